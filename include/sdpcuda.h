@@ -1,0 +1,164 @@
+/* sdpcuda.h — C ABI of the B200-native SDP relaxation solver (libsdpcuda.so).
+ *
+ * This is the drop-in boundary: plain C, plain pointers and sizes, no CUDA/torch types.  It is what the
+ * SCIP-SDP side binding `sdpisolver_cuda.c` (our fifth implementation of src/sdpi/sdpisolver.h next to
+ * sdpisolver_{dsdp.c,sdpa.cpp,mosek.c,none.c}) calls where the reference bindings call the vendor APIs:
+ *   DSDPCreate/DSDPSetup/DSDPSolve/DSDPComputeX      sdpisolver_dsdp.c:991-1004,1489-1518
+ *   SDPA::inputElement/initializeSolve/solve          sdpisolver_sdpa.cpp:981,1132-1412,1600-1670
+ *   SDPA::getResultXVec/YMat/XMat, getPhaseValue      sdpisolver_sdpa.cpp:1906-3125
+ * and what `lapack_cuda.c` calls where src/sdpi/lapack_interface.c calls DSYEVR (lapack_interface.c:178-603).
+ *
+ * Problem form handed over (SCIP-SDP's "dual", sdpisolver.h:34-43, after the binding has removed fixed variables,
+ * empty rows/cols/blocks, split LP rows into one-sided rows and turned variable bounds into LP rows exactly like
+ * sdpisolver_sdpa.cpp:1015-1412):
+ *
+ *      min  obj' y
+ *      s.t. S^(k) = sum_j y_j A_j^(k) - C^(k)  >= 0 (psd)      k = 0..nblocks-1
+ *           s     = D y - d                    >= 0            (nlp one-sided rows, CSR)
+ *
+ * with multipliers  X^(k) >= 0 (psd), x >= 0 :  sum_k A_j^(k).X^(k) + (D'x)_j = obj_j ,  max  sum_k C^(k).X^(k) + d'x.
+ * All matrices are given by their lower triangle (row >= col), 0-based, doubles; indices are 32-bit ints.
+ */
+#ifndef SDPCUDA_H
+#define SDPCUDA_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SDPCUDA_ABI_VERSION 1
+
+/* return codes of every entry point */
+#define SDPCUDA_OK            0
+#define SDPCUDA_ERR_ARG       1   /* invalid argument / inconsistent problem */
+#define SDPCUDA_ERR_NOMEM     2   /* host or device allocation failed */
+#define SDPCUDA_ERR_CUDA      3   /* CUDA runtime error (no device, launch failure); never a silent CPU fallback */
+#define SDPCUDA_ERR_STATE     4   /* result requested before a solve */
+
+/* Solver phase after a solve, in SCIP-SDP naming (p = X-problem, d = y-problem), mirroring SDPA::PhaseType as it is
+ * interpreted by sdpisolver_sdpa.cpp:1906-2317. */
+typedef enum sdpcuda_phase
+{
+   SDPCUDA_NOINFO     = 0,  /* iteration/time limit or numerical trouble, neither side feasible */
+   SDPCUDA_PFEAS      = 1,  /* X-side feasible only, not converged */
+   SDPCUDA_DFEAS      = 2,  /* y-side feasible only, not converged */
+   SDPCUDA_PDFEAS     = 3,  /* both feasible, gap not closed */
+   SDPCUDA_PDINF      = 4,  /* both sides look infeasible */
+   SDPCUDA_PFEAS_DINF = 5,  /* y-problem infeasible (certificate: X-ray) -> IsDualInfeasible / IsPrimalUnbounded */
+   SDPCUDA_PINF_DFEAS = 6,  /* y-problem unbounded (certificate: y-ray) -> IsDualUnbounded / IsPrimalInfeasible */
+   SDPCUDA_PDOPT      = 7,  /* converged to tolerances */
+   SDPCUDA_PUNBD      = 8,  /* stopped: objective limit exceeded (IsObjlimExc) */
+   SDPCUDA_DUNBD      = 9   /* stopped: y-objective fell below the lower cut */
+} sdpcuda_phase;
+
+/* why the iteration stopped (GetInternalStatus, sdpisolver.h:439-450) */
+typedef enum sdpcuda_stop
+{
+   SDPCUDA_STOP_CONVERGED = 0,
+   SDPCUDA_STOP_INFEASCERT= 1,
+   SDPCUDA_STOP_NUMERICS  = 2,
+   SDPCUDA_STOP_OBJLIMIT  = 3,
+   SDPCUDA_STOP_ITERLIMIT = 4,
+   SDPCUDA_STOP_TIMELIMIT = 5
+} sdpcuda_stop;
+
+typedef struct sdpcuda_problem
+{
+   int            m;           /* number of (active) variables y */
+   const double*  obj;         /* [m] */
+   int            nblocks;     /* SDP blocks */
+   const int*     blocksizes;  /* [nblocks] */
+   /* entries of the A_j^(k): variable j owns [varbeg[j], varbeg[j+1]) */
+   const int*     varbeg;      /* [m+1] */
+   const int*     entblk;      /* [nnz] */
+   const int*     entrow;      /* [nnz] row >= col */
+   const int*     entcol;      /* [nnz] */
+   const double*  entval;      /* [nnz] */
+   /* constant matrices C^(k) (the reference's A_0 after fixings) */
+   int            cnnz;
+   const int*     cblk;
+   const int*     crow;
+   const int*     ccol;
+   const double*  cval;
+   /* LP block: row l is  sum_{p in [lpbeg[l],lpbeg[l+1])} lpval[p]*y[lpind[p]] - lprhs[l] >= 0 */
+   int            nlp;
+   const int*     lpbeg;       /* [nlp+1] */
+   const int*     lpind;
+   const double*  lpval;
+   const double*  lprhs;       /* [nlp] */
+} sdpcuda_problem;
+
+typedef struct sdpcuda_params
+{
+   double gaptol;        /* relative duality-gap tolerance (SCIP_SDPPAR_GAPTOL, handed on like setParameterEpsilonStar) */
+   double feastol;       /* primal/dual feasibility tolerance (SCIP_SDPPAR_SDPSOLVERFEASTOL, setParameterEpsilonDash) */
+   double objlimit;      /* stop when the lower bound (X-objective) exceeds this; >= 1e20 = off (SCIP_SDPPAR_OBJLIMIT) */
+   double lambdastar;    /* scale of the initial point X = S = lambdastar*I; <= 0: computed from the data */
+   double timelimit;     /* seconds; <= 0 or >= 1e20 = none */
+   double absgaptol;     /* additionally require |pobj - dobj| <= absgaptol (the binding's post-check, sdpisolver_sdpa.cpp:449-451); <= 0 = off */
+   int    maxiter;       /* <= 0: default (100) */
+   int    setting;       /* 1 fast, 2 medium, 3 stable step-length/centering rules (SCIP_SDPSOLVERSETTING) */
+   int    verbose;       /* iteration log to stdout (SCIP_SDPPAR_SDPINFO) */
+   int    reserved;
+} sdpcuda_params;
+
+typedef struct sdpcuda_result
+{
+   int    phase;         /* sdpcuda_phase */
+   int    stop;          /* sdpcuda_stop */
+   int    iterations;
+   int    launches;      /* CUDA kernel launches issued by this solve (0 for the CPU oracle) */
+   double pobj;          /* X-side objective  sum C.X + d'x   (lower bound for the min problem) */
+   double dobj;          /* y-side objective  obj'y */
+   double relgap;
+   double pinf;          /* scaled primal residual  ||obj - A(X) - D'x|| / (1+||obj||) */
+   double dinf;          /* scaled dual residual */
+   double mu;
+   double seconds;       /* wall time of the solve including host<->device transfers */
+   double device_ms;     /* device time between the first and last kernel of the solve (CUDA events) */
+} sdpcuda_result;
+
+typedef struct sdpcuda_handle sdpcuda_handle;
+
+/* ---- life cycle (SCIPsdpiSolverCreate/Free, sdpisolver.h:126-137) ---- */
+int  sdpcuda_abi_version(void);
+const char* sdpcuda_backend_name(void);           /* "cuda-sm_100a" for the product library */
+int  sdpcuda_create(sdpcuda_handle** h, int device /* -1: round-robin over visible devices, one stream per handle */);
+int  sdpcuda_destroy(sdpcuda_handle* h);
+void sdpcuda_default_params(sdpcuda_params* p);
+
+/* ---- solve (SCIPsdpiSolverLoadAndSolveWithPenalty, sdpisolver.h:258-322) ----
+ * Copies the problem to the device, runs the primal-dual predictor-corrector iteration there and keeps the
+ * solution device-resident until the getters below fetch it.  start_y may be NULL. Blocking. */
+int  sdpcuda_solve(sdpcuda_handle* h, const sdpcuda_problem* prob, const sdpcuda_params* par,
+                   const double* start_y, sdpcuda_result* res);
+
+/* ---- solution access (GetDualSol/GetPrimal*, sdpisolver.h:484-578) ---- */
+int  sdpcuda_get_y(sdpcuda_handle* h, double* y /* [m] */);
+int  sdpcuda_get_X(sdpcuda_handle* h, int block, double* X /* [n*n] full symmetric, row-major */);
+int  sdpcuda_get_S(sdpcuda_handle* h, int block, double* S /* [n*n] */);
+int  sdpcuda_get_xlp(sdpcuda_handle* h, double* x /* [nlp] multipliers */);
+int  sdpcuda_get_slp(sdpcuda_handle* h, double* s /* [nlp] slacks */);
+
+/* ---- symmetric eigen-decomposition, batched (replaces DSYEVR behind SCIPlapackCompute*, lapack_interface.c:178-603) ----
+ * A: nbatch matrices n*n (symmetric, full storage), host memory, NOT destroyed.  w: [nbatch*n] ascending.
+ * V: NULL or [nbatch*n*n], eigenvector k of matrix b at V[b*n*n + k*n .. +n) (i.e. "as rows", lapack_interface.c:507-603). */
+int  sdpcuda_syev_batched(sdpcuda_handle* h, int n, int nbatch, const double* A, double* w, double* V);
+
+/* ---- kernel-level entry points (parity tests and roofline measurement; host buffers, column-major like BLAS) ---- */
+/* C(m x n) = alpha*op(A)*op(B) + beta*C ; transa/transb: 0 = N, 1 = T */
+int  sdpcuda_dgemm(sdpcuda_handle* h, int transa, int transb, int m, int n, int k, double alpha,
+                   const double* A, int lda, const double* B, int ldb, double beta, double* C, int ldc);
+/* lower Cholesky A = L L' in place (strict upper part left untouched); info = 0 or index (1-based) of the failing pivot */
+int  sdpcuda_dpotrf(sdpcuda_handle* h, int n, double* A, int lda, int* info);
+/* inverse of the lower-triangular factor, in place */
+int  sdpcuda_dtrtri(sdpcuda_handle* h, int n, double* L, int ldl);
+/* device-resident timing of the same kernels: runs `reps` launches on random n x n operands already in HBM and
+ * returns the mean device time per launch in ms (CUDA events on the handle's stream). kind: 0 dgemm NN, 1 dgemm NT,
+ * 2 dpotrf, 3 dtrtri, 4 DMMA register-resident peak probe (n ignored), 5 syrk-lower NT, 6 device copy (HBM probe) */
+int  sdpcuda_time_kernel(sdpcuda_handle* h, int kind, int n, int reps, double* ms_per_launch, double* flops_or_bytes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

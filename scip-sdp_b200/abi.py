@@ -1,0 +1,247 @@
+"""ctypes view of the C ABI in include/sdpcuda.h (test/bench harness side; the product host code is C:
+scip-sdp_b200/sdpi/sdpisolver_cuda.c).  The same wrapper can load the product library (lib/libsdpcuda.so) or —
+from tests and bench.py's cpu_baseline only — the CPU oracle (oracle/liboracle_sdp.so)."""
+import ctypes as C
+import os
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PRODUCT_LIB = os.path.join(ROOT, "scip-sdp_b200", "lib", "libsdpcuda.so")
+ORACLE_LIB = os.path.join(ROOT, "oracle", "liboracle_sdp.so")
+
+PHASES = ["noINFO", "pFEAS", "dFEAS", "pdFEAS", "pdINF", "pFEAS_dINF", "pINF_dFEAS", "pdOPT", "pUNBD", "dUNBD"]
+STOPS = ["converged", "infeascert", "numerics", "objlimit", "iterlimit", "timelimit"]
+
+_dp = C.POINTER(C.c_double)
+_ip = C.POINTER(C.c_int)
+
+
+class Problem(C.Structure):
+    _fields_ = [("m", C.c_int), ("obj", _dp), ("nblocks", C.c_int), ("blocksizes", _ip), ("varbeg", _ip),
+                ("entblk", _ip), ("entrow", _ip), ("entcol", _ip), ("entval", _dp),
+                ("cnnz", C.c_int), ("cblk", _ip), ("crow", _ip), ("ccol", _ip), ("cval", _dp),
+                ("nlp", C.c_int), ("lpbeg", _ip), ("lpind", _ip), ("lpval", _dp), ("lprhs", _dp)]
+
+
+class Params(C.Structure):
+    _fields_ = [("gaptol", C.c_double), ("feastol", C.c_double), ("objlimit", C.c_double), ("lambdastar", C.c_double),
+                ("timelimit", C.c_double), ("absgaptol", C.c_double), ("maxiter", C.c_int), ("setting", C.c_int),
+                ("verbose", C.c_int), ("reserved", C.c_int)]
+
+
+class Result(C.Structure):
+    _fields_ = [("phase", C.c_int), ("stop", C.c_int), ("iterations", C.c_int), ("launches", C.c_int),
+                ("pobj", C.c_double), ("dobj", C.c_double), ("relgap", C.c_double), ("pinf", C.c_double),
+                ("dinf", C.c_double), ("mu", C.c_double), ("seconds", C.c_double), ("device_ms", C.c_double)]
+
+
+def _i(a):
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
+def _d(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+class FlatProblem:
+    """Solver-form problem (see include/sdpcuda.h): numpy arrays kept alive next to the ctypes struct."""
+
+    def __init__(self, obj, blocksizes, varbeg, entblk, entrow, entcol, entval, cblk, crow, ccol, cval, lpbeg, lpind,
+                 lpval, lprhs):
+        self.obj, self.blocksizes, self.varbeg = _d(obj), _i(blocksizes), _i(varbeg)
+        self.entblk, self.entrow, self.entcol, self.entval = _i(entblk), _i(entrow), _i(entcol), _d(entval)
+        self.cblk, self.crow, self.ccol, self.cval = _i(cblk), _i(crow), _i(ccol), _d(cval)
+        self.lpbeg, self.lpind, self.lpval, self.lprhs = _i(lpbeg), _i(lpind), _d(lpval), _d(lprhs)
+        self.m, self.nblocks, self.nlp = len(self.obj), len(self.blocksizes), len(self.lprhs)
+        assert len(self.varbeg) == self.m + 1 and len(self.lpbeg) == self.nlp + 1
+
+    def struct(self):
+        p = Problem()
+        p.m, p.nblocks, p.nlp, p.cnnz = self.m, self.nblocks, self.nlp, len(self.cval)
+        for name in ("obj", "entval", "cval", "lpval", "lprhs"):
+            setattr(p, name, getattr(self, name).ctypes.data_as(_dp))
+        for name in ("blocksizes", "varbeg", "entblk", "entrow", "entcol", "cblk", "crow", "ccol", "lpbeg", "lpind"):
+            setattr(p, name, getattr(self, name).ctypes.data_as(_ip))
+        return p
+
+    # dense helpers used by the tests for a-posteriori KKT checks
+    def dense_A(self, j):
+        mats = [np.zeros((n, n)) for n in self.blocksizes]
+        for e in range(self.varbeg[j], self.varbeg[j + 1]):
+            b, r, c, v = self.entblk[e], self.entrow[e], self.entcol[e], self.entval[e]
+            mats[b][r, c] += v
+            if r != c:
+                mats[b][c, r] += v
+        return mats
+
+    def dense_C(self):
+        mats = [np.zeros((n, n)) for n in self.blocksizes]
+        for b, r, c, v in zip(self.cblk, self.crow, self.ccol, self.cval):
+            mats[b][r, c] += v
+            if r != c:
+                mats[b][c, r] += v
+        return mats
+
+    def dense_D(self):
+        D = np.zeros((self.nlp, self.m))
+        for l in range(self.nlp):
+            for p in range(self.lpbeg[l], self.lpbeg[l + 1]):
+                D[l, self.lpind[p]] += self.lpval[p]
+        return D
+
+
+class Lib:
+    """One loaded implementation of the C ABI."""
+
+    def __init__(self, path=PRODUCT_LIB):
+        if not os.path.exists(path):
+            raise FileNotFoundError(f"{path} not built: run `python -c 'import __graft_entry__ as g; g.build()'`")
+        self.path = path
+        self.lib = L = C.CDLL(path, mode=C.RTLD_GLOBAL)
+        L.sdpcuda_backend_name.restype = C.c_char_p
+        L.sdpcuda_create.argtypes = [C.POINTER(C.c_void_p), C.c_int]
+        L.sdpcuda_destroy.argtypes = [C.c_void_p]
+        L.sdpcuda_default_params.argtypes = [C.POINTER(Params)]
+        L.sdpcuda_default_params.restype = None
+        L.sdpcuda_solve.argtypes = [C.c_void_p, C.POINTER(Problem), C.POINTER(Params), _dp, C.POINTER(Result)]
+        for f in ("sdpcuda_get_y", "sdpcuda_get_xlp", "sdpcuda_get_slp"):
+            getattr(L, f).argtypes = [C.c_void_p, _dp]
+        for f in ("sdpcuda_get_X", "sdpcuda_get_S"):
+            getattr(L, f).argtypes = [C.c_void_p, C.c_int, _dp]
+        L.sdpcuda_syev_batched.argtypes = [C.c_void_p, C.c_int, C.c_int, _dp, _dp, _dp]
+        L.sdpcuda_dgemm.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, _dp, C.c_int,
+                                    _dp, C.c_int, C.c_double, _dp, C.c_int]
+        L.sdpcuda_dpotrf.argtypes = [C.c_void_p, C.c_int, _dp, C.c_int, _ip]
+        L.sdpcuda_dtrtri.argtypes = [C.c_void_p, C.c_int, _dp, C.c_int]
+        L.sdpcuda_time_kernel.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, _dp, _dp]
+
+    def backend(self):
+        return self.lib.sdpcuda_backend_name().decode()
+
+    def default_params(self, **kw):
+        p = Params()
+        self.lib.sdpcuda_default_params(C.byref(p))
+        for k, v in kw.items():
+            setattr(p, k, v)
+        return p
+
+
+class Solver:
+    def __init__(self, lib, device=-1):
+        self.L = lib
+        self.h = C.c_void_p()
+        rc = lib.lib.sdpcuda_create(C.byref(self.h), device)
+        if rc != 0:
+            raise RuntimeError(f"sdpcuda_create failed with code {rc} ({lib.path})")
+        self.prob = None
+
+    def close(self):
+        if self.h:
+            self.L.lib.sdpcuda_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def solve(self, prob, params=None, start_y=None, fetch=True, **kw):
+        params = params if params is not None else self.L.default_params(**kw)
+        self.prob = prob
+        st = prob.struct()
+        res = Result()
+        sy = _d(start_y).ctypes.data_as(_dp) if start_y is not None else None
+        rc = self.L.lib.sdpcuda_solve(self.h, C.byref(st), C.byref(params), sy, C.byref(res))
+        if rc != 0:
+            raise RuntimeError(f"sdpcuda_solve failed with code {rc}")
+        out = {f[0]: getattr(res, f[0]) for f in Result._fields_}
+        out["phase_name"], out["stop_name"] = PHASES[res.phase], STOPS[res.stop]
+        if fetch:
+            out["y"] = self.get_y()
+            out["X"] = [self.get_X(b) for b in range(prob.nblocks)]
+            out["S"] = [self.get_S(b) for b in range(prob.nblocks)]
+            out["xlp"], out["slp"] = self.get_xlp(), self.get_slp()
+        return out
+
+    def _vec(self, fn, n):
+        a = np.zeros(max(n, 1))
+        rc = fn(self.h, a.ctypes.data_as(_dp))
+        if rc != 0:
+            raise RuntimeError(f"getter failed with code {rc}")
+        return a[:n]
+
+    def get_y(self):
+        return self._vec(self.L.lib.sdpcuda_get_y, self.prob.m)
+
+    def get_xlp(self):
+        return self._vec(self.L.lib.sdpcuda_get_xlp, self.prob.nlp)
+
+    def get_slp(self):
+        return self._vec(self.L.lib.sdpcuda_get_slp, self.prob.nlp)
+
+    def _mat(self, fn, b):
+        n = int(self.prob.blocksizes[b])
+        a = np.zeros((n, n))
+        rc = fn(self.h, b, a.ctypes.data_as(_dp))
+        if rc != 0:
+            raise RuntimeError(f"getter failed with code {rc}")
+        return a
+
+    def get_X(self, b):
+        return self._mat(self.L.lib.sdpcuda_get_X, b)
+
+    def get_S(self, b):
+        return self._mat(self.L.lib.sdpcuda_get_S, b)
+
+    # ---- kernel-level entry points ----
+    def syev(self, A, vectors=True):
+        A = _d(A)
+        single = A.ndim == 2
+        A3 = A[None] if single else A
+        nb, n = A3.shape[0], A3.shape[1]
+        w = np.zeros((nb, n))
+        V = np.zeros((nb, n, n)) if vectors else None
+        rc = self.L.lib.sdpcuda_syev_batched(self.h, n, nb, A3.ctypes.data_as(_dp), w.ctypes.data_as(_dp),
+                                             V.ctypes.data_as(_dp) if vectors else None)
+        if rc != 0:
+            raise RuntimeError(f"sdpcuda_syev_batched failed with code {rc}")
+        if single:
+            return w[0], (V[0] if vectors else None)
+        return w, V
+
+    def dgemm(self, A, B, transa=False, transb=False, alpha=1.0, beta=0.0, Cin=None):
+        """column-major semantics; A, B given as numpy (row-major) arrays are passed as their Fortran copies"""
+        Af, Bf = np.asfortranarray(A, dtype=np.float64), np.asfortranarray(B, dtype=np.float64)
+        m = Af.shape[1] if transa else Af.shape[0]
+        k = Af.shape[0] if transa else Af.shape[1]
+        n = Bf.shape[0] if transb else Bf.shape[1]
+        Cf = np.asfortranarray(np.zeros((m, n)) if Cin is None else Cin, dtype=np.float64).copy(order="F")
+        rc = self.L.lib.sdpcuda_dgemm(self.h, int(transa), int(transb), m, n, k, alpha, Af.ctypes.data_as(_dp),
+                                      Af.shape[0], Bf.ctypes.data_as(_dp), Bf.shape[0], beta, Cf.ctypes.data_as(_dp), m)
+        if rc != 0:
+            raise RuntimeError(f"sdpcuda_dgemm failed with code {rc}")
+        return Cf
+
+    def dpotrf(self, A):
+        Af = np.asfortranarray(A, dtype=np.float64).copy(order="F")
+        info = C.c_int(0)
+        rc = self.L.lib.sdpcuda_dpotrf(self.h, Af.shape[0], Af.ctypes.data_as(_dp), Af.shape[0], C.byref(info))
+        if rc != 0:
+            raise RuntimeError(f"sdpcuda_dpotrf failed with code {rc}")
+        return np.tril(Af), info.value
+
+    def dtrtri(self, Lm):
+        Lf = np.asfortranarray(Lm, dtype=np.float64).copy(order="F")
+        rc = self.L.lib.sdpcuda_dtrtri(self.h, Lf.shape[0], Lf.ctypes.data_as(_dp), Lf.shape[0])
+        if rc != 0:
+            raise RuntimeError(f"sdpcuda_dtrtri failed with code {rc}")
+        return np.tril(Lf)
+
+    def time_kernel(self, kind, n, reps=10):
+        ms, work = C.c_double(0), C.c_double(0)
+        rc = self.L.lib.sdpcuda_time_kernel(self.h, kind, n, reps, C.byref(ms), C.byref(work))
+        if rc != 0:
+            raise RuntimeError(f"sdpcuda_time_kernel failed with code {rc}")
+        return ms.value, work.value
