@@ -48,7 +48,9 @@ typedef enum sdpcuda_phase
    SDPCUDA_PINF_DFEAS = 6,  /* y-problem unbounded (certificate: y-ray) -> IsDualUnbounded / IsPrimalInfeasible */
    SDPCUDA_PDOPT      = 7,  /* converged to tolerances */
    SDPCUDA_PUNBD      = 8,  /* stopped: objective limit exceeded (IsObjlimExc) */
-   SDPCUDA_DUNBD      = 9   /* stopped: y-objective fell below the lower cut */
+   SDPCUDA_DUNBD      = 9,  /* stopped: y-objective fell below the lower cut */
+   SDPCUDA_DINF       = 10  /* y-problem infeasible by an X-ray, but the X-side itself is not (yet) feasible: IsDualInfeasible
+                             * holds, primal feasibility is not claimed (both-infeasible case of checksdpi.c:656) */
 } sdpcuda_phase;
 
 /* why the iteration stopped (GetInternalStatus, sdpisolver.h:439-450) */

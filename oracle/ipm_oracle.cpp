@@ -352,6 +352,7 @@ int Solver::solve(const sdpcuda_params& par, const double* starty)
    res.phase = SDPCUDA_NOINFO; res.stop = SDPCUDA_STOP_ITERLIMIT;
    double mu = 0, pobj = 0, dobj = 0, relgap = 1e30, pinf = 1e30, dinf = 1e30, dinfabs = 1e30, pinfabs = 1e30;
    double bestmerit = 1e300; int stall = 0;
+   bool pfeasever = false, dfeasever = false;
    int iter = 0;
    for( ; ; ++iter )
    {
@@ -398,6 +399,8 @@ int Solver::solve(const sdpcuda_params& par, const double* starty)
       if( par.verbose )
          printf("  [oracle] it %3d  pobj % .10e  dobj % .10e  gap %.2e  pinf %.2e  dinf %.2e  mu %.2e\n", iter, pobj, dobj, relgap, pinf, dinf, mu);
 
+      pfeasever = pfeasever || pfeas;   /* a feasible point seen once stays a proof of feasibility when a ray shows up later */
+      dfeasever = dfeasever || dfeas;
       int ph = pfeas ? (dfeas ? SDPCUDA_PDFEAS : SDPCUDA_PFEAS) : (dfeas ? SDPCUDA_DFEAS : SDPCUDA_NOINFO);
       res.phase = ph;
       if( pfeas && dfeas && relgap <= gaptol && (par.absgaptol <= 0 || std::fabs(pobj - dobj) <= par.absgaptol) )
@@ -406,10 +409,10 @@ int Solver::solve(const sdpcuda_params& par, const double* starty)
       if( pobj > 0 )
       {
          double na = 0; for( int j = 0; j < m; ++j ) { double h = P.obj[j] - rp[j]; na += h * h; }
-         if( std::sqrt(na) / pobj < inftol ) { res.phase = SDPCUDA_PFEAS_DINF; res.stop = SDPCUDA_STOP_INFEASCERT; break; }
+         if( std::sqrt(na) / pobj < inftol ) { res.phase = pfeasever ? SDPCUDA_PFEAS_DINF : SDPCUDA_DINF; res.stop = SDPCUDA_STOP_INFEASCERT; break; }
       }
       /* y-problem unbounded: A'y - S -> 0, Dy - s -> 0 relative to -obj'y > 0 */
-      if( dobj < 0 && std::sqrt(rayd) / (-dobj) < inftol )
+      if( dfeasever && dobj < 0 && std::sqrt(rayd) / (-dobj) < inftol )
       { res.phase = SDPCUDA_PINF_DFEAS; res.stop = SDPCUDA_STOP_INFEASCERT; break; }
       if( pfeas && par.objlimit < 1e20 && pobj > par.objlimit )
       { res.phase = SDPCUDA_PUNBD; res.stop = SDPCUDA_STOP_OBJLIMIT; break; }

@@ -10,7 +10,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 PRODUCT_LIB = os.path.join(ROOT, "scip-sdp_b200", "lib", "libsdpcuda.so")
 ORACLE_LIB = os.path.join(ROOT, "oracle", "liboracle_sdp.so")
 
-PHASES = ["noINFO", "pFEAS", "dFEAS", "pdFEAS", "pdINF", "pFEAS_dINF", "pINF_dFEAS", "pdOPT", "pUNBD", "dUNBD"]
+PHASES = ["noINFO", "pFEAS", "dFEAS", "pdFEAS", "pdINF", "pFEAS_dINF", "pINF_dFEAS", "pdOPT", "pUNBD", "dUNBD", "dINF"]
 STOPS = ["converged", "infeascert", "numerics", "objlimit", "iterlimit", "timelimit"]
 
 _dp = C.POINTER(C.c_double)

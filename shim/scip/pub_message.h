@@ -2,6 +2,7 @@
 #ifndef SHIM_SCIP_PUB_MESSAGE_H
 #define SHIM_SCIP_PUB_MESSAGE_H
 #include <stdio.h>
+#include <stdlib.h>
 #include "scip/type_message.h"
 #define SCIPerrorMessage(...) do { fprintf(stderr, "[%s:%d] ERROR: ", __FILE__, __LINE__); fprintf(stderr, __VA_ARGS__); } while( 0 )
 #ifdef SCIP_DEBUG

@@ -2,6 +2,7 @@
 #ifndef SHIM_SCIP_PUB_MISC_H
 #define SHIM_SCIP_PUB_MISC_H
 #include "scip/def.h"
+#include "blockmemshell/memory.h"
 static inline void SCIPsortIntReal(int* key, SCIP_Real* f1, int len)
 {
    int i, j;
