@@ -147,6 +147,10 @@ int  sdpcuda_get_slp(sdpcuda_handle* h, double* s /* [nlp] slacks */);
  * V: NULL or [nbatch*n*n], eigenvector k of matrix b at V[b*n*n + k*n .. +n) (i.e. "as rows", lapack_interface.c:507-603). */
 int  sdpcuda_syev_batched(sdpcuda_handle* h, int n, int nbatch, const double* A, double* w, double* V);
 
+/* is A + shift*I positive definite?  (A symmetric n x n, host memory, not modified.)  Device Cholesky; used by the GPU
+ * version of SCIPsdpSolcheckerCheck (sdpsolchecker.c:58-270: lambda_min(Z(y)) >= -feastol  <=>  Z(y) + feastol*I psd). */
+int  sdpcuda_psd_check(sdpcuda_handle* h, int n, const double* A, int lda, double shift, int* is_psd);
+
 /* ---- kernel-level entry points (parity tests and roofline measurement; host buffers, column-major like BLAS) ---- */
 /* C(m x n) = alpha*op(A)*op(B) + beta*C ; transa/transb: 0 = N, 1 = T */
 int  sdpcuda_dgemm(sdpcuda_handle* h, int transa, int transb, int m, int n, int k, double alpha,

@@ -680,6 +680,18 @@ int sdpcuda_syev_batched(sdpcuda_handle* h, int n, int nbatch, const double* A, 
    return SDPCUDA_OK;
 }
 
+int sdpcuda_psd_check(sdpcuda_handle* h, int n, const double* A, int lda, double shift, int* is_psd)
+{
+   (void)h;
+   vec a((size_t)n * n);
+   for( int c = 0; c < n; ++c )
+      for( int r = 0; r < n; ++r ) a[(size_t)c * n + r] = A[(size_t)c * lda + r] + (r == c ? shift : 0.0);
+   int info = 0;
+   if( n > 0 ) scipy_dpotrf_("L", &n, a.data(), &n, &info);
+   *is_psd = (info == 0);
+   return SDPCUDA_OK;
+}
+
 int sdpcuda_dgemm(sdpcuda_handle* h, int ta, int tb, int m, int n, int k, double alpha, const double* A, int lda,
    const double* B, int ldb, double beta, double* C, int ldc)
 {

@@ -114,6 +114,7 @@ class Lib:
                                     _dp, C.c_int, C.c_double, _dp, C.c_int]
         L.sdpcuda_dpotrf.argtypes = [C.c_void_p, C.c_int, _dp, C.c_int, _ip]
         L.sdpcuda_dtrtri.argtypes = [C.c_void_p, C.c_int, _dp, C.c_int]
+        L.sdpcuda_psd_check.argtypes = [C.c_void_p, C.c_int, _dp, C.c_int, C.c_double, _ip]
         L.sdpcuda_time_kernel.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, _dp, _dp]
 
     def backend(self):
@@ -238,6 +239,14 @@ class Solver:
         if rc != 0:
             raise RuntimeError(f"sdpcuda_dtrtri failed with code {rc}")
         return np.tril(Lf)
+
+    def psd_check(self, A, shift=0.0):
+        Af = np.asfortranarray(A, dtype=np.float64)
+        ok = C.c_int(0)
+        rc = self.L.lib.sdpcuda_psd_check(self.h, Af.shape[0], Af.ctypes.data_as(_dp), Af.shape[0], shift, C.byref(ok))
+        if rc != 0:
+            raise RuntimeError(f"sdpcuda_psd_check failed with code {rc}")
+        return bool(ok.value)
 
     def time_kernel(self, kind, n, reps=10):
         ms, work = C.c_double(0), C.c_double(0)

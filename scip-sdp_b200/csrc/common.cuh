@@ -1,0 +1,52 @@
+// common.cuh — shared declarations of the libsdpcuda device library (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdio>
+#include <cstdlib>
+#include <cstdint>
+
+namespace sdpk {
+
+// every launch goes through this counter so that sdpcuda_result.launches / bench.py's gpu_launches are real counts
+struct LaunchCounter { long long n = 0; };
+extern thread_local LaunchCounter* g_counter;
+inline void count_launch(int k = 1) { if( g_counter ) g_counter->n += k; }
+
+#define SDPK_CUDA_CHECK(expr) do { cudaError_t _e = (expr); if( _e != cudaSuccess ) { \
+      fprintf(stderr, "[libsdpcuda] %s:%d CUDA error %s: %s\n", __FILE__, __LINE__, cudaGetErrorName(_e), cudaGetErrorString(_e)); \
+      return _e; } } while( 0 )
+
+inline int round_up(int x, int a) { return (x + a - 1) / a * a; }
+inline int ceil_div(int x, int a) { return (x + a - 1) / a; }
+
+// ---- gemm.cu -------------------------------------------------------------------------------------------------------
+// C(m x n) = alpha * op(A) * op(B) + beta * C, column-major, FP64 DMMA tensor-core tiles fed by cp.async.
+// flags: GEMM_LOWER computes only tiles that touch the lower triangle (row >= col) of C.
+//        GEMM_KHI_M / GEMM_KHI_N restrict the k-range of a tile to k < m0+BM / k < n0+BN (op(A) lower triangular /
+//        op(B) upper triangular), GEMM_KLO_M / GEMM_KLO_N to k >= m0 / k >= n0 (op(A) upper / op(B) lower triangular).
+enum { GEMM_LOWER = 1, GEMM_KHI_M = 2, GEMM_KHI_N = 4, GEMM_KLO_M = 8, GEMM_KLO_N = 16 };
+cudaError_t gemm(cudaStream_t st, bool transa, bool transb, int m, int n, int k, double alpha,
+   const double* A, int lda, long long strideA, const double* B, int ldb, long long strideB,
+   double beta, double* C, int ldc, long long strideC, int batch, int flags);
+cudaError_t dmma_peak_probe(cudaStream_t st, int iters, double* d_sink, double* flops);
+
+// ---- chol.cu -------------------------------------------------------------------------------------------------------
+// Cholesky A = L L' (lower, in place) by recursive blocking on DMMA GEMMs; optionally the inverse of L in Linv.
+// d_info: device int, set to the 1-based index of the first non-positive pivot (0 = success; is NOT reset here).
+// diaginv: optional workspace receiving the inverses of the NB x NB diagonal blocks of L (block b at b*NB*NB).
+constexpr int CHOL_NB = 64;
+cudaError_t potrf_lower(cudaStream_t st, int n, double* A, int lda, double* Linv, int ldi, double* diaginv, double* work, int ldw, int* d_info);
+cudaError_t trtri_lower(cudaStream_t st, int n, const double* L, int ldl, double* Linv, int ldi, double* work, int ldw);
+// solves L L' x = b for one right-hand side using the diagonal-block inverses (x overwrites b; tmp: n doubles)
+cudaError_t potrs_vec(cudaStream_t st, int n, const double* L, int ldl, const double* diaginv, double* b, double* tmp);
+
+// ---- eig.cu --------------------------------------------------------------------------------------------------------
+// batched symmetric eigen-decomposition by parallel cyclic Jacobi in shared memory (n <= JACOBI_MAX_N)
+constexpr int JACOBI_MAX_N = 96;
+cudaError_t jacobi_eig_batched(cudaStream_t st, int n, int nbatch, const double* A, int lda, long long strideA,
+   double* w, double* V /* or nullptr */, int* d_sweeps);
+// smallest eigenvalue of symmetric B (n x n, full storage) by Lanczos; result (Ritz value minus residual bound) in d_out[0]
+cudaError_t lanczos_lambda_min(cudaStream_t st, int n, const double* B, int ldb, double* work /* >= (maxit+4)*n + 4*maxit+16 */, int maxit, double* d_out);
+size_t lanczos_work_doubles(int n, int maxit);
+
+} // namespace sdpk

@@ -1,0 +1,384 @@
+// eig.cu — symmetric eigenvalue kernels.
+//
+// (1) jacobi_eig_batched: one CTA per matrix, parallel cyclic Jacobi (round-robin "chess tournament" ordering: n/2
+//     disjoint rotations per step, applied first to the columns, then to the rows) with the matrix and the accumulated
+//     eigenvectors resident in shared memory for n <= JACOBI_MAX_N.  It serves the interior-point step-length computation
+//     (smallest eigenvalue of L^-1 dX L^-T for small blocks) and replaces the DSYEVR calls behind
+//     SCIPlapackComputeIthEigenvalue / ComputeEigenvectorsNegative / ComputeEigenvectorDecomposition
+//     (lapack_interface.c:178-603): eigenvalues ascending, eigenvector k stored as row k of the output.
+//     Larger matrices run the same code on a global-memory scratch (correct, not fast; the cut-separation matrices of the
+//     reference's instances have n = 10..43).
+// (2) lanczos_lambda_min: smallest eigenvalue of a large symmetric matrix by Lanczos with full re-orthogonalisation,
+//     returning Ritz value minus residual bound, i.e. a safe value for the step length -1/lambda_min.
+#include "common.cuh"
+#include <algorithm>
+
+namespace sdpk {
+namespace {
+
+__device__ __forceinline__ double block_sum(double v, double* red)
+{
+   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+#pragma unroll
+   for( int o = 16; o > 0; o >>= 1 ) v += __shfl_xor_sync(0xffffffffu, v, o);
+   __syncthreads();
+   if( lane == 0 ) red[warp] = v;
+   __syncthreads();
+   double s = 0.0;
+   for( int w = 0; w < nw; ++w ) s += red[w];      // fixed order: deterministic
+   return s;
+}
+
+// A: n x n symmetric (full), ld = lds;  V: eigenvector accumulator or nullptr
+__global__ void __launch_bounds__(256)
+jacobi_kernel(int n, const double* __restrict__ Ain, int lda, long long strideA, double* __restrict__ wout,
+   double* __restrict__ Vout, double* __restrict__ gscratch, int use_smem, int* __restrict__ sweeps_out)
+{
+   extern __shared__ __align__(16) double jsm[];
+   const int np = (n + 1) / 2;               // rotation pairs per step
+   const int lds = n | 1;                    // odd leading dimension: conflict-free column and row walks
+   const int tid = threadIdx.x, nt = blockDim.x;
+   const int b = blockIdx.x;
+   const bool wantV = (Vout != nullptr);
+
+   double* A; double* V;
+   double* aux = jsm;                        // [0,32) reduction scratch, then c[np], s[np], then int pairs
+   double* cs = aux + 32;
+   int* top = reinterpret_cast<int*>(cs + 2 * np);
+   int* bot = top + np;
+   if( use_smem )
+   {
+      A = reinterpret_cast<double*>(bot + np + (np & 1) * 1) ;
+      A = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(A) + 15) & ~uintptr_t(15));
+      V = A + (size_t)n * lds;
+   }
+   else
+   {
+      A = gscratch + (size_t)b * 2 * n * lds;
+      V = A + (size_t)n * lds;
+   }
+   const double* Ab = Ain + (size_t)b * strideA;
+
+   double fro = 0.0;
+   for( int e = tid; e < n * n; e += nt )
+   {
+      int i = e % n, j = e / n;
+      double v = 0.5 * (Ab[(size_t)j * lda + i] + Ab[(size_t)i * lda + j]);
+      A[i * lds + j] = v;
+      fro += v * v;
+      if( wantV ) V[i * lds + j] = (i == j) ? 1.0 : 0.0;
+   }
+   for( int k = tid; k < np; k += nt ) { top[k] = 2 * k; bot[k] = 2 * k + 1; }     // index n (if n odd) is a dummy
+   fro = block_sum(fro, aux);
+   const double tol2 = fro * 1e-30 + 1e-300;
+
+   int sweep = 0;
+   for( ; sweep < 40; ++sweep )
+   {
+      double off = 0.0;
+      for( int e = tid; e < n * n; e += nt )
+      {
+         int i = e % n, j = e / n;
+         if( i != j ) off += A[i * lds + j] * A[i * lds + j];
+      }
+      off = block_sum(off, aux);
+      if( off <= tol2 ) break;
+
+      for( int step = 0; step < 2 * np - 1; ++step )
+      {
+         // rotation parameters
+         for( int k = tid; k < np; k += nt )
+         {
+            int p = min(top[k], bot[k]), q = max(top[k], bot[k]);
+            double c = 1.0, s = 0.0;
+            if( q < n )
+            {
+               double apq = A[p * lds + q];
+               if( fabs(apq) > 1e-300 )
+               {
+                  double tau = (A[q * lds + q] - A[p * lds + p]) / (2.0 * apq);
+                  double t = (tau >= 0.0 ? 1.0 : -1.0) / (fabs(tau) + sqrt(1.0 + tau * tau));
+                  c = 1.0 / sqrt(1.0 + t * t);
+                  s = t * c;
+               }
+            }
+            cs[2 * k] = c; cs[2 * k + 1] = s;
+         }
+         __syncthreads();
+         // columns: A <- A J, V <- V J
+         for( int e = tid; e < np * n; e += nt )
+         {
+            int k = e / n, i = e % n;
+            int p = min(top[k], bot[k]), q = max(top[k], bot[k]);
+            if( q >= n ) continue;
+            double c = cs[2 * k], s = cs[2 * k + 1];
+            double aip = A[i * lds + p], aiq = A[i * lds + q];
+            A[i * lds + p] = c * aip - s * aiq;
+            A[i * lds + q] = s * aip + c * aiq;
+            if( wantV )
+            {
+               double vip = V[i * lds + p], viq = V[i * lds + q];
+               V[i * lds + p] = c * vip - s * viq;
+               V[i * lds + q] = s * vip + c * viq;
+            }
+         }
+         __syncthreads();
+         // rows: A <- J' A
+         for( int e = tid; e < np * n; e += nt )
+         {
+            int k = e / n, j = e % n;
+            int p = min(top[k], bot[k]), q = max(top[k], bot[k]);
+            if( q >= n ) continue;
+            double c = cs[2 * k], s = cs[2 * k + 1];
+            double apj = A[p * lds + j], aqj = A[q * lds + j];
+            A[p * lds + j] = c * apj - s * aqj;
+            A[q * lds + j] = s * apj + c * aqj;
+         }
+         __syncthreads();
+         // next pairing: player top[0] stays, the others move one seat
+         int nt_k = -1, nb_k = -1;
+         if( tid < np )
+         {
+            int k = tid;
+            nt_k = (k == 0) ? top[0] : ((k == 1) ? bot[0] : top[k - 1]);
+            nb_k = (k == np - 1) ? top[np - 1] : bot[k + 1];
+            if( np == 1 ) { nt_k = top[0]; nb_k = bot[0]; }
+         }
+         __syncthreads();
+         if( tid < np ) { top[tid] = nt_k; bot[tid] = nb_k; }
+         __syncthreads();
+      }
+   }
+   if( sweeps_out != nullptr && tid == 0 ) sweeps_out[b] = sweep;
+
+   // ascending order by rank counting (ties broken by index), eigenvector k written as row k
+   for( int i = tid; i < n; i += nt )
+   {
+      double d = A[i * lds + i];
+      int rank = 0;
+      for( int j = 0; j < n; ++j )
+      {
+         double dj = A[j * lds + j];
+         rank += (dj < d || (dj == d && j < i)) ? 1 : 0;
+      }
+      wout[(size_t)b * n + rank] = d;
+   }
+   if( wantV )
+   {
+      __syncthreads();
+      for( int e = tid; e < n * n; e += nt )
+      {
+         int i = e / n, r = e % n;       // eigenvector of column i, component r
+         double d = A[i * lds + i];
+         int rank = 0;
+         for( int j = 0; j < n; ++j )
+         {
+            double dj = A[j * lds + j];
+            rank += (dj < d || (dj == d && j < i)) ? 1 : 0;
+         }
+         Vout[(size_t)b * n * n + (size_t)rank * n + r] = V[r * lds + i];
+      }
+   }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Lanczos
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int LZ_KSPLIT = 8;
+
+// partial products: part[ks][i] = sum_{k in slice ks} B[i + k*ld] * v[k]
+__global__ void __launch_bounds__(256)
+symv_partial_kernel(int n, const double* __restrict__ B, int ldb, const double* __restrict__ v, double* __restrict__ part)
+{
+   int i = blockIdx.x * blockDim.x + threadIdx.x;
+   int ks = blockIdx.y;
+   int chunk = (n + LZ_KSPLIT - 1) / LZ_KSPLIT;
+   int k0 = ks * chunk, k1 = min(n, k0 + chunk);
+   if( i >= n ) return;
+   double s = 0.0;
+   for( int k = k0; k < k1; ++k ) s += B[(size_t)k * ldb + i] * v[k];
+   part[(size_t)ks * n + i] = s;
+}
+
+// one CTA: w = sum of partials; alpha = w.v_j; w -= alpha v_j + beta_{j-1} v_{j-1}; re-orthogonalise against Q; beta_j = |w|;
+// v_{j+1} = w / beta_j.  Q is stored as Q[j*n ...]; alpha/beta arrays live behind Q.
+__global__ void __launch_bounds__(1024)
+lanczos_update_kernel(int n, int j, int maxit, const double* __restrict__ part, double* __restrict__ Q, double* __restrict__ ab)
+{
+   __shared__ double red[32];
+   __shared__ double coef;
+   const int tid = threadIdx.x, nt = blockDim.x;
+   double* vj = Q + (size_t)j * n;
+   double* w = Q + (size_t)(j + 1) * n;
+   double* alpha = ab;
+   double* beta = ab + maxit;
+
+   double dot = 0.0;
+   for( int i = tid; i < n; i += nt )
+   {
+      double s = 0.0;
+#pragma unroll
+      for( int ks = 0; ks < LZ_KSPLIT; ++ks ) s += part[(size_t)ks * n + i];
+      w[i] = s;
+      dot += s * vj[i];
+   }
+   double a = block_sum(dot, red);
+   if( tid == 0 ) alpha[j] = a;
+   double bprev = (j > 0) ? beta[j - 1] : 0.0;
+   const double* vprev = (j > 0) ? Q + (size_t)(j - 1) * n : nullptr;
+   for( int i = tid; i < n; i += nt )
+      w[i] -= a * vj[i] + (j > 0 ? bprev * vprev[i] : 0.0);
+   __syncthreads();
+   // full re-orthogonalisation (classical Gram-Schmidt, applied twice overall through the two passes over q)
+   for( int pass = 0; pass < 2; ++pass )
+      for( int q = 0; q <= j; ++q )
+      {
+         const double* vq = Q + (size_t)q * n;
+         double d = 0.0;
+         for( int i = tid; i < n; i += nt ) d += w[i] * vq[i];
+         d = block_sum(d, red);
+         for( int i = tid; i < n; i += nt ) w[i] -= d * vq[i];
+         __syncthreads();
+      }
+   double nr = 0.0;
+   for( int i = tid; i < n; i += nt ) nr += w[i] * w[i];
+   nr = sqrt(block_sum(nr, red));
+   if( tid == 0 ) { beta[j] = nr; coef = (nr > 1e-300) ? 1.0 / nr : 0.0; }
+   __syncthreads();
+   double cf = coef;
+   for( int i = tid; i < n; i += nt ) w[i] *= cf;
+}
+
+__global__ void lanczos_init_kernel(int n, double* __restrict__ Q)
+{
+   __shared__ double red[32];
+   double s = 0.0;
+   for( int i = threadIdx.x; i < n; i += blockDim.x )
+   {
+      // fixed pseudo-random start vector (deterministic across runs)
+      unsigned h = (unsigned)i * 2654435761u + 12345u;
+      h ^= h >> 15; h *= 2246822519u; h ^= h >> 13;
+      double v = 0.5 + (double)(h & 0xffffu) / 65536.0;
+      Q[i] = v;
+      s += v * v;
+   }
+   s = block_sum(s, red);
+   double inv = 1.0 / sqrt(s);
+   for( int i = threadIdx.x; i < n; i += blockDim.x ) Q[i] *= inv;
+}
+
+// smallest eigenvalue of the k x k tridiagonal (alpha, beta) by bisection, residual bound from inverse iteration
+__global__ void lanczos_ritz_kernel(int k, int maxit, const double* __restrict__ ab, double* __restrict__ out)
+{
+   if( threadIdx.x != 0 || blockIdx.x != 0 ) return;
+   const double* a = ab;
+   const double* bt = ab + maxit;
+   // effective size: stop at a breakdown (beta ~ 0): the Krylov space is invariant, Ritz values are exact there
+   int kk = k;
+   double scale = 0.0;
+   for( int i = 0; i < k; ++i ) scale = fmax(scale, fabs(a[i]) + (i < k ? fabs(bt[i]) : 0.0));
+   for( int i = 0; i < k - 1; ++i ) if( fabs(bt[i]) <= 1e-14 * scale ) { kk = i + 1; break; }
+   double lo = 1e300, hi = -1e300;
+   for( int i = 0; i < kk; ++i )
+   {
+      double r = (i > 0 ? fabs(bt[i - 1]) : 0.0) + (i < kk - 1 ? fabs(bt[i]) : 0.0);
+      lo = fmin(lo, a[i] - r); hi = fmax(hi, a[i] + r);
+   }
+   // bisection for the smallest eigenvalue: count of eigenvalues < x via the Sturm sequence
+   double l = lo, h = hi;
+   for( int it = 0; it < 200 && (h - l) > 1e-15 * fmax(fabs(l), fabs(h)) + 1e-300; ++it )
+   {
+      double x = 0.5 * (l + h);
+      int cnt = 0;
+      double d = 1.0;
+      for( int i = 0; i < kk; ++i )
+      {
+         double b2 = (i > 0) ? bt[i - 1] * bt[i - 1] : 0.0;
+         d = a[i] - x - (i > 0 ? b2 / d : 0.0);
+         if( d == 0.0 ) d = 1e-300;
+         if( d < 0.0 ) ++cnt;
+      }
+      if( cnt >= 1 ) h = x; else l = x;
+   }
+   double theta = 0.5 * (l + h);
+   // last component of the normalised eigenvector of T for theta via the three-term recurrence (forward)
+   double resid = 0.0;
+   if( kk == k )
+   {
+      // s_0 = 1, s_1 = (theta - a_0)/b_0 s_0, s_{i+1} = ((theta - a_i) s_i - b_{i-1} s_{i-1}) / b_i
+      double sm1 = 0.0, s0 = 1.0, nrm = 1.0, last = 1.0;
+      for( int i = 0; i < k - 1; ++i )
+      {
+         double s1 = ((theta - a[i]) * s0 - (i > 0 ? bt[i - 1] * sm1 : 0.0)) / bt[i];
+         sm1 = s0; s0 = s1;
+         nrm += s1 * s1;
+         last = s1;
+         if( nrm > 1e200 ) { sm1 *= 1e-100; s0 *= 1e-100; last *= 1e-100; nrm *= 1e-200; }
+      }
+      resid = fabs(bt[k - 1]) * fabs(last) / sqrt(nrm);
+   }
+   out[0] = theta - resid;
+   out[1] = theta;
+   out[2] = resid;
+}
+
+} // namespace
+
+cudaError_t jacobi_eig_batched(cudaStream_t st, int n, int nbatch, const double* A, int lda, long long strideA,
+   double* w, double* V, int* d_sweeps)
+{
+   if( n <= 0 || nbatch <= 0 ) return cudaSuccess;
+   const int np = (n + 1) / 2, lds = n | 1;
+   size_t aux = (32 + 2 * np) * sizeof(double) + 2 * np * sizeof(int) + 32;
+   size_t mat = 2 * (size_t)n * lds * sizeof(double);
+   static double* gscratch = nullptr;
+   static size_t gscratch_bytes = 0;
+   int use_smem = (n <= JACOBI_MAX_N) ? 1 : 0;
+   size_t smem = aux + (use_smem ? mat : 0);
+   if( !use_smem )
+   {
+      size_t need = mat * nbatch;
+      if( need > gscratch_bytes )
+      {
+         if( gscratch ) cudaFree(gscratch);
+         SDPK_CUDA_CHECK( cudaMalloc(&gscratch, need) );
+         gscratch_bytes = need;
+      }
+   }
+   static size_t configured = 0;
+   if( smem > configured )
+   {
+      SDPK_CUDA_CHECK( cudaFuncSetAttribute(jacobi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max(smem, (size_t)200 * 1024)) );
+      configured = std::max(smem, (size_t)200 * 1024);
+   }
+   jacobi_kernel<<<nbatch, 256, smem, st>>>(n, A, lda, strideA, w, V, gscratch, use_smem, d_sweeps);
+   count_launch();
+   return cudaGetLastError();
+}
+
+size_t lanczos_work_doubles(int n, int maxit)
+{
+   return (size_t)(maxit + 2) * n + (size_t)LZ_KSPLIT * n + 2 * (size_t)maxit + 16;
+}
+
+cudaError_t lanczos_lambda_min(cudaStream_t st, int n, const double* B, int ldb, double* work, int maxit, double* d_out)
+{
+   maxit = std::min(maxit, n);
+   double* Q = work;
+   double* part = Q + (size_t)(maxit + 2) * n;
+   double* ab = part + (size_t)LZ_KSPLIT * n;
+   lanczos_init_kernel<<<1, 1024, 0, st>>>(n, Q);
+   count_launch();
+   for( int j = 0; j < maxit; ++j )
+   {
+      dim3 grid(ceil_div(n, 256), LZ_KSPLIT);
+      symv_partial_kernel<<<grid, 256, 0, st>>>(n, B, ldb, Q + (size_t)j * n, part);
+      lanczos_update_kernel<<<1, 1024, 0, st>>>(n, j, maxit, part, Q, ab);
+      count_launch(2);
+   }
+   lanczos_ritz_kernel<<<1, 32, 0, st>>>(maxit, maxit, ab, d_out);
+   count_launch();
+   return cudaGetLastError();
+}
+
+} // namespace sdpk

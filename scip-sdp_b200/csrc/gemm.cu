@@ -1,0 +1,258 @@
+// gemm.cu — FP64 tensor-core GEMM for sm_100a.
+//
+// The FP64 tensor path on Blackwell is the warp-level DMMA.8x8x4 (mma.sync.aligned.m8n8k4.f64); tcgen05/TMEM have no
+// f64 kind.  One CTA computes a BM x BN tile of C with 4 warps (2 x 2), each warp a
+// (BM/2) x (BN/2) sub-tile out of 8x8 DMMA accumulators; operands are staged through a STAGES-deep cp.async
+// (LDGSTS) ring in shared memory, padded so that the fragment loads are bank-conflict free:
+//    "MN-contiguous" operand tile  [k][mn]  leading dimension BMN+4  (used for A in NN/NT and for B in NT/TT)
+//    "K-contiguous"  operand tile  [mn][k]  leading dimension BK+4   (used for A in TN/TT and for B in NN/TN)
+// Edges are handled by zero-filling cp.async (src-size < 16), so any m, n, k works as long as leading dimensions are
+// even and base pointers 16-byte aligned.  All matrices column-major; batches via blockIdx.z and element strides.
+#include "common.cuh"
+
+namespace sdpk {
+
+thread_local LaunchCounter* g_counter = nullptr;
+
+namespace {
+
+constexpr int BK = 16;
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem, int srcbytes)
+{
+   unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" :: "r"(s), "l"(gmem), "r"(srcbytes));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" :: "n"(N)); }
+
+__device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double b)
+{
+   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+
+// loads one operand tile (BMN x BK logical) of stage buffer `s` from global memory
+// KCONTIG = false: global element (mn, k) at g[mn + k*ld]   -> smem [k][mn], lds = BMN + 4
+// KCONTIG = true : global element (mn, k) at g[k + mn*ld]   -> smem [mn][k], lds = BK + 4
+template <int BMN, bool KCONTIG, int NT>
+__device__ __forceinline__ void load_tile(double* s, const double* __restrict__ g, int ld, int mn0, int k0, int MN, int K, int tid)
+{
+   if( !KCONTIG )
+   {
+      constexpr int LDS = BMN + 4;
+      constexpr int CPR = BMN / 2;               // 16-byte chunks per k-row
+      constexpr int TOTAL = BK * CPR;
+#pragma unroll
+      for( int c = tid; c < TOTAL; c += NT )
+      {
+         int k = c / CPR, mn = (c % CPR) * 2;
+         int gk = k0 + k, gmn = mn0 + mn;
+         int bytes = 0;
+         if( gk < K && gmn < MN ) bytes = (MN - gmn >= 2) ? 16 : 8;
+         const double* src = bytes ? (g + (size_t)gk * ld + gmn) : g;
+         cp_async16(s + k * LDS + mn, src, bytes);
+      }
+   }
+   else
+   {
+      constexpr int LDS = BK + 4;
+      constexpr int CPR = BK / 2;
+      constexpr int TOTAL = BMN * CPR;
+#pragma unroll
+      for( int c = tid; c < TOTAL; c += NT )
+      {
+         int mn = c / CPR, k = (c % CPR) * 2;
+         int gk = k0 + k, gmn = mn0 + mn;
+         int bytes = 0;
+         if( gk < K && gmn < MN ) bytes = (K - gk >= 2) ? 16 : 8;
+         const double* src = bytes ? (g + (size_t)gmn * ld + gk) : g;
+         cp_async16(s + mn * LDS + k, src, bytes);
+      }
+   }
+}
+
+template <int BM, int BN, bool TA, bool TB, int STAGES>
+__global__ void __launch_bounds__(128)
+gemm_dmma_kernel(int M, int N, int K, double alpha, const double* __restrict__ A, int lda, long long strideA,
+   const double* __restrict__ B, int ldb, long long strideB, double beta, double* __restrict__ C, int ldc,
+   long long strideC, int flags)
+{
+   constexpr int NT = 128;
+   constexpr int WM = BM / 2, WN = BN / 2;          // warp tile
+   constexpr int MI = WM / 8, NI = WN / 8;
+   // A is "MN-contiguous" when not transposed; B is "MN-contiguous" when transposed
+   constexpr int A_ELEMS = TA ? BM * (BK + 4) : BK * (BM + 4);
+   constexpr int B_ELEMS = TB ? BK * (BN + 4) : BN * (BK + 4);
+   extern __shared__ __align__(16) double smem[];
+   double* As = smem;
+   double* Bs = smem + STAGES * A_ELEMS;
+
+   const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+   if( (flags & GEMM_LOWER) && (m0 + BM <= n0) )
+      return;
+   A += (size_t)blockIdx.z * strideA;
+   B += (size_t)blockIdx.z * strideB;
+   C += (size_t)blockIdx.z * strideC;
+
+   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+   const int gid = lane >> 2, tig = lane & 3;
+   const int wm = (warp & 1) * WM, wn = (warp >> 1) * WN;
+
+   double acc[MI][NI][2];
+#pragma unroll
+   for( int i = 0; i < MI; ++i )
+#pragma unroll
+      for( int j = 0; j < NI; ++j ) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
+
+   // k-range of this tile: triangular operands only contribute on part of the k axis
+   int khi = K, klo = 0;
+   if( flags & GEMM_KHI_M ) khi = min(khi, m0 + BM);
+   if( flags & GEMM_KHI_N ) khi = min(khi, n0 + BN);
+   if( flags & GEMM_KLO_M ) klo = max(klo, m0);
+   if( flags & GEMM_KLO_N ) klo = max(klo, n0);
+   const int KT0 = klo / BK;
+   const int KT = max(KT0, (khi + BK - 1) / BK);
+#pragma unroll
+   for( int s = 0; s < STAGES - 1; ++s )
+   {
+      if( KT0 + s < KT )
+      {
+         load_tile<BM, TA, NT>(As + s * A_ELEMS, A, lda, m0, (KT0 + s) * BK, M, K, tid);
+         load_tile<BN, !TB, NT>(Bs + s * B_ELEMS, B, ldb, n0, (KT0 + s) * BK, N, K, tid);
+      }
+      cp_async_commit();
+   }
+
+   for( int kt = KT0; kt < KT; ++kt )
+   {
+      cp_async_wait<STAGES - 2>();
+      __syncthreads();
+      {
+         int nk = kt + STAGES - 1;
+         if( nk < KT )
+         {
+            int s = (nk - KT0) % STAGES;
+            load_tile<BM, TA, NT>(As + s * A_ELEMS, A, lda, m0, nk * BK, M, K, tid);
+            load_tile<BN, !TB, NT>(Bs + s * B_ELEMS, B, ldb, n0, nk * BK, N, K, tid);
+         }
+         cp_async_commit();
+      }
+      const double* as = As + ((kt - KT0) % STAGES) * A_ELEMS;
+      const double* bs = Bs + ((kt - KT0) % STAGES) * B_ELEMS;
+#pragma unroll
+      for( int kk = 0; kk < BK; kk += 4 )
+      {
+         double a[MI], b[NI];
+#pragma unroll
+         for( int i = 0; i < MI; ++i )
+            a[i] = TA ? as[(wm + i * 8 + gid) * (BK + 4) + kk + tig] : as[(kk + tig) * (BM + 4) + wm + i * 8 + gid];
+#pragma unroll
+         for( int j = 0; j < NI; ++j )
+            b[j] = TB ? bs[(kk + tig) * (BN + 4) + wn + j * 8 + gid] : bs[(wn + j * 8 + gid) * (BK + 4) + kk + tig];
+#pragma unroll
+         for( int i = 0; i < MI; ++i )
+#pragma unroll
+            for( int j = 0; j < NI; ++j )
+               dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+      }
+   }
+   cp_async_wait<0>();
+
+#pragma unroll
+   for( int i = 0; i < MI; ++i )
+   {
+      int row = m0 + wm + i * 8 + gid;
+      if( row >= M ) continue;
+#pragma unroll
+      for( int j = 0; j < NI; ++j )
+      {
+#pragma unroll
+         for( int e = 0; e < 2; ++e )
+         {
+            int col = n0 + wn + j * 8 + tig * 2 + e;
+            if( col < N )
+            {
+               double* p = C + (size_t)col * ldc + row;
+               double v = alpha * acc[i][j][e];
+               if( beta != 0.0 ) v += beta * (*p);
+               *p = v;
+            }
+         }
+      }
+   }
+}
+
+template <int BM, int BN, bool TA, bool TB>
+cudaError_t launch(cudaStream_t st, int m, int n, int k, double alpha, const double* A, int lda, long long sA,
+   const double* B, int ldb, long long sB, double beta, double* C, int ldc, long long sC, int batch, int flags)
+{
+   constexpr int STAGES = 3;
+   constexpr int A_ELEMS = TA ? BM * (BK + 4) : BK * (BM + 4);
+   constexpr int B_ELEMS = TB ? BK * (BN + 4) : BN * (BK + 4);
+   constexpr size_t SMEM = (size_t)STAGES * (A_ELEMS + B_ELEMS) * sizeof(double);
+   auto kern = gemm_dmma_kernel<BM, BN, TA, TB, STAGES>;
+   static bool configured = false;
+   if( !configured )
+   {
+      SDPK_CUDA_CHECK( cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM) );
+      configured = true;
+   }
+   dim3 grid(ceil_div(m, BM), ceil_div(n, BN), batch);
+   kern<<<grid, 128, SMEM, st>>>(m, n, k, alpha, A, lda, sA, B, ldb, sB, beta, C, ldc, sC, flags);
+   count_launch();
+   return cudaGetLastError();
+}
+
+// ---- register-resident DMMA throughput probe: the measured FP64 tensor roofline denominator -------------------------
+__global__ void __launch_bounds__(256) dmma_peak_kernel(int iters, double* sink)
+{
+   double acc[16][2];
+#pragma unroll
+   for( int i = 0; i < 16; ++i ) { acc[i][0] = threadIdx.x * 1e-9; acc[i][1] = i * 1e-9; }
+   double a = 1.0 + threadIdx.x * 1e-12, b = 1.0 - threadIdx.x * 1e-12;
+   for( int it = 0; it < iters; ++it )
+   {
+#pragma unroll
+      for( int i = 0; i < 16; ++i )
+         dmma884(acc[i][0], acc[i][1], a, b);
+   }
+   double s = 0.0;
+#pragma unroll
+   for( int i = 0; i < 16; ++i ) s += acc[i][0] + acc[i][1];
+   if( s == 12345.678 ) sink[0] = s;
+}
+
+} // namespace
+
+cudaError_t gemm(cudaStream_t st, bool ta, bool tb, int m, int n, int k, double alpha, const double* A, int lda,
+   long long sA, const double* B, int ldb, long long sB, double beta, double* C, int ldc, long long sC, int batch, int flags)
+{
+   if( m <= 0 || n <= 0 || batch <= 0 )
+      return cudaSuccess;
+   // small problems use 32 x 32 tiles to fill more SMs
+   bool small = ((long long)ceil_div(m, 64) * ceil_div(n, 64) * batch) < 148;
+#define SDPK_GEMM_DISPATCH(BM, BN) \
+   do { \
+      if( !ta && !tb ) return launch<BM, BN, false, false>(st, m, n, k, alpha, A, lda, sA, B, ldb, sB, beta, C, ldc, sC, batch, flags); \
+      if( !ta &&  tb ) return launch<BM, BN, false, true >(st, m, n, k, alpha, A, lda, sA, B, ldb, sB, beta, C, ldc, sC, batch, flags); \
+      if(  ta && !tb ) return launch<BM, BN, true,  false>(st, m, n, k, alpha, A, lda, sA, B, ldb, sB, beta, C, ldc, sC, batch, flags); \
+      return launch<BM, BN, true, true>(st, m, n, k, alpha, A, lda, sA, B, ldb, sB, beta, C, ldc, sC, batch, flags); \
+   } while( 0 )
+   if( small )
+      SDPK_GEMM_DISPATCH(32, 32);
+   SDPK_GEMM_DISPATCH(64, 64);
+#undef SDPK_GEMM_DISPATCH
+}
+
+cudaError_t dmma_peak_probe(cudaStream_t st, int iters, double* d_sink, double* flops)
+{
+   const int blocks = 148 * 4, threads = 256;
+   dmma_peak_kernel<<<blocks, threads, 0, st>>>(iters, d_sink);
+   count_launch();
+   // per warp and iteration: 16 DMMA.8x8x4 = 16 * 8*8*4*2 flop
+   *flops = (double)blocks * (threads / 32) * (double)iters * 16.0 * 512.0;
+   return cudaGetLastError();
+}
+
+} // namespace sdpk

@@ -1,0 +1,928 @@
+// ipm.cu — the device-resident primal-dual interior-point iteration and the C ABI of include/sdpcuda.h.
+//
+// Algorithm: infeasible-start path following with the HKM search direction and Mehrotra predictor-corrector steps for
+//      min b'y  s.t.  S_k = sum_j y_j A_j^k - C^k >= 0 (psd),  s = D y - d >= 0,
+// multipliers X_k (psd) and x >= 0.  Per iteration on the device:
+//   residuals/statistics -> Cholesky(+inverse) of S and X -> S^-1 -> Schur complement M_ij = tr(A_i X A_j S^-1) + D'diag(x/s)D
+//   -> Cholesky of M -> predictor and corrector solves -> step lengths from lambda_min(L^-1 dX L^-T) -> update.
+// The host only sees a few scalars per iteration (three small device->host copies) and steers the control flow.
+// There is NO CPU fallback: every numerical operation runs in the kernels of gemm.cu / chol.cu / eig.cu / ops.cu.
+#include "../../include/sdpcuda.h"
+#include "common.cuh"
+#include "ops.cuh"
+
+#include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <cmath>
+#include <cstring>
+#include <numeric>
+#include <vector>
+
+using namespace sdpk;
+
+namespace {
+
+#define CK(expr) do { cudaError_t _e = (expr); if( _e != cudaSuccess ) { \
+      fprintf(stderr, "[libsdpcuda] %s:%d CUDA error %s: %s\n", __FILE__, __LINE__, cudaGetErrorName(_e), cudaGetErrorString(_e)); \
+      return (_e == cudaErrorMemoryAllocation) ? SDPCUDA_ERR_NOMEM : SDPCUDA_ERR_CUDA; } } while( 0 )
+
+constexpr int NSTAT = 24;
+
+template <class T> struct DBuf
+{
+   T* p = nullptr; size_t cap = 0;
+   cudaError_t ensure(size_t n)
+   {
+      if( n <= cap ) return cudaSuccess;
+      if( p ) cudaFree(p);
+      p = nullptr; cap = 0;
+      size_t want = std::max(n, (size_t)16);
+      cudaError_t e = cudaMalloc((void**)&p, want * sizeof(T));
+      if( e == cudaSuccess ) cap = want;
+      return e;
+   }
+   template <class V> cudaError_t upload(const V& v, cudaStream_t st)
+   {
+      cudaError_t e = ensure(v.size());
+      if( e != cudaSuccess || v.empty() ) return e;
+      return cudaMemcpyAsync(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, st);
+   }
+   void release() { if( p ) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+struct Block { int n; int ld; long long off; };
+
+std::atomic<int> g_next_device{0};
+
+} // namespace
+
+struct sdpcuda_handle
+{
+   int device = 0;
+   cudaStream_t st = nullptr;
+   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+   LaunchCounter counter;
+   bool solved = false;
+
+   // problem
+   int m = 0, nb = 0, nlp = 0, ldm = 0, N = 0;
+   size_t arena = 0;
+   std::vector<Block> blk;
+   int maxn = 0;
+   int npos = 0, cnnz = 0, nheavy = 0;
+
+   // device problem data
+   DBuf<int> varbeg, erow, ecol, eld, posbeg, posvar, lpbeg, lpind, colbeg, colrow, heavy, heavylist;
+   DBuf<long long> eoff, pos, mirror, cpos, cmirror;
+   DBuf<double> eval, posval, posc, cval, lpval, colval, lprhs, b;
+   // iterate and work space
+   DBuf<double> X, S, Sinv, L, Linv, LX, LXinv, dX, dS, dXa, dSa, K, T1, T2, Rd, work;
+   DBuf<double> y, dy, g, rp, AX, DTx, tm1, tm2;
+   DBuf<double> x, s, dx, ds, dxa, dsa, klp, rdlp, Dy, Ddy;
+   DBuf<double> M, Mfac, diaginv, Mwork;
+   DBuf<double> partials, stats, scal, eigw, lzwork;
+   DBuf<int> info;
+   double* h_stats = nullptr;     // pinned
+   int* h_info = nullptr;
+
+   // generic scratch for the kernel-level entry points
+   DBuf<double> kA, kB, kC, kW;
+
+   ~sdpcuda_handle()
+   {
+      if( h_stats ) cudaFreeHost(h_stats);
+      if( h_info ) cudaFreeHost(h_info);
+   }
+};
+
+namespace {
+
+int set_device(sdpcuda_handle* h)
+{
+   CK( cudaSetDevice(h->device) );
+   g_counter = &h->counter;
+   return SDPCUDA_OK;
+}
+
+// ---- problem upload --------------------------------------------------------------------------------------------------
+int upload_problem(sdpcuda_handle* h, const sdpcuda_problem* P)
+{
+   cudaStream_t st = h->st;
+   if( P->nblocks > 4000 ) return SDPCUDA_ERR_ARG;      // pinned scalar buffer holds two eigenvalue slots per block
+   h->m = P->m; h->nb = P->nblocks; h->nlp = P->nlp;
+   h->blk.resize(h->nb);
+   long long off = 0;
+   h->maxn = 0; h->N = h->nlp;
+   for( int k = 0; k < h->nb; ++k )
+   {
+      int n = P->blocksizes[k];
+      if( n <= 0 ) return SDPCUDA_ERR_ARG;
+      h->blk[k] = Block{n, round_up(n, 4), off};
+      off += (long long)h->blk[k].ld * n;
+      off = (off + 15) / 16 * 16;                     // keep every block 128-byte aligned
+      h->maxn = std::max(h->maxn, n);
+      h->N += n;
+   }
+   h->arena = (size_t)off;
+   const int m = h->m;
+   const int nnz = P->varbeg[m];
+
+   std::vector<int> erow(nnz), ecol(nnz), eld(nnz), heavy(m, 0), heavylist;
+   std::vector<long long> eoff(nnz);
+   for( int e = 0; e < nnz; ++e )
+   {
+      int bk = P->entblk[e];
+      if( bk < 0 || bk >= h->nb ) return SDPCUDA_ERR_ARG;
+      int r = P->entrow[e], c = P->entcol[e];
+      if( r < c || c < 0 || r >= h->blk[bk].n ) return SDPCUDA_ERR_ARG;
+      erow[e] = r; ecol[e] = c; eld[e] = h->blk[bk].ld; eoff[e] = h->blk[bk].off;
+   }
+   for( int j = 0; j < m; ++j )
+      if( P->varbeg[j + 1] - P->varbeg[j] > 32 ) { heavy[j] = 1; heavylist.push_back(j); }
+   h->nheavy = (int)heavylist.size();
+
+   // position-major view of sum_j y_j A_j - C: sort entry ids by arena position
+   std::vector<long long> key(nnz + P->cnnz);
+   for( int e = 0; e < nnz; ++e ) key[e] = eoff[e] + (long long)ecol[e] * eld[e] + erow[e];
+   std::vector<long long> cposv(P->cnnz), cmirv(P->cnnz);
+   for( int e = 0; e < P->cnnz; ++e )
+   {
+      int bk = P->cblk[e];
+      if( bk < 0 || bk >= h->nb ) return SDPCUDA_ERR_ARG;
+      int r = P->crow[e], c = P->ccol[e];
+      if( r < c || c < 0 || r >= h->blk[bk].n ) return SDPCUDA_ERR_ARG;
+      cposv[e] = h->blk[bk].off + (long long)c * h->blk[bk].ld + r;
+      cmirv[e] = h->blk[bk].off + (long long)r * h->blk[bk].ld + c;
+      key[nnz + e] = cposv[e];
+   }
+   std::vector<int> order(nnz + P->cnnz);
+   std::iota(order.begin(), order.end(), 0);
+   std::sort(order.begin(), order.end(), [&](int a, int b2) { return key[a] < key[b2] || (key[a] == key[b2] && a < b2); });
+   std::vector<int> var_of(nnz);
+   for( int j = 0; j < m; ++j )
+      for( int e = P->varbeg[j]; e < P->varbeg[j + 1]; ++e ) var_of[e] = j;
+   std::vector<int> posbeg, posvar;
+   std::vector<long long> pos, mirror;
+   std::vector<double> posval, posc;
+   posbeg.push_back(0);
+   for( size_t t = 0; t < order.size(); )
+   {
+      long long kpos = key[order[t]];
+      double cv = 0.0;
+      long long mir = 0;
+      size_t u = t;
+      for( ; u < order.size() && key[order[u]] == kpos; ++u )
+      {
+         int id = order[u];
+         if( id < nnz )
+         {
+            posvar.push_back(var_of[id]);
+            posval.push_back(P->entval[id]);
+            mir = eoff[id] + (long long)erow[id] * eld[id] + ecol[id];
+         }
+         else
+         {
+            cv += P->cval[id - nnz];
+            mir = cmirv[id - nnz];
+         }
+      }
+      pos.push_back(kpos); mirror.push_back(mir); posc.push_back(cv);
+      posbeg.push_back((int)posvar.size());
+      t = u;
+   }
+   h->npos = (int)pos.size();
+   h->cnnz = P->cnnz;
+
+   // LP block CSR + CSC
+   const int nlp = h->nlp;
+   std::vector<int> lpbeg(nlp + 1, 0);
+   if( nlp > 0 ) std::copy(P->lpbeg, P->lpbeg + nlp + 1, lpbeg.begin());
+   const int lnz = lpbeg[nlp];
+   std::vector<int> colbeg(m + 1, 0), colrow(lnz);
+   std::vector<double> colval(lnz);
+   for( int p = 0; p < lnz; ++p )
+   {
+      if( P->lpind[p] < 0 || P->lpind[p] >= m ) return SDPCUDA_ERR_ARG;
+      colbeg[P->lpind[p] + 1]++;
+   }
+   for( int j = 0; j < m; ++j ) colbeg[j + 1] += colbeg[j];
+   {
+      std::vector<int> fill(colbeg.begin(), colbeg.end() - 1);
+      for( int l = 0; l < nlp; ++l )
+         for( int p = lpbeg[l]; p < lpbeg[l + 1]; ++p )
+         {
+            int q = fill[P->lpind[p]]++;
+            colrow[q] = l; colval[q] = P->lpval[p];
+         }
+   }
+
+#define UP(buf, vec) CK( h->buf.upload(vec, st) )
+   std::vector<int> varbeg(P->varbeg, P->varbeg + m + 1);
+   std::vector<double> eval(P->entval, P->entval + nnz), cval(P->cval, P->cval + P->cnnz), bvec(P->obj, P->obj + m);
+   std::vector<int> lpind(P->lpind, P->lpind + lnz);
+   std::vector<double> lpval(P->lpval, P->lpval + lnz), lprhs(P->lprhs, P->lprhs + nlp);
+   UP(varbeg, varbeg); UP(erow, erow); UP(ecol, ecol); UP(eld, eld); UP(eoff, eoff); UP(eval, eval);
+   UP(posbeg, posbeg); UP(posvar, posvar); UP(pos, pos); UP(mirror, mirror); UP(posval, posval); UP(posc, posc);
+   UP(cpos, cposv); UP(cmirror, cmirv); UP(cval, cval);
+   UP(lpbeg, lpbeg); UP(lpind, lpind); UP(lpval, lpval); UP(lprhs, lprhs);
+   UP(colbeg, colbeg); UP(colrow, colrow); UP(colval, colval);
+   UP(heavy, heavy); UP(heavylist, heavylist); UP(b, bvec);
+#undef UP
+   CK( cudaStreamSynchronize(st) );      // the host vectors above go out of scope
+
+   // work space
+   const size_t ar = h->arena;
+   for( DBuf<double>* bf : {&h->X, &h->S, &h->Sinv, &h->L, &h->Linv, &h->LX, &h->LXinv, &h->dX, &h->dS, &h->dXa, &h->dSa,
+                            &h->K, &h->T1, &h->T2, &h->Rd} )
+      CK( bf->ensure(ar) );
+   const int ldmax = round_up(std::max(h->maxn, 1), 4);
+   CK( h->work.ensure((size_t)ldmax * (h->maxn + 2 * CHOL_NB)) );
+   for( DBuf<double>* bf : {&h->y, &h->dy, &h->g, &h->rp, &h->AX, &h->DTx, &h->tm1, &h->tm2} )
+      CK( bf->ensure(m + 1) );
+   for( DBuf<double>* bf : {&h->x, &h->s, &h->dx, &h->ds, &h->dxa, &h->dsa, &h->klp, &h->rdlp, &h->Dy, &h->Ddy} )
+      CK( bf->ensure(nlp + 1) );
+   h->ldm = round_up(std::max(m, 1), 4);
+   CK( h->M.ensure((size_t)h->ldm * m) );
+   CK( h->Mfac.ensure((size_t)h->ldm * m) );
+   CK( h->diaginv.ensure((size_t)ceil_div(std::max(m, 1), CHOL_NB) * CHOL_NB * CHOL_NB) );
+   CK( h->Mwork.ensure((size_t)h->ldm * (m + 2 * CHOL_NB)) );
+   CK( h->partials.ensure((size_t)RED_BLOCKS * NSTAT) );
+   CK( h->stats.ensure(64) );
+   CK( h->scal.ensure(64 + 2 * (size_t)h->nb) );
+   CK( h->eigw.ensure((size_t)std::max(h->maxn, 1) * 4 + 16) );
+   CK( h->lzwork.ensure(lanczos_work_doubles(std::max(h->maxn, 1), 64)) );
+   CK( h->info.ensure(8) );
+   return SDPCUDA_OK;
+}
+
+DevEntries entries(sdpcuda_handle* h)
+{
+   return DevEntries{h->varbeg.p, h->erow.p, h->ecol.p, h->eld.p, h->eoff.p, h->eval.p};
+}
+
+// out_k = sum_j v_j A_j^k (cscale * C subtracted), full symmetric, everything else zero
+int assemble(sdpcuda_handle* h, const double* v, double cscale, double* T)
+{
+   CK( cudaMemsetAsync(T, 0, h->arena * sizeof(double), h->st) );
+   CK( assemble_positions(h->st, h->npos, h->posbeg.p, h->pos.p, h->mirror.p, h->posvar.p, h->posval.p, h->posc.p, v, cscale, T) );
+   return SDPCUDA_OK;
+}
+
+// factor all blocks of Src into Lout (lower) and Linvout; info slot `slot` collects a failing pivot
+int factor_blocks(sdpcuda_handle* h, const double* Src, double* Lout, double* Linvout, int slot)
+{
+   CK( cudaMemcpyAsync(Lout, Src, h->arena * sizeof(double), cudaMemcpyDeviceToDevice, h->st) );
+   for( const Block& bk : h->blk )
+      CK( potrf_lower(h->st, bk.n, Lout + bk.off, bk.ld, Linvout + bk.off, bk.ld, nullptr, h->work.p, round_up(h->maxn, 4), h->info.p + slot) );
+   return SDPCUDA_OK;
+}
+
+// Out_k = A_k * B_k for all blocks (plain products of full matrices)
+int mult_blocks(sdpcuda_handle* h, const double* A, const double* B, double* Out, double alpha, double beta)
+{
+   for( const Block& bk : h->blk )
+      CK( gemm(h->st, false, false, bk.n, bk.n, bk.n, alpha, A + bk.off, bk.ld, 0, B + bk.off, bk.ld, 0, beta, Out + bk.off, bk.ld, 0, 1, 0) );
+   return SDPCUDA_OK;
+}
+
+// lambda_min(Linv dA Linv') for every block -> scal[slot0 + k]; T1/T2 are scratch
+int step_eigs(sdpcuda_handle* h, const double* Linv, const double* dA, int slot0)
+{
+   int k = 0;
+   for( const Block& bk : h->blk )
+   {
+      double* t1 = h->T1.p + bk.off;
+      double* t2 = h->T2.p + bk.off;
+      // T1 = Linv * dA (Linv lower triangular: k < m0 + BM), T2 = T1 * Linv' (lower tiles only, k < n0 + BN)
+      CK( gemm(h->st, false, false, bk.n, bk.n, bk.n, 1.0, Linv + bk.off, bk.ld, 0, dA + bk.off, bk.ld, 0, 0.0, t1, bk.ld, 0, 1, GEMM_KHI_M) );
+      CK( gemm(h->st, false, true, bk.n, bk.n, bk.n, 1.0, t1, bk.ld, 0, Linv + bk.off, bk.ld, 0, 0.0, t2, bk.ld, 0, 1, GEMM_LOWER | GEMM_KHI_N) );
+      CK( mirror_lower(h->st, bk.n, t2, bk.ld) );
+      if( bk.n <= JACOBI_MAX_N )
+      {
+         CK( jacobi_eig_batched(h->st, bk.n, 1, t2, bk.ld, 0, h->eigw.p, nullptr, nullptr) );
+         CK( pick_value(h->st, h->eigw.p, h->scal.p + slot0 + k) );
+      }
+      else
+         CK( lanczos_lambda_min(h->st, bk.n, t2, bk.ld, h->lzwork.p, 40, h->scal.p + slot0 + k) );
+      ++k;
+   }
+   return SDPCUDA_OK;
+}
+
+double now_seconds()
+{
+   return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+} // namespace
+
+extern "C" {
+
+int sdpcuda_abi_version(void) { return SDPCUDA_ABI_VERSION; }
+const char* sdpcuda_backend_name(void) { return "cuda-sm_100a"; }
+
+void sdpcuda_default_params(sdpcuda_params* p)
+{
+   memset(p, 0, sizeof(*p));
+   p->gaptol = 1e-6; p->feastol = 1e-6; p->objlimit = 1e20; p->lambdastar = -1.0; p->timelimit = 1e20;
+   p->absgaptol = -1.0; p->maxiter = 100; p->setting = 1; p->verbose = 0;
+}
+
+int sdpcuda_create(sdpcuda_handle** out, int device)
+{
+   if( out == nullptr ) return SDPCUDA_ERR_ARG;
+   int ndev = 0;
+   cudaError_t e = cudaGetDeviceCount(&ndev);
+   if( e != cudaSuccess || ndev <= 0 )
+   {
+      fprintf(stderr, "[libsdpcuda] no CUDA device available (%s); this library has no CPU fallback\n", cudaGetErrorString(e));
+      return SDPCUDA_ERR_CUDA;
+   }
+   sdpcuda_handle* h = new (std::nothrow) sdpcuda_handle();
+   if( h == nullptr ) return SDPCUDA_ERR_NOMEM;
+   // one handle per SCIP solver thread: devices round-robin (concurrent node relaxations), a private stream each
+   h->device = (device >= 0) ? device % ndev : (g_next_device.fetch_add(1) % ndev);
+   if( cudaSetDevice(h->device) != cudaSuccess || cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking) != cudaSuccess
+      || cudaEventCreate(&h->ev0) != cudaSuccess || cudaEventCreate(&h->ev1) != cudaSuccess
+      || cudaMallocHost((void**)&h->h_stats, 8192 * sizeof(double)) != cudaSuccess
+      || cudaMallocHost((void**)&h->h_info, 8 * sizeof(int)) != cudaSuccess )
+   {
+      fprintf(stderr, "[libsdpcuda] device initialisation failed: %s\n", cudaGetErrorString(cudaGetLastError()));
+      delete h;
+      return SDPCUDA_ERR_CUDA;
+   }
+   *out = h;
+   return SDPCUDA_OK;
+}
+
+int sdpcuda_destroy(sdpcuda_handle* h)
+{
+   if( h == nullptr ) return SDPCUDA_OK;
+   cudaSetDevice(h->device);
+   cudaStreamSynchronize(h->st);
+   for( DBuf<double>* bf : {&h->eval, &h->posval, &h->posc, &h->cval, &h->lpval, &h->colval, &h->lprhs, &h->b, &h->X, &h->S, &h->Sinv,
+                            &h->L, &h->Linv, &h->LX, &h->LXinv, &h->dX, &h->dS, &h->dXa, &h->dSa, &h->K, &h->T1, &h->T2, &h->Rd, &h->work,
+                            &h->y, &h->dy, &h->g, &h->rp, &h->AX, &h->DTx, &h->tm1, &h->tm2, &h->x, &h->s, &h->dx, &h->ds, &h->dxa, &h->dsa,
+                            &h->klp, &h->rdlp, &h->Dy, &h->Ddy, &h->M, &h->Mfac, &h->diaginv, &h->Mwork, &h->partials, &h->stats, &h->scal,
+                            &h->eigw, &h->lzwork, &h->kA, &h->kB, &h->kC, &h->kW} )
+      bf->release();
+   for( DBuf<int>* bf : {&h->varbeg, &h->erow, &h->ecol, &h->eld, &h->posbeg, &h->posvar, &h->lpbeg, &h->lpind, &h->colbeg, &h->colrow,
+                         &h->heavy, &h->heavylist, &h->info} )
+      bf->release();
+   for( DBuf<long long>* bf : {&h->eoff, &h->pos, &h->mirror, &h->cpos, &h->cmirror} )
+      bf->release();
+   cudaEventDestroy(h->ev0); cudaEventDestroy(h->ev1);
+   cudaStreamDestroy(h->st);
+   if( g_counter == &h->counter ) g_counter = nullptr;
+   delete h;
+   return SDPCUDA_OK;
+}
+
+int sdpcuda_solve(sdpcuda_handle* h, const sdpcuda_problem* P, const sdpcuda_params* par, const double* start_y, sdpcuda_result* res)
+{
+   if( h == nullptr || P == nullptr || par == nullptr || P->m <= 0 ) return SDPCUDA_ERR_ARG;
+   const double t0 = now_seconds();
+   int rc = set_device(h);
+   if( rc != SDPCUDA_OK ) return rc;
+   h->solved = false;
+   h->counter.n = 0;
+   rc = upload_problem(h, P);
+   if( rc != SDPCUDA_OK ) return rc;
+
+   cudaStream_t st = h->st;
+   const int m = h->m, nb = h->nb, nlp = h->nlp;
+   const size_t ar = h->arena;
+   const double gaptol = par->gaptol > 0 ? par->gaptol : 1e-6;
+   const double feastol = par->feastol > 0 ? par->feastol : 1e-6;
+   const int maxiter = par->maxiter > 0 ? par->maxiter : 100;
+   const double inftol = 1e-8;
+   const double gammabase = par->setting >= 3 ? 0.7 : (par->setting == 2 ? 0.8 : 0.9);
+   DevEntries E = entries(h);
+
+   // ---- norms and the initial point (host side, from the problem data: O(nnz)) ----
+   double normb = 0, normC = 0;
+   for( int j = 0; j < m; ++j ) normb += P->obj[j] * P->obj[j];
+   normb = std::sqrt(normb);
+   std::vector<double> nrmC(nb, 0.0);
+   for( int e = 0; e < P->cnnz; ++e )
+      nrmC[P->cblk[e]] += (P->crow[e] == P->ccol[e] ? 1.0 : 2.0) * P->cval[e] * P->cval[e];
+   for( int k = 0; k < nb; ++k ) normC += nrmC[k];
+   for( int l = 0; l < nlp; ++l ) normC += P->lprhs[l] * P->lprhs[l];
+   normC = std::sqrt(normC);
+   {
+      std::vector<double> xi(nb), eta(nb);
+      for( int k = 0; k < nb; ++k ) { xi[k] = eta[k] = std::max(10.0, std::sqrt((double)h->blk[k].n)); eta[k] = std::max(eta[k], std::sqrt(nrmC[k])); }
+      std::vector<double> na(nb);
+      std::vector<double> nrmD(m, 0.0);
+      for( int j = 0; j < m; ++j )
+      {
+         std::fill(na.begin(), na.end(), 0.0);
+         for( int e = P->varbeg[j]; e < P->varbeg[j + 1]; ++e )
+            na[P->entblk[e]] += (P->entrow[e] == P->entcol[e] ? 1.0 : 2.0) * P->entval[e] * P->entval[e];
+         for( int e = P->varbeg[j]; e < P->varbeg[j + 1]; ++e )
+         {
+            int k = P->entblk[e];
+            if( na[k] > 0.0 )
+            {
+               double a = std::sqrt(na[k]);
+               xi[k] = std::max(xi[k], h->blk[k].n * (1.0 + std::fabs(P->obj[j])) / (1.0 + a));
+               eta[k] = std::max(eta[k], a);
+               na[k] = 0.0;      // handled
+            }
+         }
+      }
+      for( int l = 0; l < nlp; ++l )
+         for( int p = P->lpbeg[l]; p < P->lpbeg[l + 1]; ++p ) nrmD[P->lpind[p]] += P->lpval[p] * P->lpval[p];
+      double sq = std::sqrt((double)std::max(nlp, 1));
+      double xil = std::max(10.0, sq), etal = xil, nd = 0;
+      for( int l = 0; l < nlp; ++l ) nd += P->lprhs[l] * P->lprhs[l];
+      etal = std::max(etal, std::sqrt(nd));
+      for( int j = 0; j < m; ++j )
+      {
+         double a = std::sqrt(nrmD[j]);
+         if( a > 0 ) xil = std::max(xil, sq * (1.0 + std::fabs(P->obj[j])) / (1.0 + a));
+         etal = std::max(etal, a);
+      }
+      if( par->lambdastar > 0 ) { xil = etal = par->lambdastar; for( int k = 0; k < nb; ++k ) xi[k] = eta[k] = par->lambdastar; }
+      CK( cudaMemsetAsync(h->X.p, 0, ar * sizeof(double), st) );
+      CK( cudaMemsetAsync(h->S.p, 0, ar * sizeof(double), st) );
+      for( int k = 0; k < nb; ++k )
+      {
+         CK( add_diagonal(st, h->blk[k].n, h->X.p + h->blk[k].off, h->blk[k].ld, xi[k]) );
+         CK( add_diagonal(st, h->blk[k].n, h->S.p + h->blk[k].off, h->blk[k].ld, eta[k]) );
+      }
+      std::vector<double> hx(nlp, xil), hs(nlp, etal), hy(m, 0.0);
+      if( start_y != nullptr ) std::copy(start_y, start_y + m, hy.begin());
+      CK( h->x.upload(hx, st) ); CK( h->s.upload(hs, st) ); CK( h->y.upload(hy, st) );
+      CK( cudaStreamSynchronize(st) );
+   }
+   CK( cudaMemsetAsync(h->dX.p, 0, ar * sizeof(double), st) );
+   CK( cudaMemsetAsync(h->dS.p, 0, ar * sizeof(double), st) );
+
+   sdpcuda_result R;
+   memset(&R, 0, sizeof(R));
+   R.phase = SDPCUDA_NOINFO; R.stop = SDPCUDA_STOP_ITERLIMIT;
+   double mu = 0, pobj = 0, dobj = 0, relgap = 1e30, pinf = 1e30, dinf = 1e30;
+   double bestmerit = 1e300; int stall = 0;
+   bool pfeasever = false, dfeasever = false;
+   double lastap = 0.0, lastad = 0.0;           // step of the previous update (for backtracking if a factorisation fails)
+   int backtracks = 0;
+   CK( cudaEventRecord(h->ev0, st) );
+
+   int iter = 0;
+   for( ; ; ++iter )
+   {
+      // ---- residuals and statistics (one device->host copy) ----
+      CK( cudaMemsetAsync(h->partials.p, 0, sizeof(double) * RED_BLOCKS * NSTAT, st) );
+      CK( cudaMemsetAsync(h->info.p, 0, 8 * sizeof(int), st) );
+      rc = assemble(h, h->y.p, 1.0, h->K.p); if( rc ) return rc;                   // K = A'y - C (scratch use of K)
+      CK( residual_matrix(st, ar, h->K.p, h->S.p, h->X.p, h->Rd.p, h->partials.p) );
+      CK( apply_A(st, m, E, h->X.p, h->AX.p) );
+      CK( lp_cols(st, m, h->colbeg.p, h->colrow.p, h->colval.p, h->x.p, h->DTx.p, 0) );
+      CK( primal_residual(st, m, h->b.p, h->AX.p, h->DTx.p, h->y.p, h->rp.p, h->partials.p) );
+      CK( lp_rows(st, nlp, h->lpbeg.p, h->lpind.p, h->lpval.p, h->lprhs.p, h->y.p, h->x.p, h->s.p, h->Dy.p, h->rdlp.p, h->partials.p) );
+      CK( finalize_partials(st, h->partials.p, NSTAT, h->stats.p) );
+      CK( const_dots(st, h->cnnz, h->cpos.p, h->cmirror.p, h->cval.p, h->X.p, h->Rd.p, h->stats.p + NSTAT) );
+      // factorisations of S and X are issued before the sync so that their pivots are known at the same time
+      rc = factor_blocks(h, h->S.p, h->L.p, h->Linv.p, 0); if( rc ) return rc;
+      rc = factor_blocks(h, h->X.p, h->LX.p, h->LXinv.p, 1); if( rc ) return rc;
+      CK( cudaMemcpyAsync(h->h_stats, h->stats.p, (NSTAT + 2) * sizeof(double), cudaMemcpyDeviceToHost, st) );
+      CK( cudaMemcpyAsync(h->h_info, h->info.p, 8 * sizeof(int), cudaMemcpyDeviceToHost, st) );
+      CK( cudaStreamSynchronize(st) );
+
+      if( h->h_info[0] != 0 || h->h_info[1] != 0 )
+      {
+         // the last step left the cone (the step-length estimate was too optimistic): halve it and try again
+         if( iter == 0 || backtracks >= 8 ) { R.stop = SDPCUDA_STOP_NUMERICS; break; }
+         ++backtracks;
+         if( h->h_info[1] != 0 )
+         {
+            CK( axpy(st, ar, -0.5 * lastap, h->dX.p, h->X.p) );
+            CK( axpy(st, (size_t)nlp, -0.5 * lastap, h->dx.p, h->x.p) );
+            lastap *= 0.5;
+         }
+         if( h->h_info[0] != 0 )
+         {
+            CK( axpy(st, ar, -0.5 * lastad, h->dS.p, h->S.p) );
+            CK( axpy(st, (size_t)nlp, -0.5 * lastad, h->ds.p, h->s.p) );
+            CK( axpy(st, (size_t)m, -0.5 * lastad, h->dy.p, h->y.p) );
+            lastad *= 0.5;
+         }
+         --iter;
+         continue;
+      }
+      backtracks = 0;
+
+      const double* hs = h->h_stats;
+      const double nrd2 = hs[0] + hs[2], xs = hs[1] + hs[3];
+      const double CX = hs[NSTAT + 0], CRd = hs[NSTAT + 1];
+      pobj = CX + hs[4];
+      dobj = hs[8];
+      mu = h->N > 0 ? xs / h->N : 0.0;
+      const double nrp = std::sqrt(hs[6]);
+      pinf = nrp / (1.0 + normb);
+      dinf = std::sqrt(nrd2) / (1.0 + normC);
+      const double dinfabs = std::max(std::sqrt(hs[0]), hs[16]), pinfabs = hs[17];
+      relgap = std::fabs(pobj - dobj) / std::max(1.0, 0.5 * (std::fabs(pobj) + std::fabs(dobj)));
+      // |A'y - S|^2 = |Rd + C|^2 = |Rd|^2 + 2 C.Rd + |C|^2 for the SDP part, (Dy - s)^2 for the LP part
+      double normCsdp2 = 0.0; for( int k = 0; k < nb; ++k ) normCsdp2 += nrmC[k];
+      const double rayd = std::sqrt(std::max(0.0, hs[0] + 2.0 * CRd + normCsdp2 + hs[5]));
+      const bool pfeas = pinf <= feastol && pinfabs <= std::max(feastol, 1e-9 * (1 + normb));
+      const bool dfeas = dinf <= feastol && dinfabs <= feastol;
+      pfeasever = pfeasever || pfeas;
+      dfeasever = dfeasever || dfeas;
+      if( par->verbose )
+         printf("  [cuda] it %3d  pobj % .10e  dobj % .10e  gap %.2e  pinf %.2e  dinf %.2e  mu %.2e\n", iter, pobj, dobj, relgap, pinf, dinf, mu);
+
+      R.phase = pfeas ? (dfeas ? SDPCUDA_PDFEAS : SDPCUDA_PFEAS) : (dfeas ? SDPCUDA_DFEAS : SDPCUDA_NOINFO);
+      if( pfeas && dfeas && relgap <= gaptol && (par->absgaptol <= 0 || std::fabs(pobj - dobj) <= par->absgaptol) )
+      { R.phase = SDPCUDA_PDOPT; R.stop = SDPCUDA_STOP_CONVERGED; break; }
+      if( pobj > 0 && std::sqrt(hs[7]) / pobj < inftol )
+      { R.phase = pfeasever ? SDPCUDA_PFEAS_DINF : SDPCUDA_DINF; R.stop = SDPCUDA_STOP_INFEASCERT; break; }
+      if( dfeasever && dobj < 0 && rayd / (-dobj) < inftol )
+      { R.phase = SDPCUDA_PINF_DFEAS; R.stop = SDPCUDA_STOP_INFEASCERT; break; }
+      if( pfeas && par->objlimit < 1e20 && pobj > par->objlimit )
+      { R.phase = SDPCUDA_PUNBD; R.stop = SDPCUDA_STOP_OBJLIMIT; break; }
+      if( iter >= maxiter ) { R.stop = SDPCUDA_STOP_ITERLIMIT; break; }
+      if( par->timelimit > 0 && par->timelimit < 1e20 && now_seconds() - t0 > par->timelimit )
+      { R.stop = SDPCUDA_STOP_TIMELIMIT; break; }
+      {
+         double merit = std::max(relgap, std::max(pinf, dinf));
+         if( merit < 0.9 * bestmerit ) { bestmerit = merit; stall = 0; }
+         else if( ++stall >= 15 ) { R.stop = SDPCUDA_STOP_NUMERICS; break; }
+      }
+      const bool rdzero = (hs[0] <= 1e-28 * (1.0 + normCsdp2));     // dual SDP residual at round-off level: skip its GEMMs
+
+      // ---- S^-1 = Linv' Linv (lower tiles, k >= max(m0, n0)), mirrored ----
+      for( const Block& bk : h->blk )
+      {
+         CK( gemm(st, true, false, bk.n, bk.n, bk.n, 1.0, h->Linv.p + bk.off, bk.ld, 0, h->Linv.p + bk.off, bk.ld, 0, 0.0,
+               h->Sinv.p + bk.off, bk.ld, 0, 1, GEMM_LOWER | GEMM_KLO_M | GEMM_KLO_N) );
+         CK( mirror_lower(st, bk.n, h->Sinv.p + bk.off, bk.ld) );
+      }
+
+      // ---- Schur complement and its factorisation ----
+      CK( cudaMemsetAsync(h->M.p, 0, sizeof(double) * (size_t)h->ldm * m, st) );
+      CK( schur_entries(st, m, E, h->heavy.p, h->heavylist.p, h->nheavy, h->X.p, h->Sinv.p, h->M.p, h->ldm) );
+      CK( schur_lp(st, nlp, h->lpbeg.p, h->lpind.p, h->lpval.p, h->x.p, h->s.p, h->M.p, h->ldm) );
+      double reg = 0.0;
+      bool mok = false;
+      for( int tries = 0; tries < 8 && !mok; ++tries )
+      {
+         CK( cudaMemcpyAsync(h->Mfac.p, h->M.p, sizeof(double) * (size_t)h->ldm * m, cudaMemcpyDeviceToDevice, st) );
+         if( reg > 0.0 ) CK( add_diagonal(st, m, h->Mfac.p, h->ldm, reg) );
+         CK( cudaMemsetAsync(h->info.p + 2, 0, sizeof(int), st) );
+         CK( potrf_lower(st, m, h->Mfac.p, h->ldm, nullptr, 0, h->diaginv.p, h->Mwork.p, h->ldm, h->info.p + 2) );
+         CK( cudaMemcpyAsync(h->h_info, h->info.p, 8 * sizeof(int), cudaMemcpyDeviceToHost, st) );
+         CK( cudaStreamSynchronize(st) );
+         mok = (h->h_info[2] == 0);
+         if( !mok )
+         {
+            if( reg == 0.0 )
+            {
+               // scale of the regularisation: largest diagonal entry of M
+               double maxd = 0.0;
+               std::vector<double> diag(m);
+               CK( cudaMemcpy2DAsync(diag.data(), sizeof(double), h->M.p, sizeof(double) * ((size_t)h->ldm + 1), sizeof(double), m, cudaMemcpyDeviceToHost, st) );
+               CK( cudaStreamSynchronize(st) );
+               for( int j = 0; j < m; ++j ) maxd = std::max(maxd, diag[j]);
+               reg = 1e-14 * std::max(maxd, 1e-300);
+            }
+            else
+               reg *= 100.0;
+         }
+      }
+      if( !mok ) { R.stop = SDPCUDA_STOP_NUMERICS; break; }
+
+      // ---- predictor (sigma = 0) and corrector ----
+      double sigma = 0.0, ap = 0.0, ad = 0.0;
+      bool failed = false;
+      for( int pass = 0; pass < 2; ++pass )
+      {
+         // K = sym((sigma mu I - dXa dSa - X Rd) S^-1) - X
+         bool haveT = false;
+         if( !rdzero ) { rc = mult_blocks(h, h->X.p, h->Rd.p, h->T1.p, -1.0, 0.0); if( rc ) return rc; haveT = true; }
+         if( pass == 1 )
+         {
+            rc = mult_blocks(h, h->dXa.p, h->dSa.p, h->T1.p, -1.0, haveT ? 1.0 : 0.0); if( rc ) return rc;
+            for( const Block& bk : h->blk ) CK( add_diagonal(st, bk.n, h->T1.p + bk.off, bk.ld, sigma * mu) );
+            haveT = true;
+         }
+         if( haveT )
+         {
+            rc = mult_blocks(h, h->T1.p, h->Sinv.p, h->K.p, 1.0, 0.0); if( rc ) return rc;
+            for( const Block& bk : h->blk ) CK( sym_average(st, bk.n, h->K.p + bk.off, bk.ld, h->X.p + bk.off) );
+         }
+         else
+            CK( axpby_out(st, ar, -1.0, h->X.p, 0.0, h->X.p, h->K.p) );
+         CK( lp_rhs(st, nlp, pass, sigma * mu, h->x.p, h->s.p, h->rdlp.p, h->dxa.p, h->dsa.p, h->klp.p) );
+         // g = A(K) + D'klp - rp ; dy = M^-1 g with one step of iterative refinement against the unregularised M
+         CK( apply_A(st, m, E, h->K.p, h->g.p) );
+         CK( lp_cols(st, m, h->colbeg.p, h->colrow.p, h->colval.p, h->klp.p, h->g.p, 1) );
+         CK( axpy(st, (size_t)m, -1.0, h->rp.p, h->g.p) );
+         CK( cudaMemcpyAsync(h->dy.p, h->g.p, sizeof(double) * m, cudaMemcpyDeviceToDevice, st) );
+         CK( potrs_vec(st, m, h->Mfac.p, h->ldm, h->diaginv.p, h->dy.p, h->tm2.p) );
+         CK( symv_lower(st, m, h->M.p, h->ldm, h->dy.p, h->tm1.p) );
+         CK( axpby_out(st, (size_t)m, 1.0, h->g.p, -1.0, h->tm1.p, h->tm1.p) );
+         CK( potrs_vec(st, m, h->Mfac.p, h->ldm, h->diaginv.p, h->tm1.p, h->tm2.p) );
+         CK( axpy(st, (size_t)m, 1.0, h->tm1.p, h->dy.p) );
+         // dS = A'dy (+ Rd afterwards) ; dX = K - sym(X (A'dy) S^-1)
+         rc = assemble(h, h->dy.p, 0.0, h->dS.p); if( rc ) return rc;
+         rc = mult_blocks(h, h->X.p, h->dS.p, h->T1.p, 1.0, 0.0); if( rc ) return rc;
+         rc = mult_blocks(h, h->T1.p, h->Sinv.p, h->T2.p, 1.0, 0.0); if( rc ) return rc;
+         for( const Block& bk : h->blk ) CK( sym_average(st, bk.n, h->T2.p + bk.off, bk.ld, nullptr) );
+         CK( axpby_out(st, ar, 1.0, h->K.p, -1.0, h->T2.p, h->dX.p) );
+         if( !rdzero ) CK( axpy(st, ar, 1.0, h->Rd.p, h->dS.p) );
+         // LP part: Ddy = D dy, then dx, ds and the LP step lengths
+         CK( cudaMemsetAsync(h->partials.p, 0, sizeof(double) * RED_BLOCKS * NSTAT, st) );
+         {
+            // Ddy via the row kernel (its other outputs go to scratch)
+            CK( lp_rows(st, nlp, h->lpbeg.p, h->lpind.p, h->lpval.p, h->lprhs.p, h->dy.p, h->x.p, h->s.p, h->Ddy.p, h->Dy.p, h->partials.p) );
+         }
+         CK( lp_direction(st, nlp, h->x.p, h->s.p, h->rdlp.p, h->klp.p, h->Ddy.p, h->dx.p, h->ds.p, h->scal.p + 0) );
+         // SDP step lengths: lambda_min(LXinv dX LXinv') -> scal[8+k], lambda_min(Linv dS Linv') -> scal[8+nb+k]
+         rc = step_eigs(h, h->LXinv.p, h->dX.p, 8); if( rc ) return rc;
+         rc = step_eigs(h, h->Linv.p, h->dS.p, 8 + nb); if( rc ) return rc;
+         CK( cudaMemcpyAsync(h->h_stats + 32, h->scal.p, sizeof(double) * (8 + 2 * (size_t)nb), cudaMemcpyDeviceToHost, st) );
+         CK( cudaStreamSynchronize(st) );
+         double apmax = h->h_stats[32 + 0], admax = h->h_stats[32 + 1];
+         for( int k = 0; k < nb; ++k )
+         {
+            double lx = h->h_stats[32 + 8 + k], ls = h->h_stats[32 + 8 + nb + k];
+            if( !(lx == lx) || !(ls == ls) ) failed = true;
+            if( lx < -1e-300 ) apmax = std::min(apmax, -1.0 / lx);
+            if( ls < -1e-300 ) admax = std::min(admax, -1.0 / ls);
+         }
+         if( failed ) break;
+         if( pass == 0 )
+         {
+            ap = std::min(1.0, 0.98 * apmax); ad = std::min(1.0, 0.98 * admax);
+            CK( affine_mu(st, ar, h->X.p, h->dX.p, h->S.p, h->dS.p, nlp, h->x.p, h->dx.p, h->s.p, h->ds.p, ap, ad, h->partials.p) );
+            CK( finalize_partials(st, h->partials.p, NSTAT, h->stats.p) );
+            CK( cudaMemcpyAsync(h->h_stats + 64, h->stats.p, NSTAT * sizeof(double), cudaMemcpyDeviceToHost, st) );
+            CK( cudaMemcpyAsync(h->dXa.p, h->dX.p, ar * sizeof(double), cudaMemcpyDeviceToDevice, st) );
+            CK( cudaMemcpyAsync(h->dSa.p, h->dS.p, ar * sizeof(double), cudaMemcpyDeviceToDevice, st) );
+            CK( cudaMemcpyAsync(h->dxa.p, h->dx.p, (size_t)nlp * sizeof(double), cudaMemcpyDeviceToDevice, st) );
+            CK( cudaMemcpyAsync(h->dsa.p, h->ds.p, (size_t)nlp * sizeof(double), cudaMemcpyDeviceToDevice, st) );
+            CK( cudaStreamSynchronize(st) );
+            double mua = h->N > 0 ? (h->h_stats[64 + 9] + h->h_stats[64 + 10]) / h->N : 0.0;
+            double ratio = mu > 0 ? std::max(0.0, mua / mu) : 0.0;
+            double expo = (mu > 1e-6) ? std::max(1.0, 3.0 * std::min(ap, ad) * std::min(ap, ad)) : 1.0;
+            sigma = std::min(1.0, std::pow(ratio, expo));
+            if( par->setting >= 3 ) sigma = std::max(sigma, 0.1);
+         }
+         else
+         {
+            double gamma = gammabase + (0.99 - gammabase) * std::min(ap, ad);
+            ap = std::min(1.0, gamma * apmax); ad = std::min(1.0, gamma * admax);
+         }
+      }
+      if( failed || (ap < 1e-8 && ad < 1e-8) ) { R.stop = SDPCUDA_STOP_NUMERICS; break; }
+      CK( axpy(st, ar, ap, h->dX.p, h->X.p) );
+      CK( axpy(st, ar, ad, h->dS.p, h->S.p) );
+      CK( axpy(st, (size_t)nlp, ap, h->dx.p, h->x.p) );
+      CK( axpy(st, (size_t)nlp, ad, h->ds.p, h->s.p) );
+      CK( axpy(st, (size_t)m, ad, h->dy.p, h->y.p) );
+      lastap = ap; lastad = ad;
+   }
+
+   CK( cudaEventRecord(h->ev1, st) );
+   CK( cudaStreamSynchronize(st) );
+   float ms = 0.f;
+   cudaEventElapsedTime(&ms, h->ev0, h->ev1);
+   R.iterations = iter; R.launches = (int)std::min<long long>(h->counter.n, 2147483647LL);
+   R.pobj = pobj; R.dobj = dobj; R.relgap = relgap; R.pinf = pinf; R.dinf = dinf; R.mu = mu;
+   R.seconds = now_seconds() - t0;
+   R.device_ms = ms;
+   h->solved = true;
+   if( res != nullptr ) *res = R;
+   return SDPCUDA_OK;
+}
+
+int sdpcuda_get_y(sdpcuda_handle* h, double* y)
+{
+   if( h == nullptr || !h->solved ) return SDPCUDA_ERR_STATE;
+   if( set_device(h) ) return SDPCUDA_ERR_CUDA;
+   CK( cudaMemcpyAsync(y, h->y.p, sizeof(double) * h->m, cudaMemcpyDeviceToHost, h->st) );
+   CK( cudaStreamSynchronize(h->st) );
+   return SDPCUDA_OK;
+}
+
+static int get_block(sdpcuda_handle* h, const double* src, int b, double* out)
+{
+   if( h == nullptr || !h->solved ) return SDPCUDA_ERR_STATE;
+   if( b < 0 || b >= h->nb ) return SDPCUDA_ERR_ARG;
+   if( set_device(h) ) return SDPCUDA_ERR_CUDA;
+   const Block& bk = h->blk[b];
+   CK( cudaMemcpy2DAsync(out, sizeof(double) * bk.n, src + bk.off, sizeof(double) * bk.ld, sizeof(double) * bk.n, bk.n, cudaMemcpyDeviceToHost, h->st) );
+   CK( cudaStreamSynchronize(h->st) );
+   return SDPCUDA_OK;
+}
+int sdpcuda_get_X(sdpcuda_handle* h, int b, double* X) { return get_block(h, h ? h->X.p : nullptr, b, X); }
+int sdpcuda_get_S(sdpcuda_handle* h, int b, double* S) { return get_block(h, h ? h->S.p : nullptr, b, S); }
+
+int sdpcuda_get_xlp(sdpcuda_handle* h, double* x)
+{
+   if( h == nullptr || !h->solved ) return SDPCUDA_ERR_STATE;
+   if( set_device(h) ) return SDPCUDA_ERR_CUDA;
+   if( h->nlp > 0 ) CK( cudaMemcpyAsync(x, h->x.p, sizeof(double) * h->nlp, cudaMemcpyDeviceToHost, h->st) );
+   CK( cudaStreamSynchronize(h->st) );
+   return SDPCUDA_OK;
+}
+int sdpcuda_get_slp(sdpcuda_handle* h, double* s)
+{
+   if( h == nullptr || !h->solved ) return SDPCUDA_ERR_STATE;
+   if( set_device(h) ) return SDPCUDA_ERR_CUDA;
+   if( h->nlp > 0 ) CK( cudaMemcpyAsync(s, h->s.p, sizeof(double) * h->nlp, cudaMemcpyDeviceToHost, h->st) );
+   CK( cudaStreamSynchronize(h->st) );
+   return SDPCUDA_OK;
+}
+
+// ---- batched symmetric eigen-decomposition ---------------------------------------------------------------------------
+int sdpcuda_syev_batched(sdpcuda_handle* h, int n, int nbatch, const double* A, double* w, double* V)
+{
+   if( h == nullptr || n <= 0 || nbatch < 0 || A == nullptr || w == nullptr ) return SDPCUDA_ERR_ARG;
+   if( nbatch == 0 ) return SDPCUDA_OK;
+   if( set_device(h) ) return SDPCUDA_ERR_CUDA;
+   const size_t nn = (size_t)n * n;
+   CK( h->kA.ensure(nn * nbatch) ); CK( h->kB.ensure((size_t)n * nbatch) );
+   if( V != nullptr ) CK( h->kC.ensure(nn * nbatch) );
+   CK( cudaMemcpyAsync(h->kA.p, A, nn * nbatch * sizeof(double), cudaMemcpyHostToDevice, h->st) );
+   CK( jacobi_eig_batched(h->st, n, nbatch, h->kA.p, n, (long long)nn, h->kB.p, V ? h->kC.p : nullptr, nullptr) );
+   CK( cudaMemcpyAsync(w, h->kB.p, (size_t)n * nbatch * sizeof(double), cudaMemcpyDeviceToHost, h->st) );
+   if( V != nullptr ) CK( cudaMemcpyAsync(V, h->kC.p, nn * nbatch * sizeof(double), cudaMemcpyDeviceToHost, h->st) );
+   CK( cudaStreamSynchronize(h->st) );
+   return SDPCUDA_OK;
+}
+
+int sdpcuda_psd_check(sdpcuda_handle* h, int n, const double* A, int lda, double shift, int* is_psd);
+
+// ---- kernel-level entry points (host buffers) ------------------------------------------------------------------------
+static int up2d(sdpcuda_handle* h, DBuf<double>& buf, const double* src, int rows, int cols, int lds, int ldd)
+{
+   CK( buf.ensure((size_t)ldd * std::max(cols, 1)) );
+   CK( cudaMemsetAsync(buf.p, 0, sizeof(double) * (size_t)ldd * std::max(cols, 1), h->st) );
+   if( rows > 0 && cols > 0 )
+      CK( cudaMemcpy2DAsync(buf.p, sizeof(double) * ldd, src, sizeof(double) * lds, sizeof(double) * rows, cols, cudaMemcpyHostToDevice, h->st) );
+   return SDPCUDA_OK;
+}
+
+int sdpcuda_dgemm(sdpcuda_handle* h, int ta, int tb, int m, int n, int k, double alpha, const double* A, int lda,
+   const double* B, int ldb, double beta, double* C, int ldc)
+{
+   if( h == nullptr || m < 0 || n < 0 || k < 0 ) return SDPCUDA_ERR_ARG;
+   if( set_device(h) ) return SDPCUDA_ERR_CUDA;
+   const int ar = ta ? k : m, ac = ta ? m : k, br = tb ? n : k, bc = tb ? k : n;
+   const int dla = round_up(std::max(ar, 1), 4), dlb = round_up(std::max(br, 1), 4), dlc = round_up(std::max(m, 1), 4);
+   int rc;
+   if( (rc = up2d(h, h->kA, A, ar, ac, lda, dla)) || (rc = up2d(h, h->kB, B, br, bc, ldb, dlb)) || (rc = up2d(h, h->kC, C, m, n, ldc, dlc)) ) return rc;
+   CK( gemm(h->st, ta != 0, tb != 0, m, n, k, alpha, h->kA.p, dla, 0, h->kB.p, dlb, 0, beta, h->kC.p, dlc, 0, 1, 0) );
+   if( m > 0 && n > 0 )
+      CK( cudaMemcpy2DAsync(C, sizeof(double) * ldc, h->kC.p, sizeof(double) * dlc, sizeof(double) * m, n, cudaMemcpyDeviceToHost, h->st) );
+   CK( cudaStreamSynchronize(h->st) );
+   return SDPCUDA_OK;
+}
+
+int sdpcuda_dpotrf(sdpcuda_handle* h, int n, double* A, int lda, int* info)
+{
+   if( h == nullptr || n < 0 || info == nullptr ) return SDPCUDA_ERR_ARG;
+   if( set_device(h) ) return SDPCUDA_ERR_CUDA;
+   const int ld = round_up(std::max(n, 1), 4);
+   int rc;
+   if( (rc = up2d(h, h->kA, A, n, n, lda, ld)) ) return rc;
+   CK( h->kW.ensure((size_t)ld * (n + 2 * CHOL_NB)) );
+   CK( h->info.ensure(8) );
+   CK( cudaMemsetAsync(h->info.p, 0, 8 * sizeof(int), h->st) );
+   CK( h->kC.ensure((size_t)ceil_div(std::max(n, 1), CHOL_NB) * CHOL_NB * CHOL_NB) );
+   CK( potrf_lower(h->st, n, h->kA.p, ld, nullptr, 0, h->kC.p, h->kW.p, ld, h->info.p) );
+   if( n > 0 )
+      CK( cudaMemcpy2DAsync(A, sizeof(double) * lda, h->kA.p, sizeof(double) * ld, sizeof(double) * n, n, cudaMemcpyDeviceToHost, h->st) );
+   CK( cudaMemcpyAsync(h->h_info, h->info.p, sizeof(int), cudaMemcpyDeviceToHost, h->st) );
+   CK( cudaStreamSynchronize(h->st) );
+   *info = h->h_info[0];
+   return SDPCUDA_OK;
+}
+
+int sdpcuda_psd_check(sdpcuda_handle* h, int n, const double* A, int lda, double shift, int* is_psd)
+{
+   if( h == nullptr || n < 0 || is_psd == nullptr ) return SDPCUDA_ERR_ARG;
+   if( n == 0 ) { *is_psd = 1; return SDPCUDA_OK; }
+   if( set_device(h) ) return SDPCUDA_ERR_CUDA;
+   const int ld = round_up(n, 4);
+   int rc;
+   if( (rc = up2d(h, h->kA, A, n, n, lda, ld)) ) return rc;
+   CK( h->kW.ensure((size_t)ld * (n + 2 * CHOL_NB)) );
+   CK( h->info.ensure(8) );
+   CK( cudaMemsetAsync(h->info.p, 0, 8 * sizeof(int), h->st) );
+   if( shift != 0.0 ) CK( add_diagonal(h->st, n, h->kA.p, ld, shift) );
+   CK( potrf_lower(h->st, n, h->kA.p, ld, nullptr, 0, nullptr, h->kW.p, ld, h->info.p) );
+   CK( cudaMemcpyAsync(h->h_info, h->info.p, sizeof(int), cudaMemcpyDeviceToHost, h->st) );
+   CK( cudaStreamSynchronize(h->st) );
+   *is_psd = (h->h_info[0] == 0) ? 1 : 0;
+   return SDPCUDA_OK;
+}
+
+int sdpcuda_dtrtri(sdpcuda_handle* h, int n, double* L, int ldl)
+{
+   if( h == nullptr || n < 0 ) return SDPCUDA_ERR_ARG;
+   if( set_device(h) ) return SDPCUDA_ERR_CUDA;
+   const int ld = round_up(std::max(n, 1), 4);
+   int rc;
+   if( (rc = up2d(h, h->kA, L, n, n, ldl, ld)) ) return rc;
+   CK( h->kB.ensure((size_t)ld * std::max(n, 1)) );
+   CK( h->kW.ensure((size_t)ld * (n + 2 * CHOL_NB)) );
+   CK( trtri_lower(h->st, n, h->kA.p, ld, h->kB.p, ld, h->kW.p, ld) );
+   if( n > 0 )
+      CK( cudaMemcpy2DAsync(L, sizeof(double) * ldl, h->kB.p, sizeof(double) * ld, sizeof(double) * n, n, cudaMemcpyDeviceToHost, h->st) );
+   CK( cudaStreamSynchronize(h->st) );
+   return SDPCUDA_OK;
+}
+
+__global__ void fill_random_kernel(size_t n, double* a, unsigned seed, double diagboost, int ld)
+{
+   for( size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x )
+   {
+      unsigned hsh = (unsigned)(i * 2654435761ull) ^ seed;
+      hsh ^= hsh >> 15; hsh *= 2246822519u; hsh ^= hsh >> 13; hsh *= 3266489917u; hsh ^= hsh >> 16;
+      double v = (double)(hsh & 0xffffff) / 16777216.0 - 0.5;
+      if( ld > 0 && (i % ld) == (i / ld) ) v += diagboost;
+      a[i] = v;
+   }
+}
+
+int sdpcuda_time_kernel(sdpcuda_handle* h, int kind, int n, int reps, double* ms_per_launch, double* work)
+{
+   if( h == nullptr || reps <= 0 || ms_per_launch == nullptr || work == nullptr ) return SDPCUDA_ERR_ARG;
+   if( set_device(h) ) return SDPCUDA_ERR_CUDA;
+   cudaStream_t st = h->st;
+   const int ld = round_up(std::max(n, 1), 4);
+   const size_t nn = (size_t)ld * std::max(n, 1);
+   float ms = 0.f;
+   if( kind == 4 )
+   {
+      CK( h->kA.ensure(16) );
+      double fl = 0;
+      CK( dmma_peak_probe(st, 2000, h->kA.p, &fl) );       // warm-up
+      CK( cudaEventRecord(h->ev0, st) );
+      for( int r = 0; r < reps; ++r ) CK( dmma_peak_probe(st, 20000, h->kA.p, &fl) );
+      CK( cudaEventRecord(h->ev1, st) );
+      CK( cudaStreamSynchronize(st) );
+      cudaEventElapsedTime(&ms, h->ev0, h->ev1);
+      *ms_per_launch = ms / reps; *work = fl;
+      return SDPCUDA_OK;
+   }
+   if( n <= 0 ) return SDPCUDA_ERR_ARG;
+   CK( h->kA.ensure(nn) ); CK( h->kB.ensure(nn) ); CK( h->kC.ensure(nn) ); CK( h->kW.ensure((size_t)ld * (n + 2 * CHOL_NB)) );
+   CK( h->K.ensure(nn) );
+   CK( h->info.ensure(8) );
+   fill_random_kernel<<<1024, 256, 0, st>>>(nn, h->kA.p, 17u, kind == 2 || kind == 3 ? (double)n : 0.0, ld);
+   fill_random_kernel<<<1024, 256, 0, st>>>(nn, h->kB.p, 91u, 0.0, ld);
+   CK( cudaGetLastError() );
+   auto run = [&]() -> cudaError_t {
+      switch( kind )
+      {
+      case 0: return gemm(st, false, false, n, n, n, 1.0, h->kA.p, ld, 0, h->kB.p, ld, 0, 0.0, h->kC.p, ld, 0, 1, 0);
+      case 1: return gemm(st, false, true, n, n, n, 1.0, h->kA.p, ld, 0, h->kB.p, ld, 0, 0.0, h->kC.p, ld, 0, 1, 0);
+      case 5: return gemm(st, false, true, n, n, n, 1.0, h->kA.p, ld, 0, h->kA.p, ld, 0, 0.0, h->kC.p, ld, 0, 1, GEMM_LOWER);
+      case 2:
+      {
+         cudaError_t e = cudaMemcpyAsync(h->kC.p, h->kA.p, nn * sizeof(double), cudaMemcpyDeviceToDevice, st);
+         if( e != cudaSuccess ) return e;
+         return potrf_lower(st, n, h->kC.p, ld, h->K.p, ld, nullptr, h->kW.p, ld, h->info.p);
+      }
+      case 3:
+      {
+         cudaError_t e = cudaMemcpyAsync(h->kC.p, h->kA.p, nn * sizeof(double), cudaMemcpyDeviceToDevice, st);
+         if( e != cudaSuccess ) return e;
+         return potrf_lower(st, n, h->kC.p, ld, nullptr, 0, nullptr, h->kW.p, ld, h->info.p);
+      }
+      case 6: return cudaMemcpyAsync(h->kC.p, h->kA.p, nn * sizeof(double), cudaMemcpyDeviceToDevice, st);
+      default: return cudaErrorInvalidValue;
+      }
+   };
+   if( kind == 2 || kind == 3 )
+   {
+      // symmetric positive definite input: A := (A + A')/2 + n I  (diagonal boost applied by the fill kernel)
+      CK( sym_average(st, n, h->kA.p, ld, nullptr) );
+   }
+   for( int r = 0; r < 3; ++r ) CK( run() );
+   CK( cudaEventRecord(h->ev0, st) );
+   for( int r = 0; r < reps; ++r ) CK( run() );
+   CK( cudaEventRecord(h->ev1, st) );
+   CK( cudaStreamSynchronize(st) );
+   cudaEventElapsedTime(&ms, h->ev0, h->ev1);
+   *ms_per_launch = ms / reps;
+   const double dn = (double)n;
+   switch( kind )
+   {
+   case 0: case 1: *work = 2.0 * dn * dn * dn; break;
+   case 5: *work = dn * dn * dn; break;                 // algorithmic SYRK flops (lower triangle)
+   case 2: *work = 2.0 * dn * dn * dn / 3.0; break;     // Cholesky n^3/3 + triangular inverse n^3/3
+   case 3: *work = dn * dn * dn / 3.0; break;
+   case 6: *work = 2.0 * nn * sizeof(double); break;    // bytes read + written
+   }
+   return SDPCUDA_OK;
+}
+
+} // extern "C"

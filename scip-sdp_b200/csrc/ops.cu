@@ -1,0 +1,526 @@
+// ops.cu — see ops.cuh.  HBM-bound kernels: coalesced arena sweeps, grid-stride loops on a fixed grid of RED_BLOCKS CTAs
+// for everything that reduces (partials are summed in a fixed order, so results are bit-reproducible run to run).
+#include "ops.cuh"
+
+namespace sdpk {
+
+// layout of the statistics row: columns [0,16) are sums, [16,24) are maxima
+constexpr int NSTAT = 24;
+constexpr int NSUM = 16;
+
+namespace {
+
+__device__ __forceinline__ double warp_sum(double v)
+{
+#pragma unroll
+   for( int o = 16; o > 0; o >>= 1 ) v += __shfl_xor_sync(0xffffffffu, v, o);
+   return v;
+}
+__device__ __forceinline__ double warp_max(double v)
+{
+#pragma unroll
+   for( int o = 16; o > 0; o >>= 1 ) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+   return v;
+}
+// block reductions in a fixed order; blockDim.x must be a multiple of 32 and <= 1024
+__device__ double block_sum(double v, double* red)
+{
+   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+   v = warp_sum(v);
+   __syncthreads();
+   if( lane == 0 ) red[warp] = v;
+   __syncthreads();
+   double s = 0.0;
+   for( int w = 0; w < nw; ++w ) s += red[w];
+   return s;
+}
+__device__ double block_max(double v, double* red)
+{
+   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+   v = warp_max(v);
+   __syncthreads();
+   if( lane == 0 ) red[warp] = v;
+   __syncthreads();
+   double s = red[0];
+   for( int w = 1; w < nw; ++w ) s = fmax(s, red[w]);
+   return s;
+}
+
+__global__ void assemble_kernel(int npos, const int* __restrict__ posbeg, const long long* __restrict__ pos,
+   const long long* __restrict__ mirror, const int* __restrict__ posvar, const double* __restrict__ posval,
+   const double* __restrict__ posc, const double* __restrict__ y, double cscale, double* __restrict__ T)
+{
+   int p = blockIdx.x * blockDim.x + threadIdx.x;
+   if( p >= npos ) return;
+   double v = -cscale * posc[p];
+   for( int e = posbeg[p]; e < posbeg[p + 1]; ++e ) v += y[posvar[e]] * posval[e];
+   T[pos[p]] = v;
+   T[mirror[p]] = v;
+}
+
+__global__ void __launch_bounds__(256)
+residual_matrix_kernel(size_t arena, const double* __restrict__ T, const double* __restrict__ S, const double* __restrict__ X,
+   double* __restrict__ Rd, double* __restrict__ partials)
+{
+   __shared__ double red[32];
+   double s0 = 0.0, s1 = 0.0;
+   for( size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < arena; i += (size_t)gridDim.x * blockDim.x )
+   {
+      double s = S[i], r = T[i] - s;
+      Rd[i] = r;
+      s0 += r * r;
+      s1 += X[i] * s;
+   }
+   s0 = block_sum(s0, red);
+   s1 = block_sum(s1, red);
+   if( threadIdx.x == 0 ) { partials[blockIdx.x * NSTAT + 0] = s0; partials[blockIdx.x * NSTAT + 1] = s1; }
+}
+
+__global__ void apply_A_kernel(int m, DevEntries E, const double* __restrict__ X, double* __restrict__ out)
+{
+   int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+   if( warp >= m ) return;
+   double s = 0.0;
+   for( int e = E.varbeg[warp] + lane; e < E.varbeg[warp + 1]; e += 32 )
+   {
+      int r = E.row[e], c = E.col[e], ld = E.ld[e];
+      const double* Xk = X + E.off[e];
+      double v = Xk[(size_t)c * ld + r];
+      if( r != c ) v += Xk[(size_t)r * ld + c];
+      s += E.val[e] * v;
+   }
+   s = warp_sum(s);
+   if( lane == 0 ) out[warp] = s;
+}
+
+__global__ void __launch_bounds__(1024)
+const_dots_kernel(int cnnz, const long long* __restrict__ cpos, const long long* __restrict__ cmirror,
+   const double* __restrict__ cval, const double* __restrict__ X, const double* __restrict__ Y, double* __restrict__ out2)
+{
+   __shared__ double red[32];
+   double a = 0.0, b = 0.0;
+   for( int e = threadIdx.x; e < cnnz; e += blockDim.x )
+   {
+      long long p = cpos[e], q = cmirror[e];
+      double c = cval[e];
+      a += c * (X[p] + (p != q ? X[q] : 0.0));
+      if( Y != nullptr ) b += c * (Y[p] + (p != q ? Y[q] : 0.0));
+   }
+   a = block_sum(a, red);
+   b = block_sum(b, red);
+   if( threadIdx.x == 0 ) { out2[0] = a; out2[1] = b; }
+}
+
+__global__ void __launch_bounds__(256)
+lp_rows_kernel(int nlp, const int* __restrict__ lpbeg, const int* __restrict__ lpind, const double* __restrict__ lpval,
+   const double* __restrict__ lprhs, const double* __restrict__ y, const double* __restrict__ x, const double* __restrict__ s,
+   double* __restrict__ Dy, double* __restrict__ rdlp, double* __restrict__ partials)
+{
+   __shared__ double red[32];
+   double a2 = 0.0, axs = 0.0, adx = 0.0, aray = 0.0, amax = 0.0;
+   for( int l = blockIdx.x * blockDim.x + threadIdx.x; l < nlp; l += gridDim.x * blockDim.x )
+   {
+      double d = 0.0;
+      for( int p = lpbeg[l]; p < lpbeg[l + 1]; ++p ) d += lpval[p] * y[lpind[p]];
+      double r = d - lprhs[l] - s[l];
+      Dy[l] = d;
+      rdlp[l] = r;
+      a2 += r * r;
+      axs += x[l] * s[l];
+      adx += lprhs[l] * x[l];
+      double h = d - s[l];
+      aray += h * h;
+      amax = fmax(amax, fabs(r));
+   }
+   a2 = block_sum(a2, red); axs = block_sum(axs, red); adx = block_sum(adx, red); aray = block_sum(aray, red);
+   amax = block_max(amax, red);
+   if( threadIdx.x == 0 )
+   {
+      double* p = partials + blockIdx.x * NSTAT;
+      p[2] = a2; p[3] = axs; p[4] = adx; p[5] = aray; p[16] = amax;
+   }
+}
+
+__global__ void lp_cols_kernel(int m, const int* __restrict__ colbeg, const int* __restrict__ colrow, const double* __restrict__ colval,
+   const double* __restrict__ x, double* __restrict__ out, int accumulate)
+{
+   int j = blockIdx.x * blockDim.x + threadIdx.x;
+   if( j >= m ) return;
+   double s = 0.0;
+   for( int p = colbeg[j]; p < colbeg[j + 1]; ++p ) s += colval[p] * x[colrow[p]];
+   out[j] = accumulate ? out[j] + s : s;
+}
+
+__global__ void __launch_bounds__(256)
+primal_residual_kernel(int m, const double* __restrict__ b, const double* __restrict__ AX, const double* __restrict__ DTx,
+   const double* __restrict__ y, double* __restrict__ rp, double* __restrict__ partials)
+{
+   __shared__ double red[32];
+   double a2 = 0.0, aray = 0.0, aby = 0.0, amax = 0.0;
+   for( int j = blockIdx.x * blockDim.x + threadIdx.x; j < m; j += gridDim.x * blockDim.x )
+   {
+      double ax = AX[j] + DTx[j];
+      double r = b[j] - ax;
+      rp[j] = r;
+      a2 += r * r;
+      aray += ax * ax;
+      aby += b[j] * y[j];
+      amax = fmax(amax, fabs(r));
+   }
+   a2 = block_sum(a2, red); aray = block_sum(aray, red); aby = block_sum(aby, red); amax = block_max(amax, red);
+   if( threadIdx.x == 0 )
+   {
+      double* p = partials + blockIdx.x * NSTAT;
+      p[6] = a2; p[7] = aray; p[8] = aby; p[17] = amax;
+   }
+}
+
+__global__ void finalize_kernel(const double* __restrict__ partials, int nblocks, double* __restrict__ out)
+{
+   int c = threadIdx.x;
+   if( c >= NSTAT ) return;
+   double v = partials[c];
+   for( int b = 1; b < nblocks; ++b )
+   {
+      double p = partials[b * NSTAT + c];
+      v = (c < NSUM) ? v + p : fmax(v, p);
+   }
+   out[c] = v;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Schur complement, entry/gather path:  M_ij = sum over entry pairs of A_i, A_j in the same block of
+//     a_i(p,q) a_j(r,c) [ X(q,r) Z(c,p) + X(q,c) Z(r,p) + X(p,r) Z(c,q) + X(p,c) Z(r,q) ]   (terms dropped on diagonals)
+// ---------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double pair_term(const DevEntries& E, int ei, int ej, const double* __restrict__ X, const double* __restrict__ Z)
+{
+   if( E.off[ei] != E.off[ej] ) return 0.0;
+   const int ld = E.ld[ei];
+   const double* Xk = X + E.off[ei];
+   const double* Zk = Z + E.off[ei];
+   const int p = E.row[ei], q = E.col[ei], r = E.row[ej], c = E.col[ej];
+   double t = Xk[(size_t)r * ld + q] * Zk[(size_t)p * ld + c];
+   if( r != c ) t += Xk[(size_t)c * ld + q] * Zk[(size_t)p * ld + r];
+   if( p != q )
+   {
+      t += Xk[(size_t)r * ld + p] * Zk[(size_t)q * ld + c];
+      if( r != c ) t += Xk[(size_t)c * ld + p] * Zk[(size_t)q * ld + r];
+   }
+   return E.val[ei] * E.val[ej] * t;
+}
+
+// light pairs: one thread per (i, j), i >= j, both variables light
+__global__ void __launch_bounds__(256)
+schur_light_kernel(int m, DevEntries E, const int* __restrict__ heavy, const double* __restrict__ X, const double* __restrict__ Z,
+   double* __restrict__ M, int ldm)
+{
+   const int i = blockIdx.x * 32 + (threadIdx.x & 31);
+   const int j = blockIdx.y * 8 + (threadIdx.x >> 5);
+   if( blockIdx.x * 32 + 31 < blockIdx.y * 8 ) return;          // tile strictly above the diagonal
+   if( i >= m || j >= m || i < j ) return;
+   if( heavy[i] || heavy[j] ) return;
+   double v = 0.0;
+   for( int ei = E.varbeg[i]; ei < E.varbeg[i + 1]; ++ei )
+      for( int ej = E.varbeg[j]; ej < E.varbeg[j + 1]; ++ej )
+         v += pair_term(E, ei, ej, X, Z);
+   M[(size_t)j * ldm + i] = v;
+}
+
+// heavy pairs: one CTA per (heavy variable h, other variable o); the CTA splits the entry-pair product
+__global__ void __launch_bounds__(256)
+schur_heavy_kernel(int m, DevEntries E, const int* __restrict__ heavy, const int* __restrict__ heavylist,
+   const double* __restrict__ X, const double* __restrict__ Z, double* __restrict__ M, int ldm)
+{
+   __shared__ double red[32];
+   const int h = heavylist[blockIdx.y];
+   const int o = blockIdx.x;
+   if( heavy[o] && o > h ) return;                                // heavy-heavy pairs once
+   const int bh = E.varbeg[h], nh = E.varbeg[h + 1] - bh;
+   const int bo = E.varbeg[o], no = E.varbeg[o + 1] - bo;
+   double v = 0.0;
+   const long long total = (long long)nh * no;
+   for( long long t = threadIdx.x; t < total; t += blockDim.x )
+   {
+      int eh = bh + (int)(t / no), eo = bo + (int)(t % no);
+      v += pair_term(E, eh, eo, X, Z);
+   }
+   v = block_sum(v, red);
+   if( threadIdx.x == 0 )
+   {
+      int i = max(h, o), j = min(h, o);
+      M[(size_t)j * ldm + i] = v;
+   }
+}
+
+__global__ void schur_lp_kernel(int nlp, const int* __restrict__ lpbeg, const int* __restrict__ lpind, const double* __restrict__ lpval,
+   const double* __restrict__ x, const double* __restrict__ s, double* __restrict__ M, int ldm)
+{
+   int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+   if( warp >= nlp ) return;
+   const int b = lpbeg[warp], cnt = lpbeg[warp + 1] - b;
+   const double w = x[warp] / s[warp];
+   for( int t = lane; t < cnt * cnt; t += 32 )
+   {
+      int p = b + t / cnt, q = b + t % cnt;
+      int i = lpind[p], j = lpind[q];
+      if( i >= j )
+         atomicAdd(&M[(size_t)j * ldm + i], w * lpval[p] * lpval[q]);
+   }
+}
+
+__global__ void add_diagonal_kernel(int n, double* __restrict__ A, int lda, double v)
+{
+   int i = blockIdx.x * blockDim.x + threadIdx.x;
+   if( i < n ) A[(size_t)i * lda + i] += v;
+}
+
+// y = M x with M given by its lower triangle: one warp per row (row part from the row, column part from the column)
+__global__ void symv_lower_kernel(int n, const double* __restrict__ M, int ldm, const double* __restrict__ x, double* __restrict__ y)
+{
+   int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+   if( i >= n ) return;
+   double s = 0.0;
+   for( int k = lane; k < i; k += 32 ) s += M[(size_t)k * ldm + i] * x[k];          // row i, columns k < i  (strided)
+   for( int k = i + lane; k < n; k += 32 ) s += M[(size_t)i * ldm + k] * x[k];      // column i, rows k >= i (contiguous)
+   s = warp_sum(s);
+   if( lane == 0 ) y[i] = s;
+}
+
+__global__ void sym_average_kernel(int n, double* __restrict__ A, int lda, const double* __restrict__ sub)
+{
+   int i = blockIdx.x * blockDim.x + threadIdx.x;
+   int j = blockIdx.y;
+   if( i >= n || i < j ) return;
+   double v = 0.5 * (A[(size_t)j * lda + i] + A[(size_t)i * lda + j]);
+   if( sub != nullptr ) v -= sub[(size_t)j * lda + i];
+   A[(size_t)j * lda + i] = v;
+   A[(size_t)i * lda + j] = v;
+}
+
+__global__ void mirror_lower_kernel(int n, double* __restrict__ A, int lda)
+{
+   int i = blockIdx.x * blockDim.x + threadIdx.x;
+   int j = blockIdx.y;
+   if( i >= n || i <= j ) return;
+   A[(size_t)i * lda + j] = A[(size_t)j * lda + i];
+}
+
+__global__ void axpy_kernel(size_t n, double a, const double* __restrict__ x, double* __restrict__ y)
+{
+   for( size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x )
+      y[i] += a * x[i];
+}
+
+__global__ void axpby_kernel(size_t n, double a, const double* __restrict__ x, double b, const double* __restrict__ y, double* __restrict__ out)
+{
+   for( size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x )
+      out[i] = a * x[i] + b * y[i];
+}
+
+__global__ void lp_rhs_kernel(int nlp, int corr, double sigmamu, const double* __restrict__ x, const double* __restrict__ s,
+   const double* __restrict__ rd, const double* __restrict__ dxa, const double* __restrict__ dsa, double* __restrict__ klp)
+{
+   int l = blockIdx.x * blockDim.x + threadIdx.x;
+   if( l >= nlp ) return;
+   double c = -x[l] * rd[l];
+   if( corr ) c += sigmamu - dxa[l] * dsa[l];
+   klp[l] = c / s[l] - x[l];
+}
+
+__global__ void __launch_bounds__(1024)
+lp_direction_kernel(int nlp, const double* __restrict__ x, const double* __restrict__ s, const double* __restrict__ rd,
+   const double* __restrict__ klp, const double* __restrict__ Ddy, double* __restrict__ dx, double* __restrict__ ds, double* __restrict__ out2)
+{
+   __shared__ double red[32];
+   double ap = -1e300, ad = -1e300;          // we reduce max of -ratio, i.e. min ratio
+   for( int l = threadIdx.x; l < nlp; l += blockDim.x )
+   {
+      double ddy = Ddy[l];
+      double vx = klp[l] - x[l] / s[l] * ddy;
+      double vs = ddy + rd[l];
+      dx[l] = vx; ds[l] = vs;
+      if( vx < 0.0 ) ap = fmax(ap, x[l] / vx);       // x/vx is negative; the largest (closest to 0) is the binding ratio
+      if( vs < 0.0 ) ad = fmax(ad, s[l] / vs);
+   }
+   ap = block_max(ap, red);
+   ad = block_max(ad, red);
+   if( threadIdx.x == 0 ) { out2[0] = (ap > -1e299) ? -ap : 1e30; out2[1] = (ad > -1e299) ? -ad : 1e30; }
+}
+
+__global__ void __launch_bounds__(256)
+affine_mu_kernel(size_t arena, const double* __restrict__ X, const double* __restrict__ dX, const double* __restrict__ S,
+   const double* __restrict__ dS, int nlp, const double* __restrict__ x, const double* __restrict__ dx, const double* __restrict__ s,
+   const double* __restrict__ ds, double ap, double ad, double* __restrict__ partials)
+{
+   __shared__ double red[32];
+   double a = 0.0, b = 0.0;
+   for( size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < arena; i += (size_t)gridDim.x * blockDim.x )
+      a += (X[i] + ap * dX[i]) * (S[i] + ad * dS[i]);
+   for( int l = blockIdx.x * blockDim.x + threadIdx.x; l < nlp; l += gridDim.x * blockDim.x )
+      b += (x[l] + ap * dx[l]) * (s[l] + ad * ds[l]);
+   a = block_sum(a, red); b = block_sum(b, red);
+   if( threadIdx.x == 0 ) { partials[blockIdx.x * NSTAT + 9] = a; partials[blockIdx.x * NSTAT + 10] = b; }
+}
+
+__global__ void pick_kernel(const double* __restrict__ src, double* __restrict__ dst) { dst[0] = src[0]; }
+
+inline int grid_for(size_t n, int threads) { return (int)std::min<size_t>((n + threads - 1) / threads, 148 * 16); }
+
+} // namespace
+
+#define LAUNCH_END() do { count_launch(); return cudaGetLastError(); } while( 0 )
+
+cudaError_t assemble_positions(cudaStream_t st, int npos, const int* posbeg, const long long* pos, const long long* mirror,
+   const int* posvar, const double* posval, const double* posc, const double* y, double cscale, double* T)
+{
+   if( npos <= 0 ) return cudaSuccess;
+   assemble_kernel<<<ceil_div(npos, 256), 256, 0, st>>>(npos, posbeg, pos, mirror, posvar, posval, posc, y, cscale, T);
+   LAUNCH_END();
+}
+
+cudaError_t residual_matrix(cudaStream_t st, size_t arena, const double* T, const double* S, const double* X, double* Rd, double* partials)
+{
+   residual_matrix_kernel<<<RED_BLOCKS, 256, 0, st>>>(arena, T, S, X, Rd, partials);
+   LAUNCH_END();
+}
+
+cudaError_t apply_A(cudaStream_t st, int m, DevEntries E, const double* X, double* out)
+{
+   if( m <= 0 ) return cudaSuccess;
+   apply_A_kernel<<<ceil_div(m, 8), 256, 0, st>>>(m, E, X, out);
+   LAUNCH_END();
+}
+
+cudaError_t const_dots(cudaStream_t st, int cnnz, const long long* cpos, const long long* cmirror, const double* cval,
+   const double* X, const double* Y, double* out2)
+{
+   const_dots_kernel<<<1, 1024, 0, st>>>(cnnz, cpos, cmirror, cval, X, Y, out2);
+   LAUNCH_END();
+}
+
+cudaError_t lp_rows(cudaStream_t st, int nlp, const int* lpbeg, const int* lpind, const double* lpval, const double* lprhs,
+   const double* y, const double* x, const double* s, double* Dy, double* rdlp, double* partials)
+{
+   lp_rows_kernel<<<RED_BLOCKS, 256, 0, st>>>(nlp, lpbeg, lpind, lpval, lprhs, y, x, s, Dy, rdlp, partials);
+   LAUNCH_END();
+}
+
+cudaError_t lp_cols(cudaStream_t st, int m, const int* colbeg, const int* colrow, const double* colval, const double* x,
+   double* out, int accumulate)
+{
+   if( m <= 0 ) return cudaSuccess;
+   lp_cols_kernel<<<ceil_div(m, 256), 256, 0, st>>>(m, colbeg, colrow, colval, x, out, accumulate);
+   LAUNCH_END();
+}
+
+cudaError_t primal_residual(cudaStream_t st, int m, const double* b, const double* AX, const double* DTx, const double* y,
+   double* rp, double* partials)
+{
+   primal_residual_kernel<<<RED_BLOCKS, 256, 0, st>>>(m, b, AX, DTx, y, rp, partials);
+   LAUNCH_END();
+}
+
+cudaError_t finalize_partials(cudaStream_t st, const double* partials, int nstats, double* out)
+{
+   (void)nstats;
+   finalize_kernel<<<1, 32, 0, st>>>(partials, RED_BLOCKS, out);
+   LAUNCH_END();
+}
+
+cudaError_t schur_entries(cudaStream_t st, int m, DevEntries E, const int* heavy, const int* heavylist, int nheavy,
+   const double* X, const double* Z, double* M, int ldm)
+{
+   if( m <= 0 ) return cudaSuccess;
+   dim3 grid(ceil_div(m, 32), ceil_div(m, 8));
+   schur_light_kernel<<<grid, 256, 0, st>>>(m, E, heavy, X, Z, M, ldm);
+   count_launch();
+   if( nheavy > 0 )
+   {
+      dim3 g2(m, nheavy);
+      schur_heavy_kernel<<<g2, 256, 0, st>>>(m, E, heavy, heavylist, X, Z, M, ldm);
+      count_launch();
+   }
+   return cudaGetLastError();
+}
+
+cudaError_t schur_lp(cudaStream_t st, int nlp, const int* lpbeg, const int* lpind, const double* lpval, const double* x,
+   const double* s, double* M, int ldm)
+{
+   if( nlp <= 0 ) return cudaSuccess;
+   schur_lp_kernel<<<ceil_div(nlp, 8), 256, 0, st>>>(nlp, lpbeg, lpind, lpval, x, s, M, ldm);
+   LAUNCH_END();
+}
+
+cudaError_t add_diagonal(cudaStream_t st, int n, double* A, int lda, double v)
+{
+   if( n <= 0 ) return cudaSuccess;
+   add_diagonal_kernel<<<ceil_div(n, 256), 256, 0, st>>>(n, A, lda, v);
+   LAUNCH_END();
+}
+
+cudaError_t symv_lower(cudaStream_t st, int n, const double* M, int ldm, const double* x, double* y)
+{
+   if( n <= 0 ) return cudaSuccess;
+   symv_lower_kernel<<<ceil_div(n, 8), 256, 0, st>>>(n, M, ldm, x, y);
+   LAUNCH_END();
+}
+
+cudaError_t sym_average(cudaStream_t st, int n, double* A, int lda, const double* subtract)
+{
+   if( n <= 0 ) return cudaSuccess;
+   dim3 grid(ceil_div(n, 256), n);
+   sym_average_kernel<<<grid, 256, 0, st>>>(n, A, lda, subtract);
+   LAUNCH_END();
+}
+
+cudaError_t mirror_lower(cudaStream_t st, int n, double* A, int lda)
+{
+   if( n <= 1 ) return cudaSuccess;
+   dim3 grid(ceil_div(n, 256), n);
+   mirror_lower_kernel<<<grid, 256, 0, st>>>(n, A, lda);
+   LAUNCH_END();
+}
+
+cudaError_t axpy(cudaStream_t st, size_t n, double a, const double* x, double* y)
+{
+   if( n == 0 ) return cudaSuccess;
+   axpy_kernel<<<grid_for(n, 256), 256, 0, st>>>(n, a, x, y);
+   LAUNCH_END();
+}
+
+cudaError_t axpby_out(cudaStream_t st, size_t n, double a, const double* x, double b, const double* y, double* out)
+{
+   if( n == 0 ) return cudaSuccess;
+   axpby_kernel<<<grid_for(n, 256), 256, 0, st>>>(n, a, x, b, y, out);
+   LAUNCH_END();
+}
+
+cudaError_t lp_rhs(cudaStream_t st, int nlp, int corr, double sigmamu, const double* x, const double* s, const double* rd,
+   const double* dxa, const double* dsa, double* klp)
+{
+   if( nlp <= 0 ) return cudaSuccess;
+   lp_rhs_kernel<<<ceil_div(nlp, 256), 256, 0, st>>>(nlp, corr, sigmamu, x, s, rd, dxa, dsa, klp);
+   LAUNCH_END();
+}
+
+cudaError_t lp_direction(cudaStream_t st, int nlp, const double* x, const double* s, const double* rd, const double* klp,
+   const double* Ddy, double* dx, double* ds, double* out2)
+{
+   lp_direction_kernel<<<1, 1024, 0, st>>>(nlp, x, s, rd, klp, Ddy, dx, ds, out2);
+   LAUNCH_END();
+}
+
+cudaError_t affine_mu(cudaStream_t st, size_t arena, const double* X, const double* dX, const double* S, const double* dS,
+   int nlp, const double* x, const double* dx, const double* s, const double* ds, double ap, double ad, double* partials)
+{
+   affine_mu_kernel<<<RED_BLOCKS, 256, 0, st>>>(arena, X, dX, S, dS, nlp, x, dx, s, ds, ap, ad, partials);
+   LAUNCH_END();
+}
+
+cudaError_t pick_value(cudaStream_t st, const double* src, double* dst)
+{
+   pick_kernel<<<1, 1, 0, st>>>(src, dst);
+   LAUNCH_END();
+}
+
+} // namespace sdpk

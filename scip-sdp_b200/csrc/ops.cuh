@@ -1,0 +1,66 @@
+// ops.cuh — memory-bound kernels of the interior-point iteration: sparse operators A(.) and A'(.), LP-block operators,
+// Schur-complement assembly (entry/gather path and LP block), element-wise updates and deterministic reductions.
+// All dense SDP-block matrices live in one "arena" (block k at offset off[k], column-major, leading dimension ld[k]).
+#pragma once
+#include "common.cuh"
+
+namespace sdpk {
+
+struct DevEntries            // constraint-matrix entries, CSR over variables
+{
+   const int* varbeg;        // [m+1]
+   const int* row;           // [nnz]  row >= col
+   const int* col;
+   const int* ld;            // leading dimension of the entry's block
+   const long long* off;     // arena offset of the entry's block
+   const double* val;
+};
+
+constexpr int RED_BLOCKS = 256;      // partial sums per reduction (stage 1), summed in fixed order (stage 2)
+
+// T[pos] = T[mirror] = -c + sum_j y_j a_j  over the positions of the aggregate sparsity pattern (T zeroed before)
+cudaError_t assemble_positions(cudaStream_t st, int npos, const int* posbeg, const long long* pos, const long long* mirror,
+   const int* posvar, const double* posval, const double* posc, const double* y, double cscale, double* T);
+// Rd = T - S over the arena; stats[0] += sum Rd^2, stats[1] += sum X.S   (partials -> finalize)
+cudaError_t residual_matrix(cudaStream_t st, size_t arena, const double* T, const double* S, const double* X, double* Rd, double* partials);
+// out[j] = sum_e val * (X[p1] + X[p2]) per variable
+cudaError_t apply_A(cudaStream_t st, int m, DevEntries E, const double* X, double* out);
+// sparse constant matrix: stats = sum c * (X[pos] (+ X[mirror])), same for a second matrix Y (or nullptr)
+cudaError_t const_dots(cudaStream_t st, int cnnz, const long long* cpos, const long long* cmirror, const double* cval,
+   const double* X, const double* Y, double* out2);
+// LP rows: Dy, rdlp = Dy - d - s, partial statistics
+cudaError_t lp_rows(cudaStream_t st, int nlp, const int* lpbeg, const int* lpind, const double* lpval, const double* lprhs,
+   const double* y, const double* x, const double* s, double* Dy, double* rdlp, double* partials);
+// out[j] (+)= sum over column j of D: val * x[row]
+cudaError_t lp_cols(cudaStream_t st, int m, const int* colbeg, const int* colrow, const double* colval, const double* x,
+   double* out, int accumulate);
+// rp = b - AX - DTx and statistics
+cudaError_t primal_residual(cudaStream_t st, int m, const double* b, const double* AX, const double* DTx, const double* y,
+   double* rp, double* partials);
+cudaError_t finalize_partials(cudaStream_t st, const double* partials, int nstats, double* out);
+
+// Schur complement (lower triangle of M, ldm): entry/gather path over all variable pairs, LP block via atomics
+cudaError_t schur_entries(cudaStream_t st, int m, DevEntries E, const int* heavy /* [m] 0/1 */, const int* heavylist, int nheavy,
+   const double* X, const double* Z, double* M, int ldm);
+cudaError_t schur_lp(cudaStream_t st, int nlp, const int* lpbeg, const int* lpind, const double* lpval, const double* x,
+   const double* s, double* M, int ldm);
+cudaError_t add_diagonal(cudaStream_t st, int n, double* A, int lda, double v);
+cudaError_t symv_lower(cudaStream_t st, int n, const double* M, int ldm, const double* x, double* y);   // y = M x, M lower stored
+
+// dense block helpers
+cudaError_t sym_average(cudaStream_t st, int n, double* A, int lda, const double* subtract /* or nullptr */);   // A = (A+A')/2 - subtract
+cudaError_t mirror_lower(cudaStream_t st, int n, double* A, int lda);                                            // upper = lower'
+cudaError_t axpy(cudaStream_t st, size_t n, double a, const double* x, double* y);                               // y += a x
+cudaError_t axpby_out(cudaStream_t st, size_t n, double a, const double* x, double b, const double* y, double* out);
+// LP direction: klp = (sigmamu - dxa*dsa - x*rd)/s - x   (corr = 0 drops the first two terms)
+cudaError_t lp_rhs(cudaStream_t st, int nlp, int corr, double sigmamu, const double* x, const double* s, const double* rd,
+   const double* dxa, const double* dsa, double* klp);
+// ds = D dy + rd (Ddy given), dx = klp - x/s * (D dy); also max step lengths to the boundary (partials: min ratios)
+cudaError_t lp_direction(cudaStream_t st, int nlp, const double* x, const double* s, const double* rd, const double* klp,
+   const double* Ddy, double* dx, double* ds, double* out2 /* alpha_p_max, alpha_d_max */);
+// sum (x + ap dx)(s + ad ds) and sum (X + ap dX).(S + ad dS)
+cudaError_t affine_mu(cudaStream_t st, size_t arena, const double* X, const double* dX, const double* S, const double* dS,
+   int nlp, const double* x, const double* dx, const double* s, const double* ds, double ap, double ad, double* partials);
+cudaError_t pick_value(cudaStream_t st, const double* src, double* dst);
+
+} // namespace sdpk

@@ -1,0 +1,41 @@
+"""GPU suite, part 3: drop-in check.  The REFERENCE's own sdpi.c (compiled unmodified in oracle/_ref/libsdpi_cuda.so)
+drives our sdpisolver_cuda.c binding and libsdpcuda: ported checksdpi.c known answers and the B&B optima of short.solu."""
+import os
+
+import pytest
+
+from golden.checksdpi_cases import CASES
+from harness import bnb, checksdpi_port, sdpi_ref
+from scip_sdp_b200 import misdp
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+
+
+@pytest.fixture(scope="module")
+def lib():
+    os.environ.setdefault("SHIM_QUIET", "1")
+    return sdpi_ref.SdpiLib(sdpi_ref.LIB_CUDA)
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_checksdpi_known_answers_on_gpu(lib, name):
+    case = CASES[name]
+    st = checksdpi_port.run_case(lib, case, name)
+    if case["reaches_solver"]:
+        assert st["sdpcalls"] >= 1
+
+
+SHORT_SOLU = {"example_small.dat-s": -8.0, "example_inf.dat-s": None, "example_TT.dat-s.gz": 2.11803,
+              "example_CLS.dat-s.gz": 7.1485, "example_MkP.dat-s.gz": -95.0}
+
+
+@pytest.mark.parametrize("name", ["example_small.dat-s", "example_inf.dat-s", "example_CLS.dat-s.gz", "example_MkP.dat-s.gz", "example_TT.dat-s.gz"])
+def test_bnb_optimum_matches_short_solu_on_gpu(lib, name):
+    M = misdp.read_sdpa(os.path.join(GOLDEN, name))
+    r = bnb.solve_misdp(lib, M, timelimit=900)
+    if SHORT_SOLU[name] is None:
+        assert r["status"] == "infeasible"
+    else:
+        assert r["status"] == "optimal" and r["unsolved"] == 0
+        assert abs(r["objval"] - SHORT_SOLU[name]) <= 1e-4 * max(1.0, abs(SHORT_SOLU[name]))

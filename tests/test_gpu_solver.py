@@ -1,0 +1,90 @@
+"""GPU suite, part 2: the interior-point solver (sdpcuda_solve) against the CPU oracle on the BASELINE instance shapes,
+plus a-posteriori KKT residuals at sizes the oracle does not finish quickly.  Tolerance: relaxation objective within the
+solver gap tolerance 1e-5 relative (north_star), y within 1e-4 of the oracle's where the solution is unique."""
+import os
+
+import numpy as np
+import pytest
+
+from scip_sdp_b200 import abi, generators, misdp
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+
+
+@pytest.fixture(scope="module")
+def gpu():
+    return abi.Solver(abi.Lib(abi.PRODUCT_LIB), device=0)
+
+
+@pytest.fixture(scope="module")
+def cpu():
+    return abi.Solver(abi.Lib(abi.ORACLE_LIB))
+
+
+def _instances():
+    yield "example_small", lambda: misdp.read_sdpa(os.path.join(GOLDEN, "example_small.dat-s")).rows_to_bounds()
+    yield "example_TT", lambda: misdp.read_sdpa(os.path.join(GOLDEN, "example_TT.dat-s.gz")).rows_to_bounds()
+    yield "example_CLS", lambda: misdp.read_sdpa(os.path.join(GOLDEN, "example_CLS.dat-s.gz")).rows_to_bounds()
+    yield "example_MkP", lambda: misdp.read_sdpa(os.path.join(GOLDEN, "example_MkP.dat-s.gz")).rows_to_bounds()
+    yield "maxcut-150", lambda: generators.maxcut(150, 0.05, seed=11)
+    yield "mkp-24", lambda: generators.mkp(24, seed=12)
+    yield "truss-60", lambda: generators.truss(4, 4, 60, seed=13)
+    yield "cls-40", lambda: generators.cls(40, 25, 5, seed=14)
+
+
+@pytest.mark.parametrize("name,make", list(_instances()), ids=[n for n, _ in _instances()])
+def test_relaxation_matches_oracle(gpu, cpu, name, make):
+    fp, _ = make().flatten()
+    r = gpu.solve(fp, gaptol=1e-7, feastol=1e-7)
+    ref = cpu.solve(fp, gaptol=1e-7, feastol=1e-7)
+    assert r["launches"] > 0
+    assert ref["phase_name"] == "pdOPT" and r["phase_name"] == "pdOPT", (r["phase_name"], r["stop_name"])
+    assert abs(r["dobj"] - ref["dobj"]) <= 1e-5 * max(1.0, abs(ref["dobj"]))
+    assert abs(r["pobj"] - ref["pobj"]) <= 1e-5 * max(1.0, abs(ref["pobj"]))
+    _check_kkt(fp, r, 1e-6)
+
+
+def _check_kkt(fp, r, tol):
+    y = r["y"]
+    C = fp.dense_C()
+    for k in range(fp.nblocks):
+        Z = -C[k].copy()
+        for j in range(fp.m):
+            Aj = fp.dense_A(j)[k]
+            if np.any(Aj):
+                Z += y[j] * Aj
+        assert np.linalg.norm(Z - r["S"][k]) <= tol * (1 + np.linalg.norm(C[k]))
+        assert np.linalg.eigvalsh(r["X"][k]).min() >= -1e-9 and np.linalg.eigvalsh(r["S"][k]).min() >= -1e-9
+    if fp.nlp:
+        D = fp.dense_D()
+        assert np.abs(D @ y - fp.lprhs - r["slp"]).max() <= tol * (1 + np.abs(fp.lprhs).max())
+        assert r["xlp"].min() >= 0 and r["slp"].min() >= 0
+
+
+def test_infeasible_and_unbounded_certificates(gpu):
+    # y-problem infeasible: [[y1, 1], [1, 0.75 y2]] psd with |y| <= 1 (checksdpi.c test9)
+    M = misdp.Misdp(2, [-1.0, 0.0], [2])
+    M.A[0][0] = [(0, 0, 1.0)]; M.A[0][1] = [(1, 1, 0.75)]; M.C[0] = [(1, 0, -1.0)]
+    M.lb[:] = -1.0; M.ub[:] = 1.0
+    r = gpu.solve(M.flatten()[0], gaptol=1e-6, feastol=1e-6)
+    assert r["phase_name"] in ("pFEAS_dINF", "dINF")
+    # y-problem unbounded: min -3 y1 - y2 s.t. 2 y1 + y2 <= 10, y1 + 3 y2 <= 15 (checksdpi.c test2)
+    M = misdp.Misdp(2, [-3.0, -1.0], [])
+    M.add_row({0: 2.0, 1: 1.0}, rhs=10.0); M.add_row({0: 1.0, 1: 3.0}, rhs=15.0)
+    r = gpu.solve(M.flatten()[0], gaptol=1e-6, feastol=1e-6)
+    assert r["phase_name"] == "pINF_DFEAS".replace("DFEAS", "dFEAS")
+
+
+def test_maxcut_600_kkt_and_properties(gpu):
+    """size-independent checks at a size where the Lanczos step-length path and the recursive Cholesky are active"""
+    fp, _ = generators.maxcut(600, 0.02, seed=5).flatten()
+    r = gpu.solve(fp, gaptol=1e-6, feastol=1e-6)
+    assert r["phase_name"] == "pdOPT"
+    y, X, S = r["y"], r["X"][0], r["S"][0]
+    C = fp.dense_C()[0]
+    assert np.linalg.norm(np.diag(y) - C - S) <= 1e-6 * (1 + np.linalg.norm(C))
+    assert np.abs(np.diag(X) - 1.0).max() <= 1e-6                  # A_i . X = b_i = 1
+    assert np.linalg.eigvalsh(X).min() >= -1e-9 and np.linalg.eigvalsh(S).min() >= -1e-9
+    assert abs(np.vdot(X, S)) <= 1e-5 * max(1.0, abs(r["dobj"]))
+    assert abs(y.sum() - np.vdot(C, X)) <= 1e-5 * abs(y.sum())
