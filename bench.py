@@ -1,0 +1,224 @@
+#!/usr/bin/env python
+"""bench.py — SDP relaxations/sec on the max-cut n = 2000 relaxation (BASELINE.json config 5: one 2000 x 2000 block, 2000
+diagonal constraints; the configuration the north-star FP64-tensor target is quoted on).
+
+   python bench.py --gpus N --steps K --warmup W          our B200 path (one process per GPU under torchrun for N > 1)
+   python bench.py --impl reference ...                   the CPU path timed on the host cores (oracle port of the IPM;
+                                                          DSDP/SDPA/MOSEK are not installable here)
+
+A "step" is one complete interior-point solve of one relaxation.  At N > 1 every rank solves its own relaxation (the
+independent-node-relaxation partition of the B&B frontier; no data-path collective), `value` is the whole-job rate.
+`value`  : problem resident in HBM (sdpcuda_solve_resident), device time from CUDA events on the solver's stream.
+`e2e`    : the reference-facing call SCIPsdpiSolverLoadAndSolve + SCIPsdpiSolverGetDualSol with HOST buffers, wall clock.
+`roofline`: the dominant kernel (FP64 DMMA GEMM), algorithmic flops / CUDA-event time from one profiled solve, against the
+            DMMA peak measured live by a register-resident probe (MEASURED_PEAKS.json has no FP64 entry).
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+ORACLE_ITERS_FULL = 12     # iterations the CPU oracle needs on maxcut-2000 seed 4004 at gaptol = feastol = 1e-5 (measured)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--n", type=int, default=2000, help="max-cut order (2000 = the BASELINE configuration)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons of one GPU while the timed region runs"""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], False
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([t.strip() for t in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 7 for i in range(4) if r[3 + i].lower().startswith("active")})
+        return dict(sm_mhz=statistics.median(sm) if sm else None, sm_max_mhz=max(mx) if mx else None, reasons=reasons,
+                    samples=len(self.rows))
+
+
+def cpu_sample(fp, threads_note):
+    """bounded CPU sample: two interior-point iterations of the same relaxation on the oracle, extrapolated to a full solve"""
+    from scip_sdp_b200 import abi
+    cpu = abi.Solver(abi.Lib(abi.ORACLE_LIB))
+    t = time.perf_counter()
+    r = cpu.solve(fp, gaptol=1e-5, feastol=1e-5, maxiter=2, fetch=False)
+    dt = time.perf_counter() - t
+    per_iter = dt / max(1, r["iterations"])
+    return per_iter, dt, r["iterations"]
+
+
+def main():
+    a = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    from scip_sdp_b200 import generators
+    cores = os.cpu_count() or 1
+    workload = f"maxcut-{a.n} (G(n, {min(0.5, 20.0 / a.n):.4g}) unit weights, seed 4004+rank): one {a.n}x{a.n} block, m = {a.n}"
+    cfg = {"workload": workload, "tolerances": "gaptol = feastol = 1e-5 (relaxing/SDP defaults)",
+           "l2": "working set 16 arena matrices x 32 MB = 512 MB per solve, larger than the 126 MB L2 (no flush needed)",
+           "partition": "independent relaxations, one per GPU (no collective)" if world > 1 else "single relaxation"}
+
+    # ------------------------------------------------------------------ reference arm: CPU path on the host cores
+    if a.impl == "reference":
+        if rank != 0:
+            return 0
+        fp, _ = generators.maxcut(a.n, min(0.5, 20.0 / a.n), seed=4004).flatten()
+        for _ in range(a.warmup):
+            cpu_sample(fp, cores)
+        t0 = time.perf_counter()
+        per = []
+        for _ in range(a.steps):
+            per_iter, _, _ = cpu_sample(fp, cores)
+            per.append(per_iter)
+        wall = time.perf_counter() - t0
+        sec_per_relax = statistics.mean(per) * ORACLE_ITERS_FULL
+        val = 1.0 / sec_per_relax
+        line = {"impl": "reference", "metric": "SDP relaxations/sec", "value": val, "unit": "relaxations/s", "n_gpus": a.gpus,
+                "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1e3 * sec_per_relax, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": cfg,
+                "cpu_baseline": {"value": val, "unit": "relaxations/s", "cores": cores, "kind": "port",
+                                 "sample": f"each step = 2 interior-point iterations of the same relaxation on the CPU oracle "
+                                           f"(OpenBLAS, {cores} threads), scaled to the {ORACLE_ITERS_FULL} iterations a full solve takes; "
+                                           f"DSDP/SDPA are not installable in this image"},
+                "e2e": {"value": val, "unit": "relaxations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0, "wall_s": wall}
+        print(json.dumps(line))
+        return 0
+
+    # ------------------------------------------------------------------ our arm
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device visible; the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    from scip_sdp_b200 import abi, sdpisolver_host
+    M = generators.maxcut(a.n, min(0.5, 20.0 / a.n), seed=4004 + rank)
+    fp, _ = M.flatten()
+    gpu = abi.Solver(abi.Lib(abi.PRODUCT_LIB), device=local)
+    kw = dict(gaptol=1e-5, feastol=1e-5)
+
+    first = gpu.solve(fp, fetch=False, **kw)          # uploads the problem; counts as the first warm-up step
+    assert first["phase_name"] == "pdOPT", first
+    for _ in range(max(0, a.warmup - 1)):
+        gpu.solve_resident(**kw)
+    sampler = ClockSampler(local)
+    sampler.start()
+    barrier()
+    t0 = time.perf_counter()
+    dev_ms, launches, iters = 0.0, 0, 0
+    for _ in range(a.steps):
+        r = gpu.solve_resident(**kw)
+        dev_ms += r["device_ms"]; launches += r["launches"]; iters += r["iterations"]
+        assert r["phase_name"] == "pdOPT", r
+    barrier()
+    wall = time.perf_counter() - t0
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+
+    # end to end through the SCIP-SDP solver boundary with host buffers
+    bp = sdpisolver_host.BoundaryProblem(M)
+    sdpis = sdpisolver_host.SdpiSolver(gaptol=1e-5, feastol=1e-5)
+    sdpis.load_and_solve(bp); sdpis.dual_sol()
+    barrier()
+    t1 = time.perf_counter()
+    obj = None
+    for _ in range(a.steps):
+        sdpis.load_and_solve(bp)
+        obj, _y = sdpis.dual_sol()
+        assert sdpis.flag("IsAcceptable")
+    barrier()
+    e2e_wall = time.perf_counter() - t1
+    e2e_iters, e2e_calls = sdpis.iterations()
+
+    # max over ranks
+    t = torch.tensor([dev_ms / 1e3, wall, e2e_wall], dtype=torch.float64, device="cuda")
+    cnt = torch.tensor([float(launches), float(iters)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+    dev_s, wall_s, e2e_s = [float(v) for v in t.tolist()]
+    launches_all, iters_all = [float(v) for v in cnt.tolist()]
+
+    if rank == 0:
+        # roofline of the dominant kernel from one profiled solve + the measured DMMA peak
+        peak_ms, peak_fl = gpu.time_kernel(4, 0, 3)
+        peak = peak_fl / peak_ms / 1e9
+        gemm_ms, gemm_fl = gpu.time_kernel(0, 4096, 3)
+        gpu.set_profiling(True)
+        pr = gpu.solve_resident(**kw)
+        prof = gpu.get_profile()
+        gpu.set_profiling(False)
+        g = prof["gemm_dmma"]
+        achieved = g["work"] / g["ms"] / 1e9 if g["ms"] > 0 else 0.0
+        share = {c: round(v["ms"] / pr["device_ms"], 4) for c, v in prof.items()}
+        roof = {"bound": "tensor", "kernel": "gemm_dmma_kernel (FP64 DMMA.8x8x4, cp.async fed)", "achieved": achieved, "peak": max(peak, gemm_fl / gemm_ms / 1e9),
+                "unit": "TFLOP/s", "frac": achieved / max(peak, gemm_fl / gemm_ms / 1e9), "traffic": None,
+                "peak_source": "measured live: max(register-resident DMMA probe, standalone 4096^3 DGEMM of this library); MEASURED_PEAKS.json holds no FP64 figure",
+                "dmma_probe_tflops": peak, "dgemm_4096_tflops": gemm_fl / gemm_ms / 1e9,
+                "launches_per_solve": g["launches"], "algorithmic_flops_per_solve": g["work"], "device_ms_per_solve": g["ms"],
+                "share_of_step": share, "profiled_solve_ms": pr["device_ms"]}
+        line = {"metric": "SDP relaxations/sec", "value": world * a.steps / dev_s, "unit": "relaxations/s", "n_gpus": world,
+                "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1e3 * dev_s / a.steps, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": cfg,
+                "wall_ms_per_step": 1e3 * wall_s / a.steps, "iterations_per_step": iters_all / (world * a.steps),
+                "objective": r["dobj"], "gpu_launches": int(launches_all),
+                "e2e": {"value": world * a.steps / e2e_s, "unit": "relaxations/s", "h2d_bytes_per_step": int(first["h2d_bytes"]),
+                        "d2h_bytes_per_step": int(first["d2h_bytes"] + 8 * fp.m + 8), "ms_per_step": 1e3 * e2e_s / a.steps,
+                        "api": "SCIPsdpiSolverLoadAndSolve + SCIPsdpiSolverGetDualSol (libsdpisolver_cuda.so), host buffers",
+                        "objective": obj, "solver_calls_per_step": e2e_calls},
+                "roofline": roof, "clocks": sampler.summary()}
+        if world == 1 and not a.no_cpu_baseline:
+            per_iter, dt, its = cpu_sample(fp, cores)
+            line["cpu_baseline"] = {"value": 1.0 / (per_iter * ORACLE_ITERS_FULL), "unit": "relaxations/s", "cores": cores, "kind": "port",
+                                    "sample": f"{its} interior-point iterations of the same relaxation on the CPU oracle ({dt:.1f} s, OpenBLAS on "
+                                              f"{cores} threads), scaled to the {ORACLE_ITERS_FULL} iterations of a full solve; stand-in for "
+                                              f"DSDP/SDPA, which cannot be installed here"}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

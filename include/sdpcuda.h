@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define SDPCUDA_ABI_VERSION 1
+#define SDPCUDA_ABI_VERSION 2
 
 /* return codes of every entry point */
 #define SDPCUDA_OK            0
@@ -118,6 +118,8 @@ typedef struct sdpcuda_result
    double mu;
    double seconds;       /* wall time of the solve including host<->device transfers */
    double device_ms;     /* device time between the first and last kernel of the solve (CUDA events) */
+   double h2d_bytes;     /* host->device bytes moved by this call (problem upload + initial point) */
+   double d2h_bytes;     /* device->host bytes moved by this call (per-iteration scalars; solution getters add their own) */
 } sdpcuda_result;
 
 typedef struct sdpcuda_handle sdpcuda_handle;
@@ -134,6 +136,23 @@ void sdpcuda_default_params(sdpcuda_params* p);
  * solution device-resident until the getters below fetch it.  start_y may be NULL. Blocking. */
 int  sdpcuda_solve(sdpcuda_handle* h, const sdpcuda_problem* prob, const sdpcuda_params* par,
                    const double* start_y, sdpcuda_result* res);
+
+/* Same iteration on the problem that the last sdpcuda_solve left resident in HBM (no host->device traffic); used to
+ * measure the device-only throughput and for repeated solves with changed tolerances. */
+int  sdpcuda_solve_resident(sdpcuda_handle* h, const sdpcuda_params* par, sdpcuda_result* res);
+
+/* Per-kernel-class device timing of the NEXT solve (CUDA events around every launch of the class on the handle's
+ * stream; adds a little overhead, so it is off by default).  After the solve sdpcuda_get_profile fills, for each class
+ * c < SDPCUDA_NPROF, out[3*c+0] = launches, out[3*c+1] = device milliseconds, out[3*c+2] = algorithmic flops or bytes. */
+#define SDPCUDA_NPROF 6
+#define SDPCUDA_PROF_GEMM   0   /* FP64 DMMA GEMM (flops) */
+#define SDPCUDA_PROF_DIAG   1   /* 64 x 64 diagonal-block Cholesky + inverse (flops) */
+#define SDPCUDA_PROF_SCHUR  2   /* Schur complement assembly, entry/gather path + LP block (bytes) */
+#define SDPCUDA_PROF_EIG    3   /* Jacobi / Lanczos step-length kernels (bytes) */
+#define SDPCUDA_PROF_TRSV   4   /* blocked triangular solves with M (bytes) */
+#define SDPCUDA_PROF_ELEM   5   /* element-wise / reduction sweeps over the arena (bytes) */
+int  sdpcuda_set_profiling(sdpcuda_handle* h, int on);
+int  sdpcuda_get_profile(sdpcuda_handle* h, double* out /* [3*SDPCUDA_NPROF] */);
 
 /* ---- solution access (GetDualSol/GetPrimal*, sdpisolver.h:484-578) ---- */
 int  sdpcuda_get_y(sdpcuda_handle* h, double* y /* [m] */);

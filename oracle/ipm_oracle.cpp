@@ -35,6 +35,9 @@ void scipy_dtrsm_(const char* side, const char* uplo, const char* ta, const char
    const double* alpha, const double* a, const int* lda, double* b, const int* ldb);
 void scipy_dsyev_(const char* jobz, const char* uplo, const int* n, double* a, const int* lda, double* w, double* work,
    const int* lwork, int* info);
+void scipy_dsyevr_(const char* jobz, const char* range, const char* uplo, const int* n, double* a, const int* lda,
+   const double* vl, const double* vu, const int* il, const int* iu, const double* abstol, int* m, double* w, double* z,
+   const int* ldz, int* isuppz, double* work, const int* lwork, int* iwork, const int* liwork, int* info);
 void scipy_dpotrs_(const char* uplo, const int* n, const int* nrhs, const double* a, const int* lda, double* b,
    const int* ldb, int* info);
 }
@@ -123,9 +126,13 @@ double maxstep(int n, const vec& L, const vec& dA)
    scipy_dtrsm_("L", "L", "N", "N", &n, &n, &one, L.data(), &n, B.data(), &n);
    scipy_dtrsm_("R", "L", "T", "N", &n, &n, &one, L.data(), &n, B.data(), &n);
    symmetrize(n, B);
-   vec w(n), work(std::max(1, 34 * n));
-   int lwork = (int)work.size(), info = 0;
-   scipy_dsyev_("N", "L", &n, B.data(), &n, w.data(), work.data(), &lwork, &info);
+   /* only the smallest eigenvalue: DSYEVR with index range [1,1], as lapack_interface.c:178-288 does for SCIP-SDP */
+   vec w(n), work(std::max(1, 26 * n));
+   std::vector<int> iwork(std::max(1, 10 * n)), isuppz(2);
+   int lwork = (int)work.size(), liwork = (int)iwork.size(), info = 0, ione = 1, mfound = 0;
+   double zero = 0.0, zdummy = 0.0;
+   scipy_dsyevr_("N", "I", "L", &n, B.data(), &n, &zero, &zero, &ione, &ione, &zero, &mfound, w.data(), &zdummy, &ione,
+      isuppz.data(), work.data(), &lwork, iwork.data(), &liwork, &info);
    double lmin = w[0];
    if( lmin >= -1e-300 ) return 1e30;
    return -1.0 / lmin;
@@ -554,7 +561,7 @@ int Solver::solve(const sdpcuda_params& par, const double* starty)
    res.iterations = iter; res.launches = 0;
    res.pobj = pobj; res.dobj = dobj; res.relgap = relgap; res.pinf = pinf; res.dinf = dinf; res.mu = mu;
    res.seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
-   res.device_ms = 0.0;
+   res.device_ms = 0.0; res.h2d_bytes = 0.0; res.d2h_bytes = 0.0;
    solved = true;
    return SDPCUDA_OK;
 }
@@ -628,6 +635,22 @@ int sdpcuda_solve(sdpcuda_handle* h, const sdpcuda_problem* pr, const sdpcuda_pa
    int rc = h->s.solve(*par, start_y);
    if( res != NULL ) *res = h->s.res;
    return rc;
+}
+
+int sdpcuda_solve_resident(sdpcuda_handle* h, const sdpcuda_params* par, sdpcuda_result* res)
+{
+   if( h == NULL || par == NULL ) return SDPCUDA_ERR_ARG;
+   if( h->s.P.m <= 0 ) return SDPCUDA_ERR_STATE;
+   int rc = h->s.solve(*par, NULL);
+   if( res != NULL ) *res = h->s.res;
+   return rc;
+}
+int sdpcuda_set_profiling(sdpcuda_handle* h, int on) { (void)h; (void)on; return SDPCUDA_OK; }
+int sdpcuda_get_profile(sdpcuda_handle* h, double* out)
+{
+   (void)h;
+   for( int i = 0; i < 3 * SDPCUDA_NPROF; ++i ) out[i] = 0.0;
+   return SDPCUDA_OK;
 }
 
 int sdpcuda_get_y(sdpcuda_handle* h, double* y)

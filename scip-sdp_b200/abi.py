@@ -33,7 +33,8 @@ class Params(C.Structure):
 class Result(C.Structure):
     _fields_ = [("phase", C.c_int), ("stop", C.c_int), ("iterations", C.c_int), ("launches", C.c_int),
                 ("pobj", C.c_double), ("dobj", C.c_double), ("relgap", C.c_double), ("pinf", C.c_double),
-                ("dinf", C.c_double), ("mu", C.c_double), ("seconds", C.c_double), ("device_ms", C.c_double)]
+                ("dinf", C.c_double), ("mu", C.c_double), ("seconds", C.c_double), ("device_ms", C.c_double),
+                ("h2d_bytes", C.c_double), ("d2h_bytes", C.c_double)]
 
 
 def _i(a):
@@ -105,6 +106,9 @@ class Lib:
         L.sdpcuda_default_params.argtypes = [C.POINTER(Params)]
         L.sdpcuda_default_params.restype = None
         L.sdpcuda_solve.argtypes = [C.c_void_p, C.POINTER(Problem), C.POINTER(Params), _dp, C.POINTER(Result)]
+        L.sdpcuda_solve_resident.argtypes = [C.c_void_p, C.POINTER(Params), C.POINTER(Result)]
+        L.sdpcuda_set_profiling.argtypes = [C.c_void_p, C.c_int]
+        L.sdpcuda_get_profile.argtypes = [C.c_void_p, _dp]
         for f in ("sdpcuda_get_y", "sdpcuda_get_xlp", "sdpcuda_get_slp"):
             getattr(L, f).argtypes = [C.c_void_p, _dp]
         for f in ("sdpcuda_get_X", "sdpcuda_get_S"):
@@ -165,6 +169,26 @@ class Solver:
             out["S"] = [self.get_S(b) for b in range(prob.nblocks)]
             out["xlp"], out["slp"] = self.get_xlp(), self.get_slp()
         return out
+
+    def solve_resident(self, params=None, **kw):
+        params = params if params is not None else self.L.default_params(**kw)
+        res = Result()
+        rc = self.L.lib.sdpcuda_solve_resident(self.h, C.byref(params), C.byref(res))
+        if rc != 0:
+            raise RuntimeError(f"sdpcuda_solve_resident failed with code {rc}")
+        out = {f[0]: getattr(res, f[0]) for f in Result._fields_}
+        out["phase_name"], out["stop_name"] = PHASES[res.phase], STOPS[res.stop]
+        return out
+
+    PROF_CLASSES = ["gemm_dmma", "diag_block", "schur", "eig", "trsv", "elementwise"]
+
+    def set_profiling(self, on):
+        self.L.lib.sdpcuda_set_profiling(self.h, int(on))
+
+    def get_profile(self):
+        a = np.zeros(3 * len(self.PROF_CLASSES))
+        self.L.lib.sdpcuda_get_profile(self.h, a.ctypes.data_as(_dp))
+        return {c: dict(launches=int(a[3 * i]), ms=float(a[3 * i + 1]), work=float(a[3 * i + 2])) for i, c in enumerate(self.PROF_CLASSES)}
 
     def _vec(self, fn, n):
         a = np.zeros(max(n, 1))

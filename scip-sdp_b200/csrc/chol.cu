@@ -17,15 +17,27 @@ namespace {
 constexpr int NB = CHOL_NB;
 constexpr int LDSM = NB + 1;
 
+// fast reciprocal square root in double precision: float seed + two Newton steps (relative error ~1e-16)
+__device__ __forceinline__ double fast_rsqrt(double x)
+{
+   double y = (double)rsqrtf((float)x);
+   y = y * (1.5 - 0.5 * x * y * y);
+   y = y * (1.5 - 0.5 * x * y * y);
+   return y;
+}
+
 // mode 0: factorise A (nb x nb, lower) in place, optionally write inverse of L to Linv (upper part zeroed) / diaginv
 // mode 1: A holds a lower-triangular factor already; only invert it
-__global__ void __launch_bounds__(256)
+// One CTA of 128 threads; thread i < 64 owns row i (Cholesky-Crout: column k needs one dot product per row and two
+// barriers), then thread j < 64 owns column j of the inverse (forward substitution with broadcast reads of L).
+__global__ void __launch_bounds__(128)
 diag_block_kernel(int mode, int nb, double* __restrict__ A, int lda, double* __restrict__ Linv, int ldi,
    double* __restrict__ diaginv, int* __restrict__ info, int pivot_offset)
 {
    extern __shared__ __align__(16) double diag_smem[];
    double* L = diag_smem;
    double* W = diag_smem + NB * LDSM;
+   double* dinv = W + NB * LDSM;              // reciprocals of the diagonal of L
    const int tid = threadIdx.x;
 
    for( int e = tid; e < NB * NB; e += blockDim.x )
@@ -40,72 +52,85 @@ diag_block_kernel(int mode, int nb, double* __restrict__ A, int lda, double* __r
 
    if( mode == 0 )
    {
-      for( int k = 0; k < nb; ++k )
+      const int i = tid;
+      for( int k = 0; k < NB; ++k )
       {
-         if( tid == 0 )
+         double s = 0.0;
+         if( i < NB && i >= k )
          {
-            double d = L[k * LDSM + k];
-            if( !(d > 0.0) )
+            double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+            const double* ri = L + i * LDSM;
+            const double* rk = L + k * LDSM;
+            int j = 0;
+            for( ; j + 4 <= k; j += 4 )
             {
-               atomicCAS(info, 0, pivot_offset + k + 1);
-               d = 1.0;
+               s0 += ri[j] * rk[j]; s1 += ri[j + 1] * rk[j + 1]; s2 += ri[j + 2] * rk[j + 2]; s3 += ri[j + 3] * rk[j + 3];
             }
-            L[k * LDSM + k] = sqrt(d);
+            for( ; j < k; ++j ) s0 += ri[j] * rk[j];
+            s = ri[k] - ((s0 + s1) + (s2 + s3));
+            if( i == k )
+            {
+               if( !(s > 0.0) )
+               {
+                  if( k < nb ) atomicCAS(info, 0, pivot_offset + k + 1);
+                  s = 1.0;
+               }
+               double r = fast_rsqrt(s);
+               L[k * LDSM + k] = s * r;
+               dinv[k] = r;
+            }
          }
          __syncthreads();
-         double piv = L[k * LDSM + k];
-         for( int i = k + 1 + tid; i < nb; i += blockDim.x )
-            L[i * LDSM + k] /= piv;
-         __syncthreads();
-         int rem = nb - k - 1;
-         for( int e = tid; e < rem * rem; e += blockDim.x )
-         {
-            int i = k + 1 + e % rem, j = k + 1 + e / rem;
-            if( i >= j )
-               L[i * LDSM + j] -= L[i * LDSM + k] * L[j * LDSM + k];
-         }
+         if( i < NB && i > k )
+            L[i * LDSM + k] = s * dinv[k];
          __syncthreads();
       }
       for( int e = tid; e < nb * nb; e += blockDim.x )
       {
-         int i = e % nb, j = e / nb;
-         if( i >= j ) A[(size_t)j * lda + i] = L[i * LDSM + j];
+         int r = e % nb, c = e / nb;
+         if( r >= c ) A[(size_t)c * lda + r] = L[r * LDSM + c];
       }
+   }
+   else
+   {
+      if( tid < NB ) dinv[tid] = 1.0 / L[tid * LDSM + tid];
+      __syncthreads();
    }
 
    if( Linv != nullptr || diaginv != nullptr )
    {
-      // column j of W = L^-1 e_j by forward substitution; 4 threads cooperate on one column
-      const int col = tid >> 2, part = tid & 3;
-      if( col < NB )
+      // thread j: column j of W = L^-1; the k-loop starts at 0 for all threads (W is zero above the diagonal) so that the
+      // reads of L[i][k] are warp-wide broadcasts and the reads of W[k][j] are conflict free
+      const int j = tid;
+      if( j < NB )
       {
-         for( int i = 0; i < NB; ++i )
+         for( int i = 0; i < NB; ++i ) W[i * LDSM + j] = (i == j) ? dinv[j] : 0.0;
+         for( int i = 1; i < NB; ++i )
          {
-            double s = 0.0;
-            if( i > col )
-               for( int k = col + part; k < i; k += 4 ) s += L[i * LDSM + k] * W[k * LDSM + col];
-            s += __shfl_xor_sync(0xffffffffu, s, 1);
-            s += __shfl_xor_sync(0xffffffffu, s, 2);
-            if( part == 0 )
+            const double* ri = L + i * LDSM;
+            double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+            int k = 0;
+            for( ; k + 4 <= i; k += 4 )
             {
-               double v = (i < col) ? 0.0 : ((i == col) ? 1.0 / L[i * LDSM + i] : -s / L[i * LDSM + i]);
-               W[i * LDSM + col] = v;
+               s0 += ri[k] * W[k * LDSM + j]; s1 += ri[k + 1] * W[(k + 1) * LDSM + j];
+               s2 += ri[k + 2] * W[(k + 2) * LDSM + j]; s3 += ri[k + 3] * W[(k + 3) * LDSM + j];
             }
-            __syncwarp();
+            for( ; k < i; ++k ) s0 += ri[k] * W[k * LDSM + j];
+            if( i > j ) W[i * LDSM + j] = -((s0 + s1) + (s2 + s3)) * dinv[i];
          }
       }
       __syncthreads();
       if( Linv != nullptr )
          for( int e = tid; e < nb * nb; e += blockDim.x )
          {
-            int i = e % nb, j = e / nb;
-            Linv[(size_t)j * ldi + i] = W[i * LDSM + j];
+            int r = e % nb, c = e / nb;
+            Linv[(size_t)c * ldi + r] = W[r * LDSM + c];
          }
       if( diaginv != nullptr )
          for( int e = tid; e < NB * NB; e += blockDim.x )
          {
-            int i = e % NB, j = e / NB;
-            diaginv[(size_t)j * NB + i] = (i < nb && j < nb) ? W[i * LDSM + j] : 0.0;
+            int r = e % NB, c = e / NB;
+            diaginv[(size_t)c * NB + r] = (r < nb && c < nb) ? W[r * LDSM + c] : 0.0;
          }
    }
 }
@@ -126,7 +151,7 @@ cudaError_t copy2d(cudaStream_t st, int m, int n, const double* src, int lds, do
    return cudaGetLastError();
 }
 
-constexpr size_t DIAG_SMEM = 2 * NB * LDSM * sizeof(double);
+constexpr size_t DIAG_SMEM = (2 * NB * LDSM + NB) * sizeof(double);
 
 cudaError_t launch_diag(cudaStream_t st, int mode, int nb, double* A, int lda, double* Linv, int ldi, double* diaginv, int* info, int off)
 {
@@ -136,7 +161,8 @@ cudaError_t launch_diag(cudaStream_t st, int mode, int nb, double* A, int lda, d
       SDPK_CUDA_CHECK( cudaFuncSetAttribute(diag_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DIAG_SMEM) );
       configured = true;
    }
-   diag_block_kernel<<<1, 256, DIAG_SMEM, st>>>(mode, nb, A, lda, Linv, ldi, diaginv, info, off);
+   ProfScope prof(st, PROF_DIAG, (mode == 0 ? 1.0 : 0.0) * nb * (double)nb * nb / 3.0 + ((Linv || diaginv) ? nb * (double)nb * nb / 3.0 : 0.0));
+   diag_block_kernel<<<1, 128, DIAG_SMEM, st>>>(mode, nb, A, lda, Linv, ldi, diaginv, info, off);
    count_launch();
    return cudaGetLastError();
 }
@@ -293,6 +319,7 @@ cudaError_t trtri_lower(cudaStream_t st, int n, const double* L, int ldl, double
 cudaError_t potrs_vec(cudaStream_t st, int n, const double* L, int ldl, const double* diaginv, double* b, double* tmp)
 {
    const int nblk = ceil_div(n, NB);
+   ProfScope prof(st, PROF_TRSV, 8.0 * n * (double)n);      // reads the triangle of L twice
    for( int k = 0; k < nblk; ++k )
    {
       int below = n - min(n, (k + 1) * NB);

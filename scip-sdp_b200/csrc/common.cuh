@@ -4,6 +4,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstdint>
+#include <vector>
 
 namespace sdpk {
 
@@ -11,6 +12,56 @@ namespace sdpk {
 struct LaunchCounter { long long n = 0; };
 extern thread_local LaunchCounter* g_counter;
 inline void count_launch(int k = 1) { if( g_counter ) g_counter->n += k; }
+
+// optional per-class device timing (CUDA events on the launching stream around each launch / launch group)
+constexpr int NPROF = 6;
+enum { PROF_GEMM = 0, PROF_DIAG = 1, PROF_SCHUR = 2, PROF_EIG = 3, PROF_TRSV = 4, PROF_ELEM = 5 };
+struct Profiler
+{
+   bool on = false;
+   struct Rec { int cls; cudaEvent_t a, b; double work; int launches; };
+   std::vector<Rec> recs;
+   std::vector<cudaEvent_t> pool;
+   size_t used = 0;
+   double launches[NPROF] = {0}, ms[NPROF] = {0}, work[NPROF] = {0};
+   cudaEvent_t get()
+   {
+      if( used == pool.size() ) { cudaEvent_t e; cudaEventCreate(&e); pool.push_back(e); }
+      return pool[used++];
+   }
+   void reset() { recs.clear(); used = 0; for( int c = 0; c < NPROF; ++c ) launches[c] = ms[c] = work[c] = 0.0; }
+   void collect()      // call after the stream has been synchronised
+   {
+      for( const Rec& r : recs )
+      {
+         float t = 0.f;
+         cudaEventElapsedTime(&t, r.a, r.b);
+         launches[r.cls] += r.launches; ms[r.cls] += t; work[r.cls] += r.work;
+      }
+      recs.clear(); used = 0;
+   }
+   ~Profiler() { for( cudaEvent_t e : pool ) cudaEventDestroy(e); }
+};
+extern thread_local Profiler* g_prof;
+struct ProfScope
+{
+   Profiler* p; cudaStream_t st; size_t idx; long long n0;
+   ProfScope(cudaStream_t s, int cls, double work) : p((g_prof && g_prof->on) ? g_prof : nullptr), st(s), idx(0), n0(0)
+   {
+      if( !p ) return;
+      Profiler::Rec r; r.cls = cls; r.a = p->get(); r.b = p->get(); r.work = work; r.launches = 0;
+      n0 = g_counter ? g_counter->n : 0;
+      cudaEventRecord(r.a, st);
+      idx = p->recs.size();
+      p->recs.push_back(r);
+   }
+   ~ProfScope()
+   {
+      if( !p ) return;
+      cudaEventRecord(p->recs[idx].b, st);
+      p->recs[idx].launches = (int)((g_counter ? g_counter->n : 0) - n0);
+   }
+};
 
 #define SDPK_CUDA_CHECK(expr) do { cudaError_t _e = (expr); if( _e != cudaSuccess ) { \
       fprintf(stderr, "[libsdpcuda] %s:%d CUDA error %s: %s\n", __FILE__, __LINE__, cudaGetErrorName(_e), cudaGetErrorString(_e)); \
@@ -28,7 +79,7 @@ enum { GEMM_LOWER = 1, GEMM_KHI_M = 2, GEMM_KHI_N = 4, GEMM_KLO_M = 8, GEMM_KLO_
 cudaError_t gemm(cudaStream_t st, bool transa, bool transb, int m, int n, int k, double alpha,
    const double* A, int lda, long long strideA, const double* B, int ldb, long long strideB,
    double beta, double* C, int ldc, long long strideC, int batch, int flags);
-cudaError_t dmma_peak_probe(cudaStream_t st, int iters, double* d_sink, double* flops);
+cudaError_t dmma_peak_probe(cudaStream_t st, int iters, double* d_sink, double* flops, int blocks_per_sm = 4, int threads = 256);
 
 // ---- chol.cu -------------------------------------------------------------------------------------------------------
 // Cholesky A = L L' (lower, in place) by recursive blocking on DMMA GEMMs; optionally the inverse of L in Linv.

@@ -351,6 +351,7 @@ cudaError_t jacobi_eig_batched(cudaStream_t st, int n, int nbatch, const double*
       SDPK_CUDA_CHECK( cudaFuncSetAttribute(jacobi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max(smem, (size_t)200 * 1024)) );
       configured = std::max(smem, (size_t)200 * 1024);
    }
+   ProfScope prof(st, PROF_EIG, (double)nbatch * (16.0 * n * n + 8.0 * n));
    jacobi_kernel<<<nbatch, 256, smem, st>>>(n, A, lda, strideA, w, V, gscratch, use_smem, d_sweeps);
    count_launch();
    return cudaGetLastError();
@@ -364,6 +365,7 @@ size_t lanczos_work_doubles(int n, int maxit)
 cudaError_t lanczos_lambda_min(cudaStream_t st, int n, const double* B, int ldb, double* work, int maxit, double* d_out)
 {
    maxit = std::min(maxit, n);
+   ProfScope prof(st, PROF_EIG, (double)maxit * 8.0 * n * (double)n);
    double* Q = work;
    double* part = Q + (size_t)(maxit + 2) * n;
    double* ab = part + (size_t)LZ_KSPLIT * n;

@@ -13,6 +13,7 @@
 namespace sdpk {
 
 thread_local LaunchCounter* g_counter = nullptr;
+thread_local Profiler* g_prof = nullptr;
 
 namespace {
 
@@ -230,6 +231,12 @@ cudaError_t gemm(cudaStream_t st, bool ta, bool tb, int m, int n, int k, double 
 {
    if( m <= 0 || n <= 0 || batch <= 0 )
       return cudaSuccess;
+   // algorithmic flop count: triangular operands / symmetric results only need part of the 2mnk product
+   double frac = 1.0;
+   const bool kflag = (flags & (GEMM_KHI_M | GEMM_KHI_N | GEMM_KLO_M | GEMM_KLO_N)) != 0;
+   if( (flags & GEMM_LOWER) && kflag ) frac = 1.0 / 6.0;
+   else if( (flags & GEMM_LOWER) || kflag ) frac = 0.5;
+   ProfScope prof(st, PROF_GEMM, 2.0 * m * (double)n * k * batch * frac);
    // small problems use 32 x 32 tiles to fill more SMs
    bool small = ((long long)ceil_div(m, 64) * ceil_div(n, 64) * batch) < 148;
 #define SDPK_GEMM_DISPATCH(BM, BN) \
@@ -245,9 +252,9 @@ cudaError_t gemm(cudaStream_t st, bool ta, bool tb, int m, int n, int k, double 
 #undef SDPK_GEMM_DISPATCH
 }
 
-cudaError_t dmma_peak_probe(cudaStream_t st, int iters, double* d_sink, double* flops)
+cudaError_t dmma_peak_probe(cudaStream_t st, int iters, double* d_sink, double* flops, int blocks_per_sm, int threads)
 {
-   const int blocks = 148 * 4, threads = 256;
+   const int blocks = 148 * blocks_per_sm;
    dmma_peak_kernel<<<blocks, threads, 0, st>>>(iters, d_sink);
    count_launch();
    // per warp and iteration: 16 DMMA.8x8x4 = 16 * 8*8*4*2 flop

@@ -29,6 +29,8 @@ namespace {
 
 constexpr int NSTAT = 24;
 
+thread_local double g_h2d_bytes = 0.0;
+
 template <class T> struct DBuf
 {
    T* p = nullptr; size_t cap = 0;
@@ -46,6 +48,7 @@ template <class T> struct DBuf
    {
       cudaError_t e = ensure(v.size());
       if( e != cudaSuccess || v.empty() ) return e;
+      g_h2d_bytes += (double)(v.size() * sizeof(T));
       return cudaMemcpyAsync(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, st);
    }
    void release() { if( p ) cudaFree(p); p = nullptr; cap = 0; }
@@ -89,6 +92,13 @@ struct sdpcuda_handle
    // generic scratch for the kernel-level entry points
    DBuf<double> kA, kB, kC, kW;
 
+   // host-side constants of the resident problem (norms, scaling of the initial point)
+   bool resident = false;
+   double h2d = 0, d2h = 0;          // bytes moved by the current call
+   double normb = 0, normC = 0, normCsdp2 = 0, xil = 10, etal = 10;
+   std::vector<double> xi, eta;
+   Profiler prof;
+
    ~sdpcuda_handle()
    {
       if( h_stats ) cudaFreeHost(h_stats);
@@ -102,6 +112,7 @@ int set_device(sdpcuda_handle* h)
 {
    CK( cudaSetDevice(h->device) );
    g_counter = &h->counter;
+   g_prof = &h->prof;
    return SDPCUDA_OK;
 }
 
@@ -375,9 +386,65 @@ int sdpcuda_destroy(sdpcuda_handle* h)
    cudaEventDestroy(h->ev0); cudaEventDestroy(h->ev1);
    cudaStreamDestroy(h->st);
    if( g_counter == &h->counter ) g_counter = nullptr;
+   if( g_prof == &h->prof ) g_prof = nullptr;
    delete h;
    return SDPCUDA_OK;
 }
+
+// norms and the scaling of the initial point (SDPT3-style) from the host copy of the problem: O(nnz)
+static void host_constants(sdpcuda_handle* h, const sdpcuda_problem* P)
+{
+   const int m = h->m, nb = h->nb, nlp = h->nlp;
+   double normb = 0, normC = 0;
+   for( int j = 0; j < m; ++j ) normb += P->obj[j] * P->obj[j];
+   h->normb = std::sqrt(normb);
+   std::vector<double> nrmC(nb, 0.0);
+   for( int e = 0; e < P->cnnz; ++e )
+      nrmC[P->cblk[e]] += (P->crow[e] == P->ccol[e] ? 1.0 : 2.0) * P->cval[e] * P->cval[e];
+   h->normCsdp2 = 0.0;
+   for( int k = 0; k < nb; ++k ) h->normCsdp2 += nrmC[k];
+   normC = h->normCsdp2;
+   for( int l = 0; l < nlp; ++l ) normC += P->lprhs[l] * P->lprhs[l];
+   h->normC = std::sqrt(normC);
+   h->xi.assign(nb, 0.0); h->eta.assign(nb, 0.0);
+   for( int k = 0; k < nb; ++k )
+   {
+      h->xi[k] = h->eta[k] = std::max(10.0, std::sqrt((double)h->blk[k].n));
+      h->eta[k] = std::max(h->eta[k], std::sqrt(nrmC[k]));
+   }
+   std::vector<double> na(nb, 0.0), nrmD(m, 0.0);
+   for( int j = 0; j < m; ++j )
+   {
+      for( int e = P->varbeg[j]; e < P->varbeg[j + 1]; ++e )
+         na[P->entblk[e]] += (P->entrow[e] == P->entcol[e] ? 1.0 : 2.0) * P->entval[e] * P->entval[e];
+      for( int e = P->varbeg[j]; e < P->varbeg[j + 1]; ++e )
+      {
+         int k = P->entblk[e];
+         if( na[k] > 0.0 )
+         {
+            double a = std::sqrt(na[k]);
+            h->xi[k] = std::max(h->xi[k], h->blk[k].n * (1.0 + std::fabs(P->obj[j])) / (1.0 + a));
+            h->eta[k] = std::max(h->eta[k], a);
+            na[k] = 0.0;
+         }
+      }
+   }
+   for( int l = 0; l < nlp; ++l )
+      for( int p = P->lpbeg[l]; p < P->lpbeg[l + 1]; ++p ) nrmD[P->lpind[p]] += P->lpval[p] * P->lpval[p];
+   double sq = std::sqrt((double)std::max(nlp, 1));
+   double xil = std::max(10.0, sq), etal = xil, nd = 0;
+   for( int l = 0; l < nlp; ++l ) nd += P->lprhs[l] * P->lprhs[l];
+   etal = std::max(etal, std::sqrt(nd));
+   for( int j = 0; j < m; ++j )
+   {
+      double a = std::sqrt(nrmD[j]);
+      if( a > 0 ) xil = std::max(xil, sq * (1.0 + std::fabs(P->obj[j])) / (1.0 + a));
+      etal = std::max(etal, a);
+   }
+   h->xil = xil; h->etal = etal;
+}
+
+static int run_ipm(sdpcuda_handle* h, const sdpcuda_params* par, const double* start_y, sdpcuda_result* res, double t0);
 
 int sdpcuda_solve(sdpcuda_handle* h, const sdpcuda_problem* P, const sdpcuda_params* par, const double* start_y, sdpcuda_result* res)
 {
@@ -386,10 +453,47 @@ int sdpcuda_solve(sdpcuda_handle* h, const sdpcuda_problem* P, const sdpcuda_par
    int rc = set_device(h);
    if( rc != SDPCUDA_OK ) return rc;
    h->solved = false;
+   h->resident = false;
    h->counter.n = 0;
+   g_h2d_bytes = 0.0;
    rc = upload_problem(h, P);
    if( rc != SDPCUDA_OK ) return rc;
+   host_constants(h, P);
+   h->resident = true;
+   return run_ipm(h, par, start_y, res, t0);
+}
 
+int sdpcuda_solve_resident(sdpcuda_handle* h, const sdpcuda_params* par, sdpcuda_result* res)
+{
+   if( h == nullptr || par == nullptr ) return SDPCUDA_ERR_ARG;
+   if( !h->resident ) return SDPCUDA_ERR_STATE;
+   const double t0 = now_seconds();
+   int rc = set_device(h);
+   if( rc != SDPCUDA_OK ) return rc;
+   h->solved = false;
+   h->counter.n = 0;
+   g_h2d_bytes = 0.0;
+   return run_ipm(h, par, nullptr, res, t0);
+}
+
+int sdpcuda_set_profiling(sdpcuda_handle* h, int on)
+{
+   if( h == nullptr ) return SDPCUDA_ERR_ARG;
+   h->prof.on = (on != 0);
+   h->prof.reset();
+   return SDPCUDA_OK;
+}
+
+int sdpcuda_get_profile(sdpcuda_handle* h, double* out)
+{
+   if( h == nullptr || out == nullptr ) return SDPCUDA_ERR_ARG;
+   for( int c = 0; c < NPROF; ++c ) { out[3 * c] = h->prof.launches[c]; out[3 * c + 1] = h->prof.ms[c]; out[3 * c + 2] = h->prof.work[c]; }
+   return SDPCUDA_OK;
+}
+
+static int run_ipm(sdpcuda_handle* h, const sdpcuda_params* par, const double* start_y, sdpcuda_result* res, double t0)
+{
+   int rc = SDPCUDA_OK;
    cudaStream_t st = h->st;
    const int m = h->m, nb = h->nb, nlp = h->nlp;
    const size_t ar = h->arena;
@@ -399,60 +503,20 @@ int sdpcuda_solve(sdpcuda_handle* h, const sdpcuda_problem* P, const sdpcuda_par
    const double inftol = 1e-8;
    const double gammabase = par->setting >= 3 ? 0.7 : (par->setting == 2 ? 0.8 : 0.9);
    DevEntries E = entries(h);
+   const double normb = h->normb, normC = h->normC, normCsdp2 = h->normCsdp2;
+   if( h->prof.on ) h->prof.reset();
 
-   // ---- norms and the initial point (host side, from the problem data: O(nnz)) ----
-   double normb = 0, normC = 0;
-   for( int j = 0; j < m; ++j ) normb += P->obj[j] * P->obj[j];
-   normb = std::sqrt(normb);
-   std::vector<double> nrmC(nb, 0.0);
-   for( int e = 0; e < P->cnnz; ++e )
-      nrmC[P->cblk[e]] += (P->crow[e] == P->ccol[e] ? 1.0 : 2.0) * P->cval[e] * P->cval[e];
-   for( int k = 0; k < nb; ++k ) normC += nrmC[k];
-   for( int l = 0; l < nlp; ++l ) normC += P->lprhs[l] * P->lprhs[l];
-   normC = std::sqrt(normC);
+   // ---- initial point ----
    {
-      std::vector<double> xi(nb), eta(nb);
-      for( int k = 0; k < nb; ++k ) { xi[k] = eta[k] = std::max(10.0, std::sqrt((double)h->blk[k].n)); eta[k] = std::max(eta[k], std::sqrt(nrmC[k])); }
-      std::vector<double> na(nb);
-      std::vector<double> nrmD(m, 0.0);
-      for( int j = 0; j < m; ++j )
-      {
-         std::fill(na.begin(), na.end(), 0.0);
-         for( int e = P->varbeg[j]; e < P->varbeg[j + 1]; ++e )
-            na[P->entblk[e]] += (P->entrow[e] == P->entcol[e] ? 1.0 : 2.0) * P->entval[e] * P->entval[e];
-         for( int e = P->varbeg[j]; e < P->varbeg[j + 1]; ++e )
-         {
-            int k = P->entblk[e];
-            if( na[k] > 0.0 )
-            {
-               double a = std::sqrt(na[k]);
-               xi[k] = std::max(xi[k], h->blk[k].n * (1.0 + std::fabs(P->obj[j])) / (1.0 + a));
-               eta[k] = std::max(eta[k], a);
-               na[k] = 0.0;      // handled
-            }
-         }
-      }
-      for( int l = 0; l < nlp; ++l )
-         for( int p = P->lpbeg[l]; p < P->lpbeg[l + 1]; ++p ) nrmD[P->lpind[p]] += P->lpval[p] * P->lpval[p];
-      double sq = std::sqrt((double)std::max(nlp, 1));
-      double xil = std::max(10.0, sq), etal = xil, nd = 0;
-      for( int l = 0; l < nlp; ++l ) nd += P->lprhs[l] * P->lprhs[l];
-      etal = std::max(etal, std::sqrt(nd));
-      for( int j = 0; j < m; ++j )
-      {
-         double a = std::sqrt(nrmD[j]);
-         if( a > 0 ) xil = std::max(xil, sq * (1.0 + std::fabs(P->obj[j])) / (1.0 + a));
-         etal = std::max(etal, a);
-      }
-      if( par->lambdastar > 0 ) { xil = etal = par->lambdastar; for( int k = 0; k < nb; ++k ) xi[k] = eta[k] = par->lambdastar; }
       CK( cudaMemsetAsync(h->X.p, 0, ar * sizeof(double), st) );
       CK( cudaMemsetAsync(h->S.p, 0, ar * sizeof(double), st) );
       for( int k = 0; k < nb; ++k )
       {
-         CK( add_diagonal(st, h->blk[k].n, h->X.p + h->blk[k].off, h->blk[k].ld, xi[k]) );
-         CK( add_diagonal(st, h->blk[k].n, h->S.p + h->blk[k].off, h->blk[k].ld, eta[k]) );
+         double xi = par->lambdastar > 0 ? par->lambdastar : h->xi[k], eta = par->lambdastar > 0 ? par->lambdastar : h->eta[k];
+         CK( add_diagonal(st, h->blk[k].n, h->X.p + h->blk[k].off, h->blk[k].ld, xi) );
+         CK( add_diagonal(st, h->blk[k].n, h->S.p + h->blk[k].off, h->blk[k].ld, eta) );
       }
-      std::vector<double> hx(nlp, xil), hs(nlp, etal), hy(m, 0.0);
+      std::vector<double> hx(nlp, par->lambdastar > 0 ? par->lambdastar : h->xil), hs(nlp, par->lambdastar > 0 ? par->lambdastar : h->etal), hy(m, 0.0);
       if( start_y != nullptr ) std::copy(start_y, start_y + m, hy.begin());
       CK( h->x.upload(hx, st) ); CK( h->s.upload(hs, st) ); CK( h->y.upload(hy, st) );
       CK( cudaStreamSynchronize(st) );
@@ -466,6 +530,7 @@ int sdpcuda_solve(sdpcuda_handle* h, const sdpcuda_problem* P, const sdpcuda_par
    double mu = 0, pobj = 0, dobj = 0, relgap = 1e30, pinf = 1e30, dinf = 1e30;
    double bestmerit = 1e300; int stall = 0;
    bool pfeasever = false, dfeasever = false;
+   double d2h = 0.0;
    double lastap = 0.0, lastad = 0.0;           // step of the previous update (for backtracking if a factorisation fails)
    int backtracks = 0;
    CK( cudaEventRecord(h->ev0, st) );
@@ -490,6 +555,7 @@ int sdpcuda_solve(sdpcuda_handle* h, const sdpcuda_problem* P, const sdpcuda_par
       CK( cudaMemcpyAsync(h->h_stats, h->stats.p, (NSTAT + 2) * sizeof(double), cudaMemcpyDeviceToHost, st) );
       CK( cudaMemcpyAsync(h->h_info, h->info.p, 8 * sizeof(int), cudaMemcpyDeviceToHost, st) );
       CK( cudaStreamSynchronize(st) );
+      d2h += (NSTAT + 2) * sizeof(double) + 8 * sizeof(int);
 
       if( h->h_info[0] != 0 || h->h_info[1] != 0 )
       {
@@ -526,7 +592,6 @@ int sdpcuda_solve(sdpcuda_handle* h, const sdpcuda_problem* P, const sdpcuda_par
       const double dinfabs = std::max(std::sqrt(hs[0]), hs[16]), pinfabs = hs[17];
       relgap = std::fabs(pobj - dobj) / std::max(1.0, 0.5 * (std::fabs(pobj) + std::fabs(dobj)));
       // |A'y - S|^2 = |Rd + C|^2 = |Rd|^2 + 2 C.Rd + |C|^2 for the SDP part, (Dy - s)^2 for the LP part
-      double normCsdp2 = 0.0; for( int k = 0; k < nb; ++k ) normCsdp2 += nrmC[k];
       const double rayd = std::sqrt(std::max(0.0, hs[0] + 2.0 * CRd + normCsdp2 + hs[5]));
       const bool pfeas = pinf <= feastol && pinfabs <= std::max(feastol, 1e-9 * (1 + normb));
       const bool dfeas = dinf <= feastol && dinfabs <= feastol;
@@ -646,6 +711,7 @@ int sdpcuda_solve(sdpcuda_handle* h, const sdpcuda_problem* P, const sdpcuda_par
          rc = step_eigs(h, h->Linv.p, h->dS.p, 8 + nb); if( rc ) return rc;
          CK( cudaMemcpyAsync(h->h_stats + 32, h->scal.p, sizeof(double) * (8 + 2 * (size_t)nb), cudaMemcpyDeviceToHost, st) );
          CK( cudaStreamSynchronize(st) );
+         d2h += sizeof(double) * (8 + 2 * (size_t)nb) + (pass == 0 ? NSTAT * sizeof(double) : 0);
          double apmax = h->h_stats[32 + 0], admax = h->h_stats[32 + 1];
          for( int k = 0; k < nb; ++k )
          {
@@ -689,12 +755,14 @@ int sdpcuda_solve(sdpcuda_handle* h, const sdpcuda_problem* P, const sdpcuda_par
 
    CK( cudaEventRecord(h->ev1, st) );
    CK( cudaStreamSynchronize(st) );
+   if( h->prof.on ) h->prof.collect();
    float ms = 0.f;
    cudaEventElapsedTime(&ms, h->ev0, h->ev1);
    R.iterations = iter; R.launches = (int)std::min<long long>(h->counter.n, 2147483647LL);
    R.pobj = pobj; R.dobj = dobj; R.relgap = relgap; R.pinf = pinf; R.dinf = dinf; R.mu = mu;
    R.seconds = now_seconds() - t0;
    R.device_ms = ms;
+   R.h2d_bytes = g_h2d_bytes; R.d2h_bytes = d2h;
    h->solved = true;
    if( res != nullptr ) *res = R;
    return SDPCUDA_OK;
@@ -862,14 +930,23 @@ int sdpcuda_time_kernel(sdpcuda_handle* h, int kind, int n, int reps, double* ms
    if( kind == 4 )
    {
       CK( h->kA.ensure(16) );
-      double fl = 0;
-      CK( dmma_peak_probe(st, 2000, h->kA.p, &fl) );       // warm-up
-      CK( cudaEventRecord(h->ev0, st) );
-      for( int r = 0; r < reps; ++r ) CK( dmma_peak_probe(st, 20000, h->kA.p, &fl) );
-      CK( cudaEventRecord(h->ev1, st) );
-      CK( cudaStreamSynchronize(st) );
-      cudaEventElapsedTime(&ms, h->ev0, h->ev1);
-      *ms_per_launch = ms / reps; *work = fl;
+      // several occupancies; the best rate is the measured FP64 tensor peak (n > 0 selects one configuration for experiments)
+      const int cfgs[6][2] = {{1, 128}, {1, 256}, {2, 256}, {4, 256}, {2, 512}, {1, 1024}};
+      double best = 0.0, bestms = 0.0, bestfl = 0.0;
+      for( int c = 0; c < 6; ++c )
+      {
+         if( n > 0 && n != c + 1 ) continue;
+         double fl = 0;
+         CK( dmma_peak_probe(st, 2000, h->kA.p, &fl, cfgs[c][0], cfgs[c][1]) );       // warm-up
+         CK( cudaEventRecord(h->ev0, st) );
+         for( int r = 0; r < reps; ++r ) CK( dmma_peak_probe(st, 8000, h->kA.p, &fl, cfgs[c][0], cfgs[c][1]) );
+         CK( cudaEventRecord(h->ev1, st) );
+         CK( cudaStreamSynchronize(st) );
+         cudaEventElapsedTime(&ms, h->ev0, h->ev1);
+         double rate = fl / (ms / reps);
+         if( rate > best ) { best = rate; bestms = ms / reps; bestfl = fl; }
+      }
+      *ms_per_launch = bestms; *work = bestfl;
       return SDPCUDA_OK;
    }
    if( n <= 0 ) return SDPCUDA_ERR_ARG;

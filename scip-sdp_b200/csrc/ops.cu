@@ -380,6 +380,7 @@ cudaError_t assemble_positions(cudaStream_t st, int npos, const int* posbeg, con
 
 cudaError_t residual_matrix(cudaStream_t st, size_t arena, const double* T, const double* S, const double* X, double* Rd, double* partials)
 {
+   ProfScope prof(st, PROF_ELEM, 32.0 * arena);
    residual_matrix_kernel<<<RED_BLOCKS, 256, 0, st>>>(arena, T, S, X, Rd, partials);
    LAUNCH_END();
 }
@@ -431,6 +432,7 @@ cudaError_t schur_entries(cudaStream_t st, int m, DevEntries E, const int* heavy
    const double* X, const double* Z, double* M, int ldm)
 {
    if( m <= 0 ) return cudaSuccess;
+   ProfScope prof(st, PROF_SCHUR, 8.0 * m * (double)m / 2.0);
    dim3 grid(ceil_div(m, 32), ceil_div(m, 8));
    schur_light_kernel<<<grid, 256, 0, st>>>(m, E, heavy, X, Z, M, ldm);
    count_launch();
@@ -468,6 +470,7 @@ cudaError_t symv_lower(cudaStream_t st, int n, const double* M, int ldm, const d
 cudaError_t sym_average(cudaStream_t st, int n, double* A, int lda, const double* subtract)
 {
    if( n <= 0 ) return cudaSuccess;
+   ProfScope prof(st, PROF_ELEM, (subtract ? 24.0 : 16.0) * n * (double)n);
    dim3 grid(ceil_div(n, 256), n);
    sym_average_kernel<<<grid, 256, 0, st>>>(n, A, lda, subtract);
    LAUNCH_END();
@@ -476,6 +479,7 @@ cudaError_t sym_average(cudaStream_t st, int n, double* A, int lda, const double
 cudaError_t mirror_lower(cudaStream_t st, int n, double* A, int lda)
 {
    if( n <= 1 ) return cudaSuccess;
+   ProfScope prof(st, PROF_ELEM, 8.0 * n * (double)n);
    dim3 grid(ceil_div(n, 256), n);
    mirror_lower_kernel<<<grid, 256, 0, st>>>(n, A, lda);
    LAUNCH_END();
@@ -484,6 +488,7 @@ cudaError_t mirror_lower(cudaStream_t st, int n, double* A, int lda)
 cudaError_t axpy(cudaStream_t st, size_t n, double a, const double* x, double* y)
 {
    if( n == 0 ) return cudaSuccess;
+   ProfScope prof(st, PROF_ELEM, 24.0 * n);
    axpy_kernel<<<grid_for(n, 256), 256, 0, st>>>(n, a, x, y);
    LAUNCH_END();
 }
@@ -491,6 +496,7 @@ cudaError_t axpy(cudaStream_t st, size_t n, double a, const double* x, double* y
 cudaError_t axpby_out(cudaStream_t st, size_t n, double a, const double* x, double b, const double* y, double* out)
 {
    if( n == 0 ) return cudaSuccess;
+   ProfScope prof(st, PROF_ELEM, 24.0 * n);
    axpby_kernel<<<grid_for(n, 256), 256, 0, st>>>(n, a, x, b, y, out);
    LAUNCH_END();
 }
@@ -513,6 +519,7 @@ cudaError_t lp_direction(cudaStream_t st, int nlp, const double* x, const double
 cudaError_t affine_mu(cudaStream_t st, size_t arena, const double* X, const double* dX, const double* S, const double* dS,
    int nlp, const double* x, const double* dx, const double* s, const double* ds, double ap, double ad, double* partials)
 {
+   ProfScope prof(st, PROF_ELEM, 32.0 * arena);
    affine_mu_kernel<<<RED_BLOCKS, 256, 0, st>>>(arena, X, dX, S, dS, nlp, x, dx, s, ds, ap, ad, partials);
    LAUNCH_END();
 }

@@ -1,0 +1,69 @@
+"""CPU suite, part 3: the N > 1 path (independent node relaxations partitioned over ranks) with world_size 2 on gloo.
+The relaxations themselves run on the CPU oracle here; on the GPU box the same code runs with one device handle per rank."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from scip_sdp_b200 import abi, frontier, misdp
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def _nodes(M):
+    """root + the four grandchildren obtained by branching on the first two integer variables"""
+    ints = np.flatnonzero(M.integer)[:2]
+    out = [(M.lb.copy(), M.ub.copy())]
+    for a in (0, 1):
+        for b in (0, 1):
+            lb, ub = M.lb.copy(), M.ub.copy()
+            lb[ints[0]] = ub[ints[0]] = a
+            lb[ints[1]] = ub[ints[1]] = b
+            out.append((lb, ub))
+    return out
+
+
+def _worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        M = misdp.read_sdpa(os.path.join(GOLDEN, "example_TT.dat-s.gz")).rows_to_bounds()
+        solver = abi.Solver(abi.Lib(abi.ORACLE_LIB))
+        res = frontier.solve_frontier(solver, M, _nodes(M), dist=dist, gaptol=1e-6, feastol=1e-6)
+        tmax = frontier.max_over_ranks(1.0 + rank, dist=dist)
+        q.put((rank, [(r["status"], round(r["bound"], 6)) for r in res], tmax, frontier.partition(5, world, rank)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_partition_is_a_disjoint_cover():
+    for world in (1, 2, 4, 8):
+        allidx = sorted(i for r in range(world) for i in frontier.partition(13, world, r))
+        assert allidx == list(range(13))
+
+
+def test_frontier_world_size_2_matches_single_process():
+    M = misdp.read_sdpa(os.path.join(GOLDEN, "example_TT.dat-s.gz")).rows_to_bounds()
+    single = frontier.solve_frontier(abi.Solver(abi.Lib(abi.ORACLE_LIB)), M, _nodes(M), gaptol=1e-6, feastol=1e-6)
+    expect = [(r["status"], round(r["bound"], 6)) for r in single]
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, res, tmax, part in got:
+        assert res == expect                   # every rank ends up with the complete, identical result list
+        assert tmax == 2.0                     # max over ranks of (1 + rank)
+        assert part == list(range(rank, 5, 2))
+    # child bounds can only be worse (larger) than the root relaxation bound
+    assert all(b >= expect[0][1] - 1e-6 for st, b in expect[1:] if st == "pdOPT")
