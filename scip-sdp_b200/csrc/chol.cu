@@ -12,6 +12,9 @@
 #include "common.cuh"
 
 namespace sdpk {
+
+long long* g_diag_dbg = nullptr;
+
 namespace {
 
 constexpr int NB = CHOL_NB;
@@ -26,112 +29,284 @@ __device__ __forceinline__ double fast_rsqrt(double x)
    return y;
 }
 
+// inverse of a 4 x 4 lower-triangular block (fully unrolled forward substitution); rdiag = reciprocals of the diagonal
+__device__ __forceinline__ void inv4_lower(const double (&l)[4][4], const double (&rdiag)[4], double (&w)[4][4])
+{
+#pragma unroll
+   for( int c = 0; c < 4; ++c )
+   {
+#pragma unroll
+      for( int r = 0; r < 4; ++r )
+      {
+         if( r < c ) { w[r][c] = 0.0; continue; }
+         if( r == c ) { w[r][c] = rdiag[r]; continue; }
+         double s = 0.0;
+#pragma unroll
+         for( int p = 0; p < 4; ++p ) if( p >= c && p < r ) s += l[r][p] * w[p][c];
+         w[r][c] = -s * rdiag[r];
+      }
+   }
+}
+
 // mode 0: factorise A (nb x nb, lower) in place, optionally write inverse of L to Linv (upper part zeroed) / diaginv
 // mode 1: A holds a lower-triangular factor already; only invert it
-// One CTA of 128 threads; thread i < 64 owns row i (Cholesky-Crout: column k needs one dot product per row and two
-// barriers), then thread j < 64 owns column j of the inverse (forward substitution with broadcast reads of L).
-__global__ void __launch_bounds__(128)
+// One CTA of 256 threads = 16 x 16 register tiles of 4 x 4 covering the whole 64 x 64 block; everything is organised in
+// 16 macro steps over block columns of width 4 so that all register indexing is static and the updates carry no
+// predicates (published panels are zero outside their active rows):
+//   factorisation, block column t: the diagonal tile factors its 4 x 4 block and inverts it (one thread, unrolled);
+//     the tiles below form their panel block A_it L_tt^-T and publish it; every tile subtracts P_i P_j'.
+//   inverse (W = L^-1 from R = I), block row t: tiles of that row form L_tt^-1 R_t and publish it; tiles below subtract
+//     L_it W_t.  Two barriers per macro step in the first phase, one in the second (published rows double buffered).
+__global__ void __launch_bounds__(256)
 diag_block_kernel(int mode, int nb, double* __restrict__ A, int lda, double* __restrict__ Linv, int ldi,
-   double* __restrict__ diaginv, int* __restrict__ info, int pivot_offset)
+   double* __restrict__ diaginv, int* __restrict__ info, int pivot_offset, long long* __restrict__ dbg)
 {
-   extern __shared__ __align__(16) double diag_smem[];
-   double* L = diag_smem;
-   double* W = diag_smem + NB * LDSM;
-   double* dinv = W + NB * LDSM;              // reciprocals of the diagonal of L
+   __shared__ double Ls[NB * LDSM];
+   __shared__ __align__(16) double Pn[2][4][NB];      // published panel columns / inverse rows
+   __shared__ double Dinv[16][16];                    // inverses of the 4 x 4 diagonal blocks of L (row-major 4 x 4)
+   long long tc0 = clock64(), tc1 = 0, tc2 = 0, tc3 = 0;
    const int tid = threadIdx.x;
+   const int ti = tid >> 4, tj = tid & 15;
+   const int i0 = 4 * ti, j0 = 4 * tj;
 
    for( int e = tid; e < NB * NB; e += blockDim.x )
    {
       int i = e % NB, j = e / NB;
-      double v = 0.0;
+      double v = (i == j) ? 1.0 : 0.0;                 // identity padding keeps a partial block positive definite
       if( i < nb && j < nb && i >= j ) v = A[(size_t)j * lda + i];
-      else if( i == j ) v = 1.0;                      // identity padding keeps the padded block positive definite
-      L[i * LDSM + j] = v;
+      Ls[i * LDSM + j] = v;
    }
    __syncthreads();
+   tc1 = clock64();
 
+   double a[4][4];
    if( mode == 0 )
    {
-      const int i = tid;
-      for( int k = 0; k < NB; ++k )
+#pragma unroll
+      for( int r = 0; r < 4; ++r )
+#pragma unroll
+         for( int c = 0; c < 4; ++c )
+            a[r][c] = (i0 + r >= j0 + c) ? Ls[(i0 + r) * LDSM + j0 + c] : Ls[(j0 + c) * LDSM + i0 + r];
+
+      for( int t = 0; t < 16; ++t )
       {
-         double s = 0.0;
-         if( i < NB && i >= k )
+         if( ti == t && tj == t )
          {
-            double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-            const double* ri = L + i * LDSM;
-            const double* rk = L + k * LDSM;
-            int j = 0;
-            for( ; j + 4 <= k; j += 4 )
+            // 4 x 4 Cholesky of the diagonal tile, then its inverse
+            double rd[4], w[4][4];
+#pragma unroll
+            for( int q = 0; q < 4; ++q )
             {
-               s0 += ri[j] * rk[j]; s1 += ri[j + 1] * rk[j + 1]; s2 += ri[j + 2] * rk[j + 2]; s3 += ri[j + 3] * rk[j + 3];
-            }
-            for( ; j < k; ++j ) s0 += ri[j] * rk[j];
-            s = ri[k] - ((s0 + s1) + (s2 + s3));
-            if( i == k )
-            {
-               if( !(s > 0.0) )
+               double sq = a[q][q];
+#pragma unroll
+               for( int p = 0; p < 4; ++p ) if( p < q ) sq -= a[q][p] * a[q][p];
+               if( !(sq > 0.0) )
                {
-                  if( k < nb ) atomicCAS(info, 0, pivot_offset + k + 1);
-                  s = 1.0;
+                  if( 4 * t + q < nb ) atomicCAS(info, 0, pivot_offset + 4 * t + q + 1);
+                  sq = 1.0;
                }
-               double r = fast_rsqrt(s);
-               L[k * LDSM + k] = s * r;
-               dinv[k] = r;
+               rd[q] = fast_rsqrt(sq);
+               a[q][q] = sq * rd[q];
+#pragma unroll
+               for( int r = 0; r < 4; ++r )
+               {
+                  if( r > q )
+                  {
+                     double sr = a[r][q];
+#pragma unroll
+                     for( int p = 0; p < 4; ++p ) if( p < q ) sr -= a[r][p] * a[q][p];
+                     a[r][q] = sr * rd[q];
+                  }
+               }
+            }
+#pragma unroll
+            for( int r = 0; r < 4; ++r )
+#pragma unroll
+               for( int c = 0; c < 4; ++c ) if( r < c ) a[r][c] = 0.0;
+            inv4_lower(a, rd, w);
+#pragma unroll
+            for( int r = 0; r < 4; ++r )
+#pragma unroll
+               for( int c = 0; c < 4; ++c ) Dinv[t][4 * r + c] = w[r][c];
+         }
+         __syncthreads();
+         if( tj == t )
+         {
+            if( ti > t )
+            {
+               // panel block  L_it = A_it L_tt^-T :  new[r][q] = sum_{p <= q} a[r][p] * Linv_tt[q][p]
+               double li[4][4], nw[4][4];
+#pragma unroll
+               for( int q = 0; q < 4; ++q )
+#pragma unroll
+                  for( int p = 0; p < 4; ++p ) li[q][p] = Dinv[t][4 * q + p];
+#pragma unroll
+               for( int r = 0; r < 4; ++r )
+#pragma unroll
+                  for( int q = 0; q < 4; ++q )
+                  {
+                     double sacc = 0.0;
+#pragma unroll
+                     for( int p = 0; p < 4; ++p ) if( p <= q ) sacc += a[r][p] * li[q][p];
+                     nw[r][q] = sacc;
+                  }
+#pragma unroll
+               for( int r = 0; r < 4; ++r )
+#pragma unroll
+                  for( int q = 0; q < 4; ++q ) { a[r][q] = nw[r][q]; Pn[0][q][i0 + r] = nw[r][q]; }
+            }
+            else
+            {
+#pragma unroll
+               for( int r = 0; r < 4; ++r )
+#pragma unroll
+                  for( int q = 0; q < 4; ++q ) Pn[0][q][i0 + r] = 0.0;
             }
          }
          __syncthreads();
-         if( i < NB && i > k )
-            L[i * LDSM + k] = s * dinv[k];
-         __syncthreads();
+         {
+            double pi[4][4], pj[4][4];
+#pragma unroll
+            for( int q = 0; q < 4; ++q )
+#pragma unroll
+               for( int r = 0; r < 4; ++r ) { pi[q][r] = Pn[0][q][i0 + r]; pj[q][r] = Pn[0][q][j0 + r]; }
+#pragma unroll
+            for( int r = 0; r < 4; ++r )
+#pragma unroll
+               for( int c = 0; c < 4; ++c )
+               {
+                  double sacc = a[r][c];
+#pragma unroll
+                  for( int q = 0; q < 4; ++q ) sacc -= pi[q][r] * pj[q][c];
+                  a[r][c] = sacc;
+               }
+         }
       }
+      __syncthreads();
+      if( ti >= tj )
+      {
+#pragma unroll
+         for( int r = 0; r < 4; ++r )
+#pragma unroll
+            for( int c = 0; c < 4; ++c )
+               if( ti > tj || r >= c ) Ls[(i0 + r) * LDSM + j0 + c] = a[r][c];
+      }
+      __syncthreads();
       for( int e = tid; e < nb * nb; e += blockDim.x )
       {
-         int r = e % nb, c = e / nb;
-         if( r >= c ) A[(size_t)c * lda + r] = L[r * LDSM + c];
+         int i = e % nb, j = e / nb;
+         if( i >= j ) A[(size_t)j * lda + i] = Ls[i * LDSM + j];
       }
    }
    else
    {
-      if( tid < NB ) dinv[tid] = 1.0 / L[tid * LDSM + tid];
+      if( tid < 16 )
+      {
+         double l[4][4], rd[4], w[4][4];
+#pragma unroll
+         for( int r = 0; r < 4; ++r )
+#pragma unroll
+            for( int c = 0; c < 4; ++c ) l[r][c] = (r >= c) ? Ls[(4 * tid + r) * LDSM + 4 * tid + c] : 0.0;
+#pragma unroll
+         for( int r = 0; r < 4; ++r ) rd[r] = 1.0 / l[r][r];
+         inv4_lower(l, rd, w);
+#pragma unroll
+         for( int r = 0; r < 4; ++r )
+#pragma unroll
+            for( int c = 0; c < 4; ++c ) Dinv[tid][4 * r + c] = w[r][c];
+      }
       __syncthreads();
    }
 
+   tc2 = clock64();
    if( Linv != nullptr || diaginv != nullptr )
    {
-      // thread j: column j of W = L^-1; the k-loop starts at 0 for all threads (W is zero above the diagonal) so that the
-      // reads of L[i][k] are warp-wide broadcasts and the reads of W[k][j] are conflict free
-      const int j = tid;
-      if( j < NB )
+      // R = I, turned into W = L^-1 block row by block row
+#pragma unroll
+      for( int r = 0; r < 4; ++r )
+#pragma unroll
+         for( int c = 0; c < 4; ++c )
+            a[r][c] = (i0 + r == j0 + c) ? 1.0 : 0.0;
+
+      for( int t = 0; t < 16; ++t )
       {
-         for( int i = 0; i < NB; ++i ) W[i * LDSM + j] = (i == j) ? dinv[j] : 0.0;
-         for( int i = 1; i < NB; ++i )
+         const int buf = t & 1;
+         if( ti == t )
          {
-            const double* ri = L + i * LDSM;
-            double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-            int k = 0;
-            for( ; k + 4 <= i; k += 4 )
+            if( tj <= t )
             {
-               s0 += ri[k] * W[k * LDSM + j]; s1 += ri[k + 1] * W[(k + 1) * LDSM + j];
-               s2 += ri[k + 2] * W[(k + 2) * LDSM + j]; s3 += ri[k + 3] * W[(k + 3) * LDSM + j];
+               double li[4][4], nw[4][4];
+#pragma unroll
+               for( int r = 0; r < 4; ++r )
+#pragma unroll
+                  for( int p = 0; p < 4; ++p ) li[r][p] = Dinv[t][4 * r + p];
+#pragma unroll
+               for( int r = 0; r < 4; ++r )
+#pragma unroll
+                  for( int c = 0; c < 4; ++c )
+                  {
+                     double sacc = 0.0;
+#pragma unroll
+                     for( int p = 0; p < 4; ++p ) if( p <= r ) sacc += li[r][p] * a[p][c];
+                     nw[r][c] = sacc;
+                  }
+#pragma unroll
+               for( int r = 0; r < 4; ++r )
+#pragma unroll
+                  for( int c = 0; c < 4; ++c ) { a[r][c] = nw[r][c]; Pn[buf][r][j0 + c] = nw[r][c]; }
             }
-            for( ; k < i; ++k ) s0 += ri[k] * W[k * LDSM + j];
-            if( i > j ) W[i * LDSM + j] = -((s0 + s1) + (s2 + s3)) * dinv[i];
+            else
+            {
+#pragma unroll
+               for( int r = 0; r < 4; ++r )
+#pragma unroll
+                  for( int c = 0; c < 4; ++c ) Pn[buf][r][j0 + c] = 0.0;
+            }
+         }
+         __syncthreads();
+         if( ti > t )
+         {
+            double lb[4][4], wk[4][4];
+#pragma unroll
+            for( int r = 0; r < 4; ++r )
+#pragma unroll
+               for( int q = 0; q < 4; ++q ) { lb[r][q] = Ls[(i0 + r) * LDSM + 4 * t + q]; wk[q][r] = Pn[buf][q][j0 + r]; }
+#pragma unroll
+            for( int r = 0; r < 4; ++r )
+#pragma unroll
+               for( int c = 0; c < 4; ++c )
+               {
+                  double sacc = a[r][c];
+#pragma unroll
+                  for( int q = 0; q < 4; ++q ) sacc -= lb[r][q] * wk[q][c];
+                  a[r][c] = sacc;
+               }
          }
       }
+      __syncthreads();                                  // all reads of L are done: reuse Ls for W
+      tc3 = clock64();
+#pragma unroll
+      for( int r = 0; r < 4; ++r )
+#pragma unroll
+         for( int c = 0; c < 4; ++c )
+            Ls[(i0 + r) * LDSM + j0 + c] = (i0 + r >= j0 + c) ? a[r][c] : 0.0;
       __syncthreads();
       if( Linv != nullptr )
          for( int e = tid; e < nb * nb; e += blockDim.x )
          {
-            int r = e % nb, c = e / nb;
-            Linv[(size_t)c * ldi + r] = W[r * LDSM + c];
+            int i = e % nb, j = e / nb;
+            Linv[(size_t)j * ldi + i] = Ls[i * LDSM + j];
          }
       if( diaginv != nullptr )
          for( int e = tid; e < NB * NB; e += blockDim.x )
          {
-            int r = e % NB, c = e / NB;
-            diaginv[(size_t)c * NB + r] = (r < nb && c < nb) ? W[r * LDSM + c] : 0.0;
+            int i = e % NB, j = e / NB;
+            diaginv[(size_t)j * NB + i] = (i < nb && j < nb) ? Ls[i * LDSM + j] : 0.0;
          }
+   }
+   if( dbg != nullptr && tid == 0 )
+   {
+      dbg[0] = tc1 - tc0; dbg[1] = tc2 - tc1; dbg[2] = tc3 - tc2; dbg[3] = clock64() - tc3;
    }
 }
 
@@ -151,18 +326,12 @@ cudaError_t copy2d(cudaStream_t st, int m, int n, const double* src, int lds, do
    return cudaGetLastError();
 }
 
-constexpr size_t DIAG_SMEM = (2 * NB * LDSM + NB) * sizeof(double);
+constexpr size_t DIAG_SMEM = 0;
 
 cudaError_t launch_diag(cudaStream_t st, int mode, int nb, double* A, int lda, double* Linv, int ldi, double* diaginv, int* info, int off)
 {
-   static bool configured = false;
-   if( !configured )
-   {
-      SDPK_CUDA_CHECK( cudaFuncSetAttribute(diag_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DIAG_SMEM) );
-      configured = true;
-   }
    ProfScope prof(st, PROF_DIAG, (mode == 0 ? 1.0 : 0.0) * nb * (double)nb * nb / 3.0 + ((Linv || diaginv) ? nb * (double)nb * nb / 3.0 : 0.0));
-   diag_block_kernel<<<1, 128, DIAG_SMEM, st>>>(mode, nb, A, lda, Linv, ldi, diaginv, info, off);
+   diag_block_kernel<<<1, 256, DIAG_SMEM, st>>>(mode, nb, A, lda, Linv, ldi, diaginv, info, off, g_diag_dbg);
    count_launch();
    return cudaGetLastError();
 }

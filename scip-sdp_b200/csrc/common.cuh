@@ -86,6 +86,7 @@ cudaError_t dmma_peak_probe(cudaStream_t st, int iters, double* d_sink, double* 
 // d_info: device int, set to the 1-based index of the first non-positive pivot (0 = success; is NOT reset here).
 // diaginv: optional workspace receiving the inverses of the NB x NB diagonal blocks of L (block b at b*NB*NB).
 constexpr int CHOL_NB = 64;
+extern long long* g_diag_dbg;      // optional device buffer (4 x int64) receiving the phase cycle counts of the diagonal-block kernel
 cudaError_t potrf_lower(cudaStream_t st, int n, double* A, int lda, double* Linv, int ldi, double* diaginv, double* work, int ldw, int* d_info);
 cudaError_t trtri_lower(cudaStream_t st, int n, const double* L, int ldl, double* Linv, int ldi, double* work, int ldw);
 // solves L L' x = b for one right-hand side using the diagonal-block inverses (x overwrites b; tmp: n doubles)
@@ -99,5 +100,10 @@ cudaError_t jacobi_eig_batched(cudaStream_t st, int n, int nbatch, const double*
 // smallest eigenvalue of symmetric B (n x n, full storage) by Lanczos; result (Ritz value minus residual bound) in d_out[0]
 cudaError_t lanczos_lambda_min(cudaStream_t st, int n, const double* B, int ldb, double* work /* >= (maxit+4)*n + 4*maxit+16 */, int maxit, double* d_out);
 size_t lanczos_work_doubles(int n, int maxit);
+// batched, adaptive variant: all matrices advance together, convergence is checked on the host every 8 steps
+constexpr int LZB_MAXIT = 64;
+struct LzDesc { int n; int ld; const double* B; double* Q /* (LZB_MAXIT+2)*n */; double* ab /* 2*LZB_MAXIT */; double* out /* 3 */; };
+cudaError_t lanczos_batched(cudaStream_t st, int nmat, const LzDesc* h_desc, LzDesc* d_desc, int maxit, double* d_out3,
+   double* h_out3, int* steps_done);
 
 } // namespace sdpk

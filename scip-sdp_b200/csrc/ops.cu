@@ -286,6 +286,42 @@ __global__ void symv_lower_kernel(int n, const double* __restrict__ M, int ldm, 
    if( lane == 0 ) y[i] = s;
 }
 
+// y_i = sum_{k <= i} T[i + k ld] x_k : one thread per row, coalesced across rows for every k
+__global__ void trmv_lower_n_kernel(int n, const double* __restrict__ T, int ldt, const double* __restrict__ x, double* __restrict__ y)
+{
+   __shared__ double xs[256];
+   const int i = blockIdx.x * blockDim.x + threadIdx.x;
+   const int imax = min(n, (blockIdx.x + 1) * (int)blockDim.x);        // largest row of this CTA + 1
+   double s0 = 0.0, s1 = 0.0;
+   for( int k0 = 0; k0 < imax; k0 += 256 )
+   {
+      __syncthreads();
+      if( k0 + threadIdx.x < n ) xs[threadIdx.x] = x[k0 + threadIdx.x];
+      __syncthreads();
+      if( i < n )
+      {
+         int kend = min(256, i + 1 - k0);
+         const double* p = T + (size_t)k0 * ldt + i;
+         int k = 0;
+         for( ; k + 2 <= kend; k += 2 ) { s0 += p[(size_t)k * ldt] * xs[k]; s1 += p[(size_t)(k + 1) * ldt] * xs[k + 1]; }
+         if( k < kend ) s0 += p[(size_t)k * ldt] * xs[k];
+      }
+   }
+   if( i < n ) y[i] = s0 + s1;
+}
+
+// y_k = sum_{i >= k} T[i + k ld] x_i : one warp per column (contiguous)
+__global__ void trmv_lower_t_kernel(int n, const double* __restrict__ T, int ldt, const double* __restrict__ x, double* __restrict__ y)
+{
+   int k = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+   if( k >= n ) return;
+   const double* col = T + (size_t)k * ldt;
+   double s = 0.0;
+   for( int i = k + lane; i < n; i += 32 ) s += col[i] * x[i];
+   s = warp_sum(s);
+   if( lane == 0 ) y[k] = s;
+}
+
 __global__ void sym_average_kernel(int n, double* __restrict__ A, int lda, const double* __restrict__ sub)
 {
    int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -464,6 +500,15 @@ cudaError_t symv_lower(cudaStream_t st, int n, const double* M, int ldm, const d
 {
    if( n <= 0 ) return cudaSuccess;
    symv_lower_kernel<<<ceil_div(n, 8), 256, 0, st>>>(n, M, ldm, x, y);
+   LAUNCH_END();
+}
+
+cudaError_t trmv_lower(cudaStream_t st, int n, const double* T, int ldt, int trans, const double* x, double* y)
+{
+   if( n <= 0 ) return cudaSuccess;
+   ProfScope prof(st, PROF_TRSV, 4.0 * n * (double)n);
+   if( trans ) trmv_lower_t_kernel<<<ceil_div(n, 8), 256, 0, st>>>(n, T, ldt, x, y);
+   else trmv_lower_n_kernel<<<ceil_div(n, 256), 256, 0, st>>>(n, T, ldt, x, y);
    LAUNCH_END();
 }
 

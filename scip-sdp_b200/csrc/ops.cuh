@@ -46,6 +46,8 @@ cudaError_t schur_lp(cudaStream_t st, int nlp, const int* lpbeg, const int* lpin
    const double* s, double* M, int ldm);
 cudaError_t add_diagonal(cudaStream_t st, int n, double* A, int lda, double v);
 cudaError_t symv_lower(cudaStream_t st, int n, const double* M, int ldm, const double* x, double* y);   // y = M x, M lower stored
+// y = T x (trans = 0) or y = T' x (trans = 1) for a lower-triangular T (upper part never read)
+cudaError_t trmv_lower(cudaStream_t st, int n, const double* T, int ldt, int trans, const double* x, double* y);
 
 // dense block helpers
 cudaError_t sym_average(cudaStream_t st, int n, double* A, int lda, const double* subtract /* or nullptr */);   // A = (A+A')/2 - subtract

@@ -12,6 +12,8 @@ S = abi.Solver(L, 0)
 out = {}
 ms, fl = S.time_kernel(4, 0, 5)
 out["dmma_peak_tflops"] = fl / ms / 1e9
+ms, w = S.time_kernel(2, 64, 20)
+print("diag64 potrf+inv (memset + one diag kernel) ms", ms, flush=True)
 for n in (512, 1024, 2000, 4096):
     for kind, name in ((0, "gemm_nn"), (1, "gemm_nt"), (5, "syrk_nt_lower"), (2, "potrf_inv"), (3, "potrf"), (6, "copy")):
         ms, w = S.time_kernel(kind, n, 5)
