@@ -25,7 +25,8 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-ORACLE_ITERS_FULL = 12     # iterations the CPU oracle needs on maxcut-2000 seed 4004 at gaptol = feastol = 1e-5 (measured)
+ORACLE_ITERS_FULL = 18     # iterations the CPU oracle needs on maxcut-2000 seed 4004 under the binding's acceptance rule (measured)
+TOL = dict(gaptol=1e-5, feastol=1e-5, absgaptol=5e-6)   # what sdpisolver_cuda.c hands to the solver for relaxing/SDP defaults
 
 
 def parse():
@@ -73,7 +74,7 @@ def cpu_sample(fp, threads_note):
     from scip_sdp_b200 import abi
     cpu = abi.Solver(abi.Lib(abi.ORACLE_LIB))
     t = time.perf_counter()
-    r = cpu.solve(fp, gaptol=1e-5, feastol=1e-5, maxiter=2, fetch=False)
+    r = cpu.solve(fp, maxiter=2, fetch=False, **TOL)
     dt = time.perf_counter() - t
     per_iter = dt / max(1, r["iterations"])
     return per_iter, dt, r["iterations"]
@@ -87,7 +88,7 @@ def main():
     from scip_sdp_b200 import generators
     cores = os.cpu_count() or 1
     workload = f"maxcut-{a.n} (G(n, {min(0.5, 20.0 / a.n):.4g}) unit weights, seed 4004+rank): one {a.n}x{a.n} block, m = {a.n}"
-    cfg = {"workload": workload, "tolerances": "gaptol = feastol = 1e-5 (relaxing/SDP defaults)",
+    cfg = {"workload": workload, "tolerances": "relaxing/SDP defaults gaptol = feastol = 1e-5 and the binding's absolute post-check |pobj-dobj| < gaptol (sdpisolver_sdpa.cpp:449-451), i.e. 3.5e-10 relative on this instance",
            "l2": "working set 16 arena matrices x 32 MB = 512 MB per solve, larger than the 126 MB L2 (no flush needed)",
            "partition": "independent relaxations, one per GPU (no collective)" if world > 1 else "single relaxation"}
 
@@ -136,7 +137,7 @@ def main():
     M = generators.maxcut(a.n, min(0.5, 20.0 / a.n), seed=4004 + rank)
     fp, _ = M.flatten()
     gpu = abi.Solver(abi.Lib(abi.PRODUCT_LIB), device=local)
-    kw = dict(gaptol=1e-5, feastol=1e-5)
+    kw = dict(TOL)
 
     first = gpu.solve(fp, fetch=False, **kw)          # uploads the problem; counts as the first warm-up step
     assert first["phase_name"] == "pdOPT", first
@@ -206,7 +207,7 @@ def main():
                 "e2e": {"value": world * a.steps / e2e_s, "unit": "relaxations/s", "h2d_bytes_per_step": int(first["h2d_bytes"]),
                         "d2h_bytes_per_step": int(first["d2h_bytes"] + 8 * fp.m + 8), "ms_per_step": 1e3 * e2e_s / a.steps,
                         "api": "SCIPsdpiSolverLoadAndSolve + SCIPsdpiSolverGetDualSol (libsdpisolver_cuda.so), host buffers",
-                        "objective": obj, "solver_calls_per_step": e2e_calls},
+                        "objective": obj, "solver_calls_per_step": e2e_calls, "iterations_per_step": e2e_iters},
                 "roofline": roof, "clocks": sampler.summary()}
         if world == 1 and not a.no_cpu_baseline:
             per_iter, dt, its = cpu_sample(fp, cores)

@@ -371,7 +371,7 @@ cudaError_t chol_rec(cudaStream_t st, int n, double* A, int lda, double* Linv, i
    }
    if( e != cudaSuccess ) return e;
    // L21 = A21 * Linv11'
-   SDPK_CUDA_CHECK( gemm(st, false, true, n2, n1, n1, 1.0, A21, lda, 0, Li11, ldi11, 0, 0.0, wrk, ldw, 0, 1, 0) );
+   SDPK_CUDA_CHECK( gemm(st, false, true, n2, n1, n1, 1.0, A21, lda, 0, Li11, ldi11, 0, 0.0, wrk, ldw, 0, 1, GEMM_KHI_N) );
    SDPK_CUDA_CHECK( copy2d(st, n2, n1, wrk, ldw, A21, lda) );
    // A22 -= L21 L21'
    SDPK_CUDA_CHECK( gemm(st, false, true, n2, n2, n1, -1.0, A21, lda, 0, A21, lda, 0, 1.0, A22, lda, 0, 1, GEMM_LOWER) );
@@ -381,8 +381,8 @@ cudaError_t chol_rec(cudaStream_t st, int n, double* A, int lda, double* Linv, i
       double* Li21 = Linv + n1;
       SDPK_CUDA_CHECK( chol_rec(st, n2, A22, lda, Li22, ldi, diaginv, work, ldw, d_info, off + n1) );
       // Linv21 = -Linv22 * (L21 * Linv11)
-      SDPK_CUDA_CHECK( gemm(st, false, false, n2, n1, n1, 1.0, A21, lda, 0, Linv, ldi, 0, 0.0, work, ldw, 0, 1, 0) );
-      SDPK_CUDA_CHECK( gemm(st, false, false, n2, n1, n2, -1.0, Li22, ldi, 0, work, ldw, 0, 0.0, Li21, ldi, 0, 1, 0) );
+      SDPK_CUDA_CHECK( gemm(st, false, false, n2, n1, n1, 1.0, A21, lda, 0, Linv, ldi, 0, 0.0, work, ldw, 0, 1, GEMM_KLO_N) );
+      SDPK_CUDA_CHECK( gemm(st, false, false, n2, n1, n2, -1.0, Li22, ldi, 0, work, ldw, 0, 0.0, Li21, ldi, 0, 1, GEMM_KHI_M) );
    }
    else
    {
@@ -402,8 +402,8 @@ cudaError_t trtri_rec(cudaStream_t st, int n, const double* L, int ldl, double* 
    double* Li22 = Linv + (size_t)n1 * ldi + n1;
    SDPK_CUDA_CHECK( trtri_rec(st, n1, L, ldl, Linv, ldi, work, ldw) );
    SDPK_CUDA_CHECK( trtri_rec(st, n2, L + (size_t)n1 * ldl + n1, ldl, Li22, ldi, work, ldw) );
-   SDPK_CUDA_CHECK( gemm(st, false, false, n2, n1, n1, 1.0, L21, ldl, 0, Linv, ldi, 0, 0.0, work, ldw, 0, 1, 0) );
-   SDPK_CUDA_CHECK( gemm(st, false, false, n2, n1, n2, -1.0, Li22, ldi, 0, work, ldw, 0, 0.0, Linv + n1, ldi, 0, 1, 0) );
+   SDPK_CUDA_CHECK( gemm(st, false, false, n2, n1, n1, 1.0, L21, ldl, 0, Linv, ldi, 0, 0.0, work, ldw, 0, 1, GEMM_KLO_N) );
+   SDPK_CUDA_CHECK( gemm(st, false, false, n2, n1, n2, -1.0, Li22, ldi, 0, work, ldw, 0, 0.0, Linv + n1, ldi, 0, 1, GEMM_KHI_M) );
    return cudaSuccess;
 }
 

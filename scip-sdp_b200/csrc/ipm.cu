@@ -84,6 +84,8 @@ struct sdpcuda_handle
    DBuf<double> y, dy, g, rp, AX, DTx, tm1, tm2;
    DBuf<double> x, s, dx, ds, dxa, dsa, klp, rdlp, Dy, Ddy;
    DBuf<double> M, Mfac, diaginv, Mwork, MLinv;
+   DBuf<int> patcol, patrow;          // column-wise pattern of sum_j y_j A_j - C (+ diagonal) per block, if sparse
+   std::vector<long long> patcoloff, patrowoff;   // per block offsets into patcol / patrow (-1: block is treated as dense)
    DBuf<LzDesc> lzdesc;
    std::vector<LzDesc> h_lzdesc;
    bool minv = false;                // explicit inverse factor of M (m <= 4096): solves become two triangular mat-vecs
@@ -101,6 +103,7 @@ struct sdpcuda_handle
    double normb = 0, normC = 0, normCsdp2 = 0, xil = 10, etal = 10;
    std::vector<double> xi, eta;
    Profiler prof;
+   cudaEvent_t phev[12] = {nullptr};   // phase boundaries of one iteration (verbose >= 2)
 
    ~sdpcuda_handle()
    {
@@ -208,6 +211,40 @@ int upload_problem(sdpcuda_handle* h, const sdpcuda_problem* P)
    h->npos = (int)pos.size();
    h->cnnz = P->cnnz;
 
+   // column-wise symmetric pattern per block for the sparse products X*dS, dXa*dSa, Linv*dS (only for sparse blocks)
+   {
+      std::vector<std::vector<std::pair<int, int>>> ent(h->nb);       // (col, row) incl. mirrored entries
+      std::vector<long long> cnt(h->nb, 0);
+      for( int e = 0; e < nnz; ++e ) cnt[P->entblk[e]] += 2;
+      for( int e = 0; e < P->cnnz; ++e ) cnt[P->cblk[e]] += 2;
+      std::vector<int> pc, pr;
+      h->patcoloff.assign(h->nb, -1); h->patrowoff.assign(h->nb, -1);
+      for( int k = 0; k < h->nb; ++k )
+      {
+         const int n = h->blk[k].n;
+         if( n < 256 || (double)cnt[k] + n > 0.125 * (double)n * n ) continue;      // small or dense block: GEMM path
+         std::vector<std::pair<int, int>>& v = ent[k];
+         v.reserve((size_t)cnt[k] + n);
+         for( int i = 0; i < n; ++i ) v.emplace_back(i, i);
+         for( int e = 0; e < nnz; ++e )
+            if( P->entblk[e] == k && P->entrow[e] != P->entcol[e] ) { v.emplace_back(P->entcol[e], P->entrow[e]); v.emplace_back(P->entrow[e], P->entcol[e]); }
+         for( int e = 0; e < P->cnnz; ++e )
+            if( P->cblk[e] == k && P->crow[e] != P->ccol[e] ) { v.emplace_back(P->ccol[e], P->crow[e]); v.emplace_back(P->crow[e], P->ccol[e]); }
+         std::sort(v.begin(), v.end());
+         v.erase(std::unique(v.begin(), v.end()), v.end());
+         h->patcoloff[k] = (long long)pc.size();
+         h->patrowoff[k] = (long long)pr.size();
+         std::vector<int> cp(n + 1, 0);
+         for( const auto& pr2 : v ) cp[pr2.first + 1]++;
+         for( int c = 0; c < n; ++c ) cp[c + 1] += cp[c];
+         pc.insert(pc.end(), cp.begin(), cp.end());
+         for( const auto& pr2 : v ) pr.push_back(pr2.second);
+      }
+      CK( h->patcol.upload(pc, st) );
+      CK( h->patrow.upload(pr, st) );
+      CK( cudaStreamSynchronize(st) );
+   }
+
    // LP block CSR + CSC
    const int nlp = h->nlp;
    std::vector<int> lpbeg(nlp + 1, 0);
@@ -310,12 +347,32 @@ int mult_blocks(sdpcuda_handle* h, const double* A, const double* B, double* Out
    return SDPCUDA_OK;
 }
 
+// Out_k = alpha * A_k * D_k where D lives on the aggregate sparsity pattern (dS, Rd, dSa): sparse gather for sparse blocks
+int mult_blocks_pattern(sdpcuda_handle* h, const double* A, const double* D, double* Out, double alpha)
+{
+   int k = 0;
+   for( const Block& bk : h->blk )
+   {
+      if( h->patcoloff[k] >= 0 )
+         CK( spmm_pattern(h->st, bk.n, A + bk.off, bk.ld, D + bk.off, bk.ld, h->patcol.p + h->patcoloff[k], h->patrow.p + h->patrowoff[k],
+               alpha, Out + bk.off, bk.ld) );
+      else
+         CK( gemm(h->st, false, false, bk.n, bk.n, bk.n, alpha, A + bk.off, bk.ld, 0, D + bk.off, bk.ld, 0, 0.0, Out + bk.off, bk.ld, 0, 1, 0) );
+      ++k;
+   }
+   return SDPCUDA_OK;
+}
+
 // B = Linv dA Linv' for one block into Bout (T1 is scratch): Linv lower triangular -> k < m0 + BM for the first product,
 // lower tiles and k < n0 + BN for the second, then mirrored to full storage
-int form_scaled(sdpcuda_handle* h, const Block& bk, const double* Linv, const double* dA, double* Bout)
+int form_scaled(sdpcuda_handle* h, const Block& bk, int k, bool sparse_dA, const double* Linv, const double* dA, double* Bout)
 {
    double* t1 = h->T1.p + bk.off;
-   CK( gemm(h->st, false, false, bk.n, bk.n, bk.n, 1.0, Linv + bk.off, bk.ld, 0, dA + bk.off, bk.ld, 0, 0.0, t1, bk.ld, 0, 1, GEMM_KHI_M) );
+   if( sparse_dA && h->patcoloff[k] >= 0 )
+      CK( spmm_pattern(h->st, bk.n, Linv + bk.off, bk.ld, dA + bk.off, bk.ld, h->patcol.p + h->patcoloff[k], h->patrow.p + h->patrowoff[k],
+            1.0, t1, bk.ld) );
+   else
+      CK( gemm(h->st, false, false, bk.n, bk.n, bk.n, 1.0, Linv + bk.off, bk.ld, 0, dA + bk.off, bk.ld, 0, 0.0, t1, bk.ld, 0, 1, GEMM_KHI_M) );
    CK( gemm(h->st, false, true, bk.n, bk.n, bk.n, 1.0, t1, bk.ld, 0, Linv + bk.off, bk.ld, 0, 0.0, Bout + bk.off, bk.ld, 0, 1, GEMM_LOWER | GEMM_KHI_N) );
    CK( mirror_lower(h->st, bk.n, Bout + bk.off, bk.ld) );
    return SDPCUDA_OK;
@@ -324,7 +381,7 @@ int form_scaled(sdpcuda_handle* h, const Block& bk, const double* Linv, const do
 // lambda_min(LXinv dX LXinv') -> scal[8 + k], lambda_min(Linv dS Linv') -> scal[8 + nb + k] for every block k.
 // Small blocks: Jacobi kernel (values only); large blocks: all Lanczos runs of the pass advance together.
 // Scratch: T1 (intermediate), T2 (X-side matrices), K (S-side matrices; K is free once dX has been formed).
-int step_eigs(sdpcuda_handle* h)
+int step_eigs(sdpcuda_handle* h, const double* dXdir, const double* dSdir, int maxsteps)
 {
    const int nb = h->nb;
    h->h_lzdesc.clear();
@@ -333,8 +390,8 @@ int step_eigs(sdpcuda_handle* h)
    for( const Block& bk : h->blk )
    {
       int rc;
-      if( (rc = form_scaled(h, bk, h->LXinv.p, h->dX.p, h->T2.p)) ) return rc;
-      if( (rc = form_scaled(h, bk, h->Linv.p, h->dS.p, h->K.p)) ) return rc;
+      if( (rc = form_scaled(h, bk, k, false, h->LXinv.p, dXdir, h->T2.p)) ) return rc;
+      if( (rc = form_scaled(h, bk, k, true, h->Linv.p, dSdir, h->K.p)) ) return rc;
       if( bk.n <= JACOBI_MAX_N )
       {
          CK( jacobi_eig_batched(h->st, bk.n, 1, h->T2.p + bk.off, bk.ld, 0, h->eigw.p, nullptr, nullptr) );
@@ -365,7 +422,7 @@ int step_eigs(sdpcuda_handle* h)
       CK( h->scal.ensure(64 + 2 * (size_t)nb + 3 * (size_t)nmat) );
       double* out3 = h->scal.p + 64 + 2 * nb;
       for( int i = 0; i < nmat; ++i ) h->h_lzdesc[i].out = out3 + 3 * i;
-      CK( lanczos_batched(h->st, nmat, h->h_lzdesc.data(), h->lzdesc.p, LZB_MAXIT, out3, h->h_stats + 2048, nullptr) );
+      CK( lanczos_batched(h->st, nmat, h->h_lzdesc.data(), h->lzdesc.p, maxsteps, out3, h->h_stats + 2048, nullptr) );
       int i = 0; k = 0;
       for( const Block& bk : h->blk )
       {
@@ -441,7 +498,7 @@ int sdpcuda_destroy(sdpcuda_handle* h)
                             &h->eigw, &h->lzwork, &h->kA, &h->kB, &h->kC, &h->kW} )
       bf->release();
    for( DBuf<int>* bf : {&h->varbeg, &h->erow, &h->ecol, &h->eld, &h->posbeg, &h->posvar, &h->lpbeg, &h->lpind, &h->colbeg, &h->colrow,
-                         &h->heavy, &h->heavylist, &h->info} )
+                         &h->heavy, &h->heavylist, &h->info, &h->patcol, &h->patrow} )
       bf->release();
    for( DBuf<long long>* bf : {&h->eoff, &h->pos, &h->mirror, &h->cpos, &h->cmirror} )
       bf->release();
@@ -598,9 +655,13 @@ static int run_ipm(sdpcuda_handle* h, const sdpcuda_params* par, const double* s
    int backtracks = 0;
    CK( cudaEventRecord(h->ev0, st) );
 
+   const bool phases = par->verbose >= 2;
+   if( phases ) for( int e = 0; e < 12; ++e ) if( h->phev[e] == nullptr ) CK( cudaEventCreate(&h->phev[e]) );
+#define PHASE(k) do { if( phases ) CK( cudaEventRecord(h->phev[k], st) ); } while( 0 )
    int iter = 0;
    for( ; ; ++iter )
    {
+      PHASE(0);
       // ---- residuals and statistics (one device->host copy) ----
       CK( cudaMemsetAsync(h->partials.p, 0, sizeof(double) * RED_BLOCKS * NSTAT, st) );
       CK( cudaMemsetAsync(h->info.p, 0, 8 * sizeof(int), st) );
@@ -612,6 +673,7 @@ static int run_ipm(sdpcuda_handle* h, const sdpcuda_params* par, const double* s
       CK( lp_rows(st, nlp, h->lpbeg.p, h->lpind.p, h->lpval.p, h->lprhs.p, h->y.p, h->x.p, h->s.p, h->Dy.p, h->rdlp.p, h->partials.p) );
       CK( finalize_partials(st, h->partials.p, NSTAT, h->stats.p) );
       CK( const_dots(st, h->cnnz, h->cpos.p, h->cmirror.p, h->cval.p, h->X.p, h->Rd.p, h->stats.p + NSTAT) );
+      PHASE(1);
       // factorisations of S and X are issued before the sync so that their pivots are known at the same time
       // the two factorisations are latency bound (chains of small kernels) and independent: run them side by side
       CK( cudaEventRecord(h->evFork, st) );
@@ -619,18 +681,22 @@ static int run_ipm(sdpcuda_handle* h, const sdpcuda_params* par, const double* s
       rc = factor_blocks(h, h->st2, h->work2.p, h->X.p, h->LX.p, h->LXinv.p, 1); if( rc ) return rc;
       CK( cudaEventRecord(h->evJoin, h->st2) );
       rc = factor_blocks(h, st, h->work.p, h->S.p, h->L.p, h->Linv.p, 0); if( rc ) return rc;
-      CK( cudaStreamWaitEvent(st, h->evJoin, 0) );
+      // the factor of X is first needed for the primal step length: the main stream joins the side stream only there,
+      // so that the X factorisation hides behind S^-1, the Schur complement, its factorisation and the predictor solve
+      PHASE(2);
       CK( cudaMemcpyAsync(h->h_stats, h->stats.p, (NSTAT + 2) * sizeof(double), cudaMemcpyDeviceToHost, st) );
       CK( cudaMemcpyAsync(h->h_info, h->info.p, 8 * sizeof(int), cudaMemcpyDeviceToHost, st) );
       CK( cudaStreamSynchronize(st) );
       d2h += (NSTAT + 2) * sizeof(double) + 8 * sizeof(int);
 
-      if( h->h_info[0] != 0 || h->h_info[1] != 0 )
+      bool xfail = false;
+   BACKTRACK:
+      if( h->h_info[0] != 0 || xfail )
       {
          // the last step left the cone (the step-length estimate was too optimistic): halve it and try again
          if( iter == 0 || backtracks >= 8 ) { R.stop = SDPCUDA_STOP_NUMERICS; break; }
          ++backtracks;
-         if( h->h_info[1] != 0 )
+         if( xfail )
          {
             CK( axpy(st, ar, -0.5 * lastap, h->dX.p, h->X.p) );
             CK( axpy(st, (size_t)nlp, -0.5 * lastap, h->dx.p, h->x.p) );
@@ -695,10 +761,12 @@ static int run_ipm(sdpcuda_handle* h, const sdpcuda_params* par, const double* s
          CK( mirror_lower(st, bk.n, h->Sinv.p + bk.off, bk.ld) );
       }
 
+      PHASE(3);
       // ---- Schur complement and its factorisation ----
       CK( cudaMemsetAsync(h->M.p, 0, sizeof(double) * (size_t)h->ldm * m, st) );
       CK( schur_entries(st, m, E, h->heavy.p, h->heavylist.p, h->nheavy, h->X.p, h->Sinv.p, h->M.p, h->ldm) );
       CK( schur_lp(st, nlp, h->lpbeg.p, h->lpind.p, h->lpval.p, h->x.p, h->s.p, h->M.p, h->ldm) );
+      PHASE(4);
       double reg = 0.0;
       bool mok = false;
       for( int tries = 0; tries < 8 && !mok; ++tries )
@@ -727,18 +795,34 @@ static int run_ipm(sdpcuda_handle* h, const sdpcuda_params* par, const double* s
          }
       }
       if( !mok ) { R.stop = SDPCUDA_STOP_NUMERICS; break; }
+      if( h->minv ) CK( transpose(st, m, h->MLinv.p, h->ldm, h->Mfac.p, h->ldm) );   // L itself is not needed any more
 
+      PHASE(5);
       // ---- predictor (sigma = 0) and corrector ----
       double sigma = 0.0, ap = 0.0, ad = 0.0;
       bool failed = false;
       for( int pass = 0; pass < 2; ++pass )
       {
+         // the predictor writes into the dXa/dSa/dxa/dsa buffers, the corrector into dX/dS/dx/ds: the previous
+         // iteration's step stays intact until the factor of X has been checked (backtracking needs it)
+         double* oX = pass == 0 ? h->dXa.p : h->dX.p;
+         double* oS = pass == 0 ? h->dSa.p : h->dS.p;
+         double* ox = pass == 0 ? h->dxa.p : h->dx.p;
+         double* os = pass == 0 ? h->dsa.p : h->ds.p;
          // K = sym((sigma mu I - dXa dSa - X Rd) S^-1) - X
          bool haveT = false;
-         if( !rdzero ) { rc = mult_blocks(h, h->X.p, h->Rd.p, h->T1.p, -1.0, 0.0); if( rc ) return rc; haveT = true; }
+         if( !rdzero ) { rc = mult_blocks_pattern(h, h->X.p, h->Rd.p, h->T1.p, -1.0); if( rc ) return rc; haveT = true; }
          if( pass == 1 )
          {
-            rc = mult_blocks(h, h->dXa.p, h->dSa.p, h->T1.p, -1.0, haveT ? 1.0 : 0.0); if( rc ) return rc;
+            if( haveT )
+            {
+               rc = mult_blocks_pattern(h, h->dXa.p, h->dSa.p, h->T2.p, -1.0); if( rc ) return rc;
+               CK( axpy(st, ar, 1.0, h->T2.p, h->T1.p) );
+            }
+            else
+            {
+               rc = mult_blocks_pattern(h, h->dXa.p, h->dSa.p, h->T1.p, -1.0); if( rc ) return rc;
+            }
             for( const Block& bk : h->blk ) CK( add_diagonal(st, bk.n, h->T1.p + bk.off, bk.ld, sigma * mu) );
             haveT = true;
          }
@@ -757,8 +841,8 @@ static int run_ipm(sdpcuda_handle* h, const sdpcuda_params* par, const double* s
          auto msolve = [&](double* v) -> int {        // v <- M^-1 v
             if( h->minv )
             {
-               CK( trmv_lower(st, m, h->MLinv.p, h->ldm, 0, v, h->tm2.p) );
-               CK( trmv_lower(st, m, h->MLinv.p, h->ldm, 1, h->tm2.p, v) );
+               CK( trmv_upper_t(st, m, h->Mfac.p, h->ldm, v, h->tm2.p) );          // Linv v, via the transposed copy (coalesced)
+               CK( trmv_lower(st, m, h->MLinv.p, h->ldm, 1, h->tm2.p, v) );       // Linv' (Linv v)
             }
             else
                CK( potrs_vec(st, m, h->Mfac.p, h->ldm, h->diaginv.p, v, h->tm2.p) );
@@ -771,23 +855,29 @@ static int run_ipm(sdpcuda_handle* h, const sdpcuda_params* par, const double* s
          rc = msolve(h->tm1.p); if( rc ) return rc;
          CK( axpy(st, (size_t)m, 1.0, h->tm1.p, h->dy.p) );
          // dS = A'dy (+ Rd afterwards) ; dX = K - sym(X (A'dy) S^-1)
-         rc = assemble(h, h->dy.p, 0.0, h->dS.p); if( rc ) return rc;
-         rc = mult_blocks(h, h->X.p, h->dS.p, h->T1.p, 1.0, 0.0); if( rc ) return rc;
+         rc = assemble(h, h->dy.p, 0.0, oS); if( rc ) return rc;
+         rc = mult_blocks_pattern(h, h->X.p, oS, h->T1.p, 1.0); if( rc ) return rc;
          rc = mult_blocks(h, h->T1.p, h->Sinv.p, h->T2.p, 1.0, 0.0); if( rc ) return rc;
          for( const Block& bk : h->blk ) CK( sym_average(st, bk.n, h->T2.p + bk.off, bk.ld, nullptr) );
-         CK( axpby_out(st, ar, 1.0, h->K.p, -1.0, h->T2.p, h->dX.p) );
-         if( !rdzero ) CK( axpy(st, ar, 1.0, h->Rd.p, h->dS.p) );
+         CK( axpby_out(st, ar, 1.0, h->K.p, -1.0, h->T2.p, oX) );
+         if( !rdzero ) CK( axpy(st, ar, 1.0, h->Rd.p, oS) );
          // LP part: Ddy = D dy, then dx, ds and the LP step lengths
          CK( cudaMemsetAsync(h->partials.p, 0, sizeof(double) * RED_BLOCKS * NSTAT, st) );
          {
             // Ddy via the row kernel (its other outputs go to scratch)
             CK( lp_rows(st, nlp, h->lpbeg.p, h->lpind.p, h->lpval.p, h->lprhs.p, h->dy.p, h->x.p, h->s.p, h->Ddy.p, h->Dy.p, h->partials.p) );
          }
-         CK( lp_direction(st, nlp, h->x.p, h->s.p, h->rdlp.p, h->klp.p, h->Ddy.p, h->dx.p, h->ds.p, h->scal.p + 0) );
+         CK( lp_direction(st, nlp, h->x.p, h->s.p, h->rdlp.p, h->klp.p, h->Ddy.p, ox, os, h->scal.p + 0) );
          // SDP step lengths: lambda_min(LXinv dX LXinv') -> scal[8+k], lambda_min(Linv dS Linv') -> scal[8+nb+k]
-         rc = step_eigs(h); if( rc ) return rc;
+         PHASE(6 + 2 * pass);
+         if( pass == 0 ) CK( cudaStreamWaitEvent(st, h->evJoin, 0) );          // join: the factor of X is needed from here on
+         // the predictor step lengths only steer the centring parameter: a short Lanczos run (safe, slightly pessimistic) suffices
+         rc = step_eigs(h, oX, oS, pass == 0 ? 8 : LZB_MAXIT); if( rc ) return rc;
          CK( cudaMemcpyAsync(h->h_stats + 32, h->scal.p, sizeof(double) * (8 + 2 * (size_t)nb), cudaMemcpyDeviceToHost, st) );
+         PHASE(7 + 2 * pass);
+         if( pass == 0 ) CK( cudaMemcpyAsync(h->h_info, h->info.p, 8 * sizeof(int), cudaMemcpyDeviceToHost, st) );
          CK( cudaStreamSynchronize(st) );
+         if( pass == 0 && h->h_info[1] != 0 ) { xfail = true; break; }
          d2h += sizeof(double) * (8 + 2 * (size_t)nb) + (pass == 0 ? NSTAT * sizeof(double) : 0);
          double apmax = h->h_stats[32 + 0], admax = h->h_stats[32 + 1];
          for( int k = 0; k < nb; ++k )
@@ -801,13 +891,9 @@ static int run_ipm(sdpcuda_handle* h, const sdpcuda_params* par, const double* s
          if( pass == 0 )
          {
             ap = std::min(1.0, 0.98 * apmax); ad = std::min(1.0, 0.98 * admax);
-            CK( affine_mu(st, ar, h->X.p, h->dX.p, h->S.p, h->dS.p, nlp, h->x.p, h->dx.p, h->s.p, h->ds.p, ap, ad, h->partials.p) );
+            CK( affine_mu(st, ar, h->X.p, oX, h->S.p, oS, nlp, h->x.p, ox, h->s.p, os, ap, ad, h->partials.p) );
             CK( finalize_partials(st, h->partials.p, NSTAT, h->stats.p) );
             CK( cudaMemcpyAsync(h->h_stats + 64, h->stats.p, NSTAT * sizeof(double), cudaMemcpyDeviceToHost, st) );
-            CK( cudaMemcpyAsync(h->dXa.p, h->dX.p, ar * sizeof(double), cudaMemcpyDeviceToDevice, st) );
-            CK( cudaMemcpyAsync(h->dSa.p, h->dS.p, ar * sizeof(double), cudaMemcpyDeviceToDevice, st) );
-            CK( cudaMemcpyAsync(h->dxa.p, h->dx.p, (size_t)nlp * sizeof(double), cudaMemcpyDeviceToDevice, st) );
-            CK( cudaMemcpyAsync(h->dsa.p, h->ds.p, (size_t)nlp * sizeof(double), cudaMemcpyDeviceToDevice, st) );
             CK( cudaStreamSynchronize(st) );
             double mua = h->N > 0 ? (h->h_stats[64 + 9] + h->h_stats[64 + 10]) / h->N : 0.0;
             double ratio = mu > 0 ? std::max(0.0, mua / mu) : 0.0;
@@ -821,6 +907,7 @@ static int run_ipm(sdpcuda_handle* h, const sdpcuda_params* par, const double* s
             ap = std::min(1.0, gamma * apmax); ad = std::min(1.0, gamma * admax);
          }
       }
+      if( xfail ) goto BACKTRACK;
       if( failed || (ap < 1e-8 && ad < 1e-8) ) { R.stop = SDPCUDA_STOP_NUMERICS; break; }
       CK( axpy(st, ar, ap, h->dX.p, h->X.p) );
       CK( axpy(st, ar, ad, h->dS.p, h->S.p) );
@@ -828,10 +915,20 @@ static int run_ipm(sdpcuda_handle* h, const sdpcuda_params* par, const double* s
       CK( axpy(st, (size_t)nlp, ad, h->ds.p, h->s.p) );
       CK( axpy(st, (size_t)m, ad, h->dy.p, h->y.p) );
       lastap = ap; lastad = ad;
+      if( phases )
+      {
+         PHASE(10);
+         CK( cudaStreamSynchronize(st) );
+         float t[10];
+         for( int e = 0; e < 10; ++e ) cudaEventElapsedTime(&t[e], h->phev[e], h->phev[e + 1]);
+         printf("  [phases ms] resid %.3f | factS %.3f | sync+Sinv %.3f | schur %.3f | factM %.3f | pred dir %.3f | pred eig %.3f | corr dir %.3f | corr eig %.3f | upd %.3f\n",
+            t[0], t[1], t[2], t[3], t[4], t[5], t[6], t[7], t[8], t[9]);
+      }
    }
 
    CK( cudaEventRecord(h->ev1, st) );
    CK( cudaStreamSynchronize(st) );
+   CK( cudaStreamSynchronize(h->st2) );
    if( h->prof.on ) h->prof.collect();
    float ms = 0.f;
    cudaEventElapsedTime(&ms, h->ev0, h->ev1);

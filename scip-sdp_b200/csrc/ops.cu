@@ -322,6 +322,58 @@ __global__ void trmv_lower_t_kernel(int n, const double* __restrict__ T, int ldt
    if( lane == 0 ) y[k] = s;
 }
 
+__global__ void __launch_bounds__(256)
+spmm_pattern_kernel(int n, const double* __restrict__ A, int lda, const double* __restrict__ D, int ldd,
+   const int* __restrict__ colptr, const int* __restrict__ rowidx, double alpha, double* __restrict__ Out, int ldo)
+{
+   const int c = blockIdx.y;
+   const int i = blockIdx.x * blockDim.x + threadIdx.x;
+   const int b = colptr[c], e = colptr[c + 1];
+   double s0 = 0.0, s1 = 0.0;
+   if( i < n )
+   {
+      int p = b;
+      for( ; p + 2 <= e; p += 2 )
+      {
+         int r0 = rowidx[p], r1 = rowidx[p + 1];
+         s0 += A[(size_t)r0 * lda + i] * D[(size_t)c * ldd + r0];
+         s1 += A[(size_t)r1 * lda + i] * D[(size_t)c * ldd + r1];
+      }
+      if( p < e ) { int r0 = rowidx[p]; s0 += A[(size_t)r0 * lda + i] * D[(size_t)c * ldd + r0]; }
+      Out[(size_t)c * ldo + i] = alpha * (s0 + s1);
+   }
+}
+
+__global__ void trmv_upper_t_kernel(int n, const double* __restrict__ U, int ldu, const double* __restrict__ x, double* __restrict__ y)
+{
+   int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+   if( i >= n ) return;
+   const double* col = U + (size_t)i * ldu;
+   double s0 = 0.0, s1 = 0.0;
+   int k = lane;
+   for( ; k + 32 <= i; k += 64 ) { s0 += col[k] * x[k]; s1 += col[k + 32] * x[k + 32]; }
+   for( ; k <= i; k += 32 ) s0 += col[k] * x[k];
+   double s = warp_sum(s0 + s1);
+   if( lane == 0 ) y[i] = s;
+}
+
+__global__ void transpose_kernel(int n, const double* __restrict__ A, int lda, double* __restrict__ B, int ldb)
+{
+   __shared__ double tile[32][33];
+   int bx = blockIdx.x * 32, by = blockIdx.y * 32;
+   for( int r = threadIdx.y; r < 32; r += 8 )
+   {
+      int i = bx + threadIdx.x, j = by + r;
+      tile[r][threadIdx.x] = (i < n && j < n) ? A[(size_t)j * lda + i] : 0.0;
+   }
+   __syncthreads();
+   for( int r = threadIdx.y; r < 32; r += 8 )
+   {
+      int i = by + threadIdx.x, j = bx + r;      // B(i, j) = A(j, i)
+      if( i < n && j < n ) B[(size_t)j * ldb + i] = tile[threadIdx.x][r];
+   }
+}
+
 __global__ void sym_average_kernel(int n, double* __restrict__ A, int lda, const double* __restrict__ sub)
 {
    int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -509,6 +561,33 @@ cudaError_t trmv_lower(cudaStream_t st, int n, const double* T, int ldt, int tra
    ProfScope prof(st, PROF_TRSV, 4.0 * n * (double)n);
    if( trans ) trmv_lower_t_kernel<<<ceil_div(n, 8), 256, 0, st>>>(n, T, ldt, x, y);
    else trmv_lower_n_kernel<<<ceil_div(n, 256), 256, 0, st>>>(n, T, ldt, x, y);
+   LAUNCH_END();
+}
+
+cudaError_t spmm_pattern(cudaStream_t st, int n, const double* A, int lda, const double* D, int ldd, const int* colptr,
+   const int* rowidx, double alpha, double* Out, int ldo)
+{
+   if( n <= 0 ) return cudaSuccess;
+   ProfScope prof(st, PROF_ELEM, 16.0 * n * (double)n);
+   dim3 grid(ceil_div(n, 256), n);
+   spmm_pattern_kernel<<<grid, 256, 0, st>>>(n, A, lda, D, ldd, colptr, rowidx, alpha, Out, ldo);
+   LAUNCH_END();
+}
+
+cudaError_t trmv_upper_t(cudaStream_t st, int n, const double* U, int ldu, const double* x, double* y)
+{
+   if( n <= 0 ) return cudaSuccess;
+   ProfScope prof(st, PROF_TRSV, 4.0 * n * (double)n);
+   trmv_upper_t_kernel<<<ceil_div(n, 8), 256, 0, st>>>(n, U, ldu, x, y);
+   LAUNCH_END();
+}
+
+cudaError_t transpose(cudaStream_t st, int n, const double* A, int lda, double* B, int ldb)
+{
+   if( n <= 0 ) return cudaSuccess;
+   ProfScope prof(st, PROF_ELEM, 16.0 * n * (double)n);
+   dim3 grid(ceil_div(n, 32), ceil_div(n, 32)), block(32, 8);
+   transpose_kernel<<<grid, block, 0, st>>>(n, A, lda, B, ldb);
    LAUNCH_END();
 }
 

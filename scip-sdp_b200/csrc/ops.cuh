@@ -48,6 +48,15 @@ cudaError_t add_diagonal(cudaStream_t st, int n, double* A, int lda, double v);
 cudaError_t symv_lower(cudaStream_t st, int n, const double* M, int ldm, const double* x, double* y);   // y = M x, M lower stored
 // y = T x (trans = 0) or y = T' x (trans = 1) for a lower-triangular T (upper part never read)
 cudaError_t trmv_lower(cudaStream_t st, int n, const double* T, int ldt, int trans, const double* x, double* y);
+// y = U' x for an upper-triangular U (lower part never read): one warp per (contiguous) column
+cudaError_t trmv_upper_t(cudaStream_t st, int n, const double* U, int ldu, const double* x, double* y);
+// B = A' (n x n, out of place)
+cudaError_t transpose(cudaStream_t st, int n, const double* A, int lda, double* B, int ldb);
+
+// Out = A * D for one block, D symmetric and sparse: its pattern is given column-wise (colptr[n+1], rowidx), its values
+// are read from the dense array D itself.  One CTA per (256-row slab, column): gathers columns of A (coalesced).
+cudaError_t spmm_pattern(cudaStream_t st, int n, const double* A, int lda, const double* D, int ldd, const int* colptr,
+   const int* rowidx, double alpha, double* Out, int ldo);
 
 // dense block helpers
 cudaError_t sym_average(cudaStream_t st, int n, double* A, int lda, const double* subtract /* or nullptr */);   // A = (A+A')/2 - subtract
