@@ -144,8 +144,9 @@ int  sdpcuda_solve_resident(sdpcuda_handle* h, const sdpcuda_params* par, sdpcud
 /* Per-kernel-class device timing of the NEXT solve (CUDA events around every launch of the class on the handle's
  * stream; adds a little overhead, so it is off by default).  After the solve sdpcuda_get_profile fills, for each class
  * c < SDPCUDA_NPROF, out[3*c+0] = launches, out[3*c+1] = device milliseconds, out[3*c+2] = algorithmic flops or bytes. */
-#define SDPCUDA_NPROF 6
-#define SDPCUDA_PROF_GEMM   0   /* FP64 DMMA GEMM (flops) */
+#define SDPCUDA_NPROF 7
+#define SDPCUDA_PROF_GEMM   0   /* FP64 DMMA GEMM, 64 x 64 CTA tiles (flops) */
+#define SDPCUDA_PROF_GEMM_SMALL 6 /* the 32 x 32-tile instantiation used for the small products of the blocked factorisations (flops) */
 #define SDPCUDA_PROF_DIAG   1   /* 64 x 64 diagonal-block Cholesky + inverse (flops) */
 #define SDPCUDA_PROF_SCHUR  2   /* Schur complement assembly, entry/gather path + LP block (bytes) */
 #define SDPCUDA_PROF_EIG    3   /* Jacobi / Lanczos step-length kernels (bytes) */

@@ -180,7 +180,7 @@ class Solver:
         out["phase_name"], out["stop_name"] = PHASES[res.phase], STOPS[res.stop]
         return out
 
-    PROF_CLASSES = ["gemm_dmma", "diag_block", "schur", "eig", "trsv", "elementwise"]
+    PROF_CLASSES = ["gemm_dmma", "diag_block", "schur", "eig", "trsv", "elementwise", "gemm_dmma_small"]
 
     def set_profiling(self, on):
         self.L.lib.sdpcuda_set_profiling(self.h, int(on))

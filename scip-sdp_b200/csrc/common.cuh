@@ -14,8 +14,8 @@ extern thread_local LaunchCounter* g_counter;
 inline void count_launch(int k = 1) { if( g_counter ) g_counter->n += k; }
 
 // optional per-class device timing (CUDA events on the launching stream around each launch / launch group)
-constexpr int NPROF = 6;
-enum { PROF_GEMM = 0, PROF_DIAG = 1, PROF_SCHUR = 2, PROF_EIG = 3, PROF_TRSV = 4, PROF_ELEM = 5 };
+constexpr int NPROF = 7;
+enum { PROF_GEMM = 0, PROF_DIAG = 1, PROF_SCHUR = 2, PROF_EIG = 3, PROF_TRSV = 4, PROF_ELEM = 5, PROF_GEMM_SMALL = 6 };
 struct Profiler
 {
    bool on = false;

@@ -478,25 +478,31 @@ cudaError_t jacobi_eig_batched(cudaStream_t st, int n, int nbatch, const double*
    const int np = (n + 1) / 2, lds = n | 1;
    size_t aux = (32 + 2 * np) * sizeof(double) + 2 * np * sizeof(int) + 32;
    size_t mat = 2 * (size_t)n * lds * sizeof(double);
-   static double* gscratch = nullptr;
-   static size_t gscratch_bytes = 0;
+   static thread_local double* gscratch = nullptr;      // large-matrix fallback scratch (one per host thread / device use)
+   static thread_local size_t gscratch_bytes = 0;
+   static thread_local int gscratch_dev = -1;
    int use_smem = (n <= JACOBI_MAX_N) ? 1 : 0;
    size_t smem = aux + (use_smem ? mat : 0);
    if( !use_smem )
    {
       size_t need = mat * nbatch;
-      if( need > gscratch_bytes )
+      int curdev = 0;
+      SDPK_CUDA_CHECK( cudaGetDevice(&curdev) );
+      if( need > gscratch_bytes || curdev != gscratch_dev )
       {
+         gscratch_dev = curdev;
          if( gscratch ) cudaFree(gscratch);
          SDPK_CUDA_CHECK( cudaMalloc(&gscratch, need) );
          gscratch_bytes = need;
       }
    }
-   static size_t configured = 0;
-   if( smem > configured )
+   static bool configured[64] = {false};        // per-device function attribute
+   int dev = 0;
+   SDPK_CUDA_CHECK( cudaGetDevice(&dev) );
+   if( !configured[dev & 63] )
    {
-      SDPK_CUDA_CHECK( cudaFuncSetAttribute(jacobi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max(smem, (size_t)200 * 1024)) );
-      configured = std::max(smem, (size_t)200 * 1024);
+      SDPK_CUDA_CHECK( cudaFuncSetAttribute(jacobi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) );
+      configured[dev & 63] = true;
    }
    ProfScope prof(st, PROF_EIG, (double)nbatch * (16.0 * n * n + 8.0 * n));
    jacobi_kernel<<<nbatch, 256, smem, st>>>(n, A, lda, strideA, w, V, gscratch, use_smem, d_sweeps);

@@ -193,11 +193,14 @@ cudaError_t launch(cudaStream_t st, int m, int n, int k, double alpha, const dou
    constexpr int B_ELEMS = TB ? BK * (BN + 4) : BN * (BK + 4);
    constexpr size_t SMEM = (size_t)STAGES * (A_ELEMS + B_ELEMS) * sizeof(double);
    auto kern = gemm_dmma_kernel<BM, BN, TA, TB, STAGES>;
-   static bool configured = false;
-   if( !configured )
+   // the opt-in shared-memory size is a per-device function attribute
+   static bool configured[64] = {false};
+   int dev = 0;
+   SDPK_CUDA_CHECK( cudaGetDevice(&dev) );
+   if( !configured[dev & 63] )
    {
       SDPK_CUDA_CHECK( cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM) );
-      configured = true;
+      configured[dev & 63] = true;
    }
    dim3 grid(ceil_div(m, BM), ceil_div(n, BN), batch);
    kern<<<grid, 128, SMEM, st>>>(m, n, k, alpha, A, lda, sA, B, ldb, sB, beta, C, ldc, sC, flags);
@@ -236,9 +239,9 @@ cudaError_t gemm(cudaStream_t st, bool ta, bool tb, int m, int n, int k, double 
    const bool kflag = (flags & (GEMM_KHI_M | GEMM_KHI_N | GEMM_KLO_M | GEMM_KLO_N)) != 0;
    if( (flags & GEMM_LOWER) && kflag ) frac = 1.0 / 6.0;
    else if( (flags & GEMM_LOWER) || kflag ) frac = 0.5;
-   ProfScope prof(st, PROF_GEMM, 2.0 * m * (double)n * k * batch * frac);
    // small problems use 32 x 32 tiles to fill more SMs
-   bool small = ((long long)ceil_div(m, 64) * ceil_div(n, 64) * batch) < 148;
+   const bool small = ((long long)ceil_div(m, 64) * ceil_div(n, 64) * batch) < 148;
+   ProfScope prof(st, small ? PROF_GEMM_SMALL : PROF_GEMM, 2.0 * m * (double)n * k * batch * frac);
 #define SDPK_GEMM_DISPATCH(BM, BN) \
    do { \
       if( !ta && !tb ) return launch<BM, BN, false, false>(st, m, n, k, alpha, A, lda, sA, B, ldb, sB, beta, C, ldc, sC, batch, flags); \

@@ -469,6 +469,13 @@ int sdpcuda_create(sdpcuda_handle** out, int device)
    sdpcuda_handle* h = new (std::nothrow) sdpcuda_handle();
    if( h == nullptr ) return SDPCUDA_ERR_NOMEM;
    // one handle per SCIP solver thread: devices round-robin (concurrent node relaxations), a private stream each
+   // device choice: explicit argument, else SDPCUDA_DEVICE, else LOCAL_RANK (one process per GPU under torchrun), else round-robin
+   if( device < 0 )
+   {
+      const char* e = getenv("SDPCUDA_DEVICE");
+      if( e == nullptr || e[0] == 0 ) e = getenv("LOCAL_RANK");
+      if( e != nullptr && e[0] >= '0' && e[0] <= '9' ) device = atoi(e);
+   }
    h->device = (device >= 0) ? device % ndev : (g_next_device.fetch_add(1) % ndev);
    if( cudaSetDevice(h->device) != cudaSuccess || cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking) != cudaSuccess
       || cudaStreamCreateWithFlags(&h->st2, cudaStreamNonBlocking) != cudaSuccess
