@@ -74,6 +74,10 @@ struct sdpcuda_handle
    std::vector<Block> blk;
    int maxn = 0;
    int npos = 0, cnnz = 0, nheavy = 0;
+   // dense Schur path: per block the list of dense variables (device list index range) and the expanded matrices
+   struct DenseGroup { int blk; int first; int count; };
+   std::vector<DenseGroup> dgroups;
+   int ndense = 0; int dchunk = 0;
 
    // device problem data
    DBuf<int> varbeg, erow, ecol, eld, posbeg, posvar, lpbeg, lpind, colbeg, colrow, heavy, heavylist;
@@ -83,7 +87,8 @@ struct sdpcuda_handle
    DBuf<double> X, S, Sinv, L, Linv, LX, LXinv, dX, dS, dXa, dSa, K, T1, T2, Rd, work, work2;
    DBuf<double> y, dy, g, rp, AX, DTx, tm1, tm2;
    DBuf<double> x, s, dx, ds, dxa, dsa, klp, rdlp, Dy, Ddy;
-   DBuf<double> M, Mfac, diaginv, Mwork, MLinv;
+   DBuf<double> M, Mfac, diaginv, Mwork, MLinv, Adense, Hd, Ud;
+   DBuf<int> denselist;
    DBuf<int> patcol, patrow;          // column-wise pattern of sum_j y_j A_j - C (+ diagonal) per block, if sparse
    std::vector<long long> patcoloff, patrowoff;   // per block offsets into patcol / patrow (-1: block is treated as dense)
    DBuf<LzDesc> lzdesc;
@@ -155,9 +160,32 @@ int upload_problem(sdpcuda_handle* h, const sdpcuda_problem* P)
       if( r < c || c < 0 || r >= h->blk[bk].n ) return SDPCUDA_ERR_ARG;
       erow[e] = r; ecol[e] = c; eld[e] = h->blk[bk].ld; eoff[e] = h->blk[bk].off;
    }
+   // variable classes for the Schur complement: 0 light (thread per pair), 1 heavy (CTA per pair), 2 dense (GEMM path:
+   // all entries in one block and at least 5 % of its lower triangle)
+   std::vector<std::vector<int>> dense_in(h->nb);
    for( int j = 0; j < m; ++j )
-      if( P->varbeg[j + 1] - P->varbeg[j] > 32 ) { heavy[j] = 1; heavylist.push_back(j); }
+   {
+      const int cntj = P->varbeg[j + 1] - P->varbeg[j];
+      if( cntj <= 32 ) continue;
+      const int b0 = P->entblk[P->varbeg[j]];
+      bool oneblock = true;
+      for( int e = P->varbeg[j]; e < P->varbeg[j + 1] && oneblock; ++e ) oneblock = (P->entblk[e] == b0);
+      const double nn = (double)h->blk[b0].n * h->blk[b0].n;
+      if( oneblock && cntj >= 64 && cntj >= 0.05 * nn ) { heavy[j] = 2; dense_in[b0].push_back(j); }
+      else { heavy[j] = 1; heavylist.push_back(j); }
+   }
    h->nheavy = (int)heavylist.size();
+   std::vector<int> denselist;
+   h->dgroups.clear();
+   size_t maxmat = 1;
+   for( int k = 0; k < h->nb; ++k )
+   {
+      if( dense_in[k].empty() ) continue;
+      h->dgroups.push_back({k, (int)denselist.size(), (int)dense_in[k].size()});
+      denselist.insert(denselist.end(), dense_in[k].begin(), dense_in[k].end());
+      maxmat = std::max(maxmat, (size_t)h->blk[k].ld * h->blk[k].n);
+   }
+   h->ndense = (int)denselist.size();
 
    // position-major view of sum_j y_j A_j - C: sort entry ids by arena position
    std::vector<long long> key(nnz + P->cnnz);
@@ -278,9 +306,30 @@ int upload_problem(sdpcuda_handle* h, const sdpcuda_problem* P)
    UP(cpos, cposv); UP(cmirror, cmirv); UP(cval, cval);
    UP(lpbeg, lpbeg); UP(lpind, lpind); UP(lpval, lpval); UP(lprhs, lprhs);
    UP(colbeg, colbeg); UP(colrow, colrow); UP(colval, colval);
-   UP(heavy, heavy); UP(heavylist, heavylist); UP(b, bvec);
+   UP(heavy, heavy); UP(heavylist, heavylist); UP(b, bvec); UP(denselist, denselist);
 #undef UP
    CK( cudaStreamSynchronize(st) );      // the host vectors above go out of scope
+
+   // dense Schur path: expanded constraint matrices and the two batched-GEMM result buffers (chunks of <= 256 MB)
+   if( h->ndense > 0 )
+   {
+      size_t total = 0;
+      int maxcount = 0;
+      for( const auto& g : h->dgroups ) { total += (size_t)g.count * h->blk[g.blk].ld * h->blk[g.blk].n; maxcount = std::max(maxcount, g.count); }
+      CK( h->Adense.ensure(total) );
+      CK( cudaMemsetAsync(h->Adense.p, 0, total * sizeof(double), st) );
+      h->dchunk = (int)std::max<size_t>(1, std::min<size_t>((size_t)maxcount, ((size_t)32 << 20) / maxmat));
+      CK( h->Hd.ensure((size_t)h->dchunk * maxmat) );
+      CK( h->Ud.ensure((size_t)h->dchunk * maxmat) );
+      size_t offm = 0;
+      DevEntries E{h->varbeg.p, h->erow.p, h->ecol.p, h->eld.p, h->eoff.p, h->eval.p};
+      for( const auto& g : h->dgroups )
+      {
+         const long long stride = (long long)h->blk[g.blk].ld * h->blk[g.blk].n;
+         CK( scatter_dense(st, g.count, h->denselist.p + g.first, E, h->blk[g.blk].ld, stride, h->Adense.p + offm) );
+         offm += (size_t)g.count * stride;
+      }
+   }
 
    // work space
    const size_t ar = h->arena;
@@ -501,11 +550,11 @@ int sdpcuda_destroy(sdpcuda_handle* h)
    for( DBuf<double>* bf : {&h->eval, &h->posval, &h->posc, &h->cval, &h->lpval, &h->colval, &h->lprhs, &h->b, &h->X, &h->S, &h->Sinv,
                             &h->L, &h->Linv, &h->LX, &h->LXinv, &h->dX, &h->dS, &h->dXa, &h->dSa, &h->K, &h->T1, &h->T2, &h->Rd, &h->work, &h->work2,
                             &h->y, &h->dy, &h->g, &h->rp, &h->AX, &h->DTx, &h->tm1, &h->tm2, &h->x, &h->s, &h->dx, &h->ds, &h->dxa, &h->dsa,
-                            &h->klp, &h->rdlp, &h->Dy, &h->Ddy, &h->M, &h->Mfac, &h->diaginv, &h->Mwork, &h->MLinv, &h->partials, &h->stats, &h->scal,
+                            &h->klp, &h->rdlp, &h->Dy, &h->Ddy, &h->M, &h->Mfac, &h->diaginv, &h->Mwork, &h->MLinv, &h->Adense, &h->Hd, &h->Ud, &h->partials, &h->stats, &h->scal,
                             &h->eigw, &h->lzwork, &h->kA, &h->kB, &h->kC, &h->kW} )
       bf->release();
    for( DBuf<int>* bf : {&h->varbeg, &h->erow, &h->ecol, &h->eld, &h->posbeg, &h->posvar, &h->lpbeg, &h->lpind, &h->colbeg, &h->colrow,
-                         &h->heavy, &h->heavylist, &h->info, &h->patcol, &h->patrow} )
+                         &h->heavy, &h->heavylist, &h->info, &h->patcol, &h->patrow, &h->denselist} )
       bf->release();
    for( DBuf<long long>* bf : {&h->eoff, &h->pos, &h->mirror, &h->cpos, &h->cmirror} )
       bf->release();
@@ -772,6 +821,25 @@ static int run_ipm(sdpcuda_handle* h, const sdpcuda_params* par, const double* s
       // ---- Schur complement and its factorisation ----
       CK( cudaMemsetAsync(h->M.p, 0, sizeof(double) * (size_t)h->ldm * m, st) );
       CK( schur_entries(st, m, E, h->heavy.p, h->heavylist.p, h->nheavy, h->X.p, h->Sinv.p, h->M.p, h->ldm) );
+      if( h->ndense > 0 )
+      {
+         // U_j = X A_j S^-1 for the dense variables (batched DMMA GEMMs), then M_ij = A_i . U_j for every i
+         size_t offm = 0;
+         for( const auto& g : h->dgroups )
+         {
+            const Block& bk = h->blk[g.blk];
+            const long long stride = (long long)bk.ld * bk.n;
+            for( int d0 = 0; d0 < g.count; d0 += h->dchunk )
+            {
+               const int cnt = std::min(h->dchunk, g.count - d0);
+               const double* Ad = h->Adense.p + offm + (size_t)d0 * stride;
+               CK( gemm(st, false, false, bk.n, bk.n, bk.n, 1.0, h->X.p + bk.off, bk.ld, 0, Ad, bk.ld, stride, 0.0, h->Hd.p, bk.ld, stride, cnt, 0) );
+               CK( gemm(st, false, false, bk.n, bk.n, bk.n, 1.0, h->Hd.p, bk.ld, stride, h->Sinv.p + bk.off, bk.ld, 0, 0.0, h->Ud.p, bk.ld, stride, cnt, 0) );
+               CK( schur_dense_dots(st, m, cnt, g.first + d0, h->denselist.p, h->heavy.p, E, bk.off, h->Ud.p, bk.ld, stride, h->M.p, h->ldm) );
+            }
+            offm += (size_t)g.count * stride;
+         }
+      }
       CK( schur_lp(st, nlp, h->lpbeg.p, h->lpind.p, h->lpval.p, h->x.p, h->s.p, h->M.p, h->ldm) );
       PHASE(4);
       double reg = 0.0;

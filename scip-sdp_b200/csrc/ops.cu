@@ -218,7 +218,7 @@ schur_light_kernel(int m, DevEntries E, const int* __restrict__ heavy, const dou
    const int j = blockIdx.y * 8 + (threadIdx.x >> 5);
    if( blockIdx.x * 32 + 31 < blockIdx.y * 8 ) return;          // tile strictly above the diagonal
    if( i >= m || j >= m || i < j ) return;
-   if( heavy[i] || heavy[j] ) return;
+   if( heavy[i] || heavy[j] ) return;             // classes 1 (heavy) and 2 (dense) are handled elsewhere
    double v = 0.0;
    for( int ei = E.varbeg[i]; ei < E.varbeg[i + 1]; ++ei )
       for( int ej = E.varbeg[j]; ej < E.varbeg[j + 1]; ++ej )
@@ -234,7 +234,8 @@ schur_heavy_kernel(int m, DevEntries E, const int* __restrict__ heavy, const int
    __shared__ double red[32];
    const int h = heavylist[blockIdx.y];
    const int o = blockIdx.x;
-   if( heavy[o] && o > h ) return;                                // heavy-heavy pairs once
+   if( heavy[o] == 2 ) return;                                    // pairs with a dense variable belong to the dense path
+   if( heavy[o] == 1 && o > h ) return;                           // heavy-heavy pairs once
    const int bh = E.varbeg[h], nh = E.varbeg[h + 1] - bh;
    const int bo = E.varbeg[o], no = E.varbeg[o + 1] - bo;
    double v = 0.0;
@@ -249,6 +250,49 @@ schur_heavy_kernel(int m, DevEntries E, const int* __restrict__ heavy, const int
    {
       int i = max(h, o), j = min(h, o);
       M[(size_t)j * ldm + i] = v;
+   }
+}
+
+// ---- dense path ----
+__global__ void scatter_dense_kernel(int nd, const int* __restrict__ denselist, DevEntries E, int ld, long long stride, double* __restrict__ Adense)
+{
+   const int d = blockIdx.x;
+   const int j = denselist[d];
+   double* Ad = Adense + (size_t)d * stride;
+   for( int e = E.varbeg[j] + threadIdx.x; e < E.varbeg[j + 1]; e += blockDim.x )
+   {
+      int r = E.row[e], c = E.col[e];
+      double v = E.val[e];
+      Ad[(size_t)c * ld + r] = v;
+      Ad[(size_t)r * ld + c] = v;
+   }
+}
+
+// one warp per (variable i, dense variable d): M[max(i,j), min(i,j)] = sum over entries of A_i in the block of a (U_j(r,c) + U_j(c,r))
+__global__ void __launch_bounds__(256)
+schur_dense_dots_kernel(int m, int nd, int d0, const int* __restrict__ denselist, const int* __restrict__ cls, DevEntries E, long long blockoff,
+   const double* __restrict__ U, int ld, long long stride, double* __restrict__ M, int ldm)
+{
+   const int i = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+   const int d = blockIdx.y;
+   if( i >= m ) return;
+   const int j = denselist[d0 + d];
+   if( cls[i] == 2 && i < j ) return;             // dense-dense pairs are computed once, from the side with the larger index
+   const double* Uj = U + (size_t)d * stride;
+   double s = 0.0;
+   for( int e = E.varbeg[i] + lane; e < E.varbeg[i + 1]; e += 32 )
+   {
+      if( E.off[e] != blockoff ) continue;
+      int r = E.row[e], c = E.col[e];
+      double u = Uj[(size_t)c * ld + r];
+      if( r != c ) u += Uj[(size_t)r * ld + c];
+      s += E.val[e] * u;
+   }
+   s = warp_sum(s);
+   if( lane == 0 )
+   {
+      int a = max(i, j), b = min(i, j);
+      M[(size_t)b * ldm + a] = s;
    }
 }
 
@@ -531,6 +575,23 @@ cudaError_t schur_entries(cudaStream_t st, int m, DevEntries E, const int* heavy
       count_launch();
    }
    return cudaGetLastError();
+}
+
+cudaError_t scatter_dense(cudaStream_t st, int nd, const int* denselist, DevEntries E, int ld, long long stride, double* Adense)
+{
+   if( nd <= 0 ) return cudaSuccess;
+   scatter_dense_kernel<<<nd, 256, 0, st>>>(nd, denselist, E, ld, stride, Adense);
+   LAUNCH_END();
+}
+
+cudaError_t schur_dense_dots(cudaStream_t st, int m, int nd, int d0, const int* denselist, const int* cls, DevEntries E, long long blockoff,
+   const double* U, int ld, long long stride, double* M, int ldm)
+{
+   if( nd <= 0 || m <= 0 ) return cudaSuccess;
+   ProfScope prof(st, PROF_SCHUR, 8.0 * m * (double)nd);
+   dim3 grid(ceil_div(m, 8), nd);
+   schur_dense_dots_kernel<<<grid, 256, 0, st>>>(m, nd, d0, denselist, cls, E, blockoff, U, ld, stride, M, ldm);
+   LAUNCH_END();
 }
 
 cudaError_t schur_lp(cudaStream_t st, int nlp, const int* lpbeg, const int* lpind, const double* lpval, const double* x,
