@@ -416,6 +416,71 @@ lzb_update_kernel(const LzDesc* __restrict__ D, int j, int maxit)
    for( int i = tid; i < n; i += nt ) w[i] *= cf;
 }
 
+// one Lanczos step in ONE launch: every CTA forms 8 rows of u = B v_j (warp per row, contiguous column of the symmetric
+// matrix) and its share of alpha = u.v_j; the CTA that finishes last (atomic ticket) completes the step for the whole vector:
+// alpha, w = u - alpha v_j - beta_{j-1} v_{j-1}, beta_j = |w|, v_{j+1} = w / beta_j.  Plain three-term recurrence (no
+// re-orthogonalisation: the extreme Ritz value and its residual bound do not need it); partial sums are added in a fixed order.
+__global__ void __launch_bounds__(256)
+lzb_step_kernel(const LzDesc* __restrict__ D, int j, int maxit, unsigned* __restrict__ tickets, double* __restrict__ partials, int pstride)
+{
+   __shared__ double red[32];
+   __shared__ bool last;
+   const LzDesc d = D[blockIdx.y];
+   const int n = d.n, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+   const int nblk = (n + 7) / 8;
+   if( (int)blockIdx.x >= nblk || j >= n ) return;
+   const int i = blockIdx.x * 8 + wid;
+   double* Q = d.Q;
+   const double* __restrict__ v = Q + (size_t)j * n;
+   double* w = Q + (size_t)(j + 1) * n;
+   double contrib = 0.0;
+   if( i < n )
+   {
+      const double* __restrict__ col = d.B + (size_t)i * d.ld;
+      double s0 = 0.0, s1 = 0.0;
+      int k = lane;
+      for( ; k + 32 < n; k += 64 ) { s0 += col[k] * v[k]; s1 += col[k + 32] * v[k + 32]; }
+      for( ; k < n; k += 32 ) s0 += col[k] * v[k];
+      double sum = s0 + s1;
+#pragma unroll
+      for( int o = 16; o > 0; o >>= 1 ) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+      if( lane == 0 ) { w[i] = sum; contrib = sum * v[i]; }
+   }
+   if( lane == 0 ) red[wid] = contrib;
+   __syncthreads();
+   if( tid == 0 )
+   {
+      double a = 0.0;
+      for( int q = 0; q < 8; ++q ) a += red[q];
+      partials[(size_t)blockIdx.y * pstride + blockIdx.x] = a;
+      __threadfence();
+      unsigned t = atomicAdd(&tickets[blockIdx.y], 1u);
+      last = (t == (unsigned)nblk - 1);
+   }
+   __syncthreads();
+   if( !last ) return;
+   __threadfence();
+   // ---- tail: the whole vector, one CTA ----
+   double a = 0.0;
+   for( int b = tid; b < nblk; b += 256 ) a += __ldcg(&partials[(size_t)blockIdx.y * pstride + b]);
+   a = block_sum(a, red);
+   double* alpha = d.ab;
+   double* beta = d.ab + maxit;
+   const double bprev = (j > 0) ? beta[j - 1] : 0.0;
+   const double* vprev = (j > 0) ? Q + (size_t)(j - 1) * n : nullptr;
+   double nr = 0.0;
+   for( int r = tid; r < n; r += 256 )
+   {
+      double x = __ldcg(&w[r]) - a * v[r] - (j > 0 ? bprev * vprev[r] : 0.0);
+      w[r] = x;
+      nr += x * x;
+   }
+   nr = sqrt(block_sum(nr, red));
+   const double cf = (nr > 1e-300) ? 1.0 / nr : 0.0;
+   for( int r = tid; r < n; r += 256 ) w[r] *= cf;
+   if( tid == 0 ) { alpha[j] = a; beta[j] = nr; tickets[blockIdx.y] = 0u; }
+}
+
 __global__ void lzb_ritz_kernel(const LzDesc* __restrict__ D, int k, int maxit)
 {
    const LzDesc d = D[blockIdx.x];
@@ -541,7 +606,7 @@ cudaError_t lanczos_lambda_min(cudaStream_t st, int n, const double* B, int ldb,
 namespace sdpk {
 
 cudaError_t lanczos_batched(cudaStream_t st, int nmat, const LzDesc* h_desc, LzDesc* d_desc, int maxit, double* d_out3,
-   double* h_out3, int* steps_done)
+   double* h_out3, int* steps_done, unsigned* tickets, double* partials, int pstride)
 {
    if( nmat <= 0 ) return cudaSuccess;
    int maxn = 0, minn = 1 << 30;
@@ -560,9 +625,8 @@ cudaError_t lanczos_batched(cudaStream_t st, int nmat, const LzDesc* h_desc, LzD
       for( ; j < jend; ++j )
       {
          dim3 grid(ceil_div(maxn, 8), nmat);
-         lzb_symv_kernel<<<grid, 256, 0, st>>>(d_desc, j);
-         lzb_update_kernel<<<nmat, 1024, 0, st>>>(d_desc, j, LZB_MAXIT);
-         count_launch(2);
+         lzb_step_kernel<<<grid, 256, 0, st>>>(d_desc, j, LZB_MAXIT, tickets, partials, pstride);
+         count_launch();
       }
       lzb_ritz_kernel<<<nmat, 32, 0, st>>>(d_desc, j, LZB_MAXIT);
       count_launch();

@@ -92,6 +92,8 @@ struct sdpcuda_handle
    DBuf<int> patcol, patrow;          // column-wise pattern of sum_j y_j A_j - C (+ diagonal) per block, if sparse
    std::vector<long long> patcoloff, patrowoff;   // per block offsets into patcol / patrow (-1: block is treated as dense)
    DBuf<LzDesc> lzdesc;
+   DBuf<unsigned> lztickets;
+   DBuf<double> lzpart;
    std::vector<LzDesc> h_lzdesc;
    bool minv = false;                // explicit inverse factor of M (m <= 4096): solves become two triangular mat-vecs
    DBuf<double> partials, stats, scal, eigw, lzwork;
@@ -108,6 +110,9 @@ struct sdpcuda_handle
    double normb = 0, normC = 0, normCsdp2 = 0, xil = 10, etal = 10;
    std::vector<double> xi, eta;
    Profiler prof;
+   // CUDA graphs of the three factorisation launch sequences (identical arguments in every iteration of one solve)
+   struct GraphCache { cudaGraphExec_t exec = nullptr; long long launches = 0; };
+   GraphCache gS, gX, gM;
    cudaEvent_t phev[12] = {nullptr};   // phase boundaries of one iteration (verbose >= 2)
 
    ~sdpcuda_handle()
@@ -118,6 +123,8 @@ struct sdpcuda_handle
 };
 
 namespace {
+
+void drop_graph(sdpcuda_handle::GraphCache& g);
 
 int set_device(sdpcuda_handle* h)
 {
@@ -131,6 +138,7 @@ int set_device(sdpcuda_handle* h)
 int upload_problem(sdpcuda_handle* h, const sdpcuda_problem* P)
 {
    cudaStream_t st = h->st;
+   drop_graph(h->gS); drop_graph(h->gX); drop_graph(h->gM);      // buffers may move: captured sequences are stale
    if( P->nblocks > 4000 ) return SDPCUDA_ERR_ARG;      // pinned scalar buffer holds two eigenvalue slots per block
    h->m = P->m; h->nb = P->nblocks; h->nlp = P->nlp;
    h->blk.resize(h->nb);
@@ -351,6 +359,9 @@ int upload_problem(sdpcuda_handle* h, const sdpcuda_problem* P)
    h->minv = (m <= 4096);
    if( h->minv ) CK( h->MLinv.ensure((size_t)h->ldm * m) );
    CK( h->lzdesc.ensure(2 * (size_t)std::max(h->nb, 1)) );
+   CK( h->lztickets.ensure(2 * (size_t)std::max(h->nb, 1)) );
+   CK( cudaMemsetAsync(h->lztickets.p, 0, sizeof(unsigned) * 2 * (size_t)std::max(h->nb, 1), st) );
+   CK( h->lzpart.ensure(2 * (size_t)std::max(h->nb, 1) * (size_t)ceil_div(std::max(h->maxn, 8), 8)) );
    CK( h->partials.ensure((size_t)RED_BLOCKS * NSTAT) );
    CK( h->stats.ensure(64) );
    CK( h->scal.ensure(64 + 8 * (size_t)std::max(h->nb, 1)) );
@@ -376,6 +387,43 @@ int assemble(sdpcuda_handle* h, const double* v, double cscale, double* T)
 {
    CK( cudaMemsetAsync(T, 0, h->arena * sizeof(double), h->st) );
    CK( assemble_positions(h->st, h->npos, h->posbeg.p, h->pos.p, h->mirror.p, h->posvar.p, h->posval.p, h->posc.p, v, cscale, T) );
+   return SDPCUDA_OK;
+}
+
+void drop_graph(sdpcuda_handle::GraphCache& g)
+{
+   if( g.exec ) cudaGraphExecDestroy(g.exec);
+   g.exec = nullptr; g.launches = 0;
+}
+
+// runs `issue` (a fixed sequence of launches on stream st) through a captured CUDA graph: captured on first use, replayed
+// afterwards.  The sequences are chains of ~200 tiny dependent kernels; replaying removes the host launch cost.
+template <class F> int run_graphed(sdpcuda_handle* h, sdpcuda_handle::GraphCache& g, cudaStream_t st, bool allow, F issue)
+{
+   if( !allow || h->prof.on )
+      return issue();
+   if( g.exec == nullptr )
+   {
+      const long long n0 = h->counter.n;
+      cudaGraph_t graph = nullptr;
+      CK( cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) );
+      int rc = issue();
+      cudaError_t e = cudaStreamEndCapture(st, &graph);
+      if( rc != SDPCUDA_OK || e != cudaSuccess || graph == nullptr )
+      {
+         if( graph ) cudaGraphDestroy(graph);
+         cudaGetLastError();
+         h->counter.n = n0;
+         return issue();                               // capture refused: plain launches
+      }
+      e = cudaGraphInstantiate(&g.exec, graph, 0);
+      cudaGraphDestroy(graph);
+      g.launches = h->counter.n - n0;
+      h->counter.n = n0;
+      if( e != cudaSuccess ) { g.exec = nullptr; cudaGetLastError(); return issue(); }
+   }
+   CK( cudaGraphLaunch(g.exec, st) );
+   h->counter.n += g.launches;
    return SDPCUDA_OK;
 }
 
@@ -471,7 +519,8 @@ int step_eigs(sdpcuda_handle* h, const double* dXdir, const double* dSdir, int m
       CK( h->scal.ensure(64 + 2 * (size_t)nb + 3 * (size_t)nmat) );
       double* out3 = h->scal.p + 64 + 2 * nb;
       for( int i = 0; i < nmat; ++i ) h->h_lzdesc[i].out = out3 + 3 * i;
-      CK( lanczos_batched(h->st, nmat, h->h_lzdesc.data(), h->lzdesc.p, maxsteps, out3, h->h_stats + 2048, nullptr) );
+      CK( lanczos_batched(h->st, nmat, h->h_lzdesc.data(), h->lzdesc.p, maxsteps, out3, h->h_stats + 2048, nullptr,
+            h->lztickets.p, h->lzpart.p, ceil_div(std::max(h->maxn, 8), 8)) );
       int i = 0; k = 0;
       for( const Block& bk : h->blk )
       {
@@ -558,7 +607,8 @@ int sdpcuda_destroy(sdpcuda_handle* h)
       bf->release();
    for( DBuf<long long>* bf : {&h->eoff, &h->pos, &h->mirror, &h->cpos, &h->cmirror} )
       bf->release();
-   h->lzdesc.release();
+   h->lzdesc.release(); h->lztickets.release(); h->lzpart.release();
+   drop_graph(h->gS); drop_graph(h->gX); drop_graph(h->gM);
    cudaEventDestroy(h->ev0); cudaEventDestroy(h->ev1); cudaEventDestroy(h->evFork); cudaEventDestroy(h->evJoin);
    cudaStreamDestroy(h->st); cudaStreamDestroy(h->st2);
    if( g_counter == &h->counter ) g_counter = nullptr;
@@ -731,12 +781,14 @@ static int run_ipm(sdpcuda_handle* h, const sdpcuda_params* par, const double* s
       CK( const_dots(st, h->cnnz, h->cpos.p, h->cmirror.p, h->cval.p, h->X.p, h->Rd.p, h->stats.p + NSTAT) );
       PHASE(1);
       // factorisations of S and X are issued before the sync so that their pivots are known at the same time
-      // the two factorisations are latency bound (chains of small kernels) and independent: run them side by side
+      // the two factorisations are latency bound (chains of small kernels) and independent: run them side by side.  The
+      // launches of the critical one (S, main stream) are issued first so that the host does not delay it.
       CK( cudaEventRecord(h->evFork, st) );
+      const bool graphs = (iter >= 1);      // the first iteration runs plain launches (one-time kernel attribute set-up)
+      rc = run_graphed(h, h->gS, st, graphs, [&]() { return factor_blocks(h, st, h->work.p, h->S.p, h->L.p, h->Linv.p, 0); }); if( rc ) return rc;
       CK( cudaStreamWaitEvent(h->st2, h->evFork, 0) );
-      rc = factor_blocks(h, h->st2, h->work2.p, h->X.p, h->LX.p, h->LXinv.p, 1); if( rc ) return rc;
+      rc = run_graphed(h, h->gX, h->st2, graphs, [&]() { return factor_blocks(h, h->st2, h->work2.p, h->X.p, h->LX.p, h->LXinv.p, 1); }); if( rc ) return rc;
       CK( cudaEventRecord(h->evJoin, h->st2) );
-      rc = factor_blocks(h, st, h->work.p, h->S.p, h->L.p, h->Linv.p, 0); if( rc ) return rc;
       // the factor of X is first needed for the primal step length: the main stream joins the side stream only there,
       // so that the X factorisation hides behind S^-1, the Schur complement, its factorisation and the predictor solve
       PHASE(2);
@@ -849,7 +901,10 @@ static int run_ipm(sdpcuda_handle* h, const sdpcuda_params* par, const double* s
          CK( cudaMemcpyAsync(h->Mfac.p, h->M.p, sizeof(double) * (size_t)h->ldm * m, cudaMemcpyDeviceToDevice, st) );
          if( reg > 0.0 ) CK( add_diagonal(st, m, h->Mfac.p, h->ldm, reg) );
          CK( cudaMemsetAsync(h->info.p + 2, 0, sizeof(int), st) );
-         CK( potrf_lower(st, m, h->Mfac.p, h->ldm, h->minv ? h->MLinv.p : nullptr, h->ldm, h->diaginv.p, h->Mwork.p, h->ldm, h->info.p + 2) );
+         rc = run_graphed(h, h->gM, st, graphs, [&]() -> int {
+            CK( potrf_lower(st, m, h->Mfac.p, h->ldm, h->minv ? h->MLinv.p : nullptr, h->ldm, h->diaginv.p, h->Mwork.p, h->ldm, h->info.p + 2) );
+            return SDPCUDA_OK; });
+         if( rc ) return rc;
          CK( cudaMemcpyAsync(h->h_info, h->info.p, 8 * sizeof(int), cudaMemcpyDeviceToHost, st) );
          CK( cudaStreamSynchronize(st) );
          mok = (h->h_info[2] == 0);
