@@ -99,7 +99,7 @@ class Lib:
         if not os.path.exists(path):
             raise FileNotFoundError(f"{path} not built: run `python -c 'import __graft_entry__ as g; g.build()'`")
         self.path = path
-        self.lib = L = C.CDLL(path, mode=C.RTLD_GLOBAL)
+        self.lib = L = C.CDLL(path, mode=C.RTLD_LOCAL)
         L.sdpcuda_backend_name.restype = C.c_char_p
         L.sdpcuda_create.argtypes = [C.POINTER(C.c_void_p), C.c_int]
         L.sdpcuda_destroy.argtypes = [C.c_void_p]

@@ -436,12 +436,23 @@ lzb_step_kernel(const LzDesc* __restrict__ D, int j, int maxit, unsigned* __rest
    double contrib = 0.0;
    if( i < n )
    {
-      const double* __restrict__ col = d.B + (size_t)i * d.ld;
-      double s0 = 0.0, s1 = 0.0;
+      // the column is 16-byte aligned (leading dimensions are multiples of 4, blocks 128-byte aligned): 4 independent
+      // 16-byte loads per lane and iteration keep enough bytes in flight to run at memory speed
+      const double2* __restrict__ col2 = reinterpret_cast<const double2*>(d.B + (size_t)i * d.ld);
+      const int n2 = n >> 1;
+      double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
       int k = lane;
-      for( ; k + 32 < n; k += 64 ) { s0 += col[k] * v[k]; s1 += col[k + 32] * v[k + 32]; }
-      for( ; k < n; k += 32 ) s0 += col[k] * v[k];
-      double sum = s0 + s1;
+      for( ; k + 96 < n2; k += 128 )
+      {
+         double2 c0 = col2[k], c1 = col2[k + 32], c2 = col2[k + 64], c3 = col2[k + 96];
+         s0 += c0.x * v[2 * k] + c0.y * v[2 * k + 1];
+         s1 += c1.x * v[2 * k + 64] + c1.y * v[2 * k + 65];
+         s2 += c2.x * v[2 * k + 128] + c2.y * v[2 * k + 129];
+         s3 += c3.x * v[2 * k + 192] + c3.y * v[2 * k + 193];
+      }
+      for( ; k < n2; k += 32 ) { double2 c0 = col2[k]; s0 += c0.x * v[2 * k] + c0.y * v[2 * k + 1]; }
+      if( (n & 1) && lane == 0 ) s1 += d.B[(size_t)i * d.ld + n - 1] * v[n - 1];
+      double sum = (s0 + s1) + (s2 + s3);
 #pragma unroll
       for( int o = 16; o > 0; o >>= 1 ) sum += __shfl_xor_sync(0xffffffffu, sum, o);
       if( lane == 0 ) { w[i] = sum; contrib = sum * v[i]; }

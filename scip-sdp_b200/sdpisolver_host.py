@@ -86,7 +86,7 @@ class SdpiSolver:
     def __init__(self, path=BINDING_LIB, gaptol=1e-5, feastol=1e-5):
         if not os.path.exists(path):
             raise FileNotFoundError(f"{path} not built: run __graft_entry__.build()")
-        self.lib = L = C.CDLL(path, mode=C.RTLD_GLOBAL)
+        self.lib = L = C.CDLL(path, mode=C.RTLD_LOCAL)
         L.BMScreateBlockMemory.restype = C.c_void_p
         L.BMScreateBufferMemory.restype = C.c_void_p
         L.BMScreateBufferMemory.argtypes = [C.c_double, C.c_int, C.c_uint]

@@ -55,7 +55,7 @@ class SdpiLib:
     def __init__(self, path):
         if not os.path.exists(path):
             raise FileNotFoundError(path)
-        self.lib = L = C.CDLL(path, mode=C.RTLD_GLOBAL)
+        self.lib = L = C.CDLL(path, mode=C.RTLD_LOCAL)
         L.SCIPsdpiGetSolverName.restype = C.c_char_p
         L.BMSgetMemoryUsed.restype = C.c_longlong
         L.BMScreateBlockMemory.restype = C.c_void_p

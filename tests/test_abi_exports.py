@@ -62,3 +62,24 @@ def test_product_library_does_not_link_the_oracle():
     for name in ["libsdpcuda.so", "libsdpisolver_cuda.so"]:
         out = subprocess.run(["ldd", os.path.join(PKG, "lib", name)], capture_output=True, text=True).stdout
         assert "oracle" not in out and "openblas" not in out, out
+
+
+def test_checker_libraries_bind_their_own_backend():
+    """libsdpi_oracle.so and libsdpi_cuda.so both reference sdpcuda_* symbols: each must resolve them inside its own
+    dependency tree (RTLD_LOCAL loads), never through whichever implementation happened to be loaded first"""
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from harness import sdpi_ref
+    from scip_sdp_b200 import abi
+    if not os.path.exists(sdpi_ref.LIB_ORACLE):
+        pytest.skip("oracle/_ref not built")
+    ctypes.CDLL(os.path.join(PKG, "lib", "libsdpcuda.so"), mode=ctypes.RTLD_LOCAL)      # product library loaded first on purpose
+    lib = sdpi_ref.SdpiLib(sdpi_ref.LIB_ORACLE)
+    name = ctypes.CDLL(sdpi_ref.LIB_ORACLE, mode=ctypes.RTLD_LOCAL).sdpcuda_backend_name
+    name.restype = ctypes.c_char_p
+    assert name() == b"cpu-oracle"
+    # and a solve through the reference's sdpi.c really runs (no CUDA device exists in the CPU test environment)
+    from golden.checksdpi_cases import CASES
+    from harness import checksdpi_port
+    os.environ.setdefault("SHIM_QUIET", "1")
+    checksdpi_port.run_case(lib, CASES["test1"], "test1")
