@@ -10,6 +10,7 @@
 #include "../../include/sdpcuda.h"
 #include "common.cuh"
 #include "ops.cuh"
+#include "ipm_small.cuh"
 
 #include <algorithm>
 #include <atomic>
@@ -91,6 +92,8 @@ struct sdpcuda_handle
    DBuf<int> denselist;
    DBuf<int> patcol, patrow;          // column-wise pattern of sum_j y_j A_j - C (+ diagonal) per block, if sparse
    std::vector<long long> patcoloff, patrowoff;   // per block offsets into patcol / patrow (-1: block is treated as dense)
+   DBuf<SmallResult> smallres;
+   int force_path = 0;               // 0 auto, 1 always multi-kernel, 2 always single-CTA (tests)
    DBuf<LzDesc> lzdesc;
    DBuf<unsigned> lztickets;
    DBuf<double> lzpart;
@@ -557,6 +560,9 @@ void sdpcuda_default_params(sdpcuda_params* p)
 int sdpcuda_create(sdpcuda_handle** out, int device)
 {
    if( out == nullptr ) return SDPCUDA_ERR_ARG;
+   // concurrent solver handles (one per SCIP solver thread) run on separate streams; the default of 8 hardware work queues
+   // would serialise more than 8 of them.  Only effective if set before the CUDA context of this process is created.
+   setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0);
    int ndev = 0;
    cudaError_t e = cudaGetDeviceCount(&ndev);
    if( e != cudaSuccess || ndev <= 0 )
@@ -607,7 +613,7 @@ int sdpcuda_destroy(sdpcuda_handle* h)
       bf->release();
    for( DBuf<long long>* bf : {&h->eoff, &h->pos, &h->mirror, &h->cpos, &h->cmirror} )
       bf->release();
-   h->lzdesc.release(); h->lztickets.release(); h->lzpart.release();
+   h->lzdesc.release(); h->lztickets.release(); h->lzpart.release(); h->smallres.release();
    drop_graph(h->gS); drop_graph(h->gX); drop_graph(h->gM);
    cudaEventDestroy(h->ev0); cudaEventDestroy(h->ev1); cudaEventDestroy(h->evFork); cudaEventDestroy(h->evJoin);
    cudaStreamDestroy(h->st); cudaStreamDestroy(h->st2);
@@ -747,6 +753,77 @@ static int run_ipm(sdpcuda_handle* h, const sdpcuda_params* par, const double* s
       CK( h->x.upload(hx, st) ); CK( h->s.upload(hs, st) ); CK( h->y.upload(hy, st) );
       CK( cudaStreamSynchronize(st) );
    }
+   // ---- small relaxations: the whole iteration in one launch (ipm_small.cu) ----
+   {
+      const char* env = getenv("SDPCUDA_PATH");
+      int force = h->force_path;
+      if( env != nullptr && env[0] == 'm' ) force = 1;
+      if( env != nullptr && env[0] == 's' ) force = 2;
+      long long multirows = 0;
+      bool eligible = (h->maxn <= SMALL_MAX_N && m <= SMALL_MAX_M && nb <= SMALL_MAX_BLOCKS && (int)h->dgroups.size() <= SMALL_MAX_GROUPS
+         && ar <= ((size_t)1 << 20) && nlp <= (1 << 20) && !h->prof.on);
+      if( eligible && h->ndense > 0 )
+         for( const auto& g : h->dgroups ) if( g.count > h->dchunk ) eligible = false;
+      // measured on the shipped instances: the one-launch kernel wins while the Schur complement is small (m <= 64); above that
+      // the serial Cholesky of M inside a single CTA loses against the multi-kernel pipeline
+      if( eligible && force != 1 && (force == 2 || m <= 64) )
+      {
+         SmallArgs a;
+         memset(&a, 0, sizeof(a));
+         a.m = m; a.nb = nb; a.nlp = nlp; a.N = h->N; a.ldm = h->ldm; a.npos = h->npos; a.cnnz = h->cnnz; a.ndense = h->ndense;
+         a.ngroups = (int)h->dgroups.size(); a.maxiter = maxiter; a.setting = par->setting; a.verbose = par->verbose; a.arena = (long long)ar;
+         long long lzoff = 0;
+         for( int k = 0; k < nb; ++k )
+         {
+            a.blk[k].n = h->blk[k].n; a.blk[k].ld = h->blk[k].ld; a.blk[k].off = h->blk[k].off; a.blk[k].lzoff = lzoff;
+            lzoff += (long long)(SMALL_LZ_STEPS + 2) * h->blk[k].n;
+         }
+         CK( h->lzwork.ensure((size_t)lzoff + 16) );
+         CK( h->smallres.ensure(1) );
+         a.E = E; a.cls = h->heavy.p;
+         a.posbeg = h->posbeg.p; a.pos = h->pos.p; a.mirror = h->mirror.p; a.posvar = h->posvar.p; a.posval = h->posval.p; a.posc = h->posc.p;
+         a.cpos = h->cpos.p; a.cmirror = h->cmirror.p; a.cval = h->cval.p;
+         a.lpbeg = h->lpbeg.p; a.lpind = h->lpind.p; a.lpval = h->lpval.p; a.lprhs = h->lprhs.p;
+         a.colbeg = h->colbeg.p; a.colrow = h->colrow.p; a.colval = h->colval.p; a.b = h->b.p;
+         a.denselist = h->denselist.p; a.Adense = h->Adense.p;
+         {
+            long long offm = 0; int gi = 0;
+            for( const auto& g : h->dgroups )
+            {
+               a.gblk[gi] = g.blk; a.gfirst[gi] = g.first; a.gcount[gi] = g.count; a.gaoff[gi] = offm;
+               offm += (long long)g.count * h->blk[g.blk].ld * h->blk[g.blk].n; ++gi;
+            }
+         }
+         a.X = h->X.p; a.S = h->S.p; a.Sinv = h->Sinv.p; a.L = h->L.p; a.Linv = h->Linv.p; a.LX = h->LX.p; a.LXinv = h->LXinv.p;
+         a.dX = h->dX.p; a.dS = h->dS.p; a.dXa = h->dXa.p; a.dSa = h->dSa.p; a.K = h->K.p; a.T1 = h->T1.p; a.T2 = h->T2.p; a.Rd = h->Rd.p;
+         a.y = h->y.p; a.dy = h->dy.p; a.g = h->g.p; a.rp = h->rp.p; a.AX = h->AX.p; a.DTx = h->DTx.p; a.tm1 = h->tm1.p; a.tm2 = h->tm2.p;
+         a.x = h->x.p; a.s = h->s.p; a.dx = h->dx.p; a.ds = h->ds.p; a.dxa = h->dxa.p; a.dsa = h->dsa.p; a.klp = h->klp.p; a.rdlp = h->rdlp.p;
+         a.Dy = h->Dy.p; a.Ddy = h->Ddy.p; a.M = h->M.p; a.Mfac = h->Mfac.p; a.Hd = h->Hd.p; a.Ud = h->Ud.p; a.lz = h->lzwork.p;
+         a.gaptol = gaptol; a.feastol = feastol; a.absgaptol = par->absgaptol; a.objlimit = par->objlimit;
+         a.normb = normb; a.normC = normC; a.normCsdp2 = normCsdp2; a.gammabase = gammabase;
+         a.out = h->smallres.p;
+         (void)multirows;
+         CK( cudaEventRecord(h->ev0, st) );
+         CK( launch_ipm_small(st, a) );
+         CK( cudaEventRecord(h->ev1, st) );
+         SmallResult sr;
+         CK( cudaMemcpyAsync(&sr, h->smallres.p, sizeof(sr), cudaMemcpyDeviceToHost, st) );
+         CK( cudaStreamSynchronize(st) );
+         float ms = 0.f;
+         cudaEventElapsedTime(&ms, h->ev0, h->ev1);
+         sdpcuda_result R;
+         memset(&R, 0, sizeof(R));
+         R.phase = sr.phase; R.stop = sr.stop; R.iterations = sr.iterations;
+         R.launches = (int)std::min<long long>(h->counter.n, 2147483647LL);
+         R.pobj = sr.pobj; R.dobj = sr.dobj; R.relgap = sr.relgap; R.pinf = sr.pinf; R.dinf = sr.dinf; R.mu = sr.mu;
+         R.seconds = now_seconds() - t0; R.device_ms = ms; R.h2d_bytes = g_h2d_bytes; R.d2h_bytes = sizeof(sr);
+         h->solved = true;
+         if( res != nullptr ) *res = R;
+         return SDPCUDA_OK;
+      }
+      if( force == 2 ) return SDPCUDA_ERR_ARG;      // single-CTA path requested for a problem it cannot take
+   }
+
    CK( cudaMemsetAsync(h->dX.p, 0, ar * sizeof(double), st) );
    CK( cudaMemsetAsync(h->dS.p, 0, ar * sizeof(double), st) );
 

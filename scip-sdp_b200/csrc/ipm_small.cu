@@ -1,0 +1,1117 @@
+// ipm_small.cu — the whole interior-point solve of a small relaxation in ONE kernel launch.
+//
+// SCIP-SDP's branch-and-bound solves thousands of tiny relaxations (shipped instances: blocks of order 2..43, 3..105
+// variables).  On that scale a kernel-per-operation pipeline is pure launch latency (hundreds of launches and three
+// host round trips per iteration).  Here one CTA of 1024 threads runs the complete predictor-corrector iteration -
+// residuals, Cholesky factors and inverses of S and X, Schur complement, its factorisation, both solves, the HKM
+// directions, Lanczos step lengths, the update and all termination tests - with __syncthreads() as the only
+// synchronisation.  Data stay in the same HBM/L2-resident buffers as in the multi-kernel path (ipm.cu), small blocks are
+// factorised in shared memory.  The numerical recipe is identical to ipm.cu (same formulas, same status rules), so both
+// paths are interchangeable behind sdpcuda_solve; other CTAs/SMs stay free for other solver handles (concurrent nodes).
+#include "ipm_small.cuh"
+#include "../../include/sdpcuda.h"
+
+namespace sdpk {
+namespace {
+
+constexpr int NT = 1024;
+constexpr int LDS = SMALL_MAX_N + 1;
+
+struct Ctl                      // control block in shared memory, written by thread 0
+{
+   double st[40];
+   double mu, pobj, dobj, relgap, pinf, dinf, sigma, ap, ad, apmax, admax, lastap, lastad, bestmerit, lam;
+   int iter, stall, backtracks, phase, stop, done, rdzero, failS, failX, failM, pfeasever, dfeasever, xfail;
+};
+
+__device__ __forceinline__ double wsum(double v)
+{
+#pragma unroll
+   for( int o = 16; o > 0; o >>= 1 ) v += __shfl_xor_sync(0xffffffffu, v, o);
+   return v;
+}
+
+__device__ double bsum(double v, double* red)
+{
+   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+   v = wsum(v);
+   __syncthreads();
+   if( lane == 0 ) red[w] = v;
+   __syncthreads();
+   double s = 0.0;
+#pragma unroll
+   for( int q = 0; q < NT / 32; ++q ) s += red[q];
+   return s;
+}
+
+__device__ double bmax(double v, double* red)
+{
+   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+   for( int o = 16; o > 0; o >>= 1 ) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+   __syncthreads();
+   if( lane == 0 ) red[w] = v;
+   __syncthreads();
+   double s = red[0];
+#pragma unroll
+   for( int q = 1; q < NT / 32; ++q ) s = fmax(s, red[q]);
+   return s;
+}
+
+__device__ __forceinline__ double frsqrt(double x)
+{
+   double y = (double)rsqrtf((float)x);
+   y = y * (1.5 - 0.5 * x * y * y);
+   y = y * (1.5 - 0.5 * x * y * y);
+   return y;
+}
+
+// T = sum_j v_j A_j - cscale * C  (full symmetric, zero elsewhere)
+__device__ void assemble(const SmallArgs& a, const double* v, double cscale, double* T)
+{
+   for( long long i = threadIdx.x; i < a.arena; i += NT ) T[i] = 0.0;
+   __syncthreads();
+   for( int p = threadIdx.x; p < a.npos; p += NT )
+   {
+      double s = -cscale * a.posc[p];
+      for( int e = a.posbeg[p]; e < a.posbeg[p + 1]; ++e ) s += v[a.posvar[e]] * a.posval[e];
+      T[a.pos[p]] = s;
+      T[a.mirror[p]] = s;
+   }
+   __syncthreads();
+}
+
+// out_j = A_j . Xm : one warp per variable
+__device__ void applyA(const SmallArgs& a, const double* Xm, double* out)
+{
+   const int lane = threadIdx.x & 31;
+   for( int j = threadIdx.x >> 5; j < a.m; j += NT / 32 )
+   {
+      double s = 0.0;
+      for( int e = a.E.varbeg[j] + lane; e < a.E.varbeg[j + 1]; e += 32 )
+      {
+         int r = a.E.row[e], c = a.E.col[e], ld = a.E.ld[e];
+         const double* Xk = Xm + a.E.off[e];
+         double u = Xk[(size_t)c * ld + r];
+         if( r != c ) u += Xk[(size_t)r * ld + c];
+         s += a.E.val[e] * u;
+      }
+      s = wsum(s);
+      if( lane == 0 ) out[j] = s;
+   }
+   __syncthreads();
+}
+
+__device__ void lpcols(const SmallArgs& a, const double* xv, double* out, bool accumulate)
+{
+   for( int j = threadIdx.x; j < a.m; j += NT )
+   {
+      double s = 0.0;
+      for( int p = a.colbeg[j]; p < a.colbeg[j + 1]; ++p ) s += a.colval[p] * xv[a.colrow[p]];
+      out[j] = accumulate ? out[j] + s : s;
+   }
+   __syncthreads();
+}
+
+__device__ void lprows(const SmallArgs& a, const double* yv, double* out)
+{
+   for( int l = threadIdx.x; l < a.nlp; l += NT )
+   {
+      double s = 0.0;
+      for( int p = a.lpbeg[l]; p < a.lpbeg[l + 1]; ++p ) s += a.lpval[p] * yv[a.lpind[p]];
+      out[l] = s;
+   }
+   __syncthreads();
+}
+
+// C = alpha * op(A) * op(B) + beta * C for one block (n <= 64), all matrices n x n with leading dimension ld
+__device__ void gemmb(int n, int ld, bool ta, bool tb, double alpha, const double* A, const double* B, double beta, double* C)
+{
+   for( int e = threadIdx.x; e < n * n; e += NT )
+   {
+      const int i = e % n, j = e / n;
+      double s0 = 0.0, s1 = 0.0;
+      int k = 0;
+      for( ; k + 2 <= n; k += 2 )
+      {
+         double a0 = ta ? A[(size_t)i * ld + k] : A[(size_t)k * ld + i];
+         double a1 = ta ? A[(size_t)i * ld + k + 1] : A[(size_t)(k + 1) * ld + i];
+         double b0 = tb ? B[(size_t)k * ld + j] : B[(size_t)j * ld + k];
+         double b1 = tb ? B[(size_t)(k + 1) * ld + j] : B[(size_t)j * ld + k + 1];
+         s0 += a0 * b0; s1 += a1 * b1;
+      }
+      if( k < n )
+      {
+         double a0 = ta ? A[(size_t)i * ld + k] : A[(size_t)k * ld + i];
+         double b0 = tb ? B[(size_t)k * ld + j] : B[(size_t)j * ld + k];
+         s0 += a0 * b0;
+      }
+      double v = alpha * (s0 + s1);
+      if( beta != 0.0 ) v += beta * C[(size_t)j * ld + i];
+      C[(size_t)j * ld + i] = v;
+   }
+   __syncthreads();
+}
+
+// A = (A + A')/2 - sub
+__device__ void symavg(int n, int ld, double* A, const double* sub)
+{
+   for( int e = threadIdx.x; e < n * n; e += NT )
+   {
+      const int i = e % n, j = e / n;
+      if( i < j ) continue;
+      double v = 0.5 * (A[(size_t)j * ld + i] + A[(size_t)i * ld + j]);
+      if( sub != nullptr ) v -= sub[(size_t)j * ld + i];
+      A[(size_t)j * ld + i] = v;
+      A[(size_t)i * ld + j] = v;
+   }
+   __syncthreads();
+}
+
+// Cholesky factor and its inverse of one block in shared memory; returns false (to all threads) on a non-positive pivot
+__device__ bool cholinv(int n, int ld, const double* src, double* Lout, double* Linvout, double* sh, double* sh2, double* rdiag, int* flag)
+{
+   for( int e = threadIdx.x; e < n * n; e += NT )
+   {
+      const int i = e % n, j = e / n;
+      sh[i * LDS + j] = (i >= j) ? src[(size_t)j * ld + i] : 0.0;
+      sh2[i * LDS + j] = (i == j) ? 1.0 : 0.0;
+   }
+   if( threadIdx.x == 0 ) *flag = 0;
+   __syncthreads();
+   for( int k = 0; k < n; ++k )
+   {
+      if( threadIdx.x == 0 )
+      {
+         double d = sh[k * LDS + k];
+         if( !(d > 0.0) ) { *flag = 1; d = 1.0; }
+         double r = frsqrt(d);
+         rdiag[k] = r;
+         sh[k * LDS + k] = d * r;
+      }
+      __syncthreads();
+      const double r = rdiag[k];
+      for( int i = k + 1 + threadIdx.x; i < n; i += NT ) sh[i * LDS + k] *= r;
+      __syncthreads();
+      const int rem = n - k - 1;
+      for( int e = threadIdx.x; e < rem * rem; e += NT )
+      {
+         const int i = k + 1 + e % rem, j = k + 1 + e / rem;
+         if( i >= j ) sh[i * LDS + j] -= sh[i * LDS + k] * sh[j * LDS + k];
+      }
+      __syncthreads();
+   }
+   // W = L^-1 from R = I, row by row
+   for( int k = 0; k < n; ++k )
+   {
+      const double r = rdiag[k];
+      for( int j = threadIdx.x; j <= k; j += NT ) sh2[k * LDS + j] *= r;
+      __syncthreads();
+      const int below = n - k - 1;
+      for( int e = threadIdx.x; e < below * (k + 1); e += NT )
+      {
+         const int i = k + 1 + e / (k + 1), j = e % (k + 1);
+         sh2[i * LDS + j] -= sh[i * LDS + k] * sh2[k * LDS + j];
+      }
+      __syncthreads();
+   }
+   for( int e = threadIdx.x; e < n * n; e += NT )
+   {
+      const int i = e % n, j = e / n;
+      Lout[(size_t)j * ld + i] = (i >= j) ? sh[i * LDS + j] : 0.0;
+      Linvout[(size_t)j * ld + i] = (i >= j) ? sh2[i * LDS + j] : 0.0;
+   }
+   __syncthreads();
+   const bool ok = (*flag == 0);
+   __syncthreads();                 // the flag is reused by the next call
+   return ok;
+}
+
+// Schur complement entry formula for one pair of variables (same as ops.cu)
+__device__ __forceinline__ double pairterm(const DevEntries& E, int ei, int ej, const double* X, const double* Z)
+{
+   if( E.off[ei] != E.off[ej] ) return 0.0;
+   const int ld = E.ld[ei];
+   const double* Xk = X + E.off[ei];
+   const double* Zk = Z + E.off[ei];
+   const int p = E.row[ei], q = E.col[ei], r = E.row[ej], c = E.col[ej];
+   double t = Xk[(size_t)r * ld + q] * Zk[(size_t)p * ld + c];
+   if( r != c ) t += Xk[(size_t)c * ld + q] * Zk[(size_t)p * ld + r];
+   if( p != q )
+   {
+      t += Xk[(size_t)r * ld + p] * Zk[(size_t)q * ld + c];
+      if( r != c ) t += Xk[(size_t)c * ld + p] * Zk[(size_t)q * ld + r];
+   }
+   return E.val[ei] * E.val[ej] * t;
+}
+
+__device__ void schur(const SmallArgs& a)
+{
+   const int m = a.m, ldm = a.ldm;
+   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+   for( int e = threadIdx.x; e < ldm * m; e += NT ) a.M[e] = 0.0;
+   __syncthreads();
+   // pairs without a dense variable: one warp per pair (i >= j), lanes split the entry-pair product
+   const int npairs = m * (m + 1) / 2;
+   for( int p = wid; p < npairs; p += NT / 32 )
+   {
+      int i = (int)((sqrt(8.0 * p + 1.0) - 1.0) * 0.5);
+      while( (i + 1) * (i + 2) / 2 <= p ) ++i;
+      while( i * (i + 1) / 2 > p ) --i;
+      const int j = p - i * (i + 1) / 2;
+      if( a.cls[i] == 2 || a.cls[j] == 2 ) continue;
+      const int bi = a.E.varbeg[i], ni = a.E.varbeg[i + 1] - bi;
+      const int bj = a.E.varbeg[j], nj = a.E.varbeg[j + 1] - bj;
+      double v = 0.0;
+      for( int t = lane; t < ni * nj; t += 32 ) v += pairterm(a.E, bi + t / nj, bj + t % nj, a.X, a.Sinv);
+      v = wsum(v);
+      if( lane == 0 ) a.M[(size_t)j * ldm + i] = v;
+   }
+   __syncthreads();
+   // dense variables: U_d = X A_d S^-1 for all of them, then M_id = A_i . U_d
+   for( int g = 0; g < a.ngroups; ++g )
+   {
+      const SmallBlock bk = a.blk[a.gblk[g]];
+      const int n = bk.n, ld = bk.ld, cnt = a.gcount[g];
+      const long long stride = (long long)ld * n;
+      const double* Ad = a.Adense + a.gaoff[g];
+      const double* Xk = a.X + bk.off;
+      const double* Zk = a.Sinv + bk.off;
+      for( int e = threadIdx.x; e < cnt * n * n; e += NT )         // H_d = X A_d
+      {
+         const int d = e / (n * n), r = e % (n * n), i = r % n, j = r / n;
+         const double* Aj = Ad + (size_t)d * stride + (size_t)j * ld;
+         double s0 = 0.0;
+         for( int k = 0; k < n; ++k ) s0 += Xk[(size_t)k * ld + i] * Aj[k];
+         a.Hd[(size_t)d * stride + (size_t)j * ld + i] = s0;
+      }
+      __syncthreads();
+      for( int e = threadIdx.x; e < cnt * n * n; e += NT )         // U_d = H_d S^-1
+      {
+         const int d = e / (n * n), r = e % (n * n), i = r % n, j = r / n;
+         const double* Hd = a.Hd + (size_t)d * stride;
+         const double* Zj = Zk + (size_t)j * ld;
+         double s0 = 0.0;
+         for( int k = 0; k < n; ++k ) s0 += Hd[(size_t)k * ld + i] * Zj[k];
+         a.Ud[(size_t)d * stride + (size_t)j * ld + i] = s0;
+      }
+      __syncthreads();
+      for( int p = wid; p < m * cnt; p += NT / 32 )
+      {
+         const int i = p / cnt, d = p % cnt;
+         const int j = a.denselist[a.gfirst[g] + d];
+         if( a.cls[i] == 2 && i < j ) continue;
+         const double* Uj = a.Ud + (size_t)d * stride;
+         double s0 = 0.0;
+         for( int e = a.E.varbeg[i] + lane; e < a.E.varbeg[i + 1]; e += 32 )
+         {
+            if( a.E.off[e] != bk.off ) continue;
+            int r = a.E.row[e], c = a.E.col[e];
+            double u = Uj[(size_t)c * ld + r];
+            if( r != c ) u += Uj[(size_t)r * ld + c];
+            s0 += a.E.val[e] * u;
+         }
+         s0 = wsum(s0);
+         if( lane == 0 ) a.M[(size_t)min(i, j) * ldm + max(i, j)] = s0;
+      }
+      __syncthreads();
+   }
+   // LP block: single-variable rows through the column view (one thread per variable), longer rows one after the other
+   for( int j = threadIdx.x; j < m; j += NT )
+   {
+      double s0 = 0.0;
+      for( int p = a.colbeg[j]; p < a.colbeg[j + 1]; ++p )
+      {
+         const int l = a.colrow[p];
+         if( a.lpbeg[l + 1] - a.lpbeg[l] == 1 ) s0 += a.colval[p] * a.colval[p] * a.x[l] / a.s[l];
+      }
+      a.M[(size_t)j * ldm + j] += s0;
+   }
+   __syncthreads();
+   for( int l = 0; l < a.nlp; ++l )
+   {
+      const int b = a.lpbeg[l], cnt = a.lpbeg[l + 1] - b;
+      if( cnt < 2 ) continue;                               // uniform branch
+      const double w = a.x[l] / a.s[l];
+      for( int t = threadIdx.x; t < cnt * cnt; t += NT )
+      {
+         const int p = b + t / cnt, q = b + t % cnt;
+         const int i = a.lpind[p], j = a.lpind[q];
+         if( i >= j ) a.M[(size_t)j * ldm + i] += w * a.lpval[p] * a.lpval[q];
+      }
+      __syncthreads();
+   }
+}
+
+// Cholesky of M (lower, global memory) with diagonal regularisation `reg`; rdiag receives 1 / l_kk
+__device__ bool cholM(const SmallArgs& a, double reg, double* rdiag, int* flag)
+{
+   const int m = a.m, ldm = a.ldm;
+   for( int e = threadIdx.x; e < m * m; e += NT )
+   {
+      const int i = e % m, j = e / m;
+      if( i >= j ) a.Mfac[(size_t)j * ldm + i] = a.M[(size_t)j * ldm + i] + ((i == j) ? reg : 0.0);
+   }
+   if( threadIdx.x == 0 ) *flag = 0;
+   __syncthreads();
+   double* F = a.Mfac;
+   for( int k = 0; k < m; ++k )
+   {
+      if( threadIdx.x == 0 )
+      {
+         double d = F[(size_t)k * ldm + k];
+         if( !(d > 0.0) ) { *flag = 1; d = 1.0; }
+         double r = frsqrt(d);
+         rdiag[k] = r;
+         F[(size_t)k * ldm + k] = d * r;
+      }
+      __syncthreads();
+      const double r = rdiag[k];
+      for( int i = k + 1 + threadIdx.x; i < m; i += NT ) F[(size_t)k * ldm + i] *= r;
+      __syncthreads();
+      const int rem = m - k - 1;
+      for( int e = threadIdx.x; e < rem * rem; e += NT )
+      {
+         const int i = k + 1 + e % rem, j = k + 1 + e / rem;
+         if( i >= j ) F[(size_t)j * ldm + i] -= F[(size_t)k * ldm + i] * F[(size_t)k * ldm + j];
+      }
+      __syncthreads();
+   }
+   const bool ok = (*flag == 0);
+   __syncthreads();
+   return ok;
+}
+
+// v <- (L L')^-1 v with one warp: lane owns the rows r = lane, lane + 32, ... (m <= 256 -> 8 registers)
+__device__ void solveM(const SmallArgs& a, const double* rdiag, double* v)
+{
+   __syncthreads();
+   if( threadIdx.x < 32 )
+   {
+      const int lane = threadIdx.x, m = a.m, ldm = a.ldm;
+      const double* F = a.Mfac;
+      double r[SMALL_MAX_M / 32];
+#pragma unroll
+      for( int q = 0; q < SMALL_MAX_M / 32; ++q ) { int i = lane + 32 * q; r[q] = (i < m) ? v[i] : 0.0; }
+      for( int k = 0; k < m; ++k )                 // forward substitution, column oriented
+      {
+         double xk = 0.0;
+#pragma unroll
+         for( int q = 0; q < SMALL_MAX_M / 32; ++q ) if( q == (k >> 5) ) xk = r[q];
+         xk = __shfl_sync(0xffffffffu, xk, k & 31) * rdiag[k];
+#pragma unroll
+         for( int q = 0; q < SMALL_MAX_M / 32; ++q )
+         {
+            const int i = lane + 32 * q;
+            if( i == k ) r[q] = xk;
+            else if( i > k && i < m ) r[q] -= F[(size_t)k * ldm + i] * xk;
+         }
+      }
+      for( int k = m - 1; k >= 0; --k )            // backward substitution with L'
+      {
+         double xk = 0.0;
+#pragma unroll
+         for( int q = 0; q < SMALL_MAX_M / 32; ++q ) if( q == (k >> 5) ) xk = r[q];
+         xk = __shfl_sync(0xffffffffu, xk, k & 31) * rdiag[k];
+#pragma unroll
+         for( int q = 0; q < SMALL_MAX_M / 32; ++q )
+         {
+            const int i = lane + 32 * q;
+            if( i == k ) r[q] = xk;
+            else if( i < k ) r[q] -= F[(size_t)i * ldm + k] * xk;
+         }
+      }
+#pragma unroll
+      for( int q = 0; q < SMALL_MAX_M / 32; ++q ) { int i = lane + 32 * q; if( i < m ) v[i] = r[q]; }
+   }
+   __syncthreads();
+}
+
+// y = M x with M given by its lower triangle
+__device__ void symvM(const SmallArgs& a, const double* x, double* y)
+{
+   const int lane = threadIdx.x & 31, m = a.m, ldm = a.ldm;
+   for( int i = threadIdx.x >> 5; i < m; i += NT / 32 )
+   {
+      double s = 0.0;
+      for( int k = lane; k < i; k += 32 ) s += a.M[(size_t)k * ldm + i] * x[k];
+      for( int k = i + lane; k < m; k += 32 ) s += a.M[(size_t)i * ldm + k] * x[k];
+      s = wsum(s);
+      if( lane == 0 ) y[i] = s;
+   }
+   __syncthreads();
+}
+
+// smallest eigenvalue (safe estimate: Ritz value minus residual bound) of the symmetric n x n matrix B by Lanczos with full
+// re-orthogonalisation; Q: scratch of (steps + 2) * n doubles.  Result to all threads.
+__device__ double lanczos_min(int n, int ld, const double* B, double* Q, double* red, double* al, double* be, double* coef, double* shs)
+{
+   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+   const int steps = min(n, SMALL_LZ_STEPS);
+   double nr = 0.0;
+   for( int i = tid; i < n; i += NT )
+   {
+      unsigned h = (unsigned)i * 2654435761u + 12345u;
+      h ^= h >> 15; h *= 2246822519u; h ^= h >> 13;
+      double v = 0.5 + (double)(h & 0xffffu) / 65536.0;
+      Q[i] = v;
+      nr += v * v;
+   }
+   nr = bsum(nr, red);
+   const double inv0 = 1.0 / sqrt(nr);
+   for( int i = tid; i < n; i += NT ) Q[i] *= inv0;
+   __syncthreads();
+   int kdone = 0;
+   for( int j = 0; j < steps; ++j )
+   {
+      const double* v = Q + (size_t)j * n;
+      double* w = Q + (size_t)(j + 1) * n;
+      for( int i = wid; i < n; i += NT / 32 )               // w = B v (column i of the symmetric matrix is contiguous)
+      {
+         const double* col = B + (size_t)i * ld;
+         double s = 0.0;
+         for( int k = lane; k < n; k += 32 ) s += col[k] * v[k];
+         s = wsum(s);
+         if( lane == 0 ) w[i] = s;
+      }
+      __syncthreads();
+      double d = 0.0;
+      for( int i = tid; i < n; i += NT ) d += w[i] * v[i];
+      const double alpha = bsum(d, red);
+      const double bprev = (j > 0) ? be[j - 1] : 0.0;
+      for( int i = tid; i < n; i += NT ) w[i] -= alpha * v[i] + (j > 0 ? bprev * Q[(size_t)(j - 1) * n + i] : 0.0);
+      __syncthreads();
+      for( int pass = 0; pass < 2; ++pass )
+      {
+         for( int q = wid; q <= j; q += NT / 32 )
+         {
+            const double* vq = Q + (size_t)q * n;
+            double dd = 0.0;
+            for( int i = lane; i < n; i += 32 ) dd += w[i] * vq[i];
+            dd = wsum(dd);
+            if( lane == 0 ) coef[q] = dd;
+         }
+         __syncthreads();
+         for( int i = tid; i < n; i += NT )
+         {
+            double sacc = 0.0;
+            for( int q = 0; q <= j; ++q ) sacc += coef[q] * Q[(size_t)q * n + i];
+            w[i] -= sacc;
+         }
+         __syncthreads();
+      }
+      double nn = 0.0;
+      for( int i = tid; i < n; i += NT ) nn += w[i] * w[i];
+      const double beta = sqrt(bsum(nn, red));
+      if( tid == 0 ) { al[j] = alpha; be[j] = beta; }
+      kdone = j + 1;
+      if( beta <= 1e-13 * (fabs(alpha) + bprev + 1e-300) ) break;          // invariant subspace: Ritz values are exact
+      const double cf = 1.0 / beta;
+      for( int i = tid; i < n; i += NT ) w[i] *= cf;
+      __syncthreads();
+   }
+   __syncthreads();
+   // smallest eigenvalue of the kdone x kdone tridiagonal matrix: parallel multisection on Sturm counts
+   const int k = kdone;
+   double lo = 1e300, hi = -1e300;
+   for( int i = 0; i < k; ++i )
+   {
+      double r = (i > 0 ? fabs(be[i - 1]) : 0.0) + (i < k - 1 ? fabs(be[i]) : 0.0);
+      lo = fmin(lo, al[i] - r); hi = fmax(hi, al[i] + r);
+   }
+   const double width0 = hi - lo;
+   for( int round = 0; round < 4 && (hi - lo) > 1e-12 * width0 + 1e-300; ++round )
+   {
+      // thread t tests x_t = lo + (t+1) (hi - lo) / (NT + 1): smallest eigenvalue < x_t ?
+      const double xt = lo + (tid + 1) * (hi - lo) / (NT + 1);
+      int cnt = 0;
+      double dd = 1.0;
+      for( int i = 0; i < k; ++i )
+      {
+         double b2 = (i > 0) ? be[i - 1] * be[i - 1] : 0.0;
+         dd = al[i] - xt - (i > 0 ? b2 / dd : 0.0);
+         if( dd == 0.0 ) dd = 1e-300;
+         if( dd < 0.0 ) ++cnt;
+      }
+      // the bracket becomes [largest x_t with cnt == 0, smallest x_t with cnt >= 1]
+      double below = (cnt == 0) ? xt : lo;
+      double above = (cnt >= 1) ? -xt : -hi;
+      below = bmax(below, red);
+      above = -bmax(above, red);
+      lo = below; hi = above;
+   }
+   double theta = lo;
+   double resid = 0.0;
+   if( k < n )
+   {
+      // |beta_k s_k| with s from the three-term recurrence (thread-uniform, cheap: k <= 32)
+      double sm1 = 0.0, s0 = 1.0, nrm = 1.0, last = 1.0;
+      for( int i = 0; i < k - 1; ++i )
+      {
+         double s1 = ((theta - al[i]) * s0 - (i > 0 ? be[i - 1] * sm1 : 0.0)) / be[i];
+         sm1 = s0; s0 = s1; nrm += s1 * s1; last = s1;
+         if( nrm > 1e200 ) { sm1 *= 1e-100; s0 *= 1e-100; last *= 1e-100; nrm *= 1e-200; }
+      }
+      if( be[k - 1] > 1e-13 * (fabs(al[k - 1]) + 1e-300) ) resid = fabs(be[k - 1]) * fabs(last) / sqrt(nrm);
+   }
+   (void)shs;
+   __syncthreads();
+   return theta - resid;
+}
+
+
+// ---- warp-level Lanczos: the matrix (n <= 64) and the Krylov vectors live in shared memory, one warp does everything ----
+// Bs: n x n symmetric, row stride LDS.  Qs: (SMALL_LZ_STEPS + 2) vectors with stride LDS.  ab: alpha[32], beta[32], w[64] scratch.
+// Returns (to all lanes) the safe estimate Ritz value - residual bound of the smallest eigenvalue.
+__device__ double lanczos_warp(int n, const double* Bs, double* Qs, double* ab)
+{
+   const int lane = threadIdx.x & 31;
+   const int r0 = lane, r1 = lane + 32;
+   const bool h0 = r0 < n, h1 = r1 < n;
+   double* al = ab;
+   double* be = ab + SMALL_LZ_STEPS;
+   double* ws = ab + 2 * SMALL_LZ_STEPS;            // 64 doubles: current w, shared between the lanes
+   const int steps = min(n, SMALL_LZ_STEPS);
+   double v0 = 0.0, v1 = 0.0;
+   {
+      unsigned h = (unsigned)r0 * 2654435761u + 12345u; h ^= h >> 15; h *= 2246822519u; h ^= h >> 13;
+      if( h0 ) v0 = 0.5 + (double)(h & 0xffffu) / 65536.0;
+      h = (unsigned)r1 * 2654435761u + 12345u; h ^= h >> 15; h *= 2246822519u; h ^= h >> 13;
+      if( h1 ) v1 = 0.5 + (double)(h & 0xffffu) / 65536.0;
+      double nr = wsum(v0 * v0 + v1 * v1);
+      double inv = 1.0 / sqrt(nr);
+      v0 *= inv; v1 *= inv;
+      if( h0 ) Qs[r0] = v0;
+      if( h1 ) Qs[r1] = v1;
+   }
+   __syncwarp();
+   double p0 = 0.0, p1 = 0.0, bprev = 0.0;          // previous Lanczos vector (this lane's rows)
+   int kdone = 0;
+   for( int j = 0; j < steps; ++j )
+   {
+      const double* vj = Qs + j * LDS;
+      double w0 = 0.0, w1 = 0.0;
+      for( int k = 0; k < n; ++k )
+      {
+         const double vk = vj[k];
+         if( h0 ) w0 += Bs[r0 * LDS + k] * vk;
+         if( h1 ) w1 += Bs[r1 * LDS + k] * vk;
+      }
+      const double alpha = wsum(w0 * v0 + w1 * v1);
+      w0 -= alpha * v0 + bprev * p0;
+      w1 -= alpha * v1 + bprev * p1;
+      // full re-orthogonalisation, twice: lane q forms the inner product with vector q (q <= j <= 31), then all lanes update
+      for( int pass = 0; pass < 2; ++pass )
+      {
+         if( h0 ) ws[r0] = w0;
+         if( h1 ) ws[r1] = w1;
+         __syncwarp();
+         double cq = 0.0;
+         if( lane <= j )
+         {
+            const double* vq = Qs + lane * LDS;
+            for( int i = 0; i < n; ++i ) cq += ws[i] * vq[i];
+         }
+         for( int q = 0; q <= j; ++q )
+         {
+            const double c = __shfl_sync(0xffffffffu, cq, q);
+            if( h0 ) w0 -= c * Qs[q * LDS + r0];
+            if( h1 ) w1 -= c * Qs[q * LDS + r1];
+         }
+         __syncwarp();
+      }
+      const double beta = sqrt(wsum(w0 * w0 + w1 * w1));
+      if( lane == 0 ) { al[j] = alpha; be[j] = beta; }
+      kdone = j + 1;
+      if( beta <= 1e-13 * (fabs(alpha) + bprev + 1e-300) ) break;
+      const double cf = 1.0 / beta;
+      p0 = v0; p1 = v1; bprev = beta;
+      v0 = w0 * cf; v1 = w1 * cf;
+      if( h0 ) Qs[(j + 1) * LDS + r0] = v0;
+      if( h1 ) Qs[(j + 1) * LDS + r1] = v1;
+      __syncwarp();
+   }
+   __syncwarp();
+   const int k = kdone;
+   double lo = 1e300, hi = -1e300;
+   for( int i = 0; i < k; ++i )
+   {
+      double r = (i > 0 ? fabs(be[i - 1]) : 0.0) + (i < k - 1 ? fabs(be[i]) : 0.0);
+      lo = fmin(lo, al[i] - r); hi = fmax(hi, al[i] + r);
+   }
+   const double width0 = hi - lo;
+   for( int round = 0; round < 6 && (hi - lo) > 1e-9 * width0 + 1e-300; ++round )
+   {
+      const double xt = lo + (lane + 1) * (hi - lo) / 33.0;
+      int cnt = 0;
+      double dd = 1.0;
+      for( int i = 0; i < k; ++i )
+      {
+         double b2 = (i > 0) ? be[i - 1] * be[i - 1] : 0.0;
+         dd = al[i] - xt - (i > 0 ? b2 / dd : 0.0);
+         if( dd == 0.0 ) dd = 1e-300;
+         if( dd < 0.0 ) ++cnt;
+      }
+      double below = (cnt == 0) ? xt : lo;
+      double above = (cnt >= 1) ? xt : hi;
+#pragma unroll
+      for( int o = 16; o > 0; o >>= 1 )
+      {
+         below = fmax(below, __shfl_xor_sync(0xffffffffu, below, o));
+         above = fmin(above, __shfl_xor_sync(0xffffffffu, above, o));
+      }
+      lo = below; hi = above;
+   }
+   const double theta = lo;
+   double resid = 0.0;
+   if( k < n && be[k - 1] > 1e-13 * (fabs(al[k - 1]) + 1e-300) )
+   {
+      double sm1 = 0.0, s0 = 1.0, nrm = 1.0, last = 1.0;
+      for( int i = 0; i < k - 1; ++i )
+      {
+         double s1 = ((theta - al[i]) * s0 - (i > 0 ? be[i - 1] * sm1 : 0.0)) / be[i];
+         sm1 = s0; s0 = s1; nrm += s1 * s1; last = s1;
+         if( nrm > 1e200 ) { sm1 *= 1e-100; s0 *= 1e-100; last *= 1e-100; nrm *= 1e-200; }
+      }
+      resid = fabs(be[k - 1]) * fabs(last) / sqrt(nrm);
+   }
+   return theta - resid;
+}
+
+// Cholesky of M + reg I entirely in shared memory (m <= 64, row stride LDS); rdiag receives 1 / l_kk
+__device__ bool cholM_smem(const SmallArgs& a, double reg, double* Ms, double* rdiag, int* flag)
+{
+   const int m = a.m, ldm = a.ldm;
+   for( int e = threadIdx.x; e < m * m; e += NT )
+   {
+      const int i = e % m, j = e / m;
+      if( i >= j ) Ms[i * LDS + j] = a.M[(size_t)j * ldm + i] + ((i == j) ? reg : 0.0);
+   }
+   if( threadIdx.x == 0 ) *flag = 0;
+   __syncthreads();
+   for( int k = 0; k < m; ++k )
+   {
+      if( threadIdx.x == 0 )
+      {
+         double d = Ms[k * LDS + k];
+         if( !(d > 0.0) ) { *flag = 1; d = 1.0; }
+         double r = frsqrt(d);
+         rdiag[k] = r;
+         Ms[k * LDS + k] = d * r;
+      }
+      __syncthreads();
+      const double r = rdiag[k];
+      for( int i = k + 1 + threadIdx.x; i < m; i += NT ) Ms[i * LDS + k] *= r;
+      __syncthreads();
+      const int rem = m - k - 1;
+      for( int e = threadIdx.x; e < rem * rem; e += NT )
+      {
+         const int i = k + 1 + e % rem, j = k + 1 + e / rem;
+         if( i >= j ) Ms[i * LDS + j] -= Ms[i * LDS + k] * Ms[j * LDS + k];
+      }
+      __syncthreads();
+   }
+   const bool ok = (*flag == 0);
+   __syncthreads();
+   return ok;
+}
+
+// v <- (L L')^-1 v with L in shared memory (m <= 64): one warp, lane owns rows lane and lane + 32
+__device__ void solveM_smem(int m, const double* Ms, const double* rdiag, double* v)
+{
+   __syncthreads();
+   if( threadIdx.x < 32 )
+   {
+      const int lane = threadIdx.x;
+      double r0 = (lane < m) ? v[lane] : 0.0, r1 = (lane + 32 < m) ? v[lane + 32] : 0.0;
+      for( int k = 0; k < m; ++k )
+      {
+         double xk = __shfl_sync(0xffffffffu, (k < 32) ? r0 : r1, k & 31) * rdiag[k];
+         if( lane == k ) r0 = xk; else if( lane > k && lane < m ) r0 -= Ms[lane * LDS + k] * xk;
+         if( lane + 32 == k ) r1 = xk; else if( lane + 32 > k && lane + 32 < m ) r1 -= Ms[(lane + 32) * LDS + k] * xk;
+      }
+      for( int k = m - 1; k >= 0; --k )
+      {
+         double xk = __shfl_sync(0xffffffffu, (k < 32) ? r0 : r1, k & 31) * rdiag[k];
+         if( lane == k ) r0 = xk; else if( lane < k ) r0 -= Ms[k * LDS + lane] * xk;
+         if( lane + 32 == k ) r1 = xk; else if( lane + 32 < k ) r1 -= Ms[k * LDS + lane + 32] * xk;
+      }
+      if( lane < m ) v[lane] = r0;
+      if( lane + 32 < m ) v[lane + 32] = r1;
+   }
+   __syncthreads();
+}
+
+__global__ void __launch_bounds__(NT, 1)
+ipm_small_kernel(const SmallArgs a)
+{
+   extern __shared__ __align__(16) double smem[];
+   double* sh = smem;                               // 64 x 65
+   double* sh2 = sh + SMALL_MAX_N * LDS;            // 64 x 65
+   double* red = sh2 + SMALL_MAX_N * LDS;           // 32
+   double* rdiag = red + 32;                        // 64
+   double* rdiagM = rdiag + SMALL_MAX_N;            // 256
+   double* al = rdiagM + SMALL_MAX_M;               // 32 + 32 + 40
+   double* be = al + SMALL_LZ_STEPS;
+   double* coef = be + SMALL_LZ_STEPS;
+   double* lzq = coef + SMALL_LZ_STEPS + 8;         // 2 x (SMALL_LZ_STEPS + 2) x 65 : Krylov vectors of the two warp-level Lanczos runs
+   double* lzab = lzq + 2 * (SMALL_LZ_STEPS + 2) * LDS;   // 2 x (32 + 32 + 64)
+   double* Msh = lzab + 2 * (2 * SMALL_LZ_STEPS + 64);     // 64 x 65 : factor of the Schur complement when m <= 64
+   double* lam2 = Msh + SMALL_MAX_N * LDS;          // 2 results
+   Ctl* c = reinterpret_cast<Ctl*>(lam2 + 8);
+   int* flag = reinterpret_cast<int*>(c + 1);
+   const bool msmall = (a.m <= SMALL_MAX_N);
+   const int tid = threadIdx.x;
+   const int m = a.m, nb = a.nb, nlp = a.nlp;
+   const double inftol = 1e-8;
+   long long pc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+   long long tq = clock64();
+#define TICK(k) do { long long _n = clock64(); pc[k] += _n - tq; tq = _n; } while( 0 )
+
+   if( tid == 0 )
+   {
+      c->iter = 0; c->stall = 0; c->backtracks = 0; c->phase = SDPCUDA_NOINFO; c->stop = SDPCUDA_STOP_ITERLIMIT; c->done = 0;
+      c->pfeasever = 0; c->dfeasever = 0; c->bestmerit = 1e300; c->lastap = 0.0; c->lastad = 0.0; c->xfail = 0;
+      c->mu = 0; c->pobj = 0; c->dobj = 0; c->relgap = 1e30; c->pinf = 1e30; c->dinf = 1e30;
+   }
+   for( long long i = tid; i < a.arena; i += NT ) { a.dX[i] = 0.0; a.dS[i] = 0.0; }
+   __syncthreads();
+
+   for( ; ; )
+   {
+      // ---------------- residuals and statistics ----------------
+      assemble(a, a.y, 1.0, a.K);
+      double sRd = 0.0, sXS = 0.0;
+      for( long long i = tid; i < a.arena; i += NT )
+      {
+         double sv = a.S[i], r = a.K[i] - sv;
+         a.Rd[i] = r;
+         sRd += r * r;
+         sXS += a.X[i] * sv;
+      }
+      sRd = bsum(sRd, red); sXS = bsum(sXS, red);
+      applyA(a, a.X, a.AX);
+      lpcols(a, a.x, a.DTx, false);
+      double s6 = 0, s7 = 0, s8 = 0, m17 = 0;
+      for( int j = tid; j < m; j += NT )
+      {
+         double ax = a.AX[j] + a.DTx[j];
+         double r = a.b[j] - ax;
+         a.rp[j] = r;
+         s6 += r * r; s7 += ax * ax; s8 += a.b[j] * a.y[j]; m17 = fmax(m17, fabs(r));
+      }
+      s6 = bsum(s6, red); s7 = bsum(s7, red); s8 = bsum(s8, red); m17 = bmax(m17, red);
+      lprows(a, a.y, a.Dy);
+      double s2 = 0, s3 = 0, s4 = 0, s5 = 0, m16 = 0;
+      for( int l = tid; l < nlp; l += NT )
+      {
+         double d = a.Dy[l], r = d - a.lprhs[l] - a.s[l];
+         a.rdlp[l] = r;
+         s2 += r * r; s3 += a.x[l] * a.s[l]; s4 += a.lprhs[l] * a.x[l];
+         double hh = d - a.s[l]; s5 += hh * hh; m16 = fmax(m16, fabs(r));
+      }
+      s2 = bsum(s2, red); s3 = bsum(s3, red); s4 = bsum(s4, red); s5 = bsum(s5, red); m16 = bmax(m16, red);
+      double cx = 0.0, crd = 0.0;
+      for( int e = tid; e < a.cnnz; e += NT )
+      {
+         long long p = a.cpos[e], q = a.cmirror[e];
+         double cv = a.cval[e];
+         cx += cv * (a.X[p] + (p != q ? a.X[q] : 0.0));
+         crd += cv * (a.Rd[p] + (p != q ? a.Rd[q] : 0.0));
+      }
+      cx = bsum(cx, red); crd = bsum(crd, red);
+
+      TICK(0);
+      // ---------------- factorisations of S and X (their failure means the last step left the cone) ----------------
+      bool okS = true, okX = true;
+      for( int k = 0; k < nb; ++k )
+      {
+         const SmallBlock bk = a.blk[k];
+         okS = cholinv(bk.n, bk.ld, a.S + bk.off, a.L + bk.off, a.Linv + bk.off, sh, sh2, rdiag, flag) && okS;
+         okX = cholinv(bk.n, bk.ld, a.X + bk.off, a.LX + bk.off, a.LXinv + bk.off, sh, sh2, rdiag, flag) && okX;
+      }
+      if( !okS || !okX )
+      {
+         if( tid == 0 )
+         {
+            if( c->iter == 0 || c->backtracks >= 8 ) { c->stop = SDPCUDA_STOP_NUMERICS; c->done = 1; }
+            ++c->backtracks;
+         }
+         __syncthreads();
+         if( c->done ) break;
+         if( !okX )
+         {
+            const double h = -0.5 * c->lastap;
+            for( long long i = tid; i < a.arena; i += NT ) a.X[i] += h * a.dX[i];
+            for( int l = tid; l < nlp; l += NT ) a.x[l] += h * a.dx[l];
+         }
+         if( !okS )
+         {
+            const double h = -0.5 * c->lastad;
+            for( long long i = tid; i < a.arena; i += NT ) a.S[i] += h * a.dS[i];
+            for( int l = tid; l < nlp; l += NT ) a.s[l] += h * a.ds[l];
+            for( int j = tid; j < m; j += NT ) a.y[j] += h * a.dy[j];
+         }
+         __syncthreads();
+         if( tid == 0 ) { if( !okX ) c->lastap *= 0.5; if( !okS ) c->lastad *= 0.5; }
+         __syncthreads();
+         continue;
+      }
+
+      TICK(1);
+      // ---------------- termination tests (same rules as ipm.cu) ----------------
+      if( tid == 0 )
+      {
+         c->backtracks = 0;
+         const double nrd2 = sRd + s2, xs = sXS + s3;
+         c->pobj = cx + s4;
+         c->dobj = s8;
+         c->mu = a.N > 0 ? xs / a.N : 0.0;
+         c->pinf = sqrt(s6) / (1.0 + a.normb);
+         c->dinf = sqrt(nrd2) / (1.0 + a.normC);
+         const double dinfabs = fmax(sqrt(sRd), m16), pinfabs = m17;
+         c->relgap = fabs(c->pobj - c->dobj) / fmax(1.0, 0.5 * (fabs(c->pobj) + fabs(c->dobj)));
+         const double rayd = sqrt(fmax(0.0, sRd + 2.0 * crd + a.normCsdp2 + s5));
+         const bool pfeas = c->pinf <= a.feastol && pinfabs <= fmax(a.feastol, 1e-9 * (1 + a.normb));
+         const bool dfeas = c->dinf <= a.feastol && dinfabs <= a.feastol;
+         c->pfeasever |= pfeas ? 1 : 0;
+         c->dfeasever |= dfeas ? 1 : 0;
+         c->phase = pfeas ? (dfeas ? SDPCUDA_PDFEAS : SDPCUDA_PFEAS) : (dfeas ? SDPCUDA_DFEAS : SDPCUDA_NOINFO);
+         c->rdzero = (sRd <= 1e-28 * (1.0 + a.normCsdp2)) ? 1 : 0;
+         if( a.verbose )
+            printf("  [cuda-1cta] it %3d  pobj % .10e  dobj % .10e  gap %.2e  pinf %.2e  dinf %.2e  mu %.2e\n", c->iter, c->pobj, c->dobj, c->relgap, c->pinf, c->dinf, c->mu);
+         if( pfeas && dfeas && c->relgap <= a.gaptol && (a.absgaptol <= 0 || fabs(c->pobj - c->dobj) <= a.absgaptol) )
+         { c->phase = SDPCUDA_PDOPT; c->stop = SDPCUDA_STOP_CONVERGED; c->done = 1; }
+         else if( c->pobj > 0 && sqrt(s7) / c->pobj < inftol )
+         { c->phase = c->pfeasever ? SDPCUDA_PFEAS_DINF : SDPCUDA_DINF; c->stop = SDPCUDA_STOP_INFEASCERT; c->done = 1; }
+         else if( c->dfeasever && c->dobj < 0 && rayd / (-c->dobj) < inftol )
+         { c->phase = SDPCUDA_PINF_DFEAS; c->stop = SDPCUDA_STOP_INFEASCERT; c->done = 1; }
+         else if( pfeas && a.objlimit < 1e20 && c->pobj > a.objlimit )
+         { c->phase = SDPCUDA_PUNBD; c->stop = SDPCUDA_STOP_OBJLIMIT; c->done = 1; }
+         else if( c->iter >= a.maxiter ) { c->stop = SDPCUDA_STOP_ITERLIMIT; c->done = 1; }
+         else
+         {
+            double merit = fmax(c->relgap, fmax(c->pinf, c->dinf));
+            if( merit < 0.9 * c->bestmerit ) { c->bestmerit = merit; c->stall = 0; }
+            else if( ++c->stall >= 15 ) { c->stop = SDPCUDA_STOP_NUMERICS; c->done = 1; }
+         }
+      }
+      __syncthreads();
+      if( c->done ) break;
+      const bool rdzero = c->rdzero != 0;
+      const double mu = c->mu;
+
+      // ---------------- S^-1, Schur complement, its factorisation ----------------
+      for( int k = 0; k < nb; ++k )
+      {
+         const SmallBlock bk = a.blk[k];
+         gemmb(bk.n, bk.ld, true, false, 1.0, a.Linv + bk.off, a.Linv + bk.off, 0.0, a.Sinv + bk.off);
+      }
+      TICK(2);
+      schur(a);
+      TICK(3);
+      {
+         double maxd = 0.0;
+         for( int j = tid; j < m; j += NT ) maxd = fmax(maxd, a.M[(size_t)j * a.ldm + j]);
+         maxd = bmax(maxd, red);
+         double reg = 0.0;
+         bool mok = false;
+         for( int tries = 0; tries < 8 && !mok; ++tries )
+         {
+            mok = msmall ? cholM_smem(a, reg, Msh, rdiagM, flag) : cholM(a, reg, rdiagM, flag);
+            if( !mok ) reg = (reg == 0.0) ? 1e-14 * fmax(maxd, 1e-300) : reg * 100.0;
+         }
+         if( !mok )
+         {
+            if( tid == 0 ) { c->stop = SDPCUDA_STOP_NUMERICS; c->done = 1; }
+            __syncthreads();
+            break;
+         }
+      }
+
+      TICK(4);
+      // ---------------- predictor and corrector ----------------
+      bool failed = false;
+      for( int pass = 0; pass < 2; ++pass )
+      {
+         double* oX = pass == 0 ? a.dXa : a.dX;
+         double* oS = pass == 0 ? a.dSa : a.dS;
+         double* ox = pass == 0 ? a.dxa : a.dx;
+         double* os = pass == 0 ? a.dsa : a.ds;
+         const double sigmamu = (pass == 1) ? c->sigma * mu : 0.0;
+         // K = sym((sigma mu I - dXa dSa - X Rd) S^-1) - X
+         const bool haveT = (!rdzero) || pass == 1;
+         for( int k = 0; k < nb; ++k )
+         {
+            const SmallBlock bk = a.blk[k];
+            if( haveT )
+            {
+               if( !rdzero ) gemmb(bk.n, bk.ld, false, false, -1.0, a.X + bk.off, a.Rd + bk.off, 0.0, a.T1 + bk.off);
+               if( pass == 1 )
+               {
+                  gemmb(bk.n, bk.ld, false, false, -1.0, a.dXa + bk.off, a.dSa + bk.off, rdzero ? 0.0 : 1.0, a.T1 + bk.off);
+                  for( int i = tid; i < bk.n; i += NT ) a.T1[bk.off + (size_t)i * bk.ld + i] += sigmamu;
+                  __syncthreads();
+               }
+               gemmb(bk.n, bk.ld, false, false, 1.0, a.T1 + bk.off, a.Sinv + bk.off, 0.0, a.K + bk.off);
+               symavg(bk.n, bk.ld, a.K + bk.off, a.X + bk.off);
+            }
+            else
+            {
+               for( int e = tid; e < bk.n * bk.ld; e += NT ) a.K[bk.off + e] = -a.X[bk.off + e];
+               __syncthreads();
+            }
+         }
+         for( int l = tid; l < nlp; l += NT )
+         {
+            double cc = -a.x[l] * a.rdlp[l];
+            if( pass == 1 ) cc += sigmamu - a.dxa[l] * a.dsa[l];
+            a.klp[l] = cc / a.s[l] - a.x[l];
+         }
+         __syncthreads();
+         applyA(a, a.K, a.g);
+         lpcols(a, a.klp, a.g, true);
+         for( int j = tid; j < m; j += NT ) { a.g[j] -= a.rp[j]; a.dy[j] = a.g[j]; }
+         if( msmall ) solveM_smem(m, Msh, rdiagM, a.dy); else solveM(a, rdiagM, a.dy);
+         symvM(a, a.dy, a.tm1);
+         for( int j = tid; j < m; j += NT ) a.tm1[j] = a.g[j] - a.tm1[j];
+         if( msmall ) solveM_smem(m, Msh, rdiagM, a.tm1); else solveM(a, rdiagM, a.tm1);
+         for( int j = tid; j < m; j += NT ) a.dy[j] += a.tm1[j];
+         __syncthreads();
+         // dS = A'dy (+ Rd), dX = K - sym(X (A'dy) S^-1)
+         assemble(a, a.dy, 0.0, oS);
+         for( int k = 0; k < nb; ++k )
+         {
+            const SmallBlock bk = a.blk[k];
+            gemmb(bk.n, bk.ld, false, false, 1.0, a.X + bk.off, oS + bk.off, 0.0, a.T1 + bk.off);
+            gemmb(bk.n, bk.ld, false, false, 1.0, a.T1 + bk.off, a.Sinv + bk.off, 0.0, a.T2 + bk.off);
+            symavg(bk.n, bk.ld, a.T2 + bk.off, nullptr);
+         }
+         for( long long i = tid; i < a.arena; i += NT )
+         {
+            oX[i] = a.K[i] - a.T2[i];
+            if( !rdzero ) oS[i] += a.Rd[i];
+         }
+         __syncthreads();
+         lprows(a, a.dy, a.Ddy);
+         double rp1 = -1e300, rd1 = -1e300;
+         for( int l = tid; l < nlp; l += NT )
+         {
+            const double ddy = a.Ddy[l];
+            const double vx = a.klp[l] - a.x[l] / a.s[l] * ddy;
+            const double vs = ddy + a.rdlp[l];
+            ox[l] = vx; os[l] = vs;
+            if( vx < 0.0 ) rp1 = fmax(rp1, a.x[l] / vx);
+            if( vs < 0.0 ) rd1 = fmax(rd1, a.s[l] / vs);
+         }
+         rp1 = bmax(rp1, red); rd1 = bmax(rd1, red);
+         double apmax = (rp1 > -1e299) ? -rp1 : 1e30, admax = (rd1 > -1e299) ? -rd1 : 1e30;
+         TICK(5);
+         // SDP step lengths from lambda_min(LXinv dX LXinv') and lambda_min(Linv dS Linv')
+         for( int k = 0; k < nb; ++k )
+         {
+            const SmallBlock bk = a.blk[k];
+            gemmb(bk.n, bk.ld, false, false, 1.0, a.LXinv + bk.off, oX + bk.off, 0.0, a.T1 + bk.off);
+            gemmb(bk.n, bk.ld, false, true, 1.0, a.T1 + bk.off, a.LXinv + bk.off, 0.0, a.T2 + bk.off);
+            gemmb(bk.n, bk.ld, false, false, 1.0, a.Linv + bk.off, oS + bk.off, 0.0, a.T1 + bk.off);
+            gemmb(bk.n, bk.ld, false, true, 1.0, a.T1 + bk.off, a.Linv + bk.off, 0.0, a.K + bk.off);
+            // symmetrised copies into shared memory (sh: X side, sh2: S side), then one warp per matrix
+            for( int e = tid; e < bk.n * bk.n; e += NT )
+            {
+               const int i = e % bk.n, j = e / bk.n;
+               sh[i * LDS + j] = 0.5 * (a.T2[bk.off + (size_t)j * bk.ld + i] + a.T2[bk.off + (size_t)i * bk.ld + j]);
+               sh2[i * LDS + j] = 0.5 * (a.K[bk.off + (size_t)j * bk.ld + i] + a.K[bk.off + (size_t)i * bk.ld + j]);
+            }
+            __syncthreads();
+            if( tid < 64 )
+            {
+               const int wv = tid >> 5;
+               const double lv = lanczos_warp(bk.n, wv == 0 ? sh : sh2, lzq + wv * (SMALL_LZ_STEPS + 2) * LDS, lzab + wv * (2 * SMALL_LZ_STEPS + 64));
+               if( (tid & 31) == 0 ) lam2[wv] = lv;
+            }
+            __syncthreads();
+            const double lx = lam2[0], ls = lam2[1];
+            __syncthreads();
+            if( !(lx == lx) || !(ls == ls) ) failed = true;
+            if( lx < -1e-300 ) apmax = fmin(apmax, -1.0 / lx);
+            if( ls < -1e-300 ) admax = fmin(admax, -1.0 / ls);
+         }
+         TICK(6);
+         if( failed ) break;
+         if( pass == 0 )
+         {
+            const double ap = fmin(1.0, 0.98 * apmax), ad = fmin(1.0, 0.98 * admax);
+            double sa = 0.0;
+            for( long long i = tid; i < a.arena; i += NT ) sa += (a.X[i] + ap * oX[i]) * (a.S[i] + ad * oS[i]);
+            for( int l = tid; l < nlp; l += NT ) sa += (a.x[l] + ap * ox[l]) * (a.s[l] + ad * os[l]);
+            sa = bsum(sa, red);
+            if( tid == 0 )
+            {
+               const double mua = a.N > 0 ? sa / a.N : 0.0;
+               const double ratio = mu > 0 ? fmax(0.0, mua / mu) : 0.0;
+               const double mn = fmin(ap, ad);
+               const double expo = (mu > 1e-6) ? fmax(1.0, 3.0 * mn * mn) : 1.0;
+               double sg = fmin(1.0, pow(ratio, expo));
+               if( a.setting >= 3 ) sg = fmax(sg, 0.1);
+               c->sigma = sg; c->ap = ap; c->ad = ad;
+            }
+            __syncthreads();
+         }
+         else
+         {
+            if( tid == 0 )
+            {
+               const double gamma = a.gammabase + (0.99 - a.gammabase) * fmin(c->ap, c->ad);
+               c->ap = fmin(1.0, gamma * apmax); c->ad = fmin(1.0, gamma * admax);
+            }
+            __syncthreads();
+         }
+      }
+      if( failed || (c->ap < 1e-8 && c->ad < 1e-8) )
+      {
+         __syncthreads();
+         if( tid == 0 ) { c->stop = SDPCUDA_STOP_NUMERICS; c->done = 1; }
+         __syncthreads();
+         break;
+      }
+      const double ap = c->ap, ad = c->ad;
+      for( long long i = tid; i < a.arena; i += NT ) { a.X[i] += ap * a.dX[i]; a.S[i] += ad * a.dS[i]; }
+      for( int l = tid; l < nlp; l += NT ) { a.x[l] += ap * a.dx[l]; a.s[l] += ad * a.ds[l]; }
+      for( int j = tid; j < m; j += NT ) a.y[j] += ad * a.dy[j];
+      __syncthreads();
+      if( tid == 0 ) { c->lastap = ap; c->lastad = ad; ++c->iter; }
+      __syncthreads();
+   }
+   __syncthreads();
+   if( tid == 0 )
+   {
+      SmallResult r;
+      r.phase = c->phase; r.stop = c->stop; r.iterations = c->iter; r.backtracks = c->backtracks;
+      r.pobj = c->pobj; r.dobj = c->dobj; r.relgap = c->relgap; r.pinf = c->pinf; r.dinf = c->dinf; r.mu = c->mu;
+      *a.out = r;
+      if( a.verbose >= 2 )
+         printf("  [cuda-1cta cycles] resid %lld | fact S,X %lld | tests+Sinv %lld | schur %lld | chol M %lld | directions %lld | step lengths %lld\n",
+            pc[0], pc[1], pc[2], pc[3], pc[4], pc[5], pc[6]);
+   }
+}
+
+} // namespace
+
+cudaError_t launch_ipm_small(cudaStream_t st, const SmallArgs& a)
+{
+   const size_t smem = (2 * SMALL_MAX_N * LDS + 32 + SMALL_MAX_N + SMALL_MAX_M + 3 * SMALL_LZ_STEPS + 8 + 2 * (SMALL_LZ_STEPS + 2) * LDS
+      + 2 * (2 * SMALL_LZ_STEPS + 64) + SMALL_MAX_N * LDS + 8) * sizeof(double) + sizeof(Ctl) + 64;
+   static bool configured[64] = {false};
+   int dev = 0;
+   SDPK_CUDA_CHECK( cudaGetDevice(&dev) );
+   if( !configured[dev & 63] )
+   {
+      SDPK_CUDA_CHECK( cudaFuncSetAttribute(ipm_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) );
+      configured[dev & 63] = true;
+   }
+   ipm_small_kernel<<<1, NT, smem, st>>>(a);
+   count_launch();
+   return cudaGetLastError();
+}
+
+} // namespace sdpk

@@ -1,0 +1,48 @@
+// ipm_small.cuh — single-launch interior-point solver for small relaxations (the B&B node regime of SCIP-SDP's shipped
+// instances: blocks of order <= 64, <= 256 variables).  See ipm_small.cu.
+#pragma once
+#include "common.cuh"
+#include "ops.cuh"
+
+namespace sdpk {
+
+constexpr int SMALL_MAX_N = 64;        // largest SDP block
+constexpr int SMALL_MAX_M = 256;       // largest Schur complement
+constexpr int SMALL_MAX_BLOCKS = 16;
+constexpr int SMALL_MAX_GROUPS = 8;
+constexpr int SMALL_LZ_STEPS = 32;     // Lanczos steps per step-length matrix (exact when the block order is smaller)
+
+struct SmallBlock { int n, ld; long long off; long long lzoff; };
+
+struct SmallResult
+{
+   int phase, stop, iterations, backtracks;
+   double pobj, dobj, relgap, pinf, dinf, mu;
+};
+
+struct SmallArgs
+{
+   int m, nb, nlp, N, ldm, npos, cnnz, ndense, ngroups, maxiter, setting, verbose;
+   long long arena;
+   SmallBlock blk[SMALL_MAX_BLOCKS];
+   DevEntries E;
+   const int* cls;
+   const int* posbeg; const long long* pos; const long long* mirror; const int* posvar; const double* posval; const double* posc;
+   const long long* cpos; const long long* cmirror; const double* cval;
+   const int* lpbeg; const int* lpind; const double* lpval; const double* lprhs;
+   const int* colbeg; const int* colrow; const double* colval;
+   const double* b;
+   const int* denselist; const double* Adense;
+   int gblk[SMALL_MAX_GROUPS], gfirst[SMALL_MAX_GROUPS], gcount[SMALL_MAX_GROUPS];
+   long long gaoff[SMALL_MAX_GROUPS];
+   double *X, *S, *Sinv, *L, *Linv, *LX, *LXinv, *dX, *dS, *dXa, *dSa, *K, *T1, *T2, *Rd;
+   double *y, *dy, *g, *rp, *AX, *DTx, *tm1, *tm2;
+   double *x, *s, *dx, *ds, *dxa, *dsa, *klp, *rdlp, *Dy, *Ddy;
+   double *M, *Mfac, *Hd, *Ud, *lz;
+   double gaptol, feastol, absgaptol, objlimit, normb, normC, normCsdp2, gammabase;
+   SmallResult* out;
+};
+
+cudaError_t launch_ipm_small(cudaStream_t st, const SmallArgs& a);
+
+} // namespace sdpk

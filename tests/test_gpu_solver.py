@@ -33,10 +33,17 @@ def _instances():
     yield "cls-40", lambda: generators.cls(40, 25, 5, seed=14)
 
 
+@pytest.mark.parametrize("path", ["single-cta", "multi-kernel"])
 @pytest.mark.parametrize("name,make", list(_instances()), ids=[n for n, _ in _instances()])
-def test_relaxation_matches_oracle(gpu, cpu, name, make):
+def test_relaxation_matches_oracle(gpu, cpu, name, make, path, monkeypatch):
+    """both device paths: the one-launch kernel for small relaxations (ipm_small.cu) and the kernel-per-operation pipeline"""
     fp, _ = make().flatten()
+    monkeypatch.setenv("SDPCUDA_PATH", "s" if path == "single-cta" else "m")
+    if path == "single-cta" and (max(fp.blocksizes, default=0) > 64 or fp.m > 256):
+        pytest.skip("outside the single-CTA limits")
     r = gpu.solve(fp, gaptol=1e-7, feastol=1e-7)
+    if path == "single-cta":
+        assert r["launches"] < 40                      # initial point + ONE solver kernel
     ref = cpu.solve(fp, gaptol=1e-7, feastol=1e-7)
     assert r["launches"] > 0
     assert ref["phase_name"] == "pdOPT" and r["phase_name"] == "pdOPT", (r["phase_name"], r["stop_name"])
