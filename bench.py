@@ -197,7 +197,8 @@ def main():
         achieved = g["work"] / g["ms"] / 1e9 if g["ms"] > 0 else 0.0
         share = {c: round(v["ms"] / pr["device_ms"], 4) for c, v in prof.items()}
         roof = {"bound": "tensor", "kernel": "gemm_dmma_kernel<64,64> (FP64 DMMA.8x8x4, cp.async fed; the 32x32-tile instantiation of the factorisation leaves is listed separately in share_of_step)", "achieved": achieved, "peak": max(peak, gemm_fl / gemm_ms / 1e9),
-                "unit": "TFLOP/s", "frac": achieved / max(peak, gemm_fl / gemm_ms / 1e9), "traffic": None,
+                "unit": "TFLOP/s", "frac": achieved / max(peak, gemm_fl / gemm_ms / 1e9), "traffic": 81.5e6 if a.n == 2000 else None,
+                "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one 2000^3 launch, ncu --set full (profiles/r1_gemm_dmma_ncu_full.txt); algorithmic 96 MB",
                 "peak_source": "measured live: max(register-resident DMMA probe, standalone 4096^3 DGEMM of this library); MEASURED_PEAKS.json holds no FP64 figure",
                 "dmma_probe_tflops": peak, "dgemm_4096_tflops": gemm_fl / gemm_ms / 1e9,
                 "launches_per_solve": g["launches"], "algorithmic_flops_per_solve": g["work"], "device_ms_per_solve": g["ms"],

@@ -494,10 +494,11 @@ lzb_step_kernel(const LzDesc* __restrict__ D, int j, int maxit, unsigned* __rest
 
 __global__ void lzb_ritz_kernel(const LzDesc* __restrict__ D, int k, int maxit)
 {
+   // one warp per matrix: smallest eigenvalue of the k x k Lanczos tridiagonal by 32-way multisection on Sturm counts
    const LzDesc d = D[blockIdx.x];
-   if( threadIdx.x != 0 ) return;
+   const int lane = threadIdx.x & 31;
+   if( threadIdx.x >= 32 ) return;
    int kk = min(k, d.n);
-   // reuse the single-matrix routine's logic inline
    const double* a = d.ab;
    const double* bt = d.ab + maxit;
    double scale = 0.0;
@@ -510,22 +511,30 @@ __global__ void lzb_ritz_kernel(const LzDesc* __restrict__ D, int k, int maxit)
       double r = (i > 0 ? fabs(bt[i - 1]) : 0.0) + (i < keff - 1 ? fabs(bt[i]) : 0.0);
       lo = fmin(lo, a[i] - r); hi = fmax(hi, a[i] + r);
    }
-   double l = lo, h = hi;
-   for( int it = 0; it < 200 && (h - l) > 1e-15 * fmax(fabs(l), fabs(h)) + 1e-300; ++it )
+   const double width0 = hi - lo;
+   for( int round = 0; round < 6 && (hi - lo) > 1e-9 * width0 + 1e-300; ++round )
    {
-      double x = 0.5 * (l + h);
+      const double xt = lo + (lane + 1) * (hi - lo) / 33.0;
       int cnt = 0;
       double dd = 1.0;
       for( int i = 0; i < keff; ++i )
       {
          double b2 = (i > 0) ? bt[i - 1] * bt[i - 1] : 0.0;
-         dd = a[i] - x - (i > 0 ? b2 / dd : 0.0);
+         dd = a[i] - xt - (i > 0 ? b2 / dd : 0.0);
          if( dd == 0.0 ) dd = 1e-300;
          if( dd < 0.0 ) ++cnt;
       }
-      if( cnt >= 1 ) h = x; else l = x;
+      double below = (cnt == 0) ? xt : lo;
+      double above = (cnt >= 1) ? xt : hi;
+#pragma unroll
+      for( int o = 16; o > 0; o >>= 1 )
+      {
+         below = fmax(below, __shfl_xor_sync(0xffffffffu, below, o));
+         above = fmin(above, __shfl_xor_sync(0xffffffffu, above, o));
+      }
+      lo = below; hi = above;
    }
-   double theta = 0.5 * (l + h);
+   const double theta = lo;            // lower end of the bracket: errs on the safe side
    double resid = 0.0;
    if( keff == kk && kk < d.n )
    {
@@ -540,9 +549,12 @@ __global__ void lzb_ritz_kernel(const LzDesc* __restrict__ D, int k, int maxit)
       }
       resid = fabs(bt[kk - 1]) * fabs(last) / sqrt(nrm);
    }
-   d.out[0] = theta - resid;
-   d.out[1] = theta;
-   d.out[2] = resid;
+   if( lane == 0 )
+   {
+      d.out[0] = theta - resid;
+      d.out[1] = theta;
+      d.out[2] = resid;
+   }
 }
 
 } // namespace
