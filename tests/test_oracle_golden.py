@@ -66,3 +66,29 @@ def test_oracle_relaxation_kkt():
     AX = np.array([sum(np.vdot(fp.dense_A(j)[k], X[k]) for k in range(fp.nblocks)) for j in range(fp.m)]) + D.T @ r["xlp"]
     assert np.linalg.norm(AX - fp.obj) <= 1e-6 * (1 + np.linalg.norm(fp.obj))
     assert abs(r["pobj"] - r["dobj"]) <= 1e-6 * max(1, abs(r["dobj"]))
+
+
+def test_oracle_eigen_matches_reference_lapack_interface():
+    """the reference's own lapack_interface.c (oracle/_ref/liblapack_ref.so): SURVEY.md section 0 probe values and random matrices"""
+    import ctypes as C
+    ref_path = os.path.join(os.path.dirname(GOLDEN), "..", "oracle", "_ref", "liblapack_ref.so")
+    if not os.path.exists(ref_path):
+        pytest.skip("oracle/_ref/liblapack_ref.so not built")
+    L = C.CDLL(ref_path, mode=C.RTLD_LOCAL)
+    dp = C.POINTER(C.c_double)
+    L.BMScreateBufferMemory.restype = C.c_void_p
+    L.BMScreateBufferMemory.argtypes = [C.c_double, C.c_int, C.c_uint]
+    L.SCIPlapackComputeEigenvectorDecomposition.argtypes = [C.c_void_p, C.c_int, dp, dp, dp]
+    buf = C.c_void_p(L.BMScreateBufferMemory(1.2, 4, 0))
+    cpu = abi.Solver(abi.Lib(abi.ORACLE_LIB))
+    rng = np.random.default_rng(0)
+    for A in [np.array([[1.0, 2.0], [2.0, 4.0]])] + [(lambda G: G + G.T)(rng.standard_normal((n, n))) for n in (10, 15, 43)]:
+        n = A.shape[0]
+        Ac, w, V = A.copy(), np.zeros(n), np.zeros(n * n)
+        assert L.SCIPlapackComputeEigenvectorDecomposition(buf, n, Ac.ctypes.data_as(dp), w.ctypes.data_as(dp), V.ctypes.data_as(dp)) == 1
+        wo, Vo = cpu.syev(A)
+        assert np.abs(w - wo).max() <= 1e-10 * max(1.0, np.abs(w).max())
+        V = V.reshape(n, n)
+        for k in range(n):                      # eigenvectors as rows, equal up to sign where the eigenvalue is simple
+            assert abs(abs(V[k] @ Vo[k]) - 1.0) <= 1e-6
+    assert np.allclose(w[:0], [])               # (keeps flake8 quiet about w)
