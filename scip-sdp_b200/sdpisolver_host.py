@@ -97,6 +97,13 @@ class SdpiSolver:
                                                  C.c_int, _ipp, _ipp, _ippp, _ippp, _dppp, _ipp, _ip, _ip, C.c_int,
                                                  C.c_int, _ip, _dp, _dp, C.c_int, _ip, _ip, _dp,
                                                  _dp, _ip, _ipp, _ipp, _dpp, _ip, _ipp, _ipp, _dpp, C.c_int, C.c_double, C.c_void_p]
+        L.SCIPsdpiSolverLoadAndSolveWithPenalty.argtypes = [C.c_void_p, C.c_double, C.c_uint, C.c_uint] + L.SCIPsdpiSolverLoadAndSolve.argtypes[1:] + \
+            [C.POINTER(C.c_uint), C.POINTER(C.c_uint)]
+        L.SCIPsdpiSolverGetObjval.argtypes = [C.c_void_p, _dp]
+        L.SCIPsdpiSolverGetPrimalBoundVars.argtypes = [C.c_void_p, _dp, _dp]
+        L.SCIPsdpiSolverGetPrimalNonzeros.argtypes = [C.c_void_p, C.c_int, _ip]
+        L.SCIPsdpiSolverGetPrimalMatrix.argtypes = [C.c_void_p, C.c_int, _ip, _ipp, _ipp, _dpp]
+        L.SCIPsdpiSolverSettingsUsed.argtypes = [C.c_void_p, _ip]
         L.SCIPsdpiSolverSetRealpar.argtypes = [C.c_void_p, C.c_int, C.c_double]
         L.SCIPsdpiSolverGetDualSol.argtypes = [C.c_void_p, _dp, _dp]
         L.SCIPsdpiSolverGetIterations.argtypes = [C.c_void_p, _ip]
@@ -123,6 +130,60 @@ class SdpiSolver:
         rc = self.lib.SCIPsdpiSolverLoadAndSolve(self.s, *bp.args)
         if rc != SCIP_OKAY:
             raise RuntimeError(f"SCIPsdpiSolverLoadAndSolve returned SCIP_RETCODE {rc}")
+
+    def load_and_solve_with_penalty(self, bp, penaltyparam, withobj, rbound):
+        """-> (feasorig, penaltybound) of SCIPsdpiSolverLoadAndSolveWithPenalty (sdpisolver.h:258-322)"""
+        self.nvars = bp.nvars
+        self.bp = bp
+        fo, pb = C.c_uint(0), C.c_uint(0)
+        rc = self.lib.SCIPsdpiSolverLoadAndSolveWithPenalty(self.s, float(penaltyparam), int(withobj), int(rbound), *bp.args, C.byref(fo), C.byref(pb))
+        if rc != SCIP_OKAY:
+            raise RuntimeError(f"SCIPsdpiSolverLoadAndSolveWithPenalty returned SCIP_RETCODE {rc}")
+        return bool(fo.value), bool(pb.value)
+
+    def objval(self):
+        v = C.c_double(0)
+        rc = self.lib.SCIPsdpiSolverGetObjval(self.s, C.byref(v))
+        if rc != SCIP_OKAY:
+            raise RuntimeError(f"SCIPsdpiSolverGetObjval returned {rc}")
+        return v.value
+
+    def primal_matrix_sparse(self, bp):
+        """SCIPsdpiSolverGetPrimalNonzeros + GetPrimalMatrix -> list of (rows, cols, vals) per block, LP block last"""
+        nb = bp.nblocks + 1
+        cnt = (C.c_int * nb)()
+        rc = self.lib.SCIPsdpiSolverGetPrimalNonzeros(self.s, nb, cnt)
+        if rc != SCIP_OKAY:
+            raise RuntimeError(f"SCIPsdpiSolverGetPrimalNonzeros returned {rc}")
+        rows = [np.zeros(max(c, 1), dtype=np.int32) for c in cnt]
+        cols = [np.zeros(max(c, 1), dtype=np.int32) for c in cnt]
+        vals = [np.zeros(max(c, 1)) for c in cnt]
+        rp = (_ip * nb)(*[r.ctypes.data_as(_ip) for r in rows])
+        cp = (_ip * nb)(*[c.ctypes.data_as(_ip) for c in cols])
+        vp = (_dp * nb)(*[v.ctypes.data_as(_dp) for v in vals])
+        rc = self.lib.SCIPsdpiSolverGetPrimalMatrix(self.s, nb, cnt, C.cast(rp, _ipp), C.cast(cp, _ipp), C.cast(vp, _dpp))
+        if rc != SCIP_OKAY:
+            raise RuntimeError(f"SCIPsdpiSolverGetPrimalMatrix returned {rc}")
+        return [(rows[b][:cnt[b]], cols[b][:cnt[b]], vals[b][:cnt[b]]) for b in range(nb)]
+
+    def primal_matrix_dense(self, bp):
+        mats = [np.zeros((n, n)) for n in bp.blocksizes]
+        k = _Keep()
+        arr = (_dp * max(len(mats), 1))(*[m.ctypes.data_as(_dp) for m in mats])
+        ind = k.pp([k.i(np.zeros(n, dtype=np.int32)) for n in bp.blocksizes], _ip, _ipp)
+        rc = self.lib.SCIPsdpiSolverGetPrimalSolutionMatrix(self.s, bp.nblocks, k.i(bp.blocksizes if bp.blocksizes else [0]), ind,
+                                                           k.i(np.zeros(max(bp.nblocks, 1), dtype=np.int32)),
+                                                           k.i(np.zeros(max(bp.nblocks, 1), dtype=np.int32)), C.cast(arr, _dpp))
+        if rc != SCIP_OKAY:
+            raise RuntimeError(f"SCIPsdpiSolverGetPrimalSolutionMatrix returned {rc}")
+        return mats
+
+    def bound_multipliers(self):
+        lbv, ubv = np.zeros(self.nvars), np.zeros(self.nvars)
+        rc = self.lib.SCIPsdpiSolverGetPrimalBoundVars(self.s, lbv.ctypes.data_as(_dp), ubv.ctypes.data_as(_dp))
+        if rc != SCIP_OKAY:
+            raise RuntimeError(f"SCIPsdpiSolverGetPrimalBoundVars returned {rc}")
+        return lbv, ubv
 
     def flag(self, name):
         return bool(getattr(self.lib, "SCIPsdpiSolver" + name)(self.s))

@@ -1,0 +1,15 @@
+"""GPU suite, part 5: the same boundary checks on the product library lib/libsdpisolver_cuda.so (binding + GPU checker + CUDA)."""
+import pytest
+
+from harness import boundary_cases
+from scip_sdp_b200 import sdpisolver_host
+
+pytestmark = pytest.mark.gpu
+
+
+def test_penalty_formulation_call_patterns_on_gpu():
+    boundary_cases.run_penalty_patterns(sdpisolver_host.BINDING_LIB)
+
+
+def test_primal_matrix_getters_are_consistent_on_gpu():
+    boundary_cases.run_primal_getters(sdpisolver_host.BINDING_LIB)
