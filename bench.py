@@ -37,7 +37,65 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--n", type=int, default=2000, help="max-cut order (2000 = the BASELINE configuration)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="maxcut", choices=["maxcut", "frontier-tt500", "frontier-cls", "frontier-mkp120", "frontier-mkp60"],
+                    help="maxcut = the headline relaxation benchmark; frontier-* = B&B nodes/sec over a fixed frontier of node relaxations")
+    ap.add_argument("--nodes-per-gpu", type=int, default=8)
     return ap.parse_args()
+
+
+def frontier_bench(a, rank, local, world):
+    """B&B nodes/sec: a frontier of open nodes (all 0/1 fixings of the first q integer variables of the instance) is partitioned
+    round-robin over the ranks (scip_sdp_b200.frontier), every rank solves its nodes on its own GPU; weak scaling (nodes_per_gpu
+    nodes per rank).  Reported: nodes/s = total nodes / max-over-ranks wall time, plus the CPU oracle on a bounded sample."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from scip_sdp_b200 import abi, frontier, generators
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    make = {"frontier-tt500": lambda: generators.truss(6, 6, 500, seed=1001), "frontier-cls": lambda: generators.cls(199, 99, 10, seed=2002),
+            "frontier-mkp120": lambda: generators.mkp(120, seed=3003), "frontier-mkp60": lambda: generators.mkp(60, seed=3003)}[a.workload]
+    M = make()
+    nnodes = a.nodes_per_gpu * world
+    q = max(1, int(np.ceil(np.log2(nnodes))))
+    ints = np.flatnonzero(M.integer)[:q]
+    nodes = []
+    for code in range(nnodes):
+        lb, ub = M.lb.copy(), M.ub.copy()
+        for b, j in enumerate(ints):
+            v = (code >> b) & 1
+            lb[j] = ub[j] = float(v)
+        nodes.append((lb, ub))
+    os.environ["SDPCUDA_DEVICE"] = str(local)
+    gpu = abi.Solver(abi.Lib(abi.PRODUCT_LIB), device=local)
+    kw = dict(gaptol=1e-5, feastol=1e-5)
+    frontier.solve_frontier(gpu, M, nodes[:world], dist=dist if world > 1 else None, **kw)      # warm-up
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    res = frontier.solve_frontier(gpu, M, nodes, dist=dist if world > 1 else None, **kw)
+    torch.cuda.synchronize()
+    wall = frontier.max_over_ranks(time.perf_counter() - t0, dist=dist if world > 1 else None, device="cuda")
+    if rank == 0:
+        line = {"metric": "B&B nodes/sec", "value": nnodes / wall, "unit": "nodes/s", "n_gpus": world, "scaling": "weak", "dtype": "f64",
+                "data": "synthetic", "higher_is_better": True, "ms_per_node": 1e3 * wall * world / nnodes,
+                "config": {"workload": a.workload, "nodes": nnodes, "partition": "frontier nodes round-robin over ranks, no collective on the data path",
+                           "instance": f"m = {M.nvars}, blocks = {M.blocksizes}, rows = {len(M.rows)}"},
+                "statuses": sorted({r["status"] for r in res}), "bounds_min_max": [min(r["bound"] for r in res), max(r["bound"] for r in res)]}
+        if not a.no_cpu_baseline:
+            cpu = abi.Solver(abi.Lib(abi.ORACLE_LIB))
+            t1 = time.perf_counter()
+            rc = frontier.solve_frontier(cpu, M, nodes[:2], **kw)
+            dt = (time.perf_counter() - t1) / 2
+            line["cpu_baseline"] = {"value": 1.0 / dt, "unit": "nodes/s", "cores": os.cpu_count(), "kind": "port",
+                                    "sample": "the first 2 frontier nodes on the CPU oracle (OpenBLAS, all host threads)",
+                                    "bounds": [r["bound"] for r in rc], "gpu_bounds": [r["bound"] for r in res[:2]]}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
 
 
 class ClockSampler(threading.Thread):
@@ -120,6 +178,10 @@ def main():
         return 0
 
     # ------------------------------------------------------------------ our arm
+    if a.workload != "maxcut":
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"
+        return frontier_bench(a, rank, local, world)
     if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
         os.environ["NCCL_DEBUG"] = "WARN"          # keep stdout to the one JSON line (NCCL prints its version banner there)
     import torch
