@@ -53,7 +53,9 @@ def frontier_bench(a, rank, local, world):
     from scip_sdp_b200 import abi, frontier, generators
     torch.cuda.set_device(local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        with stdout_to_stderr():
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+            dist.barrier()
     make = {"frontier-tt500": lambda: generators.truss(6, 6, 500, seed=1001), "frontier-cls": lambda: generators.cls(199, 99, 10, seed=2002),
             "frontier-mkp120": lambda: generators.mkp(120, seed=3003), "frontier-mkp60": lambda: generators.mkp(60, seed=3003)}[a.workload]
     M = make()
@@ -96,6 +98,22 @@ def frontier_bench(a, rank, local, world):
     if world > 1:
         dist.destroy_process_group()
     return 0
+
+
+class stdout_to_stderr:
+    """NCCL prints its version banner on stdout at the first collective: keep stdout for the one JSON line"""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+        return self
+
+    def __exit__(self, *exc):
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+        return False
 
 
 class ClockSampler(threading.Thread):
@@ -190,7 +208,9 @@ def main():
         raise SystemExit("bench.py: no CUDA device visible; the product path has no CPU fallback")
     torch.cuda.set_device(local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        with stdout_to_stderr():
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+            dist.barrier()
 
     def barrier():
         if world > 1:
