@@ -102,7 +102,10 @@ cudaError_t lanczos_lambda_min(cudaStream_t st, int n, const double* B, int ldb,
 size_t lanczos_work_doubles(int n, int maxit);
 // batched, adaptive variant: all matrices advance together, convergence is checked on the host every 8 steps
 constexpr int LZB_MAXIT = 64;
-struct LzDesc { int n; int ld; const double* B; double* Q /* (LZB_MAXIT+2)*n */; double* ab /* 2*LZB_MAXIT */; double* out /* 3 */; };
+struct LzDesc { int n; int ld; const double* B; double* Q /* (LZB_MAXIT+2)*n */; double* ab /* 2*LZB_MAXIT */; double* out /* 3 */; double* safe /* extra destination of out[0], or nullptr */; };
+// blocks of order <= LZS_MAX_N: one CTA per matrix runs the whole recurrence out of shared memory (one launch, no host check)
+constexpr int LZS_MAX_N = 128;
+cudaError_t lanczos_small_batched(cudaStream_t st, int nmat, int maxn, const LzDesc* d_desc, int maxit);
 // tickets: nmat zero-initialised counters; partials: nmat * pstride doubles with pstride >= ceil(max n / 8)
 cudaError_t lanczos_batched(cudaStream_t st, int nmat, const LzDesc* h_desc, LzDesc* d_desc, int maxit, double* d_out3,
    double* h_out3, int* steps_done, unsigned* tickets, double* partials, int pstride);

@@ -492,15 +492,10 @@ lzb_step_kernel(const LzDesc* __restrict__ D, int j, int maxit, unsigned* __rest
    if( tid == 0 ) { alpha[j] = a; beta[j] = nr; tickets[blockIdx.y] = 0u; }
 }
 
-__global__ void lzb_ritz_kernel(const LzDesc* __restrict__ D, int k, int maxit)
+// smallest eigenvalue of the kk x kk Lanczos tridiagonal (a, bt) by 32-way multisection on Sturm counts, one warp;
+// theta = lower end of the final bracket, resid = |beta_kk s_kk| (0 when the Krylov space is exhausted or kk = n)
+__device__ __forceinline__ void ritz_warp(const double* a, const double* bt, int kk, int n, int lane, double& theta, double& resid)
 {
-   // one warp per matrix: smallest eigenvalue of the k x k Lanczos tridiagonal by 32-way multisection on Sturm counts
-   const LzDesc d = D[blockIdx.x];
-   const int lane = threadIdx.x & 31;
-   if( threadIdx.x >= 32 ) return;
-   int kk = min(k, d.n);
-   const double* a = d.ab;
-   const double* bt = d.ab + maxit;
    double scale = 0.0;
    for( int i = 0; i < kk; ++i ) scale = fmax(scale, fabs(a[i]) + fabs(bt[i]));
    int keff = kk;
@@ -534,9 +529,9 @@ __global__ void lzb_ritz_kernel(const LzDesc* __restrict__ D, int k, int maxit)
       }
       lo = below; hi = above;
    }
-   const double theta = lo;            // lower end of the bracket: errs on the safe side
-   double resid = 0.0;
-   if( keff == kk && kk < d.n )
+   theta = lo;            // lower end of the bracket: errs on the safe side
+   resid = 0.0;
+   if( keff == kk && kk < n )
    {
       double sm1 = 0.0, s0 = 1.0, nrm = 1.0, last = 1.0;
       for( int i = 0; i < kk - 1; ++i )
@@ -549,12 +544,104 @@ __global__ void lzb_ritz_kernel(const LzDesc* __restrict__ D, int k, int maxit)
       }
       resid = fabs(bt[kk - 1]) * fabs(last) / sqrt(nrm);
    }
+}
+
+__global__ void lzb_ritz_kernel(const LzDesc* __restrict__ D, int k, int maxit)
+{
+   const LzDesc d = D[blockIdx.x];
+   const int lane = threadIdx.x & 31;
+   if( threadIdx.x >= 32 ) return;
+   double theta, resid;
+   ritz_warp(d.ab, d.ab + maxit, min(k, d.n), d.n, lane, theta, resid);
    if( lane == 0 )
    {
       d.out[0] = theta - resid;
       d.out[1] = theta;
       d.out[2] = resid;
+      if( d.safe ) *d.safe = theta - resid;
    }
+}
+
+// ---- small blocks (n <= LZS_MAX_N): the whole Lanczos run of one matrix in ONE CTA, matrix and vectors in shared memory -----
+// Same recurrence, start vector and stopping rule as the batched multi-launch version above; the Ritz value is checked
+// (warp 0) after 8, 16, 24, 32, 48, 64, 96 and 128 steps.
+__global__ void __launch_bounds__(256)
+lz_smem_kernel(const LzDesc* __restrict__ D, int maxit)
+{
+   extern __shared__ __align__(16) double lsm[];
+   __shared__ double red[32];
+   __shared__ double res3[3];
+   __shared__ int done;
+   const LzDesc d = D[blockIdx.x];
+   const int n = d.n, lds = n | 1, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+   double* Bs = lsm;
+   double* v = Bs + (size_t)n * lds;
+   double* vprev = v + LZS_MAX_N;
+   double* w = vprev + LZS_MAX_N;
+   double* alpha = w + LZS_MAX_N;
+   double* beta = alpha + LZS_MAX_N + 1;
+   for( int e = tid; e < n * n; e += 256 )
+   {
+      const int r = e % n, c = e / n;
+      Bs[c * lds + r] = d.B[(size_t)c * d.ld + r];
+   }
+   double s = 0.0;
+   if( tid < n )
+   {
+      unsigned h = (unsigned)tid * 2654435761u + 12345u;
+      h ^= h >> 15; h *= 2246822519u; h ^= h >> 13;
+      const double x = 0.5 + (double)(h & 0xffffu) / 65536.0;
+      v[tid] = x; vprev[tid] = 0.0;
+      s = x * x;
+   }
+   if( tid == 0 ) done = 0;
+   s = block_sum(s, red);
+   if( tid < n ) v[tid] *= 1.0 / sqrt(s);
+   __syncthreads();
+   const int kmax = min(maxit, min(n, LZS_MAX_N));
+   double bprev = 0.0;
+   int j = 0;
+   for( ; j < kmax; )
+   {
+      for( int i = wid; i < n; i += 8 )
+      {
+         const double* col = Bs + i * lds;        // symmetric: column i = row i
+         double acc = 0.0;
+         for( int k = lane; k < n; k += 32 ) acc += col[k] * v[k];
+#pragma unroll
+         for( int o = 16; o > 0; o >>= 1 ) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+         if( lane == 0 ) w[i] = acc;
+      }
+      __syncthreads();
+      const double a = block_sum(tid < n ? w[tid] * v[tid] : 0.0, red);
+      double x = 0.0;
+      if( tid < n ) x = w[tid] - a * v[tid] - bprev * vprev[tid];
+      const double nr = sqrt(block_sum(x * x, red));
+      const double cf = (nr > 1e-300) ? 1.0 / nr : 0.0;
+      if( tid < n ) { vprev[tid] = v[tid]; v[tid] = x * cf; }
+      if( tid == 0 ) { alpha[j] = a; beta[j] = nr; }
+      bprev = nr;
+      ++j;
+      __syncthreads();
+      const bool check = (j == kmax) || (j >= 8 && ((j <= 32 && (j & 7) == 0) || (j <= 64 && (j & 15) == 0) || (j & 31) == 0));
+      if( check )
+      {
+         if( wid == 0 )
+         {
+            double theta, resid;
+            ritz_warp(alpha, beta, j, n, lane, theta, resid);
+            if( lane == 0 )
+            {
+               res3[0] = theta - resid; res3[1] = theta; res3[2] = resid;
+               done = (resid <= 0.01 * fabs(theta) || theta - resid >= -0.5) ? 1 : 0;
+            }
+         }
+         __syncthreads();
+         if( done ) break;
+      }
+   }
+   if( tid < 3 ) d.out[tid] = res3[tid];
+   if( tid == 0 && d.safe ) *d.safe = res3[0];
 }
 
 } // namespace
@@ -594,6 +681,25 @@ cudaError_t jacobi_eig_batched(cudaStream_t st, int n, int nbatch, const double*
    }
    ProfScope prof(st, PROF_EIG, (double)nbatch * (16.0 * n * n + 8.0 * n));
    jacobi_kernel<<<nbatch, 256, smem, st>>>(n, A, lda, strideA, w, V, gscratch, use_smem, d_sweeps);
+   count_launch();
+   return cudaGetLastError();
+}
+
+cudaError_t lanczos_small_batched(cudaStream_t st, int nmat, int maxn, const LzDesc* d_desc, int maxit)
+{
+   if( nmat <= 0 ) return cudaSuccess;
+   if( maxn > LZS_MAX_N ) return cudaErrorInvalidValue;
+   static bool configured[64] = {false};        // per-device function attribute
+   int dev = 0;
+   SDPK_CUDA_CHECK( cudaGetDevice(&dev) );
+   if( !configured[dev & 63] )
+   {
+      SDPK_CUDA_CHECK( cudaFuncSetAttribute(lz_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024) );
+      configured[dev & 63] = true;
+   }
+   const size_t smem = sizeof(double) * ((size_t)maxn * (maxn | 1) + 5 * (size_t)LZS_MAX_N + 8);
+   ProfScope prof(st, PROF_EIG, 8.0 * nmat * (double)maxn * maxn);
+   lz_smem_kernel<<<nmat, 256, smem, st>>>(d_desc, maxit);
    count_launch();
    return cudaGetLastError();
 }

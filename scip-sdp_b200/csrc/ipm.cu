@@ -97,8 +97,8 @@ struct sdpcuda_handle
    DBuf<LzDesc> lzdesc;
    DBuf<unsigned> lztickets;
    DBuf<double> lzpart;
-   std::vector<LzDesc> h_lzdesc;
-   bool minv = false;                // explicit inverse factor of M (m <= 4096): solves become two triangular mat-vecs
+   std::vector<LzDesc> h_lzdesc, h_lzsmall;
+   bool minv = false;                // explicit inverse factor of M (m <= 16384): solves become two triangular mat-vecs
    DBuf<double> partials, stats, scal, eigw, lzwork;
    DBuf<int> info;
    double* h_stats = nullptr;     // pinned
@@ -359,7 +359,7 @@ int upload_problem(sdpcuda_handle* h, const sdpcuda_problem* P)
    CK( h->Mfac.ensure((size_t)h->ldm * m) );
    CK( h->diaginv.ensure((size_t)ceil_div(std::max(m, 1), CHOL_NB) * CHOL_NB * CHOL_NB) );
    CK( h->Mwork.ensure((size_t)h->ldm * (m + 2 * CHOL_NB)) );
-   h->minv = (m <= 4096);
+   h->minv = (m <= 16384);      // 2 GB at the limit; the blocked substitution (one launch per 64 rows) is latency bound
    if( h->minv ) CK( h->MLinv.ensure((size_t)h->ldm * m) );
    CK( h->lzdesc.ensure(2 * (size_t)std::max(h->nb, 1)) );
    CK( h->lztickets.ensure(2 * (size_t)std::max(h->nb, 1)) );
@@ -485,56 +485,53 @@ int step_eigs(sdpcuda_handle* h, const double* dXdir, const double* dSdir, int m
 {
    const int nb = h->nb;
    h->h_lzdesc.clear();
+   h->h_lzsmall.clear();
    double* lzw = h->lzwork.p;
-   int k = 0;
+   // results land in scal[64 + 2 nb ...] (3 doubles per matrix: small blocks first), then the safe values go to their slots
+   CK( h->scal.ensure(64 + 2 * (size_t)nb + 6 * (size_t)nb) );
+   double* out3 = h->scal.p + 64 + 2 * nb;
+   int nsmall = 0, maxsmall = 0, k = 0;
+   for( const Block& bk : h->blk ) if( bk.n <= LZS_MAX_N ) nsmall += 2;
+   int ismall = 0, ibig = nsmall;
    for( const Block& bk : h->blk )
    {
       int rc;
       if( (rc = form_scaled(h, bk, k, false, h->LXinv.p, dXdir, h->T2.p)) ) return rc;
       if( (rc = form_scaled(h, bk, k, true, h->Linv.p, dSdir, h->K.p)) ) return rc;
-      if( bk.n <= JACOBI_MAX_N )
+      for( int side = 0; side < 2; ++side )
       {
-         CK( jacobi_eig_batched(h->st, bk.n, 1, h->T2.p + bk.off, bk.ld, 0, h->eigw.p, nullptr, nullptr) );
-         CK( pick_value(h->st, h->eigw.p, h->scal.p + 8 + k) );
-         CK( jacobi_eig_batched(h->st, bk.n, 1, h->K.p + bk.off, bk.ld, 0, h->eigw.p, nullptr, nullptr) );
-         CK( pick_value(h->st, h->eigw.p, h->scal.p + 8 + nb + k) );
-      }
-      else
-      {
-         for( int side = 0; side < 2; ++side )
+         LzDesc d;
+         d.n = bk.n; d.ld = bk.ld;
+         d.B = (side == 0 ? h->T2.p : h->K.p) + bk.off;
+         d.safe = h->scal.p + 8 + side * nb + k;
+         if( bk.n <= LZS_MAX_N )
          {
-            LzDesc d;
-            d.n = bk.n; d.ld = bk.ld;
-            d.B = (side == 0 ? h->T2.p : h->K.p) + bk.off;
+            d.Q = nullptr; d.ab = nullptr;
+            d.out = out3 + 3 * (ismall++);
+            h->h_lzsmall.push_back(d);
+            maxsmall = std::max(maxsmall, bk.n);
+         }
+         else
+         {
             d.Q = lzw; lzw += (size_t)(LZB_MAXIT + 2) * bk.n;
             d.ab = lzw; lzw += 2 * LZB_MAXIT + 8;
-            d.out = nullptr;
+            d.out = out3 + 3 * (ibig++);
             h->h_lzdesc.push_back(d);
          }
       }
       ++k;
    }
-   const int nmat = (int)h->h_lzdesc.size();
-   if( nmat > 2000 ) return SDPCUDA_ERR_ARG;      // pinned result buffer: 3 doubles per matrix
-   if( nmat > 0 )
+   const int nbig = (int)h->h_lzdesc.size();
+   if( nsmall + nbig > 600 ) return SDPCUDA_ERR_ARG;      // pinned result buffer: 3 doubles per matrix
+   if( nsmall > 0 )
    {
-      // results land in scal[64 + 2 nb ...] (3 doubles per matrix), then the safe values are copied to their slots
-      CK( h->scal.ensure(64 + 2 * (size_t)nb + 3 * (size_t)nmat) );
-      double* out3 = h->scal.p + 64 + 2 * nb;
-      for( int i = 0; i < nmat; ++i ) h->h_lzdesc[i].out = out3 + 3 * i;
-      CK( lanczos_batched(h->st, nmat, h->h_lzdesc.data(), h->lzdesc.p, maxsteps, out3, h->h_stats + 2048, nullptr,
-            h->lztickets.p, h->lzpart.p, ceil_div(std::max(h->maxn, 8), 8)) );
-      int i = 0; k = 0;
-      for( const Block& bk : h->blk )
-      {
-         if( bk.n > JACOBI_MAX_N )
-         {
-            CK( pick_value(h->st, out3 + 3 * i, h->scal.p + 8 + k) ); ++i;
-            CK( pick_value(h->st, out3 + 3 * i, h->scal.p + 8 + nb + k) ); ++i;
-         }
-         ++k;
-      }
+      // blocks of order <= LZS_MAX_N: whole Lanczos run per matrix in one CTA (shared memory), a single launch
+      CK( cudaMemcpyAsync(h->lzdesc.p, h->h_lzsmall.data(), sizeof(LzDesc) * nsmall, cudaMemcpyHostToDevice, h->st) );
+      CK( lanczos_small_batched(h->st, nsmall, maxsmall, h->lzdesc.p, maxsteps <= 8 ? 16 : LZS_MAX_N) );
    }
+   if( nbig > 0 )
+      CK( lanczos_batched(h->st, nbig, h->h_lzdesc.data(), h->lzdesc.p + nsmall, maxsteps, out3 + 3 * nsmall, h->h_stats + 2048, nullptr,
+            h->lztickets.p, h->lzpart.p, ceil_div(std::max(h->maxn, 8), 8)) );
    return SDPCUDA_OK;
 }
 
