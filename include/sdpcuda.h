@@ -177,6 +177,9 @@ int  sdpcuda_dgemm(sdpcuda_handle* h, int transa, int transb, int m, int n, int 
                    const double* A, int lda, const double* B, int ldb, double beta, double* C, int ldc);
 /* lower Cholesky A = L L' in place (strict upper part left untouched); info = 0 or index (1-based) of the failing pivot */
 int  sdpcuda_dpotrf(sdpcuda_handle* h, int n, double* A, int lda, int* info);
+/* the same factorisation together with the inverse factor (what the interior-point iteration computes for S and X):
+ * A <- L, Linv <- L^-1 (lower triangle, strict upper part zero) */
+int  sdpcuda_dpotrf_inv(sdpcuda_handle* h, int n, double* A, int lda, double* Linv, int ldi, int* info);
 /* inverse of the lower-triangular factor, in place */
 int  sdpcuda_dtrtri(sdpcuda_handle* h, int n, double* L, int ldl);
 /* device-resident timing of the same kernels: runs `reps` launches on random n x n operands already in HBM and

@@ -728,6 +728,17 @@ int sdpcuda_dpotrf(sdpcuda_handle* h, int n, double* A, int lda, int* info)
    scipy_dpotrf_("L", &n, A, &lda, info);
    return SDPCUDA_OK;
 }
+int sdpcuda_dpotrf_inv(sdpcuda_handle* h, int n, double* A, int lda, double* Linv, int ldi, int* info)
+{
+   (void)h;
+   scipy_dpotrf_("L", &n, A, &lda, info);
+   if( *info != 0 ) return SDPCUDA_OK;
+   for( int j = 0; j < n; ++j )
+      for( int i = 0; i < n; ++i ) Linv[(size_t)j * ldi + i] = (i >= j) ? A[(size_t)j * lda + i] : 0.0;
+   int info2 = 0;
+   scipy_dtrtri_("L", "N", &n, Linv, &ldi, &info2);
+   return info2 == 0 ? SDPCUDA_OK : SDPCUDA_ERR_ARG;
+}
 int sdpcuda_dtrtri(sdpcuda_handle* h, int n, double* L, int ldl)
 {
    (void)h;

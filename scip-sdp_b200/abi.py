@@ -118,6 +118,7 @@ class Lib:
                                     _dp, C.c_int, C.c_double, _dp, C.c_int]
         L.sdpcuda_dpotrf.argtypes = [C.c_void_p, C.c_int, _dp, C.c_int, _ip]
         L.sdpcuda_dtrtri.argtypes = [C.c_void_p, C.c_int, _dp, C.c_int]
+        L.sdpcuda_dpotrf_inv.argtypes = [C.c_void_p, C.c_int, _dp, C.c_int, _dp, C.c_int, _ip]
         L.sdpcuda_psd_check.argtypes = [C.c_void_p, C.c_int, _dp, C.c_int, C.c_double, _ip]
         L.sdpcuda_time_kernel.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, _dp, _dp]
 
@@ -256,6 +257,16 @@ class Solver:
         if rc != 0:
             raise RuntimeError(f"sdpcuda_dpotrf failed with code {rc}")
         return np.tril(Af), info.value
+
+    def dpotrf_inv(self, A):
+        Af = np.asfortranarray(A, dtype=np.float64).copy(order="F")
+        Li = np.zeros_like(Af, order="F")
+        info = C.c_int(0)
+        n = Af.shape[0]
+        rc = self.L.lib.sdpcuda_dpotrf_inv(self.h, n, Af.ctypes.data_as(_dp), n, Li.ctypes.data_as(_dp), n, C.byref(info))
+        if rc != 0:
+            raise RuntimeError(f"sdpcuda_dpotrf_inv failed with code {rc}")
+        return np.tril(Af), Li, info.value
 
     def dtrtri(self, Lm):
         Lf = np.asfortranarray(Lm, dtype=np.float64).copy(order="F")

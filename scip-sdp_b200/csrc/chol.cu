@@ -10,6 +10,8 @@
 // (and inverted) inside one CTA in shared memory.  The interior-point iteration needs L and L^-1 of S (for S^-1 and the
 // dual step length) and of X (primal step length), and L of the Schur complement M.
 #include "common.cuh"
+#include <cstdlib>
+#include <cstring>
 
 namespace sdpk {
 
@@ -310,6 +312,266 @@ diag_block_kernel(int mode, int nb, double* __restrict__ A, int lda, double* __r
    }
 }
 
+// ---- leaf kernel, DMMA version -----------------------------------------------------------------------------------------------
+// One CTA factorises (mode 0) and/or inverts (mode 1: A already holds L) a diagonal block of order nb <= NBL, NBL = 64 or 128.
+// NBL/8 warps; warp w keeps the 8-row strip w of the block as DMMA accumulator fragments (lower tiles j <= w) in registers.
+// Factorisation = NBL/4 macro steps over block columns of width 4 (fully unrolled, two barriers each):
+//   (1) the owners of block column t put it into shared memory;
+//   (2) one thread per row: 4 x 4 Cholesky of the diagonal block (every row thread redundantly - no extra barrier), forward
+//       substitution of its own row -> panel row P_r = L[r, 4t..4t+3]; stored to global memory and to the row-major copy of L;
+//   (3) rank-4 update C -= P P' of the not yet finished tiles: ONE DMMA.8x8x4 per tile, both operands read from the contiguous
+//       64 x 4 panel (conflict-free fragment loads).
+// Inverse W = L^-1 by recursive doubling: 8 x 8 diagonal inverses (one thread per column), then for s = 8, 16, .., NBL/2
+//   W21 = -W22 (L21 W11) for all adjacent pairs of s-blocks at once, the products again on DMMA fragments.
+// Shared memory: G[(NBL+1) x (NBL+4)] holds L row-major (element (r,c) at row r+1) and W transposed (element (r,c) at row c)
+// in the two triangles of one array.
+// reciprocal square root: MUFU.RSQ64H seed (rsqrt.approx.ftz.f64, about 22 bits over the whole double range, no
+// float conversions) + two Newton steps
+__device__ __forceinline__ double fast_rsqrt64(double x)
+{
+   double y;
+   asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+   const double hx = 0.5 * x;
+   y = y * (1.5 - hx * y * y);
+   y = y * (1.5 - hx * y * y);
+   return y;
+}
+
+// one product tile of the inverse recursion: D = sum_k A[.][k] B[k][.] over k in [klo, khi) (multiples of 8), operands via
+// the two loader functors; two interleaved accumulators shorten the DMMA dependency chain
+template <class FA, class FB>
+__device__ __forceinline__ void tile_product(int klo, int khi, FA fa, FB fb, double& d0, double& d1)
+{
+   double e0 = 0.0, e1 = 0.0;
+   d0 = 0.0; d1 = 0.0;
+   for( int k0 = klo; k0 < khi; k0 += 8 )
+   {
+      const double a0 = fa(k0), b0 = fb(k0), a1 = fa(k0 + 4), b1 = fb(k0 + 4);
+      dmma884(d0, d1, a0, b0);
+      dmma884(e0, e1, a1, b1);
+   }
+   d0 += e0; d1 += e1;
+}
+
+template <int NBL>
+__global__ void __launch_bounds__(NBL * 4)
+leaf_kernel(int mode, int nb, double* __restrict__ A, int lda, double* __restrict__ Linv, int ldi,
+   double* __restrict__ diaginv, int* __restrict__ info, int pivot_offset, long long* __restrict__ dbg)
+{
+   long long tc0 = clock64(), tc1 = 0, tc2 = 0, tc3 = 0;
+   constexpr int NTILE = NBL / 8, LD = NBL + 4, NSTEP = NBL / 4, NTHREADS = NBL * 4, NWARP = NBL / 8;
+   extern __shared__ __align__(16) double lsm[];
+   __shared__ int sbad;
+   double* G = lsm;                              // (NBL + 1) x LD
+   double* Tr = G + (NBL + 1) * LD;              // (NBL / 2) x LD
+   double* Pcol = Tr + (NBL / 2) * LD;           // NBL x 4  current block column
+   double* P = Pcol + NBL * 4;                   // NBL x 4  panel
+   double* rdg = P + NBL * 4;                    // NBL      reciprocals of the diagonal of L
+   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+   const int fr = lane >> 2, fc = lane & 3;
+
+   if( mode == 0 )
+   {
+      double c[NTILE][2];
+#pragma unroll
+      for( int j = 0; j < NTILE; ++j )
+      {
+         c[j][0] = 0.0; c[j][1] = 0.0;
+         if( j <= w )
+         {
+            const int row = 8 * w + fr;
+#pragma unroll
+            for( int e = 0; e < 2; ++e )
+            {
+               const int col = 8 * j + 2 * fc + e;
+               double v = (row == col) ? 1.0 : 0.0;      // identity padding keeps a partial block positive definite
+               if( row < nb && col < nb && row >= col ) v = A[(size_t)col * lda + row];
+               c[j][e] = v;
+            }
+         }
+      }
+      P[tid] = 0.0;                                      // NTHREADS = 4 NBL
+      if( tid == 0 ) sbad = 0x7fffffff;                  // smallest index of a non-positive pivot
+      __syncthreads();
+      tc1 = clock64();
+
+#pragma unroll
+      for( int t = 0; t < NSTEP; ++t )
+      {
+         const int jt = t >> 1, half = t & 1;
+         // (1) block column t -> shared memory (rows of the strips w >= jt)
+         if( w >= jt && (fc >> 1) == half )
+            *reinterpret_cast<double2*>(Pcol + (8 * w + fr) * 4 + 2 * (fc & 1)) = make_double2(c[jt][0], c[jt][1]);
+         __syncthreads();
+         // (2) panel row of every row r >= 4t
+         if( tid < NBL && tid >= 4 * t )
+         {
+            const int r = tid;
+            const double4* Dg = reinterpret_cast<const double4*>(Pcol + 16 * t);
+            const double4 g0 = Dg[0], g1 = Dg[1], g2 = Dg[2], g3 = Dg[3], av = *reinterpret_cast<const double4*>(Pcol + 4 * r);
+            // 4 x 4 Cholesky, branch free (a non-positive pivot is replaced by 1 and reported after the loop)
+            double s0 = g0.x;
+            const bool b0 = !(s0 > 0.0); s0 = b0 ? 1.0 : s0;
+            const double r0 = fast_rsqrt64(s0);
+            const double l10 = g1.x * r0, l20 = g2.x * r0, l30 = g3.x * r0;
+            double s1 = g1.y - l10 * l10;
+            const bool b1 = !(s1 > 0.0); s1 = b1 ? 1.0 : s1;
+            const double r1 = fast_rsqrt64(s1);
+            const double l21 = (g2.y - l20 * l10) * r1, l31 = (g3.y - l30 * l10) * r1;
+            double s2 = g2.z - l20 * l20 - l21 * l21;
+            const bool b2 = !(s2 > 0.0); s2 = b2 ? 1.0 : s2;
+            const double r2 = fast_rsqrt64(s2);
+            const double l32 = (g3.z - l30 * l20 - l31 * l21) * r2;
+            double s3 = g3.w - l30 * l30 - l31 * l31 - l32 * l32;
+            const bool b3 = !(s3 > 0.0); s3 = b3 ? 1.0 : s3;
+            const double r3 = fast_rsqrt64(s3);
+            if( r == 4 * t && (b0 || b1 || b2 || b3) )
+            {
+               const int q = b0 ? 0 : (b1 ? 1 : (b2 ? 2 : 3));
+               if( 4 * t + q < nb ) atomicMin(&sbad, 4 * t + q);
+            }
+            double4 pr;
+            if( r >= 4 * t + 4 )
+            {
+               pr.x = av.x * r0;
+               pr.y = (av.y - pr.x * l10) * r1;
+               pr.z = (av.z - pr.x * l20 - pr.y * l21) * r2;
+               pr.w = (av.w - pr.x * l30 - pr.y * l31 - pr.z * l32) * r3;
+               *reinterpret_cast<double4*>(P + 4 * r) = pr;
+            }
+            else
+            {
+               const int q = r - 4 * t;
+               const double d0 = s0 * r0, d1 = s1 * r1, d2 = s2 * r2, d3 = s3 * r3;
+               pr.x = (q == 0) ? d0 : (q == 1 ? l10 : (q == 2 ? l20 : l30));
+               pr.y = (q == 0) ? 0.0 : (q == 1 ? d1 : (q == 2 ? l21 : l31));
+               pr.z = (q <= 1) ? 0.0 : (q == 2 ? d2 : l32);
+               pr.w = (q <= 2) ? 0.0 : d3;
+               *reinterpret_cast<double4*>(P + 4 * r) = make_double4(0.0, 0.0, 0.0, 0.0);
+               rdg[r] = (q == 0) ? r0 : (q == 1 ? r1 : (q == 2 ? r2 : r3));
+            }
+            // row-major copy of L (zeros above the diagonal land in the triangle that the inverse fills later)
+            *reinterpret_cast<double4*>(G + (r + 1) * LD + 4 * t) = pr;
+         }
+         __syncthreads();
+         // (3) rank-4 update of the tiles that still change: rows >= 4t+4, columns >= 4t+4, lower tiles
+         {
+            const int jlo = (t + 1) >> 1;
+            if( w >= jlo )
+            {
+               const double a = -P[(8 * w + fr) * 4 + fc];
+#pragma unroll
+               for( int j = 0; j < NTILE; ++j )
+               {
+                  if( j >= jlo && j <= w )
+                  {
+                     const double b = P[(8 * j + fr) * 4 + fc];
+                     dmma884(c[j][0], c[j][1], a, b);
+                  }
+               }
+            }
+         }
+      }
+      __syncthreads();
+      if( tid == 0 && sbad != 0x7fffffff ) atomicCAS(info, 0, pivot_offset + sbad + 1);
+      tc2 = clock64();
+      // L -> global memory, lower triangle, column by column (coalesced)
+      for( int e = tid; e < nb * nb; e += NTHREADS )
+      {
+         const int i = e % nb, j = e / nb;
+         if( i >= j ) A[(size_t)j * lda + i] = G[(i + 1) * LD + j];
+      }
+   }
+   else
+   {
+      for( int e = tid; e < NBL * NBL; e += NTHREADS )
+      {
+         const int i = e % NBL, j = e / NBL;
+         if( i >= j )
+         {
+            double v = (i == j) ? 1.0 : 0.0;
+            if( i < nb && j < nb ) v = A[(size_t)j * lda + i];
+            G[(i + 1) * LD + j] = v;
+            if( i == j ) rdg[i] = 1.0 / v;
+         }
+      }
+      __syncthreads();
+      tc2 = clock64();
+   }
+   if( Linv == nullptr && diaginv == nullptr ) return;
+
+   // ---- inverse: 8 x 8 diagonal blocks, one thread per column ----
+   if( tid < NBL )
+   {
+      const int b8 = tid >> 3, cq = tid & 7, o = 8 * b8;
+      double x[8];
+#pragma unroll
+      for( int i = 0; i < 8; ++i )
+      {
+         double sacc = 0.0;
+#pragma unroll
+         for( int p2 = 0; p2 < 8; ++p2 ) if( p2 < i ) sacc += G[(o + i + 1) * LD + o + p2] * x[p2];
+         x[i] = (i == cq) ? rdg[o + i] : ((i > cq) ? -rdg[o + i] * sacc : 0.0);
+      }
+#pragma unroll
+      for( int i = 0; i < 8; ++i ) if( i >= cq ) G[(o + cq) * LD + o + i] = x[i];
+   }
+   __syncthreads();
+#pragma unroll
+   for( int ls = 3; (1 << ls) < NBL; ++ls )
+   {
+      const int s = 1 << ls, lt = ls - 3;                        // s-blocks, (s/8)^2 = 4^lt tiles per pair
+      const int total = (NBL / (2 * s)) << (2 * lt);
+      // T = L21 W11   (W11 lower triangular: k >= column tile)
+      for( int idx = w; idx < total; idx += NWARP )
+      {
+         const int pr = idx >> (2 * lt), rem = idx & ((1 << (2 * lt)) - 1), ti = rem >> lt, tj = rem & ((1 << lt) - 1);
+         const int o = 2 * s * pr;
+         const double* Lrow = G + (size_t)(o + s + 8 * ti + fr + 1) * LD + o + fc;
+         const double* Wcol = G + (size_t)(o + 8 * tj + fr) * LD + o + fc;
+         const int cdiag = 8 * tj + fr - fc;
+         double d0, d1;
+         tile_product(8 * tj, s, [&](int k0) { return Lrow[k0]; }, [&](int k0) { return (k0 >= cdiag) ? Wcol[k0] : 0.0; }, d0, d1);
+         *reinterpret_cast<double2*>(Tr + (size_t)(pr * s + 8 * ti + fr) * LD + 8 * tj + 2 * fc) = make_double2(d0, d1);
+      }
+      __syncthreads();
+      // W21 = -W22 T  (W22 lower triangular: k <= row tile)
+      for( int idx = w; idx < total; idx += NWARP )
+      {
+         const int pr = idx >> (2 * lt), rem = idx & ((1 << (2 * lt)) - 1), ti = rem >> lt, tj = rem & ((1 << lt) - 1);
+         const int o = 2 * s * pr;
+         const int rrow = o + s + 8 * ti + fr;
+         const double* W2 = G + (size_t)(o + s + fc) * LD + rrow;
+         const double* Tc = Tr + (size_t)(pr * s + fc) * LD + 8 * tj + fr;
+         const int rdiag = 8 * ti + fr - fc;
+         double d0, d1;
+         tile_product(0, 8 * ti + 8, [&](int k0) { return (k0 <= rdiag) ? -W2[(size_t)k0 * LD] : 0.0; }, [&](int k0) { return Tc[(size_t)k0 * LD]; }, d0, d1);
+         G[(size_t)(o + 8 * tj + 2 * fc) * LD + rrow] = d0;
+         G[(size_t)(o + 8 * tj + 2 * fc + 1) * LD + rrow] = d1;
+      }
+      __syncthreads();
+   }
+   tc3 = clock64();
+   if( Linv != nullptr )
+      for( int e = tid; e < nb * nb; e += NTHREADS )
+      {
+         const int i = e % nb, j = e / nb;
+         Linv[(size_t)j * ldi + i] = (i >= j) ? G[j * LD + i] : 0.0;
+      }
+   if( diaginv != nullptr )
+      for( int e = tid; e < NBL * NBL; e += NTHREADS )
+      {
+         const int i = e % NBL, j = e / NBL;
+         diaginv[(size_t)j * NBL + i] = (i < nb && j < nb && i >= j) ? G[j * LD + i] : 0.0;
+      }
+   if( dbg != nullptr && tid == 0 )
+   {
+      dbg[0] = tc1 - tc0; dbg[1] = tc2 - tc1; dbg[2] = tc3 - tc2; dbg[3] = clock64() - tc3;
+   }
+}
+
+template <int NBL> constexpr size_t leaf_smem() { return sizeof(double) * ((size_t)(NBL + 1) * (NBL + 4) + (size_t)(NBL / 2) * (NBL + 4) + 9 * (size_t)NBL); }
+
 __global__ void copy2d_kernel(int m, int n, const double* __restrict__ src, int lds, double* __restrict__ dst, int ldd)
 {
    int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -326,31 +588,62 @@ cudaError_t copy2d(cudaStream_t st, int m, int n, const double* src, int lds, do
    return cudaGetLastError();
 }
 
-constexpr size_t DIAG_SMEM = 0;
+// leaf order of the recursion: 128 (default) or 64; SDPCUDA_LEAF=old selects the previous register-tile kernel (A/B timing)
+int leaf_config()
+{
+   const char* e = getenv("SDPCUDA_LEAF");      // read on every call (tests switch it between solves)
+   if( e != nullptr && strcmp(e, "64") == 0 ) return 64;
+   if( e != nullptr && strcmp(e, "old") == 0 ) return 0;
+   return 128;
+}
 
 cudaError_t launch_diag(cudaStream_t st, int mode, int nb, double* A, int lda, double* Linv, int ldi, double* diaginv, int* info, int off)
 {
    ProfScope prof(st, PROF_DIAG, (mode == 0 ? 1.0 : 0.0) * nb * (double)nb * nb / 3.0 + ((Linv || diaginv) ? nb * (double)nb * nb / 3.0 : 0.0));
-   diag_block_kernel<<<1, 256, DIAG_SMEM, st>>>(mode, nb, A, lda, Linv, ldi, diaginv, info, off, g_diag_dbg);
+   if( leaf_config() == 0 && nb <= NB )
+   {
+      diag_block_kernel<<<1, 256, 0, st>>>(mode, nb, A, lda, Linv, ldi, diaginv, info, off, g_diag_dbg);
+      count_launch();
+      return cudaGetLastError();
+   }
+   static bool configured[64] = {false};        // per-device function attributes
+   int dev = 0;
+   SDPK_CUDA_CHECK( cudaGetDevice(&dev) );
+   if( !configured[dev & 63] )
+   {
+      SDPK_CUDA_CHECK( cudaFuncSetAttribute(leaf_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)leaf_smem<64>()) );
+      SDPK_CUDA_CHECK( cudaFuncSetAttribute(leaf_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)leaf_smem<128>()) );
+      configured[dev & 63] = true;
+   }
+   if( nb <= 64 )
+      leaf_kernel<64><<<1, 256, leaf_smem<64>(), st>>>(mode, nb, A, lda, Linv, ldi, diaginv, info, off, g_diag_dbg);
+   else if( nb <= 128 && diaginv == nullptr )
+      leaf_kernel<128><<<1, 512, leaf_smem<128>(), st>>>(mode, nb, A, lda, Linv, ldi, diaginv, info, off, g_diag_dbg);
+   else
+      return cudaErrorInvalidValue;
    count_launch();
    return cudaGetLastError();
 }
 
-int split_point(int n)
+// largest block handled by one leaf launch (the packed 64 x 64 diagonal inverses of the substitution path need 64)
+int leaf_order(const double* diaginv) { return (diaginv == nullptr && leaf_config() == 128) ? 128 : NB; }
+
+int split_point(int n, int leaf)
 {
-   int n1 = round_up(n / 2, NB);
-   if( n1 >= n ) n1 -= NB;
+   int n1 = round_up(n / 2, leaf);
+   if( n1 >= n ) n1 -= leaf;
    return n1;
 }
 
 cudaError_t chol_rec(cudaStream_t st, int n, double* A, int lda, double* Linv, int ldi, double* diaginv, double* work,
    int ldw, int* d_info, int off)
 {
-   if( n <= NB )
+   const int leaf = leaf_order(diaginv);
+   if( n <= leaf )
    {
       return launch_diag(st, 0, n, A, lda, Linv, ldi, diaginv ? diaginv + (size_t)(off / NB) * NB * NB : nullptr, d_info, off);
    }
-   const int n1 = split_point(n), n2 = n - n1;
+   const int n1 = split_point(n, leaf), n2 = n - n1;
    double* A21 = A + n1;
    double* A22 = A + (size_t)n1 * lda + n1;
    // without a wanted inverse the inverse of the leading block is still needed for L21: it goes to the work space
@@ -393,11 +686,12 @@ cudaError_t chol_rec(cudaStream_t st, int n, double* A, int lda, double* Linv, i
 
 cudaError_t trtri_rec(cudaStream_t st, int n, const double* L, int ldl, double* Linv, int ldi, double* work, int ldw)
 {
-   if( n <= NB )
+   const int leaf = leaf_order(nullptr);
+   if( n <= leaf )
    {
       return launch_diag(st, 1, n, const_cast<double*>(L), ldl, Linv, ldi, nullptr, nullptr, 0);
    }
-   const int n1 = split_point(n), n2 = n - n1;
+   const int n1 = split_point(n, leaf), n2 = n - n1;
    const double* L21 = L + n1;
    double* Li22 = Linv + (size_t)n1 * ldi + n1;
    SDPK_CUDA_CHECK( trtri_rec(st, n1, L, ldl, Linv, ldi, work, ldw) );

@@ -8,6 +8,16 @@
 
 namespace sdpk {
 
+// FP64 tensor-core instruction of sm_100a: D(8x8) += A(8x4) B(4x8); lane l holds A[l/4][l%4], B[l%4][l/4], D[l/4][2(l%4)+{0,1}]
+#ifdef __CUDACC__
+__device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double b)
+{
+   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+#endif
+
+
 // every launch goes through this counter so that sdpcuda_result.launches / bench.py's gpu_launches are real counts
 struct LaunchCounter { long long n = 0; };
 extern thread_local LaunchCounter* g_counter;
@@ -86,6 +96,7 @@ cudaError_t dmma_peak_probe(cudaStream_t st, int iters, double* d_sink, double* 
 // d_info: device int, set to the 1-based index of the first non-positive pivot (0 = success; is NOT reset here).
 // diaginv: optional workspace receiving the inverses of the NB x NB diagonal blocks of L (block b at b*NB*NB).
 constexpr int CHOL_NB = 64;
+constexpr int CHOL_LEAF_MAX = 128;   // largest diagonal block factorised by one CTA; work spaces are sized n + 2 * CHOL_LEAF_MAX columns
 extern long long* g_diag_dbg;      // optional device buffer (4 x int64) receiving the phase cycle counts of the diagonal-block kernel
 cudaError_t potrf_lower(cudaStream_t st, int n, double* A, int lda, double* Linv, int ldi, double* diaginv, double* work, int ldw, int* d_info);
 cudaError_t trtri_lower(cudaStream_t st, int n, const double* L, int ldl, double* Linv, int ldi, double* work, int ldw);

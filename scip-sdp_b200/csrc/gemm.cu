@@ -27,11 +27,6 @@ __device__ __forceinline__ void cp_async16(void* smem, const void* gmem, int src
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" :: "n"(N)); }
 
-__device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double b)
-{
-   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
-                : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
-}
 
 // loads one operand tile (BMN x BK logical) of stage buffer `s` from global memory
 // KCONTIG = false: global element (mn, k) at g[mn + k*ld]   -> smem [k][mn], lds = BMN + 4

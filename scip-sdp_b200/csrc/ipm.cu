@@ -348,8 +348,8 @@ int upload_problem(sdpcuda_handle* h, const sdpcuda_problem* P)
                             &h->K, &h->T1, &h->T2, &h->Rd} )
       CK( bf->ensure(ar) );
    const int ldmax = round_up(std::max(h->maxn, 1), 4);
-   CK( h->work.ensure((size_t)ldmax * (h->maxn + 2 * CHOL_NB)) );
-   CK( h->work2.ensure((size_t)ldmax * (h->maxn + 2 * CHOL_NB)) );
+   CK( h->work.ensure((size_t)ldmax * (h->maxn + 2 * CHOL_LEAF_MAX)) );
+   CK( h->work2.ensure((size_t)ldmax * (h->maxn + 2 * CHOL_LEAF_MAX)) );
    for( DBuf<double>* bf : {&h->y, &h->dy, &h->g, &h->rp, &h->AX, &h->DTx, &h->tm1, &h->tm2} )
       CK( bf->ensure(m + 1) );
    for( DBuf<double>* bf : {&h->x, &h->s, &h->dx, &h->ds, &h->dxa, &h->dsa, &h->klp, &h->rdlp, &h->Dy, &h->Ddy} )
@@ -358,8 +358,11 @@ int upload_problem(sdpcuda_handle* h, const sdpcuda_problem* P)
    CK( h->M.ensure((size_t)h->ldm * m) );
    CK( h->Mfac.ensure((size_t)h->ldm * m) );
    CK( h->diaginv.ensure((size_t)ceil_div(std::max(m, 1), CHOL_NB) * CHOL_NB * CHOL_NB) );
-   CK( h->Mwork.ensure((size_t)h->ldm * (m + 2 * CHOL_NB)) );
-   h->minv = (m <= 16384);      // 2 GB at the limit; the blocked substitution (one launch per 64 rows) is latency bound
+   CK( h->Mwork.ensure((size_t)h->ldm * (m + 2 * CHOL_LEAF_MAX)) );
+   {
+      const char* e = getenv("SDPCUDA_MINV_MAX");      // test knob: 0 forces the blocked substitution path
+      h->minv = (m <= (e != nullptr ? atoi(e) : 16384));
+   }      // 2 GB at the limit; the blocked substitution (one launch per 64 rows) is latency bound
    if( h->minv ) CK( h->MLinv.ensure((size_t)h->ldm * m) );
    CK( h->lzdesc.ensure(2 * (size_t)std::max(h->nb, 1)) );
    CK( h->lztickets.ensure(2 * (size_t)std::max(h->nb, 1)) );
@@ -1237,13 +1240,42 @@ int sdpcuda_dpotrf(sdpcuda_handle* h, int n, double* A, int lda, int* info)
    const int ld = round_up(std::max(n, 1), 4);
    int rc;
    if( (rc = up2d(h, h->kA, A, n, n, lda, ld)) ) return rc;
-   CK( h->kW.ensure((size_t)ld * (n + 2 * CHOL_NB)) );
+   CK( h->kW.ensure((size_t)ld * (n + 2 * CHOL_LEAF_MAX)) );
    CK( h->info.ensure(8) );
    CK( cudaMemsetAsync(h->info.p, 0, 8 * sizeof(int), h->st) );
-   CK( h->kC.ensure((size_t)ceil_div(std::max(n, 1), CHOL_NB) * CHOL_NB * CHOL_NB) );
-   CK( potrf_lower(h->st, n, h->kA.p, ld, nullptr, 0, h->kC.p, h->kW.p, ld, h->info.p) );
+   // even n: plain factor (widest leaf); odd n: with the packed 64 x 64 diagonal inverses of the substitution path
+   double* dinv = nullptr;
+   if( n & 1 )
+   {
+      CK( h->kC.ensure((size_t)ceil_div(std::max(n, 1), CHOL_NB) * CHOL_NB * CHOL_NB) );
+      dinv = h->kC.p;
+   }
+   CK( potrf_lower(h->st, n, h->kA.p, ld, nullptr, 0, dinv, h->kW.p, ld, h->info.p) );
    if( n > 0 )
       CK( cudaMemcpy2DAsync(A, sizeof(double) * lda, h->kA.p, sizeof(double) * ld, sizeof(double) * n, n, cudaMemcpyDeviceToHost, h->st) );
+   CK( cudaMemcpyAsync(h->h_info, h->info.p, sizeof(int), cudaMemcpyDeviceToHost, h->st) );
+   CK( cudaStreamSynchronize(h->st) );
+   *info = h->h_info[0];
+   return SDPCUDA_OK;
+}
+
+int sdpcuda_dpotrf_inv(sdpcuda_handle* h, int n, double* A, int lda, double* Linv, int ldi, int* info)
+{
+   if( h == nullptr || n < 0 || info == nullptr || Linv == nullptr ) return SDPCUDA_ERR_ARG;
+   if( set_device(h) ) return SDPCUDA_ERR_CUDA;
+   const int ld = round_up(std::max(n, 1), 4);
+   int rc;
+   if( (rc = up2d(h, h->kA, A, n, n, lda, ld)) ) return rc;
+   CK( h->kB.ensure((size_t)ld * std::max(n, 1)) );
+   CK( h->kW.ensure((size_t)ld * (n + 2 * CHOL_LEAF_MAX)) );
+   CK( h->info.ensure(8) );
+   CK( cudaMemsetAsync(h->info.p, 0, 8 * sizeof(int), h->st) );
+   CK( potrf_lower(h->st, n, h->kA.p, ld, h->kB.p, ld, nullptr, h->kW.p, ld, h->info.p) );
+   if( n > 0 )
+   {
+      CK( cudaMemcpy2DAsync(A, sizeof(double) * lda, h->kA.p, sizeof(double) * ld, sizeof(double) * n, n, cudaMemcpyDeviceToHost, h->st) );
+      CK( cudaMemcpy2DAsync(Linv, sizeof(double) * ldi, h->kB.p, sizeof(double) * ld, sizeof(double) * n, n, cudaMemcpyDeviceToHost, h->st) );
+   }
    CK( cudaMemcpyAsync(h->h_info, h->info.p, sizeof(int), cudaMemcpyDeviceToHost, h->st) );
    CK( cudaStreamSynchronize(h->st) );
    *info = h->h_info[0];
@@ -1258,7 +1290,7 @@ int sdpcuda_psd_check(sdpcuda_handle* h, int n, const double* A, int lda, double
    const int ld = round_up(n, 4);
    int rc;
    if( (rc = up2d(h, h->kA, A, n, n, lda, ld)) ) return rc;
-   CK( h->kW.ensure((size_t)ld * (n + 2 * CHOL_NB)) );
+   CK( h->kW.ensure((size_t)ld * (n + 2 * CHOL_LEAF_MAX)) );
    CK( h->info.ensure(8) );
    CK( cudaMemsetAsync(h->info.p, 0, 8 * sizeof(int), h->st) );
    if( shift != 0.0 ) CK( add_diagonal(h->st, n, h->kA.p, ld, shift) );
@@ -1277,7 +1309,7 @@ int sdpcuda_dtrtri(sdpcuda_handle* h, int n, double* L, int ldl)
    int rc;
    if( (rc = up2d(h, h->kA, L, n, n, ldl, ld)) ) return rc;
    CK( h->kB.ensure((size_t)ld * std::max(n, 1)) );
-   CK( h->kW.ensure((size_t)ld * (n + 2 * CHOL_NB)) );
+   CK( h->kW.ensure((size_t)ld * (n + 2 * CHOL_LEAF_MAX)) );
    CK( trtri_lower(h->st, n, h->kA.p, ld, h->kB.p, ld, h->kW.p, ld) );
    if( n > 0 )
       CK( cudaMemcpy2DAsync(L, sizeof(double) * ldl, h->kB.p, sizeof(double) * ld, sizeof(double) * n, n, cudaMemcpyDeviceToHost, h->st) );
@@ -1374,22 +1406,24 @@ int sdpcuda_time_kernel(sdpcuda_handle* h, int kind, int n, int reps, double* ms
    }
    if( kind == 9 )
    {
-      // phase timing of the diagonal-block kernel on a 64 x 64 SPD matrix
-      CK( h->kA.ensure(64 * 64) ); CK( h->kB.ensure(64 * 64) ); CK( h->kC.ensure(64) ); CK( h->info.ensure(8) );
-      CK( h->kW.ensure(64 * 256) ); CK( h->K.ensure(64 * 64) );
-      fill_random_kernel<<<16, 256, 0, st>>>(64 * 64, h->kA.p, 17u, 64.0, 64);
-      CK( sym_average(st, 64, h->kA.p, 64, nullptr) );
-      long long hv[4];
+      // phase timing of the leaf kernel on an nl x nl SPD matrix (nl = 64 or 128)
+      const int nl = (n == 128) ? 128 : 64;
+      CK( h->kA.ensure(nl * nl) ); CK( h->kB.ensure(nl * nl) ); CK( h->kC.ensure(64) ); CK( h->info.ensure(8) );
+      CK( cudaMemsetAsync(h->kC.p, 0, 64 * sizeof(double), st) );
+      CK( h->kW.ensure(nl * 512) ); CK( h->K.ensure(nl * nl) );
+      fill_random_kernel<<<16, 256, 0, st>>>(nl * nl, h->kA.p, 17u, (double)nl, nl);
+      CK( sym_average(st, nl, h->kA.p, nl, nullptr) );
+      long long hv[12] = {0};
       g_diag_dbg = reinterpret_cast<long long*>(h->kC.p);
       for( int r = 0; r < 3; ++r )
       {
-         CK( cudaMemcpyAsync(h->kB.p, h->kA.p, 64 * 64 * sizeof(double), cudaMemcpyDeviceToDevice, st) );
-         CK( potrf_lower(st, 64, h->kB.p, 64, h->K.p, 64, nullptr, h->kW.p, 64, h->info.p) );
+         CK( cudaMemcpyAsync(h->kB.p, h->kA.p, nl * nl * sizeof(double), cudaMemcpyDeviceToDevice, st) );
+         CK( potrf_lower(st, nl, h->kB.p, nl, h->K.p, nl, nullptr, h->kW.p, nl, h->info.p) );
          CK( cudaMemcpyAsync(hv, h->kC.p, sizeof(hv), cudaMemcpyDeviceToHost, st) );
          CK( cudaStreamSynchronize(st) );
       }
       g_diag_dbg = nullptr;
-      printf("[diag kernel phases, cycles] load %lld  factor %lld  inverse %lld  store %lld\n", hv[0], hv[1], hv[2], hv[3]);
+      printf("[leaf kernel %d phases, cycles] load %lld  factor %lld  store L + inverse %lld  store inverse %lld\n", nl, hv[0], hv[1], hv[2], hv[3]);
       *ms_per_launch = (double)hv[1]; *work = (double)hv[2];
       return SDPCUDA_OK;
    }
@@ -1411,7 +1445,7 @@ int sdpcuda_time_kernel(sdpcuda_handle* h, int kind, int n, int reps, double* ms
       return SDPCUDA_OK;
    }
    if( n <= 0 ) return SDPCUDA_ERR_ARG;
-   CK( h->kA.ensure(nn) ); CK( h->kB.ensure(nn) ); CK( h->kC.ensure(nn) ); CK( h->kW.ensure((size_t)ld * (n + 2 * CHOL_NB)) );
+   CK( h->kA.ensure(nn) ); CK( h->kB.ensure(nn) ); CK( h->kC.ensure(nn) ); CK( h->kW.ensure((size_t)ld * (n + 2 * CHOL_LEAF_MAX)) );
    CK( h->K.ensure(nn) );
    CK( h->info.ensure(8) );
    fill_random_kernel<<<1024, 256, 0, st>>>(nn, h->kA.p, 17u, kind == 2 || kind == 3 ? (double)n : 0.0, ld);
@@ -1450,6 +1484,7 @@ int sdpcuda_time_kernel(sdpcuda_handle* h, int kind, int n, int reps, double* ms
    CK( cudaEventRecord(h->ev1, st) );
    CK( cudaStreamSynchronize(st) );
    cudaEventElapsedTime(&ms, h->ev0, h->ev1);
+   if( h->prof.on ) h->prof.collect();
    *ms_per_launch = ms / reps;
    const double dn = (double)n;
    switch( kind )

@@ -53,6 +53,43 @@ def test_potrf_and_trtri_match_lapack(gpu, cpu, n):
     assert np.abs(Li @ Lr - np.eye(n)).max() <= 1e-11
 
 
+@pytest.mark.parametrize("n", [1, 3, 8, 63, 64, 65, 100, 127, 128, 129, 192, 250, 257, 700, 1501])
+def test_potrf_with_inverse_factor(gpu, cpu, n):
+    rng = np.random.default_rng(7000 + n)
+    G = rng.standard_normal((n, n))
+    A = G @ G.T + n * np.eye(n)
+    L, Li, info = gpu.dpotrf_inv(A)
+    Lr, Lir, infor = cpu.dpotrf_inv(A)
+    assert info == 0 and infor == 0
+    assert np.abs(L - Lr).max() <= 1e-12 * np.abs(Lr).max()
+    assert np.abs(Li - Lir).max() <= 1e-11 * np.abs(Lir).max()
+    assert np.abs(np.triu(Li, 1)).max() == 0.0
+    assert np.abs(Li @ L - np.eye(n)).max() <= 1e-11
+
+
+def test_potrf_with_inverse_badly_scaled(gpu, cpu):
+    # diagonal scaling over 12 orders of magnitude: pivots must stay accurate relative to their own size
+    rng = np.random.default_rng(99)
+    n = 128
+    G = rng.standard_normal((n, n))
+    D = np.diag(10.0 ** rng.uniform(-6, 6, n))
+    A = D @ (G @ G.T + n * np.eye(n)) @ D
+    L, Li, info = gpu.dpotrf_inv(A)
+    Lr, Lir, _ = cpu.dpotrf_inv(A)
+    assert info == 0
+    assert (np.abs(L - Lr) <= 1e-11 * np.abs(np.diag(Lr))[:, None] + 1e-300).all()
+    assert np.abs(Li @ L - np.eye(n)).max() <= 1e-9
+
+
+@pytest.mark.parametrize("n,bad", [(64, 0), (100, 70), (128, 127), (300, 129), (300, 64)])
+def test_potrf_pivot_index(gpu, n, bad):
+    A = np.eye(n); A[bad, bad] = -1.0
+    _, info = gpu.dpotrf(A)
+    assert info == bad + 1
+    _, _, info = gpu.dpotrf_inv(A)
+    assert info == bad + 1
+
+
 def test_potrf_reports_indefinite_matrix(gpu):
     A = np.eye(100); A[70, 70] = -1.0
     _, info = gpu.dpotrf(A)

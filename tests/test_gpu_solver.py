@@ -33,6 +33,21 @@ def _instances():
     yield "cls-40", lambda: generators.cls(40, 25, 5, seed=14)
 
 
+@pytest.mark.parametrize("leaf", ["128", "64"])
+def test_substitution_path_for_the_schur_system(gpu, cpu, leaf, monkeypatch):
+    """M dy = g by blocked forward/backward substitution (the path of Schur complements too large for an explicit inverse
+    factor), forced on a small instance; also covers both leaf orders of the recursive Cholesky"""
+    fp, _ = generators.mkp(24, seed=11).flatten()
+    monkeypatch.setenv("SDPCUDA_PATH", "m")
+    monkeypatch.setenv("SDPCUDA_MINV_MAX", "0")
+    monkeypatch.setenv("SDPCUDA_LEAF", leaf)
+    r = gpu.solve(fp, gaptol=1e-7, feastol=1e-7)
+    ref = cpu.solve(fp, gaptol=1e-7, feastol=1e-7)
+    assert ref["phase_name"] == "pdOPT" and r["phase_name"] == "pdOPT", (r["phase_name"], r["stop_name"])
+    assert abs(r["dobj"] - ref["dobj"]) <= 1e-5 * max(1.0, abs(ref["dobj"]))
+    _check_kkt(fp, r, 1e-6)
+
+
 @pytest.mark.parametrize("path", ["single-cta", "multi-kernel"])
 @pytest.mark.parametrize("name,make", list(_instances()), ids=[n for n, _ in _instances()])
 def test_relaxation_matches_oracle(gpu, cpu, name, make, path, monkeypatch):
