@@ -113,7 +113,18 @@ cudaError_t lanczos_lambda_min(cudaStream_t st, int n, const double* B, int ldb,
 size_t lanczos_work_doubles(int n, int maxit);
 // batched, adaptive variant: all matrices advance together, convergence is checked on the host every 8 steps
 constexpr int LZB_MAXIT = 64;
-struct LzDesc { int n; int ld; const double* B; double* Q /* (LZB_MAXIT+2)*n */; double* ab /* 2*LZB_MAXIT */; double* out /* 3 */; double* safe /* extra destination of out[0], or nullptr */; };
+struct LzDesc
+{
+   int n; int ld;
+   const double* B;      // explicit symmetric matrix (full storage), or nullptr when the operator is implicit
+   double* Q;            // (LZB_MAXIT+2)*n Lanczos vectors
+   double* ab;           // 2*LZB_MAXIT recurrence coefficients
+   double* out;          // 3 results: safe value, Ritz value, residual bound
+   double* safe;         // extra destination of out[0], or nullptr
+   // implicit operator  v -> W (D (W' v))  with W lower triangular, WT = W' stored, D symmetric (all n x n, leading dimension ld)
+   const double* W; const double* WT; const double* D;
+   double* t1; double* t2;
+};
 // blocks of order <= LZS_MAX_N: one CTA per matrix runs the whole recurrence out of shared memory (one launch, no host check)
 constexpr int LZS_MAX_N = 128;
 cudaError_t lanczos_small_batched(cudaStream_t st, int nmat, int maxn, const LzDesc* d_desc, int maxit);

@@ -416,6 +416,98 @@ lzb_update_kernel(const LzDesc* __restrict__ D, int j, int maxit)
    for( int i = tid; i < n; i += nt ) w[i] *= cf;
 }
 
+// Dot products of 8 consecutive columns i0 .. i0+7 of a column-major matrix with a vector, by one CTA of 256 threads.
+// mode 0: full column; mode 1: entries k >= column index (lower triangular W); mode 2: entries k <= column index (upper
+// triangular W').  All 256 threads sweep every column together (16-byte loads, 8 columns x 2 chunks issued before the first
+// use), so that a whole 8-column panel is in flight at once instead of one 16 KB column per warp; the 8 sums are reduced
+// through shared memory in a fixed order.  Results in res[0..7] (valid after the trailing barrier).
+__device__ __forceinline__ void coldot8(const double* __restrict__ Mx, int ld, int n, int i0, int mode,
+   const double* __restrict__ vin, double* res /* shared, 8 */, double (*part)[8] /* shared, [8 warps][8] */)
+{
+   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+   double acc[8];
+#pragma unroll
+   for( int c = 0; c < 8; ++c ) acc[c] = 0.0;
+   const int ncol = min(8, n - i0);
+   const int nev = n & ~1;
+   // triangular operands: whole 1024-row chunks outside the non-zero range of these 8 columns are skipped
+   const int kbeg = (mode == 1) ? (i0 / 1024) * 1024 : 0;
+   const int kfin = (mode == 2) ? min(nev, i0 + 8) : nev;
+   for( int k = kbeg + 2 * tid; k < kfin; k += 1024 )
+   {
+      const int k2 = k + 512;
+      const bool in2 = k2 < kfin;
+      // the vector may start at an odd element: scalar loads (cached), 16-byte loads only for the matrix columns
+      const double2 v0 = make_double2(vin[k], vin[k + 1]);
+      const double2 v1 = in2 ? make_double2(vin[k2], vin[k2 + 1]) : make_double2(0.0, 0.0);
+      double2 m0[8], m1[8];
+#pragma unroll
+      for( int c = 0; c < 8; ++c )
+      {
+         const double* col = Mx + (size_t)(i0 + c) * ld;
+         m0[c] = (c < ncol) ? *reinterpret_cast<const double2*>(col + k) : make_double2(0.0, 0.0);
+         m1[c] = (c < ncol && in2) ? *reinterpret_cast<const double2*>(col + k2) : make_double2(0.0, 0.0);
+      }
+#pragma unroll
+      for( int c = 0; c < 8; ++c )
+      {
+         const int i = i0 + c;
+         if( mode == 0 )
+            acc[c] += m0[c].x * v0.x + m0[c].y * v0.y + m1[c].x * v1.x + m1[c].y * v1.y;
+         else if( mode == 1 )
+            acc[c] += (k >= i ? m0[c].x * v0.x : 0.0) + (k + 1 >= i ? m0[c].y * v0.y : 0.0)
+                    + (k2 >= i ? m1[c].x * v1.x : 0.0) + (k2 + 1 >= i ? m1[c].y * v1.y : 0.0);
+         else
+            acc[c] += (k <= i ? m0[c].x * v0.x : 0.0) + (k + 1 <= i ? m0[c].y * v0.y : 0.0)
+                    + (k2 <= i ? m1[c].x * v1.x : 0.0) + (k2 + 1 <= i ? m1[c].y * v1.y : 0.0);
+      }
+   }
+   if( (n & 1) && tid == 0 )
+   {
+      const int k = n - 1;
+#pragma unroll
+      for( int c = 0; c < 8; ++c )
+      {
+         const int i = i0 + c;
+         if( c < ncol && (mode == 0 || (mode == 1 && k >= i) || (mode == 2 && k <= i)) )
+            acc[c] += Mx[(size_t)i * ld + k] * vin[k];
+      }
+   }
+#pragma unroll
+   for( int c = 0; c < 8; ++c )
+   {
+      double v = acc[c];
+#pragma unroll
+      for( int o = 16; o > 0; o >>= 1 ) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if( lane == 0 ) part[wid][c] = v;
+   }
+   __syncthreads();
+   if( tid < 8 )
+   {
+      double v = 0.0;
+#pragma unroll
+      for( int q = 0; q < 8; ++q ) v += part[q][tid];
+      res[tid] = v;
+   }
+   __syncthreads();
+}
+
+// first two stages of the implicit operator v -> W (D (W' v)).  stage 0: t1 = W' v_j (column i of W, entries i..n-1);
+// stage 1: t2 = D t1 (full column of D)
+__global__ void __launch_bounds__(256)
+lz_coldot_kernel(const LzDesc* __restrict__ D, int j, int stage)
+{
+   __shared__ double res[8];
+   __shared__ double part[8][8];
+   const LzDesc d = D[blockIdx.y];
+   const int n = d.n, i0 = blockIdx.x * 8;
+   if( i0 >= n || j >= n || d.B != nullptr ) return;
+   const double* vin = (stage == 0) ? d.Q + (size_t)j * n : d.t1;
+   coldot8(stage == 0 ? d.W : d.D, d.ld, n, i0, stage == 0 ? 1 : 0, vin, res, part);
+   double* out = (stage == 0) ? d.t1 : d.t2;
+   if( threadIdx.x < 8 && i0 + (int)threadIdx.x < n ) out[i0 + threadIdx.x] = res[threadIdx.x];
+}
+
 // one Lanczos step in ONE launch: every CTA forms 8 rows of u = B v_j (warp per row, contiguous column of the symmetric
 // matrix) and its share of alpha = u.v_j; the CTA that finishes last (atomic ticket) completes the step for the whole vector:
 // alpha, w = u - alpha v_j - beta_{j-1} v_{j-1}, beta_j = |w|, v_{j+1} = w / beta_j.  Plain three-term recurrence (no
@@ -426,38 +518,25 @@ lzb_step_kernel(const LzDesc* __restrict__ D, int j, int maxit, unsigned* __rest
    __shared__ double red[32];
    __shared__ bool last;
    const LzDesc d = D[blockIdx.y];
-   const int n = d.n, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+   const int n = d.n, tid = threadIdx.x;
    const int nblk = (n + 7) / 8;
    if( (int)blockIdx.x >= nblk || j >= n ) return;
-   const int i = blockIdx.x * 8 + wid;
+   __shared__ double res[8];
+   __shared__ double part[8][8];
    double* Q = d.Q;
    const double* __restrict__ v = Q + (size_t)j * n;
    double* w = Q + (size_t)(j + 1) * n;
-   double contrib = 0.0;
-   if( i < n )
+   // explicit matrix: u = B v_j.  Implicit operator: last stage u = W t2, row i of W = column i of WT, entries 0..i
+   const bool implicit = (d.B == nullptr);
+   const int i0 = blockIdx.x * 8;
+   coldot8(implicit ? d.WT : d.B, d.ld, n, i0, implicit ? 2 : 0, implicit ? d.t2 : v, res, part);
+   if( tid < 8 )
    {
-      // the column is 16-byte aligned (leading dimensions are multiples of 4, blocks 128-byte aligned): 4 independent
-      // 16-byte loads per lane and iteration keep enough bytes in flight to run at memory speed
-      const double2* __restrict__ col2 = reinterpret_cast<const double2*>(d.B + (size_t)i * d.ld);
-      const int n2 = n >> 1;
-      double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-      int k = lane;
-      for( ; k + 96 < n2; k += 128 )
-      {
-         double2 c0 = col2[k], c1 = col2[k + 32], c2 = col2[k + 64], c3 = col2[k + 96];
-         s0 += c0.x * v[2 * k] + c0.y * v[2 * k + 1];
-         s1 += c1.x * v[2 * k + 64] + c1.y * v[2 * k + 65];
-         s2 += c2.x * v[2 * k + 128] + c2.y * v[2 * k + 129];
-         s3 += c3.x * v[2 * k + 192] + c3.y * v[2 * k + 193];
-      }
-      for( ; k < n2; k += 32 ) { double2 c0 = col2[k]; s0 += c0.x * v[2 * k] + c0.y * v[2 * k + 1]; }
-      if( (n & 1) && lane == 0 ) s1 += d.B[(size_t)i * d.ld + n - 1] * v[n - 1];
-      double sum = (s0 + s1) + (s2 + s3);
-#pragma unroll
-      for( int o = 16; o > 0; o >>= 1 ) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-      if( lane == 0 ) { w[i] = sum; contrib = sum * v[i]; }
+      const int i = i0 + tid;
+      double contrib = 0.0;
+      if( i < n ) { w[i] = res[tid]; contrib = res[tid] * v[i]; }
+      red[tid] = contrib;
    }
-   if( lane == 0 ) red[wid] = contrib;
    __syncthreads();
    if( tid == 0 )
    {
@@ -740,7 +819,13 @@ cudaError_t lanczos_batched(cudaStream_t st, int nmat, const LzDesc* h_desc, LzD
    if( nmat <= 0 ) return cudaSuccess;
    int maxn = 0, minn = 1 << 30;
    double bytes = 0.0;
-   for( int i = 0; i < nmat; ++i ) { maxn = std::max(maxn, h_desc[i].n); minn = std::min(minn, h_desc[i].n); bytes += 8.0 * h_desc[i].n * (double)h_desc[i].n; }
+   bool any_implicit = false;
+   for( int i = 0; i < nmat; ++i )
+   {
+      maxn = std::max(maxn, h_desc[i].n); minn = std::min(minn, h_desc[i].n);
+      bytes += 8.0 * h_desc[i].n * (double)h_desc[i].n * (h_desc[i].B == nullptr ? 2.0 : 1.0);
+      any_implicit = any_implicit || (h_desc[i].B == nullptr);
+   }
    maxit = std::min(maxit, minn);
    SDPK_CUDA_CHECK( cudaMemcpyAsync(d_desc, h_desc, sizeof(LzDesc) * nmat, cudaMemcpyHostToDevice, st) );
    ProfScope prof(st, PROF_EIG, 0.0);
@@ -754,6 +839,12 @@ cudaError_t lanczos_batched(cudaStream_t st, int nmat, const LzDesc* h_desc, LzD
       for( ; j < jend; ++j )
       {
          dim3 grid(ceil_div(maxn, 8), nmat);
+         if( any_implicit )
+         {
+            lz_coldot_kernel<<<grid, 256, 0, st>>>(d_desc, j, 0);
+            lz_coldot_kernel<<<grid, 256, 0, st>>>(d_desc, j, 1);
+            count_launch(2);
+         }
          lzb_step_kernel<<<grid, 256, 0, st>>>(d_desc, j, LZB_MAXIT, tickets, partials, pstride);
          count_launch();
       }

@@ -179,11 +179,10 @@ gemm_dmma_kernel(int M, int N, int K, double alpha, const double* __restrict__ A
    }
 }
 
-template <int BM, int BN, bool TA, bool TB>
+template <int BM, int BN, bool TA, bool TB, int STAGES>
 cudaError_t launch(cudaStream_t st, int m, int n, int k, double alpha, const double* A, int lda, long long sA,
    const double* B, int ldb, long long sB, double beta, double* C, int ldc, long long sC, int batch, int flags)
 {
-   constexpr int STAGES = 3;
    constexpr int A_ELEMS = TA ? BM * (BK + 4) : BK * (BM + 4);
    constexpr int B_ELEMS = TB ? BK * (BN + 4) : BN * (BK + 4);
    constexpr size_t SMEM = (size_t)STAGES * (A_ELEMS + B_ELEMS) * sizeof(double);
@@ -237,16 +236,23 @@ cudaError_t gemm(cudaStream_t st, bool ta, bool tb, int m, int n, int k, double 
    // small problems use 32 x 32 tiles to fill more SMs
    const bool small = ((long long)ceil_div(m, 64) * ceil_div(n, 64) * batch) < 148;
    ProfScope prof(st, small ? PROF_GEMM_SMALL : PROF_GEMM, 2.0 * m * (double)n * k * batch * frac);
-#define SDPK_GEMM_DISPATCH(BM, BN) \
+#define SDPK_GEMM_DISPATCH(BM, BN, ST) \
    do { \
-      if( !ta && !tb ) return launch<BM, BN, false, false>(st, m, n, k, alpha, A, lda, sA, B, ldb, sB, beta, C, ldc, sC, batch, flags); \
-      if( !ta &&  tb ) return launch<BM, BN, false, true >(st, m, n, k, alpha, A, lda, sA, B, ldb, sB, beta, C, ldc, sC, batch, flags); \
-      if(  ta && !tb ) return launch<BM, BN, true,  false>(st, m, n, k, alpha, A, lda, sA, B, ldb, sB, beta, C, ldc, sC, batch, flags); \
-      return launch<BM, BN, true, true>(st, m, n, k, alpha, A, lda, sA, B, ldb, sB, beta, C, ldc, sC, batch, flags); \
+      if( !ta && !tb ) return launch<BM, BN, false, false, ST>(st, m, n, k, alpha, A, lda, sA, B, ldb, sB, beta, C, ldc, sC, batch, flags); \
+      if( !ta &&  tb ) return launch<BM, BN, false, true,  ST>(st, m, n, k, alpha, A, lda, sA, B, ldb, sB, beta, C, ldc, sC, batch, flags); \
+      if(  ta && !tb ) return launch<BM, BN, true,  false, ST>(st, m, n, k, alpha, A, lda, sA, B, ldb, sB, beta, C, ldc, sC, batch, flags); \
+      return launch<BM, BN, true, true, ST>(st, m, n, k, alpha, A, lda, sA, B, ldb, sB, beta, C, ldc, sC, batch, flags); \
    } while( 0 )
    if( small )
-      SDPK_GEMM_DISPATCH(32, 32);
-   SDPK_GEMM_DISPATCH(64, 64);
+   {
+      // few CTAs (the GEMMs inside the factorisation chains): latency bound, so keep the whole k range in flight with a deep
+      // cp.async ring; many small CTAs (batched products): shallower ring, more CTAs per SM
+      const long long ctas = (long long)ceil_div(m, 32) * ceil_div(n, 32) * batch;
+      if( ctas <= 2 * 148 )
+         SDPK_GEMM_DISPATCH(32, 32, 8);
+      SDPK_GEMM_DISPATCH(32, 32, 4);
+   }
+   SDPK_GEMM_DISPATCH(64, 64, 3);
 #undef SDPK_GEMM_DISPATCH
 }
 

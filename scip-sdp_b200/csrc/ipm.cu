@@ -98,6 +98,9 @@ struct sdpcuda_handle
    DBuf<unsigned> lztickets;
    DBuf<double> lzpart;
    std::vector<LzDesc> h_lzdesc, h_lzsmall;
+   DBuf<double> LinvT, LXinvT;       // transposed inverse factors of the large blocks (implicit step-length operators)
+   bool lzimplicit = false;
+   int lzsteps = 0;                  // Lanczos steps of the last batched run (diagnostics)
    bool minv = false;                // explicit inverse factor of M (m <= 16384): solves become two triangular mat-vecs
    DBuf<double> partials, stats, scal, eigw, lzwork;
    DBuf<int> info;
@@ -375,9 +378,13 @@ int upload_problem(sdpcuda_handle* h, const sdpcuda_problem* P)
    {
       // Lanczos work space for the X-side and S-side matrices of every large block
       size_t need = 16;
+      bool anybig = false;
       for( const Block& bk : h->blk )
-         if( bk.n > JACOBI_MAX_N ) need += 2 * ((size_t)(LZB_MAXIT + 2) * bk.n + 2 * LZB_MAXIT + 8);
+         if( bk.n > LZS_MAX_N ) { need += 2 * ((size_t)(LZB_MAXIT + 4) * bk.n + 2 * LZB_MAXIT + 8); anybig = true; }
       CK( h->lzwork.ensure(need) );
+      const char* e = getenv("SDPCUDA_LZ_IMPLICIT");      // 0: always explicit matrices, 1 (default): implicit for the short predictor runs, 2: always
+      h->lzimplicit = anybig && !(e != nullptr && atoi(e) == 0);
+      if( h->lzimplicit ) { CK( h->LinvT.ensure(h->arena) ); CK( h->LXinvT.ensure(h->arena) ); }
    }
    CK( h->info.ensure(8) );
    return SDPCUDA_OK;
@@ -434,11 +441,15 @@ template <class F> int run_graphed(sdpcuda_handle* h, sdpcuda_handle::GraphCache
 }
 
 // factor all blocks of Src into Lout (lower) and Linvout; info slot `slot` collects a failing pivot
-int factor_blocks(sdpcuda_handle* h, cudaStream_t st, double* work, const double* Src, double* Lout, double* Linvout, int slot)
+int factor_blocks(sdpcuda_handle* h, cudaStream_t st, double* work, const double* Src, double* Lout, double* Linvout, double* LinvTout, int slot)
 {
    CK( cudaMemcpyAsync(Lout, Src, h->arena * sizeof(double), cudaMemcpyDeviceToDevice, st) );
    for( const Block& bk : h->blk )
+   {
       CK( potrf_lower(st, bk.n, Lout + bk.off, bk.ld, Linvout + bk.off, bk.ld, nullptr, work, round_up(h->maxn, 4), h->info.p + slot) );
+      if( LinvTout != nullptr && bk.n > LZS_MAX_N )
+         CK( transpose(st, bk.n, Linvout + bk.off, bk.ld, LinvTout + bk.off, bk.ld) );
+   }
    return SDPCUDA_OK;
 }
 
@@ -496,18 +507,28 @@ int step_eigs(sdpcuda_handle* h, const double* dXdir, const double* dSdir, int m
    int nsmall = 0, maxsmall = 0, k = 0;
    for( const Block& bk : h->blk ) if( bk.n <= LZS_MAX_N ) nsmall += 2;
    int ismall = 0, ibig = nsmall;
+   bool implicit = h->lzimplicit && maxsteps <= 8;
+   {
+      const char* e = getenv("SDPCUDA_LZ_IMPLICIT");
+      if( h->lzimplicit && e != nullptr && atoi(e) == 2 ) implicit = true;
+   }
    for( const Block& bk : h->blk )
    {
       int rc;
-      if( (rc = form_scaled(h, bk, k, false, h->LXinv.p, dXdir, h->T2.p)) ) return rc;
-      if( (rc = form_scaled(h, bk, k, true, h->Linv.p, dSdir, h->K.p)) ) return rc;
+      const bool big = bk.n > LZS_MAX_N;
+      if( !(big && implicit) )
+      {
+         if( (rc = form_scaled(h, bk, k, false, h->LXinv.p, dXdir, h->T2.p)) ) return rc;
+         if( (rc = form_scaled(h, bk, k, true, h->Linv.p, dSdir, h->K.p)) ) return rc;
+      }
       for( int side = 0; side < 2; ++side )
       {
          LzDesc d;
          d.n = bk.n; d.ld = bk.ld;
          d.B = (side == 0 ? h->T2.p : h->K.p) + bk.off;
+         d.W = d.WT = d.D = nullptr; d.t1 = d.t2 = nullptr;
          d.safe = h->scal.p + 8 + side * nb + k;
-         if( bk.n <= LZS_MAX_N )
+         if( !big )
          {
             d.Q = nullptr; d.ab = nullptr;
             d.out = out3 + 3 * (ismall++);
@@ -517,8 +538,19 @@ int step_eigs(sdpcuda_handle* h, const double* dXdir, const double* dSdir, int m
          else
          {
             d.Q = lzw; lzw += (size_t)(LZB_MAXIT + 2) * bk.n;
+            d.t1 = lzw; lzw += bk.n;
+            d.t2 = lzw; lzw += bk.n;
             d.ab = lzw; lzw += 2 * LZB_MAXIT + 8;
             d.out = out3 + 3 * (ibig++);
+            if( implicit )
+            {
+               // lambda_min(W dA W') by Lanczos on the operator itself: three triangular / symmetric mat-vecs per step
+               // instead of two n^3 products up front (pays off for the short predictor runs)
+               d.B = nullptr;
+               d.W = (side == 0 ? h->LXinv.p : h->Linv.p) + bk.off;
+               d.WT = (side == 0 ? h->LXinvT.p : h->LinvT.p) + bk.off;
+               d.D = (side == 0 ? dXdir : dSdir) + bk.off;
+            }
             h->h_lzdesc.push_back(d);
          }
       }
@@ -533,7 +565,7 @@ int step_eigs(sdpcuda_handle* h, const double* dXdir, const double* dSdir, int m
       CK( lanczos_small_batched(h->st, nsmall, maxsmall, h->lzdesc.p, maxsteps <= 8 ? 16 : LZS_MAX_N) );
    }
    if( nbig > 0 )
-      CK( lanczos_batched(h->st, nbig, h->h_lzdesc.data(), h->lzdesc.p + nsmall, maxsteps, out3 + 3 * nsmall, h->h_stats + 2048, nullptr,
+      CK( lanczos_batched(h->st, nbig, h->h_lzdesc.data(), h->lzdesc.p + nsmall, maxsteps, out3 + 3 * nsmall, h->h_stats + 2048, &h->lzsteps,
             h->lztickets.p, h->lzpart.p, ceil_div(std::max(h->maxn, 8), 8)) );
    return SDPCUDA_OK;
 }
@@ -614,6 +646,7 @@ int sdpcuda_destroy(sdpcuda_handle* h)
    for( DBuf<long long>* bf : {&h->eoff, &h->pos, &h->mirror, &h->cpos, &h->cmirror} )
       bf->release();
    h->lzdesc.release(); h->lztickets.release(); h->lzpart.release(); h->smallres.release();
+   h->LinvT.release(); h->LXinvT.release();
    drop_graph(h->gS); drop_graph(h->gX); drop_graph(h->gM);
    cudaEventDestroy(h->ev0); cudaEventDestroy(h->ev1); cudaEventDestroy(h->evFork); cudaEventDestroy(h->evJoin);
    cudaStreamDestroy(h->st); cudaStreamDestroy(h->st2);
@@ -862,9 +895,9 @@ static int run_ipm(sdpcuda_handle* h, const sdpcuda_params* par, const double* s
       // launches of the critical one (S, main stream) are issued first so that the host does not delay it.
       CK( cudaEventRecord(h->evFork, st) );
       const bool graphs = (iter >= 1);      // the first iteration runs plain launches (one-time kernel attribute set-up)
-      rc = run_graphed(h, h->gS, st, graphs, [&]() { return factor_blocks(h, st, h->work.p, h->S.p, h->L.p, h->Linv.p, 0); }); if( rc ) return rc;
+      rc = run_graphed(h, h->gS, st, graphs, [&]() { return factor_blocks(h, st, h->work.p, h->S.p, h->L.p, h->Linv.p, h->lzimplicit ? h->LinvT.p : nullptr, 0); }); if( rc ) return rc;
       CK( cudaStreamWaitEvent(h->st2, h->evFork, 0) );
-      rc = run_graphed(h, h->gX, h->st2, graphs, [&]() { return factor_blocks(h, h->st2, h->work2.p, h->X.p, h->LX.p, h->LXinv.p, 1); }); if( rc ) return rc;
+      rc = run_graphed(h, h->gX, h->st2, graphs, [&]() { return factor_blocks(h, h->st2, h->work2.p, h->X.p, h->LX.p, h->LXinv.p, h->lzimplicit ? h->LXinvT.p : nullptr, 1); }); if( rc ) return rc;
       CK( cudaEventRecord(h->evJoin, h->st2) );
       // the factor of X is first needed for the primal step length: the main stream joins the side stream only there,
       // so that the X factorisation hides behind S^-1, the Schur complement, its factorisation and the predictor solve
@@ -979,7 +1012,7 @@ static int run_ipm(sdpcuda_handle* h, const sdpcuda_params* par, const double* s
          if( reg > 0.0 ) CK( add_diagonal(st, m, h->Mfac.p, h->ldm, reg) );
          CK( cudaMemsetAsync(h->info.p + 2, 0, sizeof(int), st) );
          rc = run_graphed(h, h->gM, st, graphs, [&]() -> int {
-            CK( potrf_lower(st, m, h->Mfac.p, h->ldm, h->minv ? h->MLinv.p : nullptr, h->ldm, h->diaginv.p, h->Mwork.p, h->ldm, h->info.p + 2) );
+            CK( potrf_lower(st, m, h->Mfac.p, h->ldm, h->minv ? h->MLinv.p : nullptr, h->ldm, h->minv ? nullptr : h->diaginv.p, h->Mwork.p, h->ldm, h->info.p + 2) );
             return SDPCUDA_OK; });
          if( rc ) return rc;
          CK( cudaMemcpyAsync(h->h_info, h->info.p, 8 * sizeof(int), cudaMemcpyDeviceToHost, st) );
@@ -1128,8 +1161,8 @@ static int run_ipm(sdpcuda_handle* h, const sdpcuda_params* par, const double* s
          CK( cudaStreamSynchronize(st) );
          float t[10];
          for( int e = 0; e < 10; ++e ) cudaEventElapsedTime(&t[e], h->phev[e], h->phev[e + 1]);
-         printf("  [phases ms] resid %.3f | factS %.3f | sync+Sinv %.3f | schur %.3f | factM %.3f | pred dir %.3f | pred eig %.3f | corr dir %.3f | corr eig %.3f | upd %.3f\n",
-            t[0], t[1], t[2], t[3], t[4], t[5], t[6], t[7], t[8], t[9]);
+         printf("  [phases ms] resid %.3f | factS %.3f | sync+Sinv %.3f | schur %.3f | factM %.3f | pred dir %.3f | pred eig %.3f | corr dir %.3f | corr eig %.3f (%d Lanczos steps) | upd %.3f\n",
+            t[0], t[1], t[2], t[3], t[4], t[5], t[6], t[7], t[8], h->lzsteps, t[9]);
       }
    }
 
