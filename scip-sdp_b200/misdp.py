@@ -28,6 +28,12 @@ class Misdp:
         self.ub = np.full(nvars, INF)
         self.integer = np.zeros(nvars, dtype=bool)
         self.rank1 = []
+        self.objsense = 1          # +1: the file asked for min obj'y; -1: it asked for max (obj is stored negated)
+        self.objoffset = 0.0       # constant term of the file's objective (in the file's sense)
+
+    def file_objective(self, value):
+        """objective value in the sense and with the constant of the input file, from the internal min-form value"""
+        return self.objsense * value + self.objoffset
 
     def add_entry(self, j, b, r, c, v):
         if r < c:
@@ -262,3 +268,150 @@ def read_sdpa(path):
         coefs, rhs = lprows[key]
         M.add_row(coefs, lhs=rhs)      # all LP-block inequalities are  a'y - a_0 >= 0
     return M
+
+
+# ---------------------------------------------------------------------- CBF (conic benchmark format)
+def read_cbf(path):
+    """Reader for the subset of CBF that src/scipsdp/reader_cbf.c accepts (VER 1-3): scalar variables in the cones F/L+/L-/L=,
+    matrix variables PSDVAR, scalar constraints CON in L=/L+/L-, LMIs PSDCON, INT, and the coordinate sections
+    OBJFCOORD/OBJACOORD/OBJBCOORD/FCOORD/ACOORD/BCOORD/HCOORD/DCOORD.  Conventions as in the reference:
+      * constraint i:  sum_j a_ij x_j + sum_v <F_iv, X_v> + b_i  in  its cone   (reader_cbf.c:720-853, 1512-1744)
+      * LMI k:         sum_j H_kj x_j + D_k  psd                                   (reader_cbf.c:1744-2160)  => A_0 = -D_k
+      * a matrix variable X_v of order n becomes n(n+1)/2 scalar variables (lower triangle) and an LMI sum x_ij E_ij psd;
+        off-diagonal coefficients of F / the objective count twice (reader_cbf.c:521-720, 1195-1211, 1479-1492)
+      * OBJSENSE MAX is turned into min of the negated objective (Misdp.objsense = -1).
+    Second-order cones and the RANK1 sections are recorded but not supported by the B&B harness."""
+    opener = gzip.open if str(path).endswith(".gz") else open
+    with opener(path, "rt") as f:
+        raw = [ln.split('#')[0].strip() for ln in f.read().splitlines()]
+    lines = [ln for ln in raw if ln]
+    pos = 0
+
+    def take():
+        nonlocal pos
+        ln = lines[pos]; pos += 1
+        return ln.split()
+
+    sense = 1
+    nscal = 0
+    varcones, concones = [], []
+    psdvar, psdcon = [], []
+    ints = []
+    sec = {k: [] for k in ("OBJFCOORD", "OBJACOORD", "OBJBCOORD", "FCOORD", "ACOORD", "BCOORD", "HCOORD", "DCOORD")}
+    rank1con, rank1var = [], []
+    ncons = 0
+    while pos < len(lines):
+        key = take()[0].upper()
+        if key == "VER":
+            ver = int(take()[0])
+            if ver not in (1, 2, 3):
+                raise ValueError(f"unsupported CBF version {ver}")
+        elif key == "OBJSENSE":
+            sense = -1 if take()[0].upper() == "MAX" else 1
+        elif key == "VAR":
+            nscal, nc = (int(t) for t in take())
+            for _ in range(nc):
+                cone, cnt = take()
+                varcones.append((cone.upper(), int(cnt)))
+        elif key == "CON":
+            ncons, nc = (int(t) for t in take())
+            for _ in range(nc):
+                cone, cnt = take()
+                concones.append((cone.upper(), int(cnt)))
+        elif key in ("PSDVAR", "PSDCON"):
+            cnt = int(take()[0])
+            (psdvar if key == "PSDVAR" else psdcon).extend(int(take()[0]) for _ in range(cnt))
+        elif key == "INT":
+            cnt = int(take()[0])
+            ints.extend(int(take()[0]) for _ in range(cnt))
+        elif key in ("PSDCONRANK1", "PSDVARRANK1"):
+            cnt = int(take()[0])
+            (rank1con if key == "PSDCONRANK1" else rank1var).extend(int(take()[0]) for _ in range(cnt))
+        elif key == "OBJBCOORD":
+            sec[key].append(take())
+        elif key in sec:
+            cnt = int(take()[0])
+            sec[key].extend(take() for _ in range(cnt))
+        else:
+            raise ValueError(f"CBF section {key} is not supported")
+
+    # scalar variables of the file, then the entries of the matrix variables
+    psdoff, nvars = [], nscal
+    for n in psdvar:
+        psdoff.append(nvars)
+        nvars += n * (n + 1) // 2
+
+    def xidx(v, r, c):
+        if r < c:
+            r, c = c, r
+        return psdoff[v] + r * (r + 1) // 2 + c
+
+    M = Misdp(nvars, np.zeros(nvars), list(psdcon) + list(psdvar))
+    M.objsense = sense
+    j = 0
+    for cone, cnt in varcones:
+        for _ in range(cnt):
+            if cone == "L+":
+                M.lb[j] = 0.0
+            elif cone == "L-":
+                M.ub[j] = 0.0
+            elif cone == "L=":
+                M.lb[j] = M.ub[j] = 0.0
+            elif cone != "F":
+                raise ValueError(f"variable cone {cone} is not supported")
+            j += 1
+    assert j == nscal, "VAR cone sizes do not add up"
+    for i in ints:
+        M.integer[i] = True
+    obj = np.zeros(nvars)
+    for v, r, c, val in sec["OBJFCOORD"]:
+        v, r, c, val = int(v), int(r), int(c), float(val)
+        obj[xidx(v, r, c)] += val if r == c else 2.0 * val
+    for jv, val in sec["OBJACOORD"]:
+        obj[int(jv)] += float(val)
+    for t in sec["OBJBCOORD"]:
+        M.objoffset += float(t[0])
+    M.obj = sense * obj
+    rows = [dict() for _ in range(ncons)]
+    bconst = np.zeros(ncons)
+    for i, v, r, c, val in sec["FCOORD"]:
+        i, v, r, c, val = int(i), int(v), int(r), int(c), float(val)
+        k = xidx(v, r, c)
+        rows[i][k] = rows[i].get(k, 0.0) + (val if r == c else 2.0 * val)
+    for i, jv, val in sec["ACOORD"]:
+        i, jv = int(i), int(jv)
+        rows[i][jv] = rows[i].get(jv, 0.0) + float(val)
+    for i, val in sec["BCOORD"]:
+        bconst[int(i)] += float(val)
+    i = 0
+    for cone, cnt in concones:
+        for _ in range(cnt):
+            if cone == "L+":
+                M.add_row(rows[i], lhs=-bconst[i])
+            elif cone == "L-":
+                M.add_row(rows[i], rhs=-bconst[i])
+            elif cone == "L=":
+                M.add_row(rows[i], lhs=-bconst[i], rhs=-bconst[i])
+            else:
+                raise ValueError(f"constraint cone {cone} is not supported")
+            i += 1
+    assert i == ncons, "CON cone sizes do not add up"
+    for k, jv, r, c, val in sec["HCOORD"]:
+        M.add_entry(int(jv), int(k), int(r), int(c), float(val))
+    for k, r, c, val in sec["DCOORD"]:
+        M.add_entry(-1, int(k), int(r), int(c), -float(val))
+    for v, n in enumerate(psdvar):
+        b = len(psdcon) + v
+        for r in range(n):
+            for c in range(r + 1):
+                M.add_entry(xidx(v, r, c), b, r, c, 1.0)
+    M.rank1 = list(rank1con) + [len(psdcon) + v for v in rank1var]
+    return M
+
+
+def read_instance(path):
+    """dispatch on the file name like the reference's reader plugins (reader_sdpa.c: dat-s, reader_cbf.c: cbf)"""
+    name = str(path)
+    if name.endswith(".gz"):
+        name = name[:-3]
+    return read_cbf(path) if name.endswith(".cbf") else read_sdpa(path)

@@ -1,0 +1,102 @@
+"""CPU suite: instance readers (the data formats in front of the hot path).
+CBF semantics follow src/scipsdp/reader_cbf.c (file:line in scip_sdp_b200/misdp.py:read_cbf); SDPA semantics reader_sdpa.c."""
+import os
+
+import numpy as np
+import pytest
+
+from scip_sdp_b200 import abi, misdp
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+
+CBF_PSDVAR = """
+# min <C, X> + 3 x0  with C = [[1, 0.5], [0.5, 2]]  s.t.  X_01 = 1 (as <F, X> - 1 = 0, F_10 = 0.5),  x0 - 2 >= 0,  X psd
+VER
+2
+
+OBJSENSE
+MAX
+
+VAR
+1 1
+L+ 1
+
+PSDVAR
+1
+2
+
+CON
+2 2
+L= 1
+L+ 1
+
+OBJFCOORD
+3
+0 0 0 -1.0
+0 1 0 -0.5
+0 1 1 -2.0
+
+OBJACOORD
+1
+0 -3.0
+
+OBJBCOORD
+10.0
+
+FCOORD
+1
+0 0 1 0 0.5
+
+ACOORD
+1
+1 0 1.0
+
+BCOORD
+2
+0 -1.0
+1 -2.0
+"""
+
+
+def test_cbf_matrix_variable_and_max_sense(tmp_path):
+    p = tmp_path / "tiny.cbf"
+    p.write_text(CBF_PSDVAR)
+    M = misdp.read_cbf(p)
+    # one scalar variable + the lower triangle (0,0), (1,0), (1,1) of X
+    assert M.nvars == 4 and M.blocksizes == [2] and M.objsense == -1 and M.objoffset == 10.0
+    assert M.lb[0] == 0.0 and M.ub[0] >= 1e20 and (M.lb[1:] <= -1e20).all()
+    # max of the negated file objective = min of: 3 x0 + X00 + 2*0.5 X10 + 2 X11 ; off-diagonals count twice
+    assert np.allclose(M.obj, [3.0, 1.0, 1.0, 2.0])
+    (c0, lhs0, rhs0), (c1, lhs1, rhs1) = M.rows
+    assert c0 == {2: 1.0} and lhs0 == rhs0 == 1.0            # 2 * 0.5 * X10 = 1
+    assert c1 == {0: 1.0} and lhs1 == 2.0 and rhs1 >= 1e20
+    assert M.A[0] == {1: [(0, 0, 1.0)], 2: [(1, 0, 1.0)], 3: [(1, 1, 1.0)]} and M.C[0] == []
+    # optimum: x0 = 2, X = [[a, 1], [1, 1/a]] minimising a + 2/a -> a = sqrt 2: value 6 + 1 + 2 sqrt 2; file sense: 10 - that
+    if os.path.exists(abi.ORACLE_LIB):
+        fp, info = M.rows_to_bounds().flatten()
+        r = abi.Solver(abi.Lib(abi.ORACLE_LIB)).solve(fp, gaptol=1e-8, feastol=1e-8)
+        assert r["phase_name"] == "pdOPT"
+        val = M.file_objective(r["dobj"] + info["fixedobj"])
+        assert abs(val - (10.0 - (7.0 + 2.0 * np.sqrt(2.0)))) <= 1e-5
+
+
+def test_cbf_lmi_constant_sign_and_integrality():
+    M = misdp.read_cbf(os.path.join(GOLDEN, "example_small_cbf.cbf"))
+    S = misdp.read_sdpa(os.path.join(GOLDEN, "example_small.dat-s"))
+    # the CBF twin of example_small: same LMIs (D = -A_0), same integrality, same objective
+    assert M.blocksizes == S.blocksizes and (M.integer == S.integer).all() and np.allclose(M.obj, S.obj)
+    y = np.array([0.3, -1.2, 2.5])
+    for Zc, Zs in zip(M.dense_Z(y), S.dense_Z(y)):
+        assert np.allclose(Zc, Zs)
+
+
+def test_cbf_rejects_unsupported_cones(tmp_path):
+    p = tmp_path / "soc.cbf"
+    p.write_text("VER\n1\nOBJSENSE\nMIN\nVAR\n3 1\nQ 3\n")
+    with pytest.raises(ValueError):
+        misdp.read_cbf(p)
+
+
+def test_read_instance_dispatch():
+    assert misdp.read_instance(os.path.join(GOLDEN, "example_cbf_dual.cbf")).blocksizes == [2, 2]
+    assert misdp.read_instance(os.path.join(GOLDEN, "example_TT.dat-s.gz")).nvars == 37
