@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define SDPCUDA_ABI_VERSION 2
+#define SDPCUDA_ABI_VERSION 3
 
 /* return codes of every entry point */
 #define SDPCUDA_OK            0
@@ -102,6 +102,8 @@ typedef struct sdpcuda_params
    int    setting;       /* 1 fast, 2 medium, 3 stable step-length/centering rules (SCIP_SDPSOLVERSETTING) */
    int    verbose;       /* iteration log to stdout (SCIP_SDPPAR_SDPINFO) */
    int    reserved;
+   double preoptgap;     /* > 0: keep a copy of the first iterate whose relative gap and scaled infeasibilities are <= preoptgap
+                            (SCIP_SDPPAR_WARMSTARTPOGAP; sdpisolver_sdpa.cpp:1611-1653); <= 0 = off */
 } sdpcuda_params;
 
 typedef struct sdpcuda_result
@@ -136,6 +138,18 @@ void sdpcuda_default_params(sdpcuda_params* p);
  * solution device-resident until the getters below fetch it.  start_y may be NULL. Blocking. */
 int  sdpcuda_solve(sdpcuda_handle* h, const sdpcuda_problem* prob, const sdpcuda_params* par,
                    const double* start_y, sdpcuda_result* res);
+
+/* ---- warm start (start point of SCIPsdpiSolverLoadAndSolve, sdpisolver.h:160-175; use in sdpisolver_sdpa.cpp:1481-1600) ----
+ * Dense start matrices for the NEXT sdpcuda_solve on this handle (one shot, used together with its start_y):
+ * which = 0: X_block (the reference's "startX", multiplier of the LMI), which = 1: S_block (its "startZ", the slack
+ * sum A_j y_j - C).  A: n x n, full symmetric.  Both must be positive definite; if the first factorisation fails the
+ * solve silently restarts from the default point.  All blocks and the LP part must be given, otherwise the point is ignored. */
+int  sdpcuda_set_start_block(sdpcuda_handle* h, int which, int block, int n, const double* A);
+int  sdpcuda_set_start_lp(sdpcuda_handle* h, int nlp, const double* xlp, const double* slp);
+/* preoptimal point saved by the last solve when params.preoptgap > 0 (SCIPsdpiSolverGetPreoptimalSol, sdpisolver.h:492-515):
+ * returns 1 / 0 in *exists; y [m], xlp [nlp] may be NULL; the X blocks come from sdpcuda_get_preopt_X (row-major, full) */
+int  sdpcuda_get_preopt(sdpcuda_handle* h, int* exists, double* y, double* xlp);
+int  sdpcuda_get_preopt_X(sdpcuda_handle* h, int block, double* X);
 
 /* Same iteration on the problem that the last sdpcuda_solve left resident in HBM (no host->device traffic); used to
  * measure the device-only throughput and for repeated solves with changed tolerances. */

@@ -144,6 +144,12 @@ struct Solver
    Iterate it;
    sdpcuda_result res;
    bool solved = false;
+   /* warm start staged by sdpcuda_set_start_* (one shot) and the preoptimal copy of the last solve */
+   std::vector<vec> startX, startS;
+   vec startx, starts;
+   bool havestartlp = false;
+   Iterate pre;
+   bool preexists = false;
 
    /* --- operators --- */
    void AT(const vec& y, std::vector<vec>& out) const   /* out_k = sum_j y_j A_j^k (full symmetric) */
@@ -351,6 +357,21 @@ int Solver::solve(const sdpcuda_params& par, const double* starty)
       if( par.lambdastar > 0 ) xi = eta = par.lambdastar;
       it.x.assign(nlp, xi); it.s.assign(nlp, eta);
    }
+   Iterate cold = it;
+   bool warm = false;
+   if( starty != NULL && (int)startX.size() == nb && (int)startS.size() == nb && (nlp == 0 || (havestartlp && (int)startx.size() == nlp)) )
+   {
+      warm = true;
+      for( int k = 0; k < nb; ++k )
+         if( startX[k].size() != it.X[k].size() || startS[k].size() != it.S[k].size() ) warm = false;
+      if( warm )
+      {
+         for( int k = 0; k < nb; ++k ) { it.X[k] = startX[k]; it.S[k] = startS[k]; }
+         if( nlp > 0 ) { it.x = startx; it.s = starts; }
+      }
+   }
+   startX.clear(); startS.clear(); startx.clear(); starts.clear(); havestartlp = false;
+   preexists = false;
 
    std::vector<vec> ATy, Rd(nb), L(nb), Linv(nb), Sinv(nb), LX(nb), LXinv(nb), dXa(nb), dSa(nb), dX(nb), dS(nb), K(nb), T1(nb), T2(nb);
    vec rp(m), rdlp(nlp), Dy, AX, Mmat, Mfac, g(m), dy(m), dya(m), dxa(nlp), dsa(nlp), dx(nlp), ds(nlp), klp(nlp), tmpm(m);
@@ -410,6 +431,9 @@ int Solver::solve(const sdpcuda_params& par, const double* starty)
       dfeasever = dfeasever || dfeas;
       int ph = pfeas ? (dfeas ? SDPCUDA_PDFEAS : SDPCUDA_PFEAS) : (dfeas ? SDPCUDA_DFEAS : SDPCUDA_NOINFO);
       res.phase = ph;
+      if( par.preoptgap > 0 && !preexists && relgap <= par.preoptgap && pinf <= std::max(feastol, par.preoptgap)
+         && dinf <= std::max(feastol, par.preoptgap) )
+      { pre = it; preexists = true; }
       if( pfeas && dfeas && relgap <= gaptol && (par.absgaptol <= 0 || std::fabs(pobj - dobj) <= par.absgaptol) )
       { res.phase = SDPCUDA_PDOPT; res.stop = SDPCUDA_STOP_CONVERGED; break; }
       /* y-problem infeasible: (X,x) >= 0 with A(X)+D'x -> 0 relative to C.X + d'x > 0 */
@@ -439,6 +463,15 @@ int Solver::solve(const sdpcuda_params& par, const double* starty)
       {
          ok = chol(P.bs[k], it.S[k], L[k]) && chol(P.bs[k], it.X[k], LX[k]);
          if( ok ) cholinv(P.bs[k], L[k], Sinv[k], Linv[k]);
+      }
+      if( !ok && warm && iter == 0 )
+      {
+         /* the given start point is not interior: start again from the default point */
+         vec keepy = it.y;
+         it = cold; it.y = keepy;
+         warm = false;
+         --iter;
+         continue;
       }
       if( !ok ) { res.stop = SDPCUDA_STOP_NUMERICS; break; }
       schur(it.X, Sinv, it.x, it.s, Mmat);
@@ -588,7 +621,7 @@ int sdpcuda_destroy(sdpcuda_handle* h) { delete h; return SDPCUDA_OK; }
 void sdpcuda_default_params(sdpcuda_params* p)
 {
    memset(p, 0, sizeof(*p));
-   p->gaptol = 1e-6; p->feastol = 1e-6; p->objlimit = 1e20; p->lambdastar = -1.0; p->timelimit = 1e20;
+   p->gaptol = 1e-6; p->feastol = 1e-6; p->objlimit = 1e20; p->lambdastar = -1.0; p->timelimit = 1e20; p->preoptgap = -1.0;
    p->absgaptol = -1.0; p->maxiter = 100; p->setting = 1; p->verbose = 0;
 }
 
@@ -671,6 +704,40 @@ int sdpcuda_get_S(sdpcuda_handle* h, int b, double* S)
    if( h == NULL || !h->s.solved ) return SDPCUDA_ERR_STATE;
    if( b < 0 || b >= h->s.P.nblocks ) return SDPCUDA_ERR_ARG;
    std::copy(h->s.it.S[b].begin(), h->s.it.S[b].end(), S);
+   return SDPCUDA_OK;
+}
+int sdpcuda_set_start_block(sdpcuda_handle* h, int which, int block, int n, const double* A)
+{
+   if( h == NULL || A == NULL || block < 0 || n < 0 || which < 0 || which > 1 ) return SDPCUDA_ERR_ARG;
+   std::vector<vec>& dst = (which == 0) ? h->s.startX : h->s.startS;
+   if( (int)dst.size() <= block ) dst.resize(block + 1);
+   dst[block].assign(A, A + (size_t)n * n);
+   return SDPCUDA_OK;
+}
+int sdpcuda_set_start_lp(sdpcuda_handle* h, int nlp, const double* xlp, const double* slp)
+{
+   if( h == NULL || nlp < 0 || (nlp > 0 && (xlp == NULL || slp == NULL)) ) return SDPCUDA_ERR_ARG;
+   h->s.startx.assign(xlp, xlp + nlp);
+   h->s.starts.assign(slp, slp + nlp);
+   h->s.havestartlp = true;
+   return SDPCUDA_OK;
+}
+int sdpcuda_get_preopt(sdpcuda_handle* h, int* exists, double* y, double* xlp)
+{
+   if( h == NULL || exists == NULL ) return SDPCUDA_ERR_ARG;
+   *exists = (h->s.solved && h->s.preexists) ? 1 : 0;
+   if( *exists )
+   {
+      if( y != NULL ) std::copy(h->s.pre.y.begin(), h->s.pre.y.end(), y);
+      if( xlp != NULL ) std::copy(h->s.pre.x.begin(), h->s.pre.x.end(), xlp);
+   }
+   return SDPCUDA_OK;
+}
+int sdpcuda_get_preopt_X(sdpcuda_handle* h, int b, double* X)
+{
+   if( h == NULL || !h->s.solved || !h->s.preexists ) return SDPCUDA_ERR_STATE;
+   if( b < 0 || b >= h->s.P.nblocks ) return SDPCUDA_ERR_ARG;
+   std::copy(h->s.pre.X[b].begin(), h->s.pre.X[b].end(), X);
    return SDPCUDA_OK;
 }
 int sdpcuda_get_xlp(sdpcuda_handle* h, double* x)

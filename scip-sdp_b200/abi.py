@@ -27,7 +27,7 @@ class Problem(C.Structure):
 class Params(C.Structure):
     _fields_ = [("gaptol", C.c_double), ("feastol", C.c_double), ("objlimit", C.c_double), ("lambdastar", C.c_double),
                 ("timelimit", C.c_double), ("absgaptol", C.c_double), ("maxiter", C.c_int), ("setting", C.c_int),
-                ("verbose", C.c_int), ("reserved", C.c_int)]
+                ("verbose", C.c_int), ("reserved", C.c_int), ("preoptgap", C.c_double)]
 
 
 class Result(C.Structure):
@@ -118,6 +118,10 @@ class Lib:
                                     _dp, C.c_int, C.c_double, _dp, C.c_int]
         L.sdpcuda_dpotrf.argtypes = [C.c_void_p, C.c_int, _dp, C.c_int, _ip]
         L.sdpcuda_dtrtri.argtypes = [C.c_void_p, C.c_int, _dp, C.c_int]
+        L.sdpcuda_set_start_block.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, _dp]
+        L.sdpcuda_set_start_lp.argtypes = [C.c_void_p, C.c_int, _dp, _dp]
+        L.sdpcuda_get_preopt.argtypes = [C.c_void_p, _ip, _dp, _dp]
+        L.sdpcuda_get_preopt_X.argtypes = [C.c_void_p, C.c_int, _dp]
         L.sdpcuda_dpotrf_inv.argtypes = [C.c_void_p, C.c_int, _dp, C.c_int, _dp, C.c_int, _ip]
         L.sdpcuda_psd_check.argtypes = [C.c_void_p, C.c_int, _dp, C.c_int, C.c_double, _ip]
         L.sdpcuda_time_kernel.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, _dp, _dp]
@@ -152,6 +156,38 @@ class Solver:
             self.close()
         except Exception:
             pass
+
+    def set_start(self, X, S, xlp=None, slp=None):
+        """stage a warm start (dense blocks, LP multipliers/slacks) for the next solve(); it is used only together with start_y"""
+        for which, blocks in ((0, X), (1, S)):
+            for b, A in enumerate(blocks):
+                Af = np.ascontiguousarray(A, dtype=np.float64)
+                rc = self.L.lib.sdpcuda_set_start_block(self.h, which, b, Af.shape[0], Af.ctypes.data_as(_dp))
+                if rc != 0:
+                    raise RuntimeError(f"sdpcuda_set_start_block failed with code {rc}")
+        if xlp is not None:
+            xf, sf = _d(xlp), _d(slp)
+            rc = self.L.lib.sdpcuda_set_start_lp(self.h, len(xf), xf.ctypes.data_as(_dp), sf.ctypes.data_as(_dp))
+            if rc != 0:
+                raise RuntimeError(f"sdpcuda_set_start_lp failed with code {rc}")
+
+    def get_preopt(self):
+        """-> None or dict(y, X, xlp): the iterate saved when the gap first dropped below params.preoptgap"""
+        ex = C.c_int(0)
+        y = np.zeros(max(self.prob.m, 1)); x = np.zeros(max(self.prob.nlp, 1))
+        rc = self.L.lib.sdpcuda_get_preopt(self.h, C.byref(ex), y.ctypes.data_as(_dp), x.ctypes.data_as(_dp))
+        if rc != 0:
+            raise RuntimeError(f"sdpcuda_get_preopt failed with code {rc}")
+        if not ex.value:
+            return None
+        X = []
+        for b, n in enumerate(self.prob.blocksizes):
+            A = np.zeros((int(n), int(n)))
+            rc = self.L.lib.sdpcuda_get_preopt_X(self.h, b, A.ctypes.data_as(_dp))
+            if rc != 0:
+                raise RuntimeError(f"sdpcuda_get_preopt_X failed with code {rc}")
+            X.append(A)
+        return dict(y=y[:self.prob.m], X=X, xlp=x[:self.prob.nlp])
 
     def solve(self, prob, params=None, start_y=None, fetch=True, **kw):
         params = params if params is not None else self.L.default_params(**kw)

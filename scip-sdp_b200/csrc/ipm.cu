@@ -98,6 +98,12 @@ struct sdpcuda_handle
    DBuf<unsigned> lztickets;
    DBuf<double> lzpart;
    std::vector<LzDesc> h_lzdesc, h_lzsmall;
+   // warm start staged by sdpcuda_set_start_* (host, one shot) and the preoptimal copy of the last solve (device)
+   std::vector<std::vector<double>> startX, startS;
+   std::vector<double> startx, starts;
+   bool havestartlp = false;
+   DBuf<double> preX, prey, prex;
+   bool preexists = false;
    DBuf<double> LinvT, LXinvT;       // transposed inverse factors of the large blocks (implicit step-length operators)
    bool lzimplicit = false;
    int lzsteps = 0;                  // Lanczos steps of the last batched run (diagnostics)
@@ -586,7 +592,7 @@ void sdpcuda_default_params(sdpcuda_params* p)
 {
    memset(p, 0, sizeof(*p));
    p->gaptol = 1e-6; p->feastol = 1e-6; p->objlimit = 1e20; p->lambdastar = -1.0; p->timelimit = 1e20;
-   p->absgaptol = -1.0; p->maxiter = 100; p->setting = 1; p->verbose = 0;
+   p->absgaptol = -1.0; p->maxiter = 100; p->setting = 1; p->verbose = 0; p->preoptgap = -1.0;
 }
 
 int sdpcuda_create(sdpcuda_handle** out, int device)
@@ -647,6 +653,7 @@ int sdpcuda_destroy(sdpcuda_handle* h)
       bf->release();
    h->lzdesc.release(); h->lztickets.release(); h->lzpart.release(); h->smallres.release();
    h->LinvT.release(); h->LXinvT.release();
+   h->preX.release(); h->prey.release(); h->prex.release();
    drop_graph(h->gS); drop_graph(h->gX); drop_graph(h->gM);
    cudaEventDestroy(h->ev0); cudaEventDestroy(h->ev1); cudaEventDestroy(h->evFork); cudaEventDestroy(h->evJoin);
    cudaStreamDestroy(h->st); cudaStreamDestroy(h->st2);
@@ -786,6 +793,48 @@ static int run_ipm(sdpcuda_handle* h, const sdpcuda_params* par, const double* s
       CK( h->x.upload(hx, st) ); CK( h->s.upload(hs, st) ); CK( h->y.upload(hy, st) );
       CK( cudaStreamSynchronize(st) );
    }
+   // ---- warm start: dense X, S blocks and LP parts staged by sdpcuda_set_start_* (used only together with start_y) ----
+   bool warm = false;
+   auto cold_start = [&]() -> int {
+      CK( cudaMemsetAsync(h->X.p, 0, ar * sizeof(double), st) );
+      CK( cudaMemsetAsync(h->S.p, 0, ar * sizeof(double), st) );
+      for( int k = 0; k < nb; ++k )
+      {
+         double xi = par->lambdastar > 0 ? par->lambdastar : h->xi[k], eta = par->lambdastar > 0 ? par->lambdastar : h->eta[k];
+         CK( add_diagonal(st, h->blk[k].n, h->X.p + h->blk[k].off, h->blk[k].ld, xi) );
+         CK( add_diagonal(st, h->blk[k].n, h->S.p + h->blk[k].off, h->blk[k].ld, eta) );
+      }
+      std::vector<double> hx(nlp, par->lambdastar > 0 ? par->lambdastar : h->xil), hs(nlp, par->lambdastar > 0 ? par->lambdastar : h->etal);
+      CK( h->x.upload(hx, st) ); CK( h->s.upload(hs, st) );
+      CK( cudaStreamSynchronize(st) );
+      return SDPCUDA_OK;
+   };
+   if( start_y != nullptr && (int)h->startX.size() == nb && (int)h->startS.size() == nb
+      && (nlp == 0 || (h->havestartlp && (int)h->startx.size() == nlp)) )
+   {
+      warm = true;
+      for( int k = 0; k < nb; ++k )
+      {
+         const size_t nn = (size_t)h->blk[k].n * h->blk[k].n;
+         if( h->startX[k].size() != nn || h->startS[k].size() != nn ) warm = false;
+      }
+      if( warm )
+      {
+         for( int k = 0; k < nb; ++k )
+         {
+            const Block& bk = h->blk[k];
+            CK( cudaMemcpy2DAsync(h->X.p + bk.off, sizeof(double) * bk.ld, h->startX[k].data(), sizeof(double) * bk.n, sizeof(double) * bk.n, bk.n, cudaMemcpyHostToDevice, st) );
+            CK( cudaMemcpy2DAsync(h->S.p + bk.off, sizeof(double) * bk.ld, h->startS[k].data(), sizeof(double) * bk.n, sizeof(double) * bk.n, bk.n, cudaMemcpyHostToDevice, st) );
+            g_h2d_bytes += 16.0 * bk.n * bk.n;
+         }
+         if( nlp > 0 ) { CK( h->x.upload(h->startx, st) ); CK( h->s.upload(h->starts, st) ); }
+         CK( cudaStreamSynchronize(st) );
+      }
+   }
+   h->startX.clear(); h->startS.clear(); h->startx.clear(); h->starts.clear(); h->havestartlp = false;
+   h->preexists = false;
+   const bool wantpre = par->preoptgap > 0;
+   if( wantpre ) { CK( h->preX.ensure(ar) ); CK( h->prey.ensure(m + 1) ); CK( h->prex.ensure(nlp + 1) ); }
    // ---- small relaxations: the whole iteration in one launch (ipm_small.cu) ----
    {
       const char* env = getenv("SDPCUDA_PATH");
@@ -794,7 +843,7 @@ static int run_ipm(sdpcuda_handle* h, const sdpcuda_params* par, const double* s
       if( env != nullptr && env[0] == 's' ) force = 2;
       long long multirows = 0;
       bool eligible = (h->maxn <= SMALL_MAX_N && m <= SMALL_MAX_M && nb <= SMALL_MAX_BLOCKS && (int)h->dgroups.size() <= SMALL_MAX_GROUPS
-         && ar <= ((size_t)1 << 20) && nlp <= (1 << 20) && !h->prof.on);
+         && ar <= ((size_t)1 << 20) && nlp <= (1 << 20) && !h->prof.on && !wantpre && !warm);
       if( eligible && h->ndense > 0 )
          for( const auto& g : h->dgroups ) if( g.count > h->dchunk ) eligible = false;
       // measured on the shipped instances: the one-launch kernel wins while the Schur complement is small (m <= 64); above that
@@ -911,6 +960,15 @@ static int run_ipm(sdpcuda_handle* h, const sdpcuda_params* par, const double* s
    BACKTRACK:
       if( h->h_info[0] != 0 || xfail )
       {
+         if( iter == 0 && warm )
+         {
+            // the given start point is not interior: start again from the default point (y is kept)
+            warm = false;
+            CK( cudaStreamSynchronize(h->st2) );       // the side stream may still be reading X
+            rc = cold_start(); if( rc ) return rc;
+            --iter;
+            continue;
+         }
          // the last step left the cone (the step-length estimate was too optimistic): halve it and try again
          if( iter == 0 || backtracks >= 8 ) { R.stop = SDPCUDA_STOP_NUMERICS; break; }
          ++backtracks;
@@ -952,6 +1010,15 @@ static int run_ipm(sdpcuda_handle* h, const sdpcuda_params* par, const double* s
       if( par->verbose )
          printf("  [cuda] it %3d  pobj % .10e  dobj % .10e  gap %.2e  pinf %.2e  dinf %.2e  mu %.2e\n", iter, pobj, dobj, relgap, pinf, dinf, mu);
 
+      if( wantpre && !h->preexists && relgap <= par->preoptgap && pinf <= std::max(feastol, par->preoptgap)
+         && dinf <= std::max(feastol, par->preoptgap) )
+      {
+         // first iterate inside the preoptimal gap: keep (y, X, x) for the caller's warm starts
+         CK( cudaMemcpyAsync(h->preX.p, h->X.p, ar * sizeof(double), cudaMemcpyDeviceToDevice, st) );
+         CK( cudaMemcpyAsync(h->prey.p, h->y.p, m * sizeof(double), cudaMemcpyDeviceToDevice, st) );
+         if( nlp > 0 ) CK( cudaMemcpyAsync(h->prex.p, h->x.p, nlp * sizeof(double), cudaMemcpyDeviceToDevice, st) );
+         h->preexists = true;
+      }
       R.phase = pfeas ? (dfeas ? SDPCUDA_PDFEAS : SDPCUDA_PFEAS) : (dfeas ? SDPCUDA_DFEAS : SDPCUDA_NOINFO);
       if( pfeas && dfeas && relgap <= gaptol && (par->absgaptol <= 0 || std::fabs(pobj - dobj) <= par->absgaptol) )
       { R.phase = SDPCUDA_PDOPT; R.stop = SDPCUDA_STOP_CONVERGED; break; }
@@ -1203,6 +1270,42 @@ static int get_block(sdpcuda_handle* h, const double* src, int b, double* out)
 }
 int sdpcuda_get_X(sdpcuda_handle* h, int b, double* X) { return get_block(h, h ? h->X.p : nullptr, b, X); }
 int sdpcuda_get_S(sdpcuda_handle* h, int b, double* S) { return get_block(h, h ? h->S.p : nullptr, b, S); }
+
+int sdpcuda_set_start_block(sdpcuda_handle* h, int which, int block, int n, const double* A)
+{
+   if( h == nullptr || A == nullptr || block < 0 || n < 0 || which < 0 || which > 1 ) return SDPCUDA_ERR_ARG;
+   std::vector<std::vector<double>>& dst = (which == 0) ? h->startX : h->startS;
+   if( (int)dst.size() <= block ) dst.resize(block + 1);
+   dst[block].assign(A, A + (size_t)n * n);
+   return SDPCUDA_OK;
+}
+
+int sdpcuda_set_start_lp(sdpcuda_handle* h, int nlp, const double* xlp, const double* slp)
+{
+   if( h == nullptr || nlp < 0 || (nlp > 0 && (xlp == nullptr || slp == nullptr)) ) return SDPCUDA_ERR_ARG;
+   h->startx.assign(xlp, xlp + nlp);
+   h->starts.assign(slp, slp + nlp);
+   h->havestartlp = true;
+   return SDPCUDA_OK;
+}
+
+int sdpcuda_get_preopt(sdpcuda_handle* h, int* exists, double* y, double* xlp)
+{
+   if( h == nullptr || exists == nullptr ) return SDPCUDA_ERR_ARG;
+   *exists = (h->solved && h->preexists) ? 1 : 0;
+   if( !*exists ) return SDPCUDA_OK;
+   if( set_device(h) ) return SDPCUDA_ERR_CUDA;
+   if( y != nullptr ) CK( cudaMemcpyAsync(y, h->prey.p, sizeof(double) * h->m, cudaMemcpyDeviceToHost, h->st) );
+   if( xlp != nullptr && h->nlp > 0 ) CK( cudaMemcpyAsync(xlp, h->prex.p, sizeof(double) * h->nlp, cudaMemcpyDeviceToHost, h->st) );
+   CK( cudaStreamSynchronize(h->st) );
+   return SDPCUDA_OK;
+}
+
+int sdpcuda_get_preopt_X(sdpcuda_handle* h, int b, double* X)
+{
+   if( h == nullptr || !h->solved || !h->preexists ) return SDPCUDA_ERR_STATE;
+   return get_block(h, h->preX.p, b, X);
+}
 
 int sdpcuda_get_xlp(sdpcuda_handle* h, double* x)
 {

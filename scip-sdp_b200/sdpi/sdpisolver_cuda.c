@@ -85,6 +85,15 @@ struct SCIP_SDPiSolver
    SCIP_Real*            xlp;                /**< [nlprows] multipliers of the device LP block (lazily fetched) */
    int                   xlpcap;
    SCIP_Bool             xlpvalid;
+   /* preoptimal point of the last solve (host copies, reduced sizes; sdpisolver_sdpa.cpp:191-195) */
+   SCIP_Bool             preoptexists;
+   SCIP_Real*            preopty;            /**< [nactive] */
+   int                   preoptycap;
+   SCIP_Real**           preoptX;            /**< [nsdpblocks] dense reduced blocks */
+   int*                  preoptXcap;
+   SCIP_Real*            preoptxlp;          /**< [nlprows] */
+   int                   preoptxlpcap;
+   SCIP_Bool             wantpreopt;         /**< ask the device for a preoptimal point in the next run */
    SCIP_Real**           X;                  /**< [nsdpblocks] dense reduced multiplier blocks (lazily fetched) */
    int*                  Xcap;
    SCIP_Bool*            Xvalid;
@@ -175,22 +184,26 @@ static SCIP_RETCODE ensureMaps(SCIP_SDPISOLVER* s, int nvars, int nsdpblocks, co
       c = oldcap; SCIP_CALL( growInt(s->blkmem, &s->origsize, &c, newcap) );
       c = oldcap; SCIP_CALL( growInt(s->blkmem, &s->red2origcap, &c, newcap) );
       c = oldcap; SCIP_CALL( growInt(s->blkmem, &s->Xcap, &c, newcap) );
+      c = oldcap; SCIP_CALL( growInt(s->blkmem, &s->preoptXcap, &c, newcap) );
       if( s->red2orig == NULL )
       {
          MEM_CALL( BMSallocBlockMemoryArray(s->blkmem, &s->red2orig, newcap) );
          MEM_CALL( BMSallocBlockMemoryArray(s->blkmem, &s->X, newcap) );
+         MEM_CALL( BMSallocBlockMemoryArray(s->blkmem, &s->preoptX, newcap) );
          MEM_CALL( BMSallocBlockMemoryArray(s->blkmem, &s->Xvalid, newcap) );
       }
       else
       {
          MEM_CALL( BMSreallocBlockMemoryArray(s->blkmem, &s->red2orig, oldcap, newcap) );
          MEM_CALL( BMSreallocBlockMemoryArray(s->blkmem, &s->X, oldcap, newcap) );
+         MEM_CALL( BMSreallocBlockMemoryArray(s->blkmem, &s->preoptX, oldcap, newcap) );
          MEM_CALL( BMSreallocBlockMemoryArray(s->blkmem, &s->Xvalid, oldcap, newcap) );
       }
       for( b = oldcap; b < newcap; ++b )
       {
          s->red2orig[b] = NULL; s->red2origcap[b] = 0;
          s->X[b] = NULL; s->Xcap[b] = 0; s->Xvalid[b] = FALSE;
+         s->preoptX[b] = NULL; s->preoptXcap[b] = 0;
       }
       s->blockcap = newcap;
    }
@@ -252,6 +265,7 @@ static SCIP_RETCODE runDevice(SCIP_SDPISOLVER* s, const sdpcuda_problem* prob, S
    par.timelimit = timeleft;
    par.setting = setting;
    par.verbose = s->sdpinfo ? 1 : 0;
+   par.preoptgap = s->wantpreopt ? s->preoptimalgap : -1.0;
 
    rc = sdpcuda_solve(s->dev, prob, &par, starty, &s->res);
    if( rc == SDPCUDA_ERR_NOMEM )
@@ -273,6 +287,29 @@ static SCIP_RETCODE runDevice(SCIP_SDPISOLVER* s, const sdpcuda_problem* prob, S
    SCIP_CALL( growReal(s->blkmem, &s->y, &s->ycap, prob->m + 1) );
    if( prob->m > 0 && sdpcuda_get_y(s->dev, s->y) != SDPCUDA_OK )
       return SCIP_LPERROR;
+   if( s->wantpreopt )
+   {
+      /* pull the preoptimal iterate right away: later runs of the settings ladder overwrite it on the device
+       * (the reference keeps host copies as well, sdpisolver_sdpa.cpp:1622-1653) */
+      int exists = 0;
+      s->wantpreopt = FALSE;
+      SCIP_CALL( growReal(s->blkmem, &s->preopty, &s->preoptycap, prob->m + 1) );
+      SCIP_CALL( growReal(s->blkmem, &s->preoptxlp, &s->preoptxlpcap, MAX(s->nlprows, 1)) );
+      if( sdpcuda_get_preopt(s->dev, &exists, s->preopty, s->preoptxlp) != SDPCUDA_OK )
+         return SCIP_LPERROR;
+      if( exists )
+      {
+         for( b = 0; b < s->nsdpblocks; ++b )
+         {
+            if( s->blk2dev[b] < 0 )
+               continue;
+            SCIP_CALL( growReal(s->blkmem, &s->preoptX[b], &s->preoptXcap[b], s->devsize[b] * s->devsize[b]) );
+            if( sdpcuda_get_preopt_X(s->dev, s->blk2dev[b], s->preoptX[b]) != SDPCUDA_OK )
+               return SCIP_LPERROR;
+         }
+         s->preoptexists = TRUE;
+      }
+   }
    return SCIP_OKAY;
 }
 
@@ -371,9 +408,14 @@ SCIP_RETCODE SCIPsdpiSolverFree(SCIP_SDPISOLVER** sdpisolver)
    {
       BMSfreeBlockMemoryArrayNull(s->blkmem, &s->red2orig[b], s->red2origcap[b]);
       BMSfreeBlockMemoryArrayNull(s->blkmem, &s->X[b], s->Xcap[b]);
+      BMSfreeBlockMemoryArrayNull(s->blkmem, &s->preoptX[b], s->preoptXcap[b]);
    }
    BMSfreeBlockMemoryArrayNull(s->blkmem, &s->red2orig, s->blockcap);
    BMSfreeBlockMemoryArrayNull(s->blkmem, &s->X, s->blockcap);
+   BMSfreeBlockMemoryArrayNull(s->blkmem, &s->preoptX, s->blockcap);
+   BMSfreeBlockMemoryArrayNull(s->blkmem, &s->preoptXcap, s->blockcap);
+   BMSfreeBlockMemoryArrayNull(s->blkmem, &s->preopty, s->preoptycap);
+   BMSfreeBlockMemoryArrayNull(s->blkmem, &s->preoptxlp, s->preoptxlpcap);
    BMSfreeBlockMemoryArrayNull(s->blkmem, &s->Xvalid, s->blockcap);
    BMSfreeBlockMemoryArrayNull(s->blkmem, &s->Xcap, s->blockcap);
    BMSfreeBlockMemoryArrayNull(s->blkmem, &s->red2origcap, s->blockcap);
@@ -489,8 +531,8 @@ SCIP_RETCODE SCIPsdpiSolverLoadAndSolveWithPenalty(
    assert( nlpcons >= 0 );
    (void) sdpnnonz; (void) nremovedblocks;
    (void) startZnblocknonz; (void) startZrow; (void) startZcol; (void) startZval;
-   (void) startXnblocknonz; (void) startXrow; (void) startXcol; (void) startXval;
-
+   s->preoptexists = FALSE;
+   s->wantpreopt = FALSE;
    s->niterations = 0;
    s->nsdpcalls = 0;
    s->opttime = 0.0;
@@ -758,6 +800,78 @@ SCIP_RETCODE SCIPsdpiSolverLoadAndSolveWithPenalty(
       for( j = 0; j < s->nactive; ++j )
          devstart[j] = starty[s->act2var[j]];
    }
+   /* full primal-dual start point (sdpisolver_sdpa.cpp:1481-1600): startZ = slack matrix, startX = multiplier matrix, both
+    * sparse lower triangles in ORIGINAL indices, last block = LP block with the index convention of sdpisolver.h:171-173 */
+   if( starty != NULL && startZnblocknonz != NULL && startXnblocknonz != NULL && !withr && penaltyparam < s->epsilon )
+   {
+      SCIP_Real* dense = NULL;
+      SCIP_Real* lpx = NULL;
+      SCIP_Real* lps = NULL;
+      int which;
+      int maxn = 1;
+
+      for( b = 0; b < nsdpblocks; ++b )
+         maxn = MAX(maxn, s->devsize[b]);
+      MEM_CALL( BMSallocBufferMemoryArray(s->bufmem, &dense, maxn * maxn) );
+      MEM_CALL( BMSallocBufferMemoryArray(s->bufmem, &lpx, nrows + 1) );
+      MEM_CALL( BMSallocBufferMemoryArray(s->bufmem, &lps, nrows + 1) );
+      for( which = 0; which < 2 && retcode == SCIP_OKAY; ++which )
+      {
+         const int* nnz = (which == 0) ? startXnblocknonz : startZnblocknonz;
+         int* const* rws = (which == 0) ? startXrow : startZrow;
+         int* const* cls = (which == 0) ? startXcol : startZcol;
+         SCIP_Real* const* vls = (which == 0) ? startXval : startZval;
+         SCIP_Real* lp = (which == 0) ? lpx : lps;
+
+         for( b = 0; b < nsdpblocks; ++b )
+         {
+            int n = s->devsize[b];
+            if( s->blk2dev[b] < 0 )
+               continue;
+            for( i = 0; i < n * n; ++i )
+               dense[i] = 0.0;
+            for( i = 0; i < nnz[b]; ++i )
+            {
+               int r = rws[b][i];
+               int c = cls[b][i];
+               /* the row/column may have been removed in the meantime */
+               if( indchanges[b][r] > -1 && indchanges[b][c] > -1 )
+               {
+                  r -= indchanges[b][r];
+                  c -= indchanges[b][c];
+                  dense[r * n + c] = vls[b][i];
+                  dense[c * n + r] = vls[b][i];
+               }
+            }
+            if( sdpcuda_set_start_block(s->dev, which, s->blk2dev[b], n, dense) != SDPCUDA_OK )
+               retcode = SCIP_LPERROR;
+         }
+         for( i = 0; i < nrows; ++i )
+            lp[i] = 0.0;
+         for( i = 0; i < nnz[nsdpblocks]; ++i )
+         {
+            int idx = rws[nsdpblocks][i];
+            int slot = -1;
+            assert( idx == cls[nsdpblocks][i] );
+            if( idx < 2 * nlpcons )
+               slot = (idx >= 0 && idx < 2 * s->nlpcons) ? s->rowslot[idx] : -1;
+            else if( idx - 2 * nlpcons < 2 * nvars )
+               slot = s->boundslot[idx - 2 * nlpcons];
+            if( slot >= 0 )
+               lp[slot] = vls[nsdpblocks][i];
+         }
+      }
+      if( retcode == SCIP_OKAY && sdpcuda_set_start_lp(s->dev, nrows, lpx, lps) != SDPCUDA_OK )
+         retcode = SCIP_LPERROR;
+      BMSfreeBufferMemoryArrayNull(s->bufmem, &lps);
+      BMSfreeBufferMemoryArrayNull(s->bufmem, &lpx);
+      BMSfreeBufferMemoryArrayNull(s->bufmem, &dense);
+      if( retcode != SCIP_OKAY )
+         goto TERMINATE;
+   }
+   /* a preoptimal point is only recorded by the first run and only without penalty formulation (sdpisolver_sdpa.cpp:1612) */
+   s->wantpreopt = (s->preoptimalgap >= 0.0 && !s->penalty
+      && (startsettings == SCIP_SDPSOLVERSETTING_UNSOLVED || startsettings == SCIP_SDPSOLVERSETTING_FAST));
 
    prob.m = m;
    prob.obj = devobj;
@@ -1134,23 +1248,64 @@ SCIP_RETCODE SCIPsdpiSolverGetDualSol(SCIP_SDPISOLVER* sdpisolver, SCIP_Real* ob
    return SCIP_OKAY;
 }
 
+static SCIP_RETCODE sparsePrimal(SCIP_SDPISOLVER* s, SCIP_Bool preopt, int nblocks, int* nnonz, int** rows, int** cols, SCIP_Real** vals, SCIP_Bool* toosmall);
+
 SCIP_RETCODE SCIPsdpiSolverGetPreoptimalPrimalNonzeros(SCIP_SDPISOLVER* sdpisolver, int nblocks, int* startXnblocknonz)
 {
-   (void) sdpisolver; (void) nblocks;
-   /* no preoptimal point is stored yet: signalled by -1 in the first entry (sdpisolver.h:492-499) */
-   if( startXnblocknonz != NULL && nblocks > 0 )
+   SCIP_Bool toosmall;
+
+   assert( sdpisolver != NULL );
+   assert( nblocks > 0 );
+   assert( startXnblocknonz != NULL );
+   NEED_SOLVED( sdpisolver );
+
+   /* no preoptimal point: signalled by -1 in the first entry (sdpisolver.h:492-499, sdpisolver_sdpa.cpp:2446-2451) */
+   if( !sdpisolver->preoptexists )
+   {
       startXnblocknonz[0] = -1;
-   return SCIP_OKAY;
+      return SCIP_OKAY;
+   }
+   return sparsePrimal(sdpisolver, TRUE, nblocks, startXnblocknonz, NULL, NULL, NULL, &toosmall);
 }
 
 SCIP_RETCODE SCIPsdpiSolverGetPreoptimalSol(SCIP_SDPISOLVER* sdpisolver, SCIP_Bool* success, SCIP_Real* dualsol, int nblocks,
    int* startXnblocknonz, int** startXrow, int** startXcol, SCIP_Real** startXval)
 {
-   (void) sdpisolver; (void) dualsol; (void) startXrow; (void) startXcol; (void) startXval;
+   SCIP_SDPISOLVER* s = sdpisolver;
+   SCIP_Bool toosmall;
+   int j;
+
+   assert( s != NULL );
    assert( success != NULL );
-   *success = FALSE;
-   if( startXnblocknonz != NULL && nblocks > 0 )
-      startXnblocknonz[0] = -1;
+   assert( startXnblocknonz != NULL || nblocks == -1 );
+
+   /* like sdpisolver_sdpa.cpp:2531-2536: no error, only *success = FALSE */
+   if( !s->solved || !s->preoptexists )
+   {
+      *success = FALSE;
+      if( startXnblocknonz != NULL && nblocks > 0 )
+         startXnblocknonz[0] = -1;
+      return SCIP_OKAY;
+   }
+   if( dualsol != NULL )
+   {
+      for( j = 0; j < s->nvars; ++j )
+      {
+         int act = s->var2act[j];
+         dualsol[j] = (act >= 0) ? s->preopty[act] : s->fixedval[-act - 1];
+      }
+   }
+   if( nblocks > -1 )
+   {
+      assert( startXrow != NULL && startXcol != NULL && startXval != NULL );
+      SCIP_CALL( sparsePrimal(s, TRUE, nblocks, startXnblocknonz, startXrow, startXcol, startXval, &toosmall) );
+      if( toosmall )
+      {
+         *success = FALSE;
+         return SCIP_OKAY;
+      }
+   }
+   *success = TRUE;
    return SCIP_OKAY;
 }
 
@@ -1195,8 +1350,10 @@ SCIP_RETCODE SCIPsdpiSolverGetPrimalLPSides(SCIP_SDPISOLVER* sdpisolver, int nlp
 }
 
 /** walks over the multiplier matrix X in sparse form; with rows == NULL only counts (shared by the two getters below) */
-static SCIP_RETCODE sparsePrimal(SCIP_SDPISOLVER* s, int nblocks, int* nnonz, int** rows, int** cols, SCIP_Real** vals, SCIP_Bool* toosmall)
+static SCIP_RETCODE sparsePrimal(SCIP_SDPISOLVER* s, SCIP_Bool preopt, int nblocks, int* nnonz, int** rows, int** cols, SCIP_Real** vals, SCIP_Bool* toosmall)
 {
+   SCIP_Real** Xsrc = preopt ? s->preoptX : s->X;
+   SCIP_Real* xlpsrc;
    int b;
    int i;
    int j;
@@ -1216,12 +1373,13 @@ static SCIP_RETCODE sparsePrimal(SCIP_SDPISOLVER* s, int nblocks, int* nnonz, in
       cnt = 0;
       if( s->blk2dev[b] >= 0 )
       {
-         SCIP_CALL( fetchX(s, b) );
+         if( !preopt )
+            SCIP_CALL( fetchX(s, b) );
          for( i = 0; i < n; ++i )
          {
             for( j = 0; j <= i; ++j )
             {
-               SCIP_Real val = s->X[b][i * n + j];
+               SCIP_Real val = Xsrc[b][i * n + j];
                if( REALABS(val) > s->epsilon )
                {
                   if( rows != NULL && cnt < cap )
@@ -1243,26 +1401,28 @@ static SCIP_RETCODE sparsePrimal(SCIP_SDPISOLVER* s, int nblocks, int* nnonz, in
    {
       int cap = nnonz[nblocks - 1];
       cnt = 0;
-      SCIP_CALL( fetchXlp(s) );
+      if( !preopt )
+         SCIP_CALL( fetchXlp(s) );
+      xlpsrc = preopt ? s->preoptxlp : s->xlp;
       for( i = 0; i < 2 * s->nlpcons; ++i )
       {
-         if( s->rowslot[i] >= 0 && REALABS(s->xlp[s->rowslot[i]]) > s->epsilon )
+         if( s->rowslot[i] >= 0 && REALABS(xlpsrc[s->rowslot[i]]) > s->epsilon )
          {
             if( rows != NULL && cnt < cap )
             {
-               rows[nblocks - 1][cnt] = i; cols[nblocks - 1][cnt] = i; vals[nblocks - 1][cnt] = s->xlp[s->rowslot[i]];
+               rows[nblocks - 1][cnt] = i; cols[nblocks - 1][cnt] = i; vals[nblocks - 1][cnt] = xlpsrc[s->rowslot[i]];
             }
             ++cnt;
          }
       }
       for( i = 0; i < 2 * s->nvars; ++i )
       {
-         if( s->boundslot[i] >= 0 && REALABS(s->xlp[s->boundslot[i]]) > s->epsilon )
+         if( s->boundslot[i] >= 0 && REALABS(xlpsrc[s->boundslot[i]]) > s->epsilon )
          {
             if( rows != NULL && cnt < cap )
             {
                rows[nblocks - 1][cnt] = 2 * s->nlpcons + i; cols[nblocks - 1][cnt] = 2 * s->nlpcons + i;
-               vals[nblocks - 1][cnt] = s->xlp[s->boundslot[i]];
+               vals[nblocks - 1][cnt] = xlpsrc[s->boundslot[i]];
             }
             ++cnt;
          }
@@ -1280,7 +1440,7 @@ SCIP_RETCODE SCIPsdpiSolverGetPrimalNonzeros(SCIP_SDPISOLVER* sdpisolver, int nb
    assert( sdpisolver != NULL );
    assert( startXnblocknonz != NULL );
    NEED_SOLVED( sdpisolver );
-   return sparsePrimal(sdpisolver, nblocks, startXnblocknonz, NULL, NULL, NULL, &toosmall);
+   return sparsePrimal(sdpisolver, FALSE, nblocks, startXnblocknonz, NULL, NULL, NULL, &toosmall);
 }
 
 SCIP_RETCODE SCIPsdpiSolverGetPrimalMatrix(SCIP_SDPISOLVER* sdpisolver, int nblocks, int* startXnblocknonz, int** startXrow,
@@ -1290,7 +1450,7 @@ SCIP_RETCODE SCIPsdpiSolverGetPrimalMatrix(SCIP_SDPISOLVER* sdpisolver, int nblo
    assert( sdpisolver != NULL );
    assert( startXnblocknonz != NULL && startXrow != NULL && startXcol != NULL && startXval != NULL );
    NEED_SOLVED( sdpisolver );
-   SCIP_CALL( sparsePrimal(sdpisolver, nblocks, startXnblocknonz, startXrow, startXcol, startXval, &toosmall) );
+   SCIP_CALL( sparsePrimal(sdpisolver, FALSE, nblocks, startXnblocknonz, startXrow, startXcol, startXval, &toosmall) );
    if( toosmall )
       SCIPdebugMessage("Insufficient memory for the primal matrix, needed sizes are returned in startXnblocknonz.\n");
    return SCIP_OKAY;

@@ -109,6 +109,9 @@ class SdpiSolver:
         L.SCIPsdpiSolverGetIterations.argtypes = [C.c_void_p, _ip]
         L.SCIPsdpiSolverGetSdpCalls.argtypes = [C.c_void_p, _ip]
         L.SCIPsdpiSolverGetPrimalSolutionMatrix.argtypes = [C.c_void_p, C.c_int, _ip, _ipp, _ip, _ip, _dpp]
+        L.SCIPsdpiSolverGetPreoptimalPrimalNonzeros.argtypes = [C.c_void_p, C.c_int, _ip]
+        L.SCIPsdpiSolverGetPreoptimalSol.argtypes = [C.c_void_p, C.POINTER(C.c_uint), _dp, C.c_int, _ip, _ipp, _ipp, _dpp]
+        L.SCIPsdpiSolverDoesWarmstartNeedPrimal.restype = C.c_uint
         for f in ("WasSolved", "IsAcceptable", "IsOptimal", "IsDualInfeasible", "IsDualFeasible", "IsPrimalFeasible", "IsConverged"):
             fn = getattr(L, "SCIPsdpiSolver" + f)
             fn.argtypes = [C.c_void_p]; fn.restype = C.c_uint
@@ -125,11 +128,54 @@ class SdpiSolver:
     def name(self):
         return self.lib.SCIPsdpiSolverGetSolverName().decode()
 
-    def load_and_solve(self, bp):
+    def load_and_solve(self, bp, start=None):
+        """start = None or dict(y=[nvars], Z=[(rows, cols, vals)] * (nblocks + 1), X=likewise): the starting point of
+        SCIPsdpiSolverLoadAndSolve (sdpisolver.h:160-175; sparse lower triangles, LP block last, indices 2i / 2i+1 for lhs / rhs of
+        row i and 2 nlpcons + 2j (+1) for lb (ub) of variable j)"""
         self.nvars = bp.nvars
-        rc = self.lib.SCIPsdpiSolverLoadAndSolve(self.s, *bp.args)
+        args = list(bp.args)
+        if start is not None:
+            k = _Keep()
+            args[30] = k.d(start["y"])
+            for base, key in ((31, "Z"), (35, "X")):
+                blocks = start[key]
+                assert len(blocks) == bp.nblocks + 1
+                args[base] = k.i([len(t[0]) for t in blocks])
+                args[base + 1] = k.pp([k.i(t[0] if len(t[0]) else [0]) for t in blocks], _ip, _ipp)
+                args[base + 2] = k.pp([k.i(t[1] if len(t[1]) else [0]) for t in blocks], _ip, _ipp)
+                args[base + 3] = k.pp([k.d(t[2] if len(t[2]) else [0.0]) for t in blocks], _dp, _dpp)
+        rc = self.lib.SCIPsdpiSolverLoadAndSolve(self.s, *args)
         if rc != SCIP_OKAY:
             raise RuntimeError(f"SCIPsdpiSolverLoadAndSolve returned SCIP_RETCODE {rc}")
+
+    def set_warmstart_pogap(self, gap):
+        rc = self.lib.SCIPsdpiSolverSetRealpar(self.s, 12, float(gap))      # SCIP_SDPPAR_WARMSTARTPOGAP
+        if rc != SCIP_OKAY:
+            raise RuntimeError(f"SCIPsdpiSolverSetRealpar(WARMSTARTPOGAP) returned {rc}")
+
+    def preoptimal_sol(self, bp):
+        """SCIPsdpiSolverGetPreoptimalPrimalNonzeros + GetPreoptimalSol -> None or (y, [(rows, cols, vals)] per block, LP block last)"""
+        nb = bp.nblocks + 1
+        cnt = (C.c_int * nb)()
+        rc = self.lib.SCIPsdpiSolverGetPreoptimalPrimalNonzeros(self.s, nb, cnt)
+        if rc != SCIP_OKAY:
+            raise RuntimeError(f"SCIPsdpiSolverGetPreoptimalPrimalNonzeros returned {rc}")
+        if cnt[0] == -1:
+            return None
+        rows = [np.zeros(max(c, 1), dtype=np.int32) for c in cnt]
+        cols = [np.zeros(max(c, 1), dtype=np.int32) for c in cnt]
+        vals = [np.zeros(max(c, 1)) for c in cnt]
+        rp = (_ip * nb)(*[r.ctypes.data_as(_ip) for r in rows])
+        cp = (_ip * nb)(*[c.ctypes.data_as(_ip) for c in cols])
+        vp = (_dp * nb)(*[v.ctypes.data_as(_dp) for v in vals])
+        ok = C.c_uint(0)
+        y = np.zeros(self.nvars)
+        rc = self.lib.SCIPsdpiSolverGetPreoptimalSol(self.s, C.byref(ok), y.ctypes.data_as(_dp), nb, cnt, C.cast(rp, _ipp), C.cast(cp, _ipp), C.cast(vp, _dpp))
+        if rc != SCIP_OKAY:
+            raise RuntimeError(f"SCIPsdpiSolverGetPreoptimalSol returned {rc}")
+        if not ok.value:
+            return None
+        return y, [(rows[b][:cnt[b]], cols[b][:cnt[b]], vals[b][:cnt[b]]) for b in range(nb)]
 
     def load_and_solve_with_penalty(self, bp, penaltyparam, withobj, rbound):
         """-> (feasorig, penaltybound) of SCIPsdpiSolverLoadAndSolveWithPenalty (sdpisolver.h:258-322)"""

@@ -79,3 +79,88 @@ def run_primal_getters(libpath):
             assert abs(t - M.obj[j]) <= 1e-6 * max(1.0, abs(M.obj[j]))
     finally:
         s.close()
+
+
+def _sparse_lower(A, tol=0.0):
+    r, c = np.nonzero(np.tril(np.abs(A) > tol))
+    return r.astype(np.int32), c.astype(np.int32), A[r, c]
+
+
+def run_warmstart_and_preoptimal(libpath):
+    """row a10 of the scope table: (1) WARMSTARTPOGAP makes the solver keep the first iterate inside that gap and
+    GetPreoptimalSol returns it (y with fixed variables filled, X sparse in original indices, LP block with the 2i/2i+1
+    convention); (2) a primal-dual start point (y, Z, X) is used: starting next to the optimum needs fewer iterations than the
+    cold start and ends at the same optimum; (3) a start point outside the cone is ignored, not fatal."""
+    M = misdp.read_sdpa(os.path.join(GOLDEN, "example_TT.dat-s.gz")).rows_to_bounds()
+    bp = sdpisolver_host.BoundaryProblem(M)
+    s = sdpisolver_host.SdpiSolver(libpath, gaptol=1e-6, feastol=1e-6)
+    try:
+        assert s.lib.SCIPsdpiSolverDoesWarmstartNeedPrimal()
+        s.load_and_solve(bp)
+        assert s.flag("IsOptimal")
+        assert s.preoptimal_sol(bp) is None                     # not asked for: first entry -1 / success FALSE
+        obj0, y0 = s.dual_sol()
+        it_cold, _ = s.iterations()
+
+        s.set_warmstart_pogap(1e-2)
+        s.load_and_solve(bp)
+        assert s.flag("IsOptimal")
+        obj1, y1 = s.dual_sol()
+        assert abs(obj1 - obj0) <= 1e-6 * max(1.0, abs(obj0))
+        pre = s.preoptimal_sol(bp)
+        assert pre is not None
+        ypre, Xpre = pre
+        objpre = float(np.dot(M.obj, ypre))
+        # an earlier iterate: close to the optimum within the requested gap, but not the final point
+        assert abs(objpre - obj0) <= 5e-2 * max(1.0, abs(obj0)) and abs(objpre - obj0) > 1e-7
+        for b, n in enumerate(M.blocksizes):
+            r, c, v = Xpre[b]
+            assert np.all(r >= c) and np.all(r < n)
+            X = np.zeros((n, n)); X[r, c] = v; X[c, r] = v
+            assert np.linalg.eigvalsh(X).min() > 0.0             # an interior iterate
+        assert np.all(Xpre[-1][2] > 0.0)                         # LP multipliers of an interior iterate
+        s.set_warmstart_pogap(-1.0)
+
+        # start point next to the optimum, pushed into the cone like relax_sdp.c does (convex combination with the identity)
+        dense = s.primal_matrix_dense(bp)
+        lp = s.primal_matrix_sparse(bp)[-1]
+        lam = 0.05
+        Zs, Xs = [], []
+        Zopt = M.dense_Z(y0)
+        for b, n in enumerate(M.blocksizes):
+            Zs.append(_sparse_lower((1 - lam) * Zopt[b] + lam * np.eye(n)))
+            Xs.append(_sparse_lower((1 - lam) * dense[b] + lam * np.eye(n)))
+        # LP block: slack of every finite side / bound (Z part) and its multiplier (X part), all made positive
+        idx, zval, xval = [], [], []
+        xmap = dict(zip(lp[0].tolist(), lp[2].tolist()))
+        nrows = len(M.rows)
+        for i, (coefs, lhs, rhs) in enumerate(M.rows):
+            act = sum(a * y0[j] for j, a in coefs.items())
+            if lhs > -1e20:
+                idx.append(2 * i); zval.append(act - lhs)
+            if rhs < 1e20:
+                idx.append(2 * i + 1); zval.append(rhs - act)
+        for j in range(M.nvars):
+            if M.lb[j] > -1e20:
+                idx.append(2 * nrows + 2 * j); zval.append(y0[j] - M.lb[j])
+            if M.ub[j] < 1e20:
+                idx.append(2 * nrows + 2 * j + 1); zval.append(M.ub[j] - y0[j])
+        idx = np.array(idx, dtype=np.int32)
+        zval = (1 - lam) * np.maximum(np.array(zval), 0.0) + lam
+        xval = (1 - lam) * np.array([max(xmap.get(int(i), 0.0), 0.0) for i in idx]) + lam
+        Zs.append((idx, idx, zval)); Xs.append((idx, idx, xval))
+        s.load_and_solve(bp, start=dict(y=y0, Z=Zs, X=Xs))
+        assert s.flag("IsOptimal")
+        obj2, _ = s.dual_sol()
+        it_warm, _ = s.iterations()
+        assert abs(obj2 - obj0) <= 1e-5 * max(1.0, abs(obj0))
+        assert it_warm < it_cold, (it_warm, it_cold)
+
+        # a start point outside the cone: solved from the default point instead
+        Xbad = [(r, c, -v) for (r, c, v) in Xs]
+        s.load_and_solve(bp, start=dict(y=y0, Z=Zs, X=Xbad))
+        assert s.flag("IsOptimal")
+        obj3, _ = s.dual_sol()
+        assert abs(obj3 - obj0) <= 1e-5 * max(1.0, abs(obj0))
+    finally:
+        s.close()

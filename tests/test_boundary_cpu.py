@@ -14,3 +14,7 @@ def test_penalty_formulation_call_patterns():
 
 def test_primal_matrix_getters_are_consistent():
     boundary_cases.run_primal_getters(sdpi_ref.LIB_ORACLE)
+
+
+def test_warmstart_and_preoptimal_solution():
+    boundary_cases.run_warmstart_and_preoptimal(sdpi_ref.LIB_ORACLE)

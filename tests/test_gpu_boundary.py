@@ -13,3 +13,7 @@ def test_penalty_formulation_call_patterns_on_gpu():
 
 def test_primal_matrix_getters_are_consistent_on_gpu():
     boundary_cases.run_primal_getters(sdpisolver_host.BINDING_LIB)
+
+
+def test_warmstart_and_preoptimal_solution_on_gpu():
+    boundary_cases.run_warmstart_and_preoptimal(sdpisolver_host.BINDING_LIB)
