@@ -37,10 +37,64 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--n", type=int, default=2000, help="max-cut order (2000 = the BASELINE configuration)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--workload", default="maxcut", choices=["maxcut", "frontier-tt500", "frontier-cls", "frontier-mkp120", "frontier-mkp60"],
+    ap.add_argument("--workload", default="maxcut", choices=["maxcut", "frontier-tt500", "frontier-cls", "frontier-mkp120", "frontier-mkp60", "sharded-maxcut", "sharded-dense", "sharded-mkp120"],
                     help="maxcut = the headline relaxation benchmark; frontier-* = B&B nodes/sec over a fixed frontier of node relaxations")
     ap.add_argument("--nodes-per-gpu", type=int, default=8)
     return ap.parse_args()
+
+
+def sharded_bench(a, rank, local, world):
+    """ONE relaxation over all N GPUs (strong scaling): every rank holds the whole problem and forms its share of
+    the Schur complement; an NCCL all-reduce over NVLink adds the shares; the rest of the iteration runs replicated.
+    sharded-maxcut is the BASELINE shape (its Schur complement is a Hadamard product: nothing to gain, reported as measured);
+    sharded-dense is a random SDP with 600 dense constraint matrices of order 300, where the Schur complement dominates."""
+    import torch
+    import torch.distributed as dist
+    from scip_sdp_b200 import abi, frontier, generators
+    torch.cuda.set_device(local)
+    if world > 1:
+        with stdout_to_stderr():
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+            dist.barrier()
+    make = {"sharded-maxcut": lambda: generators.maxcut(a.n, min(0.5, 20.0 / a.n), seed=4004),
+            "sharded-dense": lambda: generators.dense_sdp_flat(600, 300, seed=5005),
+            "sharded-mkp120": lambda: generators.mkp(120, seed=3003)}[a.workload]
+    M = make()
+    fp = M if a.workload == "sharded-dense" else M.flatten()[0]
+    os.environ["SDPCUDA_DEVICE"] = str(local)
+    os.environ["SDPCUDA_PATH"] = "m"
+    gpu = abi.Solver(abi.Lib(abi.PRODUCT_LIB), device=local)
+    if world > 1:
+        frontier.shard_one_sdp(gpu, dist, device=f"cuda:{local}")
+    kw = dict(gaptol=1e-5, feastol=1e-5)
+    first = gpu.solve(fp, fetch=False, **kw)
+    assert first["phase_name"] == "pdOPT", first
+    for _ in range(max(0, a.warmup - 1)):
+        gpu.solve_resident(**kw)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    dev_ms, iters, launches = 0.0, 0, 0
+    for _ in range(a.steps):
+        r = gpu.solve_resident(**kw)
+        dev_ms += r["device_ms"]; iters += r["iterations"]; launches += r["launches"]
+    torch.cuda.synchronize()
+    wall = frontier.max_over_ranks(time.perf_counter() - t0, dist=dist if world > 1 else None, device="cuda")
+    devmax = frontier.max_over_ranks(dev_ms, dist=dist if world > 1 else None, device="cuda")
+    if rank == 0:
+        print(json.dumps({"metric": "SDP relaxations/sec", "value": a.steps / (devmax / 1e3), "unit": "relaxations/s", "n_gpus": world,
+                          "steps": a.steps, "warmup": a.warmup, "ms_per_step": devmax / a.steps, "wall_ms_per_step": 1e3 * wall / a.steps,
+                          "higher_is_better": True, "scaling": "strong", "dtype": "f64", "data": "synthetic", "vs_baseline": None,
+                          "iterations_per_step": iters / a.steps, "objective": r["dobj"], "gpu_launches": launches,
+                          "config": {"workload": a.workload, "instance": f"m = {fp.m}, blocks = {list(map(int, fp.blocksizes))}, LP rows = {fp.nlp}",
+                                     "partition": "Schur complement shares per rank (column strips / dense chunks), one NCCL all-reduce of "
+                                                  f"{8 * fp.m * fp.m / 1e6:.1f} MB per iteration, everything else replicated"}}))
+    if world > 1:
+        gpu.dist_finalize()
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
 
 
 def frontier_bench(a, rank, local, world):
@@ -199,6 +253,8 @@ def main():
     if a.workload != "maxcut":
         if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
             os.environ["NCCL_DEBUG"] = "WARN"
+        if a.workload.startswith("sharded-"):
+            return sharded_bench(a, rank, local, world)
         return frontier_bench(a, rank, local, world)
     if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
         os.environ["NCCL_DEBUG"] = "WARN"          # keep stdout to the one JSON line (NCCL prints its version banner there)

@@ -151,6 +151,15 @@ int  sdpcuda_set_start_lp(sdpcuda_handle* h, int nlp, const double* xlp, const d
 int  sdpcuda_get_preopt(sdpcuda_handle* h, int* exists, double* y, double* xlp);
 int  sdpcuda_get_preopt_X(sdpcuda_handle* h, int block, double* X);
 
+/* ---- one large SDP over several GPUs: one process and one handle per GPU, all ranks call sdpcuda_solve with
+ * the SAME problem; every rank forms its share of the Schur complement (column strips of the entry path, chunks of the dense
+ * path), one NCCL all-reduce over NVLink adds the disjoint shares, the remaining iteration runs replicated and bit-identical.
+ * sdpcuda_dist_unique_id: called on rank 0, the 128 bytes travel to the other ranks over the caller's own channel
+ * (torch.distributed broadcast in bench.py).  NCCL is bound with dlopen at the first call; without it these return ERR_STATE. */
+int  sdpcuda_dist_unique_id(void* id128);
+int  sdpcuda_dist_init(sdpcuda_handle* h, int nranks, int rank, const void* id128);
+int  sdpcuda_dist_finalize(sdpcuda_handle* h);
+
 /* Same iteration on the problem that the last sdpcuda_solve left resident in HBM (no host->device traffic); used to
  * measure the device-only throughput and for repeated solves with changed tolerances. */
 int  sdpcuda_solve_resident(sdpcuda_handle* h, const sdpcuda_params* par, sdpcuda_result* res);

@@ -706,6 +706,14 @@ int sdpcuda_get_S(sdpcuda_handle* h, int b, double* S)
    std::copy(h->s.it.S[b].begin(), h->s.it.S[b].end(), S);
    return SDPCUDA_OK;
 }
+/* the CPU restatement is a single-process checker: no sharded path */
+int sdpcuda_dist_unique_id(void* id128) { (void)id128; return SDPCUDA_ERR_STATE; }
+int sdpcuda_dist_init(sdpcuda_handle* h, int nranks, int rank, const void* id128)
+{
+   (void)id128;
+   return (h != NULL && nranks == 1 && rank == 0) ? SDPCUDA_OK : SDPCUDA_ERR_STATE;
+}
+int sdpcuda_dist_finalize(sdpcuda_handle* h) { (void)h; return SDPCUDA_OK; }
 int sdpcuda_set_start_block(sdpcuda_handle* h, int which, int block, int n, const double* A)
 {
    if( h == NULL || A == NULL || block < 0 || n < 0 || which < 0 || which > 1 ) return SDPCUDA_ERR_ARG;

@@ -122,6 +122,9 @@ class Lib:
         L.sdpcuda_set_start_lp.argtypes = [C.c_void_p, C.c_int, _dp, _dp]
         L.sdpcuda_get_preopt.argtypes = [C.c_void_p, _ip, _dp, _dp]
         L.sdpcuda_get_preopt_X.argtypes = [C.c_void_p, C.c_int, _dp]
+        L.sdpcuda_dist_unique_id.argtypes = [C.c_void_p]
+        L.sdpcuda_dist_init.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+        L.sdpcuda_dist_finalize.argtypes = [C.c_void_p]
         L.sdpcuda_dpotrf_inv.argtypes = [C.c_void_p, C.c_int, _dp, C.c_int, _dp, C.c_int, _ip]
         L.sdpcuda_psd_check.argtypes = [C.c_void_p, C.c_int, _dp, C.c_int, C.c_double, _ip]
         L.sdpcuda_time_kernel.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, _dp, _dp]
@@ -156,6 +159,22 @@ class Solver:
             self.close()
         except Exception:
             pass
+
+    def dist_unique_id(self):
+        """rank 0: the 128-byte NCCL id that the other ranks need for dist_init"""
+        buf = C.create_string_buffer(128)
+        rc = self.L.lib.sdpcuda_dist_unique_id(buf)
+        if rc != 0:
+            raise RuntimeError(f"sdpcuda_dist_unique_id failed with code {rc} (NCCL missing?)")
+        return buf.raw
+
+    def dist_init(self, nranks, rank, idbytes):
+        rc = self.L.lib.sdpcuda_dist_init(self.h, nranks, rank, C.create_string_buffer(idbytes, 128) if idbytes is not None else None)
+        if rc != 0:
+            raise RuntimeError(f"sdpcuda_dist_init failed with code {rc}")
+
+    def dist_finalize(self):
+        self.L.lib.sdpcuda_dist_finalize(self.h)
 
     def set_start(self, X, S, xlp=None, slp=None):
         """stage a warm start (dense blocks, LP multipliers/slacks) for the next solve(); it is used only together with start_y"""

@@ -11,6 +11,8 @@
 #include "common.cuh"
 #include "ops.cuh"
 #include "ipm_small.cuh"
+#include <dlfcn.h>
+#include <nccl.h>
 
 #include <algorithm>
 #include <atomic>
@@ -88,7 +90,7 @@ struct sdpcuda_handle
    DBuf<double> X, S, Sinv, L, Linv, LX, LXinv, dX, dS, dXa, dSa, K, T1, T2, Rd, work, work2;
    DBuf<double> y, dy, g, rp, AX, DTx, tm1, tm2;
    DBuf<double> x, s, dx, ds, dxa, dsa, klp, rdlp, Dy, Ddy;
-   DBuf<double> M, Mfac, diaginv, Mwork, MLinv, Adense, Hd, Ud;
+   DBuf<double> M, Mfac, diaginv, Mwork, MLinv, Adense, Hd, Ud, Cd;
    DBuf<int> denselist;
    DBuf<int> patcol, patrow;          // column-wise pattern of sum_j y_j A_j - C (+ diagonal) per block, if sparse
    std::vector<long long> patcoloff, patrowoff;   // per block offsets into patcol / patrow (-1: block is treated as dense)
@@ -98,6 +100,10 @@ struct sdpcuda_handle
    DBuf<unsigned> lztickets;
    DBuf<double> lzpart;
    std::vector<LzDesc> h_lzdesc, h_lzsmall;
+   // one large SDP over several GPUs: every rank forms its share of the Schur complement, NCCL sums the shares
+   ncclComm_t comm = nullptr;
+   int nranks = 1, rank = 0;
+   int emulate_ranks = 0;            // test knob SDPCUDA_SHARD_EMULATE: form the shares of G ranks one after the other on this GPU
    // warm start staged by sdpcuda_set_start_* (host, one shot) and the preoptimal copy of the last solve (device)
    std::vector<std::vector<double>> startX, startS;
    std::vector<double> startx, starts;
@@ -341,6 +347,10 @@ int upload_problem(sdpcuda_handle* h, const sdpcuda_problem* P)
       h->dchunk = (int)std::max<size_t>(1, std::min<size_t>((size_t)maxcount, ((size_t)32 << 20) / maxmat));
       CK( h->Hd.ensure((size_t)h->dchunk * maxmat) );
       CK( h->Ud.ensure((size_t)h->dchunk * maxmat) );
+      // the padding rows (leading dimension > order) take part in the long dot products of the dense x dense pairs: keep them zero
+      CK( cudaMemsetAsync(h->Hd.p, 0, (size_t)h->dchunk * maxmat * sizeof(double), st) );
+      CK( cudaMemsetAsync(h->Ud.p, 0, (size_t)h->dchunk * maxmat * sizeof(double), st) );
+      CK( h->Cd.ensure((size_t)maxcount * h->dchunk + 4) );
       size_t offm = 0;
       DevEntries E{h->varbeg.p, h->erow.p, h->ecol.p, h->eld.p, h->eoff.p, h->eval.p};
       for( const auto& g : h->dgroups )
@@ -576,6 +586,57 @@ int step_eigs(sdpcuda_handle* h, const double* dXdir, const double* dSdir, int m
    return SDPCUDA_OK;
 }
 
+// ---- NCCL, bound at run time (the library must load and run on one GPU without it) -----------------------------------------
+struct NcclApi
+{
+   void* lib = nullptr;
+   ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+   ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+   ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+   ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+   const char* (*GetErrorString)(ncclResult_t) = nullptr;
+};
+
+NcclApi* nccl_api()
+{
+   static NcclApi api;
+   static bool tried = false;
+   if( !tried )
+   {
+      tried = true;
+      // an NCCL that the process has already loaded (torch brings its own) is found first under the same soname
+      const char* names[] = {"libnccl.so.2", "libnccl.so"};
+      for( const char* nm : names )
+      {
+         api.lib = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+         if( api.lib ) break;
+      }
+      if( api.lib )
+      {
+         api.GetUniqueId = (decltype(api.GetUniqueId))dlsym(api.lib, "ncclGetUniqueId");
+         api.CommInitRank = (decltype(api.CommInitRank))dlsym(api.lib, "ncclCommInitRank");
+         api.CommDestroy = (decltype(api.CommDestroy))dlsym(api.lib, "ncclCommDestroy");
+         api.AllReduce = (decltype(api.AllReduce))dlsym(api.lib, "ncclAllReduce");
+         api.GetErrorString = (decltype(api.GetErrorString))dlsym(api.lib, "ncclGetErrorString");
+         if( !api.GetUniqueId || !api.CommInitRank || !api.CommDestroy || !api.AllReduce ) api.lib = nullptr;
+      }
+   }
+   return api.lib ? &api : nullptr;
+}
+
+int dist_allreduce_sum(sdpcuda_handle* h, double* buf, size_t count)
+{
+   NcclApi* api = nccl_api();
+   if( api == nullptr || h->comm == nullptr ) return SDPCUDA_ERR_STATE;
+   ncclResult_t r = api->AllReduce(buf, buf, count, ncclDouble, ncclSum, h->comm, h->st);
+   if( r != ncclSuccess )
+   {
+      fprintf(stderr, "[sdpcuda] ncclAllReduce failed: %s\n", api->GetErrorString ? api->GetErrorString(r) : "?");
+      return SDPCUDA_ERR_CUDA;
+   }
+   return SDPCUDA_OK;
+}
+
 double now_seconds()
 {
    return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
@@ -638,12 +699,13 @@ int sdpcuda_create(sdpcuda_handle** out, int device)
 int sdpcuda_destroy(sdpcuda_handle* h)
 {
    if( h == nullptr ) return SDPCUDA_OK;
+   sdpcuda_dist_finalize(h);
    cudaSetDevice(h->device);
    cudaStreamSynchronize(h->st);
    for( DBuf<double>* bf : {&h->eval, &h->posval, &h->posc, &h->cval, &h->lpval, &h->colval, &h->lprhs, &h->b, &h->X, &h->S, &h->Sinv,
                             &h->L, &h->Linv, &h->LX, &h->LXinv, &h->dX, &h->dS, &h->dXa, &h->dSa, &h->K, &h->T1, &h->T2, &h->Rd, &h->work, &h->work2,
                             &h->y, &h->dy, &h->g, &h->rp, &h->AX, &h->DTx, &h->tm1, &h->tm2, &h->x, &h->s, &h->dx, &h->ds, &h->dxa, &h->dsa,
-                            &h->klp, &h->rdlp, &h->Dy, &h->Ddy, &h->M, &h->Mfac, &h->diaginv, &h->Mwork, &h->MLinv, &h->Adense, &h->Hd, &h->Ud, &h->partials, &h->stats, &h->scal,
+                            &h->klp, &h->rdlp, &h->Dy, &h->Ddy, &h->M, &h->Mfac, &h->diaginv, &h->Mwork, &h->MLinv, &h->Adense, &h->Hd, &h->Ud, &h->Cd, &h->partials, &h->stats, &h->scal,
                             &h->eigw, &h->lzwork, &h->kA, &h->kB, &h->kC, &h->kW} )
       bf->release();
    for( DBuf<int>* bf : {&h->varbeg, &h->erow, &h->ecol, &h->eld, &h->posbeg, &h->posvar, &h->lpbeg, &h->lpind, &h->colbeg, &h->colrow,
@@ -833,6 +895,10 @@ static int run_ipm(sdpcuda_handle* h, const sdpcuda_params* par, const double* s
    }
    h->startX.clear(); h->startS.clear(); h->startx.clear(); h->starts.clear(); h->havestartlp = false;
    h->preexists = false;
+   {
+      const char* e = getenv("SDPCUDA_SHARD_EMULATE");
+      h->emulate_ranks = (e != nullptr) ? atoi(e) : 0;
+   }
    const bool wantpre = par->preoptgap > 0;
    if( wantpre ) { CK( h->preX.ensure(ar) ); CK( h->prey.ensure(m + 1) ); CK( h->prex.ensure(nlp + 1) ); }
    // ---- small relaxations: the whole iteration in one launch (ipm_small.cu) ----
@@ -843,7 +909,7 @@ static int run_ipm(sdpcuda_handle* h, const sdpcuda_params* par, const double* s
       if( env != nullptr && env[0] == 's' ) force = 2;
       long long multirows = 0;
       bool eligible = (h->maxn <= SMALL_MAX_N && m <= SMALL_MAX_M && nb <= SMALL_MAX_BLOCKS && (int)h->dgroups.size() <= SMALL_MAX_GROUPS
-         && ar <= ((size_t)1 << 20) && nlp <= (1 << 20) && !h->prof.on && !wantpre && !warm);
+         && ar <= ((size_t)1 << 20) && nlp <= (1 << 20) && !h->prof.on && !wantpre && !warm && h->nranks == 1 && h->emulate_ranks <= 1);
       if( eligible && h->ndense > 0 )
          for( const auto& g : h->dgroups ) if( g.count > h->dchunk ) eligible = false;
       // measured on the shipped instances: the one-launch kernel wins while the Schur complement is small (m <= 64); above that
@@ -1049,27 +1115,53 @@ static int run_ipm(sdpcuda_handle* h, const sdpcuda_params* par, const double* s
       PHASE(3);
       // ---- Schur complement and its factorisation ----
       CK( cudaMemsetAsync(h->M.p, 0, sizeof(double) * (size_t)h->ldm * m, st) );
-      CK( schur_entries(st, m, E, h->heavy.p, h->heavylist.p, h->nheavy, h->X.p, h->Sinv.p, h->M.p, h->ldm) );
-      if( h->ndense > 0 )
       {
-         // U_j = X A_j S^-1 for the dense variables (batched DMMA GEMMs), then M_ij = A_i . U_j for every i
-         size_t offm = 0;
-         for( const auto& g : h->dgroups )
+         // shares: with several ranks each one forms a disjoint part of the entries (column strips of the entry path,
+         // chunks of the dense path, the LP block on rank 0) and an all-reduce over NVLink adds them up.  Every entry is
+         // non-zero on one rank only (plus the LP term from rank 0), so the sum is exact and identical on all ranks.
+         const int G = h->emulate_ranks > 1 ? h->emulate_ranks : h->nranks;
+         const int gfirst = h->emulate_ranks > 1 ? 0 : h->rank;
+         const int glast = h->emulate_ranks > 1 ? G - 1 : h->rank;
+         for( int gr = gfirst; gr <= glast; ++gr )
          {
-            const Block& bk = h->blk[g.blk];
-            const long long stride = (long long)bk.ld * bk.n;
-            for( int d0 = 0; d0 < g.count; d0 += h->dchunk )
+            CK( schur_entries(st, m, E, h->heavy.p, h->heavylist.p, h->nheavy, h->X.p, h->Sinv.p, h->M.p, h->ldm, G, gr) );
+            if( h->ndense > 0 )
             {
-               const int cnt = std::min(h->dchunk, g.count - d0);
-               const double* Ad = h->Adense.p + offm + (size_t)d0 * stride;
-               CK( gemm(st, false, false, bk.n, bk.n, bk.n, 1.0, h->X.p + bk.off, bk.ld, 0, Ad, bk.ld, stride, 0.0, h->Hd.p, bk.ld, stride, cnt, 0) );
-               CK( gemm(st, false, false, bk.n, bk.n, bk.n, 1.0, h->Hd.p, bk.ld, stride, h->Sinv.p + bk.off, bk.ld, 0, 0.0, h->Ud.p, bk.ld, stride, cnt, 0) );
-               CK( schur_dense_dots(st, m, cnt, g.first + d0, h->denselist.p, h->heavy.p, E, bk.off, h->Ud.p, bk.ld, stride, h->M.p, h->ldm) );
+               // U_j = X A_j S^-1 for the dense variables (batched DMMA GEMMs), then M_ij = A_i . U_j for every i
+               size_t offm = 0;
+               int chunkno = 0;
+               for( const auto& g : h->dgroups )
+               {
+                  const Block& bk = h->blk[g.blk];
+                  const long long stride = (long long)bk.ld * bk.n;
+                  // with several ranks the chunks shrink so that every rank gets work
+                  const int chunk = (G > 1) ? std::max(1, std::min(h->dchunk, ceil_div(g.count, G))) : h->dchunk;
+                  for( int d0 = 0; d0 < g.count; d0 += chunk, ++chunkno )
+                  {
+                     if( chunkno % G != gr ) continue;
+                     const int cnt = std::min(chunk, g.count - d0);
+                     const double* Ad = h->Adense.p + offm + (size_t)d0 * stride;
+                     CK( gemm(st, false, false, bk.n, bk.n, bk.n, 1.0, h->X.p + bk.off, bk.ld, 0, Ad, bk.ld, stride, 0.0, h->Hd.p, bk.ld, stride, cnt, 0) );
+                     CK( gemm(st, false, false, bk.n, bk.n, bk.n, 1.0, h->Hd.p, bk.ld, stride, h->Sinv.p + bk.off, bk.ld, 0, 0.0, h->Ud.p, bk.ld, stride, cnt, 0) );
+                     // M_ij = <A_i, U_j>: sparse A_i by gathered dots; dense A_i of the same block as ONE tensor-core product
+                     // Adense' (count x n^2) * U (n^2 x cnt), scattered into the lower triangle (each pair once)
+                     CK( schur_dense_dots(st, m, cnt, g.first + d0, h->denselist.p, h->heavy.p, E, bk.off, h->Ud.p, bk.ld, stride, h->M.p, h->ldm) );
+                     CK( gemm(st, true, false, g.count, cnt, (int)stride, 1.0, h->Adense.p + offm, (int)stride, 0, h->Ud.p, (int)stride, 0, 0.0,
+                           h->Cd.p, round_up(g.count, 2), 0, 1, 0) );
+                     CK( schur_dense_scatter(st, g.count, cnt, g.first, g.first + d0, h->denselist.p, h->Cd.p, round_up(g.count, 2), h->M.p, h->ldm) );
+                  }
+                  offm += (size_t)g.count * stride;
+               }
             }
-            offm += (size_t)g.count * stride;
+         }
+         // the LP block is added on top of the entries (atomics): after all plain stores into this buffer, on one rank only
+         if( h->emulate_ranks > 1 || h->rank == 0 )
+            CK( schur_lp(st, nlp, h->lpbeg.p, h->lpind.p, h->lpval.p, h->x.p, h->s.p, h->M.p, h->ldm) );
+         if( h->nranks > 1 )
+         {
+            rc = dist_allreduce_sum(h, h->M.p, (size_t)h->ldm * m); if( rc ) return rc;
          }
       }
-      CK( schur_lp(st, nlp, h->lpbeg.p, h->lpind.p, h->lpval.p, h->x.p, h->s.p, h->M.p, h->ldm) );
       PHASE(4);
       double reg = 0.0;
       bool mok = false;
@@ -1270,6 +1362,58 @@ static int get_block(sdpcuda_handle* h, const double* src, int b, double* out)
 }
 int sdpcuda_get_X(sdpcuda_handle* h, int b, double* X) { return get_block(h, h ? h->X.p : nullptr, b, X); }
 int sdpcuda_get_S(sdpcuda_handle* h, int b, double* S) { return get_block(h, h ? h->S.p : nullptr, b, S); }
+
+int sdpcuda_dist_unique_id(void* id128)
+{
+   NcclApi* api = nccl_api();
+   if( api == nullptr || id128 == nullptr ) return SDPCUDA_ERR_STATE;
+   static_assert(sizeof(ncclUniqueId) == 128, "NCCL unique id size");
+   ncclUniqueId id;
+   if( api->GetUniqueId(&id) != ncclSuccess ) return SDPCUDA_ERR_CUDA;
+   memcpy(id128, &id, sizeof(id));
+   return SDPCUDA_OK;
+}
+
+int sdpcuda_dist_init(sdpcuda_handle* h, int nranks, int rank, const void* id128)
+{
+   if( h == nullptr || nranks < 1 || rank < 0 || rank >= nranks || (nranks > 1 && id128 == nullptr) ) return SDPCUDA_ERR_ARG;
+   if( set_device(h) ) return SDPCUDA_ERR_CUDA;
+   if( h->comm != nullptr ) return SDPCUDA_ERR_STATE;
+   h->nranks = nranks; h->rank = rank;
+   if( nranks == 1 ) return SDPCUDA_OK;
+   NcclApi* api = nccl_api();
+   if( api == nullptr )
+   {
+      fprintf(stderr, "[sdpcuda] libnccl.so.2 not found: the sharded Schur path needs NCCL\n");
+      h->nranks = 1; h->rank = 0;
+      return SDPCUDA_ERR_STATE;
+   }
+   ncclUniqueId id;
+   memcpy(&id, id128, sizeof(id));
+   ncclResult_t r = api->CommInitRank(&h->comm, nranks, id, rank);
+   if( r != ncclSuccess )
+   {
+      fprintf(stderr, "[sdpcuda] ncclCommInitRank failed: %s\n", api->GetErrorString ? api->GetErrorString(r) : "?");
+      h->comm = nullptr; h->nranks = 1; h->rank = 0;
+      return SDPCUDA_ERR_CUDA;
+   }
+   return SDPCUDA_OK;
+}
+
+int sdpcuda_dist_finalize(sdpcuda_handle* h)
+{
+   if( h == nullptr ) return SDPCUDA_ERR_ARG;
+   if( h->comm != nullptr )
+   {
+      NcclApi* api = nccl_api();
+      if( set_device(h) ) return SDPCUDA_ERR_CUDA;
+      cudaStreamSynchronize(h->st);
+      if( api != nullptr ) api->CommDestroy(h->comm);
+      h->comm = nullptr;
+   }
+   h->nranks = 1; h->rank = 0;
+   return SDPCUDA_OK;
+}
 
 int sdpcuda_set_start_block(sdpcuda_handle* h, int which, int block, int n, const double* A)
 {

@@ -212,11 +212,12 @@ __device__ __forceinline__ double pair_term(const DevEntries& E, int ei, int ej,
 // light pairs: one thread per (i, j), i >= j, both variables light
 __global__ void __launch_bounds__(256)
 schur_light_kernel(int m, DevEntries E, const int* __restrict__ heavy, const double* __restrict__ X, const double* __restrict__ Z,
-   double* __restrict__ M, int ldm)
+   double* __restrict__ M, int ldm, int nranks, int rank)
 {
    const int i = blockIdx.x * 32 + (threadIdx.x & 31);
    const int j = blockIdx.y * 8 + (threadIdx.x >> 5);
    if( blockIdx.x * 32 + 31 < blockIdx.y * 8 ) return;          // tile strictly above the diagonal
+   if( (int)(blockIdx.y % nranks) != rank ) return;             // column strips of 8 are dealt round-robin to the ranks
    if( i >= m || j >= m || i < j ) return;
    if( heavy[i] || heavy[j] ) return;             // classes 1 (heavy) and 2 (dense) are handled elsewhere
    double v = 0.0;
@@ -229,9 +230,10 @@ schur_light_kernel(int m, DevEntries E, const int* __restrict__ heavy, const dou
 // heavy pairs: one CTA per (heavy variable h, other variable o); the CTA splits the entry-pair product
 __global__ void __launch_bounds__(256)
 schur_heavy_kernel(int m, DevEntries E, const int* __restrict__ heavy, const int* __restrict__ heavylist,
-   const double* __restrict__ X, const double* __restrict__ Z, double* __restrict__ M, int ldm)
+   const double* __restrict__ X, const double* __restrict__ Z, double* __restrict__ M, int ldm, int nranks, int rank)
 {
    __shared__ double red[32];
+   if( (int)(blockIdx.x % nranks) != rank ) return;               // partner variables are dealt round-robin to the ranks
    const int h = heavylist[blockIdx.y];
    const int o = blockIdx.x;
    if( heavy[o] == 2 ) return;                                    // pairs with a dense variable belong to the dense path
@@ -277,7 +279,7 @@ schur_dense_dots_kernel(int m, int nd, int d0, const int* __restrict__ denselist
    const int d = blockIdx.y;
    if( i >= m ) return;
    const int j = denselist[d0 + d];
-   if( cls[i] == 2 && i < j ) return;             // dense-dense pairs are computed once, from the side with the larger index
+   if( cls[i] == 2 ) return;                      // dense x dense pairs: tensor-core product + schur_dense_scatter
    const double* Uj = U + (size_t)d * stride;
    double s = 0.0;
    for( int e = E.varbeg[i] + lane; e < E.varbeg[i + 1]; e += 32 )
@@ -294,6 +296,16 @@ schur_dense_dots_kernel(int m, int nd, int d0, const int* __restrict__ denselist
       int a = max(i, j), b = min(i, j);
       M[(size_t)b * ldm + a] = s;
    }
+}
+
+// C(a, b) = <A_i, U_j> for dense i = denselist[first + a], dense j = denselist[first_j + b] -> M[i, j] for i >= j (each pair once)
+__global__ void schur_dense_scatter_kernel(int count, int cnt, int first, int first_j, const int* __restrict__ denselist,
+   const double* __restrict__ C, int ldc, double* __restrict__ M, int ldm)
+{
+   const int a = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y;
+   if( a >= count || b >= cnt ) return;
+   const int i = denselist[first + a], j = denselist[first_j + b];
+   if( i >= j ) M[(size_t)j * ldm + i] = C[(size_t)b * ldc + a];
 }
 
 __global__ void schur_lp_kernel(int nlp, const int* __restrict__ lpbeg, const int* __restrict__ lpind, const double* __restrict__ lpval,
@@ -561,17 +573,17 @@ cudaError_t finalize_partials(cudaStream_t st, const double* partials, int nstat
 }
 
 cudaError_t schur_entries(cudaStream_t st, int m, DevEntries E, const int* heavy, const int* heavylist, int nheavy,
-   const double* X, const double* Z, double* M, int ldm)
+   const double* X, const double* Z, double* M, int ldm, int nranks, int rank)
 {
    if( m <= 0 ) return cudaSuccess;
    ProfScope prof(st, PROF_SCHUR, 8.0 * m * (double)m / 2.0);
    dim3 grid(ceil_div(m, 32), ceil_div(m, 8));
-   schur_light_kernel<<<grid, 256, 0, st>>>(m, E, heavy, X, Z, M, ldm);
+   schur_light_kernel<<<grid, 256, 0, st>>>(m, E, heavy, X, Z, M, ldm, nranks, rank);
    count_launch();
    if( nheavy > 0 )
    {
       dim3 g2(m, nheavy);
-      schur_heavy_kernel<<<g2, 256, 0, st>>>(m, E, heavy, heavylist, X, Z, M, ldm);
+      schur_heavy_kernel<<<g2, 256, 0, st>>>(m, E, heavy, heavylist, X, Z, M, ldm, nranks, rank);
       count_launch();
    }
    return cudaGetLastError();
@@ -591,6 +603,15 @@ cudaError_t schur_dense_dots(cudaStream_t st, int m, int nd, int d0, const int* 
    ProfScope prof(st, PROF_SCHUR, 8.0 * m * (double)nd);
    dim3 grid(ceil_div(m, 8), nd);
    schur_dense_dots_kernel<<<grid, 256, 0, st>>>(m, nd, d0, denselist, cls, E, blockoff, U, ld, stride, M, ldm);
+   LAUNCH_END();
+}
+
+cudaError_t schur_dense_scatter(cudaStream_t st, int count, int cnt, int first, int first_j, const int* denselist, const double* C, int ldc,
+   double* M, int ldm)
+{
+   if( count <= 0 || cnt <= 0 ) return cudaSuccess;
+   dim3 grid(ceil_div(count, 256), cnt);
+   schur_dense_scatter_kernel<<<grid, 256, 0, st>>>(count, cnt, first, first_j, denselist, C, ldc, M, ldm);
    LAUNCH_END();
 }
 

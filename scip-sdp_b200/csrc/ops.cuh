@@ -40,14 +40,19 @@ cudaError_t primal_residual(cudaStream_t st, int m, const double* b, const doubl
 cudaError_t finalize_partials(cudaStream_t st, const double* partials, int nstats, double* out);
 
 // Schur complement (lower triangle of M, ldm): entry/gather path over all variable pairs, LP block via atomics
+// (nranks, rank): this launch only forms the share of `rank` out of `nranks` (column strips / partner variables dealt
+// round-robin; every entry of M belongs to exactly one rank); (1, 0) = everything
 cudaError_t schur_entries(cudaStream_t st, int m, DevEntries E, const int* heavy /* [m] 0/1 */, const int* heavylist, int nheavy,
-   const double* X, const double* Z, double* M, int ldm);
+   const double* X, const double* Z, double* M, int ldm, int nranks = 1, int rank = 0);
 // dense path: variables whose constraint matrix is dense in one block.  scatter_dense expands them into full n x n matrices
 // (Adense, matrix d at d*stride); schur_dense_dots then forms M_ij = A_i . U_j for every variable i and every dense j from
 // U_j = X A_j S^-1 (two batched DMMA GEMMs in between), lower triangle only, each entry written exactly once.
 cudaError_t scatter_dense(cudaStream_t st, int nd, const int* denselist, DevEntries E, int ld, long long stride, double* Adense);
 cudaError_t schur_dense_dots(cudaStream_t st, int m, int nd, int d0, const int* denselist, const int* cls, DevEntries E, long long blockoff,
    const double* U, int ld, long long stride, double* M, int ldm);
+// dense x dense pairs: C = Adense' U (count x cnt, from the DMMA GEMM) scattered to M[i, j], i >= j
+cudaError_t schur_dense_scatter(cudaStream_t st, int count, int cnt, int first, int first_j, const int* denselist, const double* C, int ldc,
+   double* M, int ldm);
 cudaError_t schur_lp(cudaStream_t st, int nlp, const int* lpbeg, const int* lpind, const double* lpval, const double* x,
    const double* s, double* M, int ldm);
 cudaError_t add_diagonal(cudaStream_t st, int n, double* A, int lda, double v);

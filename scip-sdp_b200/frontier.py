@@ -41,3 +41,30 @@ def max_over_ranks(value, dist=None, device="cpu"):
     if dist is not None and dist.is_initialized() and dist.get_world_size() > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     return float(t.item())
+
+
+# ---------------------------------------------------------------------- one large SDP over several GPUs
+def schur_shares(nstrips, world):
+    """host-side mirror of the device partition of the Schur complement: strip t (8 columns of the entry path, or one chunk
+    of dense variables) belongs to rank t % world (ops.cu: schur_light_kernel / ipm.cu: dense chunks)"""
+    return [list(range(r, nstrips, world)) for r in range(world)]
+
+
+def broadcast_bytes(payload, nbytes, dist, src=0, device="cpu"):
+    """rank `src` passes `payload` (bytes of length nbytes) to every rank over the job's process group: used for the
+    128-byte NCCL unique id that sdpcuda_dist_init needs"""
+    import torch
+    buf = torch.zeros(nbytes, dtype=torch.uint8, device=device)
+    if dist.get_rank() == src:
+        buf.copy_(torch.frombuffer(bytearray(payload), dtype=torch.uint8))
+    dist.broadcast(buf, src=src)
+    return bytes(buf.cpu().numpy().tobytes())
+
+
+def shard_one_sdp(solver, dist, device="cpu"):
+    """joins the rank's device handle to the NCCL clique of the job: afterwards all ranks call solver.solve with the SAME problem
+    and every rank forms only its share of the Schur complement"""
+    world, rank = dist.get_world_size(), dist.get_rank()
+    ident = solver.dist_unique_id() if rank == 0 else None
+    ident = broadcast_bytes(ident, 128, dist, src=0, device=device)
+    solver.dist_init(world, rank, ident)

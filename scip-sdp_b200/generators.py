@@ -119,3 +119,24 @@ def cls(nfeat=199, nsamp=99, k=10, seed=2002):
         M.C[0].append((n - 1, r, -bvec[r]))
     M.add_row({j: 1.0 for j in range(nfeat)}, rhs=float(k))
     return M
+
+
+def dense_sdp_flat(m, n, seed=5005):
+    """Random SDP with m dense constraint matrices of order n in solver form (abi.FlatProblem), strictly feasible on both sides
+    by construction: X0 = I, y0 random, S0 = I:  C = sum_j y0_j A_j - S0,  obj_j = <A_j, X0>.  This is the shape whose
+    Schur complement costs O(m n^3 + m^2 n^2) flops per iteration (the dense route of SURVEY.md 8d), used for the
+    one-SDP-over-several-GPUs measurement; built with numpy arrays directly (m n^2 / 2 entries)."""
+    from .abi import FlatProblem
+    rng = np.random.default_rng(seed)
+    r, c = np.tril_indices(n)
+    r, c = r.astype(np.int32), c.astype(np.int32)
+    per = len(r)
+    vals = rng.standard_normal((m, per)) / np.sqrt(n)
+    y0 = rng.standard_normal(m)
+    # C = sum y0_j A_j - I (lower triangle)
+    cval = y0 @ vals
+    cval[r == c] -= 1.0
+    obj = vals[:, r == c].sum(axis=1)              # <A_j, I> = trace
+    varbeg = np.arange(m + 1, dtype=np.int64) * per
+    return FlatProblem(obj, [n], varbeg, np.zeros(m * per, dtype=np.int32), np.tile(r, m), np.tile(c, m), vals.reshape(-1),
+                       np.zeros(per, dtype=np.int32), r, c, cval, [0], [], [], [])

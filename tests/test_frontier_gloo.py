@@ -34,6 +34,9 @@ def _worker(rank, world, port, q):
         solver = abi.Solver(abi.Lib(abi.ORACLE_LIB))
         res = frontier.solve_frontier(solver, M, _nodes(M), dist=dist, gaptol=1e-6, feastol=1e-6)
         tmax = frontier.max_over_ranks(1.0 + rank, dist=dist)
+        # the channel that carries the NCCL id of the sharded-Schur path (rank 0 -> all)
+        ident = frontier.broadcast_bytes(bytes(range(128)) if rank == 0 else None, 128, dist)
+        assert ident == bytes(range(128))
         q.put((rank, [(r["status"], round(r["bound"], 6)) for r in res], tmax, frontier.partition(5, world, rank)))
     finally:
         dist.destroy_process_group()
@@ -43,6 +46,20 @@ def test_partition_is_a_disjoint_cover():
     for world in (1, 2, 4, 8):
         allidx = sorted(i for r in range(world) for i in frontier.partition(13, world, r))
         assert allidx == list(range(13))
+
+
+def test_schur_shares_are_a_disjoint_cover():
+    for world in (1, 2, 3, 8):
+        shares = frontier.schur_shares(251, world)
+        assert sorted(t for sh in shares for t in sh) == list(range(251))
+        assert max(len(sh) for sh in shares) - min(len(sh) for sh in shares) <= 1
+
+
+def test_oracle_has_no_sharded_path():
+    s = abi.Solver(abi.Lib(abi.ORACLE_LIB))
+    s.dist_init(1, 0, None)                      # a clique of one is fine
+    with pytest.raises(RuntimeError):
+        s.dist_init(2, 0, bytes(128))
 
 
 def test_frontier_world_size_2_matches_single_process():

@@ -110,3 +110,32 @@ def test_maxcut_600_kkt_and_properties(gpu):
     assert np.linalg.eigvalsh(X).min() >= -1e-9 and np.linalg.eigvalsh(S).min() >= -1e-9
     assert abs(np.vdot(X, S)) <= 1e-5 * max(1.0, abs(r["dobj"]))
     assert abs(y.sum() - np.vdot(C, X)) <= 1e-5 * abs(y.sum())
+
+
+@pytest.mark.parametrize("name,make", list(_instances()), ids=[n for n, _ in _instances()])
+def test_schur_shares_add_up_to_the_unsharded_complement(gpu, name, make, monkeypatch):
+    """the partition of the Schur complement used by the multi-GPU path, emulated on one GPU: forming the shares of
+    three ranks one after the other must give the same iterates (every entry belongs to exactly one share): bit-identical
+    without LP rows; the LP block of M is accumulated with atomics, whose order differs from run to run in the last bits"""
+    fp, _ = make().flatten()
+    monkeypatch.setenv("SDPCUDA_PATH", "m")
+    a = gpu.solve(fp, gaptol=1e-7, feastol=1e-7, fetch=False)
+    monkeypatch.setenv("SDPCUDA_SHARD_EMULATE", "3")
+    b = gpu.solve(fp, gaptol=1e-7, feastol=1e-7, fetch=False)
+    assert a["phase_name"] == b["phase_name"] == "pdOPT"
+    assert a["iterations"] == b["iterations"]
+    tol = 0.0 if fp.nlp == 0 else 1e-8 * max(1.0, abs(a["dobj"]))     # ill-conditioned instances amplify the last-bit differences
+    assert abs(a["dobj"] - b["dobj"]) <= tol and abs(a["pobj"] - b["pobj"]) <= tol
+
+
+def test_sharded_schur_on_two_gpus():
+    """one SDP over two GPUs with the NCCL all-reduce of the Schur shares (needs two devices; tools/dist_check.py)"""
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                          "--master-port", "29533", os.path.join(root, "tools", "dist_check.py")], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and "DIST_CHECK PASS" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]

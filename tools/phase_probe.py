@@ -17,7 +17,7 @@ for name in which:
             ms, work = gpu.time_kernel(kind, n, 5)
             print(f"{label} n={n}: {ms:.3f} ms  {work / ms * 1e-9:.2f} TFLOP/s", flush=True)
         continue
-    fp, _ = make[name]().flatten()
+    fp = generators.dense_sdp_flat(600, 300) if name == "dense600" else make[name]().flatten()[0]
     kw = dict(gaptol=1e-5, feastol=1e-5)
     gpu.solve(fp, fetch=False, **kw)
     print("====", name, "m", fp.m, "blocks", list(fp.blocksizes), "nlp", fp.nlp, flush=True)
