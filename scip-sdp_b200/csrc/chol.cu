@@ -797,4 +797,156 @@ cudaError_t potrs_vec(cudaStream_t st, int n, const double* L, int ldl, const do
    return cudaGetLastError();
 }
 
+
+// ---- large orders: right-looking blocked factorisation with one panel of look-ahead ---------------------------------------
+// Panels of width PB.  Step k on the main stream: factor the diagonal block (recursive kernel chain above, with its inverse
+// P_k), L(below, k) = A(below, k) P_k' (GEMM), update of the NEXT panel's columns with panel k (GEMM).  The update of all
+// later columns with panel k (the bulk of the n^3/3 flops, one large lower-triangular GEMM) goes to the side stream, so that
+// the latency-bound factorisation of panel k+1 hides behind it.  Dependencies: update_rest(k) needs the panel-k solve;
+// update_next(k+1) needs update_rest(k).  The inverse of L is NOT formed: solves use the panel inverses (potrs_panels below).
+namespace {
+
+// out[i] = (bin ? bin[i] : 0) - sign * dot(column i of Mx restricted by mode, vin) for the columns i0 .. of one panel
+// mode 0: rows [0, len); mode 1: rows >= local column index (lower triangular panel inverse);
+// mode 2: rows <= local column index (transposed panel inverse)
+__global__ void __launch_bounds__(256)
+panel_dot_kernel(const double* __restrict__ Mx, int ld, int ncols, int len, int mode, const double* __restrict__ vin,
+   const double* __restrict__ bin, double sign, double* __restrict__ out)
+{
+   __shared__ double part[8][8];
+   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+   const int i0 = blockIdx.x * 8;
+   if( i0 >= ncols ) return;
+   const int nc = min(8, ncols - i0);
+   double acc[8];
+#pragma unroll
+   for( int c = 0; c < 8; ++c ) acc[c] = 0.0;
+   int kbeg = 0, kend = len;
+   if( mode == 1 ) kbeg = i0;                 // entries k >= i
+   if( mode == 2 ) kend = min(len, i0 + 8);   // entries k <= i
+   for( int k = kbeg + tid; k < kend; k += 512 )
+   {
+      const int k2 = k + 256;
+      const bool in2 = k2 < kend;
+      const double v0 = vin[k], v1 = in2 ? vin[k2] : 0.0;
+      double m0[8], m1[8];
+#pragma unroll
+      for( int c = 0; c < 8; ++c )
+      {
+         const double* col = Mx + (size_t)(i0 + c) * ld;
+         m0[c] = (c < nc) ? col[k] : 0.0;
+         m1[c] = (c < nc && in2) ? col[k2] : 0.0;
+      }
+#pragma unroll
+      for( int c = 0; c < 8; ++c )
+      {
+         const int i = i0 + c;
+         const bool ok0 = (mode == 0) || (mode == 1 ? k >= i : k <= i);
+         const bool ok1 = (mode == 0) || (mode == 1 ? k2 >= i : k2 <= i);
+         acc[c] += (ok0 ? m0[c] * v0 : 0.0) + (ok1 ? m1[c] * v1 : 0.0);
+      }
+   }
+#pragma unroll
+   for( int c = 0; c < 8; ++c )
+   {
+      double v = acc[c];
+#pragma unroll
+      for( int o = 16; o > 0; o >>= 1 ) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if( lane == 0 ) part[wid][c] = v;
+   }
+   __syncthreads();
+   if( tid < nc )
+   {
+      double v = 0.0;
+#pragma unroll
+      for( int q = 0; q < 8; ++q ) v += part[q][tid];
+      out[i0 + tid] = (bin != nullptr ? bin[i0 + tid] : 0.0) - sign * v;
+   }
+}
+
+__global__ void transpose_small_kernel(int n, const double* __restrict__ A, int lda, double* __restrict__ B, int ldb)
+{
+   __shared__ double tile[32][33];
+   const int x = blockIdx.x * 32 + threadIdx.x, y0 = blockIdx.y * 32;
+   for( int r = threadIdx.y; r < 32; r += blockDim.y )
+      tile[r][threadIdx.x] = (x < n && y0 + r < n) ? A[(size_t)(y0 + r) * lda + x] : 0.0;
+   __syncthreads();
+   const int xo = blockIdx.y * 32 + threadIdx.x, yo0 = blockIdx.x * 32;
+   for( int r = threadIdx.y; r < 32; r += blockDim.y )
+      if( xo < n && yo0 + r < n ) B[(size_t)(yo0 + r) * ldb + xo] = tile[threadIdx.x][r];
+}
+
+} // namespace
+
+cudaError_t potrf_lower_lookahead(cudaStream_t st, cudaStream_t side, cudaEvent_t* ev, int nev, int pb, int n, double* A, int lda,
+   double* pinv, double* pinvT, double* work, int ldw, int* d_info)
+{
+   const int nblk = ceil_div(n, pb);
+   if( 2 * nblk + 2 > nev ) return cudaErrorInvalidValue;
+   cudaEvent_t* evT = ev;              // panel solve of step k done (main stream)
+   cudaEvent_t* evB = ev + nblk;       // update of the later columns with panel k done (side stream)
+   int lastB = -1;
+   for( int k = 0; k < nblk; ++k )
+   {
+      const int j0 = k * pb, kb = min(pb, n - j0), rem = n - j0 - kb;
+      double* Pk = pinv + (size_t)k * pb * pb;
+      double* PkT = pinvT + (size_t)k * pb * pb;
+      SDPK_CUDA_CHECK( cudaMemsetAsync(Pk, 0, sizeof(double) * (size_t)pb * pb, st) );
+      SDPK_CUDA_CHECK( chol_rec(st, kb, A + (size_t)j0 * lda + j0, lda, Pk, pb, nullptr, work, ldw, d_info, j0) );
+      {
+         dim3 grid(ceil_div(kb, 32), ceil_div(kb, 32)), block(32, 8);
+         transpose_small_kernel<<<grid, block, 0, st>>>(kb, Pk, pb, PkT, pb);
+         count_launch();
+      }
+      if( rem == 0 ) break;
+      const int j1 = j0 + kb, kb1 = min(pb, rem), rem2 = rem - kb1, j2 = j1 + kb1;
+      double* A21 = A + (size_t)j0 * lda + j1;
+      SDPK_CUDA_CHECK( gemm(st, false, true, rem, kb, kb, 1.0, A21, lda, 0, Pk, pb, 0, 0.0, work, ldw, 0, 1, GEMM_KHI_N) );
+      SDPK_CUDA_CHECK( copy2d(st, rem, kb, work, ldw, A21, lda) );
+      SDPK_CUDA_CHECK( cudaEventRecord(evT[k], st) );
+      if( lastB >= 0 ) SDPK_CUDA_CHECK( cudaStreamWaitEvent(st, evB[lastB], 0) );
+      // next panel: A(j1.., j1..j2) -= L(j1.., k) L(j1..j2, k)'
+      SDPK_CUDA_CHECK( gemm(st, false, true, rem, kb1, kb, -1.0, A21, lda, 0, A21, lda, 0, 1.0, A + (size_t)j1 * lda + j1, lda, 0, 1, GEMM_LOWER) );
+      if( rem2 > 0 )
+      {
+         SDPK_CUDA_CHECK( cudaStreamWaitEvent(side, evT[k], 0) );
+         const double* L2 = A + (size_t)j0 * lda + j2;
+         SDPK_CUDA_CHECK( gemm(side, false, true, rem2, rem2, kb, -1.0, L2, lda, 0, L2, lda, 0, 1.0, A + (size_t)j2 * lda + j2, lda, 0, 1, GEMM_LOWER) );
+         SDPK_CUDA_CHECK( cudaEventRecord(evB[k], side) );
+         lastB = k;
+      }
+   }
+   if( lastB >= 0 ) SDPK_CUDA_CHECK( cudaStreamWaitEvent(st, evB[lastB], 0) );
+   return cudaSuccess;
+}
+
+// b <- (L L')^-1 b with the panel inverses of potrf_lower_lookahead; LT = L' (n x n, ldl) for the contiguous row access of the
+// forward sweep.  Two launches per panel and sweep, every one a set of dot products with contiguous columns.
+cudaError_t potrs_panels(cudaStream_t st, int pb, int n, const double* L, const double* LT, int ldl, const double* pinv, const double* pinvT,
+   double* b, double* tmp)
+{
+   const int nblk = ceil_div(n, pb);
+   ProfScope prof(st, PROF_TRSV, 8.0 * n * (double)n);
+   // forward: z_k = P_k (b_k - L(k, 0:j0) z(0:j0))
+   for( int k = 0; k < nblk; ++k )
+   {
+      const int j0 = k * pb, kb = min(pb, n - j0);
+      // (with j0 = 0 the first launch only copies: the second one must not read and write the same vector)
+      panel_dot_kernel<<<ceil_div(kb, 8), 256, 0, st>>>(LT + (size_t)j0 * ldl, ldl, kb, j0, 0, b, b + j0, 1.0, tmp + j0);
+      // row r of P_k = column r of P_k', entries <= r
+      panel_dot_kernel<<<ceil_div(kb, 8), 256, 0, st>>>(pinvT + (size_t)k * pb * pb, pb, kb, kb, 2, tmp + j0, nullptr, -1.0, b + j0);
+      count_launch(2);
+   }
+   // backward: x_k = P_k' (z_k - L(j1:, k)' x(j1:))
+   for( int k = nblk - 1; k >= 0; --k )
+   {
+      const int j0 = k * pb, kb = min(pb, n - j0), j1 = j0 + kb, rem = n - j1;
+      panel_dot_kernel<<<ceil_div(kb, 8), 256, 0, st>>>(L + (size_t)j0 * ldl + j1, ldl, kb, rem, 0, b + j1, b + j0, 1.0, tmp + j0);
+      // column r of P_k, entries >= r
+      panel_dot_kernel<<<ceil_div(kb, 8), 256, 0, st>>>(pinv + (size_t)k * pb * pb, pb, kb, kb, 1, tmp + j0, nullptr, -1.0, b + j0);
+      count_launch(2);
+   }
+   return cudaGetLastError();
+}
+
 } // namespace sdpk

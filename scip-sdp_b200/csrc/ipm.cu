@@ -67,6 +67,10 @@ struct sdpcuda_handle
 {
    int device = 0;
    cudaStream_t st = nullptr, st2 = nullptr;      // st2: second lane for the factorisation of X next to that of S
+   cudaStream_t st3 = nullptr;                    // side lane of the look-ahead factorisation of large Schur complements
+   cudaEvent_t evp[70] = {nullptr};
+   int panel = 0;                                 // > 0: panel width of the look-ahead path (Schur complements without explicit inverse)
+   DBuf<double> pinv, pinvT;
    cudaEvent_t ev0 = nullptr, ev1 = nullptr, evFork = nullptr, evJoin = nullptr;
    LaunchCounter counter;
    bool solved = false;
@@ -113,7 +117,7 @@ struct sdpcuda_handle
    DBuf<double> LinvT, LXinvT;       // transposed inverse factors of the large blocks (implicit step-length operators)
    bool lzimplicit = false;
    int lzsteps = 0;                  // Lanczos steps of the last batched run (diagnostics)
-   bool minv = false;                // explicit inverse factor of M (m <= 16384): solves become two triangular mat-vecs
+   bool minv = false;                // explicit inverse factor of M (m <= 4096): solves become two triangular mat-vecs; above: look-ahead panels + panel substitution
    DBuf<double> partials, stats, scal, eigw, lzwork;
    DBuf<int> info;
    double* h_stats = nullptr;     // pinned
@@ -380,9 +384,22 @@ int upload_problem(sdpcuda_handle* h, const sdpcuda_problem* P)
    CK( h->Mwork.ensure((size_t)h->ldm * (m + 2 * CHOL_LEAF_MAX)) );
    {
       const char* e = getenv("SDPCUDA_MINV_MAX");      // test knob: 0 forces the blocked substitution path
-      h->minv = (m <= (e != nullptr ? atoi(e) : 16384));
+      h->minv = (m <= (e != nullptr ? atoi(e) : 4096));
    }      // 2 GB at the limit; the blocked substitution (one launch per 64 rows) is latency bound
+   h->panel = 0;
    if( h->minv ) CK( h->MLinv.ensure((size_t)h->ldm * m) );
+   else
+   {
+      // large Schur complements: look-ahead panel factorisation, solves by panel substitution (needs L' next to L)
+      const char* e = getenv("SDPCUDA_PANEL");         // test knob: small panels on small problems
+      int pb = (e != nullptr && atoi(e) >= 8) ? atoi(e) : (m > 6144 ? 1024 : 512);
+      while( ceil_div(m, pb) > 32 ) pb *= 2;
+      h->panel = pb;
+      const size_t np = (size_t)ceil_div(m, pb) * pb * pb;
+      CK( h->pinv.ensure(np) ); CK( h->pinvT.ensure(np) );
+      CK( h->MLinv.ensure((size_t)h->ldm * m) );       // holds L'
+      for( cudaEvent_t& ev : h->evp ) if( ev == nullptr ) CK( cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) );
+   }
    CK( h->lzdesc.ensure(2 * (size_t)std::max(h->nb, 1)) );
    CK( h->lztickets.ensure(2 * (size_t)std::max(h->nb, 1)) );
    CK( cudaMemsetAsync(h->lztickets.p, 0, sizeof(unsigned) * 2 * (size_t)std::max(h->nb, 1), st) );
@@ -680,8 +697,13 @@ int sdpcuda_create(sdpcuda_handle** out, int device)
       if( e != nullptr && e[0] >= '0' && e[0] <= '9' ) device = atoi(e);
    }
    h->device = (device >= 0) ? device % ndev : (g_next_device.fetch_add(1) % ndev);
+   // the side lane of the look-ahead factorisation carries the bulk GEMMs: lowest priority, so that the latency-bound panel
+   // kernels of the main lane get SM slots first
+   int lowprio = 0, highprio = 0;
+   if( cudaSetDevice(h->device) == cudaSuccess ) cudaDeviceGetStreamPriorityRange(&lowprio, &highprio);
    if( cudaSetDevice(h->device) != cudaSuccess || cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking) != cudaSuccess
       || cudaStreamCreateWithFlags(&h->st2, cudaStreamNonBlocking) != cudaSuccess
+      || cudaStreamCreateWithPriority(&h->st3, cudaStreamNonBlocking, lowprio) != cudaSuccess
       || cudaEventCreate(&h->ev0) != cudaSuccess || cudaEventCreate(&h->ev1) != cudaSuccess
       || cudaEventCreateWithFlags(&h->evFork, cudaEventDisableTiming) != cudaSuccess
       || cudaEventCreateWithFlags(&h->evJoin, cudaEventDisableTiming) != cudaSuccess
@@ -714,11 +736,12 @@ int sdpcuda_destroy(sdpcuda_handle* h)
    for( DBuf<long long>* bf : {&h->eoff, &h->pos, &h->mirror, &h->cpos, &h->cmirror} )
       bf->release();
    h->lzdesc.release(); h->lztickets.release(); h->lzpart.release(); h->smallres.release();
-   h->LinvT.release(); h->LXinvT.release();
+   h->LinvT.release(); h->LXinvT.release(); h->pinv.release(); h->pinvT.release();
+   for( cudaEvent_t& e : h->evp ) if( e != nullptr ) { cudaEventDestroy(e); e = nullptr; }
    h->preX.release(); h->prey.release(); h->prex.release();
    drop_graph(h->gS); drop_graph(h->gX); drop_graph(h->gM);
    cudaEventDestroy(h->ev0); cudaEventDestroy(h->ev1); cudaEventDestroy(h->evFork); cudaEventDestroy(h->evJoin);
-   cudaStreamDestroy(h->st); cudaStreamDestroy(h->st2);
+   cudaStreamDestroy(h->st); cudaStreamDestroy(h->st2); cudaStreamDestroy(h->st3);
    if( g_counter == &h->counter ) g_counter = nullptr;
    if( g_prof == &h->prof ) g_prof = nullptr;
    delete h;
@@ -1171,7 +1194,10 @@ static int run_ipm(sdpcuda_handle* h, const sdpcuda_params* par, const double* s
          if( reg > 0.0 ) CK( add_diagonal(st, m, h->Mfac.p, h->ldm, reg) );
          CK( cudaMemsetAsync(h->info.p + 2, 0, sizeof(int), st) );
          rc = run_graphed(h, h->gM, st, graphs, [&]() -> int {
-            CK( potrf_lower(st, m, h->Mfac.p, h->ldm, h->minv ? h->MLinv.p : nullptr, h->ldm, h->minv ? nullptr : h->diaginv.p, h->Mwork.p, h->ldm, h->info.p + 2) );
+            if( h->minv )
+               CK( potrf_lower(st, m, h->Mfac.p, h->ldm, h->MLinv.p, h->ldm, nullptr, h->Mwork.p, h->ldm, h->info.p + 2) );
+            else
+               CK( potrf_lower_lookahead(st, h->st3, h->evp, 70, h->panel, m, h->Mfac.p, h->ldm, h->pinv.p, h->pinvT.p, h->Mwork.p, h->ldm, h->info.p + 2) );
             return SDPCUDA_OK; });
          if( rc ) return rc;
          CK( cudaMemcpyAsync(h->h_info, h->info.p, 8 * sizeof(int), cudaMemcpyDeviceToHost, st) );
@@ -1195,6 +1221,7 @@ static int run_ipm(sdpcuda_handle* h, const sdpcuda_params* par, const double* s
       }
       if( !mok ) { R.stop = SDPCUDA_STOP_NUMERICS; break; }
       if( h->minv ) CK( transpose(st, m, h->MLinv.p, h->ldm, h->Mfac.p, h->ldm) );   // L itself is not needed any more
+      else CK( transpose(st, m, h->Mfac.p, h->ldm, h->MLinv.p, h->ldm) );            // L' for the forward panel sweeps
 
       PHASE(5);
       // ---- predictor (sigma = 0) and corrector ----
@@ -1244,7 +1271,7 @@ static int run_ipm(sdpcuda_handle* h, const sdpcuda_params* par, const double* s
                CK( trmv_lower(st, m, h->MLinv.p, h->ldm, 1, h->tm2.p, v) );       // Linv' (Linv v)
             }
             else
-               CK( potrs_vec(st, m, h->Mfac.p, h->ldm, h->diaginv.p, v, h->tm2.p) );
+               CK( potrs_panels(st, h->panel, m, h->Mfac.p, h->MLinv.p, h->ldm, h->pinv.p, h->pinvT.p, v, h->tm2.p) );
             return SDPCUDA_OK;
          };
          CK( cudaMemcpyAsync(h->dy.p, h->g.p, sizeof(double) * m, cudaMemcpyDeviceToDevice, st) );

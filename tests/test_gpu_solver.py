@@ -33,14 +33,15 @@ def _instances():
     yield "cls-40", lambda: generators.cls(40, 25, 5, seed=14)
 
 
-@pytest.mark.parametrize("leaf", ["128", "64"])
-def test_substitution_path_for_the_schur_system(gpu, cpu, leaf, monkeypatch):
-    """M dy = g by blocked forward/backward substitution (the path of Schur complements too large for an explicit inverse
-    factor), forced on a small instance; also covers both leaf orders of the recursive Cholesky"""
-    fp, _ = generators.mkp(24, seed=11).flatten()
+@pytest.mark.parametrize("leaf,panel,nodes", [("128", "64", 24), ("64", "128", 40), ("128", "512", 24)])
+def test_lookahead_factorisation_and_panel_substitution(gpu, cpu, leaf, panel, nodes, monkeypatch):
+    """the path of large Schur complements (no explicit inverse factor): right-looking panels with look-ahead on a side stream and
+    M dy = g by panel substitution, forced on small instances with small panels; also covers both leaf orders of the recursion"""
+    fp, _ = generators.mkp(nodes, seed=11).flatten()
     monkeypatch.setenv("SDPCUDA_PATH", "m")
     monkeypatch.setenv("SDPCUDA_MINV_MAX", "0")
     monkeypatch.setenv("SDPCUDA_LEAF", leaf)
+    monkeypatch.setenv("SDPCUDA_PANEL", panel)
     r = gpu.solve(fp, gaptol=1e-7, feastol=1e-7)
     ref = cpu.solve(fp, gaptol=1e-7, feastol=1e-7)
     assert ref["phase_name"] == "pdOPT" and r["phase_name"] == "pdOPT", (r["phase_name"], r["stop_name"])
