@@ -33,6 +33,7 @@ namespace {
 constexpr int NSTAT = 24;
 
 thread_local double g_h2d_bytes = 0.0;
+thread_local long long g_realloc_epoch = 0;      // bumped whenever a device buffer moves (captured graphs hold raw pointers)
 
 template <class T> struct DBuf
 {
@@ -42,6 +43,7 @@ template <class T> struct DBuf
       if( n <= cap ) return cudaSuccess;
       if( p ) cudaFree(p);
       p = nullptr; cap = 0;
+      ++g_realloc_epoch;
       size_t want = std::max(n, (size_t)16);
       cudaError_t e = cudaMalloc((void**)&p, want * sizeof(T));
       if( e == cudaSuccess ) cap = want;
@@ -69,6 +71,7 @@ struct sdpcuda_handle
    cudaStream_t st = nullptr, st2 = nullptr;      // st2: second lane for the factorisation of X next to that of S
    cudaStream_t st3 = nullptr;                    // side lane of the look-ahead factorisation of large Schur complements
    cudaEvent_t evp[70] = {nullptr};
+   std::vector<long long> shapesig;               // shapes the captured graphs were recorded for
    int panel = 0;                                 // > 0: panel width of the look-ahead path (Schur complements without explicit inverse)
    DBuf<double> pinv, pinvT;
    cudaEvent_t ev0 = nullptr, ev1 = nullptr, evFork = nullptr, evJoin = nullptr;
@@ -160,7 +163,10 @@ int set_device(sdpcuda_handle* h)
 int upload_problem(sdpcuda_handle* h, const sdpcuda_problem* P)
 {
    cudaStream_t st = h->st;
-   drop_graph(h->gS); drop_graph(h->gX); drop_graph(h->gM);      // buffers may move: captured sequences are stale
+   // the captured factorisation sequences stay valid across uploads as long as no device buffer moved and the shapes are the
+   // same (the usual case between branch-and-bound nodes): checked at the end of this function
+   const long long epoch0 = g_realloc_epoch;
+   const std::vector<long long> oldsig = h->shapesig;
    if( P->nblocks > 4000 ) return SDPCUDA_ERR_ARG;      // pinned scalar buffer holds two eigenvalue slots per block
    h->m = P->m; h->nb = P->nblocks; h->nlp = P->nlp;
    h->blk.resize(h->nb);
@@ -232,8 +238,19 @@ int upload_problem(sdpcuda_handle* h, const sdpcuda_problem* P)
       key[nnz + e] = cposv[e];
    }
    std::vector<int> order(nnz + P->cnnz);
-   std::iota(order.begin(), order.end(), 0);
-   std::sort(order.begin(), order.end(), [&](int a, int b2) { return key[a] < key[b2] || (key[a] == key[b2] && a < b2); });
+   if( h->arena <= ((size_t)1 << 26) )
+   {
+      // counting sort by arena position (stable in the entry id): linear in the number of entries
+      std::vector<int> cntpos(h->arena + 1, 0);
+      for( long long kk : key ) cntpos[(size_t)kk + 1]++;
+      for( size_t a = 0; a < h->arena; ++a ) cntpos[a + 1] += cntpos[a];
+      for( int id = 0; id < nnz + P->cnnz; ++id ) order[cntpos[(size_t)key[id]]++] = id;
+   }
+   else
+   {
+      std::iota(order.begin(), order.end(), 0);
+      std::sort(order.begin(), order.end(), [&](int a, int b2) { return key[a] < key[b2] || (key[a] == key[b2] && a < b2); });
+   }
    std::vector<int> var_of(nnz);
    for( int j = 0; j < m; ++j )
       for( int e = P->varbeg[j]; e < P->varbeg[j + 1]; ++e ) var_of[e] = j;
@@ -354,7 +371,7 @@ int upload_problem(sdpcuda_handle* h, const sdpcuda_problem* P)
       // the padding rows (leading dimension > order) take part in the long dot products of the dense x dense pairs: keep them zero
       CK( cudaMemsetAsync(h->Hd.p, 0, (size_t)h->dchunk * maxmat * sizeof(double), st) );
       CK( cudaMemsetAsync(h->Ud.p, 0, (size_t)h->dchunk * maxmat * sizeof(double), st) );
-      CK( h->Cd.ensure((size_t)maxcount * h->dchunk + 4) );
+      CK( h->Cd.ensure((size_t)round_up(maxcount, 2) * h->dchunk + 4) );       // leading dimension of the product is even
       size_t offm = 0;
       DevEntries E{h->varbeg.p, h->erow.p, h->ecol.p, h->eld.p, h->eoff.p, h->eval.p};
       for( const auto& g : h->dgroups )
@@ -420,6 +437,20 @@ int upload_problem(sdpcuda_handle* h, const sdpcuda_problem* P)
       if( h->lzimplicit ) { CK( h->LinvT.ensure(h->arena) ); CK( h->LXinvT.ensure(h->arena) ); }
    }
    CK( h->info.ensure(8) );
+   {
+      // keep the captured graphs only if nothing they refer to has changed
+      std::vector<long long> sig = {(long long)m, (long long)h->nb, (long long)h->ldm, (long long)h->minv, (long long)h->panel, (long long)h->lzimplicit};
+      {
+         const char* e = getenv("SDPCUDA_LEAF");
+         sig.push_back(e != nullptr ? (long long)e[0] * 256 + e[1] : 0);
+      }
+      for( const Block& bk : h->blk ) { sig.push_back(bk.n); sig.push_back(bk.off); }
+      if( sig != oldsig || g_realloc_epoch != epoch0 )
+      {
+         drop_graph(h->gS); drop_graph(h->gX); drop_graph(h->gM);
+      }
+      h->shapesig = sig;
+   }
    return SDPCUDA_OK;
 }
 
@@ -1032,7 +1063,9 @@ static int run_ipm(sdpcuda_handle* h, const sdpcuda_params* par, const double* s
       // the two factorisations are latency bound (chains of small kernels) and independent: run them side by side.  The
       // launches of the critical one (S, main stream) are issued first so that the host does not delay it.
       CK( cudaEventRecord(h->evFork, st) );
-      const bool graphs = (iter >= 1);      // the first iteration runs plain launches (one-time kernel attribute set-up)
+      // the first iteration of a fresh shape runs plain launches (one-time kernel attribute set-up); graphs recorded for the
+      // same shapes by an earlier solve are reused from the start
+      const bool graphs = (iter >= 1) || (h->gS.exec != nullptr && h->gX.exec != nullptr && h->gM.exec != nullptr);
       rc = run_graphed(h, h->gS, st, graphs, [&]() { return factor_blocks(h, st, h->work.p, h->S.p, h->L.p, h->Linv.p, h->lzimplicit ? h->LinvT.p : nullptr, 0); }); if( rc ) return rc;
       CK( cudaStreamWaitEvent(h->st2, h->evFork, 0) );
       rc = run_graphed(h, h->gX, h->st2, graphs, [&]() { return factor_blocks(h, h->st2, h->work2.p, h->X.p, h->LX.p, h->LXinv.p, h->lzimplicit ? h->LXinvT.p : nullptr, 1); }); if( rc ) return rc;

