@@ -20,297 +20,6 @@ long long* g_diag_dbg = nullptr;
 namespace {
 
 constexpr int NB = CHOL_NB;
-constexpr int LDSM = NB + 1;
-
-// fast reciprocal square root in double precision: float seed + two Newton steps (relative error ~1e-16)
-__device__ __forceinline__ double fast_rsqrt(double x)
-{
-   double y = (double)rsqrtf((float)x);
-   y = y * (1.5 - 0.5 * x * y * y);
-   y = y * (1.5 - 0.5 * x * y * y);
-   return y;
-}
-
-// inverse of a 4 x 4 lower-triangular block (fully unrolled forward substitution); rdiag = reciprocals of the diagonal
-__device__ __forceinline__ void inv4_lower(const double (&l)[4][4], const double (&rdiag)[4], double (&w)[4][4])
-{
-#pragma unroll
-   for( int c = 0; c < 4; ++c )
-   {
-#pragma unroll
-      for( int r = 0; r < 4; ++r )
-      {
-         if( r < c ) { w[r][c] = 0.0; continue; }
-         if( r == c ) { w[r][c] = rdiag[r]; continue; }
-         double s = 0.0;
-#pragma unroll
-         for( int p = 0; p < 4; ++p ) if( p >= c && p < r ) s += l[r][p] * w[p][c];
-         w[r][c] = -s * rdiag[r];
-      }
-   }
-}
-
-// mode 0: factorise A (nb x nb, lower) in place, optionally write inverse of L to Linv (upper part zeroed) / diaginv
-// mode 1: A holds a lower-triangular factor already; only invert it
-// One CTA of 256 threads = 16 x 16 register tiles of 4 x 4 covering the whole 64 x 64 block; everything is organised in
-// 16 macro steps over block columns of width 4 so that all register indexing is static and the updates carry no
-// predicates (published panels are zero outside their active rows):
-//   factorisation, block column t: the diagonal tile factors its 4 x 4 block and inverts it (one thread, unrolled);
-//     the tiles below form their panel block A_it L_tt^-T and publish it; every tile subtracts P_i P_j'.
-//   inverse (W = L^-1 from R = I), block row t: tiles of that row form L_tt^-1 R_t and publish it; tiles below subtract
-//     L_it W_t.  Two barriers per macro step in the first phase, one in the second (published rows double buffered).
-__global__ void __launch_bounds__(256)
-diag_block_kernel(int mode, int nb, double* __restrict__ A, int lda, double* __restrict__ Linv, int ldi,
-   double* __restrict__ diaginv, int* __restrict__ info, int pivot_offset, long long* __restrict__ dbg)
-{
-   __shared__ double Ls[NB * LDSM];
-   __shared__ __align__(16) double Pn[2][4][NB];      // published panel columns / inverse rows
-   __shared__ double Dinv[16][16];                    // inverses of the 4 x 4 diagonal blocks of L (row-major 4 x 4)
-   long long tc0 = clock64(), tc1 = 0, tc2 = 0, tc3 = 0;
-   const int tid = threadIdx.x;
-   const int ti = tid >> 4, tj = tid & 15;
-   const int i0 = 4 * ti, j0 = 4 * tj;
-
-   for( int e = tid; e < NB * NB; e += blockDim.x )
-   {
-      int i = e % NB, j = e / NB;
-      double v = (i == j) ? 1.0 : 0.0;                 // identity padding keeps a partial block positive definite
-      if( i < nb && j < nb && i >= j ) v = A[(size_t)j * lda + i];
-      Ls[i * LDSM + j] = v;
-   }
-   __syncthreads();
-   tc1 = clock64();
-
-   double a[4][4];
-   if( mode == 0 )
-   {
-#pragma unroll
-      for( int r = 0; r < 4; ++r )
-#pragma unroll
-         for( int c = 0; c < 4; ++c )
-            a[r][c] = (i0 + r >= j0 + c) ? Ls[(i0 + r) * LDSM + j0 + c] : Ls[(j0 + c) * LDSM + i0 + r];
-
-      for( int t = 0; t < 16; ++t )
-      {
-         if( ti == t && tj == t )
-         {
-            // 4 x 4 Cholesky of the diagonal tile, then its inverse
-            double rd[4], w[4][4];
-#pragma unroll
-            for( int q = 0; q < 4; ++q )
-            {
-               double sq = a[q][q];
-#pragma unroll
-               for( int p = 0; p < 4; ++p ) if( p < q ) sq -= a[q][p] * a[q][p];
-               if( !(sq > 0.0) )
-               {
-                  if( 4 * t + q < nb ) atomicCAS(info, 0, pivot_offset + 4 * t + q + 1);
-                  sq = 1.0;
-               }
-               rd[q] = fast_rsqrt(sq);
-               a[q][q] = sq * rd[q];
-#pragma unroll
-               for( int r = 0; r < 4; ++r )
-               {
-                  if( r > q )
-                  {
-                     double sr = a[r][q];
-#pragma unroll
-                     for( int p = 0; p < 4; ++p ) if( p < q ) sr -= a[r][p] * a[q][p];
-                     a[r][q] = sr * rd[q];
-                  }
-               }
-            }
-#pragma unroll
-            for( int r = 0; r < 4; ++r )
-#pragma unroll
-               for( int c = 0; c < 4; ++c ) if( r < c ) a[r][c] = 0.0;
-            inv4_lower(a, rd, w);
-#pragma unroll
-            for( int r = 0; r < 4; ++r )
-#pragma unroll
-               for( int c = 0; c < 4; ++c ) Dinv[t][4 * r + c] = w[r][c];
-         }
-         __syncthreads();
-         if( tj == t )
-         {
-            if( ti > t )
-            {
-               // panel block  L_it = A_it L_tt^-T :  new[r][q] = sum_{p <= q} a[r][p] * Linv_tt[q][p]
-               double li[4][4], nw[4][4];
-#pragma unroll
-               for( int q = 0; q < 4; ++q )
-#pragma unroll
-                  for( int p = 0; p < 4; ++p ) li[q][p] = Dinv[t][4 * q + p];
-#pragma unroll
-               for( int r = 0; r < 4; ++r )
-#pragma unroll
-                  for( int q = 0; q < 4; ++q )
-                  {
-                     double sacc = 0.0;
-#pragma unroll
-                     for( int p = 0; p < 4; ++p ) if( p <= q ) sacc += a[r][p] * li[q][p];
-                     nw[r][q] = sacc;
-                  }
-#pragma unroll
-               for( int r = 0; r < 4; ++r )
-#pragma unroll
-                  for( int q = 0; q < 4; ++q ) { a[r][q] = nw[r][q]; Pn[0][q][i0 + r] = nw[r][q]; }
-            }
-            else
-            {
-#pragma unroll
-               for( int r = 0; r < 4; ++r )
-#pragma unroll
-                  for( int q = 0; q < 4; ++q ) Pn[0][q][i0 + r] = 0.0;
-            }
-         }
-         __syncthreads();
-         {
-            double pi[4][4], pj[4][4];
-#pragma unroll
-            for( int q = 0; q < 4; ++q )
-#pragma unroll
-               for( int r = 0; r < 4; ++r ) { pi[q][r] = Pn[0][q][i0 + r]; pj[q][r] = Pn[0][q][j0 + r]; }
-#pragma unroll
-            for( int r = 0; r < 4; ++r )
-#pragma unroll
-               for( int c = 0; c < 4; ++c )
-               {
-                  double sacc = a[r][c];
-#pragma unroll
-                  for( int q = 0; q < 4; ++q ) sacc -= pi[q][r] * pj[q][c];
-                  a[r][c] = sacc;
-               }
-         }
-      }
-      __syncthreads();
-      if( ti >= tj )
-      {
-#pragma unroll
-         for( int r = 0; r < 4; ++r )
-#pragma unroll
-            for( int c = 0; c < 4; ++c )
-               if( ti > tj || r >= c ) Ls[(i0 + r) * LDSM + j0 + c] = a[r][c];
-      }
-      __syncthreads();
-      for( int e = tid; e < nb * nb; e += blockDim.x )
-      {
-         int i = e % nb, j = e / nb;
-         if( i >= j ) A[(size_t)j * lda + i] = Ls[i * LDSM + j];
-      }
-   }
-   else
-   {
-      if( tid < 16 )
-      {
-         double l[4][4], rd[4], w[4][4];
-#pragma unroll
-         for( int r = 0; r < 4; ++r )
-#pragma unroll
-            for( int c = 0; c < 4; ++c ) l[r][c] = (r >= c) ? Ls[(4 * tid + r) * LDSM + 4 * tid + c] : 0.0;
-#pragma unroll
-         for( int r = 0; r < 4; ++r ) rd[r] = 1.0 / l[r][r];
-         inv4_lower(l, rd, w);
-#pragma unroll
-         for( int r = 0; r < 4; ++r )
-#pragma unroll
-            for( int c = 0; c < 4; ++c ) Dinv[tid][4 * r + c] = w[r][c];
-      }
-      __syncthreads();
-   }
-
-   tc2 = clock64();
-   if( Linv != nullptr || diaginv != nullptr )
-   {
-      // R = I, turned into W = L^-1 block row by block row
-#pragma unroll
-      for( int r = 0; r < 4; ++r )
-#pragma unroll
-         for( int c = 0; c < 4; ++c )
-            a[r][c] = (i0 + r == j0 + c) ? 1.0 : 0.0;
-
-      for( int t = 0; t < 16; ++t )
-      {
-         const int buf = t & 1;
-         if( ti == t )
-         {
-            if( tj <= t )
-            {
-               double li[4][4], nw[4][4];
-#pragma unroll
-               for( int r = 0; r < 4; ++r )
-#pragma unroll
-                  for( int p = 0; p < 4; ++p ) li[r][p] = Dinv[t][4 * r + p];
-#pragma unroll
-               for( int r = 0; r < 4; ++r )
-#pragma unroll
-                  for( int c = 0; c < 4; ++c )
-                  {
-                     double sacc = 0.0;
-#pragma unroll
-                     for( int p = 0; p < 4; ++p ) if( p <= r ) sacc += li[r][p] * a[p][c];
-                     nw[r][c] = sacc;
-                  }
-#pragma unroll
-               for( int r = 0; r < 4; ++r )
-#pragma unroll
-                  for( int c = 0; c < 4; ++c ) { a[r][c] = nw[r][c]; Pn[buf][r][j0 + c] = nw[r][c]; }
-            }
-            else
-            {
-#pragma unroll
-               for( int r = 0; r < 4; ++r )
-#pragma unroll
-                  for( int c = 0; c < 4; ++c ) Pn[buf][r][j0 + c] = 0.0;
-            }
-         }
-         __syncthreads();
-         if( ti > t )
-         {
-            double lb[4][4], wk[4][4];
-#pragma unroll
-            for( int r = 0; r < 4; ++r )
-#pragma unroll
-               for( int q = 0; q < 4; ++q ) { lb[r][q] = Ls[(i0 + r) * LDSM + 4 * t + q]; wk[q][r] = Pn[buf][q][j0 + r]; }
-#pragma unroll
-            for( int r = 0; r < 4; ++r )
-#pragma unroll
-               for( int c = 0; c < 4; ++c )
-               {
-                  double sacc = a[r][c];
-#pragma unroll
-                  for( int q = 0; q < 4; ++q ) sacc -= lb[r][q] * wk[q][c];
-                  a[r][c] = sacc;
-               }
-         }
-      }
-      __syncthreads();                                  // all reads of L are done: reuse Ls for W
-      tc3 = clock64();
-#pragma unroll
-      for( int r = 0; r < 4; ++r )
-#pragma unroll
-         for( int c = 0; c < 4; ++c )
-            Ls[(i0 + r) * LDSM + j0 + c] = (i0 + r >= j0 + c) ? a[r][c] : 0.0;
-      __syncthreads();
-      if( Linv != nullptr )
-         for( int e = tid; e < nb * nb; e += blockDim.x )
-         {
-            int i = e % nb, j = e / nb;
-            Linv[(size_t)j * ldi + i] = Ls[i * LDSM + j];
-         }
-      if( diaginv != nullptr )
-         for( int e = tid; e < NB * NB; e += blockDim.x )
-         {
-            int i = e % NB, j = e / NB;
-            diaginv[(size_t)j * NB + i] = (i < nb && j < nb) ? Ls[i * LDSM + j] : 0.0;
-         }
-   }
-   if( dbg != nullptr && tid == 0 )
-   {
-      dbg[0] = tc1 - tc0; dbg[1] = tc2 - tc1; dbg[2] = tc3 - tc2; dbg[3] = clock64() - tc3;
-   }
-}
 
 // ---- leaf kernel, DMMA version -----------------------------------------------------------------------------------------------
 // One CTA factorises (mode 0) and/or inverts (mode 1: A already holds L) a diagonal block of order nb <= NBL, NBL = 64 or 128.
@@ -588,24 +297,17 @@ cudaError_t copy2d(cudaStream_t st, int m, int n, const double* src, int lds, do
    return cudaGetLastError();
 }
 
-// leaf order of the recursion: 128 (default) or 64; SDPCUDA_LEAF=old selects the previous register-tile kernel (A/B timing)
+// leaf order of the recursion: 128 (default) or 64 (SDPCUDA_LEAF=64, tests)
 int leaf_config()
 {
    const char* e = getenv("SDPCUDA_LEAF");      // read on every call (tests switch it between solves)
    if( e != nullptr && strcmp(e, "64") == 0 ) return 64;
-   if( e != nullptr && strcmp(e, "old") == 0 ) return 0;
    return 128;
 }
 
 cudaError_t launch_diag(cudaStream_t st, int mode, int nb, double* A, int lda, double* Linv, int ldi, double* diaginv, int* info, int off)
 {
    ProfScope prof(st, PROF_DIAG, (mode == 0 ? 1.0 : 0.0) * nb * (double)nb * nb / 3.0 + ((Linv || diaginv) ? nb * (double)nb * nb / 3.0 : 0.0));
-   if( leaf_config() == 0 && nb <= NB )
-   {
-      diag_block_kernel<<<1, 256, 0, st>>>(mode, nb, A, lda, Linv, ldi, diaginv, info, off, g_diag_dbg);
-      count_launch();
-      return cudaGetLastError();
-   }
    static bool configured[64] = {false};        // per-device function attributes
    int dev = 0;
    SDPK_CUDA_CHECK( cudaGetDevice(&dev) );
@@ -701,67 +403,6 @@ cudaError_t trtri_rec(cudaStream_t st, int n, const double* L, int ldl, double* 
    return cudaSuccess;
 }
 
-// ---- blocked triangular solves with one right-hand side, one launch per diagonal block ------------------------------
-// forward step for block b:  x_b = Linv_bb * rhs_b (every CTA redundantly), then rhs_r -= L[r, b-block] x_b for r below
-__global__ void __launch_bounds__(256)
-fwd_step_kernel(int n, int b, const double* __restrict__ L, int ldl, const double* __restrict__ diaginv, double* __restrict__ x,
-   double* __restrict__ out)
-{
-   __shared__ double xb[NB];
-   const int r0 = b * NB, nb = min(NB, n - r0);
-   const double* Di = diaginv + (size_t)b * NB * NB;
-   const int tid = threadIdx.x;
-   if( tid < NB )
-   {
-      double s = 0.0;
-      if( tid < nb )
-         for( int k = 0; k <= tid; ++k ) s += Di[(size_t)k * NB + tid] * x[r0 + k];
-      xb[tid] = s;
-   }
-   __syncthreads();
-   int row = r0 + nb + blockIdx.x * blockDim.x + tid;
-   if( row < n )
-   {
-      double s = 0.0;
-      for( int k = 0; k < nb; ++k ) s += L[(size_t)(r0 + k) * ldl + row] * xb[k];
-      x[row] -= s;
-   }
-   if( blockIdx.x == 0 && tid < nb )
-      out[r0 + tid] = xb[tid];      // separate output: other CTAs may still be reading the right-hand side block
-}
-
-// backward step for block b:  x_b = Linv_bb' * rhs_b, then rhs_c -= L[b-block, c]' x_b for columns c left of the block
-__global__ void __launch_bounds__(256)
-bwd_step_kernel(int n, int b, const double* __restrict__ L, int ldl, const double* __restrict__ diaginv, double* __restrict__ x,
-   double* __restrict__ out)
-{
-   __shared__ double xb[NB];
-   const int r0 = b * NB, nb = min(NB, n - r0);
-   const double* Di = diaginv + (size_t)b * NB * NB;
-   const int tid = threadIdx.x;
-   if( tid < NB )
-   {
-      double s = 0.0;
-      if( tid < nb )
-         for( int k = tid; k < nb; ++k ) s += Di[(size_t)tid * NB + k] * x[r0 + k];
-      xb[tid] = s;
-   }
-   __syncthreads();
-   // each warp handles columns c = blockIdx.x*8 + warp, ... ; column c of L is contiguous over the block rows
-   const int lane = tid & 31, warp = tid >> 5;
-   int c = blockIdx.x * 8 + warp;
-   if( c < r0 )
-   {
-      double s = 0.0;
-      for( int k = lane; k < nb; k += 32 ) s += L[(size_t)c * ldl + r0 + k] * xb[k];
-#pragma unroll
-      for( int o = 16; o > 0; o >>= 1 ) s += __shfl_xor_sync(0xffffffffu, s, o);
-      if( lane == 0 ) x[c] -= s;
-   }
-   if( blockIdx.x == 0 && tid < nb )
-      out[r0 + tid] = xb[tid];
-}
-
 } // namespace
 
 cudaError_t potrf_lower(cudaStream_t st, int n, double* A, int lda, double* Linv, int ldi, double* diaginv, double* work, int ldw, int* d_info)
@@ -777,24 +418,6 @@ cudaError_t trtri_lower(cudaStream_t st, int n, const double* L, int ldl, double
    if( n <= 0 ) return cudaSuccess;
    SDPK_CUDA_CHECK( cudaMemsetAsync(Linv, 0, sizeof(double) * (size_t)ldi * n, st) );
    return trtri_rec(st, n, L, ldl, Linv, ldi, work, ldw);
-}
-
-cudaError_t potrs_vec(cudaStream_t st, int n, const double* L, int ldl, const double* diaginv, double* b, double* tmp)
-{
-   const int nblk = ceil_div(n, NB);
-   ProfScope prof(st, PROF_TRSV, 8.0 * n * (double)n);      // reads the triangle of L twice
-   for( int k = 0; k < nblk; ++k )
-   {
-      int below = n - min(n, (k + 1) * NB);
-      fwd_step_kernel<<<max(1, ceil_div(below, 256)), 256, 0, st>>>(n, k, L, ldl, diaginv, b, tmp);
-      count_launch();
-   }
-   for( int k = nblk - 1; k >= 0; --k )
-   {
-      bwd_step_kernel<<<max(1, ceil_div(k * NB, 8)), 256, 0, st>>>(n, k, L, ldl, diaginv, tmp, b);
-      count_launch();
-   }
-   return cudaGetLastError();
 }
 
 

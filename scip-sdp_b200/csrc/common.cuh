@@ -101,7 +101,6 @@ extern long long* g_diag_dbg;      // optional device buffer (4 x int64) receivi
 cudaError_t potrf_lower(cudaStream_t st, int n, double* A, int lda, double* Linv, int ldi, double* diaginv, double* work, int ldw, int* d_info);
 cudaError_t trtri_lower(cudaStream_t st, int n, const double* L, int ldl, double* Linv, int ldi, double* work, int ldw);
 // solves L L' x = b for one right-hand side using the diagonal-block inverses (x overwrites b; tmp: n doubles)
-cudaError_t potrs_vec(cudaStream_t st, int n, const double* L, int ldl, const double* diaginv, double* b, double* tmp);
 // large orders: right-looking panels (width pb) with one panel of look-ahead on a side stream; pinv / pinvT receive the inverses
 // of the diagonal panel blocks and their transposes (ceil(n/pb) blocks of pb x pb); ev: 2*ceil(n/pb)+2 events without timing
 cudaError_t potrf_lower_lookahead(cudaStream_t st, cudaStream_t side, cudaEvent_t* ev, int nev, int pb, int n, double* A, int lda,
@@ -114,9 +113,6 @@ cudaError_t potrs_panels(cudaStream_t st, int pb, int n, const double* L, const 
 constexpr int JACOBI_MAX_N = 96;
 cudaError_t jacobi_eig_batched(cudaStream_t st, int n, int nbatch, const double* A, int lda, long long strideA,
    double* w, double* V /* or nullptr */, int* d_sweeps);
-// smallest eigenvalue of symmetric B (n x n, full storage) by Lanczos; result (Ritz value minus residual bound) in d_out[0]
-cudaError_t lanczos_lambda_min(cudaStream_t st, int n, const double* B, int ldb, double* work /* >= (maxit+4)*n + 4*maxit+16 */, int maxit, double* d_out);
-size_t lanczos_work_doubles(int n, int maxit);
 // batched, adaptive variant: all matrices advance together, convergence is checked on the host every 8 steps
 constexpr int LZB_MAXIT = 64;
 struct LzDesc

@@ -2,14 +2,15 @@
 //
 // (1) jacobi_eig_batched: one CTA per matrix, parallel cyclic Jacobi (round-robin "chess tournament" ordering: n/2
 //     disjoint rotations per step, applied first to the columns, then to the rows) with the matrix and the accumulated
-//     eigenvectors resident in shared memory for n <= JACOBI_MAX_N.  It serves the interior-point step-length computation
-//     (smallest eigenvalue of L^-1 dX L^-T for small blocks) and replaces the DSYEVR calls behind
+//     eigenvectors resident in shared memory for n <= JACOBI_MAX_N.  It replaces the DSYEVR calls behind
 //     SCIPlapackComputeIthEigenvalue / ComputeEigenvectorsNegative / ComputeEigenvectorDecomposition
 //     (lapack_interface.c:178-603): eigenvalues ascending, eigenvector k stored as row k of the output.
 //     Larger matrices run the same code on a global-memory scratch (correct, not fast; the cut-separation matrices of the
 //     reference's instances have n = 10..43).
-// (2) lanczos_lambda_min: smallest eigenvalue of a large symmetric matrix by Lanczos with full re-orthogonalisation,
-//     returning Ritz value minus residual bound, i.e. a safe value for the step length -1/lambda_min.
+// (2) lanczos_small_batched / lanczos_batched: smallest eigenvalue of the step-length matrices L^-1 dX L^-T by Lanczos (plain
+//     three-term recurrence), returning Ritz value minus residual bound, i.e. a safe value for the step length -1/lambda_min:
+//     one CTA per matrix out of shared memory for orders <= 128, one launch per step over all matrices above, either on the
+//     explicit matrix or on the operator v -> W (D (W' v)).
 #include "common.cuh"
 #include <algorithm>
 
@@ -182,147 +183,6 @@ jacobi_kernel(int n, const double* __restrict__ Ain, int lda, long long strideA,
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-// Lanczos
-// ------------------------------------------------------------------------------------------------------------------
-constexpr int LZ_KSPLIT = 8;
-
-// partial products: part[ks][i] = sum_{k in slice ks} B[i + k*ld] * v[k]
-__global__ void __launch_bounds__(256)
-symv_partial_kernel(int n, const double* __restrict__ B, int ldb, const double* __restrict__ v, double* __restrict__ part)
-{
-   int i = blockIdx.x * blockDim.x + threadIdx.x;
-   int ks = blockIdx.y;
-   int chunk = (n + LZ_KSPLIT - 1) / LZ_KSPLIT;
-   int k0 = ks * chunk, k1 = min(n, k0 + chunk);
-   if( i >= n ) return;
-   double s = 0.0;
-   for( int k = k0; k < k1; ++k ) s += B[(size_t)k * ldb + i] * v[k];
-   part[(size_t)ks * n + i] = s;
-}
-
-// one CTA: w = sum of partials; alpha = w.v_j; w -= alpha v_j + beta_{j-1} v_{j-1}; re-orthogonalise against Q; beta_j = |w|;
-// v_{j+1} = w / beta_j.  Q is stored as Q[j*n ...]; alpha/beta arrays live behind Q.
-__global__ void __launch_bounds__(1024)
-lanczos_update_kernel(int n, int j, int maxit, const double* __restrict__ part, double* __restrict__ Q, double* __restrict__ ab)
-{
-   __shared__ double red[32];
-   __shared__ double coef;
-   const int tid = threadIdx.x, nt = blockDim.x;
-   double* vj = Q + (size_t)j * n;
-   double* w = Q + (size_t)(j + 1) * n;
-   double* alpha = ab;
-   double* beta = ab + maxit;
-
-   double dot = 0.0;
-   for( int i = tid; i < n; i += nt )
-   {
-      double s = 0.0;
-#pragma unroll
-      for( int ks = 0; ks < LZ_KSPLIT; ++ks ) s += part[(size_t)ks * n + i];
-      w[i] = s;
-      dot += s * vj[i];
-   }
-   double a = block_sum(dot, red);
-   if( tid == 0 ) alpha[j] = a;
-   double bprev = (j > 0) ? beta[j - 1] : 0.0;
-   const double* vprev = (j > 0) ? Q + (size_t)(j - 1) * n : nullptr;
-   for( int i = tid; i < n; i += nt )
-      w[i] -= a * vj[i] + (j > 0 ? bprev * vprev[i] : 0.0);
-   __syncthreads();
-   // full re-orthogonalisation (classical Gram-Schmidt, applied twice overall through the two passes over q)
-   for( int pass = 0; pass < 2; ++pass )
-      for( int q = 0; q <= j; ++q )
-      {
-         const double* vq = Q + (size_t)q * n;
-         double d = 0.0;
-         for( int i = tid; i < n; i += nt ) d += w[i] * vq[i];
-         d = block_sum(d, red);
-         for( int i = tid; i < n; i += nt ) w[i] -= d * vq[i];
-         __syncthreads();
-      }
-   double nr = 0.0;
-   for( int i = tid; i < n; i += nt ) nr += w[i] * w[i];
-   nr = sqrt(block_sum(nr, red));
-   if( tid == 0 ) { beta[j] = nr; coef = (nr > 1e-300) ? 1.0 / nr : 0.0; }
-   __syncthreads();
-   double cf = coef;
-   for( int i = tid; i < n; i += nt ) w[i] *= cf;
-}
-
-__global__ void lanczos_init_kernel(int n, double* __restrict__ Q)
-{
-   __shared__ double red[32];
-   double s = 0.0;
-   for( int i = threadIdx.x; i < n; i += blockDim.x )
-   {
-      // fixed pseudo-random start vector (deterministic across runs)
-      unsigned h = (unsigned)i * 2654435761u + 12345u;
-      h ^= h >> 15; h *= 2246822519u; h ^= h >> 13;
-      double v = 0.5 + (double)(h & 0xffffu) / 65536.0;
-      Q[i] = v;
-      s += v * v;
-   }
-   s = block_sum(s, red);
-   double inv = 1.0 / sqrt(s);
-   for( int i = threadIdx.x; i < n; i += blockDim.x ) Q[i] *= inv;
-}
-
-// smallest eigenvalue of the k x k tridiagonal (alpha, beta) by bisection, residual bound from inverse iteration
-__global__ void lanczos_ritz_kernel(int k, int maxit, const double* __restrict__ ab, double* __restrict__ out)
-{
-   if( threadIdx.x != 0 || blockIdx.x != 0 ) return;
-   const double* a = ab;
-   const double* bt = ab + maxit;
-   // effective size: stop at a breakdown (beta ~ 0): the Krylov space is invariant, Ritz values are exact there
-   int kk = k;
-   double scale = 0.0;
-   for( int i = 0; i < k; ++i ) scale = fmax(scale, fabs(a[i]) + (i < k ? fabs(bt[i]) : 0.0));
-   for( int i = 0; i < k - 1; ++i ) if( fabs(bt[i]) <= 1e-14 * scale ) { kk = i + 1; break; }
-   double lo = 1e300, hi = -1e300;
-   for( int i = 0; i < kk; ++i )
-   {
-      double r = (i > 0 ? fabs(bt[i - 1]) : 0.0) + (i < kk - 1 ? fabs(bt[i]) : 0.0);
-      lo = fmin(lo, a[i] - r); hi = fmax(hi, a[i] + r);
-   }
-   // bisection for the smallest eigenvalue: count of eigenvalues < x via the Sturm sequence
-   double l = lo, h = hi;
-   for( int it = 0; it < 200 && (h - l) > 1e-15 * fmax(fabs(l), fabs(h)) + 1e-300; ++it )
-   {
-      double x = 0.5 * (l + h);
-      int cnt = 0;
-      double d = 1.0;
-      for( int i = 0; i < kk; ++i )
-      {
-         double b2 = (i > 0) ? bt[i - 1] * bt[i - 1] : 0.0;
-         d = a[i] - x - (i > 0 ? b2 / d : 0.0);
-         if( d == 0.0 ) d = 1e-300;
-         if( d < 0.0 ) ++cnt;
-      }
-      if( cnt >= 1 ) h = x; else l = x;
-   }
-   double theta = 0.5 * (l + h);
-   // last component of the normalised eigenvector of T for theta via the three-term recurrence (forward)
-   double resid = 0.0;
-   if( kk == k )
-   {
-      // s_0 = 1, s_1 = (theta - a_0)/b_0 s_0, s_{i+1} = ((theta - a_i) s_i - b_{i-1} s_{i-1}) / b_i
-      double sm1 = 0.0, s0 = 1.0, nrm = 1.0, last = 1.0;
-      for( int i = 0; i < k - 1; ++i )
-      {
-         double s1 = ((theta - a[i]) * s0 - (i > 0 ? bt[i - 1] * sm1 : 0.0)) / bt[i];
-         sm1 = s0; s0 = s1;
-         nrm += s1 * s1;
-         last = s1;
-         if( nrm > 1e200 ) { sm1 *= 1e-100; s0 *= 1e-100; last *= 1e-100; nrm *= 1e-200; }
-      }
-      resid = fabs(bt[k - 1]) * fabs(last) / sqrt(nrm);
-   }
-   out[0] = theta - resid;
-   out[1] = theta;
-   out[2] = resid;
-}
-
-
 // ---- batched Lanczos: all step-length matrices of one predictor/corrector pass advance together ---------------------
 __global__ void lzb_init_kernel(const LzDesc* __restrict__ D)
 {
@@ -340,80 +200,6 @@ __global__ void lzb_init_kernel(const LzDesc* __restrict__ D)
    s = block_sum(s, red);
    double inv = 1.0 / sqrt(s);
    for( int i = threadIdx.x; i < d.n; i += blockDim.x ) d.Q[i] *= inv;
-}
-
-// w = B v_j: one warp per row, reading the (contiguous) column i of the symmetric matrix
-__global__ void __launch_bounds__(256)
-lzb_symv_kernel(const LzDesc* __restrict__ D, int j)
-{
-   const LzDesc d = D[blockIdx.y];
-   const int i = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-   if( i >= d.n || j >= d.n ) return;
-   const double* __restrict__ col = d.B + (size_t)i * d.ld;
-   const double* __restrict__ v = d.Q + (size_t)j * d.n;
-   double s0 = 0.0, s1 = 0.0;
-   int k = lane;
-   for( ; k + 32 < d.n; k += 64 ) { s0 += col[k] * v[k]; s1 += col[k + 32] * v[k + 32]; }
-   for( ; k < d.n; k += 32 ) s0 += col[k] * v[k];
-   double sum = s0 + s1;
-#pragma unroll
-   for( int o = 16; o > 0; o >>= 1 ) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-   if( lane == 0 ) d.Q[(size_t)(j + 1) * d.n + i] = sum;
-}
-
-__global__ void __launch_bounds__(1024)
-lzb_update_kernel(const LzDesc* __restrict__ D, int j, int maxit)
-{
-   __shared__ double red[32];
-   __shared__ double coef;
-   const LzDesc d = D[blockIdx.x];
-   const int n = d.n, tid = threadIdx.x, nt = blockDim.x;
-   if( j >= n ) return;
-   double* Q = d.Q;
-   double* vj = Q + (size_t)j * n;
-   double* w = Q + (size_t)(j + 1) * n;
-   double* alpha = d.ab;
-   double* beta = d.ab + maxit;
-   double dot = 0.0;
-   for( int i = tid; i < n; i += nt ) dot += w[i] * vj[i];
-   double a = block_sum(dot, red);
-   if( tid == 0 ) alpha[j] = a;
-   double bprev = (j > 0) ? beta[j - 1] : 0.0;
-   const double* vprev = (j > 0) ? Q + (size_t)(j - 1) * n : nullptr;
-   for( int i = tid; i < n; i += nt )
-      w[i] -= a * vj[i] + (j > 0 ? bprev * vprev[i] : 0.0);
-   __syncthreads();
-   // full re-orthogonalisation (classical Gram-Schmidt, twice): all inner products of a pass are formed concurrently,
-   // warp q' handles the vectors q = q', q' + 32, ...; then every thread updates its elements with all coefficients
-   __shared__ double dots[LZB_MAXIT + 2];
-   const int lane = tid & 31, wid = tid >> 5, nw = nt >> 5;
-   for( int pass = 0; pass < 2; ++pass )
-   {
-      for( int q = wid; q <= j; q += nw )
-      {
-         const double* vq = Q + (size_t)q * n;
-         double dd = 0.0;
-         for( int i = lane; i < n; i += 32 ) dd += w[i] * vq[i];
-#pragma unroll
-         for( int o = 16; o > 0; o >>= 1 ) dd += __shfl_xor_sync(0xffffffffu, dd, o);
-         if( lane == 0 ) dots[q] = dd;
-      }
-      __syncthreads();
-      for( int i = tid; i < n; i += nt )
-      {
-         double sacc = 0.0;
-         for( int q = 0; q <= j; ++q ) sacc += dots[q] * Q[(size_t)q * n + i];
-         w[i] -= sacc;
-      }
-      __syncthreads();
-   }
-   double nr = 0.0;
-   for( int i = tid; i < n; i += nt ) nr += w[i] * w[i];
-   nr = sqrt(block_sum(nr, red));
-   if( tid == 0 ) { beta[j] = nr; coef = (nr > 1e-300) ? 1.0 / nr : 0.0; }
-   __syncthreads();
-   double cf = coef;
-   for( int i = tid; i < n; i += nt ) w[i] *= cf;
 }
 
 // Dot products of 8 consecutive columns i0 .. i0+7 of a column-major matrix with a vector, by one CTA of 256 threads.
@@ -779,32 +565,6 @@ cudaError_t lanczos_small_batched(cudaStream_t st, int nmat, int maxn, const LzD
    const size_t smem = sizeof(double) * ((size_t)maxn * (maxn | 1) + 5 * (size_t)LZS_MAX_N + 8);
    ProfScope prof(st, PROF_EIG, 8.0 * nmat * (double)maxn * maxn);
    lz_smem_kernel<<<nmat, 256, smem, st>>>(d_desc, maxit);
-   count_launch();
-   return cudaGetLastError();
-}
-
-size_t lanczos_work_doubles(int n, int maxit)
-{
-   return (size_t)(maxit + 2) * n + (size_t)LZ_KSPLIT * n + 2 * (size_t)maxit + 16;
-}
-
-cudaError_t lanczos_lambda_min(cudaStream_t st, int n, const double* B, int ldb, double* work, int maxit, double* d_out)
-{
-   maxit = std::min(maxit, n);
-   ProfScope prof(st, PROF_EIG, (double)maxit * 8.0 * n * (double)n);
-   double* Q = work;
-   double* part = Q + (size_t)(maxit + 2) * n;
-   double* ab = part + (size_t)LZ_KSPLIT * n;
-   lanczos_init_kernel<<<1, 1024, 0, st>>>(n, Q);
-   count_launch();
-   for( int j = 0; j < maxit; ++j )
-   {
-      dim3 grid(ceil_div(n, 256), LZ_KSPLIT);
-      symv_partial_kernel<<<grid, 256, 0, st>>>(n, B, ldb, Q + (size_t)j * n, part);
-      lanczos_update_kernel<<<1, 1024, 0, st>>>(n, j, maxit, part, Q, ab);
-      count_launch(2);
-   }
-   lanczos_ritz_kernel<<<1, 32, 0, st>>>(maxit, maxit, ab, d_out);
    count_launch();
    return cudaGetLastError();
 }

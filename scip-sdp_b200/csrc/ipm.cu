@@ -961,7 +961,6 @@ static int run_ipm(sdpcuda_handle* h, const sdpcuda_params* par, const double* s
       int force = h->force_path;
       if( env != nullptr && env[0] == 'm' ) force = 1;
       if( env != nullptr && env[0] == 's' ) force = 2;
-      long long multirows = 0;
       bool eligible = (h->maxn <= SMALL_MAX_N && m <= SMALL_MAX_M && nb <= SMALL_MAX_BLOCKS && (int)h->dgroups.size() <= SMALL_MAX_GROUPS
          && ar <= ((size_t)1 << 20) && nlp <= (1 << 20) && !h->prof.on && !wantpre && !warm && h->nranks == 1 && h->emulate_ranks <= 1);
       if( eligible && h->ndense > 0 )
@@ -1004,7 +1003,6 @@ static int run_ipm(sdpcuda_handle* h, const sdpcuda_params* par, const double* s
          a.gaptol = gaptol; a.feastol = feastol; a.absgaptol = par->absgaptol; a.objlimit = par->objlimit;
          a.normb = normb; a.normC = normC; a.normCsdp2 = normCsdp2; a.gammabase = gammabase;
          a.out = h->smallres.p;
-         (void)multirows;
          CK( cudaEventRecord(h->ev0, st) );
          CK( launch_ipm_small(st, a) );
          CK( cudaEventRecord(h->ev1, st) );

@@ -442,124 +442,6 @@ __device__ void symvM(const SmallArgs& a, const double* x, double* y)
    __syncthreads();
 }
 
-// smallest eigenvalue (safe estimate: Ritz value minus residual bound) of the symmetric n x n matrix B by Lanczos with full
-// re-orthogonalisation; Q: scratch of (steps + 2) * n doubles.  Result to all threads.
-__device__ double lanczos_min(int n, int ld, const double* B, double* Q, double* red, double* al, double* be, double* coef, double* shs)
-{
-   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-   const int steps = min(n, SMALL_LZ_STEPS);
-   double nr = 0.0;
-   for( int i = tid; i < n; i += NT )
-   {
-      unsigned h = (unsigned)i * 2654435761u + 12345u;
-      h ^= h >> 15; h *= 2246822519u; h ^= h >> 13;
-      double v = 0.5 + (double)(h & 0xffffu) / 65536.0;
-      Q[i] = v;
-      nr += v * v;
-   }
-   nr = bsum(nr, red);
-   const double inv0 = 1.0 / sqrt(nr);
-   for( int i = tid; i < n; i += NT ) Q[i] *= inv0;
-   __syncthreads();
-   int kdone = 0;
-   for( int j = 0; j < steps; ++j )
-   {
-      const double* v = Q + (size_t)j * n;
-      double* w = Q + (size_t)(j + 1) * n;
-      for( int i = wid; i < n; i += NT / 32 )               // w = B v (column i of the symmetric matrix is contiguous)
-      {
-         const double* col = B + (size_t)i * ld;
-         double s = 0.0;
-         for( int k = lane; k < n; k += 32 ) s += col[k] * v[k];
-         s = wsum(s);
-         if( lane == 0 ) w[i] = s;
-      }
-      __syncthreads();
-      double d = 0.0;
-      for( int i = tid; i < n; i += NT ) d += w[i] * v[i];
-      const double alpha = bsum(d, red);
-      const double bprev = (j > 0) ? be[j - 1] : 0.0;
-      for( int i = tid; i < n; i += NT ) w[i] -= alpha * v[i] + (j > 0 ? bprev * Q[(size_t)(j - 1) * n + i] : 0.0);
-      __syncthreads();
-      for( int pass = 0; pass < 2; ++pass )
-      {
-         for( int q = wid; q <= j; q += NT / 32 )
-         {
-            const double* vq = Q + (size_t)q * n;
-            double dd = 0.0;
-            for( int i = lane; i < n; i += 32 ) dd += w[i] * vq[i];
-            dd = wsum(dd);
-            if( lane == 0 ) coef[q] = dd;
-         }
-         __syncthreads();
-         for( int i = tid; i < n; i += NT )
-         {
-            double sacc = 0.0;
-            for( int q = 0; q <= j; ++q ) sacc += coef[q] * Q[(size_t)q * n + i];
-            w[i] -= sacc;
-         }
-         __syncthreads();
-      }
-      double nn = 0.0;
-      for( int i = tid; i < n; i += NT ) nn += w[i] * w[i];
-      const double beta = sqrt(bsum(nn, red));
-      if( tid == 0 ) { al[j] = alpha; be[j] = beta; }
-      kdone = j + 1;
-      if( beta <= 1e-13 * (fabs(alpha) + bprev + 1e-300) ) break;          // invariant subspace: Ritz values are exact
-      const double cf = 1.0 / beta;
-      for( int i = tid; i < n; i += NT ) w[i] *= cf;
-      __syncthreads();
-   }
-   __syncthreads();
-   // smallest eigenvalue of the kdone x kdone tridiagonal matrix: parallel multisection on Sturm counts
-   const int k = kdone;
-   double lo = 1e300, hi = -1e300;
-   for( int i = 0; i < k; ++i )
-   {
-      double r = (i > 0 ? fabs(be[i - 1]) : 0.0) + (i < k - 1 ? fabs(be[i]) : 0.0);
-      lo = fmin(lo, al[i] - r); hi = fmax(hi, al[i] + r);
-   }
-   const double width0 = hi - lo;
-   for( int round = 0; round < 4 && (hi - lo) > 1e-12 * width0 + 1e-300; ++round )
-   {
-      // thread t tests x_t = lo + (t+1) (hi - lo) / (NT + 1): smallest eigenvalue < x_t ?
-      const double xt = lo + (tid + 1) * (hi - lo) / (NT + 1);
-      int cnt = 0;
-      double dd = 1.0;
-      for( int i = 0; i < k; ++i )
-      {
-         double b2 = (i > 0) ? be[i - 1] * be[i - 1] : 0.0;
-         dd = al[i] - xt - (i > 0 ? b2 / dd : 0.0);
-         if( dd == 0.0 ) dd = 1e-300;
-         if( dd < 0.0 ) ++cnt;
-      }
-      // the bracket becomes [largest x_t with cnt == 0, smallest x_t with cnt >= 1]
-      double below = (cnt == 0) ? xt : lo;
-      double above = (cnt >= 1) ? -xt : -hi;
-      below = bmax(below, red);
-      above = -bmax(above, red);
-      lo = below; hi = above;
-   }
-   double theta = lo;
-   double resid = 0.0;
-   if( k < n )
-   {
-      // |beta_k s_k| with s from the three-term recurrence (thread-uniform, cheap: k <= 32)
-      double sm1 = 0.0, s0 = 1.0, nrm = 1.0, last = 1.0;
-      for( int i = 0; i < k - 1; ++i )
-      {
-         double s1 = ((theta - al[i]) * s0 - (i > 0 ? be[i - 1] * sm1 : 0.0)) / be[i];
-         sm1 = s0; s0 = s1; nrm += s1 * s1; last = s1;
-         if( nrm > 1e200 ) { sm1 *= 1e-100; s0 *= 1e-100; last *= 1e-100; nrm *= 1e-200; }
-      }
-      if( be[k - 1] > 1e-13 * (fabs(al[k - 1]) + 1e-300) ) resid = fabs(be[k - 1]) * fabs(last) / sqrt(nrm);
-   }
-   (void)shs;
-   __syncthreads();
-   return theta - resid;
-}
-
-
 // ---- warp-level Lanczos: the matrix (n <= 64) and the Krylov vectors live in shared memory, one warp does everything ----
 // Bs: n x n symmetric, row stride LDS.  Qs: (SMALL_LZ_STEPS + 2) vectors with stride LDS.  ab: alpha[32], beta[32], w[64] scratch.
 // Returns (to all lanes) the safe estimate Ritz value - residual bound of the smallest eigenvalue.

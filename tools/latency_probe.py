@@ -6,7 +6,7 @@ print(S.time_kernel(8, 0, 1)); print(S.time_kernel(9, 0, 1))
 for rep in range(3):
     print("diag64", S.time_kernel(2, 64, 50))
 print("potrf 128", S.time_kernel(2, 128, 20), "potrf 256", S.time_kernel(2, 256, 20))
-for leaf in ("old", "64", "128"):
+for leaf in ("64", "128"):
     os.environ["SDPCUDA_LEAF"] = leaf
     for n in (64, 128, 256, 512, 1024, 1501, 2000, 4096, 7140):
         ms, work = S.time_kernel(2, n, 10)
