@@ -90,9 +90,9 @@ struct sdpcuda_handle
    int ndense = 0; int dchunk = 0;
 
    // device problem data
-   DBuf<int> varbeg, erow, ecol, eld, posbeg, posvar, lpbeg, lpind, colbeg, colrow, heavy, heavylist;
+   DBuf<int> varbeg, erow, ecol, eld, posbeg, posvar, posbeg2, posvar2, lpbeg, lpind, colbeg, colrow, heavy, heavylist;
    DBuf<long long> eoff, pos, mirror, cpos, cmirror;
-   DBuf<double> eval, posval, posc, cval, lpval, colval, lprhs, b;
+   DBuf<double> eval, posval, posval2, posc, cval, lpval, colval, lprhs, b;
    // iterate and work space
    DBuf<double> X, S, Sinv, L, Linv, LX, LXinv, dX, dS, dXa, dSa, K, T1, T2, Rd, work, work2;
    DBuf<double> y, dy, g, rp, AX, DTx, tm1, tm2;
@@ -254,10 +254,10 @@ int upload_problem(sdpcuda_handle* h, const sdpcuda_problem* P)
    std::vector<int> var_of(nnz);
    for( int j = 0; j < m; ++j )
       for( int e = P->varbeg[j]; e < P->varbeg[j + 1]; ++e ) var_of[e] = j;
-   std::vector<int> posbeg, posvar;
+   std::vector<int> posbeg, posvar, posbeg2, posvar2;      // "2": the same lists without the dense variables (streamed separately)
    std::vector<long long> pos, mirror;
-   std::vector<double> posval, posc;
-   posbeg.push_back(0);
+   std::vector<double> posval, posc, posval2;
+   posbeg.push_back(0); posbeg2.push_back(0);
    for( size_t t = 0; t < order.size(); )
    {
       long long kpos = key[order[t]];
@@ -271,6 +271,7 @@ int upload_problem(sdpcuda_handle* h, const sdpcuda_problem* P)
          {
             posvar.push_back(var_of[id]);
             posval.push_back(P->entval[id]);
+            if( h->ndense > 0 && heavy[var_of[id]] != 2 ) { posvar2.push_back(var_of[id]); posval2.push_back(P->entval[id]); }
             mir = eoff[id] + (long long)erow[id] * eld[id] + ecol[id];
          }
          else
@@ -281,6 +282,7 @@ int upload_problem(sdpcuda_handle* h, const sdpcuda_problem* P)
       }
       pos.push_back(kpos); mirror.push_back(mir); posc.push_back(cv);
       posbeg.push_back((int)posvar.size());
+      posbeg2.push_back((int)posvar2.size());
       t = u;
    }
    h->npos = (int)pos.size();
@@ -350,6 +352,7 @@ int upload_problem(sdpcuda_handle* h, const sdpcuda_problem* P)
    std::vector<double> lpval(P->lpval, P->lpval + lnz), lprhs(P->lprhs, P->lprhs + nlp);
    UP(varbeg, varbeg); UP(erow, erow); UP(ecol, ecol); UP(eld, eld); UP(eoff, eoff); UP(eval, eval);
    UP(posbeg, posbeg); UP(posvar, posvar); UP(pos, pos); UP(mirror, mirror); UP(posval, posval); UP(posc, posc);
+   if( h->ndense > 0 ) { UP(posbeg2, posbeg2); UP(posvar2, posvar2); UP(posval2, posval2); }
    UP(cpos, cposv); UP(cmirror, cmirv); UP(cval, cval);
    UP(lpbeg, lpbeg); UP(lpind, lpind); UP(lpval, lpval); UP(lprhs, lprhs);
    UP(colbeg, colbeg); UP(colrow, colrow); UP(colval, colval);
@@ -463,7 +466,37 @@ DevEntries entries(sdpcuda_handle* h)
 int assemble(sdpcuda_handle* h, const double* v, double cscale, double* T)
 {
    CK( cudaMemsetAsync(T, 0, h->arena * sizeof(double), h->st) );
-   CK( assemble_positions(h->st, h->npos, h->posbeg.p, h->pos.p, h->mirror.p, h->posvar.p, h->posval.p, h->posc.p, v, cscale, T) );
+   if( h->ndense == 0 )
+   {
+      CK( assemble_positions(h->st, h->npos, h->posbeg.p, h->pos.p, h->mirror.p, h->posvar.p, h->posval.p, h->posc.p, v, cscale, T) );
+      return SDPCUDA_OK;
+   }
+   // sparse variables and the constant part by position lists, dense constraint matrices streamed from their expanded copies
+   CK( assemble_positions(h->st, h->npos, h->posbeg2.p, h->pos.p, h->mirror.p, h->posvar2.p, h->posval2.p, h->posc.p, v, cscale, T) );
+   size_t offm = 0;
+   for( const auto& g : h->dgroups )
+   {
+      const Block& bk = h->blk[g.blk];
+      const long long stride = (long long)bk.ld * bk.n;
+      CK( assemble_dense(h->st, g.count, g.first, h->denselist.p, h->Adense.p + offm, stride, v, T + bk.off) );
+      offm += (size_t)g.count * stride;
+   }
+   return SDPCUDA_OK;
+}
+
+// out_j = <A_j, X> for all variables
+int apply_A_all(sdpcuda_handle* h, const double* X, double* out)
+{
+   DevEntries E{h->varbeg.p, h->erow.p, h->ecol.p, h->eld.p, h->eoff.p, h->eval.p};
+   CK( apply_A(h->st, h->m, E, X, out, h->ndense > 0 ? h->heavy.p : nullptr) );
+   size_t offm = 0;
+   for( const auto& g : h->dgroups )
+   {
+      const Block& bk = h->blk[g.blk];
+      const long long stride = (long long)bk.ld * bk.n;
+      CK( apply_A_dense(h->st, g.count, g.first, h->denselist.p, h->Adense.p + offm, stride, X + bk.off, out) );
+      offm += (size_t)g.count * stride;
+   }
    return SDPCUDA_OK;
 }
 
@@ -755,13 +788,13 @@ int sdpcuda_destroy(sdpcuda_handle* h)
    sdpcuda_dist_finalize(h);
    cudaSetDevice(h->device);
    cudaStreamSynchronize(h->st);
-   for( DBuf<double>* bf : {&h->eval, &h->posval, &h->posc, &h->cval, &h->lpval, &h->colval, &h->lprhs, &h->b, &h->X, &h->S, &h->Sinv,
+   for( DBuf<double>* bf : {&h->eval, &h->posval, &h->posval2, &h->posc, &h->cval, &h->lpval, &h->colval, &h->lprhs, &h->b, &h->X, &h->S, &h->Sinv,
                             &h->L, &h->Linv, &h->LX, &h->LXinv, &h->dX, &h->dS, &h->dXa, &h->dSa, &h->K, &h->T1, &h->T2, &h->Rd, &h->work, &h->work2,
                             &h->y, &h->dy, &h->g, &h->rp, &h->AX, &h->DTx, &h->tm1, &h->tm2, &h->x, &h->s, &h->dx, &h->ds, &h->dxa, &h->dsa,
                             &h->klp, &h->rdlp, &h->Dy, &h->Ddy, &h->M, &h->Mfac, &h->diaginv, &h->Mwork, &h->MLinv, &h->Adense, &h->Hd, &h->Ud, &h->Cd, &h->partials, &h->stats, &h->scal,
                             &h->eigw, &h->lzwork, &h->kA, &h->kB, &h->kC, &h->kW} )
       bf->release();
-   for( DBuf<int>* bf : {&h->varbeg, &h->erow, &h->ecol, &h->eld, &h->posbeg, &h->posvar, &h->lpbeg, &h->lpind, &h->colbeg, &h->colrow,
+   for( DBuf<int>* bf : {&h->varbeg, &h->erow, &h->ecol, &h->eld, &h->posbeg, &h->posvar, &h->posbeg2, &h->posvar2, &h->lpbeg, &h->lpind, &h->colbeg, &h->colrow,
                          &h->heavy, &h->heavylist, &h->info, &h->patcol, &h->patrow, &h->denselist} )
       bf->release();
    for( DBuf<long long>* bf : {&h->eoff, &h->pos, &h->mirror, &h->cpos, &h->cmirror} )
@@ -1050,7 +1083,7 @@ static int run_ipm(sdpcuda_handle* h, const sdpcuda_params* par, const double* s
       CK( cudaMemsetAsync(h->info.p, 0, 8 * sizeof(int), st) );
       rc = assemble(h, h->y.p, 1.0, h->K.p); if( rc ) return rc;                   // K = A'y - C (scratch use of K)
       CK( residual_matrix(st, ar, h->K.p, h->S.p, h->X.p, h->Rd.p, h->partials.p) );
-      CK( apply_A(st, m, E, h->X.p, h->AX.p) );
+      rc = apply_A_all(h, h->X.p, h->AX.p); if( rc ) return rc;
       CK( lp_cols(st, m, h->colbeg.p, h->colrow.p, h->colval.p, h->x.p, h->DTx.p, 0) );
       CK( primal_residual(st, m, h->b.p, h->AX.p, h->DTx.p, h->y.p, h->rp.p, h->partials.p) );
       CK( lp_rows(st, nlp, h->lpbeg.p, h->lpind.p, h->lpval.p, h->lprhs.p, h->y.p, h->x.p, h->s.p, h->Dy.p, h->rdlp.p, h->partials.p) );
@@ -1292,7 +1325,7 @@ static int run_ipm(sdpcuda_handle* h, const sdpcuda_params* par, const double* s
             CK( axpby_out(st, ar, -1.0, h->X.p, 0.0, h->X.p, h->K.p) );
          CK( lp_rhs(st, nlp, pass, sigma * mu, h->x.p, h->s.p, h->rdlp.p, h->dxa.p, h->dsa.p, h->klp.p) );
          // g = A(K) + D'klp - rp ; dy = M^-1 g with one step of iterative refinement against the unregularised M
-         CK( apply_A(st, m, E, h->K.p, h->g.p) );
+         rc = apply_A_all(h, h->K.p, h->g.p); if( rc ) return rc;
          CK( lp_cols(st, m, h->colbeg.p, h->colrow.p, h->colval.p, h->klp.p, h->g.p, 1) );
          CK( axpy(st, (size_t)m, -1.0, h->rp.p, h->g.p) );
          auto msolve = [&](double* v) -> int {        // v <- M^-1 v

@@ -76,10 +76,11 @@ residual_matrix_kernel(size_t arena, const double* __restrict__ T, const double*
    if( threadIdx.x == 0 ) { partials[blockIdx.x * NSTAT + 0] = s0; partials[blockIdx.x * NSTAT + 1] = s1; }
 }
 
-__global__ void apply_A_kernel(int m, DevEntries E, const double* __restrict__ X, double* __restrict__ out)
+__global__ void apply_A_kernel(int m, DevEntries E, const int* __restrict__ skipcls, const double* __restrict__ X, double* __restrict__ out)
 {
    int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
    if( warp >= m ) return;
+   if( skipcls != nullptr && skipcls[warp] == 2 ) return;       // dense constraint matrices: apply_A_dense_kernel
    double s = 0.0;
    for( int e = E.varbeg[warp] + lane; e < E.varbeg[warp + 1]; e += 32 )
    {
@@ -529,10 +530,65 @@ cudaError_t residual_matrix(cudaStream_t st, size_t arena, const double* T, cons
    LAUNCH_END();
 }
 
-cudaError_t apply_A(cudaStream_t st, int m, DevEntries E, const double* X, double* out)
+cudaError_t apply_A(cudaStream_t st, int m, DevEntries E, const double* X, double* out, const int* skipcls)
 {
    if( m <= 0 ) return cudaSuccess;
-   apply_A_kernel<<<ceil_div(m, 8), 256, 0, st>>>(m, E, X, out);
+   apply_A_kernel<<<ceil_div(m, 8), 256, 0, st>>>(m, E, skipcls, X, out);
+   LAUNCH_END();
+}
+
+// dense constraint matrices (expanded n x n copies, matrix d at Ad + d*stride): streaming kernels instead of index gathers
+// out[denselist[first + d]] = <A_d, Xk>   (one CTA per matrix, fixed-order reduction)
+__global__ void __launch_bounds__(256)
+apply_A_dense_kernel(int first, const int* __restrict__ denselist, const double* __restrict__ Ad, long long stride,
+   const double* __restrict__ Xk, double* __restrict__ out)
+{
+   __shared__ double red[32];
+   const double* A = Ad + (size_t)blockIdx.x * stride;
+   double s0 = 0.0, s1 = 0.0;
+   long long e = threadIdx.x;
+   for( ; e + 256 < stride; e += 512 ) { s0 += A[e] * Xk[e]; s1 += A[e + 256] * Xk[e + 256]; }
+   if( e < stride ) s0 += A[e] * Xk[e];
+   const double s = block_sum(s0 + s1, red);
+   if( threadIdx.x == 0 ) out[denselist[first + blockIdx.x]] = s;
+}
+
+// Tk[e] += sum_d v[denselist[first + d]] * A_d[e]   (one thread per element of the block, coalesced over e)
+__global__ void __launch_bounds__(256)
+assemble_dense_kernel(int count, int first, const int* __restrict__ denselist, const double* __restrict__ Ad, long long stride,
+   const double* __restrict__ v, double* __restrict__ Tk)
+{
+   __shared__ double vs[256];
+   const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+   double a0 = 0.0, a1 = 0.0;
+   for( int d0 = 0; d0 < count; d0 += 256 )
+   {
+      const int nd = min(256, count - d0);
+      __syncthreads();
+      if( (int)threadIdx.x < nd ) vs[threadIdx.x] = v[denselist[first + d0 + threadIdx.x]];
+      __syncthreads();
+      if( e < stride )
+      {
+         const double* A = Ad + (size_t)d0 * stride + e;
+         int d = 0;
+         for( ; d + 1 < nd; d += 2 ) { a0 += vs[d] * A[(size_t)d * stride]; a1 += vs[d + 1] * A[(size_t)(d + 1) * stride]; }
+         if( d < nd ) a0 += vs[d] * A[(size_t)d * stride];
+      }
+   }
+   if( e < stride ) Tk[e] += a0 + a1;
+}
+
+cudaError_t apply_A_dense(cudaStream_t st, int count, int first, const int* denselist, const double* Ad, long long stride, const double* Xk, double* out)
+{
+   if( count <= 0 ) return cudaSuccess;
+   apply_A_dense_kernel<<<count, 256, 0, st>>>(first, denselist, Ad, stride, Xk, out);
+   LAUNCH_END();
+}
+
+cudaError_t assemble_dense(cudaStream_t st, int count, int first, const int* denselist, const double* Ad, long long stride, const double* v, double* Tk)
+{
+   if( count <= 0 ) return cudaSuccess;
+   assemble_dense_kernel<<<(unsigned)((stride + 255) / 256), 256, 0, st>>>(count, first, denselist, Ad, stride, v, Tk);
    LAUNCH_END();
 }
 

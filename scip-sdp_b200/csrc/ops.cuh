@@ -24,7 +24,12 @@ cudaError_t assemble_positions(cudaStream_t st, int npos, const int* posbeg, con
 // Rd = T - S over the arena; stats[0] += sum Rd^2, stats[1] += sum X.S   (partials -> finalize)
 cudaError_t residual_matrix(cudaStream_t st, size_t arena, const double* T, const double* S, const double* X, double* Rd, double* partials);
 // out[j] = sum_e val * (X[p1] + X[p2]) per variable
-cudaError_t apply_A(cudaStream_t st, int m, DevEntries E, const double* X, double* out);
+// skipcls (or nullptr): variables with skipcls[j] == 2 are left to apply_A_dense
+cudaError_t apply_A(cudaStream_t st, int m, DevEntries E, const double* X, double* out, const int* skipcls = nullptr);
+// dense constraint matrices of one block (expanded copies, matrix d at Ad + d*stride, stride = ld*n of the block):
+// out[denselist[first + d]] = <A_d, Xk>  and  Tk += sum_d v[denselist[first + d]] A_d   -- streamed, no index arrays
+cudaError_t apply_A_dense(cudaStream_t st, int count, int first, const int* denselist, const double* Ad, long long stride, const double* Xk, double* out);
+cudaError_t assemble_dense(cudaStream_t st, int count, int first, const int* denselist, const double* Ad, long long stride, const double* v, double* Tk);
 // sparse constant matrix: stats = sum c * (X[pos] (+ X[mirror])), same for a second matrix Y (or nullptr)
 cudaError_t const_dots(cudaStream_t st, int cnnz, const long long* cpos, const long long* cmirror, const double* cval,
    const double* X, const double* Y, double* out2);
