@@ -374,7 +374,7 @@ int upload_problem(sdpcuda_handle* h, const sdpcuda_problem* P)
       // the padding rows (leading dimension > order) take part in the long dot products of the dense x dense pairs: keep them zero
       CK( cudaMemsetAsync(h->Hd.p, 0, (size_t)h->dchunk * maxmat * sizeof(double), st) );
       CK( cudaMemsetAsync(h->Ud.p, 0, (size_t)h->dchunk * maxmat * sizeof(double), st) );
-      CK( h->Cd.ensure((size_t)round_up(maxcount, 2) * h->dchunk + 4) );       // leading dimension of the product is even
+      CK( h->Cd.ensure((size_t)16 * round_up(maxcount, 2) * h->dchunk + 4) );  // even leading dimension, up to 16 k-slices
       size_t offm = 0;
       DevEntries E{h->varbeg.p, h->erow.p, h->ecol.p, h->eld.p, h->eoff.p, h->eval.p};
       for( const auto& g : h->dgroups )
@@ -1233,9 +1233,23 @@ static int run_ipm(sdpcuda_handle* h, const sdpcuda_params* par, const double* s
                      // M_ij = <A_i, U_j>: sparse A_i by gathered dots; dense A_i of the same block as ONE tensor-core product
                      // Adense' (count x n^2) * U (n^2 x cnt), scattered into the lower triangle (each pair once)
                      CK( schur_dense_dots(st, m, cnt, g.first + d0, h->denselist.p, h->heavy.p, E, bk.off, h->Ud.p, bk.ld, stride, h->M.p, h->ldm) );
-                     CK( gemm(st, true, false, g.count, cnt, (int)stride, 1.0, h->Adense.p + offm, (int)stride, 0, h->Ud.p, (int)stride, 0, 0.0,
-                           h->Cd.p, round_up(g.count, 2), 0, 1, 0) );
-                     CK( schur_dense_scatter(st, g.count, cnt, g.first, g.first + d0, h->denselist.p, h->Cd.p, round_up(g.count, 2), h->M.p, h->ldm) );
+                     {
+                        // few output tiles, very long k (= n^2): split k over up to 16 slices (batched launch, partial products
+                        // added in slice order by the scatter kernel) so that the product fills the GPU
+                        const int ldc = round_up(g.count, 2);
+                        const long long ctas = (long long)ceil_div(g.count, 32) * ceil_div(cnt, 32);
+                        int nsl = (int)std::max<long long>(1, std::min<long long>(16, (2 * 148) / std::max<long long>(ctas, 1)));
+                        const long long kc = round_up((int)ceil_div((int)stride, nsl), 16);
+                        nsl = ceil_div((int)stride, (int)kc);
+                        const long long cs = (long long)ldc * cnt;
+                        if( nsl > 1 )
+                           CK( gemm(st, true, false, g.count, cnt, (int)kc, 1.0, h->Adense.p + offm, (int)stride, kc, h->Ud.p, (int)stride, kc, 0.0,
+                                 h->Cd.p, ldc, cs, nsl - 1, 0) );
+                        const long long k0 = (long long)(nsl - 1) * kc;
+                        CK( gemm(st, true, false, g.count, cnt, (int)(stride - k0), 1.0, h->Adense.p + offm + k0, (int)stride, 0, h->Ud.p + k0, (int)stride, 0, 0.0,
+                              h->Cd.p + (size_t)(nsl - 1) * cs, ldc, 0, 1, 0) );
+                        CK( schur_dense_scatter(st, g.count, cnt, g.first, g.first + d0, h->denselist.p, h->Cd.p, ldc, nsl, cs, h->M.p, h->ldm) );
+                     }
                   }
                   offm += (size_t)g.count * stride;
                }

@@ -301,12 +301,15 @@ schur_dense_dots_kernel(int m, int nd, int d0, const int* __restrict__ denselist
 
 // C(a, b) = <A_i, U_j> for dense i = denselist[first + a], dense j = denselist[first_j + b] -> M[i, j] for i >= j (each pair once)
 __global__ void schur_dense_scatter_kernel(int count, int cnt, int first, int first_j, const int* __restrict__ denselist,
-   const double* __restrict__ C, int ldc, double* __restrict__ M, int ldm)
+   const double* __restrict__ C, int ldc, int nslices, long long slicestride, double* __restrict__ M, int ldm)
 {
    const int a = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y;
    if( a >= count || b >= cnt ) return;
    const int i = denselist[first + a], j = denselist[first_j + b];
-   if( i >= j ) M[(size_t)j * ldm + i] = C[(size_t)b * ldc + a];
+   if( i < j ) return;
+   double v = 0.0;
+   for( int sl = 0; sl < nslices; ++sl ) v += C[(size_t)sl * slicestride + (size_t)b * ldc + a];      // k-slices in fixed order
+   M[(size_t)j * ldm + i] = v;
 }
 
 __global__ void schur_lp_kernel(int nlp, const int* __restrict__ lpbeg, const int* __restrict__ lpind, const double* __restrict__ lpval,
@@ -663,11 +666,11 @@ cudaError_t schur_dense_dots(cudaStream_t st, int m, int nd, int d0, const int* 
 }
 
 cudaError_t schur_dense_scatter(cudaStream_t st, int count, int cnt, int first, int first_j, const int* denselist, const double* C, int ldc,
-   double* M, int ldm)
+   int nslices, long long slicestride, double* M, int ldm)
 {
    if( count <= 0 || cnt <= 0 ) return cudaSuccess;
    dim3 grid(ceil_div(count, 256), cnt);
-   schur_dense_scatter_kernel<<<grid, 256, 0, st>>>(count, cnt, first, first_j, denselist, C, ldc, M, ldm);
+   schur_dense_scatter_kernel<<<grid, 256, 0, st>>>(count, cnt, first, first_j, denselist, C, ldc, nslices, slicestride, M, ldm);
    LAUNCH_END();
 }
 

@@ -55,9 +55,10 @@ cudaError_t schur_entries(cudaStream_t st, int m, DevEntries E, const int* heavy
 cudaError_t scatter_dense(cudaStream_t st, int nd, const int* denselist, DevEntries E, int ld, long long stride, double* Adense);
 cudaError_t schur_dense_dots(cudaStream_t st, int m, int nd, int d0, const int* denselist, const int* cls, DevEntries E, long long blockoff,
    const double* U, int ld, long long stride, double* M, int ldm);
-// dense x dense pairs: C = Adense' U (count x cnt, from the DMMA GEMM) scattered to M[i, j], i >= j
+// dense x dense pairs: C = Adense' U (count x cnt, from the DMMA GEMM, possibly as nslices partial products over k) scattered
+// to M[i, j], i >= j
 cudaError_t schur_dense_scatter(cudaStream_t st, int count, int cnt, int first, int first_j, const int* denselist, const double* C, int ldc,
-   double* M, int ldm);
+   int nslices, long long slicestride, double* M, int ldm);
 cudaError_t schur_lp(cudaStream_t st, int nlp, const int* lpbeg, const int* lpind, const double* lpval, const double* x,
    const double* s, double* M, int ldm);
 cudaError_t add_diagonal(cudaStream_t st, int n, double* A, int lda, double v);
