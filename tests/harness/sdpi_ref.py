@@ -88,6 +88,10 @@ class SdpiLib:
         L.SCIPsdpiGetTime.argtypes = [C.c_void_p, _dp]
         L.SCIPsdpiSetRealpar.argtypes = [C.c_void_p, C.c_int, C.c_double]
         L.SCIPsdpiSetIntpar.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        L.SCIPsdpiGetPreoptimalPrimalNonzeros.argtypes = [C.c_void_p, C.c_int, _ip]
+        L.SCIPsdpiGetPreoptimalSol.argtypes = [C.c_void_p, C.POINTER(C.c_uint), _dp, C.c_int, _ip, _ipp, _ipp, _dpp]
+        L.SCIPsdpiGetPrimalNonzeros.argtypes = [C.c_void_p, C.c_int, _ip]
+        L.SCIPsdpiGetPrimalMatrix.argtypes = [C.c_void_p, C.c_int, _ip, _ipp, _ipp, _dpp]
         L.SCIPsdpiGetNLPRows.argtypes = [C.c_void_p, _ip]
         L.SCIPsdpiGetNVars.argtypes = [C.c_void_p, _ip]
 
@@ -184,11 +188,54 @@ class Sdpi:
         _ok(self.L.lib.SCIPsdpiChgBounds(self.sdpi, len(idx), k.i(idx), k.d(lb), k.d(ub)), "SCIPsdpiChgBounds")
 
     # -------------------------------------------------------------- solving
-    def solve(self, starty=None, startsettings=SETTING_UNSOLVED, enforceslater=False, timelimit=1e20):
+    def solve(self, starty=None, startsettings=SETTING_UNSOLVED, enforceslater=False, timelimit=1e20, startZ=None, startX=None):
+        """startZ / startX: lists of (rows, cols, vals) per SDP block + the LP block last (sdpi.h: SCIPsdpiSolve start point)"""
         sy = _d(starty).ctypes.data_as(_dp) if starty is not None else None
-        rc = self.L.lib.SCIPsdpiSolve(self.sdpi, sy, None, None, None, None, None, None, None, None, startsettings,
+        k = _Keep()
+        za = [None] * 4
+        xa = [None] * 4
+        if startZ is not None and startX is not None:
+            for arr, blocks in ((za, startZ), (xa, startX)):
+                arr[0] = k.i([len(t[0]) for t in blocks])
+                arr[1] = k.pp([k.i(t[0] if len(t[0]) else [0]) for t in blocks], _ip)
+                arr[2] = k.pp([k.i(t[1] if len(t[1]) else [0]) for t in blocks], _ip)
+                arr[3] = k.pp([k.d(t[2] if len(t[2]) else [0.0]) for t in blocks], _dp)
+        rc = self.L.lib.SCIPsdpiSolve(self.sdpi, sy, za[0], za[1], za[2], za[3], xa[0], xa[1], xa[2], xa[3], startsettings,
                                       int(enforceslater), timelimit)
         _ok(rc, "SCIPsdpiSolve")
+
+    def _sparse_blocks(self, counter, getter, what):
+        nb = len(self.blocksizes) + 1
+        cnt = (C.c_int * nb)()
+        _ok(counter(self.sdpi, nb, cnt), what + "Nonzeros")
+        if cnt[0] == -1:
+            return None, None
+        rows = [np.zeros(max(c, 1), dtype=np.int32) for c in cnt]
+        cols = [np.zeros(max(c, 1), dtype=np.int32) for c in cnt]
+        vals = [np.zeros(max(c, 1)) for c in cnt]
+        rp = (_ip * nb)(*[r.ctypes.data_as(_ip) for r in rows])
+        cp = (_ip * nb)(*[c.ctypes.data_as(_ip) for c in cols])
+        vp = (_dp * nb)(*[v.ctypes.data_as(_dp) for v in vals])
+        extra = getter(nb, cnt, C.cast(rp, _ipp), C.cast(cp, _ipp), C.cast(vp, _dpp))
+        return extra, [(rows[b][:cnt[b]], cols[b][:cnt[b]], vals[b][:cnt[b]]) for b in range(nb)]
+
+    def primal_matrix_sparse(self):
+        """SCIPsdpiGetPrimalNonzeros + SCIPsdpiGetPrimalMatrix"""
+        def get(nb, cnt, rp, cp, vp):
+            _ok(self.L.lib.SCIPsdpiGetPrimalMatrix(self.sdpi, nb, cnt, rp, cp, vp), "SCIPsdpiGetPrimalMatrix")
+            return True
+        return self._sparse_blocks(self.L.lib.SCIPsdpiGetPrimalNonzeros, get, "SCIPsdpiGetPrimal")[1]
+
+    def preoptimal_sol(self):
+        """SCIPsdpiGetPreoptimalPrimalNonzeros + SCIPsdpiGetPreoptimalSol -> None or (y, blocks)"""
+        y = np.zeros(self.nvars)
+
+        def get(nb, cnt, rp, cp, vp):
+            ok = C.c_uint(0)
+            _ok(self.L.lib.SCIPsdpiGetPreoptimalSol(self.sdpi, C.byref(ok), y.ctypes.data_as(_dp), nb, cnt, rp, cp, vp), "SCIPsdpiGetPreoptimalSol")
+            return bool(ok.value)
+        ok, blocks = self._sparse_blocks(self.L.lib.SCIPsdpiGetPreoptimalPrimalNonzeros, get, "SCIPsdpiGetPreoptimalPrimal")
+        return (y, blocks) if ok else None
 
     def flag(self, name):
         return bool(getattr(self.L.lib, "SCIPsdpi" + name)(self.sdpi))

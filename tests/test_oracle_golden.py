@@ -95,3 +95,76 @@ def test_oracle_eigen_matches_reference_lapack_interface():
         for k in range(n):                      # eigenvectors as rows, equal up to sign where the eigenvalue is simple
             assert abs(abs(V[k] @ Vo[k]) - 1.0) <= 1e-6
     assert np.allclose(w[:0], [])               # (keeps flake8 quiet about w)
+
+
+@needs_ref
+def test_warmstart_and_preoptimal_through_the_reference_sdpi_layer(lib):
+    """row a10 driven through the REFERENCE's sdpi.c (SCIPsdpiSolve start point, SCIPsdpiGetPreoptimalSol, sdpi.c:3123-3405,
+    4250-4370) on top of our binding: WARMSTARTPOGAP gives an earlier interior iterate; a start point next to the optimum
+    (y*, Z*, X* pushed into the cone, as relax_sdp.c does) converges in fewer iterations to the same optimum"""
+    M = misdp.read_sdpa(os.path.join(GOLDEN, "example_TT.dat-s.gz"))
+    s = sdpi_ref.Sdpi(lib, gaptol=1e-6, sdpsolverfeastol=1e-6, feastol=1e-6)
+    try:
+        s.load_model(M)
+        s.solve()
+        assert s.flag("IsOptimal")
+        obj0, y0 = s.dual_sol()
+        it_cold = s.stats()["iterations"]
+        assert s.preoptimal_sol() is None
+
+        s.set_real("WARMSTARTPOGAP", 1e-2)
+        s.solve()
+        pre = s.preoptimal_sol()
+        assert pre is not None
+        ypre, Xpre = pre
+        objpre = float(np.dot(M.obj, ypre))
+        assert 1e-7 < abs(objpre - obj0) <= 5e-2 * max(1.0, abs(obj0))
+        for b, n in enumerate(M.blocksizes):
+            r, c, v = Xpre[b]
+            X = np.zeros((n, n)); X[r, c] = v; X[c, r] = v
+            assert np.linalg.eigvalsh(X).min() > 0.0
+        s.set_real("WARMSTARTPOGAP", -1.0)
+
+        # start point: the optimal (y, Z, X) moved 5 % towards the identity
+        s.solve()
+        Xopt = s.primal_matrix_sparse()
+        lam = 0.05
+        Zd = M.dense_Z(y0)
+        startZ, startX = [], []
+        for b, n in enumerate(M.blocksizes):
+            r, c, v = Xopt[b]
+            X = np.zeros((n, n)); X[r, c] = v; X[c, r] = v
+            for A, out in (((1 - lam) * Zd[b] + lam * np.eye(n), startZ), ((1 - lam) * X + lam * np.eye(n), startX)):
+                rr, cc = np.nonzero(np.tril(np.ones((n, n))))
+                out.append((rr.astype(np.int32), cc.astype(np.int32), A[rr, cc]))
+        # LP block: index 2i / 2i+1 for lhs / rhs of the ORIGINAL row i (sdpi.c hands all rows on and marks the removed ones in
+        # lpindchanges; rows with one nonzero were turned into bounds, sdpi.c:1131), then 2 nrows + 2j (+1) for lb (ub) of
+        # variable j; every finite side and bound gets a positive slack and multiplier
+        lp = dict(zip(Xopt[-1][0].tolist(), Xopt[-1][2].tolist()))
+        Mb = misdp.read_sdpa(os.path.join(GOLDEN, "example_TT.dat-s.gz")).rows_to_bounds()
+        nrows = len(M.rows)
+        idx, zval = [], []
+        for i, (coefs, lhs, rhs) in enumerate(M.rows):
+            if sum(1 for a in coefs.values() if a != 0.0) <= 1:
+                continue
+            act = sum(a * y0[j] for j, a in coefs.items())
+            if lhs > -1e20:
+                idx.append(2 * i); zval.append(act - lhs)
+            if rhs < 1e20:
+                idx.append(2 * i + 1); zval.append(rhs - act)
+        for j in range(M.nvars):
+            if Mb.lb[j] > -1e20:
+                idx.append(2 * nrows + 2 * j); zval.append(y0[j] - Mb.lb[j])
+            if Mb.ub[j] < 1e20:
+                idx.append(2 * nrows + 2 * j + 1); zval.append(Mb.ub[j] - y0[j])
+        idx = np.array(idx, dtype=np.int32)
+        zval = (1 - lam) * np.maximum(np.array(zval), 0.0) + lam
+        xval = (1 - lam) * np.array([max(lp.get(int(i), 0.0), 0.0) for i in idx]) + lam
+        startZ.append((idx, idx, zval)); startX.append((idx, idx, xval))
+        s.solve(starty=y0, startZ=startZ, startX=startX)
+        assert s.flag("IsOptimal")
+        obj2, _ = s.dual_sol()
+        assert abs(obj2 - obj0) <= 1e-5 * max(1.0, abs(obj0))
+        assert s.stats()["iterations"] < it_cold, (s.stats()["iterations"], it_cold)
+    finally:
+        s.close()
