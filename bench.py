@@ -12,6 +12,12 @@ independent-node-relaxation partition of the B&B frontier; no data-path collecti
 `e2e`    : the reference-facing call SCIPsdpiSolverLoadAndSolve + SCIPsdpiSolverGetDualSol with HOST buffers, wall clock.
 `roofline`: the dominant kernel (FP64 DMMA GEMM), algorithmic flops / CUDA-event time from one profiled solve, against the
             DMMA peak measured live by a register-resident probe (MEASURED_PEAKS.json has no FP64 entry).
+
+Further workloads (not the driver's default):
+   --workload frontier-{tt500,cls,mkp60,mkp120}   B&B nodes/sec: a frontier of open nodes partitioned round-robin over the ranks
+                                                   (upload + solve per node through the C ABI; weak scaling)
+   --workload sharded-{dense,maxcut,mkp120}       ONE relaxation over all N GPUs: Schur-complement shares per rank + one NCCL
+                                                   all-reduce per iteration (strong scaling)
 """
 import argparse
 import json
