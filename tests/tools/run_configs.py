@@ -1,10 +1,11 @@
-"""Solves the synthetic BASELINE.json shapes on the GPU and (optionally) on the CPU oracle; prints objective, iterations, time."""
+"""Checker-side comparison (lives under tests/ because it loads the CPU oracle): solves the synthetic BASELINE.json shapes on the
+GPU and (optionally) on the CPU oracle; prints objective, iterations, time."""
 import json
 import os
 import sys
 import time
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from scip_sdp_b200 import abi, generators  # noqa: E402
 
 which = sys.argv[1:] or ["tt500", "cls", "mkp120"]

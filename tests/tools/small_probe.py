@@ -1,6 +1,6 @@
 """Timing of the single-launch path on the shipped instances: device time of the kernel vs wall time of sdpcuda_solve."""
 import os, sys, time
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 from scip_sdp_b200 import abi, misdp
 G = os.path.join(ROOT, "tests", "golden")

@@ -2,7 +2,7 @@ set -x
 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_final.log 2>&1; tail -3 gpurun_out/pytest_final.log
 python bench.py > gpurun_out/r1b_bench_n1.json 2> gpurun_out/r1b_bench_n1.err
 python bench.py --impl reference --steps 1 --warmup 0 > gpurun_out/r1b_bench_ref.json 2> gpurun_out/r1b_bench_ref.err
-ORACLE=1 python tools/run_configs.py tt500 cls mkp120 mkp60 > gpurun_out/r1b_configs.log 2>&1
+ORACLE=1 python tests/tools/run_configs.py tt500 cls mkp120 mkp60 > gpurun_out/r1b_configs.log 2>&1
 for w in frontier-tt500 frontier-cls frontier-mkp60 frontier-mkp120; do python bench.py --workload $w > gpurun_out/r1b_$w.json 2>> gpurun_out/r1b_frontier.err; done
 ncu --metrics gpu__time_duration.sum --clock-control none -c 12000 --csv --log-file gpurun_out/r1b_launches.csv python tools/ncu_target.py 2000 100 > gpurun_out/ncu_list.log 2>&1
 python tools/summarize_launches.py gpurun_out/r1b_launches.csv > gpurun_out/r1b_launches_maxcut2000.txt 2>/dev/null
