@@ -226,6 +226,13 @@ class Sdpi:
             return True
         return self._sparse_blocks(self.L.lib.SCIPsdpiGetPrimalNonzeros, get, "SCIPsdpiGetPrimal")[1]
 
+    def preoptimal_y_only(self):
+        """SCIPsdpiGetPreoptimalSol with nblocks = -1 (only the dual vector is wanted, relax_sdp.c:3907)"""
+        y = np.zeros(self.nvars)
+        ok = C.c_uint(0)
+        _ok(self.L.lib.SCIPsdpiGetPreoptimalSol(self.sdpi, C.byref(ok), y.ctypes.data_as(_dp), -1, None, None, None, None), "SCIPsdpiGetPreoptimalSol")
+        return y if ok.value else None
+
     def preoptimal_sol(self):
         """SCIPsdpiGetPreoptimalPrimalNonzeros + SCIPsdpiGetPreoptimalSol -> None or (y, blocks)"""
         y = np.zeros(self.nvars)

@@ -98,14 +98,22 @@ def test_oracle_eigen_matches_reference_lapack_interface():
 
 
 @needs_ref
-def test_warmstart_and_preoptimal_through_the_reference_sdpi_layer(lib):
+@pytest.mark.parametrize("nfixed", [0, 20])
+def test_warmstart_and_preoptimal_through_the_reference_sdpi_layer(lib, nfixed):
     """row a10 driven through the REFERENCE's sdpi.c (SCIPsdpiSolve start point, SCIPsdpiGetPreoptimalSol, sdpi.c:3123-3405,
     4250-4370) on top of our binding: WARMSTARTPOGAP gives an earlier interior iterate; a start point next to the optimum
-    (y*, Z*, X* pushed into the cone, as relax_sdp.c does) converges in fewer iterations to the same optimum"""
+    (y*, Z*, X* pushed into the cone, as relax_sdp.c does) converges in fewer iterations to the same optimum.
+    nfixed = 20: a B&B node with 20 bars fixed to zero, where sdpi.c removes two rows/columns of the block (indchanges), so the
+    start matrices in ORIGINAL indices have to be compressed by the binding (and entries of removed rows ignored)"""
     M = misdp.read_sdpa(os.path.join(GOLDEN, "example_TT.dat-s.gz"))
+    Mb = misdp.read_sdpa(os.path.join(GOLDEN, "example_TT.dat-s.gz")).rows_to_bounds()
     s = sdpi_ref.Sdpi(lib, gaptol=1e-6, sdpsolverfeastol=1e-6, feastol=1e-6)
     try:
         s.load_model(M)
+        if nfixed:
+            fix = np.flatnonzero(M.integer)[:nfixed]
+            Mb.lb[fix] = 0.0; Mb.ub[fix] = 0.0
+            s.chg_bounds(np.arange(M.nvars, dtype=np.int32), Mb.lb, Mb.ub)
         s.solve()
         assert s.flag("IsOptimal")
         obj0, y0 = s.dual_sol()
@@ -117,12 +125,15 @@ def test_warmstart_and_preoptimal_through_the_reference_sdpi_layer(lib):
         pre = s.preoptimal_sol()
         assert pre is not None
         ypre, Xpre = pre
+        assert np.array_equal(s.preoptimal_y_only(), ypre)
         objpre = float(np.dot(M.obj, ypre))
         assert 1e-7 < abs(objpre - obj0) <= 5e-2 * max(1.0, abs(obj0))
         for b, n in enumerate(M.blocksizes):
             r, c, v = Xpre[b]
             X = np.zeros((n, n)); X[r, c] = v; X[c, r] = v
-            assert np.linalg.eigvalsh(X).min() > 0.0
+            kept = np.flatnonzero(np.abs(X).sum(axis=0) > 0)          # removed rows/columns come back as zero rows (original indices)
+            assert len(kept) == (n if nfixed == 0 else n - 2)
+            assert np.linalg.eigvalsh(X[np.ix_(kept, kept)]).min() > 0.0
         s.set_real("WARMSTARTPOGAP", -1.0)
 
         # start point: the optimal (y, Z, X) moved 5 % towards the identity
@@ -141,7 +152,6 @@ def test_warmstart_and_preoptimal_through_the_reference_sdpi_layer(lib):
         # lpindchanges; rows with one nonzero were turned into bounds, sdpi.c:1131), then 2 nrows + 2j (+1) for lb (ub) of
         # variable j; every finite side and bound gets a positive slack and multiplier
         lp = dict(zip(Xopt[-1][0].tolist(), Xopt[-1][2].tolist()))
-        Mb = misdp.read_sdpa(os.path.join(GOLDEN, "example_TT.dat-s.gz")).rows_to_bounds()
         nrows = len(M.rows)
         idx, zval = [], []
         for i, (coefs, lhs, rhs) in enumerate(M.rows):
@@ -153,6 +163,8 @@ def test_warmstart_and_preoptimal_through_the_reference_sdpi_layer(lib):
             if rhs < 1e20:
                 idx.append(2 * i + 1); zval.append(rhs - act)
         for j in range(M.nvars):
+            if Mb.ub[j] - Mb.lb[j] <= 1e-9:
+                continue                                        # fixed: not a variable of the solver problem
             if Mb.lb[j] > -1e20:
                 idx.append(2 * nrows + 2 * j); zval.append(y0[j] - Mb.lb[j])
             if Mb.ub[j] < 1e20:
