@@ -107,6 +107,7 @@ def test_warmstart_and_preoptimal_through_the_reference_sdpi_layer(lib, nfixed):
     start matrices in ORIGINAL indices have to be compressed by the binding (and entries of removed rows ignored)"""
     M = misdp.read_sdpa(os.path.join(GOLDEN, "example_TT.dat-s.gz"))
     Mb = misdp.read_sdpa(os.path.join(GOLDEN, "example_TT.dat-s.gz")).rows_to_bounds()
+    mem_before = lib.memory_used()
     s = sdpi_ref.Sdpi(lib, gaptol=1e-6, sdpsolverfeastol=1e-6, feastol=1e-6)
     try:
         s.load_model(M)
@@ -180,3 +181,4 @@ def test_warmstart_and_preoptimal_through_the_reference_sdpi_layer(lib, nfixed):
         assert s.stats()["iterations"] < it_cold, (s.stats()["iterations"], it_cold)
     finally:
         s.close()
+    assert lib.memory_used() == mem_before, "BMS memory leak (preoptimal buffers?)"      # like unittests/src/checksdpi.c:117
