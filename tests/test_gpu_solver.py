@@ -145,3 +145,24 @@ def test_sharded_schur_on_two_gpus():
     out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
                           "--master-port", "29533", os.path.join(root, "tools", "dist_check.py")], capture_output=True, text=True, timeout=600)
     assert out.returncode == 0 and "DIST_CHECK PASS" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
+
+
+@pytest.mark.parametrize("name", ["tt500", "cls", "mkp60", "mkp120", "maxcut2000"])
+def test_full_size_shapes_match_pinned_oracle_objectives(gpu, name):
+    """the synthetic BASELINE.json shapes at FULL size against root-relaxation objectives pinned with the CPU oracle
+    (tests/golden/relaxation_values.json, made by tests/golden/make_relaxation_values.py; the oracle needs 2-40 s per shape, too
+    slow to repeat in every GPU run).  Tolerance: 1e-5 relative, the north-star gap tolerance both sides were solved to."""
+    import json
+    from golden.make_relaxation_values import SHAPES
+    with open(os.path.join(os.path.dirname(__file__), "golden", "relaxation_values.json")) as f:
+        pinned = json.load(f)[name]
+    fp, _ = SHAPES[name]().flatten()
+    assert (fp.m, [int(b) for b in fp.blocksizes], fp.nlp) == (pinned["m"], pinned["blocks"], pinned["nlp"])
+    r = gpu.solve(fp, gaptol=1e-5, feastol=1e-5, fetch=False)
+    assert r["phase_name"] == "pdOPT", (r["phase_name"], r["stop_name"])
+    scale = max(1.0, abs(pinned["dobj"]))
+    assert abs(r["dobj"] - pinned["dobj"]) <= 1e-5 * scale
+    # size-independent properties: small relative gap and residuals, X-side value (a lower bound) not above the y-side value
+    assert r["relgap"] <= 1e-5 and r["pinf"] <= 1e-5 and r["dinf"] <= 1e-5
+    assert r["pobj"] <= r["dobj"] + 2e-5 * scale
+    assert abs(r["iterations"] - pinned["iterations"]) <= 5
