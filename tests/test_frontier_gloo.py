@@ -37,6 +37,17 @@ def _worker(rank, world, port, q):
         # the channel that carries the NCCL id of the sharded-Schur path (rank 0 -> all)
         ident = frontier.broadcast_bytes(bytes(range(128)) if rank == 0 else None, 128, dist)
         assert ident == bytes(range(128))
+
+        class FakeHandle:          # stands in for abi.Solver: records what shard_one_sdp hands to sdpcuda_dist_init
+            def dist_unique_id(self):
+                return bytes([7 + rank]) * 128          # only rank 0's id may be used
+
+            def dist_init(self, nranks, r, idbytes):
+                self.args = (nranks, r, idbytes)
+
+        fake = FakeHandle()
+        frontier.shard_one_sdp(fake, dist)
+        assert fake.args == (world, rank, bytes([7]) * 128)
         q.put((rank, [(r["status"], round(r["bound"], 6)) for r in res], tmax, frontier.partition(5, world, rank)))
     finally:
         dist.destroy_process_group()
