@@ -163,15 +163,15 @@ class Misdp:
         out.write(" ".join(repr(float(v)) for v in self.obj) + "\n")
         for b in range(len(self.blocksizes)):
             for (r, c, v) in self.C[b]:
-                out.write(f"0 {b + 1} {c + 1} {r + 1} {v!r}\n")
+                out.write(f"0 {b + 1} {c + 1} {r + 1} {float(v)!r}\n")
             for j in sorted(self.A[b]):
                 for (r, c, v) in self.A[b][j]:
-                    out.write(f"{j + 1} {b + 1} {c + 1} {r + 1} {v!r}\n")
+                    out.write(f"{j + 1} {b + 1} {c + 1} {r + 1} {float(v)!r}\n")
         for i, (coefs, side, sgn) in enumerate(rows):
             for j in sorted(coefs):
-                out.write(f"{j + 1} {nb} {i + 1} {i + 1} {sgn * coefs[j]!r}\n")
+                out.write(f"{j + 1} {nb} {i + 1} {i + 1} {float(sgn * coefs[j])!r}\n")
             if side != 0.0:
-                out.write(f"0 {nb} {i + 1} {i + 1} {sgn * side!r}\n")
+                out.write(f"0 {nb} {i + 1} {i + 1} {float(sgn * side)!r}\n")
         if self.integer.any():
             out.write("*INTEGER\n")
             for j in np.flatnonzero(self.integer):

@@ -100,3 +100,38 @@ def test_cbf_rejects_unsupported_cones(tmp_path):
 def test_read_instance_dispatch():
     assert misdp.read_instance(os.path.join(GOLDEN, "example_cbf_dual.cbf")).blocksizes == [2, 2]
     assert misdp.read_instance(os.path.join(GOLDEN, "example_TT.dat-s.gz")).nvars == 37
+
+
+@pytest.mark.parametrize("make", [lambda: misdp.read_sdpa(os.path.join(GOLDEN, "example_TT.dat-s.gz")),
+                                  lambda: __import__("scip_sdp_b200.generators", fromlist=["x"]).mkp(12, seed=3),
+                                  lambda: __import__("scip_sdp_b200.generators", fromlist=["x"]).truss(3, 3, 20, seed=4),
+                                  lambda: __import__("scip_sdp_b200.generators", fromlist=["x"]).maxcut(30, 0.2, seed=5)],
+                         ids=["example_TT", "mkp-12", "truss-20", "maxcut-30"])
+def test_sdpa_writer_reader_round_trip(tmp_path, make):
+    """the synthetic generators write the reference's extended SDPA format (`.dat-s` files the reference readers
+    could consume): writing and reading back gives the same model (LMIs, objective, integrality) and the same flattened problem"""
+    M = make()
+    path = tmp_path / "inst.dat-s.gz"
+    M.write_sdpa(path)
+    R = misdp.read_sdpa(path)
+    assert R.nvars == M.nvars and R.blocksizes == M.blocksizes and np.allclose(R.obj, M.obj) and (R.integer == M.integer).all()
+    rng = np.random.default_rng(1)
+    y = rng.standard_normal(M.nvars)
+    for Za, Zb in zip(M.dense_Z(y), R.dense_Z(y)):
+        assert np.allclose(Za, Zb)
+    fa, _ = M.rows_to_bounds().flatten()
+    fb, _ = R.rows_to_bounds().flatten()
+    assert fa.m == fb.m and fa.nlp == fb.nlp and list(fa.blocksizes) == list(fb.blocksizes)
+    # the LP blocks describe the same polyhedron row by row (the writer emits one-sided rows, bounds last)
+    assert np.allclose(np.sort(fa.lprhs), np.sort(fb.lprhs))
+
+
+def test_generators_are_deterministic():
+    from scip_sdp_b200 import generators
+    for make in (lambda: generators.maxcut(40, 0.2, seed=9), lambda: generators.mkp(10, seed=9), lambda: generators.truss(3, 3, 15, seed=9),
+                 lambda: generators.cls(12, 8, 3, seed=9)):
+        a, _ = make().flatten()
+        b, _ = make().flatten()
+        assert np.array_equal(a.entval, b.entval) and np.array_equal(a.obj, b.obj) and np.array_equal(a.lprhs, b.lprhs)
+    fa, fb = generators.dense_sdp_flat(5, 4, seed=1), generators.dense_sdp_flat(5, 4, seed=1)
+    assert np.array_equal(fa.entval, fb.entval) and np.array_equal(fa.cval, fb.cval)
