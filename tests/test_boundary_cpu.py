@@ -18,3 +18,45 @@ def test_primal_matrix_getters_are_consistent():
 
 def test_warmstart_and_preoptimal_solution():
     boundary_cases.run_warmstart_and_preoptimal(sdpi_ref.LIB_ORACLE)
+
+
+def test_parameters_and_penalty_formulas():
+    """row a11: Get/SetRealpar, Get/SetIntpar, Infinity and the penalty-parameter policy (same constants as the SDPA binding,
+    sdpisolver_sdpa.cpp:101-105: Gamma = clamp(10 maxcoeff, 1e5, 1e12), max Gamma = min(1e6 Gamma, 1e15))"""
+    import ctypes as C
+    from scip_sdp_b200 import sdpisolver_host
+    s = sdpisolver_host.SdpiSolver(sdpi_ref.LIB_ORACLE)
+    L = s.lib
+    try:
+        L.SCIPsdpiSolverGetRealpar.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_double)]
+        L.SCIPsdpiSolverGetIntpar.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int)]
+        L.SCIPsdpiSolverSetIntpar.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        L.SCIPsdpiSolverInfinity.restype = C.c_double
+        L.SCIPsdpiSolverInfinity.argtypes = [C.c_void_p]
+        L.SCIPsdpiSolverIsInfinity.restype = C.c_uint
+        L.SCIPsdpiSolverIsInfinity.argtypes = [C.c_void_p, C.c_double]
+        L.SCIPsdpiSolverComputePenaltyparam.argtypes = [C.c_void_p, C.c_double, C.POINTER(C.c_double)]
+        L.SCIPsdpiSolverComputeMaxPenaltyparam.argtypes = [C.c_void_p, C.c_double, C.POINTER(C.c_double)]
+        L.SCIPsdpiSolverGetDefaultSdpiSolverNpenaltyIncreases.restype = C.c_int
+        v = C.c_double(0)
+        # EPSILON 0, GAPTOL 1, FEASTOL 2, SDPSOLVERFEASTOL 3, OBJLIMIT 4, LAMBDASTAR 10, WARMSTARTPOGAP 12 (type_sdpi.h:49-66)
+        for par, val in ((0, 1e-8), (1, 3e-5), (2, 2e-6), (3, 4e-7), (4, 123.5), (10, 7.0), (12, 0.01)):
+            assert L.SCIPsdpiSolverSetRealpar(s.s, par, val) == sdpisolver_host.SCIP_OKAY
+            assert L.SCIPsdpiSolverGetRealpar(s.s, par, C.byref(v)) == sdpisolver_host.SCIP_OKAY and v.value == val
+        for par in (14, 15, 16):                  # USEPRESOLVING, USESCALING, SCALEOBJ: unknown like in the DSDP/SDPA bindings
+            assert L.SCIPsdpiSolverSetRealpar(s.s, par, 1.0) == -12 or L.SCIPsdpiSolverSetIntpar(s.s, par, 1) == -12
+        iv = C.c_int(-7)
+        assert L.SCIPsdpiSolverSetIntpar(s.s, 5, 1) == sdpisolver_host.SCIP_OKAY            # SDPINFO
+        assert L.SCIPsdpiSolverGetIntpar(s.s, 5, C.byref(iv)) == sdpisolver_host.SCIP_OKAY and iv.value == 1
+        assert L.SCIPsdpiSolverSetIntpar(s.s, 5, 0) == sdpisolver_host.SCIP_OKAY
+        assert L.SCIPsdpiSolverSetIntpar(s.s, 11, 4) == sdpisolver_host.SCIP_OKAY           # NTHREADS: accepted, no effect
+        assert L.SCIPsdpiSolverInfinity(s.s) == 1e20
+        assert L.SCIPsdpiSolverIsInfinity(s.s, 1e20) and L.SCIPsdpiSolverIsInfinity(s.s, -3e20) and not L.SCIPsdpiSolverIsInfinity(s.s, 9e19)
+        for maxcoeff, expect in ((1.0, 1e5), (5e4, 5e5), (1e13, 1e12)):
+            assert L.SCIPsdpiSolverComputePenaltyparam(s.s, maxcoeff, C.byref(v)) == sdpisolver_host.SCIP_OKAY and v.value == expect
+        for gamma, expect in ((1e5, 1e11), (1e10, 1e15)):
+            assert L.SCIPsdpiSolverComputeMaxPenaltyparam(s.s, gamma, C.byref(v)) == sdpisolver_host.SCIP_OKAY and v.value == expect
+        assert L.SCIPsdpiSolverGetDefaultSdpiSolverNpenaltyIncreases() == 8
+        assert s.name() == "CUDA-IPM"
+    finally:
+        s.close()
