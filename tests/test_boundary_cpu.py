@@ -60,3 +60,29 @@ def test_parameters_and_penalty_formulas():
         assert s.name() == "CUDA-IPM"
     finally:
         s.close()
+
+
+def test_getters_before_a_solve_return_lperror():
+    """error behaviour of the boundary: SCIP_LPERROR for "asked for a solution before a solve" (CHECK_IF_SOLVED,
+    sdpisolver_dsdp.c:145-164) and for the unimplemented file interface, never a crash"""
+    import ctypes as C
+    import numpy as np
+    from scip_sdp_b200 import sdpisolver_host
+    SCIP_LPERROR = -6
+    s = sdpisolver_host.SdpiSolver(sdpi_ref.LIB_ORACLE)
+    L = s.lib
+    try:
+        assert not s.flag("WasSolved")
+        v = C.c_double(0)
+        assert L.SCIPsdpiSolverGetObjval(s.s, C.byref(v)) == SCIP_LPERROR
+        y = np.zeros(4)
+        assert L.SCIPsdpiSolverGetDualSol(s.s, C.byref(v), y.ctypes.data_as(C.POINTER(C.c_double))) == SCIP_LPERROR
+        cnt = (C.c_int * 2)()
+        assert L.SCIPsdpiSolverGetPrimalNonzeros(s.s, 2, cnt) == SCIP_LPERROR
+        L.SCIPsdpiSolverReadSDP.argtypes = [C.c_void_p, C.c_char_p]
+        L.SCIPsdpiSolverWriteSDP.argtypes = [C.c_void_p, C.c_char_p]
+        assert L.SCIPsdpiSolverReadSDP(s.s, b"x.dat-s") == SCIP_LPERROR and L.SCIPsdpiSolverWriteSDP(s.s, b"x.dat-s") == SCIP_LPERROR
+        it = C.c_int(-1)
+        assert L.SCIPsdpiSolverGetIterations(s.s, C.byref(it)) in (sdpisolver_host.SCIP_OKAY, SCIP_LPERROR)
+    finally:
+        s.close()
