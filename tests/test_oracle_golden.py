@@ -182,3 +182,22 @@ def test_warmstart_and_preoptimal_through_the_reference_sdpi_layer(lib, nfixed):
     finally:
         s.close()
     assert lib.memory_used() == mem_before, "BMS memory leak (preoptimal buffers?)"      # like unittests/src/checksdpi.c:117
+
+
+@needs_ref
+def test_exhausted_time_limit_is_not_an_error(lib):
+    """SURVEY.md 8b: time limit already exhausted => SCIP_OKAY, timelimit flag set, nothing acceptable (sdpisolver_dsdp.c:880-890);
+    the same object solves normally afterwards"""
+    M = misdp.read_sdpa(os.path.join(GOLDEN, "example_TT.dat-s.gz"))
+    s = sdpi_ref.Sdpi(lib, gaptol=1e-6, sdpsolverfeastol=1e-6, feastol=1e-6)
+    try:
+        s.load_model(M)
+        s.solve(timelimit=1e-12)
+        assert s.flag("IsTimelimExc") and not s.flag("IsAcceptable") and not s.flag("IsConverged")
+        assert s.stats()["sdpcalls"] == 0
+        s.solve()
+        assert not s.flag("IsTimelimExc") and s.flag("IsOptimal")
+        obj, _ = s.dual_sol()
+        assert abs(obj - 0.16447) <= 1e-4          # root relaxation of example_TT
+    finally:
+        s.close()
