@@ -201,3 +201,28 @@ def test_exhausted_time_limit_is_not_an_error(lib):
         assert abs(obj - 0.16447) <= 1e-4          # root relaxation of example_TT
     finally:
         s.close()
+
+
+@needs_ref
+@pytest.mark.parametrize("name,dual_expected", [("example_small.dat-s", 1), ("example_TT.dat-s.gz", 1), ("example_MkP.dat-s.gz", 1),
+                                                ("example_CLS.dat-s.gz", 1), ("example_inf.dat-s", -2)])
+def test_slater_checks_of_the_reference_run_through_the_binding(lib, name, dual_expected):
+    """SURVEY.md 8b invocation patterns (iv) and (v): sdpi.c's dual Slater check (penalty formulation, r free, no objective) and
+    primal Slater check (LoadAndSolve without constant matrices, all sides 0, one extra LP row; sdpi.c:1518-1870) with
+    relaxing/SDP/slatercheck = 2: SCIP_SDPSLATER_HOLDS (1) for the feasible instances, SCIP_SDPSLATER_INF (-2) on the dual side
+    of example_inf; the main solve is unaffected"""
+    import ctypes as C
+    M = misdp.read_instance(os.path.join(GOLDEN, name))
+    s = sdpi_ref.Sdpi(lib, gaptol=1e-6, sdpsolverfeastol=1e-6, feastol=1e-6)
+    try:
+        s.load_model(M)
+        assert s.L.lib.SCIPsdpiSetIntpar(s.sdpi, sdpi_ref.PAR["SLATERCHECK"], 2) == sdpi_ref.SCIP_OKAY
+        s.solve(enforceslater=True)
+        p, d = C.c_int(-9), C.c_int(-9)
+        s.L.lib.SCIPsdpiSlater.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+        assert s.L.lib.SCIPsdpiSlater(s.sdpi, C.byref(p), C.byref(d)) == sdpi_ref.SCIP_OKAY
+        assert p.value == 1 and d.value == dual_expected
+        assert s.flag("IsAcceptable")
+        assert s.flag("IsDualInfeasible") == (dual_expected == -2)
+    finally:
+        s.close()
