@@ -140,6 +140,12 @@ def test_warmstart_and_preoptimal_through_the_reference_sdpi_layer(lib, nfixed):
         # start point: the optimal (y, Z, X) moved 5 % towards the identity
         s.solve()
         Xopt = s.primal_matrix_sparse()
+        dense, ok = s.primal_matrices()            # GetPrimalSolutionMatrix: original size, zero rows where sdpi.c removed them
+        assert ok
+        for b, n in enumerate(M.blocksizes):
+            r, c, v = Xopt[b]
+            R = np.zeros((n, n)); R[r, c] = v; R[c, r] = v
+            assert np.abs(R - dense[b]).max() <= 1e-8
         lam = 0.05
         Zd = M.dense_Z(y0)
         startZ, startX = [], []
