@@ -28,6 +28,7 @@ class Misdp:
         self.ub = np.full(nvars, INF)
         self.integer = np.zeros(nvars, dtype=bool)
         self.rank1 = []
+        self.indicators = []       # (slack variable, binary variable): binary = 1  =>  slack = 0   (reader_sdpa.c:1195-1246)
         self.objsense = 1          # +1: the file asked for min obj'y; -1: it asked for max (obj is stored negated)
         self.objoffset = 0.0       # constant term of the file's objective (in the file's sense)
 
@@ -45,6 +46,14 @@ class Misdp:
 
     def add_row(self, coefs, lhs=-INF, rhs=INF):
         self.rows.append((dict(coefs), lhs, rhs))
+
+    def add_variable(self, obj=0.0, lb=-INF, ub=INF, integer=False):
+        """appends a scalar variable (no SDP entries) and returns its index"""
+        self.obj = np.append(self.obj, float(obj))
+        self.lb = np.append(self.lb, float(lb)); self.ub = np.append(self.ub, float(ub))
+        self.integer = np.append(self.integer, bool(integer))
+        self.nvars += 1
+        return self.nvars - 1
 
     def rows_to_bounds(self):
         """single-variable rows become variable bounds (what sdpi.c:prepareLPData does for every solve, sdpi.c:1131)"""
@@ -233,6 +242,7 @@ def read_sdpa(path):
     bmap = {b: i for i, b in enumerate(sdpidx)}
     M = Misdp(nvars, obj, [sizes[b] for b in sdpidx])
     lprows = {}
+    indrows = []
     section = None
     for s in lines[k:]:
         s = s.strip()
@@ -260,10 +270,19 @@ def read_sdpa(path):
         else:
             assert b in lpidx and r == c, "LP block entries must be diagonal"
             row = lprows.setdefault((b, r), [dict(), 0.0])
-            if j < 0:
+            if j < -1:
+                # indicator constraint (file index -k, k >= 2): variable k-1 becomes binary, the row gets a slack variable s >= 0
+                # and "variable = 1 => s = 0" (reader_sdpa.c:1195-1246; the value of the entry is not used there either)
+                indrows.append(((b, r), -j - 2))
+            elif j < 0:
                 row[1] = v
             else:
                 row[0][j] = row[0].get(j, 0.0) + v
+    for key, z in indrows:
+        sl = M.add_variable(obj=0.0, lb=0.0)
+        lprows[key][0][sl] = 1.0
+        M.lb[z], M.ub[z], M.integer[z] = max(M.lb[z], 0.0), min(M.ub[z], 1.0), True
+        M.indicators.append((sl, z))
     for key in sorted(lprows):
         coefs, rhs = lprows[key]
         M.add_row(coefs, lhs=rhs)      # all LP-block inequalities are  a'y - a_0 >= 0

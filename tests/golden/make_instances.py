@@ -9,6 +9,6 @@ SRC = "/root/reference/instances"
 DST = os.path.dirname(os.path.abspath(__file__))
 for name in ["example_small.dat-s", "example_inf.dat-s", "example_TT.dat-s.gz", "example_CLS.dat-s.gz", "example_MkP.dat-s.gz",
              "example_small_cbf.cbf", "example_cbf_primal.cbf", "example_cbf_mix.cbf", "example_cbf_dual.cbf", "example_multaggr.cbf",
-             "example_diagzeroimpl.cbf", "example_tightenmatrices.dat-s"]:
+             "example_diagzeroimpl.cbf", "example_tightenmatrices.dat-s", "example_small_ind.dat-s"]:
     shutil.copyfile(os.path.join(SRC, name), os.path.join(DST, name))
     print("copied", name)

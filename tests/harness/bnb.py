@@ -32,6 +32,10 @@ def solve_misdp(lib, M, gaptol=1e-5, feastol=1e-5, inttol=1e-5, maxnodes=100000,
             if bound >= best - 1e-6 * max(1.0, abs(best)):
                 continue
             nodes += 1
+            # indicator constraints (binary = 1 => slack = 0, SCIP's cons_indicator): enforced through the slack's upper bound
+            for sl, z in getattr(M, "indicators", []):
+                if lb[z] > 0.5:
+                    ub = ub.copy(); ub[sl] = 0.0
             s.chg_bounds(idx, lb, ub)
             s.solve()
             st = s.stats()
@@ -53,6 +57,16 @@ def solve_misdp(lib, M, gaptol=1e-5, feastol=1e-5, inttol=1e-5, maxnodes=100000,
             if obj >= best - 1e-6 * max(1.0, abs(best)):
                 continue
             frac = np.abs(y[ints] - np.round(y[ints]))
+            violated = [z for sl, z in getattr(M, "indicators", []) if frac.max(initial=0.0) <= inttol and y[z] > 0.5 and ub[z] - lb[z] > 0.5
+                        and y[sl] > 1e-6]
+            if violated:
+                # integral but an indicator with value 1 has a positive slack: branch on that binary variable
+                j = violated[0]
+                dn_ub = ub.copy(); dn_ub[j] = 0.0
+                up_lb = lb.copy(); up_lb[j] = 1.0
+                heapq.heappush(heap, (obj, next(counter), lb, dn_ub))
+                heapq.heappush(heap, (obj, next(counter), up_lb, ub))
+                continue
             if len(ints) == 0 or frac.max() <= inttol:
                 best, bestsol = obj, y.copy()
                 if verbose:

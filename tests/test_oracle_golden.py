@@ -38,7 +38,8 @@ def test_checksdpi_known_answers(lib, name):
 SHORT_SOLU = {"example_small.dat-s": -8.0, "example_inf.dat-s": None, "example_TT.dat-s.gz": 2.11803,
               "example_CLS.dat-s.gz": 7.1485, "example_MkP.dat-s.gz": -95.0,
               "example_small_cbf.cbf": -8.0, "example_cbf_primal.cbf": 0.75, "example_cbf_mix.cbf": 4.0, "example_cbf_dual.cbf": 4.0,
-              "example_multaggr.cbf": -1.0, "example_diagzeroimpl.cbf": -1.0, "example_tightenmatrices.dat-s": -9.0}
+              "example_multaggr.cbf": -1.0, "example_diagzeroimpl.cbf": -1.0, "example_tightenmatrices.dat-s": -9.0,
+              "example_small_ind.dat-s": -18.0}      # indicator constraint (binary = 1 => slack = 0), handled by the harness
 
 
 @needs_ref

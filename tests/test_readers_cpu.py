@@ -135,3 +135,14 @@ def test_generators_are_deterministic():
         assert np.array_equal(a.entval, b.entval) and np.array_equal(a.obj, b.obj) and np.array_equal(a.lprhs, b.lprhs)
     fa, fb = generators.dense_sdp_flat(5, 4, seed=1), generators.dense_sdp_flat(5, 4, seed=1)
     assert np.array_equal(fa.entval, fb.entval) and np.array_equal(fa.cval, fb.cval)
+
+
+def test_sdpa_indicator_entries():
+    """extended SDPA format: a negative variable index -k (k >= 2) in the LP block marks an indicator constraint
+    (reader_sdpa.c:1147-1246): variable k-1 becomes binary and the row gets a slack variable with "variable = 1 => slack = 0" """
+    M = misdp.read_sdpa(os.path.join(GOLDEN, "example_small_ind.dat-s"))
+    assert M.nvars == 5 and M.indicators == [(4, 3)]
+    assert M.integer.tolist() == [True, True, True, True, False]
+    assert (M.lb[3], M.ub[3], M.lb[4]) == (0.0, 1.0, 0.0) and M.ub[4] >= 1e20
+    rows_with_slack = [coefs for coefs, lhs, rhs in M.rows if 4 in coefs]
+    assert len(rows_with_slack) == 1 and rows_with_slack[0][4] == 1.0
