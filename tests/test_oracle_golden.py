@@ -233,3 +233,55 @@ def test_slater_checks_of_the_reference_run_through_the_binding(lib, name, dual_
         assert s.flag("IsDualInfeasible") == (dual_expected == -2)
     finally:
         s.close()
+
+
+# unittests/src/check1dsdp.c:122-400: one-variable SDPs  min x  s.t.  A x - B psd, lb <= x <= ub  (lower triangles, 0-based)
+CHECK1D = {
+    "test1": dict(lb=0.0, ub=1.0, n=2, B=[(0, 0, 1.0)], A=[(0, 0, 1.0)], x=1.0),
+    "test2": dict(lb=0.0, ub=1.5, n=2, B=[(0, 0, 1.0), (1, 1, -1.0)], A=[(0, 0, 1.0), (1, 1, -1.0)], x=1.0),
+    "test3": dict(lb=0.0, ub=2.0, n=2, B=[(0, 0, 1.0), (1, 1, -0.99)], A=[(0, 0, 1.0), (1, 1, -1.0)], x=None),
+    "test4": dict(lb=0.0, ub=2.0, n=2, B=[(0, 0, 0.89496), (1, 0, -0.44498), (1, 1, -0.88496)],
+                  A=[(0, 0, 0.89443), (1, 0, -0.44721), (1, 1, -0.89443)], x=None),
+    "test5": dict(lb=0.0, ub=2.0, n=2, B=[(0, 0, -2.0), (1, 0, 1.0), (1, 1, 3.0)], A=[(0, 0, 1.0), (1, 0, -2.0), (1, 1, 5.0)], x=1.541381),
+}
+
+
+@needs_ref
+@pytest.mark.parametrize("name", sorted(CHECK1D))
+def test_check1dsdp_known_answers(lib, name):
+    """the five known answers of unittests/src/check1dsdp.c: (a) the reference's own SCIPsolveOneVarSDP (solveonevarsdp.c,
+    compiled in place; the shortcut sdpi.c takes for one-variable problems), (b) where the problem has an interior, the same
+    answer from the interior-point oracle through the C ABI (this is what the GPU path is compared with)"""
+    import ctypes as C
+    c = CHECK1D[name]
+    L = lib.lib
+    _dp, _ip = C.POINTER(C.c_double), C.POINTER(C.c_int)
+    L.SCIPsolveOneVarSDP.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_int, C.c_int, _ip, _ip, _dp, C.c_int, _ip, _ip, _dp,
+                                     C.c_double, C.c_double, _dp, _dp, _dp, _dp]
+    buf = C.c_void_p(L.BMScreateBufferMemory(1.2, 4, 0))
+
+    def arrs(ents):
+        r = (C.c_int * len(ents))(*[e[0] for e in ents]); cc = (C.c_int * len(ents))(*[e[1] for e in ents])
+        v = (C.c_double * len(ents))(*[e[2] for e in ents])
+        return len(ents), r, cc, v
+    nb, br, bc, bv = arrs(c["B"])
+    na, ar, ac, av = arrs(c["A"])
+    objval, optval = C.c_double(0), C.c_double(0)
+    rc = L.SCIPsolveOneVarSDP(buf, 1.0, c["lb"], c["ub"], c["n"], nb, br, bc, bv, na, ar, ac, av, 1e20, 1e-6, None, None,
+                              C.byref(objval), C.byref(optval))
+    assert rc == sdpi_ref.SCIP_OKAY
+    L.BMSdestroyBufferMemory(C.byref(buf))
+    if c["x"] is None:
+        assert objval.value >= 1e20                        # infeasible (check1dsdp.c:306, 334)
+    else:
+        assert abs(optval.value - c["x"]) <= 1e-6
+    # (b) the same problem through the interior-point oracle
+    M = misdp.Misdp(1, [1.0], [c["n"]])
+    M.A[0][0] = list(c["A"]); M.C[0] = list(c["B"])
+    M.lb[0], M.ub[0] = c["lb"], c["ub"]
+    fp, _ = M.flatten()
+    r = abi.Solver(abi.Lib(abi.ORACLE_LIB)).solve(fp, gaptol=1e-8, feastol=1e-8)
+    if name == "test5":
+        assert r["phase_name"] == "pdOPT" and abs(r["y"][0] - c["x"]) <= 1e-5
+    elif c["x"] is None:
+        assert r["phase_name"] in ("pFEAS_dINF", "dINF", "noINFO", "pFEAS")        # never reported optimal
