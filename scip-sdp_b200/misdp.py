@@ -202,82 +202,146 @@ def _tokens(line):
     return line.split()
 
 
+class SdpaFormatError(ValueError):
+    """malformed extended-SDPA file (what reader_sdpa.c answers with SCIP_READERROR)"""
+
+
+def _numbers(line, what, lineno, count=None, integer=False):
+    """leading numbers of a header line; the rest of the line (after '=', '*' or '"') is a comment like in the shipped instances"""
+    for ch in '=*"':
+        line = line.split(ch)[0]
+    out = []
+    for t in _tokens(line):
+        try:
+            out.append(int(t) if integer else float(t))
+        except ValueError:
+            raise SdpaFormatError(f"line {lineno}: invalid symbol '{t}' in {what}") from None
+    if count is not None and len(out) != count:
+        raise SdpaFormatError(f"line {lineno}: expected {count} value(s) for {what}, found {len(out)}")
+    return out
+
+
 def read_sdpa(path):
+    """Reader for the extended SDPA format of SCIP-SDP (sdpa_format.txt; checks as in src/scipsdp/reader_sdpa.c:500-1660, whose
+    malformed unit-test files unittests/instances/*.dat-s must be rejected): 1-based indices, one LP block given by a negative
+    block size with the linear constraints on its diagonal, `*INTEGER` then `*RANK1` sections, indicator entries (variable -k)."""
     opener = gzip.open if str(path).endswith(".gz") else open
     with opener(path, "rt") as f:
         lines = f.read().splitlines()
-    header = []
     k = 0
-    # header: nvars, nblocks, block sizes, objective — comment lines start with '*' or '"'
-    while len(header) < 2:
-        s = lines[k].strip(); k += 1
-        if not s or s[0] in '*"':
-            continue
-        header.append(int(_tokens(s)[0]))
-    nvars, nblocks = header
-    sizes = []
-    while len(sizes) < nblocks:
-        s = lines[k].strip(); k += 1
-        if not s or s[0] in '*"':
-            continue
-        for t in _tokens(s):
-            if len(sizes) < nblocks:
-                try:
-                    sizes.append(int(float(t)))
-                except ValueError:
-                    break
-    obj = []
-    while len(obj) < nvars:
-        s = lines[k].strip(); k += 1
-        if not s or s[0] in '*"':
-            continue
-        for t in _tokens(s):
-            if len(obj) < nvars:
-                try:
-                    obj.append(float(t))
-                except ValueError:
-                    break
+
+    def next_data_line(what):
+        nonlocal k
+        while k < len(lines):
+            s = lines[k].strip(); k += 1
+            if s and s[0] not in '*"':
+                return s, k
+        raise SdpaFormatError(f"unexpected end of file while reading {what}")
+
+    s, ln = next_data_line("the number of variables")
+    nvars = _numbers(s, "the number of variables", ln, integer=True)[:1]
+    if not nvars or nvars[0] < 0:
+        raise SdpaFormatError(f"line {ln}: the number of variables must be a non-negative integer")
+    nvars = nvars[0]
+    s, ln = next_data_line("the number of blocks")
+    nblocks = _numbers(s, "the number of blocks", ln, integer=True)[:1]
+    if not nblocks or nblocks[0] < 0:
+        raise SdpaFormatError(f"line {ln}: the number of blocks must be a non-negative integer")
+    nblocks = nblocks[0]
+    s, ln = next_data_line("the block sizes")
+    sizes = _numbers(s, "the block sizes", ln, count=nblocks, integer=True)
+    if any(n == 0 for n in sizes):
+        raise SdpaFormatError(f"line {ln}: a block size of 0 is not valid")
+    if sum(1 for n in sizes if n < 0) > 1:
+        raise SdpaFormatError(f"line {ln}: only one LP block can be defined")
+    s, ln = next_data_line("the objective")
+    obj = _numbers(s, "the objective coefficients", ln, count=nvars)
     sdpidx = [b for b, n in enumerate(sizes) if n > 0]
     lpidx = [b for b, n in enumerate(sizes) if n < 0]
+    nlin = -sizes[lpidx[0]] if lpidx else 0
     bmap = {b: i for i, b in enumerate(sdpidx)}
     M = Misdp(nvars, obj, [sizes[b] for b in sdpidx])
     lprows = {}
+    lpcoefs = [0] * nlin
+    blocknnz = [0] * len(sdpidx)
     indrows = []
     section = None
-    for s in lines[k:]:
-        s = s.strip()
+    for ln, raw in enumerate(lines[k:], start=k + 1):
+        s = raw.strip()
         if not s:
             continue
-        if s[0] == '*':
-            up = s.upper()
-            if up.startswith("*INTEGER"):
-                section = "int"
-            elif up.startswith("*RANK1"):
-                section = "rank1"
-            elif section is not None and len(s) > 1 and s[1:].strip().split()[0].isdigit():
-                idx = int(s[1:].strip().split()[0]) - 1
-                if section == "int":
-                    M.integer[idx] = True
-                else:
-                    M.rank1.append(bmap[idx])
+        up = s.upper()
+        if up.startswith("*INTEGER"):
+            if section == "rank1":
+                raise SdpaFormatError(f"line {ln}: the integer section has to be in front of the rank-1 section")
+            section = "int"
             continue
-        t = _tokens(s.split('*')[0])
+        if up.startswith("*RANK1"):
+            section = "rank1"
+            continue
+        if section is not None:
+            # inside a section every entry is '*<index>'
+            if s[0] != '*':
+                raise SdpaFormatError(f"line {ln}: expected '*' at the beginning of the line in the {section.upper()} section")
+            tok = s[1:].split()
+            if not tok or not tok[0].lstrip("+-").isdigit():
+                raise SdpaFormatError(f"line {ln}: could not read the index in the {section.upper()} section")
+            idx = int(tok[0]) - 1
+            if section == "int":
+                if idx < 0 or idx >= nvars:
+                    raise SdpaFormatError(f"line {ln}: integrality given for variable {idx + 1} which does not exist")
+                M.integer[idx] = True
+            else:
+                if idx in lpidx:
+                    raise SdpaFormatError(f"line {ln}: rank-1 given for the LP block")
+                if idx not in bmap:
+                    raise SdpaFormatError(f"line {ln}: rank-1 given for SDP block {idx + 1} which does not exist")
+                M.rank1.append(bmap[idx])
+            continue
+        if s[0] in '*"':
+            continue                                  # comment line
+        t = _numbers(s, "a block entry", ln)
         if len(t) < 5:
-            continue
+            raise SdpaFormatError(f"line {ln}: could not read block entry (variable block row column value)")
+        if any(x != int(x) for x in t[:4]):
+            raise SdpaFormatError(f"line {ln}: indices of a block entry must be integers")
         j, b, r, c, v = int(t[0]) - 1, int(t[1]) - 1, int(t[2]) - 1, int(t[3]) - 1, float(t[4])
         if b in bmap:
+            n = sizes[b]
+            if j < -1 or j >= nvars:
+                raise SdpaFormatError(f"line {ln}: coefficient for variable {j + 1} which does not exist")
+            if r < 0 or r >= n or c < 0 or c >= n:
+                raise SdpaFormatError(f"line {ln}: row/column index outside the block of size {n}")
             M.add_entry(j, bmap[b], r, c, v)
-        else:
-            assert b in lpidx and r == c, "LP block entries must be diagonal"
+            if j >= 0:
+                blocknnz[bmap[b]] += 1
+        elif b in lpidx:
+            if j >= nvars:
+                raise SdpaFormatError(f"line {ln}: linear coefficient for variable {j + 1} which does not exist")
+            if r != c:
+                raise SdpaFormatError(f"line {ln}: linear coefficient is not located on the diagonal of the LP block")
+            if r < 0 or r >= nlin:
+                raise SdpaFormatError(f"line {ln}: linear constraint {r + 1} does not exist")
             row = lprows.setdefault((b, r), [dict(), 0.0])
             if j < -1:
                 # indicator constraint (file index -k, k >= 2): variable k-1 becomes binary, the row gets a slack variable s >= 0
                 # and "variable = 1 => s = 0" (reader_sdpa.c:1195-1246; the value of the entry is not used there either)
+                if -j - 2 >= nvars:
+                    raise SdpaFormatError(f"line {ln}: indicator variable {-j - 1} does not exist")
                 indrows.append(((b, r), -j - 2))
             elif j < 0:
                 row[1] = v
             else:
                 row[0][j] = row[0].get(j, 0.0) + v
+                lpcoefs[r] += 1
+        else:
+            raise SdpaFormatError(f"line {ln}: coefficient for block {b + 1} which does not exist")
+    for i, cnt in enumerate(blocknnz):
+        if cnt == 0:
+            raise SdpaFormatError(f"SDP block {sdpidx[i] + 1} does not contain any nonzero entries")
+    for r, cnt in enumerate(lpcoefs):
+        if cnt == 0:
+            raise SdpaFormatError(f"linear constraint {r + 1} does not contain nonzero entries")
     for key, z in indrows:
         sl = M.add_variable(obj=0.0, lb=0.0)
         lprows[key][0][sl] = 1.0

@@ -146,3 +146,77 @@ def test_sdpa_indicator_entries():
     assert (M.lb[3], M.ub[3], M.lb[4]) == (0.0, 1.0, 0.0) and M.ub[4] >= 1e20
     rows_with_slack = [coefs for coefs, lhs, rhs in M.rows if 4 in coefs]
     assert len(rows_with_slack) == 1 and rows_with_slack[0][4] == 1.0
+
+
+# the defect classes of unittests/src/readerrors.c (28 malformed files in unittests/instances, each must give SCIP_READERROR),
+# re-created as edits of a small valid file: 3 variables, blocks (2, LP with 2 rows, 2), all integer, block 3 rank-1
+_VALID = """3
+3
+2 -2 2
+1 1 1
+1 1 1 1 1
+1 3 2 1 1
+1 2 1 1 1
+2 2 1 1 1
+3 2 1 1 1
+0 2 1 1 1
+1 2 2 2 -1
+2 2 2 2 -1
+3 2 2 2 -1
+0 2 2 2 -1
+*INTEGER
+*1
+*2
+*3
+*RANK1
+*3
+"""
+
+
+def _edit(old, new):
+    assert old in _VALID
+    return _VALID.replace(old, new, 1)
+
+
+_DEFECTS = {
+    "nvars_invalidsymb": _edit("3\n3\n", "?\n3\n"), "nvars_neg": _edit("3\n3\n", "-3\n3\n"),
+    "nblocks_invalidsymb": _edit("3\n3\n", "3\n?\n"), "nblocks_neg": _edit("3\n3\n", "3\n-3\n"),
+    "blocksizes_0": _edit("2 -2 2", "2 -2 0"), "blocksizes_invalidsymb": _edit("2 -2 2", "2 -2 ?"),
+    "blocksizes_LPblocks": _edit("2 -2 2", "2 -2 -2"), "blocksizes_toofew": _edit("2 -2 2", "2 -2"),
+    "objcoeff_invalidsymb": _edit("1 1 1\n1 1 1 1 1", "1 ? 1\n1 1 1 1 1"), "objcoeff_toofew": _edit("1 1 1\n1 1 1 1 1", "1 1\n1 1 1 1 1"),
+    "blocks_col": _edit("1 1 1 1 1", "1 1 1 3 1"), "blocks_row": _edit("1 1 1 1 1", "1 1 -1 1 1"), "blocks_var": _edit("1 1 1 1 1", "4 1 1 1 1"),
+    "blocks_sdpblock": _edit("1 1 1 1 1", "1 4 1 1 1"), "blocks_invalidline": _edit("1 1 1 1 1", "1 1 1 1"),
+    "blocks_SDPnononz": _edit("1 1 1 1 1\n", ""), "blocks_LPnononz": _edit("1 2 1 1 1\n2 2 1 1 1\n3 2 1 1 1\n0 2 1 1 1\n", ""),
+    "LPblock_LPcons": _edit("1 2 1 1 1", "1 2 3 3 1"), "LPblock_nondiag": _edit("1 2 1 1 1", "1 2 1 0 1"), "LPblock_var": _edit("1 2 1 1 1", "4 2 1 1 1"),
+    "int_invalid": _edit("*INTEGER\n*1", "*INTEGER\n*"), "int_noast": _edit("*INTEGER\n*1", "*INTEGER\n1"), "int_var": _edit("*2\n*3\n*RANK1", "*2\n*4\n*RANK1"),
+    "rnk1_before_int": "\n".join(_VALID.splitlines()[:14] + ["*RANK1", "*1", "*INTEGER", "*1", "*2", "*3"]) + "\n",
+    "rnk1_block": _edit("*RANK1\n*3", "*RANK1\n*4"), "rnk1_forLP": _edit("*RANK1\n*3", "*RANK1\n*2"),
+    "rnk1_invalid": _edit("*RANK1\n*3", "*RANK1\n*"), "rnk1_noast": _edit("*RANK1\n*3", "*RANK1\n3"),
+}
+
+
+def test_valid_base_file_of_the_defect_tests(tmp_path):
+    p = tmp_path / "valid.dat-s"
+    p.write_text(_VALID)
+    M = misdp.read_sdpa(p)
+    assert M.nvars == 3 and M.blocksizes == [2, 2] and len(M.rows) == 2 and M.integer.all() and M.rank1 == [1]
+
+
+@pytest.mark.parametrize("defect", sorted(_DEFECTS))
+def test_malformed_sdpa_files_are_rejected(tmp_path, defect):
+    assert len(_DEFECTS) == 28
+    p = tmp_path / (defect + ".dat-s")
+    p.write_text(_DEFECTS[defect])
+    with pytest.raises(misdp.SdpaFormatError):
+        misdp.read_sdpa(p)
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/unittests/instances"), reason="reference tree not present")
+def test_reference_malformed_files_are_rejected():
+    """the reference's own 28 malformed files (unittests/src/readerrors.c) where the reference tree is available"""
+    import glob
+    files = [f for f in sorted(glob.glob("/root/reference/unittests/instances/*.dat-s")) if "example_small" not in f]
+    assert len(files) == 28
+    for f in files:
+        with pytest.raises(misdp.SdpaFormatError):
+            misdp.read_sdpa(f)
