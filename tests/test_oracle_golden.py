@@ -212,14 +212,20 @@ def test_exhausted_time_limit_is_not_an_error(lib):
 
 @needs_ref
 @pytest.mark.parametrize("name,dual_expected", [("example_small.dat-s", 1), ("example_TT.dat-s.gz", 1), ("example_MkP.dat-s.gz", 1),
-                                                ("example_CLS.dat-s.gz", 1), ("example_inf.dat-s", -2)])
+                                                ("example_CLS.dat-s.gz", 1), ("example_inf.dat-s", 1), ("example_inf.dat-s:relaxation-infeasible", -2)])
 def test_slater_checks_of_the_reference_run_through_the_binding(lib, name, dual_expected):
     """SURVEY.md 8b invocation patterns (iv) and (v): sdpi.c's dual Slater check (penalty formulation, r free, no objective) and
     primal Slater check (LoadAndSolve without constant matrices, all sides 0, one extra LP row; sdpi.c:1518-1870) with
-    relaxing/SDP/slatercheck = 2: SCIP_SDPSLATER_HOLDS (1) for the feasible instances, SCIP_SDPSLATER_INF (-2) on the dual side
-    of example_inf; the main solve is unaffected"""
+    relaxing/SDP/slatercheck = 2: SCIP_SDPSLATER_HOLDS (1) for the instances with a strictly feasible relaxation (example_inf is
+    infeasible only in the integers: y1 y2 >= 4/3 with |y| <= sqrt 2), SCIP_SDPSLATER_INF (-2) on the dual side of a variant of
+    example_inf whose first block loses its constant entry (1,1) (then S_11 = 0 forces y1 = 0 and block 2 cannot be psd);
+    the main solve is unaffected"""
     import ctypes as C
+    name, _, variant = name.partition(":")
     M = misdp.read_instance(os.path.join(GOLDEN, name))
+    if variant:
+        assert M.C[0][0] == (0, 0, -1.0)
+        del M.C[0][0]
     s = sdpi_ref.Sdpi(lib, gaptol=1e-6, sdpsolverfeastol=1e-6, feastol=1e-6)
     try:
         s.load_model(M)
