@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define SDPCUDA_ABI_VERSION 3
+#define SDPCUDA_ABI_VERSION 4
 
 /* return codes of every entry point */
 #define SDPCUDA_OK            0
@@ -163,6 +163,16 @@ int  sdpcuda_dist_finalize(sdpcuda_handle* h);
 /* Same iteration on the problem that the last sdpcuda_solve left resident in HBM (no host->device traffic); used to
  * measure the device-only throughput and for repeated solves with changed tolerances. */
 int  sdpcuda_solve_resident(sdpcuda_handle* h, const sdpcuda_params* par, sdpcuda_result* res);
+
+/* ---- a frontier of independent node relaxations in one call (the open B&B nodes that SCIP-SDP's concurrent
+ * solver threads would each hand to SCIPsdpiSolverLoadAndSolve, sdpi.c:3399) ----
+ * hs[i] solves probs[i]; the handles must be distinct and live on the same device (one handle = one set of device buffers, so
+ * the getters of handle i return the solution of node i afterwards).  Every relaxation that fits the single-CTA kernel (blocks of
+ * order <= 64, m <= 256) is uploaded, and then ALL of them are solved by ONE kernel launch, one CTA (= one SM) per node; larger
+ * nodes are solved one after the other by the multi-kernel path.  Cold start for every node.  res: [count] or NULL.
+ * device_ms / seconds of the batched nodes are those of the whole batch (the nodes run side by side). */
+int  sdpcuda_solve_batch(int count, sdpcuda_handle* const* hs, const sdpcuda_problem* const* probs, const sdpcuda_params* par,
+                         sdpcuda_result* res);
 
 /* Per-kernel-class device timing of the NEXT solve (CUDA events around every launch of the class on the handle's
  * stream; adds a little overhead, so it is off by default).  After the solve sdpcuda_get_profile fills, for each class

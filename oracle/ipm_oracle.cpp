@@ -678,6 +678,23 @@ int sdpcuda_solve_resident(sdpcuda_handle* h, const sdpcuda_params* par, sdpcuda
    if( res != NULL ) *res = h->s.res;
    return rc;
 }
+/* checker-side stand-in of the frontier batch: the nodes one after the other */
+int sdpcuda_solve_batch(int count, sdpcuda_handle* const* hs, const sdpcuda_problem* const* probs, const sdpcuda_params* par,
+   sdpcuda_result* res)
+{
+   if( count < 0 || par == nullptr || (count > 0 && (hs == nullptr || probs == nullptr)) ) return SDPCUDA_ERR_ARG;
+   for( int i = 0; i < count; ++i )
+   {
+      if( hs[i] == nullptr || probs[i] == nullptr ) return SDPCUDA_ERR_ARG;
+      for( int k = 0; k < i; ++k ) if( hs[k] == hs[i] ) return SDPCUDA_ERR_ARG;
+   }
+   for( int i = 0; i < count; ++i )
+   {
+      int rc = sdpcuda_solve(hs[i], probs[i], par, nullptr, res != nullptr ? &res[i] : nullptr);
+      if( rc != SDPCUDA_OK ) return rc;
+   }
+   return SDPCUDA_OK;
+}
 int sdpcuda_set_profiling(sdpcuda_handle* h, int on) { (void)h; (void)on; return SDPCUDA_OK; }
 int sdpcuda_get_profile(sdpcuda_handle* h, double* out)
 {

@@ -107,6 +107,7 @@ class Lib:
         L.sdpcuda_default_params.restype = None
         L.sdpcuda_solve.argtypes = [C.c_void_p, C.POINTER(Problem), C.POINTER(Params), _dp, C.POINTER(Result)]
         L.sdpcuda_solve_resident.argtypes = [C.c_void_p, C.POINTER(Params), C.POINTER(Result)]
+        L.sdpcuda_solve_batch.argtypes = [C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.POINTER(Problem)), C.POINTER(Params), C.POINTER(Result)]
         L.sdpcuda_set_profiling.argtypes = [C.c_void_p, C.c_int]
         L.sdpcuda_get_profile.argtypes = [C.c_void_p, _dp]
         for f in ("sdpcuda_get_y", "sdpcuda_get_xlp", "sdpcuda_get_slp"):
@@ -138,6 +139,34 @@ class Lib:
         for k, v in kw.items():
             setattr(p, k, v)
         return p
+
+
+def solve_batch(solvers, probs, params=None, **kw):
+    """sdpcuda_solve_batch: solvers[i] (distinct handles of ONE library on one device) solves probs[i]; all relaxations that fit the
+    single-CTA kernel run in one launch, one CTA per node.  Returns one result dict per node; the getters of solvers[i] serve
+    node i afterwards."""
+    n = len(probs)
+    if n == 0:
+        return []
+    if len(solvers) < n:
+        raise ValueError(f"{n} nodes need {n} solver handles, got {len(solvers)}")
+    lib = solvers[0].L
+    params = params if params is not None else lib.default_params(**kw)
+    structs = [p.struct() for p in probs]
+    hs = (C.c_void_p * n)(*[s.h for s in solvers[:n]])
+    ps = (C.POINTER(Problem) * n)(*[C.pointer(st) for st in structs])
+    res = (Result * n)()
+    for s, p in zip(solvers, probs):
+        s.prob = p
+    rc = lib.lib.sdpcuda_solve_batch(n, hs, ps, C.byref(params), res)
+    if rc != 0:
+        raise RuntimeError(f"sdpcuda_solve_batch failed with code {rc}")
+    out = []
+    for r in res:
+        d = {f[0]: getattr(r, f[0]) for f in Result._fields_}
+        d["phase_name"], d["stop_name"] = PHASES[r.phase], STOPS[r.stop]
+        out.append(d)
+    return out
 
 
 class Solver:

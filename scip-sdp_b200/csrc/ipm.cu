@@ -102,6 +102,8 @@ struct sdpcuda_handle
    DBuf<int> patcol, patrow;          // column-wise pattern of sum_j y_j A_j - C (+ diagonal) per block, if sparse
    std::vector<long long> patcoloff, patrowoff;   // per block offsets into patcol / patrow (-1: block is treated as dense)
    DBuf<SmallResult> smallres;
+   DBuf<SmallArgs> batchargs;        // descriptors of a frontier batch (sdpcuda_solve_batch; held by the first handle of the batch)
+   DBuf<SmallResult> batchres;
    int force_path = 0;               // 0 auto, 1 always multi-kernel, 2 always single-CTA (tests)
    DBuf<LzDesc> lzdesc;
    DBuf<unsigned> lztickets;
@@ -799,7 +801,7 @@ int sdpcuda_destroy(sdpcuda_handle* h)
       bf->release();
    for( DBuf<long long>* bf : {&h->eoff, &h->pos, &h->mirror, &h->cpos, &h->cmirror} )
       bf->release();
-   h->lzdesc.release(); h->lztickets.release(); h->lzpart.release(); h->smallres.release();
+   h->lzdesc.release(); h->lztickets.release(); h->lzpart.release(); h->smallres.release(); h->batchargs.release(); h->batchres.release();
    h->LinvT.release(); h->LXinvT.release(); h->pinv.release(); h->pinvT.release();
    for( cudaEvent_t& e : h->evp ) if( e != nullptr ) { cudaEventDestroy(e); e = nullptr; }
    h->preX.release(); h->prey.release(); h->prex.release();
@@ -865,7 +867,10 @@ static void host_constants(sdpcuda_handle* h, const sdpcuda_problem* P)
    h->xil = xil; h->etal = etal;
 }
 
-static int run_ipm(sdpcuda_handle* h, const sdpcuda_params* par, const double* start_y, sdpcuda_result* res, double t0);
+// defer != nullptr (frontier batch): a relaxation that fits the single-CTA kernel is only PREPARED (initial point on the device,
+// descriptor in *defer, *deferred = true) and launched by the caller together with the other nodes; anything else is solved here
+static int run_ipm(sdpcuda_handle* h, const sdpcuda_params* par, const double* start_y, sdpcuda_result* res, double t0,
+   SmallArgs* defer = nullptr, bool* deferred = nullptr);
 
 int sdpcuda_solve(sdpcuda_handle* h, const sdpcuda_problem* P, const sdpcuda_params* par, const double* start_y, sdpcuda_result* res)
 {
@@ -897,6 +902,78 @@ int sdpcuda_solve_resident(sdpcuda_handle* h, const sdpcuda_params* par, sdpcuda
    return run_ipm(h, par, nullptr, res, t0);
 }
 
+int sdpcuda_solve_batch(int count, sdpcuda_handle* const* hs, const sdpcuda_problem* const* probs, const sdpcuda_params* par,
+   sdpcuda_result* res)
+{
+   if( count < 0 || par == nullptr || (count > 0 && (hs == nullptr || probs == nullptr)) ) return SDPCUDA_ERR_ARG;
+   if( count == 0 ) return SDPCUDA_OK;
+   for( int i = 0; i < count; ++i )
+   {
+      if( hs[i] == nullptr || probs[i] == nullptr || probs[i]->m <= 0 || hs[i]->device != hs[0]->device ) return SDPCUDA_ERR_ARG;
+      for( int k = 0; k < i; ++k ) if( hs[k] == hs[i] ) return SDPCUDA_ERR_ARG;      // one handle (= one set of device buffers) per node
+   }
+   const double t0 = now_seconds();
+   std::vector<SmallArgs> args;
+   std::vector<int> who;
+   std::vector<double> h2d(count, 0.0);
+   args.reserve(count); who.reserve(count);
+   for( int i = 0; i < count; ++i )
+   {
+      sdpcuda_handle* h = hs[i];
+      int rc = set_device(h);
+      if( rc != SDPCUDA_OK ) return rc;
+      h->solved = false; h->resident = false; h->counter.n = 0;
+      g_h2d_bytes = 0.0;
+      rc = upload_problem(h, probs[i]);
+      if( rc != SDPCUDA_OK ) return rc;
+      host_constants(h, probs[i]);
+      h->resident = true;
+      SmallArgs a;
+      bool deferred = false;
+      sdpcuda_result R;
+      memset(&R, 0, sizeof(R));
+      rc = run_ipm(h, par, nullptr, &R, now_seconds(), &a, &deferred);
+      if( rc != SDPCUDA_OK ) return rc;
+      h2d[i] = g_h2d_bytes;
+      if( deferred ) { args.push_back(a); who.push_back(i); }
+      else if( res != nullptr ) res[i] = R;          // too large for one CTA: solved on its own by the multi-kernel path
+   }
+   if( args.empty() ) return SDPCUDA_OK;
+   // ---- one launch for all prepared nodes: CTA k works on the buffers of handle who[k]; every handle's stream is idle here
+   sdpcuda_handle* lead = hs[who[0]];
+   int rc = set_device(lead);
+   if( rc != SDPCUDA_OK ) return rc;
+   const int nd = (int)args.size();
+   CK( lead->batchargs.ensure(nd) );
+   CK( lead->batchres.ensure(nd) );
+   for( int k = 0; k < nd; ++k ) args[k].out = lead->batchres.p + k;
+   CK( cudaMemcpyAsync(lead->batchargs.p, args.data(), sizeof(SmallArgs) * nd, cudaMemcpyHostToDevice, lead->st) );
+   CK( cudaEventRecord(lead->ev0, lead->st) );
+   CK( launch_ipm_small_batch(lead->st, nd, lead->batchargs.p) );
+   CK( cudaEventRecord(lead->ev1, lead->st) );
+   std::vector<SmallResult> sr(nd);
+   CK( cudaMemcpyAsync(sr.data(), lead->batchres.p, sizeof(SmallResult) * nd, cudaMemcpyDeviceToHost, lead->st) );
+   CK( cudaStreamSynchronize(lead->st) );
+   float ms = 0.f;
+   cudaEventElapsedTime(&ms, lead->ev0, lead->ev1);
+   const double wall = now_seconds() - t0;
+   for( int k = 0; k < nd; ++k )
+   {
+      sdpcuda_handle* h = hs[who[k]];
+      h->solved = true;
+      if( res == nullptr ) continue;
+      sdpcuda_result R;
+      memset(&R, 0, sizeof(R));
+      R.phase = sr[k].phase; R.stop = sr[k].stop; R.iterations = sr[k].iterations;
+      R.launches = (int)std::min<long long>(h->counter.n, 2147483647LL);      // initial-point kernels; the lead handle also counts the batch launch
+      R.pobj = sr[k].pobj; R.dobj = sr[k].dobj; R.relgap = sr[k].relgap; R.pinf = sr[k].pinf; R.dinf = sr[k].dinf; R.mu = sr[k].mu;
+      R.seconds = wall; R.device_ms = ms;            // of the whole batch: the nodes ran side by side
+      R.h2d_bytes = h2d[who[k]] + sizeof(SmallArgs); R.d2h_bytes = sizeof(SmallResult);
+      res[who[k]] = R;
+   }
+   return SDPCUDA_OK;
+}
+
 int sdpcuda_set_profiling(sdpcuda_handle* h, int on)
 {
    if( h == nullptr ) return SDPCUDA_ERR_ARG;
@@ -912,7 +989,8 @@ int sdpcuda_get_profile(sdpcuda_handle* h, double* out)
    return SDPCUDA_OK;
 }
 
-static int run_ipm(sdpcuda_handle* h, const sdpcuda_params* par, const double* start_y, sdpcuda_result* res, double t0)
+static int run_ipm(sdpcuda_handle* h, const sdpcuda_params* par, const double* start_y, sdpcuda_result* res, double t0,
+   SmallArgs* defer, bool* deferred)
 {
    int rc = SDPCUDA_OK;
    cudaStream_t st = h->st;
@@ -1000,7 +1078,8 @@ static int run_ipm(sdpcuda_handle* h, const sdpcuda_params* par, const double* s
          for( const auto& g : h->dgroups ) if( g.count > h->dchunk ) eligible = false;
       // measured on the shipped instances: the one-launch kernel wins while the Schur complement is small (m <= 64); above that
       // the serial Cholesky of M inside a single CTA loses against the multi-kernel pipeline
-      if( eligible && force != 1 && (force == 2 || m <= 64) )
+      // inside a frontier batch every CTA has an SM of its own, so the single-CTA kernel is taken whenever the relaxation fits
+      if( eligible && force != 1 && (force == 2 || m <= 64 || defer != nullptr) )
       {
          SmallArgs a;
          memset(&a, 0, sizeof(a));
@@ -1036,6 +1115,12 @@ static int run_ipm(sdpcuda_handle* h, const sdpcuda_params* par, const double* s
          a.gaptol = gaptol; a.feastol = feastol; a.absgaptol = par->absgaptol; a.objlimit = par->objlimit;
          a.normb = normb; a.normC = normC; a.normCsdp2 = normCsdp2; a.gammabase = gammabase;
          a.out = h->smallres.p;
+         if( defer != nullptr )
+         {
+            *defer = a;
+            *deferred = true;
+            return SDPCUDA_OK;
+         }
          CK( cudaEventRecord(h->ev0, st) );
          CK( launch_ipm_small(st, a) );
          CK( cudaEventRecord(h->ev1, st) );

@@ -624,8 +624,8 @@ __device__ void solveM_smem(int m, const double* Ms, const double* rdiag, double
    __syncthreads();
 }
 
-__global__ void __launch_bounds__(NT, 1)
-ipm_small_kernel(const SmallArgs a)
+// the complete solve of ONE relaxation by the calling CTA (shared by the one-relaxation kernel and the frontier-batch kernel)
+__device__ __forceinline__ void ipm_small_body(const SmallArgs& a)
 {
    extern __shared__ __align__(16) double smem[];
    double* sh = smem;                               // 64 x 65
@@ -977,21 +977,58 @@ ipm_small_kernel(const SmallArgs a)
    }
 }
 
+__global__ void __launch_bounds__(NT, 1)
+ipm_small_kernel(const SmallArgs a)
+{
+   ipm_small_body(a);
+}
+
+// frontier batch: CTA i solves the relaxation described by all[i] (its own device buffers); the descriptor is staged in shared
+// memory once, the CTAs never communicate
+__global__ void __launch_bounds__(NT, 1)
+ipm_small_batch_kernel(const SmallArgs* __restrict__ all)
+{
+   __shared__ SmallArgs sa;
+   static_assert(sizeof(SmallArgs) % sizeof(int) == 0, "descriptor is copied in 4-byte words");
+   const int* src = reinterpret_cast<const int*>(all + blockIdx.x);
+   int* dst = reinterpret_cast<int*>(&sa);
+   for( int i = threadIdx.x; i < (int)(sizeof(SmallArgs) / sizeof(int)); i += NT ) dst[i] = src[i];
+   __syncthreads();
+   ipm_small_body(sa);
+}
+
+constexpr size_t SMALL_SMEM = (2 * SMALL_MAX_N * LDS + 32 + SMALL_MAX_N + SMALL_MAX_M + 3 * SMALL_LZ_STEPS + 8 + 2 * (SMALL_LZ_STEPS + 2) * LDS
+   + 2 * (2 * SMALL_LZ_STEPS + 64) + SMALL_MAX_N * LDS + 8) * sizeof(double) + sizeof(Ctl) + 64;
+
 } // namespace
 
 cudaError_t launch_ipm_small(cudaStream_t st, const SmallArgs& a)
 {
-   const size_t smem = (2 * SMALL_MAX_N * LDS + 32 + SMALL_MAX_N + SMALL_MAX_M + 3 * SMALL_LZ_STEPS + 8 + 2 * (SMALL_LZ_STEPS + 2) * LDS
-      + 2 * (2 * SMALL_LZ_STEPS + 64) + SMALL_MAX_N * LDS + 8) * sizeof(double) + sizeof(Ctl) + 64;
    static bool configured[64] = {false};
    int dev = 0;
    SDPK_CUDA_CHECK( cudaGetDevice(&dev) );
    if( !configured[dev & 63] )
    {
-      SDPK_CUDA_CHECK( cudaFuncSetAttribute(ipm_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) );
+      SDPK_CUDA_CHECK( cudaFuncSetAttribute(ipm_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMALL_SMEM) );
       configured[dev & 63] = true;
    }
-   ipm_small_kernel<<<1, NT, smem, st>>>(a);
+   ipm_small_kernel<<<1, NT, SMALL_SMEM, st>>>(a);
+   count_launch();
+   return cudaGetLastError();
+}
+
+cudaError_t launch_ipm_small_batch(cudaStream_t st, int count, const SmallArgs* dev_args)
+{
+   static bool configured[64] = {false};
+   int dev = 0;
+   if( count <= 0 ) return cudaSuccess;
+   SDPK_CUDA_CHECK( cudaGetDevice(&dev) );
+   if( !configured[dev & 63] )
+   {
+      SDPK_CUDA_CHECK( cudaFuncSetAttribute(ipm_small_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMALL_SMEM) );
+      configured[dev & 63] = true;
+   }
+   ipm_small_batch_kernel<<<count, NT, SMALL_SMEM, st>>>(dev_args);
    count_launch();
    return cudaGetLastError();
 }

@@ -44,5 +44,7 @@ struct SmallArgs
 };
 
 cudaError_t launch_ipm_small(cudaStream_t st, const SmallArgs& a);
+// one launch for a whole frontier of small relaxations: CTA i solves dev_args[i] (device array of `count` descriptors)
+cudaError_t launch_ipm_small_batch(cudaStream_t st, int count, const SmallArgs* dev_args);
 
 } // namespace sdpk

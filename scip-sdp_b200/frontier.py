@@ -16,20 +16,69 @@ def flatten_nodes(model, node_bounds, world=1, rank=0):
     return {i: model.flatten(*node_bounds[i]) for i in partition(len(node_bounds), world, rank)}
 
 
-def solve_frontier(solver, model, node_bounds, dist=None, flat=None, **solve_kw):
+def _solve_nodes_batched(pool, todo, solve_kw):
+    """chunks of len(pool) nodes through sdpcuda_solve_batch: one kernel launch per chunk, one CTA per node (relaxations that fit
+    the single-CTA kernel; others are solved one by one inside the call)"""
+    from . import abi
+    out = {}
+    for c in range(0, len(todo), len(pool)):
+        chunk = todo[c:c + len(pool)]
+        res = abi.solve_batch(pool, [fp for _, fp, _ in chunk], **solve_kw)
+        for (i, _, info), r in zip(chunk, res):
+            out[i] = dict(status=r["phase_name"], bound=float(r["dobj"] + info["fixedobj"]), iterations=int(r["iterations"]))
+    return out
+
+
+def _solve_nodes_threaded(pool, todo, solve_kw):
+    """one host thread per handle (what SCIP's concurrent solver threads do through SCIPsdpiSolverCreate): the handles own
+    their streams, so the latency-bound kernel chains of different nodes overlap on the device; ctypes releases the GIL"""
+    import threading
+    out, errors = {}, []
+
+    def work(k):
+        try:
+            for i, fp, info in todo[k::len(pool)]:
+                r = pool[k].solve(fp, fetch=False, **solve_kw)
+                out[i] = dict(status=r["phase_name"], bound=float(r["dobj"] + info["fixedobj"]), iterations=int(r["iterations"]))
+        except Exception as e:                       # noqa: BLE001 - re-raised on the calling thread
+            errors.append(e)
+
+    threads = [threading.Thread(target=work, args=(k,)) for k in range(min(len(pool), len(todo)))]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    if errors:
+        raise errors[0]
+    return out
+
+
+def solve_frontier(solver, model, node_bounds, dist=None, flat=None, pool=None, mode="serial", **solve_kw):
     """solver: scip_sdp_b200.abi.Solver bound to this rank's device; node_bounds: list of (lb, ub) arrays, identical on all ranks;
-    flat: optional result of flatten_nodes for this rank.  Returns a list with one dict(status, bound) per node (complete on every rank)."""
+    flat: optional result of flatten_nodes for this rank.  pool: further handles on the same device for mode "batch" (all nodes
+    of a chunk in one kernel launch, sdpcuda_solve_batch) or "threads" (one host thread and stream per handle); mode "serial"
+    solves the nodes one after the other on `solver`.  Returns a list with one dict(status, bound) per node (complete on every rank)."""
     world = dist.get_world_size() if dist is not None and dist.is_initialized() else 1
     rank = dist.get_rank() if world > 1 else 0
-    mine = {}
+    mine, todo = {}, []
     for i in partition(len(node_bounds), world, rank):
         lb, ub = node_bounds[i]
         fp, info = flat[i] if flat is not None else model.flatten(lb, ub)
         if fp.m == 0:
             mine[i] = dict(status="allfixed", bound=float(info["fixedobj"]))
             continue
-        r = solver.solve(fp, fetch=False, **solve_kw)
-        mine[i] = dict(status=r["phase_name"], bound=float(r["dobj"] + info["fixedobj"]), iterations=int(r["iterations"]))
+        todo.append((i, fp, info))
+    if mode not in ("serial", "batch", "threads"):
+        raise ValueError(f"unknown frontier mode {mode!r}")
+    handles = [solver] + list(pool or [])
+    if mode == "batch":
+        mine.update(_solve_nodes_batched(handles, todo, solve_kw))
+    elif mode == "threads" and len(handles) > 1:
+        mine.update(_solve_nodes_threaded(handles, todo, solve_kw))
+    else:
+        for i, fp, info in todo:
+            r = solver.solve(fp, fetch=False, **solve_kw)
+            mine[i] = dict(status=r["phase_name"], bound=float(r["dobj"] + info["fixedobj"]), iterations=int(r["iterations"]))
     if world == 1:
         return [mine[i] for i in range(len(node_bounds))]
     gathered = [None] * world

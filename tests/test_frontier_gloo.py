@@ -95,3 +95,42 @@ def test_frontier_world_size_2_matches_single_process():
         assert part == list(range(rank, 5, 2))
     # child bounds can only be worse (larger) than the root relaxation bound
     assert all(b >= expect[0][1] - 1e-6 for st, b in expect[1:] if st == "pdOPT")
+
+
+@pytest.mark.parametrize("mode", ["batch", "threads"])
+def test_frontier_modes_agree_with_serial(mode):
+    """the two ways of running several frontier nodes on ONE device at a time — sdpcuda_solve_batch (one launch, one CTA per node
+    on the GPU; the oracle's stand-in loops) and one host thread per handle — return exactly what the serial loop returns"""
+    M = misdp.read_sdpa(os.path.join(GOLDEN, "example_TT.dat-s.gz")).rows_to_bounds()
+    lib = abi.Lib(abi.ORACLE_LIB)
+    kw = dict(gaptol=1e-6, feastol=1e-6)
+    serial = frontier.solve_frontier(abi.Solver(lib), M, _nodes(M), **kw)
+    pool = [abi.Solver(lib) for _ in range(3)]             # fewer handles than nodes: chunks / strided work lists
+    got = frontier.solve_frontier(pool[0], M, _nodes(M), pool=pool[1:], mode=mode, **kw)
+    assert [(r["status"], r["bound"]) for r in got] == [(r["status"], r["bound"]) for r in serial]
+    with pytest.raises(ValueError):
+        frontier.solve_frontier(pool[0], M, _nodes(M), mode="nonsense", **kw)
+
+
+def test_solve_batch_boundary():
+    """argument checks of sdpcuda_solve_batch (include/sdpcuda.h) and the per-handle getters after a batch"""
+    import ctypes as C
+    M = misdp.read_sdpa(os.path.join(GOLDEN, "example_small.dat-s"))
+    lib = abi.Lib(abi.ORACLE_LIB)
+    nodes = [M.flatten(lb, ub)[0] for lb, ub in _nodes(M)]
+    solvers = [abi.Solver(lib) for _ in nodes]
+    res = abi.solve_batch(solvers, nodes, gaptol=1e-6, feastol=1e-6)
+    ref = abi.Solver(lib)
+    for s, fp, r in zip(solvers, nodes, res):
+        q = ref.solve(fp, gaptol=1e-6, feastol=1e-6)
+        assert r["phase_name"] == q["phase_name"] and r["dobj"] == q["dobj"]
+        assert np.array_equal(s.get_y(), q["y"]) and np.array_equal(s.get_X(0), q["X"][0])
+    assert abi.solve_batch(solvers, []) == []
+    with pytest.raises(ValueError):
+        abi.solve_batch(solvers[:2], nodes)                # fewer handles than nodes
+    with pytest.raises(RuntimeError):
+        abi.solve_batch([solvers[0], solvers[0]], nodes[:2])    # the same handle twice: SDPCUDA_ERR_ARG
+    par = lib.default_params()
+    assert lib.lib.sdpcuda_solve_batch(-1, None, None, C.byref(par), None) == 1
+    assert lib.lib.sdpcuda_solve_batch(0, None, None, C.byref(par), None) == 0
+    assert lib.lib.sdpcuda_solve_batch(2, None, None, C.byref(par), None) == 1
