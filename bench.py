@@ -16,6 +16,8 @@ independent-node-relaxation partition of the B&B frontier; no data-path collecti
 Further workloads (not the driver's default):
    --workload frontier-{tt500,cls,mkp60,mkp120}   B&B nodes/sec: a frontier of open nodes partitioned round-robin over the ranks
                                                    (upload + solve per node through the C ABI; weak scaling)
+   --workload frontier-example-{small,tt,cls,mkp} the same over nodes of the shipped instances (BASELINE configs 1-4); with
+                                                   --frontier-mode batch all nodes of a rank run in ONE launch, one CTA per node
    --workload sharded-{dense,maxcut,mkp120}       ONE relaxation over all N GPUs: Schur-complement shares per rank + one NCCL
                                                    all-reduce per iteration (strong scaling)
 """
@@ -43,9 +45,15 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--n", type=int, default=2000, help="max-cut order (2000 = the BASELINE configuration)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--workload", default="maxcut", choices=["maxcut", "frontier-tt500", "frontier-cls", "frontier-mkp120", "frontier-mkp60", "sharded-maxcut", "sharded-dense", "sharded-mkp120"],
+    ap.add_argument("--workload", default="maxcut", choices=["maxcut", "frontier-tt500", "frontier-cls", "frontier-mkp120", "frontier-mkp60",
+                                                             "frontier-example-small", "frontier-example-tt", "frontier-example-cls", "frontier-example-mkp",
+                                                             "sharded-maxcut", "sharded-dense", "sharded-mkp120"],
                     help="maxcut = the headline relaxation benchmark; frontier-* = B&B nodes/sec over a fixed frontier of node relaxations")
     ap.add_argument("--nodes-per-gpu", type=int, default=8)
+    ap.add_argument("--frontier-mode", default="serial", choices=["serial", "batch", "threads"],
+                    help="frontier workloads: nodes one after the other on one handle, all nodes of a chunk in ONE launch (sdpcuda_solve_batch, "
+                         "one CTA per node; for the shipped instances), or one host thread + stream per handle")
+    ap.add_argument("--handles-per-gpu", type=int, default=0, help="size of the handle pool of --frontier-mode batch/threads (default: 148 / 4)")
     return ap.parse_args()
 
 
@@ -116,23 +124,33 @@ def frontier_bench(a, rank, local, world):
         with stdout_to_stderr():
             dist.init_process_group("nccl", device_id=torch.device("cuda", local))
             dist.barrier()
+    from scip_sdp_b200 import misdp
+    golden = os.path.join(ROOT, "tests", "golden")
+    shipped = lambda f: (lambda: misdp.read_sdpa(os.path.join(golden, f)).rows_to_bounds())       # noqa: E731
     make = {"frontier-tt500": lambda: generators.truss(6, 6, 500, seed=1001), "frontier-cls": lambda: generators.cls(199, 99, 10, seed=2002),
-            "frontier-mkp120": lambda: generators.mkp(120, seed=3003), "frontier-mkp60": lambda: generators.mkp(60, seed=3003)}[a.workload]
+            "frontier-mkp120": lambda: generators.mkp(120, seed=3003), "frontier-mkp60": lambda: generators.mkp(60, seed=3003),
+            "frontier-example-small": shipped("example_small.dat-s"), "frontier-example-tt": shipped("example_TT.dat-s.gz"),
+            "frontier-example-cls": shipped("example_CLS.dat-s.gz"), "frontier-example-mkp": shipped("example_MkP.dat-s.gz")}[a.workload]
     M = make()
     nnodes = a.nodes_per_gpu * world
     q = max(1, int(np.ceil(np.log2(nnodes))))
-    ints = np.flatnonzero(M.integer)[:q]
+    ints = np.flatnonzero(M.integer)[:min(q, max(1, int(M.integer.sum()) - 1))]      # keep at least one variable free
     nodes = []
     for code in range(nnodes):
         lb, ub = M.lb.copy(), M.ub.copy()
         for b, j in enumerate(ints):
-            v = (code >> b) & 1
+            v = (code >> b) & 1                      # fewer integer variables than bits (example_small): the fixings repeat
             lb[j] = ub[j] = float(v)
         nodes.append((lb, ub))
     os.environ["SDPCUDA_DEVICE"] = str(local)
-    gpu = abi.Solver(abi.Lib(abi.PRODUCT_LIB), device=local)
-    kw = dict(gaptol=1e-5, feastol=1e-5)
-    frontier.solve_frontier(gpu, M, nodes[:world], dist=dist if world > 1 else None, **kw)      # warm-up
+    lib = abi.Lib(abi.PRODUCT_LIB)
+    gpu = abi.Solver(lib, device=local)
+    npool = 1 if a.frontier_mode == "serial" else (a.handles_per_gpu or (148 if a.frontier_mode == "batch" else 4))
+    npool = max(1, min(npool, a.nodes_per_gpu))
+    pool = [abi.Solver(lib, device=local) for _ in range(npool - 1)]
+    kw = dict(gaptol=1e-5, feastol=1e-5, pool=pool, mode=a.frontier_mode)
+    # warm-up: every handle of the pool sees one node of the final shapes (buffer allocation, kernel attributes, captured graphs)
+    frontier.solve_frontier(gpu, M, nodes[:world * npool], dist=dist if world > 1 else None, **kw)
     # the solver-form problems of this rank's nodes are marshalled before the clock starts (sdpi.c does this in C inside SCIP-SDP;
     # here it is Python); the timed region is upload + solve per node through the C ABI
     flat = frontier.flatten_nodes(M, nodes, world, rank)
@@ -147,12 +165,13 @@ def frontier_bench(a, rank, local, world):
         line = {"metric": "B&B nodes/sec", "value": nnodes / wall, "unit": "nodes/s", "n_gpus": world, "scaling": "weak", "dtype": "f64",
                 "data": "synthetic", "higher_is_better": True, "ms_per_node": 1e3 * wall * world / nnodes,
                 "config": {"workload": a.workload, "nodes": nnodes, "partition": "frontier nodes round-robin over ranks, no collective on the data path",
+                           "frontier_mode": a.frontier_mode, "handles_per_gpu": npool,
                            "instance": f"m = {M.nvars}, blocks = {M.blocksizes}, rows = {len(M.rows)}"},
                 "statuses": sorted({r["status"] for r in res}), "bounds_min_max": [min(r["bound"] for r in res), max(r["bound"] for r in res)]}
         if not a.no_cpu_baseline:
             cpu = abi.Solver(abi.Lib(abi.ORACLE_LIB))
             t1 = time.perf_counter()
-            rc = frontier.solve_frontier(cpu, M, nodes[:2], **kw)
+            rc = frontier.solve_frontier(cpu, M, nodes[:2], gaptol=1e-5, feastol=1e-5)
             dt = (time.perf_counter() - t1) / 2
             line["cpu_baseline"] = {"value": 1.0 / dt, "unit": "nodes/s", "cores": os.cpu_count(), "kind": "port",
                                     "sample": "the first 2 frontier nodes on the CPU oracle (OpenBLAS, all host threads)",
