@@ -53,7 +53,7 @@ def parse():
     ap.add_argument("--frontier-mode", default="serial", choices=["serial", "batch", "threads"],
                     help="frontier workloads: nodes one after the other on one handle, all nodes of a chunk in ONE launch (sdpcuda_solve_batch, "
                          "one CTA per node; for the shipped instances), or one host thread + stream per handle")
-    ap.add_argument("--handles-per-gpu", type=int, default=0, help="size of the handle pool of --frontier-mode batch/threads (default: 148 / 4)")
+    ap.add_argument("--handles-per-gpu", type=int, default=0, help="handles (host threads + streams) per GPU of --frontier-mode threads (default 4)")
     return ap.parse_args()
 
 
@@ -145,7 +145,7 @@ def frontier_bench(a, rank, local, world):
     os.environ["SDPCUDA_DEVICE"] = str(local)
     lib = abi.Lib(abi.PRODUCT_LIB)
     gpu = abi.Solver(lib, device=local)
-    npool = 1 if a.frontier_mode == "serial" else (a.handles_per_gpu or (148 if a.frontier_mode == "batch" else 4))
+    npool = (a.handles_per_gpu or 4) if a.frontier_mode == "threads" else 1
     npool = max(1, min(npool, a.nodes_per_gpu))
     pool = [abi.Solver(lib, device=local) for _ in range(npool - 1)]
     kw = dict(gaptol=1e-5, feastol=1e-5, pool=pool, mode=a.frontier_mode)

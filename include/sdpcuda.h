@@ -166,13 +166,14 @@ int  sdpcuda_solve_resident(sdpcuda_handle* h, const sdpcuda_params* par, sdpcud
 
 /* ---- a frontier of independent node relaxations in one call (the open B&B nodes that SCIP-SDP's concurrent
  * solver threads would each hand to SCIPsdpiSolverLoadAndSolve, sdpi.c:3399) ----
- * hs[i] solves probs[i]; the handles must be distinct and live on the same device (one handle = one set of device buffers, so
- * the getters of handle i return the solution of node i afterwards).  Every relaxation that fits the single-CTA kernel (blocks of
- * order <= 64, m <= 256) is uploaded, and then ALL of them are solved by ONE kernel launch, one CTA (= one SM) per node; larger
- * nodes are solved one after the other by the multi-kernel path.  Cold start for every node.  res: [count] or NULL.
- * device_ms / seconds of the batched nodes are those of the whole batch (the nodes run side by side). */
-int  sdpcuda_solve_batch(int count, sdpcuda_handle* const* hs, const sdpcuda_problem* const* probs, const sdpcuda_params* par,
-                         sdpcuda_result* res);
+ * Every relaxation that fits the single-CTA kernel (blocks of order <= 64, m <= 256, <= 16 blocks) is packed into one host image;
+ * the device sees ONE host->device copy, ONE kernel launch (one CTA = one SM per node, cold start set up by the CTA itself) and
+ * ONE device->host copy of the results and the y vectors for the whole batch.  Larger relaxations are solved one after the other
+ * by sdpcuda_solve on the same handle.  res: [count] or NULL; y_out: NULL or [count] pointers (each NULL or room for m_i doubles).
+ * The getters of the handle do not refer to batched nodes afterwards (the batch has its own device buffers).
+ * device_ms / seconds of the batched nodes are those of the whole batch (the nodes run side by side); launches = 1 on the first. */
+int  sdpcuda_solve_batch(sdpcuda_handle* h, int count, const sdpcuda_problem* const* probs, const sdpcuda_params* par,
+                         sdpcuda_result* res, double* const* y_out);
 
 /* Per-kernel-class device timing of the NEXT solve (CUDA events around every launch of the class on the handle's
  * stream; adds a little overhead, so it is off by default).  After the solve sdpcuda_get_profile fills, for each class

@@ -679,19 +679,16 @@ int sdpcuda_solve_resident(sdpcuda_handle* h, const sdpcuda_params* par, sdpcuda
    return rc;
 }
 /* checker-side stand-in of the frontier batch: the nodes one after the other */
-int sdpcuda_solve_batch(int count, sdpcuda_handle* const* hs, const sdpcuda_problem* const* probs, const sdpcuda_params* par,
-   sdpcuda_result* res)
+int sdpcuda_solve_batch(sdpcuda_handle* h, int count, const sdpcuda_problem* const* probs, const sdpcuda_params* par,
+   sdpcuda_result* res, double* const* y_out)
 {
-   if( count < 0 || par == nullptr || (count > 0 && (hs == nullptr || probs == nullptr)) ) return SDPCUDA_ERR_ARG;
+   if( h == nullptr || count < 0 || par == nullptr || (count > 0 && probs == nullptr) ) return SDPCUDA_ERR_ARG;
+   for( int i = 0; i < count; ++i ) if( probs[i] == nullptr || probs[i]->m <= 0 ) return SDPCUDA_ERR_ARG;
    for( int i = 0; i < count; ++i )
    {
-      if( hs[i] == nullptr || probs[i] == nullptr ) return SDPCUDA_ERR_ARG;
-      for( int k = 0; k < i; ++k ) if( hs[k] == hs[i] ) return SDPCUDA_ERR_ARG;
-   }
-   for( int i = 0; i < count; ++i )
-   {
-      int rc = sdpcuda_solve(hs[i], probs[i], par, nullptr, res != nullptr ? &res[i] : nullptr);
+      int rc = sdpcuda_solve(h, probs[i], par, nullptr, res != nullptr ? &res[i] : nullptr);
       if( rc != SDPCUDA_OK ) return rc;
+      if( y_out != nullptr && y_out[i] != nullptr ) { rc = sdpcuda_get_y(h, y_out[i]); if( rc != SDPCUDA_OK ) return rc; }
    }
    return SDPCUDA_OK;
 }

@@ -107,7 +107,7 @@ class Lib:
         L.sdpcuda_default_params.restype = None
         L.sdpcuda_solve.argtypes = [C.c_void_p, C.POINTER(Problem), C.POINTER(Params), _dp, C.POINTER(Result)]
         L.sdpcuda_solve_resident.argtypes = [C.c_void_p, C.POINTER(Params), C.POINTER(Result)]
-        L.sdpcuda_solve_batch.argtypes = [C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.POINTER(Problem)), C.POINTER(Params), C.POINTER(Result)]
+        L.sdpcuda_solve_batch.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.POINTER(Problem)), C.POINTER(Params), C.POINTER(Result), C.POINTER(_dp)]
         L.sdpcuda_set_profiling.argtypes = [C.c_void_p, C.c_int]
         L.sdpcuda_get_profile.argtypes = [C.c_void_p, _dp]
         for f in ("sdpcuda_get_y", "sdpcuda_get_xlp", "sdpcuda_get_slp"):
@@ -139,34 +139,6 @@ class Lib:
         for k, v in kw.items():
             setattr(p, k, v)
         return p
-
-
-def solve_batch(solvers, probs, params=None, **kw):
-    """sdpcuda_solve_batch: solvers[i] (distinct handles of ONE library on one device) solves probs[i]; all relaxations that fit the
-    single-CTA kernel run in one launch, one CTA per node.  Returns one result dict per node; the getters of solvers[i] serve
-    node i afterwards."""
-    n = len(probs)
-    if n == 0:
-        return []
-    if len(solvers) < n:
-        raise ValueError(f"{n} nodes need {n} solver handles, got {len(solvers)}")
-    lib = solvers[0].L
-    params = params if params is not None else lib.default_params(**kw)
-    structs = [p.struct() for p in probs]
-    hs = (C.c_void_p * n)(*[s.h for s in solvers[:n]])
-    ps = (C.POINTER(Problem) * n)(*[C.pointer(st) for st in structs])
-    res = (Result * n)()
-    for s, p in zip(solvers, probs):
-        s.prob = p
-    rc = lib.lib.sdpcuda_solve_batch(n, hs, ps, C.byref(params), res)
-    if rc != 0:
-        raise RuntimeError(f"sdpcuda_solve_batch failed with code {rc}")
-    out = []
-    for r in res:
-        d = {f[0]: getattr(r, f[0]) for f in Result._fields_}
-        d["phase_name"], d["stop_name"] = PHASES[r.phase], STOPS[r.stop]
-        out.append(d)
-    return out
 
 
 class Solver:
@@ -253,6 +225,32 @@ class Solver:
             out["X"] = [self.get_X(b) for b in range(prob.nblocks)]
             out["S"] = [self.get_S(b) for b in range(prob.nblocks)]
             out["xlp"], out["slp"] = self.get_xlp(), self.get_slp()
+        return out
+
+    def solve_batch(self, probs, params=None, fetch=True, **kw):
+        """sdpcuda_solve_batch: all relaxations in `probs` that fit the single-CTA kernel in ONE launch (one CTA per node), the others
+        one by one on this handle.  Returns one result dict per node (with "y" unless fetch=False).  The matrix getters of the
+        handle do not refer to batched nodes."""
+        n = len(probs)
+        if n == 0:
+            return []
+        params = params if params is not None else self.L.default_params(**kw)
+        structs = [p.struct() for p in probs]
+        ps = (C.POINTER(Problem) * n)(*[C.pointer(st) for st in structs])
+        res = (Result * n)()
+        ys = [np.zeros(max(p.m, 1)) for p in probs] if fetch else None
+        yp = (_dp * n)(*[y.ctypes.data_as(_dp) for y in ys]) if fetch else None
+        rc = self.L.lib.sdpcuda_solve_batch(self.h, n, ps, C.byref(params), res, yp)
+        if rc != 0:
+            raise RuntimeError(f"sdpcuda_solve_batch failed with code {rc}")
+        self.prob = probs[-1]
+        out = []
+        for i, r in enumerate(res):
+            d = {f[0]: getattr(r, f[0]) for f in Result._fields_}
+            d["phase_name"], d["stop_name"] = PHASES[r.phase], STOPS[r.stop]
+            if fetch:
+                d["y"] = ys[i][:probs[i].m]
+            out.append(d)
         return out
 
     def solve_resident(self, params=None, **kw):

@@ -102,8 +102,11 @@ struct sdpcuda_handle
    DBuf<int> patcol, patrow;          // column-wise pattern of sum_j y_j A_j - C (+ diagonal) per block, if sparse
    std::vector<long long> patcoloff, patrowoff;   // per block offsets into patcol / patrow (-1: block is treated as dense)
    DBuf<SmallResult> smallres;
-   DBuf<SmallArgs> batchargs;        // descriptors of a frontier batch (sdpcuda_solve_batch; held by the first handle of the batch)
+   // frontier batch (sdpcuda_solve_batch): descriptors, results, the packed read-only problem data, work space and y of all nodes
+   DBuf<SmallArgs> batchargs;
    DBuf<SmallResult> batchres;
+   DBuf<unsigned char> batchimg;
+   DBuf<double> batchwork, batchy;
    int force_path = 0;               // 0 auto, 1 always multi-kernel, 2 always single-CTA (tests)
    DBuf<LzDesc> lzdesc;
    DBuf<unsigned> lztickets;
@@ -240,9 +243,11 @@ int upload_problem(sdpcuda_handle* h, const sdpcuda_problem* P)
       key[nnz + e] = cposv[e];
    }
    std::vector<int> order(nnz + P->cnnz);
-   if( h->arena <= ((size_t)1 << 26) )
+   if( h->arena <= ((size_t)1 << 26) && h->arena <= 16 * (size_t)(nnz + P->cnnz) + 4096 )
    {
-      // counting sort by arena position (stable in the entry id): linear in the number of entries
+      // counting sort by arena position (stable in the entry id): linear in the number of entries; only while the arena is not
+      // much larger than the entry list (max-cut n = 2000: 4 M positions for 24 k entries, where the pass over the counters
+      // alone cost ~10 ms per upload — there the comparison sort below is the cheaper one)
       std::vector<int> cntpos(h->arena + 1, 0);
       for( long long kk : key ) cntpos[(size_t)kk + 1]++;
       for( size_t a = 0; a < h->arena; ++a ) cntpos[a + 1] += cntpos[a];
@@ -801,7 +806,7 @@ int sdpcuda_destroy(sdpcuda_handle* h)
       bf->release();
    for( DBuf<long long>* bf : {&h->eoff, &h->pos, &h->mirror, &h->cpos, &h->cmirror} )
       bf->release();
-   h->lzdesc.release(); h->lztickets.release(); h->lzpart.release(); h->smallres.release(); h->batchargs.release(); h->batchres.release();
+   h->lzdesc.release(); h->lztickets.release(); h->lzpart.release(); h->smallres.release(); h->batchargs.release(); h->batchres.release(); h->batchimg.release(); h->batchwork.release(); h->batchy.release();
    h->LinvT.release(); h->LXinvT.release(); h->pinv.release(); h->pinvT.release();
    for( cudaEvent_t& e : h->evp ) if( e != nullptr ) { cudaEventDestroy(e); e = nullptr; }
    h->preX.release(); h->prey.release(); h->prex.release();
@@ -867,10 +872,7 @@ static void host_constants(sdpcuda_handle* h, const sdpcuda_problem* P)
    h->xil = xil; h->etal = etal;
 }
 
-// defer != nullptr (frontier batch): a relaxation that fits the single-CTA kernel is only PREPARED (initial point on the device,
-// descriptor in *defer, *deferred = true) and launched by the caller together with the other nodes; anything else is solved here
-static int run_ipm(sdpcuda_handle* h, const sdpcuda_params* par, const double* start_y, sdpcuda_result* res, double t0,
-   SmallArgs* defer = nullptr, bool* deferred = nullptr);
+static int run_ipm(sdpcuda_handle* h, const sdpcuda_params* par, const double* start_y, sdpcuda_result* res, double t0);
 
 int sdpcuda_solve(sdpcuda_handle* h, const sdpcuda_problem* P, const sdpcuda_params* par, const double* start_y, sdpcuda_result* res)
 {
@@ -902,74 +904,315 @@ int sdpcuda_solve_resident(sdpcuda_handle* h, const sdpcuda_params* par, sdpcuda
    return run_ipm(h, par, nullptr, res, t0);
 }
 
-int sdpcuda_solve_batch(int count, sdpcuda_handle* const* hs, const sdpcuda_problem* const* probs, const sdpcuda_params* par,
-   sdpcuda_result* res)
+// ---- frontier batch: all small node relaxations of a frontier in ONE launch, one CTA per node ------------------------------------
+// The per-node host work is pure CPU (the same derived arrays as upload_problem, appended to one image); the device sees one
+// host->device copy of the image, one of the descriptors, one launch and one device->host copy of results and y for the whole batch.
+} // extern "C"
+
+struct BatchImage
 {
-   if( count < 0 || par == nullptr || (count > 0 && (hs == nullptr || probs == nullptr)) ) return SDPCUDA_ERR_ARG;
+   std::vector<unsigned char> buf;
+   size_t put(const void* src, size_t bytes)
+   {
+      const size_t off = (buf.size() + 15) & ~(size_t)15;
+      buf.resize(off + std::max<size_t>(bytes, 16));
+      if( bytes > 0 ) memcpy(buf.data() + off, src, bytes);
+      return off;
+   }
+   template <class T> size_t putv(const std::vector<T>& v) { return put(v.data(), v.size() * sizeof(T)); }
+};
+
+struct BatchNode          // offsets of one node: bytes into the image, doubles into the work space / the y buffer
+{
+   SmallArgs a;           // scalars and block table are final; the pointers are set once the device addresses are known
+   size_t varbeg, erow, ecol, eld, eoff, eval, cls, posbeg, pos, mirror, posvar, posval, posc, cpos, cmirror, cval;
+   size_t lpbeg, lpind, lpval, lprhs, colbeg, colrow, colval, b, denselist;
+   size_t work, worklen, yoff, hdlen, lzlen;
+};
+
+// builds the image of one node; returns SDPCUDA_OK and *fits = false when the relaxation is outside the single-CTA limits
+static int batch_prepare_node(const sdpcuda_problem* P, const sdpcuda_params* par, BatchImage& img, BatchNode& nd, bool* fits)
+{
+   *fits = false;
+   const int m = P->m, nb = P->nblocks, nlp = P->nlp;
+   if( m <= 0 || nb < 0 || nlp < 0 ) return SDPCUDA_ERR_ARG;
+   if( nb > SMALL_MAX_BLOCKS || m > SMALL_MAX_M || nlp > (1 << 20) ) return SDPCUDA_OK;
+   SmallArgs& a = nd.a;
+   memset(&a, 0, sizeof(a));
+   long long off = 0, lzoff = 0;
+   int maxn = 0, N = nlp;
+   for( int k = 0; k < nb; ++k )
+   {
+      const int n = P->blocksizes[k];
+      if( n <= 0 ) return SDPCUDA_ERR_ARG;
+      if( n > SMALL_MAX_N ) return SDPCUDA_OK;
+      a.blk[k].n = n; a.blk[k].ld = round_up(n, 4); a.blk[k].off = off; a.blk[k].lzoff = lzoff;
+      off += (long long)a.blk[k].ld * n;
+      off = (off + 15) / 16 * 16;
+      lzoff += (long long)(SMALL_LZ_STEPS + 2) * n;
+      maxn = std::max(maxn, n);
+      N += n;
+   }
+   const long long ar = off;
+   if( ar > ((long long)1 << 20) ) return SDPCUDA_OK;
+   const int nnz = P->varbeg[m];
+   std::vector<int> erow(nnz), ecol(nnz), eld(nnz), heavy(m, 0);
+   std::vector<long long> eoff(nnz);
+   for( int e = 0; e < nnz; ++e )
+   {
+      const int bk = P->entblk[e];
+      if( bk < 0 || bk >= nb ) return SDPCUDA_ERR_ARG;
+      const int r = P->entrow[e], c = P->entcol[e];
+      if( r < c || c < 0 || r >= a.blk[bk].n ) return SDPCUDA_ERR_ARG;
+      erow[e] = r; ecol[e] = c; eld[e] = a.blk[bk].ld; eoff[e] = a.blk[bk].off;
+   }
+   // variable classes as in upload_problem: 2 = dense (all entries in one block, >= 64 of them and >= 5 % of the block)
+   std::vector<std::vector<int>> dense_in(nb);
+   for( int j = 0; j < m; ++j )
+   {
+      const int cntj = P->varbeg[j + 1] - P->varbeg[j];
+      if( cntj <= 32 ) continue;
+      const int b0 = P->entblk[P->varbeg[j]];
+      bool oneblock = true;
+      for( int e = P->varbeg[j]; e < P->varbeg[j + 1] && oneblock; ++e ) oneblock = (P->entblk[e] == b0);
+      const double nn = (double)a.blk[b0].n * a.blk[b0].n;
+      if( oneblock && cntj >= 64 && cntj >= 0.05 * nn ) { heavy[j] = 2; dense_in[b0].push_back(j); }
+      else heavy[j] = 1;
+   }
+   std::vector<int> denselist;
+   int ngroups = 0, maxcount = 0;
+   long long adense_total = 0;
+   size_t maxmat = 1;
+   for( int k = 0; k < nb; ++k )
+   {
+      if( dense_in[k].empty() ) continue;
+      if( ngroups >= SMALL_MAX_GROUPS ) return SDPCUDA_OK;
+      a.gblk[ngroups] = k; a.gfirst[ngroups] = (int)denselist.size(); a.gcount[ngroups] = (int)dense_in[k].size(); a.gaoff[ngroups] = adense_total;
+      adense_total += (long long)dense_in[k].size() * a.blk[k].ld * a.blk[k].n;
+      maxcount = std::max(maxcount, (int)dense_in[k].size());
+      maxmat = std::max(maxmat, (size_t)a.blk[k].ld * a.blk[k].n);
+      denselist.insert(denselist.end(), dense_in[k].begin(), dense_in[k].end());
+      ++ngroups;
+   }
+   // position-major view of sum_j y_j A_j - C (one slot per distinct arena position, entries in input order)
+   std::vector<long long> key(nnz + P->cnnz), cposv(P->cnnz), cmirv(P->cnnz);
+   for( int e = 0; e < nnz; ++e ) key[e] = eoff[e] + (long long)ecol[e] * eld[e] + erow[e];
+   for( int e = 0; e < P->cnnz; ++e )
+   {
+      const int bk = P->cblk[e];
+      if( bk < 0 || bk >= nb ) return SDPCUDA_ERR_ARG;
+      const int r = P->crow[e], c = P->ccol[e];
+      if( r < c || c < 0 || r >= a.blk[bk].n ) return SDPCUDA_ERR_ARG;
+      cposv[e] = a.blk[bk].off + (long long)c * a.blk[bk].ld + r;
+      cmirv[e] = a.blk[bk].off + (long long)r * a.blk[bk].ld + c;
+      key[nnz + e] = cposv[e];
+   }
+   std::vector<int> order(nnz + P->cnnz);
+   std::iota(order.begin(), order.end(), 0);
+   std::stable_sort(order.begin(), order.end(), [&](int x, int y2) { return key[x] < key[y2]; });
+   std::vector<int> var_of(nnz);
+   for( int j = 0; j < m; ++j )
+      for( int e = P->varbeg[j]; e < P->varbeg[j + 1]; ++e ) var_of[e] = j;
+   std::vector<int> posbeg(1, 0), posvar;
+   std::vector<long long> pos, mirror;
+   std::vector<double> posval, posc;
+   for( size_t t = 0; t < order.size(); )
+   {
+      const long long kpos = key[order[t]];
+      double cv = 0.0;
+      long long mir = 0;
+      size_t u = t;
+      for( ; u < order.size() && key[order[u]] == kpos; ++u )
+      {
+         const int id = order[u];
+         if( id < nnz )
+         {
+            posvar.push_back(var_of[id]); posval.push_back(P->entval[id]);
+            mir = eoff[id] + (long long)erow[id] * eld[id] + ecol[id];
+         }
+         else { cv += P->cval[id - nnz]; mir = cmirv[id - nnz]; }
+      }
+      pos.push_back(kpos); mirror.push_back(mir); posc.push_back(cv);
+      posbeg.push_back((int)posvar.size());
+      t = u;
+   }
+   // LP block: CSR as given, CSC built here
+   std::vector<int> lpbeg(nlp + 1, 0);
+   if( nlp > 0 ) std::copy(P->lpbeg, P->lpbeg + nlp + 1, lpbeg.begin());
+   const int lnz = lpbeg[nlp];
+   std::vector<int> colbeg(m + 1, 0), colrow(lnz);
+   std::vector<double> colval(lnz);
+   for( int p = 0; p < lnz; ++p )
+   {
+      if( P->lpind[p] < 0 || P->lpind[p] >= m ) return SDPCUDA_ERR_ARG;
+      colbeg[P->lpind[p] + 1]++;
+   }
+   for( int j = 0; j < m; ++j ) colbeg[j + 1] += colbeg[j];
+   {
+      std::vector<int> fill(colbeg.begin(), colbeg.end() - 1);
+      for( int l = 0; l < nlp; ++l )
+         for( int p = lpbeg[l]; p < lpbeg[l + 1]; ++p )
+         {
+            const int q = fill[P->lpind[p]]++;
+            colrow[q] = l; colval[q] = P->lpval[p];
+         }
+   }
+   // norms and the scale of the cold start: host_constants on a scratch handle that owns no device resources
+   {
+      static thread_local sdpcuda_handle* scratch = nullptr;
+      if( scratch == nullptr ) scratch = new sdpcuda_handle();
+      scratch->m = m; scratch->nb = nb; scratch->nlp = nlp;
+      scratch->blk.resize(nb);
+      for( int k = 0; k < nb; ++k ) scratch->blk[k] = Block{a.blk[k].n, a.blk[k].ld, a.blk[k].off};
+      host_constants(scratch, P);
+      a.normb = scratch->normb; a.normC = scratch->normC; a.normCsdp2 = scratch->normCsdp2;
+      for( int k = 0; k < nb; ++k )
+      {
+         a.xi[k] = par->lambdastar > 0 ? par->lambdastar : scratch->xi[k];
+         a.eta[k] = par->lambdastar > 0 ? par->lambdastar : scratch->eta[k];
+      }
+      a.xil = par->lambdastar > 0 ? par->lambdastar : scratch->xil;
+      a.etal = par->lambdastar > 0 ? par->lambdastar : scratch->etal;
+   }
+   a.m = m; a.nb = nb; a.nlp = nlp; a.N = N; a.ldm = round_up(std::max(m, 1), 4); a.npos = (int)pos.size(); a.cnnz = P->cnnz;
+   a.ndense = (int)denselist.size(); a.ngroups = ngroups;
+   a.maxiter = par->maxiter > 0 ? par->maxiter : 100; a.setting = par->setting; a.verbose = par->verbose; a.arena = ar;
+   a.gaptol = par->gaptol > 0 ? par->gaptol : 1e-6; a.feastol = par->feastol > 0 ? par->feastol : 1e-6;
+   a.absgaptol = par->absgaptol; a.objlimit = par->objlimit;
+   a.gammabase = par->setting >= 3 ? 0.7 : (par->setting == 2 ? 0.8 : 0.9);
+   a.selfinit = 1; a.adense_total = adense_total;
+   // read-only data -> image
+   std::vector<int> varbeg(P->varbeg, P->varbeg + m + 1);
+   nd.varbeg = img.putv(varbeg); nd.erow = img.putv(erow); nd.ecol = img.putv(ecol); nd.eld = img.putv(eld); nd.eoff = img.putv(eoff);
+   nd.eval = img.put(P->entval, sizeof(double) * nnz); nd.cls = img.putv(heavy);
+   nd.posbeg = img.putv(posbeg); nd.pos = img.putv(pos); nd.mirror = img.putv(mirror); nd.posvar = img.putv(posvar);
+   nd.posval = img.putv(posval); nd.posc = img.putv(posc);
+   nd.cpos = img.putv(cposv); nd.cmirror = img.putv(cmirv); nd.cval = img.put(P->cval, sizeof(double) * P->cnnz);
+   nd.lpbeg = img.putv(lpbeg); nd.lpind = img.put(P->lpind, sizeof(int) * lnz); nd.lpval = img.put(P->lpval, sizeof(double) * lnz);
+   nd.lprhs = img.put(P->lprhs, sizeof(double) * nlp);
+   nd.colbeg = img.putv(colbeg); nd.colrow = img.putv(colrow); nd.colval = img.putv(colval);
+   nd.b = img.put(P->obj, sizeof(double) * m); nd.denselist = img.putv(denselist);
+   // work space in doubles (every array starts on a 128-byte boundary)
+   auto r16 = [](size_t v) { return (v + 15) / 16 * 16; };
+   nd.hdlen = (a.ndense > 0) ? r16((size_t)maxcount * maxmat) : 0;
+   nd.lzlen = r16((size_t)lzoff + 16);
+   nd.worklen = 15 * r16((size_t)ar) + 7 * r16((size_t)m + 1) + 10 * r16((size_t)nlp + 1) + 2 * r16((size_t)a.ldm * m)
+      + r16((size_t)adense_total) + 2 * nd.hdlen + nd.lzlen;
+   *fits = true;
+   return SDPCUDA_OK;
+}
+
+// device addresses of one node: image base (bytes), the node's slice of the work space, its y, its result slot
+static void batch_bind_node(BatchNode& nd, unsigned char* img, double* work, double* y, SmallResult* out)
+{
+   SmallArgs& a = nd.a;
+   auto r16 = [](size_t v) { return (v + 15) / 16 * 16; };
+#define IMG(T, f) reinterpret_cast<const T*>(img + nd.f)
+   a.E = DevEntries{IMG(int, varbeg), IMG(int, erow), IMG(int, ecol), IMG(int, eld), IMG(long long, eoff), IMG(double, eval)};
+   a.cls = IMG(int, cls);
+   a.posbeg = IMG(int, posbeg); a.pos = IMG(long long, pos); a.mirror = IMG(long long, mirror); a.posvar = IMG(int, posvar);
+   a.posval = IMG(double, posval); a.posc = IMG(double, posc);
+   a.cpos = IMG(long long, cpos); a.cmirror = IMG(long long, cmirror); a.cval = IMG(double, cval);
+   a.lpbeg = IMG(int, lpbeg); a.lpind = IMG(int, lpind); a.lpval = IMG(double, lpval); a.lprhs = IMG(double, lprhs);
+   a.colbeg = IMG(int, colbeg); a.colrow = IMG(int, colrow); a.colval = IMG(double, colval);
+   a.b = IMG(double, b); a.denselist = IMG(int, denselist);
+#undef IMG
+   double* w = work;
+   auto take = [&](size_t len) { double* p = w; w += r16(len); return p; };
+   const size_t ar = (size_t)a.arena, mv = (size_t)a.m + 1, lv = (size_t)a.nlp + 1, mm = (size_t)a.ldm * a.m;
+   a.X = take(ar); a.S = take(ar); a.Sinv = take(ar); a.L = take(ar); a.Linv = take(ar); a.LX = take(ar); a.LXinv = take(ar);
+   a.dX = take(ar); a.dS = take(ar); a.dXa = take(ar); a.dSa = take(ar); a.K = take(ar); a.T1 = take(ar); a.T2 = take(ar); a.Rd = take(ar);
+   a.y = y; a.dy = take(mv); a.g = take(mv); a.rp = take(mv); a.AX = take(mv); a.DTx = take(mv); a.tm1 = take(mv); a.tm2 = take(mv);
+   a.x = take(lv); a.s = take(lv); a.dx = take(lv); a.ds = take(lv); a.dxa = take(lv); a.dsa = take(lv); a.klp = take(lv); a.rdlp = take(lv);
+   a.Dy = take(lv); a.Ddy = take(lv);
+   a.M = take(mm); a.Mfac = take(mm);
+   double* ad = take((size_t)a.adense_total);
+   a.Adense = ad;
+   a.Hd = w; w += nd.hdlen; a.Ud = w; w += nd.hdlen;
+   a.lz = w; w += nd.lzlen;
+   a.out = out;
+}
+
+extern "C" {
+
+int sdpcuda_solve_batch(sdpcuda_handle* h, int count, const sdpcuda_problem* const* probs, const sdpcuda_params* par,
+   sdpcuda_result* res, double* const* y_out)
+{
+   if( h == nullptr || count < 0 || par == nullptr || (count > 0 && probs == nullptr) ) return SDPCUDA_ERR_ARG;
    if( count == 0 ) return SDPCUDA_OK;
-   for( int i = 0; i < count; ++i )
-   {
-      if( hs[i] == nullptr || probs[i] == nullptr || probs[i]->m <= 0 || hs[i]->device != hs[0]->device ) return SDPCUDA_ERR_ARG;
-      for( int k = 0; k < i; ++k ) if( hs[k] == hs[i] ) return SDPCUDA_ERR_ARG;      // one handle (= one set of device buffers) per node
-   }
+   for( int i = 0; i < count; ++i ) if( probs[i] == nullptr || probs[i]->m <= 0 ) return SDPCUDA_ERR_ARG;
    const double t0 = now_seconds();
-   std::vector<SmallArgs> args;
-   std::vector<int> who;
-   std::vector<double> h2d(count, 0.0);
-   args.reserve(count); who.reserve(count);
+   int rc = set_device(h);
+   if( rc != SDPCUDA_OK ) return rc;
+   BatchImage img;
+   std::vector<BatchNode> nodes;
+   std::vector<int> who, loners;
+   nodes.reserve(count);
+   size_t worktotal = 0, ytotal = 0;
    for( int i = 0; i < count; ++i )
    {
-      sdpcuda_handle* h = hs[i];
-      int rc = set_device(h);
+      BatchNode nd;
+      bool fits = false;
+      rc = batch_prepare_node(probs[i], par, img, nd, &fits);
       if( rc != SDPCUDA_OK ) return rc;
-      h->solved = false; h->resident = false; h->counter.n = 0;
-      g_h2d_bytes = 0.0;
-      rc = upload_problem(h, probs[i]);
-      if( rc != SDPCUDA_OK ) return rc;
-      host_constants(h, probs[i]);
-      h->resident = true;
-      SmallArgs a;
-      bool deferred = false;
-      sdpcuda_result R;
-      memset(&R, 0, sizeof(R));
-      rc = run_ipm(h, par, nullptr, &R, now_seconds(), &a, &deferred);
-      if( rc != SDPCUDA_OK ) return rc;
-      h2d[i] = g_h2d_bytes;
-      if( deferred ) { args.push_back(a); who.push_back(i); }
-      else if( res != nullptr ) res[i] = R;          // too large for one CTA: solved on its own by the multi-kernel path
+      if( !fits ) { loners.push_back(i); continue; }
+      nd.work = worktotal; worktotal += nd.worklen;
+      nd.yoff = ytotal; ytotal += ((size_t)nd.a.m + 1 + 15) / 16 * 16;
+      nodes.push_back(nd); who.push_back(i);
    }
-   if( args.empty() ) return SDPCUDA_OK;
-   // ---- one launch for all prepared nodes: CTA k works on the buffers of handle who[k]; every handle's stream is idle here
-   sdpcuda_handle* lead = hs[who[0]];
-   int rc = set_device(lead);
-   if( rc != SDPCUDA_OK ) return rc;
-   const int nd = (int)args.size();
-   CK( lead->batchargs.ensure(nd) );
-   CK( lead->batchres.ensure(nd) );
-   for( int k = 0; k < nd; ++k ) args[k].out = lead->batchres.p + k;
-   CK( cudaMemcpyAsync(lead->batchargs.p, args.data(), sizeof(SmallArgs) * nd, cudaMemcpyHostToDevice, lead->st) );
-   CK( cudaEventRecord(lead->ev0, lead->st) );
-   CK( launch_ipm_small_batch(lead->st, nd, lead->batchargs.p) );
-   CK( cudaEventRecord(lead->ev1, lead->st) );
-   std::vector<SmallResult> sr(nd);
-   CK( cudaMemcpyAsync(sr.data(), lead->batchres.p, sizeof(SmallResult) * nd, cudaMemcpyDeviceToHost, lead->st) );
-   CK( cudaStreamSynchronize(lead->st) );
-   float ms = 0.f;
-   cudaEventElapsedTime(&ms, lead->ev0, lead->ev1);
-   const double wall = now_seconds() - t0;
-   for( int k = 0; k < nd; ++k )
+   const int nd = (int)nodes.size();
+   if( nd > 0 )
    {
-      sdpcuda_handle* h = hs[who[k]];
-      h->solved = true;
-      if( res == nullptr ) continue;
+      cudaStream_t st = h->st;
+      h->counter.n = 0;
+      CK( h->batchimg.ensure(img.buf.size()) );
+      CK( h->batchwork.ensure(worktotal) );
+      CK( h->batchy.ensure(ytotal) );
+      CK( h->batchargs.ensure(nd) );
+      CK( h->batchres.ensure(nd) );
+      std::vector<SmallArgs> args(nd);
+      for( int k = 0; k < nd; ++k )
+      {
+         batch_bind_node(nodes[k], h->batchimg.p, h->batchwork.p + nodes[k].work, h->batchy.p + nodes[k].yoff, h->batchres.p + k);
+         args[k] = nodes[k].a;
+      }
+      CK( cudaMemcpyAsync(h->batchimg.p, img.buf.data(), img.buf.size(), cudaMemcpyHostToDevice, st) );
+      CK( cudaMemcpyAsync(h->batchargs.p, args.data(), sizeof(SmallArgs) * nd, cudaMemcpyHostToDevice, st) );
+      CK( cudaEventRecord(h->ev0, st) );
+      CK( launch_ipm_small_batch(st, nd, h->batchargs.p) );
+      CK( cudaEventRecord(h->ev1, st) );
+      std::vector<SmallResult> sr(nd);
+      std::vector<double> ys(ytotal);
+      CK( cudaMemcpyAsync(sr.data(), h->batchres.p, sizeof(SmallResult) * nd, cudaMemcpyDeviceToHost, st) );
+      CK( cudaMemcpyAsync(ys.data(), h->batchy.p, sizeof(double) * ytotal, cudaMemcpyDeviceToHost, st) );
+      CK( cudaStreamSynchronize(st) );
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, h->ev0, h->ev1);
+      const double wall = now_seconds() - t0;
+      for( int k = 0; k < nd; ++k )
+      {
+         const int i = who[k];
+         if( y_out != nullptr && y_out[i] != nullptr ) std::copy(ys.begin() + nodes[k].yoff, ys.begin() + nodes[k].yoff + nodes[k].a.m, y_out[i]);
+         if( res == nullptr ) continue;
+         sdpcuda_result R;
+         memset(&R, 0, sizeof(R));
+         R.phase = sr[k].phase; R.stop = sr[k].stop; R.iterations = sr[k].iterations;
+         R.launches = (k == 0) ? 1 : 0;                  // the one launch is shared by all batched nodes
+         R.pobj = sr[k].pobj; R.dobj = sr[k].dobj; R.relgap = sr[k].relgap; R.pinf = sr[k].pinf; R.dinf = sr[k].dinf; R.mu = sr[k].mu;
+         R.seconds = wall; R.device_ms = ms;             // of the whole batch: the nodes run side by side
+         R.h2d_bytes = (double)(img.buf.size() + sizeof(SmallArgs) * nd) / nd;
+         R.d2h_bytes = (double)(sizeof(SmallResult) * nd + sizeof(double) * ytotal) / nd;
+         res[i] = R;
+      }
+   }
+   // relaxations outside the single-CTA limits: one after the other through the ordinary solve on this handle
+   for( int i : loners )
+   {
       sdpcuda_result R;
-      memset(&R, 0, sizeof(R));
-      R.phase = sr[k].phase; R.stop = sr[k].stop; R.iterations = sr[k].iterations;
-      R.launches = (int)std::min<long long>(h->counter.n, 2147483647LL);      // initial-point kernels; the lead handle also counts the batch launch
-      R.pobj = sr[k].pobj; R.dobj = sr[k].dobj; R.relgap = sr[k].relgap; R.pinf = sr[k].pinf; R.dinf = sr[k].dinf; R.mu = sr[k].mu;
-      R.seconds = wall; R.device_ms = ms;            // of the whole batch: the nodes ran side by side
-      R.h2d_bytes = h2d[who[k]] + sizeof(SmallArgs); R.d2h_bytes = sizeof(SmallResult);
-      res[who[k]] = R;
+      rc = sdpcuda_solve(h, probs[i], par, nullptr, &R);
+      if( rc != SDPCUDA_OK ) return rc;
+      if( res != nullptr ) res[i] = R;
+      if( y_out != nullptr && y_out[i] != nullptr ) { rc = sdpcuda_get_y(h, y_out[i]); if( rc != SDPCUDA_OK ) return rc; }
    }
    return SDPCUDA_OK;
 }
@@ -989,8 +1232,7 @@ int sdpcuda_get_profile(sdpcuda_handle* h, double* out)
    return SDPCUDA_OK;
 }
 
-static int run_ipm(sdpcuda_handle* h, const sdpcuda_params* par, const double* start_y, sdpcuda_result* res, double t0,
-   SmallArgs* defer, bool* deferred)
+static int run_ipm(sdpcuda_handle* h, const sdpcuda_params* par, const double* start_y, sdpcuda_result* res, double t0)
 {
    int rc = SDPCUDA_OK;
    cudaStream_t st = h->st;
@@ -1078,8 +1320,7 @@ static int run_ipm(sdpcuda_handle* h, const sdpcuda_params* par, const double* s
          for( const auto& g : h->dgroups ) if( g.count > h->dchunk ) eligible = false;
       // measured on the shipped instances: the one-launch kernel wins while the Schur complement is small (m <= 64); above that
       // the serial Cholesky of M inside a single CTA loses against the multi-kernel pipeline
-      // inside a frontier batch every CTA has an SM of its own, so the single-CTA kernel is taken whenever the relaxation fits
-      if( eligible && force != 1 && (force == 2 || m <= 64 || defer != nullptr) )
+      if( eligible && force != 1 && (force == 2 || m <= 64) )
       {
          SmallArgs a;
          memset(&a, 0, sizeof(a));
@@ -1115,12 +1356,6 @@ static int run_ipm(sdpcuda_handle* h, const sdpcuda_params* par, const double* s
          a.gaptol = gaptol; a.feastol = feastol; a.absgaptol = par->absgaptol; a.objlimit = par->objlimit;
          a.normb = normb; a.normC = normC; a.normCsdp2 = normCsdp2; a.gammabase = gammabase;
          a.out = h->smallres.p;
-         if( defer != nullptr )
-         {
-            *defer = a;
-            *deferred = true;
-            return SDPCUDA_OK;
-         }
          CK( cudaEventRecord(h->ev0, st) );
          CK( launch_ipm_small(st, a) );
          CK( cudaEventRecord(h->ev1, st) );

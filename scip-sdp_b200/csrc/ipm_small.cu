@@ -656,6 +656,44 @@ __device__ __forceinline__ void ipm_small_body(const SmallArgs& a)
       c->pfeasever = 0; c->dfeasever = 0; c->bestmerit = 1e300; c->lastap = 0.0; c->lastad = 0.0; c->xfail = 0;
       c->mu = 0; c->pobj = 0; c->dobj = 0; c->relgap = 1e30; c->pinf = 1e30; c->dinf = 1e30;
    }
+   if( a.selfinit )
+   {
+      // cold start and expanded dense matrices written by the CTA itself (what run_ipm / upload_problem do with memsets,
+      // add_diagonal and scatter_dense launches for a single relaxation)
+      for( long long i = tid; i < a.arena; i += NT ) { a.X[i] = 0.0; a.S[i] = 0.0; }
+      double* AdW = const_cast<double*>(a.Adense);       // written only here, read-only for the iteration
+      for( long long i = tid; i < a.adense_total; i += NT ) AdW[i] = 0.0;
+      for( int l = tid; l < nlp; l += NT ) { a.x[l] = a.xil; a.s[l] = a.etal; }
+      for( int j = tid; j < m; j += NT ) a.y[j] = 0.0;
+      __syncthreads();
+      for( int k = 0; k < nb; ++k )
+      {
+         const SmallBlock bk = a.blk[k];
+         for( int i = tid; i < bk.n; i += NT )
+         {
+            a.X[bk.off + (long long)i * bk.ld + i] = a.xi[k];
+            a.S[bk.off + (long long)i * bk.ld + i] = a.eta[k];
+         }
+      }
+      for( int g = 0; g < a.ngroups; ++g )
+      {
+         const SmallBlock bk = a.blk[a.gblk[g]];
+         const long long stride = (long long)bk.ld * bk.n;
+         for( int d = 0; d < a.gcount[g]; ++d )
+         {
+            const int j = a.denselist[a.gfirst[g] + d];
+            double* Ad = AdW + a.gaoff[g] + (long long)d * stride;
+            for( int e = a.E.varbeg[j] + tid; e < a.E.varbeg[j + 1]; e += NT )
+            {
+               const int r = a.E.row[e], cc = a.E.col[e];
+               const double v = a.E.val[e];
+               Ad[(long long)cc * bk.ld + r] = v;
+               Ad[(long long)r * bk.ld + cc] = v;
+            }
+         }
+      }
+      __syncthreads();
+   }
    for( long long i = tid; i < a.arena; i += NT ) { a.dX[i] = 0.0; a.dS[i] = 0.0; }
    __syncthreads();
 

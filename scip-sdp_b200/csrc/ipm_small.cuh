@@ -41,6 +41,12 @@ struct SmallArgs
    double *M, *Mfac, *Hd, *Ud, *lz;
    double gaptol, feastol, absgaptol, objlimit, normb, normC, normCsdp2, gammabase;
    SmallResult* out;
+   // frontier batch (sdpcuda_solve_batch): the CTA sets up its own cold start X = xi I, S = eta I, x = xil, s = etal, y = 0 and
+   // expands its dense constraint matrices into Adense itself, so that a node costs the host no launch and no copy of its own
+   int selfinit;
+   long long adense_total;
+   double xil, etal;
+   double xi[SMALL_MAX_BLOCKS], eta[SMALL_MAX_BLOCKS];
 };
 
 cudaError_t launch_ipm_small(cudaStream_t st, const SmallArgs& a);

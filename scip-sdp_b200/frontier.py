@@ -16,15 +16,14 @@ def flatten_nodes(model, node_bounds, world=1, rank=0):
     return {i: model.flatten(*node_bounds[i]) for i in partition(len(node_bounds), world, rank)}
 
 
-def _solve_nodes_batched(pool, todo, solve_kw):
-    """chunks of len(pool) nodes through sdpcuda_solve_batch: one kernel launch per chunk, one CTA per node (relaxations that fit
-    the single-CTA kernel; others are solved one by one inside the call)"""
-    from . import abi
+def _solve_nodes_batched(solver, todo, chunk, solve_kw):
+    """chunks of `chunk` nodes through sdpcuda_solve_batch: one host->device copy, one kernel launch (one CTA per node) and one
+    device->host copy per chunk for the relaxations that fit the single-CTA kernel; others are solved one by one inside the call"""
     out = {}
-    for c in range(0, len(todo), len(pool)):
-        chunk = todo[c:c + len(pool)]
-        res = abi.solve_batch(pool, [fp for _, fp, _ in chunk], **solve_kw)
-        for (i, _, info), r in zip(chunk, res):
+    for c in range(0, len(todo), chunk):
+        part = todo[c:c + chunk]
+        res = solver.solve_batch([fp for _, fp, _ in part], fetch=False, **solve_kw)
+        for (i, _, info), r in zip(part, res):
             out[i] = dict(status=r["phase_name"], bound=float(r["dobj"] + info["fixedobj"]), iterations=int(r["iterations"]))
     return out
 
@@ -53,11 +52,11 @@ def _solve_nodes_threaded(pool, todo, solve_kw):
     return out
 
 
-def solve_frontier(solver, model, node_bounds, dist=None, flat=None, pool=None, mode="serial", **solve_kw):
+def solve_frontier(solver, model, node_bounds, dist=None, flat=None, pool=None, mode="serial", chunk=1184, **solve_kw):
     """solver: scip_sdp_b200.abi.Solver bound to this rank's device; node_bounds: list of (lb, ub) arrays, identical on all ranks;
-    flat: optional result of flatten_nodes for this rank.  pool: further handles on the same device for mode "batch" (all nodes
-    of a chunk in one kernel launch, sdpcuda_solve_batch) or "threads" (one host thread and stream per handle); mode "serial"
-    solves the nodes one after the other on `solver`.  Returns a list with one dict(status, bound) per node (complete on every rank)."""
+    flat: optional result of flatten_nodes for this rank.  mode "serial": the nodes one after the other on `solver`; "batch": chunks
+    of `chunk` nodes (default 8 per SM) in one kernel launch each (sdpcuda_solve_batch); "threads": one host thread and stream per
+    handle of [solver] + pool.  Returns a list with one dict(status, bound) per node (complete on every rank)."""
     world = dist.get_world_size() if dist is not None and dist.is_initialized() else 1
     rank = dist.get_rank() if world > 1 else 0
     mine, todo = {}, []
@@ -72,7 +71,7 @@ def solve_frontier(solver, model, node_bounds, dist=None, flat=None, pool=None, 
         raise ValueError(f"unknown frontier mode {mode!r}")
     handles = [solver] + list(pool or [])
     if mode == "batch":
-        mine.update(_solve_nodes_batched(handles, todo, solve_kw))
+        mine.update(_solve_nodes_batched(solver, todo, max(1, int(chunk)), solve_kw))
     elif mode == "threads" and len(handles) > 1:
         mine.update(_solve_nodes_threaded(handles, todo, solve_kw))
     else:

@@ -105,32 +105,30 @@ def test_frontier_modes_agree_with_serial(mode):
     lib = abi.Lib(abi.ORACLE_LIB)
     kw = dict(gaptol=1e-6, feastol=1e-6)
     serial = frontier.solve_frontier(abi.Solver(lib), M, _nodes(M), **kw)
-    pool = [abi.Solver(lib) for _ in range(3)]             # fewer handles than nodes: chunks / strided work lists
-    got = frontier.solve_frontier(pool[0], M, _nodes(M), pool=pool[1:], mode=mode, **kw)
+    pool = [abi.Solver(lib) for _ in range(3)]             # fewer handles than nodes: strided work lists
+    got = frontier.solve_frontier(pool[0], M, _nodes(M), pool=pool[1:], mode=mode, chunk=2, **kw)      # chunks of 2: 2 + 2 + 1 nodes
     assert [(r["status"], r["bound"]) for r in got] == [(r["status"], r["bound"]) for r in serial]
     with pytest.raises(ValueError):
         frontier.solve_frontier(pool[0], M, _nodes(M), mode="nonsense", **kw)
 
 
 def test_solve_batch_boundary():
-    """argument checks of sdpcuda_solve_batch (include/sdpcuda.h) and the per-handle getters after a batch"""
+    """argument checks of sdpcuda_solve_batch (include/sdpcuda.h) and its outputs"""
     import ctypes as C
     M = misdp.read_sdpa(os.path.join(GOLDEN, "example_small.dat-s"))
     lib = abi.Lib(abi.ORACLE_LIB)
     nodes = [M.flatten(lb, ub)[0] for lb, ub in _nodes(M)]
-    solvers = [abi.Solver(lib) for _ in nodes]
-    res = abi.solve_batch(solvers, nodes, gaptol=1e-6, feastol=1e-6)
-    ref = abi.Solver(lib)
-    for s, fp, r in zip(solvers, nodes, res):
+    s, ref = abi.Solver(lib), abi.Solver(lib)
+    res = s.solve_batch(nodes, gaptol=1e-6, feastol=1e-6)
+    for fp, r in zip(nodes, res):
         q = ref.solve(fp, gaptol=1e-6, feastol=1e-6)
-        assert r["phase_name"] == q["phase_name"] and r["dobj"] == q["dobj"]
-        assert np.array_equal(s.get_y(), q["y"]) and np.array_equal(s.get_X(0), q["X"][0])
-    assert abi.solve_batch(solvers, []) == []
-    with pytest.raises(ValueError):
-        abi.solve_batch(solvers[:2], nodes)                # fewer handles than nodes
-    with pytest.raises(RuntimeError):
-        abi.solve_batch([solvers[0], solvers[0]], nodes[:2])    # the same handle twice: SDPCUDA_ERR_ARG
+        assert r["phase_name"] == q["phase_name"] and r["dobj"] == q["dobj"] and np.array_equal(r["y"], q["y"])
+    assert s.solve_batch([]) == []
+    assert "y" not in s.solve_batch(nodes[:2], fetch=False)[0]
     par = lib.default_params()
-    assert lib.lib.sdpcuda_solve_batch(-1, None, None, C.byref(par), None) == 1
-    assert lib.lib.sdpcuda_solve_batch(0, None, None, C.byref(par), None) == 0
-    assert lib.lib.sdpcuda_solve_batch(2, None, None, C.byref(par), None) == 1
+    batch = lib.lib.sdpcuda_solve_batch
+    assert batch(s.h, -1, None, C.byref(par), None, None) == 1          # SDPCUDA_ERR_ARG
+    assert batch(s.h, 0, None, C.byref(par), None, None) == 0
+    assert batch(s.h, 2, None, C.byref(par), None, None) == 1
+    assert batch(None, 0, None, C.byref(par), None, None) == 1
+    assert batch(s.h, 0, None, None, None, None) == 1

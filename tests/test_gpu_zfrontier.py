@@ -39,16 +39,16 @@ def cpu():
 @pytest.mark.parametrize("name,q", [("example_small.dat-s", 2), ("example_TT.dat-s.gz", 4), ("example_CLS.dat-s.gz", 3), ("example_MkP.dat-s.gz", 3)])
 def test_batched_nodes_match_oracle_and_single_solves(lib, cpu, name, q, monkeypatch):
     """2^q nodes of a shipped instance in ONE launch: statuses and bounds as the oracle's (1e-5 relative, north_star tolerance),
-    and the same numbers as the one-relaxation launch of the same kernel; y of handle i belongs to node i"""
+    and the same numbers as the one-relaxation launch of the same kernel (the batch only differs in who writes the cold start)"""
     M = misdp.read_sdpa(os.path.join(GOLDEN, name)).rows_to_bounds()
     flat = [M.flatten(lb, ub) for lb, ub in _frontier(M, q)]
-    keep = [(fp, info) for fp, info in flat if fp.m > 0]
-    pool = [abi.Solver(lib, device=0) for _ in keep]
-    res = abi.solve_batch(pool, [fp for fp, _ in keep], **KW)
-    assert sum(r["launches"] for r in res) > 0
+    keep = [fp for fp, _ in flat if fp.m > 0]
+    gpu = abi.Solver(lib, device=0)
+    res = gpu.solve_batch(keep, **KW)
+    assert sum(r["launches"] for r in res) == 1            # ONE kernel launch for the whole frontier
     monkeypatch.setenv("SDPCUDA_PATH", "s")
     one = abi.Solver(lib, device=0)
-    for s, (fp, info), r in zip(pool, keep, res):
+    for fp, r in zip(keep, res):
         ref = cpu.solve(fp, **KW)
         # optimal nodes must be optimal; for infeasible nodes any certificate phase counts (the two back ends may stop one iteration apart)
         assert (r["phase_name"] == "pdOPT") == (ref["phase_name"] == "pdOPT"), (r["phase_name"], r["stop_name"], ref["phase_name"])
@@ -56,31 +56,48 @@ def test_batched_nodes_match_oracle_and_single_solves(lib, cpu, name, q, monkeyp
             assert r["phase_name"] in ("pFEAS_dINF", "dINF")
         if ref["phase_name"] == "pdOPT":
             assert abs(r["dobj"] - ref["dobj"]) <= 1e-5 * max(1.0, abs(ref["dobj"]))
-            assert np.allclose(s.get_y(), ref["y"], atol=1e-3 * max(1.0, np.abs(ref["y"]).max()))
+            assert np.allclose(r["y"], ref["y"], atol=1e-3 * max(1.0, np.abs(ref["y"]).max()))
         single = one.solve(fp, **KW)
         assert single["phase_name"] == r["phase_name"] and single["iterations"] == r["iterations"]
         assert abs(single["dobj"] - r["dobj"]) <= 1e-9 * max(1.0, abs(r["dobj"]))
-    for s in pool:
-        s.close()
+        assert np.allclose(single["y"], r["y"], rtol=0, atol=1e-9 * max(1.0, np.abs(r["y"]).max()))
+    gpu.close(); one.close()
 
 
 def test_batch_with_a_node_outside_the_single_cta_limits(lib, cpu):
     """a block of order 96 does not fit the one-CTA kernel: that node is solved by the multi-kernel path inside the same call"""
     big, _ = generators.maxcut(96, 0.1, seed=7).flatten()
     small, _ = misdp.read_sdpa(os.path.join(GOLDEN, "example_small.dat-s")).rows_to_bounds().flatten()
-    pool = [abi.Solver(lib, device=0) for _ in range(3)]
-    res = abi.solve_batch(pool, [small, big, small], **KW)
+    gpu = abi.Solver(lib, device=0)
+    res = gpu.solve_batch([small, big, small], **KW)
     for fp, r in zip([small, big, small], res):
         ref = cpu.solve(fp, **KW)
         assert r["phase_name"] == ref["phase_name"] == "pdOPT"
         assert abs(r["dobj"] - ref["dobj"]) <= 1e-5 * max(1.0, abs(ref["dobj"]))
+        assert np.allclose(r["y"], ref["y"], atol=1e-3 * max(1.0, np.abs(ref["y"]).max()))
     assert res[1]["launches"] > 100 and res[0]["dobj"] == res[2]["dobj"]
+    gpu.close()
+
+
+def test_batch_larger_than_the_sm_count(lib, cpu):
+    """300 nodes (two waves of CTAs on 148 SMs) of example_TT: every node's bound equals the one of its duplicate"""
+    M = misdp.read_sdpa(os.path.join(GOLDEN, "example_TT.dat-s.gz")).rows_to_bounds()
+    flat = [M.flatten(lb, ub)[0] for lb, ub in _frontier(M, 3)]
+    probs = [flat[i % 8] for i in range(300)]
+    gpu = abi.Solver(lib, device=0)
+    res = gpu.solve_batch(probs, **KW)
+    for i, r in enumerate(res):
+        assert r["phase_name"] == res[i % 8]["phase_name"] and r["dobj"] == res[i % 8]["dobj"] and np.array_equal(r["y"], res[i % 8]["y"])
+    for i in range(8):
+        ref = cpu.solve(flat[i], **KW)
+        assert abs(res[i]["dobj"] - ref["dobj"]) <= 1e-5 * max(1.0, abs(ref["dobj"]))
+    gpu.close()
 
 
 @pytest.mark.parametrize("mode", ["batch", "threads"])
 def test_frontier_modes_on_one_gpu(lib, mode, monkeypatch):
-    """frontier.solve_frontier with a pool of handles on one device: same statuses and bounds (1e-7 relative) as the serial loop;
-    "threads" runs a mid-size truss relaxation (multi-kernel path, CUDA graphs captured per thread) on 4 host threads"""
+    """frontier.solve_frontier on one device: same statuses and bounds (1e-7 relative) as the serial loop; "threads" runs a
+    mid-size truss relaxation (multi-kernel path, CUDA graphs captured per thread) on 4 host threads"""
     if mode == "batch":
         M = misdp.read_sdpa(os.path.join(GOLDEN, "example_TT.dat-s.gz")).rows_to_bounds()
     else:
