@@ -22,6 +22,8 @@
 #ifndef SDPCUDA_H
 #define SDPCUDA_H
 
+#include <stddef.h>
+
 #ifdef __cplusplus
 extern "C" {
 #endif
@@ -174,6 +176,13 @@ int  sdpcuda_solve_resident(sdpcuda_handle* h, const sdpcuda_params* par, sdpcud
  * device_ms / seconds of the batched nodes are those of the whole batch (the nodes run side by side); launches = 1 on the first. */
 int  sdpcuda_solve_batch(sdpcuda_handle* h, int count, const sdpcuda_problem* const* probs, const sdpcuda_params* par,
                          sdpcuda_result* res, double* const* y_out);
+
+/* test hook (no device needed): packs ONE node exactly like sdpcuda_solve_batch does and returns the host image of its read-only
+ * data, the length of its work space and its kernel descriptor bound to the given (fake) device addresses; *fits = 0 when the
+ * relaxation is outside the single-CTA limits.  tests/test_batch_pack.py re-derives the operators from these arrays. */
+int  sdpcuda_debug_pack_node(const sdpcuda_problem* prob, const sdpcuda_params* par, unsigned long long img_base,
+                             unsigned long long work_base, unsigned long long y_base, unsigned char* image, size_t image_cap,
+                             size_t* image_bytes, size_t* work_doubles, void* descriptor, size_t desc_cap, size_t* desc_bytes, int* fits);
 
 /* Per-kernel-class device timing of the NEXT solve (CUDA events around every launch of the class on the handle's
  * stream; adds a little overhead, so it is off by default).  After the solve sdpcuda_get_profile fills, for each class

@@ -692,6 +692,16 @@ int sdpcuda_solve_batch(sdpcuda_handle* h, int count, const sdpcuda_problem* con
    }
    return SDPCUDA_OK;
 }
+/* the packed image is a device-side layout of the product library: nothing to pack on the checker side */
+int sdpcuda_debug_pack_node(const sdpcuda_problem* P, const sdpcuda_params* par, unsigned long long img_base, unsigned long long work_base,
+   unsigned long long y_base, unsigned char* image, size_t image_cap, size_t* image_bytes, size_t* work_doubles,
+   void* descriptor, size_t desc_cap, size_t* desc_bytes, int* fits)
+{
+   (void)P; (void)par; (void)img_base; (void)work_base; (void)y_base; (void)image; (void)image_cap; (void)image_bytes; (void)work_doubles;
+   (void)descriptor; (void)desc_cap; (void)desc_bytes;
+   if( fits != nullptr ) *fits = 0;
+   return SDPCUDA_ERR_STATE;
+}
 int sdpcuda_set_profiling(sdpcuda_handle* h, int on) { (void)h; (void)on; return SDPCUDA_OK; }
 int sdpcuda_get_profile(sdpcuda_handle* h, double* out)
 {

@@ -11,6 +11,7 @@
 #include "common.cuh"
 #include "ops.cuh"
 #include "ipm_small.cuh"
+#include <cstdint>
 #include <dlfcn.h>
 #include <nccl.h>
 
@@ -1134,6 +1135,27 @@ static void batch_bind_node(BatchNode& nd, unsigned char* img, double* work, dou
 }
 
 extern "C" {
+
+int sdpcuda_debug_pack_node(const sdpcuda_problem* P, const sdpcuda_params* par, unsigned long long img_base, unsigned long long work_base,
+   unsigned long long y_base, unsigned char* image, size_t image_cap, size_t* image_bytes, size_t* work_doubles,
+   void* descriptor, size_t desc_cap, size_t* desc_bytes, int* fits)
+{
+   if( P == nullptr || par == nullptr || image_bytes == nullptr || work_doubles == nullptr || desc_bytes == nullptr || fits == nullptr ) return SDPCUDA_ERR_ARG;
+   BatchImage img;
+   BatchNode nd;
+   bool ok = false;
+   int rc = batch_prepare_node(P, par, img, nd, &ok);
+   if( rc != SDPCUDA_OK ) return rc;
+   *fits = ok ? 1 : 0;
+   *image_bytes = ok ? img.buf.size() : 0; *work_doubles = ok ? nd.worklen : 0; *desc_bytes = sizeof(SmallArgs);
+   if( !ok ) return SDPCUDA_OK;
+   // fake device addresses: nothing is dereferenced here
+   batch_bind_node(nd, reinterpret_cast<unsigned char*>((uintptr_t)img_base), reinterpret_cast<double*>((uintptr_t)work_base),
+      reinterpret_cast<double*>((uintptr_t)y_base), nullptr);
+   if( image != nullptr && image_cap >= img.buf.size() ) memcpy(image, img.buf.data(), img.buf.size());
+   if( descriptor != nullptr && desc_cap >= sizeof(SmallArgs) ) memcpy(descriptor, &nd.a, sizeof(SmallArgs));
+   return SDPCUDA_OK;
+}
 
 int sdpcuda_solve_batch(sdpcuda_handle* h, int count, const sdpcuda_problem* const* probs, const sdpcuda_params* par,
    sdpcuda_result* res, double* const* y_out)
