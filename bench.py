@@ -18,6 +18,8 @@ Further workloads (not the driver's default):
                                                    (upload + solve per node through the C ABI; weak scaling)
    --workload frontier-example-{small,tt,cls,mkp} the same over nodes of the shipped instances (BASELINE configs 1-4); with
                                                    --frontier-mode batch all nodes of a rank run in ONE launch, one CTA per node
+   --workload bnb-example-{small,tt,cls,mkp}      complete B&B runs on the shipped instances with the frontier-synchronous driver
+                                                   (--frontier-mode batch: all open nodes of a round in one launch)
    --workload sharded-{dense,maxcut,mkp120}       ONE relaxation over all N GPUs: Schur-complement shares per rank + one NCCL
                                                    all-reduce per iteration (strong scaling)
 """
@@ -47,6 +49,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--workload", default="maxcut", choices=["maxcut", "frontier-tt500", "frontier-cls", "frontier-mkp120", "frontier-mkp60",
                                                              "frontier-example-small", "frontier-example-tt", "frontier-example-cls", "frontier-example-mkp",
+                                                             "bnb-example-small", "bnb-example-tt", "bnb-example-cls", "bnb-example-mkp",
                                                              "sharded-maxcut", "sharded-dense", "sharded-mkp120"],
                     help="maxcut = the headline relaxation benchmark; frontier-* = B&B nodes/sec over a fixed frontier of node relaxations")
     ap.add_argument("--nodes-per-gpu", type=int, default=8)
@@ -107,6 +110,63 @@ def sharded_bench(a, rank, local, world):
     if world > 1:
         gpu.dist_finalize()
         dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def bnb_bench(a, rank, local, world):
+    """Complete branch-and-bound runs on the shipped instances (BASELINE configs 1-4) with the frontier-synchronous driver
+    (scip_sdp_b200.frontier.branch_and_bound): B&B nodes/sec = nodes of the whole tree / wall time, every rank solving the same
+    instance on its own GPU (replicas; the tree of these instances is too small to be worth partitioning), next to the same driver
+    on the CPU oracle.  A step is one complete B&B run; the optimum is compared with check/testset/short.solu."""
+    import torch
+    import torch.distributed as dist
+    from scip_sdp_b200 import abi, frontier, misdp
+    torch.cuda.set_device(local)
+    if world > 1:
+        with stdout_to_stderr():
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+            dist.barrier()
+    inst = {"bnb-example-small": ("example_small.dat-s", -8.0), "bnb-example-tt": ("example_TT.dat-s.gz", 2.11803),
+            "bnb-example-cls": ("example_CLS.dat-s.gz", 7.1485), "bnb-example-mkp": ("example_MkP.dat-s.gz", -95.0)}[a.workload]
+    M = misdp.read_instance(os.path.join(ROOT, "tests", "golden", inst[0]))
+    os.environ["SDPCUDA_DEVICE"] = str(local)
+    lib = abi.Lib(abi.PRODUCT_LIB)
+    gpu = abi.Solver(lib, device=local)
+    mode = a.frontier_mode
+    npool = (a.handles_per_gpu or 4) if mode == "threads" else 1
+    pool = [abi.Solver(lib, device=local) for _ in range(npool - 1)]
+    width = {"serial": 1, "threads": 4 * npool, "batch": 592}[mode]
+    run = lambda s, p, md, w: frontier.branch_and_bound(s, M, mode=md, width=w, pool=p, gaptol=1e-5, feastol=1e-5)      # noqa: E731
+    for _ in range(max(1, a.warmup)):
+        r = run(gpu, pool, mode, width)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    nodes = 0
+    for _ in range(a.steps):
+        r = run(gpu, pool, mode, width)
+        nodes += r["nodes"]
+    torch.cuda.synchronize()
+    wall = frontier.max_over_ranks(time.perf_counter() - t0, dist=dist if world > 1 else None, device="cuda")
+    if rank == 0:
+        line = {"metric": "B&B nodes/sec", "value": world * nodes / wall, "unit": "nodes/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+                "scaling": "weak", "dtype": "f64", "data": "reference instance", "higher_is_better": True, "ms_per_step": 1e3 * wall / a.steps,
+                "config": {"workload": a.workload, "instance": inst[0], "frontier_mode": mode, "width": width, "handles_per_gpu": npool,
+                           "partition": "replicas (one complete tree per GPU)"},
+                "nodes_per_run": r["nodes"], "rounds_per_run": r["rounds"], "unsolved": r["unsolved"], "status": r["status"],
+                "objective": M.file_objective(r["objval"]), "short_solu": inst[1]}
+        if not a.no_cpu_baseline:
+            cpu = abi.Solver(abi.Lib(abi.ORACLE_LIB))
+            t1 = time.perf_counter()
+            rc = run(cpu, None, "serial", 1)
+            dt = time.perf_counter() - t1
+            line["cpu_baseline"] = {"value": rc["nodes"] / dt, "unit": "nodes/s", "cores": os.cpu_count(), "kind": "port",
+                                    "sample": "one complete best-first B&B run of the same driver on the CPU oracle (one node at a time)",
+                                    "nodes": rc["nodes"], "objective": M.file_objective(rc["objval"])}
+        print(json.dumps(line))
+    if world > 1:
         dist.destroy_process_group()
     return 0
 
@@ -283,6 +343,8 @@ def main():
             os.environ["NCCL_DEBUG"] = "WARN"
         if a.workload.startswith("sharded-"):
             return sharded_bench(a, rank, local, world)
+        if a.workload.startswith("bnb-"):
+            return bnb_bench(a, rank, local, world)
         return frontier_bench(a, rank, local, world)
     if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
         os.environ["NCCL_DEBUG"] = "WARN"          # keep stdout to the one JSON line (NCCL prints its version banner there)

@@ -88,6 +88,154 @@ def solve_frontier(solver, model, node_bounds, dist=None, flat=None, pool=None, 
     return [merged[i] for i in range(len(node_bounds))]
 
 
+def _penalty_ladder(solver, model, lb, ub, r, kw, penaltyparam=1e5, maxpenaltyparam=1e10, npenaltyincr=8, peninfeasadjust=10.0):
+    """what SCIPsdpiSolve does after an unacceptable solve (sdpi.c:3437-3619): (ii) min r over the constraints + r I, r free, no
+    objective: optimal with r > peninfeasadjust * max(feastol, gaptol), or infeasible => the node is infeasible; otherwise (iii) the
+    penalty formulation with objective, r >= 0 and growing Gamma until r < feastol, whose y and bound are then those of the node.
+    Returns a result dict like a solve ("pFEAS_dINF" for a node found infeasible, the original r if nothing worked)."""
+    fp, info = model.flatten(lb, ub, compress=True, skip_single_rows=True, penalty=(1.0, False, False))
+    q = solver.solve(fp, fetch=False, **kw)
+    tol = max(kw.get("feastol", 1e-6), kw.get("gaptol", 1e-6))
+    if (q["phase_name"] == "pdOPT" and q["dobj"] > peninfeasadjust * tol) or q["phase_name"] in ("pFEAS_dINF", "dINF"):
+        return dict(r, phase_name="pFEAS_dINF")
+    gamma, fact = penaltyparam, (maxpenaltyparam / penaltyparam) ** (1.0 / npenaltyincr)
+    for _ in range(npenaltyincr + 1):
+        fp, info = model.flatten(lb, ub, compress=True, skip_single_rows=True, penalty=(gamma, True, True))
+        q = solver.solve(fp, fetch=False, **kw)
+        if q["phase_name"] == "pdOPT":
+            y = solver.get_y()
+            if y[-1] < kw.get("feastol", 1e-6):          # feasorig: the solution is feasible for the node itself
+                return dict(q, phase_name="pdOPT", dobj=float(q["dobj"] - gamma * y[-1]), y=y[:-1])
+        elif q["phase_name"] in ("pFEAS_dINF", "dINF"):
+            return dict(r, phase_name="pFEAS_dINF")
+        gamma *= fact
+    return r
+
+
+def branch_and_bound(solver, model, mode="batch", width=1184, pool=None, gaptol=1e-5, feastol=1e-5, inttol=1e-5, maxnodes=1000000,
+                     timelimit=600.0, verbose=False):
+    """Frontier-synchronous branch-and-bound on the C ABI: in every round the (at most `width`) best open nodes are prepared like
+    sdpi.c prepares a node (Misdp.node_problem), their relaxations are solved TOGETHER — mode "batch": one kernel launch, one CTA
+    per node (sdpcuda_solve_batch); "threads": one host thread + stream per handle; "serial" — and the results are dispatched like
+    relax_sdp.c does (relax_sdp.c:4180-4346): infeasibility certificate => cutoff, bound >= incumbent => cutoff, integral => new
+    incumbent, otherwise most-infeasible branching (branch_sdpmostinf.c).  A relaxation that does not end optimal or with a
+    certificate is solved again alone with the stable settings (the first rung of sdpi.c's ladder); if that fails too the node is
+    branched on its first free integer variable with its parent's bound (nothing is lost, the count is reported as `unsolved`).
+    -> dict(status, objval, sol, nodes, rounds, unsolved, seconds)"""
+    import heapq
+    import itertools
+    import math
+    import time
+    t0 = time.time()
+    ints = np.flatnonzero(model.integer)
+    indicators = list(getattr(model, "indicators", []))
+    lb0, ub0 = model.lb.copy(), model.ub.copy()
+    lb0[ints] = np.ceil(lb0[ints] - inttol)
+    ub0[ints] = np.floor(ub0[ints] + inttol)
+    best, bestsol = math.inf, None
+    tick = itertools.count()
+    heap = [(-math.inf, next(tick), lb0, ub0)]
+    nodes = rounds = unsolved = 0
+    kw = dict(gaptol=gaptol, feastol=feastol)
+    handles = [solver] + list(pool or [])
+
+    def cutoff(bound):
+        return bound >= best - 1e-6 * max(1.0, abs(best))
+
+    def push_children(bound, lb, ub, j, value):
+        dn_ub = ub.copy(); dn_ub[j] = math.floor(value)
+        up_lb = lb.copy(); up_lb[j] = math.ceil(value)
+        if math.floor(value) == math.ceil(value):            # integral value (unsolved node / indicator): split below and above it
+            up_lb[j] = value + 1.0
+        if dn_ub[j] >= lb[j] - inttol:
+            heapq.heappush(heap, (bound, next(tick), lb, dn_ub))
+        if up_lb[j] <= ub[j] + inttol:
+            heapq.heappush(heap, (bound, next(tick), up_lb, ub))
+
+    while heap and nodes < maxnodes and time.time() - t0 < timelimit:
+        rounds += 1
+        todo = []
+        while heap and len(todo) < width:
+            bound, _, lb, ub = heapq.heappop(heap)
+            if cutoff(bound):
+                continue
+            nodes += 1
+            for sl, z in indicators:                         # binary = 1 => slack = 0 (cons_indicator), through the slack's bound
+                if lb[z] > 0.5 and ub[sl] > 0.0:
+                    ub = ub.copy(); ub[sl] = 0.0
+            status, fp, info = model.node_problem(lb, ub, feastol=feastol)
+            if status == "infeasible":
+                continue
+            if status == "allfixed":
+                if info["fixedobj"] < best and not cutoff(info["fixedobj"]):
+                    best, bestsol = info["fixedobj"], info["y"]
+                continue
+            todo.append((bound, fp, info))
+        if not todo:
+            continue
+        if mode == "batch":
+            results = []
+            for c in range(0, len(todo), width):
+                results += solver.solve_batch([fp for _, fp, _ in todo[c:c + width]], **kw)
+        elif mode == "threads" and len(handles) > 1:
+            import threading
+            results = [None] * len(todo)
+
+            def work(k):
+                for i in range(k, len(todo), len(handles)):
+                    results[i] = handles[k].solve(todo[i][1], fetch=False, **kw)
+                    results[i]["y"] = handles[k].get_y()
+
+            th = [threading.Thread(target=work, args=(k,)) for k in range(min(len(handles), len(todo)))]
+            for t in th:
+                t.start()
+            for t in th:
+                t.join()
+        else:
+            results = []
+            for _, fp, _ in todo:
+                r = solver.solve(fp, fetch=False, **kw)
+                r["y"] = solver.get_y()
+                results.append(r)
+        for (bound, fp, info), r in zip(todo, results):
+            lb, ub = info["lb"], info["ub"]
+            if r["phase_name"] not in ("pdOPT", "pFEAS_dINF", "dINF", "pINF_dFEAS"):
+                r = solver.solve(fp, fetch=False, setting=3, **kw)
+                r["y"] = solver.get_y()
+            if r["phase_name"] not in ("pdOPT", "pFEAS_dINF", "dINF", "pINF_dFEAS"):
+                r = _penalty_ladder(solver, model, lb, ub, r, kw)
+            if r["phase_name"] in ("pFEAS_dINF", "dINF"):
+                continue
+            if r["phase_name"] == "pINF_dFEAS":
+                return dict(status="unbounded", objval=-math.inf, sol=None, nodes=nodes, rounds=rounds, unsolved=unsolved, seconds=time.time() - t0)
+            y = lb.copy()
+            y[info["active"]] = r["y"]
+            free = [j for j in ints if ub[j] - lb[j] > 0.5]
+            if r["phase_name"] != "pdOPT":
+                unsolved += 1
+                if free:
+                    push_children(bound, lb, ub, free[0], math.floor(0.5 * (lb[free[0]] + ub[free[0]])) + 0.5)
+                continue
+            obj = r["dobj"] + info["fixedobj"]
+            if cutoff(obj):
+                continue
+            frac = np.abs(y[ints] - np.round(y[ints])) if len(ints) else np.zeros(0)
+            if len(ints) and frac.max() > inttol:
+                j = ints[int(np.argmax(frac))]
+                push_children(obj, lb, ub, j, y[j])
+                continue
+            viol = [z for sl, z in indicators if y[z] > 0.5 and ub[z] - lb[z] > 0.5 and y[sl] > 1e-6]
+            if viol:
+                push_children(obj, lb, ub, viol[0], 0.5)
+                continue
+            best, bestsol = obj, y
+            if verbose:
+                print(f"round {rounds}: incumbent {best:.8g} ({nodes} nodes)")
+    done = not heap or all(cutoff(h[0]) for h in heap)
+    status = ("optimal" if bestsol is not None else "infeasible") if done else "limit"
+    return dict(status=status, objval=best, sol=bestsol, nodes=nodes, rounds=rounds, unsolved=unsolved, seconds=time.time() - t0)
+
+
 def max_over_ranks(value, dist=None, device="cpu"):
     """the timing rule of bench.py: a multi-GPU time is the maximum over ranks"""
     import torch

@@ -76,9 +76,53 @@ class Misdp:
         return self
 
     # ------------------------------------------------------------------ flattening
-    def flatten(self, lb=None, ub=None, epsilon=1e-9, penalty=None):
+    def node_problem(self, lb, ub, epsilon=1e-9, feastol=1e-6):
+        """What sdpi.c does to a branch-and-bound node before the solver sees it (SCIPsdpiSolve, sdpi.c:3123-3399), for drivers that
+        talk to the C ABI directly: rows without active variables are checked and dropped, rows with one active variable tighten
+        its bounds (prepareLPData, sdpi.c:1131-1290), empty rows/columns of the SDP blocks and empty blocks are removed
+        (findEmptyRowColsSDP, sdpi.c:691-810), and a node whose variables are all fixed is decided on the spot (sdpi.c:3219-3290).
+        -> (status, FlatProblem or None, info); status: "solve" | "infeasible" | "allfixed" (feasible, info["fixedobj"] is its value)"""
+        lb, ub = np.array(lb, dtype=float), np.array(ub, dtype=float)
+        for _ in range(4):
+            if np.any(lb > ub + epsilon):
+                return "infeasible", None, {}
+            fixed = (ub - lb) <= epsilon
+            changed = False
+            for coefs, lhs, rhs in self.rows:
+                const = sum(a * lb[j] for j, a in coefs.items() if fixed[j])
+                act = [(j, a) for j, a in coefs.items() if not fixed[j] and a != 0.0]
+                if not act:
+                    if const < lhs - feastol or const > rhs + feastol:
+                        return "infeasible", None, {}
+                elif len(act) == 1:
+                    j, a = act[0]
+                    lo = (lhs - const) / a if lhs > -INF else -INF
+                    hi = (rhs - const) / a if rhs < INF else INF
+                    if a < 0:
+                        lo, hi = (hi if hi < INF else -INF), (lo if lo > -INF else INF)
+                    if lo > lb[j] + epsilon:
+                        lb[j] = lo; changed = True
+                    if hi < ub[j] - epsilon:
+                        ub[j] = hi; changed = True
+            if not changed:
+                break
+        if np.any(lb > ub + epsilon):
+            return "infeasible", None, {}
+        fixed = (ub - lb) <= epsilon
+        if fixed.all():
+            Z = self.dense_Z(lb)
+            ok = all(np.linalg.eigvalsh(z)[0] >= -feastol for z in Z if z.size)
+            return ("allfixed" if ok else "infeasible"), None, dict(fixedobj=float(np.dot(self.obj, lb)), y=lb.copy())
+        fp, info = self.flatten(lb, ub, epsilon=epsilon, compress=True, skip_single_rows=True)
+        info["lb"], info["ub"] = lb, ub
+        return "solve", fp, info
+
+    def flatten(self, lb=None, ub=None, epsilon=1e-9, penalty=None, compress=False, skip_single_rows=False):
         """-> (FlatProblem, info) for the given bounds; variables with ub-lb <= epsilon are fixed and eliminated.
-        info: active (indices), fixedobj, rowmap [(input row, +1 lhs / -1 rhs)], boundmap [(var, +1 lb / -1 ub)]"""
+        info: active (indices), fixedobj, rowmap [(input row, +1 lhs / -1 rhs)], boundmap [(var, +1 lb / -1 ub)].
+        compress: rows/columns of a block that carry no entry of an active variable and no constant entry are removed, blocks
+        without entries too (sdpi.c:691-810); skip_single_rows: rows with one active variable are left out (node_problem has
+        turned them into bounds)"""
         lb = self.lb if lb is None else np.asarray(lb, dtype=float)
         ub = self.ub if ub is None else np.asarray(ub, dtype=float)
         fixed = (ub - lb) <= epsilon
@@ -103,6 +147,23 @@ class Misdp:
         for (b, r, c, v) in cent:
             cm[(b, r, c)] = cm.get((b, r, c), 0.0) + v
         cent = [(b, r, c, v) for (b, r, c), v in sorted(cm.items()) if v != 0.0]
+        blocksizes = list(self.blocksizes)
+        if compress:
+            used = [set() for _ in blocksizes]
+            for ents in per_var:
+                for (b, r, c, v) in ents:
+                    used[b].update((r, c))
+            for (b, r, c, v) in cent:
+                if abs(v) > epsilon:
+                    used[b].update((r, c))
+            bmap, imap, blocksizes = {}, {}, []
+            for b, u in enumerate(used):
+                if u:
+                    bmap[b] = len(blocksizes)
+                    imap[b] = {i: k for k, i in enumerate(sorted(u))}
+                    blocksizes.append(len(u))
+            per_var = [[(bmap[b], imap[b][r], imap[b][c], v) for (b, r, c, v) in ents] for ents in per_var]
+            cent = [(bmap[b], imap[b][r], imap[b][c], v) for (b, r, c, v) in cent if abs(v) > epsilon]
         varbeg = [0]
         eb, er, ec, ev = [], [], [], []
         for j in range(m):
@@ -114,7 +175,7 @@ class Misdp:
         for i, (coefs, lhs, rhs) in enumerate(self.rows):
             const = sum(a * lb[j] for j, a in coefs.items() if fixed[j])
             act = [(amap[j], a) for j, a in sorted(coefs.items()) if not fixed[j] and a != 0.0]
-            if not act:
+            if not act or (skip_single_rows and len(act) == 1):
                 continue
             if lhs > -INF:
                 for j, a in act:
@@ -129,7 +190,30 @@ class Misdp:
                 lpind.append(amap[j]); lpval.append(1.0); lpbeg.append(len(lpind)); lprhs.append(lb[j]); boundmap.append((j, +1))
             if ub[j] < INF:
                 lpind.append(amap[j]); lpval.append(-1.0); lpbeg.append(len(lpind)); lprhs.append(-ub[j]); boundmap.append((j, -1))
-        fp = FlatProblem(self.obj[active], self.blocksizes, varbeg, eb, er, ec, ev,
+        objv = self.obj[active]
+        if penalty is not None:
+            # penalty formulation (SCIPsdpiSolverLoadAndSolveWithPenalty, sdpisolver.h:258-322; sdpisolver_sdpa.cpp:1232-1239,
+            # 1338-1357,1405-1410): one more variable r with objective gamma, + r I on every block and + r in every LP row (not in
+            # the variable bounds); withobj=False drops the original objective, rbound adds r >= 0
+            gamma, withobj, rbound = penalty
+            nrows = len(rowmap)
+            for b, n in enumerate(blocksizes):
+                for i in range(n):
+                    eb.append(b); er.append(i); ec.append(i); ev.append(1.0)
+            varbeg.append(len(eb))
+            newbeg, newind, newval = [0], [], []
+            for l in range(len(lprhs)):
+                newind += lpind[lpbeg[l]:lpbeg[l + 1]]; newval += lpval[lpbeg[l]:lpbeg[l + 1]]
+                if l < nrows:
+                    newind.append(m); newval.append(1.0)
+                newbeg.append(len(newind))
+            lpbeg, lpind, lpval = newbeg, newind, newval
+            if rbound:
+                lpind.append(m); lpval.append(1.0); lpbeg.append(len(lpind)); lprhs.append(0.0)
+            objv = np.concatenate([objv if withobj else np.zeros(m), [gamma]])
+            if not withobj:
+                fixedobj = 0.0
+        fp = FlatProblem(objv, blocksizes, varbeg, eb, er, ec, ev,
                          [t[0] for t in cent], [t[1] for t in cent], [t[2] for t in cent], [t[3] for t in cent],
                          lpbeg, lpind, lpval, lprhs)
         return fp, dict(active=active, fixedobj=fixedobj, rowmap=rowmap, boundmap=boundmap, fixed=fixed)

@@ -132,3 +132,77 @@ def test_solve_batch_boundary():
     assert batch(s.h, 2, None, C.byref(par), None, None) == 1
     assert batch(None, 0, None, C.byref(par), None, None) == 1
     assert batch(s.h, 0, None, None, None, None) == 1
+
+
+# check/testset/short.solu (reference): B&B optima of the short.test instances the harness can read (the same 13 that
+# tests/test_oracle_golden.py checks through the reference's sdpi.c; None = infeasible)
+SHORT_SOLU = {"example_small.dat-s": -8.0, "example_inf.dat-s": None, "example_TT.dat-s.gz": 2.11803,
+              "example_CLS.dat-s.gz": 7.1485, "example_MkP.dat-s.gz": -95.0,
+              "example_small_cbf.cbf": -8.0, "example_cbf_primal.cbf": 0.75, "example_cbf_mix.cbf": 4.0, "example_cbf_dual.cbf": 4.0,
+              "example_multaggr.cbf": -1.0, "example_diagzeroimpl.cbf": -1.0, "example_tightenmatrices.dat-s": -9.0,
+              "example_small_ind.dat-s": -18.0}
+
+
+@pytest.mark.parametrize("name", sorted(SHORT_SOLU))
+def test_frontier_branch_and_bound_reaches_short_solu(name):
+    """frontier-synchronous B&B straight on the C ABI (node presolve of sdpi.c restated in Misdp.node_problem, all open nodes of a
+    round solved by one sdpcuda_solve_batch call, penalty ladder for unacceptable solves): the reference's optimal values"""
+    M = misdp.read_instance(os.path.join(GOLDEN, name))
+    r = frontier.branch_and_bound(abi.Solver(abi.Lib(abi.ORACLE_LIB)), M, mode="batch", width=64, timelimit=300)
+    if SHORT_SOLU[name] is None:
+        assert r["status"] == "infeasible"
+    else:
+        assert r["status"] == "optimal" and r["unsolved"] == 0
+        assert abs(M.file_objective(r["objval"]) - SHORT_SOLU[name]) <= 1e-4 * max(1.0, abs(SHORT_SOLU[name]))
+        # the incumbent is integral and feasible for the original model
+        y = r["sol"]
+        assert np.abs(y[M.integer] - np.round(y[M.integer])).max(initial=0.0) <= 1e-5
+        assert all(np.linalg.eigvalsh(Z)[0] >= -1e-5 for Z in M.dense_Z(y))
+
+
+@pytest.mark.parametrize("mode", ["serial", "threads"])
+def test_frontier_branch_and_bound_other_modes(mode):
+    lib = abi.Lib(abi.ORACLE_LIB)
+    M = misdp.read_instance(os.path.join(GOLDEN, "example_MkP.dat-s.gz"))
+    r = frontier.branch_and_bound(abi.Solver(lib), M, mode=mode, width=1 if mode == "serial" else 8, pool=[abi.Solver(lib) for _ in range(3)])
+    assert r["status"] == "optimal" and abs(r["objval"] + 95.0) <= 1e-2
+
+
+def test_node_problem_follows_sdpi_presolve():
+    """Misdp.node_problem: rows without active variables decide or vanish, one-variable rows become bounds, empty block rows/columns
+    are removed (sdpi.c:691-810,1131-1290,3219-3290)"""
+    M = misdp.read_sdpa(os.path.join(GOLDEN, "example_TT.dat-s.gz"))
+    ints = np.flatnonzero(M.integer)
+    lb, ub = M.lb.copy(), M.ub.copy()
+    ub[ints[:30]] = 0.0
+    st, fp, info = M.node_problem(lb, ub)
+    full, _ = M.flatten(lb, ub)
+    assert st == "solve" and fp.m <= full.m and fp.blocksizes[0] < full.blocksizes[0] and fp.nlp < full.nlp
+    lb2 = M.lb.copy(); lb2[ints] = 1.0                       # every bar at every size: the one-size-per-bar rows are violated
+    assert M.node_problem(lb2, M.ub.copy())[0] == "infeasible"
+    lb3, ub3 = M.lb.copy(), M.ub.copy()
+    lb3[0] = 1.0; ub3[0] = 0.0
+    assert M.node_problem(lb3, ub3)[0] == "infeasible"       # crossed bounds
+    S = misdp.read_sdpa(os.path.join(GOLDEN, "example_small.dat-s"))
+    y = np.array([1.0, 1.0, 1.0])
+    st, fp, info = S.node_problem(y, y)
+    assert st in ("allfixed", "infeasible") and fp is None
+
+
+def test_penalty_form_of_flatten():
+    """the penalty formulation (sdpisolver.h:258-322): r with objective Gamma on every block diagonal and LP row, not on bounds"""
+    M = misdp.read_sdpa(os.path.join(GOLDEN, "example_small.dat-s"))
+    fp0, _ = M.flatten()
+    fp, info = M.flatten(penalty=(7.0, True, True))
+    assert fp.m == fp0.m + 1 and fp.obj[-1] == 7.0 and np.array_equal(fp.obj[:-1], fp0.obj)
+    r_ent = range(fp.varbeg[fp.m - 1], fp.varbeg[fp.m])
+    assert [(fp.entblk[e], fp.entrow[e], fp.entcol[e], fp.entval[e]) for e in r_ent] == [(b, i, i, 1.0) for b, n in enumerate(fp.blocksizes) for i in range(n)]
+    nrows = len(info["rowmap"])
+    D = fp.dense_D()
+    assert np.all(D[:nrows, -1] == 1.0) and np.all(D[nrows:-1, -1] == 0.0) and D[-1, -1] == 1.0 and fp.lprhs[-1] == 0.0
+    assert fp.nlp == fp0.nlp + 1
+    fpf, _ = M.flatten(penalty=(1.0, False, False))
+    assert fpf.nlp == fp0.nlp and np.all(fpf.obj[:-1] == 0.0) and fpf.obj[-1] == 1.0
+    # feasible problem: min r is (clearly) negative, i.e. a strictly feasible point exists
+    q = abi.Solver(abi.Lib(abi.ORACLE_LIB)).solve(fpf, gaptol=1e-6, feastol=1e-6)
+    assert q["phase_name"] == "pdOPT" and q["dobj"] < -1e-3

@@ -112,3 +112,18 @@ def test_frontier_modes_on_one_gpu(lib, mode, monkeypatch):
         assert abs(a["bound"] - b["bound"]) <= 1e-7 * max(1.0, abs(a["bound"]))
     for s in pool:
         s.close()
+
+
+@pytest.mark.parametrize("name,want", [("example_small.dat-s", -8.0), ("example_inf.dat-s", None), ("example_TT.dat-s.gz", 2.11803),
+                                       ("example_CLS.dat-s.gz", 7.1485), ("example_MkP.dat-s.gz", -95.0), ("example_small_ind.dat-s", -18.0)])
+def test_frontier_branch_and_bound_on_gpu(lib, name, want):
+    """frontier-synchronous B&B with all open nodes of a round in one launch: the optimal values of check/testset/short.solu"""
+    M = misdp.read_instance(os.path.join(GOLDEN, name))
+    gpu = abi.Solver(lib, device=0)
+    r = frontier.branch_and_bound(gpu, M, mode="batch", width=592, timelimit=300)
+    if want is None:
+        assert r["status"] == "infeasible"
+    else:
+        assert r["status"] == "optimal", r
+        assert abs(M.file_objective(r["objval"]) - want) <= 1e-4 * max(1.0, abs(want))
+    gpu.close()
