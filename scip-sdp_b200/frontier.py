@@ -13,7 +13,7 @@ def partition(nnodes, world, rank):
 def flatten_nodes(model, node_bounds, world=1, rank=0):
     """solver-form problems of this rank's nodes ({node index: (FlatProblem, info)}): the host-side marshalling that sdpi.c does
     in C for SCIP-SDP; bench.py does it before the timed region"""
-    return {i: model.flatten(*node_bounds[i]) for i in partition(len(node_bounds), world, rank)}
+    return {i: model.flatten_fast(*node_bounds[i]) for i in partition(len(node_bounds), world, rank)}
 
 
 def _solve_nodes_batched(solver, todo, chunk, solve_kw):
@@ -163,7 +163,7 @@ def branch_and_bound(solver, model, mode="batch", width=1184, pool=None, gaptol=
             for sl, z in indicators:                         # binary = 1 => slack = 0 (cons_indicator), through the slack's bound
                 if lb[z] > 0.5 and ub[sl] > 0.0:
                     ub = ub.copy(); ub[sl] = 0.0
-            status, fp, info = model.node_problem(lb, ub, feastol=feastol)
+            status, fp, info = model.node_problem_fast(lb, ub, feastol=feastol)
             if status == "infeasible":
                 continue
             if status == "allfixed":

@@ -37,6 +37,7 @@ class Misdp:
         return self.objsense * value + self.objoffset
 
     def add_entry(self, j, b, r, c, v):
+        self._fast = None
         if r < c:
             r, c = c, r
         if j < 0:
@@ -45,6 +46,7 @@ class Misdp:
             self.A[b].setdefault(j, []).append((r, c, v))
 
     def add_row(self, coefs, lhs=-INF, rhs=INF):
+        self._fast = None
         self.rows.append((dict(coefs), lhs, rhs))
 
     def add_variable(self, obj=0.0, lb=-INF, ub=INF, integer=False):
@@ -53,6 +55,7 @@ class Misdp:
         self.lb = np.append(self.lb, float(lb)); self.ub = np.append(self.ub, float(ub))
         self.integer = np.append(self.integer, bool(integer))
         self.nvars += 1
+        self._fast = None
         return self.nvars - 1
 
     def rows_to_bounds(self):
@@ -73,6 +76,7 @@ class Misdp:
             elif len(nz) > 1:
                 keep.append((dict(nz), lhs, rhs))
         self.rows = keep
+        self._fast = None
         return self
 
     # ------------------------------------------------------------------ flattening
@@ -114,6 +118,175 @@ class Misdp:
             ok = all(np.linalg.eigvalsh(z)[0] >= -feastol for z in Z if z.size)
             return ("allfixed" if ok else "infeasible"), None, dict(fixedobj=float(np.dot(self.obj, lb)), y=lb.copy())
         fp, info = self.flatten(lb, ub, epsilon=epsilon, compress=True, skip_single_rows=True)
+        info["lb"], info["ub"] = lb, ub
+        return "solve", fp, info
+
+    # ------------------------------------------------------------------ vectorised node marshalling (same results as flatten)
+    def _arrays(self):
+        """flat numpy views of the model, cached (rebuilt when the entry counts change); orders follow flatten's loops so that
+        sums are formed in the same order"""
+        sig = (self.nvars, len(self.rows), tuple(map(len, self.C)), tuple(map(len, self.A)))
+        cache = getattr(self, "_fast", None)
+        if cache is not None and cache["sig"] == sig:
+            return cache
+        ev, eb, er, ec, ex = [], [], [], [], []            # block-major, constants (var -1) first: the order flatten builds `cent` in
+        for b in range(len(self.blocksizes)):
+            for (r, c, v) in self.C[b]:
+                ev.append(-1); eb.append(b); er.append(r); ec.append(c); ex.append(v)
+            for j, ents in self.A[b].items():
+                for (r, c, v) in ents:
+                    ev.append(j); eb.append(b); er.append(r); ec.append(c); ex.append(v)
+        ev, eb, er, ec = (np.asarray(a, dtype=np.int64) for a in (ev, eb, er, ec))
+        ex = np.asarray(ex, dtype=float)
+        var_order = np.lexsort((ex, ec, er, eb, ev))       # per variable sorted by (block, row, col, value) like sorted(per_var[j])
+        var_order = var_order[ev[var_order] >= 0]
+        rid, rj, ra = [], [], []                           # row nonzeros in dict order (constants of fixed variables)
+        for i, (coefs, lhs, rhs) in enumerate(self.rows):
+            for j, a in coefs.items():
+                rid.append(i); rj.append(j); ra.append(a)
+        rid, rj = np.asarray(rid, dtype=np.int64), np.asarray(rj, dtype=np.int64)
+        ra = np.asarray(ra, dtype=float)
+        srt = np.lexsort((rj, rid))                        # per row sorted by variable (emission order)
+        cache = dict(sig=sig, ev=ev, eb=eb, er=er, ec=ec, ex=ex, var_order=var_order, rid=rid, rj=rj, ra=ra, srt=srt,
+                     lhs=np.array([r[1] for r in self.rows], dtype=float), rhs=np.array([r[2] for r in self.rows], dtype=float),
+                     maxn=max(self.blocksizes, default=1))
+        self._fast = cache
+        return cache
+
+    def flatten_fast(self, lb=None, ub=None, epsilon=1e-9, compress=False, skip_single_rows=False, maps=True):
+        """flatten(...) without Python loops over entries (identical arrays; tests/test_readers_cpu.py compares them)"""
+        F = self._arrays()
+        lb = self.lb if lb is None else np.asarray(lb, dtype=float)
+        ub = self.ub if ub is None else np.asarray(ub, dtype=float)
+        fixed = (ub - lb) <= epsilon
+        active = np.flatnonzero(~fixed)
+        m = len(active)
+        amap = -np.ones(self.nvars + 1, dtype=np.int64)
+        amap[active] = np.arange(m)
+        fixedobj = float(np.dot(self.obj[fixed], lb[fixed]))
+        ev, eb, er, ec, ex, maxn = F["ev"], F["eb"], F["er"], F["ec"], F["ex"], F["maxn"]
+        # entries of active variables
+        vo = F["var_order"]
+        vo = vo[~fixed[ev[vo]]]
+        aj, ab, arow, acol, aval = amap[ev[vo]], eb[vo], er[vo], ec[vo], ex[vo]
+        varbeg = np.concatenate([[0], np.cumsum(np.bincount(aj, minlength=m))]).astype(np.int32) if m else np.zeros(1, dtype=np.int32)
+        # constant part: A_0 and the fixed variables, duplicates summed in input order
+        isc = ev < 0
+        sel = np.flatnonzero(isc | fixed[np.where(isc, 0, ev)])
+        cval = np.where(isc[sel], ex[sel], -lb[np.where(isc[sel], 0, ev[sel])] * ex[sel])
+        key = (eb[sel] * maxn + er[sel]) * maxn + ec[sel]
+        ukey, inv = np.unique(key, return_inverse=True)
+        csum = np.zeros(len(ukey))
+        np.add.at(csum, inv, cval)
+        keepc = csum != 0.0
+        if compress:
+            keepc &= np.abs(csum) > epsilon
+        ukey, csum = ukey[keepc], csum[keepc]
+        cb, cr, cc = ukey // (maxn * maxn), (ukey // maxn) % maxn, ukey % maxn
+        blocksizes = list(self.blocksizes)
+        if compress:
+            nb = len(blocksizes)
+            used = np.zeros((nb, maxn), dtype=bool)
+            used[ab, arow] = True; used[ab, acol] = True
+            used[cb, cr] = True; used[cb, cc] = True
+            newidx = np.cumsum(used, axis=1) - 1
+            keepb = used.any(axis=1)
+            bmap = np.cumsum(keepb) - 1
+            blocksizes = [int(x) for x in used.sum(axis=1)[keepb]]
+            arow, acol, ab = newidx[ab, arow], newidx[ab, acol], bmap[ab]
+            cr, cc, cb = newidx[cb, cr], newidx[cb, cc], bmap[cb]
+        # LP rows: constants of the fixed variables (dict order), active entries sorted by variable
+        rid, rj, ra, srt = F["rid"], F["rj"], F["ra"], F["srt"]
+        nrows = len(self.rows)
+        fx = fixed[rj] if len(rj) else np.zeros(0, dtype=bool)
+        const = np.bincount(rid[fx], weights=ra[fx] * lb[rj[fx]], minlength=nrows) if nrows else np.zeros(0)
+        srid, srj, sra = rid[srt], rj[srt], ra[srt]
+        actm = ~fixed[srj] & (sra != 0.0) if len(srj) else np.zeros(0, dtype=bool)
+        srid, srj, sra = srid[actm], amap[srj[actm]], sra[actm]
+        nact = np.bincount(srid, minlength=nrows) if nrows else np.zeros(0, dtype=np.int64)
+        rbeg = np.concatenate([[0], np.cumsum(nact)])
+        keep = nact >= (2 if skip_single_rows else 1)
+        el = np.flatnonzero(keep & (F["lhs"] > -INF))
+        eh = np.flatnonzero(keep & (F["rhs"] < INF))
+        erow = np.concatenate([el, eh])
+        esgn = np.concatenate([np.ones(len(el)), -np.ones(len(eh))])
+        order = np.lexsort((-esgn, erow))                  # per row: lhs part first
+        erow, esgn = erow[order], esgn[order]
+        cnt = nact[erow]
+        start = np.repeat(rbeg[erow], cnt)
+        within = np.arange(int(cnt.sum())) - np.repeat(np.cumsum(cnt) - cnt, cnt)
+        src = start + within
+        lpind = srj[src]
+        lpval = sra[src] * np.repeat(esgn, cnt)
+        lprhs = np.where(esgn > 0, F["lhs"][erow] - const[erow], -(F["rhs"][erow] - const[erow]))
+        rowmap = [(int(i), int(sg)) for i, sg in zip(erow, esgn)] if maps else None
+        # variable bounds as rows: per active variable lb first, then ub
+        hl = lb[active] > -INF
+        hu = ub[active] < INF
+        bj = np.concatenate([np.flatnonzero(hl), np.flatnonzero(hu)])
+        bs = np.concatenate([np.ones(int(hl.sum())), -np.ones(int(hu.sum()))])
+        order = np.lexsort((-bs, bj))
+        bj, bs = bj[order], bs[order]
+        brhs = np.where(bs > 0, lb[active][bj], -ub[active][bj])
+        lpbeg = np.concatenate([[0], np.cumsum(cnt), int(cnt.sum()) + 1 + np.arange(len(bj))]).astype(np.int32)
+        boundmap = [(int(active[j]), int(sg)) for j, sg in zip(bj, bs)] if maps else None
+        fp = FlatProblem(self.obj[active], blocksizes, varbeg, ab, arow, acol, aval, cb, cr, cc, csum,
+                         lpbeg, np.concatenate([lpind, bj]), np.concatenate([lpval, bs]), np.concatenate([lprhs, brhs]))
+        return fp, dict(active=active, fixedobj=fixedobj, rowmap=rowmap, boundmap=boundmap, fixed=fixed)
+
+    def node_problem_fast(self, lb, ub, epsilon=1e-9, feastol=1e-6):
+        """node_problem(...) on the cached arrays (identical results)"""
+        F = self._arrays()
+        lb, ub = np.array(lb, dtype=float), np.array(ub, dtype=float)
+        rid, rj, ra = F["rid"], F["rj"], F["ra"]
+        nrows = len(self.rows)
+        for _ in range(4):
+            if np.any(lb > ub + epsilon):
+                return "infeasible", None, {}
+            if nrows == 0:
+                break
+            fixed = (ub - lb) <= epsilon
+            fx = fixed[rj]
+            const = np.bincount(rid[fx], weights=ra[fx] * lb[rj[fx]], minlength=nrows)
+            am = ~fx & (ra != 0.0)
+            nact = np.bincount(rid[am], minlength=nrows)
+            none = nact == 0
+            if np.any(none & ((const < F["lhs"] - feastol) | (const > F["rhs"] + feastol))):
+                return "infeasible", None, {}
+            one = np.flatnonzero(am & (nact[rid] == 1))
+            if len(one) == 0:
+                break
+            # rows that can tighten anything at all (bounds only move inwards during the pass), then sequentially like node_problem
+            i1, j1, a1 = rid[one], rj[one], ra[one]
+            with np.errstate(over="ignore", invalid="ignore"):
+                lo1 = np.where(F["lhs"][i1] > -INF, (F["lhs"][i1] - const[i1]) / a1, -INF)
+                hi1 = np.where(F["rhs"][i1] < INF, (F["rhs"][i1] - const[i1]) / a1, INF)
+            neg = a1 < 0
+            lo2 = np.where(neg, np.where(hi1 < INF, hi1, -INF), lo1)
+            hi2 = np.where(neg, np.where(lo1 > -INF, lo1, INF), hi1)
+            one = one[(lo2 > lb[j1] + epsilon) | (hi2 < ub[j1] - epsilon)]
+            changed = False
+            for t in one:
+                i, j, a = rid[t], rj[t], ra[t]
+                lhs, rhs = F["lhs"][i], F["rhs"][i]
+                lo = (lhs - const[i]) / a if lhs > -INF else -INF
+                hi = (rhs - const[i]) / a if rhs < INF else INF
+                if a < 0:
+                    lo, hi = (hi if hi < INF else -INF), (lo if lo > -INF else INF)
+                if lo > lb[j] + epsilon:
+                    lb[j] = lo; changed = True
+                if hi < ub[j] - epsilon:
+                    ub[j] = hi; changed = True
+            if not changed:
+                break
+        if np.any(lb > ub + epsilon):
+            return "infeasible", None, {}
+        fixed = (ub - lb) <= epsilon
+        if fixed.all():
+            Z = self.dense_Z(lb)
+            ok = all(np.linalg.eigvalsh(z)[0] >= -feastol for z in Z if z.size)
+            return ("allfixed" if ok else "infeasible"), None, dict(fixedobj=float(np.dot(self.obj, lb)), y=lb.copy())
+        fp, info = self.flatten_fast(lb, ub, epsilon=epsilon, compress=True, skip_single_rows=True, maps=False)
         info["lb"], info["ub"] = lb, ub
         return "solve", fp, info
 

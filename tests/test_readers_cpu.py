@@ -220,3 +220,33 @@ def test_reference_malformed_files_are_rejected():
     for f in files:
         with pytest.raises(misdp.SdpaFormatError):
             misdp.read_sdpa(f)
+
+
+def test_vectorised_node_marshalling_equals_the_loop_version():
+    """Misdp.flatten_fast / node_problem_fast (numpy, used by the frontier drivers) produce exactly the arrays of flatten /
+    node_problem (plain loops, the documented restatement of sdpisolver_sdpa.cpp:1015-1412 and sdpi.c's node presolve)"""
+    import glob
+    from scip_sdp_b200 import generators
+    rng = np.random.default_rng(0)
+    models = [misdp.read_instance(f) for f in sorted(glob.glob(os.path.join(GOLDEN, "example_*")))]
+    models += [generators.truss(4, 4, 60, seed=13), generators.cls(20, 12, 4, seed=3), generators.mkp(12, seed=2), generators.maxcut(30, 0.2, seed=1)]
+    fields = "obj blocksizes varbeg entblk entrow entcol entval cblk crow ccol cval lpbeg lpind lpval lprhs".split()
+    for M in models:
+        for to_bounds in (False, True):
+            if to_bounds:
+                M = M.rows_to_bounds()
+            ints = np.flatnonzero(M.integer)
+            for trial in range(6):
+                lb, ub = M.lb.copy(), M.ub.copy()
+                for j in rng.permutation(ints)[:rng.integers(0, len(ints) + 1)]:
+                    lb[j] = ub[j] = float(np.clip(rng.integers(0, 2), max(lb[j], -5), min(ub[j], 5)))
+                for compress, skip in ((False, False), (True, True)):
+                    a, ia = M.flatten(lb, ub, compress=compress, skip_single_rows=skip)
+                    b, ib = M.flatten_fast(lb, ub, compress=compress, skip_single_rows=skip)
+                    assert all(np.array_equal(getattr(a, k), getattr(b, k)) for k in fields)
+                    assert ia["fixedobj"] == ib["fixedobj"] and ia["rowmap"] == ib["rowmap"] and ia["boundmap"] == ib["boundmap"]
+                s1, s2 = M.node_problem(lb, ub), M.node_problem_fast(lb, ub)
+                assert s1[0] == s2[0]
+                if s1[0] == "solve":
+                    assert all(np.array_equal(getattr(s1[1], k), getattr(s2[1], k)) for k in fields)
+                    assert np.array_equal(s1[2]["lb"], s2[2]["lb"]) and np.array_equal(s1[2]["ub"], s2[2]["ub"])
