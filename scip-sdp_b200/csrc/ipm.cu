@@ -1198,6 +1198,9 @@ int sdpcuda_solve_batch(sdpcuda_handle* h, int count, const sdpcuda_problem* con
          batch_bind_node(nodes[k], h->batchimg.p, h->batchwork.p + nodes[k].work, h->batchy.p + nodes[k].yoff, h->batchres.p + k);
          args[k] = nodes[k].a;
       }
+      // the work space is shared by batches of different layouts: start from zeros (padding rows and alignment gaps are never
+      // written by the kernel; a few tens of MB at most)
+      CK( cudaMemsetAsync(h->batchwork.p, 0, sizeof(double) * worktotal, st) );
       CK( cudaMemcpyAsync(h->batchimg.p, img.buf.data(), img.buf.size(), cudaMemcpyHostToDevice, st) );
       CK( cudaMemcpyAsync(h->batchargs.p, args.data(), sizeof(SmallArgs) * nd, cudaMemcpyHostToDevice, st) );
       CK( cudaEventRecord(h->ev0, st) );
