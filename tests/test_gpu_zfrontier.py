@@ -127,3 +127,19 @@ def test_frontier_branch_and_bound_on_gpu(lib, name, want):
         assert r["status"] == "optimal", r
         assert abs(M.file_objective(r["objval"]) - want) <= 1e-4 * max(1.0, abs(want))
     gpu.close()
+
+
+@pytest.mark.parametrize("name,want", [("example_inf.dat-s", None), ("example_small_ind.dat-s", -18.0)])
+def test_bnb_through_the_reference_sdpi_layer_later_cases(name, want):
+    """the two short.test instances whose harness-level reading changed after the last GPU run of round 1 (example_inf: block-size
+    line with a glued comment, now read like reader_sdpa.c does; example_small_ind: indicator entries), through the reference's
+    sdpi.c + sdpisolver_cuda.c + libsdpcuda exactly like tests/test_gpu_sdpi.py"""
+    from harness import bnb, sdpi_ref
+    os.environ.setdefault("SHIM_QUIET", "1")
+    M = misdp.read_instance(os.path.join(GOLDEN, name))
+    r = bnb.solve_misdp(sdpi_ref.SdpiLib(sdpi_ref.LIB_CUDA), M, timelimit=900)
+    if want is None:
+        assert r["status"] == "infeasible"
+    else:
+        assert r["status"] == "optimal" and r["unsolved"] == 0
+        assert abs(M.file_objective(r["objval"]) - want) <= 1e-4 * max(1.0, abs(want))
