@@ -214,6 +214,12 @@ int  sdpcuda_syev_batched(sdpcuda_handle* h, int n, int nbatch, const double* A,
  * version of SCIPsdpSolcheckerCheck (sdpsolchecker.c:58-270: lambda_min(Z(y)) >= -feastol  <=>  Z(y) + feastol*I psd). */
 int  sdpcuda_psd_check(sdpcuda_handle* h, int n, const double* A, int lda, double shift, int* is_psd);
 
+/* the same test for the problem that is RESIDENT on the device (the reduced problem of the last sdpcuda_solve): is
+ * sum_j y_j A_j^(k) - C^(k) + shift*I positive definite for every block?  y: [m] host vector or NULL = the solution of the last
+ * solve (already on the device).  Nothing but y travels to the device — no dense matrix is formed on the host (SURVEY.md 8f.3:
+ * the block part of SCIPsdpSolcheckerCheck, sdpsolchecker.c:166-260, after every converged solve). */
+int  sdpcuda_check_psd_resident(sdpcuda_handle* h, const double* y, double shift, int* is_psd);
+
 /* ---- kernel-level entry points (parity tests and roofline measurement; host buffers, column-major like BLAS) ---- */
 /* C(m x n) = alpha*op(A)*op(B) + beta*C ; transa/transb: 0 = N, 1 = T */
 int  sdpcuda_dgemm(sdpcuda_handle* h, int transa, int transb, int m, int n, int k, double alpha,

@@ -678,6 +678,27 @@ int sdpcuda_solve_resident(sdpcuda_handle* h, const sdpcuda_params* par, sdpcuda
    if( res != NULL ) *res = h->s.res;
    return rc;
 }
+/* is sum_j y_j A_j - C + shift I positive definite for every block of the loaded problem?  (LAPACK Cholesky) */
+int sdpcuda_check_psd_resident(sdpcuda_handle* h, const double* y, double shift, int* is_psd)
+{
+   if( h == NULL || is_psd == NULL ) return SDPCUDA_ERR_ARG;
+   if( h->s.P.m <= 0 || (y == NULL && !h->s.solved) ) return SDPCUDA_ERR_STATE;
+   const Problem& P = h->s.P;
+   vec yy = (y != NULL) ? vec(y, y + P.m) : h->s.it.y;
+   std::vector<vec> Z, C;
+   h->s.AT(yy, Z);
+   h->s.Cmat(C);
+   *is_psd = 1;
+   for( int k = 0; k < P.nblocks && *is_psd; ++k )
+   {
+      int n = P.bs[k], info = 0;
+      for( size_t e = 0; e < Z[k].size(); ++e ) Z[k][e] -= C[k][e];
+      for( int i = 0; i < n; ++i ) Z[k][(size_t)i * n + i] += shift;
+      scipy_dpotrf_("L", &n, Z[k].data(), &n, &info);
+      if( info != 0 ) *is_psd = 0;
+   }
+   return SDPCUDA_OK;
+}
 /* checker-side stand-in of the frontier batch: the nodes one after the other */
 int sdpcuda_solve_batch(sdpcuda_handle* h, int count, const sdpcuda_problem* const* probs, const sdpcuda_params* par,
    sdpcuda_result* res, double* const* y_out)

@@ -129,6 +129,7 @@ class Lib:
         L.sdpcuda_dpotrf_inv.argtypes = [C.c_void_p, C.c_int, _dp, C.c_int, _dp, C.c_int, _ip]
         L.sdpcuda_psd_check.argtypes = [C.c_void_p, C.c_int, _dp, C.c_int, C.c_double, _ip]
         L.sdpcuda_time_kernel.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, _dp, _dp]
+        L.sdpcuda_check_psd_resident.argtypes = [C.c_void_p, _dp, C.c_double, _ip]
 
     def backend(self):
         return self.lib.sdpcuda_backend_name().decode()
@@ -363,6 +364,16 @@ class Solver:
         rc = self.L.lib.sdpcuda_psd_check(self.h, Af.shape[0], Af.ctypes.data_as(_dp), Af.shape[0], shift, C.byref(ok))
         if rc != 0:
             raise RuntimeError(f"sdpcuda_psd_check failed with code {rc}")
+        return bool(ok.value)
+
+    def check_psd_resident(self, y=None, shift=0.0):
+        """is sum_j y_j A_j - C + shift I positive definite for every block of the problem resident from the last solve?
+        y = None: the solution of the last solve (already on the device)"""
+        ok = C.c_int(0)
+        yp = _d(y).ctypes.data_as(_dp) if y is not None else None
+        rc = self.L.lib.sdpcuda_check_psd_resident(self.h, yp, shift, C.byref(ok))
+        if rc != 0:
+            raise RuntimeError(f"sdpcuda_check_psd_resident failed with code {rc}")
         return bool(ok.value)
 
     def time_kernel(self, kind, n, reps=10):

@@ -2031,6 +2031,32 @@ int sdpcuda_psd_check(sdpcuda_handle* h, int n, const double* A, int lda, double
    return SDPCUDA_OK;
 }
 
+int sdpcuda_check_psd_resident(sdpcuda_handle* h, const double* y, double shift, int* is_psd)
+{
+   if( h == nullptr || is_psd == nullptr ) return SDPCUDA_ERR_ARG;
+   if( !h->resident || (y == nullptr && !h->solved) ) return SDPCUDA_ERR_STATE;
+   if( set_device(h) ) return SDPCUDA_ERR_CUDA;
+   cudaStream_t st = h->st;
+   const double* yd = h->y.p;
+   if( y != nullptr )
+   {
+      CK( cudaMemcpyAsync(h->tm1.p, y, sizeof(double) * h->m, cudaMemcpyHostToDevice, st) );      // tm1: scratch of m + 1 doubles
+      yd = h->tm1.p;
+   }
+   int rc = assemble(h, yd, 1.0, h->K.p);                  // K = sum_j y_j A_j - C (scratch matrix of the iteration)
+   if( rc != SDPCUDA_OK ) return rc;
+   CK( cudaMemsetAsync(h->info.p, 0, 8 * sizeof(int), st) );
+   for( const Block& bk : h->blk )
+   {
+      if( shift != 0.0 ) CK( add_diagonal(st, bk.n, h->K.p + bk.off, bk.ld, shift) );
+      CK( potrf_lower(st, bk.n, h->K.p + bk.off, bk.ld, nullptr, 0, nullptr, h->work.p, round_up(h->maxn, 4), h->info.p) );
+   }
+   CK( cudaMemcpyAsync(h->h_info, h->info.p, sizeof(int), cudaMemcpyDeviceToHost, st) );
+   CK( cudaStreamSynchronize(st) );
+   *is_psd = (h->h_info[0] == 0) ? 1 : 0;
+   return SDPCUDA_OK;
+}
+
 int sdpcuda_dtrtri(sdpcuda_handle* h, int n, double* L, int ldl)
 {
    if( h == nullptr || n < 0 ) return SDPCUDA_ERR_ARG;

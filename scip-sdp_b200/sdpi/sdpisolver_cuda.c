@@ -19,6 +19,7 @@
  *      settings MEDIUM and STABLE are tried (sdpisolver_sdpa.cpp:1698-1795).
  */
 #include <assert.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "sdpi/sdpisolver.h"
@@ -97,6 +98,8 @@ struct SCIP_SDPiSolver
    SCIP_Real**           X;                  /**< [nsdpblocks] dense reduced multiplier blocks (lazily fetched) */
    int*                  Xcap;
    SCIP_Bool*            Xvalid;
+
+   SCIP_Bool             devicecheck;        /**< post-check of the SDP blocks on the problem resident on the device (SDPCUDA_DEVICE_CHECK=1) */
 
    /* status */
    sdpcuda_result        res;
@@ -386,6 +389,11 @@ SCIP_RETCODE SCIPsdpiSolverCreate(SCIP_SDPISOLVER** sdpisolver, SCIP_MESSAGEHDLR
    s->objlimit = CUDASDP_INF;
    s->lambdastar = -1.0;
    s->preoptimalgap = -1.0;
+   {
+      /* off by default in round 1 (written after the last GPU run): the checker then builds Z(y) on the host and ships it */
+      const char* e = getenv("SDPCUDA_DEVICE_CHECK");
+      s->devicecheck = (e != NULL && e[0] == '1');
+   }
    s->sdpinfo = FALSE;
    s->nthreads = -1;
 
@@ -918,7 +926,43 @@ SCIP_RETCODE SCIPsdpiSolverLoadAndSolveWithPenalty(
 
          MEM_CALL( BMSallocBufferMemoryArray(s->bufmem, &solvector, nvars) );
          retcode = SCIPsdpiSolverGetDualSol(s, NULL, solvector);
-         if( retcode == SCIP_OKAY )
+         if( retcode == SCIP_OKAY && s->devicecheck )
+         {
+            /* same contract as SCIPsdpSolcheckerCheck (sdpsolchecker.c:58-270): bounds and rows here (O(nnz)), the blocks as a
+             * device Cholesky of Z(y) + feastol I assembled from the problem that is already resident in HBM */
+            int psd = 1;
+
+            infeasible = FALSE;
+            for( i = 0; i < nvars && !infeasible; ++i )
+               infeasible = (solvector[i] < lb[i] - s->feastol || solvector[i] > ub[i] + s->feastol);
+            for( i = 0; i < nlpcons && !infeasible; ++i )
+            {
+               SCIP_Real act = 0.0;
+               int last = (i == nlpcons - 1) ? lpnnonz : lpbeg[i + 1];
+               int p;
+
+               if( lpindchanges[i] < 0 )
+                  continue;
+               for( p = lpbeg[i]; p < last; ++p )
+               {
+                  if( lb[lpind[p]] < ub[lpind[p]] - s->epsilon )
+                     act += solvector[lpind[p]] * lpval[p];
+               }
+               infeasible = (act < lplhs[i] - s->feastol || act > lprhs[i] + s->feastol);
+            }
+            if( !infeasible && s->ndevblocks > 0 )
+            {
+               if( sdpcuda_check_psd_resident(s->dev, NULL, s->feastol * (1.0 + 1e-6) + 1e-13, &psd) != SDPCUDA_OK )
+               {
+                  BMSfreeBufferMemoryArray(s->bufmem, &solvector);
+                  SCIPerrorMessage("sdpcuda_check_psd_resident failed.\n");
+                  retcode = SCIP_LPERROR;
+                  goto TERMINATE;
+               }
+               infeasible = !psd;
+            }
+         }
+         else if( retcode == SCIP_OKAY )
          {
             retcode = SCIPsdpSolcheckerCheck(s->bufmem, nvars, lb, ub, nsdpblocks, sdpblocksizes, sdpnblockvars, sdpconstnnonz,
                sdpconstnblocknonz, sdpconstrow, sdpconstcol, sdpconstval, sdpnnonz, sdpnblockvarnonz, sdpvar, sdprow, sdpcol, sdpval,

@@ -86,3 +86,46 @@ def test_getters_before_a_solve_return_lperror():
         assert L.SCIPsdpiSolverGetIterations(s.s, C.byref(it)) in (sdpisolver_host.SCIP_OKAY, SCIP_LPERROR)
     finally:
         s.close()
+
+
+def _resident_check_cases(solver, tol=1e-9):
+    """sdpcuda_check_psd_resident against numpy's eigenvalues: the solution of the last solve, shifted copies of it and random
+    vectors, on instances with one and with several blocks (shared by the CPU-oracle and the GPU suite)"""
+    import os
+    import numpy as np
+    from scip_sdp_b200 import generators, misdp
+    golden = os.path.join(os.path.dirname(__file__), "golden")
+    rng = np.random.default_rng(5)
+    for make in (lambda: misdp.read_sdpa(os.path.join(golden, "example_small.dat-s")).rows_to_bounds(),
+                 lambda: misdp.read_sdpa(os.path.join(golden, "example_MkP.dat-s.gz")).rows_to_bounds(),
+                 lambda: generators.cls(12, 9, 3, seed=5), lambda: generators.maxcut(150, 0.05, seed=11)):
+        M = make()
+        fp, _ = M.flatten()
+        r = solver.solve(fp, gaptol=1e-7, feastol=1e-7)
+        assert r["phase_name"] == "pdOPT"
+
+        def lam_min(y):
+            Cd = fp.dense_C()
+            Z = [sum(y[j] * fp.dense_A(j)[k] for j in range(fp.m)) - Cd[k] for k in range(fp.nblocks)]
+            return min(float(np.linalg.eigvalsh(z)[0]) for z in Z)
+
+        lam = lam_min(r["y"])
+        assert lam >= -1e-6                                     # the solution is (nearly) feasible
+        assert solver.check_psd_resident(None, shift=1e-5)      # ... and the device says so for the y it holds
+        assert solver.check_psd_resident(r["y"], shift=1e-5)
+        for _ in range(4):
+            y = r["y"] + rng.standard_normal(fp.m) * 0.3 * max(1.0, np.abs(r["y"]).max())
+            lam = lam_min(y)
+            for shift in (0.0, -lam + 1e-3 * max(1.0, abs(lam)), -lam - 1e-3 * max(1.0, abs(lam))):
+                if abs(lam + shift) > tol:
+                    assert solver.check_psd_resident(y, shift=shift) == (lam + shift > 0), (lam, shift)
+
+
+def test_resident_psd_check_on_the_oracle():
+    from scip_sdp_b200 import abi
+    s = abi.Solver(abi.Lib(abi.ORACLE_LIB))
+    import ctypes as C
+    ok = C.c_int(0)
+    assert s.L.lib.sdpcuda_check_psd_resident(s.h, None, 0.0, C.byref(ok)) == 4      # SDPCUDA_ERR_STATE: nothing loaded
+    assert s.L.lib.sdpcuda_check_psd_resident(s.h, None, 0.0, None) == 1             # SDPCUDA_ERR_ARG
+    _resident_check_cases(s)

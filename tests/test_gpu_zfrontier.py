@@ -143,3 +143,25 @@ def test_bnb_through_the_reference_sdpi_layer_later_cases(name, want):
     else:
         assert r["status"] == "optimal" and r["unsolved"] == 0
         assert abs(M.file_objective(r["objval"]) - want) <= 1e-4 * max(1.0, abs(want))
+
+
+def test_resident_psd_check_on_gpu(lib):
+    """sdpcuda_check_psd_resident (device assemble + Cholesky of the resident problem) against numpy's eigenvalues"""
+    from test_boundary_cpu import _resident_check_cases
+    gpu = abi.Solver(lib, device=0)
+    _resident_check_cases(gpu)
+    gpu.close()
+
+
+def test_checksdpi_known_answers_with_the_device_resident_post_check(monkeypatch):
+    """the ported unittests/src/checksdpi.c cases with SDPCUDA_DEVICE_CHECK=1: the binding's post-check of every converged solve
+    then runs on the device-resident problem instead of shipping a dense Z(y)"""
+    from golden.checksdpi_cases import CASES
+    from harness import checksdpi_port, sdpi_ref
+    os.environ.setdefault("SHIM_QUIET", "1")
+    monkeypatch.setenv("SDPCUDA_DEVICE_CHECK", "1")
+    L = sdpi_ref.SdpiLib(sdpi_ref.LIB_CUDA)
+    for name in sorted(CASES):
+        if L.solver_name() in CASES[name].get("skip_for", []):
+            continue
+        checksdpi_port.run_case(L, CASES[name], name)
