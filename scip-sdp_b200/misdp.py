@@ -452,6 +452,76 @@ class Misdp:
             f.write(data)
 
 
+    def write_cbf(self, path):
+        """CBF version 2 in the dual form that reader_cbf.c writes (reader_cbf.c:2780-3440): scalar variables with their sign cones
+        (L+ / L- / L= / F; other finite bounds become linear constraints), INT, linear constraints grouped as L= , L+ , L-,
+        one PSDCON per block with HCOORD (the A_j) and DCOORD (= -A_0), PSDCONRANK1, objective in the file's own sense"""
+        if self.indicators:
+            raise ValueError("indicator constraints cannot be written in CBF")
+        cones, extra = [], []
+        for j in range(self.nvars):
+            lo, hi = self.lb[j], self.ub[j]
+            if lo == 0.0 and hi == 0.0:
+                cone = "L="
+            elif lo == 0.0:
+                cone = "L+"
+            elif hi == 0.0:
+                cone = "L-"
+            else:
+                cone = "F"
+            if lo > -INF and lo != 0.0:
+                extra.append(({j: 1.0}, lo, INF))
+            if hi < INF and hi != 0.0:
+                extra.append(({j: 1.0}, -INF, hi))
+            if cones and cones[-1][0] == cone:
+                cones[-1][1] += 1
+            else:
+                cones.append([cone, 1])
+        eq, ge, le = [], [], []              # (coefficients, constant b) of  a'x + b  in  L= / L+ / L-
+        for coefs, lhs, rhs in list(self.rows) + extra:
+            if lhs > -INF and rhs < INF and lhs == rhs:
+                eq.append((coefs, -lhs))
+            else:
+                if lhs > -INF:
+                    ge.append((coefs, -lhs))
+                if rhs < INF:
+                    le.append((coefs, -rhs))
+        cons = eq + ge + le
+        out = io.StringIO()
+        out.write("VER\n2\n\nOBJSENSE\n" + ("MIN" if self.objsense == 1 else "MAX") + "\n\n")
+        out.write(f"VAR\n{self.nvars} {len(cones)}\n" + "".join(f"{c} {n}\n" for c, n in cones) + "\n")
+        ints = np.flatnonzero(self.integer)
+        if len(ints):
+            out.write(f"INT\n{len(ints)}\n" + "".join(f"{j}\n" for j in ints) + "\n")
+        if cons:
+            groups = [(c, len(g)) for c, g in (("L=", eq), ("L+", ge), ("L-", le)) if g]
+            out.write(f"CON\n{len(cons)} {len(groups)}\n" + "".join(f"{c} {n}\n" for c, n in groups) + "\n")
+        if self.blocksizes:
+            out.write(f"PSDCON\n{len(self.blocksizes)}\n" + "".join(f"{n}\n" for n in self.blocksizes) + "\n")
+        if self.rank1:
+            out.write(f"PSDCONRANK1\n{len(self.rank1)}\n" + "".join(f"{b}\n" for b in self.rank1) + "\n")
+        objfile = self.objsense * self.obj
+        nz = np.flatnonzero(objfile)
+        out.write(f"OBJACOORD\n{len(nz)}\n" + "".join(f"{j} {float(objfile[j])!r}\n" for j in nz) + "\n")
+        if self.objoffset != 0.0:
+            out.write(f"OBJBCOORD\n{float(self.objoffset)!r}\n\n")
+        if cons:
+            ac = [(i, j, a) for i, (coefs, b) in enumerate(cons) for j, a in sorted(coefs.items()) if a != 0.0]
+            out.write(f"ACOORD\n{len(ac)}\n" + "".join(f"{i} {j} {float(a)!r}\n" for i, j, a in ac) + "\n")
+            bc = [(i, b) for i, (coefs, b) in enumerate(cons) if b != 0.0]
+            if bc:
+                out.write(f"BCOORD\n{len(bc)}\n" + "".join(f"{i} {float(b)!r}\n" for i, b in bc) + "\n")
+        hc = [(b, j, r, c, v) for b in range(len(self.blocksizes)) for j in sorted(self.A[b]) for (r, c, v) in self.A[b][j]]
+        if hc:
+            out.write(f"HCOORD\n{len(hc)}\n" + "".join(f"{b} {j} {r} {c} {float(v)!r}\n" for b, j, r, c, v in hc) + "\n")
+        dc = [(b, r, c, -v) for b in range(len(self.blocksizes)) for (r, c, v) in self.C[b]]
+        if dc:
+            out.write(f"DCOORD\n{len(dc)}\n" + "".join(f"{b} {r} {c} {float(v)!r}\n" for b, r, c, v in dc) + "\n")
+        opener = gzip.open if str(path).endswith(".gz") else open
+        with opener(path, "wt") as f:
+            f.write(out.getvalue())
+
+
 def _tokens(line):
     # SDPA files may separate numbers by blanks, commas, braces or parentheses
     for ch in ",(){}":

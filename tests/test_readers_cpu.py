@@ -250,3 +250,28 @@ def test_vectorised_node_marshalling_equals_the_loop_version():
                 if s1[0] == "solve":
                     assert all(np.array_equal(getattr(s1[1], k), getattr(s2[1], k)) for k in fields)
                     assert np.array_equal(s1[2]["lb"], s2[2]["lb"]) and np.array_equal(s1[2]["ub"], s2[2]["ub"])
+
+
+# unittests/src/readwrite.c:66-140 (runTests): read an instance, write it as CBF and as SDPA, read both files again, solve all three:
+# the optimal values agree (the SDPA format has no objective sense, so its value is compared in the internal min form)
+READWRITE = ["example_small.dat-s", "example_small_cbf.cbf", "example_inf.dat-s", "example_TT.dat-s.gz", "example_MkP.dat-s.gz",
+             "example_cbf_primal.cbf", "example_cbf_mix.cbf", "example_cbf_dual.cbf", "example_multaggr.cbf", "example_diagzeroimpl.cbf",
+             "example_tightenmatrices.dat-s"]
+
+
+@pytest.mark.parametrize("name", READWRITE)
+def test_read_write_read_gives_the_same_optimum(tmp_path, name):
+    from scip_sdp_b200 import frontier
+    lib = abi.Lib(abi.ORACLE_LIB)
+    M = misdp.read_instance(os.path.join(GOLDEN, name))
+    M.write_cbf(tmp_path / "t.cbf")
+    M.write_sdpa(tmp_path / "t.dat-s")
+    Mc, Ms = misdp.read_cbf(tmp_path / "t.cbf"), misdp.read_sdpa(tmp_path / "t.dat-s")
+    assert (Mc.nvars, Mc.blocksizes, Mc.objsense) == (M.nvars, M.blocksizes, M.objsense) and np.array_equal(Mc.integer, M.integer)
+    assert np.allclose(Mc.obj, M.obj) and Mc.objoffset == M.objoffset
+    runs = [frontier.branch_and_bound(abi.Solver(lib), X, mode="batch", width=64, timelimit=120) for X in (M, Mc, Ms)]
+    assert len({r["status"] for r in runs}) == 1
+    if runs[0]["status"] == "optimal":
+        v = [runs[0]["objval"], runs[1]["objval"], runs[2]["objval"]]
+        assert abs(M.file_objective(v[0]) - Mc.file_objective(v[1])) <= 1e-4 * max(1.0, abs(v[0]))
+        assert abs(v[0] - v[2]) <= 1e-4 * max(1.0, abs(v[0]))
