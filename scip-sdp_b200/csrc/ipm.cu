@@ -1192,11 +1192,30 @@ int sdpcuda_solve_batch(sdpcuda_handle* h, int count, const sdpcuda_problem* con
       CK( h->batchy.ensure(ytotal) );
       CK( h->batchargs.ensure(nd) );
       CK( h->batchres.ensure(nd) );
+      // SDPCUDA_BATCH_TINY=1: relaxations whose blocks all have order <= 16 go to the 256-thread instantiation (four per SM);
+      // off by default until it has run on a GPU.  The descriptors are ordered tiny first, then the others: two launches.
+      const char* te = getenv("SDPCUDA_BATCH_TINY");
+      const bool usetiny = (te != nullptr && te[0] == '1');
+      std::vector<int> slot(nd);
+      int ntiny = 0;
+      {
+         std::vector<int> tiny, rest;
+         for( int k = 0; k < nd; ++k )
+         {
+            int mx = 0;
+            for( int b = 0; b < nodes[k].a.nb; ++b ) mx = std::max(mx, nodes[k].a.blk[b].n);
+            (usetiny && mx <= TINY_MAX_N ? tiny : rest).push_back(k);
+         }
+         ntiny = (int)tiny.size();
+         int pos = 0;
+         for( int k : tiny ) slot[k] = pos++;
+         for( int k : rest ) slot[k] = pos++;
+      }
       std::vector<SmallArgs> args(nd);
       for( int k = 0; k < nd; ++k )
       {
          batch_bind_node(nodes[k], h->batchimg.p, h->batchwork.p + nodes[k].work, h->batchy.p + nodes[k].yoff, h->batchres.p + k);
-         args[k] = nodes[k].a;
+         args[slot[k]] = nodes[k].a;
       }
       // the work space is shared by batches of different layouts: start from zeros (padding rows and alignment gaps are never
       // written by the kernel; a few tens of MB at most)
@@ -1204,7 +1223,8 @@ int sdpcuda_solve_batch(sdpcuda_handle* h, int count, const sdpcuda_problem* con
       CK( cudaMemcpyAsync(h->batchimg.p, img.buf.data(), img.buf.size(), cudaMemcpyHostToDevice, st) );
       CK( cudaMemcpyAsync(h->batchargs.p, args.data(), sizeof(SmallArgs) * nd, cudaMemcpyHostToDevice, st) );
       CK( cudaEventRecord(h->ev0, st) );
-      CK( launch_ipm_small_batch(st, nd, h->batchargs.p) );
+      CK( launch_ipm_tiny_batch(st, ntiny, h->batchargs.p) );
+      CK( launch_ipm_small_batch(st, nd - ntiny, h->batchargs.p + ntiny) );
       CK( cudaEventRecord(h->ev1, st) );
       std::vector<SmallResult> sr(nd);
       std::vector<double> ys(ytotal);
@@ -1222,7 +1242,7 @@ int sdpcuda_solve_batch(sdpcuda_handle* h, int count, const sdpcuda_problem* con
          sdpcuda_result R;
          memset(&R, 0, sizeof(R));
          R.phase = sr[k].phase; R.stop = sr[k].stop; R.iterations = sr[k].iterations;
-         R.launches = (k == 0) ? 1 : 0;                  // the one launch is shared by all batched nodes
+         R.launches = (k == 0) ? (int)h->counter.n : 0;   // the launch (two with the tiny instantiation) is shared by all batched nodes
          R.pobj = sr[k].pobj; R.dobj = sr[k].dobj; R.relgap = sr[k].relgap; R.pinf = sr[k].pinf; R.dinf = sr[k].dinf; R.mu = sr[k].mu;
          R.seconds = wall; R.device_ms = ms;             // of the whole batch: the nodes run side by side
          R.h2d_bytes = (double)(img.buf.size() + sizeof(SmallArgs) * nd) / nd;

@@ -14,8 +14,22 @@
 namespace sdpk {
 namespace {
 
+#ifdef SDPK_VARIANT_TINY
+// second instantiation of this file (ipm_tiny.cu) for frontier batches of relaxations with blocks of order <= 16: 256 threads and
+// 41 KB of shared memory per CTA, so that four CTAs (= four nodes) share an SM; the Schur factor still fits shared memory up to m = 64
+constexpr int NT = 256;
+constexpr int VMAXN = TINY_MAX_N;
+constexpr int MSN = 64;
+constexpr int MINB = 4;
+#define ipm_small_batch_kernel ipm_tiny_batch_kernel
+#else
 constexpr int NT = 1024;
-constexpr int LDS = SMALL_MAX_N + 1;
+constexpr int VMAXN = SMALL_MAX_N;       // largest block
+constexpr int MSN = SMALL_MAX_N;         // largest Schur complement whose factor lives in shared memory
+constexpr int MINB = 1;
+#endif
+constexpr int LDS = VMAXN + 1;
+constexpr int LDMS = MSN + 1;
 
 struct Ctl                      // control block in shared memory, written by thread 0
 {
@@ -560,14 +574,14 @@ __device__ double lanczos_warp(int n, const double* Bs, double* Qs, double* ab)
    return theta - resid;
 }
 
-// Cholesky of M + reg I entirely in shared memory (m <= 64, row stride LDS); rdiag receives 1 / l_kk
+// Cholesky of M + reg I entirely in shared memory (m <= 64, row stride LDMS); rdiag receives 1 / l_kk
 __device__ bool cholM_smem(const SmallArgs& a, double reg, double* Ms, double* rdiag, int* flag)
 {
    const int m = a.m, ldm = a.ldm;
    for( int e = threadIdx.x; e < m * m; e += NT )
    {
       const int i = e % m, j = e / m;
-      if( i >= j ) Ms[i * LDS + j] = a.M[(size_t)j * ldm + i] + ((i == j) ? reg : 0.0);
+      if( i >= j ) Ms[i * LDMS + j] = a.M[(size_t)j * ldm + i] + ((i == j) ? reg : 0.0);
    }
    if( threadIdx.x == 0 ) *flag = 0;
    __syncthreads();
@@ -575,21 +589,21 @@ __device__ bool cholM_smem(const SmallArgs& a, double reg, double* Ms, double* r
    {
       if( threadIdx.x == 0 )
       {
-         double d = Ms[k * LDS + k];
+         double d = Ms[k * LDMS + k];
          if( !(d > 0.0) ) { *flag = 1; d = 1.0; }
          double r = frsqrt(d);
          rdiag[k] = r;
-         Ms[k * LDS + k] = d * r;
+         Ms[k * LDMS + k] = d * r;
       }
       __syncthreads();
       const double r = rdiag[k];
-      for( int i = k + 1 + threadIdx.x; i < m; i += NT ) Ms[i * LDS + k] *= r;
+      for( int i = k + 1 + threadIdx.x; i < m; i += NT ) Ms[i * LDMS + k] *= r;
       __syncthreads();
       const int rem = m - k - 1;
       for( int e = threadIdx.x; e < rem * rem; e += NT )
       {
          const int i = k + 1 + e % rem, j = k + 1 + e / rem;
-         if( i >= j ) Ms[i * LDS + j] -= Ms[i * LDS + k] * Ms[j * LDS + k];
+         if( i >= j ) Ms[i * LDMS + j] -= Ms[i * LDMS + k] * Ms[j * LDMS + k];
       }
       __syncthreads();
    }
@@ -609,14 +623,14 @@ __device__ void solveM_smem(int m, const double* Ms, const double* rdiag, double
       for( int k = 0; k < m; ++k )
       {
          double xk = __shfl_sync(0xffffffffu, (k < 32) ? r0 : r1, k & 31) * rdiag[k];
-         if( lane == k ) r0 = xk; else if( lane > k && lane < m ) r0 -= Ms[lane * LDS + k] * xk;
-         if( lane + 32 == k ) r1 = xk; else if( lane + 32 > k && lane + 32 < m ) r1 -= Ms[(lane + 32) * LDS + k] * xk;
+         if( lane == k ) r0 = xk; else if( lane > k && lane < m ) r0 -= Ms[lane * LDMS + k] * xk;
+         if( lane + 32 == k ) r1 = xk; else if( lane + 32 > k && lane + 32 < m ) r1 -= Ms[(lane + 32) * LDMS + k] * xk;
       }
       for( int k = m - 1; k >= 0; --k )
       {
          double xk = __shfl_sync(0xffffffffu, (k < 32) ? r0 : r1, k & 31) * rdiag[k];
-         if( lane == k ) r0 = xk; else if( lane < k ) r0 -= Ms[k * LDS + lane] * xk;
-         if( lane + 32 == k ) r1 = xk; else if( lane + 32 < k ) r1 -= Ms[k * LDS + lane + 32] * xk;
+         if( lane == k ) r0 = xk; else if( lane < k ) r0 -= Ms[k * LDMS + lane] * xk;
+         if( lane + 32 == k ) r1 = xk; else if( lane + 32 < k ) r1 -= Ms[k * LDMS + lane + 32] * xk;
       }
       if( lane < m ) v[lane] = r0;
       if( lane + 32 < m ) v[lane + 32] = r1;
@@ -629,20 +643,20 @@ __device__ __forceinline__ void ipm_small_body(const SmallArgs& a)
 {
    extern __shared__ __align__(16) double smem[];
    double* sh = smem;                               // 64 x 65
-   double* sh2 = sh + SMALL_MAX_N * LDS;            // 64 x 65
-   double* red = sh2 + SMALL_MAX_N * LDS;           // 32
+   double* sh2 = sh + VMAXN * LDS;                  // 64 x 65
+   double* red = sh2 + VMAXN * LDS;                 // 32
    double* rdiag = red + 32;                        // 64
-   double* rdiagM = rdiag + SMALL_MAX_N;            // 256
+   double* rdiagM = rdiag + VMAXN;                  // 256
    double* al = rdiagM + SMALL_MAX_M;               // 32 + 32 + 40
    double* be = al + SMALL_LZ_STEPS;
    double* coef = be + SMALL_LZ_STEPS;
    double* lzq = coef + SMALL_LZ_STEPS + 8;         // 2 x (SMALL_LZ_STEPS + 2) x 65 : Krylov vectors of the two warp-level Lanczos runs
    double* lzab = lzq + 2 * (SMALL_LZ_STEPS + 2) * LDS;   // 2 x (32 + 32 + 64)
    double* Msh = lzab + 2 * (2 * SMALL_LZ_STEPS + 64);     // 64 x 65 : factor of the Schur complement when m <= 64
-   double* lam2 = Msh + SMALL_MAX_N * LDS;          // 2 results
+   double* lam2 = Msh + MSN * LDMS;                 // 2 results
    Ctl* c = reinterpret_cast<Ctl*>(lam2 + 8);
    int* flag = reinterpret_cast<int*>(c + 1);
-   const bool msmall = (a.m <= SMALL_MAX_N);
+   const bool msmall = (a.m <= MSN);
    const int tid = threadIdx.x;
    const int m = a.m, nb = a.nb, nlp = a.nlp;
    const double inftol = 1e-8;
@@ -1015,15 +1029,17 @@ __device__ __forceinline__ void ipm_small_body(const SmallArgs& a)
    }
 }
 
-__global__ void __launch_bounds__(NT, 1)
+#ifndef SDPK_VARIANT_TINY
+__global__ void __launch_bounds__(NT, MINB)
 ipm_small_kernel(const SmallArgs a)
 {
    ipm_small_body(a);
 }
+#endif
 
 // frontier batch: CTA i solves the relaxation described by all[i] (its own device buffers); the descriptor is staged in shared
 // memory once, the CTAs never communicate
-__global__ void __launch_bounds__(NT, 1)
+__global__ void __launch_bounds__(NT, MINB)
 ipm_small_batch_kernel(const SmallArgs* __restrict__ all)
 {
    __shared__ SmallArgs sa;
@@ -1035,11 +1051,12 @@ ipm_small_batch_kernel(const SmallArgs* __restrict__ all)
    ipm_small_body(sa);
 }
 
-constexpr size_t SMALL_SMEM = (2 * SMALL_MAX_N * LDS + 32 + SMALL_MAX_N + SMALL_MAX_M + 3 * SMALL_LZ_STEPS + 8 + 2 * (SMALL_LZ_STEPS + 2) * LDS
-   + 2 * (2 * SMALL_LZ_STEPS + 64) + SMALL_MAX_N * LDS + 8) * sizeof(double) + sizeof(Ctl) + 64;
+constexpr size_t SMALL_SMEM = (2 * VMAXN * LDS + 32 + VMAXN + SMALL_MAX_M + 3 * SMALL_LZ_STEPS + 8 + 2 * (SMALL_LZ_STEPS + 2) * LDS
+   + 2 * (2 * SMALL_LZ_STEPS + 64) + MSN * LDMS + 8) * sizeof(double) + sizeof(Ctl) + 64;
 
 } // namespace
 
+#ifndef SDPK_VARIANT_TINY
 cudaError_t launch_ipm_small(cudaStream_t st, const SmallArgs& a)
 {
    static bool configured[64] = {false};
@@ -1070,5 +1087,25 @@ cudaError_t launch_ipm_small_batch(cudaStream_t st, int count, const SmallArgs* 
    count_launch();
    return cudaGetLastError();
 }
+
+#else
+
+cudaError_t launch_ipm_tiny_batch(cudaStream_t st, int count, const SmallArgs* dev_args)
+{
+   static bool configured[64] = {false};
+   int dev = 0;
+   if( count <= 0 ) return cudaSuccess;
+   SDPK_CUDA_CHECK( cudaGetDevice(&dev) );
+   if( !configured[dev & 63] )
+   {
+      SDPK_CUDA_CHECK( cudaFuncSetAttribute(ipm_tiny_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMALL_SMEM) );
+      configured[dev & 63] = true;
+   }
+   ipm_tiny_batch_kernel<<<count, NT, SMALL_SMEM, st>>>(dev_args);
+   count_launch();
+   return cudaGetLastError();
+}
+
+#endif
 
 } // namespace sdpk

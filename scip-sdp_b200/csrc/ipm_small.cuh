@@ -8,6 +8,7 @@ namespace sdpk {
 
 constexpr int SMALL_MAX_N = 64;        // largest SDP block
 constexpr int SMALL_MAX_M = 256;       // largest Schur complement
+constexpr int TINY_MAX_N = 16;         // blocks of the second instantiation (ipm_tiny.cu): four relaxations per SM
 constexpr int SMALL_MAX_BLOCKS = 16;
 constexpr int SMALL_MAX_GROUPS = 8;
 constexpr int SMALL_LZ_STEPS = 32;     // Lanczos steps per step-length matrix (exact when the block order is smaller)
@@ -52,5 +53,7 @@ struct SmallArgs
 cudaError_t launch_ipm_small(cudaStream_t st, const SmallArgs& a);
 // one launch for a whole frontier of small relaxations: CTA i solves dev_args[i] (device array of `count` descriptors)
 cudaError_t launch_ipm_small_batch(cudaStream_t st, int count, const SmallArgs* dev_args);
+// the same for relaxations whose blocks all have order <= TINY_MAX_N: CTAs of 256 threads, four per SM (ipm_tiny.cu)
+cudaError_t launch_ipm_tiny_batch(cudaStream_t st, int count, const SmallArgs* dev_args);
 
 } // namespace sdpk

@@ -165,3 +165,23 @@ def test_checksdpi_known_answers_with_the_device_resident_post_check(monkeypatch
         if L.solver_name() in CASES[name].get("skip_for", []):
             continue
         checksdpi_port.run_case(L, CASES[name], name)
+
+
+@pytest.mark.parametrize("name,q", [("example_small.dat-s", 2), ("example_TT.dat-s.gz", 4), ("example_MkP.dat-s.gz", 3)])
+def test_tiny_instantiation_of_the_batch_kernel(lib, cpu, name, q, monkeypatch):
+    """SDPCUDA_BATCH_TINY=1: relaxations with blocks of order <= 16 run in the 256-thread instantiation (four nodes per SM,
+    csrc/ipm_tiny.cu): same statuses, bounds within 1e-7 relative of the 1024-thread kernel (reduction orders differ) and within
+    the north-star tolerance of the oracle"""
+    M = misdp.read_sdpa(os.path.join(GOLDEN, name)).rows_to_bounds()
+    keep = [fp for fp, _ in (M.flatten(lb, ub) for lb, ub in _frontier(M, q)) if fp.m > 0]
+    gpu = abi.Solver(lib, device=0)
+    regular = gpu.solve_batch(keep, **KW)
+    monkeypatch.setenv("SDPCUDA_BATCH_TINY", "1")
+    tiny = gpu.solve_batch(keep, **KW)
+    for fp, a, b in zip(keep, regular, tiny):
+        assert a["phase_name"] == b["phase_name"], (a["phase_name"], b["phase_name"], b["stop_name"])
+        if a["phase_name"] == "pdOPT":
+            assert abs(a["dobj"] - b["dobj"]) <= 1e-7 * max(1.0, abs(a["dobj"]))
+            ref = cpu.solve(fp, **KW)
+            assert abs(b["dobj"] - ref["dobj"]) <= 1e-5 * max(1.0, abs(ref["dobj"]))
+    gpu.close()
