@@ -58,12 +58,15 @@ class FlatProblem:
         assert len(self.varbeg) == self.m + 1 and len(self.lpbeg) == self.nlp + 1
 
     def struct(self):
+        if getattr(self, "_struct", None) is not None:      # the arrays are never modified after construction
+            return self._struct
         p = Problem()
         p.m, p.nblocks, p.nlp, p.cnnz = self.m, self.nblocks, self.nlp, len(self.cval)
         for name in ("obj", "entval", "cval", "lpval", "lprhs"):
             setattr(p, name, getattr(self, name).ctypes.data_as(_dp))
         for name in ("blocksizes", "varbeg", "entblk", "entrow", "entcol", "cblk", "crow", "ccol", "lpbeg", "lpind"):
             setattr(p, name, getattr(self, name).ctypes.data_as(_ip))
+        self._struct = p
         return p
 
     # dense helpers used by the tests for a-posteriori KKT checks
