@@ -56,6 +56,8 @@ def parse():
     ap.add_argument("--frontier-mode", default="serial", choices=["serial", "batch", "threads"],
                     help="frontier workloads: nodes one after the other on one handle, all nodes of a chunk in ONE launch (sdpcuda_solve_batch, "
                          "one CTA per node; for the shipped instances), or one host thread + stream per handle")
+    ap.add_argument("--bnb-partition", default="replicas", choices=["replicas", "rounds"],
+                    help="bnb-* workloads at N > 1: one complete tree per GPU, or ONE tree whose rounds are partitioned over the ranks")
     ap.add_argument("--handles-per-gpu", type=int, default=0, help="handles (host threads + streams) per GPU of --frontier-mode threads (default 4)")
     return ap.parse_args()
 
@@ -137,24 +139,25 @@ def bnb_bench(a, rank, local, world):
     npool = (a.handles_per_gpu or 4) if mode == "threads" else 1
     pool = [abi.Solver(lib, device=local) for _ in range(npool - 1)]
     width = {"serial": 1, "threads": 4 * npool, "batch": 592}[mode]
-    run = lambda s, p, md, w: frontier.branch_and_bound(s, M, mode=md, width=w, pool=p, gaptol=1e-5, feastol=1e-5)      # noqa: E731
+    shared = world > 1 and a.bnb_partition == "rounds"
+    run = lambda s, p, md, w, d=None: frontier.branch_and_bound(s, M, mode=md, width=w, pool=p, gaptol=1e-5, feastol=1e-5, dist=d)      # noqa: E731
     for _ in range(max(1, a.warmup)):
-        r = run(gpu, pool, mode, width)
+        r = run(gpu, pool, mode, width, dist if shared else None)
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     nodes = 0
     for _ in range(a.steps):
-        r = run(gpu, pool, mode, width)
+        r = run(gpu, pool, mode, width, dist if shared else None)
         nodes += r["nodes"]
     torch.cuda.synchronize()
     wall = frontier.max_over_ranks(time.perf_counter() - t0, dist=dist if world > 1 else None, device="cuda")
     if rank == 0:
-        line = {"metric": "B&B nodes/sec", "value": world * nodes / wall, "unit": "nodes/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
-                "scaling": "weak", "dtype": "f64", "data": "reference instance", "higher_is_better": True, "ms_per_step": 1e3 * wall / a.steps,
+        line = {"metric": "B&B nodes/sec", "value": (1 if shared else world) * nodes / wall, "unit": "nodes/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+                "scaling": "strong" if shared else "weak", "dtype": "f64", "data": "reference instance", "higher_is_better": True, "ms_per_step": 1e3 * wall / a.steps,
                 "config": {"workload": a.workload, "instance": inst[0], "frontier_mode": mode, "width": width, "handles_per_gpu": npool,
-                           "partition": "replicas (one complete tree per GPU)"},
+                           "partition": "one tree, the nodes of every round dealt round-robin to the ranks" if shared else "replicas (one complete tree per GPU)"},
                 "nodes_per_run": r["nodes"], "rounds_per_run": r["rounds"], "unsolved": r["unsolved"], "status": r["status"],
                 "objective": M.file_objective(r["objval"]), "short_solu": inst[1]}
         if not a.no_cpu_baseline:

@@ -113,7 +113,7 @@ def _penalty_ladder(solver, model, lb, ub, r, kw, penaltyparam=1e5, maxpenaltypa
 
 
 def branch_and_bound(solver, model, mode="batch", width=1184, pool=None, gaptol=1e-5, feastol=1e-5, inttol=1e-5, maxnodes=1000000,
-                     timelimit=600.0, verbose=False):
+                     timelimit=600.0, verbose=False, dist=None):
     """Frontier-synchronous branch-and-bound on the C ABI: in every round the (at most `width`) best open nodes are prepared like
     sdpi.c prepares a node (Misdp.node_problem), their relaxations are solved TOGETHER — mode "batch": one kernel launch, one CTA
     per node (sdpcuda_solve_batch); "threads": one host thread + stream per handle; "serial" — and the results are dispatched like
@@ -121,6 +121,9 @@ def branch_and_bound(solver, model, mode="batch", width=1184, pool=None, gaptol=
     incumbent, otherwise most-infeasible branching (branch_sdpmostinf.c).  A relaxation that does not end optimal or with a
     certificate is solved again alone with the stable settings (the first rung of sdpi.c's ladder); if that fails too the node is
     branched on its first free integer variable with its parent's bound (nothing is lost, the count is reported as `unsolved`).
+    dist: torch.distributed with world size N > 1 (one process per GPU): every rank runs the same deterministic tree, in each round
+    rank r solves the nodes r, r + N, ... of the round on its own device and the results (status, bound, y) are all-gathered — the
+    partition of SURVEY.md 8e.1, no collective on the data path of a relaxation.
     -> dict(status, objval, sol, nodes, rounds, unsolved, seconds)"""
     import heapq
     import itertools
@@ -138,6 +141,8 @@ def branch_and_bound(solver, model, mode="batch", width=1184, pool=None, gaptol=
     nodes = rounds = unsolved = 0
     kw = dict(gaptol=gaptol, feastol=feastol)
     handles = [solver] + list(pool or [])
+    world = dist.get_world_size() if dist is not None and dist.is_initialized() else 1
+    rank = dist.get_rank() if world > 1 else 0
 
     def cutoff(bound):
         return bound >= best - 1e-6 * max(1.0, abs(best))
@@ -152,8 +157,10 @@ def branch_and_bound(solver, model, mode="batch", width=1184, pool=None, gaptol=
         if up_lb[j] <= ub[j] + inttol:
             heapq.heappush(heap, (bound, next(tick), up_lb, ub))
 
-    while heap and nodes < maxnodes and time.time() - t0 < timelimit:
+    expired = False
+    while heap and nodes < maxnodes and not expired:
         rounds += 1
+        expired = time.time() - t0 >= timelimit            # acted upon after this round (and, with several ranks, agreed upon)
         todo = []
         while heap and len(todo) < width:
             bound, _, lb, ub = heapq.heappop(heap)
@@ -173,7 +180,12 @@ def branch_and_bound(solver, model, mode="batch", width=1184, pool=None, gaptol=
             todo.append((bound, fp, info))
         if not todo:
             continue
-        if mode == "batch":
+        alltodo = todo
+        if world > 1:
+            todo = alltodo[rank::world]
+        if not todo:
+            results = []
+        elif mode == "batch":
             results = []
             for c in range(0, len(todo), width):
                 results += solver.solve_batch([fp for _, fp, _ in todo[c:c + width]], **kw)
@@ -197,13 +209,24 @@ def branch_and_bound(solver, model, mode="batch", width=1184, pool=None, gaptol=
                 r = solver.solve(fp, fetch=False, **kw)
                 r["y"] = solver.get_y()
                 results.append(r)
-        for (bound, fp, info), r in zip(todo, results):
-            lb, ub = info["lb"], info["ub"]
+        for k, ((bound, fp, info), r) in enumerate(zip(todo, results)):       # repair unacceptable solves on the rank that owns the node
             if r["phase_name"] not in ("pdOPT", "pFEAS_dINF", "dINF", "pINF_dFEAS"):
                 r = solver.solve(fp, fetch=False, setting=3, **kw)
                 r["y"] = solver.get_y()
             if r["phase_name"] not in ("pdOPT", "pFEAS_dINF", "dINF", "pINF_dFEAS"):
-                r = _penalty_ladder(solver, model, lb, ub, r, kw)
+                r = _penalty_ladder(solver, model, info["lb"], info["ub"], r, kw)
+            results[k] = r
+        if world > 1:
+            slim = [dict(phase_name=r["phase_name"], dobj=float(r["dobj"]), y=np.asarray(r["y"], dtype=float)) for r in results]
+            gathered = [None] * world
+            dist.all_gather_object(gathered, (expired, slim))
+            results = [None] * len(alltodo)
+            for q, (flag, part) in enumerate(gathered):
+                results[q::world] = part
+                expired = expired or flag
+            todo = alltodo
+        for (bound, fp, info), r in zip(todo, results):
+            lb, ub = info["lb"], info["ub"]
             if r["phase_name"] in ("pFEAS_dINF", "dINF"):
                 continue
             if r["phase_name"] == "pINF_dFEAS":

@@ -206,3 +206,35 @@ def test_penalty_form_of_flatten():
     # feasible problem: min r is (clearly) negative, i.e. a strictly feasible point exists
     q = abi.Solver(abi.Lib(abi.ORACLE_LIB)).solve(fpf, gaptol=1e-6, feastol=1e-6)
     assert q["phase_name"] == "pdOPT" and q["dobj"] < -1e-3
+
+
+def _bnb_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        M = misdp.read_instance(os.path.join(GOLDEN, "example_MkP.dat-s.gz"))
+        r = frontier.branch_and_bound(abi.Solver(abi.Lib(abi.ORACLE_LIB)), M, mode="batch", width=64, dist=dist)
+        q.put((rank, r["status"], r["objval"], r["nodes"], r["rounds"]))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_branch_and_bound_world_size_2_runs_the_same_tree():
+    """the rounds of the B&B driver partitioned over two ranks (gloo): both ranks end with the tree of the single-process run"""
+    M = misdp.read_instance(os.path.join(GOLDEN, "example_MkP.dat-s.gz"))
+    single = frontier.branch_and_bound(abi.Solver(abi.Lib(abi.ORACLE_LIB)), M, mode="batch", width=64)
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_bnb_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = [q.get(timeout=300) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, status, objval, nodes, rounds in got:
+        assert (status, nodes, rounds) == (single["status"], single["nodes"], single["rounds"])
+        assert objval == single["objval"]
