@@ -1,0 +1,169 @@
+"""CPU suite, part 6: the frontier-batch kernel executed on the CPU.  tests/harness/cuemu compiles the SOURCE of csrc/ipm_small.cu
+(both instantiations) against a fiber-based emulation of a CUDA thread block (every thread a fiber, __syncthreads / warp shuffles as
+scheduler barriers); the descriptors and the packed image come from the product library's own packing code
+(sdpcuda_debug_pack_node, the host half of sdpcuda_solve_batch) bound to host buffers.  Together this runs the whole batch path —
+packing, descriptor staging in shared memory, in-kernel cold start and dense-matrix expansion, the interior-point iteration, the
+result and y write-back — without a GPU, and compares with the CPU oracle at the north-star tolerance (1e-5 relative).
+It checks logic, not timing or races; the GPU suite (tests/test_gpu_zfrontier.py) remains the parity test proper."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from scip_sdp_b200 import abi, generators, misdp
+from test_batch_pack import SmallArgs
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+EMUDIR = os.path.join(os.path.dirname(__file__), "harness", "cuemu")
+KW = dict(gaptol=1e-6, feastol=1e-6)
+
+
+class SmallResult(C.Structure):      # sdpk::SmallResult (csrc/ipm_small.cuh)
+    _fields_ = [("phase", C.c_int), ("stop", C.c_int), ("iterations", C.c_int), ("backtracks", C.c_int),
+                ("pobj", C.c_double), ("dobj", C.c_double), ("relgap", C.c_double), ("pinf", C.c_double), ("dinf", C.c_double), ("mu", C.c_double)]
+
+
+@pytest.fixture(scope="module")
+def emu():
+    r = subprocess.run(["make", "-C", EMUDIR], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-2000:]
+    L = C.CDLL(os.path.join(EMUDIR, "_build", "libcuemu_ipm.so"))
+    for f in (L.cuemu_run_small_batch, L.cuemu_run_tiny_batch):
+        f.argtypes = [C.c_int, C.c_void_p, C.c_size_t]
+    return L
+
+
+@pytest.fixture(scope="module")
+def lib():
+    L = abi.Lib(abi.PRODUCT_LIB)
+    L.lib.sdpcuda_debug_pack_node.argtypes = [C.POINTER(abi.Problem), C.POINTER(abi.Params), C.c_ulonglong, C.c_ulonglong, C.c_ulonglong,
+                                              C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t),
+                                              C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t), C.POINTER(C.c_int)]
+    return L
+
+
+CANARY = 1.2345e300
+
+
+def run_batch(lib, emu, probs, tiny=False, **kw):
+    """the device half of sdpcuda_solve_batch on the emulator: -> list of dict(phase_name, dobj, ..., y)"""
+    par = lib.default_params(**kw)
+    n = len(probs)
+    descs = (SmallArgs * n)()
+    res = (SmallResult * n)()
+    keep = []
+    for i, fp in enumerate(probs):
+        st = fp.struct()
+        nimg, nwork, ndesc, fits = C.c_size_t(0), C.c_size_t(0), C.c_size_t(0), C.c_int(-1)
+        assert lib.lib.sdpcuda_debug_pack_node(C.byref(st), C.byref(par), 0, 0, 0, None, 0, C.byref(nimg), C.byref(nwork), None, 0,
+                                               C.byref(ndesc), C.byref(fits)) == 0
+        assert fits.value == 1 and ndesc.value == C.sizeof(SmallArgs)
+        img = np.zeros(nimg.value + 64, dtype=np.uint8)
+        work = np.zeros(nwork.value + 64)
+        work[nwork.value:] = CANARY
+        y = np.full(fp.m + 17, CANARY)
+        assert lib.lib.sdpcuda_debug_pack_node(C.byref(st), C.byref(par), img.ctypes.data, work.ctypes.data, y.ctypes.data, img.ctypes.data,
+                                               img.size, C.byref(nimg), C.byref(nwork), C.byref(descs[i]), C.sizeof(SmallArgs),
+                                               C.byref(ndesc), C.byref(fits)) == 0
+        descs[i].out = C.addressof(res[i])
+        keep.append((img, work, y, nwork.value))
+    run = emu.cuemu_run_tiny_batch if tiny else emu.cuemu_run_small_batch
+    assert run(n, C.addressof(descs), C.sizeof(SmallArgs)) == 0, "emulator reported a deadlock or a shared-memory overrun"
+    out = []
+    for i, fp in enumerate(probs):
+        img, work, y, nw = keep[i]
+        assert np.all(work[nw:] == CANARY), "the kernel wrote behind the node's work space"
+        assert np.all(y[fp.m + 1:] == CANARY), "the kernel wrote behind the node's y"
+        r = res[i]
+        out.append(dict(phase_name=abi.PHASES[r.phase], stop_name=abi.STOPS[r.stop], iterations=r.iterations, pobj=r.pobj, dobj=r.dobj,
+                        relgap=r.relgap, pinf=r.pinf, dinf=r.dinf, y=y[:fp.m].copy()))
+    return out
+
+
+def _nodes(M, q):
+    ints = np.flatnonzero(M.integer)[:q]
+    for code in range(1 << q):
+        lb, ub = M.lb.copy(), M.ub.copy()
+        for b, j in enumerate(ints):
+            lb[j] = ub[j] = float((code >> b) & 1)
+        fp, info = M.flatten_fast(lb, ub)
+        if fp.m > 0:
+            yield fp
+
+
+def _compare(fp, r, ref):
+    assert (r["phase_name"] == "pdOPT") == (ref["phase_name"] == "pdOPT"), (r["phase_name"], r["stop_name"], ref["phase_name"])
+    if ref["phase_name"] in ("pFEAS_dINF", "dINF"):
+        assert r["phase_name"] in ("pFEAS_dINF", "dINF")
+    if ref["phase_name"] == "pdOPT":
+        assert abs(r["dobj"] - ref["dobj"]) <= 1e-5 * max(1.0, abs(ref["dobj"]))
+        assert np.allclose(r["y"], ref["y"], atol=1e-3 * max(1.0, np.abs(ref["y"]).max()))
+        assert r["relgap"] <= 1e-5 and r["pinf"] <= 1e-5 and r["dinf"] <= 1e-5
+
+
+@pytest.mark.parametrize("tiny", [False, True], ids=["1024-threads", "256-threads"])
+@pytest.mark.parametrize("name,q", [("example_small.dat-s", 2), ("example_TT.dat-s.gz", 2), ("example_MkP.dat-s.gz", 1)])
+def test_batch_kernel_on_the_emulator(lib, emu, name, q, tiny):
+    """nodes of the shipped instances with blocks of order <= 16 through both instantiations of the batch kernel"""
+    M = misdp.read_sdpa(os.path.join(GOLDEN, name)).rows_to_bounds()
+    probs = list(_nodes(M, q))
+    got = run_batch(lib, emu, probs, tiny=tiny, **KW)
+    cpu = abi.Solver(abi.Lib(abi.ORACLE_LIB))
+    for fp, r in zip(probs, got):
+        _compare(fp, r, cpu.solve(fp, **KW))
+
+
+def test_batch_kernel_with_dense_constraint_matrices_on_the_emulator(lib, emu):
+    """a small cardinality-constrained least-squares relaxation: dense constraint matrices expanded by the CTA itself, block of
+    order 13, and a max-cut relaxation without LP block"""
+    cpu = abi.Solver(abi.Lib(abi.ORACLE_LIB))
+    probs = [generators.cls(12, 9, 3, seed=5).flatten()[0], generators.maxcut(24, 0.3, seed=3).flatten()[0]]
+    for fp, r in zip(probs, run_batch(lib, emu, probs, **KW)):
+        _compare(fp, r, cpu.solve(fp, **KW))
+
+
+def test_root_relaxations_of_the_larger_shipped_instances_on_the_emulator(lib, emu):
+    """example_CLS (block of order 43, dense constraint matrices) and example_MkP (m = 105 > 64: Schur factor in global memory) in
+    ONE emulated launch of two CTAs: same iteration counts as the oracle, objectives within 1e-7 relative"""
+    cpu = abi.Solver(abi.Lib(abi.ORACLE_LIB))
+    probs = [misdp.read_sdpa(os.path.join(GOLDEN, f)).rows_to_bounds().flatten()[0] for f in ("example_CLS.dat-s.gz", "example_MkP.dat-s.gz")]
+    for fp, r in zip(probs, run_batch(lib, emu, probs, **KW)):
+        ref = cpu.solve(fp, **KW)
+        _compare(fp, r, ref)
+        assert abs(r["iterations"] - ref["iterations"]) <= 1 and abs(r["dobj"] - ref["dobj"]) <= 1e-7 * max(1.0, abs(ref["dobj"]))
+
+
+class EmuSolver:
+    """stands in for abi.Solver in frontier.branch_and_bound: batches run on the emulated kernel, single solves (stable-settings
+    retries, penalty ladder) on the oracle"""
+
+    def __init__(self, lib, emu, tiny):
+        self.lib, self.emu, self.tiny = lib, emu, tiny
+        self.cpu = abi.Solver(abi.Lib(abi.ORACLE_LIB))
+        self.batches = 0
+
+    def solve_batch(self, probs, fetch=True, **kw):
+        self.batches += 1
+        return run_batch(self.lib, self.emu, probs, tiny=self.tiny, **kw)
+
+    def solve(self, fp, **kw):
+        return self.cpu.solve(fp, **kw)
+
+    def get_y(self):
+        return self.cpu.get_y()
+
+
+@pytest.mark.parametrize("name,want", [("example_small.dat-s", -8.0), ("example_inf.dat-s", None), ("example_small_ind.dat-s", -18.0)])
+def test_branch_and_bound_on_the_emulated_batch_kernel(lib, emu, name, want):
+    """complete frontier-synchronous trees with every round solved by one emulated launch of the 256-thread instantiation"""
+    from scip_sdp_b200 import frontier
+    M = misdp.read_instance(os.path.join(GOLDEN, name))
+    s = EmuSolver(lib, emu, tiny=True)
+    r = frontier.branch_and_bound(s, M, mode="batch", width=64, gaptol=1e-5, feastol=1e-5)
+    assert s.batches == r["rounds"] or s.batches <= r["rounds"]
+    if want is None:
+        assert r["status"] == "infeasible"
+    else:
+        assert r["status"] == "optimal" and abs(M.file_objective(r["objval"]) - want) <= 1e-4 * max(1.0, abs(want))
