@@ -86,6 +86,10 @@ int run_grid(void (*fn)(void*), void* arg, int nblocks, int nthreads, size_t sme
    std::vector<uint64_t> smem(nsm + guard);
    g_smem = (double*)smem.data();
    int rc = 0;
+   /* CUEMU_REVERSE=1: warps and lanes are visited in descending order.  A result that depends on the visiting order means that two
+    * threads touch the same location without a barrier in between (the one kind of race this emulator can expose). */
+   const char* rev = getenv("CUEMU_REVERSE");
+   const bool reverse = (rev != nullptr && rev[0] == '1');
    for( int b = 0; b < nblocks && rc == 0; ++b )
    {
       cur_block = b;
@@ -95,13 +99,16 @@ int run_grid(void (*fn)(void*), void* arg, int nblocks, int nthreads, size_t sme
       while( live > 0 )
       {
          bool progress = false;
-         for( int w = 0; w < nwarps; ++w )
+         for( int wi = 0; wi < nwarps; ++wi )
          {
+            const int w = reverse ? nwarps - 1 - wi : wi;
             const int t0 = w * 32, t1 = (t0 + 32 < nthreads) ? t0 + 32 : nthreads;
             for( ; ; )                           /* let the warp run until all its lanes wait at the block barrier or are done */
             {
                bool ran = false;
-               for( int t = t0; t < t1; ++t )
+               for( int ti = t0; ti < t1; ++ti )
+               {
+                  const int t = reverse ? t1 - 1 - (ti - t0) : ti;
                   if( fibers[t].state == 0 )
                   {
                      cur = &fibers[t];
@@ -109,6 +116,7 @@ int run_grid(void (*fn)(void*), void* arg, int nblocks, int nthreads, size_t sme
                      if( fibers[t].state == 3 ) --live;
                      ran = true; progress = true;
                   }
+               }
                int waitw = 0, alive = 0;
                for( int t = t0; t < t1; ++t ) { if( fibers[t].state != 3 ) ++alive; if( fibers[t].state == 2 ) ++waitw; }
                if( waitw > 0 && waitw == alive ) { for( int t = t0; t < t1; ++t ) if( fibers[t].state == 2 ) fibers[t].state = 0; continue; }

@@ -167,3 +167,16 @@ def test_branch_and_bound_on_the_emulated_batch_kernel(lib, emu, name, want):
         assert r["status"] == "infeasible"
     else:
         assert r["status"] == "optimal" and abs(M.file_objective(r["objval"]) - want) <= 1e-4 * max(1.0, abs(want))
+
+
+@pytest.mark.parametrize("tiny", [False, True], ids=["1024-threads", "256-threads"])
+def test_result_does_not_depend_on_the_thread_visiting_order(lib, emu, tiny, monkeypatch):
+    """the emulator visits warps and lanes in ascending or (CUEMU_REVERSE=1) descending order between barriers: bit-identical results
+    mean that no two threads exchange data through memory without a barrier in between on these inputs"""
+    probs = [misdp.read_sdpa(os.path.join(GOLDEN, "example_TT.dat-s.gz")).rows_to_bounds().flatten()[0], generators.cls(12, 9, 3, seed=5).flatten()[0]]
+    fwd = run_batch(lib, emu, probs, tiny=tiny, **KW)
+    monkeypatch.setenv("CUEMU_REVERSE", "1")
+    rev = run_batch(lib, emu, probs, tiny=tiny, **KW)
+    for a, b in zip(fwd, rev):
+        assert a["phase_name"] == b["phase_name"] and a["iterations"] == b["iterations"]
+        assert a["dobj"] == b["dobj"] and a["pobj"] == b["pobj"] and np.array_equal(a["y"], b["y"])
