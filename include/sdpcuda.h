@@ -184,6 +184,16 @@ int  sdpcuda_debug_pack_node(const sdpcuda_problem* prob, const sdpcuda_params* 
                              unsigned long long work_base, unsigned long long y_base, unsigned char* image, size_t image_cap,
                              size_t* image_bytes, size_t* work_doubles, void* descriptor, size_t desc_cap, size_t* desc_bytes, int* fits);
 
+/* the same for a whole batch: everything sdpcuda_solve_batch decides on the host (which problems are batched, one image, one work
+ * space, one y buffer, descriptor order with the 256-thread relaxations first) for the given (fake or host) base addresses.
+ * descriptors: nbatched kernel descriptors in launch order; result k (at res_base + k) belongs to input problem
+ * problem_of_result[k], its y starts yoff_of_result[k] doubles behind y_base. */
+int  sdpcuda_debug_pack_batch(int count, const sdpcuda_problem* const* probs, const sdpcuda_params* par, int usetiny,
+                              unsigned long long img_base, unsigned long long work_base, unsigned long long y_base,
+                              unsigned long long res_base, unsigned char* image, size_t image_cap, size_t* image_bytes,
+                              size_t* work_doubles, size_t* y_doubles, void* descriptors, size_t desc_cap, int* nbatched, int* ntiny,
+                              int* problem_of_result, size_t* yoff_of_result);
+
 /* Per-kernel-class device timing of the NEXT solve (CUDA events around every launch of the class on the handle's
  * stream; adds a little overhead, so it is off by default).  After the solve sdpcuda_get_profile fills, for each class
  * c < SDPCUDA_NPROF, out[3*c+0] = launches, out[3*c+1] = device milliseconds, out[3*c+2] = algorithmic flops or bytes. */

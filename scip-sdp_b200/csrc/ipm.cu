@@ -1134,7 +1134,89 @@ static void batch_bind_node(BatchNode& nd, unsigned char* img, double* work, dou
    a.out = out;
 }
 
+// the host half of a batch: which nodes fit the single-CTA kernel, their images, where their work space / y / result live, and
+// the order of the descriptors (relaxations for the 256-thread instantiation first).  Pure CPU work: no CUDA call in here.
+struct BatchPlan
+{
+   BatchImage img;
+   std::vector<BatchNode> nodes;      // the batched nodes
+   std::vector<int> who;              // nodes[k] is input problem who[k]
+   std::vector<int> loners;           // input problems outside the single-CTA limits
+   std::vector<int> slot;             // descriptor position of nodes[k]
+   size_t worktotal = 0, ytotal = 0;
+   int ntiny = 0;
+};
+
+static int batch_plan(int count, const sdpcuda_problem* const* probs, const sdpcuda_params* par, bool usetiny, BatchPlan& P)
+{
+   P.nodes.reserve(count);
+   for( int i = 0; i < count; ++i )
+   {
+      BatchNode nd;
+      bool fits = false;
+      int rc = batch_prepare_node(probs[i], par, P.img, nd, &fits);
+      if( rc != SDPCUDA_OK ) return rc;
+      if( !fits ) { P.loners.push_back(i); continue; }
+      nd.work = P.worktotal; P.worktotal += nd.worklen;
+      nd.yoff = P.ytotal; P.ytotal += ((size_t)nd.a.m + 1 + 15) / 16 * 16;
+      P.nodes.push_back(nd); P.who.push_back(i);
+   }
+   const int nd = (int)P.nodes.size();
+   P.slot.assign(nd, 0);
+   std::vector<int> tiny, rest;
+   for( int k = 0; k < nd; ++k )
+   {
+      int mx = 0;
+      for( int b = 0; b < P.nodes[k].a.nb; ++b ) mx = std::max(mx, P.nodes[k].a.blk[b].n);
+      (usetiny && mx <= TINY_MAX_N ? tiny : rest).push_back(k);
+   }
+   P.ntiny = (int)tiny.size();
+   int pos = 0;
+   for( int k : tiny ) P.slot[k] = pos++;
+   for( int k : rest ) P.slot[k] = pos++;
+   return SDPCUDA_OK;
+}
+
+// descriptors of all batched nodes for the given device addresses, in launch order (args[slot[k]] describes nodes[k]; its result
+// goes to res[k])
+static void batch_bind_all(BatchPlan& P, unsigned char* img, double* work, double* y, SmallResult* res, std::vector<SmallArgs>& args)
+{
+   const int nd = (int)P.nodes.size();
+   args.resize(nd);
+   for( int k = 0; k < nd; ++k )
+   {
+      batch_bind_node(P.nodes[k], img, work + P.nodes[k].work, y + P.nodes[k].yoff, res + k);
+      args[P.slot[k]] = P.nodes[k].a;
+   }
+}
+
 extern "C" {
+
+int sdpcuda_debug_pack_batch(int count, const sdpcuda_problem* const* probs, const sdpcuda_params* par, int usetiny,
+   unsigned long long img_base, unsigned long long work_base, unsigned long long y_base, unsigned long long res_base,
+   unsigned char* image, size_t image_cap, size_t* image_bytes, size_t* work_doubles, size_t* y_doubles,
+   void* descriptors, size_t desc_cap, int* nbatched, int* ntiny, int* problem_of_result, size_t* yoff_of_result)
+{
+   if( count < 0 || par == nullptr || (count > 0 && probs == nullptr) || image_bytes == nullptr || work_doubles == nullptr
+      || y_doubles == nullptr || nbatched == nullptr || ntiny == nullptr ) return SDPCUDA_ERR_ARG;
+   for( int i = 0; i < count; ++i ) if( probs[i] == nullptr || probs[i]->m <= 0 ) return SDPCUDA_ERR_ARG;
+   BatchPlan P;
+   int rc = batch_plan(count, probs, par, usetiny != 0, P);
+   if( rc != SDPCUDA_OK ) return rc;
+   const int nd = (int)P.nodes.size();
+   *image_bytes = P.img.buf.size(); *work_doubles = P.worktotal; *y_doubles = P.ytotal; *nbatched = nd; *ntiny = P.ntiny;
+   std::vector<SmallArgs> args;
+   batch_bind_all(P, reinterpret_cast<unsigned char*>((uintptr_t)img_base), reinterpret_cast<double*>((uintptr_t)work_base),
+      reinterpret_cast<double*>((uintptr_t)y_base), reinterpret_cast<SmallResult*>((uintptr_t)res_base), args);
+   if( image != nullptr && image_cap >= P.img.buf.size() ) memcpy(image, P.img.buf.data(), P.img.buf.size());
+   if( descriptors != nullptr && desc_cap >= sizeof(SmallArgs) * nd ) memcpy(descriptors, args.data(), sizeof(SmallArgs) * nd);
+   for( int k = 0; k < nd; ++k )
+   {
+      if( problem_of_result != nullptr ) problem_of_result[k] = P.who[k];
+      if( yoff_of_result != nullptr ) yoff_of_result[k] = P.nodes[k].yoff;
+   }
+   return SDPCUDA_OK;
+}
 
 int sdpcuda_debug_pack_node(const sdpcuda_problem* P, const sdpcuda_params* par, unsigned long long img_base, unsigned long long work_base,
    unsigned long long y_base, unsigned char* image, size_t image_cap, size_t* image_bytes, size_t* work_doubles,
@@ -1166,22 +1248,18 @@ int sdpcuda_solve_batch(sdpcuda_handle* h, int count, const sdpcuda_problem* con
    const double t0 = now_seconds();
    int rc = set_device(h);
    if( rc != SDPCUDA_OK ) return rc;
-   BatchImage img;
-   std::vector<BatchNode> nodes;
-   std::vector<int> who, loners;
-   nodes.reserve(count);
-   size_t worktotal = 0, ytotal = 0;
-   for( int i = 0; i < count; ++i )
-   {
-      BatchNode nd;
-      bool fits = false;
-      rc = batch_prepare_node(probs[i], par, img, nd, &fits);
-      if( rc != SDPCUDA_OK ) return rc;
-      if( !fits ) { loners.push_back(i); continue; }
-      nd.work = worktotal; worktotal += nd.worklen;
-      nd.yoff = ytotal; ytotal += ((size_t)nd.a.m + 1 + 15) / 16 * 16;
-      nodes.push_back(nd); who.push_back(i);
-   }
+   // SDPCUDA_BATCH_TINY=1: relaxations whose blocks all have order <= 16 go to the 256-thread instantiation (four per SM);
+   // off by default until it has run on a GPU.  The descriptors are ordered tiny first, then the others: two launches.
+   const char* te = getenv("SDPCUDA_BATCH_TINY");
+   BatchPlan plan;
+   rc = batch_plan(count, probs, par, te != nullptr && te[0] == '1', plan);
+   if( rc != SDPCUDA_OK ) return rc;
+   BatchImage& img = plan.img;
+   std::vector<BatchNode>& nodes = plan.nodes;
+   const std::vector<int>& who = plan.who;
+   const std::vector<int>& loners = plan.loners;
+   const size_t worktotal = plan.worktotal, ytotal = plan.ytotal;
+   const int ntiny = plan.ntiny;
    const int nd = (int)nodes.size();
    if( nd > 0 )
    {
@@ -1192,31 +1270,8 @@ int sdpcuda_solve_batch(sdpcuda_handle* h, int count, const sdpcuda_problem* con
       CK( h->batchy.ensure(ytotal) );
       CK( h->batchargs.ensure(nd) );
       CK( h->batchres.ensure(nd) );
-      // SDPCUDA_BATCH_TINY=1: relaxations whose blocks all have order <= 16 go to the 256-thread instantiation (four per SM);
-      // off by default until it has run on a GPU.  The descriptors are ordered tiny first, then the others: two launches.
-      const char* te = getenv("SDPCUDA_BATCH_TINY");
-      const bool usetiny = (te != nullptr && te[0] == '1');
-      std::vector<int> slot(nd);
-      int ntiny = 0;
-      {
-         std::vector<int> tiny, rest;
-         for( int k = 0; k < nd; ++k )
-         {
-            int mx = 0;
-            for( int b = 0; b < nodes[k].a.nb; ++b ) mx = std::max(mx, nodes[k].a.blk[b].n);
-            (usetiny && mx <= TINY_MAX_N ? tiny : rest).push_back(k);
-         }
-         ntiny = (int)tiny.size();
-         int pos = 0;
-         for( int k : tiny ) slot[k] = pos++;
-         for( int k : rest ) slot[k] = pos++;
-      }
-      std::vector<SmallArgs> args(nd);
-      for( int k = 0; k < nd; ++k )
-      {
-         batch_bind_node(nodes[k], h->batchimg.p, h->batchwork.p + nodes[k].work, h->batchy.p + nodes[k].yoff, h->batchres.p + k);
-         args[slot[k]] = nodes[k].a;
-      }
+      std::vector<SmallArgs> args;
+      batch_bind_all(plan, h->batchimg.p, h->batchwork.p, h->batchy.p, h->batchres.p, args);
       // the work space is shared by batches of different layouts: start from zeros (padding rows and alignment gaps are never
       // written by the kernel; a few tens of MB at most)
       CK( cudaMemsetAsync(h->batchwork.p, 0, sizeof(double) * worktotal, st) );

@@ -180,3 +180,56 @@ def test_result_does_not_depend_on_the_thread_visiting_order(lib, emu, tiny, mon
     for a, b in zip(fwd, rev):
         assert a["phase_name"] == b["phase_name"] and a["iterations"] == b["iterations"]
         assert a["dobj"] == b["dobj"] and a["pobj"] == b["pobj"] and np.array_equal(a["y"], b["y"])
+
+
+def run_planned_batch(lib, emu, probs, usetiny, **kw):
+    """exactly what sdpcuda_solve_batch does, with the CUDA calls replaced: ONE image, ONE zeroed work buffer, ONE y buffer and the
+    descriptor order come from the library's own plan (sdpcuda_debug_pack_batch); the two launches run on the emulator"""
+    par = lib.default_params(**kw)
+    n = len(probs)
+    F = lib.lib.sdpcuda_debug_pack_batch
+    F.argtypes = [C.c_int, C.POINTER(C.POINTER(abi.Problem)), C.POINTER(abi.Params), C.c_int, C.c_ulonglong, C.c_ulonglong, C.c_ulonglong,
+                  C.c_ulonglong, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t), C.POINTER(C.c_size_t), C.c_void_p,
+                  C.c_size_t, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_size_t)]
+    structs = [p.struct() for p in probs]
+    ps = (C.POINTER(abi.Problem) * n)(*[C.pointer(s) for s in structs])
+    nimg, nwork, ny, nb, nt = C.c_size_t(0), C.c_size_t(0), C.c_size_t(0), C.c_int(0), C.c_int(0)
+    assert F(n, ps, C.byref(par), int(usetiny), 0, 0, 0, 0, None, 0, C.byref(nimg), C.byref(nwork), C.byref(ny), None, 0, C.byref(nb), C.byref(nt), None, None) == 0
+    img = np.zeros(nimg.value + 64, dtype=np.uint8)
+    work = np.zeros(nwork.value + 64); work[nwork.value:] = CANARY
+    ybuf = np.full(ny.value + 64, CANARY)
+    res = (SmallResult * max(nb.value, 1))()
+    descs = (SmallArgs * max(nb.value, 1))()
+    owner = (C.c_int * max(nb.value, 1))()
+    yoff = (C.c_size_t * max(nb.value, 1))()
+    assert F(n, ps, C.byref(par), int(usetiny), img.ctypes.data, work.ctypes.data, ybuf.ctypes.data, C.addressof(res), img.ctypes.data, img.size,
+             C.byref(nimg), C.byref(nwork), C.byref(ny), C.byref(descs), C.sizeof(descs), C.byref(nb), C.byref(nt), owner, yoff) == 0
+    base = C.addressof(descs)
+    if nt.value:
+        assert emu.cuemu_run_tiny_batch(nt.value, base, C.sizeof(SmallArgs)) == 0
+    if nb.value - nt.value:
+        assert emu.cuemu_run_small_batch(nb.value - nt.value, base + nt.value * C.sizeof(SmallArgs), C.sizeof(SmallArgs)) == 0
+    assert np.all(work[nwork.value:] == CANARY) and np.all(ybuf[ny.value:] == CANARY)
+    out = {}
+    for k in range(nb.value):
+        fp, r = probs[owner[k]], res[k]
+        out[owner[k]] = dict(phase_name=abi.PHASES[r.phase], stop_name=abi.STOPS[r.stop], iterations=r.iterations, pobj=r.pobj, dobj=r.dobj,
+                             relgap=r.relgap, pinf=r.pinf, dinf=r.dinf, y=ybuf[yoff[k]:yoff[k] + fp.m].copy())
+    return out, nb.value, nt.value
+
+
+@pytest.mark.parametrize("usetiny", [False, True])
+def test_planned_batch_with_mixed_sizes(lib, emu, usetiny):
+    """one plan for nodes of different shapes — blocks of order 2, 10, 13 (dense) and 24, one relaxation outside the limits —
+    executed as the two launches of sdpcuda_solve_batch: every batched node matches the oracle, the large one is left to the
+    ordinary solve, and with SDPCUDA_BATCH_TINY the three relaxations with blocks <= 16 go first"""
+    S = misdp.read_sdpa(os.path.join(GOLDEN, "example_small.dat-s")).rows_to_bounds().flatten()[0]
+    T = misdp.read_sdpa(os.path.join(GOLDEN, "example_TT.dat-s.gz")).rows_to_bounds().flatten()[0]
+    probs = [generators.maxcut(24, 0.3, seed=3).flatten()[0], S, generators.maxcut(96, 0.1, seed=7).flatten()[0], T,
+             generators.cls(12, 9, 3, seed=5).flatten()[0], S]
+    got, nbatched, ntiny = run_planned_batch(lib, emu, probs, usetiny, **KW)
+    assert nbatched == 5 and sorted(got) == [0, 1, 3, 4, 5] and ntiny == (4 if usetiny else 0)
+    cpu = abi.Solver(abi.Lib(abi.ORACLE_LIB))
+    for i, r in got.items():
+        _compare(probs[i], r, cpu.solve(probs[i], **KW))
+    assert got[1]["dobj"] == got[5]["dobj"] and np.array_equal(got[1]["y"], got[5]["y"])
