@@ -188,11 +188,12 @@ int  sdpcuda_debug_pack_node(const sdpcuda_problem* prob, const sdpcuda_params* 
  * space, one y buffer, descriptor order with the 256-thread relaxations first) for the given (fake or host) base addresses.
  * descriptors: nbatched kernel descriptors in launch order; result k (at res_base + k) belongs to input problem
  * problem_of_result[k], its y starts yoff_of_result[k] doubles behind y_base. */
-int  sdpcuda_debug_pack_batch(int count, const sdpcuda_problem* const* probs, const sdpcuda_params* par, int usetiny,
+int  sdpcuda_debug_pack_batch(int count, const sdpcuda_problem* const* probs, const sdpcuda_params* par, int flags /* 1: SDPCUDA_BATCH_TINY, 2: SDPCUDA_BATCH_SMEM */,
                               unsigned long long img_base, unsigned long long work_base, unsigned long long y_base,
                               unsigned long long res_base, unsigned char* image, size_t image_cap, size_t* image_bytes,
                               size_t* work_doubles, size_t* y_doubles, void* descriptors, size_t desc_cap, int* nbatched, int* ntiny,
-                              int* problem_of_result, size_t* yoff_of_result);
+                              int* problem_of_result, size_t* yoff_of_result,
+                              size_t* stage_bytes /* [2] or NULL: shared memory of the two launches on top of the kernels' own */);
 
 /* Per-kernel-class device timing of the NEXT solve (CUDA events around every launch of the class on the handle's
  * stream; adds a little overhead, so it is off by default).  After the solve sdpcuda_get_profile fills, for each class

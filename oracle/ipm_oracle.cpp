@@ -723,12 +723,12 @@ int sdpcuda_debug_pack_node(const sdpcuda_problem* P, const sdpcuda_params* par,
    if( fits != nullptr ) *fits = 0;
    return SDPCUDA_ERR_STATE;
 }
-int sdpcuda_debug_pack_batch(int count, const sdpcuda_problem* const* probs, const sdpcuda_params* par, int usetiny,
+int sdpcuda_debug_pack_batch(int count, const sdpcuda_problem* const* probs, const sdpcuda_params* par, int flags,
    unsigned long long img_base, unsigned long long work_base, unsigned long long y_base, unsigned long long res_base,
    unsigned char* image, size_t image_cap, size_t* image_bytes, size_t* work_doubles, size_t* y_doubles,
-   void* descriptors, size_t desc_cap, int* nbatched, int* ntiny, int* problem_of_result, size_t* yoff_of_result)
+   void* descriptors, size_t desc_cap, int* nbatched, int* ntiny, int* problem_of_result, size_t* yoff_of_result, size_t* stage_bytes)
 {
-   (void)count; (void)probs; (void)par; (void)usetiny; (void)img_base; (void)work_base; (void)y_base; (void)res_base; (void)image; (void)image_cap;
+   (void)count; (void)probs; (void)par; (void)flags; (void)stage_bytes; (void)img_base; (void)work_base; (void)y_base; (void)res_base; (void)image; (void)image_cap;
    (void)image_bytes; (void)work_doubles; (void)y_doubles; (void)descriptors; (void)desc_cap; (void)ntiny; (void)problem_of_result; (void)yoff_of_result;
    if( nbatched != nullptr ) *nbatched = 0;
    return SDPCUDA_ERR_STATE;

@@ -929,7 +929,12 @@ struct BatchNode          // offsets of one node: bytes into the image, doubles 
    size_t varbeg, erow, ecol, eld, eoff, eval, cls, posbeg, pos, mirror, posvar, posval, posc, cpos, cmirror, cval;
    size_t lpbeg, lpind, lpval, lprhs, colbeg, colrow, colval, b, denselist;
    size_t work, worklen, yoff, hdlen, lzlen;
+   size_t stagelen;      // doubles of the work space staged in shared memory (0 = none)
 };
+
+// budgets of shared memory for the staged head of a node's work space (SDPCUDA_BATCH_SMEM=1): two CTAs per SM stay possible for the
+// 256-thread instantiation (2 x (53 + 58) KB), the 1024-thread kernel takes what is left of the 227 KB of its SM
+constexpr size_t STAGE_BUDGET_TINY = 58 * 1024, STAGE_BUDGET_SMALL = 80 * 1024;
 
 // builds the image of one node; returns SDPCUDA_OK and *fits = false when the relaxation is outside the single-CTA limits
 static int batch_prepare_node(const sdpcuda_problem* P, const sdpcuda_params* par, BatchImage& img, BatchNode& nd, bool* fits)
@@ -1099,6 +1104,7 @@ static int batch_prepare_node(const sdpcuda_problem* P, const sdpcuda_params* pa
    nd.lzlen = r16((size_t)lzoff + 16);
    nd.worklen = 15 * r16((size_t)ar) + 7 * r16((size_t)m + 1) + 10 * r16((size_t)nlp + 1) + 2 * r16((size_t)a.ldm * m)
       + r16((size_t)adense_total) + 2 * nd.hdlen + nd.lzlen;
+   nd.stagelen = 0;
    *fits = true;
    return SDPCUDA_OK;
 }
@@ -1121,17 +1127,41 @@ static void batch_bind_node(BatchNode& nd, unsigned char* img, double* work, dou
    double* w = work;
    auto take = [&](size_t len) { double* p = w; w += r16(len); return p; };
    const size_t ar = (size_t)a.arena, mv = (size_t)a.m + 1, lv = (size_t)a.nlp + 1, mm = (size_t)a.ldm * a.m;
-   a.X = take(ar); a.S = take(ar); a.Sinv = take(ar); a.L = take(ar); a.Linv = take(ar); a.LX = take(ar); a.LXinv = take(ar);
-   a.dX = take(ar); a.dS = take(ar); a.dXa = take(ar); a.dSa = take(ar); a.K = take(ar); a.T1 = take(ar); a.T2 = take(ar); a.Rd = take(ar);
+   // order = staging priority (batch_stage_prefix): vectors, block matrices, Schur complement and its factor, dense-path buffers
+   a.workbase = work;
    a.y = y; a.dy = take(mv); a.g = take(mv); a.rp = take(mv); a.AX = take(mv); a.DTx = take(mv); a.tm1 = take(mv); a.tm2 = take(mv);
    a.x = take(lv); a.s = take(lv); a.dx = take(lv); a.ds = take(lv); a.dxa = take(lv); a.dsa = take(lv); a.klp = take(lv); a.rdlp = take(lv);
    a.Dy = take(lv); a.Ddy = take(lv);
+   a.X = take(ar); a.S = take(ar); a.Sinv = take(ar); a.L = take(ar); a.Linv = take(ar); a.LX = take(ar); a.LXinv = take(ar);
+   a.dX = take(ar); a.dS = take(ar); a.dXa = take(ar); a.dSa = take(ar); a.K = take(ar); a.T1 = take(ar); a.T2 = take(ar); a.Rd = take(ar);
    a.M = take(mm); a.Mfac = take(mm);
    double* ad = take((size_t)a.adense_total);
    a.Adense = ad;
    a.Hd = w; w += nd.hdlen; a.Ud = w; w += nd.hdlen;
    a.lz = w; w += nd.lzlen;
    a.out = out;
+   a.stage_doubles = (long long)nd.stagelen;
+}
+
+// the longest head of the work space, cut at an array boundary, that fits `budget` bytes (same order as batch_bind_node)
+static size_t batch_stage_prefix(const BatchNode& nd, size_t budget)
+{
+   const SmallArgs& a = nd.a;
+   auto r16 = [](size_t v) { return (v + 15) / 16 * 16; };
+   std::vector<size_t> len;
+   len.insert(len.end(), 7, r16((size_t)a.m + 1));
+   len.insert(len.end(), 10, r16((size_t)a.nlp + 1));
+   len.insert(len.end(), 15, r16((size_t)a.arena));
+   len.insert(len.end(), 2, r16((size_t)a.ldm * a.m));
+   len.push_back(r16((size_t)a.adense_total));
+   len.insert(len.end(), 2, nd.hdlen);
+   size_t tot = 0;
+   for( size_t l : len )
+   {
+      if( (tot + l) * sizeof(double) > budget ) break;
+      tot += l;
+   }
+   return tot;
 }
 
 // the host half of a batch: which nodes fit the single-CTA kernel, their images, where their work space / y / result live, and
@@ -1145,9 +1175,10 @@ struct BatchPlan
    std::vector<int> slot;             // descriptor position of nodes[k]
    size_t worktotal = 0, ytotal = 0;
    int ntiny = 0;
+   size_t stagebytes[2] = {0, 0};     // dynamic shared memory on top of the kernels' own, per launch (tiny, regular)
 };
 
-static int batch_plan(int count, const sdpcuda_problem* const* probs, const sdpcuda_params* par, bool usetiny, BatchPlan& P)
+static int batch_plan(int count, const sdpcuda_problem* const* probs, const sdpcuda_params* par, bool usetiny, bool stage, BatchPlan& P)
 {
    P.nodes.reserve(count);
    for( int i = 0; i < count; ++i )
@@ -1174,6 +1205,11 @@ static int batch_plan(int count, const sdpcuda_problem* const* probs, const sdpc
    int pos = 0;
    for( int k : tiny ) P.slot[k] = pos++;
    for( int k : rest ) P.slot[k] = pos++;
+   if( stage )
+   {
+      for( int k : tiny ) { P.nodes[k].stagelen = batch_stage_prefix(P.nodes[k], STAGE_BUDGET_TINY); P.stagebytes[0] = std::max(P.stagebytes[0], P.nodes[k].stagelen * sizeof(double)); }
+      for( int k : rest ) { P.nodes[k].stagelen = batch_stage_prefix(P.nodes[k], STAGE_BUDGET_SMALL); P.stagebytes[1] = std::max(P.stagebytes[1], P.nodes[k].stagelen * sizeof(double)); }
+   }
    return SDPCUDA_OK;
 }
 
@@ -1192,18 +1228,19 @@ static void batch_bind_all(BatchPlan& P, unsigned char* img, double* work, doubl
 
 extern "C" {
 
-int sdpcuda_debug_pack_batch(int count, const sdpcuda_problem* const* probs, const sdpcuda_params* par, int usetiny,
+int sdpcuda_debug_pack_batch(int count, const sdpcuda_problem* const* probs, const sdpcuda_params* par, int flags,
    unsigned long long img_base, unsigned long long work_base, unsigned long long y_base, unsigned long long res_base,
    unsigned char* image, size_t image_cap, size_t* image_bytes, size_t* work_doubles, size_t* y_doubles,
-   void* descriptors, size_t desc_cap, int* nbatched, int* ntiny, int* problem_of_result, size_t* yoff_of_result)
+   void* descriptors, size_t desc_cap, int* nbatched, int* ntiny, int* problem_of_result, size_t* yoff_of_result, size_t* stage_bytes)
 {
    if( count < 0 || par == nullptr || (count > 0 && probs == nullptr) || image_bytes == nullptr || work_doubles == nullptr
       || y_doubles == nullptr || nbatched == nullptr || ntiny == nullptr ) return SDPCUDA_ERR_ARG;
    for( int i = 0; i < count; ++i ) if( probs[i] == nullptr || probs[i]->m <= 0 ) return SDPCUDA_ERR_ARG;
    BatchPlan P;
-   int rc = batch_plan(count, probs, par, usetiny != 0, P);
+   int rc = batch_plan(count, probs, par, (flags & 1) != 0, (flags & 2) != 0, P);
    if( rc != SDPCUDA_OK ) return rc;
    const int nd = (int)P.nodes.size();
+   if( stage_bytes != nullptr ) { stage_bytes[0] = P.stagebytes[0]; stage_bytes[1] = P.stagebytes[1]; }
    *image_bytes = P.img.buf.size(); *work_doubles = P.worktotal; *y_doubles = P.ytotal; *nbatched = nd; *ntiny = P.ntiny;
    std::vector<SmallArgs> args;
    batch_bind_all(P, reinterpret_cast<unsigned char*>((uintptr_t)img_base), reinterpret_cast<double*>((uintptr_t)work_base),
@@ -1250,9 +1287,11 @@ int sdpcuda_solve_batch(sdpcuda_handle* h, int count, const sdpcuda_problem* con
    if( rc != SDPCUDA_OK ) return rc;
    // SDPCUDA_BATCH_TINY=1: relaxations whose blocks all have order <= 16 go to the 256-thread instantiation (four per SM);
    // off by default until it has run on a GPU.  The descriptors are ordered tiny first, then the others: two launches.
+   // SDPCUDA_BATCH_SMEM=1: the head of every node's work space is staged in shared memory (as many whole arrays as fit the budget)
    const char* te = getenv("SDPCUDA_BATCH_TINY");
+   const char* se = getenv("SDPCUDA_BATCH_SMEM");
    BatchPlan plan;
-   rc = batch_plan(count, probs, par, te != nullptr && te[0] == '1', plan);
+   rc = batch_plan(count, probs, par, te != nullptr && te[0] == '1', se != nullptr && se[0] == '1', plan);
    if( rc != SDPCUDA_OK ) return rc;
    BatchImage& img = plan.img;
    std::vector<BatchNode>& nodes = plan.nodes;
@@ -1278,8 +1317,8 @@ int sdpcuda_solve_batch(sdpcuda_handle* h, int count, const sdpcuda_problem* con
       CK( cudaMemcpyAsync(h->batchimg.p, img.buf.data(), img.buf.size(), cudaMemcpyHostToDevice, st) );
       CK( cudaMemcpyAsync(h->batchargs.p, args.data(), sizeof(SmallArgs) * nd, cudaMemcpyHostToDevice, st) );
       CK( cudaEventRecord(h->ev0, st) );
-      CK( launch_ipm_tiny_batch(st, ntiny, h->batchargs.p) );
-      CK( launch_ipm_small_batch(st, nd - ntiny, h->batchargs.p + ntiny) );
+      CK( launch_ipm_tiny_batch(st, ntiny, h->batchargs.p, plan.stagebytes[0]) );
+      CK( launch_ipm_small_batch(st, nd - ntiny, h->batchargs.p + ntiny, plan.stagebytes[1]) );
       CK( cudaEventRecord(h->ev1, st) );
       std::vector<SmallResult> sr(nd);
       std::vector<double> ys(ytotal);

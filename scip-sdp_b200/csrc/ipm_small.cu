@@ -638,6 +638,10 @@ __device__ void solveM_smem(int m, const double* Ms, const double* rdiag, double
    __syncthreads();
 }
 
+// dynamic shared memory of the body (layout at the top of ipm_small_body)
+constexpr size_t SMALL_SMEM = (2 * VMAXN * LDS + 32 + VMAXN + SMALL_MAX_M + 3 * SMALL_LZ_STEPS + 8 + 2 * (SMALL_LZ_STEPS + 2) * LDS
+   + 2 * (2 * SMALL_LZ_STEPS + 64) + MSN * LDMS + 8) * sizeof(double) + sizeof(Ctl) + 64;
+
 // the complete solve of ONE relaxation by the calling CTA (shared by the one-relaxation kernel and the frontier-batch kernel)
 __device__ __forceinline__ void ipm_small_body(const SmallArgs& a)
 {
@@ -1048,11 +1052,30 @@ ipm_small_batch_kernel(const SmallArgs* __restrict__ all)
    int* dst = reinterpret_cast<int*>(&sa);
    for( int i = threadIdx.x; i < (int)(sizeof(SmallArgs) / sizeof(int)); i += NT ) dst[i] = src[i];
    __syncthreads();
+   if( sa.stage_doubles > 0 )
+   {
+      // the head of the node's work space moves into shared memory (behind the SMALL_SMEM bytes of the body): zero it like the host
+      // zeroes the global work space, then point every array that lies completely inside the staged head to its shared copy
+      extern __shared__ __align__(16) double smem[];
+      double* stage = smem + (SMALL_SMEM + sizeof(double) - 1) / sizeof(double);
+      for( long long i = threadIdx.x; i < sa.stage_doubles; i += NT ) stage[i] = 0.0;
+      if( threadIdx.x == 0 )
+      {
+         double** ptrs[] = {&sa.X, &sa.S, &sa.Sinv, &sa.L, &sa.Linv, &sa.LX, &sa.LXinv, &sa.dX, &sa.dS, &sa.dXa, &sa.dSa, &sa.K, &sa.T1, &sa.T2, &sa.Rd,
+                            &sa.dy, &sa.g, &sa.rp, &sa.AX, &sa.DTx, &sa.tm1, &sa.tm2,
+                            &sa.x, &sa.s, &sa.dx, &sa.ds, &sa.dxa, &sa.dsa, &sa.klp, &sa.rdlp, &sa.Dy, &sa.Ddy, &sa.M, &sa.Mfac, &sa.Hd, &sa.Ud};
+         for( double** pp : ptrs )
+         {
+            const long long off = *pp - sa.workbase;
+            if( off >= 0 && off < sa.stage_doubles ) *pp = stage + off;
+         }
+         const long long offa = sa.Adense - sa.workbase;
+         if( offa >= 0 && offa < sa.stage_doubles ) sa.Adense = stage + offa;
+      }
+      __syncthreads();
+   }
    ipm_small_body(sa);
 }
-
-constexpr size_t SMALL_SMEM = (2 * VMAXN * LDS + 32 + VMAXN + SMALL_MAX_M + 3 * SMALL_LZ_STEPS + 8 + 2 * (SMALL_LZ_STEPS + 2) * LDS
-   + 2 * (2 * SMALL_LZ_STEPS + 64) + MSN * LDMS + 8) * sizeof(double) + sizeof(Ctl) + 64;
 
 } // namespace
 
@@ -1072,7 +1095,9 @@ cudaError_t launch_ipm_small(cudaStream_t st, const SmallArgs& a)
    return cudaGetLastError();
 }
 
-cudaError_t launch_ipm_small_batch(cudaStream_t st, int count, const SmallArgs* dev_args)
+size_t ipm_small_smem_bytes() { return SMALL_SMEM; }
+
+cudaError_t launch_ipm_small_batch(cudaStream_t st, int count, const SmallArgs* dev_args, size_t stage_bytes)
 {
    static bool configured[64] = {false};
    int dev = 0;
@@ -1080,17 +1105,21 @@ cudaError_t launch_ipm_small_batch(cudaStream_t st, int count, const SmallArgs* 
    SDPK_CUDA_CHECK( cudaGetDevice(&dev) );
    if( !configured[dev & 63] )
    {
-      SDPK_CUDA_CHECK( cudaFuncSetAttribute(ipm_small_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMALL_SMEM) );
+      // up to the 227 KB a CTA may have (1.5 KB of them static: the staged descriptor)
+      SDPK_CUDA_CHECK( cudaFuncSetAttribute(ipm_small_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024) );
       configured[dev & 63] = true;
    }
-   ipm_small_batch_kernel<<<count, NT, SMALL_SMEM, st>>>(dev_args);
+   if( SMALL_SMEM + stage_bytes > 225 * 1024 ) return cudaErrorInvalidValue;
+   ipm_small_batch_kernel<<<count, NT, SMALL_SMEM + stage_bytes, st>>>(dev_args);
    count_launch();
    return cudaGetLastError();
 }
 
 #else
 
-cudaError_t launch_ipm_tiny_batch(cudaStream_t st, int count, const SmallArgs* dev_args)
+size_t ipm_tiny_smem_bytes() { return SMALL_SMEM; }
+
+cudaError_t launch_ipm_tiny_batch(cudaStream_t st, int count, const SmallArgs* dev_args, size_t stage_bytes)
 {
    static bool configured[64] = {false};
    int dev = 0;
@@ -1098,10 +1127,11 @@ cudaError_t launch_ipm_tiny_batch(cudaStream_t st, int count, const SmallArgs* d
    SDPK_CUDA_CHECK( cudaGetDevice(&dev) );
    if( !configured[dev & 63] )
    {
-      SDPK_CUDA_CHECK( cudaFuncSetAttribute(ipm_tiny_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMALL_SMEM) );
+      SDPK_CUDA_CHECK( cudaFuncSetAttribute(ipm_tiny_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024) );
       configured[dev & 63] = true;
    }
-   ipm_tiny_batch_kernel<<<count, NT, SMALL_SMEM, st>>>(dev_args);
+   if( SMALL_SMEM + stage_bytes > 225 * 1024 ) return cudaErrorInvalidValue;
+   ipm_tiny_batch_kernel<<<count, NT, SMALL_SMEM + stage_bytes, st>>>(dev_args);
    count_launch();
    return cudaGetLastError();
 }

@@ -45,6 +45,11 @@ struct SmallArgs
    // frontier batch (sdpcuda_solve_batch): the CTA sets up its own cold start X = xi I, S = eta I, x = xil, s = etal, y = 0 and
    // expands its dense constraint matrices into Adense itself, so that a node costs the host no launch and no copy of its own
    int selfinit;
+   // frontier batch with SDPCUDA_BATCH_SMEM=1: the first stage_doubles doubles of the node's work space (starting at workbase:
+   // vectors first, then the block matrices, then M and its factor - as many whole arrays as the launch has shared memory for) live in
+   // the CTA's shared memory behind the kernel's own buffers; the entry kernel redirects the pointers, the body does not notice
+   long long stage_doubles;
+   double* workbase;
    long long adense_total;
    double xil, etal;
    double xi[SMALL_MAX_BLOCKS], eta[SMALL_MAX_BLOCKS];
@@ -52,8 +57,11 @@ struct SmallArgs
 
 cudaError_t launch_ipm_small(cudaStream_t st, const SmallArgs& a);
 // one launch for a whole frontier of small relaxations: CTA i solves dev_args[i] (device array of `count` descriptors)
-cudaError_t launch_ipm_small_batch(cudaStream_t st, int count, const SmallArgs* dev_args);
+cudaError_t launch_ipm_small_batch(cudaStream_t st, int count, const SmallArgs* dev_args, size_t stage_bytes = 0);
 // the same for relaxations whose blocks all have order <= TINY_MAX_N: CTAs of 256 threads, four per SM (ipm_tiny.cu)
-cudaError_t launch_ipm_tiny_batch(cudaStream_t st, int count, const SmallArgs* dev_args);
+cudaError_t launch_ipm_tiny_batch(cudaStream_t st, int count, const SmallArgs* dev_args, size_t stage_bytes = 0);
+// shared memory the two batch kernels use for themselves (the staged work space of a node comes on top)
+size_t ipm_small_smem_bytes();
+size_t ipm_tiny_smem_bytes();
 
 } // namespace sdpk

@@ -12,8 +12,8 @@
 
 static void block_main(void* arg) { sdpk::ipm_small_batch_kernel(static_cast<const sdpk::SmallArgs*>(arg)); }
 
-extern "C" int ENTRY(int count, const void* descriptors, size_t desc_bytes)
+extern "C" int ENTRY(int count, const void* descriptors, size_t desc_bytes, size_t stage_bytes)
 {
    if( desc_bytes != sizeof(sdpk::SmallArgs) ) return 2;
-   return cuemu::run_grid(block_main, const_cast<void*>(descriptors), count, sdpk::NT, sdpk::SMALL_SMEM);
+   return cuemu::run_grid(block_main, const_cast<void*>(descriptors), count, sdpk::NT, sdpk::SMALL_SMEM + stage_bytes);
 }

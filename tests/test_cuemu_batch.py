@@ -31,7 +31,7 @@ def emu():
     assert r.returncode == 0, r.stderr[-2000:]
     L = C.CDLL(os.path.join(EMUDIR, "_build", "libcuemu_ipm.so"))
     for f in (L.cuemu_run_small_batch, L.cuemu_run_tiny_batch):
-        f.argtypes = [C.c_int, C.c_void_p, C.c_size_t]
+        f.argtypes = [C.c_int, C.c_void_p, C.c_size_t, C.c_size_t]
     return L
 
 
@@ -70,7 +70,7 @@ def run_batch(lib, emu, probs, tiny=False, **kw):
         descs[i].out = C.addressof(res[i])
         keep.append((img, work, y, nwork.value))
     run = emu.cuemu_run_tiny_batch if tiny else emu.cuemu_run_small_batch
-    assert run(n, C.addressof(descs), C.sizeof(SmallArgs)) == 0, "emulator reported a deadlock or a shared-memory overrun"
+    assert run(n, C.addressof(descs), C.sizeof(SmallArgs), 0) == 0, "emulator reported a deadlock or a shared-memory overrun"
     out = []
     for i, fp in enumerate(probs):
         img, work, y, nw = keep[i]
@@ -182,7 +182,7 @@ def test_result_does_not_depend_on_the_thread_visiting_order(lib, emu, tiny, mon
         assert a["dobj"] == b["dobj"] and a["pobj"] == b["pobj"] and np.array_equal(a["y"], b["y"])
 
 
-def run_planned_batch(lib, emu, probs, usetiny, **kw):
+def run_planned_batch(lib, emu, probs, usetiny, stage=False, **kw):
     """exactly what sdpcuda_solve_batch does, with the CUDA calls replaced: ONE image, ONE zeroed work buffer, ONE y buffer and the
     descriptor order come from the library's own plan (sdpcuda_debug_pack_batch); the two launches run on the emulator"""
     par = lib.default_params(**kw)
@@ -190,11 +190,13 @@ def run_planned_batch(lib, emu, probs, usetiny, **kw):
     F = lib.lib.sdpcuda_debug_pack_batch
     F.argtypes = [C.c_int, C.POINTER(C.POINTER(abi.Problem)), C.POINTER(abi.Params), C.c_int, C.c_ulonglong, C.c_ulonglong, C.c_ulonglong,
                   C.c_ulonglong, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t), C.POINTER(C.c_size_t), C.c_void_p,
-                  C.c_size_t, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_size_t)]
+                  C.c_size_t, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]
+    flags = int(usetiny) + 2 * int(stage)
+    stagebytes = (C.c_size_t * 2)()
     structs = [p.struct() for p in probs]
     ps = (C.POINTER(abi.Problem) * n)(*[C.pointer(s) for s in structs])
     nimg, nwork, ny, nb, nt = C.c_size_t(0), C.c_size_t(0), C.c_size_t(0), C.c_int(0), C.c_int(0)
-    assert F(n, ps, C.byref(par), int(usetiny), 0, 0, 0, 0, None, 0, C.byref(nimg), C.byref(nwork), C.byref(ny), None, 0, C.byref(nb), C.byref(nt), None, None) == 0
+    assert F(n, ps, C.byref(par), flags, 0, 0, 0, 0, None, 0, C.byref(nimg), C.byref(nwork), C.byref(ny), None, 0, C.byref(nb), C.byref(nt), None, None, None) == 0
     img = np.zeros(nimg.value + 64, dtype=np.uint8)
     work = np.zeros(nwork.value + 64); work[nwork.value:] = CANARY
     ybuf = np.full(ny.value + 64, CANARY)
@@ -202,19 +204,26 @@ def run_planned_batch(lib, emu, probs, usetiny, **kw):
     descs = (SmallArgs * max(nb.value, 1))()
     owner = (C.c_int * max(nb.value, 1))()
     yoff = (C.c_size_t * max(nb.value, 1))()
-    assert F(n, ps, C.byref(par), int(usetiny), img.ctypes.data, work.ctypes.data, ybuf.ctypes.data, C.addressof(res), img.ctypes.data, img.size,
-             C.byref(nimg), C.byref(nwork), C.byref(ny), C.byref(descs), C.sizeof(descs), C.byref(nb), C.byref(nt), owner, yoff) == 0
+    assert F(n, ps, C.byref(par), flags, img.ctypes.data, work.ctypes.data, ybuf.ctypes.data, C.addressof(res), img.ctypes.data, img.size,
+             C.byref(nimg), C.byref(nwork), C.byref(ny), C.byref(descs), C.sizeof(descs), C.byref(nb), C.byref(nt), owner, yoff, stagebytes) == 0
+    assert (stagebytes[0] > 0 or stagebytes[1] > 0) == (stage and nb.value > 0)
     base = C.addressof(descs)
     if nt.value:
-        assert emu.cuemu_run_tiny_batch(nt.value, base, C.sizeof(SmallArgs)) == 0
+        assert emu.cuemu_run_tiny_batch(nt.value, base, C.sizeof(SmallArgs), stagebytes[0]) == 0
     if nb.value - nt.value:
-        assert emu.cuemu_run_small_batch(nb.value - nt.value, base + nt.value * C.sizeof(SmallArgs), C.sizeof(SmallArgs)) == 0
+        assert emu.cuemu_run_small_batch(nb.value - nt.value, base + nt.value * C.sizeof(SmallArgs), C.sizeof(SmallArgs), stagebytes[1]) == 0
     assert np.all(work[nwork.value:] == CANARY) and np.all(ybuf[ny.value:] == CANARY)
     out = {}
     for k in range(nb.value):
         fp, r = probs[owner[k]], res[k]
         out[owner[k]] = dict(phase_name=abi.PHASES[r.phase], stop_name=abi.STOPS[r.stop], iterations=r.iterations, pobj=r.pobj, dobj=r.dobj,
                              relgap=r.relgap, pinf=r.pinf, dinf=r.dinf, y=ybuf[yoff[k]:yoff[k] + fp.m].copy())
+    if stage:
+        # staged arrays never reach the global work space: the staged head of every node's slice is still all zeros
+        for k in range(nb.value):
+            d = descs[k]
+            lo = (d.workbase - work.ctypes.data) // 8
+            assert d.stage_doubles > 0 and not work[lo:lo + d.stage_doubles].any()
     return out, nb.value, nt.value
 
 
@@ -233,3 +242,22 @@ def test_planned_batch_with_mixed_sizes(lib, emu, usetiny):
     for i, r in got.items():
         _compare(probs[i], r, cpu.solve(probs[i], **KW))
     assert got[1]["dobj"] == got[5]["dobj"] and np.array_equal(got[1]["y"], got[5]["y"])
+
+
+@pytest.mark.parametrize("usetiny", [False, True])
+def test_work_space_staged_in_shared_memory(lib, emu, usetiny):
+    """SDPCUDA_BATCH_SMEM: the entry kernel moves the head of every node's work space (vectors, block matrices, M and its factor as far
+    as the budget reaches) into shared memory and redirects the descriptor's pointers; same results as from global memory bit for
+    bit, nothing of the staged head is ever written to the global work space, no overrun of the enlarged shared memory"""
+    T = misdp.read_sdpa(os.path.join(GOLDEN, "example_TT.dat-s.gz")).rows_to_bounds().flatten()[0]       # everything fits
+    K = misdp.read_sdpa(os.path.join(GOLDEN, "example_MkP.dat-s.gz")).rows_to_bounds().flatten()[0]      # M (2 x 88 KB) stays global
+    Cl = generators.cls(12, 9, 3, seed=5).flatten()[0]                                                   # dense-path buffers
+    W = generators.maxcut(40, 0.2, seed=3).flatten()[0]                                                  # 1024-thread kernel, partly staged
+    probs = [T, K, Cl, W]
+    plain, nb, nt = run_planned_batch(lib, emu, probs, usetiny, stage=False, **KW)
+    staged, nb2, nt2 = run_planned_batch(lib, emu, probs, usetiny, stage=True, **KW)
+    assert (nb, nt) == (nb2, nt2) == (4, 3 if usetiny else 0)
+    for i in range(4):
+        a, b = plain[i], staged[i]
+        assert a["phase_name"] == b["phase_name"] == "pdOPT" and a["iterations"] == b["iterations"]
+        assert a["dobj"] == b["dobj"] and np.array_equal(a["y"], b["y"])

@@ -185,3 +185,22 @@ def test_tiny_instantiation_of_the_batch_kernel(lib, cpu, name, q, monkeypatch):
             ref = cpu.solve(fp, **KW)
             assert abs(b["dobj"] - ref["dobj"]) <= 1e-5 * max(1.0, abs(ref["dobj"]))
     gpu.close()
+
+
+@pytest.mark.parametrize("tiny", ["0", "1"])
+def test_work_space_staged_in_shared_memory_on_gpu(lib, tiny, monkeypatch):
+    """SDPCUDA_BATCH_SMEM=1: the head of every node's work space lives in shared memory; the arithmetic is the same, so statuses,
+    iteration counts, objectives and y are bit-identical to the run from global memory (the CPU emulation shows the same)"""
+    T = misdp.read_sdpa(os.path.join(GOLDEN, "example_TT.dat-s.gz")).rows_to_bounds()
+    probs = [fp for fp, _ in (T.flatten(lb, ub) for lb, ub in _frontier(T, 3)) if fp.m > 0]
+    probs += [misdp.read_sdpa(os.path.join(GOLDEN, "example_MkP.dat-s.gz")).rows_to_bounds().flatten()[0],
+              generators.cls(12, 9, 3, seed=5).flatten()[0], generators.maxcut(40, 0.2, seed=3).flatten()[0]]
+    monkeypatch.setenv("SDPCUDA_BATCH_TINY", tiny)
+    gpu = abi.Solver(lib, device=0)
+    plain = gpu.solve_batch(probs, **KW)
+    monkeypatch.setenv("SDPCUDA_BATCH_SMEM", "1")
+    staged = gpu.solve_batch(probs, **KW)
+    for a, b in zip(plain, staged):
+        assert a["phase_name"] == b["phase_name"] and a["iterations"] == b["iterations"]
+        assert a["dobj"] == b["dobj"] and np.array_equal(a["y"], b["y"])
+    gpu.close()

@@ -17,6 +17,12 @@ for inst in tt cls mkp small; do
   SDPCUDA_BATCH_TINY=1 timeout 300 python bench.py --workload frontier-example-$inst --frontier-mode batch --nodes-per-gpu 592 --no-cpu-baseline \
       > gpurun_out/r2_frontier_example_${inst}_batch_tiny.json 2>> gpurun_out/r2_frontier_example.err
   cut -c1-160 gpurun_out/r2_frontier_example_${inst}_batch_tiny.json
+  SDPCUDA_BATCH_TINY=1 SDPCUDA_BATCH_SMEM=1 timeout 300 python bench.py --workload frontier-example-$inst --frontier-mode batch --nodes-per-gpu 592 --no-cpu-baseline \
+      > gpurun_out/r2_frontier_example_${inst}_batch_tiny_smem.json 2>> gpurun_out/r2_frontier_example.err
+  cut -c1-160 gpurun_out/r2_frontier_example_${inst}_batch_tiny_smem.json
+  SDPCUDA_BATCH_SMEM=1 timeout 300 python bench.py --workload frontier-example-$inst --frontier-mode batch --nodes-per-gpu 592 --no-cpu-baseline \
+      > gpurun_out/r2_frontier_example_${inst}_batch_smem.json 2>> gpurun_out/r2_frontier_example.err
+  cut -c1-160 gpurun_out/r2_frontier_example_${inst}_batch_smem.json
   timeout 600 python bench.py --workload bnb-example-$inst --frontier-mode batch --steps 2 --warmup 1 > gpurun_out/r2_bnb_example_${inst}_batch.json 2>> gpurun_out/r2_bnb.err
   cut -c1-300 gpurun_out/r2_bnb_example_${inst}_batch.json
 done
