@@ -32,6 +32,7 @@ namespace cuemu {
 
 Fiber* cur = nullptr;
 int cur_block = 0;
+long long barrier_releases = 0;
 static void* main_sp = nullptr;
 static void (*g_fn)(void*) = nullptr;
 static void* g_arg = nullptr;
@@ -125,7 +126,7 @@ int run_grid(void (*fn)(void*), void* arg, int nblocks, int nthreads, size_t sme
          }
          int waitb = 0;
          for( int t = 0; t < nthreads; ++t ) if( fibers[t].state == 1 ) ++waitb;
-         if( live > 0 && waitb == live ) { for( int t = 0; t < nthreads; ++t ) if( fibers[t].state == 1 ) fibers[t].state = 0; progress = true; }
+         if( live > 0 && waitb == live ) { for( int t = 0; t < nthreads; ++t ) if( fibers[t].state == 1 ) fibers[t].state = 0; progress = true; ++barrier_releases; }
          if( !progress )
          {
             fprintf(stderr, "cuemu: deadlock in block %d (%d live threads, %d at the block barrier; divergent barrier or shuffle)\n", b, live, waitb);
