@@ -108,6 +108,12 @@ struct sdpcuda_handle
    DBuf<SmallResult> batchres;
    DBuf<unsigned char> batchimg;
    DBuf<double> batchwork, batchy;
+   // SDPCUDA_PACKED_SOLVE=1: a single small relaxation goes through the same packed path (one copy, one launch); the getters
+   // then read the solution where the descriptor of that solve (device addresses) says it is
+   bool packed = false;
+   SmallArgs pk;
+   size_t pkstage = 0;
+   bool pktiny = false;
    int force_path = 0;               // 0 auto, 1 always multi-kernel, 2 always single-CTA (tests)
    DBuf<LzDesc> lzdesc;
    DBuf<unsigned> lztickets;
@@ -875,6 +881,9 @@ static void host_constants(sdpcuda_handle* h, const sdpcuda_problem* P)
 
 static int run_ipm(sdpcuda_handle* h, const sdpcuda_params* par, const double* start_y, sdpcuda_result* res, double t0);
 
+static int solve_packed(sdpcuda_handle* h, const sdpcuda_problem* P, const sdpcuda_params* par, sdpcuda_result* res, double t0, bool* done);
+static int launch_packed(sdpcuda_handle* h, sdpcuda_result* res, double t0, double h2d);
+
 int sdpcuda_solve(sdpcuda_handle* h, const sdpcuda_problem* P, const sdpcuda_params* par, const double* start_y, sdpcuda_result* res)
 {
    if( h == nullptr || P == nullptr || par == nullptr || P->m <= 0 ) return SDPCUDA_ERR_ARG;
@@ -883,8 +892,23 @@ int sdpcuda_solve(sdpcuda_handle* h, const sdpcuda_problem* P, const sdpcuda_par
    if( rc != SDPCUDA_OK ) return rc;
    h->solved = false;
    h->resident = false;
+   h->packed = false;
    h->counter.n = 0;
    g_h2d_bytes = 0.0;
+   {
+      // SDPCUDA_PACKED_SOLVE=1 (off by default until it has run on a GPU): a cold-started relaxation inside the single-CTA limits is
+      // packed like a node of a frontier batch - one host->device copy, one launch, results copied back - instead of ~35 copies,
+      // four synchronisations and six launches before the kernel
+      const char* pe = getenv("SDPCUDA_PACKED_SOLVE");
+      const char* fe = getenv("SDPCUDA_PATH");
+      if( pe != nullptr && pe[0] == '1' && !(fe != nullptr && fe[0] == 'm') && h->force_path != 1 && start_y == nullptr && h->startX.empty()
+         && h->startS.empty() && par->preoptgap <= 0 && !h->prof.on && h->nranks == 1 )
+      {
+         bool done = false;
+         rc = solve_packed(h, P, par, res, t0, &done);
+         if( rc != SDPCUDA_OK || done ) return rc;
+      }
+   }
    rc = upload_problem(h, P);
    if( rc != SDPCUDA_OK ) return rc;
    host_constants(h, P);
@@ -895,6 +919,13 @@ int sdpcuda_solve(sdpcuda_handle* h, const sdpcuda_problem* P, const sdpcuda_par
 int sdpcuda_solve_resident(sdpcuda_handle* h, const sdpcuda_params* par, sdpcuda_result* res)
 {
    if( h == nullptr || par == nullptr ) return SDPCUDA_ERR_ARG;
+   if( h->packed )
+   {
+      // the packed image and descriptor are still on the device (tolerances as in the solve that packed them)
+      if( set_device(h) ) return SDPCUDA_ERR_CUDA;
+      h->counter.n = 0;
+      return launch_packed(h, res, now_seconds(), 0.0);
+   }
    if( !h->resident ) return SDPCUDA_ERR_STATE;
    const double t0 = now_seconds();
    int rc = set_device(h);
@@ -1178,7 +1209,8 @@ struct BatchPlan
    size_t stagebytes[2] = {0, 0};     // dynamic shared memory on top of the kernels' own, per launch (tiny, regular)
 };
 
-static int batch_plan(int count, const sdpcuda_problem* const* probs, const sdpcuda_params* par, bool usetiny, bool stage, BatchPlan& P)
+static int batch_plan(int count, const sdpcuda_problem* const* probs, const sdpcuda_params* par, bool usetiny, bool stage, BatchPlan& P,
+   bool copyback = false)
 {
    P.nodes.reserve(count);
    for( int i = 0; i < count; ++i )
@@ -1205,6 +1237,7 @@ static int batch_plan(int count, const sdpcuda_problem* const* probs, const sdpc
    int pos = 0;
    for( int k : tiny ) P.slot[k] = pos++;
    for( int k : rest ) P.slot[k] = pos++;
+   for( BatchNode& n : P.nodes ) n.a.copyback = copyback ? 1 : 0;
    if( stage )
    {
       for( int k : tiny ) { P.nodes[k].stagelen = batch_stage_prefix(P.nodes[k], STAGE_BUDGET_TINY); P.stagebytes[0] = std::max(P.stagebytes[0], P.nodes[k].stagelen * sizeof(double)); }
@@ -1237,7 +1270,7 @@ int sdpcuda_debug_pack_batch(int count, const sdpcuda_problem* const* probs, con
       || y_doubles == nullptr || nbatched == nullptr || ntiny == nullptr ) return SDPCUDA_ERR_ARG;
    for( int i = 0; i < count; ++i ) if( probs[i] == nullptr || probs[i]->m <= 0 ) return SDPCUDA_ERR_ARG;
    BatchPlan P;
-   int rc = batch_plan(count, probs, par, (flags & 1) != 0, (flags & 2) != 0, P);
+   int rc = batch_plan(count, probs, par, (flags & 1) != 0, (flags & 2) != 0, P, (flags & 4) != 0);
    if( rc != SDPCUDA_OK ) return rc;
    const int nd = (int)P.nodes.size();
    if( stage_bytes != nullptr ) { stage_bytes[0] = P.stagebytes[0]; stage_bytes[1] = P.stagebytes[1]; }
@@ -1276,6 +1309,66 @@ int sdpcuda_debug_pack_node(const sdpcuda_problem* P, const sdpcuda_params* par,
    return SDPCUDA_OK;
 }
 
+static int launch_packed(sdpcuda_handle* h, sdpcuda_result* res, double t0, double h2d)
+{
+   cudaStream_t st = h->st;
+   CK( cudaMemsetAsync(h->batchwork.p, 0, sizeof(double) * h->batchwork.cap, st) );
+   CK( cudaEventRecord(h->ev0, st) );
+   if( h->pktiny ) CK( launch_ipm_tiny_batch(st, 1, h->batchargs.p, h->pkstage) );
+   else CK( launch_ipm_small_batch(st, 1, h->batchargs.p, h->pkstage) );
+   CK( cudaEventRecord(h->ev1, st) );
+   SmallResult sr;
+   CK( cudaMemcpyAsync(&sr, h->batchres.p, sizeof(sr), cudaMemcpyDeviceToHost, st) );
+   CK( cudaStreamSynchronize(st) );
+   float ms = 0.f;
+   cudaEventElapsedTime(&ms, h->ev0, h->ev1);
+   h->solved = true;
+   if( res != nullptr )
+   {
+      sdpcuda_result R;
+      memset(&R, 0, sizeof(R));
+      R.phase = sr.phase; R.stop = sr.stop; R.iterations = sr.iterations;
+      R.launches = (int)h->counter.n;
+      R.pobj = sr.pobj; R.dobj = sr.dobj; R.relgap = sr.relgap; R.pinf = sr.pinf; R.dinf = sr.dinf; R.mu = sr.mu;
+      R.seconds = now_seconds() - t0; R.device_ms = ms; R.h2d_bytes = h2d; R.d2h_bytes = sizeof(sr);
+      *res = R;
+   }
+   return SDPCUDA_OK;
+}
+
+static int solve_packed(sdpcuda_handle* h, const sdpcuda_problem* P, const sdpcuda_params* par, sdpcuda_result* res, double t0, bool* done)
+{
+   *done = false;
+   const char* te = getenv("SDPCUDA_BATCH_TINY");
+   const char* se = getenv("SDPCUDA_BATCH_SMEM");
+   BatchPlan plan;
+   const sdpcuda_problem* one[1] = {P};
+   int rc = batch_plan(1, one, par, te != nullptr && te[0] == '1', se != nullptr && se[0] == '1', plan, true);
+   if( rc != SDPCUDA_OK ) return rc;
+   if( plan.nodes.size() != 1 ) return SDPCUDA_OK;            // outside the single-CTA limits: the ordinary path takes it
+   cudaStream_t st = h->st;
+   CK( h->batchimg.ensure(plan.img.buf.size()) );
+   CK( h->batchwork.ensure(plan.worktotal) );
+   CK( h->batchy.ensure(plan.ytotal) );
+   CK( h->batchargs.ensure(1) );
+   CK( h->batchres.ensure(1) );
+   std::vector<SmallArgs> args;
+   batch_bind_all(plan, h->batchimg.p, h->batchwork.p, h->batchy.p, h->batchres.p, args);
+   CK( cudaMemcpyAsync(h->batchimg.p, plan.img.buf.data(), plan.img.buf.size(), cudaMemcpyHostToDevice, st) );
+   CK( cudaMemcpyAsync(h->batchargs.p, args.data(), sizeof(SmallArgs), cudaMemcpyHostToDevice, st) );
+   CK( cudaStreamSynchronize(st) );                           // plan goes out of scope
+   // what the getters need: sizes, block table and the device addresses of the solution
+   h->pk = args[0];
+   h->pktiny = (plan.ntiny == 1);
+   h->pkstage = plan.stagebytes[h->pktiny ? 0 : 1];
+   h->m = P->m; h->nb = P->nblocks; h->nlp = P->nlp;
+   h->blk.resize(h->nb);
+   for( int k = 0; k < h->nb; ++k ) h->blk[k] = Block{h->pk.blk[k].n, h->pk.blk[k].ld, h->pk.blk[k].off};
+   h->packed = true;
+   *done = true;
+   return launch_packed(h, res, t0, (double)(plan.img.buf.size() + sizeof(SmallArgs)));
+}
+
 int sdpcuda_solve_batch(sdpcuda_handle* h, int count, const sdpcuda_problem* const* probs, const sdpcuda_params* par,
    sdpcuda_result* res, double* const* y_out)
 {
@@ -1291,6 +1384,7 @@ int sdpcuda_solve_batch(sdpcuda_handle* h, int count, const sdpcuda_problem* con
    const char* te = getenv("SDPCUDA_BATCH_TINY");
    const char* se = getenv("SDPCUDA_BATCH_SMEM");
    BatchPlan plan;
+   if( h->packed ) { h->packed = false; h->solved = false; }      // the batch reuses the buffers of a packed single solve
    rc = batch_plan(count, probs, par, te != nullptr && te[0] == '1', se != nullptr && se[0] == '1', plan);
    if( rc != SDPCUDA_OK ) return rc;
    BatchImage& img = plan.img;
@@ -1909,7 +2003,7 @@ int sdpcuda_get_y(sdpcuda_handle* h, double* y)
 {
    if( h == nullptr || !h->solved ) return SDPCUDA_ERR_STATE;
    if( set_device(h) ) return SDPCUDA_ERR_CUDA;
-   CK( cudaMemcpyAsync(y, h->y.p, sizeof(double) * h->m, cudaMemcpyDeviceToHost, h->st) );
+   CK( cudaMemcpyAsync(y, h->packed ? h->pk.y : h->y.p, sizeof(double) * h->m, cudaMemcpyDeviceToHost, h->st) );
    CK( cudaStreamSynchronize(h->st) );
    return SDPCUDA_OK;
 }
@@ -1924,8 +2018,8 @@ static int get_block(sdpcuda_handle* h, const double* src, int b, double* out)
    CK( cudaStreamSynchronize(h->st) );
    return SDPCUDA_OK;
 }
-int sdpcuda_get_X(sdpcuda_handle* h, int b, double* X) { return get_block(h, h ? h->X.p : nullptr, b, X); }
-int sdpcuda_get_S(sdpcuda_handle* h, int b, double* S) { return get_block(h, h ? h->S.p : nullptr, b, S); }
+int sdpcuda_get_X(sdpcuda_handle* h, int b, double* X) { return get_block(h, h ? (h->packed ? h->pk.X : h->X.p) : nullptr, b, X); }
+int sdpcuda_get_S(sdpcuda_handle* h, int b, double* S) { return get_block(h, h ? (h->packed ? h->pk.S : h->S.p) : nullptr, b, S); }
 
 int sdpcuda_dist_unique_id(void* id128)
 {
@@ -2019,7 +2113,7 @@ int sdpcuda_get_xlp(sdpcuda_handle* h, double* x)
 {
    if( h == nullptr || !h->solved ) return SDPCUDA_ERR_STATE;
    if( set_device(h) ) return SDPCUDA_ERR_CUDA;
-   if( h->nlp > 0 ) CK( cudaMemcpyAsync(x, h->x.p, sizeof(double) * h->nlp, cudaMemcpyDeviceToHost, h->st) );
+   if( h->nlp > 0 ) CK( cudaMemcpyAsync(x, h->packed ? h->pk.x : h->x.p, sizeof(double) * h->nlp, cudaMemcpyDeviceToHost, h->st) );
    CK( cudaStreamSynchronize(h->st) );
    return SDPCUDA_OK;
 }
@@ -2027,7 +2121,7 @@ int sdpcuda_get_slp(sdpcuda_handle* h, double* s)
 {
    if( h == nullptr || !h->solved ) return SDPCUDA_ERR_STATE;
    if( set_device(h) ) return SDPCUDA_ERR_CUDA;
-   if( h->nlp > 0 ) CK( cudaMemcpyAsync(s, h->s.p, sizeof(double) * h->nlp, cudaMemcpyDeviceToHost, h->st) );
+   if( h->nlp > 0 ) CK( cudaMemcpyAsync(s, h->packed ? h->pk.s : h->s.p, sizeof(double) * h->nlp, cudaMemcpyDeviceToHost, h->st) );
    CK( cudaStreamSynchronize(h->st) );
    return SDPCUDA_OK;
 }

@@ -1052,6 +1052,8 @@ ipm_small_batch_kernel(const SmallArgs* __restrict__ all)
    int* dst = reinterpret_cast<int*>(&sa);
    for( int i = threadIdx.x; i < (int)(sizeof(SmallArgs) / sizeof(int)); i += NT ) dst[i] = src[i];
    __syncthreads();
+   __shared__ double* orig[4];                     // X, S, x, s as the host bound them (global memory)
+   if( threadIdx.x == 0 ) { orig[0] = sa.X; orig[1] = sa.S; orig[2] = sa.x; orig[3] = sa.s; }
    if( sa.stage_doubles > 0 )
    {
       // the head of the node's work space moves into shared memory (behind the SMALL_SMEM bytes of the body): zero it like the host
@@ -1075,6 +1077,14 @@ ipm_small_batch_kernel(const SmallArgs* __restrict__ all)
       __syncthreads();
    }
    ipm_small_body(sa);
+   if( sa.copyback && sa.stage_doubles > 0 )
+   {
+      __syncthreads();
+      if( sa.X != orig[0] ) for( long long i = threadIdx.x; i < sa.arena; i += NT ) orig[0][i] = sa.X[i];
+      if( sa.S != orig[1] ) for( long long i = threadIdx.x; i < sa.arena; i += NT ) orig[1][i] = sa.S[i];
+      if( sa.x != orig[2] ) for( int l = threadIdx.x; l < sa.nlp; l += NT ) orig[2][l] = sa.x[l];
+      if( sa.s != orig[3] ) for( int l = threadIdx.x; l < sa.nlp; l += NT ) orig[3][l] = sa.s[l];
+   }
 }
 
 } // namespace

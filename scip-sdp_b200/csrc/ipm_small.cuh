@@ -50,6 +50,8 @@ struct SmallArgs
    // the CTA's shared memory behind the kernel's own buffers; the entry kernel redirects the pointers, the body does not notice
    long long stage_doubles;
    double* workbase;
+   int copyback;            // staged X, S, x, s are copied to their global addresses when the solve ends (a single packed solve whose
+                            // multipliers the getters serve afterwards; a frontier batch only returns y and leaves this 0)
    long long adense_total;
    double xil, etal;
    double xi[SMALL_MAX_BLOCKS], eta[SMALL_MAX_BLOCKS];

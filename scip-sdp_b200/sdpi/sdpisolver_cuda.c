@@ -928,6 +928,8 @@ SCIP_RETCODE SCIPsdpiSolverLoadAndSolveWithPenalty(
          retcode = SCIPsdpiSolverGetDualSol(s, NULL, solvector);
          if( retcode == SCIP_OKAY && s->devicecheck )
          {
+            int devrc = SDPCUDA_OK;
+
             /* same contract as SCIPsdpSolcheckerCheck (sdpsolchecker.c:58-270): bounds and rows here (O(nnz)), the blocks as a
              * device Cholesky of Z(y) + feastol I assembled from the problem that is already resident in HBM */
             int psd = 1;
@@ -952,7 +954,8 @@ SCIP_RETCODE SCIPsdpiSolverLoadAndSolveWithPenalty(
             }
             if( !infeasible && s->ndevblocks > 0 )
             {
-               if( sdpcuda_check_psd_resident(s->dev, NULL, s->feastol * (1.0 + 1e-6) + 1e-13, &psd) != SDPCUDA_OK )
+               devrc = sdpcuda_check_psd_resident(s->dev, NULL, s->feastol * (1.0 + 1e-6) + 1e-13, &psd);
+               if( devrc != SDPCUDA_OK && devrc != SDPCUDA_ERR_STATE )
                {
                   BMSfreeBufferMemoryArray(s->bufmem, &solvector);
                   SCIPerrorMessage("sdpcuda_check_psd_resident failed.\n");
@@ -960,6 +963,14 @@ SCIP_RETCODE SCIPsdpiSolverLoadAndSolveWithPenalty(
                   goto TERMINATE;
                }
                infeasible = !psd;
+            }
+            if( devrc == SDPCUDA_ERR_STATE )
+            {
+               /* the last solve left no problem resident in the form this test needs (packed single solve): ship Z(y) instead */
+               retcode = SCIPsdpSolcheckerCheck(s->bufmem, nvars, lb, ub, nsdpblocks, sdpblocksizes, sdpnblockvars, sdpconstnnonz,
+                  sdpconstnblocknonz, sdpconstrow, sdpconstcol, sdpconstval, sdpnnonz, sdpnblockvarnonz, sdpvar, sdprow, sdpcol, sdpval,
+                  indchanges, nremovedinds, blockindchanges, nlpcons, lpindchanges, lplhs, lprhs, lpnnonz, lpbeg, lpind, lpval,
+                  solvector, s->feastol, s->epsilon, &infeasible);
             }
          }
          else if( retcode == SCIP_OKAY )

@@ -182,7 +182,7 @@ def test_result_does_not_depend_on_the_thread_visiting_order(lib, emu, tiny, mon
         assert a["dobj"] == b["dobj"] and a["pobj"] == b["pobj"] and np.array_equal(a["y"], b["y"])
 
 
-def run_planned_batch(lib, emu, probs, usetiny, stage=False, **kw):
+def run_planned_batch(lib, emu, probs, usetiny, stage=False, copyback=False, **kw):
     """exactly what sdpcuda_solve_batch does, with the CUDA calls replaced: ONE image, ONE zeroed work buffer, ONE y buffer and the
     descriptor order come from the library's own plan (sdpcuda_debug_pack_batch); the two launches run on the emulator"""
     par = lib.default_params(**kw)
@@ -191,7 +191,7 @@ def run_planned_batch(lib, emu, probs, usetiny, stage=False, **kw):
     F.argtypes = [C.c_int, C.POINTER(C.POINTER(abi.Problem)), C.POINTER(abi.Params), C.c_int, C.c_ulonglong, C.c_ulonglong, C.c_ulonglong,
                   C.c_ulonglong, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t), C.POINTER(C.c_size_t), C.c_void_p,
                   C.c_size_t, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]
-    flags = int(usetiny) + 2 * int(stage)
+    flags = int(usetiny) + 2 * int(stage) + 4 * int(copyback)
     stagebytes = (C.c_size_t * 2)()
     structs = [p.struct() for p in probs]
     ps = (C.POINTER(abi.Problem) * n)(*[C.pointer(s) for s in structs])
@@ -218,10 +218,16 @@ def run_planned_batch(lib, emu, probs, usetiny, stage=False, **kw):
         fp, r = probs[owner[k]], res[k]
         out[owner[k]] = dict(phase_name=abi.PHASES[r.phase], stop_name=abi.STOPS[r.stop], iterations=r.iterations, pobj=r.pobj, dobj=r.dobj,
                              relgap=r.relgap, pinf=r.pinf, dinf=r.dinf, y=ybuf[yoff[k]:yoff[k] + fp.m].copy())
-    if stage:
-        # staged arrays never reach the global work space: the staged head of every node's slice is still all zeros
-        for k in range(nb.value):
-            d = descs[k]
+    def arr(addr, n):
+        lo = (addr - work.ctypes.data) // 8
+        return work[lo:lo + n].copy()
+    for k in range(nb.value):
+        # descriptor k is in launch order; its result slot tells which node it describes
+        d = descs[k]
+        node = (d.out - C.addressof(res)) // C.sizeof(SmallResult)
+        out[owner[node]].update(X=arr(d.X, d.arena), S=arr(d.S, d.arena), x=arr(d.x, d.nlp), s=arr(d.s, d.nlp))
+        if stage and not copyback:
+            # staged arrays never reach the global work space: the staged head of the node's slice is still all zeros
             lo = (d.workbase - work.ctypes.data) // 8
             assert d.stage_doubles > 0 and not work[lo:lo + d.stage_doubles].any()
     return out, nb.value, nt.value
@@ -261,3 +267,16 @@ def test_work_space_staged_in_shared_memory(lib, emu, usetiny):
         a, b = plain[i], staged[i]
         assert a["phase_name"] == b["phase_name"] == "pdOPT" and a["iterations"] == b["iterations"]
         assert a["dobj"] == b["dobj"] and np.array_equal(a["y"], b["y"])
+
+
+@pytest.mark.parametrize("usetiny", [False, True])
+def test_staged_multipliers_are_copied_back_for_a_packed_single_solve(lib, emu, usetiny):
+    """descriptor flag copyback (SDPCUDA_PACKED_SOLVE: one relaxation through the packed path, its X, S, x, s served by the getters
+    afterwards): the staged copies reach their global addresses, bit-identical to the run without staging"""
+    probs = [misdp.read_sdpa(os.path.join(GOLDEN, "example_TT.dat-s.gz")).rows_to_bounds().flatten()[0], generators.maxcut(40, 0.2, seed=3).flatten()[0]]
+    plain, _, _ = run_planned_batch(lib, emu, probs, usetiny, stage=False, **KW)
+    staged, _, _ = run_planned_batch(lib, emu, probs, usetiny, stage=True, copyback=True, **KW)
+    for i in range(len(probs)):
+        for key in ("X", "S", "x", "s", "y"):
+            assert np.array_equal(plain[i][key], staged[i][key]), key
+        assert np.abs(plain[i]["X"]).max() > 0 and plain[i]["dobj"] == staged[i]["dobj"]

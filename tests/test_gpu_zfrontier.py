@@ -204,3 +204,49 @@ def test_work_space_staged_in_shared_memory_on_gpu(lib, tiny, monkeypatch):
         assert a["phase_name"] == b["phase_name"] and a["iterations"] == b["iterations"]
         assert a["dobj"] == b["dobj"] and np.array_equal(a["y"], b["y"])
     gpu.close()
+
+
+@pytest.mark.parametrize("smem", ["0", "1"])
+@pytest.mark.parametrize("name", ["example_small.dat-s", "example_TT.dat-s.gz", "example_CLS.dat-s.gz", "example_MkP.dat-s.gz"])
+def test_packed_single_solve(lib, cpu, name, smem, monkeypatch):
+    """SDPCUDA_PACKED_SOLVE=1: one relaxation through the packed path (one copy, one launch); objective, y and the multipliers the
+    getters return afterwards (X, S, x, s) against the oracle and the complementarity / feasibility relations"""
+    fp, _ = misdp.read_sdpa(os.path.join(GOLDEN, name)).rows_to_bounds().flatten()
+    monkeypatch.setenv("SDPCUDA_PACKED_SOLVE", "1")
+    monkeypatch.setenv("SDPCUDA_BATCH_SMEM", smem)
+    monkeypatch.setenv("SDPCUDA_BATCH_TINY", smem)
+    gpu = abi.Solver(lib, device=0)
+    r = gpu.solve(fp, **KW)
+    ref = cpu.solve(fp, **KW)
+    assert r["phase_name"] == ref["phase_name"] == "pdOPT" and r["launches"] == 1
+    assert abs(r["dobj"] - ref["dobj"]) <= 1e-5 * max(1.0, abs(ref["dobj"]))
+    Cd = fp.dense_C()
+    for k in range(fp.nblocks):
+        Z = sum(r["y"][j] * fp.dense_A(j)[k] for j in range(fp.m)) - Cd[k]
+        assert np.allclose(r["S"][k], Z, atol=1e-5 * max(1.0, np.abs(Z).max()))                     # S = A'y - C
+        assert np.linalg.eigvalsh(r["X"][k])[0] >= -1e-8 and abs(np.sum(r["X"][k] * r["S"][k])) <= 1e-4 * max(1.0, abs(ref["dobj"]))
+    if fp.nlp:
+        assert np.allclose(r["slp"], fp.dense_D() @ r["y"] - fp.lprhs, atol=1e-5 * max(1.0, np.abs(fp.lprhs).max()))
+        assert r["xlp"].min() >= -1e-9
+    again = gpu.solve_resident(**KW)
+    assert again["dobj"] == r["dobj"] and again["iterations"] == r["iterations"]
+    gpu.close()
+
+
+def test_sdpi_layer_on_the_packed_single_solve(monkeypatch):
+    """the reference's sdpi.c over the binding with packed single solves, staged work space and the device-resident post-check
+    (which falls back to the shipped Z(y) for packed solves): ported checksdpi.c answers and two B&B optima"""
+    from golden.checksdpi_cases import CASES
+    from harness import bnb, checksdpi_port, sdpi_ref
+    os.environ.setdefault("SHIM_QUIET", "1")
+    for k in ("SDPCUDA_PACKED_SOLVE", "SDPCUDA_BATCH_SMEM", "SDPCUDA_BATCH_TINY", "SDPCUDA_DEVICE_CHECK"):
+        monkeypatch.setenv(k, "1")
+    L = sdpi_ref.SdpiLib(sdpi_ref.LIB_CUDA)
+    for name in sorted(CASES):
+        if L.solver_name() in CASES[name].get("skip_for", []):
+            continue
+        checksdpi_port.run_case(L, CASES[name], name)
+    for name, want in (("example_small.dat-s", -8.0), ("example_TT.dat-s.gz", 2.11803)):
+        M = misdp.read_instance(os.path.join(GOLDEN, name))
+        r = bnb.solve_misdp(L, M, timelimit=600)
+        assert r["status"] == "optimal" and abs(M.file_objective(r["objval"]) - want) <= 1e-4 * max(1.0, abs(want))

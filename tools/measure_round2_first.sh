@@ -33,6 +33,10 @@ for w in frontier-tt500 frontier-cls frontier-mkp60; do
     cut -c1-160 gpurun_out/r2_${w}_threads$k.json
   done
 done
+# single small relaxations through the binding: classic upload vs packed path (+ staged work space)
+python tests/tools/bnb_bench.py > gpurun_out/r2_bnb_sdpi_classic.log 2>&1; tail -6 gpurun_out/r2_bnb_sdpi_classic.log
+SDPCUDA_PACKED_SOLVE=1 python tests/tools/bnb_bench.py > gpurun_out/r2_bnb_sdpi_packed.log 2>&1; tail -6 gpurun_out/r2_bnb_sdpi_packed.log
+SDPCUDA_PACKED_SOLVE=1 SDPCUDA_BATCH_SMEM=1 SDPCUDA_BATCH_TINY=1 python tests/tools/bnb_bench.py > gpurun_out/r2_bnb_sdpi_packed_smem.log 2>&1; tail -6 gpurun_out/r2_bnb_sdpi_packed_smem.log
 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file gpurun_out/r2_launches_batch.csv \
   python bench.py --workload frontier-example-tt --frontier-mode batch --nodes-per-gpu 592 --no-cpu-baseline > gpurun_out/r2_ncu_batch_list.log 2>&1
 python tools/summarize_launches.py gpurun_out/r2_launches_batch.csv > gpurun_out/r2_launches_batch.txt 2>/dev/null; cat gpurun_out/r2_launches_batch.txt
