@@ -1,4 +1,4 @@
-# First GPU call of round 2 (one B200, ~8 minutes): bash tools/measure_round2_first.sh
+# First GPU call of round 2 (one B200, ~20 minutes; every python start pays ~10 s of torch import): bash tools/measure_round2_first.sh
 # 1. the whole GPU suite (the last file, tests/test_gpu_zfrontier.py, holds everything written after the GPU budget of round 1 ran out)
 # 2. the headline bench (the upload sort changed: e2e should lose ~10 ms per solve)
 # 3. the frontier of small nodes: node-by-node vs threads vs ONE launch (sdpcuda_solve_batch), and complete B&B runs
@@ -27,7 +27,7 @@ for inst in tt cls mkp small; do
   cut -c1-300 gpurun_out/r2_bnb_example_${inst}_batch.json
 done
 for w in frontier-tt500 frontier-cls frontier-mkp60; do
-  for k in 1 4 8; do
+  for k in 1 4; do
     timeout 600 python bench.py --workload $w --frontier-mode threads --handles-per-gpu $k --nodes-per-gpu 32 --no-cpu-baseline \
       > gpurun_out/r2_${w}_threads$k.json 2>> gpurun_out/r2_frontier_threads.err
     cut -c1-160 gpurun_out/r2_${w}_threads$k.json
@@ -35,8 +35,8 @@ for w in frontier-tt500 frontier-cls frontier-mkp60; do
 done
 # single small relaxations through the binding: classic upload vs packed path (+ staged work space)
 python tests/tools/bnb_bench.py > gpurun_out/r2_bnb_sdpi_classic.log 2>&1; tail -6 gpurun_out/r2_bnb_sdpi_classic.log
-SDPCUDA_PACKED_SOLVE=1 python tests/tools/bnb_bench.py > gpurun_out/r2_bnb_sdpi_packed.log 2>&1; tail -6 gpurun_out/r2_bnb_sdpi_packed.log
-SDPCUDA_PACKED_SOLVE=1 SDPCUDA_BATCH_SMEM=1 SDPCUDA_BATCH_TINY=1 python tests/tools/bnb_bench.py > gpurun_out/r2_bnb_sdpi_packed_smem.log 2>&1; tail -6 gpurun_out/r2_bnb_sdpi_packed_smem.log
+SDPCUDA_PACKED_SOLVE=1 python tests/tools/bnb_bench.py cuda > gpurun_out/r2_bnb_sdpi_packed.log 2>&1; tail -6 gpurun_out/r2_bnb_sdpi_packed.log
+SDPCUDA_PACKED_SOLVE=1 SDPCUDA_BATCH_SMEM=1 SDPCUDA_BATCH_TINY=1 python tests/tools/bnb_bench.py cuda > gpurun_out/r2_bnb_sdpi_packed_smem.log 2>&1; tail -6 gpurun_out/r2_bnb_sdpi_packed_smem.log
 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file gpurun_out/r2_launches_batch.csv \
   python bench.py --workload frontier-example-tt --frontier-mode batch --nodes-per-gpu 592 --no-cpu-baseline > gpurun_out/r2_ncu_batch_list.log 2>&1
 python tools/summarize_launches.py gpurun_out/r2_launches_batch.csv > gpurun_out/r2_launches_batch.txt 2>/dev/null; cat gpurun_out/r2_launches_batch.txt
