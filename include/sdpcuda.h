@@ -175,7 +175,9 @@ int  sdpcuda_solve_resident(sdpcuda_handle* h, const sdpcuda_params* par, sdpcud
  * The getters of the handle do not refer to batched nodes afterwards (the batch has its own device buffers).
  * device_ms / seconds of the batched nodes are those of the whole batch (the nodes run side by side); launches = 1 on the first. */
 int  sdpcuda_solve_batch(sdpcuda_handle* h, int count, const sdpcuda_problem* const* probs, const sdpcuda_params* par,
-                         sdpcuda_result* res, double* const* y_out);
+                         sdpcuda_result* res, double* const* y_out,
+                         const double* objlimits /* NULL, or [count]: per-node value for params.objlimit — the cutoff bound of the
+                                                    node minus its fixed-variable objective (relaxing/SDP/objlimit, relax_sdp.c:4265) */);
 
 /* test hook (no device needed): packs ONE node exactly like sdpcuda_solve_batch does and returns the host image of its read-only
  * data, the length of its work space and its kernel descriptor bound to the given (fake) device addresses; *fits = 0 when the

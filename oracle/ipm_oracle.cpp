@@ -701,13 +701,15 @@ int sdpcuda_check_psd_resident(sdpcuda_handle* h, const double* y, double shift,
 }
 /* checker-side stand-in of the frontier batch: the nodes one after the other */
 int sdpcuda_solve_batch(sdpcuda_handle* h, int count, const sdpcuda_problem* const* probs, const sdpcuda_params* par,
-   sdpcuda_result* res, double* const* y_out)
+   sdpcuda_result* res, double* const* y_out, const double* objlimits)
 {
    if( h == nullptr || count < 0 || par == nullptr || (count > 0 && probs == nullptr) ) return SDPCUDA_ERR_ARG;
    for( int i = 0; i < count; ++i ) if( probs[i] == nullptr || probs[i]->m <= 0 ) return SDPCUDA_ERR_ARG;
    for( int i = 0; i < count; ++i )
    {
-      int rc = sdpcuda_solve(h, probs[i], par, nullptr, res != nullptr ? &res[i] : nullptr);
+      sdpcuda_params pi = *par;
+      if( objlimits != nullptr ) pi.objlimit = objlimits[i];
+      int rc = sdpcuda_solve(h, probs[i], &pi, nullptr, res != nullptr ? &res[i] : nullptr);
       if( rc != SDPCUDA_OK ) return rc;
       if( y_out != nullptr && y_out[i] != nullptr ) { rc = sdpcuda_get_y(h, y_out[i]); if( rc != SDPCUDA_OK ) return rc; }
    }

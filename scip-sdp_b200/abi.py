@@ -110,7 +110,7 @@ class Lib:
         L.sdpcuda_default_params.restype = None
         L.sdpcuda_solve.argtypes = [C.c_void_p, C.POINTER(Problem), C.POINTER(Params), _dp, C.POINTER(Result)]
         L.sdpcuda_solve_resident.argtypes = [C.c_void_p, C.POINTER(Params), C.POINTER(Result)]
-        L.sdpcuda_solve_batch.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.POINTER(Problem)), C.POINTER(Params), C.POINTER(Result), C.POINTER(_dp)]
+        L.sdpcuda_solve_batch.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.POINTER(Problem)), C.POINTER(Params), C.POINTER(Result), C.POINTER(_dp), _dp]
         L.sdpcuda_set_profiling.argtypes = [C.c_void_p, C.c_int]
         L.sdpcuda_get_profile.argtypes = [C.c_void_p, _dp]
         for f in ("sdpcuda_get_y", "sdpcuda_get_xlp", "sdpcuda_get_slp"):
@@ -231,10 +231,10 @@ class Solver:
             out["xlp"], out["slp"] = self.get_xlp(), self.get_slp()
         return out
 
-    def solve_batch(self, probs, params=None, fetch=True, **kw):
+    def solve_batch(self, probs, params=None, fetch=True, objlimits=None, **kw):
         """sdpcuda_solve_batch: all relaxations in `probs` that fit the single-CTA kernel in ONE launch (one CTA per node), the others
         one by one on this handle.  Returns one result dict per node (with "y" unless fetch=False).  The matrix getters of the
-        handle do not refer to batched nodes."""
+        handle do not refer to batched nodes.  objlimits: per-node stop value for the lower bound (phase pUNBD when exceeded)."""
         n = len(probs)
         if n == 0:
             return []
@@ -244,7 +244,9 @@ class Solver:
         res = (Result * n)()
         ys = [np.zeros(max(p.m, 1)) for p in probs] if fetch else None
         yp = (_dp * n)(*[y.ctypes.data_as(_dp) for y in ys]) if fetch else None
-        rc = self.L.lib.sdpcuda_solve_batch(self.h, n, ps, C.byref(params), res, yp)
+        ol = _d(objlimits) if objlimits is not None else None
+        assert ol is None or len(ol) == n
+        rc = self.L.lib.sdpcuda_solve_batch(self.h, n, ps, C.byref(params), res, yp, ol.ctypes.data_as(_dp) if ol is not None else None)
         if rc != 0:
             raise RuntimeError(f"sdpcuda_solve_batch failed with code {rc}")
         self.prob = probs[-1]

@@ -1370,7 +1370,7 @@ static int solve_packed(sdpcuda_handle* h, const sdpcuda_problem* P, const sdpcu
 }
 
 int sdpcuda_solve_batch(sdpcuda_handle* h, int count, const sdpcuda_problem* const* probs, const sdpcuda_params* par,
-   sdpcuda_result* res, double* const* y_out)
+   sdpcuda_result* res, double* const* y_out, const double* objlimits)
 {
    if( h == nullptr || count < 0 || par == nullptr || (count > 0 && probs == nullptr) ) return SDPCUDA_ERR_ARG;
    if( count == 0 ) return SDPCUDA_OK;
@@ -1387,6 +1387,8 @@ int sdpcuda_solve_batch(sdpcuda_handle* h, int count, const sdpcuda_problem* con
    if( h->packed ) { h->packed = false; h->solved = false; }      // the batch reuses the buffers of a packed single solve
    rc = batch_plan(count, probs, par, te != nullptr && te[0] == '1', se != nullptr && se[0] == '1', plan);
    if( rc != SDPCUDA_OK ) return rc;
+   if( objlimits != nullptr )
+      for( size_t k = 0; k < plan.nodes.size(); ++k ) plan.nodes[k].a.objlimit = objlimits[plan.who[k]];
    BatchImage& img = plan.img;
    std::vector<BatchNode>& nodes = plan.nodes;
    const std::vector<int>& who = plan.who;
@@ -1442,7 +1444,9 @@ int sdpcuda_solve_batch(sdpcuda_handle* h, int count, const sdpcuda_problem* con
    for( int i : loners )
    {
       sdpcuda_result R;
-      rc = sdpcuda_solve(h, probs[i], par, nullptr, &R);
+      sdpcuda_params pi = *par;
+      if( objlimits != nullptr ) pi.objlimit = objlimits[i];
+      rc = sdpcuda_solve(h, probs[i], &pi, nullptr, &R);
       if( rc != SDPCUDA_OK ) return rc;
       if( res != nullptr ) res[i] = R;
       if( y_out != nullptr && y_out[i] != nullptr ) { rc = sdpcuda_get_y(h, y_out[i]); if( rc != SDPCUDA_OK ) return rc; }

@@ -113,7 +113,7 @@ def _penalty_ladder(solver, model, lb, ub, r, kw, penaltyparam=1e5, maxpenaltypa
 
 
 def branch_and_bound(solver, model, mode="batch", width=1184, pool=None, gaptol=1e-5, feastol=1e-5, inttol=1e-5, maxnodes=1000000,
-                     timelimit=600.0, verbose=False, dist=None):
+                     timelimit=600.0, verbose=False, dist=None, use_objlimit=False):
     """Frontier-synchronous branch-and-bound on the C ABI: in every round the (at most `width`) best open nodes are prepared like
     sdpi.c prepares a node (Misdp.node_problem), their relaxations are solved TOGETHER — mode "batch": one kernel launch, one CTA
     per node (sdpcuda_solve_batch); "threads": one host thread + stream per handle; "serial" — and the results are dispatched like
@@ -121,6 +121,8 @@ def branch_and_bound(solver, model, mode="batch", width=1184, pool=None, gaptol=
     incumbent, otherwise most-infeasible branching (branch_sdpmostinf.c).  A relaxation that does not end optimal or with a
     certificate is solved again alone with the stable settings (the first rung of sdpi.c's ladder); if that fails too the node is
     branched on its first free integer variable with its parent's bound (nothing is lost, the count is reported as `unsolved`).
+    use_objlimit (relaxing/SDP/objlimit of the reference, off by default there too): once an incumbent exists every relaxation is
+    stopped as soon as its lower bound (the X-side objective of a feasible X-iterate) exceeds the cutoff — phase pUNBD => cutoff.
     dist: torch.distributed with world size N > 1 (one process per GPU): every rank runs the same deterministic tree, in each round
     rank r solves the nodes r, r + N, ... of the round on its own device and the results (status, bound, y) are all-gathered — the
     partition of SURVEY.md 8e.1, no collective on the data path of a relaxation.
@@ -138,7 +140,7 @@ def branch_and_bound(solver, model, mode="batch", width=1184, pool=None, gaptol=
     best, bestsol = math.inf, None
     tick = itertools.count()
     heap = [(-math.inf, next(tick), lb0, ub0)]
-    nodes = rounds = unsolved = 0
+    nodes = rounds = unsolved = iterations = 0
     kw = dict(gaptol=gaptol, feastol=feastol)
     handles = [solver] + list(pool or [])
     world = dist.get_world_size() if dist is not None and dist.is_initialized() else 1
@@ -188,7 +190,11 @@ def branch_and_bound(solver, model, mode="batch", width=1184, pool=None, gaptol=
         elif mode == "batch":
             results = []
             for c in range(0, len(todo), width):
-                results += solver.solve_batch([fp for _, fp, _ in todo[c:c + width]], **kw)
+                part = todo[c:c + width]
+                limits = None
+                if use_objlimit and best < math.inf:
+                    limits = [best - 1e-6 * max(1.0, abs(best)) - info["fixedobj"] for _, _, info in part]
+                results += solver.solve_batch([fp for _, fp, _ in part], objlimits=limits, **kw)
         elif mode == "threads" and len(handles) > 1:
             import threading
             results = [None] * len(todo)
@@ -210,14 +216,15 @@ def branch_and_bound(solver, model, mode="batch", width=1184, pool=None, gaptol=
                 r["y"] = solver.get_y()
                 results.append(r)
         for k, ((bound, fp, info), r) in enumerate(zip(todo, results)):       # repair unacceptable solves on the rank that owns the node
-            if r["phase_name"] not in ("pdOPT", "pFEAS_dINF", "dINF", "pINF_dFEAS"):
+            if r["phase_name"] not in ("pdOPT", "pFEAS_dINF", "dINF", "pINF_dFEAS", "pUNBD"):
                 r = solver.solve(fp, fetch=False, setting=3, **kw)
                 r["y"] = solver.get_y()
-            if r["phase_name"] not in ("pdOPT", "pFEAS_dINF", "dINF", "pINF_dFEAS"):
+            if r["phase_name"] not in ("pdOPT", "pFEAS_dINF", "dINF", "pINF_dFEAS", "pUNBD"):
                 r = _penalty_ladder(solver, model, info["lb"], info["ub"], r, kw)
             results[k] = r
         if world > 1:
-            slim = [dict(phase_name=r["phase_name"], dobj=float(r["dobj"]), y=np.asarray(r["y"], dtype=float)) for r in results]
+            slim = [dict(phase_name=r["phase_name"], dobj=float(r["dobj"]), iterations=int(r.get("iterations", 0)),
+                         y=np.asarray(r["y"], dtype=float)) for r in results]
             gathered = [None] * world
             dist.all_gather_object(gathered, (expired, slim))
             results = [None] * len(alltodo)
@@ -227,7 +234,8 @@ def branch_and_bound(solver, model, mode="batch", width=1184, pool=None, gaptol=
             todo = alltodo
         for (bound, fp, info), r in zip(todo, results):
             lb, ub = info["lb"], info["ub"]
-            if r["phase_name"] in ("pFEAS_dINF", "dINF"):
+            iterations += int(r.get("iterations", 0))
+            if r["phase_name"] in ("pFEAS_dINF", "dINF", "pUNBD"):      # infeasible, or bound above the cutoff (objective limit)
                 continue
             if r["phase_name"] == "pINF_dFEAS":
                 return dict(status="unbounded", objval=-math.inf, sol=None, nodes=nodes, rounds=rounds, unsolved=unsolved, seconds=time.time() - t0)
@@ -256,7 +264,8 @@ def branch_and_bound(solver, model, mode="batch", width=1184, pool=None, gaptol=
                 print(f"round {rounds}: incumbent {best:.8g} ({nodes} nodes)")
     done = not heap or all(cutoff(h[0]) for h in heap)
     status = ("optimal" if bestsol is not None else "infeasible") if done else "limit"
-    return dict(status=status, objval=best, sol=bestsol, nodes=nodes, rounds=rounds, unsolved=unsolved, seconds=time.time() - t0)
+    return dict(status=status, objval=best, sol=bestsol, nodes=nodes, rounds=rounds, unsolved=unsolved, iterations=iterations,
+                seconds=time.time() - t0)
 
 
 def max_over_ranks(value, dist=None, device="cpu"):

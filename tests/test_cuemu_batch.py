@@ -144,7 +144,8 @@ class EmuSolver:
         self.cpu = abi.Solver(abi.Lib(abi.ORACLE_LIB))
         self.batches = 0
 
-    def solve_batch(self, probs, fetch=True, **kw):
+    def solve_batch(self, probs, fetch=True, objlimits=None, **kw):
+        assert objlimits is None
         self.batches += 1
         return run_batch(self.lib, self.emu, probs, tiny=self.tiny, **kw)
 

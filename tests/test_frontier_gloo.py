@@ -127,11 +127,11 @@ def test_solve_batch_boundary():
     assert "y" not in s.solve_batch(nodes[:2], fetch=False)[0]
     par = lib.default_params()
     batch = lib.lib.sdpcuda_solve_batch
-    assert batch(s.h, -1, None, C.byref(par), None, None) == 1          # SDPCUDA_ERR_ARG
-    assert batch(s.h, 0, None, C.byref(par), None, None) == 0
-    assert batch(s.h, 2, None, C.byref(par), None, None) == 1
-    assert batch(None, 0, None, C.byref(par), None, None) == 1
-    assert batch(s.h, 0, None, None, None, None) == 1
+    assert batch(s.h, -1, None, C.byref(par), None, None, None) == 1          # SDPCUDA_ERR_ARG
+    assert batch(s.h, 0, None, C.byref(par), None, None, None) == 0
+    assert batch(s.h, 2, None, C.byref(par), None, None, None) == 1
+    assert batch(None, 0, None, C.byref(par), None, None, None) == 1
+    assert batch(s.h, 0, None, None, None, None, None) == 1
 
 
 # check/testset/short.solu (reference): B&B optima of the short.test instances the harness can read (the same 13 that
@@ -238,3 +238,25 @@ def test_branch_and_bound_world_size_2_runs_the_same_tree():
     for rank, status, objval, nodes, rounds in got:
         assert (status, nodes, rounds) == (single["status"], single["nodes"], single["rounds"])
         assert objval == single["objval"]
+
+
+def test_objective_limits_per_node():
+    """sdpcuda_solve_batch with per-node objective limits (relaxing/SDP/objlimit): a relaxation whose lower bound passes its limit
+    stops with phase pUNBD; the B&B driver with use_objlimit reaches the same optimum over the same tree with fewer iterations"""
+    lib = abi.Lib(abi.ORACLE_LIB)
+    M = misdp.read_sdpa(os.path.join(GOLDEN, "example_TT.dat-s.gz")).rows_to_bounds()
+    nodes = [M.flatten(lb, ub)[0] for lb, ub in _nodes(M)]
+    s = abi.Solver(lib)
+    free = s.solve_batch(nodes, gaptol=1e-6, feastol=1e-6)
+    limits = [r["dobj"] - 0.05 if i % 2 == 0 else 1e20 for i, r in enumerate(free)]
+    cut = s.solve_batch(nodes, objlimits=limits, gaptol=1e-6, feastol=1e-6)
+    for i, (a, b) in enumerate(zip(free, cut)):
+        if i % 2 == 0:
+            assert b["phase_name"] == "pUNBD" and b["stop_name"] == "objlimit" and b["iterations"] < a["iterations"] and b["pobj"] > limits[i]
+        else:
+            assert b["phase_name"] == a["phase_name"] and b["dobj"] == a["dobj"]
+    R = misdp.read_instance(os.path.join(GOLDEN, "example_TT.dat-s.gz"))
+    plain = frontier.branch_and_bound(abi.Solver(lib), R, mode="batch", width=64)
+    fast = frontier.branch_and_bound(abi.Solver(lib), R, mode="batch", width=64, use_objlimit=True)
+    assert (plain["status"], plain["nodes"]) == (fast["status"], fast["nodes"]) and abs(plain["objval"] - fast["objval"]) <= 1e-6
+    assert fast["iterations"] < plain["iterations"]

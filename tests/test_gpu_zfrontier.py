@@ -250,3 +250,19 @@ def test_sdpi_layer_on_the_packed_single_solve(monkeypatch):
         M = misdp.read_instance(os.path.join(GOLDEN, name))
         r = bnb.solve_misdp(L, M, timelimit=600)
         assert r["status"] == "optimal" and abs(M.file_objective(r["objval"]) - want) <= 1e-4 * max(1.0, abs(want))
+
+
+def test_objective_limits_per_node_on_gpu(lib):
+    """per-node objective limits in the batch call: nodes with a limit below their value stop early with phase pUNBD"""
+    M = misdp.read_sdpa(os.path.join(GOLDEN, "example_TT.dat-s.gz")).rows_to_bounds()
+    probs = [fp for fp, _ in (M.flatten(lb, ub) for lb, ub in _frontier(M, 3)) if fp.m > 0]
+    gpu = abi.Solver(lib, device=0)
+    free = gpu.solve_batch(probs, **KW)
+    limits = [r["dobj"] - 0.05 if i % 2 == 0 else 1e20 for i, r in enumerate(free)]
+    cut = gpu.solve_batch(probs, objlimits=limits, **KW)
+    for i, (a, b) in enumerate(zip(free, cut)):
+        if i % 2 == 0:
+            assert b["phase_name"] == "pUNBD" and b["iterations"] < a["iterations"] and b["pobj"] > limits[i]
+        else:
+            assert b["phase_name"] == a["phase_name"] and b["dobj"] == a["dobj"]
+    gpu.close()
