@@ -112,7 +112,7 @@ struct sdpcuda_handle
    // then read the solution where the descriptor of that solve (device addresses) says it is
    bool packed = false;
    SmallArgs pk;
-   size_t pkstage = 0;
+   size_t pkstage = 0, pkwork = 0;
    bool pktiny = false;
    int force_path = 0;               // 0 auto, 1 always multi-kernel, 2 always single-CTA (tests)
    DBuf<LzDesc> lzdesc;
@@ -1312,7 +1312,7 @@ int sdpcuda_debug_pack_node(const sdpcuda_problem* P, const sdpcuda_params* par,
 static int launch_packed(sdpcuda_handle* h, sdpcuda_result* res, double t0, double h2d)
 {
    cudaStream_t st = h->st;
-   CK( cudaMemsetAsync(h->batchwork.p, 0, sizeof(double) * h->batchwork.cap, st) );
+   CK( cudaMemsetAsync(h->batchwork.p, 0, sizeof(double) * h->pkwork, st) );
    CK( cudaEventRecord(h->ev0, st) );
    if( h->pktiny ) CK( launch_ipm_tiny_batch(st, 1, h->batchargs.p, h->pkstage) );
    else CK( launch_ipm_small_batch(st, 1, h->batchargs.p, h->pkstage) );
@@ -1361,6 +1361,7 @@ static int solve_packed(sdpcuda_handle* h, const sdpcuda_problem* P, const sdpcu
    h->pk = args[0];
    h->pktiny = (plan.ntiny == 1);
    h->pkstage = plan.stagebytes[h->pktiny ? 0 : 1];
+   h->pkwork = plan.worktotal;
    h->m = P->m; h->nb = P->nblocks; h->nlp = P->nlp;
    h->blk.resize(h->nb);
    for( int k = 0; k < h->nb; ++k ) h->blk[k] = Block{h->pk.blk[k].n, h->pk.blk[k].ld, h->pk.blk[k].off};
