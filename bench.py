@@ -58,6 +58,8 @@ def parse():
                          "one CTA per node; for the shipped instances), or one host thread + stream per handle")
     ap.add_argument("--bnb-partition", default="replicas", choices=["replicas", "rounds"],
                     help="bnb-* workloads at N > 1: one complete tree per GPU, or ONE tree whose rounds are partitioned over the ranks")
+    ap.add_argument("--native-nodes", action="store_true", help="bnb-* workloads in batch mode: node presolve and marshalling in the library (sdpcuda_solve_nodes)")
+    ap.add_argument("--objlimit", action="store_true", help="bnb-* workloads: per-node objective cutoffs (relaxing/SDP/objlimit)")
     ap.add_argument("--handles-per-gpu", type=int, default=0, help="handles (host threads + streams) per GPU of --frontier-mode threads (default 4)")
     return ap.parse_args()
 
@@ -140,7 +142,8 @@ def bnb_bench(a, rank, local, world):
     pool = [abi.Solver(lib, device=local) for _ in range(npool - 1)]
     width = {"serial": 1, "threads": 4 * npool, "batch": 592}[mode]
     shared = world > 1 and a.bnb_partition == "rounds"
-    run = lambda s, p, md, w, d=None: frontier.branch_and_bound(s, M, mode=md, width=w, pool=p, gaptol=1e-5, feastol=1e-5, dist=d)      # noqa: E731
+    run = lambda s, p, md, w, d=None: frontier.branch_and_bound(s, M, mode=md, width=w, pool=p, gaptol=1e-5, feastol=1e-5, dist=d,      # noqa: E731
+                                                              native=a.native_nodes, use_objlimit=a.objlimit)
     for _ in range(max(1, a.warmup)):
         r = run(gpu, pool, mode, width, dist if shared else None)
     if world > 1:
@@ -156,7 +159,7 @@ def bnb_bench(a, rank, local, world):
     if rank == 0:
         line = {"metric": "B&B nodes/sec", "value": (1 if shared else world) * nodes / wall, "unit": "nodes/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
                 "scaling": "strong" if shared else "weak", "dtype": "f64", "data": "reference instance", "higher_is_better": True, "ms_per_step": 1e3 * wall / a.steps,
-                "config": {"workload": a.workload, "instance": inst[0], "frontier_mode": mode, "width": width, "handles_per_gpu": npool,
+                "config": {"workload": a.workload, "instance": inst[0], "frontier_mode": mode, "width": width, "handles_per_gpu": npool, "native_nodes": bool(a.native_nodes), "objlimit": bool(a.objlimit),
                            "partition": "one tree, the nodes of every round dealt round-robin to the ranks" if shared else "replicas (one complete tree per GPU)"},
                 "nodes_per_run": r["nodes"], "rounds_per_run": r["rounds"], "unsolved": r["unsolved"], "status": r["status"],
                 "objective": M.file_objective(r["objval"]), "short_solu": inst[1]}

@@ -179,6 +179,28 @@ int  sdpcuda_solve_batch(sdpcuda_handle* h, int count, const sdpcuda_problem* co
                          const double* objlimits /* NULL, or [count]: per-node value for params.objlimit — the cutoff bound of the
                                                     node minus its fixed-variable objective (relaxing/SDP/objlimit, relax_sdp.c:4265) */);
 
+/* ---- a frontier given as NODES of one mixed-integer SDP (the form SCIP-SDP's tree has them: one model, per node a pair of bound
+ * vectors).  The model is SCIP-SDP's "dual" form (sdpi.h: min obj'y, sum_j A_j y_j - A_0 psd, lhs <= D y <= rhs, lb <= y <= ub):
+ * entries (variable or -1 for A_0, block, row >= col, value) in the caller's order, rows in CSR.  sdpcuda_solve_nodes does for every
+ * node what SCIPsdpiSolve does before the solver sees it (sdpi.c:3123-3399: rows without active variables decide or vanish, rows with
+ * one active variable tighten its bounds, fixed variables move into the constant part, empty block rows/columns are removed; csrc/
+ * node_marshal.hpp) and hands all remaining relaxations to sdpcuda_solve_batch.
+ * lb, ub: [count*nvars].  status[i]: 0 = solved (res[i], bound[i] = objective incl. the fixed variables), 1 = infeasible by the
+ * presolve, 2 = all variables fixed and feasible (bound[i] = its value).  y: NULL or [count*nvars] solution in MODEL variables;
+ * lbout/ubout: NULL or the tightened bounds; cutoff: NULL or [count] objective cutoffs in model terms (see objlimits above). ---- */
+typedef struct sdpcuda_model sdpcuda_model;
+int  sdpcuda_model_create(sdpcuda_model** model, int nvars, const double* obj, int nblocks, const int* blocksizes, int nnz,
+                          const int* entvar, const int* entblk, const int* entrow, const int* entcol, const double* entval,
+                          int nrows, const int* rowbeg, const int* rowind, const double* rowval, const double* lhs, const double* rhs);
+int  sdpcuda_model_destroy(sdpcuda_model* model);
+int  sdpcuda_solve_nodes(sdpcuda_handle* h, const sdpcuda_model* model, int count, const double* lb, const double* ub,
+                         const sdpcuda_params* par, const double* cutoff, int* status, sdpcuda_result* res, double* bound, double* y,
+                         double* lbout, double* ubout);
+/* test hook: the solver-form problem of one node as flat arrays (ibuf: blocksizes, varbeg, entblk, entrow, entcol, cblk, crow, ccol,
+ * lpbeg, lpind, active; dbuf: obj, entval, cval, lpval, lprhs; sizes: m, nblocks, nnz, cnnz, nlp, lpnnz) */
+int  sdpcuda_debug_node_problem(const sdpcuda_model* model, const double* lb, const double* ub, double feastol, int* status,
+                                double* fixedobj, int* sizes, int* ibuf, size_t icap, double* dbuf, size_t dcap, double* lbout, double* ubout);
+
 /* test hook (no device needed): packs ONE node exactly like sdpcuda_solve_batch does and returns the host image of its read-only
  * data, the length of its work space and its kernel descriptor bound to the given (fake) device addresses; *fits = 0 when the
  * relaxation is outside the single-CTA limits.  tests/test_batch_pack.py re-derives the operators from these arrays. */

@@ -17,6 +17,9 @@
  * and bench.py's cpu_baseline / --impl reference legs may load this library.
  */
 #include "../include/sdpcuda.h"
+/* node marshalling of the product (plain host code, no numerics): shared so that drivers can be tested on the checker back end */
+#define SDPNODE_EMIT_ABI 1
+#include "../scip-sdp_b200/csrc/node_marshal.hpp"
 
 #include <algorithm>
 #include <chrono>

@@ -133,6 +133,10 @@ class Lib:
         L.sdpcuda_psd_check.argtypes = [C.c_void_p, C.c_int, _dp, C.c_int, C.c_double, _ip]
         L.sdpcuda_time_kernel.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, _dp, _dp]
         L.sdpcuda_check_psd_resident.argtypes = [C.c_void_p, _dp, C.c_double, _ip]
+        L.sdpcuda_model_create.argtypes = [C.POINTER(C.c_void_p), C.c_int, _dp, C.c_int, _ip, C.c_int, _ip, _ip, _ip, _ip, _dp, C.c_int, _ip, _ip, _dp, _dp, _dp]
+        L.sdpcuda_model_destroy.argtypes = [C.c_void_p]
+        L.sdpcuda_solve_nodes.argtypes = [C.c_void_p, C.c_void_p, C.c_int, _dp, _dp, C.POINTER(Params), _dp, _ip, C.POINTER(Result), _dp, _dp, _dp, _dp]
+        L.sdpcuda_debug_node_problem.argtypes = [C.c_void_p, _dp, _dp, C.c_double, _ip, _dp, _ip, _ip, C.c_size_t, _dp, C.c_size_t, _dp, _dp]
 
     def backend(self):
         return self.lib.sdpcuda_backend_name().decode()
@@ -143,6 +147,59 @@ class Lib:
         for k, v in kw.items():
             setattr(p, k, v)
         return p
+
+
+class Model:
+    """sdpcuda_model: a mixed-integer SDP handed over once (scip_sdp_b200.misdp.Misdp), so that whole frontiers of its nodes can be
+    given to Solver.solve_nodes as bound vectors only; node presolve and marshalling then run in C++ (csrc/node_marshal.hpp)"""
+
+    def __init__(self, lib, misdp_model):
+        F = misdp_model._arrays()                  # entries block-major with the constant part first, rows in input order
+        self.L, self.nvars = lib, misdp_model.nvars
+        rowbeg = np.concatenate([[0], np.cumsum(np.bincount(F["rid"], minlength=len(misdp_model.rows)))]) if len(misdp_model.rows) else np.zeros(1)
+        keep = [_d(misdp_model.obj), _i(misdp_model.blocksizes), _i(F["ev"]), _i(F["eb"]), _i(F["er"]), _i(F["ec"]), _d(F["ex"]),
+                _i(rowbeg), _i(F["rj"]), _d(F["ra"]), _d(F["lhs"]), _d(F["rhs"])]
+        self.h = C.c_void_p()
+        ip = lambda a: a.ctypes.data_as(_ip)       # noqa: E731
+        dp = lambda a: a.ctypes.data_as(_dp)       # noqa: E731
+        rc = lib.lib.sdpcuda_model_create(C.byref(self.h), self.nvars, dp(keep[0]), len(keep[1]), ip(keep[1]), len(keep[2]), ip(keep[2]), ip(keep[3]),
+                                          ip(keep[4]), ip(keep[5]), dp(keep[6]), len(misdp_model.rows), ip(keep[7]), ip(keep[8]), dp(keep[9]),
+                                          dp(keep[10]), dp(keep[11]))
+        if rc != 0:
+            raise RuntimeError(f"sdpcuda_model_create failed with code {rc}")
+
+    def close(self):
+        if self.h:
+            self.L.lib.sdpcuda_model_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def node_problem(self, lb, ub, feastol=1e-6):
+        """test hook: -> (status 0 solve / 1 infeasible / 2 all fixed, FlatProblem or None, dict(fixedobj, active, lb, ub))"""
+        lb, ub = _d(lb), _d(ub)
+        st, fo = C.c_int(-1), C.c_double(0)
+        sizes = (C.c_int * 6)()
+        lbo, ubo = np.zeros(self.nvars), np.zeros(self.nvars)
+        F = self.L.lib.sdpcuda_debug_node_problem
+        args = (self.h, lb.ctypes.data_as(_dp), ub.ctypes.data_as(_dp), feastol, C.byref(st), C.byref(fo), sizes)
+        assert F(*args, None, 0, None, 0, lbo.ctypes.data_as(_dp), ubo.ctypes.data_as(_dp)) == 0
+        info = dict(fixedobj=fo.value, lb=lbo, ub=ubo)
+        if st.value != 0:
+            return st.value, None, info
+        m, nb, nnz, cn, nlp, lnz = [int(v) for v in sizes]
+        ib = np.zeros(nb + (m + 1) + 3 * nnz + 3 * cn + (nlp + 1) + lnz + m, dtype=np.int32)
+        db = np.zeros(m + nnz + cn + lnz + nlp)
+        assert F(*args, ib.ctypes.data_as(_ip), ib.size, db.ctypes.data_as(_dp), db.size, lbo.ctypes.data_as(_dp), ubo.ctypes.data_as(_dp)) == 0
+        it, dt = iter(np.split(ib, np.cumsum([nb, m + 1, nnz, nnz, nnz, cn, cn, cn, nlp + 1, lnz]))), iter(np.split(db, np.cumsum([m, nnz, cn, lnz])))
+        bs, varbeg, eb, er, ec, cb, cr, cc, lpbeg, lpind, active = [next(it) for _ in range(11)]
+        obj, ev, cv, lpval, lprhs = [next(dt) for _ in range(5)]
+        info["active"] = active
+        return 0, FlatProblem(obj, bs, varbeg, eb, er, ec, ev, cb, cr, cc, cv, lpbeg, lpind, lpval, lprhs), info
 
 
 class Solver:
@@ -258,6 +315,30 @@ class Solver:
                 d["y"] = ys[i][:probs[i].m]
             out.append(d)
         return out
+
+    def solve_nodes(self, model, lbs, ubs, params=None, cutoff=None, **kw):
+        """sdpcuda_solve_nodes: nodes of `model` (abi.Model) given by their bound vectors (arrays count x nvars); presolve, marshalling
+        and the batch launch happen in the library.  -> dict(status [count] (0 solved, 1 infeasible by presolve, 2 all fixed),
+        results (list of dicts), bound, y (count x nvars, model variables), lb, ub (tightened))"""
+        lbs, ubs = _d(lbs), _d(ubs)
+        n, nv = lbs.shape
+        assert nv == model.nvars and ubs.shape == lbs.shape
+        params = params if params is not None else self.L.default_params(**kw)
+        status = np.zeros(n, dtype=np.int32)
+        res = (Result * n)()
+        bound, y, lbo, ubo = np.zeros(n), np.zeros((n, nv)), np.zeros((n, nv)), np.zeros((n, nv))
+        co = _d(cutoff) if cutoff is not None else None
+        dp = lambda a: a.ctypes.data_as(_dp) if a is not None else None      # noqa: E731
+        rc = self.L.lib.sdpcuda_solve_nodes(self.h, model.h, n, dp(lbs), dp(ubs), C.byref(params), dp(co), status.ctypes.data_as(_ip), res,
+                                            dp(bound), dp(y), dp(lbo), dp(ubo))
+        if rc != 0:
+            raise RuntimeError(f"sdpcuda_solve_nodes failed with code {rc}")
+        results = []
+        for r in res:
+            d = {f[0]: getattr(r, f[0]) for f in Result._fields_}
+            d["phase_name"], d["stop_name"] = PHASES[r.phase], STOPS[r.stop]
+            results.append(d)
+        return dict(status=status, results=results, bound=bound, y=y, lb=lbo, ub=ubo)
 
     def solve_resident(self, params=None, **kw):
         params = params if params is not None else self.L.default_params(**kw)

@@ -12,6 +12,8 @@
 #include "ops.cuh"
 #include "ipm_small.cuh"
 #include <cstdint>
+#define SDPNODE_EMIT_ABI 1
+#include "node_marshal.hpp"
 #include <dlfcn.h>
 #include <nccl.h>
 

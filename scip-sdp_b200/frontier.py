@@ -113,7 +113,7 @@ def _penalty_ladder(solver, model, lb, ub, r, kw, penaltyparam=1e5, maxpenaltypa
 
 
 def branch_and_bound(solver, model, mode="batch", width=1184, pool=None, gaptol=1e-5, feastol=1e-5, inttol=1e-5, maxnodes=1000000,
-                     timelimit=600.0, verbose=False, dist=None, use_objlimit=False):
+                     timelimit=600.0, verbose=False, dist=None, use_objlimit=False, native=False):
     """Frontier-synchronous branch-and-bound on the C ABI: in every round the (at most `width`) best open nodes are prepared like
     sdpi.c prepares a node (Misdp.node_problem), their relaxations are solved TOGETHER — mode "batch": one kernel launch, one CTA
     per node (sdpcuda_solve_batch); "threads": one host thread + stream per handle; "serial" — and the results are dispatched like
@@ -123,6 +123,8 @@ def branch_and_bound(solver, model, mode="batch", width=1184, pool=None, gaptol=
     branched on its first free integer variable with its parent's bound (nothing is lost, the count is reported as `unsolved`).
     use_objlimit (relaxing/SDP/objlimit of the reference, off by default there too): once an incumbent exists every relaxation is
     stopped as soon as its lower bound (the X-side objective of a feasible X-iterate) exceeds the cutoff — phase pUNBD => cutoff.
+    native (mode "batch", one rank): the nodes of a round go to the library as bound vectors only (sdpcuda_solve_nodes); node
+    presolve and marshalling run in C++ (csrc/node_marshal.hpp, the same arrays as Misdp.node_problem), Python keeps the tree.
     dist: torch.distributed with world size N > 1 (one process per GPU): every rank runs the same deterministic tree, in each round
     rank r solves the nodes r, r + N, ... of the round on its own device and the results (status, bound, y) are all-gathered — the
     partition of SURVEY.md 8e.1, no collective on the data path of a relaxation.
@@ -160,7 +162,75 @@ def branch_and_bound(solver, model, mode="batch", width=1184, pool=None, gaptol=
             heapq.heappush(heap, (bound, next(tick), up_lb, ub))
 
     expired = False
-    while heap and nodes < maxnodes and not expired:
+    use_native = native and mode == "batch" and world == 1
+    nmodel = None
+    if use_native:
+        from . import abi
+        nmodel = abi.Model(solver.L, model)
+    while use_native and heap and nodes < maxnodes and not expired:
+        rounds += 1
+        expired = time.time() - t0 >= timelimit
+        lbs, ubs, bounds = [], [], []
+        while heap and len(lbs) < width:
+            bound, _, lb, ub = heapq.heappop(heap)
+            if cutoff(bound):
+                continue
+            nodes += 1
+            for sl, z in indicators:
+                if lb[z] > 0.5 and ub[sl] > 0.0:
+                    ub = ub.copy(); ub[sl] = 0.0
+            lbs.append(lb); ubs.append(ub); bounds.append(bound)
+        if not lbs:
+            continue
+        cut = None
+        if use_objlimit and best < math.inf:
+            cut = np.full(len(lbs), best - 1e-6 * max(1.0, abs(best)))
+        out = solver.solve_nodes(nmodel, np.array(lbs), np.array(ubs), cutoff=cut, **kw)
+        for k in range(len(lbs)):
+            st, r = int(out["status"][k]), out["results"][k]
+            lb, ub, y = out["lb"][k], out["ub"][k], out["y"][k]
+            if st == 1:
+                continue
+            if st == 2:
+                if out["bound"][k] < best and not cutoff(out["bound"][k]):
+                    best, bestsol = float(out["bound"][k]), y.copy()
+                continue
+            iterations += int(r["iterations"])
+            obj = float(out["bound"][k])
+            if r["phase_name"] not in ("pdOPT", "pFEAS_dINF", "dINF", "pINF_dFEAS", "pUNBD"):
+                # unacceptable solve: the few such nodes go through the Python path (stable settings, then the penalty ladder)
+                status, fp, info = model.node_problem_fast(lbs[k], ubs[k], feastol=feastol)
+                r = solver.solve(fp, fetch=False, setting=3, **kw)
+                r["y"] = solver.get_y()
+                if r["phase_name"] not in ("pdOPT", "pFEAS_dINF", "dINF", "pINF_dFEAS"):
+                    r = _penalty_ladder(solver, model, info["lb"], info["ub"], r, kw)
+                if r["phase_name"] == "pdOPT":
+                    y = info["lb"].copy(); y[info["active"]] = r["y"]
+                    obj = r["dobj"] + info["fixedobj"]
+            if r["phase_name"] in ("pFEAS_dINF", "dINF", "pUNBD"):
+                continue
+            if r["phase_name"] == "pINF_dFEAS":
+                return dict(status="unbounded", objval=-math.inf, sol=None, nodes=nodes, rounds=rounds, unsolved=unsolved, iterations=iterations,
+                            seconds=time.time() - t0)
+            free = [j for j in ints if ub[j] - lb[j] > 0.5]
+            if r["phase_name"] != "pdOPT":
+                unsolved += 1
+                if free:
+                    push_children(bounds[k], lb, ub, free[0], math.floor(0.5 * (lb[free[0]] + ub[free[0]])) + 0.5)
+                continue
+            if cutoff(obj):
+                continue
+            frac = np.abs(y[ints] - np.round(y[ints])) if len(ints) else np.zeros(0)
+            if len(ints) and frac.max() > inttol:
+                j = ints[int(np.argmax(frac))]
+                push_children(obj, lb, ub, j, y[j])
+                continue
+            viol = [z for sl, z in indicators if y[z] > 0.5 and ub[z] - lb[z] > 0.5 and y[sl] > 1e-6]
+            if viol:
+                push_children(obj, lb, ub, viol[0], 0.5)
+                continue
+            best, bestsol = obj, y.copy()
+    while not use_native and heap and nodes < maxnodes and not expired:
         rounds += 1
         expired = time.time() - t0 >= timelimit            # acted upon after this round (and, with several ranks, agreed upon)
         todo = []

@@ -186,6 +186,16 @@ def test_frontier_branch_and_bound_on_gpu(lib, name, want):
     gpu.close()
 
 
+@pytest.mark.parametrize("name,want", [("example_TT.dat-s.gz", 2.11803), ("example_MkP.dat-s.gz", -95.0)])
+def test_branch_and_bound_with_native_nodes_on_gpu(lib, name, want):
+    """the rounds handed to the library as bound vectors (sdpcuda_solve_nodes: C++ presolve + marshalling + one launch per round)"""
+    M = misdp.read_instance(os.path.join(GOLDEN, name))
+    gpu = abi.Solver(lib, device=0)
+    r = frontier.branch_and_bound(gpu, M, mode="batch", width=592, native=True, use_objlimit=True, timelimit=300)
+    assert r["status"] == "optimal" and abs(M.file_objective(r["objval"]) - want) <= 1e-4 * max(1.0, abs(want))
+    gpu.close()
+
+
 @pytest.mark.parametrize("name,q", [("example_small.dat-s", 2), ("example_TT.dat-s.gz", 4), ("example_MkP.dat-s.gz", 3)])
 def test_tiny_instantiation_of_the_batch_kernel(lib, cpu, name, q, monkeypatch):
     """SDPCUDA_BATCH_TINY=1: relaxations with blocks of order <= 16 run in the 256-thread instantiation (four nodes per SM,

@@ -25,6 +25,9 @@ for inst in tt cls mkp small; do
   cut -c1-160 gpurun_out/r2_frontier_example_${inst}_batch_smem.json
   timeout 600 python bench.py --workload bnb-example-$inst --frontier-mode batch --steps 2 --warmup 1 > gpurun_out/r2_bnb_example_${inst}_batch.json 2>> gpurun_out/r2_bnb.err
   cut -c1-300 gpurun_out/r2_bnb_example_${inst}_batch.json
+  timeout 600 python bench.py --workload bnb-example-$inst --frontier-mode batch --native-nodes --objlimit --steps 2 --warmup 1 --no-cpu-baseline \
+      > gpurun_out/r2_bnb_example_${inst}_batch_native.json 2>> gpurun_out/r2_bnb.err
+  cut -c1-300 gpurun_out/r2_bnb_example_${inst}_batch_native.json
 done
 for w in frontier-tt500 frontier-cls frontier-mkp60; do
   for k in 1 4; do
