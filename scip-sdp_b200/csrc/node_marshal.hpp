@@ -34,6 +34,7 @@ struct Model
    std::vector<int> ev, eb, er, ec;
    std::vector<double> ex;
    std::vector<int> var_order;
+   std::vector<int> key_order;      // all entries sorted by position (block, row, col), input order within a position
    // row nonzeros in input order and sorted by (row, variable)
    int nrows = 0;
    std::vector<int> rid, rj;
@@ -64,6 +65,12 @@ inline int model_build(Model& M, int nvars, const double* obj, int nblocks, cons
       if( M.er[a] != M.er[b] ) return M.er[a] < M.er[b];
       if( M.ec[a] != M.ec[b] ) return M.ec[a] < M.ec[b];
       return M.ex[a] < M.ex[b]; });
+   M.key_order.resize(nnz);
+   std::iota(M.key_order.begin(), M.key_order.end(), 0);
+   std::stable_sort(M.key_order.begin(), M.key_order.end(), [&](int a, int b) {
+      if( M.eb[a] != M.eb[b] ) return M.eb[a] < M.eb[b];
+      if( M.er[a] != M.er[b] ) return M.er[a] < M.er[b];
+      return M.ec[a] < M.ec[b]; });
    const int rnz = nrows > 0 ? rowbeg[nrows] : 0;
    M.rid.resize(rnz); M.rj.assign(rowind, rowind + rnz); M.ra.assign(rowval, rowval + rnz);
    for( int i = 0; i < nrows; ++i )
@@ -120,23 +127,23 @@ inline void flatten(const Model& M, const double* lb, const double* ub, double e
    for( int k = 0; k < m; ++k ) F.varbeg[k + 1] += F.varbeg[k];
    // constant part: A_0 and the fixed variables, duplicates summed in input order
    const long long mx = M.maxn;
-   std::vector<std::pair<long long, double>> cent;
-   for( size_t e = 0; e < M.ev.size(); ++e )
-   {
-      const int v = M.ev[e];
-      if( v >= 0 && !fixed[v] ) continue;
-      cent.emplace_back(((long long)M.eb[e] * mx + M.er[e]) * mx + M.ec[e], v < 0 ? M.ex[e] : -lb[v] * M.ex[e]);
-   }
-   std::stable_sort(cent.begin(), cent.end(), [](const std::pair<long long, double>& a, const std::pair<long long, double>& b) { return a.first < b.first; });
    std::vector<long long> ckey;
    std::vector<double> csum;
-   for( size_t t = 0; t < cent.size(); )
    {
+      // one pass over the entries in position order (sorted once per model): runs of equal position are summed in input order
+      long long curkey = -1;
       double s = 0.0;
-      size_t u = t;
-      for( ; u < cent.size() && cent[u].first == cent[t].first; ++u ) s += cent[u].second;
-      if( s != 0.0 && std::fabs(s) > epsilon ) { ckey.push_back(cent[t].first); csum.push_back(s); }
-      t = u;
+      bool have = false;
+      auto flush = [&]() { if( have && s != 0.0 && std::fabs(s) > epsilon ) { ckey.push_back(curkey); csum.push_back(s); } };
+      for( int e : M.key_order )
+      {
+         const int v = M.ev[e];
+         if( v >= 0 && !fixed[v] ) continue;
+         const long long key = ((long long)M.eb[e] * mx + M.er[e]) * mx + M.ec[e];
+         if( !have || key != curkey ) { flush(); curkey = key; s = 0.0; have = true; }
+         s += v < 0 ? M.ex[e] : -lb[v] * M.ex[e];
+      }
+      flush();
    }
    // rows/columns and blocks that carry nothing are removed
    std::vector<std::vector<char>> used(M.nblocks);
