@@ -281,3 +281,16 @@ def test_staged_multipliers_are_copied_back_for_a_packed_single_solve(lib, emu, 
         for key in ("X", "S", "x", "s", "y"):
             assert np.array_equal(plain[i][key], staged[i][key]), key
         assert np.abs(plain[i]["X"]).max() > 0 and plain[i]["dobj"] == staged[i]["dobj"]
+
+
+@pytest.mark.parametrize("extra", [dict(setting=2), dict(setting=3), dict(lambdastar=50.0), dict(absgaptol=1e-7), dict(objlimit=0.1), dict(maxiter=5)],
+                         ids=lambda d: "-".join(f"{k}={v}" for k, v in d.items()))
+def test_parameters_reach_the_packed_kernel(lib, emu, extra):
+    """the solver parameters as the batch descriptor carries them (settings of SCIP_SDPSOLVERSETTING, prescribed lambdastar, absolute
+    gap, objective limit, iteration limit): same status, stop reason, iteration count and objective as the oracle"""
+    fp, _ = misdp.read_sdpa(os.path.join(GOLDEN, "example_TT.dat-s.gz")).rows_to_bounds().flatten()
+    kw = dict(KW, **extra)
+    r = run_batch(lib, emu, [fp], tiny=True, **kw)[0]
+    ref = abi.Solver(abi.Lib(abi.ORACLE_LIB)).solve(fp, **kw)
+    assert (r["phase_name"], r["stop_name"], r["iterations"]) == (ref["phase_name"], ref["stop_name"], ref["iterations"])
+    assert abs(r["dobj"] - ref["dobj"]) <= 1e-7 * max(1.0, abs(ref["dobj"]))
