@@ -275,3 +275,17 @@ def test_read_write_read_gives_the_same_optimum(tmp_path, name):
         v = [runs[0]["objval"], runs[1]["objval"], runs[2]["objval"]]
         assert abs(M.file_objective(v[0]) - Mc.file_objective(v[1])) <= 1e-4 * max(1.0, abs(v[0]))
         assert abs(v[0] - v[2]) <= 1e-4 * max(1.0, abs(v[0]))
+
+
+def test_cbf_mixed_and_dual_form_have_the_same_optimum():
+    """unittests/src/mixcbf.c:70-93 (readCBFmixreadCBFdual): the same problem in mixed form (matrix variable + LMI) and in dual form;
+    plus the primal form of the same family (example_cbf_primal has its own optimum 0.75 in short.solu)"""
+    from scip_sdp_b200 import frontier
+    lib = abi.Lib(abi.ORACLE_LIB)
+    vals = []
+    for f in ("example_cbf_mix.cbf", "example_cbf_dual.cbf"):
+        M = misdp.read_instance(os.path.join(GOLDEN, f))
+        r = frontier.branch_and_bound(abi.Solver(lib), M, mode="batch", width=16)
+        assert r["status"] == "optimal"
+        vals.append(M.file_objective(r["objval"]))
+    assert abs(vals[0] - vals[1]) <= 1e-6 and abs(vals[0] - 4.0) <= 1e-4
