@@ -238,7 +238,7 @@ inline int node_problem(const Model& M, const double* lb, const double* ub, doub
    std::vector<char> fixed(nv);
    std::vector<double> rconst(M.nrows);
    std::vector<int> nact(M.nrows);
-   for( int pass = 0; pass < 4; ++pass )
+   for( ;; )                                                           // until no bound moves (sdpi.c:3220-3225: while fixingfound)
    {
       for( int j = 0; j < nv; ++j ) if( lbw[j] > ubw[j] + epsilon ) return NODE_INFEASIBLE;
       if( M.nrows == 0 ) break;

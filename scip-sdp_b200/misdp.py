@@ -87,7 +87,7 @@ class Misdp:
         (findEmptyRowColsSDP, sdpi.c:691-810), and a node whose variables are all fixed is decided on the spot (sdpi.c:3219-3290).
         -> (status, FlatProblem or None, info); status: "solve" | "infeasible" | "allfixed" (feasible, info["fixedobj"] is its value)"""
         lb, ub = np.array(lb, dtype=float), np.array(ub, dtype=float)
-        for _ in range(4):
+        while True:                                                   # until no bound moves (sdpi.c:3220-3225: while fixingfound)
             if np.any(lb > ub + epsilon):
                 return "infeasible", None, {}
             fixed = (ub - lb) <= epsilon
@@ -240,7 +240,7 @@ class Misdp:
         lb, ub = np.array(lb, dtype=float), np.array(ub, dtype=float)
         rid, rj, ra = F["rid"], F["rj"], F["ra"]
         nrows = len(self.rows)
-        for _ in range(4):
+        while True:                                                   # until no bound moves (sdpi.c:3220-3225: while fixingfound)
             if np.any(lb > ub + epsilon):
                 return "infeasible", None, {}
             if nrows == 0:

@@ -99,3 +99,37 @@ def test_branch_and_bound_with_native_node_marshalling(name, want):
     else:
         assert b["status"] == "optimal" and abs(M.file_objective(b["objval"]) - want) <= 1e-4 * max(1.0, abs(want))
         assert abs(a["objval"] - b["objval"]) <= 1e-9 * max(1.0, abs(a["objval"]))
+
+
+def _fixing_chain(n=8):
+    """binary y_0..y_{n-1}, y_0 = 1, y_j + y_{j+1} = 1: fixing y_0 fixes the whole chain, one variable per propagation pass
+    (sdpi.c:3220-3225 repeats prepareLPData while a fixing was found); a 1x1 block keeps an SDP part in the problem"""
+    M = misdp.Misdp(n, np.r_[np.zeros(5), -1.0, np.zeros(n - 6)], [1])
+    M.lb[:] = 0.0; M.ub[:] = 1.0; M.integer[:] = True
+    M.add_entry(n - 1, 0, 0, 0, 1.0); M.add_entry(-1, 0, 0, 0, -1.0)          # y_{n-1} + 1 >= 0
+    M.add_row({0: 1.0}, 1.0, 1.0)
+    for j in range(n - 1):
+        M.add_row({j: 1.0, j + 1: 1.0}, 1.0, 1.0)
+    return M
+
+
+def test_fixing_chain_longer_than_four_passes():
+    """the chain is propagated to its end by all three restatements of the node presolve (it used to stop after four passes and
+    drop the rows that were left with one active variable)"""
+    M = _fixing_chain(8)
+    want = np.array([1.0, 0.0] * 4)
+    for fn in (M.node_problem, M.node_problem_fast):
+        st, fp, info = fn(M.lb, M.ub)
+        assert st == "allfixed" and np.array_equal(info["y"], want) and info["fixedobj"] == 0.0
+    lib = abi.Lib(abi.PRODUCT_LIB)
+    model = abi.Model(lib, M)
+    st, fp, info = model.node_problem(M.lb, M.ub)
+    assert st == 2 and info["fixedobj"] == 0.0
+    model.close()
+    # the end of the chain contradicts a bound: infeasible, not "optimal with a violated row"
+    ub = M.ub.copy(); ub[6] = 0.0
+    assert M.node_problem(M.lb, ub)[0] == "infeasible" and M.node_problem_fast(M.lb, ub)[0] == "infeasible"
+    from scip_sdp_b200 import frontier
+    for native in (False, True):
+        r = frontier.branch_and_bound(abi.Solver(abi.Lib(abi.ORACLE_LIB)), M, mode="batch", width=8, native=native)
+        assert r["status"] == "optimal" and abs(r["objval"]) <= 1e-9
