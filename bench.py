@@ -8,6 +8,11 @@ diagonal constraints; the configuration the north-star FP64-tensor target is quo
 
 A "step" is one complete interior-point solve of one relaxation.  At N > 1 every rank solves its own relaxation (the
 independent-node-relaxation partition of the B&B frontier; no data-path collective), `value` is the whole-job rate.
+The same line carries the other half of BASELINE.json's metric under "bnb": B&B nodes/sec for frontiers of open nodes of
+example_TT / example_MkP / example_CLS (one launch per frontier, one CTA per node), of the synthetic TT-500 / CLS-syn / MkP-120 shapes
+and for complete B&B trees, every rank on its own slice of the frontier (scip_sdp_b200/nodesets.py), every counted node converged
+and within 1e-5 of the committed oracle bound (tests/golden/frontier_bounds.npz); and "kernels": FP64 TFLOP/s of the Cholesky and
+GEMM kernels at n = 2000 against the measured DMMA peak.
 `value`  : problem resident in HBM (sdpcuda_solve_resident), device time from CUDA events on the solver's stream.
 `e2e`    : the reference-facing call SCIPsdpiSolverLoadAndSolve + SCIPsdpiSolverGetDualSol with HOST buffers, wall clock.
 `roofline`: the dominant kernel (FP64 DMMA GEMM), algorithmic flops / CUDA-event time from one profiled solve, against the
@@ -35,7 +40,6 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-ORACLE_ITERS_FULL = 18     # iterations the CPU oracle needs on maxcut-2000 seed 4004 under the binding's acceptance rule (measured)
 TOL = dict(gaptol=1e-5, feastol=1e-5, absgaptol=5e-6)   # what sdpisolver_cuda.c hands to the solver for relaxing/SDP defaults
 
 
@@ -47,6 +51,8 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--n", type=int, default=2000, help="max-cut order (2000 = the BASELINE configuration)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-nodes", action="store_true", help="default workload: skip the B&B node workloads (\"bnb\" object of the line)")
+    ap.add_argument("--cpu-nodes-worker", default=None, help=argparse.SUPPRESS)
     ap.add_argument("--workload", default="maxcut", choices=["maxcut", "frontier-tt500", "frontier-cls", "frontier-mkp120", "frontier-mkp60",
                                                              "frontier-example-small", "frontier-example-tt", "frontier-example-cls", "frontier-example-mkp",
                                                              "bnb-example-small", "bnb-example-tt", "bnb-example-cls", "bnb-example-mkp",
@@ -293,19 +299,171 @@ class ClockSampler(threading.Thread):
                     samples=len(self.rows))
 
 
-def cpu_sample(fp, threads_note):
-    """bounded CPU sample: two interior-point iterations of the same relaxation on the oracle, extrapolated to a full solve"""
+# ---------------------------------------------------------------------- CPU legs (the only code of this file that runs the oracle)
+def oracle_lib(threads):
+    """the CPU oracle with its OpenBLAS pool set explicitly (torchrun exports OMP_NUM_THREADS=1, which OpenBLAS would obey);
+    -> (lib, threads actually in use)"""
     from scip_sdp_b200 import abi
-    cpu = abi.Solver(abi.Lib(abi.ORACLE_LIB))
+    lib = abi.Lib(abi.ORACLE_LIB)
+    lib.lib.sdporacle_set_threads.restype = int
+    return lib, int(lib.lib.sdporacle_set_threads(int(threads)))
+
+
+def cpu_relaxation(fp, cores, maxiter=0):
+    """one solve of the relaxation on the CPU oracle with all host threads, to convergence (maxiter = 0) or a bounded number of
+    iterations (warm-up); -> (seconds, result dict, OpenBLAS threads)"""
+    from scip_sdp_b200 import abi
+    lib, threads = oracle_lib(cores)
+    cpu = abi.Solver(lib)
     t = time.perf_counter()
-    r = cpu.solve(fp, maxiter=2, fetch=False, **TOL)
+    r = cpu.solve(fp, fetch=False, **(dict(TOL, maxiter=maxiter) if maxiter else TOL))
+    return time.perf_counter() - t, r, threads
+
+
+NODE_KW = dict(gaptol=1e-5, feastol=1e-5)
+PDOPT = 7          # sdpcuda_phase SDPCUDA_PDOPT
+
+
+def cpu_nodes_worker(spec):
+    """child process of cpu_nodes_baseline: solves its share of a node workload on the CPU oracle with ONE thread (sdpcuda_solve_nodes
+    of the checker library: the same C++ node presolve and marshalling as the product, the oracle's interior-point method)"""
+    os.environ["SDPCUDA_HOST_THREADS"] = "1"
+    from scip_sdp_b200 import abi, nodesets
+    lib, _ = oracle_lib(1)
+    cpu = abi.Solver(lib)
+    M = nodesets.WORKLOADS[spec["name"]][0]()
+    model = abi.Model(lib, M)
+    lbs, ubs = nodesets.node_bounds(M, spec["codes"])
+    cpu.solve_nodes(model, lbs[:1], ubs[:1], lean=True, **NODE_KW)
+    print("ready", flush=True)
+    sys.stdin.readline()
+    t = time.perf_counter()
+    out = cpu.solve_nodes(model, lbs, ubs, lean=True, **NODE_KW)
     dt = time.perf_counter() - t
-    per_iter = dt / max(1, r["iterations"])
-    return per_iter, dt, r["iterations"]
+    print(json.dumps({"seconds": dt, "bound": out["bound"].tolist(), "phase": out["results"]["phase"].tolist()}), flush=True)
+    return 0
+
+
+def cpu_nodes_baseline(name, codes, cores):
+    """B&B nodes/sec of the box's host cores on a node workload: `cores` worker processes, one OpenBLAS thread each, every worker
+    solving its share of the nodes one after the other (independent node relaxations, the way concurrent SCIP-SDP threads would);
+    the clock runs from the common start signal to the last worker's answer"""
+    nw = max(1, min(cores, len(codes)))
+    env = dict(os.environ, OMP_NUM_THREADS="1", OPENBLAS_NUM_THREADS="1")
+    procs = [subprocess.Popen([sys.executable, os.path.abspath(__file__), "--cpu-nodes-worker", json.dumps({"name": name, "codes": [int(c) for c in codes[w::nw]]})],
+                              stdin=subprocess.PIPE, stdout=subprocess.PIPE, text=True, env=env) for w in range(nw)]
+    for p in procs:
+        assert p.stdout.readline().strip() == "ready", "CPU node worker failed to start"
+    t0 = time.perf_counter()
+    for p in procs:
+        p.stdin.write("go\n"); p.stdin.flush()
+    outs = [json.loads(p.stdout.readline()) for p in procs]
+    wall = time.perf_counter() - t0
+    for p in procs:
+        p.wait()
+    bound = [None] * len(codes)
+    for w, o in enumerate(outs):
+        bound[w::nw] = o["bound"]
+    return {"value": len(codes) / wall, "unit": "nodes/s", "cores": nw, "kind": "port",
+            "sample": f"{len(codes)} nodes of this frontier on {nw} worker processes (one OpenBLAS thread each), CPU oracle behind sdpcuda_solve_nodes"}, bound
+
+
+def cpu_nodes_serial(name, codes, cores):
+    """mid-size node relaxations on the CPU: one node at a time with all host threads in OpenBLAS (bounded sample: the first node)"""
+    from scip_sdp_b200 import abi, nodesets
+    lib, threads = oracle_lib(cores)
+    cpu = abi.Solver(lib)
+    M = nodesets.WORKLOADS[name][0]()
+    model = abi.Model(lib, M)
+    lbs, ubs = nodesets.node_bounds(M, codes[:1])
+    t = time.perf_counter()
+    out = cpu.solve_nodes(model, lbs, ubs, lean=True, **NODE_KW)
+    dt = time.perf_counter() - t
+    return {"value": 1.0 / dt, "unit": "nodes/s", "cores": threads, "kind": "port",
+            "sample": f"the first node of this frontier on the CPU oracle ({dt:.1f} s, OpenBLAS on {threads} threads)"}, [float(out["bound"][0])]
+
+
+def cpu_tree(name, cores):
+    """a complete best-first B&B run of the frontier driver on the CPU oracle, one node at a time on one core"""
+    from scip_sdp_b200 import abi, frontier, misdp, nodesets
+    lib, _ = oracle_lib(1)
+    M = misdp.read_instance(os.path.join(nodesets.GOLDEN, name))
+    t = time.perf_counter()
+    r = frontier.branch_and_bound(abi.Solver(lib), M, mode="serial", width=1, **NODE_KW)
+    dt = time.perf_counter() - t
+    return {"value": r["nodes"] / dt, "unit": "nodes/s", "cores": 1, "kind": "port", "nodes": r["nodes"], "objective": M.file_objective(r["objval"]),
+            "sample": "one complete best-first B&B run of the same driver on the CPU oracle, one node at a time on one core"}
+
+
+TREES = {"example_TT tree": ("example_TT.dat-s.gz", 2.11803), "example_MkP tree": ("example_MkP.dat-s.gz", -95.0)}
+
+
+def gpu_node_workload(gpu, lib, name, rank, table, reps):
+    """one frontier on this rank's GPU through sdpcuda_solve_nodes (host bound vectors in, bounds and y out): node presolve, marshalling
+    and packing on the host threads, ONE launch for the nodes that fit the single-CTA kernels, the others one after the other on the
+    multi-kernel path; a node that ends without pdOPT is solved again with the stable settings inside the clock.  Every node is
+    compared with the committed oracle bound; only converged nodes within 1e-5 count."""
+    import numpy as np
+    import torch
+    from scip_sdp_b200 import abi, nodesets
+    M = nodesets.WORKLOADS[name][0]()
+    codes, want = nodesets.frontier_of_rank(name, rank, table=table)
+    lbs, ubs = nodesets.node_bounds(M, codes)
+    model = abi.Model(lib, M)
+    gpu.solve_nodes(model, lbs[:min(len(codes), 8)], ubs[:min(len(codes), 8)], lean=True, **NODE_KW)      # buffers, kernel attributes, graphs
+    wall = dev_ms = 0.0
+    launches = resolved = 0
+    for _ in range(reps):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        out = gpu.solve_nodes(model, lbs, ubs, lean=True, **NODE_KW)
+        bound, phase = out["bound"].copy(), out["results"]["phase"].copy()
+        again = np.flatnonzero((out["status"] == 0) & (phase != PDOPT))
+        if len(again):
+            rep = gpu.solve_nodes(model, lbs[again], ubs[again], lean=True, setting=3, **NODE_KW)
+            bound[again], phase[again] = rep["bound"], rep["results"]["phase"]
+            launches += int(rep["results"]["launches"].sum())
+        wall += time.perf_counter() - t0
+        resolved += len(again)
+        res = out["results"]
+        batched = res["launches"] == 0            # nodes of the shared launch report 0 launches except the first of them
+        dev_ms += float(res["device_ms"][~batched].sum()) if (~batched).any() else 0.0
+        launches += int(res["launches"].sum())
+    rel = np.abs(bound - want) / np.maximum(1.0, np.abs(want))
+    ok = (out["status"] == 0) & (phase == PDOPT) & (rel <= 1e-5)
+    return {"nodes": len(codes), "counted": int(ok.sum()), "wall_s": wall / reps, "device_ms": dev_ms / reps, "launches": launches // reps,
+            "resolved_with_stable_settings": resolved // reps, "max_rel_diff_to_oracle": float(rel[phase == PDOPT].max()) if (phase == PDOPT).any() else None,
+            "not_converged": int(((out["status"] == 0) & (phase != PDOPT)).sum()), "codes": codes,
+            "instance": f"m = {M.nvars}, blocks = {M.blocksizes}, rows = {len(M.rows)}"}
+
+
+def gpu_tree(gpu, lib, file, short_solu):
+    """a complete B&B run of the frontier-synchronous driver: every round's open nodes in one sdpcuda_solve_nodes call"""
+    from scip_sdp_b200 import frontier, misdp, nodesets
+    M = misdp.read_instance(os.path.join(nodesets.GOLDEN, file))
+    run = lambda: frontier.branch_and_bound(gpu, M, mode="batch", width=592, native=True, use_objlimit=True, **NODE_KW)      # noqa: E731
+    run()
+    t0 = time.perf_counter()
+    r = run()
+    dt = time.perf_counter() - t0
+    obj = M.file_objective(r["objval"])
+    assert r["status"] == "optimal" and abs(obj - short_solu) <= 1e-4 * max(1.0, abs(short_solu)), (file, r["status"], obj, short_solu)
+    return {"nodes": r["nodes"], "wall_s": dt, "rounds": r["rounds"], "unsolved": r["unsolved"], "objective": obj, "short_solu": short_solu}
+
+
+def kernel_rates(gpu, peak):
+    """FP64 rates of the factorisation and GEMM kernels at the headline order (sdpcuda_time_kernel, CUDA events on the handle's stream)"""
+    out = {}
+    for key, kind, n in (("potrf_2000", 3, 2000), ("potrf_with_inverse_2000", 2, 2000), ("dgemm_2000", 0, 2000), ("dgemm_4096", 0, 4096), ("syrk_2000", 5, 2000)):
+        ms, fl = gpu.time_kernel(kind, n, 5)              # fl: algorithmic flops (n^3/3 Cholesky, + n^3/3 inverse, 2n^3 GEMM, n^3 SYRK)
+        out[key] = {"ms": ms, "tflops": fl / ms / 1e9, "frac_of_dmma_peak": fl / ms / 1e9 / peak, "flops": fl}
+    return out
 
 
 def main():
     a = parse()
+    if a.cpu_nodes_worker:
+        return cpu_nodes_worker(json.loads(a.cpu_nodes_worker))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -320,26 +478,40 @@ def main():
     if a.impl == "reference":
         if rank != 0:
             return 0
+        # Every timed step is one COMPLETE solve of the relaxation to the same tolerances on the CPU oracle with all host threads of
+        # the box (warm-up steps are two iterations each: they only spin up the BLAS threads).  The value is the box's CPU
+        # throughput whatever N is: the GPUs of the other arm share these host cores.
         fp, _ = generators.maxcut(a.n, min(0.5, 20.0 / a.n), seed=4004).flatten()
         for _ in range(a.warmup):
-            cpu_sample(fp, cores)
-        t0 = time.perf_counter()
-        per = []
+            cpu_relaxation(fp, cores, maxiter=2)
+        secs, its, obj, threads = [], [], None, cores
         for _ in range(a.steps):
-            per_iter, _, _ = cpu_sample(fp, cores)
-            per.append(per_iter)
-        wall = time.perf_counter() - t0
-        sec_per_relax = statistics.mean(per) * ORACLE_ITERS_FULL
-        val = 1.0 / sec_per_relax
+            dt, r, threads = cpu_relaxation(fp, cores)
+            assert r["phase_name"] == "pdOPT", r
+            secs.append(dt); its.append(r["iterations"]); obj = r["dobj"]
+        wall = sum(secs)
+        val = a.steps / wall
         line = {"impl": "reference", "metric": "SDP relaxations/sec", "value": val, "unit": "relaxations/s", "n_gpus": a.gpus,
-                "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1e3 * sec_per_relax, "higher_is_better": True,
+                "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1e3 * wall / a.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": cfg,
-                "cpu_baseline": {"value": val, "unit": "relaxations/s", "cores": cores, "kind": "port",
-                                 "sample": f"each step = 2 interior-point iterations of the same relaxation on the CPU oracle "
-                                           f"(OpenBLAS, {cores} threads), scaled to the {ORACLE_ITERS_FULL} iterations a full solve takes; "
-                                           f"DSDP/SDPA are not installable in this image"},
+                "iterations_per_step": statistics.mean(its), "objective": obj,
+                "cpu_baseline": {"value": val, "unit": "relaxations/s", "cores": threads, "kind": "port",
+                                 "sample": f"every step = one complete solve of the same relaxation on the CPU oracle (OpenBLAS on {threads} threads, "
+                                           f"{os.cpu_count()} host cores; Lanczos step lengths like SDPA); the box's CPU throughput, independent of N; "
+                                           f"DSDP/SDPA/MOSEK are not installable in this image"},
                 "e2e": {"value": val, "unit": "relaxations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0, "wall_s": wall}
+        if not a.no_nodes:
+            from scip_sdp_b200 import nodesets
+            table, bnb = nodesets.golden(), {}
+            for name, (_, per, how) in nodesets.WORKLOADS.items():
+                codes, want = nodesets.frontier_of_rank(name, 0, table=table)
+                base, bound = (cpu_nodes_baseline if how == "nodes" else cpu_nodes_serial)(name, [int(c) for c in codes], cores)
+                base["max_rel_diff_to_committed_bounds"] = max(abs(b - w) / max(1.0, abs(w)) for b, w in zip(bound, want))
+                bnb[name] = base
+            for name, (file, _) in TREES.items():
+                bnb[name] = cpu_tree(file, cores)
+            line["bnb"] = bnb
         print(json.dumps(line))
         return 0
 
@@ -418,11 +590,58 @@ def main():
     dev_s, wall_s, e2e_s = [float(v) for v in t.tolist()]
     launches_all, iters_all = [float(v) for v in cnt.tolist()]
 
+    # ------------------------------------------------------------------ the other half of the metric: B&B nodes/sec (every rank its own frontier slice)
+    bnb = {}
+    if not a.no_nodes:
+        import numpy as np
+        from scip_sdp_b200 import nodesets
+        table = nodesets.golden()
+        lib = gpu.L
+        names = list(nodesets.WORKLOADS)
+        local_res = {}
+        for name in names:
+            barrier()
+            local_res[name] = gpu_node_workload(gpu, lib, name, rank, table, reps=3 if nodesets.WORKLOADS[name][2] == "nodes" else 1)
+        for name, (file, solu) in TREES.items():
+            barrier()
+            local_res[name] = gpu_tree(gpu, lib, file, solu)
+        barrier()
+        # whole-job rates: counted nodes of all ranks / the slowest rank's time
+        keys = names + list(TREES)
+        agg = torch.tensor([[local_res[k]["wall_s"], local_res[k].get("device_ms", 0.0), float(local_res[k].get("counted", local_res[k]["nodes"])),
+                             float(local_res[k]["nodes"])] for k in keys], dtype=torch.float64, device="cuda")
+        mx, sm = agg.clone(), agg.clone()
+        if world > 1:
+            dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+            dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+        for i, k in enumerate(keys):
+            lr = local_res[k]
+            wall_k, dev_k, counted, nodes = float(mx[i, 0]), float(mx[i, 1]), float(sm[i, 2]), float(sm[i, 3])
+            entry = {"value": counted / wall_k, "unit": "nodes/s", "nodes": int(nodes), "counted": int(counted), "ms_per_frontier": 1e3 * wall_k,
+                     "api": "sdpcuda_solve_nodes with host bound vectors (node presolve + marshalling + packing + H2D + launch + D2H inside the clock)"}
+            if k in nodesets.WORKLOADS:
+                entry.update({"device_nodes_per_s": (counted / (dev_k / 1e3)) if dev_k > 0 else None, "launches": lr["launches"],
+                              "not_converged": lr["not_converged"], "resolved_with_stable_settings": lr["resolved_with_stable_settings"],
+                              "max_rel_diff_to_oracle": lr["max_rel_diff_to_oracle"], "instance": lr["instance"],
+                              "parity": "every counted node ended pdOPT and is within 1e-5 (relative) of the oracle bound in tests/golden/frontier_bounds.npz"})
+            else:
+                entry.update({"rounds": lr["rounds"], "unsolved": lr["unsolved"], "objective": lr["objective"], "short_solu": lr["short_solu"],
+                              "api": "frontier.branch_and_bound(native=True, use_objlimit=True): every round's open nodes in one sdpcuda_solve_nodes call; one complete tree per GPU"})
+            bnb[k] = entry
+        if rank == 0 and world == 1 and not a.no_cpu_baseline:
+            for name, (_, per, how) in nodesets.WORKLOADS.items():
+                codes = [int(c) for c in local_res[name]["codes"]]
+                base, _ = (cpu_nodes_baseline if how == "nodes" else cpu_nodes_serial)(name, codes, cores)
+                bnb[name]["cpu_baseline"] = base
+            for name, (file, _) in TREES.items():
+                bnb[name]["cpu_baseline"] = cpu_tree(file, cores)
+
     if rank == 0:
         # roofline of the dominant kernel from one profiled solve + the measured DMMA peak
         peak_ms, peak_fl = gpu.time_kernel(4, 0, 3)
         peak = peak_fl / peak_ms / 1e9
         gemm_ms, gemm_fl = gpu.time_kernel(0, 4096, 3)
+        gpu.solve(fp, fetch=False, **kw)                 # the node workloads used the handle: make the relaxation resident again
         gpu.set_profiling(True)
         pr = gpu.solve_resident(**kw)
         prof = gpu.get_profile()
@@ -430,11 +649,12 @@ def main():
         g = prof["gemm_dmma"]
         achieved = g["work"] / g["ms"] / 1e9 if g["ms"] > 0 else 0.0
         share = {c: round(v["ms"] / pr["device_ms"], 4) for c, v in prof.items()}
-        roof = {"bound": "tensor", "kernel": "gemm_dmma_kernel<64,64> (FP64 DMMA.8x8x4, cp.async fed; the 32x32-tile instantiation of the factorisation leaves is listed separately in share_of_step)", "achieved": achieved, "peak": max(peak, gemm_fl / gemm_ms / 1e9),
-                "unit": "TFLOP/s", "frac": achieved / max(peak, gemm_fl / gemm_ms / 1e9), "traffic": 81.5e6 if a.n == 2000 else None,
+        peak = max(peak, gemm_fl / gemm_ms / 1e9)
+        roof = {"bound": "tensor", "kernel": "gemm_dmma_kernel<64,64> (FP64 DMMA.8x8x4; the 32x32-tile instantiation of the factorisation leaves is listed separately in share_of_step)", "achieved": achieved, "peak": peak,
+                "unit": "TFLOP/s", "frac": achieved / peak, "traffic": 81.5e6 if a.n == 2000 else None,
                 "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one 2000^3 launch, ncu --set full (profiles/r1_gemm_dmma_ncu_full.txt); algorithmic 96 MB",
                 "peak_source": "measured live: max(register-resident DMMA probe, standalone 4096^3 DGEMM of this library); MEASURED_PEAKS.json holds no FP64 figure",
-                "dmma_probe_tflops": peak, "dgemm_4096_tflops": gemm_fl / gemm_ms / 1e9,
+                "dmma_probe_tflops": peak_fl / peak_ms / 1e9, "dgemm_4096_tflops": gemm_fl / gemm_ms / 1e9,
                 "launches_per_solve": g["launches"], "algorithmic_flops_per_solve": g["work"], "device_ms_per_solve": g["ms"],
                 "share_of_step": share, "profiled_solve_ms": pr["device_ms"]}
         line = {"metric": "SDP relaxations/sec", "value": world * a.steps / dev_s, "unit": "relaxations/s", "n_gpus": world,
@@ -446,13 +666,15 @@ def main():
                         "d2h_bytes_per_step": int(first["d2h_bytes"] + 8 * fp.m + 8), "ms_per_step": 1e3 * e2e_s / a.steps,
                         "api": "SCIPsdpiSolverLoadAndSolve + SCIPsdpiSolverGetDualSol (libsdpisolver_cuda.so), host buffers",
                         "objective": obj, "solver_calls_per_step": e2e_calls, "iterations_per_step": e2e_iters},
-                "roofline": roof, "clocks": sampler.summary()}
+                "roofline": roof, "kernels": kernel_rates(gpu, peak), "clocks": sampler.summary()}
+        if bnb:
+            line["bnb"] = bnb
         if world == 1 and not a.no_cpu_baseline:
-            per_iter, dt, its = cpu_sample(fp, cores)
-            line["cpu_baseline"] = {"value": 1.0 / (per_iter * ORACLE_ITERS_FULL), "unit": "relaxations/s", "cores": cores, "kind": "port",
-                                    "sample": f"{its} interior-point iterations of the same relaxation on the CPU oracle ({dt:.1f} s, OpenBLAS on "
-                                              f"{cores} threads), scaled to the {ORACLE_ITERS_FULL} iterations of a full solve; stand-in for "
-                                              f"DSDP/SDPA, which cannot be installed here"}
+            dt, rc, threads = cpu_relaxation(fp, cores)
+            line["cpu_baseline"] = {"value": 1.0 / dt, "unit": "relaxations/s", "cores": threads, "kind": "port",
+                                    "sample": f"one complete solve of the same relaxation on the CPU oracle ({dt:.1f} s, {rc['iterations']} iterations, "
+                                              f"{rc['phase_name']}, objective {rc['dobj']:.6f}; OpenBLAS on {threads} threads, Lanczos step lengths like SDPA); "
+                                              f"stand-in for DSDP/SDPA, which cannot be installed here"}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define SDPCUDA_ABI_VERSION 4
+#define SDPCUDA_ABI_VERSION 5
 
 /* return codes of every entry point */
 #define SDPCUDA_OK            0
@@ -165,6 +165,15 @@ int  sdpcuda_dist_finalize(sdpcuda_handle* h);
 /* Same iteration on the problem that the last sdpcuda_solve left resident in HBM (no host->device traffic); used to
  * measure the device-only throughput and for repeated solves with changed tolerances. */
 int  sdpcuda_solve_resident(sdpcuda_handle* h, const sdpcuda_params* par, sdpcuda_result* res);
+
+/* Re-solve with a problem of the SAME STRUCTURE as the resident one (the >= 3 solves of a failing node in
+ * sdpi.c:3437-3619 - tolerance tightening, FAST/MEDIUM/STABLE ladder, growing penalty parameter Gamma - and the post-check loop of
+ * sdpisolver_sdpa.cpp:368-494 re-load everything although only tolerances, settings, the objective coefficient of r and right-hand
+ * sides change).  The caller guarantees that P differs from the problem of the last sdpcuda_solve on this handle at most in `obj`
+ * and `lprhs` (the binding compares a hash of all other arrays); only these two vectors travel to the device (8 (m + nlp) bytes),
+ * the start point is staged like for sdpcuda_solve.  Without a resident problem (or after a packed/batched solve) it is a full
+ * sdpcuda_solve. */
+int  sdpcuda_solve_patched(sdpcuda_handle* h, const sdpcuda_problem* P, const sdpcuda_params* par, const double* start_y, sdpcuda_result* res);
 
 /* ---- a frontier of independent node relaxations in one call (the open B&B nodes that SCIP-SDP's concurrent
  * solver threads would each hand to SCIPsdpiSolverLoadAndSolve, sdpi.c:3399) ----

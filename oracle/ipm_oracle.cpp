@@ -43,6 +43,11 @@ void scipy_dsyevr_(const char* jobz, const char* range, const char* uplo, const 
    const int* ldz, int* isuppz, double* work, const int* lwork, int* iwork, const int* liwork, int* info);
 void scipy_dpotrs_(const char* uplo, const int* n, const int* nrhs, const double* a, const int* lda, double* b,
    const int* ldb, int* info);
+void scipy_dsymv_(const char* uplo, const int* n, const double* alpha, const double* a, const int* lda, const double* x,
+   const int* incx, const double* beta, double* y, const int* incy);
+void scipy_dstev_(const char* jobz, const int* n, double* d, double* e, double* z, const int* ldz, double* work, int* info);
+void scipy_openblas_set_num_threads(int nthreads);
+int scipy_openblas_get_num_threads(void);
 }
 
 namespace {
@@ -120,6 +125,70 @@ double dotm(const vec& A, const vec& B)
    return s;
 }
 
+/* Smallest eigenvalue of a large symmetric matrix by Lanczos with full reorthogonalisation, the method SDPA itself uses for its
+ * step lengths (Yamashita/Fujisawa/Kojima, SDPA 6.0, section on the step-size computation; Toh, "A note on the calculation of
+ * step-lengths in interior-point methods for SDP").  The Ritz value is lowered by its residual bound |beta_k s_k|, so the
+ * returned value is a lower bound of lambda_min up to the convergence tolerance (1e-10 relative): the step stays inside the cone. */
+const int LANCZOS_MIN_ORDER = 256;
+struct Prof { const char* name; std::chrono::steady_clock::time_point t0; static double acc[16]; static const char* names[16]; int id;
+   Prof(int i, const char* n) : name(n), t0(std::chrono::steady_clock::now()), id(i) { names[i] = n; }
+   ~Prof() { acc[id] += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count(); } };
+double Prof::acc[16]; const char* Prof::names[16];
+static double g_lz_sec = 0.0; static long g_lz_steps = 0, g_lz_calls = 0;
+double lanczos_lmin_impl(int n, const vec& B);
+double lanczos_lmin(int n, const vec& B)
+{
+   auto t0 = std::chrono::steady_clock::now();
+   double v = lanczos_lmin_impl(n, B);
+   g_lz_sec += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count(); ++g_lz_calls;
+   return v;
+}
+double lanczos_lmin_impl(int n, const vec& B)
+{
+   const int kmax = std::min(n, 300);
+   std::vector<vec> Q;
+   vec alpha, beta, q(n), w(n);
+   double nrm = 0.0;
+   for( int i = 0; i < n; ++i ) { q[i] = 1.0 + 0.37 * std::sin(1.0 + 0.7 * i); nrm += q[i] * q[i]; }
+   nrm = std::sqrt(nrm);
+   for( int i = 0; i < n; ++i ) q[i] /= nrm;
+   const double one = 1.0, zero = 0.0;
+   const int ione = 1;
+   double theta = 0.0, bound = 1e300;
+   for( int k = 0; k < kmax; ++k )
+   {
+      Q.push_back(q); ++g_lz_steps;
+      scipy_dsymv_("L", &n, &one, B.data(), &n, q.data(), &ione, &zero, w.data(), &ione);
+      double a = 0.0;
+      for( int i = 0; i < n; ++i ) a += w[i] * q[i];
+      alpha.push_back(a);
+      for( int pass = 0; pass < 2; ++pass )                 /* full reorthogonalisation, twice */
+         for( size_t j = 0; j < Q.size(); ++j )
+         {
+            double d = 0.0;
+            for( int i = 0; i < n; ++i ) d += w[i] * Q[j][i];
+            for( int i = 0; i < n; ++i ) w[i] -= d * Q[j][i];
+         }
+      double b = 0.0;
+      for( int i = 0; i < n; ++i ) b += w[i] * w[i];
+      b = std::sqrt(b);
+      const int kk = k + 1;
+      if( kk % 8 == 0 || kk == kmax || b <= 1e-14 * std::max(1.0, std::fabs(a)) )
+      {
+         vec d(alpha), e(beta), Z((size_t)kk * kk), work(std::max(1, 2 * kk));
+         e.resize(std::max(1, kk));
+         int info = 0;
+         scipy_dstev_("V", &kk, d.data(), e.data(), Z.data(), &kk, work.data(), &info);
+         theta = d[0];
+         bound = std::fabs(b * Z[kk - 1]);                  /* |beta_k| * |last component of the Ritz vector| */
+         if( bound <= 1e-10 * std::max(1.0, std::fabs(theta)) || b <= 1e-14 * std::max(1.0, std::fabs(a)) ) break;
+      }
+      beta.push_back(b);
+      for( int i = 0; i < n; ++i ) q[i] = w[i] / b;
+   }
+   return theta - bound;
+}
+
 /* largest alpha in (0, inf] with  A + alpha*dA  psd, given the Cholesky factor L of A:  -1/lambda_min(L^-1 dA L^-T) */
 double maxstep(int n, const vec& L, const vec& dA)
 {
@@ -129,6 +198,11 @@ double maxstep(int n, const vec& L, const vec& dA)
    scipy_dtrsm_("L", "L", "N", "N", &n, &n, &one, L.data(), &n, B.data(), &n);
    scipy_dtrsm_("R", "L", "T", "N", &n, &n, &one, L.data(), &n, B.data(), &n);
    symmetrize(n, B);
+   double lmin;
+   if( n >= LANCZOS_MIN_ORDER )
+      lmin = lanczos_lmin(n, B);
+   else
+   {
    /* only the smallest eigenvalue: DSYEVR with index range [1,1], as lapack_interface.c:178-288 does for SCIP-SDP */
    vec w(n), work(std::max(1, 26 * n));
    std::vector<int> iwork(std::max(1, 10 * n)), isuppz(2);
@@ -136,7 +210,8 @@ double maxstep(int n, const vec& L, const vec& dA)
    double zero = 0.0, zdummy = 0.0;
    scipy_dsyevr_("N", "I", "L", &n, B.data(), &n, &zero, &zero, &ione, &ione, &zero, &mfound, w.data(), &zdummy, &ione,
       isuppz.data(), work.data(), &lwork, iwork.data(), &liwork, &info);
-   double lmin = w[0];
+   lmin = w[0];
+   }
    if( lmin >= -1e-300 ) return 1e30;
    return -1.0 / lmin;
 }
@@ -388,6 +463,7 @@ int Solver::solve(const sdpcuda_params& par, const double* starty)
    for( ; ; ++iter )
    {
       /* ---- residuals, gap, termination tests ---- */
+      Prof* pr0 = new Prof(0, "residuals");
       AT(it.y, ATy);
       Aop(it.X, AX);
       Dmul(it.y, Dy);
@@ -421,6 +497,7 @@ int Solver::solve(const sdpcuda_params& par, const double* starty)
          pobj += P.lprhs[l] * it.x[l];
       }
       dobj = 0; for( int j = 0; j < m; ++j ) dobj += P.obj[j] * it.y[j];
+      delete pr0;
       mu = P.N > 0 ? xs / P.N : 0.0;
       pinf = std::sqrt(nrp) / (1.0 + normb);
       dinf = std::sqrt(nrd) / (1.0 + normC);
@@ -464,8 +541,8 @@ int Solver::solve(const sdpcuda_params& par, const double* starty)
       bool ok = true;
       for( int k = 0; k < nb && ok; ++k )
       {
-         ok = chol(P.bs[k], it.S[k], L[k]) && chol(P.bs[k], it.X[k], LX[k]);
-         if( ok ) cholinv(P.bs[k], L[k], Sinv[k], Linv[k]);
+         { Prof p(1, "chol S,X"); ok = chol(P.bs[k], it.S[k], L[k]) && chol(P.bs[k], it.X[k], LX[k]); }
+         if( ok ) { Prof p(2, "S^-1"); cholinv(P.bs[k], L[k], Sinv[k], Linv[k]); }
       }
       if( !ok && warm && iter == 0 )
       {
@@ -477,8 +554,9 @@ int Solver::solve(const sdpcuda_params& par, const double* starty)
          continue;
       }
       if( !ok ) { res.stop = SDPCUDA_STOP_NUMERICS; break; }
-      schur(it.X, Sinv, it.x, it.s, Mmat);
+      { Prof p(3, "schur"); schur(it.X, Sinv, it.x, it.s, Mmat); }
       {
+         Prof p(4, "chol M");
          double reg = 0.0, maxd = 0.0;
          for( int j = 0; j < m; ++j ) maxd = std::max(maxd, Mmat[(size_t)j * m + j]);
          int info = 1, tries = 0;
@@ -498,6 +576,7 @@ int Solver::solve(const sdpcuda_params& par, const double* starty)
       for( int pass = 0; pass < 2; ++pass )
       {
          /* K = sym((sigma mu I - dXa dSa - X Rd) S^-1) - X ;  klp likewise */
+         Prof* pr5 = new Prof(5, "K");
          for( int k = 0; k < nb; ++k )
          {
             int n = P.bs[k];
@@ -519,6 +598,8 @@ int Solver::solve(const sdpcuda_params& par, const double* starty)
             if( pass == 1 ) c += sigma * mu - dxa[l] * dsa[l];
             klp[l] = c / it.s[l] - it.x[l];
          }
+         delete pr5;
+         Prof* pr6 = new Prof(6, "rhs+solve");
          Aop(K, g);
          DTmul(klp, g);
          for( int j = 0; j < m; ++j ) g[j] -= rp[j];
@@ -534,6 +615,8 @@ int Solver::solve(const sdpcuda_params& par, const double* starty)
             for( int j = 0; j < m; ++j ) dy[j] += r[j];
          }
          /* dS = A'dy + Rd ; dX = K - sym(X (A'dy) S^-1) */
+         delete pr6;
+         Prof* pr7 = new Prof(7, "dS,dX");
          AT(dy, dS);
          for( int k = 0; k < nb; ++k )
          {
@@ -552,9 +635,11 @@ int Solver::solve(const sdpcuda_params& par, const double* starty)
             ds[l] += rdlp[l];
          }
          /* step lengths */
+         delete pr7;
          double apmax = 1e30, admax = 1e30;
          for( int k = 0; k < nb; ++k )
          {
+            Prof p(8, "maxstep");
             apmax = std::min(apmax, maxstep(P.bs[k], LX[k], dX[k]));
             admax = std::min(admax, maxstep(P.bs[k], L[k], dS[k]));
          }
@@ -599,6 +684,12 @@ int Solver::solve(const sdpcuda_params& par, const double* starty)
    res.seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
    res.device_ms = 0.0; res.h2d_bytes = 0.0; res.d2h_bytes = 0.0;
    solved = true;
+   if( getenv("SDPORACLE_PROFILE") != NULL )
+   {
+      fprintf(stderr, "[oracle profile] %d iterations, %.3f s:", iter, res.seconds);
+      for( int i = 0; i < 16; ++i ) if( Prof::names[i] != NULL ) { fprintf(stderr, "  %s %.3f", Prof::names[i], Prof::acc[i]); Prof::acc[i] = 0.0; }
+      fprintf(stderr, "\n");
+   }
    return SDPCUDA_OK;
 }
 
@@ -609,6 +700,9 @@ struct sdpcuda_handle { Solver s; };
 extern "C" {
 
 int sdpcuda_abi_version(void) { return SDPCUDA_ABI_VERSION; }
+/* checker-only: OpenBLAS thread count actually in use (torchrun exports OMP_NUM_THREADS=1, which OpenBLAS obeys) */
+int sdporacle_set_threads(int n) { if( n > 0 ) scipy_openblas_set_num_threads(n); return scipy_openblas_get_num_threads(); }
+int sdporacle_get_threads(void) { return scipy_openblas_get_num_threads(); }
 const char* sdpcuda_backend_name(void) { return "cpu-oracle"; }
 
 int sdpcuda_create(sdpcuda_handle** h, int device)
@@ -670,6 +764,14 @@ int sdpcuda_solve(sdpcuda_handle* h, const sdpcuda_problem* pr, const sdpcuda_pa
    }
    int rc = h->s.solve(*par, start_y);
    if( res != NULL ) *res = h->s.res;
+   return rc;
+}
+
+/* checker: the same full solve; the product library only ships obj and lprhs to the device */
+int sdpcuda_solve_patched(sdpcuda_handle* h, const sdpcuda_problem* pr, const sdpcuda_params* par, const double* start_y, sdpcuda_result* res)
+{
+   int rc = sdpcuda_solve(h, pr, par, start_y, res);
+   if( rc == SDPCUDA_OK && res != NULL ) res->h2d_bytes = 0.0;
    return rc;
 }
 

@@ -37,6 +37,10 @@ class Result(C.Structure):
                 ("h2d_bytes", C.c_double), ("d2h_bytes", C.c_double)]
 
 
+RESULT_DTYPE = np.dtype([(name, np.int32 if ctype is C.c_int else np.float64) for name, ctype in Result._fields_], align=True)
+assert RESULT_DTYPE.itemsize == C.sizeof(Result)
+
+
 def _i(a):
     return np.ascontiguousarray(a, dtype=np.int32)
 
@@ -316,7 +320,7 @@ class Solver:
             out.append(d)
         return out
 
-    def solve_nodes(self, model, lbs, ubs, params=None, cutoff=None, **kw):
+    def solve_nodes(self, model, lbs, ubs, params=None, cutoff=None, lean=False, **kw):
         """sdpcuda_solve_nodes: nodes of `model` (abi.Model) given by their bound vectors (arrays count x nvars); presolve, marshalling
         and the batch launch happen in the library.  -> dict(status [count] (0 solved, 1 infeasible by presolve, 2 all fixed),
         results (list of dicts), bound, y (count x nvars, model variables), lb, ub (tightened))"""
@@ -333,6 +337,8 @@ class Solver:
                                             dp(bound), dp(y), dp(lbo), dp(ubo))
         if rc != 0:
             raise RuntimeError(f"sdpcuda_solve_nodes failed with code {rc}")
+        if lean:          # the result structs as one numpy record array (fields of sdpcuda_result), no per-node Python objects
+            return dict(status=status, results=np.frombuffer(res, dtype=RESULT_DTYPE, count=n), bound=bound, y=y, lb=lbo, ub=ubo, keep=res)
         results = []
         for r in res:
             d = {f[0]: getattr(r, f[0]) for f in Result._fields_}

@@ -137,6 +137,7 @@ struct sdpcuda_handle
    bool minv = false;                // explicit inverse factor of M (m <= 4096): solves become two triangular mat-vecs; above: look-ahead panels + panel substitution
    DBuf<double> partials, stats, scal, eigw, lzwork;
    DBuf<int> info;
+   DBuf<double> kflag;                            // one word: time-limit flag agreed between the ranks of a sharded solve
    double* h_stats = nullptr;     // pinned
    int* h_info = nullptr;
 
@@ -918,6 +919,25 @@ int sdpcuda_solve(sdpcuda_handle* h, const sdpcuda_problem* P, const sdpcuda_par
    return run_ipm(h, par, start_y, res, t0);
 }
 
+int sdpcuda_solve_patched(sdpcuda_handle* h, const sdpcuda_problem* P, const sdpcuda_params* par, const double* start_y, sdpcuda_result* res)
+{
+   if( h == nullptr || P == nullptr || par == nullptr || P->m <= 0 ) return SDPCUDA_ERR_ARG;
+   if( !h->resident || h->packed || P->m != h->m || P->nblocks != h->nb || P->nlp != h->nlp ) return sdpcuda_solve(h, P, par, start_y, res);
+   const double t0 = now_seconds();
+   int rc = set_device(h);
+   if( rc != SDPCUDA_OK ) return rc;
+   h->solved = false;
+   h->counter.n = 0;
+   g_h2d_bytes = 0.0;
+   // only the objective and the right-hand sides of the rows travel; the scale of the cold start and the norms depend on them
+   std::vector<double> bvec(P->obj, P->obj + h->m), lprhs(P->lprhs, P->lprhs + h->nlp);
+   CK( h->b.upload(bvec, h->st) );
+   if( h->nlp > 0 ) CK( h->lprhs.upload(lprhs, h->st) );
+   CK( cudaStreamSynchronize(h->st) );
+   host_constants(h, P);
+   return run_ipm(h, par, start_y, res, t0);
+}
+
 int sdpcuda_solve_resident(sdpcuda_handle* h, const sdpcuda_params* par, sdpcuda_result* res)
 {
    if( h == nullptr || par == nullptr ) return SDPCUDA_ERR_ARG;
@@ -1214,18 +1234,36 @@ struct BatchPlan
 static int batch_plan(int count, const sdpcuda_problem* const* probs, const sdpcuda_params* par, bool usetiny, bool stage, BatchPlan& P,
    bool copyback = false)
 {
-   P.nodes.reserve(count);
+   // every node is packed into its own image by the host threads (host_pool.hpp); the images are then appended in input order, so
+   // the layout is the one a serial pass over the nodes produces
+   struct Packed { BatchImage img; BatchNode nd; bool fits = false; int rc = SDPCUDA_OK; };
+   std::vector<Packed> packed(count);
+   sdphost::Pool::get().run(count, [&](int i) { packed[i].rc = batch_prepare_node(probs[i], par, packed[i].img, packed[i].nd, &packed[i].fits); });
+   size_t imgtotal = 0;
    for( int i = 0; i < count; ++i )
    {
-      BatchNode nd;
-      bool fits = false;
-      int rc = batch_prepare_node(probs[i], par, P.img, nd, &fits);
-      if( rc != SDPCUDA_OK ) return rc;
-      if( !fits ) { P.loners.push_back(i); continue; }
+      if( packed[i].rc != SDPCUDA_OK ) return packed[i].rc;
+      if( packed[i].fits ) imgtotal += (packed[i].img.buf.size() + 15) & ~(size_t)15;
+   }
+   P.img.buf.resize(imgtotal);
+   P.nodes.reserve(count);
+   std::vector<size_t> base(count, 0);
+   size_t at = 0;
+   for( int i = 0; i < count; ++i )
+   {
+      if( !packed[i].fits ) { P.loners.push_back(i); continue; }
+      BatchNode& nd = packed[i].nd;
+      base[i] = at; at += (packed[i].img.buf.size() + 15) & ~(size_t)15;
+      static_assert(offsetof(BatchNode, denselist) - offsetof(BatchNode, varbeg) == 24 * sizeof(size_t), "image offsets of BatchNode are contiguous");
+      for( size_t* f = &nd.varbeg; f <= &nd.denselist; ++f ) *f += base[i];
       nd.work = P.worktotal; P.worktotal += nd.worklen;
       nd.yoff = P.ytotal; P.ytotal += ((size_t)nd.a.m + 1 + 15) / 16 * 16;
       P.nodes.push_back(nd); P.who.push_back(i);
    }
+   sdphost::Pool::get().run(count, [&](int i)
+   {
+      if( packed[i].fits && !packed[i].img.buf.empty() ) memcpy(P.img.buf.data() + base[i], packed[i].img.buf.data(), packed[i].img.buf.size());
+   });
    const int nd = (int)P.nodes.size();
    P.slot.assign(nd, 0);
    std::vector<int> tiny, rest;
@@ -1742,8 +1780,23 @@ static int run_ipm(sdpcuda_handle* h, const sdpcuda_params* par, const double* s
       if( pfeas && par->objlimit < 1e20 && pobj > par->objlimit )
       { R.phase = SDPCUDA_PUNBD; R.stop = SDPCUDA_STOP_OBJLIMIT; break; }
       if( iter >= maxiter ) { R.stop = SDPCUDA_STOP_ITERLIMIT; break; }
-      if( par->timelimit > 0 && par->timelimit < 1e20 && now_seconds() - t0 > par->timelimit )
-      { R.stop = SDPCUDA_STOP_TIMELIMIT; break; }
+      if( par->timelimit > 0 && par->timelimit < 1e20 )
+      {
+         bool expired = now_seconds() - t0 > par->timelimit;
+         if( h->nranks > 1 )
+         {
+            // one SDP over several GPUs: every rank reads its own clock, so the ranks agree on the stop through a one-word all-reduce
+            // (a rank that left the loop alone would leave the others waiting in the all-reduce of the Schur complement)
+            double flag = expired ? 1.0 : 0.0;
+            CK( h->kflag.ensure(1) );
+            CK( cudaMemcpyAsync(h->kflag.p, &flag, sizeof(double), cudaMemcpyHostToDevice, st) );
+            rc = dist_allreduce_sum(h, h->kflag.p, 1); if( rc ) return rc;
+            CK( cudaMemcpyAsync(&flag, h->kflag.p, sizeof(double), cudaMemcpyDeviceToHost, st) );
+            CK( cudaStreamSynchronize(st) );
+            expired = flag > 0.0;
+         }
+         if( expired ) { R.stop = SDPCUDA_STOP_TIMELIMIT; break; }
+      }
       {
          double merit = std::max(relgap, std::max(pinf, dinf));
          if( merit < 0.9 * bestmerit ) { bestmerit = merit; stall = 0; }

@@ -13,6 +13,7 @@
 // array by array in tests/test_node_marshal.py); sums are formed in the same order.  Shared by libsdpcuda and, as plain marshalling
 // code without numerics, by the checker library.
 #pragma once
+#include "host_pool.hpp"
 #include <algorithm>
 #include <cmath>
 #include <cstring>
@@ -314,23 +315,24 @@ inline int solve_nodes(sdpcuda_handle* h, const sdpcuda_model* model, int count,
    const int nv = M.nvars;
    const double epsilon = 1e-9;
    const double feastol = par->feastol > 0 ? par->feastol : 1e-6;
-   std::vector<FlatNode> flats;
-   std::vector<int> owner;
-   std::vector<std::vector<double>> lbs, ubs;
-   flats.reserve(count);
-   std::vector<double> lbw, ubw;
-   for( int i = 0; i < count; ++i )
+   // presolve + marshalling of every node: independent host work, spread over the host threads (host_pool.hpp)
+   std::vector<FlatNode> all(count);
+   sdphost::Pool::get().run(count, [&](int i)
    {
-      FlatNode F;
+      std::vector<double> lbw, ubw;
+      FlatNode& F = all[i];
       status[i] = node_problem(M, lb + (size_t)i * nv, ub + (size_t)i * nv, epsilon, feastol, lbw, ubw, F);
       if( lbout != nullptr ) std::copy(lbw.begin(), lbw.end(), lbout + (size_t)i * nv);
       if( ubout != nullptr ) std::copy(ubw.begin(), ubw.end(), ubout + (size_t)i * nv);
       if( res != nullptr ) memset(&res[i], 0, sizeof(sdpcuda_result));
       if( bound != nullptr ) bound[i] = (status[i] == NODE_ALLFIXED) ? F.fixedobj : 0.0;
       if( y != nullptr && status[i] != NODE_INFEASIBLE ) std::copy(lbw.begin(), lbw.end(), y + (size_t)i * nv);   // fixed variables sit at their value
-      if( status[i] != NODE_SOLVE ) continue;
-      flats.push_back(std::move(F)); owner.push_back(i);
-   }
+   });
+   std::vector<FlatNode> flats;
+   std::vector<int> owner;
+   flats.reserve(count);
+   for( int i = 0; i < count; ++i )
+      if( status[i] == NODE_SOLVE ) { flats.push_back(std::move(all[i])); owner.push_back(i); }
    const int ns = (int)flats.size();
    if( ns == 0 ) return SDPCUDA_OK;
    std::vector<sdpcuda_problem> views(ns);

@@ -41,6 +41,8 @@
 #define CUDASDP_INF                  1e20
 
 #define MEM_CALL(x) do { if( NULL == (x) ) { SCIPerrorMessage("No memory in function call.\n"); return SCIP_NOMEMORY; } } while( FALSE )
+/* inside LoadAndSolveWithPenalty: the buffer arrays allocated so far are released at TERMINATE */
+#define MEM_GOTO(x) do { if( NULL == (x) ) { SCIPerrorMessage("No memory in function call.\n"); retcode = SCIP_NOMEMORY; goto TERMINATE; } } while( FALSE )
 #define NEED_SOLVED(s) do { if( !(s)->solved ) { \
       SCIPerrorMessage("Tried to access solution information for SDP %d ahead of solving!\n", (s)->sdpcounter); return SCIP_LPERROR; } } while( FALSE )
 #define NEED_SOLVED_BOOL(s) do { if( !(s)->solved ) { \
@@ -98,6 +100,13 @@ struct SCIP_SDPiSolver
    SCIP_Real**           X;                  /**< [nsdpblocks] dense reduced multiplier blocks (lazily fetched) */
    int*                  Xcap;
    SCIP_Bool*            Xvalid;
+
+   /* problem resident on the device: hash over every array handed to sdpcuda_solve except obj and lprhs */
+   SCIP_Bool             residentvalid;
+   unsigned long long    residenthash;
+   int                   nuploads;           /**< full uploads (sdpcuda_solve) since creation */
+   int                   npatched;           /**< re-solves on the resident problem (sdpcuda_solve_patched) since creation */
+   SCIP_Real             h2dbytes;           /**< host->device bytes of all solves since creation */
 
    SCIP_Bool             devicecheck;        /**< post-check of the SDP blocks on the problem resident on the device (SDPCUDA_DEVICE_CHECK=1) */
 
@@ -252,7 +261,28 @@ static SCIP_RETCODE fetchX(SCIP_SDPISOLVER* s, int b)
 }
 
 /** runs one device solve with the given tolerances/settings and pulls y */
-static SCIP_RETCODE runDevice(SCIP_SDPISOLVER* s, const sdpcuda_problem* prob, SCIP_Real gaptol, SCIP_Real feastol,
+/** FNV-1a over the structure of a solver-form problem: everything except the two vectors sdpcuda_solve_patched ships (obj, lprhs) */
+static unsigned long long structureHash(const sdpcuda_problem* p)
+{
+   unsigned long long h = 1469598103934665603ULL;
+   const int nnz = p->m > 0 ? p->varbeg[p->m] : 0;
+   const int lnz = p->nlp > 0 ? p->lpbeg[p->nlp] : 0;
+#define MIX(ptr, bytes) do { const unsigned char* q_ = (const unsigned char*)(ptr); size_t n_ = (size_t)(bytes); size_t t_; \
+      for( t_ = 0; t_ < n_; ++t_ ) { h ^= q_[t_]; h *= 1099511628211ULL; } } while( FALSE )
+   MIX(&p->m, sizeof(int)); MIX(&p->nblocks, sizeof(int)); MIX(&p->cnnz, sizeof(int)); MIX(&p->nlp, sizeof(int));
+   MIX(p->blocksizes, sizeof(int) * p->nblocks);
+   MIX(p->varbeg, sizeof(int) * (p->m + 1));
+   MIX(p->entblk, sizeof(int) * nnz); MIX(p->entrow, sizeof(int) * nnz); MIX(p->entcol, sizeof(int) * nnz); MIX(p->entval, sizeof(double) * nnz);
+   MIX(p->cblk, sizeof(int) * p->cnnz); MIX(p->crow, sizeof(int) * p->cnnz); MIX(p->ccol, sizeof(int) * p->cnnz); MIX(p->cval, sizeof(double) * p->cnnz);
+   if( p->nlp > 0 )
+   {
+      MIX(p->lpbeg, sizeof(int) * (p->nlp + 1)); MIX(p->lpind, sizeof(int) * lnz); MIX(p->lpval, sizeof(double) * lnz);
+   }
+#undef MIX
+   return h;
+}
+
+static SCIP_RETCODE runDevice(SCIP_SDPISOLVER* s, const sdpcuda_problem* prob, unsigned long long hash, SCIP_Real gaptol, SCIP_Real feastol,
    int setting, SCIP_Real timeleft, const SCIP_Real* starty)
 {
    sdpcuda_params par;
@@ -270,7 +300,25 @@ static SCIP_RETCODE runDevice(SCIP_SDPISOLVER* s, const sdpcuda_problem* prob, S
    par.verbose = s->sdpinfo ? 1 : 0;
    par.preoptgap = s->wantpreopt ? s->preoptimalgap : -1.0;
 
-   rc = sdpcuda_solve(s->dev, prob, &par, starty, &s->res);
+   /* the problem of the previous solve is still in HBM: tolerance tightening, the settings ladder, a growing penalty parameter
+    * (only the objective coefficient of r changes) and repeated solves of one node ship obj and lprhs only (sdpi.c:3437-3619) */
+   if( s->residentvalid && s->residenthash == hash )
+   {
+      rc = sdpcuda_solve_patched(s->dev, prob, &par, starty, &s->res);
+      ++s->npatched;
+   }
+   else
+   {
+      s->residentvalid = FALSE;
+      rc = sdpcuda_solve(s->dev, prob, &par, starty, &s->res);
+      ++s->nuploads;
+   }
+   if( rc == SDPCUDA_OK )
+   {
+      s->residentvalid = TRUE;
+      s->residenthash = hash;
+      s->h2dbytes += s->res.h2d_bytes;
+   }
    if( rc == SDPCUDA_ERR_NOMEM )
       return SCIP_NOMEMORY;
    if( rc != SDPCUDA_OK )
@@ -319,6 +367,18 @@ static SCIP_RETCODE runDevice(SCIP_SDPISOLVER* s, const sdpcuda_problem* prob, S
 /*
  * Miscellaneous Methods
  */
+
+/** not part of sdpisolver.h: transfer statistics of this solver object for the tests of the resident re-solve path */
+void SCIPsdpiSolverCudaGetTransferStats(SCIP_SDPISOLVER* sdpisolver, int* nuploads, int* npatched, SCIP_Real* h2dbytes)
+{
+   assert( sdpisolver != NULL );
+   if( nuploads != NULL )
+      *nuploads = sdpisolver->nuploads;
+   if( npatched != NULL )
+      *npatched = sdpisolver->npatched;
+   if( h2dbytes != NULL )
+      *h2dbytes = sdpisolver->h2dbytes;
+}
 
 const char* SCIPsdpiSolverGetSolverName(void)
 {
@@ -381,6 +441,11 @@ SCIP_RETCODE SCIPsdpiSolverCreate(SCIP_SDPISOLVER** sdpisolver, SCIP_MESSAGEHDLR
    s->solved = FALSE;
    s->timelimit = FALSE;
    s->sdpcounter = 0;
+   s->residentvalid = FALSE;
+   s->residenthash = 0ULL;
+   s->nuploads = 0;
+   s->npatched = 0;
+   s->h2dbytes = 0.0;
    s->usedsetting = SCIP_SDPSOLVERSETTING_UNSOLVED;
    s->epsilon = 1e-9;
    s->gaptol = 1e-4;
@@ -494,6 +559,7 @@ SCIP_RETCODE SCIPsdpiSolverLoadAndSolveWithPenalty(
 {
    SCIP_SDPISOLVER* s = sdpisolver;
    sdpcuda_problem prob;
+   unsigned long long probhash;
    SCIP_RETCODE retcode = SCIP_OKAY;
    SCIP_Real timeleft;
    SCIP_Real curgaptol;
@@ -623,7 +689,7 @@ SCIP_RETCODE SCIPsdpiSolverLoadAndSolveWithPenalty(
    }
 
    /* ---- 3. constraint-matrix entries grouped by active variable (CSR over variables) ---- */
-   MEM_CALL( BMSallocClearBufferMemoryArray(s->bufmem, &varbeg, m + 2) );
+   MEM_GOTO( BMSallocClearBufferMemoryArray(s->bufmem, &varbeg, m + 2) );
    for( b = 0; b < nsdpblocks; ++b )
    {
       if( s->blk2dev[b] < 0 )
@@ -640,11 +706,11 @@ SCIP_RETCODE SCIPsdpiSolverLoadAndSolveWithPenalty(
    for( j = 0; j < m; ++j )
       varbeg[j + 1] += varbeg[j];
    nnz = varbeg[m];
-   MEM_CALL( BMSallocBufferMemoryArray(s->bufmem, &fill, m + 1) );
-   MEM_CALL( BMSallocBufferMemoryArray(s->bufmem, &entblk, nnz + 1) );
-   MEM_CALL( BMSallocBufferMemoryArray(s->bufmem, &entrow, nnz + 1) );
-   MEM_CALL( BMSallocBufferMemoryArray(s->bufmem, &entcol, nnz + 1) );
-   MEM_CALL( BMSallocBufferMemoryArray(s->bufmem, &entval, nnz + 1) );
+   MEM_GOTO( BMSallocBufferMemoryArray(s->bufmem, &fill, m + 1) );
+   MEM_GOTO( BMSallocBufferMemoryArray(s->bufmem, &entblk, nnz + 1) );
+   MEM_GOTO( BMSallocBufferMemoryArray(s->bufmem, &entrow, nnz + 1) );
+   MEM_GOTO( BMSallocBufferMemoryArray(s->bufmem, &entcol, nnz + 1) );
+   MEM_GOTO( BMSallocBufferMemoryArray(s->bufmem, &entval, nnz + 1) );
    for( j = 0; j < m; ++j )
       fill[j] = varbeg[j];
    for( b = 0; b < nsdpblocks; ++b )
@@ -683,10 +749,10 @@ SCIP_RETCODE SCIPsdpiSolverLoadAndSolveWithPenalty(
 
    /* ---- 4. constant part (may be absent: primal Slater check passes sdpconstnnonz = 0 and NULL arrays, sdpi.c:1661-1789) ---- */
    cnnz = 0;
-   MEM_CALL( BMSallocBufferMemoryArray(s->bufmem, &cblk, sdpconstnnonz + 1) );
-   MEM_CALL( BMSallocBufferMemoryArray(s->bufmem, &crow, sdpconstnnonz + 1) );
-   MEM_CALL( BMSallocBufferMemoryArray(s->bufmem, &ccol, sdpconstnnonz + 1) );
-   MEM_CALL( BMSallocBufferMemoryArray(s->bufmem, &cval, sdpconstnnonz + 1) );
+   MEM_GOTO( BMSallocBufferMemoryArray(s->bufmem, &cblk, sdpconstnnonz + 1) );
+   MEM_GOTO( BMSallocBufferMemoryArray(s->bufmem, &crow, sdpconstnnonz + 1) );
+   MEM_GOTO( BMSallocBufferMemoryArray(s->bufmem, &ccol, sdpconstnnonz + 1) );
+   MEM_GOTO( BMSallocBufferMemoryArray(s->bufmem, &cval, sdpconstnnonz + 1) );
    if( sdpconstnnonz > 0 )
    {
       for( b = 0; b < nsdpblocks; ++b )
@@ -707,7 +773,7 @@ SCIP_RETCODE SCIPsdpiSolverLoadAndSolveWithPenalty(
          }
       }
    }
-   MEM_CALL( BMSallocBufferMemoryArray(s->bufmem, &devblocksizes, s->ndevblocks + 1) );
+   MEM_GOTO( BMSallocBufferMemoryArray(s->bufmem, &devblocksizes, s->ndevblocks + 1) );
    for( b = 0; b < nsdpblocks; ++b )
    {
       if( s->blk2dev[b] >= 0 )
@@ -717,10 +783,10 @@ SCIP_RETCODE SCIPsdpiSolverLoadAndSolveWithPenalty(
    /* ---- 5. LP block: row sides, then variable bounds, then r >= 0 ---- */
    lpcap = 2 * lpnnonz + 2 * nlpcons + 2 * s->nactive + 2;
    nrows = 2 * nlpcons + 2 * s->nactive + 1;
-   MEM_CALL( BMSallocBufferMemoryArray(s->bufmem, &rowbeg, nrows + 1) );
-   MEM_CALL( BMSallocBufferMemoryArray(s->bufmem, &rowrhs, nrows + 1) );
-   MEM_CALL( BMSallocBufferMemoryArray(s->bufmem, &rowind, lpcap) );
-   MEM_CALL( BMSallocBufferMemoryArray(s->bufmem, &rowval, lpcap) );
+   MEM_GOTO( BMSallocBufferMemoryArray(s->bufmem, &rowbeg, nrows + 1) );
+   MEM_GOTO( BMSallocBufferMemoryArray(s->bufmem, &rowrhs, nrows + 1) );
+   MEM_GOTO( BMSallocBufferMemoryArray(s->bufmem, &rowind, lpcap) );
+   MEM_GOTO( BMSallocBufferMemoryArray(s->bufmem, &rowval, lpcap) );
    nrows = 0;
    lpnz = 0;
    rowbeg[0] = 0;
@@ -797,14 +863,14 @@ SCIP_RETCODE SCIPsdpiSolverLoadAndSolveWithPenalty(
    assert( lpnz <= lpcap );
 
    /* ---- 6. objective and starting point ---- */
-   MEM_CALL( BMSallocBufferMemoryArray(s->bufmem, &devobj, m + 1) );
+   MEM_GOTO( BMSallocBufferMemoryArray(s->bufmem, &devobj, m + 1) );
    for( j = 0; j < s->nactive; ++j )
       devobj[j] = s->actobj[j];
    if( withr )
       devobj[s->nactive] = penaltyparam;
    if( starty != NULL && !withr )
    {
-      MEM_CALL( BMSallocBufferMemoryArray(s->bufmem, &devstart, m + 1) );
+      MEM_GOTO( BMSallocBufferMemoryArray(s->bufmem, &devstart, m + 1) );
       for( j = 0; j < s->nactive; ++j )
          devstart[j] = starty[s->act2var[j]];
    }
@@ -820,9 +886,9 @@ SCIP_RETCODE SCIPsdpiSolverLoadAndSolveWithPenalty(
 
       for( b = 0; b < nsdpblocks; ++b )
          maxn = MAX(maxn, s->devsize[b]);
-      MEM_CALL( BMSallocBufferMemoryArray(s->bufmem, &dense, maxn * maxn) );
-      MEM_CALL( BMSallocBufferMemoryArray(s->bufmem, &lpx, nrows + 1) );
-      MEM_CALL( BMSallocBufferMemoryArray(s->bufmem, &lps, nrows + 1) );
+      MEM_GOTO( BMSallocBufferMemoryArray(s->bufmem, &dense, maxn * maxn) );
+      MEM_GOTO( BMSallocBufferMemoryArray(s->bufmem, &lpx, nrows + 1) );
+      MEM_GOTO( BMSallocBufferMemoryArray(s->bufmem, &lps, nrows + 1) );
       for( which = 0; which < 2 && retcode == SCIP_OKAY; ++which )
       {
          const int* nnz = (which == 0) ? startXnblocknonz : startZnblocknonz;
@@ -892,6 +958,8 @@ SCIP_RETCODE SCIPsdpiSolverLoadAndSolveWithPenalty(
    prob.nlp = nrows;
    prob.lpbeg = rowbeg; prob.lpind = rowind; prob.lpval = rowval; prob.lprhs = rowrhs;
 
+   probhash = structureHash(&prob);
+
    /* ---- 7. solve: settings ladder with post-check, like sdpisolver_sdpa.cpp:1416-1795 ---- */
    if( s->penalty || startsettings == SCIP_SDPSOLVERSETTING_STABLE || startsettings == SCIP_SDPSOLVERSETTING_PENALTY )
       setting = SCIP_SDPSOLVERSETTING_STABLE;
@@ -912,7 +980,7 @@ SCIP_RETCODE SCIPsdpiSolverLoadAndSolveWithPenalty(
       curgaptol = s->gaptol;
       curfeastol = s->sdpsolverfeastol;
 
-      retcode = runDevice(s, &prob, curgaptol, curfeastol, setting, timeleft, devstart);
+      retcode = runDevice(s, &prob, probhash, curgaptol, curfeastol, setting, timeleft, devstart);
       if( retcode != SCIP_OKAY )
          goto TERMINATE;
 
@@ -924,7 +992,7 @@ SCIP_RETCODE SCIPsdpiSolverLoadAndSolveWithPenalty(
          SCIP_Bool infeasible;
          SCIP_Bool again = FALSE;
 
-         MEM_CALL( BMSallocBufferMemoryArray(s->bufmem, &solvector, nvars) );
+         MEM_GOTO( BMSallocBufferMemoryArray(s->bufmem, &solvector, nvars) );
          retcode = SCIPsdpiSolverGetDualSol(s, NULL, solvector);
          if( retcode == SCIP_OKAY && s->devicecheck )
          {
@@ -992,15 +1060,17 @@ SCIP_RETCODE SCIPsdpiSolverLoadAndSolveWithPenalty(
          }
          if( REALABS(s->res.dobj - s->res.pobj) >= s->gaptol )
          {
-            /* the device solver already iterates until the absolute gap is closed (params.absgaptol) or no further
-             * progress is possible, so unlike sdpisolver_sdpa.cpp:449-460 a repeated solve cannot improve on this */
+            /* the absolute gap is still open: tighten the gap tolerance by the same factor and solve again, like
+             * sdpisolver_sdpa.cpp:449-460 (the device solver also gets the absolute rule itself, params.absgaptol) */
             infeasible = TRUE;
-            curgaptol = 0.0;
+            curgaptol *= CUDASDP_TIGHTEN;
+            if( curgaptol >= CUDASDP_MINTOL )
+               again = TRUE;
          }
          if( again )
          {
             SCIPdebugMessage("post-check failed, solving again with feastol %g, gaptol %g\n", curfeastol, curgaptol);
-            retcode = runDevice(s, &prob, curgaptol, curfeastol, setting, timeleft, devstart);
+            retcode = runDevice(s, &prob, probhash, curgaptol, curfeastol, setting, timeleft, devstart);
             if( retcode != SCIP_OKAY )
                goto TERMINATE;
          }

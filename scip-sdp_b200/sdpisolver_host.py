@@ -248,6 +248,14 @@ class SdpiSolver:
         self.lib.SCIPsdpiSolverGetSdpCalls(self.s, C.byref(calls))
         return it.value, calls.value
 
+    def transfer_stats(self):
+        """(full uploads, re-solves on the resident problem, host->device bytes) of this solver object since creation"""
+        up, pa, by = C.c_int(0), C.c_int(0), C.c_double(0)
+        self.lib.SCIPsdpiSolverCudaGetTransferStats.argtypes = [C.c_void_p, _ip, _ip, _dp]
+        self.lib.SCIPsdpiSolverCudaGetTransferStats.restype = None
+        self.lib.SCIPsdpiSolverCudaGetTransferStats(self.s, C.byref(up), C.byref(pa), C.byref(by))
+        return up.value, pa.value, by.value
+
     def close(self):
         if self.s:
             self.lib.SCIPsdpiSolverFree(C.byref(self.s))

@@ -44,6 +44,50 @@ def run_penalty_patterns(libpath):
         s.close()
 
 
+def run_resident_resolves(libpath, device=False):
+    """the re-solves of one node (sdpi.c:3437-3619) reuse the problem that is resident on the device.  Pattern: node
+    solve, the same node again with a tighter gap tolerance, then the penalty formulation (iii) with three growing penalty
+    parameters — uploads happen only when the structure changes (node -> penalty formulation), every other solve ships obj and
+    lprhs only; the results equal those of a fresh solver object that uploads every time."""
+    M = misdp.read_sdpa(os.path.join(GOLDEN, "example_TT.dat-s.gz")).rows_to_bounds()
+    bp = sdpisolver_host.BoundaryProblem(M)
+    s = sdpisolver_host.SdpiSolver(libpath, gaptol=1e-5, feastol=1e-6)
+    try:
+        s.load_and_solve(bp)
+        obj0, y0 = s.dual_sol()
+        assert s.transfer_stats()[:2] == (1, 0)
+        bytes_first = s.transfer_stats()[2]
+        s.lib.SCIPsdpiSolverSetRealpar(s.s, 1, 1e-7)                   # GAPTOL tightened between two solves of the node (sdpi.c:3553)
+        s.load_and_solve(bp)
+        obj1, _ = s.dual_sol()
+        up, pa, by = s.transfer_stats()
+        assert (up, pa) == (1, 1) and abs(obj1 - obj0) <= 1e-5 * max(1.0, abs(obj0))
+        if device:
+            assert by - bytes_first <= 8 * (bp.nvars + 4 * bp.nvars + 2 * len(M.rows) + 64), (by, bytes_first)
+        objs = []
+        for gamma in (1e4, 1e5, 1e6):
+            feasorig, _ = s.load_and_solve_with_penalty(bp, gamma, True, True)
+            assert s.flag("IsAcceptable") and feasorig
+            objs.append(s.dual_sol()[0])
+        up, pa, by2 = s.transfer_stats()
+        assert up == 2 and pa >= 3, (up, pa)                          # one upload for the penalty structure, Gamma only changes obj
+        fresh = []
+        for gamma in (1e4, 1e5, 1e6):
+            t = sdpisolver_host.SdpiSolver(libpath, gaptol=1e-7, feastol=1e-6)
+            t.load_and_solve_with_penalty(bp, gamma, True, True)
+            fresh.append(t.dual_sol()[0])
+            assert t.transfer_stats()[0] == 1
+            t.close()
+        assert np.allclose(objs, fresh, rtol=1e-9, atol=1e-9), (objs, fresh)
+        # a different node (one more fixed variable): the structure changes, so it is uploaded
+        lb, ub = M.lb.copy(), M.ub.copy()
+        j = int(np.flatnonzero(M.integer)[0]); ub[j] = lb[j]
+        s.load_and_solve(sdpisolver_host.BoundaryProblem(M, lb, ub))
+        assert s.transfer_stats()[0] == 3
+    finally:
+        s.close()
+
+
 def run_primal_getters(libpath):
     """GetPrimalMatrix (sparse, original indices, LP block with the 2i/2i+1 convention) vs GetPrimalSolutionMatrix (dense) vs
     GetPrimalBoundVars, and dual feasibility of the multipliers: sum_k A_j.X + D'x + w - v = obj_j"""

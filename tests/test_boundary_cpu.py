@@ -16,6 +16,10 @@ def test_primal_matrix_getters_are_consistent():
     boundary_cases.run_primal_getters(sdpi_ref.LIB_ORACLE)
 
 
+def test_resolves_of_a_node_reuse_the_resident_problem():
+    boundary_cases.run_resident_resolves(sdpi_ref.LIB_ORACLE)
+
+
 def test_warmstart_and_preoptimal_solution():
     boundary_cases.run_warmstart_and_preoptimal(sdpi_ref.LIB_ORACLE)
 

@@ -17,3 +17,8 @@ def test_primal_matrix_getters_are_consistent_on_gpu():
 
 def test_warmstart_and_preoptimal_solution_on_gpu():
     boundary_cases.run_warmstart_and_preoptimal(sdpisolver_host.BINDING_LIB)
+
+
+def test_resolves_of_a_node_reuse_the_resident_problem_on_gpu():
+    """row f4: host->device traffic of the re-solves is the two patched vectors only"""
+    boundary_cases.run_resident_resolves(sdpisolver_host.BINDING_LIB, device=True)
