@@ -166,6 +166,16 @@ int  sdpcuda_dist_finalize(sdpcuda_handle* h);
  * measure the device-only throughput and for repeated solves with changed tolerances. */
 int  sdpcuda_solve_resident(sdpcuda_handle* h, const sdpcuda_params* par, sdpcuda_result* res);
 
+/* Reductions on the primal solution X that is resident on the device (computeConflictCut, relax_sdp.c:1030-1099, pulls
+ * the dense X of every block to the host after every node, forms <A_j, X> and <A_0, X> there and calls LAPACK for lambda_min(X)):
+ *   out[g] = sum over entries e in [groupbeg[g], groupbeg[g+1]) of  w_e val[e] X_{blk[e]}[row[e], col[e]],  w_e = 1 (row == col) or 2,
+ * entries in the device's block numbering and reduced indices (row >= col); 12 bytes per entry go up, 8 bytes per group come back. */
+int  sdpcuda_primal_products(sdpcuda_handle* h, int ngroups, const int* groupbeg, const int* blk, const int* row, const int* col,
+   const double* val, double* out);
+/* certified lower bound of min(lambda_min(X_block), 0): 0 when the Cholesky factorisation of X_block succeeds on the device (always
+ * the case for an interior iterate), otherwise -sigma for the smallest sigma = 1e-14 |X|_max 10^k with X + sigma I positive definite */
+int  sdpcuda_primal_mineig_bound(sdpcuda_handle* h, int block, double* bound);
+
 /* Re-solve with a problem of the SAME STRUCTURE as the resident one (the >= 3 solves of a failing node in
  * sdpi.c:3437-3619 - tolerance tightening, FAST/MEDIUM/STABLE ladder, growing penalty parameter Gamma - and the post-check loop of
  * sdpisolver_sdpa.cpp:368-494 re-load everything although only tolerances, settings, the objective coefficient of r and right-hand

@@ -869,6 +869,46 @@ int sdpcuda_get_S(sdpcuda_handle* h, int b, double* S)
    return SDPCUDA_OK;
 }
 /* the CPU restatement is a single-process checker: no sharded path */
+int sdpcuda_primal_products(sdpcuda_handle* h, int ngroups, const int* groupbeg, const int* blk, const int* row, const int* col,
+   const double* val, double* out)
+{
+   if( h == NULL || ngroups < 0 ) return SDPCUDA_ERR_ARG;
+   Solver* S = &h->s;
+   if( !S->solved ) return SDPCUDA_ERR_STATE;
+   for( int g = 0; g < ngroups; ++g )
+   {
+      double acc = 0.0;
+      for( int e = groupbeg[g]; e < groupbeg[g + 1]; ++e )
+      {
+         if( blk[e] < 0 || blk[e] >= S->P.nblocks || col[e] < 0 || row[e] < col[e] || row[e] >= S->P.bs[blk[e]] ) return SDPCUDA_ERR_ARG;
+         const int n = S->P.bs[blk[e]];
+         acc += (row[e] == col[e] ? 1.0 : 2.0) * val[e] * S->it.X[blk[e]][(size_t)col[e] * n + row[e]];
+      }
+      out[g] = acc;
+   }
+   return SDPCUDA_OK;
+}
+
+int sdpcuda_primal_mineig_bound(sdpcuda_handle* h, int block, double* bound)
+{
+   if( h == NULL || bound == NULL ) return SDPCUDA_ERR_ARG;
+   Solver* S = &h->s;
+   if( !S->solved ) return SDPCUDA_ERR_STATE;
+   if( block < 0 || block >= S->P.nblocks ) return SDPCUDA_ERR_ARG;
+   const int n = S->P.bs[block];
+   double sigma = 0.0, scale = 1e-300;
+   for( double v : S->it.X[block] ) scale = std::max(scale, std::fabs(v));
+   for( int tries = 0; tries < 40; ++tries )
+   {
+      vec A = S->it.X[block], L;
+      for( int i = 0; i < n; ++i ) A[(size_t)i * n + i] += sigma;
+      if( chol(n, A, L) ) { *bound = -sigma; return SDPCUDA_OK; }
+      sigma = (sigma == 0.0) ? 1e-14 * scale : sigma * 10.0;
+   }
+   *bound = -sigma;
+   return SDPCUDA_OK;
+}
+
 int sdpcuda_dist_unique_id(void* id128) { (void)id128; return SDPCUDA_ERR_STATE; }
 int sdpcuda_dist_init(sdpcuda_handle* h, int nranks, int rank, const void* id128)
 {

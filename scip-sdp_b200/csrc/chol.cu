@@ -10,6 +10,7 @@
 // (and inverted) inside one CTA in shared memory.  The interior-point iteration needs L and L^-1 of S (for S^-1 and the
 // dual step length) and of X (primal step length), and L of the Schur complement M.
 #include "common.cuh"
+#include <algorithm>
 #include <cstdlib>
 #include <cstring>
 
@@ -46,6 +47,16 @@ __device__ __forceinline__ double fast_rsqrt64(double x)
    return y;
 }
 
+// reciprocal: MUFU.RCP64H seed + two Newton steps
+__device__ __forceinline__ double fast_rcp64(double x)
+{
+   double y;
+   asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+   y = fma(y, fma(-x, y, 1.0), y);
+   y = fma(y, fma(-x, y, 1.0), y);
+   return y;
+}
+
 // one product tile of the inverse recursion: D = sum_k A[.][k] B[k][.] over k in [klo, khi) (multiples of 8), operands via
 // the two loader functors; two interleaved accumulators shorten the DMMA dependency chain
 template <class FA, class FB>
@@ -62,153 +73,166 @@ __device__ __forceinline__ void tile_product(int klo, int khi, FA fa, FB fb, dou
    d0 += e0; d1 += e1;
 }
 
+__device__ long long* g_leaf_stamps = nullptr;       // debug: clock64 stamps of one macro step (set by the kind-9 probe)
+
+// shared-memory carve-up and thread coordinates of the diagonal-block code (kernel below and the tile kernel potrf_dag_kernel)
 template <int NBL>
-__global__ void __launch_bounds__(NBL * 4)
-leaf_kernel(int mode, int nb, double* __restrict__ A, int lda, double* __restrict__ Linv, int ldi,
-   double* __restrict__ diaginv, int* __restrict__ info, int pivot_offset, long long* __restrict__ dbg)
+struct LeafCtx
 {
-   long long tc0 = clock64(), tc1 = 0, tc2 = 0, tc3 = 0;
-   constexpr int NTILE = NBL / 8, LD = NBL + 4, NSTEP = NBL / 4, NTHREADS = NBL * 4, NWARP = NBL / 8;
-   extern __shared__ __align__(16) double lsm[];
-   __shared__ int sbad;
-   double* G = lsm;                              // (NBL + 1) x LD
-   double* Tr = G + (NBL + 1) * LD;              // (NBL / 2) x LD
-   double* Pcol = Tr + (NBL / 2) * LD;           // NBL x 4  current block column
-   double* P = Pcol + NBL * 4;                   // NBL x 4  panel
-   double* rdg = P + NBL * 4;                    // NBL      reciprocals of the diagonal of L
-   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-   const int fr = lane >> 2, fc = lane & 3;
-
-   if( mode == 0 )
+   static constexpr int NTILE = NBL / 8, LD = NBL + 4, NSTEP = NBL / 4, NTHREADS = NBL * 4, NWARP = NBL / 8;
+   double *G, *Tr, *Pcol, *P, *rdg;
+   int tid, lane, w, fr, fc;
+   __device__ __forceinline__ LeafCtx(double* lsm)
    {
-      double c[NTILE][2];
-#pragma unroll
-      for( int j = 0; j < NTILE; ++j )
-      {
-         c[j][0] = 0.0; c[j][1] = 0.0;
-         if( j <= w )
-         {
-            const int row = 8 * w + fr;
-#pragma unroll
-            for( int e = 0; e < 2; ++e )
-            {
-               const int col = 8 * j + 2 * fc + e;
-               double v = (row == col) ? 1.0 : 0.0;      // identity padding keeps a partial block positive definite
-               if( row < nb && col < nb && row >= col ) v = A[(size_t)col * lda + row];
-               c[j][e] = v;
-            }
-         }
-      }
-      P[tid] = 0.0;                                      // NTHREADS = 4 NBL
-      if( tid == 0 ) sbad = 0x7fffffff;                  // smallest index of a non-positive pivot
-      __syncthreads();
-      tc1 = clock64();
+      G = lsm;                              // (NBL + 1) x LD
+      Tr = G + (NBL + 1) * LD;              // (NBL / 2) x LD
+      Pcol = Tr + (NBL / 2) * LD;           // 2 x (NBL x 4)  block column of the current / the next macro step
+      P = Pcol + 2 * NBL * 4;               // 2 x (NBL x 4)  panel of the current / the next macro step
+      rdg = P + 2 * NBL * 4;                // NBL      reciprocals of the diagonal of L
+      tid = threadIdx.x; lane = tid & 31; w = tid >> 5; fr = lane >> 2; fc = lane & 3;
+   }
+};
 
+// factorisation of the block held as accumulator fragments c (warp w = 8-row strip w, lower tiles j <= w): L goes to global memory
+// (lower triangle of A) and, row-major, to G; rdg receives the reciprocals of the diagonal.  sbad: shared int of the caller.
+template <int NBL>
+__device__ __forceinline__ void leaf_factor(const LeafCtx<NBL>& X, double (&c)[NBL / 8][2], int nb, double* __restrict__ A, int lda,
+   int* __restrict__ info, int pivot_offset, int& sbad)
+{
+   constexpr int NTILE = LeafCtx<NBL>::NTILE, LD = LeafCtx<NBL>::LD, NSTEP = LeafCtx<NBL>::NSTEP, NTHREADS = LeafCtx<NBL>::NTHREADS;
+   double* const G = X.G; double* const Pcol = X.Pcol; double* const P = X.P; double* const rdg = X.rdg;
+   const int tid = X.tid, w = X.w, fr = X.fr, fc = X.fc;
+   __shared__ long long lstamp[8];
+   P[tid] = 0.0; P[NTHREADS + tid] = 0.0;             // NTHREADS = 4 NBL; both panel buffers
+   if( tid == 0 ) sbad = 0x7fffffff;                  // smallest index of a non-positive pivot
+   // block column 0 -> shared memory
+   if( (fc >> 1) == 0 )
+      *reinterpret_cast<double2*>(Pcol + (8 * w + fr) * 4 + 2 * (fc & 1)) = make_double2(c[0][0], c[0][1]);
+   __syncthreads();
+
+   // Macro step t (4 columns), two barriers, ordered so that only what the NEXT step needs sits between them:
+   //   (a) row threads: 4 x 4 Cholesky of the diagonal block + their panel row            (the dependent rsqrt chain)
+   //   (b) every strip updates the ONE tile that holds block column t+1 and hands that column over
+   //   (c) the rank-4 update of all other tiles runs after the second barrier, i.e. beside (a) of step t+1
 #pragma unroll
-      for( int t = 0; t < NSTEP; ++t )
+   for( int t = 0; t < NSTEP; ++t )
+   {
+      double* const Pc = Pcol + (t & 1) * NBL * 4;
+      double* const Pp = P + (t & 1) * NBL * 4;
+      if( t == 8 && tid == 63 ) lstamp[0] = clock64();
+      // (2) panel row of every row r >= 4t
+      if( tid < NBL && tid >= 4 * t )
       {
-         const int jt = t >> 1, half = t & 1;
-         // (1) block column t -> shared memory (rows of the strips w >= jt)
-         if( w >= jt && (fc >> 1) == half )
-            *reinterpret_cast<double2*>(Pcol + (8 * w + fr) * 4 + 2 * (fc & 1)) = make_double2(c[jt][0], c[jt][1]);
-         __syncthreads();
-         // (2) panel row of every row r >= 4t
-         if( tid < NBL && tid >= 4 * t )
+         const int r = tid;
+         const double4* Dg = reinterpret_cast<const double4*>(Pc + 16 * t);
+         const double4 g0 = Dg[0], g1 = Dg[1], g2 = Dg[2], g3 = Dg[3], av = *reinterpret_cast<const double4*>(Pc + 4 * r);
+         // 4 x 4 Cholesky through the leading principal minors m1..m4 (fraction-free elimination with the exact division of
+         // Bareiss): the elimination itself needs only multiplications and two reciprocals that do not depend on each other,
+         // and the FOUR reciprocal square roots are independent, instead of the chain pivot -> rsqrt -> next pivot -> rsqrt ...
+         //    b_ij = m1 g_ij - g_i0 g_j0,   c_ij = (b_11 b_ij - b_i1 b_j1) / m1,   m4 = (c_22 c_33 - c_32^2) / m2,   m2 = b_11, m3 = c_22
+         //    L_kk = m_{k+1} q_k,  1 / L_kk = m_k q_k,  L_i1 = b_i1 q_1,  L_32 = c_32 q_2   with   q_k = rsqrt(m_k m_{k+1}), m_0 = 1
+         // (same rounding behaviour as the usual elimination: every Schur-complement entry is formed by one product and one FMA;
+         // magnitudes stay below |a|^4).  A non-positive minor = non-positive pivot: replaced by 1 and reported after the loop.
+         double m1 = g0.x;
+         const bool b0 = !(m1 > 0.0); m1 = b0 ? 1.0 : m1;
+         const double i1 = fast_rcp64(m1);
+         const double b11 = fma(m1, g1.y, -g1.x * g1.x), b21 = fma(m1, g2.y, -g2.x * g1.x), b31 = fma(m1, g3.y, -g3.x * g1.x);
+         const double b22 = fma(m1, g2.z, -g2.x * g2.x), b32 = fma(m1, g3.z, -g3.x * g2.x), b33 = fma(m1, g3.w, -g3.x * g3.x);
+         double m2 = b11;
+         const bool b1 = !(m2 > 0.0); m2 = b1 ? 1.0 : m2;
+         const double i2 = fast_rcp64(m2);
+         const double c22 = fma(m2, b22, -b21 * b21) * i1, c32 = fma(m2, b32, -b31 * b21) * i1, c33 = fma(m2, b33, -b31 * b31) * i1;
+         double m3 = c22;
+         const bool b2 = !(m3 > 0.0); m3 = b2 ? 1.0 : m3;
+         double m4 = fma(m3, c33, -c32 * c32) * i2;
+         const bool b3 = !(m4 > 0.0); m4 = b3 ? 1.0 : m4;
+         const double q0 = fast_rsqrt64(m1), q1 = fast_rsqrt64(m1 * m2), q2 = fast_rsqrt64(m2 * m3), q3 = fast_rsqrt64(m3 * m4);
+         const double r0 = q0, r1 = m1 * q1, r2 = m2 * q2, r3 = m3 * q3;                    // reciprocals of the diagonal of L
+         const double s0 = m1, s1 = m2 * i1, s2 = m3 * i2;                                  // pivots (only their products with r are used)
+         const double l10 = g1.x * q0, l20 = g2.x * q0, l30 = g3.x * q0;
+         const double l21 = b21 * q1, l31 = b31 * q1, l32 = c32 * q2;
+         const double d0v = m1 * q0, d1v = m2 * q1, d2v = m3 * q2, d3v = m4 * q3;           // diagonal of L
+         (void)s0; (void)s1; (void)s2;
+         if( r == 4 * t && (b0 || b1 || b2 || b3) )
          {
-            const int r = tid;
-            const double4* Dg = reinterpret_cast<const double4*>(Pcol + 16 * t);
-            const double4 g0 = Dg[0], g1 = Dg[1], g2 = Dg[2], g3 = Dg[3], av = *reinterpret_cast<const double4*>(Pcol + 4 * r);
-            // 4 x 4 Cholesky, branch free (a non-positive pivot is replaced by 1 and reported after the loop)
-            double s0 = g0.x;
-            const bool b0 = !(s0 > 0.0); s0 = b0 ? 1.0 : s0;
-            const double r0 = fast_rsqrt64(s0);
-            const double l10 = g1.x * r0, l20 = g2.x * r0, l30 = g3.x * r0;
-            double s1 = g1.y - l10 * l10;
-            const bool b1 = !(s1 > 0.0); s1 = b1 ? 1.0 : s1;
-            const double r1 = fast_rsqrt64(s1);
-            const double l21 = (g2.y - l20 * l10) * r1, l31 = (g3.y - l30 * l10) * r1;
-            double s2 = g2.z - l20 * l20 - l21 * l21;
-            const bool b2 = !(s2 > 0.0); s2 = b2 ? 1.0 : s2;
-            const double r2 = fast_rsqrt64(s2);
-            const double l32 = (g3.z - l30 * l20 - l31 * l21) * r2;
-            double s3 = g3.w - l30 * l30 - l31 * l31 - l32 * l32;
-            const bool b3 = !(s3 > 0.0); s3 = b3 ? 1.0 : s3;
-            const double r3 = fast_rsqrt64(s3);
-            if( r == 4 * t && (b0 || b1 || b2 || b3) )
-            {
-               const int q = b0 ? 0 : (b1 ? 1 : (b2 ? 2 : 3));
-               if( 4 * t + q < nb ) atomicMin(&sbad, 4 * t + q);
-            }
-            double4 pr;
-            if( r >= 4 * t + 4 )
-            {
-               pr.x = av.x * r0;
-               pr.y = (av.y - pr.x * l10) * r1;
-               pr.z = (av.z - pr.x * l20 - pr.y * l21) * r2;
-               pr.w = (av.w - pr.x * l30 - pr.y * l31 - pr.z * l32) * r3;
-               *reinterpret_cast<double4*>(P + 4 * r) = pr;
-            }
-            else
-            {
-               const int q = r - 4 * t;
-               const double d0 = s0 * r0, d1 = s1 * r1, d2 = s2 * r2, d3 = s3 * r3;
-               pr.x = (q == 0) ? d0 : (q == 1 ? l10 : (q == 2 ? l20 : l30));
-               pr.y = (q == 0) ? 0.0 : (q == 1 ? d1 : (q == 2 ? l21 : l31));
-               pr.z = (q <= 1) ? 0.0 : (q == 2 ? d2 : l32);
-               pr.w = (q <= 2) ? 0.0 : d3;
-               *reinterpret_cast<double4*>(P + 4 * r) = make_double4(0.0, 0.0, 0.0, 0.0);
-               rdg[r] = (q == 0) ? r0 : (q == 1 ? r1 : (q == 2 ? r2 : r3));
-            }
-            // row-major copy of L (zeros above the diagonal land in the triangle that the inverse fills later)
-            *reinterpret_cast<double4*>(G + (r + 1) * LD + 4 * t) = pr;
+            const int q = b0 ? 0 : (b1 ? 1 : (b2 ? 2 : 3));
+            if( 4 * t + q < nb ) atomicMin(&sbad, 4 * t + q);
          }
-         __syncthreads();
-         // (3) rank-4 update of the tiles that still change: rows >= 4t+4, columns >= 4t+4, lower tiles
+         double4 pr;
+         if( r >= 4 * t + 4 )
          {
-            const int jlo = (t + 1) >> 1;
-            if( w >= jlo )
-            {
-               const double a = -P[(8 * w + fr) * 4 + fc];
-#pragma unroll
-               for( int j = 0; j < NTILE; ++j )
-               {
-                  if( j >= jlo && j <= w )
-                  {
-                     const double b = P[(8 * j + fr) * 4 + fc];
-                     dmma884(c[j][0], c[j][1], a, b);
-                  }
-               }
-            }
+            pr.x = av.x * r0;
+            pr.y = (av.y - pr.x * l10) * r1;
+            pr.z = (av.z - pr.x * l20 - pr.y * l21) * r2;
+            pr.w = (av.w - pr.x * l30 - pr.y * l31 - pr.z * l32) * r3;
+            *reinterpret_cast<double4*>(Pp + 4 * r) = pr;
+         }
+         else
+         {
+            const int q = r - 4 * t;
+            const double d0 = d0v, d1 = d1v, d2 = d2v, d3 = d3v;
+            pr.x = (q == 0) ? d0 : (q == 1 ? l10 : (q == 2 ? l20 : l30));
+            pr.y = (q == 0) ? 0.0 : (q == 1 ? d1 : (q == 2 ? l21 : l31));
+            pr.z = (q <= 1) ? 0.0 : (q == 2 ? d2 : l32);
+            pr.w = (q <= 2) ? 0.0 : d3;
+            *reinterpret_cast<double4*>(Pp + 4 * r) = make_double4(0.0, 0.0, 0.0, 0.0);
+            rdg[r] = (q == 0) ? r0 : (q == 1 ? r1 : (q == 2 ? r2 : r3));
+         }
+         // row-major copy of L (zeros above the diagonal land in the triangle that the inverse fills later)
+         *reinterpret_cast<double4*>(G + (r + 1) * LD + 4 * t) = pr;
+      }
+      if( t == 8 && tid == 63 ) lstamp[1] = clock64();
+      __syncthreads();
+      if( t == 8 && tid == 63 ) lstamp[2] = clock64();
+      const int jlo = (t + 1) >> 1;                      // first tile column that still changes = the one holding block column t+1
+      double a = 0.0;
+      if( w >= jlo )
+      {
+         a = -Pp[(8 * w + fr) * 4 + fc];
+         if( jlo < NTILE )
+         {
+            const double b = Pp[(8 * jlo + fr) * 4 + fc];
+            dmma884(c[jlo][0], c[jlo][1], a, b);
+            if( t + 1 < NSTEP && (fc >> 1) == ((t + 1) & 1) )
+               *reinterpret_cast<double2*>(Pcol + ((t + 1) & 1) * NBL * 4 + (8 * w + fr) * 4 + 2 * (fc & 1)) = make_double2(c[jlo][0], c[jlo][1]);
          }
       }
+      if( t == 8 && tid == 63 ) lstamp[3] = clock64();
       __syncthreads();
-      if( tid == 0 && sbad != 0x7fffffff ) atomicCAS(info, 0, pivot_offset + sbad + 1);
-      tc2 = clock64();
-      // L -> global memory, lower triangle, column by column (coalesced)
-      for( int e = tid; e < nb * nb; e += NTHREADS )
+      if( t == 8 && tid == 63 ) lstamp[4] = clock64();
+      if( t == 9 && tid == 63 ) lstamp[5] = clock64();
+      if( w > jlo )
       {
-         const int i = e % nb, j = e / nb;
-         if( i >= j ) A[(size_t)j * lda + i] = G[(i + 1) * LD + j];
+#pragma unroll
+         for( int j = 0; j < NTILE; ++j )
+         {
+            if( j > jlo && j <= w )
+            {
+               const double b = Pp[(8 * j + fr) * 4 + fc];
+               dmma884(c[j][0], c[j][1], a, b);
+            }
+         }
       }
    }
-   else
+   __syncthreads();
+   if( tid == 0 && sbad != 0x7fffffff ) atomicCAS(info, 0, pivot_offset + sbad + 1);
+   if( tid == 0 && g_leaf_stamps != nullptr ) for( int q = 0; q < 6; ++q ) g_leaf_stamps[q] = lstamp[q];
+   // L -> global memory, lower triangle, column by column (coalesced)
+   for( int e = tid; e < nb * nb; e += NTHREADS )
    {
-      for( int e = tid; e < NBL * NBL; e += NTHREADS )
-      {
-         const int i = e % NBL, j = e / NBL;
-         if( i >= j )
-         {
-            double v = (i == j) ? 1.0 : 0.0;
-            if( i < nb && j < nb ) v = A[(size_t)j * lda + i];
-            G[(i + 1) * LD + j] = v;
-            if( i == j ) rdg[i] = 1.0 / v;
-         }
-      }
-      __syncthreads();
-      tc2 = clock64();
+      const int i = e % nb, j = e / nb;
+      if( i >= j ) A[(size_t)j * lda + i] = G[(i + 1) * LD + j];
    }
-   if( Linv == nullptr && diaginv == nullptr ) return;
+}
 
+// inverse W = L^-1 of the block whose factor sits row-major in G (with rdg): 8 x 8 diagonal inverses, then recursive doubling on
+// DMMA fragments; W ends up transposed in the upper triangle of G (element (r,c) at row c)
+template <int NBL>
+__device__ __forceinline__ void leaf_invert(const LeafCtx<NBL>& X)
+{
+   constexpr int LD = LeafCtx<NBL>::LD, NWARP = LeafCtx<NBL>::NWARP;
+   double* const G = X.G; double* const Tr = X.Tr; double* const rdg = X.rdg;
+   const int tid = X.tid, w = X.w, fr = X.fr, fc = X.fc;
    // ---- inverse: 8 x 8 diagonal blocks, one thread per column ----
    if( tid < NBL )
    {
@@ -260,6 +284,69 @@ leaf_kernel(int mode, int nb, double* __restrict__ A, int lda, double* __restric
       }
       __syncthreads();
    }
+}
+
+template <int NBL>
+__global__ void __launch_bounds__(NBL * 4)
+leaf_kernel(int mode, int nb, double* __restrict__ A, int lda, double* __restrict__ Linv, int ldi,
+   double* __restrict__ diaginv, int* __restrict__ info, int pivot_offset, long long* __restrict__ dbg)
+{
+   long long tc0 = clock64(), tc1 = 0, tc2 = 0, tc3 = 0;
+   constexpr int NTILE = NBL / 8, LD = NBL + 4, NSTEP = NBL / 4, NTHREADS = NBL * 4, NWARP = NBL / 8;
+   extern __shared__ __align__(16) double lsm[];
+   __shared__ int sbad;
+   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+   const int fr = lane >> 2, fc = lane & 3;
+
+   const LeafCtx<NBL> X(lsm);
+   double* const G = X.G;
+   double* const rdg = X.rdg;
+   if( mode == 0 )
+   {
+      double c[NTILE][2];
+#pragma unroll
+      for( int j = 0; j < NTILE; ++j )
+      {
+         c[j][0] = 0.0; c[j][1] = 0.0;
+         if( j <= w )
+         {
+            const int row = 8 * w + fr;
+#pragma unroll
+            for( int e = 0; e < 2; ++e )
+            {
+               const int col = 8 * j + 2 * fc + e;
+               double v = (row == col) ? 1.0 : 0.0;      // identity padding keeps a partial block positive definite
+               if( row < nb && col < nb && row >= col ) v = A[(size_t)col * lda + row];
+               c[j][e] = v;
+            }
+         }
+      }
+      tc1 = clock64();
+      if( tid == 0 ) g_leaf_stamps = (dbg != nullptr) ? dbg + 4 : nullptr;
+      __syncthreads();
+      leaf_factor<NBL>(X, c, nb, A, lda, info, pivot_offset, sbad);
+      if( tid == 0 ) g_leaf_stamps = nullptr;
+      tc2 = clock64();
+   }
+   else
+   {
+      for( int e = tid; e < NBL * NBL; e += NTHREADS )
+      {
+         const int i = e % NBL, j = e / NBL;
+         if( i >= j )
+         {
+            double v = (i == j) ? 1.0 : 0.0;
+            if( i < nb && j < nb ) v = A[(size_t)j * lda + i];
+            G[(i + 1) * LD + j] = v;
+            if( i == j ) rdg[i] = 1.0 / v;
+         }
+      }
+      __syncthreads();
+      tc2 = clock64();
+   }
+   if( Linv == nullptr && diaginv == nullptr ) return;
+
+   leaf_invert<NBL>(X);
    tc3 = clock64();
    if( Linv != nullptr )
       for( int e = tid; e < nb * nb; e += NTHREADS )
@@ -279,7 +366,276 @@ leaf_kernel(int mode, int nb, double* __restrict__ A, int lda, double* __restric
    }
 }
 
-template <int NBL> constexpr size_t leaf_smem() { return sizeof(double) * ((size_t)(NBL + 1) * (NBL + 4) + (size_t)(NBL / 2) * (NBL + 4) + 9 * (size_t)NBL); }
+template <int NBL> constexpr size_t leaf_smem() { return sizeof(double) * ((size_t)(NBL + 1) * (NBL + 4) + (size_t)(NBL / 2) * (NBL + 4) + 17 * (size_t)NBL); }
+
+// ---- tile-DAG Cholesky: ONE persistent kernel for the whole factorisation --------------------------------------------------------
+// The lower triangle is cut into 64 x 64 tiles, ordered column by column (diagonal tile first).  CTAs claim tiles in that order from
+// an atomic counter and compute a tile completely ("left-looking per tile"):
+//     C = A_ij - sum_{k<j} L_ik L_jk'        one DMMA accumulation over K = 64 j, operands streamed through a cp.async ring
+//     i == j:  L_jj = chol(C), W_jj = L_jj^-1  (the diagonal-block code above, on the accumulator fragments)
+//     i >  j:  L_ij = C W_jj'                 (one more 64^3 product out of shared memory)
+// and publish it through a ready flag (release/acquire at GPU scope).  A tile only depends on tiles that precede it in the claim
+// order, and a claimed tile is owned by a running CTA, so the smallest unfinished tile can always proceed: no deadlock whatever
+// part of the grid is resident (other streams may hold SMs).  The chain POTRF(j) -> TRSM(j+1,j) -> last update of (j+1,j+1) is the
+// critical path; all other tiles of later columns are claimed early and hide behind it (look-ahead without a schedule).
+constexpr int DAG_T = 64, DAG_THREADS = 256, DAG_BK = 16, DAG_STAGES = 4, DAG_LDS = DAG_T + 4;
+constexpr size_t DAG_SMEM = sizeof(double) * (size_t)DAG_STAGES * 2 * DAG_BK * DAG_LDS;      // 69632 B >= leaf_smem<64>() and the two TRSM operand tiles
+static_assert(DAG_STAGES * 2 * DAG_BK * DAG_LDS >= 2 * DAG_T * DAG_LDS, "TRSM operands fit the ring");
+
+struct DagArgs
+{
+   int n, T;
+   double* A; int lda;
+   double* Linv; int ldi;        // optional: diagonal blocks of the inverse factor are written here as well
+   double* Wd;                   // T packed 64 x 64 inverses of the diagonal blocks of L
+   int* sync;                    // [0] tile counter, [1] abort flag, [2 ..] T*T ready flags (zeroed before the launch)
+   int* info;
+   long long* dbg;               // optional: 8 timestamps (ns) per tile of the critical chain (diagonal tiles: slot 2j, tiles (j+1,j): slot 2j+1)
+};
+
+__device__ __forceinline__ long long dag_now()
+{
+   long long t;
+   asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+   return t;
+}
+
+__device__ __forceinline__ int ld_acquire(const int* p)
+{
+   int v;
+   asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+   return v;
+}
+__device__ __forceinline__ void st_release(int* p, int v)
+{
+   asm volatile("st.release.gpu.global.s32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void dag_cp16(void* smem, const void* gmem, int srcbytes)
+{
+   unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" :: "r"(sa), "l"(gmem), "r"(srcbytes));
+}
+
+// thread 0 waits until the flags f0 and f1 are set (or the kernel is being aborted), then the whole CTA passes
+__device__ __forceinline__ bool dag_wait(const int* f0, const int* f1, int* abortflag, int& s_abort)
+{
+   if( threadIdx.x == 0 )
+   {
+      const long long t0 = clock64();
+      int bad = 0;
+      while( ld_acquire(f0) == 0 || ld_acquire(f1) == 0 )
+      {
+         if( ld_acquire(abortflag) != 0 ) { bad = 1; break; }
+         if( clock64() - t0 > 4000000000LL ) { atomicExch(abortflag, 1); bad = 1; break; }     // ~2 s: a bug, not a wait
+      }
+      s_abort = bad;
+   }
+   __syncthreads();
+   return s_abort == 0;
+}
+
+// 16 columns [k0, k0+16) of the 64-row tile at (row0, .) of a column-major matrix -> smem [k][r], leading dimension DAG_LDS
+__device__ __forceinline__ void dag_load_chunk(double* s, const double* __restrict__ g, int ld, int row0, int k0, int nrows, int tid)
+{
+#pragma unroll
+   for( int c = tid; c < DAG_BK * (DAG_T / 2); c += DAG_THREADS )
+   {
+      const int k = c / (DAG_T / 2), r = (c % (DAG_T / 2)) * 2;
+      const int gr = row0 + r;
+      int bytes = 0;
+      if( gr < nrows ) bytes = (nrows - gr >= 2) ? 16 : 8;
+      const double* src = bytes ? (g + (size_t)(k0 + k) * ld + gr) : g;
+      dag_cp16(s + k * DAG_LDS + r, src, bytes);
+   }
+}
+
+__global__ void __launch_bounds__(DAG_THREADS, 2) potrf_dag_kernel(DagArgs a)
+{
+   extern __shared__ __align__(16) double dsm[];
+   __shared__ int s_tile, s_abort, sbad;
+   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, fr = lane >> 2, fc = lane & 3;
+   const int T = a.T, n = a.n, total = T * (T + 1) / 2;
+   int* const counter = a.sync;
+   int* const abortflag = a.sync + 1;
+   int* const ready = a.sync + 2;
+
+   for( ;; )
+   {
+      __syncthreads();                                   // the previous tile is done with shared memory and s_tile
+      if( tid == 0 ) s_tile = atomicAdd(counter, 1);
+      __syncthreads();
+      const int t = s_tile;
+      if( t >= total ) break;
+      int j = 0, start = 0;
+      while( start + (T - j) <= t ) { start += T - j; ++j; }
+      const int i = j + (t - start);
+      const bool diag = (i == j);
+      const int row0 = DAG_T * i, col0 = DAG_T * j;
+      long long* const dbg = (a.dbg != nullptr && tid == 0 && (diag || i == j + 1)) ? a.dbg + 8 * (2 * j + (diag ? 0 : 1)) : nullptr;
+      if( dbg ) dbg[0] = dag_now();                     // claimed
+
+      // ---- C = A_ij (diagonal tile: lower part, identity on the padding) ----
+      double c[8][2];
+#pragma unroll
+      for( int jt = 0; jt < 8; ++jt )
+      {
+         const int row = row0 + 8 * w + fr;
+#pragma unroll
+         for( int e = 0; e < 2; ++e )
+         {
+            const int col = col0 + 8 * jt + 2 * fc + e;
+            double v = 0.0;
+            if( row < n && col < n && (!diag || row >= col) ) v = a.A[(size_t)col * a.lda + row];
+            if( diag && row == col && row >= n ) v = 1.0;
+            c[jt][e] = v;
+         }
+      }
+
+      // ---- C -= sum_k L_ik L_jk' ----
+      // k-tiles 0 .. j-2 stream through the cp.async ring (their flags are usually set long before); the LAST k-tile, the one the
+      // critical chain waits for, is fetched in one go after its flags - four chunks in flight at once instead of one per ring turn
+      const int nchunks = 4 * max(j - 1, 0);
+      bool ok = true;
+      auto load_chunk = [&](int cidx, int slot)
+      {
+         const int kt = cidx >> 2, k0 = DAG_T * kt + (cidx & 3) * DAG_BK;
+         double* As = dsm + (size_t)slot * (2 * DAG_BK * DAG_LDS);
+         dag_load_chunk(As, a.A, a.lda, row0, k0, n, tid);
+         if( !diag ) dag_load_chunk(As + DAG_BK * DAG_LDS, a.A, a.lda, col0, k0, n, tid);
+      };
+      auto compute_chunk = [&](int slot)
+      {
+         const double* As = dsm + (size_t)slot * (2 * DAG_BK * DAG_LDS);
+         const double* Bs = diag ? As : As + DAG_BK * DAG_LDS;
+#pragma unroll
+         for( int kk = 0; kk < DAG_BK; kk += 4 )
+         {
+            const double av = -As[(kk + fc) * DAG_LDS + 8 * w + fr];
+#pragma unroll
+            for( int jt = 0; jt < 8; ++jt )
+            {
+               if( diag && jt > w ) continue;
+               const double bv = Bs[(kk + fc) * DAG_LDS + 8 * jt + fr];
+               dmma884(c[jt][0], c[jt][1], av, bv);
+            }
+         }
+      };
+      auto issue = [&](int cidx)
+      {
+         if( (cidx & 3) == 0 ) ok = dag_wait(ready + i * T + (cidx >> 2), ready + j * T + (cidx >> 2), abortflag, s_abort) && ok;
+         if( ok ) load_chunk(cidx, cidx % DAG_STAGES);
+      };
+#pragma unroll 1
+      for( int sidx = 0; sidx < DAG_STAGES - 1; ++sidx )
+      {
+         if( sidx < nchunks ) issue(sidx);
+         asm volatile("cp.async.commit_group;\n" ::);
+      }
+#pragma unroll 1
+      for( int cidx = 0; cidx < nchunks; ++cidx )
+      {
+         asm volatile("cp.async.wait_group %0;\n" :: "n"(DAG_STAGES - 2));
+         __syncthreads();
+         if( cidx + DAG_STAGES - 1 < nchunks ) issue(cidx + DAG_STAGES - 1);
+         asm volatile("cp.async.commit_group;\n" ::);
+         compute_chunk(cidx % DAG_STAGES);
+      }
+      asm volatile("cp.async.wait_group 0;\n" ::);
+      __syncthreads();
+      if( j > 0 && ok )
+      {
+         ok = dag_wait(ready + i * T + (j - 1), ready + j * T + (j - 1), abortflag, s_abort);
+         if( ok )
+         {
+#pragma unroll
+            for( int q = 0; q < 4; ++q ) load_chunk(4 * (j - 1) + q, q);
+            asm volatile("cp.async.commit_group;\n" ::);
+            asm volatile("cp.async.wait_group 0;\n" ::);
+            __syncthreads();
+#pragma unroll
+            for( int q = 0; q < 4; ++q ) compute_chunk(q);
+         }
+      }
+      __syncthreads();
+      if( !ok ) break;
+      if( dbg ) dbg[1] = dag_now();                     // updates done
+
+      if( diag )
+      {
+         const int nb = min(DAG_T, n - col0);
+         const LeafCtx<DAG_T> X(dsm);
+         leaf_factor<DAG_T>(X, c, nb, a.A + (size_t)col0 * a.lda + col0, a.lda, a.info, col0, sbad);
+         if( dbg ) dbg[2] = dag_now();                  // factor done
+         leaf_invert<DAG_T>(X);
+         if( dbg ) dbg[3] = dag_now();                  // inverse done
+         constexpr int LD = LeafCtx<DAG_T>::LD;
+         double* Wj = a.Wd + (size_t)j * DAG_T * DAG_T;
+         for( int e = tid; e < DAG_T * DAG_T; e += DAG_THREADS )
+         {
+            const int r = e % DAG_T, q = e / DAG_T;
+            const double v = (r < nb && q < nb && r >= q) ? X.G[q * LD + r] : 0.0;
+            Wj[(size_t)q * DAG_T + r] = v;
+            if( a.Linv != nullptr && r < nb && q < nb ) a.Linv[(size_t)(col0 + q) * a.ldi + col0 + r] = v;
+         }
+      }
+      else
+      {
+         // ---- L_ij = C W_jj' ----
+         ok = dag_wait(ready + j * T + j, ready + j * T + j, abortflag, s_abort);
+         if( !ok ) break;
+         if( dbg ) dbg[2] = dag_now();                  // saw the diagonal tile
+         double* Cs = dsm;                               // [k][r]
+         double* Ws = dsm + DAG_T * DAG_LDS;             // [k][c] = W_jj[c][k]
+         const double* Wj = a.Wd + (size_t)j * DAG_T * DAG_T;
+         for( int q = tid; q < DAG_T * (DAG_T / 2); q += DAG_THREADS )
+         {
+            const int k = q / (DAG_T / 2), r = (q % (DAG_T / 2)) * 2;
+            dag_cp16(Ws + k * DAG_LDS + r, Wj + (size_t)k * DAG_T + r, 16);
+         }
+         asm volatile("cp.async.commit_group;\n" ::);
+#pragma unroll
+         for( int jt = 0; jt < 8; ++jt )
+         {
+            Cs[(8 * jt + 2 * fc) * DAG_LDS + 8 * w + fr] = c[jt][0];
+            Cs[(8 * jt + 2 * fc + 1) * DAG_LDS + 8 * w + fr] = c[jt][1];
+         }
+         asm volatile("cp.async.wait_group 0;\n" ::);
+         __syncthreads();
+         double d[8][2];
+#pragma unroll
+         for( int jt = 0; jt < 8; ++jt ) { d[jt][0] = 0.0; d[jt][1] = 0.0; }
+#pragma unroll
+         for( int k0 = 0; k0 < DAG_T; k0 += 4 )
+         {
+            const double av = Cs[(k0 + fc) * DAG_LDS + 8 * w + fr];
+#pragma unroll
+            for( int jt = 0; jt < 8; ++jt )
+            {
+               if( k0 >= 8 * jt + 8 ) continue;          // W_jj is lower triangular: W[c][k] = 0 for k > c
+               const double bv = Ws[(k0 + fc) * DAG_LDS + 8 * jt + fr];
+               dmma884(d[jt][0], d[jt][1], av, bv);
+            }
+         }
+         if( dbg ) dbg[3] = dag_now();                  // product done
+         const int row = row0 + 8 * w + fr;
+         if( row < n )
+         {
+#pragma unroll
+            for( int jt = 0; jt < 8; ++jt )
+            {
+               const int col = col0 + 8 * jt + 2 * fc;
+               a.A[(size_t)col * a.lda + row] = d[jt][0];
+               a.A[(size_t)(col + 1) * a.lda + row] = d[jt][1];
+            }
+         }
+      }
+      if( dbg ) dbg[4] = dag_now();                     // stores issued
+      __threadfence();
+      __syncthreads();
+      if( tid == 0 ) st_release(ready + i * T + j, 1);
+      if( dbg ) dbg[5] = dag_now();                     // published
+   }
+}
 
 __global__ void copy2d_kernel(int m, int n, const double* __restrict__ src, int lds, double* __restrict__ dst, int ldd)
 {
@@ -403,6 +759,68 @@ cudaError_t trtri_rec(cudaStream_t st, int n, const double* L, int ldl, double* 
    return cudaSuccess;
 }
 
+
+
+// 0: recursive kernel chain (round 1), 1: tile-DAG kernel for n > 128 (default); SDPCUDA_CHOL=rec|dag overrides (tests compare both)
+int chol_variant()
+{
+   const char* e = getenv("SDPCUDA_CHOL");
+   if( e != nullptr && strcmp(e, "rec") == 0 ) return 0;
+   return 1;
+}
+
+// Cholesky by the tile-DAG kernel, then (if wanted) the inverse factor level by level: the diagonal 64-blocks of W = L^-1 come out
+// of the kernel, and for s = 64, 128, ... all pairs of adjacent s-blocks are joined at once, W21 = -W22 (L21 W11), as two batched
+// GEMMs per level (plus two for a shorter last pair).  work: ldw x (n + 2 CHOL_LEAF_MAX) doubles; the packed diagonal inverses and
+// the flags of the kernel live in its last 2 CHOL_LEAF_MAX columns.
+cudaError_t potrf_dag(cudaStream_t st, int n, double* A, int lda, double* Linv, int ldi, double* diaginv, double* work, int ldw, int* d_info)
+{
+   const int T = ceil_div(n, DAG_T);
+   double* Wd = diaginv != nullptr ? diaginv : work + (size_t)ldw * n;
+   int* sync = reinterpret_cast<int*>(work + (size_t)ldw * n + (diaginv != nullptr ? 0 : (size_t)T * DAG_T * DAG_T));
+   if( (size_t)T * DAG_T * DAG_T + (size_t)(T * T + 2 + 1) / 2 > (size_t)ldw * 2 * CHOL_LEAF_MAX ) return cudaErrorInvalidValue;
+   static bool configured[64] = {false};
+   static int nsm[64] = {0};
+   int dev = 0;
+   SDPK_CUDA_CHECK( cudaGetDevice(&dev) );
+   if( !configured[dev & 63] )
+   {
+      SDPK_CUDA_CHECK( cudaFuncSetAttribute(potrf_dag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DAG_SMEM) );
+      SDPK_CUDA_CHECK( cudaDeviceGetAttribute(&nsm[dev & 63], cudaDevAttrMultiProcessorCount, dev) );
+      configured[dev & 63] = true;
+   }
+   SDPK_CUDA_CHECK( cudaMemsetAsync(sync, 0, sizeof(int) * (size_t)(T * T + 2), st) );
+   DagArgs a;
+   a.n = n; a.T = T; a.A = A; a.lda = lda; a.Linv = Linv; a.ldi = ldi; a.Wd = Wd; a.sync = sync; a.info = d_info; a.dbg = g_diag_dbg;
+   const int total = T * (T + 1) / 2;
+   {
+      ProfScope prof(st, PROF_DIAG, (double)n * n * n / 3.0);
+      potrf_dag_kernel<<<std::min(total, 2 * nsm[dev & 63]), DAG_THREADS, DAG_SMEM, st>>>(a);
+      count_launch();
+      SDPK_CUDA_CHECK( cudaGetLastError() );
+   }
+   if( Linv == nullptr ) return cudaSuccess;
+   for( int s = DAG_T; s < n; s *= 2 )
+   {
+      const int full = n / (2 * s);                       // pairs with two complete s-blocks
+      const long long sl = (long long)2 * s * ((long long)lda + 1), si = (long long)2 * s * ((long long)ldi + 1);
+      if( full > 0 )
+      {
+         SDPK_CUDA_CHECK( gemm(st, false, false, s, s, s, 1.0, A + s, lda, sl, Linv, ldi, si, 0.0, work, ldw, 2 * s, full, GEMM_KLO_N) );
+         SDPK_CUDA_CHECK( gemm(st, false, false, s, s, s, -1.0, Linv + (size_t)s * ldi + s, ldi, si, work, ldw, 2 * s, 0.0, Linv + s, ldi, si, full, GEMM_KHI_M) );
+      }
+      const int o = 2 * s * full, n2 = n - (o + s);       // a last pair whose second block is shorter
+      if( n2 > 0 )
+      {
+         SDPK_CUDA_CHECK( gemm(st, false, false, n2, s, s, 1.0, A + (size_t)o * lda + o + s, lda, 0, Linv + (size_t)o * ldi + o, ldi, 0, 0.0,
+            work + o, ldw, 0, 1, GEMM_KLO_N) );
+         SDPK_CUDA_CHECK( gemm(st, false, false, n2, s, n2, -1.0, Linv + (size_t)(o + s) * ldi + o + s, ldi, 0, work + o, ldw, 0, 0.0,
+            Linv + (size_t)o * ldi + o + s, ldi, 0, 1, GEMM_KHI_M) );
+      }
+   }
+   return cudaSuccess;
+}
+
 } // namespace
 
 cudaError_t potrf_lower(cudaStream_t st, int n, double* A, int lda, double* Linv, int ldi, double* diaginv, double* work, int ldw, int* d_info)
@@ -410,6 +828,8 @@ cudaError_t potrf_lower(cudaStream_t st, int n, double* A, int lda, double* Linv
    if( n <= 0 ) return cudaSuccess;
    if( Linv )
       SDPK_CUDA_CHECK( cudaMemsetAsync(Linv, 0, sizeof(double) * (size_t)ldi * n, st) );
+   if( n > CHOL_LEAF_MAX && chol_variant() == 1 )
+      return potrf_dag(st, n, A, lda, Linv, ldi, diaginv, work, ldw, d_info);
    return chol_rec(st, n, A, lda, Linv, ldi, diaginv, work, ldw, d_info, 0);
 }
 

@@ -84,7 +84,22 @@ gemm_dmma_kernel(int M, int N, int K, double alpha, const double* __restrict__ A
    double* As = smem;
    double* Bs = smem + STAGES * A_ELEMS;
 
-   const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+   // L2-aware rasterisation: the CTAs of a wave (launch order = blockIdx.x fastest) cover bands of GROUP_M tile rows instead of whole
+   // tile columns, so that the operand panels a wave streams (GROUP_M row panels of A + the column panels of B it meets) stay
+   // inside the 126 MB L2; matters once A alone is larger than L2 (4096^3: DRAM traffic 9x the algorithmic bytes before)
+   constexpr int GROUP_M = 16;
+   int tm = blockIdx.x, tn = blockIdx.y;
+   if( gridDim.x > GROUP_M )
+   {
+      const int lin = blockIdx.x + gridDim.x * blockIdx.y;
+      const int per = GROUP_M * gridDim.y;
+      const int grp = lin / per, first = grp * GROUP_M;
+      const int gsz = min((int)gridDim.x - first, GROUP_M);
+      const int r = lin - grp * per;
+      tm = first + r % gsz;
+      tn = r / gsz;
+   }
+   const int m0 = tm * BM, n0 = tn * BN;
    if( (flags & GEMM_LOWER) && (m0 + BM <= n0) )
       return;
    A += (size_t)blockIdx.z * strideA;

@@ -137,6 +137,7 @@ struct sdpcuda_handle
    bool minv = false;                // explicit inverse factor of M (m <= 4096): solves become two triangular mat-vecs; above: look-ahead panels + panel substitution
    DBuf<double> partials, stats, scal, eigw, lzwork;
    DBuf<int> info;
+   DBuf<int> ppint; DBuf<double> ppdbl, ppout; DBuf<long long> ppoff;      // staging of sdpcuda_primal_products
    DBuf<double> kflag;                            // one word: time-limit flag agreed between the ranks of a sharded solve
    double* h_stats = nullptr;     // pinned
    int* h_info = nullptr;
@@ -820,6 +821,7 @@ int sdpcuda_destroy(sdpcuda_handle* h)
    h->LinvT.release(); h->LXinvT.release(); h->pinv.release(); h->pinvT.release();
    for( cudaEvent_t& e : h->evp ) if( e != nullptr ) { cudaEventDestroy(e); e = nullptr; }
    h->preX.release(); h->prey.release(); h->prex.release();
+   h->ppint.release(); h->ppdbl.release(); h->ppout.release(); h->ppoff.release(); h->kflag.release();
    drop_graph(h->gS); drop_graph(h->gX); drop_graph(h->gM);
    cudaEventDestroy(h->ev0); cudaEventDestroy(h->ev1); cudaEventDestroy(h->evFork); cudaEventDestroy(h->evJoin);
    cudaStreamDestroy(h->st); cudaStreamDestroy(h->st2); cudaStreamDestroy(h->st3);
@@ -2081,6 +2083,96 @@ static int get_block(sdpcuda_handle* h, const double* src, int b, double* out)
 int sdpcuda_get_X(sdpcuda_handle* h, int b, double* X) { return get_block(h, h ? (h->packed ? h->pk.X : h->X.p) : nullptr, b, X); }
 int sdpcuda_get_S(sdpcuda_handle* h, int b, double* S) { return get_block(h, h ? (h->packed ? h->pk.S : h->S.p) : nullptr, b, S); }
 
+// one warp per group: fixed summation order (lane-strided partial sums, shuffle tree), so the result is reproducible
+__global__ void primal_products_kernel(int ngroups, const int* __restrict__ groupbeg, const int* __restrict__ blk, const int* __restrict__ row,
+   const int* __restrict__ col, const double* __restrict__ val, const double* __restrict__ X, const long long* __restrict__ boff,
+   const int* __restrict__ bld, double* __restrict__ out)
+{
+   const int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+   if( g >= ngroups ) return;
+   double acc = 0.0;
+   for( int e = groupbeg[g] + lane; e < groupbeg[g + 1]; e += 32 )
+   {
+      const double x = X[boff[blk[e]] + (long long)col[e] * bld[blk[e]] + row[e]];
+      acc += (row[e] == col[e] ? 1.0 : 2.0) * val[e] * x;
+   }
+#pragma unroll
+   for( int o = 16; o > 0; o >>= 1 ) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+   if( lane == 0 ) out[g] = acc;
+}
+
+int sdpcuda_primal_products(sdpcuda_handle* h, int ngroups, const int* groupbeg, const int* blk, const int* row, const int* col,
+   const double* val, double* out)
+{
+   if( h == nullptr || ngroups < 0 || (ngroups > 0 && (groupbeg == nullptr || out == nullptr)) ) return SDPCUDA_ERR_ARG;
+   if( !h->solved || h->packed ) return SDPCUDA_ERR_STATE;
+   if( ngroups == 0 ) return SDPCUDA_OK;
+   if( set_device(h) ) return SDPCUDA_ERR_CUDA;
+   const int ne = groupbeg[ngroups];
+   for( int e = 0; e < ne; ++e )
+      if( blk[e] < 0 || blk[e] >= h->nb || col[e] < 0 || row[e] < col[e] || row[e] >= h->blk[blk[e]].n ) return SDPCUDA_ERR_ARG;
+   cudaStream_t st = h->st;
+   std::vector<long long> boff(h->nb);
+   std::vector<int> bld(h->nb);
+   for( int k = 0; k < h->nb; ++k ) { boff[k] = h->blk[k].off; bld[k] = h->blk[k].ld; }
+   // one staging image: [groupbeg | blk | row | col] ints, then [val] doubles, block table, results
+   std::vector<int> ints;
+   ints.insert(ints.end(), groupbeg, groupbeg + ngroups + 1);
+   ints.insert(ints.end(), blk, blk + ne); ints.insert(ints.end(), row, row + ne); ints.insert(ints.end(), col, col + ne);
+   ints.insert(ints.end(), bld.begin(), bld.end());
+   CK( h->ppint.upload(ints, st) );
+   std::vector<double> dbl(val, val + ne);
+   CK( h->ppdbl.upload(dbl, st) );
+   CK( h->ppoff.upload(boff, st) );
+   CK( h->ppout.ensure(ngroups) );
+   const int* di = h->ppint.p;
+   primal_products_kernel<<<ceil_div(ngroups * 32, 256), 256, 0, st>>>(ngroups, di, di + ngroups + 1, di + ngroups + 1 + ne, di + ngroups + 1 + 2 * ne,
+      h->ppdbl.p, h->X.p, h->ppoff.p, di + ngroups + 1 + 3 * ne, h->ppout.p);
+   count_launch();
+   CK( cudaGetLastError() );
+   CK( cudaMemcpyAsync(out, h->ppout.p, sizeof(double) * ngroups, cudaMemcpyDeviceToHost, st) );
+   CK( cudaStreamSynchronize(st) );
+   return SDPCUDA_OK;
+}
+
+int sdpcuda_primal_mineig_bound(sdpcuda_handle* h, int block, double* bound)
+{
+   if( h == nullptr || bound == nullptr ) return SDPCUDA_ERR_ARG;
+   if( !h->solved || h->packed ) return SDPCUDA_ERR_STATE;
+   if( block < 0 || block >= h->nb ) return SDPCUDA_ERR_ARG;
+   if( set_device(h) ) return SDPCUDA_ERR_CUDA;
+   cudaStream_t st = h->st;
+   const Block& bk = h->blk[block];
+   const size_t nn = (size_t)bk.ld * bk.n;
+   CK( h->kA.ensure(nn) );
+   CK( h->kW.ensure((size_t)bk.ld * (bk.n + 2 * CHOL_LEAF_MAX)) );
+   CK( h->info.ensure(8) );
+   double sigma = 0.0, scale = -1.0;
+   for( int tries = 0; tries < 40; ++tries )
+   {
+      CK( cudaMemcpyAsync(h->kA.p, h->X.p + bk.off, sizeof(double) * nn, cudaMemcpyDeviceToDevice, st) );
+      CK( cudaMemsetAsync(h->info.p, 0, 8 * sizeof(int), st) );
+      if( sigma > 0.0 ) CK( add_diagonal(st, bk.n, h->kA.p, bk.ld, sigma) );
+      CK( potrf_lower(st, bk.n, h->kA.p, bk.ld, nullptr, 0, nullptr, h->kW.p, bk.ld, h->info.p) );
+      CK( cudaMemcpyAsync(h->h_info, h->info.p, sizeof(int), cudaMemcpyDeviceToHost, st) );
+      CK( cudaStreamSynchronize(st) );
+      if( h->h_info[0] == 0 ) { *bound = -sigma; return SDPCUDA_OK; }
+      if( scale < 0.0 )
+      {
+         // |X|_max from the diagonal (X is symmetric; for an indefinite matrix any entry bound does: use the largest |entry| of the block)
+         std::vector<double> hx(nn);
+         CK( cudaMemcpyAsync(hx.data(), h->X.p + bk.off, sizeof(double) * nn, cudaMemcpyDeviceToHost, st) );
+         CK( cudaStreamSynchronize(st) );
+         scale = 0.0;
+         for( double v : hx ) scale = std::max(scale, std::fabs(v));
+         scale = std::max(scale, 1e-300);
+      }
+      sigma = (sigma == 0.0) ? 1e-14 * scale : sigma * 10.0;
+   }
+   *bound = -sigma;
+   return SDPCUDA_OK;
+}
+
 int sdpcuda_dist_unique_id(void* id128)
 {
    NcclApi* api = nccl_api();
@@ -2448,7 +2540,48 @@ int sdpcuda_time_kernel(sdpcuda_handle* h, int kind, int n, int reps, double* ms
       }
       g_diag_dbg = nullptr;
       printf("[leaf kernel %d phases, cycles] load %lld  factor %lld  store L + inverse %lld  store inverse %lld\n", nl, hv[0], hv[1], hv[2], hv[3]);
+      printf("[leaf kernel %d macro step 8, cycles] pivot chain + panel rows %lld  barrier %lld  first tile + hand-over %lld  barrier %lld  whole step %lld\n",
+         nl, hv[5] - hv[4], hv[6] - hv[5], hv[7] - hv[6], hv[8] - hv[7], hv[9] - hv[8]);
       *ms_per_launch = (double)hv[1]; *work = (double)hv[2];
+      return SDPCUDA_OK;
+   }
+   if( kind == 10 )
+   {
+      // critical chain of the tile-DAG Cholesky at order n: timestamps per diagonal tile and first sub-diagonal tile
+      const int T = (n + 63) / 64;
+      CK( h->kA.ensure(nn) ); CK( h->kB.ensure(nn) ); CK( h->kC.ensure((size_t)16 * T + 16) ); CK( h->kW.ensure((size_t)ld * (n + 2 * CHOL_LEAF_MAX)) ); CK( h->info.ensure(8) );
+      fill_random_kernel<<<1024, 256, 0, st>>>(nn, h->kA.p, 17u, (double)n, ld);
+      CK( sym_average(st, n, h->kA.p, ld, nullptr) );
+      std::vector<long long> hv((size_t)16 * T);
+      g_diag_dbg = reinterpret_cast<long long*>(h->kC.p);
+      for( int r = 0; r < 3; ++r )
+      {
+         CK( cudaMemsetAsync(h->kC.p, 0, sizeof(double) * 16 * T, st) );
+         CK( cudaMemcpyAsync(h->kB.p, h->kA.p, nn * sizeof(double), cudaMemcpyDeviceToDevice, st) );
+         CK( potrf_lower(st, n, h->kB.p, ld, nullptr, 0, nullptr, h->kW.p, ld, h->info.p) );
+         CK( cudaMemcpyAsync(hv.data(), h->kC.p, sizeof(long long) * 16 * T, cudaMemcpyDeviceToHost, st) );
+         CK( cudaStreamSynchronize(st) );
+      }
+      g_diag_dbg = nullptr;
+      const long long t00 = hv[0];
+      double sum[8] = {0};
+      for( int j = 0; j + 1 < T; ++j )
+      {
+         const long long* d = &hv[(size_t)16 * j];          // diagonal tile j
+         const long long* o = d + 8;                        // tile (j+1, j)
+         const long long* dn = d + 16;                      // diagonal tile j+1
+         if( j < 3 || j == T / 2 || j == T - 2 )
+            printf("[dag chain] j %2d  diag: claim %8.2f upd %8.2f factor %8.2f inverse %8.2f stores %8.2f publish %8.2f | (j+1,j): claim %8.2f upd %8.2f sawdiag %8.2f product %8.2f stores %8.2f publish %8.2f us\n",
+               j, (d[0] - t00) / 1e3, (d[1] - t00) / 1e3, (d[2] - t00) / 1e3, (d[3] - t00) / 1e3, (d[4] - t00) / 1e3, (d[5] - t00) / 1e3,
+               (o[0] - t00) / 1e3, (o[1] - t00) / 1e3, (o[2] - t00) / 1e3, (o[3] - t00) / 1e3, (o[4] - t00) / 1e3, (o[5] - t00) / 1e3);
+         sum[0] += (d[2] - d[1]) / 1e3; sum[1] += (d[3] - d[2]) / 1e3; sum[2] += (d[5] - d[3]) / 1e3;      // factor, inverse, store+publish
+         sum[3] += (o[2] - d[5]) / 1e3; sum[4] += (o[3] - o[2]) / 1e3; sum[5] += (o[5] - o[3]) / 1e3;      // hop, W load + product, store+publish
+         sum[6] += (dn[1] - o[5]) / 1e3;                                                                     // hop + last update of the next diagonal tile
+      }
+      printf("[dag chain] n %d, %d steps, mean us per step: factor %.2f  inverse %.2f  store+publish %.2f | hop %.2f  W load+product %.2f  store+publish %.2f | hop+last update %.2f   total %.2f us\n",
+         n, T - 1, sum[0] / (T - 1), sum[1] / (T - 1), sum[2] / (T - 1), sum[3] / (T - 1), sum[4] / (T - 1), sum[5] / (T - 1), sum[6] / (T - 1),
+         (hv[(size_t)16 * (T - 1) + 5] - t00) / 1e3);
+      *ms_per_launch = (hv[(size_t)16 * (T - 1) + 5] - t00) / 1e6; *work = (double)n * n * n / 3.0;
       return SDPCUDA_OK;
    }
    if( kind == 8 )

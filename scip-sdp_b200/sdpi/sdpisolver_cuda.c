@@ -380,6 +380,120 @@ void SCIPsdpiSolverCudaGetTransferStats(SCIP_SDPISOLVER* sdpisolver, int* nuploa
       *h2dbytes = sdpisolver->h2dbytes;
 }
 
+/** not part of sdpisolver.h: what computeConflictCut (relax_sdp.c:1030-1099) takes from the primal solution, computed
+ *  on the device-resident X instead of shipping every dense block to the host: for every block b and block variable v the inner
+ *  product <A_v^b, X_b> (varproducts[b][v]), <A_0^b, X_b> (constproducts[b]) and a certified lower bound of min(lambda_min(X_b), 0)
+ *  (mineigbounds[b]).  The SDP data are given like SCIPsdpiGetSDPdata returns them: original (unreduced) indices, lower triangle;
+ *  entries in rows/columns that were removed before the solve meet zeros of X.  INTEGRATION.md shows the caller-side change. */
+SCIP_RETCODE SCIPsdpiSolverGetPrimalInnerProducts(SCIP_SDPISOLVER* sdpisolver, int nsdpblocks, const int* sdpnblockvars,
+   int* const* sdpnblockvarnonz, int** const* sdprow, int** const* sdpcol, SCIP_Real** const* sdpval, const int* sdpconstnblocknonz,
+   int* const* sdpconstrow, int* const* sdpconstcol, SCIP_Real* const* sdpconstval, SCIP_Real* const* varproducts, SCIP_Real* constproducts,
+   SCIP_Real* mineigbounds)
+{
+   SCIP_SDPISOLVER* s = sdpisolver;
+   SCIP_RETCODE retcode = SCIP_OKAY;
+   int* groupbeg = NULL;
+   int* eblk = NULL;
+   int* erow = NULL;
+   int* ecol = NULL;
+   int* orig2red = NULL;
+   SCIP_Real* evalv = NULL;
+   SCIP_Real* out = NULL;
+   int ngroups = 0;
+   int nent = 0;
+   int maxsize = 0;
+   int b;
+   int v;
+   int k;
+   int g;
+
+   assert( s != NULL );
+   NEED_SOLVED(s);
+   if( nsdpblocks != s->nsdpblocks )
+      return SCIP_LPERROR;
+   for( b = 0; b < nsdpblocks; ++b )
+   {
+      ngroups += sdpnblockvars[b] + 1;
+      nent += sdpconstnblocknonz != NULL ? sdpconstnblocknonz[b] : 0;
+      for( v = 0; v < sdpnblockvars[b]; ++v )
+         nent += sdpnblockvarnonz[b][v];
+      maxsize = MAX(maxsize, s->origsize[b]);
+   }
+   MEM_CALL( BMSallocBufferMemoryArray(s->bufmem, &groupbeg, ngroups + 1) );
+   if( NULL == BMSallocBufferMemoryArray(s->bufmem, &eblk, nent + 1) || NULL == BMSallocBufferMemoryArray(s->bufmem, &erow, nent + 1)
+      || NULL == BMSallocBufferMemoryArray(s->bufmem, &ecol, nent + 1) || NULL == BMSallocBufferMemoryArray(s->bufmem, &evalv, nent + 1)
+      || NULL == BMSallocBufferMemoryArray(s->bufmem, &out, ngroups + 1) || NULL == BMSallocBufferMemoryArray(s->bufmem, &orig2red, maxsize + 1) )
+   {
+      retcode = SCIP_NOMEMORY;
+      goto DONE;
+   }
+   nent = 0;
+   g = 0;
+   for( b = 0; b < nsdpblocks; ++b )
+   {
+      const int dev = s->blk2dev[b];
+
+      for( k = 0; k < s->origsize[b]; ++k )
+         orig2red[k] = -1;
+      for( k = 0; dev >= 0 && k < s->devsize[b]; ++k )
+         orig2red[s->red2orig[b][k]] = k;
+      for( v = 0; v <= sdpnblockvars[b]; ++v )               /* v == nblockvars: the constant matrix */
+      {
+         const int cnt = v < sdpnblockvars[b] ? sdpnblockvarnonz[b][v] : (sdpconstnblocknonz != NULL ? sdpconstnblocknonz[b] : 0);
+         const int* rws = v < sdpnblockvars[b] ? sdprow[b][v] : (cnt > 0 ? sdpconstrow[b] : NULL);
+         const int* cls = v < sdpnblockvars[b] ? sdpcol[b][v] : (cnt > 0 ? sdpconstcol[b] : NULL);
+         const SCIP_Real* vls = v < sdpnblockvars[b] ? sdpval[b][v] : (cnt > 0 ? sdpconstval[b] : NULL);
+
+         groupbeg[g++] = nent;
+         for( k = 0; dev >= 0 && k < cnt; ++k )
+         {
+            const int r = orig2red[rws[k]];
+            const int c = orig2red[cls[k]];
+
+            if( r < 0 || c < 0 )
+               continue;
+            eblk[nent] = dev;
+            erow[nent] = MAX(r, c);
+            ecol[nent] = MIN(r, c);
+            evalv[nent] = vls[k];
+            ++nent;
+         }
+      }
+   }
+   groupbeg[g] = nent;
+   assert( g == ngroups );
+   if( sdpcuda_primal_products(s->dev, ngroups, groupbeg, eblk, erow, ecol, evalv, out) != SDPCUDA_OK )
+   {
+      SCIPerrorMessage("sdpcuda_primal_products failed.\n");
+      retcode = SCIP_LPERROR;
+      goto DONE;
+   }
+   g = 0;
+   for( b = 0; b < nsdpblocks; ++b )
+   {
+      for( v = 0; v < sdpnblockvars[b]; ++v )
+         varproducts[b][v] = out[g++];
+      constproducts[b] = out[g++];
+      mineigbounds[b] = 0.0;
+      if( s->blk2dev[b] >= 0 && sdpcuda_primal_mineig_bound(s->dev, s->blk2dev[b], &mineigbounds[b]) != SDPCUDA_OK )
+      {
+         SCIPerrorMessage("sdpcuda_primal_mineig_bound failed.\n");
+         retcode = SCIP_LPERROR;
+         goto DONE;
+      }
+   }
+
+DONE:
+   BMSfreeBufferMemoryArrayNull(s->bufmem, &orig2red);
+   BMSfreeBufferMemoryArrayNull(s->bufmem, &out);
+   BMSfreeBufferMemoryArrayNull(s->bufmem, &evalv);
+   BMSfreeBufferMemoryArrayNull(s->bufmem, &ecol);
+   BMSfreeBufferMemoryArrayNull(s->bufmem, &erow);
+   BMSfreeBufferMemoryArrayNull(s->bufmem, &eblk);
+   BMSfreeBufferMemoryArrayNull(s->bufmem, &groupbeg);
+   return retcode;
+}
+
 const char* SCIPsdpiSolverGetSolverName(void)
 {
    /* neither "DSDP" nor "SDPA" nor containing "Mosek": the caller then passes start settings of the parent node and

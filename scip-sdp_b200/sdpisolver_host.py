@@ -224,6 +224,23 @@ class SdpiSolver:
             raise RuntimeError(f"SCIPsdpiSolverGetPrimalSolutionMatrix returned {rc}")
         return mats
 
+    def primal_inner_products(self, bp):
+        """SCIPsdpiSolverGetPrimalInnerProducts (not part of sdpisolver.h): per block the products <A_v, X> of its block
+        variables (in the order of the block's variable list), <A_0, X> and a lower bound of min(lambda_min(X), 0), formed on the device"""
+        nb = bp.nblocks
+        nbv = [int(bp.args[6][b]) for b in range(nb)]
+        prods = [np.zeros(max(n, 1)) for n in nbv]
+        const, mineig = np.zeros(max(nb, 1)), np.zeros(max(nb, 1))
+        arr = (_dp * max(nb, 1))(*[p.ctypes.data_as(_dp) for p in prods])
+        F = self.lib.SCIPsdpiSolverGetPrimalInnerProducts
+        F.argtypes = [C.c_void_p, C.c_int, _ip, _ipp, _ippp, _ippp, _dppp, _ip, _ipp, _ipp, _dpp, _dpp, _dp, _dp]
+        a = bp.args
+        rc = F(self.s, nb, a[6], a[13], a[15], a[16], a[17], a[8], a[9], a[10], a[11], C.cast(arr, _dpp),
+               const.ctypes.data_as(_dp), mineig.ctypes.data_as(_dp))
+        if rc != SCIP_OKAY:
+            raise RuntimeError(f"SCIPsdpiSolverGetPrimalInnerProducts returned {rc}")
+        return [p[:n] for p, n in zip(prods, nbv)], const[:nb], mineig[:nb]
+
     def bound_multipliers(self):
         lbv, ubv = np.zeros(self.nvars), np.zeros(self.nvars)
         rc = self.lib.SCIPsdpiSolverGetPrimalBoundVars(self.s, lbv.ctypes.data_as(_dp), ubv.ctypes.data_as(_dp))

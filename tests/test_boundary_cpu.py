@@ -133,3 +133,7 @@ def test_resident_psd_check_on_the_oracle():
     assert s.L.lib.sdpcuda_check_psd_resident(s.h, None, 0.0, C.byref(ok)) == 4      # SDPCUDA_ERR_STATE: nothing loaded
     assert s.L.lib.sdpcuda_check_psd_resident(s.h, None, 0.0, None) == 1             # SDPCUDA_ERR_ARG
     _resident_check_cases(s)
+
+
+def test_conflict_cut_reductions_on_the_resident_primal_solution():
+    boundary_cases.run_primal_inner_products(sdpi_ref.LIB_ORACLE)

@@ -22,3 +22,7 @@ def test_warmstart_and_preoptimal_solution_on_gpu():
 def test_resolves_of_a_node_reuse_the_resident_problem_on_gpu():
     """row f4: host->device traffic of the re-solves is the two patched vectors only"""
     boundary_cases.run_resident_resolves(sdpisolver_host.BINDING_LIB, device=True)
+
+
+def test_conflict_cut_reductions_on_the_resident_primal_solution_on_gpu():
+    boundary_cases.run_primal_inner_products(sdpisolver_host.BINDING_LIB)

@@ -67,6 +67,29 @@ def test_potrf_with_inverse_factor(gpu, cpu, n):
     assert np.abs(Li @ L - np.eye(n)).max() <= 1e-11
 
 
+@pytest.mark.parametrize("n", [129, 192, 1000, 2000, 2048, 2049, 3000])
+@pytest.mark.parametrize("variant", ["dag", "rec"])
+def test_tile_dag_cholesky_matches_lapack_and_the_recursive_chain(gpu, cpu, n, variant, monkeypatch):
+    """the one-kernel tile-DAG factorisation (default for n > 128) and the recursive kernel chain of round 1 (SDPCUDA_CHOL=rec)
+    against LAPACK, with and without the inverse factor"""
+    monkeypatch.setenv("SDPCUDA_CHOL", variant)
+    rng = np.random.default_rng(31000 + n)
+    G = rng.standard_normal((n, n))
+    A = G @ G.T + n * np.eye(n)
+    Lr, Lir, _ = cpu.dpotrf_inv(A)
+    L, info = gpu.dpotrf(A)
+    assert info == 0 and np.abs(L - Lr).max() <= 1e-12 * np.abs(Lr).max()
+    L, Li, info = gpu.dpotrf_inv(A)
+    assert info == 0 and np.abs(L - Lr).max() <= 1e-12 * np.abs(Lr).max()
+    assert np.abs(Li - Lir).max() <= 1e-11 * np.abs(Lir).max() and np.abs(np.triu(Li, 1)).max() == 0.0
+
+
+def test_tile_dag_cholesky_reports_the_first_bad_pivot(gpu):
+    A = np.eye(700); A[450, 450] = -1.0; A[600, 600] = -2.0
+    _, info = gpu.dpotrf(A)
+    assert info == 451
+
+
 def test_potrf_with_inverse_badly_scaled(gpu, cpu):
     # diagonal scaling over 12 orders of magnitude: pivots must stay accurate relative to their own size
     rng = np.random.default_rng(99)

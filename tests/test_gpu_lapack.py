@@ -80,3 +80,98 @@ def test_checklapack_known_answer(libs):
         out = np.zeros(4)
         assert L.SCIPlapackMatrixMatrixMult(2, 2, _p(A), 0, 2, 2, _p(B), 1, _p(out)) == 1
         assert np.allclose(out, [26.0, 38.0, 30.0, 44.0])
+
+
+@pytest.mark.parametrize("n", [96, 97, 120, 200])
+def test_eigen_entry_points_on_larger_blocks(libs, n):
+    """orders above the shared-memory limit of the Jacobi kernel (96) take its global-memory branch"""
+    (ours, bo), (ref, br) = libs
+    rng = np.random.default_rng(9000 + n)
+    A = rng.standard_normal((n, n)); A = A + A.T
+    nrm = np.abs(np.linalg.eigvalsh(A)).max()
+    full = []
+    for L, b in ((ours, bo), (ref, br)):
+        Ac, w, V = A.copy(), np.zeros(n), np.zeros(n * n)
+        assert L.SCIPlapackComputeEigenvectorDecomposition(b, n, _p(Ac), _p(w), _p(V)) == 1
+        full.append((w, V.reshape(n, n)))
+    assert np.abs(full[0][0] - full[1][0]).max() <= 1e-10 * nrm
+    V = full[0][1]
+    assert np.abs(V @ V.T - np.eye(n)).max() <= 1e-10 * n
+    assert np.abs(A @ V.T - V.T * full[0][0][None, :]).max() <= 1e-10 * nrm * n
+
+
+def _cuts(L, buf, Z, Aj, A0, tol, batch=None):
+    """what separateSol / produceCutFromEigenvector form (cons_sdp.c:1612-1797, :896-1130) from the negative eigenpairs of Z(y):
+    for every eigenvector v the cut  sum_j (v' A_j v) y_j >= v' A_0 v  -> (eigenvalues, coefficient rows, left-hand sides)"""
+    n = Z.shape[0]
+    if batch is None:
+        Ac, cnt, w, V = Z.copy(), C.c_int(0), np.zeros(n), np.zeros(n * n)
+        assert L.SCIPlapackComputeEigenvectorsNegative(buf, n, _p(Ac), tol, C.byref(cnt), _p(w), _p(V)) == 1
+        k = cnt.value
+    else:
+        k, w, V = batch
+    V = V.reshape(n, n)[:k]
+    coef = np.array([[v @ A @ v for A in Aj] for v in V]).reshape(k, len(Aj))
+    lhs = np.array([v @ A0 @ v for v in V])
+    return w[:k].copy(), coef, lhs
+
+
+def _dense_blocks(M, y):
+    """(Z(y), [A_j], A_0) per SDP block of a Misdp, dense symmetric"""
+    out = []
+    for b, n in enumerate(M.blocksizes):
+        def dense(ents):
+            D = np.zeros((n, n))
+            for r, c, v in ents:
+                D[r, c] = v; D[c, r] = v
+            return D
+        Aj = [dense(M.A[b].get(j, [])) for j in range(M.nvars)]
+        A0 = dense(M.C[b])
+        out.append((sum(yj * A for yj, A in zip(y, Aj)) - A0, Aj, A0))
+    return out
+
+
+@pytest.mark.parametrize("name", ["example_small.dat-s", "example_TT.dat-s.gz", "example_MkP.dat-s.gz", "example_CLS.dat-s.gz"])
+def test_eigenvector_cuts_match_the_reference_lapack_path(libs, name):
+    """the cuts cons_sdp.c forms from our eigenvectors equal those from the reference's lapack_interface.c —
+    coefficient vectors and left-hand sides to 1e-8 (sums over clusters of equal eigenvalues, which are rotation invariant),
+    every cut violated by exactly its eigenvalue; and the batch entry point (one device call for all blocks of a separation
+    round) returns the same eigenpairs as the per-constraint calls."""
+    from scip_sdp_b200 import misdp
+    (ours, bo), (ref, br) = libs
+    M = misdp.read_instance(os.path.join(ROOT, "tests", "golden", name))
+    rng = np.random.default_rng(17)
+    tol = 1e-6
+    ours.SCIPlapackComputeEigenvectorsNegativeBatch.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int), C.POINTER(_dp), C.c_double,
+                                                                 C.POINTER(C.c_int), C.POINTER(_dp), C.POINTER(_dp)]
+    for trial in range(3):
+        lo = np.where(M.lb > -1e19, M.lb, -1.0); hi = np.where(M.ub < 1e19, M.ub, 1.0)
+        y = lo + (hi - lo) * rng.random(M.nvars) * (0.3 if trial else 0.0)          # an LP-relaxation-like point: Z(y) is indefinite
+        blocks = _dense_blocks(M, y)
+        # batch call over all blocks of the "separation round"
+        nb = len(blocks)
+        sizes = (C.c_int * nb)(*[Z.shape[0] for Z, _, _ in blocks])
+        mats = [Z.copy() for Z, _, _ in blocks]
+        ws = [np.zeros(Z.shape[0]) for Z, _, _ in blocks]
+        Vs = [np.zeros(Z.shape[0] ** 2) for Z, _, _ in blocks]
+        cnts = (C.c_int * nb)()
+        assert ours.SCIPlapackComputeEigenvectorsNegativeBatch(bo, nb, sizes, (_dp * nb)(*[_p(m) for m in mats]), tol, cnts,
+                                                                (_dp * nb)(*[_p(w) for w in ws]), (_dp * nb)(*[_p(v) for v in Vs])) == 1
+        for k, (Z, Aj, A0) in enumerate(blocks):
+            nrm = max(1.0, np.abs(Z).max())
+            wo, co, lo_ = _cuts(ours, bo, Z, Aj, A0, tol)
+            wr, cr, lr = _cuts(ref, br, Z, Aj, A0, tol)
+            wb, cb, lb_ = _cuts(ours, bo, Z, Aj, A0, tol, batch=(cnts[k], ws[k], Vs[k]))
+            assert len(wo) == len(wr) == len(wb)
+            if len(wo) == 0:
+                continue
+            assert np.abs(wo - wr).max() <= 1e-10 * nrm and np.abs(wb - wo).max() <= 1e-12 * nrm
+            # violation of cut i at y = coef_i . y - lhs_i = v' Z(y) v = eigenvalue i
+            assert np.abs(co @ y - lo_ - wo).max() <= 1e-9 * nrm
+            # clusters of (numerically) equal eigenvalues: the sum of their cuts does not depend on the basis chosen inside the cluster
+            edges = [0] + [i for i in range(1, len(wr)) if wr[i] - wr[i - 1] > 1e-7 * nrm] + [len(wr)]
+            for a, e in zip(edges[:-1], edges[1:]):
+                scale = max(1.0, np.abs(cr[a:e].sum(0)).max())
+                assert np.abs(co[a:e].sum(0) - cr[a:e].sum(0)).max() <= 1e-8 * scale
+                assert np.abs(cb[a:e].sum(0) - cr[a:e].sum(0)).max() <= 1e-8 * scale
+                assert abs(lo_[a:e].sum() - lr[a:e].sum()) <= 1e-8 * max(1.0, abs(lr[a:e].sum()))
