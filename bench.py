@@ -389,10 +389,10 @@ def cpu_tree(name, cores):
     lib, _ = oracle_lib(1)
     M = misdp.read_instance(os.path.join(nodesets.GOLDEN, name))
     t = time.perf_counter()
-    r = frontier.branch_and_bound(abi.Solver(lib), M, mode="serial", width=1, **NODE_KW)
+    r = frontier.branch_and_bound(abi.Solver(lib), M, mode="batch", width=1, native=True, use_objlimit=True, **NODE_KW)
     dt = time.perf_counter() - t
     return {"value": r["nodes"] / dt, "unit": "nodes/s", "cores": 1, "kind": "port", "nodes": r["nodes"], "objective": M.file_objective(r["objval"]),
-            "sample": "one complete best-first B&B run of the same driver on the CPU oracle, one node at a time on one core"}
+            "sample": "one complete best-first B&B run of the same driver on the CPU oracle (native node marshalling, objective limits), one node at a time on one core"}
 
 
 TREES = {"example_TT tree": ("example_TT.dat-s.gz", 2.11803), "example_MkP tree": ("example_MkP.dat-s.gz", -95.0)}
@@ -636,6 +636,43 @@ def main():
             for name, (file, _) in TREES.items():
                 bnb[name]["cpu_baseline"] = cpu_tree(file, cores)
 
+    # ------------------------------------------------------------------ ONE relaxation over all N GPUs, strong scaling
+    # Every rank holds the whole problem and forms its share of the Schur complement; one NCCL all-reduce per iteration adds the
+    # shares, the rest of the iteration runs replicated.  At N = 1 the same shapes are solved unsharded, so the
+    # driver's N = 1, 2, 4, 8 records give the strong-scaling curve.  Objectives are compared with tests/golden/relaxation_values.json.
+    sharded = {}
+    if not a.no_nodes:
+        from scip_sdp_b200 import frontier
+        with open(os.path.join(ROOT, "tests", "golden", "relaxation_values.json")) as f:
+            pinned = json.load(f)
+        gs = abi.Solver(gpu.L, device=local)
+        if world > 1:
+            frontier.shard_one_sdp(gs, dist, device=f"cuda:{local}")
+        for key, make in (("dense600x300", lambda: generators.dense_sdp_flat(600, 300, seed=5005)),
+                          ("maxcut2000", lambda: generators.maxcut(2000, 0.01, seed=4004).flatten()[0])):
+            sfp = make()
+            skw = dict(gaptol=1e-5, feastol=1e-5)
+            r0 = gs.solve(sfp, fetch=False, **skw)
+            barrier()
+            ms, its = 0.0, 0
+            for _ in range(3):
+                rr = gs.solve_resident(**skw)
+                ms += rr["device_ms"]; its += rr["iterations"]
+            barrier()
+            tmax = torch.tensor([ms / 3.0], dtype=torch.float64, device="cuda")
+            if world > 1:
+                dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+            want = pinned.get(key, {}).get("dobj")
+            rel = abs(rr["dobj"] - want) / max(1.0, abs(want)) if want is not None else None
+            assert rr["phase_name"] == "pdOPT" and (rel is None or rel <= 1e-5), (key, rr["phase_name"], rr["dobj"], want)
+            sharded[key] = {"value": 1e3 / float(tmax), "unit": "relaxations/s", "ms_per_relaxation": float(tmax), "iterations": its / 3, "n_gpus": world,
+                            "scaling": "strong", "objective": rr["dobj"], "rel_diff_to_oracle": rel,
+                            "instance": f"m = {sfp.m}, blocks = {[int(b) for b in sfp.blocksizes]}",
+                            "partition": ("Schur-complement shares per rank, one NCCL all-reduce of %.1f MB per iteration, rest replicated" % (8 * sfp.m * sfp.m / 1e6))
+                            if world > 1 else "one GPU (the N = 1 point of the strong-scaling curve)"}
+        if world > 1:
+            gs.dist_finalize()
+
     if rank == 0:
         # roofline of the dominant kernel from one profiled solve + the measured DMMA peak
         peak_ms, peak_fl = gpu.time_kernel(4, 0, 3)
@@ -669,6 +706,8 @@ def main():
                 "roofline": roof, "kernels": kernel_rates(gpu, peak), "clocks": sampler.summary()}
         if bnb:
             line["bnb"] = bnb
+        if sharded:
+            line["sharded"] = sharded
         if world == 1 and not a.no_cpu_baseline:
             dt, rc, threads = cpu_relaxation(fp, cores)
             line["cpu_baseline"] = {"value": 1.0 / dt, "unit": "relaxations/s", "cores": threads, "kind": "port",

@@ -151,33 +151,26 @@ __device__ __forceinline__ void leaf_factor(const LeafCtx<NBL>& X, double (&c)[N
          const double s0 = m1, s1 = m2 * i1, s2 = m3 * i2;                                  // pivots (only their products with r are used)
          const double l10 = g1.x * q0, l20 = g2.x * q0, l30 = g3.x * q0;
          const double l21 = b21 * q1, l31 = b31 * q1, l32 = c32 * q2;
-         const double d0v = m1 * q0, d1v = m2 * q1, d2v = m3 * q2, d3v = m4 * q3;           // diagonal of L
          (void)s0; (void)s1; (void)s2;
          if( r == 4 * t && (b0 || b1 || b2 || b3) )
          {
             const int q = b0 ? 0 : (b1 ? 1 : (b2 ? 2 : 3));
             if( 4 * t + q < nb ) atomicMin(&sbad, 4 * t + q);
          }
+         // forward substitution of the row; on the four rows of the diagonal block itself the same formulas give the block's
+         // own factor (entry q of row 4t+q is m_{q+1} q_q = L_qq), only the entries above the diagonal are cleared: no branch
+         const int q = r - 4 * t;                         // >= 4 for the rows below the block
          double4 pr;
-         if( r >= 4 * t + 4 )
-         {
-            pr.x = av.x * r0;
-            pr.y = (av.y - pr.x * l10) * r1;
-            pr.z = (av.z - pr.x * l20 - pr.y * l21) * r2;
-            pr.w = (av.w - pr.x * l30 - pr.y * l31 - pr.z * l32) * r3;
-            *reinterpret_cast<double4*>(Pp + 4 * r) = pr;
-         }
-         else
-         {
-            const int q = r - 4 * t;
-            const double d0 = d0v, d1 = d1v, d2 = d2v, d3 = d3v;
-            pr.x = (q == 0) ? d0 : (q == 1 ? l10 : (q == 2 ? l20 : l30));
-            pr.y = (q == 0) ? 0.0 : (q == 1 ? d1 : (q == 2 ? l21 : l31));
-            pr.z = (q <= 1) ? 0.0 : (q == 2 ? d2 : l32);
-            pr.w = (q <= 2) ? 0.0 : d3;
-            *reinterpret_cast<double4*>(Pp + 4 * r) = make_double4(0.0, 0.0, 0.0, 0.0);
-            rdg[r] = (q == 0) ? r0 : (q == 1 ? r1 : (q == 2 ? r2 : r3));
-         }
+         pr.x = av.x * r0;
+         pr.y = (av.y - pr.x * l10) * r1;
+         pr.z = (av.z - pr.x * l20 - pr.y * l21) * r2;
+         pr.w = (av.w - pr.x * l30 - pr.y * l31 - pr.z * l32) * r3;
+         pr.y = (q < 1) ? 0.0 : pr.y;
+         pr.z = (q < 2) ? 0.0 : pr.z;
+         pr.w = (q < 3) ? 0.0 : pr.w;
+         const bool below = (q >= 4);
+         *reinterpret_cast<double4*>(Pp + 4 * r) = below ? pr : make_double4(0.0, 0.0, 0.0, 0.0);
+         if( !below ) rdg[r] = (q == 0) ? r0 : (q == 1 ? r1 : (q == 2 ? r2 : r3));
          // row-major copy of L (zeros above the diagonal land in the triangle that the inverse fills later)
          *reinterpret_cast<double4*>(G + (r + 1) * LD + 4 * t) = pr;
       }
@@ -795,7 +788,10 @@ cudaError_t potrf_dag(cudaStream_t st, int n, double* A, int lda, double* Linv, 
    const int total = T * (T + 1) / 2;
    {
       ProfScope prof(st, PROF_DIAG, (double)n * n * n / 3.0);
-      potrf_dag_kernel<<<std::min(total, 2 * nsm[dev & 63]), DAG_THREADS, DAG_SMEM, st>>>(a);
+      // up to about n = 3000 the factorisation is bound by its dependency chain, not by flops: one CTA per SM is plenty and leaves the
+      // other CTA slot of every SM to the kernel of the second stream (the factorisations of S and X run side by side)
+      const int per_sm = (n <= 3072) ? 1 : 2;
+      potrf_dag_kernel<<<std::min(total, per_sm * nsm[dev & 63]), DAG_THREADS, DAG_SMEM, st>>>(a);
       count_launch();
       SDPK_CUDA_CHECK( cudaGetLastError() );
    }

@@ -22,6 +22,7 @@
 #include <chrono>
 #include <cmath>
 #include <cstring>
+#include <mutex>
 #include <numeric>
 #include <vector>
 
@@ -67,6 +68,20 @@ struct Block { int n; int ld; long long off; };
 std::atomic<int> g_next_device{0};
 
 } // namespace
+
+// one host image of a frontier batch (all read-only arrays of all nodes, 16-byte aligned pieces)
+struct BatchImage
+{
+   std::vector<unsigned char> buf;
+   size_t put(const void* src, size_t bytes)
+   {
+      const size_t off = (buf.size() + 15) & ~(size_t)15;
+      buf.resize(off + std::max<size_t>(bytes, 16));
+      if( bytes > 0 ) memcpy(buf.data() + off, src, bytes);
+      return off;
+   }
+   template <class T> size_t putv(const std::vector<T>& v) { return put(v.data(), v.size() * sizeof(T)); }
+};
 
 struct sdpcuda_handle
 {
@@ -137,6 +152,7 @@ struct sdpcuda_handle
    bool minv = false;                // explicit inverse factor of M (m <= 4096): solves become two triangular mat-vecs; above: look-ahead panels + panel substitution
    DBuf<double> partials, stats, scal, eigw, lzwork;
    DBuf<int> info;
+   BatchImage batchhost;                           // host image of the last frontier batch (kept: no page faults on the next one)
    DBuf<int> ppint; DBuf<double> ppdbl, ppout; DBuf<long long> ppoff;      // staging of sdpcuda_primal_products
    DBuf<double> kflag;                            // one word: time-limit flag agreed between the ranks of a sharded solve
    double* h_stats = nullptr;     // pinned
@@ -965,19 +981,6 @@ int sdpcuda_solve_resident(sdpcuda_handle* h, const sdpcuda_params* par, sdpcuda
 // host->device copy of the image, one of the descriptors, one launch and one device->host copy of results and y for the whole batch.
 } // extern "C"
 
-struct BatchImage
-{
-   std::vector<unsigned char> buf;
-   size_t put(const void* src, size_t bytes)
-   {
-      const size_t off = (buf.size() + 15) & ~(size_t)15;
-      buf.resize(off + std::max<size_t>(bytes, 16));
-      if( bytes > 0 ) memcpy(buf.data() + off, src, bytes);
-      return off;
-   }
-   template <class T> size_t putv(const std::vector<T>& v) { return put(v.data(), v.size() * sizeof(T)); }
-};
-
 struct BatchNode          // offsets of one node: bytes into the image, doubles into the work space / the y buffer
 {
    SmallArgs a;           // scalars and block table are final; the pointers are set once the device addresses are known
@@ -992,7 +995,17 @@ struct BatchNode          // offsets of one node: bytes into the image, doubles 
 constexpr size_t STAGE_BUDGET_TINY = 58 * 1024, STAGE_BUDGET_SMALL = 80 * 1024;
 
 // builds the image of one node; returns SDPCUDA_OK and *fits = false when the relaxation is outside the single-CTA limits
-static int batch_prepare_node(const sdpcuda_problem* P, const sdpcuda_params* par, BatchImage& img, BatchNode& nd, bool* fits)
+// S: per-worker scratch vectors (kept across nodes and calls: a CLS node has 30 k entries, and a fresh set of vectors per node costs
+// more in page faults and allocator locks than the packing itself)
+struct PrepScratch
+{
+   std::vector<int> erow, ecol, eld, heavy, order, var_of, posbeg, posvar, lpbeg, colbeg, colrow, fill, denselist, varbeg, cnt;
+   std::vector<long long> eoff, key, cposv, cmirv, pos, mirror;
+   std::vector<double> posval, posc, colval;
+   std::vector<std::vector<int>> dense_in;
+};
+
+static int batch_prepare_node(const sdpcuda_problem* P, const sdpcuda_params* par, BatchImage& img, BatchNode& nd, bool* fits, PrepScratch& S)
 {
    *fits = false;
    const int m = P->m, nb = P->nblocks, nlp = P->nlp;
@@ -1017,8 +1030,9 @@ static int batch_prepare_node(const sdpcuda_problem* P, const sdpcuda_params* pa
    const long long ar = off;
    if( ar > ((long long)1 << 20) ) return SDPCUDA_OK;
    const int nnz = P->varbeg[m];
-   std::vector<int> erow(nnz), ecol(nnz), eld(nnz), heavy(m, 0);
-   std::vector<long long> eoff(nnz);
+   std::vector<int>& erow = S.erow; std::vector<int>& ecol = S.ecol; std::vector<int>& eld = S.eld; std::vector<int>& heavy = S.heavy;
+   std::vector<long long>& eoff = S.eoff;
+   erow.resize(nnz); ecol.resize(nnz); eld.resize(nnz); eoff.resize(nnz); heavy.assign(m, 0);
    for( int e = 0; e < nnz; ++e )
    {
       const int bk = P->entblk[e];
@@ -1028,7 +1042,9 @@ static int batch_prepare_node(const sdpcuda_problem* P, const sdpcuda_params* pa
       erow[e] = r; ecol[e] = c; eld[e] = a.blk[bk].ld; eoff[e] = a.blk[bk].off;
    }
    // variable classes as in upload_problem: 2 = dense (all entries in one block, >= 64 of them and >= 5 % of the block)
-   std::vector<std::vector<int>> dense_in(nb);
+   std::vector<std::vector<int>>& dense_in = S.dense_in;
+   if( (int)dense_in.size() < nb ) dense_in.resize(nb);
+   for( int k = 0; k < nb; ++k ) dense_in[k].clear();
    for( int j = 0; j < m; ++j )
    {
       const int cntj = P->varbeg[j + 1] - P->varbeg[j];
@@ -1040,7 +1056,8 @@ static int batch_prepare_node(const sdpcuda_problem* P, const sdpcuda_params* pa
       if( oneblock && cntj >= 64 && cntj >= 0.05 * nn ) { heavy[j] = 2; dense_in[b0].push_back(j); }
       else heavy[j] = 1;
    }
-   std::vector<int> denselist;
+   std::vector<int>& denselist = S.denselist;
+   denselist.clear();
    int ngroups = 0, maxcount = 0;
    long long adense_total = 0;
    size_t maxmat = 1;
@@ -1056,7 +1073,8 @@ static int batch_prepare_node(const sdpcuda_problem* P, const sdpcuda_params* pa
       ++ngroups;
    }
    // position-major view of sum_j y_j A_j - C (one slot per distinct arena position, entries in input order)
-   std::vector<long long> key(nnz + P->cnnz), cposv(P->cnnz), cmirv(P->cnnz);
+   std::vector<long long>& key = S.key; std::vector<long long>& cposv = S.cposv; std::vector<long long>& cmirv = S.cmirv;
+   key.resize(nnz + P->cnnz); cposv.resize(P->cnnz); cmirv.resize(P->cnnz);
    for( int e = 0; e < nnz; ++e ) key[e] = eoff[e] + (long long)ecol[e] * eld[e] + erow[e];
    for( int e = 0; e < P->cnnz; ++e )
    {
@@ -1068,15 +1086,30 @@ static int batch_prepare_node(const sdpcuda_problem* P, const sdpcuda_params* pa
       cmirv[e] = a.blk[bk].off + (long long)r * a.blk[bk].ld + c;
       key[nnz + e] = cposv[e];
    }
-   std::vector<int> order(nnz + P->cnnz);
-   std::iota(order.begin(), order.end(), 0);
-   std::stable_sort(order.begin(), order.end(), [&](int x, int y2) { return key[x] < key[y2]; });
-   std::vector<int> var_of(nnz);
+   std::vector<int>& order = S.order;
+   order.resize(nnz + P->cnnz);
+   if( (long long)order.size() * 8 >= ar )
+   {
+      // dense-enough entry lists (CLS: 30 k entries on 1.9 k positions): stable counting sort over the arena positions
+      std::vector<int>& cnt = S.cnt;
+      cnt.assign((size_t)ar + 1, 0);
+      for( long long kk : key ) cnt[(size_t)kk + 1]++;
+      for( long long q = 0; q < ar; ++q ) cnt[(size_t)q + 1] += cnt[(size_t)q];
+      for( int t = 0; t < (int)order.size(); ++t ) order[cnt[(size_t)key[t]]++] = t;
+   }
+   else
+   {
+      std::iota(order.begin(), order.end(), 0);
+      std::stable_sort(order.begin(), order.end(), [&](int x, int y2) { return key[x] < key[y2]; });
+   }
+   std::vector<int>& var_of = S.var_of;
+   var_of.resize(nnz);
    for( int j = 0; j < m; ++j )
       for( int e = P->varbeg[j]; e < P->varbeg[j + 1]; ++e ) var_of[e] = j;
-   std::vector<int> posbeg(1, 0), posvar;
-   std::vector<long long> pos, mirror;
-   std::vector<double> posval, posc;
+   std::vector<int>& posbeg = S.posbeg; std::vector<int>& posvar = S.posvar;
+   std::vector<long long>& pos = S.pos; std::vector<long long>& mirror = S.mirror;
+   std::vector<double>& posval = S.posval; std::vector<double>& posc = S.posc;
+   posbeg.assign(1, 0); posvar.clear(); pos.clear(); mirror.clear(); posval.clear(); posc.clear();
    for( size_t t = 0; t < order.size(); )
    {
       const long long kpos = key[order[t]];
@@ -1098,11 +1131,13 @@ static int batch_prepare_node(const sdpcuda_problem* P, const sdpcuda_params* pa
       t = u;
    }
    // LP block: CSR as given, CSC built here
-   std::vector<int> lpbeg(nlp + 1, 0);
+   std::vector<int>& lpbeg = S.lpbeg;
+   lpbeg.assign(nlp + 1, 0);
    if( nlp > 0 ) std::copy(P->lpbeg, P->lpbeg + nlp + 1, lpbeg.begin());
    const int lnz = lpbeg[nlp];
-   std::vector<int> colbeg(m + 1, 0), colrow(lnz);
-   std::vector<double> colval(lnz);
+   std::vector<int>& colbeg = S.colbeg; std::vector<int>& colrow = S.colrow;
+   std::vector<double>& colval = S.colval;
+   colbeg.assign(m + 1, 0); colrow.resize(lnz); colval.resize(lnz);
    for( int p = 0; p < lnz; ++p )
    {
       if( P->lpind[p] < 0 || P->lpind[p] >= m ) return SDPCUDA_ERR_ARG;
@@ -1110,7 +1145,8 @@ static int batch_prepare_node(const sdpcuda_problem* P, const sdpcuda_params* pa
    }
    for( int j = 0; j < m; ++j ) colbeg[j + 1] += colbeg[j];
    {
-      std::vector<int> fill(colbeg.begin(), colbeg.end() - 1);
+      std::vector<int>& fill = S.fill;
+      fill.assign(colbeg.begin(), colbeg.end() - 1);
       for( int l = 0; l < nlp; ++l )
          for( int p = lpbeg[l]; p < lpbeg[l + 1]; ++p )
          {
@@ -1143,7 +1179,8 @@ static int batch_prepare_node(const sdpcuda_problem* P, const sdpcuda_params* pa
    a.gammabase = par->setting >= 3 ? 0.7 : (par->setting == 2 ? 0.8 : 0.9);
    a.selfinit = 1; a.adense_total = adense_total;
    // read-only data -> image
-   std::vector<int> varbeg(P->varbeg, P->varbeg + m + 1);
+   std::vector<int>& varbeg = S.varbeg;
+   varbeg.assign(P->varbeg, P->varbeg + m + 1);
    nd.varbeg = img.putv(varbeg); nd.erow = img.putv(erow); nd.ecol = img.putv(ecol); nd.eld = img.putv(eld); nd.eoff = img.putv(eoff);
    nd.eval = img.put(P->entval, sizeof(double) * nnz); nd.cls = img.putv(heavy);
    nd.posbeg = img.putv(posbeg); nd.pos = img.putv(pos); nd.mirror = img.putv(mirror); nd.posvar = img.putv(posvar);
@@ -1223,7 +1260,10 @@ static size_t batch_stage_prefix(const BatchNode& nd, size_t budget)
 // the order of the descriptors (relaxations for the 256-thread instantiation first).  Pure CPU work: no CUDA call in here.
 struct BatchPlan
 {
-   BatchImage img;
+   BatchImage own;
+   BatchImage& img;                   // the joined image: the plan's own buffer, or a buffer the caller keeps across batches
+   BatchPlan() : img(own) {}
+   explicit BatchPlan(BatchImage& keep) : img(keep) {}
    std::vector<BatchNode> nodes;      // the batched nodes
    std::vector<int> who;              // nodes[k] is input problem who[k]
    std::vector<int> loners;           // input problems outside the single-CTA limits
@@ -1236,35 +1276,45 @@ struct BatchPlan
 static int batch_plan(int count, const sdpcuda_problem* const* probs, const sdpcuda_params* par, bool usetiny, bool stage, BatchPlan& P,
    bool copyback = false)
 {
-   // every node is packed into its own image by the host threads (host_pool.hpp); the images are then appended in input order, so
-   // the layout is the one a serial pass over the nodes produces
-   struct Packed { BatchImage img; BatchNode nd; bool fits = false; int rc = SDPCUDA_OK; };
+   // the nodes are packed by the host threads (host_pool.hpp), every worker appending to its own image; the worker images are then
+   // joined (the order of the nodes inside the image depends on the scheduling, the descriptors carry the offsets)
+   // (one plan at a time: the per-worker images and scratch vectors below are shared by all handles of the process)
+   static std::mutex planmu;
+   std::lock_guard<std::mutex> planlock(planmu);
+   constexpr int NW = sdphost::Pool::MAX_WORKERS;
+   static BatchImage wimg[NW];                            // image pieces of the nodes a worker packed in this call
+   static PrepScratch wscr[NW];
+   struct Packed { BatchNode nd; bool fits = false; int rc = SDPCUDA_OK; int worker = 0; size_t at = 0, len = 0; };
    std::vector<Packed> packed(count);
-   sdphost::Pool::get().run(count, [&](int i) { packed[i].rc = batch_prepare_node(probs[i], par, packed[i].img, packed[i].nd, &packed[i].fits); });
-   size_t imgtotal = 0;
-   for( int i = 0; i < count; ++i )
+   for( int wk = 0; wk < NW; ++wk ) wimg[wk].buf.clear();
+   sdphost::Pool::get().run_indexed(count, [&](int i, int wk)
    {
-      if( packed[i].rc != SDPCUDA_OK ) return packed[i].rc;
-      if( packed[i].fits ) imgtotal += (packed[i].img.buf.size() + 15) & ~(size_t)15;
-   }
+      BatchImage& img = wimg[wk];
+      const size_t at = (img.buf.size() + 15) & ~(size_t)15;
+      img.buf.resize(at);                                 // the node's pieces start on a 16-byte boundary of the worker image
+      packed[i].rc = batch_prepare_node(probs[i], par, img, packed[i].nd, &packed[i].fits, wscr[wk]);
+      if( packed[i].rc != SDPCUDA_OK || !packed[i].fits ) { img.buf.resize(at); return; }
+      packed[i].worker = wk; packed[i].at = at; packed[i].len = img.buf.size() - at;
+   });
+   // worker images are appended one after the other; a node's offsets are relative to its worker image already
+   size_t wbase[NW], imgtotal = 0;
+   for( int wk = 0; wk < NW; ++wk ) { wbase[wk] = imgtotal; imgtotal += (wimg[wk].buf.size() + 15) & ~(size_t)15; }
+   for( int i = 0; i < count; ++i ) if( packed[i].rc != SDPCUDA_OK ) return packed[i].rc;
    P.img.buf.resize(imgtotal);
    P.nodes.reserve(count);
-   std::vector<size_t> base(count, 0);
-   size_t at = 0;
    for( int i = 0; i < count; ++i )
    {
       if( !packed[i].fits ) { P.loners.push_back(i); continue; }
       BatchNode& nd = packed[i].nd;
-      base[i] = at; at += (packed[i].img.buf.size() + 15) & ~(size_t)15;
       static_assert(offsetof(BatchNode, denselist) - offsetof(BatchNode, varbeg) == 24 * sizeof(size_t), "image offsets of BatchNode are contiguous");
-      for( size_t* f = &nd.varbeg; f <= &nd.denselist; ++f ) *f += base[i];
+      for( size_t* f = &nd.varbeg; f <= &nd.denselist; ++f ) *f += wbase[packed[i].worker];
       nd.work = P.worktotal; P.worktotal += nd.worklen;
       nd.yoff = P.ytotal; P.ytotal += ((size_t)nd.a.m + 1 + 15) / 16 * 16;
       P.nodes.push_back(nd); P.who.push_back(i);
    }
-   sdphost::Pool::get().run(count, [&](int i)
+   sdphost::Pool::get().run(NW, [&](int wk)
    {
-      if( packed[i].fits && !packed[i].img.buf.empty() ) memcpy(P.img.buf.data() + base[i], packed[i].img.buf.data(), packed[i].img.buf.size());
+      if( !wimg[wk].buf.empty() ) memcpy(P.img.buf.data() + wbase[wk], wimg[wk].buf.data(), wimg[wk].buf.size());
    });
    const int nd = (int)P.nodes.size();
    P.slot.assign(nd, 0);
@@ -1311,7 +1361,8 @@ int sdpcuda_debug_pack_batch(int count, const sdpcuda_problem* const* probs, con
    if( count < 0 || par == nullptr || (count > 0 && probs == nullptr) || image_bytes == nullptr || work_doubles == nullptr
       || y_doubles == nullptr || nbatched == nullptr || ntiny == nullptr ) return SDPCUDA_ERR_ARG;
    for( int i = 0; i < count; ++i ) if( probs[i] == nullptr || probs[i]->m <= 0 ) return SDPCUDA_ERR_ARG;
-   BatchPlan P;
+   static thread_local BatchImage keep;                  // like the handle's: repeated calls of one thread do not re-fault the pages
+   BatchPlan P(keep);
    int rc = batch_plan(count, probs, par, (flags & 1) != 0, (flags & 2) != 0, P, (flags & 4) != 0);
    if( rc != SDPCUDA_OK ) return rc;
    const int nd = (int)P.nodes.size();
@@ -1338,7 +1389,8 @@ int sdpcuda_debug_pack_node(const sdpcuda_problem* P, const sdpcuda_params* par,
    BatchImage img;
    BatchNode nd;
    bool ok = false;
-   int rc = batch_prepare_node(P, par, img, nd, &ok);
+   PrepScratch scr;
+   int rc = batch_prepare_node(P, par, img, nd, &ok, scr);
    if( rc != SDPCUDA_OK ) return rc;
    *fits = ok ? 1 : 0;
    *image_bytes = ok ? img.buf.size() : 0; *work_doubles = ok ? nd.worklen : 0; *desc_bytes = sizeof(SmallArgs);
@@ -1421,14 +1473,15 @@ int sdpcuda_solve_batch(sdpcuda_handle* h, int count, const sdpcuda_problem* con
    const double t0 = now_seconds();
    int rc = set_device(h);
    if( rc != SDPCUDA_OK ) return rc;
-   // SDPCUDA_BATCH_TINY=1: relaxations whose blocks all have order <= 16 go to the 256-thread instantiation (four per SM);
-   // off by default until it has run on a GPU.  The descriptors are ordered tiny first, then the others: two launches.
+   // Relaxations whose blocks all have order <= 16 go to the 256-thread instantiation (four per SM): measured on the B200 with 592-node
+   // frontiers, example_TT 41 k -> 84 k nodes/s on the device, example_MkP 5.3 k -> 7.9 k (profiles/r2_batch_switches.log), so it is
+   // the default; SDPCUDA_BATCH_TINY=0 turns it off.  The descriptors are ordered tiny first, then the others: two launches.
    // SDPCUDA_BATCH_SMEM=1: the head of every node's work space is staged in shared memory (as many whole arrays as fit the budget)
    const char* te = getenv("SDPCUDA_BATCH_TINY");
    const char* se = getenv("SDPCUDA_BATCH_SMEM");
-   BatchPlan plan;
+   BatchPlan plan(h->batchhost);
    if( h->packed ) { h->packed = false; h->solved = false; }      // the batch reuses the buffers of a packed single solve
-   rc = batch_plan(count, probs, par, te != nullptr && te[0] == '1', se != nullptr && se[0] == '1', plan);
+   rc = batch_plan(count, probs, par, !(te != nullptr && te[0] == '0'), se != nullptr && se[0] == '1', plan);
    if( rc != SDPCUDA_OK ) return rc;
    if( objlimits != nullptr )
       for( size_t k = 0; k < plan.nodes.size(); ++k ) plan.nodes[k].a.objlimit = objlimits[plan.who[k]];

@@ -119,6 +119,10 @@ inline void flatten(const Model& M, const double* lb, const double* ub, double e
    for( int k = 0; k < m; ++k ) F.obj[k] = M.obj[F.active[k]];
    // entries of the active variables
    F.varbeg.assign(m + 1, 0);
+   {
+      const size_t cap = M.var_order.size();            // no growth reallocations (a CLS node carries 30 k entries)
+      F.entblk.reserve(cap); F.entrow.reserve(cap); F.entcol.reserve(cap); F.entval.reserve(cap);
+   }
    for( int e : M.var_order )
    {
       if( fixed[M.ev[e]] ) continue;

@@ -13,13 +13,14 @@ from scip_sdp_b200 import abi, generators  # noqa: E402
 
 SHAPES = {"tt500": lambda: generators.truss(6, 6, 500, seed=1001), "cls": lambda: generators.cls(199, 99, 10, seed=2002),
           "mkp60": lambda: generators.mkp(60, seed=3003), "mkp120": lambda: generators.mkp(120, seed=3003),
-          "maxcut2000": lambda: generators.maxcut(2000, 0.01, seed=4004)}
+          "maxcut2000": lambda: generators.maxcut(2000, 0.01, seed=4004), "dense600x300": lambda: generators.dense_sdp_flat(600, 300, seed=5005)}
 
 if __name__ == "__main__":
     cpu = abi.Solver(abi.Lib(abi.ORACLE_LIB))
     out = {}
     for name, make in SHAPES.items():
-        fp, _ = make().flatten()
+        M = make()
+        fp = M if isinstance(M, abi.FlatProblem) else M.flatten()[0]          # dense_sdp_flat is in solver form already
         t = time.time()
         r = cpu.solve(fp, gaptol=1e-5, feastol=1e-5, fetch=False)
         assert r["phase_name"] == "pdOPT", (name, r["phase_name"])

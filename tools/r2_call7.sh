@@ -1,0 +1,15 @@
+# Round 2, GPU call 7: the driver's commands — default bench (both arms, steps 20 / warmup 5) and the whole GPU suite
+set -x
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests -m gpu -q > gpurun_out/r2d_pytest_all.log 2>&1; tail -8 gpurun_out/r2d_pytest_all.log
+( time timeout 900 python bench.py --gpus 1 --steps 20 --warmup 5 > gpurun_out/r2d_bench_n1.json 2> gpurun_out/r2d_bench_n1.err ) 2>&1 | tail -3
+tail -5 gpurun_out/r2d_bench_n1.err; python - <<'P'
+import json
+d = json.load(open("gpurun_out/r2d_bench_n1.json"))
+print({k: d[k] for k in ("value", "ms_per_step")}, d["e2e"]["value"], d["roofline"]["frac"], d.get("cpu_baseline", {}).get("value"))
+for k, v in d.get("bnb", {}).items():
+    print(k, {kk: (round(vv, 2) if isinstance(vv, float) else vv) for kk, vv in v.items() if kk in ("value", "nodes", "counted", "ms_per_frontier", "device_nodes_per_s", "not_converged", "resolved_with_stable_settings", "max_rel_diff_to_oracle", "rounds")}, "cpu", v.get("cpu_baseline", {}).get("value"))
+print(json.dumps(d["kernels"]))
+P
+( time timeout 1200 python bench.py --impl reference --gpus 1 --steps 20 --warmup 5 > gpurun_out/r2d_bench_ref_n1.json 2> gpurun_out/r2d_bench_ref_n1.err ) 2>&1 | tail -3
+cut -c1-400 gpurun_out/r2d_bench_ref_n1.json; tail -3 gpurun_out/r2d_bench_ref_n1.err
