@@ -9,6 +9,8 @@
 // Edges are handled by zero-filling cp.async (src-size < 16), so any m, n, k works as long as leading dimensions are
 // even and base pointers 16-byte aligned.  All matrices column-major; batches via blockIdx.z and element strides.
 #include "common.cuh"
+#include <cuda.h>          // CUtensorMap (types only; the encoder is fetched through cudaGetDriverEntryPoint)
+#include <cstring>
 
 namespace sdpk {
 
@@ -194,6 +196,249 @@ gemm_dmma_kernel(int M, int N, int K, double alpha, const double* __restrict__ A
    }
 }
 
+// ---- TMA-fed variant of the 64 x 64 kernel ------------------------------------------------------------------------------------------
+// Same tiling and DMMA fragment code; the operand tiles are fetched by the TMA unit instead of 128 threads issuing cp.async: one
+// elected thread arms an mbarrier with the byte count of the stage and issues two cp.async.bulk.tensor.3d (box BM x BK and BN x BK of
+// a tensor map over the whole operand, third coordinate = batch index); out-of-range rows / k are zero-filled by the hardware, so
+// there is no edge code; the other threads only wait on the mbarrier.  Shared-memory layouts:
+//    "K-contiguous" operand (A in TN/TT, B in NN/TN): box [mn][BK], BK * 8 = 128 bytes per row, SWIZZLE_128B: the 16-byte chunk index
+//        is XORed with (mn & 7), which makes the DMMA fragment loads (8 rows x 4 k) conflict free without padding;
+//    "MN-contiguous" operand (A in NN/NT, B in NT/TT): no swizzle mode covers 512-byte rows, and a dense [k][64] tile would put the
+//        four k-rows of a fragment load on the same banks (measured: SYRK 2000 25.8 -> 21.0 TFLOP/s).  The box is therefore 68 wide:
+//        four more rows of the operand than the tile needs (zero-filled beyond the matrix), which lands as [k][68] — exactly the
+//        padded, conflict-free layout of the cp.async kernel, made by the TMA unit itself.
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count)
+{
+   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" :: "r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes)
+{
+   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity)
+{
+   // bounded: a transfer that never completes (a bug) ends in a trap, not in a hung GPU
+   for( unsigned spins = 0; ; ++spins )
+   {
+      unsigned ok;
+      asm volatile(
+         "{\n"
+         ".reg .pred p;\n"
+         "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+         "selp.u32 %0, 1, 0, p;\n"
+         "}\n" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+      if( ok ) return;
+      if( spins > (1u << 26) ) asm volatile("trap;\n");
+   }
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, int c0, int c1, int c2, unsigned long long* bar)
+{
+   asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];\n"
+      :: "r"(smem_u32(dst)), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar)) : "memory");
+}
+
+template <bool TA, bool TB, int STAGES>
+__global__ void __launch_bounds__(128)
+gemm_dmma_tma_kernel(int M, int N, int K, double alpha, const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
+   double beta, double* __restrict__ C, int ldc, long long strideC, int flags)
+{
+   constexpr int BM = 64, BN = 64, NT = 128;
+   constexpr int WM = BM / 2, WN = BN / 2, MI = WM / 8, NI = WN / 8;
+   constexpr int PADW = BM + 4;                            // row length of an MN-contiguous tile
+   constexpr int TILE_A = TA ? BM * BK : BK * PADW, TILE_B = TB ? BK * PADW : BN * BK;      // doubles per operand tile
+   extern __shared__ __align__(16) unsigned char tsm_raw[];
+   __shared__ unsigned long long full[STAGES];
+   // SWIZZLE_128B repeats every 1024 bytes of shared memory: the swizzled tiles (8 KB each) come first, on a 1024-byte boundary
+   double* tsm = reinterpret_cast<double*>(tsm_raw + ((1024u - (smem_u32(tsm_raw) & 1023u)) & 1023u));
+   double* As = (TA || TB) ? tsm : tsm + STAGES * TILE_B;          // A first unless only B is swizzled
+   double* Bs = (TA || TB) ? tsm + STAGES * TILE_A : tsm;
+
+   constexpr int GROUP_M = 16;
+   int tm = blockIdx.x, tn = blockIdx.y;
+   if( gridDim.x > GROUP_M )
+   {
+      const int lin = blockIdx.x + gridDim.x * blockIdx.y;
+      const int per = GROUP_M * gridDim.y;
+      const int grp = lin / per, first = grp * GROUP_M;
+      const int gsz = min((int)gridDim.x - first, GROUP_M);
+      const int r = lin - grp * per;
+      tm = first + r % gsz;
+      tn = r / gsz;
+   }
+   const int m0 = tm * BM, n0 = tn * BN;
+   if( (flags & GEMM_LOWER) && (m0 + BM <= n0) )
+      return;
+   const int z = blockIdx.z;
+   C += (size_t)z * strideC;
+
+   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+   const int gid = lane >> 2, tig = lane & 3;
+   const int wm = (warp & 1) * WM, wn = (warp >> 1) * WN;
+
+   if( tid == 0 )
+   {
+#pragma unroll
+      for( int s = 0; s < STAGES; ++s ) mbar_init(&full[s], 1);
+      asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+   }
+   __syncthreads();
+
+   double acc[MI][NI][2];
+#pragma unroll
+   for( int i = 0; i < MI; ++i )
+#pragma unroll
+      for( int j = 0; j < NI; ++j ) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
+
+   int khi = K, klo = 0;
+   if( flags & GEMM_KHI_M ) khi = min(khi, m0 + BM);
+   if( flags & GEMM_KHI_N ) khi = min(khi, n0 + BN);
+   if( flags & GEMM_KLO_M ) klo = max(klo, m0);
+   if( flags & GEMM_KLO_N ) klo = max(klo, n0);
+   const int KT0 = klo / BK;
+   const int KT = max(KT0, (khi + BK - 1) / BK);
+
+   auto issue = [&](int kt)
+   {
+      const int s = (kt - KT0) % STAGES, k0 = kt * BK;
+      mbar_expect_tx(&full[s], (TILE_A + TILE_B) * (unsigned)sizeof(double));
+      // A: K-contiguous (TA): map dims (K, M, batch); MN-contiguous: (M, K, batch).  B: K-contiguous (!TB): (K, N, batch); else (N, K, batch)
+      if( TA ) tma_load_3d(As + s * TILE_A, &mapA, k0, m0, z, &full[s]); else tma_load_3d(As + s * TILE_A, &mapA, m0, k0, z, &full[s]);
+      if( !TB ) tma_load_3d(Bs + s * TILE_B, &mapB, k0, n0, z, &full[s]); else tma_load_3d(Bs + s * TILE_B, &mapB, n0, k0, z, &full[s]);
+   };
+   if( tid == 0 )
+   {
+#pragma unroll 1
+      for( int s = 0; s < STAGES - 1; ++s ) if( KT0 + s < KT ) issue(KT0 + s);
+   }
+
+   for( int kt = KT0; kt < KT; ++kt )
+   {
+      const int it = kt - KT0, s = it % STAGES;
+      mbar_wait(&full[s], (unsigned)((it / STAGES) & 1));
+      __syncthreads();                                      // everybody is done with the stage that is refilled next
+      if( tid == 0 && kt + STAGES - 1 < KT ) issue(kt + STAGES - 1);
+      const double* as = As + s * TILE_A;
+      const double* bs = Bs + s * TILE_B;
+#pragma unroll
+      for( int kk = 0; kk < BK; kk += 4 )
+      {
+         double a[MI], b[NI];
+         const int k = kk + tig;
+#pragma unroll
+         for( int i = 0; i < MI; ++i )
+         {
+            const int r = wm + i * 8 + gid;
+            a[i] = TA ? as[r * BK + ((((k >> 1) ^ (r & 7)) << 1) | (k & 1))] : as[k * PADW + r];
+         }
+#pragma unroll
+         for( int j = 0; j < NI; ++j )
+         {
+            const int c = wn + j * 8 + gid;
+            b[j] = TB ? bs[k * PADW + c] : bs[c * BK + ((((k >> 1) ^ (c & 7)) << 1) | (k & 1))];
+         }
+#pragma unroll
+         for( int i = 0; i < MI; ++i )
+#pragma unroll
+            for( int j = 0; j < NI; ++j )
+               dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+      }
+   }
+
+#pragma unroll
+   for( int i = 0; i < MI; ++i )
+   {
+      int row = m0 + wm + i * 8 + gid;
+      if( row >= M ) continue;
+#pragma unroll
+      for( int j = 0; j < NI; ++j )
+      {
+#pragma unroll
+         for( int e = 0; e < 2; ++e )
+         {
+            int col = n0 + wn + j * 8 + tig * 2 + e;
+            if( col < N )
+            {
+               double* p = C + (size_t)col * ldc + row;
+               double v = alpha * acc[i][j][e];
+               if( beta != 0.0 ) v += beta * (*p);
+               *p = v;
+            }
+         }
+      }
+   }
+}
+
+// tensor map of a column-major operand with `inner` contiguous elements per column, `outer` columns, `batch` matrices
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+   const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_tiled()
+{
+   static EncodeTiledFn fn = nullptr;
+   static bool tried = false;
+   if( !tried )
+   {
+      tried = true;
+      void* p = nullptr;
+      cudaDriverEntryPointQueryResult q;
+      if( cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess )
+         fn = reinterpret_cast<EncodeTiledFn>(p);
+   }
+   return fn;
+}
+
+bool make_map(CUtensorMap* map, const double* base, long long inner, long long outer, int ld, long long stride, int batch, int box_inner,
+   int box_outer, bool swizzle128)
+{
+   EncodeTiledFn fn = encode_tiled();
+   if( fn == nullptr ) return false;
+   if( (reinterpret_cast<uintptr_t>(base) & 15) != 0 || (ld & 1) != 0 || ((stride & 1) != 0 && batch > 1) || (stride <= 0 && batch > 1) ) return false;
+   cuuint64_t dims[3] = {(cuuint64_t)inner, (cuuint64_t)outer, (cuuint64_t)std::max(batch, 1)};
+   cuuint64_t strides[2] = {(cuuint64_t)ld * sizeof(double), (cuuint64_t)(batch > 1 ? stride : (long long)ld * outer) * sizeof(double)};
+   if( strides[1] == 0 ) strides[1] = 16;
+   cuuint32_t box[3] = {(cuuint32_t)box_inner, (cuuint32_t)box_outer, 1};
+   cuuint32_t estr[3] = {1, 1, 1};
+   return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, const_cast<double*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+      swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+// 0: cp.async ring (round 1), 1: TMA-fed kernel for the 64 x 64 tiles (default when the tensor maps can be built); SDPCUDA_GEMM=cpasync|tma
+int gemm_variant()
+{
+   const char* e = getenv("SDPCUDA_GEMM");
+   if( e != nullptr && strcmp(e, "cpasync") == 0 ) return 0;
+   return 1;
+}
+
+template <bool TA, bool TB>
+cudaError_t launch_tma(cudaStream_t st, int m, int n, int k, double alpha, const double* A, int lda, long long sA,
+   const double* B, int ldb, long long sB, double beta, double* C, int ldc, long long sC, int batch, int flags, bool* done)
+{
+   constexpr int STAGES = 3;          // 51.7 KB per CTA: four CTAs per SM (four stages: three CTAs, and SYRK 2000 loses a wave)
+   constexpr size_t SMEM = (size_t)STAGES * ((TA ? 64 * BK : BK * 68) + (TB ? BK * 68 : 64 * BK)) * sizeof(double) + 1024;     // + alignment slack
+   *done = false;
+   CUtensorMap mapA, mapB;
+   // A is (m x k) when not transposed: MN-contiguous, box 64 x BK; transposed: stored (k x m), K-contiguous, box BK x 64
+   if( !(TA ? make_map(&mapA, A, k, m, lda, sA, batch, BK, 64, true) : make_map(&mapA, A, m, k, lda, sA, batch, 68, BK, false)) ) return cudaSuccess;
+   // B is (k x n) when not transposed: K-contiguous; transposed: stored (n x k), MN-contiguous
+   if( !(TB ? make_map(&mapB, B, n, k, ldb, sB, batch, 68, BK, false) : make_map(&mapB, B, k, n, ldb, sB, batch, BK, 64, true)) ) return cudaSuccess;
+   auto kern = gemm_dmma_tma_kernel<TA, TB, STAGES>;
+   static bool configured[64] = {false};
+   int dev = 0;
+   SDPK_CUDA_CHECK( cudaGetDevice(&dev) );
+   if( !configured[dev & 63] )
+   {
+      SDPK_CUDA_CHECK( cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM) );
+      configured[dev & 63] = true;
+   }
+   dim3 grid(ceil_div(m, 64), ceil_div(n, 64), batch);
+   kern<<<grid, 128, SMEM, st>>>(m, n, k, alpha, mapA, mapB, beta, C, ldc, sC, flags);
+   count_launch();
+   *done = true;
+   return cudaGetLastError();
+}
+
 template <int BM, int BN, bool TA, bool TB, int STAGES>
 cudaError_t launch(cudaStream_t st, int m, int n, int k, double alpha, const double* A, int lda, long long sA,
    const double* B, int ldb, long long sB, double beta, double* C, int ldc, long long sC, int batch, int flags)
@@ -266,6 +511,16 @@ cudaError_t gemm(cudaStream_t st, bool ta, bool tb, int m, int n, int k, double 
       if( ctas <= 2 * 148 )
          SDPK_GEMM_DISPATCH(32, 32, 8);
       SDPK_GEMM_DISPATCH(32, 32, 4);
+   }
+   if( k > 0 && gemm_variant() == 1 )
+   {
+      bool done = false;
+      cudaError_t e;
+      if( !ta && !tb ) e = launch_tma<false, false>(st, m, n, k, alpha, A, lda, sA, B, ldb, sB, beta, C, ldc, sC, batch, flags, &done);
+      else if( !ta && tb ) e = launch_tma<false, true>(st, m, n, k, alpha, A, lda, sA, B, ldb, sB, beta, C, ldc, sC, batch, flags, &done);
+      else if( ta && !tb ) e = launch_tma<true, false>(st, m, n, k, alpha, A, lda, sA, B, ldb, sB, beta, C, ldc, sC, batch, flags, &done);
+      else e = launch_tma<true, true>(st, m, n, k, alpha, A, lda, sA, B, ldb, sB, beta, C, ldc, sC, batch, flags, &done);
+      if( e != cudaSuccess || done ) return e;          // otherwise (operands the tensor maps cannot describe): the cp.async kernel
    }
    SDPK_GEMM_DISPATCH(64, 64, 3);
 #undef SDPK_GEMM_DISPATCH

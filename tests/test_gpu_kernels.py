@@ -31,6 +31,22 @@ def test_dgemm_matches_blas(gpu, cpu, m, n, k, ta, tb):
     assert np.abs(got - ref).max() <= 4e-16 * k * (np.abs(A).max() * np.abs(B).max()) * 8 + 1e-13
 
 
+@pytest.mark.parametrize("m,n,k", [(1100, 900, 333), (2000, 1000, 517), (1025, 1027, 2)])
+@pytest.mark.parametrize("ta,tb", [(False, False), (False, True), (True, False), (True, True)])
+@pytest.mark.parametrize("variant", ["tma", "cpasync"])
+def test_large_dgemm_tma_and_cp_async_variants(gpu, cpu, m, n, k, ta, tb, variant, monkeypatch):
+    """products with at least 148 tiles of 64 x 64 take the large-tile kernel: fed by TMA tensor maps (default) or by the cp.async
+    ring of round 1 (SDPCUDA_GEMM=cpasync); ragged edges are zero-filled by the TMA unit / by zero-size cp.async"""
+    monkeypatch.setenv("SDPCUDA_GEMM", variant)
+    rng = np.random.default_rng(m + 3 * n + 7 * k)
+    A = rng.standard_normal((k, m) if ta else (m, k))
+    B = rng.standard_normal((n, k) if tb else (k, n))
+    C0 = rng.standard_normal((m, n))
+    got = gpu.dgemm(A, B, ta, tb, alpha=-0.75, beta=0.5, Cin=C0)
+    ref = cpu.dgemm(A, B, ta, tb, alpha=-0.75, beta=0.5, Cin=C0)
+    assert np.abs(got - ref).max() <= 4e-16 * k * (np.abs(A).max() * np.abs(B).max()) * 8 + 1e-13
+
+
 def test_dgemm_empty_and_degenerate(gpu):
     out = gpu.dgemm(np.zeros((3, 0)), np.zeros((0, 4)), Cin=np.ones((3, 4)), beta=2.0)
     assert np.allclose(out, 2.0)
