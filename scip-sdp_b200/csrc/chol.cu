@@ -371,15 +371,19 @@ template <int NBL> constexpr size_t leaf_smem() { return sizeof(double) * ((size
 // order, and a claimed tile is owned by a running CTA, so the smallest unfinished tile can always proceed: no deadlock whatever
 // part of the grid is resident (other streams may hold SMs).  The chain POTRF(j) -> TRSM(j+1,j) -> last update of (j+1,j+1) is the
 // critical path; all other tiles of later columns are claimed early and hide behind it (look-ahead without a schedule).
-constexpr int DAG_T = 64, DAG_THREADS = 256, DAG_BK = 16, DAG_STAGES = 4, DAG_LDS = DAG_T + 4;
-constexpr size_t DAG_SMEM = sizeof(double) * (size_t)DAG_STAGES * 2 * DAG_BK * DAG_LDS;      // 69632 B >= leaf_smem<64>() and the two TRSM operand tiles
-static_assert(DAG_STAGES * 2 * DAG_BK * DAG_LDS >= 2 * DAG_T * DAG_LDS, "TRSM operands fit the ring");
+constexpr int DAG_T = 64, DAG_THREADS = 256, DAG_BK = 16, DAG_STAGES = 4, DAG_LDS = DAG_T + 4, DAG_LDK = DAG_BK + 4;
+// one ring slot: an MN-contiguous chunk [k][r] (16 x 68) plus either a second one (factor tiles) or a K-contiguous chunk [c][k] (64 x 20,
+// tiles of the inverse)
+constexpr int DAG_SLOT = DAG_BK * DAG_LDS + DAG_T * DAG_LDK;
+constexpr size_t DAG_SMEM = sizeof(double) * (size_t)DAG_STAGES * DAG_SLOT;      // 75776 B >= leaf_smem<64>() and two 64 x 68 operand tiles
+static_assert(DAG_STAGES * DAG_SLOT >= 2 * DAG_T * DAG_LDS && DAG_T * DAG_LDK >= DAG_BK * DAG_LDS, "operand tiles fit the ring");
 
 struct DagArgs
 {
    int n, T;
    double* A; int lda;
-   double* Linv; int ldi;        // optional: diagonal blocks of the inverse factor are written here as well
+   double* Linv; int ldi;        // optional: the inverse factor W = L^-1 (zeroed before the launch)
+   int winv;                     // 1: the off-diagonal tiles of W are tasks of this kernel as well (ready flag of W_ij: ready[j * T + i])
    double* Wd;                   // T packed 64 x 64 inverses of the diagonal blocks of L
    int* sync;                    // [0] tile counter, [1] abort flag, [2 ..] T*T ready flags (zeroed before the launch)
    int* info;
@@ -442,26 +446,177 @@ __device__ __forceinline__ void dag_load_chunk(double* s, const double* __restri
    }
 }
 
-__global__ void __launch_bounds__(DAG_THREADS, 2) potrf_dag_kernel(DagArgs a)
+// up to two matrices per launch (S and X of an interior-point iteration): their tiles are claimed alternately from one counter, so the
+// two dependency chains advance side by side on different SMs instead of two kernels sharing every SM
+struct DagPair { DagArgs p[2]; int count; };
+
+__global__ void __launch_bounds__(DAG_THREADS, 2) potrf_dag_kernel(const __grid_constant__ DagPair pair)
 {
    extern __shared__ __align__(16) double dsm[];
    __shared__ int s_tile, s_abort, sbad;
    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, fr = lane >> 2, fc = lane & 3;
-   const int T = a.T, n = a.n, total = T * (T + 1) / 2;
-   int* const counter = a.sync;
-   int* const abortflag = a.sync + 1;
-   int* const ready = a.sync + 2;
+   int* const counter = pair.p[0].sync;                  // one claim counter and one abort flag for the launch
+   int* const abortflag = pair.p[0].sync + 1;
+   int maxtotal = 0;
+   for( int q = 0; q < pair.count; ++q )
+      maxtotal = max(maxtotal, pair.p[q].winv ? pair.p[q].T * pair.p[q].T : pair.p[q].T * (pair.p[q].T + 1) / 2);
 
    for( ;; )
    {
       __syncthreads();                                   // the previous tile is done with shared memory and s_tile
       if( tid == 0 ) s_tile = atomicAdd(counter, 1);
       __syncthreads();
-      const int t = s_tile;
-      if( t >= total ) break;
-      int j = 0, start = 0;
-      while( start + (T - j) <= t ) { start += T - j; ++j; }
-      const int i = j + (t - start);
+      if( s_tile >= maxtotal * pair.count ) break;
+      const DagArgs& a = pair.p[s_tile % pair.count];
+      const int t = s_tile / pair.count;
+      const int T = a.T, n = a.n, total = a.winv ? T * T : T * (T + 1) / 2;
+      int* const ready = a.sync + 2;
+      if( t >= total ) continue;
+      // claim order: for c = 0, 1, ...: the factor tiles of block column c, (c,c) first, then (with the inverse) the tiles of row c of W
+      int i, j;
+      bool wtile = false;
+      if( a.winv )
+      {
+         const int c0 = t / T, idx = t - c0 * T;
+         if( idx < T - c0 ) { i = c0 + idx; j = c0; }
+         else { i = c0; j = idx - (T - c0); wtile = true; }
+      }
+      else
+      {
+         int start = 0;
+         j = 0;
+         while( start + (T - j) <= t ) { start += T - j; ++j; }
+         i = j + (t - start);
+      }
+      if( wtile )
+      {
+         // ---- W_ij = -W_ii sum_{k=j}^{i-1} L_ik W_kj  (i > j): the sum streams through the ring like the factor updates (L_ik as the
+         // MN-contiguous operand, W_kj K-contiguous), its last term waits for W_{i-1,j}; then one 64^3 product with W_ii ----
+         const int row0 = DAG_T * i, col0 = DAG_T * j;
+         double sacc[8][2];
+#pragma unroll
+         for( int jt = 0; jt < 8; ++jt ) { sacc[jt][0] = 0.0; sacc[jt][1] = 0.0; }
+         bool ok = true;
+         auto wload = [&](int cidx, int slot)
+         {
+            const int k0 = DAG_T * j + cidx * DAG_BK;                 // global k of the chunk
+            double* As = dsm + (size_t)slot * DAG_SLOT;
+            double* Bs = As + DAG_BK * DAG_LDS;
+            dag_load_chunk(As, a.A, a.lda, row0, k0, n, tid);
+            // W rows [k0, k0 + 16) x the 64 columns of tile column j -> smem [c][k]
+            for( int q = tid; q < DAG_T * (DAG_BK / 2); q += DAG_THREADS )
+            {
+               const int cc = q / (DAG_BK / 2), kq = (q % (DAG_BK / 2)) * 2;
+               dag_cp16(Bs + cc * DAG_LDK + kq, a.Linv + (size_t)(col0 + cc) * a.ldi + k0 + kq, 16);
+            }
+         };
+         auto wcompute = [&](int slot)
+         {
+            const double* As = dsm + (size_t)slot * DAG_SLOT;
+            const double* Bs = As + DAG_BK * DAG_LDS;
+#pragma unroll
+            for( int kk = 0; kk < DAG_BK; kk += 4 )
+            {
+               const double av = As[(kk + fc) * DAG_LDS + 8 * w + fr];
+#pragma unroll
+               for( int jt = 0; jt < 8; ++jt )
+               {
+                  const double bv = Bs[(8 * jt + fr) * DAG_LDK + kk + fc];
+                  dmma884(sacc[jt][0], sacc[jt][1], av, bv);
+               }
+            }
+         };
+         // flags of k-tile kt (global tile index j + kt): L_{i,j+kt} and W_{j+kt,j} (the diagonal tile publishes W_jj with L_jj)
+         auto wwait = [&](int kt)
+         {
+            const int k = j + kt;
+            return dag_wait(ready + i * T + k, (k == j) ? ready + j * T + j : ready + j * T + k, abortflag, s_abort);
+         };
+         const int nkt = i - j, nchunks = 4 * (nkt - 1);
+         auto wissue = [&](int cidx)
+         {
+            if( (cidx & 3) == 0 ) ok = wwait(cidx >> 2) && ok;
+            if( ok ) wload(cidx, cidx % DAG_STAGES);
+         };
+#pragma unroll 1
+         for( int sidx = 0; sidx < DAG_STAGES - 1; ++sidx )
+         {
+            if( sidx < nchunks ) wissue(sidx);
+            asm volatile("cp.async.commit_group;\n" ::);
+         }
+#pragma unroll 1
+         for( int cidx = 0; cidx < nchunks; ++cidx )
+         {
+            asm volatile("cp.async.wait_group %0;\n" :: "n"(DAG_STAGES - 2));
+            __syncthreads();
+            if( cidx + DAG_STAGES - 1 < nchunks ) wissue(cidx + DAG_STAGES - 1);
+            asm volatile("cp.async.commit_group;\n" ::);
+            wcompute(cidx % DAG_STAGES);
+         }
+         asm volatile("cp.async.wait_group 0;\n" ::);
+         __syncthreads();
+         if( ok )
+         {
+            ok = wwait(nkt - 1);
+            if( ok )
+            {
+#pragma unroll
+               for( int q = 0; q < 4; ++q ) wload(4 * (nkt - 1) + q, q);
+               asm volatile("cp.async.commit_group;\n" ::);
+               asm volatile("cp.async.wait_group 0;\n" ::);
+               __syncthreads();
+#pragma unroll
+               for( int q = 0; q < 4; ++q ) wcompute(q);
+            }
+         }
+         __syncthreads();
+         if( ok ) ok = dag_wait(ready + i * T + i, ready + i * T + i, abortflag, s_abort);
+         if( !ok ) break;
+         double* Ws = dsm;                               // [k][r] = W_ii[r][k]
+         double* Ss = dsm + DAG_T * DAG_LDS;             // [k][c] = S[k][c]
+         const double* Wi = a.Wd + (size_t)i * DAG_T * DAG_T;
+         for( int q = tid; q < DAG_T * (DAG_T / 2); q += DAG_THREADS )
+         {
+            const int k = q / (DAG_T / 2), r = (q % (DAG_T / 2)) * 2;
+            dag_cp16(Ws + k * DAG_LDS + r, Wi + (size_t)k * DAG_T + r, 16);
+         }
+         asm volatile("cp.async.commit_group;\n" ::);
+#pragma unroll
+         for( int jt = 0; jt < 8; ++jt )
+            *reinterpret_cast<double2*>(Ss + (8 * w + fr) * DAG_LDS + 8 * jt + 2 * fc) = make_double2(sacc[jt][0], sacc[jt][1]);
+         asm volatile("cp.async.wait_group 0;\n" ::);
+         __syncthreads();
+         double d[8][2];
+#pragma unroll
+         for( int jt = 0; jt < 8; ++jt ) { d[jt][0] = 0.0; d[jt][1] = 0.0; }
+#pragma unroll
+         for( int k0 = 0; k0 < DAG_T; k0 += 4 )
+         {
+            if( k0 > 8 * w + 7 ) continue;                // W_ii is lower triangular: W[r][k] = 0 for k > r
+            const double av = -Ws[(k0 + fc) * DAG_LDS + 8 * w + fr];
+#pragma unroll
+            for( int jt = 0; jt < 8; ++jt )
+            {
+               const double bv = Ss[(k0 + fc) * DAG_LDS + 8 * jt + fr];
+               dmma884(d[jt][0], d[jt][1], av, bv);
+            }
+         }
+         const int row = row0 + 8 * w + fr;
+         if( row < n )
+         {
+#pragma unroll
+            for( int jt = 0; jt < 8; ++jt )
+            {
+               const int col = col0 + 8 * jt + 2 * fc;
+               a.Linv[(size_t)col * a.ldi + row] = d[jt][0];
+               a.Linv[(size_t)(col + 1) * a.ldi + row] = d[jt][1];
+            }
+         }
+         __threadfence();
+         __syncthreads();
+         if( tid == 0 ) st_release(ready + j * T + i, 1);
+         continue;
+      }
       const bool diag = (i == j);
       const int row0 = DAG_T * i, col0 = DAG_T * j;
       long long* const dbg = (a.dbg != nullptr && tid == 0 && (diag || i == j + 1)) ? a.dbg + 8 * (2 * j + (diag ? 0 : 1)) : nullptr;
@@ -492,13 +647,13 @@ __global__ void __launch_bounds__(DAG_THREADS, 2) potrf_dag_kernel(DagArgs a)
       auto load_chunk = [&](int cidx, int slot)
       {
          const int kt = cidx >> 2, k0 = DAG_T * kt + (cidx & 3) * DAG_BK;
-         double* As = dsm + (size_t)slot * (2 * DAG_BK * DAG_LDS);
+         double* As = dsm + (size_t)slot * DAG_SLOT;
          dag_load_chunk(As, a.A, a.lda, row0, k0, n, tid);
          if( !diag ) dag_load_chunk(As + DAG_BK * DAG_LDS, a.A, a.lda, col0, k0, n, tid);
       };
       auto compute_chunk = [&](int slot)
       {
-         const double* As = dsm + (size_t)slot * (2 * DAG_BK * DAG_LDS);
+         const double* As = dsm + (size_t)slot * DAG_SLOT;
          const double* Bs = diag ? As : As + DAG_BK * DAG_LDS;
 #pragma unroll
          for( int kk = 0; kk < DAG_BK; kk += 4 )
@@ -762,16 +917,10 @@ int chol_variant()
    return 1;
 }
 
-// Cholesky by the tile-DAG kernel, then (if wanted) the inverse factor level by level: the diagonal 64-blocks of W = L^-1 come out
-// of the kernel, and for s = 64, 128, ... all pairs of adjacent s-blocks are joined at once, W21 = -W22 (L21 W11), as two batched
-// GEMMs per level (plus two for a shorter last pair).  work: ldw x (n + 2 CHOL_LEAF_MAX) doubles; the packed diagonal inverses and
-// the flags of the kernel live in its last 2 CHOL_LEAF_MAX columns.
-cudaError_t potrf_dag(cudaStream_t st, int n, double* A, int lda, double* Linv, int ldi, double* diaginv, double* work, int ldw, int* d_info)
+struct DagProblem { int n; double* A; int lda; double* Linv; int ldi; double* diaginv; double* work; int ldw; int* d_info; };
+
+cudaError_t potrf_dag_launch(cudaStream_t st, const DagProblem* pr, int count)
 {
-   const int T = ceil_div(n, DAG_T);
-   double* Wd = diaginv != nullptr ? diaginv : work + (size_t)ldw * n;
-   int* sync = reinterpret_cast<int*>(work + (size_t)ldw * n + (diaginv != nullptr ? 0 : (size_t)T * DAG_T * DAG_T));
-   if( (size_t)T * DAG_T * DAG_T + (size_t)(T * T + 2 + 1) / 2 > (size_t)ldw * 2 * CHOL_LEAF_MAX ) return cudaErrorInvalidValue;
    static bool configured[64] = {false};
    static int nsm[64] = {0};
    int dev = 0;
@@ -782,39 +931,78 @@ cudaError_t potrf_dag(cudaStream_t st, int n, double* A, int lda, double* Linv, 
       SDPK_CUDA_CHECK( cudaDeviceGetAttribute(&nsm[dev & 63], cudaDevAttrMultiProcessorCount, dev) );
       configured[dev & 63] = true;
    }
-   SDPK_CUDA_CHECK( cudaMemsetAsync(sync, 0, sizeof(int) * (size_t)(T * T + 2), st) );
-   DagArgs a;
-   a.n = n; a.T = T; a.A = A; a.lda = lda; a.Linv = Linv; a.ldi = ldi; a.Wd = Wd; a.sync = sync; a.info = d_info; a.dbg = g_diag_dbg;
-   const int total = T * (T + 1) / 2;
+   // the inverse factor: inside the kernel where the factorisation is bound by its dependency chain (the tiles of W hide behind
+   // it: n = 2000 1.05 -> 0.83 ms), level by level with batched GEMMs afterwards for large orders (7140: 10.3 vs 12.4 ms in the
+   // kernel); SDPCUDA_CHOL_INV=levels|kernel overrides
+   const char* ie = getenv("SDPCUDA_CHOL_INV");
+   DagPair pair;
+   pair.count = count;
+   int total = 0, maxn = 0;
+   double flops = 0.0;
+   bool inkernel[2] = {false, false};
+   for( int q = 0; q < count; ++q )
    {
-      ProfScope prof(st, PROF_DIAG, (double)n * n * n / 3.0);
-      // up to about n = 3000 the factorisation is bound by its dependency chain, not by flops: one CTA per SM is plenty and leaves the
-      // other CTA slot of every SM to the kernel of the second stream (the factorisations of S and X run side by side)
-      const int per_sm = (n <= 3072) ? 1 : 2;
-      potrf_dag_kernel<<<std::min(total, per_sm * nsm[dev & 63]), DAG_THREADS, DAG_SMEM, st>>>(a);
+      const DagProblem& P = pr[q];
+      const int T = ceil_div(P.n, DAG_T);
+      double* Wd = P.diaginv != nullptr ? P.diaginv : P.work + (size_t)P.ldw * P.n;
+      int* sync = reinterpret_cast<int*>(P.work + (size_t)P.ldw * P.n + (P.diaginv != nullptr ? 0 : (size_t)T * DAG_T * DAG_T));
+      if( (size_t)T * DAG_T * DAG_T + (size_t)(T * T + 2 + 1) / 2 > (size_t)P.ldw * 2 * CHOL_LEAF_MAX ) return cudaErrorInvalidValue;
+      SDPK_CUDA_CHECK( cudaMemsetAsync(sync, 0, sizeof(int) * (size_t)(T * T + 2), st) );
+      inkernel[q] = (P.Linv != nullptr) && (ie != nullptr ? strcmp(ie, "levels") != 0 : P.n <= 3072);
+      DagArgs& a = pair.p[q];
+      a.n = P.n; a.T = T; a.A = P.A; a.lda = P.lda; a.Linv = P.Linv; a.ldi = P.ldi; a.Wd = Wd; a.sync = sync; a.info = P.d_info;
+      a.dbg = (q == 0) ? g_diag_dbg : nullptr;
+      a.winv = inkernel[q] ? 1 : 0;
+      total = std::max(total, inkernel[q] ? T * T : T * (T + 1) / 2);
+      maxn = std::max(maxn, P.n);
+      flops += (double)P.n * P.n * P.n / 3.0 * (inkernel[q] ? 2.0 : 1.0);
+   }
+   if( count == 1 ) pair.p[1] = pair.p[0];
+   {
+      ProfScope prof(st, PROF_DIAG, flops);
+      // up to about n = 3000 the factorisation is bound by its dependency chain, not by flops: one CTA per SM is plenty (and the
+      // chain runs faster on an SM of its own)
+      const int per_sm = (maxn <= 3072) ? 1 : 2;
+      potrf_dag_kernel<<<std::min(total * count, per_sm * nsm[dev & 63]), DAG_THREADS, DAG_SMEM, st>>>(pair);
       count_launch();
       SDPK_CUDA_CHECK( cudaGetLastError() );
    }
-   if( Linv == nullptr ) return cudaSuccess;
-   for( int s = DAG_T; s < n; s *= 2 )
+   for( int q = 0; q < count; ++q )
    {
-      const int full = n / (2 * s);                       // pairs with two complete s-blocks
-      const long long sl = (long long)2 * s * ((long long)lda + 1), si = (long long)2 * s * ((long long)ldi + 1);
-      if( full > 0 )
+      const DagProblem& P = pr[q];
+      if( P.Linv == nullptr || inkernel[q] ) continue;
+      const int n = P.n, lda = P.lda, ldi = P.ldi, ldw = P.ldw;
+      double* const A = P.A; double* const Linv = P.Linv; double* const work = P.work;
+      for( int s = DAG_T; s < n; s *= 2 )
       {
-         SDPK_CUDA_CHECK( gemm(st, false, false, s, s, s, 1.0, A + s, lda, sl, Linv, ldi, si, 0.0, work, ldw, 2 * s, full, GEMM_KLO_N) );
-         SDPK_CUDA_CHECK( gemm(st, false, false, s, s, s, -1.0, Linv + (size_t)s * ldi + s, ldi, si, work, ldw, 2 * s, 0.0, Linv + s, ldi, si, full, GEMM_KHI_M) );
-      }
-      const int o = 2 * s * full, n2 = n - (o + s);       // a last pair whose second block is shorter
-      if( n2 > 0 )
-      {
-         SDPK_CUDA_CHECK( gemm(st, false, false, n2, s, s, 1.0, A + (size_t)o * lda + o + s, lda, 0, Linv + (size_t)o * ldi + o, ldi, 0, 0.0,
-            work + o, ldw, 0, 1, GEMM_KLO_N) );
-         SDPK_CUDA_CHECK( gemm(st, false, false, n2, s, n2, -1.0, Linv + (size_t)(o + s) * ldi + o + s, ldi, 0, work + o, ldw, 0, 0.0,
-            Linv + (size_t)o * ldi + o + s, ldi, 0, 1, GEMM_KHI_M) );
+         const int full = n / (2 * s);                       // pairs with two complete s-blocks
+         const long long sl = (long long)2 * s * ((long long)lda + 1), si = (long long)2 * s * ((long long)ldi + 1);
+         if( full > 0 )
+         {
+            SDPK_CUDA_CHECK( gemm(st, false, false, s, s, s, 1.0, A + s, lda, sl, Linv, ldi, si, 0.0, work, ldw, 2 * s, full, GEMM_KLO_N) );
+            SDPK_CUDA_CHECK( gemm(st, false, false, s, s, s, -1.0, Linv + (size_t)s * ldi + s, ldi, si, work, ldw, 2 * s, 0.0, Linv + s, ldi, si, full, GEMM_KHI_M) );
+         }
+         const int o = 2 * s * full, n2 = n - (o + s);       // a last pair whose second block is shorter
+         if( n2 > 0 )
+         {
+            SDPK_CUDA_CHECK( gemm(st, false, false, n2, s, s, 1.0, A + (size_t)o * lda + o + s, lda, 0, Linv + (size_t)o * ldi + o, ldi, 0, 0.0,
+               work + o, ldw, 0, 1, GEMM_KLO_N) );
+            SDPK_CUDA_CHECK( gemm(st, false, false, n2, s, n2, -1.0, Linv + (size_t)(o + s) * ldi + o + s, ldi, 0, work + o, ldw, 0, 0.0,
+               Linv + (size_t)o * ldi + o + s, ldi, 0, 1, GEMM_KHI_M) );
+         }
       }
    }
    return cudaSuccess;
+}
+
+// Cholesky by the tile-DAG kernel and (if wanted) the inverse factor: the diagonal 64-blocks of W = L^-1 come out of the leaf code,
+// the other tiles either inside the kernel or, for s = 64, 128, ..., all pairs of adjacent s-blocks joined at once,
+// W21 = -W22 (L21 W11), as two batched GEMMs per level (plus two for a shorter last pair).  work: ldw x (n + 2 CHOL_LEAF_MAX) doubles;
+// the packed diagonal inverses and the flags of the kernel live in its last 2 CHOL_LEAF_MAX columns.
+cudaError_t potrf_dag(cudaStream_t st, int n, double* A, int lda, double* Linv, int ldi, double* diaginv, double* work, int ldw, int* d_info)
+{
+   DagProblem P = {n, A, lda, Linv, ldi, diaginv, work, ldw, d_info};
+   return potrf_dag_launch(st, &P, 1);
 }
 
 } // namespace
@@ -827,6 +1015,23 @@ cudaError_t potrf_lower(cudaStream_t st, int n, double* A, int lda, double* Linv
    if( n > CHOL_LEAF_MAX && chol_variant() == 1 )
       return potrf_dag(st, n, A, lda, Linv, ldi, diaginv, work, ldw, d_info);
    return chol_rec(st, n, A, lda, Linv, ldi, diaginv, work, ldw, d_info, 0);
+}
+
+// two factorisations of the same order with inverse factors in ONE launch of the tile-DAG kernel (S and X of an interior-point
+// iteration); orders the kernel does not take (n <= CHOL_LEAF_MAX, or SDPCUDA_CHOL=rec) run one after the other
+cudaError_t potrf_lower_pair(cudaStream_t st, int n, double* A0, double* Linv0, double* work0, int* info0, double* A1, double* Linv1,
+   double* work1, int* info1, int ld, int ldw)
+{
+   if( n <= 0 ) return cudaSuccess;
+   if( n > CHOL_LEAF_MAX && chol_variant() == 1 )
+   {
+      SDPK_CUDA_CHECK( cudaMemsetAsync(Linv0, 0, sizeof(double) * (size_t)ld * n, st) );
+      SDPK_CUDA_CHECK( cudaMemsetAsync(Linv1, 0, sizeof(double) * (size_t)ld * n, st) );
+      DagProblem P[2] = {{n, A0, ld, Linv0, ld, nullptr, work0, ldw, info0}, {n, A1, ld, Linv1, ld, nullptr, work1, ldw, info1}};
+      return potrf_dag_launch(st, P, 2);
+   }
+   SDPK_CUDA_CHECK( potrf_lower(st, n, A0, ld, Linv0, ld, nullptr, work0, ldw, info0) );
+   return potrf_lower(st, n, A1, ld, Linv1, ld, nullptr, work1, ldw, info1);
 }
 
 cudaError_t trtri_lower(cudaStream_t st, int n, const double* L, int ldl, double* Linv, int ldi, double* work, int ldw)

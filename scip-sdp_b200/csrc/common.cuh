@@ -100,6 +100,10 @@ constexpr int CHOL_LEAF_MAX = 128;   // largest diagonal block factorised by one
 extern long long* g_diag_dbg;      // optional device buffer (4 x int64) receiving the phase cycle counts of the diagonal-block kernel
 cudaError_t potrf_lower(cudaStream_t st, int n, double* A, int lda, double* Linv, int ldi, double* diaginv, double* work, int ldw, int* d_info);
 cudaError_t trtri_lower(cudaStream_t st, int n, const double* L, int ldl, double* Linv, int ldi, double* work, int ldw);
+// two factorisations of the same order (each with its inverse factor) in one launch of the tile kernel: the two dependency chains
+// run side by side on different SMs
+cudaError_t potrf_lower_pair(cudaStream_t st, int n, double* A0, double* Linv0, double* work0, int* info0, double* A1, double* Linv1,
+   double* work1, int* info1, int ld, int ldw);
 // solves L L' x = b for one right-hand side using the diagonal-block inverses (x overwrites b; tmp: n doubles)
 // large orders: right-looking panels (width pb) with one panel of look-ahead on a side stream; pinv / pinvT receive the inverses
 // of the diagonal panel blocks and their transposes (ceil(n/pb) blocks of pb x pb); ev: 2*ceil(n/pb)+2 events without timing
