@@ -386,6 +386,7 @@ struct DagArgs
    int winv;                     // 1: the off-diagonal tiles of W are tasks of this kernel as well (ready flag of W_ij: ready[j * T + i])
    double* Wd;                   // T packed 64 x 64 inverses of the diagonal blocks of L
    int* sync;                    // [0] tile counter, [1] abort flag, [2 ..] T*T ready flags (zeroed before the launch)
+   long long watchdog;           // cycles a flag wait may last before the kernel aborts (0: no limit; SDPCUDA_DAG_WATCHDOG_S, default 2 s)
    int* info;
    long long* dbg;               // optional: 8 timestamps (ns) per tile of the critical chain (diagonal tiles: slot 2j, tiles (j+1,j): slot 2j+1)
 };
@@ -414,7 +415,7 @@ __device__ __forceinline__ void dag_cp16(void* smem, const void* gmem, int srcby
 }
 
 // thread 0 waits until the flags f0 and f1 are set (or the kernel is being aborted), then the whole CTA passes
-__device__ __forceinline__ bool dag_wait(const int* f0, const int* f1, int* abortflag, int& s_abort)
+__device__ __forceinline__ bool dag_wait(const int* f0, const int* f1, int* abortflag, int& s_abort, long long watchdog)
 {
    if( threadIdx.x == 0 )
    {
@@ -423,7 +424,7 @@ __device__ __forceinline__ bool dag_wait(const int* f0, const int* f1, int* abor
       while( ld_acquire(f0) == 0 || ld_acquire(f1) == 0 )
       {
          if( ld_acquire(abortflag) != 0 ) { bad = 1; break; }
-         if( clock64() - t0 > 4000000000LL ) { atomicExch(abortflag, 1); bad = 1; break; }     // ~2 s: a bug, not a wait
+         if( watchdog > 0 && clock64() - t0 > watchdog ) { atomicExch(abortflag, 1); bad = 1; break; }     // a bug, not a wait
       }
       s_abort = bad;
    }
@@ -530,7 +531,7 @@ __global__ void __launch_bounds__(DAG_THREADS, 2) potrf_dag_kernel(const __grid_
          auto wwait = [&](int kt)
          {
             const int k = j + kt;
-            return dag_wait(ready + i * T + k, (k == j) ? ready + j * T + j : ready + j * T + k, abortflag, s_abort);
+            return dag_wait(ready + i * T + k, (k == j) ? ready + j * T + j : ready + j * T + k, abortflag, s_abort, pair.p[0].watchdog);
          };
          const int nkt = i - j, nchunks = 4 * (nkt - 1);
          auto wissue = [&](int cidx)
@@ -570,7 +571,7 @@ __global__ void __launch_bounds__(DAG_THREADS, 2) potrf_dag_kernel(const __grid_
             }
          }
          __syncthreads();
-         if( ok ) ok = dag_wait(ready + i * T + i, ready + i * T + i, abortflag, s_abort);
+         if( ok ) ok = dag_wait(ready + i * T + i, ready + i * T + i, abortflag, s_abort, pair.p[0].watchdog);
          if( !ok ) break;
          double* Ws = dsm;                               // [k][r] = W_ii[r][k]
          double* Ss = dsm + DAG_T * DAG_LDS;             // [k][c] = S[k][c]
@@ -670,7 +671,7 @@ __global__ void __launch_bounds__(DAG_THREADS, 2) potrf_dag_kernel(const __grid_
       };
       auto issue = [&](int cidx)
       {
-         if( (cidx & 3) == 0 ) ok = dag_wait(ready + i * T + (cidx >> 2), ready + j * T + (cidx >> 2), abortflag, s_abort) && ok;
+         if( (cidx & 3) == 0 ) ok = dag_wait(ready + i * T + (cidx >> 2), ready + j * T + (cidx >> 2), abortflag, s_abort, pair.p[0].watchdog) && ok;
          if( ok ) load_chunk(cidx, cidx % DAG_STAGES);
       };
 #pragma unroll 1
@@ -692,7 +693,7 @@ __global__ void __launch_bounds__(DAG_THREADS, 2) potrf_dag_kernel(const __grid_
       __syncthreads();
       if( j > 0 && ok )
       {
-         ok = dag_wait(ready + i * T + (j - 1), ready + j * T + (j - 1), abortflag, s_abort);
+         ok = dag_wait(ready + i * T + (j - 1), ready + j * T + (j - 1), abortflag, s_abort, pair.p[0].watchdog);
          if( ok )
          {
 #pragma unroll
@@ -729,7 +730,7 @@ __global__ void __launch_bounds__(DAG_THREADS, 2) potrf_dag_kernel(const __grid_
       else
       {
          // ---- L_ij = C W_jj' ----
-         ok = dag_wait(ready + j * T + j, ready + j * T + j, abortflag, s_abort);
+         ok = dag_wait(ready + j * T + j, ready + j * T + j, abortflag, s_abort, pair.p[0].watchdog);
          if( !ok ) break;
          if( dbg ) dbg[2] = dag_now();                  // saw the diagonal tile
          double* Cs = dsm;                               // [k][r]
@@ -952,6 +953,10 @@ cudaError_t potrf_dag_launch(cudaStream_t st, const DagProblem* pr, int count)
       DagArgs& a = pair.p[q];
       a.n = P.n; a.T = T; a.A = P.A; a.lda = P.lda; a.Linv = P.Linv; a.ldi = P.ldi; a.Wd = Wd; a.sync = sync; a.info = P.d_info;
       a.dbg = (q == 0) ? g_diag_dbg : nullptr;
+      {
+         const char* we = getenv("SDPCUDA_DAG_WATCHDOG_S");       // compute-sanitizer slows the kernel down by orders of magnitude: 0 turns the limit off
+         a.watchdog = (long long)((we != nullptr ? atof(we) : 2.0) * 2.0e9);
+      }
       a.winv = inkernel[q] ? 1 : 0;
       total = std::max(total, inkernel[q] ? T * T : T * (T + 1) / 2);
       maxn = std::max(maxn, P.n);

@@ -23,6 +23,7 @@
 #include <cmath>
 #include <cstring>
 #include <mutex>
+#include <new>
 #include <numeric>
 #include <vector>
 
@@ -70,14 +71,57 @@ std::atomic<int> g_next_device{0};
 } // namespace
 
 // one host image of a frontier batch (all read-only arrays of all nodes, 16-byte aligned pieces)
+// byte buffer that never value-initialises and can live in pinned host memory (the joined image of a batch: 141 MB for 148 CLS nodes
+// travel at the pinned-copy rate instead of through the driver's staging buffer)
+struct ByteBuf
+{
+   unsigned char* p = nullptr;
+   size_t n = 0, cap = 0;
+   bool pinned = false;
+   ByteBuf() = default;
+   ByteBuf(const ByteBuf&) = delete;
+   ByteBuf& operator=(const ByteBuf&) = delete;
+   ~ByteBuf() { release(); }
+   size_t size() const { return n; }
+   bool empty() const { return n == 0; }
+   unsigned char* data() { return p; }
+   const unsigned char* data() const { return p; }
+   void clear() { n = 0; }
+   void release()
+   {
+      if( p != nullptr ) { if( pinned_alloc ) cudaFreeHost(p); else free(p); }
+      p = nullptr; n = cap = 0;
+   }
+   void resize(size_t want)
+   {
+      if( want > cap )
+      {
+         const size_t nc = std::max<size_t>({want, cap + cap / 2, 4096});
+         unsigned char* q = nullptr;
+         bool qpinned = false;
+         if( pinned && cudaHostAlloc((void**)&q, nc, cudaHostAllocDefault) == cudaSuccess ) qpinned = true;
+         else { cudaGetLastError(); q = static_cast<unsigned char*>(malloc(nc)); }
+         if( q == nullptr ) throw std::bad_alloc();
+         if( n > 0 ) memcpy(q, p, n);
+         if( p != nullptr ) { if( pinned_alloc ) cudaFreeHost(p); else free(p); }
+         p = q; cap = nc; pinned_alloc = qpinned;
+      }
+      n = want;
+   }
+private:
+   bool pinned_alloc = false;
+};
+
 struct BatchImage
 {
-   std::vector<unsigned char> buf;
+   ByteBuf buf;
    size_t put(const void* src, size_t bytes)
    {
-      const size_t off = (buf.size() + 15) & ~(size_t)15;
-      buf.resize(off + std::max<size_t>(bytes, 16));
+      const size_t old = buf.size(), off = (old + 15) & ~(size_t)15, len = std::max<size_t>(bytes, 16);
+      buf.resize(off + len);
+      if( off > old ) memset(buf.data() + old, 0, off - old);             // alignment gap
       if( bytes > 0 ) memcpy(buf.data() + off, src, bytes);
+      if( len > bytes ) memset(buf.data() + off + bytes, 0, len - bytes);
       return off;
    }
    template <class T> size_t putv(const std::vector<T>& v) { return put(v.data(), v.size() * sizeof(T)); }
@@ -152,7 +196,8 @@ struct sdpcuda_handle
    bool minv = false;                // explicit inverse factor of M (m <= 4096): solves become two triangular mat-vecs; above: look-ahead panels + panel substitution
    DBuf<double> partials, stats, scal, eigw, lzwork;
    DBuf<int> info;
-   BatchImage batchhost;                           // host image of the last frontier batch (kept: no page faults on the next one)
+   bool lpdup = false;                            // some LP row lists a variable twice
+   BatchImage batchhost;                           // host image of the last frontier batch (kept, pinned: no page faults, fast H2D)
    DBuf<int> ppint; DBuf<double> ppdbl, ppout; DBuf<long long> ppoff;      // staging of sdpcuda_primal_products
    DBuf<double> kflag;                            // one word: time-limit flag agreed between the ranks of a sharded solve
    double* h_stats = nullptr;     // pinned
@@ -378,6 +423,12 @@ int upload_problem(sdpcuda_handle* h, const sdpcuda_problem* P)
             colrow[q] = l; colval[q] = P->lpval[p];
          }
    }
+   // a variable that occurs twice in one row would appear twice in its column list: the deterministic Schur kernel of the LP block
+   // assumes it does not (the atomic kernel takes such problems)
+   h->lpdup = false;
+   for( int j = 0; j < m && !h->lpdup; ++j )
+      for( int q = colbeg[j] + 1; q < colbeg[j + 1]; ++q )
+         if( colrow[q] == colrow[q - 1] ) { h->lpdup = true; break; }
 
 #define UP(buf, vec) CK( h->buf.upload(vec, st) )
    std::vector<int> varbeg(P->varbeg, P->varbeg + m + 1);
@@ -814,6 +865,7 @@ int sdpcuda_create(sdpcuda_handle** out, int device)
       if( e != nullptr && e[0] >= '0' && e[0] <= '9' ) device = atoi(e);
    }
    h->device = (device >= 0) ? device % ndev : (g_next_device.fetch_add(1) % ndev);
+   h->batchhost.buf.pinned = true;
    // the side lane of the look-ahead factorisation carries the bulk GEMMs: lowest priority, so that the latency-bound panel
    // kernels of the main lane get SM slots first
    int lowprio = 0, highprio = 0;
@@ -856,6 +908,7 @@ int sdpcuda_destroy(sdpcuda_handle* h)
    h->LinvT.release(); h->LXinvT.release(); h->pinv.release(); h->pinvT.release();
    for( cudaEvent_t& e : h->evp ) if( e != nullptr ) { cudaEventDestroy(e); e = nullptr; }
    h->preX.release(); h->prey.release(); h->prex.release();
+   h->batchhost.buf.release();
    h->ppint.release(); h->ppdbl.release(); h->ppout.release(); h->ppoff.release(); h->kflag.release();
    drop_graph(h->gS); drop_graph(h->gX); drop_graph(h->gM);
    cudaEventDestroy(h->ev0); cudaEventDestroy(h->ev1); cudaEventDestroy(h->evFork); cudaEventDestroy(h->evJoin);
@@ -1502,6 +1555,8 @@ int sdpcuda_solve_batch(sdpcuda_handle* h, int count, const sdpcuda_problem* con
    if( h->packed ) { h->packed = false; h->solved = false; }      // the batch reuses the buffers of a packed single solve
    rc = batch_plan(count, probs, par, !(te != nullptr && te[0] == '0'), se != nullptr && se[0] == '1', plan);
    if( rc != SDPCUDA_OK ) return rc;
+   const bool bprof = getenv("SDPCUDA_BATCH_PROFILE") != nullptr;
+   const double tplan = now_seconds();
    if( objlimits != nullptr )
       for( size_t k = 0; k < plan.nodes.size(); ++k ) plan.nodes[k].a.objlimit = objlimits[plan.who[k]];
    BatchImage& img = plan.img;
@@ -1527,6 +1582,7 @@ int sdpcuda_solve_batch(sdpcuda_handle* h, int count, const sdpcuda_problem* con
       CK( cudaMemsetAsync(h->batchwork.p, 0, sizeof(double) * worktotal, st) );
       CK( cudaMemcpyAsync(h->batchimg.p, img.buf.data(), img.buf.size(), cudaMemcpyHostToDevice, st) );
       CK( cudaMemcpyAsync(h->batchargs.p, args.data(), sizeof(SmallArgs) * nd, cudaMemcpyHostToDevice, st) );
+      if( bprof ) { CK( cudaStreamSynchronize(st) ); fprintf(stderr, "[batch] %d nodes: plan %.2f ms, bind + memset + H2D of %.1f MB %.2f ms", nd, 1e3 * (tplan - t0), img.buf.size() / 1e6, 1e3 * (now_seconds() - tplan)); }
       CK( cudaEventRecord(h->ev0, st) );
       CK( launch_ipm_tiny_batch(st, ntiny, h->batchargs.p, plan.stagebytes[0]) );
       CK( launch_ipm_small_batch(st, nd - ntiny, h->batchargs.p + ntiny, plan.stagebytes[1]) );
@@ -1539,6 +1595,7 @@ int sdpcuda_solve_batch(sdpcuda_handle* h, int count, const sdpcuda_problem* con
       float ms = 0.f;
       cudaEventElapsedTime(&ms, h->ev0, h->ev1);
       const double wall = now_seconds() - t0;
+      if( bprof ) fprintf(stderr, ", kernels %.2f ms, whole call %.2f ms\n", ms, 1e3 * wall);
       for( int k = 0; k < nd; ++k )
       {
          const int i = who[k];
@@ -1958,7 +2015,7 @@ static int run_ipm(sdpcuda_handle* h, const sdpcuda_params* par, const double* s
          }
          // the LP block is added on top of the entries (atomics): after all plain stores into this buffer, on one rank only
          if( h->emulate_ranks > 1 || h->rank == 0 )
-            CK( schur_lp(st, nlp, h->lpbeg.p, h->lpind.p, h->lpval.p, h->x.p, h->s.p, h->M.p, h->ldm) );
+            CK( schur_lp(st, nlp, h->lpbeg.p, h->lpind.p, h->lpval.p, h->x.p, h->s.p, h->M.p, h->ldm, h->lpdup ? nullptr : h->colbeg.p, h->colrow.p, h->colval.p) );
          if( h->nranks > 1 )
          {
             rc = dist_allreduce_sum(h, h->M.p, (size_t)h->ldm * m); if( rc ) return rc;

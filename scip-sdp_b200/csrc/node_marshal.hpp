@@ -15,7 +15,10 @@
 #pragma once
 #include "host_pool.hpp"
 #include <algorithm>
+#include <chrono>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <numeric>
 #include <vector>
@@ -320,6 +323,7 @@ inline int solve_nodes(sdpcuda_handle* h, const sdpcuda_model* model, int count,
    const double epsilon = 1e-9;
    const double feastol = par->feastol > 0 ? par->feastol : 1e-6;
    // presolve + marshalling of every node: independent host work, spread over the host threads (host_pool.hpp)
+   const auto tn0 = std::chrono::steady_clock::now();
    std::vector<FlatNode> all(count);
    sdphost::Pool::get().run(count, [&](int i)
    {
@@ -351,7 +355,11 @@ inline int solve_nodes(sdpcuda_handle* h, const sdpcuda_model* model, int count,
       ys[k].assign(std::max<size_t>(flats[k].obj.size(), 1), 0.0); yp[k] = ys[k].data();
       if( cutoff != nullptr && cutoff[owner[k]] < 1e20 ) limits[k] = cutoff[owner[k]] - flats[k].fixedobj;
    }
+   const bool bprof = getenv("SDPCUDA_BATCH_PROFILE") != nullptr;
+   const auto tb0 = std::chrono::steady_clock::now();
+   if( bprof ) fprintf(stderr, "[nodes] %d nodes, %d to solve: presolve + marshalling %.2f ms\n", count, ns, 1e3 * std::chrono::duration<double>(tb0 - tn0).count());
    int rc = sdpcuda_solve_batch(h, ns, vp.data(), par, rs.data(), yp.data(), cutoff != nullptr ? limits.data() : nullptr);
+   if( bprof ) fprintf(stderr, "[nodes] solve_batch %.2f ms\n", 1e3 * std::chrono::duration<double>(std::chrono::steady_clock::now() - tb0).count());
    if( rc != SDPCUDA_OK ) return rc;
    for( int k = 0; k < ns; ++k )
    {

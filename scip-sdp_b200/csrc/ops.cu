@@ -328,6 +328,40 @@ __global__ void schur_lp_kernel(int nlp, const int* __restrict__ lpbeg, const in
    }
 }
 
+// Deterministic form of the same update (no atomics): the pair (i, j) of row r is handled by the thread of the FIRST row that contains
+// both variables; it walks the two column lists (rows ascending, built at upload) once and adds the contributions of all common rows
+// in row order.  Every entry of M has one writer, so the Schur complement is bit-reproducible from run to run and across the ranks
+// of a sharded solve.  Needs row lists without repeated variables (checked at upload; otherwise the atomic kernel is used).
+__global__ void schur_lp_det_kernel(int nlp, const int* __restrict__ lpbeg, const int* __restrict__ lpind, const int* __restrict__ colbeg,
+   const int* __restrict__ colrow, const double* __restrict__ colval, const double* __restrict__ x, const double* __restrict__ s,
+   double* __restrict__ M, int ldm)
+{
+   int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+   if( warp >= nlp ) return;
+   const int b = lpbeg[warp], cnt = lpbeg[warp + 1] - b;
+   for( int t = lane; t < cnt * cnt; t += 32 )
+   {
+      const int i = lpind[b + t / cnt], j = lpind[b + t % cnt];
+      if( i < j ) continue;
+      int a = colbeg[i], ae = colbeg[i + 1], c = colbeg[j], ce = colbeg[j + 1];
+      double total = 0.0;
+      bool first = true, mine = false;
+      while( a < ae && c < ce )
+      {
+         const int ra = colrow[a], rc = colrow[c];
+         if( ra < rc ) ++a;
+         else if( rc < ra ) ++c;
+         else
+         {
+            if( first ) { first = false; mine = (ra == warp); if( !mine ) break; }
+            total += (x[ra] / s[ra]) * colval[a] * colval[c];
+            ++a; ++c;
+         }
+      }
+      if( mine ) M[(size_t)j * ldm + i] += total;
+   }
+}
+
 __global__ void add_diagonal_kernel(int n, double* __restrict__ A, int lda, double v)
 {
    int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -675,10 +709,13 @@ cudaError_t schur_dense_scatter(cudaStream_t st, int count, int cnt, int first, 
 }
 
 cudaError_t schur_lp(cudaStream_t st, int nlp, const int* lpbeg, const int* lpind, const double* lpval, const double* x,
-   const double* s, double* M, int ldm)
+   const double* s, double* M, int ldm, const int* colbeg, const int* colrow, const double* colval)
 {
    if( nlp <= 0 ) return cudaSuccess;
-   schur_lp_kernel<<<ceil_div(nlp, 8), 256, 0, st>>>(nlp, lpbeg, lpind, lpval, x, s, M, ldm);
+   if( colbeg != nullptr )
+      schur_lp_det_kernel<<<ceil_div(nlp, 8), 256, 0, st>>>(nlp, lpbeg, lpind, colbeg, colrow, colval, x, s, M, ldm);
+   else
+      schur_lp_kernel<<<ceil_div(nlp, 8), 256, 0, st>>>(nlp, lpbeg, lpind, lpval, x, s, M, ldm);
    LAUNCH_END();
 }
 
