@@ -1407,6 +1407,20 @@ static int batch_plan(int count, const sdpcuda_problem* const* probs, const sdpc
       for( int k : tiny ) { P.nodes[k].stagelen = batch_stage_prefix(P.nodes[k], STAGE_BUDGET_TINY); P.stagebytes[0] = std::max(P.stagebytes[0], P.nodes[k].stagelen * sizeof(double)); }
       for( int k : rest ) { P.nodes[k].stagelen = batch_stage_prefix(P.nodes[k], STAGE_BUDGET_SMALL); P.stagebytes[1] = std::max(P.stagebytes[1], P.nodes[k].stagelen * sizeof(double)); }
    }
+   // Schur complements of order 65 .. 112 / 128 (example_MkP: m = 105): the launch reserves room for the packed factor behind the
+   // kernel's own buffers and the staged work space; every node of the launch learns the offset
+   for( int g = 0; g < 2; ++g )
+   {
+      const std::vector<int>& grp = (g == 0) ? tiny : rest;
+      const int mpk = (g == 0) ? TINY_MPK : SMALL_MPK;
+      const size_t own = (g == 0) ? ipm_tiny_smem_bytes() : ipm_small_smem_bytes();
+      bool want = false;
+      for( int k : grp ) want = want || (P.nodes[k].a.m > SMALL_MAX_N && P.nodes[k].a.m <= mpk);
+      const size_t off = (own + P.stagebytes[g] + 15) / 16 * 16;
+      if( !want || off + small_mpk_bytes(mpk) > 225 * 1024 ) continue;
+      for( int k : grp ) P.nodes[k].a.mpk_off = (long long)(off / sizeof(double));
+      P.stagebytes[g] = off + small_mpk_bytes(mpk) - own;
+   }
    return SDPCUDA_OK;
 }
 
@@ -1729,7 +1743,9 @@ static int run_ipm(sdpcuda_handle* h, const sdpcuda_params* par, const double* s
          for( const auto& g : h->dgroups ) if( g.count > h->dchunk ) eligible = false;
       // measured on the shipped instances: the one-launch kernel wins while the Schur complement is small (m <= 64); above that
       // the serial Cholesky of M inside a single CTA loses against the multi-kernel pipeline
-      if( eligible && force != 1 && (force == 2 || m <= 64) )
+      // (SDPCUDA_SMALL_M: the largest Schur complement of the one-launch kernel)
+      static const int small_m = []() { const char* e = getenv("SDPCUDA_SMALL_M"); return e != nullptr ? atoi(e) : 64; }();
+      if( eligible && force != 1 && (force == 2 || m <= small_m) )
       {
          SmallArgs a;
          memset(&a, 0, sizeof(a));

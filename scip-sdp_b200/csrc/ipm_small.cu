@@ -30,6 +30,11 @@ constexpr int MINB = 1;
 #endif
 constexpr int LDS = VMAXN + 1;
 constexpr int LDMS = MSN + 1;
+#ifdef SDPK_VARIANT_TINY
+constexpr int MPK = TINY_MPK;
+#else
+constexpr int MPK = SMALL_MPK;
+#endif
 
 struct Ctl                      // control block in shared memory, written by thread 0
 {
@@ -265,8 +270,25 @@ __device__ void schur(const SmallArgs& a)
    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
    for( int e = threadIdx.x; e < ldm * m; e += NT ) a.M[e] = 0.0;
    __syncthreads();
-   // pairs without a dense variable: one warp per pair (i >= j), lanes split the entry-pair product
+   // pairs without a dense variable.  Light pairs (at most SCHUR_LIGHT entry-pair terms: the one-entry matrices of example_MkP, the
+   // rank-one bars of example_TT) get ONE THREAD each - a warp per pair left 31 lanes idle and made the 5565 pairs of example_MkP
+   // 174 rounds of dependent global loads per warp; heavier pairs keep one warp per pair, the lanes split the entry-pair product
+   constexpr int SCHUR_LIGHT = 16;
    const int npairs = m * (m + 1) / 2;
+   for( int p = threadIdx.x; p < npairs; p += NT )
+   {
+      int i = (int)((sqrt(8.0 * p + 1.0) - 1.0) * 0.5);
+      while( (i + 1) * (i + 2) / 2 <= p ) ++i;
+      while( i * (i + 1) / 2 > p ) --i;
+      const int j = p - i * (i + 1) / 2;
+      if( a.cls[i] == 2 || a.cls[j] == 2 ) continue;
+      const int bi = a.E.varbeg[i], ni = a.E.varbeg[i + 1] - bi;
+      const int bj = a.E.varbeg[j], nj = a.E.varbeg[j + 1] - bj;
+      if( ni * nj > SCHUR_LIGHT ) continue;
+      double v = 0.0;
+      for( int t = 0; t < ni * nj; ++t ) v += pairterm(a.E, bi + t / nj, bj + t % nj, a.X, a.Sinv);
+      a.M[(size_t)j * ldm + i] = v;
+   }
    for( int p = wid; p < npairs; p += NT / 32 )
    {
       int i = (int)((sqrt(8.0 * p + 1.0) - 1.0) * 0.5);
@@ -276,6 +298,7 @@ __device__ void schur(const SmallArgs& a)
       if( a.cls[i] == 2 || a.cls[j] == 2 ) continue;
       const int bi = a.E.varbeg[i], ni = a.E.varbeg[i + 1] - bi;
       const int bj = a.E.varbeg[j], nj = a.E.varbeg[j + 1] - bj;
+      if( ni * nj <= SCHUR_LIGHT ) continue;
       double v = 0.0;
       for( int t = lane; t < ni * nj; t += 32 ) v += pairterm(a.E, bi + t / nj, bj + t % nj, a.X, a.Sinv);
       v = wsum(v);
@@ -342,19 +365,40 @@ __device__ void schur(const SmallArgs& a)
       a.M[(size_t)j * ldm + j] += s0;
    }
    __syncthreads();
+   // longer rows: the pair (i >= j) of row l belongs to the thread that meets it in the FIRST row containing both variables; that thread
+   // walks the two column lists (rows ascending) and adds the terms of all common longer rows in row order.  One writer per entry:
+   // no barrier between the rows (example_MkP: 30 rows of 15 variables were 30 barriers and read-modify-write round trips per
+   // iteration) and the same summation order in every run.
    for( int l = 0; l < a.nlp; ++l )
    {
       const int b = a.lpbeg[l], cnt = a.lpbeg[l + 1] - b;
       if( cnt < 2 ) continue;                               // uniform branch
-      const double w = a.x[l] / a.s[l];
       for( int t = threadIdx.x; t < cnt * cnt; t += NT )
       {
-         const int p = b + t / cnt, q = b + t % cnt;
-         const int i = a.lpind[p], j = a.lpind[q];
-         if( i >= j ) a.M[(size_t)j * ldm + i] += w * a.lpval[p] * a.lpval[q];
+         const int i = a.lpind[b + t / cnt], j = a.lpind[b + t % cnt];
+         if( i < j ) continue;
+         int pa = a.colbeg[i], ea = a.colbeg[i + 1], pc = a.colbeg[j], ec = a.colbeg[j + 1];
+         double total = 0.0;
+         bool first = true, mine = false;
+         while( pa < ea && pc < ec )
+         {
+            const int ra = a.colrow[pa], rc = a.colrow[pc];
+            if( ra < rc ) ++pa;
+            else if( rc < ra ) ++pc;
+            else
+            {
+               if( a.lpbeg[ra + 1] - a.lpbeg[ra] >= 2 )
+               {
+                  if( first ) { first = false; mine = (ra == l); if( !mine ) break; }
+                  total += (a.x[ra] / a.s[ra]) * a.colval[pa] * a.colval[pc];
+               }
+               ++pa; ++pc;
+            }
+         }
+         if( mine ) a.M[(size_t)j * ldm + i] += total;
       }
-      __syncthreads();
    }
+   __syncthreads();
 }
 
 // Cholesky of M (lower, global memory) with diagonal regularisation `reg`; rdiag receives 1 / l_kk
@@ -369,28 +413,28 @@ __device__ bool cholM(const SmallArgs& a, double reg, double* rdiag, int* flag)
    if( threadIdx.x == 0 ) *flag = 0;
    __syncthreads();
    double* F = a.Mfac;
+   // one barrier per column (same arithmetic as the shared-memory variants: the column stays unscaled while it is used, the trailing
+   // update carries 1 / d_k, all columns are scaled at the end)
    for( int k = 0; k < m; ++k )
    {
-      if( threadIdx.x == 0 )
+      double d = F[(size_t)k * ldm + k];
+      if( !(d > 0.0) ) { if( threadIdx.x == 0 ) *flag = 1; d = 1.0; }
+      const double r = frsqrt(d), rr = r * r;
+      if( threadIdx.x == 0 ) rdiag[k] = r;
+      for( int j = k + 1 + (threadIdx.x >> 5); j < m; j += NT / 32 )
       {
-         double d = F[(size_t)k * ldm + k];
-         if( !(d > 0.0) ) { *flag = 1; d = 1.0; }
-         double r = frsqrt(d);
-         rdiag[k] = r;
-         F[(size_t)k * ldm + k] = d * r;
-      }
-      __syncthreads();
-      const double r = rdiag[k];
-      for( int i = k + 1 + threadIdx.x; i < m; i += NT ) F[(size_t)k * ldm + i] *= r;
-      __syncthreads();
-      const int rem = m - k - 1;
-      for( int e = threadIdx.x; e < rem * rem; e += NT )
-      {
-         const int i = k + 1 + e % rem, j = k + 1 + e / rem;
-         if( i >= j ) F[(size_t)j * ldm + i] -= F[(size_t)k * ldm + i] * F[(size_t)k * ldm + j];
+         const double lj = F[(size_t)k * ldm + j] * rr;
+         for( int i = j + (threadIdx.x & 31); i < m; i += 32 ) F[(size_t)j * ldm + i] -= F[(size_t)k * ldm + i] * lj;
       }
       __syncthreads();
    }
+   for( int e = threadIdx.x; e < m * m; e += NT )
+   {
+      const int i = e % m, k = e / m;
+      if( i > k ) F[(size_t)k * ldm + i] *= rdiag[k];
+      else if( i == k ) { const double d = F[(size_t)k * ldm + k]; F[(size_t)k * ldm + k] = (d > 0.0 ? d : 1.0) * rdiag[k]; }
+   }
+   __syncthreads();
    const bool ok = (*flag == 0);
    __syncthreads();
    return ok;
@@ -587,26 +631,24 @@ __device__ bool cholM_smem(const SmallArgs& a, double reg, double* Ms, double* r
    __syncthreads();
    for( int k = 0; k < m; ++k )
    {
-      if( threadIdx.x == 0 )
+      double d = Ms[k * LDMS + k];
+      if( !(d > 0.0) ) { if( threadIdx.x == 0 ) *flag = 1; d = 1.0; }
+      const double r = frsqrt(d), rr = r * r;
+      if( threadIdx.x == 0 ) rdiag[k] = r;
+      for( int j = k + 1 + (threadIdx.x >> 5); j < m; j += NT / 32 )
       {
-         double d = Ms[k * LDMS + k];
-         if( !(d > 0.0) ) { *flag = 1; d = 1.0; }
-         double r = frsqrt(d);
-         rdiag[k] = r;
-         Ms[k * LDMS + k] = d * r;
-      }
-      __syncthreads();
-      const double r = rdiag[k];
-      for( int i = k + 1 + threadIdx.x; i < m; i += NT ) Ms[i * LDMS + k] *= r;
-      __syncthreads();
-      const int rem = m - k - 1;
-      for( int e = threadIdx.x; e < rem * rem; e += NT )
-      {
-         const int i = k + 1 + e % rem, j = k + 1 + e / rem;
-         if( i >= j ) Ms[i * LDMS + j] -= Ms[i * LDMS + k] * Ms[j * LDMS + k];
+         const double lj = Ms[j * LDMS + k] * rr;
+         for( int i = j + (threadIdx.x & 31); i < m; i += 32 ) Ms[i * LDMS + j] -= Ms[i * LDMS + k] * lj;
       }
       __syncthreads();
    }
+   for( int e = threadIdx.x; e < m * m; e += NT )
+   {
+      const int i = e % m, k = e / m;
+      if( i > k ) Ms[i * LDMS + k] *= rdiag[k];
+      else if( i == k ) { const double d = Ms[k * LDMS + k]; Ms[k * LDMS + k] = (d > 0.0 ? d : 1.0) * rdiag[k]; }
+   }
+   __syncthreads();
    const bool ok = (*flag == 0);
    __syncthreads();
    return ok;
@@ -638,6 +680,91 @@ __device__ void solveM_smem(int m, const double* Ms, const double* rdiag, double
    __syncthreads();
 }
 
+// ---- packed variant for MSN < m <= MPK: row i of the lower triangle at Mp + i (i + 1) / 2 ----
+__device__ bool cholM_pk(const SmallArgs& a, double reg, double* Mp, double* rdiag, int* flag)
+{
+   const int m = a.m, ldm = a.ldm;
+   for( int e = threadIdx.x; e < m * m; e += NT )
+   {
+      const int i = e % m, j = e / m;
+      if( i >= j ) Mp[i * (i + 1) / 2 + j] = a.M[(size_t)j * ldm + i] + ((i == j) ? reg : 0.0);
+   }
+   if( threadIdx.x == 0 ) *flag = 0;
+   __syncthreads();
+   // right-looking with ONE barrier per column: column k stays unscaled while it is used (every thread forms 1 / pivot itself), the
+   // trailing update carries the factor 1 / d_k, and all columns are scaled by 1 / sqrt(d_k) at the end
+   for( int k = 0; k < m; ++k )
+   {
+      double d = Mp[k * (k + 1) / 2 + k];
+      if( !(d > 0.0) ) { if( threadIdx.x == 0 ) *flag = 1; d = 1.0; }
+      const double r = frsqrt(d), rr = r * r;
+      if( threadIdx.x == 0 ) rdiag[k] = r;
+      // warp per column j of the trailing block, lanes over the rows i >= j: no integer division, lower triangle only
+      for( int j = k + 1 + (threadIdx.x >> 5); j < m; j += NT / 32 )
+      {
+         const double lj = Mp[j * (j + 1) / 2 + k] * rr;
+         for( int i = j + (threadIdx.x & 31); i < m; i += 32 ) Mp[i * (i + 1) / 2 + j] -= Mp[i * (i + 1) / 2 + k] * lj;
+      }
+      __syncthreads();
+   }
+   for( int e = threadIdx.x; e < m * m; e += NT )
+   {
+      const int i = e % m, k = e / m;
+      if( i > k ) Mp[i * (i + 1) / 2 + k] *= rdiag[k];
+      else if( i == k ) { const double d = Mp[k * (k + 1) / 2 + k]; Mp[k * (k + 1) / 2 + k] = (d > 0.0 ? d : 1.0) * rdiag[k]; }
+   }
+   __syncthreads();
+   const bool ok = (*flag == 0);
+   __syncthreads();
+   return ok;
+}
+
+// v <- (L L')^-1 v with the packed factor: one warp, lane owns the rows lane + 32 q
+__device__ void solveM_pk(int m, const double* Mp, const double* rdiag, double* v)
+{
+   __syncthreads();
+   if( threadIdx.x < 32 )
+   {
+      constexpr int Q = (MPK + 31) / 32;
+      const int lane = threadIdx.x;
+      double r[Q];
+#pragma unroll
+      for( int q = 0; q < Q; ++q ) { const int i = lane + 32 * q; r[q] = (i < m) ? v[i] : 0.0; }
+      for( int k = 0; k < m; ++k )                 // forward substitution, column k of L: entries (i, k), i > k
+      {
+         double xk = 0.0;
+#pragma unroll
+         for( int q = 0; q < Q; ++q ) if( q == (k >> 5) ) xk = r[q];
+         xk = __shfl_sync(0xffffffffu, xk, k & 31) * rdiag[k];
+#pragma unroll
+         for( int q = 0; q < Q; ++q )
+         {
+            const int i = lane + 32 * q;
+            if( i == k ) r[q] = xk;
+            else if( i > k && i < m ) r[q] -= Mp[i * (i + 1) / 2 + k] * xk;
+         }
+      }
+      for( int k = m - 1; k >= 0; --k )            // backward substitution with L': row k of L, entries (k, i), i < k (contiguous)
+      {
+         double xk = 0.0;
+#pragma unroll
+         for( int q = 0; q < Q; ++q ) if( q == (k >> 5) ) xk = r[q];
+         xk = __shfl_sync(0xffffffffu, xk, k & 31) * rdiag[k];
+         const double* row = Mp + k * (k + 1) / 2;
+#pragma unroll
+         for( int q = 0; q < Q; ++q )
+         {
+            const int i = lane + 32 * q;
+            if( i == k ) r[q] = xk;
+            else if( i < k ) r[q] -= row[i] * xk;
+         }
+      }
+#pragma unroll
+      for( int q = 0; q < Q; ++q ) { const int i = lane + 32 * q; if( i < m ) v[i] = r[q]; }
+   }
+   __syncthreads();
+}
+
 // dynamic shared memory of the body (layout at the top of ipm_small_body)
 constexpr size_t SMALL_SMEM = (2 * VMAXN * LDS + 32 + VMAXN + SMALL_MAX_M + 3 * SMALL_LZ_STEPS + 8 + 2 * (SMALL_LZ_STEPS + 2) * LDS
    + 2 * (2 * SMALL_LZ_STEPS + 64) + MSN * LDMS + 8) * sizeof(double) + sizeof(Ctl) + 64;
@@ -661,6 +788,8 @@ __device__ __forceinline__ void ipm_small_body(const SmallArgs& a)
    Ctl* c = reinterpret_cast<Ctl*>(lam2 + 8);
    int* flag = reinterpret_cast<int*>(c + 1);
    const bool msmall = (a.m <= MSN);
+   double* const Mpk = smem + a.mpk_off;                                   // packed factor, reserved by the launch when mpk_off > 0
+   const bool mpacked = !msmall && a.mpk_off > 0 && a.m <= MPK;
    const int tid = threadIdx.x;
    const int m = a.m, nb = a.nb, nlp = a.nlp;
    const double inftol = 1e-8;
@@ -856,7 +985,7 @@ __device__ __forceinline__ void ipm_small_body(const SmallArgs& a)
          bool mok = false;
          for( int tries = 0; tries < 8 && !mok; ++tries )
          {
-            mok = msmall ? cholM_smem(a, reg, Msh, rdiagM, flag) : cholM(a, reg, rdiagM, flag);
+            mok = msmall ? cholM_smem(a, reg, Msh, rdiagM, flag) : (mpacked ? cholM_pk(a, reg, Mpk, rdiagM, flag) : cholM(a, reg, rdiagM, flag));
             if( !mok ) reg = (reg == 0.0) ? 1e-14 * fmax(maxd, 1e-300) : reg * 100.0;
          }
          if( !mok )
@@ -910,10 +1039,10 @@ __device__ __forceinline__ void ipm_small_body(const SmallArgs& a)
          applyA(a, a.K, a.g);
          lpcols(a, a.klp, a.g, true);
          for( int j = tid; j < m; j += NT ) { a.g[j] -= a.rp[j]; a.dy[j] = a.g[j]; }
-         if( msmall ) solveM_smem(m, Msh, rdiagM, a.dy); else solveM(a, rdiagM, a.dy);
+         if( msmall ) solveM_smem(m, Msh, rdiagM, a.dy); else if( mpacked ) solveM_pk(m, Mpk, rdiagM, a.dy); else solveM(a, rdiagM, a.dy);
          symvM(a, a.dy, a.tm1);
          for( int j = tid; j < m; j += NT ) a.tm1[j] = a.g[j] - a.tm1[j];
-         if( msmall ) solveM_smem(m, Msh, rdiagM, a.tm1); else solveM(a, rdiagM, a.tm1);
+         if( msmall ) solveM_smem(m, Msh, rdiagM, a.tm1); else if( mpacked ) solveM_pk(m, Mpk, rdiagM, a.tm1); else solveM(a, rdiagM, a.tm1);
          for( int j = tid; j < m; j += NT ) a.dy[j] += a.tm1[j];
          __syncthreads();
          // dS = A'dy (+ Rd), dX = K - sym(X (A'dy) S^-1)
@@ -1095,12 +1224,18 @@ cudaError_t launch_ipm_small(cudaStream_t st, const SmallArgs& a)
    static bool configured[64] = {false};
    int dev = 0;
    SDPK_CUDA_CHECK( cudaGetDevice(&dev) );
+   // Schur complements of order 65 .. SMALL_MPK: room for the packed factor behind the kernel's own buffers
+   const size_t off = (SMALL_SMEM + 15) / 16 * 16;
+   const bool pk = (a.m > MSN && a.m <= MPK);
+   const size_t total = pk ? off + small_mpk_bytes(MPK) : SMALL_SMEM;
    if( !configured[dev & 63] )
    {
-      SDPK_CUDA_CHECK( cudaFuncSetAttribute(ipm_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMALL_SMEM) );
+      SDPK_CUDA_CHECK( cudaFuncSetAttribute(ipm_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(off + small_mpk_bytes(MPK))) );
       configured[dev & 63] = true;
    }
-   ipm_small_kernel<<<1, NT, SMALL_SMEM, st>>>(a);
+   SmallArgs b = a;
+   b.mpk_off = pk ? (long long)(off / sizeof(double)) : 0;
+   ipm_small_kernel<<<1, NT, total, st>>>(b);
    count_launch();
    return cudaGetLastError();
 }

@@ -12,6 +12,11 @@ constexpr int TINY_MAX_N = 16;         // blocks of the second instantiation (ip
 constexpr int SMALL_MAX_BLOCKS = 16;
 constexpr int SMALL_MAX_GROUPS = 8;
 constexpr int SMALL_LZ_STEPS = 32;     // Lanczos steps per step-length matrix (exact when the block order is smaller)
+// Schur complements of order 65 .. SMALL_MPK / TINY_MPK: the factor lives in shared memory as a packed lower triangle behind the
+// kernel's own buffers (and behind a staged work space), if the launch reserves the bytes (SmallArgs::mpk_off > 0); example_MkP
+// (m = 105) spent 57 % of its cycles in the substitutions and the factorisation of a factor that lived in global memory
+constexpr int SMALL_MPK = 128, TINY_MPK = 112;
+constexpr size_t small_mpk_bytes(int mmax) { return sizeof(double) * ((size_t)mmax * (mmax + 1) / 2 + 2); }
 
 struct SmallBlock { int n, ld; long long off; long long lzoff; };
 
@@ -53,12 +58,14 @@ struct SmallArgs
    int copyback;            // staged X, S, x, s are copied to their global addresses when the solve ends (a single packed solve whose
                             // multipliers the getters serve afterwards; a frontier batch only returns y and leaves this 0)
    long long adense_total;
+   long long mpk_off;       // doubles from the start of dynamic shared memory to the packed Schur factor (0: not reserved)
    double xil, etal;
    double xi[SMALL_MAX_BLOCKS], eta[SMALL_MAX_BLOCKS];
 };
 
 cudaError_t launch_ipm_small(cudaStream_t st, const SmallArgs& a);
 // one launch for a whole frontier of small relaxations: CTA i solves dev_args[i] (device array of `count` descriptors)
+// (stage_bytes: everything the launch reserves behind the kernel's own buffers - staged work space and packed Schur factor)
 cudaError_t launch_ipm_small_batch(cudaStream_t st, int count, const SmallArgs* dev_args, size_t stage_bytes = 0);
 // the same for relaxations whose blocks all have order <= TINY_MAX_N: CTAs of 256 threads, four per SM (ipm_tiny.cu)
 cudaError_t launch_ipm_tiny_batch(cudaStream_t st, int count, const SmallArgs* dev_args, size_t stage_bytes = 0);

@@ -27,7 +27,7 @@ class SmallArgs(C.Structure):       # mirror of sdpk::SmallArgs (csrc/ipm_small.
                 + [(k, P_) for k in "X S Sinv L Linv LX LXinv dX dS dXa dSa K T1 T2 Rd y dy g rp AX DTx tm1 tm2 "
                                      "x s dx ds dxa dsa klp rdlp Dy Ddy M Mfac Hd Ud lz".split()]
                 + [(k, C.c_double) for k in "gaptol feastol absgaptol objlimit normb normC normCsdp2 gammabase".split()]
-                + [("out", P_), ("selfinit", C.c_int), ("stage_doubles", C.c_longlong), ("workbase", P_), ("copyback", C.c_int), ("adense_total", C.c_longlong), ("xil", C.c_double), ("etal", C.c_double),
+                + [("out", P_), ("selfinit", C.c_int), ("stage_doubles", C.c_longlong), ("workbase", P_), ("copyback", C.c_int), ("adense_total", C.c_longlong), ("mpk_off", C.c_longlong), ("xil", C.c_double), ("etal", C.c_double),
                    ("xi", C.c_double * MAXB), ("eta", C.c_double * MAXB)])
 
 
