@@ -410,7 +410,9 @@ def gpu_node_workload(gpu, lib, name, rank, table, reps):
     codes, want = nodesets.frontier_of_rank(name, rank, table=table)
     lbs, ubs = nodesets.node_bounds(M, codes)
     model = abi.Model(lib, M)
-    gpu.solve_nodes(model, lbs[:min(len(codes), 8)], ubs[:min(len(codes), 8)], lean=True, **NODE_KW)      # buffers, kernel attributes, graphs
+    gpu.solve_nodes(model, lbs[:min(len(codes), 8)], ubs[:min(len(codes), 8)], lean=True, **NODE_KW)      # kernel attributes, graphs
+    if nodesets.WORKLOADS[name][2] == "nodes":
+        gpu.solve_nodes(model, lbs, ubs, lean=True, **NODE_KW)            # untimed pass at full size: device buffers and the pinned host image grow once
     wall = dev_ms = 0.0
     launches = resolved = 0
     for _ in range(reps):
