@@ -95,10 +95,13 @@ struct LeafCtx
 
 // factorisation of the block held as accumulator fragments c (warp w = 8-row strip w, lower tiles j <= w): L goes to global memory
 // (lower triangle of A) and, row-major, to G; rdg receives the reciprocals of the diagonal.  sbad: shared int of the caller.
+// pf0/pf1 (optional): two flags in global memory that thread 0 reads (relaxed, nothing waits for the loads) four macro steps before
+// the end; s_flag <- both were set (with acquire semantics for the whole CTA after the function's last barrier)
 template <int NBL>
 __device__ __forceinline__ void leaf_factor(const LeafCtx<NBL>& X, double (&c)[NBL / 8][2], int nb, double* __restrict__ A, int lda,
-   int* __restrict__ info, int pivot_offset, int& sbad)
+   int* __restrict__ info, int pivot_offset, int& sbad, const int* pf0 = nullptr, const int* pf1 = nullptr, int* s_flag = nullptr)
 {
+   int polled0 = 0, polled1 = 0;
    constexpr int NTILE = LeafCtx<NBL>::NTILE, LD = LeafCtx<NBL>::LD, NSTEP = LeafCtx<NBL>::NSTEP, NTHREADS = LeafCtx<NBL>::NTHREADS;
    double* const G = X.G; double* const Pcol = X.Pcol; double* const P = X.P; double* const rdg = X.rdg;
    const int tid = X.tid, w = X.w, fr = X.fr, fc = X.fc;
@@ -119,6 +122,11 @@ __device__ __forceinline__ void leaf_factor(const LeafCtx<NBL>& X, double (&c)[N
    {
       double* const Pc = Pcol + (t & 1) * NBL * 4;
       double* const Pp = P + (t & 1) * NBL * 4;
+      if( t == NSTEP - 4 && pf0 != nullptr && tid == 0 )
+      {
+         asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(polled0) : "l"(pf0) : "memory");
+         asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(polled1) : "l"(pf1) : "memory");
+      }
       if( t == 8 && tid == 63 ) lstamp[0] = clock64();
       // (2) panel row of every row r >= 4t
       if( tid < NBL && tid >= 4 * t )
@@ -207,9 +215,252 @@ __device__ __forceinline__ void leaf_factor(const LeafCtx<NBL>& X, double (&c)[N
          }
       }
    }
+   if( pf0 != nullptr && tid == 0 )
+   {
+      const int both = (polled0 != 0 && polled1 != 0) ? 1 : 0;
+      if( both ) asm volatile("fence.acq_rel.gpu;" ::: "memory");
+      *s_flag = both;
+   }
    __syncthreads();
    if( tid == 0 && sbad != 0x7fffffff ) atomicCAS(info, 0, pivot_offset + sbad + 1);
    if( tid == 0 && g_leaf_stamps != nullptr ) for( int q = 0; q < 6; ++q ) g_leaf_stamps[q] = lstamp[q];
+   // L -> global memory, lower triangle, column by column (coalesced)
+   for( int e = tid; e < nb * nb; e += NTHREADS )
+   {
+      const int i = e % nb, j = e / nb;
+      if( i >= j ) A[(size_t)j * lda + i] = G[(i + 1) * LD + j];
+   }
+}
+
+// reciprocal: MUFU.RCP64H seed (about 22 bits) + ONE cubically convergent step  y (1 + e + e^2), e = 1 - x y  (three dependent FMAs)
+__device__ __forceinline__ double fast_rcp64_cubic(double x)
+{
+   double y;
+   asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+   const double e = fma(-x, y, 1.0);
+   const double q = fma(e, e, e);
+   return fma(y, q, y);
+}
+
+__device__ __forceinline__ int ld_acquire(const int* p)
+{
+   int v;
+   asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+   return v;
+}
+__device__ __forceinline__ void st_release(int* p, int v)
+{
+   asm volatile("st.release.gpu.global.s32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void named_bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" :: "r"(id), "r"(count) : "memory"); }
+__device__ __forceinline__ void named_bar_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" :: "r"(id), "r"(count) : "memory"); }
+
+// ---- diagonal block of order 64, second formulation: rows in lanes, columns by warp shuffles ------------------------------------
+// The macro steps of leaf_factor cost two CTA barriers and about 240 cycles per column.  Here a block column of width 16 is
+// factorised by warps that hold ONE ROW PER LANE in registers (16 entries): lanes 0-15 the rows of the 16 x 16 diagonal block
+// (every duty warp redundantly), lanes 16-31 sixteen rows of the panel below it.  Column k inside the warp, no barrier, no shared memory:
+//      d = shfl(a[k], k)   inv = 1/d   t = a[k] inv      a[j] -= t * shfl(a[k], j)   (j > k; the shuffles do not wait for inv)
+// i.e. the elimination runs on UNSCALED columns (the dependent chain per column is shuffle -> reciprocal -> two FMAs, about 75
+// cycles); L_ik = a_ik rsqrt(d_k) is formed beside the chain.  The panel rows finish together with the diagonal block: no triangular
+// solve, no inverse of the diagonal block.  Between block columns: the 64 x 16 panel goes to shared memory, every warp applies it to
+// its strip of accumulator fragments (rank-16 update, DMMA; the two tile columns of the next block column first, handed to the
+// duty warps through shared memory and a producer/consumer barrier, the other tiles behind it), two CTA-wide barriers per 16 columns.
+// Results as leaf_factor: L to global memory and row-major to G, reciprocals of the diagonal to rdg.
+__device__ __forceinline__ void leaf_factor64(const LeafCtx<64>& X, double (&c)[8][2], int nb, double* __restrict__ A, int lda,
+   int* __restrict__ info, int pivot_offset, int& sbad, const int* pf0 = nullptr, const int* pf1 = nullptr, int* s_flag = nullptr)
+{
+   constexpr int NBL = 64, LD = LeafCtx<64>::LD, NTHREADS = LeafCtx<64>::NTHREADS, LS = 18, LP = 20;
+   constexpr unsigned FULL = 0xffffffffu;
+   double* const G = X.G; double* const rdg = X.rdg;
+   double* const S = X.Tr;                    // 64 x LS: the current block column, one row per lane
+   double* const Pp = X.Tr + NBL * LS;        // 64 x LP: the finished panel (K-contiguous DMMA operand); Tr .. P are contiguous
+   double* const Bc = Pp + NBL * LP;          // 3 duty warps x 3 x (16 x 4): broadcast buffers of the column code
+   static_assert(NBL * LS + NBL * LP + 9 * 64 <= (NBL / 2) * LD + 16 * NBL, "scratch of the shuffle formulation fits Tr + Pcol + P");
+   const int tid = X.tid, lane = X.lane, fr = X.fr, fc = X.fc;
+   const int w = __shfl_sync(FULL, X.w, 0);   // warp-uniform for the compiler: the warp-level code below runs without divergence checks
+   int polled0 = 0, polled1 = 0;
+   __shared__ long long lstamp[8];
+   if( tid == 0 ) sbad = 0x7fffffff;
+   // (the loop over the block columns is NOT unrolled: 20 KB of straight-line code per block column, executed by one to three warps;
+   // unrolled fourfold the kernel streamed its instructions from L2 and the factorisation took four times as long)
+#pragma unroll 1
+   for( int b = 0; b < 4; ++b )
+   {
+      const int jt0 = 2 * b;
+      const int ngroups = 3 - b;                         // groups of 16 panel rows below the diagonal block
+      const int nduty = (ngroups > 0) ? ngroups : 1;
+      const int wd = w - jt0;
+      const bool duty = (wd >= 0 && wd < nduty);
+      if( b == 3 && pf0 != nullptr && tid == 0 )
+      {
+         polled0 = ld_acquire(pf0);           // thread 0 has nothing else to do in this block column: nobody waits for the loads
+         polled1 = ld_acquire(pf1);
+      }
+      if( b == 1 && tid == 64 ) lstamp[0] = clock64();
+      // (1) the two tile columns of block column b: rank-16 update with the previous panel, then to shared memory
+      double av[4] = {0.0, 0.0, 0.0, 0.0};
+      if( b > 0 && w >= jt0 )
+      {
+#pragma unroll
+         for( int kk = 0; kk < 4; ++kk ) av[kk] = -Pp[(8 * w + fr) * LP + 4 * kk + fc];
+      }
+#pragma unroll
+      for( int jt = 0; jt < 8; ++jt )
+      {
+         if( (jt == jt0 || jt == jt0 + 1) && jt <= w )
+         {
+            if( b > 0 )
+            {
+#pragma unroll
+               for( int kk = 0; kk < 4; ++kk ) dmma884(c[jt][0], c[jt][1], av[kk], Pp[(8 * jt + fr) * LP + 4 * kk + fc]);
+            }
+            *reinterpret_cast<double2*>(S + (8 * w + fr) * LS + 8 * (jt - jt0) + 2 * fc) = make_double2(c[jt][0], c[jt][1]);
+         }
+      }
+      if( duty ) named_bar_sync(1, NTHREADS); else named_bar_arrive(1, NTHREADS);
+      if( b == 1 && tid == 64 ) lstamp[1] = clock64();
+      if( !duty )
+      {
+         if( b > 0 )
+         {
+            // (2) the other tiles of the strip (needed two block columns later at the earliest), and the previous panel -> G
+#pragma unroll
+            for( int jt = 2; jt < 8; ++jt )
+            {
+               if( jt >= jt0 + 2 && jt <= w )
+               {
+#pragma unroll
+                  for( int kk = 0; kk < 4; ++kk ) dmma884(c[jt][0], c[jt][1], av[kk], Pp[(8 * jt + fr) * LP + 4 * kk + fc]);
+               }
+            }
+            const int rank = (w < jt0) ? w : w - nduty, nnd = 8 - nduty;
+            for( int r = 16 * (b - 1) + 4 * rank + (lane >> 3); r < NBL; r += 4 * nnd )
+               *reinterpret_cast<double2*>(G + (r + 1) * LD + 16 * (b - 1) + 2 * (lane & 7)) = *reinterpret_cast<const double2*>(Pp + r * LP + 2 * (lane & 7));
+         }
+         named_bar_arrive(2, NTHREADS);                  // done reading the previous panel
+      }
+      else
+      {
+         // (3) block column b: one row per lane
+         const bool lower = (lane < 16);
+         const bool valid = lower || (ngroups > 0);
+         const int grow = lower ? 16 * b + lane : 16 * b + 16 + 16 * wd + (lane - 16);
+         double a[16];
+#pragma unroll
+         for( int q = 0; q < 8; ++q )
+         {
+            double2 v = make_double2(0.0, 0.0);
+            if( valid ) v = *reinterpret_cast<const double2*>(S + grow * LS + 2 * q);
+            a[2 * q] = v.x; a[2 * q + 1] = v.y;
+         }
+#pragma unroll
+         for( int j = 1; j < 16; ++j ) a[j] = (lower && j > lane) ? 0.0 : a[j];       // above the diagonal: never used, kept finite
+         if( b == 1 && tid == 64 ) lstamp[2] = clock64();
+         // 16 columns as four mini blocks of 4: inside a mini block the columns go through warp shuffles (pivot, then the
+         // entries of the 4 x 4 pivot block); the finished four columns of the diagonal rows are then broadcast ONCE through shared
+         // memory (one 32-byte store per lane, two 16-byte broadcast loads per row) for the rank-4 update of the columns to the right
+         int badk = 0x7fffffff;
+         double* const Bw = Bc + wd * 3 * 64;            // broadcast buffers of this warp: 3 mini blocks x 16 rows x 4
+         double d = __shfl_sync(FULL, a[0], 0);
+         double dmine = a[0];                            // lane l < 16: its own pivot d_l (unscaled diagonal entry at elimination time)
+#pragma unroll
+         for( int mb = 0; mb < 4; ++mb )
+         {
+            const int k0 = 4 * mb;
+            double t[4];
+            double2 f01 = make_double2(0.0, 0.0), f23 = make_double2(0.0, 0.0);      // row k0 + 4 of the broadcast, fetched early
+#pragma unroll
+            for( int q = 0; q < 4; ++q )
+            {
+               const int k = k0 + q;
+               if( q == 3 && mb < 3 )
+               {
+                  // the four columns of this lane are final (the last one needs no update from column k itself): publish them
+                  if( lower )
+                  {
+                     *reinterpret_cast<double2*>(Bw + mb * 64 + lane * 4) = make_double2(a[k0], a[k0 + 1]);
+                     *reinterpret_cast<double2*>(Bw + mb * 64 + lane * 4 + 2) = make_double2(a[k0 + 2], a[k0 + 3]);
+                  }
+                  __syncwarp();
+                  f01 = *reinterpret_cast<const double2*>(Bw + mb * 64 + (k0 + 4) * 4);
+                  f23 = *reinterpret_cast<const double2*>(Bw + mb * 64 + (k0 + 4) * 4 + 2);
+               }
+               // a non-positive pivot is reported (and the results are void); the chain itself does not wait for the test
+               badk = (!(d > 0.0) && badk == 0x7fffffff) ? 16 * b + k : badk;
+               dmine = (lane == k) ? d : dmine;
+               const double inv = fast_rcp64_cubic(d);
+               double dn = 0.0;
+               if( q < 3 )
+               {
+                  const double u1 = __shfl_sync(FULL, a[k], k + 1);
+                  const double p1 = a[k] * u1;
+                  a[k + 1] = fma(-p1, inv, a[k + 1]);
+                  dn = __shfl_sync(FULL, a[k + 1], k + 1);
+               }
+               t[q] = a[k] * inv;
+#pragma unroll
+               for( int j = k + 2; j < k0 + 4; ++j )
+               {
+                  const double u = __shfl_sync(FULL, a[k], j);
+                  a[j] = fma(-t[q], u, a[j]);
+               }
+               if( q < 3 ) d = dn;
+            }
+            if( mb < 3 )
+            {
+               a[k0 + 4] = fma(-t[3], f23.y, fma(-t[2], f23.x, fma(-t[1], f01.y, fma(-t[0], f01.x, a[k0 + 4]))));
+               d = __shfl_sync(FULL, a[k0 + 4], k0 + 4);
+#pragma unroll
+               for( int j = k0 + 5; j < 16; ++j )
+               {
+                  const double2 u01 = *reinterpret_cast<const double2*>(Bw + mb * 64 + j * 4);
+                  const double2 u23 = *reinterpret_cast<const double2*>(Bw + mb * 64 + j * 4 + 2);
+                  a[j] = fma(-t[3], u23.y, fma(-t[2], u23.x, fma(-t[1], u01.y, fma(-t[0], u01.x, a[j]))));
+               }
+            }
+         }
+         // L_ik = a_ik / sqrt(d_k): ONE reciprocal square root per lane (lane l: column l), handed round through shared memory
+         {
+            const bool badp = !(dmine > 0.0);
+            const double rsl = fast_rsqrt64(badp ? 1.0 : dmine);
+            __syncwarp();
+            if( lower ) Bw[lane] = rsl;
+            if( lower && wd == 0 ) rdg[16 * b + lane] = rsl;
+            __syncwarp();
+#pragma unroll
+            for( int q = 0; q < 8; ++q )
+            {
+               const double2 r2 = *reinterpret_cast<const double2*>(Bw + 2 * q);
+               a[2 * q] *= r2.x; a[2 * q + 1] *= r2.y;
+            }
+         }
+         if( lane == 0 && wd == 0 && badk < nb ) atomicMin(&sbad, badk);
+#pragma unroll
+         for( int j = 1; j < 16; ++j ) a[j] = (lower && j > lane) ? 0.0 : a[j];
+         // (a duty warp never has tiles right of the block column: with b > 0 at most two warps are on duty, strips 2b and 2b + 1)
+         if( b == 1 && tid == 64 ) lstamp[3] = clock64();
+         named_bar_sync(2, NTHREADS);                    // everybody is done reading the previous panel
+         if( b == 1 && tid == 64 ) lstamp[4] = clock64();
+         if( valid && (!lower || wd == 0) )
+         {
+#pragma unroll
+            for( int q = 0; q < 8; ++q )
+               *reinterpret_cast<double2*>(Pp + grow * LP + 2 * q) = make_double2(a[2 * q], a[2 * q + 1]);
+         }
+      }
+      if( b == 3 && pf0 != nullptr && tid == 0 )
+      {
+         *s_flag = (polled0 != 0 && polled1 != 0) ? 1 : 0;
+      }
+      __syncthreads();
+      if( b == 1 && tid == 64 ) lstamp[5] = clock64();
+   }
+   // the last panel -> G
+   if( tid < 128 )
+      *reinterpret_cast<double2*>(G + (48 + (tid >> 3) + 1) * LD + 48 + 2 * (tid & 7)) = *reinterpret_cast<const double2*>(Pp + (48 + (tid >> 3)) * LP + 2 * (tid & 7));
+   __syncthreads();
+   if( tid == 0 && g_leaf_stamps != nullptr ) for( int q = 0; q < 6; ++q ) g_leaf_stamps[q] = lstamp[q];
+   if( tid == 0 && sbad != 0x7fffffff ) atomicCAS(info, 0, pivot_offset + sbad + 1);
    // L -> global memory, lower triangle, column by column (coalesced)
    for( int e = tid; e < nb * nb; e += NTHREADS )
    {
@@ -317,7 +568,8 @@ leaf_kernel(int mode, int nb, double* __restrict__ A, int lda, double* __restric
       tc1 = clock64();
       if( tid == 0 ) g_leaf_stamps = (dbg != nullptr) ? dbg + 4 : nullptr;
       __syncthreads();
-      leaf_factor<NBL>(X, c, nb, A, lda, info, pivot_offset, sbad);
+      if constexpr( NBL == 64 ) leaf_factor64(X, c, nb, A, lda, info, pivot_offset, sbad);
+      else leaf_factor<NBL>(X, c, nb, A, lda, info, pivot_offset, sbad);
       if( tid == 0 ) g_leaf_stamps = nullptr;
       tc2 = clock64();
    }
@@ -377,6 +629,10 @@ constexpr int DAG_T = 64, DAG_THREADS = 256, DAG_BK = 16, DAG_STAGES = 4, DAG_LD
 constexpr int DAG_SLOT = DAG_BK * DAG_LDS + DAG_T * DAG_LDK;
 constexpr size_t DAG_SMEM = sizeof(double) * (size_t)DAG_STAGES * DAG_SLOT;      // 75776 B >= leaf_smem<64>() and two 64 x 68 operand tiles
 static_assert(DAG_STAGES * DAG_SLOT >= 2 * DAG_T * DAG_LDS && DAG_T * DAG_LDK >= DAG_BK * DAG_LDS, "operand tiles fit the ring");
+// chain variant: the diagonal-block code keeps its shared memory for the whole kernel, one 64 x 68 operand tile behind it
+constexpr size_t DAG_LEAF_DOUBLES = leaf_smem<DAG_T>() / sizeof(double);
+constexpr size_t DAG_SMEM_CHAIN = leaf_smem<DAG_T>() + sizeof(double) * (size_t)DAG_T * DAG_LDS;
+static_assert(DAG_SMEM_CHAIN >= DAG_SMEM && leaf_smem<DAG_T>() % 16 == 0, "chain layout");
 
 struct DagArgs
 {
@@ -385,7 +641,8 @@ struct DagArgs
    double* Linv; int ldi;        // optional: the inverse factor W = L^-1 (zeroed before the launch)
    int winv;                     // 1: the off-diagonal tiles of W are tasks of this kernel as well (ready flag of W_ij: ready[j * T + i])
    double* Wd;                   // T packed 64 x 64 inverses of the diagonal blocks of L
-   int* sync;                    // [0] tile counter, [1] abort flag, [2 ..] T*T ready flags (zeroed before the launch)
+   int* sync;                    // [0] tile counter, [1] abort flag, [2 ..] T*T ready flags, then 2T flags of the pre-updated tiles (zeroed before the launch)
+   int chain;                    // 1: ONE CTA carries the whole critical chain (all diagonal tiles and the tiles (j+1, j)), see dag_chain
    long long watchdog;           // cycles a flag wait may last before the kernel aborts (0: no limit; SDPCUDA_DAG_WATCHDOG_S, default 2 s)
    int* info;
    long long* dbg;               // optional: 8 timestamps (ns) per tile of the critical chain (diagonal tiles: slot 2j, tiles (j+1,j): slot 2j+1)
@@ -398,16 +655,6 @@ __device__ __forceinline__ long long dag_now()
    return t;
 }
 
-__device__ __forceinline__ int ld_acquire(const int* p)
-{
-   int v;
-   asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-   return v;
-}
-__device__ __forceinline__ void st_release(int* p, int v)
-{
-   asm volatile("st.release.gpu.global.s32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
-}
 __device__ __forceinline__ void dag_cp16(void* smem, const void* gmem, int srcbytes)
 {
    unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
@@ -447,14 +694,181 @@ __device__ __forceinline__ void dag_load_chunk(double* s, const double* __restri
    }
 }
 
+// ---- the critical chain in ONE CTA (orders up to 3072, where the factorisation is bound by its dependency chain) ----------------
+// The CTA that claims task 0 keeps the diagonal-block code's shared memory for the whole kernel and walks down the diagonal:
+//     L_jj = chol(D_j), W_jj = L_jj^-1                      (leaf code, on the accumulator fragments)      -> ready[j][j]
+//     L_{j+1,j} = P_{j+1,j} W_jj'                           (W_jj' straight out of the leaf's shared memory) -> ready[j+1][j]
+//     D_{j+1} -= L_{j+1,j} L_{j+1,j}'                       (stays in the accumulator fragments: the next leaf starts at once)
+// where P_{j+1,j} = A_{j+1,j} - sum_{k<j} L_{j+1,k} L_jk' and D_{j+1} = A_{j+1,j+1} - sum_{k<j} L_{j+1,k} L_{j+1,k}' are PRE-UPDATED
+// in place by ordinary tasks of the claim order (slots of the tiles (j,j) and (j+1,j); flags pre[2(j+1)], pre[2(j+1)+1]); they only
+// need columns < j, i.e. they are ready while the chain still factorises D_j, and P is prefetched during that leaf.  Off the chain
+// compared with one task per tile: two flag hops, the reload of W_jj, the store/reload of L_{j+1,j} and of the diagonal tile.
+__device__ __forceinline__ bool dag_chain(const DagArgs& a, double* dsm, int* abortflag, int& s_abort, int& sbad, int& s_pref, long long watchdog)
+{
+   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, fr = lane >> 2, fc = lane & 3;
+   const int T = a.T, n = a.n;
+   int* const ready = a.sync + 2;
+   int* const pre = ready + T * T;
+   const LeafCtx<DAG_T> X(dsm);
+   constexpr int LD = LeafCtx<DAG_T>::LD;
+   double* const Pt = dsm + DAG_LEAF_DOUBLES;       // [k][r], leading dimension DAG_LDS
+   double c[8][2];
+   // (everything below exists ONCE in the kernel and the inner loops are not unrolled further than the tensor pipe needs: what this
+   // CTA executes per step has to stay in the instruction cache - its warps often run alone, with nobody to hide a fetch behind)
+   int jnext = 0;                                   // the diagonal tile to load into c: 0 at the start, j + 1 inside the loop
+   if( tid == 0 ) g_leaf_stamps = (a.dbg != nullptr) ? a.dbg + 16 * T : nullptr;     // the leaf's own stamps (chain profile)
+   for( int j = -1; j < T; ++j )
+   {
+      long long* const dbg = (a.dbg != nullptr && tid == 0 && j >= 0) ? a.dbg + 16 * j : nullptr;
+      const bool has_next = (j + 1 < T);
+      bool pref = false;
+      if( j >= 0 )
+      {
+         const int col0 = DAG_T * j, nb = min(DAG_T, n - col0);
+         if( dbg ) { dbg[0] = dag_now(); dbg[1] = dbg[0]; }
+         const bool poll = has_next && j > 0;
+         // (inside this kernel the macro-step code is the faster one - 10.5 against 11.8 us per block; alone in leaf_kernel<64> the
+         // shuffle formulation wins, 17.9 k against 19.7 k cycles: profiles/r2_leaf_formulations.log)
+         leaf_factor<DAG_T>(X, c, nb, a.A + (size_t)col0 * a.lda + col0, a.lda, a.info, col0, sbad,
+            poll ? pre + 2 * (j + 1) : nullptr, poll ? pre + 2 * (j + 1) + 1 : nullptr, &s_pref);
+         if( dbg ) dbg[2] = dag_now();
+         pref = has_next && (j == 0 || s_pref != 0);     // the pre-updated tiles are there (the usual case)
+      }
+      if( j >= 0 && !has_next ) pref = false;
+      // tile (j+1, j) -> Pt, in flight during the inverse
+      if( pref )
+      {
+#pragma unroll 1
+         for( int q = 0; q < 4; ++q ) dag_load_chunk(Pt + q * DAG_BK * DAG_LDS, a.A, a.lda, DAG_T * (j + 1), DAG_T * j + q * DAG_BK, n, tid);
+         asm volatile("cp.async.commit_group;\n" ::);
+      }
+      if( j >= 0 )
+      {
+         const int col0 = DAG_T * j, nb = min(DAG_T, n - col0);
+         leaf_invert<DAG_T>(X);
+         if( dbg ) dbg[3] = dag_now();
+         double* Wj = a.Wd + (size_t)j * DAG_T * DAG_T;
+#pragma unroll 2
+         for( int e = tid; e < DAG_T * DAG_T; e += DAG_THREADS )
+         {
+            const int r = e % DAG_T, q = e / DAG_T;
+            const double v = (r < nb && q < nb && r >= q) ? X.G[q * LD + r] : 0.0;
+            Wj[(size_t)q * DAG_T + r] = v;
+            if( a.Linv != nullptr && r < nb && q < nb ) a.Linv[(size_t)(col0 + q) * a.ldi + col0 + r] = v;
+         }
+         if( dbg ) dbg[4] = dag_now();
+         // Publishing without a fence on the chain: the stores are followed by a CTA barrier, and thread 0 releases the flag later
+         // (release is cumulative over what the barrier ordered before it), when its own stores have long landed.
+         if( !has_next )
+         {
+            __syncthreads();
+            if( tid == 0 ) st_release(ready + j * T + j, 1);
+            if( dbg ) dbg[5] = dag_now();
+            break;
+         }
+         // L_jj and W_jj: released at once (thread 0 waits for the tiles of the next step anyway, and their tasks are waiting for W_jj)
+         __syncthreads();
+         if( tid == 0 ) st_release(ready + j * T + j, 1);
+         if( dbg ) { dbg[5] = dag_now(); dbg[8] = dbg[5]; dbg[9] = dbg[5]; }
+         if( !pref )
+         {
+            if( !dag_wait(pre + 2 * (j + 1), pre + 2 * (j + 1) + 1, abortflag, s_abort, watchdog) ) return false;
+#pragma unroll 1
+            for( int q = 0; q < 4; ++q ) dag_load_chunk(Pt + q * DAG_BK * DAG_LDS, a.A, a.lda, DAG_T * (j + 1), DAG_T * j + q * DAG_BK, n, tid);
+            asm volatile("cp.async.commit_group;\n" ::);
+         }
+      }
+      // the next diagonal tile -> c (pre-updated by its task; the raw tile for j + 1 = 0 and 1): the loads fly during the product below
+      {
+         const int o = DAG_T * jnext, row = o + 8 * w + fr;
+#pragma unroll
+         for( int jt = 0; jt < 8; ++jt )
+#pragma unroll
+            for( int e = 0; e < 2; ++e )
+            {
+               const int col = o + 8 * jt + 2 * fc + e;
+               double v = 0.0;
+               if( row < n && col < n && row >= col ) v = __ldcg(a.A + (size_t)col * a.lda + row);
+               if( row == col && row >= n ) v = 1.0;
+               c[jt][e] = v;
+            }
+         jnext = j + 2;
+      }
+      if( j < 0 ) continue;
+      const int col0 = DAG_T * j;
+      asm volatile("cp.async.wait_group 0;\n" ::);
+      __syncthreads();
+      if( dbg ) dbg[10] = dag_now();
+      // L_{j+1,j} = P W_jj':  B operand [k][c] = W_jj[c][k] = G[k * LD + c] for k <= c (below it the array holds L)
+      double d[8][2];
+#pragma unroll
+      for( int jt = 0; jt < 8; ++jt ) { d[jt][0] = 0.0; d[jt][1] = 0.0; }
+#pragma unroll
+      for( int k0 = 0; k0 < DAG_T; k0 += 4 )
+      {
+         const double av = Pt[(k0 + fc) * DAG_LDS + 8 * w + fr];
+#pragma unroll
+         for( int jt = 0; jt < 8; ++jt )
+         {
+            if( k0 >= 8 * jt + 8 ) continue;
+            double bv = X.G[(k0 + fc) * LD + 8 * jt + fr];
+            if( k0 + 4 > 8 * jt ) bv = (k0 + fc <= 8 * jt + fr) ? bv : 0.0;
+            dmma884(d[jt][0], d[jt][1], av, bv);
+         }
+      }
+      if( dbg ) dbg[11] = dag_now();
+      const int row = DAG_T * (j + 1) + 8 * w + fr;
+      if( row < n )
+      {
+#pragma unroll
+         for( int jt = 0; jt < 8; ++jt )
+         {
+            const int col = col0 + 8 * jt + 2 * fc;
+            a.A[(size_t)col * a.lda + row] = d[jt][0];
+            a.A[(size_t)(col + 1) * a.lda + row] = d[jt][1];
+         }
+      }
+      __syncthreads();                        // everybody is done reading Pt and G
+#pragma unroll
+      for( int jt = 0; jt < 8; ++jt )
+      {
+         Pt[(8 * jt + 2 * fc) * DAG_LDS + 8 * w + fr] = d[jt][0];
+         Pt[(8 * jt + 2 * fc + 1) * DAG_LDS + 8 * w + fr] = d[jt][1];
+      }
+      if( dbg ) dbg[12] = dag_now();
+      __syncthreads();
+      if( tid == 0 ) st_release(ready + (j + 1) * T + j, 1);   // L_{j+1,j}: the pre-updates of the next step wait for it
+      if( dbg ) dbg[13] = dag_now();
+      // D_{j+1} -= L L'
+#pragma unroll
+      for( int kk = 0; kk < DAG_T; kk += 4 )
+      {
+         const double av = -Pt[(kk + fc) * DAG_LDS + 8 * w + fr];
+#pragma unroll
+         for( int jt = 0; jt < 8; ++jt )
+         {
+            if( jt > w ) continue;
+            const double bv = Pt[(kk + fc) * DAG_LDS + 8 * jt + fr];
+            dmma884(c[jt][0], c[jt][1], av, bv);
+         }
+      }
+      // (Pt is written again only after the barriers of the next diagonal block)
+   }
+   if( tid == 0 ) g_leaf_stamps = nullptr;
+   return true;
+}
+
 // up to two matrices per launch (S and X of an interior-point iteration): their tiles are claimed alternately from one counter, so the
 // two dependency chains advance side by side on different SMs instead of two kernels sharing every SM
 struct DagPair { DagArgs p[2]; int count; };
 
+// CHAIN: the variant with the critical chain in one CTA (two instantiations rather than one kernel with both paths: the instruction
+// footprint of what the chain CTA executes per step decides how fast a lone warp is fed)
+template <bool CHAIN>
 __global__ void __launch_bounds__(DAG_THREADS, 2) potrf_dag_kernel(const __grid_constant__ DagPair pair)
 {
    extern __shared__ __align__(16) double dsm[];
-   __shared__ int s_tile, s_abort, sbad;
+   __shared__ int s_tile, s_abort, sbad, s_pref;
    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, fr = lane >> 2, fc = lane & 3;
    int* const counter = pair.p[0].sync;                  // one claim counter and one abort flag for the launch
    int* const abortflag = pair.p[0].sync + 1;
@@ -618,9 +1032,31 @@ __global__ void __launch_bounds__(DAG_THREADS, 2) potrf_dag_kernel(const __grid_
          if( tid == 0 ) st_release(ready + j * T + i, 1);
          continue;
       }
+      // chain variant: task 0 is the chain itself; the slots of the other diagonal tiles and of the tiles (j+1, j) carry the
+      // pre-updates D_{j+1} (diagonal tile (j+1, j+1) with the k-tiles < j) and P_{j+1,j}, stored back in place
+      int nk = j;                                        // k-tiles of the update
+      bool pretask = false;
+      if constexpr( CHAIN )
+      {
+         if( i == j )
+         {
+            if( j == 0 )
+            {
+               if( !dag_chain(a, dsm, abortflag, s_abort, sbad, s_pref, pair.p[0].watchdog) ) break;
+               continue;
+            }
+            if( j + 1 >= T ) continue;
+            i = j + 1; j = j + 1; pretask = true;
+         }
+         else if( i == j + 1 )
+         {
+            if( j == 0 ) continue;
+            pretask = true;
+         }
+      }
       const bool diag = (i == j);
       const int row0 = DAG_T * i, col0 = DAG_T * j;
-      long long* const dbg = (a.dbg != nullptr && tid == 0 && (diag || i == j + 1)) ? a.dbg + 8 * (2 * j + (diag ? 0 : 1)) : nullptr;
+      long long* const dbg = (a.dbg != nullptr && !CHAIN && tid == 0 && (diag || i == j + 1)) ? a.dbg + 8 * (2 * j + (diag ? 0 : 1)) : nullptr;
       if( dbg ) dbg[0] = dag_now();                     // claimed
 
       // ---- C = A_ij (diagonal tile: lower part, identity on the padding) ----
@@ -643,7 +1079,7 @@ __global__ void __launch_bounds__(DAG_THREADS, 2) potrf_dag_kernel(const __grid_
       // ---- C -= sum_k L_ik L_jk' ----
       // k-tiles 0 .. j-2 stream through the cp.async ring (their flags are usually set long before); the LAST k-tile, the one the
       // critical chain waits for, is fetched in one go after its flags - four chunks in flight at once instead of one per ring turn
-      const int nchunks = 4 * max(j - 1, 0);
+      const int nchunks = 4 * max(nk - 1, 0);
       bool ok = true;
       auto load_chunk = [&](int cidx, int slot)
       {
@@ -691,13 +1127,13 @@ __global__ void __launch_bounds__(DAG_THREADS, 2) potrf_dag_kernel(const __grid_
       }
       asm volatile("cp.async.wait_group 0;\n" ::);
       __syncthreads();
-      if( j > 0 && ok )
+      if( nk > 0 && ok )
       {
-         ok = dag_wait(ready + i * T + (j - 1), ready + j * T + (j - 1), abortflag, s_abort, pair.p[0].watchdog);
+         ok = dag_wait(ready + i * T + (nk - 1), ready + j * T + (nk - 1), abortflag, s_abort, pair.p[0].watchdog);
          if( ok )
          {
 #pragma unroll
-            for( int q = 0; q < 4; ++q ) load_chunk(4 * (j - 1) + q, q);
+            for( int q = 0; q < 4; ++q ) load_chunk(4 * (nk - 1) + q, q);
             asm volatile("cp.async.commit_group;\n" ::);
             asm volatile("cp.async.wait_group 0;\n" ::);
             __syncthreads();
@@ -709,7 +1145,26 @@ __global__ void __launch_bounds__(DAG_THREADS, 2) potrf_dag_kernel(const __grid_
       if( !ok ) break;
       if( dbg ) dbg[1] = dag_now();                     // updates done
 
-      if( diag )
+      if( pretask )
+      {
+         const int row = row0 + 8 * w + fr;
+         if( row < n )
+         {
+#pragma unroll
+            for( int jt = 0; jt < 8; ++jt )
+#pragma unroll
+               for( int e = 0; e < 2; ++e )
+               {
+                  const int col = col0 + 8 * jt + 2 * fc + e;
+                  if( col < n && (!diag || row >= col) ) a.A[(size_t)col * a.lda + row] = c[jt][e];
+               }
+         }
+         __threadfence();
+         __syncthreads();
+         if( tid == 0 ) st_release(ready + T * T + 2 * i + (diag ? 1 : 0), 1);
+         continue;
+      }
+      if( !CHAIN && diag )
       {
          const int nb = min(DAG_T, n - col0);
          const LeafCtx<DAG_T> X(dsm);
@@ -928,7 +1383,8 @@ cudaError_t potrf_dag_launch(cudaStream_t st, const DagProblem* pr, int count)
    SDPK_CUDA_CHECK( cudaGetDevice(&dev) );
    if( !configured[dev & 63] )
    {
-      SDPK_CUDA_CHECK( cudaFuncSetAttribute(potrf_dag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DAG_SMEM) );
+      SDPK_CUDA_CHECK( cudaFuncSetAttribute(potrf_dag_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) );
+      SDPK_CUDA_CHECK( cudaFuncSetAttribute(potrf_dag_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DAG_SMEM) );
       SDPK_CUDA_CHECK( cudaDeviceGetAttribute(&nsm[dev & 63], cudaDevAttrMultiProcessorCount, dev) );
       configured[dev & 63] = true;
    }
@@ -939,6 +1395,10 @@ cudaError_t potrf_dag_launch(cudaStream_t st, const DagProblem* pr, int count)
    DagPair pair;
    pair.count = count;
    int total = 0, maxn = 0;
+   for( int q = 0; q < count; ++q ) maxn = std::max(maxn, pr[q].n);
+   // the chain-in-one-CTA variant where the dependency chain is the bound (SDPCUDA_CHOL_CHAIN=0: one task per tile everywhere)
+   const char* ce = getenv("SDPCUDA_CHOL_CHAIN");
+   const bool chain = (maxn <= 3072) && !(ce != nullptr && strcmp(ce, "0") == 0);
    double flops = 0.0;
    bool inkernel[2] = {false, false};
    for( int q = 0; q < count; ++q )
@@ -947,8 +1407,8 @@ cudaError_t potrf_dag_launch(cudaStream_t st, const DagProblem* pr, int count)
       const int T = ceil_div(P.n, DAG_T);
       double* Wd = P.diaginv != nullptr ? P.diaginv : P.work + (size_t)P.ldw * P.n;
       int* sync = reinterpret_cast<int*>(P.work + (size_t)P.ldw * P.n + (P.diaginv != nullptr ? 0 : (size_t)T * DAG_T * DAG_T));
-      if( (size_t)T * DAG_T * DAG_T + (size_t)(T * T + 2 + 1) / 2 > (size_t)P.ldw * 2 * CHOL_LEAF_MAX ) return cudaErrorInvalidValue;
-      SDPK_CUDA_CHECK( cudaMemsetAsync(sync, 0, sizeof(int) * (size_t)(T * T + 2), st) );
+      if( (size_t)T * DAG_T * DAG_T + (size_t)(T * T + 2 * T + 2 + 1) / 2 > (size_t)P.ldw * 2 * CHOL_LEAF_MAX ) return cudaErrorInvalidValue;
+      SDPK_CUDA_CHECK( cudaMemsetAsync(sync, 0, sizeof(int) * (size_t)(T * T + 2 * T + 2), st) );
       inkernel[q] = (P.Linv != nullptr) && (ie != nullptr ? strcmp(ie, "levels") != 0 : P.n <= 3072);
       DagArgs& a = pair.p[q];
       a.n = P.n; a.T = T; a.A = P.A; a.lda = P.lda; a.Linv = P.Linv; a.ldi = P.ldi; a.Wd = Wd; a.sync = sync; a.info = P.d_info;
@@ -958,6 +1418,7 @@ cudaError_t potrf_dag_launch(cudaStream_t st, const DagProblem* pr, int count)
          a.watchdog = (long long)((we != nullptr ? atof(we) : 2.0) * 2.0e9);
       }
       a.winv = inkernel[q] ? 1 : 0;
+      a.chain = chain ? 1 : 0;
       total = std::max(total, inkernel[q] ? T * T : T * (T + 1) / 2);
       maxn = std::max(maxn, P.n);
       flops += (double)P.n * P.n * P.n / 3.0 * (inkernel[q] ? 2.0 : 1.0);
@@ -967,8 +1428,18 @@ cudaError_t potrf_dag_launch(cudaStream_t st, const DagProblem* pr, int count)
       ProfScope prof(st, PROF_DIAG, flops);
       // up to about n = 3000 the factorisation is bound by its dependency chain, not by flops: one CTA per SM is plenty (and the
       // chain runs faster on an SM of its own)
-      const int per_sm = (maxn <= 3072) ? 1 : 2;
-      potrf_dag_kernel<<<std::min(total * count, per_sm * nsm[dev & 63]), DAG_THREADS, DAG_SMEM, st>>>(pair);
+      const char* pe = getenv("SDPCUDA_DAG_PER_SM");
+      const int per_sm = (pe != nullptr && atoi(pe) > 0) ? atoi(pe) : ((maxn <= 3072) ? 1 : 2);
+      int grid = std::min(total * count, per_sm * nsm[dev & 63]);
+      size_t smem_chain = DAG_SMEM_CHAIN;
+      {
+         const char* ge = getenv("SDPCUDA_DAG_GRID");
+         const char* se = getenv("SDPCUDA_DAG_SMEM_KB");
+         if( ge != nullptr && atoi(ge) > 0 ) grid = std::min(grid, atoi(ge));
+         if( se != nullptr && atoi(se) > 0 ) smem_chain = std::max(smem_chain, (size_t)atoi(se) * 1024);
+      }
+      if( chain ) potrf_dag_kernel<true><<<grid, DAG_THREADS, smem_chain, st>>>(pair);
+      else potrf_dag_kernel<false><<<grid, DAG_THREADS, DAG_SMEM, st>>>(pair);
       count_launch();
       SDPK_CUDA_CHECK( cudaGetLastError() );
    }

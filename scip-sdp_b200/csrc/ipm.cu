@@ -2635,6 +2635,80 @@ __global__ void latency_probe_kernel(double* out, double seed)
    if( x == 123.456 ) out[7] = x;
    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(n1));
    if( tid == 0 ) { out[5] = (double)(n1 - n0); }
+   // issue rate of independent DFMAs: one warp alone (8 chains), then all 8 warps; MUFU.RSQ64H / RCP64H dependent latency;
+   // DMMA.8x8x4 dependent latency and issue rate of one warp (4 chains)
+   __syncthreads();
+   {
+      double c0 = seed, c1 = seed + 1, c2 = seed + 2, c3 = seed + 3, c4 = seed + 4, c5 = seed + 5, c6 = seed + 6, c7 = seed + 7;
+      const double m = 1.0000001, b = 1e-9;
+      for( int pass = 0; pass < 2; ++pass )
+      {
+         __syncthreads();
+         if( pass == 1 || tid < 32 )
+         {
+            t0 = clock64();
+#pragma unroll 4
+            for( int i = 0; i < 1024; ++i )
+            {
+               c0 = fma(c0, m, b); c1 = fma(c1, m, b); c2 = fma(c2, m, b); c3 = fma(c3, m, b);
+               c4 = fma(c4, m, b); c5 = fma(c5, m, b); c6 = fma(c6, m, b); c7 = fma(c7, m, b);
+            }
+            t1 = clock64();
+            if( tid == 0 ) out[8 + pass] = (double)(t1 - t0) / (8.0 * 1024.0);
+         }
+      }
+      if( c0 + c1 + c2 + c3 + c4 + c5 + c6 + c7 == 123.456 ) out[7] = c0;
+      __syncthreads();
+      double y = seed + 3.0;
+      t0 = clock64();
+      for( int i = 0; i < 1024; ++i ) { double r; asm volatile("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(y)); y = r + 2.0; }
+      t1 = clock64();
+      if( tid == 0 ) out[10] = (double)(t1 - t0) / 1024.0;        // includes one DADD
+      if( y == 123.456 ) out[7] = y;
+      t0 = clock64();
+      for( int i = 0; i < 1024; ++i ) { double r; asm volatile("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(y)); y = r + 2.0; }
+      t1 = clock64();
+      if( tid == 0 ) out[11] = (double)(t1 - t0) / 1024.0;
+      if( y == 123.456 ) out[7] = y;
+      __syncthreads();
+      double d0 = 0, d1 = 0, e0 = 0, e1 = 0, f0 = 0, f1 = 0, g0 = 0, g1 = 0;
+      const double av = seed * 1e-3, bv = 1e-3;
+      if( tid < 32 )
+      {
+         t0 = clock64();
+         for( int i = 0; i < 1024; ++i ) dmma884(d0, d1, av, bv);
+         t1 = clock64();
+         if( tid == 0 ) out[12] = (double)(t1 - t0) / 1024.0;
+         t0 = clock64();
+         for( int i = 0; i < 1024; ++i ) { dmma884(d0, d1, av, bv); dmma884(e0, e1, av, bv); dmma884(f0, f1, av, bv); dmma884(g0, g1, av, bv); }
+         t1 = clock64();
+         if( tid == 0 ) out[13] = (double)(t1 - t0) / 4096.0;
+      }
+      if( d0 + d1 + e0 + e1 + f0 + f1 + g0 + g1 == 123.456 ) out[7] = d0;
+      // dependent chains of one warp: 64-bit shuffle (+ DADD), FP64 compare + select (+ DMUL), shared-memory store/load round trip
+      __syncthreads();
+      if( tid < 32 )
+      {
+         double z = seed + tid;
+         t0 = clock64();
+         for( int i = 0; i < 1024; ++i ) z = __shfl_sync(0xffffffffu, z, (tid + 1) & 31) + 1.0;
+         t1 = clock64();
+         if( tid == 0 ) out[14] = (double)(t1 - t0) / 1024.0;
+         if( z == 123.456 ) out[7] = z;
+         z = seed + 0.25 * tid;
+         t0 = clock64();
+         for( int i = 0; i < 1024; ++i ) { const bool bad = !(z > 0.0); z = (bad ? 1.0 : z) * 1.0000001; }
+         t1 = clock64();
+         if( tid == 0 ) out[15] = (double)(t1 - t0) / 1024.0;
+         if( z == 123.456 ) out[7] = z;
+         z = seed + tid;
+         t0 = clock64();
+         for( int i = 0; i < 1024; ++i ) { sm[tid] = z; __syncwarp(); z = sm[(tid + 1) & 31] + 1.0; __syncwarp(); }
+         t1 = clock64();
+         if( tid == 0 ) out[16] = (double)(t1 - t0) / 1024.0;
+         if( z == 123.456 ) out[7] = z;
+      }
+   }
 }
 
 __global__ void fill_random_kernel(size_t n, double* a, unsigned seed, double diagboost, int ld)
@@ -2699,8 +2773,12 @@ int sdpcuda_time_kernel(sdpcuda_handle* h, int kind, int n, int reps, double* ms
       }
       g_diag_dbg = nullptr;
       printf("[leaf kernel %d phases, cycles] load %lld  factor %lld  store L + inverse %lld  store inverse %lld\n", nl, hv[0], hv[1], hv[2], hv[3]);
-      printf("[leaf kernel %d macro step 8, cycles] pivot chain + panel rows %lld  barrier %lld  first tile + hand-over %lld  barrier %lld  whole step %lld\n",
-         nl, hv[5] - hv[4], hv[6] - hv[5], hv[7] - hv[6], hv[8] - hv[7], hv[9] - hv[8]);
+      if( nl == 64 )
+         printf("[leaf kernel 64 block column 1, cycles] update + hand-over %lld  row loads %lld  16 columns in the warp %lld  barrier %lld  panel stores + barrier %lld\n",
+            hv[5] - hv[4], hv[6] - hv[5], hv[7] - hv[6], hv[8] - hv[7], hv[9] - hv[8]);
+      else
+         printf("[leaf kernel %d macro step 8, cycles] pivot chain + panel rows %lld  barrier %lld  first tile + hand-over %lld  barrier %lld  whole step %lld\n",
+            nl, hv[5] - hv[4], hv[6] - hv[5], hv[7] - hv[6], hv[8] - hv[7], hv[9] - hv[8]);
       *ms_per_launch = (double)hv[1]; *work = (double)hv[2];
       return SDPCUDA_OK;
    }
@@ -2708,17 +2786,17 @@ int sdpcuda_time_kernel(sdpcuda_handle* h, int kind, int n, int reps, double* ms
    {
       // critical chain of the tile-DAG Cholesky at order n: timestamps per diagonal tile and first sub-diagonal tile
       const int T = (n + 63) / 64;
-      CK( h->kA.ensure(nn) ); CK( h->kB.ensure(nn) ); CK( h->kC.ensure((size_t)16 * T + 16) ); CK( h->kW.ensure((size_t)ld * (n + 2 * CHOL_LEAF_MAX)) ); CK( h->info.ensure(8) );
+      CK( h->kA.ensure(nn) ); CK( h->kB.ensure(nn) ); CK( h->kC.ensure((size_t)16 * T + 32) ); CK( h->kW.ensure((size_t)ld * (n + 2 * CHOL_LEAF_MAX)) ); CK( h->info.ensure(8) );
       fill_random_kernel<<<1024, 256, 0, st>>>(nn, h->kA.p, 17u, (double)n, ld);
       CK( sym_average(st, n, h->kA.p, ld, nullptr) );
-      std::vector<long long> hv((size_t)16 * T);
+      std::vector<long long> hv((size_t)16 * T + 8);
       g_diag_dbg = reinterpret_cast<long long*>(h->kC.p);
       for( int r = 0; r < 3; ++r )
       {
-         CK( cudaMemsetAsync(h->kC.p, 0, sizeof(double) * 16 * T, st) );
+         CK( cudaMemsetAsync(h->kC.p, 0, sizeof(double) * (16 * T + 8), st) );
          CK( cudaMemcpyAsync(h->kB.p, h->kA.p, nn * sizeof(double), cudaMemcpyDeviceToDevice, st) );
          CK( potrf_lower(st, n, h->kB.p, ld, nullptr, 0, nullptr, h->kW.p, ld, h->info.p) );
-         CK( cudaMemcpyAsync(hv.data(), h->kC.p, sizeof(long long) * 16 * T, cudaMemcpyDeviceToHost, st) );
+         CK( cudaMemcpyAsync(hv.data(), h->kC.p, sizeof(long long) * (16 * T + 8), cudaMemcpyDeviceToHost, st) );
          CK( cudaStreamSynchronize(st) );
       }
       g_diag_dbg = nullptr;
@@ -2740,14 +2818,20 @@ int sdpcuda_time_kernel(sdpcuda_handle* h, int kind, int n, int reps, double* ms
       printf("[dag chain] n %d, %d steps, mean us per step: factor %.2f  inverse %.2f  store+publish %.2f | hop %.2f  W load+product %.2f  store+publish %.2f | hop+last update %.2f   total %.2f us\n",
          n, T - 1, sum[0] / (T - 1), sum[1] / (T - 1), sum[2] / (T - 1), sum[3] / (T - 1), sum[4] / (T - 1), sum[5] / (T - 1), sum[6] / (T - 1),
          (hv[(size_t)16 * (T - 1) + 5] - t00) / 1e3);
+      {
+         const long long* ls = &hv[(size_t)16 * T];
+         if( ls[5] != 0 )
+            printf("[dag chain] diagonal-block code inside the chain, block column 1, cycles: update + hand-over %lld  row loads %lld  16 columns in the warp %lld  barrier %lld  panel stores + barrier %lld\n",
+               ls[1] - ls[0], ls[2] - ls[1], ls[3] - ls[2], ls[4] - ls[3], ls[5] - ls[4]);
+      }
       *ms_per_launch = (hv[(size_t)16 * (T - 1) + 5] - t00) / 1e6; *work = (double)n * n * n / 3.0;
       return SDPCUDA_OK;
    }
    if( kind == 8 )
    {
       // latency probe: ms_per_launch <- DFMA dependent latency (cycles), work <- packed text is printed to stdout
-      CK( h->kA.ensure(16) );
-      double hv[8];
+      CK( h->kA.ensure(32) );
+      double hv[20];
       for( int r = 0; r < 2; ++r )
       {
          latency_probe_kernel<<<1, 256, 0, st>>>(h->kA.p, 1.0);
@@ -2757,6 +2841,9 @@ int sdpcuda_time_kernel(sdpcuda_handle* h, int kind, int n, int reps, double* ms
       }
       printf("[latency probe] dependent DFMA %.1f cyc, dependent LDS %.1f cyc, __syncthreads(256) %.1f cyc, rsqrt+2 Newton chain %.1f cyc, kernel %.1f us\n",
          hv[0], hv[1], hv[2], hv[3], hv[5] / 1e3);
+      printf("[latency probe] independent DFMA issue: one warp %.2f cyc, 8 warps %.2f cyc per warp instruction; MUFU.RSQ64H+DADD %.1f cyc, MUFU.RCP64H+DADD %.1f cyc; DMMA.8x8x4 dependent %.1f cyc, 4 chains of one warp %.1f cyc per DMMA\n",
+         hv[8], hv[9], hv[10], hv[11], hv[12], hv[13]);
+      printf("[latency probe] dependent 64-bit SHFL+DADD %.1f cyc, DSETP+FSEL+DMUL %.1f cyc, STS+LDS round trip (+DADD, two __syncwarp) %.1f cyc\n", hv[14], hv[15], hv[16]);
       *ms_per_launch = hv[0]; *work = hv[1];
       return SDPCUDA_OK;
    }

@@ -1,0 +1,19 @@
+set -x
+mkdir -p gpurun_out
+timeout 600 python -m pytest tests/test_gpu_kernels.py -m gpu -q -x 2>&1 | tail -5
+cat > /tmp/potrf_t.py <<'P'
+import os, sys
+sys.path.insert(0, os.getcwd())
+from scip_sdp_b200 import abi
+g = abi.Solver(abi.Lib(abi.PRODUCT_LIB), device=0)
+for n in (1000, 2000, 3000):
+    for kind, name in ((3, "potrf"), (2, "potrf+inverse")):
+        ms, fl = g.time_kernel(kind, n, 10)
+        print(f"  {name:14s} n={n:5d} {ms:8.3f} ms {fl / ms / 1e9:6.2f} TF/s", flush=True)
+g.time_kernel(10, 2000, 1)
+P
+timeout 300 python /tmp/potrf_t.py 2>&1 | tee gpurun_out/r2o_potrf_chain.log
+SDPCUDA_CHOL_CHAIN=0 timeout 300 python /tmp/potrf_t.py 2>&1 | tee gpurun_out/r2o_potrf_nochain.log
+timeout 300 python bench.py --no-nodes --no-cpu-baseline > gpurun_out/r2o_bench.json 2>> gpurun_out/r2o_bench.err; python -c "
+import json; d=json.load(open('gpurun_out/r2o_bench.json')); r=d['roofline']; print(d['value'], d['ms_per_step'], d['e2e']['value'], r['profiled_solve_ms'], r['share_of_step'], d['kernels'])"
+tail -3 gpurun_out/r2o_bench.err
