@@ -197,6 +197,7 @@ struct sdpcuda_handle
    DBuf<double> partials, stats, scal, eigw, lzwork;
    DBuf<int> info;
    bool lpdup = false;                            // some LP row lists a variable twice
+   int lpmaxcnt = 0;                              // longest LP row (grid of the deterministic Schur kernel of the LP block)
    BatchImage batchhost;                           // host image of the last frontier batch (kept, pinned: no page faults, fast H2D)
    DBuf<int> ppint; DBuf<double> ppdbl, ppout; DBuf<long long> ppoff;      // staging of sdpcuda_primal_products
    DBuf<double> kflag;                            // one word: time-limit flag agreed between the ranks of a sharded solve
@@ -426,6 +427,8 @@ int upload_problem(sdpcuda_handle* h, const sdpcuda_problem* P)
    // a variable that occurs twice in one row would appear twice in its column list: the deterministic Schur kernel of the LP block
    // assumes it does not (the atomic kernel takes such problems)
    h->lpdup = false;
+   h->lpmaxcnt = 0;
+   for( int l = 0; l < nlp; ++l ) h->lpmaxcnt = std::max(h->lpmaxcnt, lpbeg[l + 1] - lpbeg[l]);
    for( int j = 0; j < m && !h->lpdup; ++j )
       for( int q = colbeg[j] + 1; q < colbeg[j + 1]; ++q )
          if( colrow[q] == colrow[q - 1] ) { h->lpdup = true; break; }
@@ -2031,7 +2034,7 @@ static int run_ipm(sdpcuda_handle* h, const sdpcuda_params* par, const double* s
          }
          // the LP block is added on top of the entries (atomics): after all plain stores into this buffer, on one rank only
          if( h->emulate_ranks > 1 || h->rank == 0 )
-            CK( schur_lp(st, nlp, h->lpbeg.p, h->lpind.p, h->lpval.p, h->x.p, h->s.p, h->M.p, h->ldm, h->lpdup ? nullptr : h->colbeg.p, h->colrow.p, h->colval.p) );
+            CK( schur_lp(st, nlp, h->lpbeg.p, h->lpind.p, h->lpval.p, h->x.p, h->s.p, h->M.p, h->ldm, h->lpdup ? nullptr : h->colbeg.p, h->colrow.p, h->colval.p, h->lpmaxcnt) );
          if( h->nranks > 1 )
          {
             rc = dist_allreduce_sum(h, h->M.p, (size_t)h->ldm * m); if( rc ) return rc;

@@ -336,30 +336,30 @@ __global__ void schur_lp_det_kernel(int nlp, const int* __restrict__ lpbeg, cons
    const int* __restrict__ colrow, const double* __restrict__ colval, const double* __restrict__ x, const double* __restrict__ s,
    double* __restrict__ M, int ldm)
 {
-   int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-   if( warp >= nlp ) return;
-   const int b = lpbeg[warp], cnt = lpbeg[warp + 1] - b;
-   for( int t = lane; t < cnt * cnt; t += 32 )
+   // one THREAD per pair of a row (grid.x = row, grid.y covers the cnt^2 pairs of the longest row): a row with 100 variables is 10^4
+   // independent list walks, not 300 rounds of one warp (CLS-syn: 874 -> 20 us per launch)
+   const int row = blockIdx.x;
+   const int b = lpbeg[row], cnt = lpbeg[row + 1] - b;
+   const int t = blockIdx.y * blockDim.x + threadIdx.x;
+   if( t >= cnt * cnt ) return;
+   const int i = lpind[b + t / cnt], j = lpind[b + t % cnt];
+   if( i < j ) return;
+   int a = colbeg[i], ae = colbeg[i + 1], c = colbeg[j], ce = colbeg[j + 1];
+   double total = 0.0;
+   bool first = true;
+   while( a < ae && c < ce )
    {
-      const int i = lpind[b + t / cnt], j = lpind[b + t % cnt];
-      if( i < j ) continue;
-      int a = colbeg[i], ae = colbeg[i + 1], c = colbeg[j], ce = colbeg[j + 1];
-      double total = 0.0;
-      bool first = true, mine = false;
-      while( a < ae && c < ce )
+      const int ra = colrow[a], rc = colrow[c];
+      if( ra < rc ) ++a;
+      else if( rc < ra ) ++c;
+      else
       {
-         const int ra = colrow[a], rc = colrow[c];
-         if( ra < rc ) ++a;
-         else if( rc < ra ) ++c;
-         else
-         {
-            if( first ) { first = false; mine = (ra == warp); if( !mine ) break; }
-            total += (x[ra] / s[ra]) * colval[a] * colval[c];
-            ++a; ++c;
-         }
+         if( first ) { first = false; if( ra != row ) return; }       // the pair belongs to the first row that holds both variables
+         total += (x[ra] / s[ra]) * colval[a] * colval[c];
+         ++a; ++c;
       }
-      if( mine ) M[(size_t)j * ldm + i] += total;
    }
+   if( !first ) M[(size_t)j * ldm + i] += total;
 }
 
 __global__ void add_diagonal_kernel(int n, double* __restrict__ A, int lda, double v)
@@ -709,11 +709,15 @@ cudaError_t schur_dense_scatter(cudaStream_t st, int count, int cnt, int first, 
 }
 
 cudaError_t schur_lp(cudaStream_t st, int nlp, const int* lpbeg, const int* lpind, const double* lpval, const double* x,
-   const double* s, double* M, int ldm, const int* colbeg, const int* colrow, const double* colval)
+   const double* s, double* M, int ldm, const int* colbeg, const int* colrow, const double* colval, int maxcnt)
 {
    if( nlp <= 0 ) return cudaSuccess;
-   if( colbeg != nullptr )
-      schur_lp_det_kernel<<<ceil_div(nlp, 8), 256, 0, st>>>(nlp, lpbeg, lpind, colbeg, colrow, colval, x, s, M, ldm);
+   if( colbeg != nullptr && maxcnt > 0 && maxcnt <= 2048 )
+   {
+      const int threads = (maxcnt * maxcnt >= 128) ? 128 : 32;
+      dim3 grid(nlp, ceil_div(maxcnt * maxcnt, threads));
+      schur_lp_det_kernel<<<grid, threads, 0, st>>>(nlp, lpbeg, lpind, colbeg, colrow, colval, x, s, M, ldm);
+   }
    else
       schur_lp_kernel<<<ceil_div(nlp, 8), 256, 0, st>>>(nlp, lpbeg, lpind, lpval, x, s, M, ldm);
    LAUNCH_END();
