@@ -160,6 +160,10 @@ struct sdpcuda_handle
    DBuf<double> y, dy, g, rp, AX, DTx, tm1, tm2;
    DBuf<double> x, s, dx, ds, dxa, dsa, klp, rdlp, Dy, Ddy;
    DBuf<double> M, Mfac, diaginv, Mwork, MLinv, Adense, Hd, Ud, Cd;
+   // rank-one constraint matrices A_j = sigma_j a_j a_j' of one block (class 3): their mutual Schur entries come from two GEMM pairs,
+   // M_ij = sigma_i sigma_j (a_i' X a_j)(a_i' S^-1 a_j) = [(A' X A) o (A' S^-1 A)]_ij  (SURVEY 7.5 ii)
+   int r1count = 0, r1blk = -1, r1ld = 0, r1ldg = 0;
+   DBuf<double> r1A, r1V, r1G1, r1G2, r1sig; DBuf<int> r1var;
    DBuf<int> denselist;
    DBuf<int> patcol, patrow;          // column-wise pattern of sum_j y_j A_j - C (+ diagonal) per block, if sparse
    std::vector<long long> patcoloff, patrowoff;   // per block offsets into patcol / patrow (-1: block is treated as dense)
@@ -289,6 +293,85 @@ int upload_problem(sdpcuda_handle* h, const sdpcuda_problem* P)
       else { heavy[j] = 1; heavylist.push_back(j); }
    }
    h->nheavy = (int)heavylist.size();
+   // class 3: light variables whose matrix is sigma a a' inside one block; used when the GEMM form is clearly cheaper than the
+   // entry-pair form (truss topology: 4 x 4 element matrices, 100 entry pairs per pair of variables; max-cut: a = e_i, one entry
+   // pair per pair of variables - stays on the entry path).  SDPCUDA_RANK1=0 turns the path off, =force skips the cost model.
+   h->r1count = 0; h->r1blk = -1;
+   {
+      const char* re = getenv("SDPCUDA_RANK1");
+      std::vector<std::vector<int>> r1_in(h->nb);
+      std::vector<std::vector<std::pair<int, double>>> r1vec(m);
+      std::vector<double> r1sg(m, 0.0);
+      std::vector<long long> r1nnz(h->nb, 0);
+      for( int j = 0; j < m && !(re != nullptr && strcmp(re, "0") == 0); ++j )
+      {
+         const int e0 = P->varbeg[j], cntj = P->varbeg[j + 1] - e0;
+         if( heavy[j] != 0 || cntj < 1 ) continue;
+         const int b0 = P->entblk[e0];
+         bool ok = true;
+         std::vector<int> sup;
+         for( int e = e0; e < e0 + cntj && ok; ++e )
+         {
+            ok = (P->entblk[e] == b0);
+            sup.push_back(P->entrow[e]); sup.push_back(P->entcol[e]);
+         }
+         if( !ok ) continue;
+         std::sort(sup.begin(), sup.end());
+         sup.erase(std::unique(sup.begin(), sup.end()), sup.end());
+         const int sn = (int)sup.size();
+         std::vector<double> D((size_t)sn * sn, 0.0);
+         double amax = 0.0;
+         for( int e = e0; e < e0 + cntj; ++e )
+         {
+            const int r = (int)(std::lower_bound(sup.begin(), sup.end(), P->entrow[e]) - sup.begin());
+            const int c = (int)(std::lower_bound(sup.begin(), sup.end(), P->entcol[e]) - sup.begin());
+            D[(size_t)r * sn + c] += P->entval[e];
+            if( r != c ) D[(size_t)c * sn + r] += P->entval[e];
+            amax = std::max(amax, std::fabs(P->entval[e]));
+         }
+         int pv = 0;
+         for( int i = 1; i < sn; ++i ) if( std::fabs(D[(size_t)i * sn + i]) > std::fabs(D[(size_t)pv * sn + pv]) ) pv = i;
+         const double dp = D[(size_t)pv * sn + pv];
+         if( !(std::fabs(dp) > 0.0) ) continue;
+         const double sg = dp > 0.0 ? 1.0 : -1.0, ap = std::sqrt(std::fabs(dp));
+         std::vector<double> av(sn);
+         for( int i = 0; i < sn; ++i ) av[i] = sg * D[(size_t)i * sn + pv] / ap;
+         for( int i = 0; i < sn && ok; ++i )
+            for( int k2 = 0; k2 <= i && ok; ++k2 )
+               ok = std::fabs(D[(size_t)i * sn + k2] - sg * av[i] * av[k2]) <= 1e-13 * amax;
+         if( !ok ) continue;
+         for( int i = 0; i < sn; ++i ) r1vec[j].emplace_back(sup[i], av[i]);
+         r1sg[j] = sg;
+         r1_in[b0].push_back(j);
+         r1nnz[b0] += cntj;
+      }
+      int best = -1;
+      for( int k = 0; k < h->nb; ++k ) if( best < 0 || r1_in[k].size() > r1_in[best].size() ) best = k;
+      const bool force = (re != nullptr && strcmp(re, "force") == 0);       // tests: take the path whatever the cost model says
+      if( best >= 0 && r1_in[best].size() >= (force ? 2u : 256u) )
+      {
+         const double r = (double)r1_in[best].size(), n = (double)h->blk[best].n;
+         const double t_entry = 0.5 * (double)r1nnz[best] * (double)r1nnz[best] / 1.5e11;  // measured: 6.5 ps per entry pair (TT-500: 52 M pairs, 337 us)
+         const double t_gemm = 2.0 * (2.0 * n * n * r + r * r * n) / 8.0e12 + 50e-6;       // short-k products: 8 TFLOP/s, plus launches
+         if( force || t_entry > 2.0 * t_gemm )
+         {
+            h->r1count = (int)r; h->r1blk = best;
+            h->r1ld = round_up(h->blk[best].n, 4); h->r1ldg = round_up(h->r1count, 4);
+            std::vector<double> Ar((size_t)h->r1ld * h->r1count, 0.0), sg(h->r1count);
+            for( int q = 0; q < h->r1count; ++q )
+            {
+               const int j = r1_in[best][q];
+               heavy[j] = 3;
+               sg[q] = r1sg[j];
+               for( const auto& pr2 : r1vec[j] ) Ar[(size_t)q * h->r1ld + pr2.first] = pr2.second;
+            }
+            CK( h->r1A.upload(Ar, st) ); CK( h->r1sig.upload(sg, st) ); CK( h->r1var.upload(r1_in[best], st) );
+            CK( h->r1V.ensure((size_t)h->r1ld * h->r1count) );
+            CK( h->r1G1.ensure((size_t)h->r1ldg * h->r1count) ); CK( h->r1G2.ensure((size_t)h->r1ldg * h->r1count) );
+            CK( cudaStreamSynchronize(st) );
+         }
+      }
+   }
    std::vector<int> denselist;
    h->dgroups.clear();
    size_t maxmat = 1;
@@ -900,10 +983,10 @@ int sdpcuda_destroy(sdpcuda_handle* h)
                             &h->L, &h->Linv, &h->LX, &h->LXinv, &h->dX, &h->dS, &h->dXa, &h->dSa, &h->K, &h->T1, &h->T2, &h->Rd, &h->work, &h->work2,
                             &h->y, &h->dy, &h->g, &h->rp, &h->AX, &h->DTx, &h->tm1, &h->tm2, &h->x, &h->s, &h->dx, &h->ds, &h->dxa, &h->dsa,
                             &h->klp, &h->rdlp, &h->Dy, &h->Ddy, &h->M, &h->Mfac, &h->diaginv, &h->Mwork, &h->MLinv, &h->Adense, &h->Hd, &h->Ud, &h->Cd, &h->partials, &h->stats, &h->scal,
-                            &h->eigw, &h->lzwork, &h->kA, &h->kB, &h->kC, &h->kW} )
+                            &h->eigw, &h->lzwork, &h->kA, &h->kB, &h->kC, &h->kW, &h->r1A, &h->r1V, &h->r1G1, &h->r1G2, &h->r1sig} )
       bf->release();
    for( DBuf<int>* bf : {&h->varbeg, &h->erow, &h->ecol, &h->eld, &h->posbeg, &h->posvar, &h->posbeg2, &h->posvar2, &h->lpbeg, &h->lpind, &h->colbeg, &h->colrow,
-                         &h->heavy, &h->heavylist, &h->info, &h->patcol, &h->patrow, &h->denselist} )
+                         &h->heavy, &h->heavylist, &h->info, &h->patcol, &h->patrow, &h->denselist, &h->r1var} )
       bf->release();
    for( DBuf<long long>* bf : {&h->eoff, &h->pos, &h->mirror, &h->cpos, &h->cmirror} )
       bf->release();
@@ -1989,6 +2072,17 @@ static int run_ipm(sdpcuda_handle* h, const sdpcuda_params* par, const double* s
          for( int gr = gfirst; gr <= glast; ++gr )
          {
             CK( schur_entries(st, m, E, h->heavy.p, h->heavylist.p, h->nheavy, h->X.p, h->Sinv.p, h->M.p, h->ldm, G, gr) );
+            if( h->r1count > 0 && gr == 0 )
+            {
+               // pairs of rank-one variables: G1 = A' (X A), G2 = A' (S^-1 A) (lower tiles), M_ij = sigma_i sigma_j G1_ij G2_ij
+               const Block& bk = h->blk[h->r1blk];
+               const int r = h->r1count;
+               CK( gemm(st, false, false, bk.n, r, bk.n, 1.0, h->X.p + bk.off, bk.ld, 0, h->r1A.p, h->r1ld, 0, 0.0, h->r1V.p, h->r1ld, 0, 1, 0) );
+               CK( gemm(st, true, false, r, r, bk.n, 1.0, h->r1A.p, h->r1ld, 0, h->r1V.p, h->r1ld, 0, 0.0, h->r1G1.p, h->r1ldg, 0, 1, GEMM_LOWER) );
+               CK( gemm(st, false, false, bk.n, r, bk.n, 1.0, h->Sinv.p + bk.off, bk.ld, 0, h->r1A.p, h->r1ld, 0, 0.0, h->r1V.p, h->r1ld, 0, 1, 0) );
+               CK( gemm(st, true, false, r, r, bk.n, 1.0, h->r1A.p, h->r1ld, 0, h->r1V.p, h->r1ld, 0, 0.0, h->r1G2.p, h->r1ldg, 0, 1, GEMM_LOWER) );
+               CK( schur_rank1_scatter(st, r, h->r1var.p, h->r1sig.p, h->r1G1.p, h->r1G2.p, h->r1ldg, h->M.p, h->ldm) );
+            }
             if( h->ndense > 0 )
             {
                // U_j = X A_j S^-1 for the dense variables (batched DMMA GEMMs), then M_ij = A_i . U_j for every i

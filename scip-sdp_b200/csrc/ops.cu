@@ -220,7 +220,9 @@ schur_light_kernel(int m, DevEntries E, const int* __restrict__ heavy, const dou
    if( blockIdx.x * 32 + 31 < blockIdx.y * 8 ) return;          // tile strictly above the diagonal
    if( (int)(blockIdx.y % nranks) != rank ) return;             // column strips of 8 are dealt round-robin to the ranks
    if( i >= m || j >= m || i < j ) return;
-   if( heavy[i] || heavy[j] ) return;             // classes 1 (heavy) and 2 (dense) are handled elsewhere
+   const int ci = heavy[i], cj = heavy[j];
+   if( ci == 1 || ci == 2 || cj == 1 || cj == 2 ) return;      // classes 1 (heavy) and 2 (dense) are handled elsewhere
+   if( ci == 3 && cj == 3 ) return;                            // two rank-one variables: GEMM path (schur_rank1_scatter)
    double v = 0.0;
    for( int ei = E.varbeg[i]; ei < E.varbeg[i + 1]; ++ei )
       for( int ej = E.varbeg[j]; ej < E.varbeg[j + 1]; ++ej )
@@ -310,6 +312,15 @@ __global__ void schur_dense_scatter_kernel(int count, int cnt, int first, int fi
    double v = 0.0;
    for( int sl = 0; sl < nslices; ++sl ) v += C[(size_t)sl * slicestride + (size_t)b * ldc + a];      // k-slices in fixed order
    M[(size_t)j * ldm + i] = v;
+}
+
+// M[var_a, var_b] = sigma_a sigma_b G1(a, b) G2(a, b) for the rank-one variables a >= b (list ascending in the variable index)
+__global__ void schur_rank1_scatter_kernel(int r, const int* __restrict__ var, const double* __restrict__ sig, const double* __restrict__ G1,
+   const double* __restrict__ G2, int ldg, double* __restrict__ M, int ldm)
+{
+   const int a = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y;
+   if( a >= r || a < b ) return;
+   M[(size_t)var[b] * ldm + var[a]] = sig[a] * sig[b] * G1[(size_t)b * ldg + a] * G2[(size_t)b * ldg + a];
 }
 
 __global__ void schur_lp_kernel(int nlp, const int* __restrict__ lpbeg, const int* __restrict__ lpind, const double* __restrict__ lpval,
@@ -705,6 +716,16 @@ cudaError_t schur_dense_scatter(cudaStream_t st, int count, int cnt, int first, 
    if( count <= 0 || cnt <= 0 ) return cudaSuccess;
    dim3 grid(ceil_div(count, 256), cnt);
    schur_dense_scatter_kernel<<<grid, 256, 0, st>>>(count, cnt, first, first_j, denselist, C, ldc, nslices, slicestride, M, ldm);
+   LAUNCH_END();
+}
+
+cudaError_t schur_rank1_scatter(cudaStream_t st, int r, const int* var, const double* sig, const double* G1, const double* G2, int ldg,
+   double* M, int ldm)
+{
+   if( r <= 0 ) return cudaSuccess;
+   ProfScope prof(st, PROF_SCHUR, 24.0 * r * (double)r / 2);
+   dim3 grid(ceil_div(r, 256), r);
+   schur_rank1_scatter_kernel<<<grid, 256, 0, st>>>(r, var, sig, G1, G2, ldg, M, ldm);
    LAUNCH_END();
 }
 

@@ -63,6 +63,8 @@ cudaError_t schur_dense_scatter(cudaStream_t st, int count, int cnt, int first, 
 cudaError_t schur_lp(cudaStream_t st, int nlp, const int* lpbeg, const int* lpind, const double* lpval, const double* x,
    const double* s, double* M, int ldm, const int* colbeg = nullptr, const int* colrow = nullptr, const double* colval = nullptr,
    int maxcnt = 0);
+cudaError_t schur_rank1_scatter(cudaStream_t st, int r, const int* var, const double* sig, const double* G1, const double* G2, int ldg,
+   double* M, int ldm);
 cudaError_t add_diagonal(cudaStream_t st, int n, double* A, int lda, double v);
 cudaError_t symv_lower(cudaStream_t st, int n, const double* M, int ldm, const double* x, double* y);   // y = M x, M lower stored
 // y = T x (trans = 0) or y = T' x (trans = 1) for a lower-triangular T (upper part never read)

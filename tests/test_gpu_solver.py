@@ -130,6 +130,29 @@ def test_schur_shares_add_up_to_the_unsharded_complement(gpu, name, make, monkey
     assert c["iterations"] == b["iterations"] and c["dobj"] == b["dobj"] and c["pobj"] == b["pobj"]
 
 
+def test_rank_one_schur_path_matches_the_entry_path(gpu, cpu, monkeypatch):
+    """truss topology with 300 bars: the element matrices are rank one, their mutual Schur entries come from the two GEMM pairs
+    (A' X A) o (A' S^-1 A) (SURVEY 7.5 ii); with SDPCUDA_RANK1=0 every pair goes through the entry lists.  Same optimum to 1e-9
+    relative, the same iteration count, and both within 1e-5 of the oracle; the shares of three emulated ranks reproduce the
+    unsharded iterates bit by bit with the path on"""
+    fp, _ = generators.truss(5, 5, 300, seed=21).flatten()
+    monkeypatch.setenv("SDPCUDA_PATH", "m")
+    monkeypatch.setenv("SDPCUDA_RANK1", "force")
+    on = gpu.solve(fp, gaptol=1e-7, feastol=1e-7, fetch=False)
+    monkeypatch.setenv("SDPCUDA_SHARD_EMULATE", "3")
+    on3 = gpu.solve(fp, gaptol=1e-7, feastol=1e-7, fetch=False)
+    monkeypatch.delenv("SDPCUDA_SHARD_EMULATE")
+    monkeypatch.setenv("SDPCUDA_RANK1", "0")
+    off = gpu.solve(fp, gaptol=1e-7, feastol=1e-7, fetch=False)
+    ref = cpu.solve(fp, gaptol=1e-7, feastol=1e-7)
+    assert on["phase_name"] == off["phase_name"] == ref["phase_name"] == "pdOPT"
+    assert on["launches"] != off["launches"]                       # the path was taken (five more launches per iteration)
+    assert on["iterations"] == off["iterations"]
+    assert abs(on["dobj"] - off["dobj"]) <= 1e-9 * max(1.0, abs(off["dobj"]))
+    assert abs(on["dobj"] - ref["dobj"]) <= 1e-5 * max(1.0, abs(ref["dobj"]))
+    assert on3["iterations"] == on["iterations"] and on3["dobj"] == on["dobj"] and on3["pobj"] == on["pobj"]
+
+
 def test_sharded_schur_on_two_gpus():
     """one SDP over two GPUs with the NCCL all-reduce of the Schur shares (needs two devices; tools/dist_check.py)"""
     import subprocess
