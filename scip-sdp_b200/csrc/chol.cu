@@ -111,6 +111,14 @@ __device__ __forceinline__ void leaf_factor(const LeafCtx<NBL>& X, double (&c)[N
    // block column 0 -> shared memory
    if( (fc >> 1) == 0 )
       *reinterpret_cast<double2*>(Pcol + (8 * w + fr) * 4 + 2 * (fc & 1)) = make_double2(c[0][0], c[0][1]);
+   // a partial block (order 66 in a 128-leaf: TT-500) stops after its last column group; the identity padding behind it is written here
+   const int nbr = (nb + 3) & ~3;
+   for( int e = tid; e < (NBL - nbr) * NBL; e += NTHREADS )
+   {
+      const int r = nbr + e / NBL, cc = e % NBL;
+      G[(r + 1) * LD + cc] = (cc == r) ? 1.0 : 0.0;
+      if( cc == r ) rdg[r] = 1.0;
+   }
    __syncthreads();
 
    // Macro step t (4 columns), two barriers, ordered so that only what the NEXT step needs sits between them:
@@ -120,6 +128,7 @@ __device__ __forceinline__ void leaf_factor(const LeafCtx<NBL>& X, double (&c)[N
 #pragma unroll
    for( int t = 0; t < NSTEP; ++t )
    {
+      if( 4 * t >= nb ) break;
       double* const Pc = Pcol + (t & 1) * NBL * 4;
       double* const Pp = P + (t & 1) * NBL * 4;
       if( t == NSTEP - 4 && pf0 != nullptr && tid == 0 )
