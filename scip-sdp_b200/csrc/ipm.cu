@@ -203,6 +203,12 @@ struct sdpcuda_handle
    bool lpdup = false;                            // some LP row lists a variable twice
    int lpmaxcnt = 0;                              // longest LP row (grid of the deterministic Schur kernel of the LP block)
    BatchImage batchhost;                           // host image of the last frontier batch (kept, pinned: no page faults, fast H2D)
+   // second set of batch buffers: a large frontier goes through in chunks, chunk c + 1 is packed on the host while chunk c runs
+   // (set c % 2, stream st / st2); results land in pinned host buffers so that the copies back do not block the packing
+   DBuf<SmallArgs> batchargs2; DBuf<SmallResult> batchres2; DBuf<unsigned char> batchimg2; DBuf<double> batchwork2, batchy2;
+   BatchImage batchhost2;
+   ByteBuf batchback[2];
+   cudaEvent_t evChunk[2] = {nullptr, nullptr};
    DBuf<int> ppint; DBuf<double> ppdbl, ppout; DBuf<long long> ppoff;      // staging of sdpcuda_primal_products
    DBuf<double> kflag;                            // one word: time-limit flag agreed between the ranks of a sharded solve
    double* h_stats = nullptr;     // pinned
@@ -952,6 +958,7 @@ int sdpcuda_create(sdpcuda_handle** out, int device)
    }
    h->device = (device >= 0) ? device % ndev : (g_next_device.fetch_add(1) % ndev);
    h->batchhost.buf.pinned = true;
+   h->batchhost2.buf.pinned = true; h->batchback[0].pinned = true; h->batchback[1].pinned = true;
    // the side lane of the look-ahead factorisation carries the bulk GEMMs: lowest priority, so that the latency-bound panel
    // kernels of the main lane get SM slots first
    int lowprio = 0, highprio = 0;
@@ -995,6 +1002,9 @@ int sdpcuda_destroy(sdpcuda_handle* h)
    for( cudaEvent_t& e : h->evp ) if( e != nullptr ) { cudaEventDestroy(e); e = nullptr; }
    h->preX.release(); h->prey.release(); h->prex.release();
    h->batchhost.buf.release();
+   h->batchhost2.buf.release(); h->batchback[0].release(); h->batchback[1].release();
+   h->batchargs2.release(); h->batchres2.release(); h->batchimg2.release(); h->batchwork2.release(); h->batchy2.release();
+   for( int q = 0; q < 2; ++q ) if( h->evChunk[q] ) cudaEventDestroy(h->evChunk[q]);
    h->ppint.release(); h->ppdbl.release(); h->ppout.release(); h->ppoff.release(); h->kflag.release();
    drop_graph(h->gS); drop_graph(h->gX); drop_graph(h->gM);
    cudaEventDestroy(h->ev0); cudaEventDestroy(h->ev1); cudaEventDestroy(h->evFork); cudaEventDestroy(h->evJoin);
@@ -1651,65 +1661,140 @@ int sdpcuda_solve_batch(sdpcuda_handle* h, int count, const sdpcuda_problem* con
    // SDPCUDA_BATCH_SMEM=1: the head of every node's work space is staged in shared memory (as many whole arrays as fit the budget)
    const char* te = getenv("SDPCUDA_BATCH_TINY");
    const char* se = getenv("SDPCUDA_BATCH_SMEM");
-   BatchPlan plan(h->batchhost);
    if( h->packed ) { h->packed = false; h->solved = false; }      // the batch reuses the buffers of a packed single solve
-   rc = batch_plan(count, probs, par, !(te != nullptr && te[0] == '0'), se != nullptr && se[0] == '1', plan);
-   if( rc != SDPCUDA_OK ) return rc;
+   const bool usetiny = !(te != nullptr && te[0] == '0'), stage = (se != nullptr && se[0] == '1');
    const bool bprof = getenv("SDPCUDA_BATCH_PROFILE") != nullptr;
-   const double tplan = now_seconds();
-   if( objlimits != nullptr )
-      for( size_t k = 0; k < plan.nodes.size(); ++k ) plan.nodes[k].a.objlimit = objlimits[plan.who[k]];
-   BatchImage& img = plan.img;
-   std::vector<BatchNode>& nodes = plan.nodes;
-   const std::vector<int>& who = plan.who;
-   const std::vector<int>& loners = plan.loners;
-   const size_t worktotal = plan.worktotal, ytotal = plan.ytotal;
-   const int ntiny = plan.ntiny;
-   const int nd = (int)nodes.size();
-   if( nd > 0 )
+   // Chunks: the host packs chunk c + 1 (all host threads) while the kernels of chunk c run; two sets of buffers on two streams, so
+   // that the kernels of two chunks overlap on the device as well.  This pays only for frontiers of several waves: a node takes its
+   // 5 - 40 ms of kernel time whatever else runs, so one wave (592 small or 148 large nodes) is fastest in ONE launch - measured:
+   // example_TT, 592 nodes, 6.6 ms in one launch, 10.5 ms in four chunks (profiles/r2_batch_chunks.log).  Default: chunks of two
+   // waves of the small kernel; SDPCUDA_BATCH_CHUNKS=k forces k chunks.
+   int nchunks = std::min(4, count / 1184);
    {
-      cudaStream_t st = h->st;
-      h->counter.n = 0;
-      CK( h->batchimg.ensure(img.buf.size()) );
-      CK( h->batchwork.ensure(worktotal) );
-      CK( h->batchy.ensure(ytotal) );
-      CK( h->batchargs.ensure(nd) );
-      CK( h->batchres.ensure(nd) );
+      const char* ce = getenv("SDPCUDA_BATCH_CHUNKS");
+      if( ce != nullptr && atoi(ce) > 0 ) nchunks = atoi(ce);
+   }
+   nchunks = std::max(1, std::min(nchunks, count));
+   for( int q = 0; q < 2; ++q )
+      if( h->evChunk[q] == nullptr ) CK( cudaEventCreateWithFlags(&h->evChunk[q], cudaEventDisableTiming) );
+   struct Chunk { BatchPlan* plan = nullptr; int first = 0, cnt = 0, set = 0; size_t yoff_bytes = 0; };
+   std::vector<Chunk> chunks(nchunks);
+   std::vector<int> loners;
+   h->counter.n = 0;
+   double h2d_total = 0.0, d2h_total = 0.0;
+   int nd_total = 0;
+   bool first_launch = true;
+   int rcall = SDPCUDA_OK;
+   auto submit = [&](Chunk& ck) -> int
+   {
+      const int sx = ck.set;
+      cudaStream_t st = (sx == 0) ? h->st : h->st2;
+      ck.plan = new BatchPlan(sx == 0 ? h->batchhost : h->batchhost2);
+      BatchPlan& plan = *ck.plan;
+      int rc2 = batch_plan(ck.cnt, probs + ck.first, par, usetiny, stage, plan);
+      if( rc2 != SDPCUDA_OK ) return rc2;
+      if( objlimits != nullptr )
+         for( size_t k = 0; k < plan.nodes.size(); ++k ) plan.nodes[k].a.objlimit = objlimits[ck.first + plan.who[k]];
+      for( int i : plan.loners ) loners.push_back(ck.first + i);
+      const int nd = (int)plan.nodes.size();
+      if( nd == 0 ) return SDPCUDA_OK;
+      DBuf<unsigned char>& dimg = (sx == 0) ? h->batchimg : h->batchimg2;
+      DBuf<double>& dwork = (sx == 0) ? h->batchwork : h->batchwork2;
+      DBuf<double>& dy = (sx == 0) ? h->batchy : h->batchy2;
+      DBuf<SmallArgs>& dargs = (sx == 0) ? h->batchargs : h->batchargs2;
+      DBuf<SmallResult>& dres = (sx == 0) ? h->batchres : h->batchres2;
+      CK( dimg.ensure(plan.img.buf.size()) );
+      CK( dwork.ensure(plan.worktotal) );
+      CK( dy.ensure(plan.ytotal) );
+      CK( dargs.ensure(nd) );
+      CK( dres.ensure(nd) );
       std::vector<SmallArgs> args;
-      batch_bind_all(plan, h->batchimg.p, h->batchwork.p, h->batchy.p, h->batchres.p, args);
+      batch_bind_all(plan, dimg.p, dwork.p, dy.p, dres.p, args);
+      // the descriptors travel behind the image in the same pinned buffer (the vector above dies with this call)
+      const size_t imgbytes = (plan.img.buf.size() + 15) & ~(size_t)15;
+      plan.img.buf.resize(imgbytes + sizeof(SmallArgs) * nd);
+      memcpy(plan.img.buf.data() + imgbytes, args.data(), sizeof(SmallArgs) * nd);
       // the work space is shared by batches of different layouts: start from zeros (padding rows and alignment gaps are never
       // written by the kernel; a few tens of MB at most)
-      CK( cudaMemsetAsync(h->batchwork.p, 0, sizeof(double) * worktotal, st) );
-      CK( cudaMemcpyAsync(h->batchimg.p, img.buf.data(), img.buf.size(), cudaMemcpyHostToDevice, st) );
-      CK( cudaMemcpyAsync(h->batchargs.p, args.data(), sizeof(SmallArgs) * nd, cudaMemcpyHostToDevice, st) );
-      if( bprof ) { CK( cudaStreamSynchronize(st) ); fprintf(stderr, "[batch] %d nodes: plan %.2f ms, bind + memset + H2D of %.1f MB %.2f ms", nd, 1e3 * (tplan - t0), img.buf.size() / 1e6, 1e3 * (now_seconds() - tplan)); }
-      CK( cudaEventRecord(h->ev0, st) );
-      CK( launch_ipm_tiny_batch(st, ntiny, h->batchargs.p, plan.stagebytes[0]) );
-      CK( launch_ipm_small_batch(st, nd - ntiny, h->batchargs.p + ntiny, plan.stagebytes[1]) );
-      CK( cudaEventRecord(h->ev1, st) );
-      std::vector<SmallResult> sr(nd);
-      std::vector<double> ys(ytotal);
-      CK( cudaMemcpyAsync(sr.data(), h->batchres.p, sizeof(SmallResult) * nd, cudaMemcpyDeviceToHost, st) );
-      CK( cudaMemcpyAsync(ys.data(), h->batchy.p, sizeof(double) * ytotal, cudaMemcpyDeviceToHost, st) );
-      CK( cudaStreamSynchronize(st) );
+      CK( cudaMemsetAsync(dwork.p, 0, sizeof(double) * plan.worktotal, st) );
+      CK( cudaMemcpyAsync(dimg.p, plan.img.buf.data(), imgbytes, cudaMemcpyHostToDevice, st) );
+      CK( cudaMemcpyAsync(dargs.p, plan.img.buf.data() + imgbytes, sizeof(SmallArgs) * nd, cudaMemcpyHostToDevice, st) );
+      if( first_launch ) { CK( cudaEventRecord(h->ev0, st) ); first_launch = false; }
+      CK( launch_ipm_tiny_batch(st, plan.ntiny, dargs.p, plan.stagebytes[0]) );
+      CK( launch_ipm_small_batch(st, nd - plan.ntiny, dargs.p + plan.ntiny, plan.stagebytes[1]) );
+      ck.yoff_bytes = (sizeof(SmallResult) * nd + 15) & ~(size_t)15;
+      h->batchback[sx].resize(ck.yoff_bytes + sizeof(double) * plan.ytotal);
+      CK( cudaMemcpyAsync(h->batchback[sx].data(), dres.p, sizeof(SmallResult) * nd, cudaMemcpyDeviceToHost, st) );
+      CK( cudaMemcpyAsync(h->batchback[sx].data() + ck.yoff_bytes, dy.p, sizeof(double) * plan.ytotal, cudaMemcpyDeviceToHost, st) );
+      CK( cudaEventRecord(h->evChunk[sx], st) );
+      h2d_total += (double)(imgbytes + sizeof(SmallArgs) * nd);
+      d2h_total += (double)(sizeof(SmallResult) * nd + sizeof(double) * plan.ytotal);
+      nd_total += nd;
+      if( bprof ) fprintf(stderr, "[batch] chunk of %d nodes submitted at %.2f ms (image %.1f MB)\n", nd, 1e3 * (now_seconds() - t0), imgbytes / 1e6);
+      return SDPCUDA_OK;
+   };
+   auto collect = [&](Chunk& ck) -> int
+   {
+      if( ck.plan == nullptr ) return SDPCUDA_OK;
+      BatchPlan& plan = *ck.plan;
+      const int nd = (int)plan.nodes.size();
+      if( nd > 0 )
+      {
+         CK( cudaEventSynchronize(h->evChunk[ck.set]) );
+         const SmallResult* sr = reinterpret_cast<const SmallResult*>(h->batchback[ck.set].data());
+         const double* ys = reinterpret_cast<const double*>(h->batchback[ck.set].data() + ck.yoff_bytes);
+         for( int k = 0; k < nd; ++k )
+         {
+            const int i = ck.first + plan.who[k];
+            if( y_out != nullptr && y_out[i] != nullptr ) std::copy(ys + plan.nodes[k].yoff, ys + plan.nodes[k].yoff + plan.nodes[k].a.m, y_out[i]);
+            if( res == nullptr ) continue;
+            sdpcuda_result R;
+            memset(&R, 0, sizeof(R));
+            R.phase = sr[k].phase; R.stop = sr[k].stop; R.iterations = sr[k].iterations;
+            R.pobj = sr[k].pobj; R.dobj = sr[k].dobj; R.relgap = sr[k].relgap; R.pinf = sr[k].pinf; R.dinf = sr[k].dinf; R.mu = sr[k].mu;
+            res[i] = R;
+         }
+      }
+      delete ck.plan; ck.plan = nullptr;
+      return SDPCUDA_OK;
+   };
+   for( int c = 0; c < nchunks && rcall == SDPCUDA_OK; ++c )
+   {
+      chunks[c].first = (int)((long long)count * c / nchunks);
+      chunks[c].cnt = (int)((long long)count * (c + 1) / nchunks) - chunks[c].first;
+      chunks[c].set = c & 1;
+      rcall = submit(chunks[c]);
+      if( rcall == SDPCUDA_OK && c >= 1 ) rcall = collect(chunks[c - 1]);
+   }
+   if( rcall == SDPCUDA_OK && nd_total > 0 )
+   {
+      // device time of the batch: from the first launch to the end of the last chunk (both streams)
+      CK( cudaEventRecord(h->evJoin, h->st2) );
+      CK( cudaStreamWaitEvent(h->st, h->evJoin, 0) );
+      CK( cudaEventRecord(h->ev1, h->st) );
+   }
+   if( rcall == SDPCUDA_OK ) rcall = collect(chunks[nchunks - 1]);
+   for( Chunk& ck : chunks ) { delete ck.plan; ck.plan = nullptr; }
+   if( rcall != SDPCUDA_OK ) { cudaStreamSynchronize(h->st); cudaStreamSynchronize(h->st2); return rcall; }
+   if( nd_total > 0 )
+   {
+      CK( cudaEventSynchronize(h->ev1) );
       float ms = 0.f;
       cudaEventElapsedTime(&ms, h->ev0, h->ev1);
       const double wall = now_seconds() - t0;
-      if( bprof ) fprintf(stderr, ", kernels %.2f ms, whole call %.2f ms\n", ms, 1e3 * wall);
-      for( int k = 0; k < nd; ++k )
+      if( bprof ) fprintf(stderr, "[batch] %d nodes in %d chunk(s): first launch to last result %.2f ms, whole call %.2f ms\n", nd_total, nchunks, ms, 1e3 * wall);
+      if( res != nullptr )
       {
-         const int i = who[k];
-         if( y_out != nullptr && y_out[i] != nullptr ) std::copy(ys.begin() + nodes[k].yoff, ys.begin() + nodes[k].yoff + nodes[k].a.m, y_out[i]);
-         if( res == nullptr ) continue;
-         sdpcuda_result R;
-         memset(&R, 0, sizeof(R));
-         R.phase = sr[k].phase; R.stop = sr[k].stop; R.iterations = sr[k].iterations;
-         R.launches = (k == 0) ? (int)h->counter.n : 0;   // the launch (two with the tiny instantiation) is shared by all batched nodes
-         R.pobj = sr[k].pobj; R.dobj = sr[k].dobj; R.relgap = sr[k].relgap; R.pinf = sr[k].pinf; R.dinf = sr[k].dinf; R.mu = sr[k].mu;
-         R.seconds = wall; R.device_ms = ms;             // of the whole batch: the nodes run side by side
-         R.h2d_bytes = (double)(img.buf.size() + sizeof(SmallArgs) * nd) / nd;
-         R.d2h_bytes = (double)(sizeof(SmallResult) * nd + sizeof(double) * ytotal) / nd;
-         res[i] = R;
+         bool firstres = true;
+         for( int i = 0; i < count; ++i )
+         {
+            if( std::find(loners.begin(), loners.end(), i) != loners.end() ) continue;
+            res[i].launches = firstres ? (int)h->counter.n : 0;      // the launches are shared by all batched nodes
+            firstres = false;
+            res[i].seconds = wall; res[i].device_ms = ms;          // of the whole batch: the nodes run side by side
+            res[i].h2d_bytes = h2d_total / nd_total;
+            res[i].d2h_bytes = d2h_total / nd_total;
+         }
       }
    }
    // relaxations outside the single-CTA limits: one after the other through the ordinary solve on this handle

@@ -154,6 +154,28 @@ def test_batch_larger_than_the_sm_count(lib, cpu):
     gpu.close()
 
 
+@pytest.mark.parametrize("chunks", ["2", "3", "5"])
+def test_batch_in_chunks_equals_the_single_launch(lib, chunks, monkeypatch):
+    """a frontier sent through in chunks (two buffer sets on two streams, chunk c + 1 packed while chunk c runs; the default for
+    frontiers of several waves) returns bit for bit what the single launch returns, also with a node outside the single-CTA limits"""
+    M = misdp.read_sdpa(os.path.join(GOLDEN, "example_TT.dat-s.gz")).rows_to_bounds()
+    flat = [M.flatten(lb, ub)[0] for lb, ub in _frontier(M, 3)]
+    big, _ = generators.maxcut(96, 0.1, seed=7).flatten()
+    probs = [flat[i % 8] for i in range(90)]
+    probs[41] = big
+    gpu = abi.Solver(lib, device=0)
+    monkeypatch.setenv("SDPCUDA_BATCH_CHUNKS", "1")
+    one = gpu.solve_batch(probs, **KW)
+    monkeypatch.setenv("SDPCUDA_BATCH_CHUNKS", chunks)
+    many = gpu.solve_batch(probs, **KW)
+    again = gpu.solve_batch(probs, **KW)                  # both buffer sets reused
+    for a, b, c in zip(one, many, again):
+        assert a["phase_name"] == b["phase_name"] == c["phase_name"] == "pdOPT"
+        assert a["dobj"] == b["dobj"] == c["dobj"] and a["iterations"] == b["iterations"] == c["iterations"]
+        assert np.array_equal(a["y"], b["y"]) and np.array_equal(a["y"], c["y"])
+    gpu.close()
+
+
 def test_objective_limits_per_node_on_gpu(lib):
     """per-node objective limits in the batch call: nodes with a limit below their value stop early with phase pUNBD"""
     M = misdp.read_sdpa(os.path.join(GOLDEN, "example_TT.dat-s.gz")).rows_to_bounds()
