@@ -449,6 +449,42 @@ spmm_pattern_kernel(int n, const double* __restrict__ A, int lda, const double* 
    }
 }
 
+// Sampled product on the aggregate sparsity pattern: W(p, q) = sum_k Pt(k, p) Z(k, q) = (P Z)(p, q) with Pt = P' for the pattern
+// entries (p, q) of column q only.  One CTA per column q, one warp per entry (both operand columns contiguous; the column of Z is
+// shared by the warps of the CTA and stays in L1).  A(K) only reads K on the pattern, so the n^3 product P Z is not needed for it.
+__global__ void __launch_bounds__(256)
+sddmm_pattern_kernel(int n, const double* __restrict__ Pt, int ldp, const double* __restrict__ Z, int ldz, const int* __restrict__ colptr,
+   const int* __restrict__ rowidx, double* __restrict__ W, int ldw)
+{
+   const int q = blockIdx.x, lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+   const int b = colptr[q], e = colptr[q + 1];
+   const double* zc = Z + (size_t)q * ldz;
+   for( int t = b + wid; t < e; t += 8 )
+   {
+      const int p = rowidx[t];
+      const double* pc = Pt + (size_t)p * ldp;
+      double s0 = 0.0, s1 = 0.0;
+      int k = lane;
+      for( ; k + 32 < n; k += 64 ) { s0 += pc[k] * zc[k]; s1 += pc[k + 32] * zc[k + 32]; }
+      if( k < n ) s0 += pc[k] * zc[k];
+      const double v = warp_sum(s0 + s1);
+      if( lane == 0 ) W[(size_t)q * ldw + p] = v;
+   }
+}
+
+// K(p, q) = (W(p, q) + W(q, p)) / 2 - X(p, q) on the (symmetric) pattern
+__global__ void __launch_bounds__(256)
+sym_pattern_kernel(int n, const double* __restrict__ W, int ldw, const double* __restrict__ X, int ldx, const int* __restrict__ colptr,
+   const int* __restrict__ rowidx, double* __restrict__ K, int ldk)
+{
+   const int q = blockIdx.x;
+   for( int t = colptr[q] + threadIdx.x; t < colptr[q + 1]; t += blockDim.x )
+   {
+      const int p = rowidx[t];
+      K[(size_t)q * ldk + p] = 0.5 * (W[(size_t)q * ldw + p] + W[(size_t)p * ldw + q]) - X[(size_t)q * ldx + p];
+   }
+}
+
 __global__ void trmv_upper_t_kernel(int n, const double* __restrict__ U, int ldu, const double* __restrict__ x, double* __restrict__ y)
 {
    int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
@@ -775,6 +811,17 @@ cudaError_t spmm_pattern(cudaStream_t st, int n, const double* A, int lda, const
    dim3 grid(ceil_div(n, 256), n);
    spmm_pattern_kernel<<<grid, 256, 0, st>>>(n, A, lda, D, ldd, colptr, rowidx, alpha, Out, ldo);
    LAUNCH_END();
+}
+
+cudaError_t sddmm_pattern_sym(cudaStream_t st, int n, const double* Pt, int ldp, const double* Z, int ldz, const double* X, int ldx,
+   const int* colptr, const int* rowidx, double* W, int ldw, double* K, int ldk)
+{
+   if( n <= 0 ) return cudaSuccess;
+   ProfScope prof(st, PROF_ELEM, 0.0);
+   sddmm_pattern_kernel<<<n, 256, 0, st>>>(n, Pt, ldp, Z, ldz, colptr, rowidx, W, ldw);
+   sym_pattern_kernel<<<n, 64, 0, st>>>(n, W, ldw, X, ldx, colptr, rowidx, K, ldk);
+   count_launch(2);
+   return cudaGetLastError();
 }
 
 cudaError_t trmv_upper_t(cudaStream_t st, int n, const double* U, int ldu, const double* x, double* y)

@@ -73,6 +73,9 @@ cudaError_t trmv_lower(cudaStream_t st, int n, const double* T, int ldt, int tra
 cudaError_t trmv_upper_t(cudaStream_t st, int n, const double* U, int ldu, const double* x, double* y);
 // B = A' (n x n, out of place)
 cudaError_t transpose(cudaStream_t st, int n, const double* A, int lda, double* B, int ldb);
+// K = sym(P Z) - X on the pattern entries only, P given transposed (Pt); W: scratch matrix (pattern entries written)
+cudaError_t sddmm_pattern_sym(cudaStream_t st, int n, const double* Pt, int ldp, const double* Z, int ldz, const double* X, int ldx,
+   const int* colptr, const int* rowidx, double* W, int ldw, double* K, int ldk);
 
 // Out = A * D for one block, D symmetric and sparse: its pattern is given column-wise (colptr[n+1], rowidx), its values
 // are read from the dense array D itself.  One CTA per (256-row slab, column): gathers columns of A (coalesced).
