@@ -167,7 +167,9 @@ struct sdpcuda_handle
    DBuf<int> denselist;
    DBuf<int> patcol, patrow;          // column-wise pattern of sum_j y_j A_j - C (+ diagonal) per block, if sparse
    std::vector<long long> patcoloff, patrowoff;   // per block offsets into patcol / patrow (-1: block is treated as dense)
+   std::vector<long long> patcolAoff, patrowAoff; // the same for the pattern of the A_j alone (without C, without a forced diagonal): products with A'dy
    bool sddmm = false;                            // every block has a sparse pattern: K on the pattern by sampled products (run_ipm)
+   bool apat = true;                              // products with A'dy run over the pattern of the A_j alone (SDPCUDA_APAT=0: aggregate pattern)
    DBuf<SmallResult> smallres;
    // frontier batch (sdpcuda_solve_batch): descriptors, results, the packed read-only problem data, work space and y of all nodes
    DBuf<SmallArgs> batchargs;
@@ -466,10 +468,31 @@ int upload_problem(sdpcuda_handle* h, const sdpcuda_problem* P)
       for( int e = 0; e < P->cnnz; ++e ) cnt[P->cblk[e]] += 2;
       std::vector<int> pc, pr;
       h->patcoloff.assign(h->nb, -1); h->patrowoff.assign(h->nb, -1);
+      h->patcolAoff.assign(h->nb, -1); h->patrowAoff.assign(h->nb, -1);
       for( int k = 0; k < h->nb; ++k )
       {
          const int n = h->blk[k].n;
          if( n < 256 || (double)cnt[k] + n > 0.125 * (double)n * n ) continue;      // small or dense block: GEMM path
+         {
+            // pattern of the constraint matrices alone: A'dy lives on it (max-cut: the diagonal, while C brings the edges), so that
+            // X (A'dy), dXa dSa and Linv dS cost one pass over the matrix instead of one per pattern entry of a column
+            std::vector<std::pair<int, int>> va;
+            for( int e = 0; e < nnz; ++e )
+               if( P->entblk[e] == k )
+               {
+                  va.emplace_back(P->entcol[e], P->entrow[e]);
+                  if( P->entrow[e] != P->entcol[e] ) va.emplace_back(P->entrow[e], P->entcol[e]);
+               }
+            std::sort(va.begin(), va.end());
+            va.erase(std::unique(va.begin(), va.end()), va.end());
+            h->patcolAoff[k] = (long long)pc.size();
+            h->patrowAoff[k] = (long long)pr.size();
+            std::vector<int> cpa(n + 1, 0);
+            for( const auto& pr2 : va ) cpa[pr2.first + 1]++;
+            for( int c = 0; c < n; ++c ) cpa[c + 1] += cpa[c];
+            pc.insert(pc.end(), cpa.begin(), cpa.end());
+            for( const auto& pr2 : va ) pr.push_back(pr2.second);
+         }
          std::vector<std::pair<int, int>>& v = ent[k];
          v.reserve((size_t)cnt[k] + n);
          for( int i = 0; i < n; ++i ) v.emplace_back(i, i);
@@ -491,6 +514,8 @@ int upload_problem(sdpcuda_handle* h, const sdpcuda_problem* P)
       CK( h->patrow.upload(pr, st) );
       {
          const char* se2 = getenv("SDPCUDA_SDDMM");
+         const char* se3 = getenv("SDPCUDA_APAT");
+         h->apat = !(se3 != nullptr && strcmp(se3, "0") == 0);
          h->sddmm = (h->nb > 0) && !(se2 != nullptr && strcmp(se2, "0") == 0);
          for( int k = 0; k < h->nb; ++k ) if( h->patcoloff[k] < 0 ) h->sddmm = false;
       }
@@ -761,14 +786,15 @@ int mult_blocks(sdpcuda_handle* h, const double* A, const double* B, double* Out
 }
 
 // Out_k = alpha * A_k * D_k where D lives on the aggregate sparsity pattern (dS, Rd, dSa): sparse gather for sparse blocks
-int mult_blocks_pattern(sdpcuda_handle* h, const double* A, const double* D, double* Out, double alpha)
+// apat: D = A'dy exactly (no residual part): non-zero on the pattern of the constraint matrices only
+int mult_blocks_pattern(sdpcuda_handle* h, const double* A, const double* D, double* Out, double alpha, bool apat = false)
 {
    int k = 0;
    for( const Block& bk : h->blk )
    {
       if( h->patcoloff[k] >= 0 )
-         CK( spmm_pattern(h->st, bk.n, A + bk.off, bk.ld, D + bk.off, bk.ld, h->patcol.p + h->patcoloff[k], h->patrow.p + h->patrowoff[k],
-               alpha, Out + bk.off, bk.ld) );
+         CK( spmm_pattern(h->st, bk.n, A + bk.off, bk.ld, D + bk.off, bk.ld, h->patcol.p + (apat ? h->patcolAoff[k] : h->patcoloff[k]),
+               h->patrow.p + (apat ? h->patrowAoff[k] : h->patrowoff[k]), alpha, Out + bk.off, bk.ld) );
       else
          CK( gemm(h->st, false, false, bk.n, bk.n, bk.n, alpha, A + bk.off, bk.ld, 0, D + bk.off, bk.ld, 0, 0.0, Out + bk.off, bk.ld, 0, 1, 0) );
       ++k;
@@ -778,12 +804,12 @@ int mult_blocks_pattern(sdpcuda_handle* h, const double* A, const double* D, dou
 
 // B = Linv dA Linv' for one block into Bout (T1 is scratch): Linv lower triangular -> k < m0 + BM for the first product,
 // lower tiles and k < n0 + BN for the second, then mirrored to full storage
-int form_scaled(sdpcuda_handle* h, const Block& bk, int k, bool sparse_dA, const double* Linv, const double* dA, double* Bout)
+int form_scaled(sdpcuda_handle* h, const Block& bk, int k, bool sparse_dA, const double* Linv, const double* dA, double* Bout, bool apat = false)
 {
    double* t1 = h->T1.p + bk.off;
    if( sparse_dA && h->patcoloff[k] >= 0 )
-      CK( spmm_pattern(h->st, bk.n, Linv + bk.off, bk.ld, dA + bk.off, bk.ld, h->patcol.p + h->patcoloff[k], h->patrow.p + h->patrowoff[k],
-            1.0, t1, bk.ld) );
+      CK( spmm_pattern(h->st, bk.n, Linv + bk.off, bk.ld, dA + bk.off, bk.ld, h->patcol.p + (apat ? h->patcolAoff[k] : h->patcoloff[k]),
+            h->patrow.p + (apat ? h->patrowAoff[k] : h->patrowoff[k]), 1.0, t1, bk.ld) );
    else
       CK( gemm(h->st, false, false, bk.n, bk.n, bk.n, 1.0, Linv + bk.off, bk.ld, 0, dA + bk.off, bk.ld, 0, 0.0, t1, bk.ld, 0, 1, GEMM_KHI_M) );
    CK( gemm(h->st, false, true, bk.n, bk.n, bk.n, 1.0, t1, bk.ld, 0, Linv + bk.off, bk.ld, 0, 0.0, Bout + bk.off, bk.ld, 0, 1, GEMM_LOWER | GEMM_KHI_N) );
@@ -794,7 +820,7 @@ int form_scaled(sdpcuda_handle* h, const Block& bk, int k, bool sparse_dA, const
 // lambda_min(LXinv dX LXinv') -> scal[8 + k], lambda_min(Linv dS Linv') -> scal[8 + nb + k] for every block k.
 // Small blocks: Jacobi kernel (values only); large blocks: all Lanczos runs of the pass advance together.
 // Scratch: T1 (intermediate), T2 (X-side matrices), K (S-side matrices; K is free once dX has been formed).
-int step_eigs(sdpcuda_handle* h, const double* dXdir, const double* dSdir, int maxsteps)
+int step_eigs(sdpcuda_handle* h, const double* dXdir, const double* dSdir, int maxsteps, bool apat = false)
 {
    const int nb = h->nb;
    h->h_lzdesc.clear();
@@ -818,7 +844,7 @@ int step_eigs(sdpcuda_handle* h, const double* dXdir, const double* dSdir, int m
       if( !(big && implicit) )
       {
          if( (rc = form_scaled(h, bk, k, false, h->LXinv.p, dXdir, h->T2.p)) ) return rc;
-         if( (rc = form_scaled(h, bk, k, true, h->Linv.p, dSdir, h->K.p)) ) return rc;
+         if( (rc = form_scaled(h, bk, k, true, h->Linv.p, dSdir, h->K.p, apat)) ) return rc;
       }
       for( int side = 0; side < 2; ++side )
       {
@@ -2282,12 +2308,12 @@ static int run_ipm(sdpcuda_handle* h, const sdpcuda_params* par, const double* s
          {
             if( haveT )
             {
-               rc = mult_blocks_pattern(h, h->dXa.p, h->dSa.p, h->T2.p, -1.0); if( rc ) return rc;
+               rc = mult_blocks_pattern(h, h->dXa.p, h->dSa.p, h->T2.p, -1.0, rdzero && h->apat); if( rc ) return rc;
                CK( axpy(st, ar, 1.0, h->T2.p, h->T1.p) );
             }
             else
             {
-               rc = mult_blocks_pattern(h, h->dXa.p, h->dSa.p, h->T1.p, -1.0); if( rc ) return rc;
+               rc = mult_blocks_pattern(h, h->dXa.p, h->dSa.p, h->T1.p, -1.0, rdzero && h->apat); if( rc ) return rc;
             }
             for( const Block& bk : h->blk ) CK( add_diagonal(st, bk.n, h->T1.p + bk.off, bk.ld, sigma * mu) );
             haveT = true;
@@ -2341,14 +2367,14 @@ static int run_ipm(sdpcuda_handle* h, const sdpcuda_params* par, const double* s
          if( sampled )
          {
             // dX = sym((T1 - X (A'dy)) S^-1) - X : the one n^3 product of the pass
-            rc = mult_blocks_pattern(h, h->X.p, oS, h->T2.p, 1.0); if( rc ) return rc;
+            rc = mult_blocks_pattern(h, h->X.p, oS, h->T2.p, 1.0, h->apat); if( rc ) return rc;
             CK( axpy(st, ar, -1.0, h->T2.p, h->T1.p) );
             rc = mult_blocks(h, h->T1.p, h->Sinv.p, oX, 1.0, 0.0); if( rc ) return rc;
             for( const Block& bk : h->blk ) CK( sym_average(st, bk.n, oX + bk.off, bk.ld, h->X.p + bk.off) );
          }
          else
          {
-            rc = mult_blocks_pattern(h, h->X.p, oS, h->T1.p, 1.0); if( rc ) return rc;
+            rc = mult_blocks_pattern(h, h->X.p, oS, h->T1.p, 1.0, h->apat); if( rc ) return rc;
             rc = mult_blocks(h, h->T1.p, h->Sinv.p, h->T2.p, 1.0, 0.0); if( rc ) return rc;
             for( const Block& bk : h->blk ) CK( sym_average(st, bk.n, h->T2.p + bk.off, bk.ld, nullptr) );
             CK( axpby_out(st, ar, 1.0, h->K.p, -1.0, h->T2.p, oX) );
@@ -2365,7 +2391,7 @@ static int run_ipm(sdpcuda_handle* h, const sdpcuda_params* par, const double* s
          PHASE(6 + 2 * pass);
          if( pass == 0 ) CK( cudaStreamWaitEvent(st, h->evJoin, 0) );          // join: the factor of X is needed from here on
          // the predictor step lengths only steer the centring parameter: a short Lanczos run (safe, slightly pessimistic) suffices
-         rc = step_eigs(h, oX, oS, pass == 0 ? 8 : LZB_MAXIT); if( rc ) return rc;
+         rc = step_eigs(h, oX, oS, pass == 0 ? 8 : LZB_MAXIT, rdzero && h->apat); if( rc ) return rc;
          CK( cudaMemcpyAsync(h->h_stats + 32, h->scal.p, sizeof(double) * (8 + 2 * (size_t)nb), cudaMemcpyDeviceToHost, st) );
          PHASE(7 + 2 * pass);
          if( pass == 0 ) CK( cudaMemcpyAsync(h->h_info, h->info.p, 8 * sizeof(int), cudaMemcpyDeviceToHost, st) );
