@@ -357,6 +357,139 @@ lzb_step_kernel(const LzDesc* __restrict__ D, int j, int maxit, unsigned* __rest
    if( tid == 0 ) { alpha[j] = a; beta[j] = nr; tickets[blockIdx.y] = 0u; }
 }
 
+// ---- several Lanczos steps in ONE cooperative launch (explicit matrices) ---------------------------------------------------------
+// The step kernel above moves 2 x 32 MB in 22.7 us (max-cut 2000): launch, one memory round trip per CTA, the ticket and the tail of
+// the last CTA add up to more than the streaming itself.  Here the grid stays resident for a whole chunk of steps (four CTAs per SM,
+// cooperative launch); a step is two phases separated by grid-wide barriers (arrive counter + generation word, release/acquire):
+//   A  r = B x_j for the CTA's groups of 8 rows (same coldot8 as above) and its share of x_j' B x_j
+//   B  every CTA adds the shares in the same fixed order (alpha), forms x_{j+1} = s_j r - alpha s_j x_j - beta_{j-1} s_{j-1} x_{j-1} for
+//      its rows and its share of |x_{j+1}|^2
+// where v_j = s_j x_j, s_j = 1 / |x_j|: the vectors are kept UNSCALED, so that no third phase is needed for the normalisation
+// (|x_{j+1}| = beta_j is known to every CTA after the second barrier).  Same recurrence and coefficients as the step kernel.
+__device__ __forceinline__ void lz_grid_sync(unsigned* bar, unsigned& gen, unsigned nblocks)
+{
+   __syncthreads();
+   if( threadIdx.x == 0 )
+   {
+      ++gen;
+      __threadfence();
+      const unsigned old = atomicAdd(bar, 1u);
+      if( old == gen * nblocks - 1u )
+         asm volatile("st.release.gpu.global.u32 [%0], %1;" :: "l"(bar + 1), "r"(gen) : "memory");
+      else
+      {
+         unsigned seen, spins = 0;
+         do
+         {
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(bar + 1) : "memory");
+            if( ++spins > (1u << 25) ) asm volatile("trap;");      // a bug, not a wait (the launch is cooperative: all CTAs are resident)
+         } while( seen < gen );
+      }
+   }
+   __syncthreads();
+}
+
+__global__ void __launch_bounds__(256)
+lzb_persist_kernel(const LzDesc* __restrict__ D, int nmat, int j0, int jend, int maxit, unsigned* __restrict__ bar,
+   double* __restrict__ partials, int pstride)
+{
+   __shared__ double red[32];
+   __shared__ double res[8];
+   __shared__ double part[8][8];
+   const int tid = threadIdx.x;
+   unsigned gen = 0;
+   double* const pA = partials;                                  // shares of x' B x   [mat][group]
+   double* const pB = partials + (size_t)nmat * pstride;         // shares of |x_{j+1}|^2
+   int maxgroups = 0;
+   for( int q = 0; q < nmat; ++q ) maxgroups = max(maxgroups, (D[q].n + 7) / 8);
+   const int total = nmat * maxgroups;
+   for( int j = j0; j < jend; ++j )
+   {
+      // ---- phase A ----
+      for( int g = blockIdx.x; g < total; g += gridDim.x )
+      {
+         const int q = g / maxgroups, grp = g - q * maxgroups;
+         const LzDesc d = D[q];
+         const int n = d.n, i0 = 8 * grp;
+         if( i0 >= n || j >= n ) continue;
+         const double* x = d.Q + (size_t)j * n;
+         double* w = d.Q + (size_t)(j + 1) * n;
+         coldot8(d.B, d.ld, n, i0, 0, x, res, part);
+         if( tid < 8 )
+         {
+            const int i = i0 + tid;
+            double contrib = 0.0;
+            if( i < n ) { w[i] = res[tid]; contrib = res[tid] * x[i]; }
+            red[tid] = contrib;
+         }
+         __syncthreads();
+         if( tid == 0 )
+         {
+            double a = 0.0;
+            for( int t = 0; t < 8; ++t ) a += red[t];
+            pA[(size_t)q * pstride + grp] = a;
+         }
+         __syncthreads();
+      }
+      lz_grid_sync(bar, gen, gridDim.x);
+      // ---- phase B ----
+      for( int g = blockIdx.x; g < total; g += gridDim.x )
+      {
+         const int q = g / maxgroups, grp = g - q * maxgroups;
+         const LzDesc d = D[q];
+         const int n = d.n, i0 = 8 * grp, nblk = (n + 7) / 8;
+         if( i0 >= n || j >= n ) continue;
+         double* alpha = d.ab;
+         double* beta = d.ab + maxit;
+         double a = 0.0;
+         for( int b = tid; b < nblk; b += 256 ) a += __ldcg(&pA[(size_t)q * pstride + b]);
+         a = block_sum(a, red);                                 // the same order in every CTA
+         const double bprev = (j > 0) ? __ldcg(&beta[j - 1]) : 0.0;                    // = |x_j|
+         const double sj = (j > 0) ? ((bprev > 1e-300) ? 1.0 / bprev : 0.0) : 1.0;
+         const double bpp = (j > 1) ? __ldcg(&beta[j - 2]) : 0.0;                      // = |x_{j-1}|
+         const double sjm = (j > 1) ? ((bpp > 1e-300) ? 1.0 / bpp : 0.0) : 1.0;
+         const double al = sj * sj * a;
+         const double* x = d.Q + (size_t)j * n;
+         const double* xp = d.Q + (size_t)(j > 0 ? j - 1 : 0) * n;
+         double* w = d.Q + (size_t)(j + 1) * n;
+         if( tid < 8 )
+         {
+            const int i = i0 + tid;
+            double v = 0.0;
+            if( i < n )
+            {
+               v = sj * __ldcg(&w[i]) - al * sj * __ldcg(&x[i]) - (j > 0 ? bprev * sjm * __ldcg(&xp[i]) : 0.0);
+               w[i] = v;
+            }
+            red[tid] = v * v;
+         }
+         __syncthreads();
+         if( tid == 0 )
+         {
+            double s2 = 0.0;
+            for( int t = 0; t < 8; ++t ) s2 += red[t];
+            pB[(size_t)q * pstride + grp] = s2;
+            if( grp == 0 ) alpha[j] = al;
+         }
+         __syncthreads();
+      }
+      lz_grid_sync(bar, gen, gridDim.x);
+      // ---- beta_j = |x_{j+1}|: written once per matrix (by the CTA of its first group) ----
+      for( int g = blockIdx.x; g < total; g += gridDim.x )
+      {
+         const int q = g / maxgroups, grp = g - q * maxgroups;
+         if( grp != 0 ) continue;
+         const LzDesc d = D[q];
+         const int n = d.n, nblk = (n + 7) / 8;
+         if( j >= n ) continue;
+         double s2 = 0.0;
+         for( int b = tid; b < nblk; b += 256 ) s2 += __ldcg(&pB[(size_t)q * pstride + b]);
+         s2 = block_sum(s2, red);
+         if( tid == 0 ) d.ab[maxit + j] = sqrt(s2);      // read in phase B of the next step, i.e. behind its first barrier
+      }
+   }
+}
+
 // smallest eigenvalue of the kk x kk Lanczos tridiagonal (a, bt) by 32-way multisection on Sturm counts, one warp;
 // theta = lower end of the final bracket, resid = |beta_kk s_kk| (0 when the Krylov space is exhausted or kk = n)
 __device__ __forceinline__ void ritz_warp(const double* a, const double* bt, int kk, int n, int lane, double& theta, double& resid)
@@ -591,11 +724,41 @@ cudaError_t lanczos_batched(cudaStream_t st, int nmat, const LzDesc* h_desc, LzD
    ProfScope prof(st, PROF_EIG, 0.0);
    lzb_init_kernel<<<nmat, 1024, 0, st>>>(d_desc);
    count_launch();
+   // explicit matrices: a whole chunk of steps in one cooperative launch - OFF by default: measured on max-cut 2000 a step costs
+   // about 19 us instead of 22.7 (two grid barriers over 500 CTAs eat most of what the saved launches and tails give), the solve
+   // 5.65 instead of 5.81 ms per iteration, and the differently rounded recurrence needed 19 instead of 18 iterations on the
+   // benchmark instance (107.3 vs 104.6 ms).  SDPCUDA_LZ_PERSIST=1 turns it on.
+   static int coop_blocks[64] = {0};          // 0: not asked yet, -1: unavailable
+   int dev = 0;
+   SDPK_CUDA_CHECK( cudaGetDevice(&dev) );
+   if( coop_blocks[dev & 63] == 0 )
+   {
+      int coop = 0, per_sm = 0, nsm = 0;
+      cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
+      cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
+      if( coop && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lzb_persist_kernel, 256, 0) == cudaSuccess && per_sm > 0 )
+         coop_blocks[dev & 63] = std::min(per_sm, 4) * nsm;
+      else { coop_blocks[dev & 63] = -1; cudaGetLastError(); }
+   }
+   const char* pe = getenv("SDPCUDA_LZ_PERSIST");
+   const bool persist = !any_implicit && coop_blocks[dev & 63] > 0 && (pe != nullptr && pe[0] == '1');
    int j = 0;
    const int chunk = 8;
    while( j < maxit )
    {
       int jend = std::min(maxit, j + chunk);
+      if( persist )
+      {
+         unsigned* bar = tickets + nmat;                      // two words behind the tickets of the step kernel
+         SDPK_CUDA_CHECK( cudaMemsetAsync(bar, 0, 2 * sizeof(unsigned), st) );
+         const int groups = nmat * ceil_div(maxn, 8);
+         int grid = std::min(coop_blocks[dev & 63], std::max(groups, 1));
+         int jj0 = j, mi = LZB_MAXIT;
+         void* args[] = {(void*)&d_desc, (void*)&nmat, (void*)&jj0, (void*)&jend, (void*)&mi, (void*)&bar, (void*)&partials, (void*)&pstride};
+         SDPK_CUDA_CHECK( cudaLaunchCooperativeKernel((const void*)lzb_persist_kernel, dim3(grid), dim3(256), args, 0, st) );
+         count_launch();
+         j = jend;
+      }
       for( ; j < jend; ++j )
       {
          dim3 grid(ceil_div(maxn, 8), nmat);

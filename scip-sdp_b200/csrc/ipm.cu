@@ -629,9 +629,9 @@ int upload_problem(sdpcuda_handle* h, const sdpcuda_problem* P)
       for( cudaEvent_t& ev : h->evp ) if( ev == nullptr ) CK( cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) );
    }
    CK( h->lzdesc.ensure(2 * (size_t)std::max(h->nb, 1)) );
-   CK( h->lztickets.ensure(2 * (size_t)std::max(h->nb, 1)) );
-   CK( cudaMemsetAsync(h->lztickets.p, 0, sizeof(unsigned) * 2 * (size_t)std::max(h->nb, 1), st) );
-   CK( h->lzpart.ensure(2 * (size_t)std::max(h->nb, 1) * (size_t)ceil_div(std::max(h->maxn, 8), 8)) );
+   CK( h->lztickets.ensure(2 * (size_t)std::max(h->nb, 1) + 2) );        // + the two barrier words of the persistent Lanczos kernel
+   CK( cudaMemsetAsync(h->lztickets.p, 0, sizeof(unsigned) * (2 * (size_t)std::max(h->nb, 1) + 2), st) );
+   CK( h->lzpart.ensure(4 * (size_t)std::max(h->nb, 1) * (size_t)ceil_div(std::max(h->maxn, 8), 8)) );      // two sets of shares
    CK( h->partials.ensure((size_t)RED_BLOCKS * NSTAT) );
    CK( h->stats.ensure(64) );
    CK( h->scal.ensure(64 + 8 * (size_t)std::max(h->nb, 1)) );
