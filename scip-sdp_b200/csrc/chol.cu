@@ -643,6 +643,15 @@ constexpr size_t DAG_LEAF_DOUBLES = leaf_smem<DAG_T>() / sizeof(double);
 constexpr size_t DAG_SMEM_CHAIN = leaf_smem<DAG_T>() + sizeof(double) * (size_t)DAG_T * DAG_LDS;
 static_assert(DAG_SMEM_CHAIN >= DAG_SMEM && leaf_smem<DAG_T>() % 16 == 0, "chain layout");
 
+// Row sums of W in pieces: a tile (i, j) of W with more than DAG_WSEG k-tiles hands the first pieces of its sum to HELPER tasks (up to
+// three, DAG_WSEG k-tiles each), which are claimed before the tiles of the row, add up their piece as soon as its operands exist
+// (columns far left of the chain: long before) and leave it in a scratch tile; the tile's own task keeps the last piece - the one
+// that waits for the chain - and adds the helpers' pieces in a fixed order.  Without them the last rows of W (31 k-tiles = 65 us of
+// DMMA time on one SM per tile) were still adding when the chain had ended: 0.12 ms of tail at n = 2000.
+constexpr int DAG_WSEG = 8;
+__host__ __device__ inline int dag_nhelp(int len) { const int s = (len + DAG_WSEG - 1) / DAG_WSEG - 1; return s < 0 ? 0 : (s > 3 ? 3 : s); }
+__host__ __device__ inline int dag_rowhelp(int i) { int h = 0; for( int len = 1; len <= i; ++len ) h += dag_nhelp(len); return h; }     // helpers of row i
+
 struct DagArgs
 {
    int n, T;
@@ -652,6 +661,9 @@ struct DagArgs
    double* Wd;                   // T packed 64 x 64 inverses of the diagonal blocks of L
    int* sync;                    // [0] tile counter, [1] abort flag, [2 ..] T*T ready flags, then 2T flags of the pre-updated tiles (zeroed before the launch)
    int chain;                    // 1: ONE CTA carries the whole critical chain (all diagonal tiles and the tiles (j+1, j)), see dag_chain
+   int wshift;                   // the tiles of row r of W are claimed with block column r - wshift (0, 1 or 2)
+   int whelp;                    // 1: helper tasks for the long row sums of W (scratch tiles in `wscratch`, flags behind the other flags)
+   double* wscratch;
    long long watchdog;           // cycles a flag wait may last before the kernel aborts (0: no limit; SDPCUDA_DAG_WATCHDOG_S, default 2 s)
    int* info;
    long long* dbg;               // optional: 8 timestamps (ns) per tile of the critical chain (diagonal tiles: slot 2j, tiles (j+1,j): slot 2j+1)
@@ -883,7 +895,7 @@ __global__ void __launch_bounds__(DAG_THREADS, 2) potrf_dag_kernel(const __grid_
    int* const abortflag = pair.p[0].sync + 1;
    int maxtotal = 0;
    for( int q = 0; q < pair.count; ++q )
-      maxtotal = max(maxtotal, pair.p[q].winv ? pair.p[q].T * pair.p[q].T : pair.p[q].T * (pair.p[q].T + 1) / 2);
+      maxtotal = max(maxtotal, pair.p[q].winv ? pair.p[q].T * pair.p[q].T + pair.p[q].whelp : pair.p[q].T * (pair.p[q].T + 1) / 2);
 
    for( ;; )
    {
@@ -893,17 +905,68 @@ __global__ void __launch_bounds__(DAG_THREADS, 2) potrf_dag_kernel(const __grid_
       if( s_tile >= maxtotal * pair.count ) break;
       const DagArgs& a = pair.p[s_tile % pair.count];
       const int t = s_tile / pair.count;
-      const int T = a.T, n = a.n, total = a.winv ? T * T : T * (T + 1) / 2;
+      const int T = a.T, n = a.n, total = a.winv ? T * T + a.whelp : T * (T + 1) / 2;     // whelp: number of helper tasks (0: none)
       int* const ready = a.sync + 2;
       if( t >= total ) continue;
       // claim order: for c = 0, 1, ...: the factor tiles of block column c, (c,c) first, then (with the inverse) the tiles of row c of W
       int i, j;
-      bool wtile = false;
-      if( a.winv )
+      bool wtile = false, whelper = false;
+      int hid = 0, nh = 0, kt0 = 0;                     // helper id (first helper of a tile of W), helpers of the tile, first k-tile of the task
+      if( a.winv && a.whelp > 0 )
       {
-         const int c0 = t / T, idx = t - c0 * T;
-         if( idx < T - c0 ) { i = c0 + idx; j = c0; }
-         else { i = c0; j = idx - (T - c0); wtile = true; }
+         // block c0 of the order: the factor slots of column c0, the helpers of row c0 of W, the tiles of row c0 of W
+         int c0 = 0, rem = t, Hc = 0, HB = 0;            // Hc: helpers of row c0, HB: helpers of the rows before
+         for( ;; )
+         {
+            const int size = T + Hc;
+            if( rem < size ) break;
+            rem -= size; HB += Hc; ++c0; Hc += dag_nhelp(c0);
+         }
+         if( rem < T - c0 ) { i = c0 + rem; j = c0; }
+         else if( rem < T - c0 + Hc )
+         {
+            int hidx = rem - (T - c0);
+            whelper = wtile = true;
+            i = c0; hid = HB + hidx;
+            for( j = 0; j < i; ++j ) { const int q = dag_nhelp(i - j); if( hidx < q ) break; hidx -= q; }
+            kt0 = hidx * DAG_WSEG;
+         }
+         else
+         {
+            wtile = true;
+            i = c0; j = rem - (T - c0) - Hc;
+            hid = HB;
+            for( int jj = 0; jj < j; ++jj ) hid += dag_nhelp(i - jj);
+            nh = dag_nhelp(i - j);
+            kt0 = nh * DAG_WSEG;
+         }
+      }
+      else if( a.winv )
+      {
+         // block c0 of the order: the factor slots of column c0, then the tiles of row c0 + wshift of W (block 0 also takes the rows
+         // before that).  A tile of row r needs L_{r,k}, k < r: tile (r, r-1) comes from the chain, tile (r, r-2) from block r - 2,
+         // and the rows of W above it sit in earlier blocks as well - with wshift <= 2 every dependency still points backwards.
+         // The long row sums of the last rows get two chain steps more to stream before the chain ends.
+         const int sh = a.wshift;
+         int c0 = 0, rem = t;
+         for( ;; )
+         {
+            const int size = (T - c0) + ((c0 + sh <= T - 1) ? c0 + sh : 0) + ((c0 == 0) ? sh * (sh - 1) / 2 : 0);
+            if( rem < size ) break;
+            rem -= size; ++c0;
+         }
+         if( rem < T - c0 ) { i = c0 + rem; j = c0; }
+         else
+         {
+            rem -= T - c0;
+            wtile = true;
+            i = c0 + sh;
+            if( c0 == 0 )
+            {
+               for( int r = 1; r < sh; ++r ) { if( rem < r ) { i = r; break; } rem -= r; }
+            }
+            j = rem;
+         }
       }
       else
       {
@@ -956,11 +1019,13 @@ __global__ void __launch_bounds__(DAG_THREADS, 2) potrf_dag_kernel(const __grid_
             const int k = j + kt;
             return dag_wait(ready + i * T + k, (k == j) ? ready + j * T + j : ready + j * T + k, abortflag, s_abort, pair.p[0].watchdog);
          };
-         const int nkt = i - j, nchunks = 4 * (nkt - 1);
+         // this task adds the k-tiles kt0 .. nkt - 1 of the sum (a helper: its piece of DAG_WSEG k-tiles; chunk indices below are local)
+         const int nkt = whelper ? kt0 + DAG_WSEG : i - j, nchunks = 4 * (nkt - kt0 - 1);
+         int* const hflag = ready + T * T + 2 * T;
          auto wissue = [&](int cidx)
          {
-            if( (cidx & 3) == 0 ) ok = wwait(cidx >> 2) && ok;
-            if( ok ) wload(cidx, cidx % DAG_STAGES);
+            if( (cidx & 3) == 0 ) ok = wwait(kt0 + (cidx >> 2)) && ok;
+            if( ok ) wload(4 * kt0 + cidx, cidx % DAG_STAGES);
          };
 #pragma unroll 1
          for( int sidx = 0; sidx < DAG_STAGES - 1; ++sidx )
@@ -985,7 +1050,7 @@ __global__ void __launch_bounds__(DAG_THREADS, 2) potrf_dag_kernel(const __grid_
             if( ok )
             {
 #pragma unroll
-               for( int q = 0; q < 4; ++q ) wload(4 * (nkt - 1) + q, q);
+               for( int q = 0; q < 4; ++q ) wload(4 * (nkt - 1) + q, q);      // (global chunk index)
                asm volatile("cp.async.commit_group;\n" ::);
                asm volatile("cp.async.wait_group 0;\n" ::);
                __syncthreads();
@@ -994,6 +1059,34 @@ __global__ void __launch_bounds__(DAG_THREADS, 2) potrf_dag_kernel(const __grid_
             }
          }
          __syncthreads();
+         if( !ok ) break;
+         if( whelper )
+         {
+            // the piece goes to its scratch tile (thread-major layout: the tile's own task reads it back the same way)
+            double* sc = a.wscratch + (size_t)hid * DAG_T * DAG_T;
+#pragma unroll
+            for( int jt = 0; jt < 8; ++jt )
+            {
+               sc[(2 * jt) * DAG_THREADS + tid] = sacc[jt][0];
+               sc[(2 * jt + 1) * DAG_THREADS + tid] = sacc[jt][1];
+            }
+            __threadfence();
+            __syncthreads();
+            if( tid == 0 ) st_release(hflag + hid, 1);
+            continue;
+         }
+         for( int q = 0; q < nh && ok; ++q )
+         {
+            ok = dag_wait(hflag + hid + q, hflag + hid + q, abortflag, s_abort, pair.p[0].watchdog);
+            if( !ok ) break;
+            const double* sc = a.wscratch + (size_t)(hid + q) * DAG_T * DAG_T;
+#pragma unroll
+            for( int jt = 0; jt < 8; ++jt )
+            {
+               sacc[jt][0] += __ldcg(sc + (2 * jt) * DAG_THREADS + tid);
+               sacc[jt][1] += __ldcg(sc + (2 * jt + 1) * DAG_THREADS + tid);
+            }
+         }
          if( ok ) ok = dag_wait(ready + i * T + i, ready + i * T + i, abortflag, s_abort, pair.p[0].watchdog);
          if( !ok ) break;
          double* Ws = dsm;                               // [k][r] = W_ii[r][k]
@@ -1416,9 +1509,23 @@ cudaError_t potrf_dag_launch(cudaStream_t st, const DagProblem* pr, int count)
       const int T = ceil_div(P.n, DAG_T);
       double* Wd = P.diaginv != nullptr ? P.diaginv : P.work + (size_t)P.ldw * P.n;
       int* sync = reinterpret_cast<int*>(P.work + (size_t)P.ldw * P.n + (P.diaginv != nullptr ? 0 : (size_t)T * DAG_T * DAG_T));
-      if( (size_t)T * DAG_T * DAG_T + (size_t)(T * T + 2 * T + 2 + 1) / 2 > (size_t)P.ldw * 2 * CHOL_LEAF_MAX ) return cudaErrorInvalidValue;
-      SDPK_CUDA_CHECK( cudaMemsetAsync(sync, 0, sizeof(int) * (size_t)(T * T + 2 * T + 2), st) );
       inkernel[q] = (P.Linv != nullptr) && (ie != nullptr ? strcmp(ie, "levels") != 0 : P.n <= 3072);
+      // helper tasks of the row sums of W: their scratch tiles live in the first n columns of the work space (free in this path)
+      int nhelp = 0;
+      {
+         // OFF by default (SDPCUDA_DAG_WHELP=1): measured at n = 2000 the kernel takes 0.81 instead of 0.76 ms with the helpers - the
+         // 0.11 ms that the inverse factor costs on top of the factorisation are mostly a SLOWER CHAIN (714 instead of 630 us: the
+         // tasks that feed it wait longer for a CTA, 1.6 instead of 0.6 us per step), not a tail behind it (48 us), and more tasks
+         // in the order make exactly that worse (profiles/r2_chain_cta_and_leaf_formulations.log)
+         const char* he = getenv("SDPCUDA_DAG_WHELP");
+         if( inkernel[q] && (he != nullptr && he[0] == '1') )
+         {
+            for( int i = 0; i < T; ++i ) nhelp += dag_rowhelp(i);
+            if( (size_t)nhelp * DAG_T * DAG_T > (size_t)P.ldw * P.n ) nhelp = 0;
+         }
+      }
+      if( (size_t)T * DAG_T * DAG_T + (size_t)(T * T + 2 * T + 2 + nhelp + 1) / 2 > (size_t)P.ldw * 2 * CHOL_LEAF_MAX ) return cudaErrorInvalidValue;
+      SDPK_CUDA_CHECK( cudaMemsetAsync(sync, 0, sizeof(int) * (size_t)(T * T + 2 * T + 2 + nhelp), st) );
       DagArgs& a = pair.p[q];
       a.n = P.n; a.T = T; a.A = P.A; a.lda = P.lda; a.Linv = P.Linv; a.ldi = P.ldi; a.Wd = Wd; a.sync = sync; a.info = P.d_info;
       a.dbg = (q == 0) ? g_diag_dbg : nullptr;
@@ -1427,8 +1534,14 @@ cudaError_t potrf_dag_launch(cudaStream_t st, const DagProblem* pr, int count)
          a.watchdog = (long long)((we != nullptr ? atof(we) : 2.0) * 2.0e9);
       }
       a.winv = inkernel[q] ? 1 : 0;
+      a.whelp = nhelp; a.wscratch = P.work;
       a.chain = chain ? 1 : 0;
-      total = std::max(total, inkernel[q] ? T * T : T * (T + 1) / 2);
+      {
+         const char* we2 = getenv("SDPCUDA_DAG_WSHIFT");
+         a.wshift = (we2 != nullptr) ? std::max(0, std::min(2, atoi(we2))) : 0;   // measured: earlier claims take CTAs from the tasks the chain waits for (2000: 0.77 / 0.81 / 0.86 ms for 0 / 1 / 2)
+         if( T < 4 || !chain ) a.wshift = 0;          // without the chain CTA tile (r, r-1) is a task of block r - 1 itself
+      }
+      total = std::max(total, inkernel[q] ? T * T + nhelp : T * (T + 1) / 2);
       maxn = std::max(maxn, P.n);
       flops += (double)P.n * P.n * P.n / 3.0 * (inkernel[q] ? 2.0 : 1.0);
    }

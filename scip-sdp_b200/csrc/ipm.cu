@@ -3023,7 +3023,7 @@ int sdpcuda_time_kernel(sdpcuda_handle* h, int kind, int n, int reps, double* ms
       *ms_per_launch = (double)hv[1]; *work = (double)hv[2];
       return SDPCUDA_OK;
    }
-   if( kind == 10 )
+   if( kind == 10 || kind == 11 )      // 11: the same with the inverse factor (tiles of W as tasks of the same kernel)
    {
       // critical chain of the tile-DAG Cholesky at order n: timestamps per diagonal tile and first sub-diagonal tile
       const int T = (n + 63) / 64;
@@ -3036,7 +3036,8 @@ int sdpcuda_time_kernel(sdpcuda_handle* h, int kind, int n, int reps, double* ms
       {
          CK( cudaMemsetAsync(h->kC.p, 0, sizeof(double) * (16 * T + 8), st) );
          CK( cudaMemcpyAsync(h->kB.p, h->kA.p, nn * sizeof(double), cudaMemcpyDeviceToDevice, st) );
-         CK( potrf_lower(st, n, h->kB.p, ld, nullptr, 0, nullptr, h->kW.p, ld, h->info.p) );
+         CK( h->K.ensure(nn) );
+         CK( potrf_lower(st, n, h->kB.p, ld, kind == 11 ? h->K.p : nullptr, kind == 11 ? ld : 0, nullptr, h->kW.p, ld, h->info.p) );
          CK( cudaMemcpyAsync(hv.data(), h->kC.p, sizeof(long long) * (16 * T + 8), cudaMemcpyDeviceToHost, st) );
          CK( cudaStreamSynchronize(st) );
       }
