@@ -85,7 +85,7 @@ inline int ceil_div(int x, int a) { return (x + a - 1) / a; }
 // flags: GEMM_LOWER computes only tiles that touch the lower triangle (row >= col) of C.
 //        GEMM_KHI_M / GEMM_KHI_N restrict the k-range of a tile to k < m0+BM / k < n0+BN (op(A) lower triangular /
 //        op(B) upper triangular), GEMM_KLO_M / GEMM_KLO_N to k >= m0 / k >= n0 (op(A) upper / op(B) lower triangular).
-enum { GEMM_LOWER = 1, GEMM_KHI_M = 2, GEMM_KHI_N = 4, GEMM_KLO_M = 8, GEMM_KLO_N = 16 };
+enum { GEMM_LOWER = 1, GEMM_KHI_M = 2, GEMM_KHI_N = 4, GEMM_KLO_M = 8, GEMM_KLO_N = 16, GEMM_BALANCED = 32 /* internal: set by the launcher */ };
 cudaError_t gemm(cudaStream_t st, bool transa, bool transb, int m, int n, int k, double alpha,
    const double* A, int lda, long long strideA, const double* B, int ldb, long long strideB,
    double beta, double* C, int ldc, long long strideC, int batch, int flags);

@@ -271,6 +271,23 @@ gemm_dmma_tma_kernel(int M, int N, int K, double alpha, const __grid_constant__ 
       tm = first + r % gsz;
       tn = r / gsz;
    }
+   // Products of two triangular operands into a lower triangle (S^-1 = L^-T L^-1, the scaled step-length matrices): 528 tiles at
+   // n = 2000 whose k ranges differ by a factor of 32, all resident at once - what counts is the SUM of the tiles an SM gets.  The
+   // launch has 4 CTAs per SM; the tiles are sorted by work and dealt to the SMs in snake order (CTA b sits on SM b mod #SM when
+   // the grid fits the device in one wave), so that every SM gets a long, two middle and a short tile (list-scheduling model:
+   // 61 -> 45 tile times, ideal 40).
+   if( flags & GEMM_BALANCED )
+   {
+      const int T = (M + BM - 1) / BM, nsm = (int)gridDim.x / 4;
+      const int sidx = (int)blockIdx.x % nsm, q = (int)blockIdx.x / nsm;
+      const int p = (q & 1) ? nsm * q + (nsm - 1 - sidx) : nsm * q + sidx;
+      if( p >= T * (T + 1) / 2 ) return;
+      int k = 1;
+      while( k * (k + 1) / 2 <= p ) ++k;
+      const int off = p - (k - 1) * k / 2;
+      if( flags & GEMM_KHI_N ) { tn = T - k; tm = tn + off; }      // k range 64 (tn + 1): longest first
+      else { tm = k - 1; tn = off; }                               // k range K - 64 tm: longest first
+   }
    // longest tiles first: with a triangular operand the k range of a tile grows with its row (KHI_M) or column (KHI_N); launched in
    // ascending order the longest tiles would start last and run alone at the end (Linv dX, 2000^3: 160 -> 116 units of tile time in
    // a list-scheduling model, tools/gemm_schedule_model.py)
@@ -443,6 +460,20 @@ cudaError_t launch_tma(cudaStream_t st, int m, int n, int k, double alpha, const
       configured[dev & 63] = true;
    }
    dim3 grid(ceil_div(m, 64), ceil_div(n, 64), batch);
+   {
+      // balanced dealing of the lower tiles of a triangular x triangular product (see the kernel)
+      static int nsm[64] = {0};
+      if( nsm[dev & 63] == 0 ) SDPK_CUDA_CHECK( cudaDeviceGetAttribute(&nsm[dev & 63], cudaDevAttrMultiProcessorCount, dev) );
+      const int T = ceil_div(m, 64);
+      const bool tri = (flags & GEMM_LOWER) && (((flags & GEMM_KHI_N) && !(flags & (GEMM_KHI_M | GEMM_KLO_M | GEMM_KLO_N)))
+                                                || ((flags & GEMM_KLO_M) && (flags & GEMM_KLO_N) && !(flags & (GEMM_KHI_M | GEMM_KHI_N))));
+      const char* be = getenv("SDPCUDA_GEMM_BALANCE");
+      if( tri && batch == 1 && m == n && T >= 8 && T * (T + 1) / 2 <= 4 * nsm[dev & 63] && !(be != nullptr && be[0] == '0') )
+      {
+         grid = dim3(4 * nsm[dev & 63], 1, 1);
+         flags |= GEMM_BALANCED;
+      }
+   }
    kern<<<grid, 128, SMEM, st>>>(m, n, k, alpha, mapA, mapB, beta, C, ldc, sC, flags);
    count_launch();
    *done = true;
