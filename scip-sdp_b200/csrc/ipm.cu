@@ -251,9 +251,14 @@ int set_device(sdpcuda_handle* h)
 }
 
 // ---- problem upload --------------------------------------------------------------------------------------------------
+double now_seconds();
+
 int upload_problem(sdpcuda_handle* h, const sdpcuda_problem* P)
 {
    cudaStream_t st = h->st;
+   const bool uprof = getenv("SDPCUDA_UPLOAD_PROFILE") != nullptr;      // host time of the sections below, to stderr
+   double utick = now_seconds();
+   auto usec = [&](const char* what) { if( uprof ) { const double t = now_seconds(); fprintf(stderr, "[upload] %-28s %8.3f ms\n", what, 1e3 * (t - utick)); utick = t; } };
    // the captured factorisation sequences stay valid across uploads as long as no device buffer moved and the shapes are the
    // same (the usual case between branch-and-bound nodes): checked at the end of this function
    const long long epoch0 = g_realloc_epoch;
@@ -302,6 +307,7 @@ int upload_problem(sdpcuda_handle* h, const sdpcuda_problem* P)
       else { heavy[j] = 1; heavylist.push_back(j); }
    }
    h->nheavy = (int)heavylist.size();
+   usec("entries + classes");
    // class 3: light variables whose matrix is sigma a a' inside one block; used when the GEMM form is clearly cheaper than the
    // entry-pair form (truss topology: 4 x 4 element matrices, 100 entry pairs per pair of variables; max-cut: a = e_i, one entry
    // pair per pair of variables - stays on the entry path).  SDPCUDA_RANK1=0 turns the path off, =force skips the cost model.
@@ -381,6 +387,7 @@ int upload_problem(sdpcuda_handle* h, const sdpcuda_problem* P)
          }
       }
    }
+   usec("rank-one detection");
    std::vector<int> denselist;
    h->dgroups.clear();
    size_t maxmat = 1;
@@ -407,28 +414,43 @@ int upload_problem(sdpcuda_handle* h, const sdpcuda_problem* P)
       cmirv[e] = h->blk[bk].off + (long long)r * h->blk[bk].ld + c;
       key[nnz + e] = cposv[e];
    }
-   std::vector<int> order(nnz + P->cnnz);
-   if( h->arena <= ((size_t)1 << 26) && h->arena <= 16 * (size_t)(nnz + P->cnnz) + 4096 )
+   std::vector<int> var_of(nnz);
+   for( int j = 0; j < m; ++j )
+      for( int e = P->varbeg[j]; e < P->varbeg[j + 1]; ++e ) var_of[e] = j;
+   // the entries of dense constraint matrices (class 2) are streamed from their expanded copies (assemble_dense, apply_A_dense): the
+   // position lists need them only for the one-launch kernel of small relaxations.  A dense mid-size node (CLS-syn: 10^6 entries,
+   // 5 * 10^3 of them sparse) skips them here - the sort and the lists were 30 of the 47 ms of host time per upload.
+   const bool skipdense = h->ndense > 0 && !(h->maxn <= SMALL_MAX_N && m <= SMALL_MAX_M);
+   std::vector<int> ids;
+   ids.reserve((size_t)nnz + P->cnnz);
+   for( int e = 0; e < nnz; ++e ) if( !(skipdense && heavy[var_of[e]] == 2) ) ids.push_back(e);
+   for( int e = 0; e < P->cnnz; ++e ) ids.push_back(nnz + e);
+   std::vector<int> order(ids.size());
+   if( h->arena <= ((size_t)1 << 26) && h->arena <= 16 * ids.size() + 4096 )
    {
       // counting sort by arena position (stable in the entry id): linear in the number of entries; only while the arena is not
       // much larger than the entry list (max-cut n = 2000: 4 M positions for 24 k entries, where the pass over the counters
       // alone cost ~10 ms per upload — there the comparison sort below is the cheaper one)
       std::vector<int> cntpos(h->arena + 1, 0);
-      for( long long kk : key ) cntpos[(size_t)kk + 1]++;
+      for( int id : ids ) cntpos[(size_t)key[id] + 1]++;
       for( size_t a = 0; a < h->arena; ++a ) cntpos[a + 1] += cntpos[a];
-      for( int id = 0; id < nnz + P->cnnz; ++id ) order[cntpos[(size_t)key[id]]++] = id;
+      for( int id : ids ) order[cntpos[(size_t)key[id]]++] = id;
    }
    else
    {
-      std::iota(order.begin(), order.end(), 0);
+      order = ids;
       std::sort(order.begin(), order.end(), [&](int a, int b2) { return key[a] < key[b2] || (key[a] == key[b2] && a < b2); });
    }
-   std::vector<int> var_of(nnz);
-   for( int j = 0; j < m; ++j )
-      for( int e = P->varbeg[j]; e < P->varbeg[j + 1]; ++e ) var_of[e] = j;
    std::vector<int> posbeg, posvar, posbeg2, posvar2;      // "2": the same lists without the dense variables (streamed separately)
    std::vector<long long> pos, mirror;
    std::vector<double> posval, posc, posval2;
+   {
+      // (a dense instance has 10^6 entries: without the reservations below the growing vectors cost more than the sort)
+      const size_t npmax = std::min<size_t>(h->arena, order.size()) + 1;
+      posvar.reserve(ids.size()); posval.reserve(ids.size());
+      if( h->ndense > 0 ) { posvar2.reserve(ids.size()); posval2.reserve(ids.size()); }
+      pos.reserve(npmax); mirror.reserve(npmax); posc.reserve(npmax); posbeg.reserve(npmax + 1); posbeg2.reserve(npmax + 1);
+   }
    posbeg.push_back(0); posbeg2.push_back(0);
    for( size_t t = 0; t < order.size(); )
    {
@@ -459,6 +481,7 @@ int upload_problem(sdpcuda_handle* h, const sdpcuda_problem* P)
    }
    h->npos = (int)pos.size();
    h->cnnz = P->cnnz;
+   usec("position-major lists");
 
    // column-wise symmetric pattern per block for the sparse products X*dS, dXa*dSa, Linv*dS (only for sparse blocks)
    {
@@ -522,6 +545,7 @@ int upload_problem(sdpcuda_handle* h, const sdpcuda_problem* P)
       CK( cudaStreamSynchronize(st) );
    }
 
+   usec("sparsity patterns");
    // LP block CSR + CSC
    const int nlp = h->nlp;
    std::vector<int> lpbeg(nlp + 1, 0);
@@ -553,6 +577,7 @@ int upload_problem(sdpcuda_handle* h, const sdpcuda_problem* P)
       for( int q = colbeg[j] + 1; q < colbeg[j + 1]; ++q )
          if( colrow[q] == colrow[q - 1] ) { h->lpdup = true; break; }
 
+   usec("LP lists");
 #define UP(buf, vec) CK( h->buf.upload(vec, st) )
    std::vector<int> varbeg(P->varbeg, P->varbeg + m + 1);
    std::vector<double> eval(P->entval, P->entval + nnz), cval(P->cval, P->cval + P->cnnz), bvec(P->obj, P->obj + m);
@@ -567,6 +592,7 @@ int upload_problem(sdpcuda_handle* h, const sdpcuda_problem* P)
    UP(heavy, heavy); UP(heavylist, heavylist); UP(b, bvec); UP(denselist, denselist);
 #undef UP
    CK( cudaStreamSynchronize(st) );      // the host vectors above go out of scope
+   usec("copies + H2D");
 
    // dense Schur path: expanded constraint matrices and the two batched-GEMM result buffers (chunks of <= 256 MB)
    if( h->ndense > 0 )
@@ -593,6 +619,7 @@ int upload_problem(sdpcuda_handle* h, const sdpcuda_problem* P)
       }
    }
 
+   usec("dense expansion (launches)");
    // work space
    const size_t ar = h->arena;
    for( DBuf<double>* bf : {&h->X, &h->S, &h->Sinv, &h->L, &h->Linv, &h->LX, &h->LXinv, &h->dX, &h->dS, &h->dXa, &h->dSa,

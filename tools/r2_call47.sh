@@ -1,0 +1,14 @@
+set -x
+timeout 900 python -m pytest tests/test_gpu_solver.py tests/test_gpu_zfrontier.py tests/test_gpu_sdpi.py -m gpu -q -x 2>&1 | tail -2
+cat > /tmp/fr.py <<'P'
+import os, sys, time
+sys.path.insert(0, os.getcwd())
+import bench
+from scip_sdp_b200 import abi, nodesets
+lib = abi.Lib(abi.PRODUCT_LIB); g = abi.Solver(lib, device=0); t = nodesets.golden()
+for name in sys.argv[1:]:
+    r = bench.gpu_node_workload(g, lib, name, 0, t, 2)
+    print(name, "e2e nodes/s", round(r["counted"] / r["wall_s"], 2), "device nodes/s", round(r["counted"] / (r["device_ms"] / 1e3), 2), r["max_rel_diff_to_oracle"], flush=True)
+P
+SDPCUDA_UPLOAD_PROFILE=1 timeout 300 python /tmp/fr.py CLS-syn 2>&1 | tail -9
+timeout 300 python /tmp/fr.py TT-500 example_CLS 2>&1 | tail -2
