@@ -700,9 +700,9 @@ def main():
         achieved = g["work"] / g["ms"] / 1e9 if g["ms"] > 0 else 0.0
         share = {c: round(v["ms"] / pr["device_ms"], 4) for c, v in prof.items()}
         peak = max(peak, gemm_fl / gemm_ms / 1e9)
-        roof = {"bound": "tensor", "kernel": "gemm_dmma_kernel<64,64> (FP64 DMMA.8x8x4; the 32x32-tile instantiation of the factorisation leaves is listed separately in share_of_step)", "achieved": achieved, "peak": peak,
-                "unit": "TFLOP/s", "frac": achieved / peak, "traffic": 81.5e6 if a.n == 2000 else None,
-                "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one 2000^3 launch, ncu --set full (profiles/r1_gemm_dmma_ncu_full.txt); algorithmic 96 MB",
+        roof = {"bound": "tensor", "kernel": "gemm_dmma_tma_kernel<TA,TB,3> (64x64 tiles, FP64 DMMA.8x8x4, operands by cp.async.bulk.tensor; the 32x32-tile cp.async instantiation of small products is listed separately in share_of_step)", "achieved": achieved, "peak": peak,
+                "unit": "TFLOP/s", "frac": achieved / peak, "traffic": 97.7e6 if a.n == 2000 else None,
+                "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one 2000^3 launch, ncu --set full (profiles/r2_ncu_full_gemm_tma_potrf_dag_tiny_batch.txt: 75.8 + 21.9 MB); algorithmic 96 MB",
                 "peak_source": "measured live: max(register-resident DMMA probe, standalone 4096^3 DGEMM of this library); MEASURED_PEAKS.json holds no FP64 figure",
                 "dmma_probe_tflops": peak_fl / peak_ms / 1e9, "dgemm_4096_tflops": gemm_fl / gemm_ms / 1e9,
                 "launches_per_solve": g["launches"], "algorithmic_flops_per_solve": g["work"], "device_ms_per_solve": g["ms"],

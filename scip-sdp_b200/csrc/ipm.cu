@@ -1721,7 +1721,12 @@ int sdpcuda_solve_batch(sdpcuda_handle* h, int count, const sdpcuda_problem* con
    const char* te = getenv("SDPCUDA_BATCH_TINY");
    const char* se = getenv("SDPCUDA_BATCH_SMEM");
    if( h->packed ) { h->packed = false; h->solved = false; }      // the batch reuses the buffers of a packed single solve
-   const bool usetiny = !(te != nullptr && te[0] == '0'), stage = (se != nullptr && se[0] == '1');
+   // (a frontier that fits one wave of the 1024-thread kernel - one CTA per SM - is solved faster there: a node alone on its SM takes
+   // 28 - 39 ms of example_MkP against 35 - 48 ms in the 256-thread kernel, whose gain is four nodes per SM; rounds of a B&B tree)
+   int nsm_batch = 148;
+   cudaDeviceGetAttribute(&nsm_batch, cudaDevAttrMultiProcessorCount, h->device);
+   const bool usetiny = (te != nullptr) ? (te[0] != '0') : (count > nsm_batch);
+   const bool stage = (se != nullptr && se[0] == '1');
    const bool bprof = getenv("SDPCUDA_BATCH_PROFILE") != nullptr;
    // Chunks: the host packs chunk c + 1 (all host threads) while the kernels of chunk c run; two sets of buffers on two streams, so
    // that the kernels of two chunks overlap on the device as well.  This pays only for frontiers of several waves: a node takes its
