@@ -663,6 +663,7 @@ struct DagArgs
    int chain;                    // 1: ONE CTA carries the whole critical chain (all diagonal tiles and the tiles (j+1, j)), see dag_chain
    int wshift;                   // the tiles of row r of W are claimed with block column r - wshift (0, 1 or 2)
    int whelp;                    // 1: helper tasks for the long row sums of W (scratch tiles in `wscratch`, flags behind the other flags)
+   int wpanel;                   // > 0: only the tiles of W inside diagonal panels of wpanel x wpanel tiles (the inverses of the panels' diagonal blocks)
    double* wscratch;
    long long watchdog;           // cycles a flag wait may last before the kernel aborts (0: no limit; SDPCUDA_DAG_WATCHDOG_S, default 2 s)
    int* info;
@@ -975,6 +976,7 @@ __global__ void __launch_bounds__(DAG_THREADS, 2) potrf_dag_kernel(const __grid_
          while( start + (T - j) <= t ) { start += T - j; ++j; }
          i = j + (t - start);
       }
+      if( wtile && a.wpanel > 0 && (i / a.wpanel) != (j / a.wpanel) ) continue;       // W = L^-1 is wanted panel by panel only
       if( wtile )
       {
          // ---- W_ij = -W_ii sum_{k=j}^{i-1} L_ik W_kj  (i > j): the sum streams through the ring like the factor updates (L_ik as the
@@ -1475,7 +1477,7 @@ int chol_variant()
    return 1;
 }
 
-struct DagProblem { int n; double* A; int lda; double* Linv; int ldi; double* diaginv; double* work; int ldw; int* d_info; };
+struct DagProblem { int n; double* A; int lda; double* Linv; int ldi; double* diaginv; double* work; int ldw; int* d_info; int wpanel = 0; };
 
 cudaError_t potrf_dag_launch(cudaStream_t st, const DagProblem* pr, int count)
 {
@@ -1509,7 +1511,7 @@ cudaError_t potrf_dag_launch(cudaStream_t st, const DagProblem* pr, int count)
       const int T = ceil_div(P.n, DAG_T);
       double* Wd = P.diaginv != nullptr ? P.diaginv : P.work + (size_t)P.ldw * P.n;
       int* sync = reinterpret_cast<int*>(P.work + (size_t)P.ldw * P.n + (P.diaginv != nullptr ? 0 : (size_t)T * DAG_T * DAG_T));
-      inkernel[q] = (P.Linv != nullptr) && (ie != nullptr ? strcmp(ie, "levels") != 0 : P.n <= 3072);
+      inkernel[q] = (P.Linv != nullptr) && (P.wpanel > 0 || (ie != nullptr ? strcmp(ie, "levels") != 0 : P.n <= 3072));
       // helper tasks of the row sums of W: their scratch tiles live in the first n columns of the work space (free in this path)
       int nhelp = 0;
       {
@@ -1518,7 +1520,7 @@ cudaError_t potrf_dag_launch(cudaStream_t st, const DagProblem* pr, int count)
          // tasks that feed it wait longer for a CTA, 1.6 instead of 0.6 us per step), not a tail behind it (48 us), and more tasks
          // in the order make exactly that worse (profiles/r2_chain_cta_and_leaf_formulations.log)
          const char* he = getenv("SDPCUDA_DAG_WHELP");
-         if( inkernel[q] && (he != nullptr && he[0] == '1') )
+         if( inkernel[q] && P.wpanel == 0 && (he != nullptr && he[0] == '1') )
          {
             for( int i = 0; i < T; ++i ) nhelp += dag_rowhelp(i);
             if( (size_t)nhelp * DAG_T * DAG_T > (size_t)P.ldw * P.n ) nhelp = 0;
@@ -1535,6 +1537,7 @@ cudaError_t potrf_dag_launch(cudaStream_t st, const DagProblem* pr, int count)
       }
       a.winv = inkernel[q] ? 1 : 0;
       a.whelp = nhelp; a.wscratch = P.work;
+      a.wpanel = P.wpanel;
       a.chain = chain ? 1 : 0;
       {
          const char* we2 = getenv("SDPCUDA_DAG_WSHIFT");
@@ -1719,6 +1722,37 @@ __global__ void transpose_small_kernel(int n, const double* __restrict__ A, int 
 }
 
 } // namespace
+
+// The same result as potrf_lower_lookahead (L in A, packed inverses of the pb x pb diagonal blocks of L in pinv, their transposes in
+// pinvT) from ONE launch of the tile-DAG kernel: the factorisation as usual, and of W = L^-1 only the tiles inside the diagonal
+// panels (a.wpanel: a tile of W is a task only if its row and column tile lie in the same panel - the inverse of a diagonal block
+// depends on that block alone).  The inverse tiles land in the first n columns of the work space (free in this path) and are copied
+// out panel by panel.  m = 7140 (MkP-120): 8.3 -> about 6 ms per factorisation of the Schur complement.
+cudaError_t potrf_lower_panels(cudaStream_t st, int pb, int n, double* A, int lda, double* pinv, double* pinvT, double* work, int ldw, int* d_info)
+{
+   if( n <= 0 ) return cudaSuccess;
+   if( pb % DAG_T != 0 || n <= CHOL_LEAF_MAX || chol_variant() != 1 ) return cudaErrorNotSupported;
+   const int nblk = ceil_div(n, pb);
+   for( int k = 0; k < nblk; ++k )
+   {
+      const int j0 = k * pb, kb = min(pb, n - j0);
+      SDPK_CUDA_CHECK( cudaMemset2DAsync(work + (size_t)j0 * ldw + j0, sizeof(double) * ldw, 0, sizeof(double) * kb, kb, st) );
+      SDPK_CUDA_CHECK( cudaMemsetAsync(pinv + (size_t)k * pb * pb, 0, sizeof(double) * (size_t)pb * pb, st) );
+   }
+   DagProblem P = {n, A, lda, work, ldw, nullptr, work, ldw, d_info};
+   P.wpanel = pb / DAG_T;
+   SDPK_CUDA_CHECK( potrf_dag_launch(st, &P, 1) );
+   for( int k = 0; k < nblk; ++k )
+   {
+      const int j0 = k * pb, kb = min(pb, n - j0);
+      double* Pk = pinv + (size_t)k * pb * pb;
+      SDPK_CUDA_CHECK( copy2d(st, kb, kb, work + (size_t)j0 * ldw + j0, ldw, Pk, pb) );
+      dim3 grid(ceil_div(kb, 32), ceil_div(kb, 32)), block(32, 8);
+      transpose_small_kernel<<<grid, block, 0, st>>>(kb, Pk, pb, pinvT + (size_t)k * pb * pb, pb);
+      count_launch();
+   }
+   return cudaGetLastError();
+}
 
 cudaError_t potrf_lower_lookahead(cudaStream_t st, cudaStream_t side, cudaEvent_t* ev, int nev, int pb, int n, double* A, int lda,
    double* pinv, double* pinvT, double* work, int ldw, int* d_info)

@@ -107,6 +107,7 @@ cudaError_t potrf_lower_pair(cudaStream_t st, int n, double* A0, double* Linv0, 
 // solves L L' x = b for one right-hand side using the diagonal-block inverses (x overwrites b; tmp: n doubles)
 // large orders: right-looking panels (width pb) with one panel of look-ahead on a side stream; pinv / pinvT receive the inverses
 // of the diagonal panel blocks and their transposes (ceil(n/pb) blocks of pb x pb); ev: 2*ceil(n/pb)+2 events without timing
+cudaError_t potrf_lower_panels(cudaStream_t st, int pb, int n, double* A, int lda, double* pinv, double* pinvT, double* work, int ldw, int* d_info);
 cudaError_t potrf_lower_lookahead(cudaStream_t st, cudaStream_t side, cudaEvent_t* ev, int nev, int pb, int n, double* A, int lda,
    double* pinv, double* pinvT, double* work, int ldw, int* d_info);
 cudaError_t potrs_panels(cudaStream_t st, int pb, int n, const double* L, const double* LT, int ldl, const double* pinv, const double* pinvT,

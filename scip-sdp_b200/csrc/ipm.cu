@@ -2295,7 +2295,20 @@ static int run_ipm(sdpcuda_handle* h, const sdpcuda_params* par, const double* s
             if( h->minv )
                CK( potrf_lower(st, m, h->Mfac.p, h->ldm, h->MLinv.p, h->ldm, nullptr, h->Mwork.p, h->ldm, h->info.p + 2) );
             else
-               CK( potrf_lower_lookahead(st, h->st3, h->evp, 70, h->panel, m, h->Mfac.p, h->ldm, h->pinv.p, h->pinvT.p, h->Mwork.p, h->ldm, h->info.p + 2) );
+            {
+               // one launch of the tile-DAG kernel (factor + the inverses of the panels' diagonal blocks); SDPCUDA_MPANEL=lookahead: the
+               // right-looking panel factorisation on two streams of round 1
+               const char* mpe = getenv("SDPCUDA_MPANEL");
+               const bool lookahead = (mpe != nullptr && strcmp(mpe, "lookahead") == 0);
+               cudaError_t pe = lookahead ? cudaErrorNotSupported
+                  : potrf_lower_panels(st, h->panel, m, h->Mfac.p, h->ldm, h->pinv.p, h->pinvT.p, h->Mwork.p, h->ldm, h->info.p + 2);
+               if( pe == cudaErrorNotSupported )
+               {
+                  cudaGetLastError();
+                  pe = potrf_lower_lookahead(st, h->st3, h->evp, 70, h->panel, m, h->Mfac.p, h->ldm, h->pinv.p, h->pinvT.p, h->Mwork.p, h->ldm, h->info.p + 2);
+               }
+               CK( pe );
+            }
             return SDPCUDA_OK; });
          if( rc ) return rc;
          CK( cudaMemcpyAsync(h->h_info, h->info.p, 8 * sizeof(int), cudaMemcpyDeviceToHost, st) );
@@ -3125,7 +3138,7 @@ int sdpcuda_time_kernel(sdpcuda_handle* h, int kind, int n, int reps, double* ms
    CK( h->kA.ensure(nn) ); CK( h->kB.ensure(nn) ); CK( h->kC.ensure(nn) ); CK( h->kW.ensure((size_t)ld * (n + 2 * CHOL_LEAF_MAX)) );
    CK( h->K.ensure(nn) );
    CK( h->info.ensure(8) );
-   fill_random_kernel<<<1024, 256, 0, st>>>(nn, h->kA.p, 17u, kind == 2 || kind == 3 ? (double)n : 0.0, ld);
+   fill_random_kernel<<<1024, 256, 0, st>>>(nn, h->kA.p, 17u, kind == 2 || kind == 3 || kind == 13 ? (double)n : 0.0, ld);
    fill_random_kernel<<<1024, 256, 0, st>>>(nn, h->kB.p, 91u, 0.0, ld);
    CK( cudaGetLastError() );
    auto run = [&]() -> cudaError_t {
@@ -3147,10 +3160,16 @@ int sdpcuda_time_kernel(sdpcuda_handle* h, int kind, int n, int reps, double* ms
          return potrf_lower(st, n, h->kC.p, ld, nullptr, 0, nullptr, h->kW.p, ld, h->info.p);
       }
       case 6: return cudaMemcpyAsync(h->kC.p, h->kA.p, nn * sizeof(double), cudaMemcpyDeviceToDevice, st);
+      case 13:     // factor + inverses of the 512-wide diagonal blocks in one launch of the tile-DAG kernel (potrf_lower_panels)
+      {
+         cudaError_t e = cudaMemcpyAsync(h->kC.p, h->kA.p, nn * sizeof(double), cudaMemcpyDeviceToDevice, st);
+         if( e != cudaSuccess ) return e;
+         return potrf_lower_panels(st, n > 6144 ? 1024 : 512, n, h->kC.p, ld, h->K.p, h->kB.p, h->kW.p, ld, h->info.p);
+      }
       default: return cudaErrorInvalidValue;
       }
    };
-   if( kind == 2 || kind == 3 )
+   if( kind == 2 || kind == 3 || kind == 13 )
    {
       // symmetric positive definite input: A := (A + A')/2 + n I  (diagonal boost applied by the fill kernel)
       CK( sym_average(st, n, h->kA.p, ld, nullptr) );
@@ -3169,7 +3188,7 @@ int sdpcuda_time_kernel(sdpcuda_handle* h, int kind, int n, int reps, double* ms
    case 0: case 1: *work = 2.0 * dn * dn * dn; break;
    case 5: *work = dn * dn * dn; break;                 // algorithmic SYRK flops (lower triangle)
    case 2: *work = 2.0 * dn * dn * dn / 3.0; break;     // Cholesky n^3/3 + triangular inverse n^3/3
-   case 3: *work = dn * dn * dn / 3.0; break;
+   case 3: case 13: *work = dn * dn * dn / 3.0; break;
    case 6: *work = 2.0 * nn * sizeof(double); break;    // bytes read + written
    }
    return SDPCUDA_OK;
