@@ -503,7 +503,10 @@ __device__ void symvM(const SmallArgs& a, const double* x, double* y)
 // ---- warp-level Lanczos: the matrix (n <= 64) and the Krylov vectors live in shared memory, one warp does everything ----
 // Bs: n x n symmetric, row stride LDS.  Qs: (SMALL_LZ_STEPS + 2) vectors with stride LDS.  ab: alpha[32], beta[32], w[64] scratch.
 // Returns (to all lanes) the safe estimate Ritz value - residual bound of the smallest eigenvalue.
-__device__ double lanczos_warp(int n, const double* Bs, double* Qs, double* ab)
+// maxsteps: 8 for the predictor (its step lengths only steer the centring parameter), SMALL_LZ_STEPS for the corrector, where the run
+// also ends after 8, 16 or 24 steps once the Ritz pair is good enough for a step length (residual bound below 1 % of the value, or
+// the safe value above -0.5: the full step is taken anyway) - the stopping rule of lanczos_batched in eig.cu.
+__device__ double lanczos_warp(int n, const double* Bs, double* Qs, double* ab, int maxsteps)
 {
    const int lane = threadIdx.x & 31;
    const int r0 = lane, r1 = lane + 32;
@@ -511,7 +514,8 @@ __device__ double lanczos_warp(int n, const double* Bs, double* Qs, double* ab)
    double* al = ab;
    double* be = ab + SMALL_LZ_STEPS;
    double* ws = ab + 2 * SMALL_LZ_STEPS;            // 64 doubles: current w, shared between the lanes
-   const int steps = min(n, SMALL_LZ_STEPS);
+   // (blocks of order <= 16 always run all n steps: exact values, iterate for iterate what the oracle's eigenvalue routine gives)
+   const int steps = (n <= 16) ? n : min(n, min(maxsteps, SMALL_LZ_STEPS));
    double v0 = 0.0, v1 = 0.0;
    {
       unsigned h = (unsigned)r0 * 2654435761u + 12345u; h ^= h >> 15; h *= 2246822519u; h ^= h >> 13;
@@ -525,6 +529,53 @@ __device__ double lanczos_warp(int n, const double* Bs, double* Qs, double* ab)
       if( h1 ) Qs[r1] = v1;
    }
    __syncwarp();
+   // smallest Ritz value of the k x k tridiagonal (32-way multisection on Sturm counts) and its residual bound
+   auto ritz = [&](int k, double& th_out, double& rs_out)
+   {
+      double lo = 1e300, hi = -1e300;
+      for( int i = 0; i < k; ++i )
+      {
+         double r = (i > 0 ? fabs(be[i - 1]) : 0.0) + (i < k - 1 ? fabs(be[i]) : 0.0);
+         lo = fmin(lo, al[i] - r); hi = fmax(hi, al[i] + r);
+      }
+      const double width0 = hi - lo;
+      for( int round = 0; round < 6 && (hi - lo) > 1e-9 * width0 + 1e-300; ++round )
+      {
+         const double xt = lo + (lane + 1) * (hi - lo) / 33.0;
+         int cnt = 0;
+         double dd = 1.0;
+         for( int i = 0; i < k; ++i )
+         {
+            double b2 = (i > 0) ? be[i - 1] * be[i - 1] : 0.0;
+            dd = al[i] - xt - (i > 0 ? b2 / dd : 0.0);
+            if( dd == 0.0 ) dd = 1e-300;
+            if( dd < 0.0 ) ++cnt;
+         }
+         double below = (cnt == 0) ? xt : lo;
+         double above = (cnt >= 1) ? xt : hi;
+   #pragma unroll
+         for( int o = 16; o > 0; o >>= 1 )
+         {
+            below = fmax(below, __shfl_xor_sync(0xffffffffu, below, o));
+            above = fmin(above, __shfl_xor_sync(0xffffffffu, above, o));
+         }
+         lo = below; hi = above;
+      }
+      const double theta = lo;
+      double resid = 0.0;
+      if( k < n && be[k - 1] > 1e-13 * (fabs(al[k - 1]) + 1e-300) )
+      {
+         double sm1 = 0.0, s0 = 1.0, nrm = 1.0, last = 1.0;
+         for( int i = 0; i < k - 1; ++i )
+         {
+            double s1 = ((theta - al[i]) * s0 - (i > 0 ? be[i - 1] * sm1 : 0.0)) / be[i];
+            sm1 = s0; s0 = s1; nrm += s1 * s1; last = s1;
+            if( nrm > 1e200 ) { sm1 *= 1e-100; s0 *= 1e-100; last *= 1e-100; nrm *= 1e-200; }
+         }
+         resid = fabs(be[k - 1]) * fabs(last) / sqrt(nrm);
+      }
+         th_out = theta; rs_out = resid;
+   };
    double p0 = 0.0, p1 = 0.0, bprev = 0.0;          // previous Lanczos vector (this lane's rows)
    int kdone = 0;
    for( int j = 0; j < steps; ++j )
@@ -570,51 +621,16 @@ __device__ double lanczos_warp(int n, const double* Bs, double* Qs, double* ab)
       if( h0 ) Qs[(j + 1) * LDS + r0] = v0;
       if( h1 ) Qs[(j + 1) * LDS + r1] = v1;
       __syncwarp();
+      if( n > 16 && kdone < steps && (kdone & 7) == 0 )
+      {
+         double th, rs;
+         ritz(kdone, th, rs);
+         if( rs <= 0.01 * fabs(th) || th - rs >= -0.5 ) return th - rs;
+      }
    }
    __syncwarp();
-   const int k = kdone;
-   double lo = 1e300, hi = -1e300;
-   for( int i = 0; i < k; ++i )
-   {
-      double r = (i > 0 ? fabs(be[i - 1]) : 0.0) + (i < k - 1 ? fabs(be[i]) : 0.0);
-      lo = fmin(lo, al[i] - r); hi = fmax(hi, al[i] + r);
-   }
-   const double width0 = hi - lo;
-   for( int round = 0; round < 6 && (hi - lo) > 1e-9 * width0 + 1e-300; ++round )
-   {
-      const double xt = lo + (lane + 1) * (hi - lo) / 33.0;
-      int cnt = 0;
-      double dd = 1.0;
-      for( int i = 0; i < k; ++i )
-      {
-         double b2 = (i > 0) ? be[i - 1] * be[i - 1] : 0.0;
-         dd = al[i] - xt - (i > 0 ? b2 / dd : 0.0);
-         if( dd == 0.0 ) dd = 1e-300;
-         if( dd < 0.0 ) ++cnt;
-      }
-      double below = (cnt == 0) ? xt : lo;
-      double above = (cnt >= 1) ? xt : hi;
-#pragma unroll
-      for( int o = 16; o > 0; o >>= 1 )
-      {
-         below = fmax(below, __shfl_xor_sync(0xffffffffu, below, o));
-         above = fmin(above, __shfl_xor_sync(0xffffffffu, above, o));
-      }
-      lo = below; hi = above;
-   }
-   const double theta = lo;
-   double resid = 0.0;
-   if( k < n && be[k - 1] > 1e-13 * (fabs(al[k - 1]) + 1e-300) )
-   {
-      double sm1 = 0.0, s0 = 1.0, nrm = 1.0, last = 1.0;
-      for( int i = 0; i < k - 1; ++i )
-      {
-         double s1 = ((theta - al[i]) * s0 - (i > 0 ? be[i - 1] * sm1 : 0.0)) / be[i];
-         sm1 = s0; s0 = s1; nrm += s1 * s1; last = s1;
-         if( nrm > 1e200 ) { sm1 *= 1e-100; s0 *= 1e-100; last *= 1e-100; nrm *= 1e-200; }
-      }
-      resid = fabs(be[k - 1]) * fabs(last) / sqrt(nrm);
-   }
+   double theta, resid;
+   ritz(kdone, theta, resid);
    return theta - resid;
 }
 
@@ -1093,7 +1109,7 @@ __device__ __forceinline__ void ipm_small_body(const SmallArgs& a)
             if( tid < 64 )
             {
                const int wv = tid >> 5;
-               const double lv = lanczos_warp(bk.n, wv == 0 ? sh : sh2, lzq + wv * (SMALL_LZ_STEPS + 2) * LDS, lzab + wv * (2 * SMALL_LZ_STEPS + 64));
+               const double lv = lanczos_warp(bk.n, wv == 0 ? sh : sh2, lzq + wv * (SMALL_LZ_STEPS + 2) * LDS, lzab + wv * (2 * SMALL_LZ_STEPS + 64), pass == 0 ? 8 : SMALL_LZ_STEPS);
                if( (tid & 31) == 0 ) lam2[wv] = lv;
             }
             __syncthreads();
