@@ -670,25 +670,51 @@ __device__ bool cholM_smem(const SmallArgs& a, double reg, double* Ms, double* r
    return ok;
 }
 
-// v <- (L L')^-1 v with L in shared memory (m <= 64): one warp, lane owns rows lane and lane + 32
-__device__ void solveM_smem(int m, const double* Ms, const double* rdiag, double* v)
+// v <- (L L')^-1 v with L in shared memory (m <= 64): one warp, lane owns rows lane and lane + 32.
+// The substitution is a chain of 2 m dependent steps (shuffle -> product -> FMA); everything that does not depend on the chain - the
+// loads of column / row k and of 1 / l_kk - is written so that the compiler can issue it steps ahead (k loops split at 32: the source
+// register of the shuffle is fixed inside a loop, unrolled fourfold).  Same operations in the same order as before: same bits.
+__device__ __noinline__ void solveM_smem(int m, const double* Ms, const double* rdiag, double* v)
 {
    __syncthreads();
    if( threadIdx.x < 32 )
    {
       const int lane = threadIdx.x;
       double r0 = (lane < m) ? v[lane] : 0.0, r1 = (lane + 32 < m) ? v[lane + 32] : 0.0;
-      for( int k = 0; k < m; ++k )
+      const double* row0 = Ms + min(lane, m - 1) * LDMS;
+      const double* row1 = Ms + min(lane + 32, m - 1) * LDMS;
+      const bool in0 = lane < m, in1 = lane + 32 < m;
+      const int m0 = min(m, 32);
+#pragma unroll 4
+      for( int k = 0; k < m0; ++k )
       {
-         double xk = __shfl_sync(0xffffffffu, (k < 32) ? r0 : r1, k & 31) * rdiag[k];
-         if( lane == k ) r0 = xk; else if( lane > k && lane < m ) r0 -= Ms[lane * LDMS + k] * xk;
-         if( lane + 32 == k ) r1 = xk; else if( lane + 32 > k && lane + 32 < m ) r1 -= Ms[(lane + 32) * LDMS + k] * xk;
+         const double xk = __shfl_sync(0xffffffffu, r0, k) * rdiag[k];
+         const double l0 = row0[k], l1 = row1[k];
+         if( lane == k ) r0 = xk; else if( lane > k && in0 ) r0 -= l0 * xk;
+         if( in1 ) r1 -= l1 * xk;
       }
-      for( int k = m - 1; k >= 0; --k )
+#pragma unroll 4
+      for( int k = 32; k < m; ++k )
       {
-         double xk = __shfl_sync(0xffffffffu, (k < 32) ? r0 : r1, k & 31) * rdiag[k];
-         if( lane == k ) r0 = xk; else if( lane < k ) r0 -= Ms[k * LDMS + lane] * xk;
-         if( lane + 32 == k ) r1 = xk; else if( lane + 32 < k ) r1 -= Ms[k * LDMS + lane + 32] * xk;
+         const double xk = __shfl_sync(0xffffffffu, r1, k - 32) * rdiag[k];
+         const double l1 = row1[k];
+         if( lane + 32 == k ) r1 = xk; else if( lane + 32 > k && in1 ) r1 -= l1 * xk;
+      }
+#pragma unroll 4
+      for( int k = m - 1; k >= 32; --k )
+      {
+         const double xk = __shfl_sync(0xffffffffu, r1, k - 32) * rdiag[k];
+         const double* rowk = Ms + k * LDMS;
+         const double l0 = rowk[lane], l1 = rowk[min(lane + 32, k)];
+         r0 -= l0 * xk;
+         if( lane + 32 == k ) r1 = xk; else if( lane + 32 < k ) r1 -= l1 * xk;
+      }
+#pragma unroll 4
+      for( int k = m0 - 1; k >= 0; --k )
+      {
+         const double xk = __shfl_sync(0xffffffffu, r0, k) * rdiag[k];
+         const double l0 = Ms[k * LDMS + min(lane, k)];
+         if( lane == k ) r0 = xk; else if( lane < k ) r0 -= l0 * xk;
       }
       if( lane < m ) v[lane] = r0;
       if( lane + 32 < m ) v[lane + 32] = r1;
@@ -735,8 +761,9 @@ __device__ bool cholM_pk(const SmallArgs& a, double reg, double* Mp, double* rdi
    return ok;
 }
 
-// v <- (L L')^-1 v with the packed factor: one warp, lane owns the rows lane + 32 q
-__device__ void solveM_pk(int m, const double* Mp, const double* rdiag, double* v)
+// v <- (L L')^-1 v with the packed factor: one warp, lane owns the rows lane + 32 q.  Written like solveM_smem: the k loops are split
+// at the multiples of 32 (static source register of the shuffle), the row pointers are formed once, the loads run ahead of the chain.
+__device__ __noinline__ void solveM_pk(int m, const double* Mp, const double* rdiag, double* v)
 {
    __syncthreads();
    if( threadIdx.x < 32 )
@@ -744,35 +771,53 @@ __device__ void solveM_pk(int m, const double* Mp, const double* rdiag, double* 
       constexpr int Q = (MPK + 31) / 32;
       const int lane = threadIdx.x;
       double r[Q];
+      const double* row[Q];
+      bool in[Q];
 #pragma unroll
-      for( int q = 0; q < Q; ++q ) { const int i = lane + 32 * q; r[q] = (i < m) ? v[i] : 0.0; }
-      for( int k = 0; k < m; ++k )                 // forward substitution, column k of L: entries (i, k), i > k
+      for( int q = 0; q < Q; ++q )
       {
-         double xk = 0.0;
+         const int i = lane + 32 * q, ic = min(i, m - 1);
+         in[q] = (i < m);
+         r[q] = in[q] ? v[i] : 0.0;
+         row[q] = Mp + ic * (ic + 1) / 2;
+      }
+      // forward substitution, column k of L: entries (i, k), i > k
 #pragma unroll
-         for( int q = 0; q < Q; ++q ) if( q == (k >> 5) ) xk = r[q];
-         xk = __shfl_sync(0xffffffffu, xk, k & 31) * rdiag[k];
-#pragma unroll
-         for( int q = 0; q < Q; ++q )
+      for( int kq = 0; kq < Q; ++kq )
+      {
+         const int kend = min(32, m - 32 * kq);
+#pragma unroll 4
+         for( int kl = 0; kl < kend; ++kl )
          {
-            const int i = lane + 32 * q;
-            if( i == k ) r[q] = xk;
-            else if( i > k && i < m ) r[q] -= Mp[i * (i + 1) / 2 + k] * xk;
+            const int k = 32 * kq + kl;
+            const double xk = __shfl_sync(0xffffffffu, r[kq], kl) * rdiag[k];
+#pragma unroll
+            for( int q = kq; q < Q; ++q )
+            {
+               const double l = row[q][min(k, lane + 32 * q)];
+               if( q == kq ) { if( lane == kl ) r[q] = xk; else if( lane > kl && in[q] ) r[q] -= l * xk; }
+               else if( in[q] ) r[q] -= l * xk;
+            }
          }
       }
-      for( int k = m - 1; k >= 0; --k )            // backward substitution with L': row k of L, entries (k, i), i < k (contiguous)
+      // backward substitution with L': row k of L, entries (k, i), i < k (contiguous)
+#pragma unroll
+      for( int kq = Q - 1; kq >= 0; --kq )
       {
-         double xk = 0.0;
-#pragma unroll
-         for( int q = 0; q < Q; ++q ) if( q == (k >> 5) ) xk = r[q];
-         xk = __shfl_sync(0xffffffffu, xk, k & 31) * rdiag[k];
-         const double* row = Mp + k * (k + 1) / 2;
-#pragma unroll
-         for( int q = 0; q < Q; ++q )
+         const int kend = min(32, m - 32 * kq);
+#pragma unroll 4
+         for( int kl = kend - 1; kl >= 0; --kl )
          {
-            const int i = lane + 32 * q;
-            if( i == k ) r[q] = xk;
-            else if( i < k ) r[q] -= row[i] * xk;
+            const int k = 32 * kq + kl;
+            const double xk = __shfl_sync(0xffffffffu, r[kq], kl) * rdiag[k];
+            const double* rowk = Mp + k * (k + 1) / 2;
+#pragma unroll
+            for( int q = 0; q <= kq; ++q )
+            {
+               const double l = rowk[min(lane + 32 * q, k)];
+               if( q == kq ) { if( lane == kl ) r[q] = xk; else if( lane < kl ) r[q] -= l * xk; }
+               else r[q] -= l * xk;
+            }
          }
       }
 #pragma unroll
@@ -781,6 +826,11 @@ __device__ void solveM_pk(int m, const double* Mp, const double* rdiag, double* 
    __syncthreads();
 }
 
+// (Measured and NOT kept: inverting the shared-memory factor of M in place once per iteration and solving by two matrix-vector products.
+// The substitution by one warp is a chain of 2 m dependent steps - 106 k cycles per solve at m = 96, four solves per iteration - and
+// the products took 0.3 M instead of 5.7 M cycles per example_MkP relaxation; but the in-place inversion cost 4.9 M, a frontier of
+// example_TT (m = 27, four CTAs per SM: throughput, not latency) lost 13 %, and the penalty formulations of the boundary tests
+// (Gamma = 1e4 .. 1e6) stopped converging: the substitution is backward stable, the explicit inverse is not.)
 // dynamic shared memory of the body (layout at the top of ipm_small_body)
 constexpr size_t SMALL_SMEM = (2 * VMAXN * LDS + 32 + VMAXN + SMALL_MAX_M + 3 * SMALL_LZ_STEPS + 8 + 2 * (SMALL_LZ_STEPS + 2) * LDS
    + 2 * (2 * SMALL_LZ_STEPS + 64) + MSN * LDMS + 8) * sizeof(double) + sizeof(Ctl) + 64;
@@ -812,6 +862,16 @@ __device__ __forceinline__ void ipm_small_body(const SmallArgs& a)
    long long pc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
    long long tq = clock64();
 #define TICK(k) do { long long _n = clock64(); pc[k] += _n - tq; tq = _n; } while( 0 )
+   // sub-phases of the directions: compiled in with -DSDPK_SUBTICKS only (eight more 64-bit counters cost the 256-thread instantiation,
+   // which lives on 64 registers per thread, 10 % of its frontier throughput)
+#ifdef SDPK_SUBTICKS
+   long long ps[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tq2 = 0;
+#define SUBTICK(k) do { long long _n = clock64(); ps[k] += _n - tq2; tq2 = _n; } while( 0 )
+#define SUBTICK_START() do { tq2 = clock64(); } while( 0 )
+#else
+#define SUBTICK(k) do { } while( 0 )
+#define SUBTICK_START() do { } while( 0 )
+#endif
 
    if( tid == 0 )
    {
@@ -1022,6 +1082,7 @@ __device__ __forceinline__ void ipm_small_body(const SmallArgs& a)
          double* ox = pass == 0 ? a.dxa : a.dx;
          double* os = pass == 0 ? a.dsa : a.ds;
          const double sigmamu = (pass == 1) ? c->sigma * mu : 0.0;
+         SUBTICK_START();
          // K = sym((sigma mu I - dXa dSa - X Rd) S^-1) - X
          const bool haveT = (!rdzero) || pass == 1;
          for( int k = 0; k < nb; ++k )
@@ -1052,17 +1113,23 @@ __device__ __forceinline__ void ipm_small_body(const SmallArgs& a)
             a.klp[l] = cc / a.s[l] - a.x[l];
          }
          __syncthreads();
+         SUBTICK(0);
          applyA(a, a.K, a.g);
          lpcols(a, a.klp, a.g, true);
          for( int j = tid; j < m; j += NT ) { a.g[j] -= a.rp[j]; a.dy[j] = a.g[j]; }
+         SUBTICK(1);
          if( msmall ) solveM_smem(m, Msh, rdiagM, a.dy); else if( mpacked ) solveM_pk(m, Mpk, rdiagM, a.dy); else solveM(a, rdiagM, a.dy);
+         SUBTICK(6);
          symvM(a, a.dy, a.tm1);
+         SUBTICK(7);
          for( int j = tid; j < m; j += NT ) a.tm1[j] = a.g[j] - a.tm1[j];
          if( msmall ) solveM_smem(m, Msh, rdiagM, a.tm1); else if( mpacked ) solveM_pk(m, Mpk, rdiagM, a.tm1); else solveM(a, rdiagM, a.tm1);
          for( int j = tid; j < m; j += NT ) a.dy[j] += a.tm1[j];
          __syncthreads();
+         SUBTICK(2);
          // dS = A'dy (+ Rd), dX = K - sym(X (A'dy) S^-1)
          assemble(a, a.dy, 0.0, oS);
+         SUBTICK(3);
          for( int k = 0; k < nb; ++k )
          {
             const SmallBlock bk = a.blk[k];
@@ -1076,6 +1143,7 @@ __device__ __forceinline__ void ipm_small_body(const SmallArgs& a)
             if( !rdzero ) oS[i] += a.Rd[i];
          }
          __syncthreads();
+         SUBTICK(4);
          lprows(a, a.dy, a.Ddy);
          double rp1 = -1e300, rd1 = -1e300;
          for( int l = tid; l < nlp; l += NT )
@@ -1089,6 +1157,7 @@ __device__ __forceinline__ void ipm_small_body(const SmallArgs& a)
          }
          rp1 = bmax(rp1, red); rd1 = bmax(rd1, red);
          double apmax = (rp1 > -1e299) ? -rp1 : 1e30, admax = (rd1 > -1e299) ? -rd1 : 1e30;
+         SUBTICK(5);
          TICK(5);
          // SDP step lengths from lambda_min(LXinv dX LXinv') and lambda_min(Linv dS Linv')
          for( int k = 0; k < nb; ++k )
@@ -1175,6 +1244,11 @@ __device__ __forceinline__ void ipm_small_body(const SmallArgs& a)
       if( a.verbose >= 2 )
          printf("  [cuda-1cta cycles] resid %lld | fact S,X %lld | tests+Sinv %lld | schur %lld | chol M %lld | directions %lld | step lengths %lld\n",
             pc[0], pc[1], pc[2], pc[3], pc[4], pc[5], pc[6]);
+#ifdef SDPK_SUBTICKS
+      if( a.verbose >= 2 )
+         printf("  [cuda-1cta cycles, directions] K %lld | A(K) + D'k %lld | first solve with M %lld | M dy %lld | second solve %lld | A'dy %lld | dX %lld | LP part %lld (m = %d, factor of M: %s)\n",
+            ps[0], ps[1], ps[6], ps[7], ps[2], ps[3], ps[4], ps[5], a.m, msmall ? "shared memory" : (mpacked ? "packed in shared memory" : "global memory"));
+#endif
    }
 }
 

@@ -61,6 +61,7 @@ static const cuemu::Idx3 blockIdx = {{1}};
 #undef __global__
 #undef __host__
 #undef __forceinline__
+#undef __noinline__
 #undef __shared__
 #undef __launch_bounds__
 #undef __align__
@@ -68,6 +69,7 @@ static const cuemu::Idx3 blockIdx = {{1}};
 #define __global__
 #define __host__
 #define __forceinline__ inline
+#define __noinline__
 #define __shared__ static
 #define __launch_bounds__(...)
 #define __align__(n) alignas(n)
