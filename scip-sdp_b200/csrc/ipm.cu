@@ -61,12 +61,21 @@ template <class T> struct DBuf
       g_h2d_bytes += (double)(v.size() * sizeof(T));
       return cudaMemcpyAsync(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, st);
    }
+   // the same through a pinned staging ring (anything with in(dst, src, bytes, stream))
+   template <class V, class Stage> cudaError_t upload(const V& v, cudaStream_t st, Stage& stage)
+   {
+      cudaError_t e = ensure(v.size());
+      if( e != cudaSuccess || v.empty() ) return e;
+      g_h2d_bytes += (double)(v.size() * sizeof(T));
+      return stage.in(p, v.data(), v.size() * sizeof(T), st);
+   }
    void release() { if( p ) cudaFree(p); p = nullptr; cap = 0; }
 };
 
 struct Block { int n; int ld; long long off; };
 
 std::atomic<int> g_next_device{0};
+std::atomic<int> g_live_handles{0};             // solver objects alive in this process (SCIP's concurrent mode: one per solver thread)
 
 } // namespace
 
@@ -127,9 +136,73 @@ struct BatchImage
    template <class T> size_t putv(const std::vector<T>& v) { return put(v.data(), v.size() * sizeof(T)); }
 };
 
+// Pinned staging ring of a handle.  Copies between PAGEABLE host memory and the device do not overlap with kernels of other
+// streams (the driver stages them and waits): with several solver objects at work on one GPU (SCIP's concurrent mode, one handle
+// and stream per thread) a 0.2 ms upload waited 16 ms on average behind the other threads' kernels.  Everything on the per-node
+// path therefore goes through this ring: H2D = memcpy into the ring + async copy; D2H = async copy into the ring, sync, memcpy.
+struct PinStage
+{
+   ByteBuf buf;
+   size_t off = 0;
+   PinStage() { buf.pinned = true; }
+   // a piece of the ring; a piece is reused only after a synchronisation of the stream its copy was issued on
+   unsigned char* take(size_t bytes, cudaStream_t st)
+   {
+      const size_t len = (std::max<size_t>(bytes, 16) + 63) & ~(size_t)63;
+      if( off + len > buf.cap )
+      {
+         cudaStreamSynchronize(st);
+         off = 0;
+         if( 2 * len > buf.cap ) { buf.clear(); buf.resize(std::max<size_t>(4 * len, (size_t)1 << 20)); }
+      }
+      unsigned char* q = buf.data() + off;
+      off += len;
+      return q;
+   }
+   cudaError_t in(void* dst, const void* src, size_t bytes, cudaStream_t st)
+   {
+      if( bytes == 0 ) return cudaSuccess;
+      unsigned char* q = take(bytes, st);
+      memcpy(q, src, bytes);
+      return cudaMemcpyAsync(dst, q, bytes, cudaMemcpyHostToDevice, st);
+   }
+   // synchronises the stream
+   cudaError_t out(void* dst, const void* src, size_t bytes, cudaStream_t st)
+   {
+      if( bytes == 0 ) return cudaStreamSynchronize(st);
+      unsigned char* q = take(bytes, st);
+      cudaError_t e = cudaMemcpyAsync(q, src, bytes, cudaMemcpyDeviceToHost, st);
+      if( e == cudaSuccess ) e = cudaStreamSynchronize(st);
+      if( e == cudaSuccess ) memcpy(dst, q, bytes);
+      off = 0;
+      return e;
+   }
+   // rows x cols doubles out of a device matrix with leading dimension lds into a host matrix with leading dimension ldd; synchronises
+   cudaError_t out2d(double* dst, size_t ldd, const double* src, size_t lds, size_t rows, size_t cols, cudaStream_t st)
+   {
+      if( rows == 0 || cols == 0 ) return cudaStreamSynchronize(st);
+      unsigned char* q = take(rows * cols * sizeof(double), st);
+      cudaError_t e = cudaMemcpy2DAsync(q, sizeof(double) * rows, src, sizeof(double) * lds, sizeof(double) * rows, cols, cudaMemcpyDeviceToHost, st);
+      if( e == cudaSuccess ) e = cudaStreamSynchronize(st);
+      if( e == cudaSuccess )
+         for( size_t c = 0; c < cols; ++c ) memcpy(dst + c * ldd, q + c * rows * sizeof(double), rows * sizeof(double));
+      off = 0;
+      return e;
+   }
+   cudaError_t in2d(double* dst, size_t ldd, const double* src, size_t lds, size_t rows, size_t cols, cudaStream_t st)
+   {
+      if( rows == 0 || cols == 0 ) return cudaSuccess;
+      unsigned char* q = take(rows * cols * sizeof(double), st);
+      for( size_t c = 0; c < cols; ++c ) memcpy(q + c * rows * sizeof(double), src + c * lds, rows * sizeof(double));
+      return cudaMemcpy2DAsync(dst, sizeof(double) * ldd, q, sizeof(double) * rows, sizeof(double) * rows, cols, cudaMemcpyHostToDevice, st);
+   }
+};
+
 struct sdpcuda_handle
 {
    int device = 0;
+   cudaEvent_t evblock = nullptr;                 // blocking wait for the one-launch kernels when several handles share the host cores
+   PinStage pin;                                  // pinned staging of the host <-> device copies of the per-node path
    cudaStream_t st = nullptr, st2 = nullptr;      // st2: second lane for the factorisation of X next to that of S
    cudaStream_t st3 = nullptr;                    // side lane of the look-ahead factorisation of large Schur complements
    cudaEvent_t evp[70] = {nullptr};
@@ -380,7 +453,7 @@ int upload_problem(sdpcuda_handle* h, const sdpcuda_problem* P)
                sg[q] = r1sg[j];
                for( const auto& pr2 : r1vec[j] ) Ar[(size_t)q * h->r1ld + pr2.first] = pr2.second;
             }
-            CK( h->r1A.upload(Ar, st) ); CK( h->r1sig.upload(sg, st) ); CK( h->r1var.upload(r1_in[best], st) );
+            CK( h->r1A.upload(Ar, st, h->pin) ); CK( h->r1sig.upload(sg, st, h->pin) ); CK( h->r1var.upload(r1_in[best], st, h->pin) );
             CK( h->r1V.ensure((size_t)h->r1ld * h->r1count) );
             CK( h->r1G1.ensure((size_t)h->r1ldg * h->r1count) ); CK( h->r1G2.ensure((size_t)h->r1ldg * h->r1count) );
             CK( cudaStreamSynchronize(st) );
@@ -533,8 +606,8 @@ int upload_problem(sdpcuda_handle* h, const sdpcuda_problem* P)
          pc.insert(pc.end(), cp.begin(), cp.end());
          for( const auto& pr2 : v ) pr.push_back(pr2.second);
       }
-      CK( h->patcol.upload(pc, st) );
-      CK( h->patrow.upload(pr, st) );
+      CK( h->patcol.upload(pc, st, h->pin) );
+      CK( h->patrow.upload(pr, st, h->pin) );
       {
          const char* se2 = getenv("SDPCUDA_SDDMM");
          const char* se3 = getenv("SDPCUDA_APAT");
@@ -578,7 +651,7 @@ int upload_problem(sdpcuda_handle* h, const sdpcuda_problem* P)
          if( colrow[q] == colrow[q - 1] ) { h->lpdup = true; break; }
 
    usec("LP lists");
-#define UP(buf, vec) CK( h->buf.upload(vec, st) )
+#define UP(buf, vec) CK( h->buf.upload(vec, st, h->pin) )
    std::vector<int> varbeg(P->varbeg, P->varbeg + m + 1);
    std::vector<double> eval(P->entval, P->entval + nnz), cval(P->cval, P->cval + P->cnnz), bvec(P->obj, P->obj + m);
    std::vector<int> lpind(P->lpind, P->lpind + lnz);
@@ -591,7 +664,7 @@ int upload_problem(sdpcuda_handle* h, const sdpcuda_problem* P)
    UP(colbeg, colbeg); UP(colrow, colrow); UP(colval, colval);
    UP(heavy, heavy); UP(heavylist, heavylist); UP(b, bvec); UP(denselist, denselist);
 #undef UP
-   CK( cudaStreamSynchronize(st) );      // the host vectors above go out of scope
+   // (the copies above are staged in the pinned ring of the handle: nothing to wait for here)
    usec("copies + H2D");
 
    // dense Schur path: expanded constraint matrices and the two batched-GEMM result buffers (chunks of <= 256 MB)
@@ -913,7 +986,7 @@ int step_eigs(sdpcuda_handle* h, const double* dXdir, const double* dSdir, int m
    if( nsmall > 0 )
    {
       // blocks of order <= LZS_MAX_N: whole Lanczos run per matrix in one CTA (shared memory), a single launch
-      CK( cudaMemcpyAsync(h->lzdesc.p, h->h_lzsmall.data(), sizeof(LzDesc) * nsmall, cudaMemcpyHostToDevice, h->st) );
+      CK( h->pin.in(h->lzdesc.p, h->h_lzsmall.data(), sizeof(LzDesc) * nsmall, h->st) );
       CK( lanczos_small_batched(h->st, nsmall, maxsmall, h->lzdesc.p, maxsteps <= 8 ? 16 : LZS_MAX_N) );
    }
    if( nbig > 0 )
@@ -1035,6 +1108,8 @@ int sdpcuda_create(sdpcuda_handle** out, int device)
       delete h;
       return SDPCUDA_ERR_CUDA;
    }
+   cudaEventCreateWithFlags(&h->evblock, cudaEventBlockingSync | cudaEventDisableTiming);
+   g_live_handles.fetch_add(1);
    *out = h;
    return SDPCUDA_OK;
 }
@@ -1042,6 +1117,8 @@ int sdpcuda_create(sdpcuda_handle** out, int device)
 int sdpcuda_destroy(sdpcuda_handle* h)
 {
    if( h == nullptr ) return SDPCUDA_OK;
+   g_live_handles.fetch_sub(1);
+   if( h->evblock != nullptr ) { cudaEventDestroy(h->evblock); h->evblock = nullptr; }
    sdpcuda_dist_finalize(h);
    cudaSetDevice(h->device);
    cudaStreamSynchronize(h->st);
@@ -1132,6 +1209,13 @@ static int run_ipm(sdpcuda_handle* h, const sdpcuda_params* par, const double* s
 static int solve_packed(sdpcuda_handle* h, const sdpcuda_problem* P, const sdpcuda_params* par, sdpcuda_result* res, double t0, bool* done);
 static int launch_packed(sdpcuda_handle* h, sdpcuda_result* res, double t0, double h2d);
 
+// three or more solver objects alive: the process runs node relaxations side by side (SDPCUDA_CONCURRENT=0 / 1 overrides)
+static bool concurrent_handles()
+{
+   static const int forced = []() { const char* e = getenv("SDPCUDA_CONCURRENT"); return e != nullptr ? (e[0] != '0' ? 1 : 0) : -1; }();
+   return forced >= 0 ? forced == 1 : g_live_handles.load() >= 3;
+}
+
 int sdpcuda_solve(sdpcuda_handle* h, const sdpcuda_problem* P, const sdpcuda_params* par, const double* start_y, sdpcuda_result* res)
 {
    if( h == nullptr || P == nullptr || par == nullptr || P->m <= 0 ) return SDPCUDA_ERR_ARG;
@@ -1144,10 +1228,14 @@ int sdpcuda_solve(sdpcuda_handle* h, const sdpcuda_problem* P, const sdpcuda_par
    h->counter.n = 0;
    g_h2d_bytes = 0.0;
    {
-      // SDPCUDA_PACKED_SOLVE=1 (off by default until it has run on a GPU): a cold-started relaxation inside the single-CTA limits is
-      // packed like a node of a frontier batch - one host->device copy, one launch, results copied back - instead of ~35 copies,
-      // four synchronisations and six launches before the kernel
-      const char* pe = getenv("SDPCUDA_PACKED_SOLVE");
+      // A cold-started relaxation inside the single-CTA limits can be packed like a node of a frontier batch - one host->device copy,
+      // one launch, results copied back - instead of ~35 copies and six launches before the kernel.  With several solver objects
+      // alive in the process (SCIP's concurrent mode: every solver thread owns one) the driver calls are what the threads share, and
+      // the packed path is the default (8 threads through sdpi.c, nodes/s: example_TT 1703 -> 2422, example_MkP 281 -> 575,
+      // example_CLS 383 -> 439); a lone handle keeps the problem resident for the re-solves of sdpi.c's ladder instead.
+      // SDPCUDA_PACKED_SOLVE=1 / 0 forces / forbids it.
+      const char* pe0 = getenv("SDPCUDA_PACKED_SOLVE");
+      const char* pe = pe0 != nullptr ? pe0 : (concurrent_handles() ? "1" : "0");
       const char* fe = getenv("SDPCUDA_PATH");
       if( pe != nullptr && pe[0] == '1' && !(fe != nullptr && fe[0] == 'm') && h->force_path != 1 && start_y == nullptr && h->startX.empty()
          && h->startS.empty() && par->preoptgap <= 0 && !h->prof.on && h->nranks == 1 )
@@ -1176,8 +1264,8 @@ int sdpcuda_solve_patched(sdpcuda_handle* h, const sdpcuda_problem* P, const sdp
    g_h2d_bytes = 0.0;
    // only the objective and the right-hand sides of the rows travel; the scale of the cold start and the norms depend on them
    std::vector<double> bvec(P->obj, P->obj + h->m), lprhs(P->lprhs, P->lprhs + h->nlp);
-   CK( h->b.upload(bvec, h->st) );
-   if( h->nlp > 0 ) CK( h->lprhs.upload(lprhs, h->st) );
+   CK( h->b.upload(bvec, h->st, h->pin) );
+   if( h->nlp > 0 ) CK( h->lprhs.upload(lprhs, h->st, h->pin) );
    CK( cudaStreamSynchronize(h->st) );
    host_constants(h, P);
    return run_ipm(h, par, start_y, res, t0);
@@ -1652,9 +1740,15 @@ static int launch_packed(sdpcuda_handle* h, sdpcuda_result* res, double t0, doub
    if( h->pktiny ) CK( launch_ipm_tiny_batch(st, 1, h->batchargs.p, h->pkstage) );
    else CK( launch_ipm_small_batch(st, 1, h->batchargs.p, h->pkstage) );
    CK( cudaEventRecord(h->ev1, st) );
+   static const bool blockwait = []() { const char* e = getenv("SDPCUDA_BLOCKING_WAIT"); return e == nullptr || e[0] != '0'; }();
+   if( blockwait && h->evblock != nullptr && concurrent_handles() )
+   {
+      // the kernel runs for milliseconds: sleep instead of spinning, the other solver threads need the cores
+      CK( cudaEventRecord(h->evblock, st) );
+      CK( cudaEventSynchronize(h->evblock) );
+   }
    SmallResult sr;
-   CK( cudaMemcpyAsync(&sr, h->batchres.p, sizeof(sr), cudaMemcpyDeviceToHost, st) );
-   CK( cudaStreamSynchronize(st) );
+   CK( h->pin.out(&sr, h->batchres.p, sizeof(sr), st) );
    float ms = 0.f;
    cudaEventElapsedTime(&ms, h->ev0, h->ev1);
    h->solved = true;
@@ -1689,9 +1783,8 @@ static int solve_packed(sdpcuda_handle* h, const sdpcuda_problem* P, const sdpcu
    CK( h->batchres.ensure(1) );
    std::vector<SmallArgs> args;
    batch_bind_all(plan, h->batchimg.p, h->batchwork.p, h->batchy.p, h->batchres.p, args);
-   CK( cudaMemcpyAsync(h->batchimg.p, plan.img.buf.data(), plan.img.buf.size(), cudaMemcpyHostToDevice, st) );
-   CK( cudaMemcpyAsync(h->batchargs.p, args.data(), sizeof(SmallArgs), cudaMemcpyHostToDevice, st) );
-   CK( cudaStreamSynchronize(st) );                           // plan goes out of scope
+   CK( h->pin.in(h->batchimg.p, plan.img.buf.data(), plan.img.buf.size(), st) );
+   CK( h->pin.in(h->batchargs.p, args.data(), sizeof(SmallArgs), st) );
    // what the getters need: sizes, block table and the device addresses of the solution
    h->pk = args[0];
    h->pktiny = (plan.ntiny == 1);
@@ -1917,7 +2010,7 @@ static int run_ipm(sdpcuda_handle* h, const sdpcuda_params* par, const double* s
       }
       std::vector<double> hx(nlp, par->lambdastar > 0 ? par->lambdastar : h->xil), hs(nlp, par->lambdastar > 0 ? par->lambdastar : h->etal), hy(m, 0.0);
       if( start_y != nullptr ) std::copy(start_y, start_y + m, hy.begin());
-      CK( h->x.upload(hx, st) ); CK( h->s.upload(hs, st) ); CK( h->y.upload(hy, st) );
+      CK( h->x.upload(hx, st, h->pin) ); CK( h->s.upload(hs, st, h->pin) ); CK( h->y.upload(hy, st, h->pin) );
       CK( cudaStreamSynchronize(st) );
    }
    // ---- warm start: dense X, S blocks and LP parts staged by sdpcuda_set_start_* (used only together with start_y) ----
@@ -1932,7 +2025,7 @@ static int run_ipm(sdpcuda_handle* h, const sdpcuda_params* par, const double* s
          CK( add_diagonal(st, h->blk[k].n, h->S.p + h->blk[k].off, h->blk[k].ld, eta) );
       }
       std::vector<double> hx(nlp, par->lambdastar > 0 ? par->lambdastar : h->xil), hs(nlp, par->lambdastar > 0 ? par->lambdastar : h->etal);
-      CK( h->x.upload(hx, st) ); CK( h->s.upload(hs, st) );
+      CK( h->x.upload(hx, st, h->pin) ); CK( h->s.upload(hs, st, h->pin) );
       CK( cudaStreamSynchronize(st) );
       return SDPCUDA_OK;
    };
@@ -1950,11 +2043,11 @@ static int run_ipm(sdpcuda_handle* h, const sdpcuda_params* par, const double* s
          for( int k = 0; k < nb; ++k )
          {
             const Block& bk = h->blk[k];
-            CK( cudaMemcpy2DAsync(h->X.p + bk.off, sizeof(double) * bk.ld, h->startX[k].data(), sizeof(double) * bk.n, sizeof(double) * bk.n, bk.n, cudaMemcpyHostToDevice, st) );
-            CK( cudaMemcpy2DAsync(h->S.p + bk.off, sizeof(double) * bk.ld, h->startS[k].data(), sizeof(double) * bk.n, sizeof(double) * bk.n, bk.n, cudaMemcpyHostToDevice, st) );
+            CK( h->pin.in2d(h->X.p + bk.off, bk.ld, h->startX[k].data(), bk.n, bk.n, bk.n, st) );
+            CK( h->pin.in2d(h->S.p + bk.off, bk.ld, h->startS[k].data(), bk.n, bk.n, bk.n, st) );
             g_h2d_bytes += 16.0 * bk.n * bk.n;
          }
-         if( nlp > 0 ) { CK( h->x.upload(h->startx, st) ); CK( h->s.upload(h->starts, st) ); }
+         if( nlp > 0 ) { CK( h->x.upload(h->startx, st, h->pin) ); CK( h->s.upload(h->starts, st, h->pin) ); }
          CK( cudaStreamSynchronize(st) );
       }
    }
@@ -1976,10 +2069,11 @@ static int run_ipm(sdpcuda_handle* h, const sdpcuda_params* par, const double* s
          && ar <= ((size_t)1 << 20) && nlp <= (1 << 20) && !h->prof.on && !wantpre && !warm && h->nranks == 1 && h->emulate_ranks <= 1);
       if( eligible && h->ndense > 0 )
          for( const auto& g : h->dgroups ) if( g.count > h->dchunk ) eligible = false;
-      // measured on the shipped instances: the one-launch kernel wins while the Schur complement is small (m <= 64); above that
-      // the serial Cholesky of M inside a single CTA loses against the multi-kernel pipeline
-      // (SDPCUDA_SMALL_M: the largest Schur complement of the one-launch kernel)
-      static const int small_m = []() { const char* e = getenv("SDPCUDA_SMALL_M"); return e != nullptr ? atoi(e) : 64; }();
+      // measured on the shipped instances: the one-launch kernel wins while the packed factor of the Schur complement fits into
+      // shared memory (m <= 128; example_MkP, m <= 105: 14.5 ms on the multi-kernel pipeline, 13.3 ms in one launch, and one launch
+      // instead of ~1000 when several solver threads share the driver); above that the serial Cholesky of M inside a single CTA
+      // loses against the multi-kernel pipeline (SDPCUDA_SMALL_M: the largest Schur complement of the one-launch kernel)
+      static const int small_m = []() { const char* e = getenv("SDPCUDA_SMALL_M"); return e != nullptr ? atoi(e) : 128; }();
       if( eligible && force != 1 && (force == 2 || m <= small_m) )
       {
          SmallArgs a;
@@ -2020,8 +2114,7 @@ static int run_ipm(sdpcuda_handle* h, const sdpcuda_params* par, const double* s
          CK( launch_ipm_small(st, a) );
          CK( cudaEventRecord(h->ev1, st) );
          SmallResult sr;
-         CK( cudaMemcpyAsync(&sr, h->smallres.p, sizeof(sr), cudaMemcpyDeviceToHost, st) );
-         CK( cudaStreamSynchronize(st) );
+         CK( h->pin.out(&sr, h->smallres.p, sizeof(sr), st) );
          float ms = 0.f;
          cudaEventElapsedTime(&ms, h->ev0, h->ev1);
          sdpcuda_result R;
@@ -2321,7 +2414,7 @@ static int run_ipm(sdpcuda_handle* h, const sdpcuda_params* par, const double* s
                // scale of the regularisation: largest diagonal entry of M
                double maxd = 0.0;
                std::vector<double> diag(m);
-               CK( cudaMemcpy2DAsync(diag.data(), sizeof(double), h->M.p, sizeof(double) * ((size_t)h->ldm + 1), sizeof(double), m, cudaMemcpyDeviceToHost, st) );
+               CK( cudaMemcpy2DAsync(diag.data(), sizeof(double), h->M.p, sizeof(double) * ((size_t)h->ldm + 1), sizeof(double), m, cudaMemcpyDeviceToHost, st) );      // rare path (failed factorisation): pageable is fine
                CK( cudaStreamSynchronize(st) );
                for( int j = 0; j < m; ++j ) maxd = std::max(maxd, diag[j]);
                reg = 1e-14 * std::max(maxd, 1e-300);
@@ -2510,8 +2603,7 @@ int sdpcuda_get_y(sdpcuda_handle* h, double* y)
 {
    if( h == nullptr || !h->solved ) return SDPCUDA_ERR_STATE;
    if( set_device(h) ) return SDPCUDA_ERR_CUDA;
-   CK( cudaMemcpyAsync(y, h->packed ? h->pk.y : h->y.p, sizeof(double) * h->m, cudaMemcpyDeviceToHost, h->st) );
-   CK( cudaStreamSynchronize(h->st) );
+   CK( h->pin.out(y, h->packed ? h->pk.y : h->y.p, sizeof(double) * h->m, h->st) );
    return SDPCUDA_OK;
 }
 
@@ -2521,8 +2613,7 @@ static int get_block(sdpcuda_handle* h, const double* src, int b, double* out)
    if( b < 0 || b >= h->nb ) return SDPCUDA_ERR_ARG;
    if( set_device(h) ) return SDPCUDA_ERR_CUDA;
    const Block& bk = h->blk[b];
-   CK( cudaMemcpy2DAsync(out, sizeof(double) * bk.n, src + bk.off, sizeof(double) * bk.ld, sizeof(double) * bk.n, bk.n, cudaMemcpyDeviceToHost, h->st) );
-   CK( cudaStreamSynchronize(h->st) );
+   CK( h->pin.out2d(out, bk.n, src + bk.off, bk.ld, bk.n, bk.n, h->st) );
    return SDPCUDA_OK;
 }
 int sdpcuda_get_X(sdpcuda_handle* h, int b, double* X) { return get_block(h, h ? (h->packed ? h->pk.X : h->X.p) : nullptr, b, X); }
@@ -2550,7 +2641,7 @@ int sdpcuda_primal_products(sdpcuda_handle* h, int ngroups, const int* groupbeg,
    const double* val, double* out)
 {
    if( h == nullptr || ngroups < 0 || (ngroups > 0 && (groupbeg == nullptr || out == nullptr)) ) return SDPCUDA_ERR_ARG;
-   if( !h->solved || h->packed ) return SDPCUDA_ERR_STATE;
+   if( !h->solved ) return SDPCUDA_ERR_STATE;
    if( ngroups == 0 ) return SDPCUDA_OK;
    if( set_device(h) ) return SDPCUDA_ERR_CUDA;
    const int ne = groupbeg[ngroups];
@@ -2565,37 +2656,37 @@ int sdpcuda_primal_products(sdpcuda_handle* h, int ngroups, const int* groupbeg,
    ints.insert(ints.end(), groupbeg, groupbeg + ngroups + 1);
    ints.insert(ints.end(), blk, blk + ne); ints.insert(ints.end(), row, row + ne); ints.insert(ints.end(), col, col + ne);
    ints.insert(ints.end(), bld.begin(), bld.end());
-   CK( h->ppint.upload(ints, st) );
+   CK( h->ppint.upload(ints, st, h->pin) );
    std::vector<double> dbl(val, val + ne);
-   CK( h->ppdbl.upload(dbl, st) );
-   CK( h->ppoff.upload(boff, st) );
+   CK( h->ppdbl.upload(dbl, st, h->pin) );
+   CK( h->ppoff.upload(boff, st, h->pin) );
    CK( h->ppout.ensure(ngroups) );
    const int* di = h->ppint.p;
    primal_products_kernel<<<ceil_div(ngroups * 32, 256), 256, 0, st>>>(ngroups, di, di + ngroups + 1, di + ngroups + 1 + ne, di + ngroups + 1 + 2 * ne,
-      h->ppdbl.p, h->X.p, h->ppoff.p, di + ngroups + 1 + 3 * ne, h->ppout.p);
+      h->ppdbl.p, h->packed ? h->pk.X : h->X.p, h->ppoff.p, di + ngroups + 1 + 3 * ne, h->ppout.p);
    count_launch();
    CK( cudaGetLastError() );
-   CK( cudaMemcpyAsync(out, h->ppout.p, sizeof(double) * ngroups, cudaMemcpyDeviceToHost, st) );
-   CK( cudaStreamSynchronize(st) );
+   CK( h->pin.out(out, h->ppout.p, sizeof(double) * ngroups, st) );
    return SDPCUDA_OK;
 }
 
 int sdpcuda_primal_mineig_bound(sdpcuda_handle* h, int block, double* bound)
 {
    if( h == nullptr || bound == nullptr ) return SDPCUDA_ERR_ARG;
-   if( !h->solved || h->packed ) return SDPCUDA_ERR_STATE;
+   if( !h->solved ) return SDPCUDA_ERR_STATE;
    if( block < 0 || block >= h->nb ) return SDPCUDA_ERR_ARG;
    if( set_device(h) ) return SDPCUDA_ERR_CUDA;
    cudaStream_t st = h->st;
    const Block& bk = h->blk[block];
    const size_t nn = (size_t)bk.ld * bk.n;
+   const double* Xsol = h->packed ? h->pk.X : h->X.p;      // a packed single solve keeps its X in the work space of the batch kernel
    CK( h->kA.ensure(nn) );
    CK( h->kW.ensure((size_t)bk.ld * (bk.n + 2 * CHOL_LEAF_MAX)) );
    CK( h->info.ensure(8) );
    double sigma = 0.0, scale = -1.0;
    for( int tries = 0; tries < 40; ++tries )
    {
-      CK( cudaMemcpyAsync(h->kA.p, h->X.p + bk.off, sizeof(double) * nn, cudaMemcpyDeviceToDevice, st) );
+      CK( cudaMemcpyAsync(h->kA.p, Xsol + bk.off, sizeof(double) * nn, cudaMemcpyDeviceToDevice, st) );
       CK( cudaMemsetAsync(h->info.p, 0, 8 * sizeof(int), st) );
       if( sigma > 0.0 ) CK( add_diagonal(st, bk.n, h->kA.p, bk.ld, sigma) );
       CK( potrf_lower(st, bk.n, h->kA.p, bk.ld, nullptr, 0, nullptr, h->kW.p, bk.ld, h->info.p) );
@@ -2606,8 +2697,7 @@ int sdpcuda_primal_mineig_bound(sdpcuda_handle* h, int block, double* bound)
       {
          // |X|_max from the diagonal (X is symmetric; for an indefinite matrix any entry bound does: use the largest |entry| of the block)
          std::vector<double> hx(nn);
-         CK( cudaMemcpyAsync(hx.data(), h->X.p + bk.off, sizeof(double) * nn, cudaMemcpyDeviceToHost, st) );
-         CK( cudaStreamSynchronize(st) );
+         CK( h->pin.out(hx.data(), Xsol + bk.off, sizeof(double) * nn, st) );
          scale = 0.0;
          for( double v : hx ) scale = std::max(scale, std::fabs(v));
          scale = std::max(scale, 1e-300);
@@ -2694,9 +2784,8 @@ int sdpcuda_get_preopt(sdpcuda_handle* h, int* exists, double* y, double* xlp)
    *exists = (h->solved && h->preexists) ? 1 : 0;
    if( !*exists ) return SDPCUDA_OK;
    if( set_device(h) ) return SDPCUDA_ERR_CUDA;
-   if( y != nullptr ) CK( cudaMemcpyAsync(y, h->prey.p, sizeof(double) * h->m, cudaMemcpyDeviceToHost, h->st) );
-   if( xlp != nullptr && h->nlp > 0 ) CK( cudaMemcpyAsync(xlp, h->prex.p, sizeof(double) * h->nlp, cudaMemcpyDeviceToHost, h->st) );
-   CK( cudaStreamSynchronize(h->st) );
+   if( y != nullptr ) CK( h->pin.out(y, h->prey.p, sizeof(double) * h->m, h->st) );
+   if( xlp != nullptr && h->nlp > 0 ) CK( h->pin.out(xlp, h->prex.p, sizeof(double) * h->nlp, h->st) );
    return SDPCUDA_OK;
 }
 
@@ -2710,16 +2799,14 @@ int sdpcuda_get_xlp(sdpcuda_handle* h, double* x)
 {
    if( h == nullptr || !h->solved ) return SDPCUDA_ERR_STATE;
    if( set_device(h) ) return SDPCUDA_ERR_CUDA;
-   if( h->nlp > 0 ) CK( cudaMemcpyAsync(x, h->packed ? h->pk.x : h->x.p, sizeof(double) * h->nlp, cudaMemcpyDeviceToHost, h->st) );
-   CK( cudaStreamSynchronize(h->st) );
+   if( h->nlp > 0 ) CK( h->pin.out(x, h->packed ? h->pk.x : h->x.p, sizeof(double) * h->nlp, h->st) );
    return SDPCUDA_OK;
 }
 int sdpcuda_get_slp(sdpcuda_handle* h, double* s)
 {
    if( h == nullptr || !h->solved ) return SDPCUDA_ERR_STATE;
    if( set_device(h) ) return SDPCUDA_ERR_CUDA;
-   if( h->nlp > 0 ) CK( cudaMemcpyAsync(s, h->packed ? h->pk.s : h->s.p, sizeof(double) * h->nlp, cudaMemcpyDeviceToHost, h->st) );
-   CK( cudaStreamSynchronize(h->st) );
+   if( h->nlp > 0 ) CK( h->pin.out(s, h->packed ? h->pk.s : h->s.p, sizeof(double) * h->nlp, h->st) );
    return SDPCUDA_OK;
 }
 
@@ -2732,11 +2819,10 @@ int sdpcuda_syev_batched(sdpcuda_handle* h, int n, int nbatch, const double* A, 
    const size_t nn = (size_t)n * n;
    CK( h->kA.ensure(nn * nbatch) ); CK( h->kB.ensure((size_t)n * nbatch) );
    if( V != nullptr ) CK( h->kC.ensure(nn * nbatch) );
-   CK( cudaMemcpyAsync(h->kA.p, A, nn * nbatch * sizeof(double), cudaMemcpyHostToDevice, h->st) );
+   CK( h->pin.in(h->kA.p, A, nn * nbatch * sizeof(double), h->st) );
    CK( jacobi_eig_batched(h->st, n, nbatch, h->kA.p, n, (long long)nn, h->kB.p, V ? h->kC.p : nullptr, nullptr) );
-   CK( cudaMemcpyAsync(w, h->kB.p, (size_t)n * nbatch * sizeof(double), cudaMemcpyDeviceToHost, h->st) );
-   if( V != nullptr ) CK( cudaMemcpyAsync(V, h->kC.p, nn * nbatch * sizeof(double), cudaMemcpyDeviceToHost, h->st) );
-   CK( cudaStreamSynchronize(h->st) );
+   CK( h->pin.out(w, h->kB.p, (size_t)n * nbatch * sizeof(double), h->st) );
+   if( V != nullptr ) CK( h->pin.out(V, h->kC.p, nn * nbatch * sizeof(double), h->st) );
    return SDPCUDA_OK;
 }
 
@@ -2748,7 +2834,7 @@ static int up2d(sdpcuda_handle* h, DBuf<double>& buf, const double* src, int row
    CK( buf.ensure((size_t)ldd * std::max(cols, 1)) );
    CK( cudaMemsetAsync(buf.p, 0, sizeof(double) * (size_t)ldd * std::max(cols, 1), h->st) );
    if( rows > 0 && cols > 0 )
-      CK( cudaMemcpy2DAsync(buf.p, sizeof(double) * ldd, src, sizeof(double) * lds, sizeof(double) * rows, cols, cudaMemcpyHostToDevice, h->st) );
+      CK( h->pin.in2d(buf.p, ldd, src, lds, rows, cols, h->st) );
    return SDPCUDA_OK;
 }
 
@@ -2762,9 +2848,7 @@ int sdpcuda_dgemm(sdpcuda_handle* h, int ta, int tb, int m, int n, int k, double
    int rc;
    if( (rc = up2d(h, h->kA, A, ar, ac, lda, dla)) || (rc = up2d(h, h->kB, B, br, bc, ldb, dlb)) || (rc = up2d(h, h->kC, C, m, n, ldc, dlc)) ) return rc;
    CK( gemm(h->st, ta != 0, tb != 0, m, n, k, alpha, h->kA.p, dla, 0, h->kB.p, dlb, 0, beta, h->kC.p, dlc, 0, 1, 0) );
-   if( m > 0 && n > 0 )
-      CK( cudaMemcpy2DAsync(C, sizeof(double) * ldc, h->kC.p, sizeof(double) * dlc, sizeof(double) * m, n, cudaMemcpyDeviceToHost, h->st) );
-   CK( cudaStreamSynchronize(h->st) );
+   CK( h->pin.out2d(C, ldc, h->kC.p, dlc, m, n, h->st) );
    return SDPCUDA_OK;
 }
 
@@ -2845,7 +2929,7 @@ int sdpcuda_check_psd_resident(sdpcuda_handle* h, const double* y, double shift,
    const double* yd = h->y.p;
    if( y != nullptr )
    {
-      CK( cudaMemcpyAsync(h->tm1.p, y, sizeof(double) * h->m, cudaMemcpyHostToDevice, st) );      // tm1: scratch of m + 1 doubles
+      CK( h->pin.in(h->tm1.p, y, sizeof(double) * h->m, st) );      // tm1: scratch of m + 1 doubles
       yd = h->tm1.p;
    }
    int rc = assemble(h, yd, 1.0, h->K.p);                  // K = sum_j y_j A_j - C (scratch matrix of the iteration)
