@@ -423,6 +423,16 @@ def gpu_node_workload(gpu, lib, name, rank, table, reps):
         shared = first["results"]["launches"] != 0
         one_launch_ms = float(first["results"]["device_ms"][shared].sum()) if shared.any() else None
         gpu.solve_nodes(model, lbs, ubs, lean=True, **NODE_KW)
+    else:
+        # mid-size nodes (multi-kernel path): the timed calls run them on several lanes side by side (helper handles on threads of
+        # their own, SDPCUDA_LONER_LANES); the device-only figure is the sum of the nodes' device times when one runs after the other
+        os.environ["SDPCUDA_LONER_LANES"] = "1"
+        try:
+            first = gpu.solve_nodes(model, lbs, ubs, lean=True, **NODE_KW)
+        finally:
+            del os.environ["SDPCUDA_LONER_LANES"]
+        one_launch_ms = float(first["results"]["device_ms"].sum())
+        gpu.solve_nodes(model, lbs, ubs, lean=True, **NODE_KW)          # the helper handles grow their buffers once
     wall = dev_ms = 0.0
     launches = resolved = 0
     for _ in range(reps):

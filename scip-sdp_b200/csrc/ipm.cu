@@ -23,6 +23,7 @@
 #include <cmath>
 #include <cstring>
 #include <mutex>
+#include <thread>
 #include <new>
 #include <numeric>
 #include <vector>
@@ -201,6 +202,8 @@ struct PinStage
 struct sdpcuda_handle
 {
    int device = 0;
+   std::vector<sdpcuda_handle*> helpers;          // further lanes for the mid-size nodes of a frontier (sdpcuda_solve_batch), created on demand
+   bool helper = false;
    cudaEvent_t evblock = nullptr;                 // blocking wait for the one-launch kernels when several handles share the host cores
    PinStage pin;                                  // pinned staging of the host <-> device copies of the per-node path
    cudaStream_t st = nullptr, st2 = nullptr;      // st2: second lane for the factorisation of X next to that of S
@@ -1117,7 +1120,9 @@ int sdpcuda_create(sdpcuda_handle** out, int device)
 int sdpcuda_destroy(sdpcuda_handle* h)
 {
    if( h == nullptr ) return SDPCUDA_OK;
-   g_live_handles.fetch_sub(1);
+   if( !h->helper ) g_live_handles.fetch_sub(1);
+   for( sdpcuda_handle* hh : h->helpers ) sdpcuda_destroy(hh);
+   h->helpers.clear();
    if( h->evblock != nullptr ) { cudaEventDestroy(h->evblock); h->evblock = nullptr; }
    sdpcuda_dist_finalize(h);
    cudaSetDevice(h->device);
@@ -1954,17 +1959,54 @@ int sdpcuda_solve_batch(sdpcuda_handle* h, int count, const sdpcuda_problem* con
          }
       }
    }
-   // relaxations outside the single-CTA limits: one after the other through the ordinary solve on this handle
-   for( int i : loners )
+   // relaxations outside the single-CTA limits go through the ordinary solve.  Mid-size nodes leave most of the GPU idle and spend a
+   // third of their time on the host (upload lists of 10^6 entries), so two or more of them run side by side: lane 0 is this handle
+   // on the calling thread, the other lanes are helper handles (own streams and buffers on the same device) on threads of their own.
+   // SDPCUDA_LONER_LANES=k sets the number of lanes (default 4; 1 = one node after the other); Schur complements above 4096
+   // (hundreds of MB of work space per lane, kernels that fill the GPU anyway) stay on one lane.
+   int lanes = 1;
+   if( loners.size() >= 2 && h->nranks == 1 )
    {
-      sdpcuda_result R;
-      sdpcuda_params pi = *par;
-      if( objlimits != nullptr ) pi.objlimit = objlimits[i];
-      rc = sdpcuda_solve(h, probs[i], &pi, nullptr, &R);
-      if( rc != SDPCUDA_OK ) return rc;
-      if( res != nullptr ) res[i] = R;
-      if( y_out != nullptr && y_out[i] != nullptr ) { rc = sdpcuda_get_y(h, y_out[i]); if( rc != SDPCUDA_OK ) return rc; }
+      const char* e = getenv("SDPCUDA_LONER_LANES");
+      lanes = e != nullptr ? std::max(1, std::min(atoi(e), 8)) : 4;
+      lanes = std::min<int>(lanes, (int)loners.size());
+      for( int i : loners ) if( probs[i]->m > 4096 ) lanes = 1;
    }
+   while( lanes > 1 && (int)h->helpers.size() < lanes - 1 )
+   {
+      sdpcuda_handle* hh = nullptr;
+      if( sdpcuda_create(&hh, h->device) != SDPCUDA_OK ) { lanes = (int)h->helpers.size() + 1; break; }
+      g_live_handles.fetch_sub(1);          // not a solver object of the caller
+      hh->helper = true;
+      h->helpers.push_back(hh);
+   }
+   std::atomic<int> nextloner{0};
+   std::vector<int> lanerc(lanes, SDPCUDA_OK);
+   auto lane_work = [&](int lane)
+   {
+      sdpcuda_handle* hh = lane == 0 ? h : h->helpers[lane - 1];
+      hh->force_path = h->force_path;
+      for( ;; )
+      {
+         const int k = nextloner.fetch_add(1);
+         if( k >= (int)loners.size() ) break;
+         const int i = loners[k];
+         sdpcuda_result R;
+         sdpcuda_params pi = *par;
+         if( objlimits != nullptr ) pi.objlimit = objlimits[i];
+         int lrc = sdpcuda_solve(hh, probs[i], &pi, nullptr, &R);
+         if( lrc == SDPCUDA_OK && res != nullptr ) res[i] = R;
+         if( lrc == SDPCUDA_OK && y_out != nullptr && y_out[i] != nullptr ) lrc = sdpcuda_get_y(hh, y_out[i]);
+         if( lrc != SDPCUDA_OK ) { lanerc[lane] = lrc; break; }
+      }
+   };
+   {
+      std::vector<std::thread> lanethreads;
+      for( int lane = 1; lane < lanes; ++lane ) lanethreads.emplace_back(lane_work, lane);
+      lane_work(0);
+      for( std::thread& t : lanethreads ) t.join();
+   }
+   for( int lrc : lanerc ) if( lrc != SDPCUDA_OK ) return lrc;
    return SDPCUDA_OK;
 }
 

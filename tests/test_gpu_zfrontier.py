@@ -176,6 +176,32 @@ def test_batch_in_chunks_equals_the_single_launch(lib, chunks, monkeypatch):
     gpu.close()
 
 
+@pytest.mark.parametrize("lanes", ["2", "4"])
+def test_midsize_nodes_on_several_lanes_equal_one_after_the_other(lib, lanes, monkeypatch):
+    """nodes outside the single-CTA limits run side by side on helper handles (SDPCUDA_LONER_LANES, default 4): bit for bit the
+    results of one node after the other on the caller's handle, small nodes of the same call untouched, handle reusable afterwards"""
+    M = misdp.read_sdpa(os.path.join(GOLDEN, "example_TT.dat-s.gz")).rows_to_bounds()
+    flat = [M.flatten(lb, ub)[0] for lb, ub in _frontier(M, 3)]
+    mids = [generators.maxcut(80 + 8 * k, 0.1, seed=11 + k).flatten()[0] for k in range(5)] + [generators.truss(4, 4, 150, seed=5).flatten()[0]]
+    probs = [flat[i % 8] for i in range(12)]
+    for k, q in enumerate(mids):
+        probs.insert(2 * k + 1, q)
+    gpu = abi.Solver(lib, device=0)
+    monkeypatch.setenv("SDPCUDA_LONER_LANES", "1")
+    one = gpu.solve_batch(probs, **KW)
+    monkeypatch.setenv("SDPCUDA_LONER_LANES", lanes)
+    many = gpu.solve_batch(probs, **KW)
+    again = gpu.solve_batch(probs, **KW)
+    assert sum(1 for r in one if r["launches"] > 100) >= len(mids) - 1      # the mid-size nodes took the multi-kernel path
+    for a, b, c in zip(one, many, again):
+        assert a["phase_name"] == b["phase_name"] == c["phase_name"] == "pdOPT"
+        assert a["dobj"] == b["dobj"] == c["dobj"] and a["iterations"] == b["iterations"] == c["iterations"]
+        assert np.array_equal(a["y"], b["y"]) and np.array_equal(a["y"], c["y"])
+    single = gpu.solve(mids[0], **KW)                                       # the caller's handle after the lanes
+    assert single["dobj"] == one[1]["dobj"]
+    gpu.close()
+
+
 def test_objective_limits_per_node_on_gpu(lib):
     """per-node objective limits in the batch call: nodes with a limit below their value stop early with phase pUNBD"""
     M = misdp.read_sdpa(os.path.join(GOLDEN, "example_TT.dat-s.gz")).rows_to_bounds()
