@@ -50,7 +50,10 @@ template <class T> struct DBuf
       if( p ) cudaFree(p);
       p = nullptr; cap = 0;
       ++g_realloc_epoch;
+      // a quarter of headroom on everything below 64 MB: the nodes of a tree differ by a few per cent in size, and every growth
+      // is a cudaFree + cudaMalloc that synchronises the device (with several handles at work: hundreds of ms for all of them)
       size_t want = std::max(n, (size_t)16);
+      if( want * sizeof(T) < ((size_t)64 << 20) ) want += want / 4;
       cudaError_t e = cudaMalloc((void**)&p, want * sizeof(T));
       if( e == cudaSuccess ) cap = want;
       return e;
@@ -204,6 +207,7 @@ struct sdpcuda_handle
    int device = 0;
    std::vector<sdpcuda_handle*> helpers;          // further lanes for the mid-size nodes of a frontier (sdpcuda_solve_batch), created on demand
    bool helper = false;
+   double last_upload_s = 0.0;       // host time of the last upload (diagnostics)
    cudaEvent_t evblock = nullptr;                 // blocking wait for the one-launch kernels when several handles share the host cores
    PinStage pin;                                  // pinned staging of the host <-> device copies of the per-node path
    cudaStream_t st = nullptr, st2 = nullptr;      // st2: second lane for the factorisation of X next to that of S
@@ -1252,6 +1256,7 @@ int sdpcuda_solve(sdpcuda_handle* h, const sdpcuda_problem* P, const sdpcuda_par
    }
    rc = upload_problem(h, P);
    if( rc != SDPCUDA_OK ) return rc;
+   h->last_upload_s = now_seconds() - t0;
    host_constants(h, P);
    h->resident = true;
    return run_ipm(h, par, start_y, res, t0);
@@ -1980,22 +1985,26 @@ int sdpcuda_solve_batch(sdpcuda_handle* h, int count, const sdpcuda_problem* con
       hh->helper = true;
       h->helpers.push_back(hh);
    }
-   std::atomic<int> nextloner{0};
+   const double tlanes0 = now_seconds();
    std::vector<int> lanerc(lanes, SDPCUDA_OK);
    auto lane_work = [&](int lane)
    {
       sdpcuda_handle* hh = lane == 0 ? h : h->helpers[lane - 1];
       hh->force_path = h->force_path;
-      for( ;; )
+      // dealt round-robin, not first come first served: a lane sees the same nodes when the call is repeated (buffers sized once)
+      for( int k = lane; k < (int)loners.size(); k += lanes )
       {
-         const int k = nextloner.fetch_add(1);
-         if( k >= (int)loners.size() ) break;
          const int i = loners[k];
          sdpcuda_result R;
          sdpcuda_params pi = *par;
          if( objlimits != nullptr ) pi.objlimit = objlimits[i];
+         const double tl0 = now_seconds();
          int lrc = sdpcuda_solve(hh, probs[i], &pi, nullptr, &R);
+         const double tl1 = now_seconds();
          if( lrc == SDPCUDA_OK && res != nullptr ) res[i] = R;
+         if( getenv("SDPCUDA_LANE_TRACE") != nullptr )
+            fprintf(stderr, "[lanes] node %d lane %d/%d: start %.3f ms, solve %.2f ms (upload %.2f, device %.2f, %d iterations, %d launches)\n", i, lane, lanes,
+               1e3 * (tl0 - tlanes0), 1e3 * (tl1 - tl0), 1e3 * hh->last_upload_s, R.device_ms, R.iterations, R.launches);
          if( lrc == SDPCUDA_OK && y_out != nullptr && y_out[i] != nullptr ) lrc = sdpcuda_get_y(hh, y_out[i]);
          if( lrc != SDPCUDA_OK ) { lanerc[lane] = lrc; break; }
       }

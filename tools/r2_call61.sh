@@ -1,0 +1,13 @@
+set -x
+mkdir -p gpurun_out
+( time timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29533 bench.py --gpus 2 --steps 10 --warmup 3 > gpurun_out/r2aq_bench_n2.json 2> gpurun_out/r2aq_bench_n2.err ) 2>&1 | tail -3
+tail -2 gpurun_out/r2aq_bench_n2.err; python - <<'P'
+import json
+d = json.loads(open("gpurun_out/r2aq_bench_n2.json").read().strip().splitlines()[-1])
+print({k: d[k] for k in ("value", "ms_per_step", "n_gpus")}, d["e2e"]["value"])
+for k, v in d.get("bnb", {}).items():
+    print(k, {kk: (round(vv, 2) if isinstance(vv, float) else vv) for kk, vv in v.items() if kk in ("value", "nodes", "counted", "not_converged")})
+print(json.dumps(d.get("sharded"))[:600])
+P
+timeout 300 python -m pytest tests -m gpu -q -x -k "nccl or two_gpus or 2_gpus or sharded" 2>&1 | tail -2
+timeout 300 python -c "import __graft_entry__ as g; g.smoke(); g.smoke()"
