@@ -163,9 +163,17 @@ struct PinStage
       off += len;
       return q;
    }
+   // pieces above 16 MB (dense constraint matrices of large relaxations) are copied directly: such a solve fills the GPU by itself,
+   // and a ring of four times the piece would pin hundreds of MB
+   static constexpr size_t DIRECT = (size_t)16 << 20;
    cudaError_t in(void* dst, const void* src, size_t bytes, cudaStream_t st)
    {
       if( bytes == 0 ) return cudaSuccess;
+      if( bytes > DIRECT )
+      {
+         cudaError_t e = cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, st);
+         return e == cudaSuccess ? cudaStreamSynchronize(st) : e;      // the source may go out of scope
+      }
       unsigned char* q = take(bytes, st);
       memcpy(q, src, bytes);
       return cudaMemcpyAsync(dst, q, bytes, cudaMemcpyHostToDevice, st);
@@ -174,6 +182,11 @@ struct PinStage
    cudaError_t out(void* dst, const void* src, size_t bytes, cudaStream_t st)
    {
       if( bytes == 0 ) return cudaStreamSynchronize(st);
+      if( bytes > DIRECT )
+      {
+         cudaError_t e = cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, st);
+         return e == cudaSuccess ? cudaStreamSynchronize(st) : e;
+      }
       unsigned char* q = take(bytes, st);
       cudaError_t e = cudaMemcpyAsync(q, src, bytes, cudaMemcpyDeviceToHost, st);
       if( e == cudaSuccess ) e = cudaStreamSynchronize(st);
@@ -185,6 +198,11 @@ struct PinStage
    cudaError_t out2d(double* dst, size_t ldd, const double* src, size_t lds, size_t rows, size_t cols, cudaStream_t st)
    {
       if( rows == 0 || cols == 0 ) return cudaStreamSynchronize(st);
+      if( rows * cols * sizeof(double) > DIRECT )
+      {
+         cudaError_t e = cudaMemcpy2DAsync(dst, sizeof(double) * ldd, src, sizeof(double) * lds, sizeof(double) * rows, cols, cudaMemcpyDeviceToHost, st);
+         return e == cudaSuccess ? cudaStreamSynchronize(st) : e;
+      }
       unsigned char* q = take(rows * cols * sizeof(double), st);
       cudaError_t e = cudaMemcpy2DAsync(q, sizeof(double) * rows, src, sizeof(double) * lds, sizeof(double) * rows, cols, cudaMemcpyDeviceToHost, st);
       if( e == cudaSuccess ) e = cudaStreamSynchronize(st);
@@ -196,6 +214,11 @@ struct PinStage
    cudaError_t in2d(double* dst, size_t ldd, const double* src, size_t lds, size_t rows, size_t cols, cudaStream_t st)
    {
       if( rows == 0 || cols == 0 ) return cudaSuccess;
+      if( rows * cols * sizeof(double) > DIRECT )
+      {
+         cudaError_t e = cudaMemcpy2DAsync(dst, sizeof(double) * ldd, src, sizeof(double) * lds, sizeof(double) * rows, cols, cudaMemcpyHostToDevice, st);
+         return e == cudaSuccess ? cudaStreamSynchronize(st) : e;
+      }
       unsigned char* q = take(rows * cols * sizeof(double), st);
       for( size_t c = 0; c < cols; ++c ) memcpy(q + c * rows * sizeof(double), src + c * lds, rows * sizeof(double));
       return cudaMemcpy2DAsync(dst, sizeof(double) * ldd, q, sizeof(double) * rows, sizeof(double) * rows, cols, cudaMemcpyHostToDevice, st);

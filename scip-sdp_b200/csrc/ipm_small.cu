@@ -264,8 +264,131 @@ __device__ __forceinline__ double pairterm(const DevEntries& E, int ei, int ej, 
    return E.val[ei] * E.val[ej] * t;
 }
 
+// C_d = A_d B_d for d < cnt, all n x n with leading dimension ld; 4 x 2 register tiles, rows up to ld (padding rows of C become zero),
+// ends with a barrier.  One operand is the same matrix for all d (SHARED_A: A, else B): it is staged in the scratch tile at the head
+// of the shared memory (free between the phases), the other one streams from global memory, 16 bytes per load.
+__device__ __forceinline__ void ld2(const double* p, double& x, double& y)
+{
+#ifdef __CUDA_ARCH__
+   const double2 v = *reinterpret_cast<const double2*>(p);
+   x = v.x; y = v.y;
+#else
+   x = p[0]; y = p[1];
+#endif
+}
+template <bool SHARED_A>
+__device__ __noinline__ void dense_product(int n, int ld, int cnt, long long stride, const double* A, const double* B, double* C)
+{
+   extern __shared__ __align__(16) double smem[];
+   double* sh = smem;                                // VMAXN x (VMAXN + 1) doubles, n * ld fits
+   {
+      const double* S = SHARED_A ? A : B;
+      for( int e = threadIdx.x; e < n * ld; e += NT ) sh[e] = S[e];
+   }
+   __syncthreads();
+   const int rt = ld / 4, ct = (n + 1) / 2, per = rt * ct;
+   for( int t = threadIdx.x; t < cnt * per; t += NT )
+   {
+      const int d = t / per, r = t % per, i0 = 4 * (r % rt), j0 = 2 * (r / rt);
+      const bool two = j0 + 1 < n;
+      const double* Ad = (SHARED_A ? sh : A + (size_t)d * stride) + i0;
+      const double* B0 = (SHARED_A ? B + (size_t)d * stride : sh) + (size_t)j0 * ld;
+      const double* B1 = B0 + (two ? ld : 0);
+      double c00 = 0.0, c10 = 0.0, c20 = 0.0, c30 = 0.0, c01 = 0.0, c11 = 0.0, c21 = 0.0, c31 = 0.0;
+      int k = 0;
+      for( ; k + 2 <= n; k += 2 )                   // two steps of k per round: the columns of B come in pairs (ld and j0 * ld are even)
+      {
+         double a0, a1, a2, a3, e0, e1, e2, e3, b00, b01, b10, b11;
+         ld2(Ad + (size_t)k * ld, a0, a1); ld2(Ad + (size_t)k * ld + 2, a2, a3);
+         ld2(Ad + (size_t)(k + 1) * ld, e0, e1); ld2(Ad + (size_t)(k + 1) * ld + 2, e2, e3);
+         ld2(B0 + k, b00, b01); ld2(B1 + k, b10, b11);
+         c00 += a0 * b00; c10 += a1 * b00; c20 += a2 * b00; c30 += a3 * b00;
+         c01 += a0 * b10; c11 += a1 * b10; c21 += a2 * b10; c31 += a3 * b10;
+         c00 += e0 * b01; c10 += e1 * b01; c20 += e2 * b01; c30 += e3 * b01;
+         c01 += e0 * b11; c11 += e1 * b11; c21 += e2 * b11; c31 += e3 * b11;
+      }
+      if( k < n )
+      {
+         double a0, a1, a2, a3;
+         ld2(Ad + (size_t)k * ld, a0, a1); ld2(Ad + (size_t)k * ld + 2, a2, a3);
+         const double b0 = B0[k], b1 = B1[k];
+         c00 += a0 * b0; c10 += a1 * b0; c20 += a2 * b0; c30 += a3 * b0;
+         c01 += a0 * b1; c11 += a1 * b1; c21 += a2 * b1; c31 += a3 * b1;
+      }
+      // the padding rows of C are written as zeros whatever the padding rows of A hold (they take part in the long dot products)
+      if( i0 + 1 >= n ) { c10 = 0.0; c11 = 0.0; }
+      if( i0 + 2 >= n ) { c20 = 0.0; c21 = 0.0; }
+      if( i0 + 3 >= n ) { c30 = 0.0; c31 = 0.0; }
+      double* C0 = C + (size_t)d * stride + (size_t)j0 * ld + i0;
+      C0[0] = c00; C0[1] = c10; C0[2] = c20; C0[3] = c30;
+      if( two ) { C0[ld] = c01; C0[ld + 1] = c11; C0[ld + 2] = c21; C0[ld + 3] = c31; }
+   }
+   __syncthreads();
+}
+
+// M[v_i, v_j] = <A_i, U_j> for the dense variables of one group (v = their variable indices, pairs with v_i >= v_j), A and U stored
+// as cnt contiguous matrices of `stride` doubles with zero padding rows.  One warp per tile of 4 x 4 pairs, the lanes split the
+// elements: every matrix is read once per tile instead of once per pair - with a whole frontier at work (one node per SM) the
+// pair-by-pair version read 17 MB per node and iteration through the L2 and was bound by it.  No barrier at the end.
+__device__ __noinline__ void dense_pair_dots(const int* vars, int cnt, long long stride, const double* A, const double* U, double* M, int ldm)
+{
+   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+   const int nt = (cnt + 3) / 4;
+   for( int t = wid; t < nt * nt; t += NT / 32 )
+   {
+      const int d1 = 4 * (t / nt), d2 = 4 * (t % nt);
+      int imax = -1, jmin = 0x7fffffff;
+      for( int q = 0; q < 4; ++q )
+      {
+         if( d1 + q < cnt ) imax = max(imax, vars[d1 + q]);
+         if( d2 + q < cnt ) jmin = min(jmin, vars[d2 + q]);
+      }
+      if( imax < jmin ) continue;                    // no pair of this tile belongs to the lower triangle
+      // rows beyond cnt repeat the last matrix (computed, not stored)
+      const double* Ab = A + (size_t)d1 * stride;
+      const double* Ub = U + (size_t)d2 * stride;
+      const int st = (int)stride;
+      const int oa1 = (min(d1 + 1, cnt - 1) - d1) * st, oa2 = (min(d1 + 2, cnt - 1) - d1) * st, oa3 = (min(d1 + 3, cnt - 1) - d1) * st;
+      const int ou1 = (min(d2 + 1, cnt - 1) - d2) * st, ou2 = (min(d2 + 2, cnt - 1) - d2) * st, ou3 = (min(d2 + 3, cnt - 1) - d2) * st;
+      double c00 = 0.0, c10 = 0.0, c20 = 0.0, c30 = 0.0, c01 = 0.0, c11 = 0.0, c21 = 0.0, c31 = 0.0;
+      double c02 = 0.0, c12 = 0.0, c22 = 0.0, c32 = 0.0, c03 = 0.0, c13 = 0.0, c23 = 0.0, c33 = 0.0;
+#pragma unroll 1
+      for( int e = lane; e < st; e += 32 )
+      {
+         const double* Ae = Ab + e;
+         const double* Ue = Ub + e;
+         const double a0 = Ae[0], a1 = Ae[oa1], a2 = Ae[oa2], a3 = Ae[oa3];
+         double u = Ue[0];
+         c00 += a0 * u; c10 += a1 * u; c20 += a2 * u; c30 += a3 * u;
+         u = Ue[ou1];
+         c01 += a0 * u; c11 += a1 * u; c21 += a2 * u; c31 += a3 * u;
+         u = Ue[ou2];
+         c02 += a0 * u; c12 += a1 * u; c22 += a2 * u; c32 += a3 * u;
+         u = Ue[ou3];
+         c03 += a0 * u; c13 += a1 * u; c23 += a2 * u; c33 += a3 * u;
+      }
+#define SDPK_PAIR_OUT(q1, q2, acc) do { const double sum_ = wsum(acc); \
+         if( lane == 0 && d1 + q1 < cnt && d2 + q2 < cnt ) { const int vi_ = vars[d1 + q1], vj_ = vars[d2 + q2]; \
+            if( vi_ >= vj_ ) M[(size_t)vj_ * ldm + vi_] = sum_; } } while( 0 )
+      SDPK_PAIR_OUT(0, 0, c00); SDPK_PAIR_OUT(1, 0, c10); SDPK_PAIR_OUT(2, 0, c20); SDPK_PAIR_OUT(3, 0, c30);
+      SDPK_PAIR_OUT(0, 1, c01); SDPK_PAIR_OUT(1, 1, c11); SDPK_PAIR_OUT(2, 1, c21); SDPK_PAIR_OUT(3, 1, c31);
+      SDPK_PAIR_OUT(0, 2, c02); SDPK_PAIR_OUT(1, 2, c12); SDPK_PAIR_OUT(2, 2, c22); SDPK_PAIR_OUT(3, 2, c32);
+      SDPK_PAIR_OUT(0, 3, c03); SDPK_PAIR_OUT(1, 3, c13); SDPK_PAIR_OUT(2, 3, c23); SDPK_PAIR_OUT(3, 3, c33);
+#undef SDPK_PAIR_OUT
+   }
+}
+
+#ifdef SDPK_SCHURTICKS
+__device__ long long g_schur_ticks[8];
+#define SCHURTICK(k) do { __syncthreads(); if( threadIdx.x == 0 ) { long long n_ = clock64(); g_schur_ticks[k] += n_ - tq_; tq_ = n_; } } while( 0 )
+#else
+#define SCHURTICK(k) do { } while( 0 )
+#endif
 __device__ void schur(const SmallArgs& a)
 {
+#ifdef SDPK_SCHURTICKS
+   long long tq_ = clock64();
+#endif
    const int m = a.m, ldm = a.ldm;
    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
    for( int e = threadIdx.x; e < ldm * m; e += NT ) a.M[e] = 0.0;
@@ -289,6 +412,7 @@ __device__ void schur(const SmallArgs& a)
       for( int t = 0; t < ni * nj; ++t ) v += pairterm(a.E, bi + t / nj, bj + t % nj, a.X, a.Sinv);
       a.M[(size_t)j * ldm + i] = v;
    }
+   SCHURTICK(0);
    for( int p = wid; p < npairs; p += NT / 32 )
    {
       int i = (int)((sqrt(8.0 * p + 1.0) - 1.0) * 0.5);
@@ -305,6 +429,7 @@ __device__ void schur(const SmallArgs& a)
       if( lane == 0 ) a.M[(size_t)j * ldm + i] = v;
    }
    __syncthreads();
+   SCHURTICK(1);
    // dense variables: U_d = X A_d S^-1 for all of them, then M_id = A_i . U_d
    for( int g = 0; g < a.ngroups; ++g )
    {
@@ -314,30 +439,24 @@ __device__ void schur(const SmallArgs& a)
       const double* Ad = a.Adense + a.gaoff[g];
       const double* Xk = a.X + bk.off;
       const double* Zk = a.Sinv + bk.off;
-      for( int e = threadIdx.x; e < cnt * n * n; e += NT )         // H_d = X A_d
-      {
-         const int d = e / (n * n), r = e % (n * n), i = r % n, j = r / n;
-         const double* Aj = Ad + (size_t)d * stride + (size_t)j * ld;
-         double s0 = 0.0;
-         for( int k = 0; k < n; ++k ) s0 += Xk[(size_t)k * ld + i] * Aj[k];
-         a.Hd[(size_t)d * stride + (size_t)j * ld + i] = s0;
-      }
-      __syncthreads();
-      for( int e = threadIdx.x; e < cnt * n * n; e += NT )         // U_d = H_d S^-1
-      {
-         const int d = e / (n * n), r = e % (n * n), i = r % n, j = r / n;
-         const double* Hd = a.Hd + (size_t)d * stride;
-         const double* Zj = Zk + (size_t)j * ld;
-         double s0 = 0.0;
-         for( int k = 0; k < n; ++k ) s0 += Hd[(size_t)k * ld + i] * Zj[k];
-         a.Ud[(size_t)d * stride + (size_t)j * ld + i] = s0;
-      }
-      __syncthreads();
+      // H_d = X A_d and U_d = H_d S^-1 with 4 x 2 register tiles, X and S^-1 staged in shared memory (one output per thread with both
+      // operands from global memory made the two products of example_CLS, 33 matrices of order 43, the largest phase of the
+      // iteration: bound by the load path of the SM).  Every output is still one sum over k in ascending order: the values are those of the
+      // one-output loop, bit for bit.  Rows n .. ld - 1 of H_d and U_d are written as zeros (ld is a multiple of 4).
+      dense_product<true>(n, ld, cnt, stride, Xk, Ad, a.Hd);
+      SCHURTICK(2);
+      dense_product<false>(n, ld, cnt, stride, a.Hd, Zk, a.Ud);
+      SCHURTICK(3);
+      // dense x dense pairs of the group: <A_i, U_d> as contiguous dot products over the expanded matrices (the entry list of a dense
+      // matrix costs four index loads and two scattered loads of U per entry), 4 x 4 pairs per warp
+      dense_pair_dots(a.denselist + a.gfirst[g], cnt, stride, Ad, a.Ud, a.M, ldm);
+      SCHURTICK(4);
+      // the other variables against the dense ones of the group: entry lists
       for( int p = wid; p < m * cnt; p += NT / 32 )
       {
          const int i = p / cnt, d = p % cnt;
          const int j = a.denselist[a.gfirst[g] + d];
-         if( a.cls[i] == 2 && i < j ) continue;
+         if( a.cls[i] == 2 && (i < j || a.E.off[a.E.varbeg[i]] == bk.off) ) continue;      // dense of this group: done above
          const double* Uj = a.Ud + (size_t)d * stride;
          double s0 = 0.0;
          for( int e = a.E.varbeg[i] + lane; e < a.E.varbeg[i + 1]; e += 32 )
@@ -353,6 +472,7 @@ __device__ void schur(const SmallArgs& a)
       }
       __syncthreads();
    }
+   SCHURTICK(5);
    // LP block: single-variable rows through the column view (one thread per variable), longer rows one after the other
    for( int j = threadIdx.x; j < m; j += NT )
    {
@@ -399,6 +519,7 @@ __device__ void schur(const SmallArgs& a)
       }
    }
    __syncthreads();
+   SCHURTICK(6);
 }
 
 // Cholesky of M (lower, global memory) with diagonal regularisation `reg`; rdiag receives 1 / l_kk
@@ -1241,6 +1362,11 @@ __device__ __forceinline__ void ipm_small_body(const SmallArgs& a)
       r.phase = c->phase; r.stop = c->stop; r.iterations = c->iter; r.backtracks = c->backtracks;
       r.pobj = c->pobj; r.dobj = c->dobj; r.relgap = c->relgap; r.pinf = c->pinf; r.dinf = c->dinf; r.mu = c->mu;
       *a.out = r;
+#ifdef SDPK_SCHURTICKS
+      if( a.verbose >= 2 )
+         printf("  [schur cycles] zero + light pairs %lld | heavy pairs %lld | X A_d %lld | H_d S^-1 %lld | dense pair dots %lld | entry lists x dense %lld | LP %lld\n",
+            g_schur_ticks[0], g_schur_ticks[1], g_schur_ticks[2], g_schur_ticks[3], g_schur_ticks[4], g_schur_ticks[5], g_schur_ticks[6]);
+#endif
       if( a.verbose >= 2 )
          printf("  [cuda-1cta cycles] resid %lld | fact S,X %lld | tests+Sinv %lld | schur %lld | chol M %lld | directions %lld | step lengths %lld\n",
             pc[0], pc[1], pc[2], pc[3], pc[4], pc[5], pc[6]);
