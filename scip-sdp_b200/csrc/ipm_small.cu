@@ -276,6 +276,9 @@ __device__ __forceinline__ void ld2(const double* p, double& x, double& y)
    x = p[0]; y = p[1];
 #endif
 }
+// (Measured and not kept: staging the streamed operand as well, two matrices at a time by the whole CTA - only 484 of the 1024
+// threads have a tile then, and the 17 stages of example_CLS cost more in barriers than the loads from the L2 did: Schur phase
+// 12.4 M -> 13.7 M cycles.)
 template <bool SHARED_A>
 __device__ __noinline__ void dense_product(int n, int ld, int cnt, long long stride, const double* A, const double* B, double* C)
 {
