@@ -98,7 +98,9 @@ typedef struct sdpcuda_params
    double feastol;       /* primal/dual feasibility tolerance (SCIP_SDPPAR_SDPSOLVERFEASTOL, setParameterEpsilonDash) */
    double objlimit;      /* stop when the lower bound (X-objective) exceeds this; >= 1e20 = off (SCIP_SDPPAR_OBJLIMIT) */
    double lambdastar;    /* scale of the initial point X = S = lambdastar*I; <= 0: computed from the data */
-   double timelimit;     /* seconds; <= 0 or >= 1e20 = none */
+   double timelimit;     /* seconds; <= 0 or >= 1e20 = none.  Checked between the iterations of the multi-kernel path; the one-launch
+                          * kernels (relaxations inside the single-CTA limits, frontier batches, packed solves) run to completion -
+                          * milliseconds, bounded by maxiter - and never report SDPCUDA_STOP_TIMELIMIT */
    double absgaptol;     /* additionally require |pobj - dobj| <= absgaptol (the binding's post-check, sdpisolver_sdpa.cpp:449-451); <= 0 = off */
    int    maxiter;       /* <= 0: default (100) */
    int    setting;       /* 1 fast, 2 medium, 3 stable step-length/centering rules (SCIP_SDPSOLVERSETTING) */
