@@ -416,20 +416,30 @@ __device__ void schur(const SmallArgs& a)
       a.M[(size_t)j * ldm + i] = v;
    }
    SCHURTICK(0);
-   for( int p = wid; p < npairs; p += NT / 32 )
+   // heavier pairs: one warp per pair, the lanes split the entry-pair product.  A warp takes the rows i = wid, wid + 32 warps, ... and
+   // looks at 32 columns j at a time (one per lane, ballot of the heavy ones): walking the pairs one by one cost a square root, six
+   // dependent loads and a branch per pair and warp just to find out that a pair is light (example_MkP: all 4656 of them)
+   for( int i = wid; i < m; i += NT / 32 )
    {
-      int i = (int)((sqrt(8.0 * p + 1.0) - 1.0) * 0.5);
-      while( (i + 1) * (i + 2) / 2 <= p ) ++i;
-      while( i * (i + 1) / 2 > p ) --i;
-      const int j = p - i * (i + 1) / 2;
-      if( a.cls[i] == 2 || a.cls[j] == 2 ) continue;
+      if( a.cls[i] == 2 ) continue;
       const int bi = a.E.varbeg[i], ni = a.E.varbeg[i + 1] - bi;
-      const int bj = a.E.varbeg[j], nj = a.E.varbeg[j + 1] - bj;
-      if( ni * nj <= SCHUR_LIGHT ) continue;
-      double v = 0.0;
-      for( int t = lane; t < ni * nj; t += 32 ) v += pairterm(a.E, bi + t / nj, bj + t % nj, a.X, a.Sinv);
-      v = wsum(v);
-      if( lane == 0 ) a.M[(size_t)j * ldm + i] = v;
+      for( int j0 = 0; j0 <= i; j0 += 32 )
+      {
+         const int jl = j0 + lane;
+         bool heavy = false;
+         if( jl <= i && a.cls[jl] != 2 ) heavy = ni * (a.E.varbeg[jl + 1] - a.E.varbeg[jl]) > SCHUR_LIGHT;
+         unsigned mask = __ballot_sync(0xffffffffu, heavy);
+         while( mask != 0 )
+         {
+            const int j = j0 + __ffs(mask) - 1;
+            mask &= mask - 1;
+            const int bj = a.E.varbeg[j], nj = a.E.varbeg[j + 1] - bj;
+            double v = 0.0;
+            for( int t = lane; t < ni * nj; t += 32 ) v += pairterm(a.E, bi + t / nj, bj + t % nj, a.X, a.Sinv);
+            v = wsum(v);
+            if( lane == 0 ) a.M[(size_t)j * ldm + i] = v;
+         }
+      }
    }
    __syncthreads();
    SCHURTICK(1);
@@ -492,10 +502,43 @@ __device__ void schur(const SmallArgs& a)
    // walks the two column lists (rows ascending) and adds the terms of all common longer rows in row order.  One writer per entry:
    // no barrier between the rows (example_MkP: 30 rows of 15 variables were 30 barriers and read-modify-write round trips per
    // iteration) and the same summation order in every run.
+   // Rows of up to 16 variables go one per warp, all rows side by side (example_MkP: 30 rows of 15 variables were 30 rounds of the
+   // whole CTA with 225 busy threads each: 44 % of its Schur phase); longer rows take the whole CTA, one after the other (the
+   // cardinality row of example_CLS, 33 variables, would keep one warp busy for 34 rounds).
+   constexpr int LP_WARP_PAIRS = 256;
+   for( int l = wid; l < a.nlp; l += NT / 32 )
+   {
+      const int b = a.lpbeg[l], cnt = a.lpbeg[l + 1] - b;
+      if( cnt < 2 || cnt * cnt > LP_WARP_PAIRS ) continue;
+      for( int t = lane; t < cnt * cnt; t += 32 )
+      {
+         const int i = a.lpind[b + t / cnt], j = a.lpind[b + t % cnt];
+         if( i < j ) continue;
+         int pa = a.colbeg[i], ea = a.colbeg[i + 1], pc = a.colbeg[j], ec = a.colbeg[j + 1];
+         double total = 0.0;
+         bool first = true, mine = false;
+         while( pa < ea && pc < ec )
+         {
+            const int ra = a.colrow[pa], rc = a.colrow[pc];
+            if( ra < rc ) ++pa;
+            else if( rc < ra ) ++pc;
+            else
+            {
+               if( a.lpbeg[ra + 1] - a.lpbeg[ra] >= 2 )
+               {
+                  if( first ) { first = false; mine = (ra == l); if( !mine ) break; }
+                  total += (a.x[ra] / a.s[ra]) * a.colval[pa] * a.colval[pc];
+               }
+               ++pa; ++pc;
+            }
+         }
+         if( mine ) a.M[(size_t)j * ldm + i] += total;
+      }
+   }
    for( int l = 0; l < a.nlp; ++l )
    {
       const int b = a.lpbeg[l], cnt = a.lpbeg[l + 1] - b;
-      if( cnt < 2 ) continue;                               // uniform branch
+      if( cnt * cnt <= LP_WARP_PAIRS ) continue;            // uniform branch
       for( int t = threadIdx.x; t < cnt * cnt; t += NT )
       {
          const int i = a.lpind[b + t / cnt], j = a.lpind[b + t % cnt];

@@ -49,6 +49,18 @@ template <class T> inline T shfl(T v, int src)
    return r;
 }
 
+/* every lane of the warp takes part (the kernels only use full masks) */
+inline unsigned ballot(bool pred)
+{
+   Fiber* f = cur;
+   const int ph = f->shflphase++ & 1;
+   warp_slots(ph)[f->tid & 31] = pred ? 1u : 0u;
+   warp_barrier();
+   unsigned m = 0;
+   for( int l = 0; l < 32; ++l ) if( warp_slots(ph)[l] != 0 ) m |= 1u << l;
+   return m;
+}
+
 struct IdxProxy { int which; operator int() const { return which == 0 ? cur->tid : cur_block; } };
 struct Idx3 { IdxProxy x; };
 
@@ -77,6 +89,8 @@ static const cuemu::Idx3 blockIdx = {{1}};
 #define __syncwarp() cuemu::warp_barrier()
 #define __shfl_sync(mask, v, src) cuemu::shfl((v), (src))
 #define __shfl_xor_sync(mask, v, o) cuemu::shfl((v), (cuemu::cur->tid & 31) ^ (o))
+#define __ballot_sync(mask, pred) cuemu::ballot((pred))
+#define __ffs(x) __builtin_ffs((int)(x))
 namespace cuemu { extern long long barrier_releases; }
 /* the kernel's own phase profile (verbose >= 2) then counts block-barrier releases per phase instead of cycles */
 static inline long long clock64() { return cuemu::barrier_releases; }
