@@ -1683,19 +1683,25 @@ static int batch_plan(int count, const sdpcuda_problem* const* probs, const sdpc
       for( int k : tiny ) { P.nodes[k].stagelen = batch_stage_prefix(P.nodes[k], STAGE_BUDGET_TINY); P.stagebytes[0] = std::max(P.stagebytes[0], P.nodes[k].stagelen * sizeof(double)); }
       for( int k : rest ) { P.nodes[k].stagelen = batch_stage_prefix(P.nodes[k], STAGE_BUDGET_SMALL); P.stagebytes[1] = std::max(P.stagebytes[1], P.nodes[k].stagelen * sizeof(double)); }
    }
-   // Schur complements of order 65 .. 112 / 128 (example_MkP: m = 105): the launch reserves room for the packed factor behind the
-   // kernel's own buffers and the staged work space; every node of the launch learns the offset
+   // Schur complements of order 65 .. 112 / 128 (example_MkP: m = 105): the launch reserves room for the packed factor, sized by the
+   // largest such m of the group, and every node of the launch learns the offset.  Without a staged work space the factor starts where
+   // the 64 x 65 tile of the m <= 64 variant lives (the last of the kernel's own buffers; a node uses one of the two) and only the excess
+   // is added to the launch: 64 KB instead of 103 KB per CTA of the 256-thread kernel for example_MkP, three CTAs per SM instead of two
+   // (ncu: profiles/r2c_ncu_full_frontier_kernels_mkp_cls.txt).  With a staged work space the factor goes behind it.
    for( int g = 0; g < 2; ++g )
    {
       const std::vector<int>& grp = (g == 0) ? tiny : rest;
       const int mpk = (g == 0) ? TINY_MPK : SMALL_MPK;
       const size_t own = (g == 0) ? ipm_tiny_smem_bytes() : ipm_small_smem_bytes();
-      bool want = false;
-      for( int k : grp ) want = want || (P.nodes[k].a.m > SMALL_MAX_N && P.nodes[k].a.m <= mpk);
-      const size_t off = (own + P.stagebytes[g] + 15) / 16 * 16;
-      if( !want || off + small_mpk_bytes(mpk) > 225 * 1024 ) continue;
+      int mmax = 0;
+      for( int k : grp ) if( P.nodes[k].a.m > SMALL_MAX_N && P.nodes[k].a.m <= mpk ) mmax = std::max(mmax, P.nodes[k].a.m);
+      if( mmax == 0 ) continue;
+      const size_t off = (P.stagebytes[g] == 0) ? ((g == 0) ? ipm_tiny_msh_offset_bytes() : ipm_small_msh_offset_bytes())
+         : (own + P.stagebytes[g] + 15) / 16 * 16;
+      const size_t end = off + small_mpk_bytes(mmax);
+      if( end > 225 * 1024 ) continue;
       for( int k : grp ) P.nodes[k].a.mpk_off = (long long)(off / sizeof(double));
-      P.stagebytes[g] = off + small_mpk_bytes(mpk) - own;
+      P.stagebytes[g] = end > own ? end - own : 0;
    }
    return SDPCUDA_OK;
 }

@@ -999,8 +999,10 @@ __device__ __noinline__ void solveM_pk(int m, const double* Mp, const double* rd
 // example_TT (m = 27, four CTAs per SM: throughput, not latency) lost 13 %, and the penalty formulations of the boundary tests
 // (Gamma = 1e4 .. 1e6) stopped converging: the substitution is backward stable, the explicit inverse is not.)
 // dynamic shared memory of the body (layout at the top of ipm_small_body)
-constexpr size_t SMALL_SMEM = (2 * VMAXN * LDS + 32 + VMAXN + SMALL_MAX_M + 3 * SMALL_LZ_STEPS + 8 + 2 * (SMALL_LZ_STEPS + 2) * LDS
-   + 2 * (2 * SMALL_LZ_STEPS + 64) + MSN * LDMS + 8) * sizeof(double) + sizeof(Ctl) + 64;
+constexpr size_t SMALL_CTL_BYTES = (8 * sizeof(double) + sizeof(Ctl) + 16 + 15) / 16 * 16;      // lam2, Ctl, flag
+constexpr size_t SMALL_MSH_OFF = 2 * VMAXN * LDS + 32 + VMAXN + SMALL_MAX_M + 3 * SMALL_LZ_STEPS + 8 + 2 * (SMALL_LZ_STEPS + 2) * LDS
+   + 2 * (2 * SMALL_LZ_STEPS + 64) + SMALL_CTL_BYTES / sizeof(double);                             // in doubles
+constexpr size_t SMALL_SMEM = (SMALL_MSH_OFF + MSN * LDMS) * sizeof(double) + 64;
 
 // the complete solve of ONE relaxation by the calling CTA (shared by the one-relaxation kernel and the frontier-batch kernel)
 __device__ __forceinline__ void ipm_small_body(const SmallArgs& a)
@@ -1016,10 +1018,12 @@ __device__ __forceinline__ void ipm_small_body(const SmallArgs& a)
    double* coef = be + SMALL_LZ_STEPS;
    double* lzq = coef + SMALL_LZ_STEPS + 8;         // 2 x (SMALL_LZ_STEPS + 2) x 65 : Krylov vectors of the two warp-level Lanczos runs
    double* lzab = lzq + 2 * (SMALL_LZ_STEPS + 2) * LDS;   // 2 x (32 + 32 + 64)
-   double* Msh = lzab + 2 * (2 * SMALL_LZ_STEPS + 64);     // 64 x 65 : factor of the Schur complement when m <= 64
-   double* lam2 = Msh + MSN * LDMS;                 // 2 results
+   double* lam2 = lzab + 2 * (2 * SMALL_LZ_STEPS + 64);   // 2 results
    Ctl* c = reinterpret_cast<Ctl*>(lam2 + 8);
-   int* flag = reinterpret_cast<int*>(c + 1);
+   int* flag = reinterpret_cast<int*>(reinterpret_cast<char*>(lam2) + SMALL_CTL_BYTES - 16);
+   // 64 x 65 : factor of the Schur complement when m <= 64.  LAST of the kernel's own buffers: a frontier launch that stages no work
+   // space puts the packed factor of the nodes with m > 64 at the same place (a node needs one of the two), see batch_plan
+   double* Msh = smem + SMALL_MSH_OFF;
    const bool msmall = (a.m <= MSN);
    double* const Mpk = smem + a.mpk_off;                                   // packed factor, reserved by the launch when mpk_off > 0
    const bool mpacked = !msmall && a.mpk_off > 0 && a.m <= MPK;
@@ -1503,6 +1507,7 @@ cudaError_t launch_ipm_small(cudaStream_t st, const SmallArgs& a)
 }
 
 size_t ipm_small_smem_bytes() { return SMALL_SMEM; }
+size_t ipm_small_msh_offset_bytes() { return SMALL_MSH_OFF * sizeof(double); }
 
 cudaError_t launch_ipm_small_batch(cudaStream_t st, int count, const SmallArgs* dev_args, size_t stage_bytes)
 {
@@ -1525,6 +1530,7 @@ cudaError_t launch_ipm_small_batch(cudaStream_t st, int count, const SmallArgs* 
 #else
 
 size_t ipm_tiny_smem_bytes() { return SMALL_SMEM; }
+size_t ipm_tiny_msh_offset_bytes() { return SMALL_MSH_OFF * sizeof(double); }
 
 cudaError_t launch_ipm_tiny_batch(cudaStream_t st, int count, const SmallArgs* dev_args, size_t stage_bytes)
 {

@@ -71,6 +71,8 @@ cudaError_t launch_ipm_small_batch(cudaStream_t st, int count, const SmallArgs* 
 cudaError_t launch_ipm_tiny_batch(cudaStream_t st, int count, const SmallArgs* dev_args, size_t stage_bytes = 0);
 // shared memory the two batch kernels use for themselves (the staged work space of a node comes on top)
 size_t ipm_small_smem_bytes();
+size_t ipm_small_msh_offset_bytes();      // where the 64 x 65 tile of the Schur factor (m <= 64) starts: the last of the kernel's own buffers
+size_t ipm_tiny_msh_offset_bytes();
 size_t ipm_tiny_smem_bytes();
 
 } // namespace sdpk
