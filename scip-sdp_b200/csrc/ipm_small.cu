@@ -758,7 +758,11 @@ __device__ double lanczos_warp(int n, const double* Bs, double* Qs, double* ab, 
       const double alpha = wsum(w0 * v0 + w1 * v1);
       w0 -= alpha * v0 + bprev * p0;
       w1 -= alpha * v1 + bprev * p1;
-      // full re-orthogonalisation, twice: lane q forms the inner product with vector q (q <= j <= 31), then all lanes update
+      // full re-orthogonalisation: lane q forms the inner product with vector q (q <= j <= 31), then all lanes update.  A second pass
+      // only if the first one took away more than half of the squared norm ("twice is enough", Daniel-Gragg-Kaufman-Stewart: without
+      // cancellation the second pass changes w by rounding errors only; it was a third of the cost of a step)
+      double nrm2 = wsum(w0 * w0 + w1 * w1);
+      double beta = 0.0;
       for( int pass = 0; pass < 2; ++pass )
       {
          if( h0 ) ws[r0] = w0;
@@ -777,8 +781,11 @@ __device__ double lanczos_warp(int n, const double* Bs, double* Qs, double* ab, 
             if( h1 ) w1 -= c * Qs[q * LDS + r1];
          }
          __syncwarp();
+         const double after2 = wsum(w0 * w0 + w1 * w1);
+         beta = sqrt(after2);
+         if( after2 >= 0.5 * nrm2 ) break;            // uniform over the warp (wsum leaves the same value in every lane)
+         nrm2 = after2;
       }
-      const double beta = sqrt(wsum(w0 * w0 + w1 * w1));
       if( lane == 0 ) { al[j] = alpha; be[j] = beta; }
       kdone = j + 1;
       if( beta <= 1e-13 * (fabs(alpha) + bprev + 1e-300) ) break;
