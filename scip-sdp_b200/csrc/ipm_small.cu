@@ -774,9 +774,14 @@ __device__ double lanczos_warp(int n, const double* Bs, double* Qs, double* ab, 
             const double* vq = Qs + lane * LDS;
             for( int i = 0; i < n; ++i ) cq += ws[i] * vq[i];
          }
+         // the j + 1 coefficients go through shared memory (w has been read by everybody): a broadcast load per term instead of a
+         // shuffle in the dependent chain
+         __syncwarp();
+         if( lane <= j ) ws[lane] = cq;
+         __syncwarp();
          for( int q = 0; q <= j; ++q )
          {
-            const double c = __shfl_sync(0xffffffffu, cq, q);
+            const double c = ws[q];
             if( h0 ) w0 -= c * Qs[q * LDS + r0];
             if( h1 ) w1 -= c * Qs[q * LDS + r1];
          }
