@@ -295,3 +295,31 @@ def test_parameters_reach_the_packed_kernel(lib, emu, extra):
     ref = abi.Solver(abi.Lib(abi.ORACLE_LIB)).solve(fp, **kw)
     assert (r["phase_name"], r["stop_name"], r["iterations"]) == (ref["phase_name"], ref["stop_name"], ref["iterations"])
     assert abs(r["dobj"] - ref["dobj"]) <= 1e-7 * max(1.0, abs(ref["dobj"]))
+
+
+def test_packed_factor_shares_the_tile_of_the_small_schur_complements(lib, emu):
+    """frontier launch of the 256-thread kernel with Schur complements above 64 (example_MkP, m = 105) next to small ones (example_TT):
+    the plan puts the packed factor where the 64 x 65 tile of the m <= 64 variant lives and adds only the excess to the launch
+    (three CTAs per SM instead of two on a B200: 64 KB instead of 103 KB per CTA); the emulator guards the shared memory, the bounds
+    match the oracle"""
+    K = misdp.read_sdpa(os.path.join(GOLDEN, "example_MkP.dat-s.gz")).rows_to_bounds().flatten()[0]
+    T = misdp.read_sdpa(os.path.join(GOLDEN, "example_TT.dat-s.gz")).rows_to_bounds().flatten()[0]
+    assert K.m == 105
+    probs = [T, K, T]
+    par = lib.default_params(**KW)
+    F = lib.lib.sdpcuda_debug_pack_batch
+    structs = [p.struct() for p in probs]
+    ps = (C.POINTER(abi.Problem) * 3)(*[C.pointer(s) for s in structs])
+    nimg, nwork, ny, nb, nt = C.c_size_t(0), C.c_size_t(0), C.c_size_t(0), C.c_int(0), C.c_int(0)
+    stagebytes = (C.c_size_t * 2)()
+    got, nbatched, ntiny = run_planned_batch(lib, emu, probs, True, **KW)        # sets the argument types of F
+    assert nbatched == 3 and ntiny == 3
+    assert F(3, ps, C.byref(par), 1, 0, 0, 0, 0, None, 0, C.byref(nimg), C.byref(nwork), C.byref(ny), None, 0, C.byref(nb), C.byref(nt), None, None,
+             stagebytes) == 0
+    packed = 8 * (105 * 106 // 2 + 2)
+    tile = 8 * 64 * 65
+    assert stagebytes[1] == 0 and packed - tile - 64 <= stagebytes[0] <= packed - tile + 256, (stagebytes[0], packed - tile)      # (64 bytes of slack end the kernel's own buffers)
+    cpu = abi.Solver(abi.Lib(abi.ORACLE_LIB))
+    for i, r in got.items():
+        _compare(probs[i], r, cpu.solve(probs[i], **KW))
+    assert got[0]["dobj"] == got[2]["dobj"] and np.array_equal(got[0]["y"], got[2]["y"])
